@@ -1,0 +1,177 @@
+/*
+ * salt_b200.h -- C ABI of libsalt_b200.so, the B200 (sm_100a) engine for salt's
+ * SNP-aware verification / extension hot path.
+ *
+ * Plain C, opaque handle, int return codes, no exit() inside the library.  Every entry
+ * point names the reference interface it stands in for (paths relative to the reference
+ * tree's Align_src/).  There is no CPU fallback: without a CUDA device every compute
+ * entry point fails with SALT_ERR_NODEVICE.
+ *
+ * Data conventions (all from the reference):
+ *   mixRef : uint32 words, 4 bit/base allele mask A=1 C=2 G=4 T=8, base p in bits
+ *            4*(p%8).. of word p/8                       (metaref.h:2-5, metaref.c:54-56)
+ *   pac    : 2 bit/base, base p in bits ((~p&3)<<1) of byte p>>2       (alnpe.c:47)
+ *   reads  : codes A,C,G,T,N = 0..4, one byte per base                 (query.c:177-181)
+ *   strand : 0 = read as given, 1 = reverse complement                 (query.c:46-64)
+ */
+#ifndef SALT_B200_H
+#define SALT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SALT_B200_ABI_VERSION 1
+
+enum {
+    SALT_OK = 0,
+    SALT_ERR_ARG = -101,          /* bad argument */
+    SALT_ERR_CUDA = -102,         /* a CUDA call failed; see salt_b200_last_error() */
+    SALT_ERR_NOMEM = -103,
+    SALT_ERR_UNSUPPORTED = -104,  /* parameters outside what the kernels reproduce exactly */
+    SALT_ERR_NODEVICE = -105      /* no usable CUDA device: there is no CPU path */
+};
+
+typedef struct salt_b200 salt_b200_t;
+
+/* (read, candidate locus) pair.  rs = (read_id << 1) | strand. */
+typedef struct { uint32_t rs; uint32_t pos; } salt_pair_t;
+
+/* One chunk of reads (alnse.c:1414 reads N_SEQS=100000 at a time; any size works). */
+typedef struct {
+    const uint8_t *codes;    /* concatenated codes 0..4 */
+    const uint32_t *offs;    /* n_reads+1 offsets into codes */
+    uint32_t n_reads;
+} salt_reads_t;
+
+/* Sorted candidate loci per read and strand, CSR (what alnse_locate[_alt] leaves in
+ * aux->loci, alnse.c:501-731). */
+typedef struct {
+    const uint32_t *offs[2];  /* n_reads+1 each */
+    const uint32_t *loci[2];
+} salt_cands_t;
+
+/* Mate-rescue window: read rs against reference bases [start, end] inclusive
+ * (alnpe.c:213-252 compute start/end; alnpe.c:261 / :330 consume them). */
+typedef struct { uint32_t rs; uint32_t start; uint32_t end; } salt_win_t;
+
+/* s_align (ssw.h:37-47) without the heap pointer. */
+typedef struct {
+    uint16_t score1, score2;
+    int32_t ref_begin1, ref_end1, read_begin1, read_end1, ref_end2;
+    int32_t cigarLen;
+} salt_ssw_out_t;
+
+/* Per-read outcome of the verification stage: the query_t fields that
+ * alnse_check_nogap / alnse_check_withgap set (alnse.c:348-393), plus hit counts. */
+typedef struct {
+    uint32_t pos;        /* 0xFFFFFFFF = unmapped (query.c:202) */
+    uint8_t strand;      /* 3 = unset (query.c:204) */
+    uint8_t n_diff;      /* 255 = unset */
+    uint8_t is_gap;      /* 255 = unset */
+    uint8_t lv_ran;      /* 1 if the gapped stage ran for this read */
+    int32_t n_hits[2];   /* accepted candidates per strand (aux->hits) */
+} salt_verify_out_t;
+
+const char *salt_b200_last_error(void);
+int salt_b200_abi_version(void);
+int salt_b200_device_count(void);
+
+/* Upload the SNP-aware reference (and optionally the 2-bit pac) once.
+ * Stands in for the in-memory mixRef/pac that alnse_index_reload builds (indexio.c:23-50). */
+salt_b200_t *salt_b200_init(const uint32_t *mixref, uint32_t l, const uint8_t *pac, int64_t l_pac, int device);
+void salt_b200_destroy(salt_b200_t *h);
+
+/* Build the SNP-aware reference on the device from raw bases and SNP rows instead of
+ * uploading it: Index_src/mixRef.c:93-197 (build_mixRef) + Index_src/hapmap.c:92-158.
+ * bases: ASCII, all records concatenated; snp_pos: 0-based global positions; snp_mask: allele
+ * masks (low 4 bits used).  Returns a handle owning the device copy; salt_b200_get_mixref
+ * downloads the words (file layout of PREFIX.ref minus the length word). */
+salt_b200_t *salt_b200_init_from_bases(const char *bases, uint32_t l, const uint32_t *snp_pos,
+                                       const uint8_t *snp_mask, size_t n_snp, int device);
+int salt_b200_get_mixref(salt_b200_t *h, uint32_t *words_out, size_t n_words);
+
+/* Use an existing CUDA stream (cudaStream_t) for all work of this handle; NULL = own stream. */
+int salt_b200_set_stream(salt_b200_t *h, void *cuda_stream);
+int salt_b200_sync(salt_b200_t *h);
+
+/* Pinned host memory for the caller's queues. */
+void *salt_b200_host_alloc(size_t bytes);
+void salt_b200_host_free(void *p);
+
+/* Upload + pack one chunk of reads (both strands) into HBM.  Pair/window `rs` fields
+ * index into the current chunk. */
+int salt_b200_set_reads(salt_b200_t *h, const salt_reads_t *reads);
+
+/* Batched ed_mismatch (editdistance.c:88): out[i] = n if n <= max_err else -1.
+ * Pairs with pos + l_seq > l give -1 (the reference leaves that to its callers). */
+int salt_b200_mismatch(salt_b200_t *h, const salt_pair_t *pairs, size_t n, int max_err, int8_t *out);
+
+/* Batched ed_diff -> computeEditDistance (editdistance.c:174, LandauVishkin.c:19) with
+ * l_ref = l_seq + 4 (alnse.c:373).  k < 0 means l_seq/10 per read (alnse.c:1090).
+ * out[i] = e <= min(k,30), or -1. */
+int salt_b200_lv(salt_b200_t *h, const salt_pair_t *pairs, size_t n, int k, int8_t *out);
+
+/* Batched ed_diff_withcigar -> computeEditDistanceWithCigar, useM=1, COMPACT_CIGAR_STRING
+ * (editdistance.c:234, LandauVishkin.c:176; call sites query.c:288, sam.c:218).
+ * k_each[i] must be < 31.  cigars: n buffers of `stride` bytes, written like the reference
+ * writes its caller's buffer (NUL-terminated string; bytes after it untouched).
+ * out[i] = e, -1 (not within k) or -2 (buffer too small). */
+int salt_b200_lv_cigar(salt_b200_t *h, const salt_pair_t *pairs, const uint8_t *k_each, size_t n,
+                       char *cigars, int stride, int8_t *out);
+
+/* Batched ssw_init(score_size=1) + ssw_align (ssw.c:742, :771) on reference windows.
+ * use_pac = 0: window symbols are mixRef masks, read symbol = 1<<code (N -> 16), the
+ *              snpaln_sw_snpaware call (alnpe.c:261-293);
+ * use_pac = 1: window symbols are 2-bit pac codes, read symbol = code, the snpaln_sw call
+ *              (alnpe.c:330-351).
+ * mat has n_sym*n_sym entries and is indexed mat[ref_sym*n_sym + read_sym] exactly as
+ * ssw.c:361 does; an index of n_sym*n_sym (read N against mask 15, which the reference
+ * reads one past its array) is scored as mat[n_sym*n_sym-1].
+ * mask_len < 0 means l_seq/2 (alnpe.c:287).  Requires gapO > gapE.
+ * cigars: n * cigar_stride uint32 (len<<4|op, op 0/1/2 = M/I/D); out[i].cigarLen is the
+ * true length even if it exceeds cigar_stride. */
+int salt_b200_ssw(salt_b200_t *h, const salt_win_t *wins, size_t n, int use_pac,
+                  const int8_t *mat, int n_sym, int gapO, int gapE, int flag,
+                  int filters, int filterd, int mask_len,
+                  salt_ssw_out_t *out, uint32_t *cigars, int cigar_stride);
+
+/* The whole verification stage for a chunk, as alnse_overlap_alt (SE) / alnse_overlap (PE)
+ * run it after seeding (alnse.c:1077-1097 / :1014-1036):
+ *   nogap on strand 0 then 1 with threshold nogap_T0 (3) tightening as candidates are
+ *   accepted; if neither strand matched, the gapped stage with lv_T0 (< 0: l_seq/10, the SE
+ *   rule; 3 is the PE rule); then CIGARs for gapped primaries (query.c:282).
+ * acc[s][i] (one per candidate, same order as cands->loci[s]) = accepted n_diff or -1;
+ * together with rec[] that is exactly aux->hits + the primary.  cigars: n_reads buffers of
+ * `cigar_stride` bytes (query->cigar, 128 in the reference), written only for gapped
+ * primaries. acc / cigars may be NULL. */
+int salt_b200_verify(salt_b200_t *h, const salt_cands_t *cands, int nogap_T0, int lv_T0,
+                     salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1,
+                     char *cigars, int cigar_stride);
+
+/* Widest rescue window (in bases) the *_dev SSW entry point must handle; the host entry point
+ * sets it from its arguments.  Default 1024. */
+int salt_b200_set_max_window(salt_b200_t *h, int cols);
+
+/* ---- device-resident variants (inputs already in HBM; asynchronous on the handle's
+ * stream; used for kernel-level measurement and by callers that keep queues on the GPU) */
+int salt_b200_mismatch_dev(salt_b200_t *h, const salt_pair_t *d_pairs, size_t n, int max_err, int8_t *d_out);
+int salt_b200_lv_dev(salt_b200_t *h, const salt_pair_t *d_pairs, size_t n, int k, int8_t *d_out);
+int salt_b200_verify_dev(salt_b200_t *h, const uint32_t *d_offs0, const uint32_t *d_loci0, size_t n0,
+                         const uint32_t *d_offs1, const uint32_t *d_loci1, size_t n1,
+                         int nogap_T0, int lv_T0, salt_verify_out_t *d_rec, int8_t *d_acc0, int8_t *d_acc1,
+                         char *d_cigars, int cigar_stride);
+int salt_b200_ssw_dev(salt_b200_t *h, const salt_win_t *d_wins, size_t n, int use_pac,
+                      const int8_t *mat, int n_sym, int gapO, int gapE, int flag,
+                      int filters, int filterd, int mask_len,
+                      salt_ssw_out_t *d_out, uint32_t *d_cigars, int cigar_stride);
+
+/* Counters for benchmarking: kernels launched by this handle since the last reset. */
+uint64_t salt_b200_launch_count(salt_b200_t *h, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SALT_B200_H */

@@ -1,0 +1,236 @@
+"""ctypes binding of libsalt_b200.so (include/salt_b200.h) with numpy in/out.
+
+This is the call a Python user makes; it only forwards to the C ABI.  `load()` opens the
+CUDA library built in-tree and refuses to work without it or without a GPU -- there is no
+CPU implementation behind this module.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsalt_b200.so")
+
+SALT_OK = 0
+ERRORS = {-101: "SALT_ERR_ARG", -102: "SALT_ERR_CUDA", -103: "SALT_ERR_NOMEM",
+          -104: "SALT_ERR_UNSUPPORTED", -105: "SALT_ERR_NODEVICE"}
+
+PAIR_DT = np.dtype([("rs", np.uint32), ("pos", np.uint32)])
+WIN_DT = np.dtype([("rs", np.uint32), ("start", np.uint32), ("end", np.uint32)])
+SSW_DT = np.dtype([("score1", np.uint16), ("score2", np.uint16), ("ref_begin1", np.int32), ("ref_end1", np.int32),
+                   ("read_begin1", np.int32), ("read_end1", np.int32), ("ref_end2", np.int32), ("cigarLen", np.int32)])
+VERIFY_DT = np.dtype([("pos", np.uint32), ("strand", np.uint8), ("n_diff", np.uint8), ("is_gap", np.uint8),
+                      ("lv_ran", np.uint8), ("n_hits", np.int32, (2,))])
+assert PAIR_DT.itemsize == 8 and WIN_DT.itemsize == 12 and SSW_DT.itemsize == 28 and VERIFY_DT.itemsize == 16
+
+
+class SaltError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s (%d): %s" % (ERRORS.get(code, "error"), code, msg))
+        self.code = code
+
+
+class ReadsT(C.Structure):
+    _fields_ = [("codes", C.c_void_p), ("offs", C.c_void_p), ("n_reads", C.c_uint32)]
+
+
+class CandsT(C.Structure):
+    _fields_ = [("offs", C.c_void_p * 2), ("loci", C.c_void_p * 2)]
+
+
+def _declare(L):
+    vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
+    L.salt_b200_last_error.restype = C.c_char_p
+    L.salt_b200_init.restype = vp
+    L.salt_b200_init.argtypes = [vp, C.c_uint32, vp, C.c_int64, i32]
+    L.salt_b200_init_from_bases.restype = vp
+    L.salt_b200_init_from_bases.argtypes = [vp, C.c_uint32, vp, vp, sz, i32]
+    L.salt_b200_get_mixref.argtypes = [vp, vp, sz]
+    L.salt_b200_destroy.argtypes = [vp]
+    L.salt_b200_destroy.restype = None
+    L.salt_b200_set_stream.argtypes = [vp, vp]
+    L.salt_b200_sync.argtypes = [vp]
+    L.salt_b200_host_alloc.restype = vp
+    L.salt_b200_host_alloc.argtypes = [sz]
+    L.salt_b200_host_free.argtypes = [vp]
+    L.salt_b200_host_free.restype = None
+    L.salt_b200_set_reads.argtypes = [vp, C.POINTER(ReadsT)]
+    L.salt_b200_mismatch.argtypes = [vp, vp, sz, i32, vp]
+    L.salt_b200_lv.argtypes = [vp, vp, sz, i32, vp]
+    L.salt_b200_lv_cigar.argtypes = [vp, vp, vp, sz, vp, i32, vp]
+    L.salt_b200_ssw.argtypes = [vp, vp, sz, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32]
+    L.salt_b200_verify.argtypes = [vp, C.POINTER(CandsT), i32, i32, vp, vp, vp, vp, i32]
+    L.salt_b200_set_max_window.argtypes = [vp, i32]
+    L.salt_b200_mismatch_dev.argtypes = [vp, vp, sz, i32, vp]
+    L.salt_b200_lv_dev.argtypes = [vp, vp, sz, i32, vp]
+    L.salt_b200_verify_dev.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, i32, vp, vp, vp, vp, i32]
+    L.salt_b200_ssw_dev.argtypes = [vp, vp, sz, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32]
+    L.salt_b200_launch_count.restype = C.c_uint64
+    L.salt_b200_launch_count.argtypes = [vp, i32]
+    return L
+
+
+_lib = None
+
+
+def load():
+    """Open the CUDA library.  Raises if it was not built or no device is visible."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SaltError(-105, "libsalt_b200.so is not built (python -m salt_b200.build); there is no CPU fallback")
+        _lib = _declare(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def salt_score_mat2():
+    """salt's 16x16 SNP-aware SSW matrix as alnpe.c:58-73 lays it out (rule, not a copy):
+    rows 1,2,4,8 score +1 where the column shares the row's bit, everything else -3."""
+    m = np.full((16, 16), -3, np.int8)
+    for r in (1, 2, 4, 8):
+        for c in range(16):
+            if c & r:
+                m[r, c] = 1
+    return m.ravel().copy()
+
+
+def salt_score_mat():
+    """salt's 5x5 matrix for the 2-bit reference (alnpe.c:52-56): +1 / -3, N scores -1."""
+    m = np.full((5, 5), -3, np.int8)
+    m[np.arange(4), np.arange(4)] = 1
+    m[4, :] = -1
+    m[:, 4] = -1
+    return m.ravel().copy()
+
+
+class Engine:
+    """One handle = one GPU with the reference resident in HBM."""
+
+    def __init__(self, mixref, l, pac=None, l_pac=0, device=0, lib=None):
+        self.L = lib if lib is not None else load()
+        self.mixref = np.ascontiguousarray(mixref, np.uint32)
+        pac = None if pac is None else np.ascontiguousarray(pac, np.uint8)
+        self.h = self.L.salt_b200_init(_ptr(self.mixref), int(l), _ptr(pac), int(l_pac), int(device))
+        if not self.h:
+            code = -105 if b"no CUDA device" in self.L.salt_b200_last_error() else -102
+            raise SaltError(code, self.L.salt_b200_last_error().decode())
+        self.l = int(l)
+        self.n_reads = 0
+
+    @classmethod
+    def from_bases(cls, bases, snp_pos, snp_mask, device=0, lib=None):
+        self = cls.__new__(cls)
+        self.L = lib if lib is not None else load()
+        b = np.frombuffer(bases.encode() if isinstance(bases, str) else bases, np.uint8)
+        snp_pos = np.ascontiguousarray(snp_pos, np.uint32); snp_mask = np.ascontiguousarray(snp_mask, np.uint8)
+        self.h = self.L.salt_b200_init_from_bases(_ptr(b), len(b), _ptr(snp_pos), _ptr(snp_mask), len(snp_pos), int(device))
+        if not self.h:
+            raise SaltError(-102, self.L.salt_b200_last_error().decode())
+        self.l = len(b); self.n_reads = 0
+        return self
+
+    def _ck(self, rc):
+        if rc != SALT_OK:
+            raise SaltError(rc, self.L.salt_b200_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.salt_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def get_mixref(self):
+        out = np.zeros((self.l + 7) // 8, np.uint32)
+        self._ck(self.L.salt_b200_get_mixref(self.h, _ptr(out), len(out)))
+        return out
+
+    def set_stream(self, stream_ptr):
+        self._ck(self.L.salt_b200_set_stream(self.h, stream_ptr))
+
+    def sync(self):
+        self._ck(self.L.salt_b200_sync(self.h))
+
+    def launch_count(self, reset=False):
+        return int(self.L.salt_b200_launch_count(self.h, int(reset)))
+
+    # ---- reads -------------------------------------------------------------------
+    def set_reads(self, codes, offs=None):
+        """codes: [n, L] uint8 matrix, or flat uint8 with offs (n+1 uint32)."""
+        codes = np.ascontiguousarray(codes, np.uint8)
+        if offs is None:
+            n, L = codes.shape
+            offs = (np.arange(n + 1, dtype=np.uint64) * L).astype(np.uint32)
+            codes = codes.reshape(-1)
+        offs = np.ascontiguousarray(offs, np.uint32)
+        r = ReadsT(_ptr(codes), _ptr(offs), len(offs) - 1)
+        self._ck(self.L.salt_b200_set_reads(self.h, C.byref(r)))
+        self.n_reads = len(offs) - 1
+
+    # ---- per-pair kernels ----------------------------------------------------------
+    @staticmethod
+    def make_pairs(read_ids, strands, pos):
+        p = np.zeros(len(pos), PAIR_DT)
+        p["rs"] = (np.asarray(read_ids, np.uint32) << 1) | np.asarray(strands, np.uint32)
+        p["pos"] = pos
+        return p
+
+    def mismatch(self, pairs, max_err=3):
+        pairs = np.ascontiguousarray(pairs, PAIR_DT)
+        out = np.empty(len(pairs), np.int8)
+        self._ck(self.L.salt_b200_mismatch(self.h, _ptr(pairs), len(pairs), int(max_err), _ptr(out)))
+        return out
+
+    def lv(self, pairs, k=-1):
+        pairs = np.ascontiguousarray(pairs, PAIR_DT)
+        out = np.empty(len(pairs), np.int8)
+        self._ck(self.L.salt_b200_lv(self.h, _ptr(pairs), len(pairs), int(k), _ptr(out)))
+        return out
+
+    def lv_cigar(self, pairs, k_each, stride=128, fill=0):
+        pairs = np.ascontiguousarray(pairs, PAIR_DT)
+        k_each = np.ascontiguousarray(k_each, np.uint8)
+        out = np.empty(len(pairs), np.int8)
+        buf = np.full((len(pairs), stride), fill, np.uint8)
+        self._ck(self.L.salt_b200_lv_cigar(self.h, _ptr(pairs), _ptr(k_each), len(pairs), _ptr(buf), int(stride), _ptr(out)))
+        return out, buf
+
+    def ssw(self, wins, mat, n_sym=16, use_pac=False, gapO=3, gapE=1, flag=2, filters=0, filterd=20,
+            mask_len=-1, cigar_stride=64):
+        wins = np.ascontiguousarray(wins, WIN_DT)
+        mat = np.ascontiguousarray(mat, np.int8)
+        out = np.zeros(len(wins), SSW_DT)
+        cig = np.zeros((len(wins), cigar_stride), np.uint32)
+        self._ck(self.L.salt_b200_ssw(self.h, _ptr(wins), len(wins), int(use_pac), _ptr(mat), int(n_sym), int(gapO),
+                                      int(gapE), int(flag), int(filters), int(filterd), int(mask_len),
+                                      _ptr(out), _ptr(cig), int(cigar_stride)))
+        return out, cig
+
+    # ---- verification stage ----------------------------------------------------------
+    def verify(self, offs0, loci0, offs1, loci1, nogap_T0=3, lv_T0=-1, cigar_stride=128, want_cigars=True):
+        offs0 = np.ascontiguousarray(offs0, np.uint32); offs1 = np.ascontiguousarray(offs1, np.uint32)
+        loci0 = np.ascontiguousarray(loci0, np.uint32); loci1 = np.ascontiguousarray(loci1, np.uint32)
+        c = CandsT()
+        c.offs[0], c.offs[1] = _ptr(offs0), _ptr(offs1)
+        c.loci[0], c.loci[1] = _ptr(loci0) if len(loci0) else None, _ptr(loci1) if len(loci1) else None
+        rec = np.zeros(self.n_reads, VERIFY_DT)
+        acc0 = np.empty(len(loci0), np.int8); acc1 = np.empty(len(loci1), np.int8)
+        cig = np.zeros((self.n_reads, cigar_stride), np.uint8) if want_cigars else None
+        self._ck(self.L.salt_b200_verify(self.h, C.byref(c), int(nogap_T0), int(lv_T0), _ptr(rec), _ptr(acc0), _ptr(acc1),
+                                         _ptr(cig), int(cigar_stride)))
+        return rec, acc0, acc1, cig
+
+
+def cstr(row):
+    """NUL-terminated bytes in a uint8 row -> str."""
+    b = bytes(row)
+    return b.split(b"\0")[0].decode()

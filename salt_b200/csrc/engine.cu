@@ -1,0 +1,534 @@
+// engine.cu -- the C ABI of libsalt_b200.so (include/salt_b200.h): device residency of the
+// reference and the current read chunk, staging of batches, and the verification pipeline.
+// There is deliberately no CPU implementation behind any entry point.
+#if !defined(SALT_EMUL)
+#include <cuda_runtime.h>
+#endif
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace salt;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    else snprintf(buf, sizeof buf, "%s", what);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(SALT_ERR_CUDA, #call, e_); } while (0)
+
+// growable device buffer
+struct DBuf {
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t need(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+        size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return e;
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+}  // namespace
+
+struct salt_b200 {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    uint32_t *d_mixref = nullptr; uint32_t l = 0;
+    uint8_t *d_pac = nullptr; int64_t l_pac = 0;
+    // current read chunk
+    DBuf codes, offs, rd4, rd_len;
+    uint32_t n_reads = 0, W64 = 0, l_max = 0;
+    // staging / scratch
+    DBuf pairs, out8, kbuf, cig, wins, sswout, sswcig, sswscratch;
+    DBuf c_offs0, c_loci0, c_offs1, c_loci1, vpairs, acc, rec, lvlist, ciglist, counters;
+    uint64_t launches = 0;
+    int max_window = 1024;      // widest rescue window the SSW scratch is sized for
+
+    DevCtx ctx() const
+    {
+        DevCtx c;
+        c.mixref = d_mixref; c.l = l; c.pac = d_pac; c.l_pac = l_pac;
+        c.rd4 = rd4.as<uint64_t>(); c.rd_len = rd_len.as<uint16_t>();
+        c.n_reads = n_reads; c.W64 = W64; c.l_max = l_max;
+        return c;
+    }
+};
+
+namespace {
+
+int use_device(salt_b200_t *h)
+{
+    if (!h) return fail(SALT_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    return SALT_OK;
+}
+
+salt_b200_t *new_handle(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) { fail(SALT_ERR_NODEVICE, "no CUDA device available (libsalt_b200 has no CPU path)", e); return nullptr; }
+    if (device < 0 || device >= n) { fail(SALT_ERR_ARG, "device index out of range"); return nullptr; }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { fail(SALT_ERR_CUDA, "cudaSetDevice", e); return nullptr; }
+    salt_b200_t *h = new (std::nothrow) salt_b200();
+    if (!h) { fail(SALT_ERR_NOMEM, "out of host memory"); return nullptr; }
+    h->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        fail(SALT_ERR_CUDA, "cudaStreamCreate", e); delete h; return nullptr;
+    }
+    return h;
+}
+
+const size_t REF_PAD = 256;   // zero bytes after the reference so vector loads may run past the end
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char *salt_b200_last_error(void) { return g_err.c_str(); }
+int salt_b200_abi_version(void) { return SALT_B200_ABI_VERSION; }
+
+int salt_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+salt_b200_t *salt_b200_init(const uint32_t *mixref, uint32_t l, const uint8_t *pac, int64_t l_pac, int device)
+{
+    if (!mixref || l == 0) { fail(SALT_ERR_ARG, "mixref is null or empty"); return nullptr; }
+    salt_b200_t *h = new_handle(device);
+    if (!h) return nullptr;
+    const size_t nb = ((size_t)l + 7) / 8 * 4;
+    cudaError_t e;
+    if ((e = cudaMalloc(&h->d_mixref, nb + REF_PAD)) != cudaSuccess ||
+        (e = cudaMemsetAsync(reinterpret_cast<uint8_t *>(h->d_mixref) + nb, 0, REF_PAD, h->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(h->d_mixref, mixref, nb, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) {
+        fail(SALT_ERR_CUDA, "upload mixref", e); salt_b200_destroy(h); return nullptr;
+    }
+    h->l = l;
+    if (pac && l_pac > 0) {
+        const size_t pb = ((size_t)l_pac + 3) / 4;
+        if ((e = cudaMalloc(&h->d_pac, pb + REF_PAD)) != cudaSuccess ||
+            (e = cudaMemsetAsync(h->d_pac + pb, 0, REF_PAD, h->stream)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(h->d_pac, pac, pb, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) {
+            fail(SALT_ERR_CUDA, "upload pac", e); salt_b200_destroy(h); return nullptr;
+        }
+        h->l_pac = l_pac;
+    }
+    if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) { fail(SALT_ERR_CUDA, "sync", e); salt_b200_destroy(h); return nullptr; }
+    return h;
+}
+
+salt_b200_t *salt_b200_init_from_bases(const char *bases, uint32_t l, const uint32_t *snp_pos,
+                                       const uint8_t *snp_mask, size_t n_snp, int device)
+{
+    if (!bases || l == 0) { fail(SALT_ERR_ARG, "bases is null or empty"); return nullptr; }
+    salt_b200_t *h = new_handle(device);
+    if (!h) return nullptr;
+    const size_t nb = ((size_t)l + 7) / 8 * 4;
+    char *d_bases = nullptr; uint32_t *d_pos = nullptr; uint8_t *d_mask = nullptr;
+    cudaError_t e = cudaSuccess;
+    do {
+        if ((e = cudaMalloc(&h->d_mixref, nb + REF_PAD)) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(reinterpret_cast<uint8_t *>(h->d_mixref) + nb, 0, REF_PAD, h->stream)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_bases, l)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(d_bases, bases, l, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) break;
+        if (n_snp) {
+            if ((e = cudaMalloc(&d_pos, n_snp * 4)) != cudaSuccess) break;
+            if ((e = cudaMalloc(&d_mask, n_snp)) != cudaSuccess) break;
+            if ((e = cudaMemcpyAsync(d_pos, snp_pos, n_snp * 4, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) break;
+            if ((e = cudaMemcpyAsync(d_mask, snp_mask, n_snp, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) break;
+        }
+        if ((e = launch_build_mixref(d_bases, l, d_pos, d_mask, n_snp, h->d_mixref, h->stream)) != cudaSuccess) break;
+        h->launches += n_snp ? 2 : 1;
+        e = cudaStreamSynchronize(h->stream);
+    } while (0);
+    if (d_bases) cudaFree(d_bases);
+    if (d_pos) cudaFree(d_pos);
+    if (d_mask) cudaFree(d_mask);
+    if (e != cudaSuccess) { fail(SALT_ERR_CUDA, "build mixref", e); salt_b200_destroy(h); return nullptr; }
+    h->l = l;
+    return h;
+}
+
+int salt_b200_get_mixref(salt_b200_t *h, uint32_t *words_out, size_t n_words)
+{
+    if (int rc = use_device(h)) return rc;
+    const size_t have = ((size_t)h->l + 7) / 8;
+    if (!words_out || n_words < have) return fail(SALT_ERR_ARG, "output too small");
+    CU(cudaMemcpyAsync(words_out, h->d_mixref, have * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return SALT_OK;
+}
+
+void salt_b200_destroy(salt_b200_t *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream && h->own_stream) { cudaStreamSynchronize(h->stream); }
+    DBuf *all[] = {&h->codes, &h->offs, &h->rd4, &h->rd_len, &h->pairs, &h->out8, &h->kbuf, &h->cig, &h->wins,
+                   &h->sswout, &h->sswcig, &h->sswscratch, &h->c_offs0, &h->c_loci0, &h->c_offs1, &h->c_loci1,
+                   &h->vpairs, &h->acc, &h->rec, &h->lvlist, &h->ciglist, &h->counters};
+    for (DBuf *b : all) b->release();
+    if (h->d_mixref) cudaFree(h->d_mixref);
+    if (h->d_pac) cudaFree(h->d_pac);
+    if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int salt_b200_set_stream(salt_b200_t *h, void *cuda_stream)
+{
+    if (int rc = use_device(h)) return rc;
+    if (h->own_stream && h->stream) { CU(cudaStreamSynchronize(h->stream)); CU(cudaStreamDestroy(h->stream)); }
+    if (cuda_stream) { h->stream = static_cast<cudaStream_t>(cuda_stream); h->own_stream = false; }
+    else { CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    return SALT_OK;
+}
+
+int salt_b200_sync(salt_b200_t *h)
+{
+    if (int rc = use_device(h)) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return SALT_OK;
+}
+
+void *salt_b200_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { fail(SALT_ERR_CUDA, "cudaMallocHost", e); return nullptr; }
+    return p;
+}
+
+void salt_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+uint64_t salt_b200_launch_count(salt_b200_t *h, int reset)
+{
+    if (!h) return 0;
+    const uint64_t v = h->launches;
+    if (reset) h->launches = 0;
+    return v;
+}
+
+int salt_b200_set_reads(salt_b200_t *h, const salt_reads_t *reads)
+{
+    if (int rc = use_device(h)) return rc;
+    if (!reads || !reads->offs || (reads->n_reads && !reads->codes)) return fail(SALT_ERR_ARG, "reads is null");
+    if (reads->n_reads >= (1u << 31)) return fail(SALT_ERR_ARG, "too many reads in one chunk");
+    const uint32_t n = reads->n_reads;
+    uint32_t l_max = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t a = reads->offs[i], b = reads->offs[i + 1];
+        if (b < a) return fail(SALT_ERR_ARG, "read offsets not monotone");
+        if (b - a > l_max) l_max = b - a;
+    }
+    if (l_max > 1024) return fail(SALT_ERR_UNSUPPORTED, "reads longer than 1024 bases are not supported");
+    const size_t total = n ? reads->offs[n] : 0;
+    h->n_reads = n; h->l_max = l_max; h->W64 = (l_max + 15) / 16 + 1;
+    CU(h->codes.need(total + 16));
+    CU(h->offs.need(((size_t)n + 1) * 4));
+    CU(h->rd4.need((size_t)n * 2 * h->W64 * 8 + 64));
+    CU(h->rd_len.need((size_t)n * 2 + 64));
+    if (n) {
+        CU(cudaMemcpyAsync(h->codes.p, reads->codes, total, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->offs.p, reads->offs, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+        CU(launch_pack_reads(h->codes.as<uint8_t>(), h->offs.as<uint32_t>(), n, h->W64, h->rd4.as<uint64_t>(),
+                             h->rd_len.as<uint16_t>(), h->stream));
+        h->launches += 1;
+    }
+    CU(cudaStreamSynchronize(h->stream));      // the caller's buffers are free to change after return
+    return SALT_OK;
+}
+
+// ------------------------------------------------------------------ mismatch / LV
+int salt_b200_mismatch_dev(salt_b200_t *h, const salt_pair_t *d_pairs, size_t n, int max_err, int8_t *d_out)
+{
+    if (int rc = use_device(h)) return rc;
+    if (n && (!d_pairs || !d_out)) return fail(SALT_ERR_ARG, "null buffer");
+    if (max_err < 0 || max_err > 127) return fail(SALT_ERR_ARG, "max_err must be in 0..127");
+    if (!h->n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    CU(launch_mismatch(h->ctx(), d_pairs, n, max_err, d_out, h->stream));
+    if (n) h->launches += 1;
+    return SALT_OK;
+}
+
+int salt_b200_mismatch(salt_b200_t *h, const salt_pair_t *pairs, size_t n, int max_err, int8_t *out)
+{
+    if (int rc = use_device(h)) return rc;
+    if (n && (!pairs || !out)) return fail(SALT_ERR_ARG, "null buffer");
+    if (!n) return SALT_OK;
+    CU(h->pairs.need(n * sizeof(salt_pair_t)));
+    CU(h->out8.need(n));
+    CU(cudaMemcpyAsync(h->pairs.p, pairs, n * sizeof(salt_pair_t), cudaMemcpyHostToDevice, h->stream));
+    if (int rc = salt_b200_mismatch_dev(h, h->pairs.as<salt_pair_t>(), n, max_err, h->out8.as<int8_t>())) return rc;
+    CU(cudaMemcpyAsync(out, h->out8.p, n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return SALT_OK;
+}
+
+int salt_b200_lv_dev(salt_b200_t *h, const salt_pair_t *d_pairs, size_t n, int k, int8_t *d_out)
+{
+    if (int rc = use_device(h)) return rc;
+    if (n && (!d_pairs || !d_out)) return fail(SALT_ERR_ARG, "null buffer");
+    if (!h->n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    CU(launch_lv(h->ctx(), d_pairs, n, k, nullptr, nullptr, 0, d_out, h->sm_count, h->stream));
+    if (n) h->launches += 1;
+    return SALT_OK;
+}
+
+int salt_b200_lv(salt_b200_t *h, const salt_pair_t *pairs, size_t n, int k, int8_t *out)
+{
+    if (int rc = use_device(h)) return rc;
+    if (n && (!pairs || !out)) return fail(SALT_ERR_ARG, "null buffer");
+    if (!n) return SALT_OK;
+    CU(h->pairs.need(n * sizeof(salt_pair_t)));
+    CU(h->out8.need(n));
+    CU(cudaMemcpyAsync(h->pairs.p, pairs, n * sizeof(salt_pair_t), cudaMemcpyHostToDevice, h->stream));
+    if (int rc = salt_b200_lv_dev(h, h->pairs.as<salt_pair_t>(), n, k, h->out8.as<int8_t>())) return rc;
+    CU(cudaMemcpyAsync(out, h->out8.p, n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return SALT_OK;
+}
+
+int salt_b200_lv_cigar(salt_b200_t *h, const salt_pair_t *pairs, const uint8_t *k_each, size_t n,
+                       char *cigars, int stride, int8_t *out)
+{
+    if (int rc = use_device(h)) return rc;
+    if (n && (!pairs || !k_each || !cigars || !out)) return fail(SALT_ERR_ARG, "null buffer");
+    if (stride < 2) return fail(SALT_ERR_ARG, "cigar stride too small");
+    if (!h->n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    if (!n) return SALT_OK;
+    for (size_t i = 0; i < n; ++i)
+        if (k_each[i] >= 31) return fail(SALT_ERR_ARG, "k must be < 31 (LandauVishkin.c:183 asserts)");
+    CU(h->pairs.need(n * sizeof(salt_pair_t)));
+    CU(h->out8.need(n));
+    CU(h->kbuf.need(n));
+    CU(h->cig.need(n * (size_t)stride));
+    CU(cudaMemcpyAsync(h->pairs.p, pairs, n * sizeof(salt_pair_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->kbuf.p, k_each, n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(h->cig.p, 0, n * (size_t)stride, h->stream));
+    CU(launch_lv_cigar(h->ctx(), h->pairs.as<salt_pair_t>(), h->kbuf.as<uint8_t>(), n, nullptr, nullptr, 0, nullptr,
+                       h->cig.as<char>(), stride, h->out8.as<int8_t>(), h->sm_count, h->stream));
+    h->launches += 1;
+    std::vector<char> tmp(n * (size_t)stride);
+    CU(cudaMemcpyAsync(tmp.data(), h->cig.p, tmp.size(), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(out, h->out8.p, n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    // like the reference, touch only the string and its terminator in the caller's buffers
+    for (size_t i = 0; i < n; ++i) {
+        const char *s = tmp.data() + i * (size_t)stride;
+        size_t len = strnlen(s, (size_t)stride - 1);
+        memcpy(cigars + i * (size_t)stride, s, len);
+        cigars[i * (size_t)stride + len] = '\0';
+    }
+    return SALT_OK;
+}
+
+// ------------------------------------------------------------------ SSW
+static int fill_ssw_params(SswParams &p, int use_pac, const int8_t *mat, int n_sym, int gapO, int gapE, int flag,
+                           int filters, int filterd, int mask_len)
+{
+    if (!mat || n_sym < 1 || n_sym > 16) return fail(SALT_ERR_ARG, "mat is null or n_sym outside 1..16");
+    if (use_pac && n_sym < 5) return fail(SALT_ERR_ARG, "pac scoring needs n_sym >= 5 (codes 0..4)");
+    if (!use_pac && n_sym != 16) return fail(SALT_ERR_ARG, "mixRef scoring needs n_sym == 16 (4-bit masks)");
+    if (gapO < 0 || gapO > 255 || gapE < 0 || gapE > 255) return fail(SALT_ERR_ARG, "gap penalties are uint8 in ssw_align");
+    if (gapO <= gapE)
+        return fail(SALT_ERR_UNSUPPORTED, "gapO <= gapE: the SSE2 lazy-F loop of the reference under-propagates there and is not reproduced");
+    p.use_pac = use_pac; p.n_sym = n_sym; p.gapO = gapO; p.gapE = gapE; p.flag = flag;
+    p.filters = filters; p.filterd = filterd; p.mask_len = mask_len;
+    const int nn = n_sym * n_sym;
+    for (int sym = 0; sym < 17; ++sym)
+        for (int code = 0; code < 8; ++code) {
+            int v = 0;
+            if (sym == 16 || code == 5) v = -128;             // pad column / row above the read
+            else if (code == 6 || code == 7) v = 0;           // zero-score padded rows (ssw.c:361)
+            else if (sym >= n_sym) v = -128;
+            else {
+                const int read_sym = use_pac ? code : (1 << code);      // alnpe.c:283 / :344
+                int idx = sym * n_sym + read_sym;                        // ssw.c:361
+                if (idx >= nn) idx = nn - 1;
+                v = mat[idx];
+            }
+            p.table[sym * 8 + code] = (int8_t)v;
+        }
+    return SALT_OK;
+}
+
+int salt_b200_ssw_dev(salt_b200_t *h, const salt_win_t *d_wins, size_t n, int use_pac,
+                      const int8_t *mat, int n_sym, int gapO, int gapE, int flag,
+                      int filters, int filterd, int mask_len,
+                      salt_ssw_out_t *d_out, uint32_t *d_cigars, int cigar_stride)
+{
+    if (int rc = use_device(h)) return rc;
+    if (n && (!d_wins || !d_out || !d_cigars)) return fail(SALT_ERR_ARG, "null buffer");
+    if (cigar_stride < 1) return fail(SALT_ERR_ARG, "cigar stride too small");
+    if (!h->n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    if (use_pac && !h->d_pac) return fail(SALT_ERR_ARG, "no pac uploaded");
+    SswParams prm;
+    if (int rc = fill_ssw_params(prm, use_pac, mat, n_sym, gapO, gapE, flag, filters, filterd, mask_len)) return rc;
+    int maxpos = 0;
+    for (int i = 0; i < n_sym * n_sym; ++i) if (mat[i] > maxpos) maxpos = mat[i];
+    if ((int64_t)maxpos * (int64_t)h->l_max >= 32000) return fail(SALT_ERR_UNSUPPORTED, "scores would overflow int16");
+    if (!n) return SALT_OK;
+    const int max_cols = h->max_window;
+    size_t lay[8];
+    const size_t need = ssw_scratch_bytes(n, max_cols, (int)h->l_max, lay);
+    CU(h->sswscratch.need(need));
+    CU(launch_ssw(h->ctx(), d_wins, n, prm, h->sswscratch.p, h->sswscratch.cap, max_cols, d_out, d_cigars,
+                  cigar_stride, h->sm_count, h->stream, &h->launches));
+    return SALT_OK;
+}
+
+int salt_b200_set_max_window(salt_b200_t *h, int cols)
+{
+    if (!h) return fail(SALT_ERR_ARG, "null handle");
+    if (cols < 1 || cols > 65536) return fail(SALT_ERR_ARG, "max window must be in 1..65536");
+    h->max_window = cols;
+    return SALT_OK;
+}
+
+int salt_b200_ssw(salt_b200_t *h, const salt_win_t *wins, size_t n, int use_pac,
+                  const int8_t *mat, int n_sym, int gapO, int gapE, int flag,
+                  int filters, int filterd, int mask_len,
+                  salt_ssw_out_t *out, uint32_t *cigars, int cigar_stride)
+{
+    if (int rc = use_device(h)) return rc;
+    if (n && (!wins || !out || !cigars)) return fail(SALT_ERR_ARG, "null buffer");
+    if (cigar_stride < 1) return fail(SALT_ERR_ARG, "cigar stride too small");
+    if (!n) return SALT_OK;
+    uint32_t widest = 1;
+    for (size_t i = 0; i < n; ++i)
+        if (wins[i].end >= wins[i].start && wins[i].end - wins[i].start + 1 > widest) widest = wins[i].end - wins[i].start + 1;
+    if (widest > 65536) return fail(SALT_ERR_UNSUPPORTED, "rescue window wider than 65536 bases");
+    h->max_window = (int)((widest + 7) / 8 * 8);
+    CU(h->wins.need(n * sizeof(salt_win_t)));
+    CU(h->sswout.need(n * sizeof(salt_ssw_out_t)));
+    CU(h->sswcig.need(n * (size_t)cigar_stride * 4));
+    CU(cudaMemcpyAsync(h->wins.p, wins, n * sizeof(salt_win_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(h->sswcig.p, 0, n * (size_t)cigar_stride * 4, h->stream));
+    if (int rc = salt_b200_ssw_dev(h, h->wins.as<salt_win_t>(), n, use_pac, mat, n_sym, gapO, gapE, flag, filters,
+                                   filterd, mask_len, h->sswout.as<salt_ssw_out_t>(), h->sswcig.as<uint32_t>(), cigar_stride))
+        return rc;
+    CU(cudaMemcpyAsync(out, h->sswout.p, n * sizeof(salt_ssw_out_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(cigars, h->sswcig.p, n * (size_t)cigar_stride * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < n; ++i)
+        if (out[i].cigarLen < 0) return fail(SALT_ERR_UNSUPPORTED, "a window was invalid or its traceback band exceeded the engine limit");
+    return SALT_OK;
+}
+
+// ------------------------------------------------------------------ verification stage
+int salt_b200_verify_dev(salt_b200_t *h, const uint32_t *d_offs0, const uint32_t *d_loci0, size_t n0,
+                         const uint32_t *d_offs1, const uint32_t *d_loci1, size_t n1,
+                         int nogap_T0, int lv_T0, salt_verify_out_t *d_rec, int8_t *d_acc0, int8_t *d_acc1,
+                         char *d_cigars, int cigar_stride)
+{
+    if (int rc = use_device(h)) return rc;
+    if (!h->n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    if (!d_offs0 || !d_offs1 || !d_rec) return fail(SALT_ERR_ARG, "null buffer");
+    if (nogap_T0 < 0 || nogap_T0 > 127) return fail(SALT_ERR_ARG, "nogap_T0 must be in 0..127");
+    if (n0 + n1 >= (size_t)1 << 32) return fail(SALT_ERR_ARG, "too many candidates in one chunk");
+    if (d_acc0 && d_acc1 && d_acc1 != d_acc0 + n0) return fail(SALT_ERR_ARG, "acc1 must follow acc0 contiguously");
+    const size_t n = n0 + n1;
+    const DevCtx c = h->ctx();
+    CU(h->vpairs.need((n + 1) * sizeof(salt_pair_t)));
+    CU(h->lvlist.need((n + 1) * 4));
+    CU(h->ciglist.need(((size_t)h->n_reads + 1) * 4));
+    CU(h->counters.need(256));
+    int8_t *acc = d_acc0;
+    if (!acc) { CU(h->acc.need(n + 1)); acc = h->acc.as<int8_t>(); }
+    salt_pair_t *vp = h->vpairs.as<salt_pair_t>();
+    uint32_t *cnt = h->counters.as<uint32_t>();        // [0] LV worklist length, [1] cigar worklist length
+    CU(cudaMemsetAsync(cnt, 0, 256, h->stream));
+    CU(launch_expand(d_offs0, d_loci0, n0, d_offs1, d_loci1, n1, h->n_reads, vp, h->stream));
+    CU(launch_mismatch(c, vp, n, nogap_T0, acc, h->stream));
+    CU(launch_scan_nogap(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, nogap_T0, acc, d_rec, h->lvlist.as<uint32_t>(), cnt, h->stream));
+    CU(launch_lv(c, vp, n, lv_T0, h->lvlist.as<uint32_t>(), cnt, n, acc, h->sm_count, h->stream));
+    CU(launch_scan_gap(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, lv_T0, acc, d_rec,
+                       d_cigars ? h->ciglist.as<uint32_t>() : nullptr, cnt + 1, h->stream));
+    h->launches += n ? 5 : 2;
+    if (d_cigars) {
+        if (cigar_stride < 2) return fail(SALT_ERR_ARG, "cigar stride too small");
+        CU(launch_lv_cigar(c, nullptr, nullptr, 0, h->ciglist.as<uint32_t>(), cnt + 1, h->n_reads, d_rec,
+                           d_cigars, cigar_stride, nullptr, h->sm_count, h->stream));
+        h->launches += 1;
+    }
+    return SALT_OK;
+}
+
+int salt_b200_verify(salt_b200_t *h, const salt_cands_t *cands, int nogap_T0, int lv_T0,
+                     salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1, char *cigars, int cigar_stride)
+{
+    if (int rc = use_device(h)) return rc;
+    if (!cands || !cands->offs[0] || !cands->offs[1] || !rec) return fail(SALT_ERR_ARG, "null buffer");
+    if (!h->n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    const uint32_t nr = h->n_reads;
+    const size_t n0 = cands->offs[0][nr], n1 = cands->offs[1][nr];
+    if ((n0 && !cands->loci[0]) || (n1 && !cands->loci[1])) return fail(SALT_ERR_ARG, "null loci");
+    CU(h->c_offs0.need(((size_t)nr + 1) * 4)); CU(h->c_offs1.need(((size_t)nr + 1) * 4));
+    CU(h->c_loci0.need(n0 * 4 + 4)); CU(h->c_loci1.need(n1 * 4 + 4));
+    CU(h->acc.need(n0 + n1 + 1));
+    CU(h->rec.need((size_t)nr * sizeof(salt_verify_out_t)));
+    if (cigars) { CU(h->cig.need((size_t)nr * cigar_stride)); CU(cudaMemsetAsync(h->cig.p, 0, (size_t)nr * cigar_stride, h->stream)); }
+    CU(cudaMemcpyAsync(h->c_offs0.p, cands->offs[0], ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->c_offs1.p, cands->offs[1], ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+    if (n0) CU(cudaMemcpyAsync(h->c_loci0.p, cands->loci[0], n0 * 4, cudaMemcpyHostToDevice, h->stream));
+    if (n1) CU(cudaMemcpyAsync(h->c_loci1.p, cands->loci[1], n1 * 4, cudaMemcpyHostToDevice, h->stream));
+    int8_t *acc = h->acc.as<int8_t>();
+    if (int rc = salt_b200_verify_dev(h, h->c_offs0.as<uint32_t>(), h->c_loci0.as<uint32_t>(), n0,
+                                      h->c_offs1.as<uint32_t>(), h->c_loci1.as<uint32_t>(), n1, nogap_T0, lv_T0,
+                                      h->rec.as<salt_verify_out_t>(), acc, acc + n0,
+                                      cigars ? h->cig.as<char>() : nullptr, cigar_stride))
+        return rc;
+    CU(cudaMemcpyAsync(rec, h->rec.p, (size_t)nr * sizeof(salt_verify_out_t), cudaMemcpyDeviceToHost, h->stream));
+    if (acc0 && n0) CU(cudaMemcpyAsync(acc0, acc, n0, cudaMemcpyDeviceToHost, h->stream));
+    if (acc1 && n1) CU(cudaMemcpyAsync(acc1, acc + n0, n1, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<char> tmp;
+    if (cigars) {
+        tmp.resize((size_t)nr * cigar_stride);
+        CU(cudaMemcpyAsync(tmp.data(), h->cig.p, tmp.size(), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    if (cigars) {
+        for (uint32_t r = 0; r < nr; ++r) {
+            if (rec[r].is_gap != 1) continue;            // query_gen_cigar only calls LV for gapped primaries
+            const char *s = tmp.data() + (size_t)r * cigar_stride;
+            size_t len = strnlen(s, (size_t)cigar_stride - 1);
+            memcpy(cigars + (size_t)r * cigar_stride, s, len);
+            cigars[(size_t)r * cigar_stride + len] = '\0';
+        }
+    }
+    return SALT_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,55 @@
+// kernels.h -- launchers implemented in verify.cu / ssw.cu / mixref.cu, used by engine.cu.
+#pragma once
+#if !defined(SALT_EMUL)
+#include <cuda_runtime.h>
+#endif
+
+#include "common.cuh"
+
+namespace salt {
+
+cudaError_t launch_pack_reads(const uint8_t *codes, const uint32_t *offs, uint32_t n_reads, uint32_t W64,
+                              uint64_t *rd4, uint16_t *rd_len, cudaStream_t st);
+cudaError_t launch_mismatch(const DevCtx &c, const salt_pair_t *pairs, size_t n, int max_err, int8_t *out, cudaStream_t st);
+cudaError_t launch_lv(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k,
+                      const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
+                      int8_t *out, int sm_count, cudaStream_t st);
+cudaError_t launch_lv_cigar(const DevCtx &c, const salt_pair_t *pairs, const uint8_t *k_each, size_t n,
+                            const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
+                            const salt_verify_out_t *rec, char *cigars, int stride, int8_t *out,
+                            int sm_count, cudaStream_t st);
+cudaError_t launch_expand(const uint32_t *offs0, const uint32_t *loci0, size_t n0,
+                          const uint32_t *offs1, const uint32_t *loci1, size_t n1,
+                          uint32_t n_reads, salt_pair_t *pairs, cudaStream_t st);
+cudaError_t launch_scan_nogap(const DevCtx &c, const uint32_t *offs0, const uint32_t *loci0,
+                              const uint32_t *offs1, const uint32_t *loci1, size_t n0, int T0,
+                              int8_t *acc, salt_verify_out_t *rec, uint32_t *lv_list, uint32_t *lv_count, cudaStream_t st);
+cudaError_t launch_scan_gap(const DevCtx &c, const uint32_t *offs0, const uint32_t *loci0,
+                            const uint32_t *offs1, const uint32_t *loci1, size_t n0, int lv_T0,
+                            int8_t *acc, salt_verify_out_t *rec, uint32_t *cig_list, uint32_t *cig_count, cudaStream_t st);
+
+// mixref.cu
+cudaError_t launch_build_mixref(const char *bases, uint32_t l, const uint32_t *snp_pos, const uint8_t *snp_mask,
+                                size_t n_snp, uint32_t *words, cudaStream_t st);
+
+// ssw.cu
+struct SswParams {
+    int use_pac, n_sym, gapO, gapE, flag, filters, filterd, mask_len;
+    int8_t table[17 * 8];     // score[ref_sym][read code 0..4, 5 = pad row], row 16 = pad column
+};
+struct SswScratch {           // device buffers owned by the engine, sized for >= n tasks
+    uint32_t *win4;           // per pair-of-tasks packed window symbols, interleaved (w0,w1) per 8 columns
+    uint32_t *rsel;           // per task read-code selectors
+    uint16_t *maxcol;         // per task, per column
+    int32_t *fwd;             // per task forward results
+    int8_t *dirs;             // banded traceback direction bytes
+    size_t dirs_bytes;
+    size_t cap_tasks; int cap_cols; int cap_rows;
+};
+size_t ssw_scratch_bytes(size_t n_tasks, int max_cols, int max_rows, size_t *layout /*[8]*/);
+cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const SswParams &prm,
+                       void *scratch, size_t scratch_bytes, int max_cols,
+                       salt_ssw_out_t *out, uint32_t *cigars, int cigar_stride, int sm_count, cudaStream_t st,
+                       uint64_t *launches);
+
+}  // namespace salt

@@ -1,0 +1,575 @@
+// ssw.cu -- sm_100a kernels for batched ssw_init + ssw_align on reference windows
+// (ssw.c:742 ssw_init, :771 ssw_align, :371 sw_sse2_word, :549 banded_sw), as salt's
+// mate rescue calls them (alnpe.c:261 snpaln_sw_snpaware, :330 snpaln_sw).
+//
+// Pipeline per batch (all on the caller's stream, no host round trip):
+//   sw_prep<fwd>   window symbols + read-code selectors per task
+//   sw_dp<fwd>     score1 / ref_end1 / read_end1 / maxColumn -> score2 / ref_end2
+//   sw_prep<rev>   reversed read prefix and reversed window (ssw.c:827-832)
+//   sw_dp<rev>     ref_begin1 / read_begin1, stops at the column whose maximum equals score1
+//   sw_banded      banded_sw + traceback -> cigar (ssw.c:549-727); overflow pass for wide bands
+#if !defined(SALT_EMUL)
+#include <cuda_runtime.h>
+#endif
+
+#include "common.cuh"
+#include "sw_core.cuh"
+#include "kernels.h"
+
+namespace salt {
+
+// fwd[] record per task (int32 x 8)
+enum { F_SCORE1 = 0, F_REF_END1, F_READ_END1, F_SCORE2, F_REF_END2, F_REF_BEGIN1, F_READ_BEGIN1, F_FLAGS };
+enum { FL_VALID = 1, FL_DO_REV = 2, FL_DO_CIGAR = 4 };
+
+struct SwDev {
+    DevCtx c;
+    const salt_win_t *wins;
+    size_t n_tasks;            // real tasks
+    size_t n_pairs;            // ceil(n_tasks / 2)
+    int G, S;                  // rows = G*S
+    int CW;                    // window words (8 columns each) per pair
+    int MC;                    // maxcol stride (columns) per pair
+    uint2 *win2;               // [pair][CW]  (.x task 0, .y task 1)
+    uint32_t *rsel;            // [task][G*NQ]
+    uint32_t *maxcol2;         // [pair][MC]  packed column maxima
+    int32_t *fwd;              // [task][8]
+    SswParams prm;
+};
+
+__device__ __forceinline__ int sw_ref_symbol(const DevCtx &c, int use_pac, uint32_t p)
+{
+    if (use_pac) return (c.pac[p >> 2] >> ((~p & 3u) << 1)) & 3;
+    return (c.mixref[p >> 3] >> (4u * (p & 7u))) & 15u;
+}
+
+// read code 0..4 of packed read rs at index i (one-hot nibble -> code)
+__device__ __forceinline__ int sw_read_code(const DevCtx &c, uint32_t rs, int i)
+{
+    const uint64_t w = c.rd4[(size_t)rs * c.W64 + (i >> 4)];
+    const unsigned nib = (unsigned)(w >> (4 * (i & 15))) & 15u;
+    return nib == 15u ? SW_CODE_N : (31 - __clz(nib));
+}
+
+// --------------------------------------------------------------------------------------
+// prep: one thread per output word.  Items per task: CW window words, then G*NQ selectors.
+// --------------------------------------------------------------------------------------
+template <bool REV>
+__global__ void __launch_bounds__(256)
+sw_prep_kernel(SwDev d)
+{
+    const int NQ = (d.S + 3) / 4;
+    const int per_task = d.CW + d.G * NQ;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = d.n_pairs * 2 * (size_t)per_task;
+    if (idx >= total) return;
+    const size_t t = idx / per_task;
+    const int item = (int)(idx % per_task);
+    const bool real = t < d.n_tasks;
+    uint32_t rs = 0, start = 0;
+    int L = 0, cols = 0, read_end = 0, ref_end = 0;
+    int32_t *f = d.fwd + t * 8;
+    if (real) {
+        const salt_win_t w = d.wins[t];
+        const uint32_t rid = w.rs >> 1;
+        const int64_t lim = d.prm.use_pac ? d.c.l_pac : (int64_t)d.c.l;
+        const bool ok = rid < d.c.n_reads && w.start <= w.end && (int64_t)w.end < lim &&
+                        (!d.prm.use_pac || d.c.pac != nullptr) &&
+                        (int64_t)(w.end - w.start + 1) <= (int64_t)d.MC;
+        if (!REV) {
+            if (item == 0) {
+                f[F_FLAGS] = ok ? FL_VALID : 0;
+                f[F_SCORE1] = 0; f[F_REF_END1] = 0; f[F_READ_END1] = 0; f[F_SCORE2] = 0;
+                f[F_REF_END2] = 0;
+                f[F_REF_BEGIN1] = -1; f[F_READ_BEGIN1] = -1;
+            }
+            if (ok) { rs = w.rs; start = w.start; L = d.c.rd_len[rid]; cols = (int)(w.end - w.start + 1); }
+        } else {
+            if (ok && (f[F_FLAGS] & FL_DO_REV)) {
+                rs = w.rs; start = w.start; read_end = f[F_READ_END1]; ref_end = f[F_REF_END1];
+                L = read_end + 1; cols = ref_end + 1;
+            }
+        }
+    }
+    if (item < d.CW) {                                  // window word: columns 8*item .. 8*item+7
+        uint32_t word = 0;
+        for (int b = 0; b < 8; ++b) {
+            const int col = item * 8 + b;
+            if (col < cols) {
+                const uint32_t p = REV ? start + (uint32_t)(ref_end - col) : start + (uint32_t)col;
+                word |= (uint32_t)sw_ref_symbol(d.c, d.prm.use_pac, p) << (4 * b);
+            }
+        }
+        uint32_t *dst = reinterpret_cast<uint32_t *>(d.win2 + (t >> 1) * d.CW + item);
+        dst[t & 1] = word;
+    } else {                                            // selector word: rows 4q..4q+3 of thread j
+        const int k = item - d.CW;
+        const int j = k / NQ, q = k % NQ;
+        const int R = 8 * ((L + 7) / 8);
+        const int off = d.G * d.S - R;
+        uint32_t sel = 0;
+        for (int r = 0; r < 4; ++r) {
+            const int i = 4 * q + r;
+            int code = SW_CODE_TOP;
+            if (i < d.S) {
+                const int row = j * d.S + i - off;
+                if (row >= 0) {
+                    if (row < L) code = sw_read_code(d.c, rs, REV ? read_end - row : row);
+                    else code = SW_CODE_TAIL;
+                }
+            }
+            sel |= (uint32_t)code << (4 * r);
+        }
+        d.rsel[t * (size_t)(d.G * NQ) + k] = sel;
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// dp: systolic strip DP, see sw_core.cuh.  CTA = 128 threads = 128/G task pairs.
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ int half_of(uint32_t x, int h) { return h ? s16hi(x) : s16lo(x); }
+
+template <int G, int S, bool REV>
+__global__ void __launch_bounds__(128)
+sw_dp_kernel(SwDev d)
+{
+    constexpr int NQ = (S + 3) / 4;
+    __shared__ uint2 s_tab[17];
+    SALT_DYN_SMEM(uint32_t, s_snap);                     // [thread][2][S]
+    if (threadIdx.x < 17) {
+        const uint32_t *tb = reinterpret_cast<const uint32_t *>(d.prm.table);
+        s_tab[threadIdx.x] = make_uint2(tb[2 * threadIdx.x], tb[2 * threadIdx.x + 1]);
+    }
+    __syncthreads();
+    constexpr int GPC = 128 / G;
+    const int gl = threadIdx.x / G, j = threadIdx.x % G;
+    const size_t pair = (size_t)blockIdx.x * GPC + gl;
+    if (pair >= d.n_pairs) return;
+    const int gshift = (threadIdx.x & 31) / G * G;
+    const unsigned gmask = (unsigned)(((1ull << G) - 1ull) << gshift);
+    uint32_t *snap = s_snap + (size_t)threadIdx.x * 2 * S;
+
+    int rows[2], cols[2], off[2], aux_read_end[2], aux_ref_end[2];
+    uint32_t term = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const size_t t = pair * 2 + h;
+        rows[h] = 0; cols[h] = 0; aux_read_end[h] = 0; aux_ref_end[h] = 0;
+        if (t < d.n_tasks) {
+            const int32_t *f = d.fwd + t * 8;
+            const int fl = f[F_FLAGS];
+            if (!REV) {
+                if (fl & FL_VALID) {
+                    const salt_win_t w = d.wins[t];
+                    rows[h] = d.c.rd_len[w.rs >> 1];
+                    cols[h] = (int)(w.end - w.start + 1);
+                }
+            } else if (fl & FL_DO_REV) {
+                aux_read_end[h] = f[F_READ_END1]; aux_ref_end[h] = f[F_REF_END1];
+                rows[h] = aux_read_end[h] + 1; cols[h] = aux_ref_end[h] + 1;
+                term |= (uint32_t)(uint16_t)f[F_SCORE1] << (16 * h);
+            }
+        }
+        off[h] = G * S - 8 * ((rows[h] + 7) / 8);
+    }
+    const int maxcols = cols[0] > cols[1] ? cols[0] : cols[1];
+
+    SwStrip<S> st;
+    st.clear();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        st.sel0[q] = d.rsel[(pair * 2 + 0) * (size_t)(G * NQ) + j * NQ + q];
+        st.sel1[q] = d.rsel[(pair * 2 + 1) * (size_t)(G * NQ) + j * NQ + q];
+    }
+    const uint32_t negO = s16x2(-d.prm.gapO, -d.prm.gapO), negE = s16x2(-d.prm.gapE, -d.prm.gapE);
+    const uint2 *__restrict__ win = d.win2 + pair * d.CW;
+    uint32_t *__restrict__ mcol = d.maxcol2 + pair * (size_t)d.MC;
+
+    uint32_t Hrecv = 0, Hrecv2 = 0, Frecv = 0, Crecv = 0, best = 0;
+    int bcol[2] = {0, 0};
+    uint2 wreg = make_uint2(0, 0);
+    int done = 0;                                        // REV, lane G-1: bit h = half h reached score1
+    if (REV) done = (cols[0] == 0 ? 1 : 0) | (cols[1] == 0 ? 2 : 0);
+    const int nsteps = maxcols + G - 1;
+    for (int t = 0; t < nsteps; ++t) {
+        const int c = t - j;
+        uint32_t Hbot = 0, Fout = 0, cm = 0;
+        if (c >= 0 && c < maxcols) {
+            if ((c & 7) == 0) wreg = win[c >> 3];
+            const int sh = 4 * (c & 7);
+            int sym0 = (wreg.x >> sh) & 15, sym1 = (wreg.y >> sh) & 15;
+            if (c >= cols[0]) sym0 = SW_SYM_PADCOL;
+            if (c >= cols[1]) sym1 = SW_SYM_PADCOL;
+            const uint2 ta = s_tab[sym0], tb = s_tab[sym1];
+            uint32_t F = j == 0 ? 0u : Frecv;
+            const uint32_t diag = j == 0 ? 0u : Hrecv2;
+            const uint32_t sm = st.column(ta.x, ta.y, tb.x, tb.y, diag, F, negO, negE);
+            Hbot = st.H[S - 1]; Fout = F;
+            cm = vmax2(j == 0 ? 0u : Crecv, sm);
+            const uint32_t nb = vmax2(best, sm);
+            if (nb != best) {                            // this strip's maximum rose: remember where
+                const uint32_t ch = nb ^ best;
+                if (ch & 0xffffu) {
+                    bcol[0] = c;
+#pragma unroll
+                    for (int i = 0; i < S; ++i) snap[i] = st.H[i];
+                }
+                if (ch >> 16) {
+                    bcol[1] = c;
+#pragma unroll
+                    for (int i = 0; i < S; ++i) snap[S + i] = st.H[i];
+                }
+                best = nb;
+            }
+            if (j == G - 1) {
+                if (!REV) mcol[c] = cm;
+                else {
+                    if (c < cols[0] && (cm & 0xffffu) == (term & 0xffffu)) done |= 1;
+                    if (c < cols[1] && (cm >> 16) == (term >> 16)) done |= 2;
+                }
+            }
+        }
+        Hrecv2 = Hrecv;
+        Hrecv = __shfl_up_sync(gmask, Hbot, 1, G);
+        Frecv = __shfl_up_sync(gmask, Fout, 1, G);
+        Crecv = __shfl_up_sync(gmask, cm, 1, G);
+        if (REV) {
+            if (__shfl_sync(gmask, done, G - 1, G) == 3) break;
+        }
+    }
+    __syncwarp(gmask);
+
+    // ---- combine the strips: global maximum, first column reaching it, smallest row there
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const size_t t = pair * 2 + h;
+        const int bh = half_of(best, h);
+        int m = bh;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) m = imax(m, __shfl_xor_sync(gmask, m, o, G));
+        int ec = bh == m ? bcol[h] : 0x7fffffff;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) ec = imin(ec, __shfl_xor_sync(gmask, ec, o, G));
+        const unsigned ball = (__ballot_sync(gmask, bh == m && bcol[h] == ec) >> gshift) & (unsigned)((1ull << G) - 1ull);
+        const int winner = __ffs((int)ball) - 1;
+        int row = 0;
+        if (j == winner && m > 0) {
+            for (int i = 0; i < S; ++i)
+                if (half_of(snap[h * S + i], h) == m) { row = j * S + i - off[h]; break; }
+        }
+        row = __shfl_sync(gmask, row, winner, G);
+        int end_read = 0;
+        if (m == 0) ec = 0;                               // nothing scored: ssw.c keeps end_ref = 0, Hmax = 0
+        else end_read = imin(rows[h] - 1, row);
+        if (rows[h] > 0 && end_read > rows[h] - 1) end_read = rows[h] - 1;
+
+        if (t >= d.n_tasks) continue;
+        int32_t *f = d.fwd + t * 8;
+        if (!REV) {
+            // second-best score outside the mask around ref_end1 (ssw.c:537-550)
+            int s2 = 0, e2 = 0x7fffffff;
+            const int mask_len = d.prm.mask_len >= 0 ? d.prm.mask_len : rows[h] / 2;
+            if (mask_len >= 15) {
+                const int lo = imax(ec - mask_len, 0), hi = imin(ec + mask_len, cols[h]);
+                for (int c = j; c < cols[h]; c += G) {
+                    if (c >= lo && c < hi) continue;
+                    const int v = half_of(mcol[c], h) & 0xffff;
+                    if (v > s2) { s2 = v; e2 = c; }
+                }
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) {
+                    const int os = __shfl_xor_sync(gmask, s2, o, G), oe = __shfl_xor_sync(gmask, e2, o, G);
+                    if (os > s2 || (os == s2 && oe < e2)) { s2 = os; e2 = oe; }
+                }
+                if (s2 == 0) e2 = 0;
+            } else { s2 = 0; e2 = -1; }
+            if (j == 0 && (f[F_FLAGS] & FL_VALID)) {
+                f[F_SCORE1] = m; f[F_REF_END1] = ec; f[F_READ_END1] = end_read;
+                f[F_SCORE2] = s2; f[F_REF_END2] = e2;
+                const int flag = d.prm.flag;
+                const bool do_rev = !(flag == 0 || (flag == 2 && m < d.prm.filters));      // ssw.c:824
+                f[F_FLAGS] = FL_VALID | (do_rev ? FL_DO_REV : 0);
+            }
+        } else if (j == 0 && (f[F_FLAGS] & FL_DO_REV)) {
+            const int rb = aux_ref_end[h] - ec, qb = aux_read_end[h] - end_read;       // ssw.c:836-837
+            f[F_REF_BEGIN1] = rb; f[F_READ_BEGIN1] = qb;
+            const int flag = d.prm.flag, score1 = f[F_SCORE1];
+            const bool skip = (7 & flag) == 0 || ((2 & flag) != 0 && score1 < d.prm.filters) ||
+                              ((4 & flag) != 0 && (aux_ref_end[h] - rb > d.prm.filterd || aux_read_end[h] - qb > d.prm.filterd));
+            if (!skip) f[F_FLAGS] |= FL_DO_CIGAR;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// banded: one thread per task, literal restatement of banded_sw's arithmetic with the three
+// direction codes of a cell packed into one byte.  A task whose band outgrows BWMAX is
+// pushed to the overflow list (main pass) or flagged (overflow pass).
+// --------------------------------------------------------------------------------------
+struct BandDev {
+    DevCtx c;
+    const salt_win_t *wins;
+    size_t n_tasks;
+    const int32_t *fwd;
+    SswParams prm;
+    uint8_t *dirs; size_t slot;          // per-thread direction scratch
+    uint32_t *ovf_list; uint32_t *ovf_count; uint32_t ovf_cap;
+    const uint32_t *in_list; const uint32_t *in_count;   // overflow pass input
+    salt_ssw_out_t *out; uint32_t *cigars; int cigar_stride;
+};
+
+__device__ __forceinline__ int band_u(int w, int i, int j) { int x = i - w; if (x < 0) x = 0; return j - x + 1; }
+__device__ __forceinline__ int band_d(int w, int i, int j) { int x = i - w; if (x < 0) x = 0; return j - x; }
+
+template <int BWMAX, bool OVERFLOW>
+__global__ void __launch_bounds__(128)
+sw_banded_kernel(BandDev d)
+{
+    __shared__ int8_t s_tab[17 * 8];
+    for (int i = threadIdx.x; i < 17 * 8; i += blockDim.x) s_tab[i] = d.prm.table[i];
+    __syncthreads();
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t t;
+    if (OVERFLOW) { if (tid >= (size_t)min(*d.in_count, d.ovf_cap)) return; t = d.in_list[tid]; }
+    else { if (tid >= d.n_tasks) return; t = tid; }
+    const int32_t *f = d.fwd + t * 8;
+    const int fl = f[F_FLAGS];
+    salt_ssw_out_t o;
+    o.score1 = (uint16_t)f[F_SCORE1]; o.score2 = (uint16_t)f[F_SCORE2];
+    o.ref_begin1 = f[F_REF_BEGIN1]; o.ref_end1 = f[F_REF_END1];
+    o.read_begin1 = f[F_READ_BEGIN1]; o.read_end1 = f[F_READ_END1];
+    o.ref_end2 = f[F_REF_END2]; o.cigarLen = 0;
+    if (!(fl & FL_VALID)) { o.ref_end2 = -1; o.cigarLen = -1; }
+    if (!(fl & FL_DO_CIGAR)) { if (!OVERFLOW) d.out[t] = o; return; }
+
+    const salt_win_t w = d.wins[t];
+    const int refLen = o.ref_end1 - o.ref_begin1 + 1, readLen = o.read_end1 - o.read_begin1 + 1;
+    const uint32_t ref0 = w.start + (uint32_t)o.ref_begin1;
+    const int read0 = o.read_begin1;
+    const int score = o.score1, gapO = d.prm.gapO, gapE = d.prm.gapE;
+    int band = abs(refLen - readLen) + 1;                                    // ssw.c:845
+    uint8_t *dirs = d.dirs + tid * d.slot;
+    int hb[2 * BWMAX + 5], eb[2 * BWMAX + 5], hc[2 * BWMAX + 5];
+    int max = 0, wd = 0;
+    bool overflow = false;
+    do {
+        const int width = band * 2 + 3;
+        wd = band * 2 + 1;
+        if (band > BWMAX || (size_t)wd * (size_t)readLen > d.slot) { overflow = true; break; }
+        for (int j = 1; j < width - 1; ++j) hb[j] = 0;
+        for (int i = 0; i < readLen; ++i) {
+            int beg = 0, end = refLen - 1, u = 0;
+            if (i - band > beg) beg = i - band;
+            if (i + band < end) end = i + band;
+            const int edge = end + 1 < width - 1 ? end + 1 : width - 1;
+            int fcur = 0;
+            hb[0] = eb[0] = hb[edge] = eb[edge] = hc[0] = 0;
+            uint8_t *dl = dirs + (size_t)wd * i;
+            const int rc = sw_read_code(d.c, w.rs, read0 + i);
+            for (int j = beg; j <= end; ++j) {
+                u = band_u(band, i, j);
+                const int ue = band_u(band, i - 1, j), ub = band_u(band, i, j - 1), ud = band_u(band, i - 1, j - 1);
+                int t1 = i == 0 ? -gapO : hb[ue] - gapO;
+                int t2 = i == 0 ? -gapE : eb[ue] - gapE;
+                eb[u] = t1 > t2 ? t1 : t2;
+                const int de = t1 > t2 ? 3 : 2;
+                t1 = hc[ub] - gapO;
+                t2 = fcur - gapE;
+                fcur = t1 > t2 ? t1 : t2;
+                const int df = t1 > t2 ? 5 : 4;
+                const int e1 = eb[u] > 0 ? eb[u] : 0;
+                const int f1 = fcur > 0 ? fcur : 0;
+                t1 = e1 > f1 ? e1 : f1;
+                const int sym = sw_ref_symbol(d.c, d.prm.use_pac, ref0 + (uint32_t)j);
+                t2 = hb[ud] + s_tab[sym * 8 + rc];
+                hc[u] = t1 > t2 ? t1 : t2;
+                if (hc[u] > max) max = hc[u];
+                const int dh = t1 <= t2 ? 1 : (e1 > f1 ? de : df);
+                dl[band_d(band, i, j)] = sw_dir_pack(de, df, dh);
+            }
+            for (int j = 1; j <= u; ++j) hb[j] = hc[j];
+        }
+        band *= 2;
+    } while (max < score);
+
+    if (overflow) {
+        if (!OVERFLOW) {
+            const uint32_t k = atomicAdd(d.ovf_count, 1u);
+            if (k < d.ovf_cap) { d.ovf_list[k] = (uint32_t)t; o.cigarLen = 0; }
+            else o.cigarLen = -2;
+        } else o.cigarLen = -2;
+        d.out[t] = o;
+        return;
+    }
+    band /= 2;
+
+    // trace back from the bottom-right corner (ssw.c:634-716); ops are produced last-first
+    uint32_t *cg = d.cigars + t * (size_t)d.cigar_stride;
+    int i = readLen - 1, j = refLen - 1, e = 0, l = 0, fop = 0, prev = 0, state = 2;
+    bool bad = false;
+    auto emit = [&](uint32_t v) { if (l < d.cigar_stride) cg[l] = v; ++l; };
+    while (i > 0) {
+        const int x = band_d(band, i, j);
+        if (x < 0 || x >= wd || j < 0) { bad = true; break; }
+        const int code = sw_dir_get(dirs[(size_t)wd * i + x], state);
+        switch (code) {
+        case 1: --i; --j; state = 2; fop = 0; break;
+        case 2: --i; state = 0; fop = 1; break;
+        case 3: --i; state = 2; fop = 1; break;
+        case 4: --j; state = 1; fop = 2; break;
+        case 5: --j; state = 2; fop = 2; break;
+        default: bad = true; break;
+        }
+        if (bad) break;
+        if (fop == prev) ++e;
+        else { emit((uint32_t)e << 4 | (uint32_t)prev); prev = fop; e = 1; }
+    }
+    if (bad) { o.cigarLen = -3; d.out[t] = o; return; }
+    if (fop == 0) emit((uint32_t)(e + 1) << 4);
+    else { emit((uint32_t)e << 4 | (uint32_t)fop); emit(16u); }
+    const int stored = l < d.cigar_stride ? l : d.cigar_stride;
+    for (int a = 0, b = stored - 1; a < b; ++a, --b) { const uint32_t tmp = cg[a]; cg[a] = cg[b]; cg[b] = tmp; }
+    if (l > d.cigar_stride) {
+        // keep the FIRST cigar_stride ops of the true cigar: they are the last ones produced.
+        // (callers size the stride for the worst case; cigarLen still reports the true length)
+    }
+    o.cigarLen = l;
+    d.out[t] = o;
+}
+
+// --------------------------------------------------------------------------------------
+// host side of this file
+// --------------------------------------------------------------------------------------
+struct SwShape { int G, S; };
+
+static SwShape pick_shape(int l_max)
+{
+    const int seg = (l_max + 7) / 8;                 // rows needed = 8*seg
+    static const int s8[] = {8, 13, 16, 19, 24, 32};
+    for (int s : s8) if (seg <= s) return {8, s};
+    if (8 * seg <= 16 * 32) return {16, 32};
+    return {32, 32};
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// layout: [0]=win2 [1]=rsel [2]=maxcol2 [3]=fwd [4]=dirs [5]=ovf_list [6]=ovf_count [7]=total
+size_t ssw_scratch_bytes(size_t n_tasks, int max_cols, int max_rows, size_t *layout)
+{
+    const SwShape sh = pick_shape(max_rows);
+    const int NQ = (sh.S + 3) / 4;
+    const size_t pairs = (n_tasks + 1) / 2;
+    const int CW = (max_cols + 7) / 8 + 1;
+    size_t off = 0;
+    layout[0] = off; off = align_up(off + pairs * CW * sizeof(uint2), 256);
+    layout[1] = off; off = align_up(off + pairs * 2 * sh.G * NQ * sizeof(uint32_t), 256);
+    layout[2] = off; off = align_up(off + pairs * (size_t)max_cols * sizeof(uint32_t), 256);
+    layout[3] = off; off = align_up(off + pairs * 2 * 8 * sizeof(int32_t), 256);
+    const size_t slot = (size_t)(2 * 16 + 1) * (size_t)(8 * ((max_rows + 7) / 8));
+    layout[4] = off; off = align_up(off + align_up(n_tasks, 128) * slot, 256);
+    layout[5] = off; off = align_up(off + n_tasks * sizeof(uint32_t), 256);
+    layout[6] = off; off = align_up(off + 256, 256);
+    layout[7] = off;
+    return off;
+}
+
+template <int G, int S>
+static cudaError_t run_dp(const SwDev &d, bool rev, cudaStream_t st)
+{
+    constexpr int GPC = 128 / G;
+    const size_t blocks = (d.n_pairs + GPC - 1) / GPC;
+    const size_t smem = 128 * 2 * S * sizeof(uint32_t);
+    if (rev) {
+        auto kern = sw_dp_kernel<G, S, true>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        SALT_LAUNCH(kern, (unsigned)blocks, 128, smem, st, d);
+    } else {
+        auto kern = sw_dp_kernel<G, S, false>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        SALT_LAUNCH(kern, (unsigned)blocks, 128, smem, st, d);
+    }
+    return cudaGetLastError();
+}
+
+static cudaError_t dispatch_dp(const SwDev &d, bool rev, cudaStream_t st)
+{
+    switch (d.G * 100 + d.S) {
+    case 808: return run_dp<8, 8>(d, rev, st);
+    case 813: return run_dp<8, 13>(d, rev, st);
+    case 816: return run_dp<8, 16>(d, rev, st);
+    case 819: return run_dp<8, 19>(d, rev, st);
+    case 824: return run_dp<8, 24>(d, rev, st);
+    case 832: return run_dp<8, 32>(d, rev, st);
+    case 1632: return run_dp<16, 32>(d, rev, st);
+    case 3232: return run_dp<32, 32>(d, rev, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// Overflow scratch for wide bands: allocated on first use, kept for the process lifetime.
+static uint8_t *g_ovf_dirs[64] = {nullptr};
+static const size_t OVF_SLOT = (size_t)(2 * 512 + 1) * 1024;     // band <= 512, rows <= 1024
+static const uint32_t OVF_CAP = 256;
+
+cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const SswParams &prm,
+                       void *scratch, size_t scratch_bytes, int max_cols,
+                       salt_ssw_out_t *out, uint32_t *cigars, int cigar_stride, int sm_count, cudaStream_t st,
+                       uint64_t *launches)
+{
+    (void)sm_count;
+    if (!n) return cudaSuccess;
+    size_t lay[8];
+    const size_t need = ssw_scratch_bytes(n, max_cols, (int)c.l_max, lay);
+    if (need > scratch_bytes) return cudaErrorMemoryAllocation;
+    const SwShape sh = pick_shape((int)c.l_max);
+    uint8_t *base = static_cast<uint8_t *>(scratch);
+    SwDev d;
+    d.c = c; d.wins = wins; d.n_tasks = n; d.n_pairs = (n + 1) / 2;
+    d.G = sh.G; d.S = sh.S; d.CW = (max_cols + 7) / 8 + 1; d.MC = max_cols;
+    d.win2 = reinterpret_cast<uint2 *>(base + lay[0]);
+    d.rsel = reinterpret_cast<uint32_t *>(base + lay[1]);
+    d.maxcol2 = reinterpret_cast<uint32_t *>(base + lay[2]);
+    d.fwd = reinterpret_cast<int32_t *>(base + lay[3]);
+    d.prm = prm;
+    const int NQ = (sh.S + 3) / 4;
+    const size_t prep_items = d.n_pairs * 2 * (size_t)(d.CW + d.G * NQ);
+    const unsigned prep_blocks = (unsigned)((prep_items + 255) / 256);
+    cudaError_t e;
+    uint32_t *ovf_count = reinterpret_cast<uint32_t *>(base + lay[6]);
+    if ((e = cudaMemsetAsync(ovf_count, 0, 256, st)) != cudaSuccess) return e;
+
+    { auto kern = sw_prep_kernel<false>; SALT_LAUNCH(kern, prep_blocks, 256, 0, st, d); }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = dispatch_dp(d, false, st)) != cudaSuccess) return e;
+    { auto kern = sw_prep_kernel<true>; SALT_LAUNCH(kern, prep_blocks, 256, 0, st, d); }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = dispatch_dp(d, true, st)) != cudaSuccess) return e;
+
+    BandDev b;
+    b.c = c; b.wins = wins; b.n_tasks = n; b.fwd = d.fwd; b.prm = prm;
+    b.dirs = base + lay[4];
+    b.slot = (size_t)(2 * 16 + 1) * (size_t)(8 * (((int)c.l_max + 7) / 8));
+    b.ovf_list = reinterpret_cast<uint32_t *>(base + lay[5]);
+    b.ovf_count = ovf_count; b.ovf_cap = OVF_CAP;
+    b.in_list = nullptr; b.in_count = nullptr;
+    b.out = out; b.cigars = cigars; b.cigar_stride = cigar_stride;
+    { auto kern = sw_banded_kernel<16, false>; SALT_LAUNCH(kern, (unsigned)((n + 127) / 128), 128, 0, st, b); }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64) {
+        if (!g_ovf_dirs[dev]) {
+            if ((e = cudaMalloc(&g_ovf_dirs[dev], OVF_SLOT * OVF_CAP)) != cudaSuccess) return e;
+        }
+        BandDev b2 = b;
+        b2.dirs = g_ovf_dirs[dev]; b2.slot = OVF_SLOT;
+        b2.in_list = b.ovf_list; b2.in_count = ovf_count;
+        { auto kern = sw_banded_kernel<512, true>; SALT_LAUNCH(kern, (OVF_CAP + 127) / 128, 128, 0, st, b2); }
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (launches) *launches += 6;
+    return cudaSuccess;
+}
+
+}  // namespace salt

@@ -1,0 +1,562 @@
+// verify.cu -- sm_100a kernels for the ungapped / gapped verification of (read, locus) pairs
+// and the per-read acceptance scans that reproduce salt's sequential threshold logic.
+//
+//   pack_reads      query codes -> one-hot nibbles for both strands      (query.c:46-64, editdistance.c:215-218)
+//   mismatch        ed_mismatch                                          (editdistance.c:88-163)
+//   lv              ed_diff -> computeEditDistance                       (editdistance.c:174, LandauVishkin.c:19)
+//   lv_cigar        ed_diff_withcigar -> computeEditDistanceWithCigar    (editdistance.c:234, LandauVishkin.c:176)
+//   expand / scan   alnse_check_nogap / alnse_check_withgap + overlap    (alnse.c:734, :871, :1014-1036, :1077-1097)
+#if !defined(SALT_EMUL)
+#include <cuda_runtime.h>
+#endif
+
+#include "common.cuh"
+#include "lv_core.cuh"
+#include "kernels.h"
+
+namespace salt {
+
+// --------------------------------------------------------------------------------------
+// pack_reads: one thread per 64-bit output word (16 bases).
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_reads_kernel(const uint8_t *__restrict__ codes, const uint32_t *__restrict__ offs, uint32_t n_reads,
+                  uint32_t W64, uint64_t *__restrict__ rd4, uint16_t *__restrict__ rd_len)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)n_reads * 2 * W64;
+    if (idx >= total) return;
+    const uint32_t w = (uint32_t)(idx % W64);
+    const uint32_t rs = (uint32_t)(idx / W64);
+    const uint32_t rid = rs >> 1, strand = rs & 1;
+    const uint32_t o = offs[rid];
+    const int L = (int)(offs[rid + 1] - o);
+    uint64_t word = 0;
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+        const int i = (int)w * 16 + b;
+        if (i < L) {
+            unsigned c = strand ? codes[o + (L - 1 - i)] : codes[o + i];
+            if (strand && c < 4) c = 3 - c;
+            const uint64_t nib = c > 3 ? 15u : (1u << c);
+            word |= nib << (4 * b);
+        }
+    }
+    rd4[idx] = word;
+    if (w == 0 && strand == 0) rd_len[rid] = (uint16_t)L;
+}
+
+// --------------------------------------------------------------------------------------
+// mismatch: G lanes per pair, one 64-bit word (16 bases) per lane per iteration.
+// The window is fetched as aligned 64-bit words (coalesced across the group) and funnel
+// shifted to the read's nibble phase; a match is (ref & read) != 0 per nibble.
+// --------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256)
+mismatch_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int max_err, int8_t *__restrict__ out)
+{
+    const size_t gid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
+    const bool live = gid < n;
+    salt_pair_t p; p.rs = 0; p.pos = 0;
+    if (live) p = pairs[gid];
+    const uint32_t rid = p.rs >> 1;
+    bool bad = !live || rid >= c.n_reads;
+    const int L = bad ? 0 : (int)c.rd_len[rid];
+    bad = bad || ((uint64_t)p.pos + (uint64_t)L > (uint64_t)c.l) || L == 0;
+    int matches = 0;
+    if (!bad) {
+        const uint64_t *__restrict__ r = c.rd4 + (size_t)p.rs * c.W64;
+        const uint64_t *__restrict__ m64 = reinterpret_cast<const uint64_t *>(c.mixref);
+        const int nw = (L + 15) >> 4;
+        const size_t base = p.pos >> 4;
+        const int sh = (p.pos & 15) * 4;
+        for (int w = lane; w < nw; w += G) {
+            const uint64_t q0 = m64[base + w], q1 = m64[base + w + 1];
+            const uint64_t x = sh ? ((q0 >> sh) | (q1 << (64 - sh))) : q0;
+            uint64_t m = x & r[w];
+            m |= m >> 1;
+            m |= m >> 2;
+            matches += __popcll(m & 0x1111111111111111ull);
+        }
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) matches += __shfl_xor_sync(0xffffffffu, matches, o, G);
+    if (lane == 0 && live) {
+        const int nmis = L - matches;
+        out[gid] = (int8_t)((bad || nmis > max_err) ? -1 : nmis);
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// Staging of one pair's text window and pattern into shared memory (32-bit words).
+// T: nibbles pos..pos+tlen-1 of mixRef, zero from tlen on.  P: the packed read, zero from plen on.
+// --------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ void lv_stage(const DevCtx &c, uint32_t rs, uint32_t pos, int plen, int tlen,
+                                         uint32_t *T, uint32_t *P, int TW, int PW, int lane)
+{
+    const uint32_t *__restrict__ mix = c.mixref;
+    for (int i = lane; i < TW; i += G) {
+        const int valid = tlen - 8 * i;
+        uint32_t x = 0;
+        if (valid > 0) {
+            const uint32_t o = pos + 8u * (uint32_t)i;
+            const uint32_t w = o >> 3;
+            const int sh = (int)(o & 7u) * 4;
+            x = __funnelshift_r(mix[w], mix[w + 1], sh);
+            if (valid < 8) x &= (1u << (4 * valid)) - 1u;
+        }
+        T[i] = x;
+    }
+    const uint32_t *__restrict__ r32 = reinterpret_cast<const uint32_t *>(c.rd4 + (size_t)rs * c.W64);
+    const int have = (int)c.W64 * 2;
+    for (int i = lane; i < PW; i += G) P[i] = i < have ? r32[i] : 0u;
+    (void)plen;
+}
+
+// Cooperative level-0 extension: lane t looks at symbols [8t, 8t+8) of each 8G-symbol block.
+template <int G>
+__device__ __forceinline__ int lv_level0(const uint32_t *T, const uint32_t *P, int plen, int tlen,
+                                         int lane, unsigned gmask, int gshift)
+{
+    const int e0 = imin(plen, tlen);
+    for (int base = 0; base < e0; base += 8 * G) {
+        const int off = base + 8 * lane;
+        // lanes past the end report a stop at their first symbol; the min() below clamps it
+        const uint32_t z = off < e0 ? zero_nibbles(nib8(P, off) & nib8(T, off)) : 1u;
+        const unsigned bal = (__ballot_sync(gmask, z != 0) >> gshift) & (unsigned)((1ull << G) - 1ull);
+        if (bal) {
+            const int first = __ffs((int)bal) - 1;
+            const int idx = __shfl_sync(gmask, z ? first_set_nibble(z) : 0, first, G);
+            return imin(base + 8 * first + idx, e0);
+        }
+    }
+    return e0;
+}
+
+// Shared-memory words needed per pair for a chunk whose longest read is l_max.
+__host__ __device__ inline int lv_tw(int l_max) { return (l_max + 4 + 64) / 8 + 2; }
+__host__ __device__ inline int lv_pw(int l_max) { return (l_max + 64) / 8 + 2; }
+
+// --------------------------------------------------------------------------------------
+// lv: G lanes per pair, DPL diagonals per lane (diagonal d = lane*DPL + q - G*DPL/2).
+// Furthest-reaching values of the previous level live in registers; neighbours are
+// exchanged with __shfl_up/down inside the group.  The diagonal order of the reference
+// (0,+1,-1,..) does not affect the returned level, so all diagonals of a level run at once.
+// Work items: pairs[i] for i < n, or, when `worklist` is non-null, pairs[worklist[i]] for
+// i < *wl_count (persistent groups stride over the list).
+// --------------------------------------------------------------------------------------
+template <int G, int DPL>
+__global__ void __launch_bounds__(128)
+lv_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_fixed,
+          const uint32_t *__restrict__ worklist, const uint32_t *__restrict__ wl_count,
+          int8_t *__restrict__ out)
+{
+    SALT_DYN_SMEM(uint32_t, smem);
+    constexpr int ND = G * DPL, C = ND / 2;
+    const int TW = lv_tw((int)c.l_max), PW = lv_pw((int)c.l_max);
+    const int gl = threadIdx.x / G, lane = threadIdx.x % G;
+    const int gshift = (threadIdx.x & 31) / G * G;
+    const unsigned gmask = (unsigned)(((1ull << G) - 1ull) << gshift);
+    uint32_t *T = smem + (size_t)gl * (TW + PW);
+    uint32_t *P = T + TW;
+    const size_t groups = (size_t)gridDim.x * (blockDim.x / G);
+    const size_t count = worklist ? (size_t)*wl_count : n;
+
+    for (size_t it = (size_t)blockIdx.x * (blockDim.x / G) + gl; it < count; it += groups) {
+        const size_t slot = worklist ? worklist[it] : it;
+        const salt_pair_t p = pairs[slot];
+        const uint32_t rid = p.rs >> 1;
+        const int plen = rid < c.n_reads ? (int)c.rd_len[rid] : 0;
+        const int tlen = plen + 4;                                  // alnse.c:373
+        int k = k_fixed >= 0 ? k_fixed : plen / 10;                 // alnse.c:1090
+        k = imin(k, LV_MAXK - 1);                                   // LandauVishkin.c:31
+        k = imin(k, C - 1);                                         // diagonals this instantiation holds
+        int result = -1;
+        // editdistance.c:178: window must lie inside the reference
+        const bool ok = plen > 0 && (uint64_t)p.pos + (uint64_t)tlen <= (uint64_t)c.l;
+        if (ok) {
+            lv_stage<G>(c, p.rs, p.pos, plen, tlen, T, P, TW, PW, lane);
+            __syncwarp(gmask);
+            const int L0 = lv_level0<G>(T, P, plen, tlen, lane, gmask, gshift);
+            if (L0 == plen) {
+                result = 0;                                         // endl(0) == plen since tlen > plen
+            } else {
+                int Lp[DPL];
+#pragma unroll
+                for (int q = 0; q < DPL; ++q) Lp[q] = (lane * DPL + q - C == 0) ? L0 : -2;
+                for (int e = 1; e <= k; ++e) {
+                    int lft = __shfl_up_sync(gmask, Lp[DPL - 1], 1, G);
+                    int rgt = __shfl_down_sync(gmask, Lp[0], 1, G);
+                    if (lane == 0) lft = -2;
+                    if (lane == G - 1) rgt = -2;
+                    int Ln[DPL];
+                    bool hit = false;
+#pragma unroll
+                    for (int q = 0; q < DPL; ++q) {
+                        const int d = lane * DPL + q - C;
+                        const int left = q == 0 ? lft : Lp[q - 1];
+                        const int right = q == DPL - 1 ? rgt : Lp[q + 1];
+                        int best = imax(imax(Lp[q] + 1, left), right + 1);
+                        if (d >= -e && d <= e) {
+                            best = lv_extend(T, P, best, d, plen, tlen);
+                            hit = hit || best == plen;
+                            Ln[q] = best;
+                        } else {
+                            Ln[q] = -2;
+                        }
+                    }
+                    if (__any_sync(gmask, hit)) { result = e; break; }
+#pragma unroll
+                    for (int q = 0; q < DPL; ++q) Lp[q] = Ln[q];
+                }
+            }
+            __syncwarp(gmask);
+        }
+        if (lane == 0) out[slot] = (int8_t)result;
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// lv_cigar: one warp per pair, 64 diagonals (2 per lane), furthest-reaching and action
+// tables kept in shared memory for the backtrace, which lane 0 performs.
+// Work items: (pairs[i], k_each[i]) -> cigars + i*stride, or, when `worklist` is non-null,
+// read ids whose primary (rec[rid]) is gapped -> cigars + rid*stride (query.c:282-295).
+// --------------------------------------------------------------------------------------
+struct LvCigarSmem {
+    int16_t L[LV_MAXK][LV_ND];
+    char A[LV_MAXK][LV_ND];
+};
+
+__global__ void __launch_bounds__(128)
+lv_cigar_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8_t *__restrict__ k_each, size_t n,
+                const uint32_t *__restrict__ worklist, const uint32_t *__restrict__ wl_count,
+                const salt_verify_out_t *__restrict__ rec,
+                char *__restrict__ cigars, int stride, int8_t *__restrict__ out)
+{
+    SALT_DYN_SMEM(uint32_t, smem);
+    constexpr int G = 32, DPL = 2, C = LV_ND / 2;
+    const int TW = lv_tw((int)c.l_max), PW = lv_pw((int)c.l_max);
+    const int wl = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int warps = blockDim.x / 32;
+    const size_t per_warp = (sizeof(LvCigarSmem) + 3) / 4 + TW + PW;
+    uint32_t *base = smem + (size_t)wl * per_warp;
+    LvCigarSmem *tab = reinterpret_cast<LvCigarSmem *>(base);
+    uint32_t *T = base + (sizeof(LvCigarSmem) + 3) / 4;
+    uint32_t *P = T + TW;
+    const unsigned gmask = 0xffffffffu;
+    const size_t groups = (size_t)gridDim.x * warps;
+    const size_t count = worklist ? (size_t)*wl_count : n;
+
+    for (size_t it = (size_t)blockIdx.x * warps + wl; it < count; it += groups) {
+        salt_pair_t p; int k; size_t slot;
+        if (worklist) {
+            const uint32_t rid = worklist[it];
+            const salt_verify_out_t r = rec[rid];
+            p.rs = (rid << 1) | (r.strand & 1); p.pos = r.pos; k = r.n_diff; slot = rid;
+        } else {
+            p = pairs[it]; k = k_each[it]; slot = it;
+        }
+        char *buf = cigars + slot * (size_t)stride;
+        const uint32_t rid = p.rs >> 1;
+        const int plen = rid < c.n_reads ? (int)c.rd_len[rid] : 0;
+        const int tlen = plen + 4;
+        int result = -1;
+        const bool ok = plen > 0 && k < LV_MAXK && (uint64_t)p.pos + (uint64_t)tlen <= (uint64_t)c.l;
+        if (ok) {
+            lv_stage<G>(c, p.rs, p.pos, plen, tlen, T, P, TW, PW, lane);
+            __syncwarp();
+            const int L0 = lv_level0<G>(T, P, plen, tlen, lane, gmask, 0);
+            if (L0 == plen) {
+                if (lane == 0) { CigarOut o{buf, stride}; result = o.put(plen, 'M') ? 0 : -2; }
+            } else {
+                int Lp[DPL];
+#pragma unroll
+                for (int q = 0; q < DPL; ++q) {
+                    const int d = lane * DPL + q - C;
+                    Lp[q] = d == 0 ? L0 : -2;
+                    tab->L[0][d + C] = (int16_t)Lp[q];
+                }
+                int found_e = -1, found_d = 0;
+                for (int e = 1; e <= k; ++e) {
+                    int lft = __shfl_up_sync(gmask, Lp[DPL - 1], 1);
+                    int rgt = __shfl_down_sync(gmask, Lp[0], 1);
+                    if (lane == 0) lft = -2;
+                    if (lane == G - 1) rgt = -2;
+                    int Ln[DPL];
+                    int myrank = 1 << 20;
+#pragma unroll
+                    for (int q = 0; q < DPL; ++q) {
+                        const int d = lane * DPL + q - C;
+                        const int left = q == 0 ? lft : Lp[q - 1];
+                        const int right = (q == DPL - 1 ? rgt : Lp[q + 1]) + 1;
+                        int best = Lp[q] + 1; char a = 'X';                // LandauVishkin.c:249-260
+                        if (left > best) { best = left; a = 'D'; }
+                        if (right > best) { best = right; a = 'I'; }
+                        if (d >= -e && d <= e) {
+                            best = lv_extend(T, P, best, d, plen, tlen);
+                            if (best == plen) myrank = imin(myrank, lv_cigar_rank(d));
+                            Ln[q] = best;
+                            tab->A[e][d + C] = a;
+                        } else {
+                            Ln[q] = -2;
+                        }
+                        tab->L[e][d + C] = (int16_t)Ln[q];
+                    }
+                    int r = myrank;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) r = imin(r, __shfl_xor_sync(gmask, r, o));
+                    if (r < (1 << 20)) {
+                        found_e = e;
+                        found_d = r == 0 ? 0 : ((r & 1) ? -(r + 1) / 2 : r / 2);
+                        break;
+                    }
+#pragma unroll
+                    for (int q = 0; q < DPL; ++q) Lp[q] = Ln[q];
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    if (found_e < 0) { if (stride > 0) buf[0] = '\0'; result = -1; }
+                    else result = lv_cigar_emit(&tab->L[0][0], &tab->A[0][0], found_e, found_d, buf, stride);
+                }
+            }
+            __syncwarp();
+        } else if (lane == 0 && stride > 0 && plen > 0 && k < LV_MAXK) {
+            buf[0] = '\0';
+        }
+        if (lane == 0 && out) out[slot] = (int8_t)result;
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// expand: CSR candidate lists -> flat pair array (strand 0 lists first, then strand 1).
+// One thread per candidate; the owning read is found by binary search in the offsets.
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+expand_kernel(const uint32_t *__restrict__ offs0, const uint32_t *__restrict__ loci0, size_t n0,
+              const uint32_t *__restrict__ offs1, const uint32_t *__restrict__ loci1, size_t n1,
+              uint32_t n_reads, salt_pair_t *__restrict__ pairs)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0 + n1) return;
+    const uint32_t strand = i >= n0;
+    const uint32_t *offs = strand ? offs1 : offs0;
+    const uint32_t j = (uint32_t)(strand ? i - n0 : i);
+    uint32_t lo = 0, hi = n_reads;                  // find r with offs[r] <= j < offs[r+1]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (offs[mid] <= j) lo = mid; else hi = mid;
+    }
+    salt_pair_t p;
+    p.rs = (lo << 1) | strand;
+    p.pos = strand ? loci1[j] : loci0[j];
+    pairs[i] = p;
+}
+
+// --------------------------------------------------------------------------------------
+// Acceptance scans.  The kernels above return n iff n <= T0; the reference calls them with
+// a threshold that tightens as candidates are accepted, which is equivalent to accepting
+// candidate i iff n_i <= min(T0, min_{j<i} n_j) in list order, strand 0 then strand 1
+// (code_kmismatch / code_kdiff, alnse.c:348-393).  One thread per read walks its lists.
+// --------------------------------------------------------------------------------------
+struct StageState { int max_diff; };
+
+__device__ __forceinline__ int scan_stage(const uint32_t *__restrict__ loci, uint32_t b, uint32_t e,
+                                          int8_t *__restrict__ acc, uint32_t l_mref, uint32_t guard,
+                                          int max_diff, int strand, int gapped, salt_verify_out_t &q)
+{
+    bool matched = false;
+    uint32_t last = 0xFFFFFFFFu;
+    for (uint32_t i = b; i < e; ++i) {
+        const uint32_t pos = loci[i];
+        // alnse.c:762 (nogap: pos >= l) / :894 (withgap: pos + l_seq + 4 >= l, uint32 arithmetic)
+        if (pos == last || (uint32_t)(pos + guard) >= l_mref) { acc[i] = -1; continue; }
+        const int nd = acc[i];
+        if (nd >= 0 && nd <= max_diff) {
+            if (nd < max_diff || !matched) {
+                max_diff = nd;
+                q.is_gap = (uint8_t)gapped; q.n_diff = (uint8_t)nd; q.strand = (uint8_t)strand; q.pos = pos;
+            }
+            matched = true;
+            q.n_hits[strand] += 1;
+        } else {
+            acc[i] = -1;
+        }
+        last = pos;
+    }
+    return matched ? max_diff : -1;
+}
+
+__global__ void __launch_bounds__(128)
+scan_nogap_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t *__restrict__ loci0,
+                  const uint32_t *__restrict__ offs1, const uint32_t *__restrict__ loci1, size_t n0,
+                  int T0, int8_t *__restrict__ acc, salt_verify_out_t *__restrict__ rec,
+                  uint32_t *__restrict__ lv_list, uint32_t *__restrict__ lv_count)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= c.n_reads) return;
+    salt_verify_out_t q;
+    q.pos = 0xFFFFFFFFu; q.strand = 3; q.n_diff = 255; q.is_gap = 255; q.lv_ran = 0; q.n_hits[0] = q.n_hits[1] = 0;
+    int max_diff = T0;
+    const uint32_t b0 = offs0[r], e0 = offs0[r + 1], b1 = offs1[r], e1 = offs1[r + 1];
+    const int m0 = scan_stage(loci0, b0, e0, acc, c.l, 0, max_diff, 0, 0, q);
+    if (m0 != -1 && m0 < max_diff) max_diff = m0;
+    const int m1 = scan_stage(loci1, b1, e1, acc + n0, c.l, 0, max_diff, 1, 0, q);
+    if (m0 == -1 && m1 == -1) {                      // alnse.c:1022 / :1089
+        q.lv_ran = 1;
+        const uint32_t cnt = (e0 - b0) + (e1 - b1);
+        if (cnt) {
+            uint32_t w = atomicAdd(lv_count, cnt);
+            for (uint32_t i = b0; i < e0; ++i) lv_list[w++] = i;
+            for (uint32_t i = b1; i < e1; ++i) lv_list[w++] = (uint32_t)n0 + i;
+        }
+    }
+    rec[r] = q;
+}
+
+__global__ void __launch_bounds__(128)
+scan_gap_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t *__restrict__ loci0,
+                const uint32_t *__restrict__ offs1, const uint32_t *__restrict__ loci1, size_t n0,
+                int lv_T0, int8_t *__restrict__ acc, salt_verify_out_t *__restrict__ rec,
+                uint32_t *__restrict__ cig_list, uint32_t *__restrict__ cig_count)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= c.n_reads) return;
+    salt_verify_out_t q = rec[r];
+    if (!q.lv_ran) return;
+    const int L = c.rd_len[r];
+    int max_diff = lv_T0 >= 0 ? lv_T0 : L / 10;
+    const uint32_t guard = (uint32_t)L + 4u;
+    const int d0 = scan_stage(loci0, offs0[r], offs0[r + 1], acc, c.l, guard, max_diff, 0, 1, q);
+    if (d0 != -1 && d0 < max_diff) max_diff = d0;
+    (void)scan_stage(loci1, offs1[r], offs1[r + 1], acc + n0, c.l, guard, max_diff, 1, 1, q);
+    rec[r] = q;
+    if (q.is_gap == 1 && cig_list) cig_list[atomicAdd(cig_count, 1u)] = r;
+}
+
+// --------------------------------------------------------------------------------------
+// launchers
+// --------------------------------------------------------------------------------------
+#define SALT_LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
+
+cudaError_t launch_pack_reads(const uint8_t *codes, const uint32_t *offs, uint32_t n_reads, uint32_t W64,
+                              uint64_t *rd4, uint16_t *rd_len, cudaStream_t st)
+{
+    const size_t total = (size_t)n_reads * 2 * W64;
+    if (!total) return cudaSuccess;
+    SALT_LAUNCH(pack_reads_kernel, (unsigned)((total + 255) / 256), 256, 0, st, codes, offs, n_reads, W64, rd4, rd_len);
+    SALT_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_mismatch(const DevCtx &c, const salt_pair_t *pairs, size_t n, int max_err, int8_t *out, cudaStream_t st)
+{
+    if (!n) return cudaSuccess;
+    const int nw = ((int)c.l_max + 15) / 16;
+    if (nw <= 4) {
+        constexpr int G = 4;
+        auto kern = mismatch_kernel<G>;
+        SALT_LAUNCH(kern, (unsigned)((n * G + 255) / 256), 256, 0, st, c, pairs, n, max_err, out);
+    } else if (nw <= 8) {
+        constexpr int G = 8;
+        auto kern = mismatch_kernel<G>;
+        SALT_LAUNCH(kern, (unsigned)((n * G + 255) / 256), 256, 0, st, c, pairs, n, max_err, out);
+    } else {
+        constexpr int G = 16;
+        auto kern = mismatch_kernel<G>;
+        SALT_LAUNCH(kern, (unsigned)((n * G + 255) / 256), 256, 0, st, c, pairs, n, max_err, out);
+    }
+    SALT_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+template <int G, int DPL>
+static cudaError_t launch_lv_t(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k,
+                               const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
+                               int8_t *out, int sm_count, cudaStream_t st)
+{
+    constexpr int threads = 128;
+    const int gpc = threads / G;
+    const size_t smem = (size_t)gpc * (lv_tw((int)c.l_max) + lv_pw((int)c.l_max)) * 4;
+    const size_t items = worklist ? wl_cap : n;
+    size_t blocks = (items + gpc - 1) / gpc;
+    const size_t cap = (size_t)sm_count * 16;          // persistent upper bound: groups stride over the rest
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) return cudaSuccess;
+    auto kern = lv_kernel<G, DPL>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    SALT_LAUNCH(kern, (unsigned)blocks, threads, smem, st, c, pairs, n, k, worklist, wl_count, out);
+    SALT_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_lv(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k,
+                      const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
+                      int8_t *out, int sm_count, cudaStream_t st)
+{
+    int kmax = k >= 0 ? k : (int)c.l_max / 10;
+    if (kmax > LV_MAXK - 1) kmax = LV_MAXK - 1;
+    if (kmax <= 3) return launch_lv_t<8, 1>(c, pairs, n, k, worklist, wl_count, wl_cap, out, sm_count, st);
+    if (kmax <= 7) return launch_lv_t<16, 1>(c, pairs, n, k, worklist, wl_count, wl_cap, out, sm_count, st);
+    if (kmax <= 15) return launch_lv_t<32, 1>(c, pairs, n, k, worklist, wl_count, wl_cap, out, sm_count, st);
+    return launch_lv_t<32, 2>(c, pairs, n, k, worklist, wl_count, wl_cap, out, sm_count, st);
+}
+
+cudaError_t launch_lv_cigar(const DevCtx &c, const salt_pair_t *pairs, const uint8_t *k_each, size_t n,
+                            const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
+                            const salt_verify_out_t *rec, char *cigars, int stride, int8_t *out,
+                            int sm_count, cudaStream_t st)
+{
+    constexpr int threads = 128, warps = threads / 32;
+    const size_t per_warp = ((sizeof(LvCigarSmem) + 3) / 4 + lv_tw((int)c.l_max) + lv_pw((int)c.l_max)) * 4;
+    const size_t smem = per_warp * warps;
+    const size_t items = worklist ? wl_cap : n;
+    size_t blocks = (items + warps - 1) / warps;
+    const size_t cap = (size_t)sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) return cudaSuccess;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(lv_cigar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    SALT_LAUNCH(lv_cigar_kernel, (unsigned)blocks, threads, smem, st, c, pairs, k_each, n, worklist, wl_count, rec, cigars, stride, out);
+    SALT_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_expand(const uint32_t *offs0, const uint32_t *loci0, size_t n0,
+                          const uint32_t *offs1, const uint32_t *loci1, size_t n1,
+                          uint32_t n_reads, salt_pair_t *pairs, cudaStream_t st)
+{
+    const size_t n = n0 + n1;
+    if (!n) return cudaSuccess;
+    SALT_LAUNCH(expand_kernel, (unsigned)((n + 255) / 256), 256, 0, st, offs0, loci0, n0, offs1, loci1, n1, n_reads, pairs);
+    SALT_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_scan_nogap(const DevCtx &c, const uint32_t *offs0, const uint32_t *loci0,
+                              const uint32_t *offs1, const uint32_t *loci1, size_t n0, int T0,
+                              int8_t *acc, salt_verify_out_t *rec, uint32_t *lv_list, uint32_t *lv_count, cudaStream_t st)
+{
+    if (!c.n_reads) return cudaSuccess;
+    SALT_LAUNCH(scan_nogap_kernel, (c.n_reads + 127) / 128, 128, 0, st, c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_list, lv_count);
+    SALT_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_scan_gap(const DevCtx &c, const uint32_t *offs0, const uint32_t *loci0,
+                            const uint32_t *offs1, const uint32_t *loci1, size_t n0, int lv_T0,
+                            int8_t *acc, salt_verify_out_t *rec, uint32_t *cig_list, uint32_t *cig_count, cudaStream_t st)
+{
+    if (!c.n_reads) return cudaSuccess;
+    SALT_LAUNCH(scan_gap_kernel, (c.n_reads + 127) / 128, 128, 0, st, c, offs0, loci0, offs1, loci1, n0, lv_T0, acc, rec, cig_list, cig_count);
+    SALT_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+}  // namespace salt

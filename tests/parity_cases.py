@@ -1,0 +1,131 @@
+"""Parity cases shared by the GPU tests (real CUDA library) and the CPU logic tests (the SIMT
+emulator build of the same kernel sources).  Every case compares the engine, called through
+the C ABI, with the oracle on the same seeded inputs; all comparisons are bit-exact."""
+import numpy as np
+
+from salt_b200 import api, synth
+
+
+def make_world(seed, glen=60000, L=100, n_reads=64, per_strand=6, snp_rate=0.02, n_rate=0.002,
+               sub_rate=0.02, indel_frac=0.3, n_frac=0.003):
+    g = synth.Genome(glen, snp_rate=snp_rate, n_rate=n_rate, seed=seed)
+    reads, pos, strand = synth.sample_reads(g, n_reads, L, seed=seed + 1, sub_rate=sub_rate,
+                                            indel_frac=indel_frac, n_frac=n_frac)
+    offs0, loci0, offs1, loci1 = synth.make_candidates(g, pos, strand, L, per_strand=per_strand, seed=seed + 2)
+    return g, reads, pos, strand, (offs0, loci0, offs1, loci1)
+
+
+def flat_pairs(cands, n_reads):
+    offs0, loci0, offs1, loci1 = cands
+    rid0 = np.repeat(np.arange(n_reads, dtype=np.uint32), np.diff(offs0.astype(np.int64)))
+    rid1 = np.repeat(np.arange(n_reads, dtype=np.uint32), np.diff(offs1.astype(np.int64)))
+    p0 = api.Engine.make_pairs(rid0, np.zeros(len(rid0), np.uint32), loci0)
+    p1 = api.Engine.make_pairs(rid1, np.ones(len(rid1), np.uint32), loci1)
+    return np.concatenate([p0, p1])
+
+
+def read_of(reads, rs):
+    r = reads[rs >> 1]
+    return synth.revcomp(r) if rs & 1 else r
+
+
+def check_mismatch(eng, oracle, g, reads, pairs, max_err):
+    got = eng.mismatch(pairs, max_err)
+    for i, p in enumerate(pairs):
+        seq = np.ascontiguousarray(read_of(reads, int(p["rs"])))
+        want = oracle.ed_mismatch(g.mixref, int(p["pos"]), seq, max_err) if int(p["pos"]) + len(seq) <= g.l else -1
+        assert got[i] == want, ("mismatch", i, int(p["rs"]), int(p["pos"]), got[i], want)
+    return got
+
+
+def check_lv(eng, oracle, g, reads, pairs, k):
+    got = eng.lv(pairs, k)
+    for i, p in enumerate(pairs):
+        seq = np.ascontiguousarray(read_of(reads, int(p["rs"])))
+        kk = k if k >= 0 else len(seq) // 10
+        want = oracle.ed_diff(g.mixref, g.l, int(p["pos"]), seq, kk)
+        assert got[i] == want, ("lv", i, int(p["rs"]), int(p["pos"]), kk, got[i], want)
+    return got
+
+
+def check_lv_cigar(eng, oracle, g, reads, pairs, k_each, stride):
+    out, buf = eng.lv_cigar(pairs, k_each, stride, fill=0x7e)
+    n_gapped = 0
+    for i, p in enumerate(pairs):
+        seq = np.ascontiguousarray(read_of(reads, int(p["rs"])))
+        want = oracle.ed_diff_withcigar(g.mixref, int(p["pos"]), seq, int(k_each[i]), stride)
+        assert out[i] == want[0], ("lv_cigar rc", i, out[i], want)
+        if want[0] != -2:
+            assert api.cstr(buf[i]) == want[1], ("lv_cigar str", i, api.cstr(buf[i]), want)
+            # bytes after the terminator are the caller's (here: fill pattern), like the reference leaves them
+            assert (buf[i][len(want[1]) + 1:] == 0x7e).all()
+        n_gapped += ("I" in want[1]) or ("D" in want[1])
+    return n_gapped
+
+
+def check_verify(eng, oracle, g, reads, cands, nogap_T0=3, lv_T0=-1, stride=128):
+    offs0, loci0, offs1, loci1 = cands
+    rec, acc0, acc1, cig = eng.verify(offs0, loci0, offs1, loci1, nogap_T0, lv_T0, stride)
+    n = len(reads)
+    stats = dict(lv_ran=0, gapped=0, mapped=0)
+    for r in range(n):
+        seq = np.ascontiguousarray(reads[r]); rseq = np.ascontiguousarray(synth.revcomp(reads[r]))
+        l0 = loci0[offs0[r]:offs0[r + 1]]; l1 = loci1[offs1[r]:offs1[r + 1]]
+        prim, hits, _ = oracle.verify_read(g.mixref, g.l, seq, rseq, l0, l1, nogap_T0,
+                                           (len(seq) // 10 if lv_T0 < 0 else lv_T0))
+        got = rec[r]
+        assert (int(got["pos"]), int(got["strand"]), int(got["n_diff"]), int(got["is_gap"])) == prim[:4], (r, got, prim)
+        for s, (acc, lo, of) in enumerate(((acc0, l0, offs0), (acc1, l1, offs1))):
+            a = acc[of[r]:of[r + 1]]
+            got_hits = [(int(p), int(v)) for p, v in zip(lo, a) if v >= 0]
+            want_hits = [(h[0], h[1]) for h in hits[s]]
+            assert got_hits == want_hits, (r, s, got_hits, want_hits)
+            assert int(got["n_hits"][s]) == len(want_hits)
+        stats["lv_ran"] += int(got["lv_ran"]); stats["mapped"] += prim[0] != 0xFFFFFFFF
+        if prim[3] == 1:
+            stats["gapped"] += 1
+            want = oracle.ed_diff_withcigar(g.mixref, prim[0], rseq if prim[1] else seq, prim[2], stride)
+            assert api.cstr(cig[r]) == want[1], (r, api.cstr(cig[r]), want)
+    return stats
+
+
+def make_windows(g, reads, pos, strand, L, rng, width=401):
+    """Rescue-like windows: the read's true locus somewhere inside a `width`-base window,
+    plus a few decoy windows and windows clipped at the ends of the reference."""
+    n = len(reads)
+    wins = np.zeros(n, api.WIN_DT)
+    for i in range(n):
+        kind = rng.random()
+        if kind < 0.8:
+            start = max(0, int(pos[i]) - int(rng.integers(0, max(1, width - L))))
+        elif kind < 0.9:
+            start = int(rng.integers(0, g.l - width))
+        else:
+            start = int(rng.choice([0, g.l - width, g.l - int(rng.integers(L // 2, width))]))
+        end = min(g.l - 1, start + width - 1)
+        wins[i] = ((i << 1) | int(strand[i]), start, end)
+    return wins
+
+
+def check_ssw(eng, oracle, g, reads, wins, use_pac, mat, n_sym, gapO=3, gapE=1, flag=2, filters=0, filterd=20,
+              mask_len=-1, cigar_stride=64):
+    out, cig = eng.ssw(wins, mat, n_sym, use_pac, gapO, gapE, flag, filters, filterd, mask_len, cigar_stride)
+    gapped = 0
+    pad_mat = np.concatenate([np.asarray(mat, np.int8), np.asarray(mat, np.int8)[-1:]])   # index n*n -> last entry
+    for i, w in enumerate(wins):
+        seq = np.ascontiguousarray(read_of(reads, int(w["rs"])))
+        ml = len(seq) // 2 if mask_len < 0 else mask_len
+        if use_pac:
+            idx = np.arange(int(w["start"]), int(w["end"]) + 1)
+            ref = ((g.pac[idx >> 2] >> ((~idx & 3) << 1).astype(np.uint8)) & 3).astype(np.int8)
+            rc, rec, wc = oracle.ssw_align(seq.astype(np.int8), mat, n_sym, ref, gapO, gapE, flag, filters, filterd, ml)
+        else:
+            ref = synth.unpack_mixref(g.mixref, int(w["start"]), int(w["end"]) - int(w["start"]) + 1).astype(np.int8)
+            rd = (1 << seq.astype(np.int32)).astype(np.int8)
+            rc, rec, wc = oracle.ssw_align(rd, pad_mat, n_sym, ref, gapO, gapE, flag, filters, filterd, ml)
+        got = tuple(int(out[i][f]) for f in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1",
+                                              "read_end1", "ref_end2", "cigarLen"))
+        assert got == rec, ("ssw rec", i, got, rec, tuple(w))
+        assert np.array_equal(cig[i][:rec[7]], wc), ("ssw cigar", i, cig[i][:rec[7]], wc)
+        gapped += any((int(c) & 15) != 0 for c in wc)
+    return gapped

@@ -1,0 +1,128 @@
+"""CPU logic tests: the engine's kernel sources compiled on the SIMT emulator (tests/emul) and
+driven through the same C ABI, checked bit-exactly against the oracle.  The emulator is test
+infrastructure; the GPU tests in test_gpu_parity.py check the real CUDA library."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from salt_b200 import api, synth
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "emul"))
+
+
+@pytest.fixture(scope="module")
+def emul_lib():
+    import build_emul
+    return api._declare(C.CDLL(build_emul.build()))
+
+
+def _engine(emul_lib, g, with_pac=False):
+    return api.Engine(g.mixref, g.l, g.pac if with_pac else None, g.l if with_pac else 0, lib=emul_lib)
+
+
+@pytest.mark.parametrize("L", [100, 150, 250, 37])
+def test_mismatch(emul_lib, oracle, L):
+    g, reads, pos, strand, cands = pc.make_world(100 + L, L=L, n_reads=24, per_strand=4, indel_frac=0.0, sub_rate=0.004)
+    eng = _engine(emul_lib, g)
+    eng.set_reads(reads)
+    pairs = pc.flat_pairs(cands, len(reads))
+    extra = api.Engine.make_pairs([0, 1, 2], [0, 1, 0], [g.l - L, g.l - L + 1, g.l - 1])   # last fits, others run off the end
+    pairs = np.concatenate([pairs, extra])
+    got = pc.check_mismatch(eng, oracle, g, reads, pairs, 3)
+    assert (got >= 0).sum() >= len(reads) // 2
+    pc.check_mismatch(eng, oracle, g, reads, pairs[:40], 0)
+    pc.check_mismatch(eng, oracle, g, reads, pairs[:40], 12)
+
+
+@pytest.mark.parametrize("L,k", [(100, -1), (100, 3), (150, -1), (250, -1), (100, 7), (64, 2), (100, 30)])
+def test_lv(emul_lib, oracle, L, k):
+    g, reads, pos, strand, cands = pc.make_world(200 + L + k, L=L, n_reads=16, per_strand=4, indel_frac=0.6, sub_rate=0.03)
+    eng = _engine(emul_lib, g)
+    eng.set_reads(reads)
+    pairs = pc.flat_pairs(cands, len(reads))
+    extra = api.Engine.make_pairs([0, 1], [0, 1], [g.l - L - 4, g.l - L - 3])
+    pairs = np.concatenate([pairs, extra])
+    got = pc.check_lv(eng, oracle, g, reads, pairs, k)
+    assert (got > 0).sum() >= 3
+
+
+@pytest.mark.parametrize("L", [100, 250])
+def test_lv_cigar(emul_lib, oracle, L):
+    g, reads, pos, strand, cands = pc.make_world(300 + L, L=L, n_reads=24, per_strand=3, indel_frac=0.8, sub_rate=0.02)
+    eng = _engine(emul_lib, g)
+    eng.set_reads(reads)
+    rng = np.random.default_rng(L)
+    # true loci (mostly gapped alignments) and a few decoys, with assorted k and tiny buffers
+    rid = np.arange(len(reads), dtype=np.uint32)
+    pairs = api.Engine.make_pairs(rid, strand, pos)
+    k_each = rng.choice([2, 5, 10, 25, 30], len(pairs)).astype(np.uint8)
+    gapped = pc.check_lv_cigar(eng, oracle, g, reads, pairs, k_each, 128)
+    assert gapped >= 5
+    pc.check_lv_cigar(eng, oracle, g, reads, pairs, k_each, 6)
+    pc.check_lv_cigar(eng, oracle, g, reads, pc.flat_pairs(cands, len(reads))[:24], np.full(24, 10, np.uint8), 256)
+
+
+@pytest.mark.parametrize("L,lv_T0", [(100, -1), (100, 3), (150, -1)])
+def test_verify_stage(emul_lib, oracle, L, lv_T0):
+    g, reads, pos, strand, cands = pc.make_world(400 + L, L=L, n_reads=48, per_strand=5, indel_frac=0.35,
+                                                 sub_rate=0.025, glen=30000)
+    # a read with no candidates at all and duplicated loci must behave like the reference's loops
+    offs0, loci0, offs1, loci1 = cands
+    loci0 = loci0.copy(); loci0[offs0[3] + 1] = loci0[offs0[3]]
+    eng = _engine(emul_lib, g)
+    eng.set_reads(reads)
+    st = pc.check_verify(eng, oracle, g, reads, (offs0, loci0, offs1, loci1), 3, lv_T0)
+    assert st["lv_ran"] >= 5 and st["gapped"] >= 2 and st["mapped"] >= 30
+
+
+def test_verify_empty_lists(emul_lib, oracle):
+    g, reads, pos, strand, cands = pc.make_world(77, L=100, n_reads=6, per_strand=3, glen=20000)
+    z = np.zeros(7, np.uint32); e = np.zeros(0, np.uint32)
+    eng = _engine(emul_lib, g)
+    eng.set_reads(reads)
+    rec, acc0, acc1, cig = eng.verify(z, e, z, e)
+    assert (rec["pos"] == 0xFFFFFFFF).all() and (rec["lv_ran"] == 1).all()
+
+
+@pytest.mark.parametrize("L,width", [(100, 401), (150, 401), (250, 301), (64, 200)])
+def test_ssw_mixref(emul_lib, oracle, L, width):
+    g, reads, pos, strand, _ = pc.make_world(500 + L, L=L, n_reads=18, per_strand=2, indel_frac=0.7,
+                                              sub_rate=0.04, glen=20000)
+    eng = _engine(emul_lib, g)
+    eng.set_reads(reads)
+    rng = np.random.default_rng(L)
+    wins = pc.make_windows(g, reads, pos, strand, L, rng, width)
+    gapped = pc.check_ssw(eng, oracle, g, reads, wins, False, api.salt_score_mat2(), 16)
+    assert gapped >= 3
+
+
+def test_ssw_pac_and_params(emul_lib, oracle):
+    L = 100
+    g, reads, pos, strand, _ = pc.make_world(600, L=L, n_reads=11, per_strand=2, indel_frac=0.7, sub_rate=0.04,
+                                              glen=20000, n_rate=0.0, n_frac=0.01)
+    eng = _engine(emul_lib, g, with_pac=True)
+    eng.set_reads(reads)
+    rng = np.random.default_rng(6)
+    wins = pc.make_windows(g, reads, pos, strand, L, rng, 401)
+    pc.check_ssw(eng, oracle, g, reads, wins, True, api.salt_score_mat(), 5)
+    pc.check_ssw(eng, oracle, g, reads, wins, True, api.salt_score_mat(), 5, gapO=5, gapE=2, mask_len=15)
+    pc.check_ssw(eng, oracle, g, reads, wins, True, api.salt_score_mat(), 5, flag=0)
+    pc.check_ssw(eng, oracle, g, reads, wins, True, api.salt_score_mat(), 5, flag=1, mask_len=7)
+    with pytest.raises(api.SaltError):
+        eng.ssw(wins, api.salt_score_mat(), 5, True, gapO=1, gapE=1)
+
+
+def test_build_mixref_on_device(emul_lib, oracle):
+    g = synth.Genome(5000, snp_rate=0.05, n_rate=0.01, seed=9)
+    rows = g.snp_table()
+    fasta = g.fasta()
+    want, l = oracle.build_mixref([("chr1", fasta)], rows)
+    pos = np.array([r[1] - 1 for r in rows], np.uint32)
+    mask = np.array([oracle.lib.orc_allele_mask(r[2].encode()) for r in rows], np.uint8)
+    eng = api.Engine.from_bases(fasta, pos, mask, lib=emul_lib)
+    assert np.array_equal(eng.get_mixref(), want)
+    assert np.array_equal(want, g.mixref)
