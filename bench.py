@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of salt's SNP-aware verification hot path on B200.
+
+Workload (BASELINE.json configs[1]): synthetic 50 Mbp genome + 1 % synthetic SNPs, 2 M single-end
+100 bp reads per GPU, each with --cands candidate loci per strand (true locus + decoys).  One
+"step" = one pass of the whole verification stage over the 2 M-read batch:
+    expand -> ed_mismatch on every candidate -> acceptance scan -> Landau-Vishkin on the
+    candidates of unmatched reads -> acceptance scan -> CIGARs for gapped primaries.
+
+  value : reads/s with reads, candidate lists and outputs resident in HBM (CUDA events on the
+          stream the kernels run on, max over ranks)
+  e2e   : the same pass through the C ABI from pinned HOST buffers (salt_b200_set_reads +
+          salt_b200_verify), H2D and D2H inside the timed region
+  roofline / kernels : per-kernel device time from the library's own CUDA events
+  sw / lv           : kernel-level sweeps of the mate-rescue Smith-Waterman and Landau-Vishkin
+  cpu_baseline      : the reference's own C functions (oracle/_ref) on the host cores, bounded sample
+
+`--impl reference` times only that CPU path (rank 0), K steps of the bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reads/s (SNP-aware verify stage: ed_mismatch + Landau-Vishkin + CIGAR)"
+UNIT = "reads/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=2_000_000)
+    ap.add_argument("--genome", type=int, default=50_000_000)
+    ap.add_argument("--read-len", type=int, default=100)
+    ap.add_argument("--cands", type=int, default=8, help="candidate loci per read per strand")
+    ap.add_argument("--snp-rate", type=float, default=0.01)
+    ap.add_argument("--cpu-sample", type=int, default=400_000, help="reads in the bounded CPU-baseline sample")
+    ap.add_argument("--sw-tasks", type=int, default=200_000)
+    ap.add_argument("--skip-extras", action="store_true", help="skip the sw/lv kernel sweeps")
+    return ap.parse_args()
+
+
+def make_workload(args, seed):
+    from salt_b200 import synth
+    t0 = time.time()
+    g = synth.Genome(args.genome, snp_rate=args.snp_rate, seed=seed)
+    n, L = args.reads, args.read_len
+    reads = np.empty((n, L), np.uint8); pos = np.empty(n, np.uint32); strand = np.empty(n, np.uint8)
+    chunk = 250_000
+    for i in range(0, n, chunk):
+        m = min(chunk, n - i)
+        r, p, s = synth.sample_reads(g, m, L, seed=seed * 1000 + i // chunk, sub_rate=0.01, indel_frac=0.02)
+        reads[i:i + m], pos[i:i + m], strand[i:i + m] = r, p, s
+    offs0, loci0, offs1, loci1 = synth.make_candidates(g, pos, strand, L, per_strand=args.cands, seed=seed + 7)
+    return dict(g=g, reads=reads, pos=pos, strand=strand, offs0=offs0, loci0=loci0, offs1=offs1, loci1=loci1,
+                gen_s=time.time() - t0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, dev):
+        self.dev = dev; self.rows = []; self.p = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        busy = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+def cpu_reference_run(args, wl, n_sample, steps, warmup):
+    """The reference's verification loop (oracle/_ref when present, else the port) on all host threads."""
+    from oracle import orc
+    o = orc.Oracle()
+    ref = orc.Ref() if orc.ref_available() else None
+    kind = "reference" if ref is not None else "port"
+    cores = os.cpu_count() or 1
+    n = min(n_sample, len(wl["reads"]))
+    L = args.read_len
+    codes = np.ascontiguousarray(wl["reads"][:n]).reshape(-1)
+    roffs = (np.arange(n + 1, dtype=np.uint64) * L).astype(np.uint32)
+    o0 = wl["offs0"][:n + 1].copy(); o1 = wl["offs1"][:n + 1].copy()
+    l0 = wl["loci0"][:o0[-1]]; l1 = wl["loci1"][:o1[-1]]
+    g = wl["g"]
+    times = []
+    for it in range(warmup + steps):
+        sec, recs, a0, a1, cig = o.verify_batch(g.mixref, g.l, codes, roffs, o0, l0, o1, l1, 3, -1, n_threads=cores, ref=ref)
+        if it >= warmup:
+            times.append(sec)
+    pairs = int(o0[-1]) + int(o1[-1])
+    return dict(kind=kind, cores=cores, n=n, pairs=pairs, sec=float(np.mean(times)), times=times,
+                sample="first %d of %d reads of the same workload (%d candidate pairs), verify stage with the reference's "
+                       "running thresholds, %d host threads, gcc -O2" % (n, len(wl["reads"]), pairs, cores))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = {"workload": "configs[1]: synthetic %d Mbp genome + %.1f%% SNPs, %d x %d bp SE reads per GPU, %d candidates/read/strand "
+                       "(true locus + decoys), sub 1%%, 2%% reads with an indel" % (args.genome // 1_000_000, args.snp_rate * 100,
+                                                                                  args.reads, args.read_len, args.cands),
+           "nogap_T0": 3, "lv_T0": "l_seq/10", "parallelism": "reads sharded per GPU, reference replicated, no collective on the data path",
+           "l2": "per-step inputs+outputs (~0.7 GB) exceed the 126 MB L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        wl = make_workload(args, seed=11)
+        r = cpu_reference_run(args, wl, args.cpu_sample, args.steps, args.warmup)
+        val = r["n"] / r["sec"]
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec"] * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": cfg,
+                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from salt_b200 import api
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    wl = make_workload(args, seed=11 + rank)
+    g = wl["g"]; n = args.reads; L = args.read_len
+    eng = api.Engine(g.mixref, g.l, g.pac, g.l, device=local)
+    stream = torch.cuda.current_stream(dev)
+    eng.set_stream(stream.cuda_stream)
+    lib, h = eng.L, eng.h
+
+    # ---------------- pinned host buffers (e2e) and device-resident copies (value)
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t
+    h_codes = pin(wl["reads"].reshape(-1)); h_roffs = pin((np.arange(n + 1, dtype=np.uint64) * L).astype(np.uint32))
+    h_o0, h_l0, h_o1, h_l1 = pin(wl["offs0"]), pin(wl["loci0"]), pin(wl["offs1"]), pin(wl["loci1"])
+    n0, n1 = len(wl["loci0"]), len(wl["loci1"])
+    h_rec = torch.empty(n * 16, dtype=torch.uint8).pin_memory()
+    h_acc0 = torch.empty(n0, dtype=torch.int8).pin_memory(); h_acc1 = torch.empty(n1, dtype=torch.int8).pin_memory()
+    h_cig = torch.zeros(n * 128, dtype=torch.uint8).pin_memory()
+    reads_t = api.ReadsT(h_codes.data_ptr(), h_roffs.data_ptr(), n)
+    cands = api.CandsT()
+    cands.offs[0], cands.offs[1] = h_o0.data_ptr(), h_o1.data_ptr()
+    cands.loci[0], cands.loci[1] = h_l0.data_ptr(), h_l1.data_ptr()
+
+    def ck(rc):
+        if rc != 0:
+            raise RuntimeError(lib.salt_b200_last_error().decode())
+
+    ck(lib.salt_b200_set_reads(h, C.byref(reads_t)))
+    d_o0, d_l0, d_o1, d_l1 = (t.to(dev) for t in (h_o0, h_l0, h_o1, h_l1))
+    d_rec = torch.empty(n * 16, dtype=torch.uint8, device=dev)
+    d_acc = torch.empty(n0 + n1 + 16, dtype=torch.int8, device=dev)
+    d_cig = torch.empty(n * 128, dtype=torch.uint8, device=dev)
+    d_cigreads = torch.empty(n + 2, dtype=torch.int32, device=dev); d_cigcnt = torch.zeros(4, dtype=torch.int32, device=dev)
+
+    def step_dev():
+        ck(lib.salt_b200_verify_dev(h, d_o0.data_ptr(), d_l0.data_ptr(), n0, d_o1.data_ptr(), d_l1.data_ptr(), n1, 3, -1,
+                                    d_rec.data_ptr(), d_acc.data_ptr(), d_acc.data_ptr() + n0,
+                                    d_cig.data_ptr(), 128, d_cigreads.data_ptr(), d_cigcnt.data_ptr()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- value: device-resident pass
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    eng.launch_count(reset=True)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count()
+    clocks = sampler.stop()
+    tmax = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax.item()) / args.steps
+    value = world * n / (ms_step * 1e-3)
+
+    # per-kernel times from the library's own events (separate, untimed-for-value pass)
+    eng.profile(True)
+    prof = {}
+    for _ in range(3):
+        step_dev()
+        for k, v in eng.profile_read().items():
+            prof.setdefault(k, []).append(v)
+    eng.profile(False)
+    kernels = {k: float(np.mean(v)) for k, v in prof.items()}
+    n_lv = int(np.frombuffer(d_rec.cpu().numpy().tobytes(), api.VERIFY_DT)["lv_ran"].sum())
+    n_gapped = int(d_cigcnt[0].item())
+
+    # ---------------- e2e: host buffers through the C ABI
+    def step_host():
+        ck(lib.salt_b200_set_reads(h, C.byref(reads_t)))
+        ck(lib.salt_b200_verify(h, C.byref(cands), 3, -1, h_rec.data_ptr(), h_acc0.data_ptr(), h_acc1.data_ptr(), h_cig.data_ptr(), 128))
+    for _ in range(max(1, args.warmup - 1)):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    te = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    h2d = h_codes.numel() + 4 * (h_roffs.numel() + h_o0.numel() + h_o1.numel() + n0 + n1)
+    d2h = n * 16 + n0 + n1 + n_gapped * (128 + 4) + 4
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+           "data": "synthetic", "config": cfg, "clocks": clocks, "gpu_launches": int(launches),
+           "e2e": {"value": world * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": e2e_s * 1e3},
+           "pairs_per_step": int(n0 + n1), "pairs_per_s": world * (n0 + n1) / (ms_step * 1e-3),
+           "lv_reads_per_step": n_lv, "gapped_primaries_per_step": n_gapped, "kernels_ms": kernels}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        # dominant kernel of the step; its algorithmic bytes per pair are stated in DESIGN.md §4
+        dom = max(kernels, key=kernels.get) if kernels else "mismatch"
+        bytes_per_pair = (L + 1) // 2 + 8 + 2          # window nibbles + pair descriptor + result (60 B at L=100)
+        mm_ms = kernels.get("mismatch", float("nan"))
+        ach = (n0 + n1) * bytes_per_pair / (mm_ms * 1e-3) / 1e9
+        out["roofline"] = {"kernel": "mismatch_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                           "frac": ach / hbm, "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                           "algorithmic_bytes_per_pair": bytes_per_pair, "kernel_ms": mm_ms, "dominant_kernel_of_step": dom}
+
+    # ---------------- kernel-level extras: LV and SW sweeps (N=1 only)
+    if world == 1 and not args.skip_extras:
+        out["lv"] = bench_lv(eng, lib, h, wl, args, dev, stream)
+        out["sw"] = bench_sw(eng, lib, h, wl, args, dev, stream)
+
+    if rank == 0 and world == 1:
+        try:
+            r = cpu_reference_run(args, wl, args.cpu_sample, 1, 0)
+            out["cpu_baseline"] = {"value": r["n"] / r["sec"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                   "sample": r["sample"], "pairs_per_s": r["pairs"] / r["sec"]}
+        except Exception as ex:   # the checker is optional for the bench line
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_lv(eng, lib, h, wl, args, dev, stream):
+    """Landau-Vishkin kernel alone on decoy-heavy pair lists (every candidate of the first reads), k = 2..10."""
+    import torch
+    from salt_b200 import api
+    n = min(len(wl["reads"]), 500_000)
+    n0 = int(wl["offs0"][n]); n1 = int(wl["offs1"][n])
+    rid0 = np.repeat(np.arange(n, dtype=np.uint32), np.diff(wl["offs0"][:n + 1].astype(np.int64)))
+    rid1 = np.repeat(np.arange(n, dtype=np.uint32), np.diff(wl["offs1"][:n + 1].astype(np.int64)))
+    pairs = np.concatenate([api.Engine.make_pairs(rid0, np.zeros(n0, np.uint32), wl["loci0"][:n0]),
+                            api.Engine.make_pairs(rid1, np.ones(n1, np.uint32), wl["loci1"][:n1])])
+    d_pairs = torch.from_numpy(pairs.view(np.uint8)).to(dev)
+    d_out = torch.empty(len(pairs), dtype=torch.int8, device=dev)
+    L = args.read_len
+    res = {}
+    for k in (2, 3, 5, 8, 10):
+        for _ in range(2):
+            lib.salt_b200_lv_dev(h, d_pairs.data_ptr(), len(pairs), k, d_out.data_ptr())
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record(stream)
+        for _ in range(3):
+            lib.salt_b200_lv_dev(h, d_pairs.data_ptr(), len(pairs), k, d_out.data_ptr())
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        sec = e0.elapsed_time(e1) * 1e-3 / 3
+        res["k%d" % k] = {"pairs_per_s": len(pairs) / sec, "gcups_equiv": len(pairs) * L * (L + 4) / sec / 1e9, "ms": sec * 1e3}
+    res["pairs"] = len(pairs)
+    res["note"] = "GCUPS-equivalent = L*(L+4) DP cells per pair (SURVEY §8d); ~94% of pairs are decoys (worst case for LV)"
+    return res
+
+
+def bench_sw(eng, lib, h, wl, args, dev, stream):
+    """Mate-rescue SSW (forward + reverse + banded traceback) on 401-wide windows around the true loci."""
+    import torch
+    from salt_b200 import api
+    nt = min(args.sw_tasks, len(wl["reads"]))
+    g = wl["g"]; L = args.read_len; W = 401
+    rng = np.random.default_rng(5)
+    start = np.maximum(0, wl["pos"][:nt].astype(np.int64) - rng.integers(0, W - L, nt))
+    end = np.minimum(g.l - 1, start + W - 1)
+    wins = np.zeros(nt, api.WIN_DT)
+    wins["rs"] = (np.arange(nt, dtype=np.uint32) << 1) | wl["strand"][:nt]
+    wins["start"] = start; wins["end"] = end
+    d_w = torch.from_numpy(wins.view(np.uint8)).to(dev)
+    d_out = torch.empty(nt * 28, dtype=torch.uint8, device=dev)
+    d_cig = torch.empty(nt * 32, dtype=torch.int32, device=dev)
+    mat = api.salt_score_mat2()
+    lib.salt_b200_set_max_window(h, 408)
+
+    def run():
+        rc = lib.salt_b200_ssw_dev(h, d_w.data_ptr(), nt, 0, mat.ctypes.data, 16, 3, 1, 2, 0, 20, -1, d_out.data_ptr(), d_cig.data_ptr(), 32)
+        if rc != 0:
+            raise RuntimeError(lib.salt_b200_last_error().decode())
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize(dev)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(3):
+        run()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    sec = e0.elapsed_time(e1) * 1e-3 / 3
+    eng.profile(True); run(); st = {k: v for k, v in eng.profile_read().items() if k.startswith("ssw")}; eng.profile(False)
+    cells = nt * (8 * ((L + 7) // 8)) * W          # forward cells, the convention of the CPU probe
+    res = {"tasks": nt, "window": W, "read_len": L, "ms": sec * 1e3, "tasks_per_s": nt / sec,
+           "gcups_fwd_cells_whole_pipeline": cells / sec / 1e9,
+           "gcups_fwd_kernel": cells / (st.get("ssw_dp_fwd", float("nan")) * 1e-3) / 1e9, "stages_ms": st}
+    # CPU beside it: the reference's ssw on a bounded sample
+    try:
+        from oracle import orc
+        o = orc.Oracle(); ref = orc.Ref() if orc.ref_available() else None
+        m = min(nt, 4000 * (os.cpu_count() or 1))
+        rd = wl["reads"][:m]
+        rd = np.where(wl["strand"][:m, None] == 1, __import__("salt_b200.synth", fromlist=["revcomp"]).revcomp(rd), rd)
+        s, chk = o.ssw_batch(g.mixref, np.ascontiguousarray(rd).reshape(-1), L, wins["start"][:m].copy(), wins["end"][:m].copy(),
+                             o.score_mat2(), 3, 1, n_threads=os.cpu_count() or 1, ref=ref)
+        res["cpu"] = {"gcups_fwd_cells": m * (8 * ((L + 7) // 8)) * W / s / 1e9, "tasks_per_s": m / s, "cores": os.cpu_count(),
+                      "kind": "reference" if ref else "port", "sample": "%d tasks" % m}
+    except Exception as ex:
+        res["cpu"] = {"error": repr(ex)}
+    return res
+
+
+if __name__ == "__main__":
+    main()

@@ -159,14 +159,25 @@ int salt_b200_set_max_window(salt_b200_t *h, int cols);
  * stream; used for kernel-level measurement and by callers that keep queues on the GPU) */
 int salt_b200_mismatch_dev(salt_b200_t *h, const salt_pair_t *d_pairs, size_t n, int max_err, int8_t *d_out);
 int salt_b200_lv_dev(salt_b200_t *h, const salt_pair_t *d_pairs, size_t n, int k, int8_t *d_out);
+/* Device variant of salt_b200_verify.  CIGARs come back compact: d_cigars[i*stride] belongs to
+ * read d_cig_reads[i], i < *d_cig_count (only gapped primaries have one).  Pass d_cigars = NULL
+ * to skip them. */
 int salt_b200_verify_dev(salt_b200_t *h, const uint32_t *d_offs0, const uint32_t *d_loci0, size_t n0,
                          const uint32_t *d_offs1, const uint32_t *d_loci1, size_t n1,
                          int nogap_T0, int lv_T0, salt_verify_out_t *d_rec, int8_t *d_acc0, int8_t *d_acc1,
-                         char *d_cigars, int cigar_stride);
+                         char *d_cigars, int cigar_stride, uint32_t *d_cig_reads, uint32_t *d_cig_count);
 int salt_b200_ssw_dev(salt_b200_t *h, const salt_win_t *d_wins, size_t n, int use_pac,
                       const int8_t *mat, int n_sym, int gapO, int gapE, int flag,
                       int filters, int filterd, int mask_len,
                       salt_ssw_out_t *d_out, uint32_t *d_cigars, int cigar_stride);
+
+/* Per-stage device timing (CUDA events on the handle's stream around each kernel).
+ * After a verify / ssw call with profiling enabled, salt_b200_profile_read synchronises and fills
+ * ms[0..5]  = expand, mismatch, scan_nogap, lv, scan_gap, lv_cigar      (verify stage)
+ * ms[6..11] = prep_fwd, dp_fwd, prep_rev, dp_rev, banded, banded_overflow (ssw)
+ * with -1 for stages that did not run. */
+int salt_b200_profile(salt_b200_t *h, int enable);
+int salt_b200_profile_read(salt_b200_t *h, float *ms);
 
 /* Counters for benchmarking: kernels launched by this handle since the last reset. */
 uint64_t salt_b200_launch_count(salt_b200_t *h, int reset);

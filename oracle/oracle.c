@@ -674,3 +674,179 @@ ORC_EXPORT void orc_verify_read(const uint32_t *mixref, uint32_t l_mref,
 done:
     q->mapq = orc_gen_mapq((uint32_t)q->b0, (uint32_t)q->b1);
 }
+
+/* ------------------------------------------------------------------------ */
+/* Threaded batch drivers for the CPU baseline (bench.py cpu_baseline and    */
+/* --impl reference).  The per-pair functions are passed in as pointers so   */
+/* the same loop can time either this file's restatement ("port") or the     */
+/* reference's own compiled functions from oracle/_ref ("reference").  The   */
+/* loop itself is the reference's: one worker per thread, reads dealt        */
+/* round-robin (alnse.c:1316-1350 alnse_core1: i % n_threads == tid).        */
+/* ------------------------------------------------------------------------ */
+#include <pthread.h>
+#include <time.h>
+
+typedef int (*orc_mm_fn)(const uint32_t *, uint32_t, const uint8_t *, uint32_t, int);
+typedef int (*orc_diff_fn)(const uint32_t *, uint32_t, uint32_t, uint32_t, const uint8_t *, uint32_t, int);
+typedef int (*orc_cig_fn)(const uint32_t *, uint32_t, uint32_t, const uint8_t *, uint32_t, int, char *, int, int, int);
+
+typedef struct {
+    const uint32_t *mixref; uint32_t l;
+    const uint8_t *codes; const uint32_t *roffs; uint32_t n_reads;
+    const uint32_t *offs[2]; const uint32_t *loci[2];
+    int nogap_T0, lv_T0;
+    orc_mm_fn mm; orc_diff_fn df; orc_cig_fn cg;
+    orc_verify_t *out; int8_t *acc[2]; char *cigars; int cigar_stride;
+    int tid, n_threads;
+} vb_job_t;
+
+static int vb_stage(const vb_job_t *J, const uint8_t *seq, uint32_t l_seq, int s, uint32_t r, int max_diff, int gapped, orc_verify_t *q)
+{
+    int matched = 0;
+    uint32_t last = (uint32_t)-1;
+    for (uint32_t i = J->offs[s][r]; i < J->offs[s][r + 1]; ++i) {
+        uint32_t pos = J->loci[s][i];
+        if (pos == last || (gapped ? (uint32_t)(pos + l_seq + 4) >= J->l : pos >= J->l)) { if (J->acc[s]) J->acc[s][i] = -1; continue; }
+        int nd = gapped ? J->df(J->mixref, J->l, pos, l_seq + 4, seq, l_seq, max_diff) : J->mm(J->mixref, pos, seq, l_seq, max_diff);
+        if (nd >= 0) {
+            if (nd < max_diff || !matched) { max_diff = nd; q->is_gap = (uint8_t)gapped; q->n_diff = (uint8_t)nd; q->strand = s; q->pos = pos; }
+            matched = 1; q->n_hits[s]++;
+        }
+        if (J->acc[s]) J->acc[s][i] = (int8_t)nd;
+        last = pos;
+    }
+    return matched ? max_diff : -1;
+}
+
+static void *vb_worker(void *arg)
+{
+    const vb_job_t *J = (const vb_job_t *)arg;
+    uint8_t rbuf[2048];
+    for (uint32_t r = (uint32_t)J->tid; r < J->n_reads; r += (uint32_t)J->n_threads) {
+        const uint8_t *seq = J->codes + J->roffs[r];
+        uint32_t L = J->roffs[r + 1] - J->roffs[r];
+        for (uint32_t i = 0; i < L; ++i) { uint8_t c = seq[L - 1 - i]; rbuf[i] = c < 4 ? (uint8_t)(3 - c) : c; }
+        orc_verify_t *q = J->out + r;
+        memset(q, 0, sizeof *q);
+        q->pos = 0xFFFFFFFFu; q->strand = 3; q->n_diff = 255; q->is_gap = 255;
+        int max_diff = J->nogap_T0;
+        int m0 = vb_stage(J, seq, L, 0, r, max_diff, 0, q);
+        if (m0 != -1 && m0 < max_diff) max_diff = m0;
+        int m1 = vb_stage(J, rbuf, L, 1, r, max_diff, 0, q);
+        if (m0 == -1 && m1 == -1) {
+            max_diff = J->lv_T0 >= 0 ? J->lv_T0 : (int)L / 10;
+            int d0 = vb_stage(J, seq, L, 0, r, max_diff, 1, q);
+            if (d0 != -1 && d0 < max_diff) max_diff = d0;
+            (void)vb_stage(J, rbuf, L, 1, r, max_diff, 1, q);
+        }
+        if (q->is_gap == 1 && J->cigars && J->cg)      /* query_gen_cigar, query.c:282-295 */
+            J->cg(J->mixref, q->pos, L + 4, q->strand ? rbuf : seq, L, q->n_diff,
+                  J->cigars + (size_t)r * J->cigar_stride, J->cigar_stride, 1, 0);
+    }
+    return NULL;
+}
+
+/* Returns wall seconds of the threaded region. */
+ORC_EXPORT double orc_verify_batch(const uint32_t *mixref, uint32_t l, const uint8_t *codes, const uint32_t *roffs,
+                                   uint32_t n_reads, const uint32_t *offs0, const uint32_t *loci0,
+                                   const uint32_t *offs1, const uint32_t *loci1, int nogap_T0, int lv_T0,
+                                   void *mm, void *df, void *cg, int n_threads,
+                                   orc_verify_t *out, int8_t *acc0, int8_t *acc1, char *cigars, int cigar_stride)
+{
+    if (n_threads < 1) n_threads = 1;
+    vb_job_t *jobs = (vb_job_t *)calloc((size_t)n_threads, sizeof(vb_job_t));
+    pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
+    struct timespec a, b;
+    clock_gettime(CLOCK_MONOTONIC, &a);
+    for (int t = 0; t < n_threads; ++t) {
+        vb_job_t *J = jobs + t;
+        J->mixref = mixref; J->l = l; J->codes = codes; J->roffs = roffs; J->n_reads = n_reads;
+        J->offs[0] = offs0; J->offs[1] = offs1; J->loci[0] = loci0; J->loci[1] = loci1;
+        J->nogap_T0 = nogap_T0; J->lv_T0 = lv_T0;
+        J->mm = mm ? (orc_mm_fn)mm : orc_ed_mismatch;
+        J->df = df ? (orc_diff_fn)df : orc_ed_diff;
+        J->cg = (orc_cig_fn)cg;
+        J->out = out; J->acc[0] = acc0; J->acc[1] = acc1; J->cigars = cigars; J->cigar_stride = cigar_stride;
+        J->tid = t; J->n_threads = n_threads;
+        pthread_create(&th[t], NULL, vb_worker, J);
+    }
+    for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    free(jobs); free(th);
+    return (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec);
+}
+
+/* SSW batch: ssw_init + ssw_align + destroys per task through function pointers (the
+ * reference's own, from oracle/_ref), or this file's orc_ssw_align when they are NULL. */
+typedef void *(*orc_sswinit_fn)(const int8_t *, int32_t, const int8_t *, int32_t, int8_t);
+typedef void *(*orc_sswalign_fn)(const void *, const int8_t *, int32_t, uint8_t, uint8_t, uint8_t, uint16_t, int32_t, int32_t);
+typedef void (*orc_free_fn)(void *);
+typedef struct {
+    const uint32_t *mixref; const uint8_t *codes; int L; const uint32_t *starts; const uint32_t *ends; uint32_t n;
+    const int8_t *mat; int gapO, gapE;
+    orc_sswinit_fn init; orc_sswalign_fn align; orc_free_fn idestroy, adestroy;
+    uint64_t *checksum; int tid, n_threads;
+} sb_job_t;
+
+static void *sb_worker(void *arg)
+{
+    const sb_job_t *J = (const sb_job_t *)arg;
+    int8_t ref[4096], read[2048];
+    uint64_t sum = 0;
+    for (uint32_t t = (uint32_t)J->tid; t < J->n; t += (uint32_t)J->n_threads) {
+        int l_ref = (int)(J->ends[t] - J->starts[t] + 1);
+        if (l_ref > 4096) l_ref = 4096;
+        for (int i = 0; i < l_ref; ++i) ref[i] = (int8_t)orc_nib(J->mixref, J->starts[t] + (uint32_t)i);
+        for (int i = 0; i < J->L; ++i) read[i] = (int8_t)(1 << J->codes[(size_t)t * J->L + i]);
+        if (J->init) {
+            void *p = J->init(read, J->L, J->mat, 16, 1);
+            uint16_t *res = (uint16_t *)J->align(p, ref, l_ref, (uint8_t)J->gapO, (uint8_t)J->gapE, 2, 0, 20, J->L / 2);
+            sum += res[0];
+            J->adestroy(res); J->idestroy(p);
+        } else {
+            orc_align_t r; uint32_t cig[256];
+            orc_ssw_align(read, J->L, J->mat, 16, ref, l_ref, J->gapO, J->gapE, 2, 0, 20, J->L / 2, &r, cig, 256);
+            sum += r.score1;
+        }
+    }
+    J->checksum[J->tid] = sum;
+    return NULL;
+}
+
+ORC_EXPORT double orc_ssw_batch(const uint32_t *mixref, const uint8_t *codes, int L, const uint32_t *starts,
+                                const uint32_t *ends, uint32_t n, const int8_t *mat, int gapO, int gapE,
+                                void *init, void *align, void *idestroy, void *adestroy, int n_threads, uint64_t *checksum)
+{
+    if (n_threads < 1) n_threads = 1;
+    sb_job_t *jobs = (sb_job_t *)calloc((size_t)n_threads, sizeof(sb_job_t));
+    pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
+    uint64_t *sums = (uint64_t *)calloc((size_t)n_threads, sizeof(uint64_t));
+    struct timespec a, b;
+    clock_gettime(CLOCK_MONOTONIC, &a);
+    for (int t = 0; t < n_threads; ++t) {
+        sb_job_t *J = jobs + t;
+        J->mixref = mixref; J->codes = codes; J->L = L; J->starts = starts; J->ends = ends; J->n = n;
+        J->mat = mat; J->gapO = gapO; J->gapE = gapE;
+        J->init = (orc_sswinit_fn)init; J->align = (orc_sswalign_fn)align;
+        J->idestroy = (orc_free_fn)idestroy; J->adestroy = (orc_free_fn)adestroy;
+        J->checksum = sums; J->tid = t; J->n_threads = n_threads;
+        pthread_create(&th[t], NULL, sb_worker, J);
+    }
+    for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    uint64_t tot = 0;
+    for (int t = 0; t < n_threads; ++t) tot += sums[t];
+    if (checksum) *checksum = tot;
+    free(jobs); free(th); free(sums);
+    return (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec);
+}
+
+/* orc_ed_diff_withcigar with the reference's 10-argument signature (editdistance.h:22), so the
+ * batch driver can call either implementation through one pointer type. */
+ORC_EXPORT int orc_ed_diff_withcigar_ref_abi(const uint32_t *mixref, uint32_t ref_st, uint32_t l_ref,
+                                             const uint8_t *seq, uint32_t l_seq, int max_k_diff,
+                                             char *cigarBuf, int cigarLen, int useM, int fmt)
+{
+    (void)useM; (void)fmt;
+    return orc_ed_diff_withcigar(mixref, ref_st, l_ref, seq, l_seq, max_k_diff, cigarBuf, cigarLen);
+}

@@ -78,6 +78,48 @@ class Oracle:
                                       C.c_int, C.c_int, C.c_int, C.POINTER(VerifyRec),
                                       C.POINTER(Hit), C.POINTER(Hit), C.POINTER(Hit), C.POINTER(Hit)]
 
+    # --- threaded CPU baselines (bench.py) ----------------------------------
+    def verify_batch(self, mixref, l, codes, roffs, offs0, loci0, offs1, loci1, nogap_T0=3, lv_T0=-1,
+                     n_threads=1, ref=None, want_acc=True, cigar_stride=128):
+        """The reference's verification loop over a batch on n_threads host threads.
+        ref=None times this file's port; ref=Ref() times the reference's own compiled functions.
+        Returns (seconds, recs, acc0, acc1, cigars)."""
+        L = self.lib
+        L.orc_verify_batch.restype = C.c_double
+        L.orc_verify_batch.argtypes = [u32p, C.c_uint32, u8p, u32p, C.c_uint32, u32p, u32p, u32p, u32p, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(VerifyRec), C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int]
+        n = len(roffs) - 1
+        recs = (VerifyRec * n)()
+        acc0 = np.empty(len(loci0), np.int8) if want_acc else None
+        acc1 = np.empty(len(loci1), np.int8) if want_acc else None
+        cig = np.zeros((n, cigar_stride), np.uint8)
+        if ref is not None:
+            fn = [C.cast(getattr(ref.lib, f), C.c_void_p) for f in ("ed_mismatch", "ed_diff", "ed_diff_withcigar")]
+        else:
+            fn = [None, None, C.cast(L.orc_ed_diff_withcigar_ref_abi, C.c_void_p)]
+        sec = L.orc_verify_batch(_p(mixref, u32p), int(l), _p(codes, u8p), _p(roffs, u32p), n,
+                                 _p(offs0, u32p), _p(loci0, u32p), _p(offs1, u32p), _p(loci1, u32p),
+                                 nogap_T0, lv_T0, fn[0], fn[1], fn[2], int(n_threads), recs,
+                                 None if acc0 is None else acc0.ctypes.data, None if acc1 is None else acc1.ctypes.data,
+                                 cig.ctypes.data, cigar_stride)
+        return sec, recs, acc0, acc1, cig
+
+    def ssw_batch(self, mixref, codes, L_read, starts, ends, mat, gapO=3, gapE=1, n_threads=1, ref=None):
+        """ssw_init + ssw_align(flag=2) + destroys per task on n_threads host threads; returns (seconds, checksum)."""
+        L = self.lib
+        L.orc_ssw_batch.restype = C.c_double
+        L.orc_ssw_batch.argtypes = [u32p, u8p, C.c_int, u32p, u32p, C.c_uint32, i8p, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+        fn = [None] * 4
+        if ref is not None:
+            fn = [C.cast(getattr(ref.lib, f), C.c_void_p) for f in ("ssw_init", "ssw_align", "init_destroy", "align_destroy")]
+        chk = C.c_uint64(0)
+        mat = np.ascontiguousarray(mat, np.int8)
+        sec = L.orc_ssw_batch(_p(mixref, u32p), _p(codes, u8p), int(L_read), _p(starts, u32p), _p(ends, u32p), len(starts),
+                              _p(mat, i8p), gapO, gapE, fn[0], fn[1], fn[2], fn[3], int(n_threads), C.byref(chk))
+        return sec, chk.value
+
     # --- scoring matrices -------------------------------------------------
     def score_mat2(self, pad=-3):
         """256 entries + one pad entry (the reference reads mat[256] for read-N vs mask 15)."""

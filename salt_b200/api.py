@@ -64,7 +64,9 @@ def _declare(L):
     L.salt_b200_set_max_window.argtypes = [vp, i32]
     L.salt_b200_mismatch_dev.argtypes = [vp, vp, sz, i32, vp]
     L.salt_b200_lv_dev.argtypes = [vp, vp, sz, i32, vp]
-    L.salt_b200_verify_dev.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, i32, vp, vp, vp, vp, i32]
+    L.salt_b200_verify_dev.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, i32, vp, vp, vp, vp, i32, vp, vp]
+    L.salt_b200_profile.argtypes = [vp, i32]
+    L.salt_b200_profile_read.argtypes = [vp, vp]
     L.salt_b200_ssw_dev.argtypes = [vp, vp, sz, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32]
     L.salt_b200_launch_count.restype = C.c_uint64
     L.salt_b200_launch_count.argtypes = [vp, i32]
@@ -159,6 +161,17 @@ class Engine:
 
     def sync(self):
         self._ck(self.L.salt_b200_sync(self.h))
+
+    STAGES = ("expand", "mismatch", "scan_nogap", "lv", "scan_gap", "lv_cigar",
+              "ssw_prep_fwd", "ssw_dp_fwd", "ssw_prep_rev", "ssw_dp_rev", "ssw_banded", "ssw_banded_ovf")
+
+    def profile(self, enable=True):
+        self._ck(self.L.salt_b200_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        ms = np.zeros(12, np.float32)
+        self._ck(self.L.salt_b200_profile_read(self.h, _ptr(ms)))
+        return {k: float(v) for k, v in zip(self.STAGES, ms) if v >= 0}
 
     def launch_count(self, reset=False):
         return int(self.L.salt_b200_launch_count(self.h, int(reset)))

@@ -67,6 +67,10 @@ struct salt_b200 {
     DBuf c_offs0, c_loci0, c_offs1, c_loci1, vpairs, acc, rec, lvlist, ciglist, counters;
     uint64_t launches = 0;
     int max_window = 1024;      // widest rescue window the SSW scratch is sized for
+    // optional per-stage timing (salt_b200_profile): events at the boundaries of the stages
+    bool profiling = false;
+    cudaEvent_t ev_verify[7] = {nullptr}, ev_ssw[7] = {nullptr};
+    bool have_verify_prof = false, have_ssw_prof = false, verify_prof_cigar = false;
 
     DevCtx ctx() const
     {
@@ -199,6 +203,7 @@ void salt_b200_destroy(salt_b200_t *h)
                    &h->sswout, &h->sswcig, &h->sswscratch, &h->c_offs0, &h->c_loci0, &h->c_offs1, &h->c_loci1,
                    &h->vpairs, &h->acc, &h->rec, &h->lvlist, &h->ciglist, &h->counters};
     for (DBuf *b : all) b->release();
+    for (int i = 0; i < 7; ++i) { if (h->ev_verify[i]) cudaEventDestroy(h->ev_verify[i]); if (h->ev_ssw[i]) cudaEventDestroy(h->ev_ssw[i]); }
     if (h->d_mixref) cudaFree(h->d_mixref);
     if (h->d_pac) cudaFree(h->d_pac);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
@@ -404,7 +409,8 @@ int salt_b200_ssw_dev(salt_b200_t *h, const salt_win_t *d_wins, size_t n, int us
     const size_t need = ssw_scratch_bytes(n, max_cols, (int)h->l_max, lay);
     CU(h->sswscratch.need(need));
     CU(launch_ssw(h->ctx(), d_wins, n, prm, h->sswscratch.p, h->sswscratch.cap, max_cols, d_out, d_cigars,
-                  cigar_stride, h->sm_count, h->stream, &h->launches));
+                  cigar_stride, h->sm_count, h->stream, &h->launches, h->profiling ? h->ev_ssw : nullptr));
+    h->have_ssw_prof = h->profiling;
     return SALT_OK;
 }
 
@@ -450,7 +456,7 @@ int salt_b200_ssw(salt_b200_t *h, const salt_win_t *wins, size_t n, int use_pac,
 int salt_b200_verify_dev(salt_b200_t *h, const uint32_t *d_offs0, const uint32_t *d_loci0, size_t n0,
                          const uint32_t *d_offs1, const uint32_t *d_loci1, size_t n1,
                          int nogap_T0, int lv_T0, salt_verify_out_t *d_rec, int8_t *d_acc0, int8_t *d_acc1,
-                         char *d_cigars, int cigar_stride)
+                         char *d_cigars, int cigar_stride, uint32_t *d_cig_reads, uint32_t *d_cig_count)
 {
     if (int rc = use_device(h)) return rc;
     if (!h->n_reads) return fail(SALT_ERR_ARG, "no reads set");
@@ -458,30 +464,42 @@ int salt_b200_verify_dev(salt_b200_t *h, const uint32_t *d_offs0, const uint32_t
     if (nogap_T0 < 0 || nogap_T0 > 127) return fail(SALT_ERR_ARG, "nogap_T0 must be in 0..127");
     if (n0 + n1 >= (size_t)1 << 32) return fail(SALT_ERR_ARG, "too many candidates in one chunk");
     if (d_acc0 && d_acc1 && d_acc1 != d_acc0 + n0) return fail(SALT_ERR_ARG, "acc1 must follow acc0 contiguously");
+    if (d_cigars && (!d_cig_reads || !d_cig_count)) return fail(SALT_ERR_ARG, "cigars need d_cig_reads and d_cig_count");
+    if (d_cigars && cigar_stride < 2) return fail(SALT_ERR_ARG, "cigar stride too small");
     const size_t n = n0 + n1;
     const DevCtx c = h->ctx();
     CU(h->vpairs.need((n + 1) * sizeof(salt_pair_t)));
     CU(h->lvlist.need((n + 1) * 4));
-    CU(h->ciglist.need(((size_t)h->n_reads + 1) * 4));
     CU(h->counters.need(256));
     int8_t *acc = d_acc0;
     if (!acc) { CU(h->acc.need(n + 1)); acc = h->acc.as<int8_t>(); }
     salt_pair_t *vp = h->vpairs.as<salt_pair_t>();
-    uint32_t *cnt = h->counters.as<uint32_t>();        // [0] LV worklist length, [1] cigar worklist length
+    uint32_t *cnt = h->counters.as<uint32_t>();        // [0] LV worklist length
+    cudaEvent_t *ev = h->profiling ? h->ev_verify : nullptr;
+#define SALT_EV(i) do { if (ev) CU(cudaEventRecord(ev[i], h->stream)); } while (0)
     CU(cudaMemsetAsync(cnt, 0, 256, h->stream));
+    if (d_cig_count) CU(cudaMemsetAsync(d_cig_count, 0, 4, h->stream));
+    SALT_EV(0);
     CU(launch_expand(d_offs0, d_loci0, n0, d_offs1, d_loci1, n1, h->n_reads, vp, h->stream));
+    SALT_EV(1);
     CU(launch_mismatch(c, vp, n, nogap_T0, acc, h->stream));
+    SALT_EV(2);
     CU(launch_scan_nogap(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, nogap_T0, acc, d_rec, h->lvlist.as<uint32_t>(), cnt, h->stream));
+    SALT_EV(3);
     CU(launch_lv(c, vp, n, lv_T0, h->lvlist.as<uint32_t>(), cnt, n, acc, h->sm_count, h->stream));
+    SALT_EV(4);
     CU(launch_scan_gap(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, lv_T0, acc, d_rec,
-                       d_cigars ? h->ciglist.as<uint32_t>() : nullptr, cnt + 1, h->stream));
+                       d_cigars ? d_cig_reads : nullptr, d_cig_count, h->stream));
+    SALT_EV(5);
     h->launches += n ? 5 : 2;
     if (d_cigars) {
-        if (cigar_stride < 2) return fail(SALT_ERR_ARG, "cigar stride too small");
-        CU(launch_lv_cigar(c, nullptr, nullptr, 0, h->ciglist.as<uint32_t>(), cnt + 1, h->n_reads, d_rec,
+        CU(launch_lv_cigar(c, nullptr, nullptr, 0, d_cig_reads, d_cig_count, h->n_reads, d_rec,
                            d_cigars, cigar_stride, nullptr, h->sm_count, h->stream));
         h->launches += 1;
     }
+    SALT_EV(6);
+#undef SALT_EV
+    h->have_verify_prof = h->profiling;
     return SALT_OK;
 }
 
@@ -498,35 +516,71 @@ int salt_b200_verify(salt_b200_t *h, const salt_cands_t *cands, int nogap_T0, in
     CU(h->c_loci0.need(n0 * 4 + 4)); CU(h->c_loci1.need(n1 * 4 + 4));
     CU(h->acc.need(n0 + n1 + 1));
     CU(h->rec.need((size_t)nr * sizeof(salt_verify_out_t)));
-    if (cigars) { CU(h->cig.need((size_t)nr * cigar_stride)); CU(cudaMemsetAsync(h->cig.p, 0, (size_t)nr * cigar_stride, h->stream)); }
+    if (cigars) {
+        if (cigar_stride < 2) return fail(SALT_ERR_ARG, "cigar stride too small");
+        CU(h->cig.need((size_t)nr * cigar_stride));
+        CU(h->ciglist.need(((size_t)nr + 2) * 4));      // [0] count, [1..] read ids
+    }
     CU(cudaMemcpyAsync(h->c_offs0.p, cands->offs[0], ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->c_offs1.p, cands->offs[1], ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, h->stream));
     if (n0) CU(cudaMemcpyAsync(h->c_loci0.p, cands->loci[0], n0 * 4, cudaMemcpyHostToDevice, h->stream));
     if (n1) CU(cudaMemcpyAsync(h->c_loci1.p, cands->loci[1], n1 * 4, cudaMemcpyHostToDevice, h->stream));
     int8_t *acc = h->acc.as<int8_t>();
+    uint32_t *cl = cigars ? h->ciglist.as<uint32_t>() : nullptr;
     if (int rc = salt_b200_verify_dev(h, h->c_offs0.as<uint32_t>(), h->c_loci0.as<uint32_t>(), n0,
                                       h->c_offs1.as<uint32_t>(), h->c_loci1.as<uint32_t>(), n1, nogap_T0, lv_T0,
                                       h->rec.as<salt_verify_out_t>(), acc, acc + n0,
-                                      cigars ? h->cig.as<char>() : nullptr, cigar_stride))
+                                      cigars ? h->cig.as<char>() : nullptr, cigar_stride, cl ? cl + 1 : nullptr, cl))
         return rc;
     CU(cudaMemcpyAsync(rec, h->rec.p, (size_t)nr * sizeof(salt_verify_out_t), cudaMemcpyDeviceToHost, h->stream));
     if (acc0 && n0) CU(cudaMemcpyAsync(acc0, acc, n0, cudaMemcpyDeviceToHost, h->stream));
     if (acc1 && n1) CU(cudaMemcpyAsync(acc1, acc + n0, n1, cudaMemcpyDeviceToHost, h->stream));
-    std::vector<char> tmp;
-    if (cigars) {
-        tmp.resize((size_t)nr * cigar_stride);
-        CU(cudaMemcpyAsync(tmp.data(), h->cig.p, tmp.size(), cudaMemcpyDeviceToHost, h->stream));
-    }
+    uint32_t n_cig = 0;
+    if (cigars) CU(cudaMemcpyAsync(&n_cig, cl, 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    if (cigars) {
-        for (uint32_t r = 0; r < nr; ++r) {
-            if (rec[r].is_gap != 1) continue;            // query_gen_cigar only calls LV for gapped primaries
-            const char *s = tmp.data() + (size_t)r * cigar_stride;
-            size_t len = strnlen(s, (size_t)cigar_stride - 1);
-            memcpy(cigars + (size_t)r * cigar_stride, s, len);
-            cigars[(size_t)r * cigar_stride + len] = '\0';
+    if (cigars && n_cig) {
+        // only gapped primaries have a CIGAR to fetch (query_gen_cigar, query.c:282-295): bring back
+        // the compact list and copy each string into the caller's per-read buffer
+        std::vector<uint32_t> ids(n_cig);
+        std::vector<char> tmp((size_t)n_cig * cigar_stride);
+        CU(cudaMemcpyAsync(ids.data(), cl + 1, (size_t)n_cig * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(tmp.data(), h->cig.p, tmp.size(), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (uint32_t i = 0; i < n_cig; ++i) {
+            const char *sp = tmp.data() + (size_t)i * cigar_stride;
+            const size_t len = strnlen(sp, (size_t)cigar_stride - 1);
+            char *dst = cigars + (size_t)ids[i] * cigar_stride;
+            memcpy(dst, sp, len);
+            dst[len] = '\0';
         }
     }
+    return SALT_OK;
+}
+
+int salt_b200_profile(salt_b200_t *h, int enable)
+{
+    if (int rc = use_device(h)) return rc;
+    if (enable) {
+        for (int i = 0; i < 7; ++i) {
+            if (!h->ev_verify[i]) CU(cudaEventCreate(&h->ev_verify[i]));
+            if (!h->ev_ssw[i]) CU(cudaEventCreate(&h->ev_ssw[i]));
+        }
+    }
+    h->profiling = enable != 0;
+    h->have_verify_prof = h->have_ssw_prof = false;
+    return SALT_OK;
+}
+
+int salt_b200_profile_read(salt_b200_t *h, float *ms /* [12] */)
+{
+    if (int rc = use_device(h)) return rc;
+    if (!ms) return fail(SALT_ERR_ARG, "null buffer");
+    CU(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 12; ++i) ms[i] = -1.f;
+    if (h->have_verify_prof)
+        for (int i = 0; i < 6; ++i) CU(cudaEventElapsedTime(&ms[i], h->ev_verify[i], h->ev_verify[i + 1]));
+    if (h->have_ssw_prof)
+        for (int i = 0; i < 6; ++i) CU(cudaEventElapsedTime(&ms[6 + i], h->ev_ssw[i], h->ev_ssw[i + 1]));
     return SALT_OK;
 }
 

@@ -514,8 +514,9 @@ static const uint32_t OVF_CAP = 256;
 cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const SswParams &prm,
                        void *scratch, size_t scratch_bytes, int max_cols,
                        salt_ssw_out_t *out, uint32_t *cigars, int cigar_stride, int sm_count, cudaStream_t st,
-                       uint64_t *launches)
+                       uint64_t *launches, cudaEvent_t *ev)
 {
+#define SALT_EV(i) do { if (ev) cudaEventRecord(ev[i], st); } while (0)
     (void)sm_count;
     if (!n) return cudaSuccess;
     size_t lay[8];
@@ -538,12 +539,17 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
     uint32_t *ovf_count = reinterpret_cast<uint32_t *>(base + lay[6]);
     if ((e = cudaMemsetAsync(ovf_count, 0, 256, st)) != cudaSuccess) return e;
 
+    SALT_EV(0);
     { auto kern = sw_prep_kernel<false>; SALT_LAUNCH(kern, prep_blocks, 256, 0, st, d); }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    SALT_EV(1);
     if ((e = dispatch_dp(d, false, st)) != cudaSuccess) return e;
+    SALT_EV(2);
     { auto kern = sw_prep_kernel<true>; SALT_LAUNCH(kern, prep_blocks, 256, 0, st, d); }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    SALT_EV(3);
     if ((e = dispatch_dp(d, true, st)) != cudaSuccess) return e;
+    SALT_EV(4);
 
     BandDev b;
     b.c = c; b.wins = wins; b.n_tasks = n; b.fwd = d.fwd; b.prm = prm;
@@ -555,6 +561,7 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
     b.out = out; b.cigars = cigars; b.cigar_stride = cigar_stride;
     { auto kern = sw_banded_kernel<16, false>; SALT_LAUNCH(kern, (unsigned)((n + 127) / 128), 128, 0, st, b); }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    SALT_EV(5);
 
     int dev = 0;
     cudaGetDevice(&dev);
@@ -568,8 +575,10 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
         { auto kern = sw_banded_kernel<512, true>; SALT_LAUNCH(kern, (OVF_CAP + 127) / 128, 128, 0, st, b2); }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
+    SALT_EV(6);
     if (launches) *launches += 6;
     return cudaSuccess;
+#undef SALT_EV
 }
 
 }  // namespace salt

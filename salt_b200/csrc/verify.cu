@@ -222,7 +222,7 @@ lv_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_fixed
 // lv_cigar: one warp per pair, 64 diagonals (2 per lane), furthest-reaching and action
 // tables kept in shared memory for the backtrace, which lane 0 performs.
 // Work items: (pairs[i], k_each[i]) -> cigars + i*stride, or, when `worklist` is non-null,
-// read ids whose primary (rec[rid]) is gapped -> cigars + rid*stride (query.c:282-295).
+// read ids whose primary (rec[rid]) is gapped -> cigars + (list index)*stride (query.c:282-295).
 // --------------------------------------------------------------------------------------
 struct LvCigarSmem {
     int16_t L[LV_MAXK][LV_ND];
@@ -254,7 +254,7 @@ lv_cigar_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8_t *
         if (worklist) {
             const uint32_t rid = worklist[it];
             const salt_verify_out_t r = rec[rid];
-            p.rs = (rid << 1) | (r.strand & 1); p.pos = r.pos; k = r.n_diff; slot = rid;
+            p.rs = (rid << 1) | (r.strand & 1); p.pos = r.pos; k = r.n_diff; slot = it;   // compact: slot = list index
         } else {
             p = pairs[it]; k = k_each[it]; slot = it;
         }

@@ -1,0 +1,153 @@
+"""GPU parity tests: the real CUDA library through the C ABI against the oracle, bit-exact.
+Sizes are what the oracle finishes in seconds; the full-size properties are in test_gpu_full.py."""
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from salt_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def world100():
+    return pc.make_world(31, glen=400000, L=100, n_reads=3000, per_strand=8, indel_frac=0.2, sub_rate=0.02)
+
+
+def _engine(g, pac=True):
+    return api.Engine(g.mixref, g.l, g.pac if pac else None, g.l if pac else 0, device=0)
+
+
+@pytest.mark.parametrize("L", [100, 150, 250, 37, 64])
+def test_mismatch(oracle, L):
+    g, reads, pos, strand, cands = pc.make_world(100 + L, glen=300000, L=L, n_reads=600, per_strand=6, indel_frac=0.0, sub_rate=0.006)
+    eng = _engine(g)
+    eng.set_reads(reads)
+    pairs = pc.flat_pairs(cands, len(reads))
+    extra = api.Engine.make_pairs([0, 1, 2], [0, 1, 0], [g.l - L, g.l - L + 1, g.l - 1])
+    pairs = np.concatenate([pairs, extra])
+    got = pc.check_mismatch(eng, oracle, g, reads, pairs, 3)
+    assert (got >= 0).sum() >= len(reads) // 2
+    pc.check_mismatch(eng, oracle, g, reads, pairs[:500], 0)
+    pc.check_mismatch(eng, oracle, g, reads, pairs[:500], 40)
+
+
+@pytest.mark.parametrize("L,k", [(100, -1), (100, 2), (100, 3), (100, 5), (100, 8), (150, -1), (250, -1), (100, 30), (64, 6)])
+def test_lv(oracle, L, k):
+    g, reads, pos, strand, cands = pc.make_world(200 + L + k, glen=300000, L=L, n_reads=300, per_strand=5, indel_frac=0.6, sub_rate=0.03)
+    eng = _engine(g)
+    eng.set_reads(reads)
+    pairs = pc.flat_pairs(cands, len(reads))
+    extra = api.Engine.make_pairs([0, 1], [0, 1], [g.l - L - 4, g.l - L - 3])
+    pairs = np.concatenate([pairs, extra])
+    got = pc.check_lv(eng, oracle, g, reads, pairs, k)
+    assert (got > 0).sum() >= 10
+
+
+@pytest.mark.parametrize("L", [100, 150, 250])
+def test_lv_cigar(oracle, L):
+    g, reads, pos, strand, cands = pc.make_world(300 + L, glen=300000, L=L, n_reads=400, per_strand=3, indel_frac=0.8, sub_rate=0.02)
+    eng = _engine(g)
+    eng.set_reads(reads)
+    rng = np.random.default_rng(L)
+    pairs = api.Engine.make_pairs(np.arange(len(reads), dtype=np.uint32), strand, pos)
+    k_each = rng.choice([2, 5, 10, 25, 30], len(pairs)).astype(np.uint8)
+    assert pc.check_lv_cigar(eng, oracle, g, reads, pairs, k_each, 128) >= 100
+    pc.check_lv_cigar(eng, oracle, g, reads, pairs, k_each, 6)
+    pc.check_lv_cigar(eng, oracle, g, reads, pc.flat_pairs(cands, len(reads))[:300], np.full(300, 10, np.uint8), 256)
+
+
+@pytest.mark.parametrize("L,lv_T0", [(100, -1), (100, 3), (150, -1), (250, -1)])
+def test_verify_stage(oracle, L, lv_T0):
+    g, reads, pos, strand, cands = pc.make_world(400 + L, glen=300000, L=L, n_reads=1500, per_strand=6, indel_frac=0.3, sub_rate=0.025)
+    offs0, loci0, offs1, loci1 = cands
+    loci0 = loci0.copy(); loci0[offs0[3] + 1] = loci0[offs0[3]]
+    eng = _engine(g)
+    eng.set_reads(reads)
+    st = pc.check_verify(eng, oracle, g, reads, (offs0, loci0, offs1, loci1), 3, lv_T0)
+    assert st["lv_ran"] >= 100 and st["gapped"] >= 30 and st["mapped"] >= 1000
+
+
+def test_verify_ragged_and_empty(oracle):
+    """ragged read lengths in one chunk, reads without candidates, an empty chunk of lists"""
+    rng = np.random.default_rng(5)
+    g = synth.Genome(200000, snp_rate=0.02, seed=12)
+    lens = rng.choice([36, 50, 75, 100, 101, 125, 150], 400)
+    reads, poss, strands = [], [], []
+    for i, L in enumerate(lens):
+        r, p, s = synth.sample_reads(g, 1, int(L), seed=1000 + i, sub_rate=0.02, indel_frac=0.3)
+        reads.append(r[0]); poss.append(p[0]); strands.append(s[0])
+    codes = np.concatenate(reads); roffs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    offs = [[0], [0]]; loci = [[], []]
+    for i, L in enumerate(lens):
+        for s in (0, 1):
+            c = set(rng.integers(0, g.l - 160, 4).tolist()) if i % 7 else set()
+            if strands[i] == s and i % 7:
+                c.add(int(poss[i]))
+            loci[s] += sorted(c); offs[s].append(len(loci[s]))
+    eng = _engine(g)
+    eng.set_reads(codes, roffs)
+    o0, o1 = np.array(offs[0], np.uint32), np.array(offs[1], np.uint32)
+    l0, l1 = np.array(loci[0], np.uint32), np.array(loci[1], np.uint32)
+    rec, acc0, acc1, cig = eng.verify(o0, l0, o1, l1, 3, -1)
+    for r in range(len(lens)):
+        seq = np.ascontiguousarray(reads[r]); rseq = np.ascontiguousarray(synth.revcomp(reads[r]))
+        prim, hits, _ = oracle.verify_read(g.mixref, g.l, seq, rseq, l0[o0[r]:o0[r + 1]], l1[o1[r]:o1[r + 1]], 3, len(seq) // 10)
+        got = rec[r]
+        assert (int(got["pos"]), int(got["strand"]), int(got["n_diff"]), int(got["is_gap"])) == prim[:4], (r, got, prim)
+
+
+@pytest.mark.parametrize("L,width", [(100, 401), (150, 401), (250, 301), (250, 551), (64, 200), (300, 700)])
+def test_ssw_mixref(oracle, L, width):
+    g, reads, pos, strand, _ = pc.make_world(500 + L, glen=200000, L=L, n_reads=301, per_strand=2, indel_frac=0.7, sub_rate=0.04)
+    eng = _engine(g)
+    eng.set_reads(reads)
+    rng = np.random.default_rng(L)
+    wins = pc.make_windows(g, reads, pos, strand, L, rng, width)
+    assert pc.check_ssw(eng, oracle, g, reads, wins, False, api.salt_score_mat2(), 16, cigar_stride=96) >= 60
+
+
+def test_ssw_pac_and_params(oracle):
+    L = 100
+    g, reads, pos, strand, _ = pc.make_world(600, glen=200000, L=L, n_reads=200, per_strand=2, indel_frac=0.7, sub_rate=0.04,
+                                              n_rate=0.0, n_frac=0.01)
+    eng = _engine(g)
+    eng.set_reads(reads)
+    rng = np.random.default_rng(6)
+    wins = pc.make_windows(g, reads, pos, strand, L, rng, 401)
+    pc.check_ssw(eng, oracle, g, reads, wins, True, api.salt_score_mat(), 5)
+    pc.check_ssw(eng, oracle, g, reads, wins, True, api.salt_score_mat(), 5, gapO=5, gapE=2, mask_len=15)
+    pc.check_ssw(eng, oracle, g, reads, wins, True, api.salt_score_mat(), 5, flag=0)
+    pc.check_ssw(eng, oracle, g, reads, wins, True, api.salt_score_mat(), 5, flag=1, mask_len=7)
+    with pytest.raises(api.SaltError):
+        eng.ssw(wins, api.salt_score_mat(), 5, True, gapO=1, gapE=1)
+
+
+def test_ssw_known_answer():
+    """Align_src/test/test_ssw_snp.c:81-87 through the engine: needs its own matrix and window."""
+    mat = np.full(256, -3, np.int8)
+    for m in range(16):
+        for b in range(4):
+            if m >> b & 1:
+                mat[m * 16 + (1 << b)] = 1       # our read symbols are one-hot, the test file's are 0..3
+    Ref = np.array([1, 3, 5, 7, 2, 4, 8, 9, 10, 11, 12, 13, 14, 15, 1, 2, 4, 6, 1], np.uint8)
+    Seq = np.array([0, 0, 0, 0, 1, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 0, 1, 2, 1, 0], np.uint8)
+    masks = np.concatenate([Ref, np.zeros(45, np.uint8)])
+    eng = api.Engine(synth.pack_mixref(masks), len(masks))
+    eng.set_reads(Seq[None, :])
+    wins = np.zeros(1, api.WIN_DT); wins[0] = (0, 0, 18)
+    out, cig = eng.ssw(wins, mat, 16, False, gapO=5, gapE=2, flag=2, filters=0, filterd=100, mask_len=10)
+    o = out[0]
+    assert (int(o["score1"]), int(o["ref_begin1"]), int(o["ref_end1"]), int(o["read_begin1"]), int(o["read_end1"])) == (15, 0, 18, 1, 19)
+    assert int(o["cigarLen"]) == 1 and int(cig[0][0]) == (19 << 4)
+
+
+def test_build_mixref_on_device(oracle):
+    g = synth.Genome(300000, snp_rate=0.03, n_rate=0.01, seed=9)
+    rows = g.snp_table()
+    fasta = g.fasta()
+    want, l = oracle.build_mixref([("chr1", fasta)], rows)
+    pos = np.array([r[1] - 1 for r in rows], np.uint32)
+    mask = np.array([oracle.lib.orc_allele_mask(r[2].encode()) for r in rows], np.uint8)
+    eng = api.Engine.from_bases(fasta, pos, mask)
+    assert np.array_equal(eng.get_mixref(), want)
