@@ -163,7 +163,10 @@ def main():
     wl = make_workload(args, seed=11 + rank)
     g = wl["g"]; n = args.reads; L = args.read_len
     eng = api.Engine(g.mixref, g.l, g.pac, g.l, device=local)
-    stream = torch.cuda.current_stream(dev)
+    # a real (non-default) stream: handle 0 would mean "library-owned stream" to salt_b200_set_stream
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
     lib, h = eng.L, eng.h
 
