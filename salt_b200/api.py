@@ -162,7 +162,7 @@ class Engine:
     def sync(self):
         self._ck(self.L.salt_b200_sync(self.h))
 
-    STAGES = ("expand", "mismatch", "scan_nogap", "lv", "scan_gap", "lv_cigar",
+    STAGES = ("_a", "nogap_fused", "_b", "lv", "scan_gap", "lv_cigar",
               "ssw_prep_fwd", "ssw_dp_fwd", "ssw_prep_rev", "ssw_dp_rev", "ssw_banded", "ssw_banded_ovf")
 
     def profile(self, enable=True):

@@ -468,30 +468,29 @@ int salt_b200_verify_dev(salt_b200_t *h, const uint32_t *d_offs0, const uint32_t
     if (d_cigars && cigar_stride < 2) return fail(SALT_ERR_ARG, "cigar stride too small");
     const size_t n = n0 + n1;
     const DevCtx c = h->ctx();
-    CU(h->vpairs.need((n + 1) * sizeof(salt_pair_t)));
-    CU(h->lvlist.need((n + 1) * 4));
+    CU(h->vpairs.need((n + 1) * sizeof(salt_pair_t)));      // LV worklist: pairs ...
+    CU(h->lvlist.need((n + 1) * 4));                         // ... and the acc slot each one reports to
     CU(h->counters.need(256));
     int8_t *acc = d_acc0;
     if (!acc) { CU(h->acc.need(n + 1)); acc = h->acc.as<int8_t>(); }
-    salt_pair_t *vp = h->vpairs.as<salt_pair_t>();
+    salt_pair_t *lvp = h->vpairs.as<salt_pair_t>();
+    uint32_t *lvs = h->lvlist.as<uint32_t>();
     uint32_t *cnt = h->counters.as<uint32_t>();        // [0] LV worklist length
     cudaEvent_t *ev = h->profiling ? h->ev_verify : nullptr;
 #define SALT_EV(i) do { if (ev) CU(cudaEventRecord(ev[i], h->stream)); } while (0)
     CU(cudaMemsetAsync(cnt, 0, 256, h->stream));
     if (d_cig_count) CU(cudaMemsetAsync(d_cig_count, 0, 4, h->stream));
     SALT_EV(0);
-    CU(launch_expand(d_offs0, d_loci0, n0, d_offs1, d_loci1, n1, h->n_reads, vp, h->stream));
     SALT_EV(1);
-    CU(launch_mismatch(c, vp, n, nogap_T0, acc, h->stream));
+    CU(launch_nogap_fused(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, nogap_T0, acc, d_rec, lvp, lvs, cnt, h->stream));
     SALT_EV(2);
-    CU(launch_scan_nogap(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, nogap_T0, acc, d_rec, h->lvlist.as<uint32_t>(), cnt, h->stream));
     SALT_EV(3);
-    CU(launch_lv(c, vp, n, lv_T0, h->lvlist.as<uint32_t>(), cnt, n, acc, h->sm_count, h->stream));
+    CU(launch_lv(c, lvp, n, lv_T0, lvs, cnt, n, acc, h->sm_count, h->stream));
     SALT_EV(4);
     CU(launch_scan_gap(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, lv_T0, acc, d_rec,
                        d_cigars ? d_cig_reads : nullptr, d_cig_count, h->stream));
     SALT_EV(5);
-    h->launches += n ? 5 : 2;
+    h->launches += 3;
     if (d_cigars) {
         CU(launch_lv_cigar(c, nullptr, nullptr, 0, d_cig_reads, d_cig_count, h->n_reads, d_rec,
                            d_cigars, cigar_stride, nullptr, h->sm_count, h->stream));

@@ -144,8 +144,8 @@ __host__ __device__ inline int lv_pw(int l_max) { return (l_max + 64) / 8 + 2; }
 // Furthest-reaching values of the previous level live in registers; neighbours are
 // exchanged with __shfl_up/down inside the group.  The diagonal order of the reference
 // (0,+1,-1,..) does not affect the returned level, so all diagonals of a level run at once.
-// Work items: pairs[i] for i < n, or, when `worklist` is non-null, pairs[worklist[i]] for
-// i < *wl_count (persistent groups stride over the list).
+// Work items: pairs[i] -> out[i] for i < n; with `slots` non-null the list length is read from
+// *wl_count on the device and pairs[i] -> out[slots[i]] (persistent groups stride over the list).
 // --------------------------------------------------------------------------------------
 template <int G, int DPL>
 __global__ void __launch_bounds__(128)
@@ -166,7 +166,7 @@ lv_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_fixed
 
     for (size_t it = (size_t)blockIdx.x * (blockDim.x / G) + gl; it < count; it += groups) {
         const size_t slot = worklist ? worklist[it] : it;
-        const salt_pair_t p = pairs[slot];
+        const salt_pair_t p = pairs[it];
         const uint32_t rid = p.rs >> 1;
         const int plen = rid < c.n_reads ? (int)c.rd_len[rid] : 0;
         const int tlen = plen + 4;                                  // alnse.c:373
@@ -327,6 +327,140 @@ lv_cigar_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8_t *
         }
         if (lane == 0 && out) out[slot] = (int8_t)result;
     }
+}
+
+// --------------------------------------------------------------------------------------
+// nogap_fused: the whole ungapped stage of one read in one group of G lanes
+// (alnse_check_nogap on strand 0 then strand 1, alnse.c:734-782 + :1079-1083):
+//   - the read's packed words stay in registers while its candidate list is walked, so a
+//     candidate costs one coalesced 8-byte window load per lane (neighbour word by shuffle)
+//   - candidates are fetched G at a time, windows for 4 candidates are in flight together
+//   - the running threshold / primary / hit count are kept redundantly by all lanes
+//   - reads with no ungapped hit append their candidates to the Landau-Vishkin worklist
+// WPL = 64-bit words of the read per lane (reads up to 16*G*WPL bases).
+// --------------------------------------------------------------------------------------
+template <int G, int WPL>
+__global__ void __launch_bounds__(256)
+nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t *__restrict__ loci0,
+                   const uint32_t *__restrict__ offs1, const uint32_t *__restrict__ loci1, size_t n0,
+                   int T0, int8_t *__restrict__ acc, salt_verify_out_t *__restrict__ rec,
+                   salt_pair_t *__restrict__ lv_pairs, uint32_t *__restrict__ lv_slots, uint32_t *__restrict__ lv_count)
+{
+    const uint32_t r = (uint32_t)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
+    const int lane = threadIdx.x % G;
+    if (r >= c.n_reads) return;                         // whole groups leave together
+    const int gshift = (threadIdx.x & 31) / G * G;
+    const unsigned gmask = (unsigned)(((1ull << G) - 1ull) << gshift);
+    const int L = c.rd_len[r];
+    const int nw = (L + 15) >> 4;
+    const uint64_t *__restrict__ m64 = reinterpret_cast<const uint64_t *>(c.mixref);
+
+    salt_verify_out_t q;
+    q.pos = 0xFFFFFFFFu; q.strand = 3; q.n_diff = 255; q.is_gap = 255; q.lv_ran = 0; q.n_hits[0] = q.n_hits[1] = 0;
+    int max_diff = T0;
+    bool any = false;
+    uint32_t lb[2], le[2];
+    lb[0] = offs0[r]; le[0] = offs0[r + 1]; lb[1] = offs1[r]; le[1] = offs1[r + 1];
+
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const uint32_t *__restrict__ loci = s ? loci1 : loci0;
+        int8_t *__restrict__ accs = s ? acc + n0 : acc;
+        uint64_t rw[WPL];
+        const uint64_t *__restrict__ rrow = c.rd4 + ((size_t)r * 2 + s) * c.W64;
+#pragma unroll
+        for (int w = 0; w < WPL; ++w) rw[w] = (lane + w * G) < nw ? rrow[lane + w * G] : 0ull;
+        bool matched = false;
+        uint32_t last = 0xFFFFFFFFu;
+        for (uint32_t base = lb[s]; base < le[s]; base += G) {
+            const int cnt = (int)min((uint32_t)G, le[s] - base);
+            const uint32_t mypos = lane < cnt ? loci[base + lane] : 0u;
+            int myacc = -1;
+            for (int j0 = 0; j0 < cnt; j0 += 4) {
+                uint32_t pos[4]; bool ok[4]; int mt[4];
+                uint64_t q0[4][WPL];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    pos[u] = __shfl_sync(gmask, mypos, (j0 + u) & (G - 1), G);
+                    ok[u] = (j0 + u) < cnt && (uint64_t)pos[u] + (uint64_t)L <= (uint64_t)c.l;
+#pragma unroll
+                    for (int w = 0; w < WPL; ++w) {
+                        const int wi = lane + w * G;
+                        q0[u][w] = (ok[u] && wi <= nw) ? m64[(size_t)(pos[u] >> 4) + wi] : 0ull;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int sh = (int)(pos[u] & 15u) * 4;
+                    int m = 0;
+#pragma unroll
+                    for (int w = 0; w < WPL; ++w) {
+                        // word wi+1 lives in the next lane; for the last lane it is lane 0's next slot
+                        uint64_t nx = __shfl_down_sync(gmask, q0[u][w], 1, G);
+                        if (WPL > 1) {
+                            const uint64_t wrap = __shfl_sync(gmask, q0[u][(w + 1 < WPL) ? w + 1 : w], 0, G);
+                            if (lane == G - 1) nx = (w + 1 < WPL) ? wrap : 0ull;
+                        }
+                        const uint64_t x = sh ? ((q0[u][w] >> sh) | (nx << (64 - sh))) : q0[u][w];
+                        uint64_t a = x & rw[w];
+                        a |= a >> 1;
+                        a |= a >> 2;
+                        m += __popcll(a & 0x1111111111111111ull);
+                    }
+                    mt[u] = m;
+                }
+                // two 16-bit counts per register: two group reductions for four candidates
+                int p01 = mt[0] | (mt[1] << 16), p23 = mt[2] | (mt[3] << 16);
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) {
+                    p01 += __shfl_xor_sync(gmask, p01, o, G);
+                    p23 += __shfl_xor_sync(gmask, p23, o, G);
+                }
+                mt[0] = p01 & 0xffff; mt[1] = p01 >> 16; mt[2] = p23 & 0xffff; mt[3] = p23 >> 16;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (j0 + u >= cnt) break;
+                    int v = -1;
+                    // alnse.c:762: duplicates and loci past the end are skipped without touching pos0
+                    if (!(pos[u] == last || pos[u] >= c.l)) {
+                        const int nmis = L - mt[u];
+                        const int nd = (ok[u] && nmis <= T0) ? nmis : -1;
+                        if (nd >= 0 && nd <= max_diff) {                    // code_kmismatch, alnse.c:348-370
+                            if (nd < max_diff || !matched) {
+                                max_diff = nd;
+                                q.is_gap = 0; q.n_diff = (uint8_t)nd; q.strand = (uint8_t)s; q.pos = pos[u];
+                            }
+                            matched = true;
+                            q.n_hits[s] += 1;
+                            v = nd;
+                        }
+                        last = pos[u];
+                    }
+                    if (lane == j0 + u) myacc = v;
+                }
+            }
+            if (lane < cnt) accs[base + lane] = (int8_t)myacc;
+        }
+        any = any || matched;
+    }
+    if (!any) {                                          // alnse.c:1022 / :1089: gapped stage for this read
+        q.lv_ran = 1;
+        const uint32_t c0 = le[0] - lb[0], c1 = le[1] - lb[1];
+        if (c0 + c1) {
+            uint32_t w = 0;
+            if (lane == 0) w = atomicAdd(lv_count, c0 + c1);
+            w = __shfl_sync(gmask, w, 0, G);
+            for (uint32_t i = lane; i < c0; i += G) {
+                salt_pair_t p; p.rs = r << 1; p.pos = loci0[lb[0] + i];
+                lv_pairs[w + i] = p; lv_slots[w + i] = lb[0] + i;
+            }
+            for (uint32_t i = lane; i < c1; i += G) {
+                salt_pair_t p; p.rs = (r << 1) | 1u; p.pos = loci1[lb[1] + i];
+                lv_pairs[w + c0 + i] = p; lv_slots[w + c0 + i] = (uint32_t)n0 + lb[1] + i;
+            }
+        }
+    }
+    if (lane == 0) rec[r] = q;
 }
 
 // --------------------------------------------------------------------------------------
@@ -547,6 +681,33 @@ cudaError_t launch_scan_nogap(const DevCtx &c, const uint32_t *offs0, const uint
     SALT_LAUNCH(scan_nogap_kernel, (c.n_reads + 127) / 128, 128, 0, st, c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_list, lv_count);
     SALT_LAUNCH_CHECK();
     return cudaSuccess;
+}
+
+template <int G, int WPL>
+static cudaError_t launch_nogap_t(const DevCtx &c, const uint32_t *offs0, const uint32_t *loci0,
+                                  const uint32_t *offs1, const uint32_t *loci1, size_t n0, int T0,
+                                  int8_t *acc, salt_verify_out_t *rec, salt_pair_t *lv_pairs, uint32_t *lv_slots,
+                                  uint32_t *lv_count, cudaStream_t st)
+{
+    auto kern = nogap_fused_kernel<G, WPL>;
+    const size_t threads = (size_t)c.n_reads * G;
+    SALT_LAUNCH(kern, (unsigned)((threads + 255) / 256), 256, 0, st, c, offs0, loci0, offs1, loci1, n0, T0, acc, rec,
+                lv_pairs, lv_slots, lv_count);
+    SALT_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_nogap_fused(const DevCtx &c, const uint32_t *offs0, const uint32_t *loci0,
+                               const uint32_t *offs1, const uint32_t *loci1, size_t n0, int T0,
+                               int8_t *acc, salt_verify_out_t *rec, salt_pair_t *lv_pairs, uint32_t *lv_slots,
+                               uint32_t *lv_count, cudaStream_t st)
+{
+    if (!c.n_reads) return cudaSuccess;
+    const int nw = ((int)c.l_max + 15) / 16;
+    if (nw < 8) return launch_nogap_t<8, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
+    if (nw < 16) return launch_nogap_t<16, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
+    if (nw < 32) return launch_nogap_t<32, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
+    return launch_nogap_t<32, 3>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
 }
 
 cudaError_t launch_scan_gap(const DevCtx &c, const uint32_t *offs0, const uint32_t *loci0,

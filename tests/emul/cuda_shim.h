@@ -115,34 +115,39 @@ static inline void launch(dim3 grid, dim3 block, size_t smem, F body)
 #define SALT_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(emu::t_cta->dyn)
 
 // ---- warp collectives -------------------------------------------------------------
+namespace emu {
+// value of lane `s` (absolute lane index in the warp) for every participating lane; 4- or 8-byte T
+template <class T> static inline T pick(unsigned mask, T v, int s)
+{
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "4- or 8-byte shuffles only");
+    uint32_t part[2] = {0, 0}, res[2] = {0, 0};
+    memcpy(part, &v, sizeof(T));
+    for (unsigned k = 0; k < sizeof(T) / 4; ++k) { uint32_t tab[32]; gather(mask, part[k], tab); res[k] = tab[s]; }
+    T r; memcpy(&r, res, sizeof(T)); return r;
+}
+}  // namespace emu
 template <class T> static inline T __shfl_sync(unsigned mask, T v, int src, int width = 32)
 {
-    uint32_t tab[32]; uint32_t u; static_assert(sizeof(T) == 4, "32-bit shuffles only");
-    memcpy(&u, &v, 4); emu::gather(mask, u, tab);
     const int lane = threadIdx.x % 32, base = lane / width * width;
-    const int s = base + ((src % width) + width) % width;
-    T r; memcpy(&r, &tab[s], 4); return r;
+    return emu::pick(mask, v, base + ((src % width) + width) % width);
 }
 template <class T> static inline T __shfl_up_sync(unsigned mask, T v, unsigned d, int width = 32)
 {
-    uint32_t tab[32]; uint32_t u; memcpy(&u, &v, 4); emu::gather(mask, u, tab);
     const int lane = threadIdx.x % 32, base = lane / width * width;
     const int s = lane - (int)d;
-    T r; memcpy(&r, &tab[s < base ? lane : s], 4); return r;
+    return emu::pick(mask, v, s < base ? lane : s);
 }
 template <class T> static inline T __shfl_down_sync(unsigned mask, T v, unsigned d, int width = 32)
 {
-    uint32_t tab[32]; uint32_t u; memcpy(&u, &v, 4); emu::gather(mask, u, tab);
     const int lane = threadIdx.x % 32, base = lane / width * width;
     const int s = lane + (int)d;
-    T r; memcpy(&r, &tab[s >= base + width ? lane : s], 4); return r;
+    return emu::pick(mask, v, s >= base + width ? lane : s);
 }
 template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int x, int width = 32)
 {
-    uint32_t tab[32]; uint32_t u; memcpy(&u, &v, 4); emu::gather(mask, u, tab);
     const int lane = threadIdx.x % 32, base = lane / width * width;
     const int s = lane ^ x;
-    T r; memcpy(&r, &tab[(s >= base && s < base + width) ? s : lane], 4); return r;
+    return emu::pick(mask, v, (s >= base && s < base + width) ? s : lane);
 }
 static inline unsigned __ballot_sync(unsigned mask, int pred)
 {
