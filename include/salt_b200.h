@@ -151,6 +151,11 @@ int salt_b200_verify(salt_b200_t *h, const salt_cands_t *cands, int nogap_T0, in
                      salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1,
                      char *cigars, int cigar_stride);
 
+/* Landau-Vishkin work mapping: 0 = automatic (one thread per pair with all diagonals in
+ * registers for k <= 15, one warp per pair with lanes over diagonals beyond), 1 = always one
+ * warp (or sub-warp group) per pair.  Results are identical; this exists for measurement. */
+int salt_b200_set_lv_mapping(salt_b200_t *h, int mapping);
+
 /* Widest rescue window (in bases) the *_dev SSW entry point must handle; the host entry point
  * sets it from its arguments.  Default 1024. */
 int salt_b200_set_max_window(salt_b200_t *h, int cols);

@@ -62,6 +62,7 @@ def _declare(L):
     L.salt_b200_ssw.argtypes = [vp, vp, sz, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32]
     L.salt_b200_verify.argtypes = [vp, C.POINTER(CandsT), i32, i32, vp, vp, vp, vp, i32]
     L.salt_b200_set_max_window.argtypes = [vp, i32]
+    L.salt_b200_set_lv_mapping.argtypes = [vp, i32]
     L.salt_b200_mismatch_dev.argtypes = [vp, vp, sz, i32, vp]
     L.salt_b200_lv_dev.argtypes = [vp, vp, sz, i32, vp]
     L.salt_b200_verify_dev.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, i32, vp, vp, vp, vp, i32, vp, vp]
@@ -172,6 +173,9 @@ class Engine:
         ms = np.zeros(12, np.float32)
         self._ck(self.L.salt_b200_profile_read(self.h, _ptr(ms)))
         return {k: float(v) for k, v in zip(self.STAGES, ms) if v >= 0}
+
+    def set_lv_mapping(self, mapping):
+        self._ck(self.L.salt_b200_set_lv_mapping(self.h, int(mapping)))
 
     def launch_count(self, reset=False):
         return int(self.L.salt_b200_launch_count(self.h, int(reset)))

@@ -66,6 +66,7 @@ struct salt_b200 {
     DBuf pairs, out8, kbuf, cig, wins, sswout, sswcig, sswscratch;
     DBuf c_offs0, c_loci0, c_offs1, c_loci1, vpairs, acc, rec, lvlist, ciglist, counters;
     uint64_t launches = 0;
+    int lv_mapping = 0;         // 0 = auto, 1 = force warp-per-pair (salt_b200_set_lv_mapping)
     int max_window = 1024;      // widest rescue window the SSW scratch is sized for
     // optional per-stage timing (salt_b200_profile): events at the boundaries of the stages
     bool profiling = false;
@@ -305,7 +306,7 @@ int salt_b200_lv_dev(salt_b200_t *h, const salt_pair_t *d_pairs, size_t n, int k
     if (int rc = use_device(h)) return rc;
     if (n && (!d_pairs || !d_out)) return fail(SALT_ERR_ARG, "null buffer");
     if (!h->n_reads) return fail(SALT_ERR_ARG, "no reads set");
-    CU(launch_lv(h->ctx(), d_pairs, n, k, nullptr, nullptr, 0, d_out, h->sm_count, h->stream));
+    CU(launch_lv(h->ctx(), d_pairs, n, k, nullptr, nullptr, 0, d_out, h->sm_count, h->stream, h->lv_mapping));
     if (n) h->launches += 1;
     return SALT_OK;
 }
@@ -414,6 +415,14 @@ int salt_b200_ssw_dev(salt_b200_t *h, const salt_win_t *d_wins, size_t n, int us
     return SALT_OK;
 }
 
+int salt_b200_set_lv_mapping(salt_b200_t *h, int mapping)
+{
+    if (!h) return fail(SALT_ERR_ARG, "null handle");
+    if (mapping != 0 && mapping != 1) return fail(SALT_ERR_ARG, "mapping must be 0 (auto) or 1 (warp per pair)");
+    h->lv_mapping = mapping;
+    return SALT_OK;
+}
+
 int salt_b200_set_max_window(salt_b200_t *h, int cols)
 {
     if (!h) return fail(SALT_ERR_ARG, "null handle");
@@ -485,7 +494,7 @@ int salt_b200_verify_dev(salt_b200_t *h, const uint32_t *d_offs0, const uint32_t
     CU(launch_nogap_fused(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, nogap_T0, acc, d_rec, lvp, lvs, cnt, h->stream));
     SALT_EV(2);
     SALT_EV(3);
-    CU(launch_lv(c, lvp, n, lv_T0, lvs, cnt, n, acc, h->sm_count, h->stream));
+    CU(launch_lv(c, lvp, n, lv_T0, lvs, cnt, n, acc, h->sm_count, h->stream, h->lv_mapping));
     SALT_EV(4);
     CU(launch_scan_gap(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, lv_T0, acc, d_rec,
                        d_cigars ? d_cig_reads : nullptr, d_cig_count, h->stream));

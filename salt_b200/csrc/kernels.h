@@ -13,7 +13,7 @@ cudaError_t launch_pack_reads(const uint8_t *codes, const uint32_t *offs, uint32
 cudaError_t launch_mismatch(const DevCtx &c, const salt_pair_t *pairs, size_t n, int max_err, int8_t *out, cudaStream_t st);
 cudaError_t launch_lv(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k,
                       const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
-                      int8_t *out, int sm_count, cudaStream_t st);
+                      int8_t *out, int sm_count, cudaStream_t st, int mapping = 0);
 cudaError_t launch_lv_cigar(const DevCtx &c, const salt_pair_t *pairs, const uint8_t *k_each, size_t n,
                             const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
                             const salt_verify_out_t *rec, char *cigars, int stride, int8_t *out,

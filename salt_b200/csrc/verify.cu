@@ -219,6 +219,105 @@ lv_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_fixed
 }
 
 // --------------------------------------------------------------------------------------
+// lv_tpp: one THREAD per pair, all 2K+1 diagonals of a level in registers (loops over the
+// diagonals are fully unrolled, so L[e-1][d-1], L[e-1][d], L[e-1][d+1] are plain registers).
+// The warp-per-pair kernel above keeps at most 2e+1 of its 32 lanes busy at level e; here every
+// lane works on its own pair, which costs ~6x fewer issue slots per pair for k <= 15.  Windows
+// and reads are staged per warp: for each of its 32 pairs the lanes copy the pair's text and
+// pattern words to shared memory with coalesced loads (row stride odd => conflict-free columns).
+// Work items as in lv_kernel.
+// --------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(128)
+lv_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_fixed,
+              const uint32_t *__restrict__ slots, const uint32_t *__restrict__ wl_count,
+              int8_t *__restrict__ out)
+{
+    SALT_DYN_SMEM(uint32_t, smem);
+    const int TW = lv_tw((int)c.l_max), PW = lv_pw((int)c.l_max);
+    const int stride = (TW + PW) | 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *wbase = smem + (size_t)warp * 32 * stride;
+    uint32_t *T = wbase + (size_t)lane * stride;
+    uint32_t *P = T + TW;
+    const size_t count = slots ? (size_t)*wl_count : n;
+    const size_t step = (size_t)gridDim.x * blockDim.x;
+    const uint32_t *__restrict__ mix = c.mixref;
+
+    for (size_t base = (size_t)blockIdx.x * blockDim.x + (size_t)warp * 32; base < count; base += step) {
+        const size_t it = base + lane;
+        const bool live = it < count;
+        salt_pair_t p; p.rs = 0; p.pos = 0;
+        if (live) p = pairs[it];
+        const uint32_t rid = p.rs >> 1;
+        const int plen = (live && rid < c.n_reads) ? (int)c.rd_len[rid] : 0;
+        const int tlen = plen + 4;                                  // alnse.c:373
+        const bool ok = plen > 0 && (uint64_t)p.pos + (uint64_t)tlen <= (uint64_t)c.l;   // editdistance.c:178
+        // ---- cooperative staging of the warp's 32 windows and reads
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t pos_j = __shfl_sync(0xffffffffu, p.pos, j);
+            const uint32_t rs_j = __shfl_sync(0xffffffffu, p.rs, j);
+            const int tlen_j = __shfl_sync(0xffffffffu, ok ? tlen : 0, j);
+            if (tlen_j == 0) continue;
+            uint32_t *Tj = wbase + (size_t)j * stride;
+            uint32_t *Pj = Tj + TW;
+            const uint32_t *__restrict__ r32 = reinterpret_cast<const uint32_t *>(c.rd4 + (size_t)rs_j * c.W64);
+            const int have = (int)c.W64 * 2;
+            for (int i = lane; i < TW + PW; i += 32) {
+                if (i < TW) {
+                    const int valid = tlen_j - 8 * i;
+                    uint32_t x = 0;
+                    if (valid > 0) {
+                        const uint32_t o = pos_j + 8u * (uint32_t)i;
+                        x = __funnelshift_r(mix[o >> 3], mix[(o >> 3) + 1], (int)(o & 7u) * 4);
+                        if (valid < 8) x &= (1u << (4 * valid)) - 1u;
+                    }
+                    Tj[i] = x;
+                } else {
+                    const int pi = i - TW;
+                    Pj[pi] = pi < have ? r32[pi] : 0u;
+                }
+            }
+        }
+        __syncwarp();
+        int result = -1;
+        if (ok) {
+            int k = k_fixed >= 0 ? k_fixed : plen / 10;             // alnse.c:1090
+            k = imin(imin(k, LV_MAXK - 1), K);                      // LandauVishkin.c:31
+            const int L0 = lv_extend0(T, P, plen, tlen);
+            if (L0 == plen) result = 0;
+            else {
+                int Lp[2 * K + 1];
+#pragma unroll
+                for (int i = 0; i < 2 * K + 1; ++i) Lp[i] = -2;
+                Lp[K] = L0;
+                for (int e = 1; e <= k; ++e) {
+                    int Ln[2 * K + 1];
+                    bool hit = false;
+#pragma unroll
+                    for (int di = 0; di < 2 * K + 1; ++di) {
+                        const int d = di - K;
+                        int v = -2;
+                        if (d >= -e && d <= e) {
+                            const int left = di > 0 ? Lp[di > 0 ? di - 1 : 0] : -2;
+                            const int right = di < 2 * K ? Lp[di < 2 * K ? di + 1 : 0] + 1 : -1;
+                            v = lv_extend(T, P, imax(imax(Lp[di] + 1, left), right), d, plen, tlen);
+                            hit = hit || v == plen;
+                        }
+                        Ln[di] = v;
+                    }
+                    if (hit) { result = e; break; }
+#pragma unroll
+                    for (int i = 0; i < 2 * K + 1; ++i) Lp[i] = Ln[i];
+                }
+            }
+        }
+        if (live) out[slots ? slots[it] : it] = (int8_t)result;
+        __syncwarp();
+    }
+}
+
+// --------------------------------------------------------------------------------------
 // lv_cigar: one warp per pair, 64 diagonals (2 per lane), furthest-reaching and action
 // tables kept in shared memory for the backtrace, which lane 0 performs.
 // Work items: (pairs[i], k_each[i]) -> cigars + i*stride, or, when `worklist` is non-null,
@@ -331,13 +430,16 @@ lv_cigar_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8_t *
 
 // --------------------------------------------------------------------------------------
 // nogap_fused: the whole ungapped stage of one read in one group of G lanes
-// (alnse_check_nogap on strand 0 then strand 1, alnse.c:734-782 + :1079-1083):
-//   - the read's packed words stay in registers while its candidate list is walked, so a
-//     candidate costs one coalesced 8-byte window load per lane (neighbour word by shuffle)
-//   - candidates are fetched G at a time, windows for 4 candidates are in flight together
-//   - the running threshold / primary / hit count are kept redundantly by all lanes
+// (alnse_check_nogap on strand 0 then strand 1, alnse.c:734-782 + :1079-1083).
+//   - lane i keeps 32-bit words i, i+G, .. of the packed read (8 bases each) in registers while
+//     the read's candidate list is walked, so a candidate costs one coalesced 4-byte window
+//     load per lane; the neighbouring word arrives by shuffle and one funnel shift aligns it
+//   - a read base is one-hot, so popc(window & read) counts matches directly; reads that
+//     contain N (nibble 15) take the nibble-OR path instead (group-uniform choice)
+//   - candidates are fetched G at a time, four windows are in flight together, and their four
+//     counts are reduced across the group packed two per register
+//   - threshold / primary / hit counts follow code_kmismatch (alnse.c:348-370) in list order
 //   - reads with no ungapped hit append their candidates to the Landau-Vishkin worklist
-// WPL = 64-bit words of the read per lane (reads up to 16*G*WPL bases).
 // --------------------------------------------------------------------------------------
 template <int G, int WPL>
 __global__ void __launch_bounds__(256)
@@ -352,8 +454,8 @@ nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t 
     const int gshift = (threadIdx.x & 31) / G * G;
     const unsigned gmask = (unsigned)(((1ull << G) - 1ull) << gshift);
     const int L = c.rd_len[r];
-    const int nw = (L + 15) >> 4;
-    const uint64_t *__restrict__ m64 = reinterpret_cast<const uint64_t *>(c.mixref);
+    const int nw = (L + 7) >> 3;                        // 32-bit words of the read
+    const uint32_t *__restrict__ mix = c.mixref;
 
     salt_verify_out_t q;
     q.pos = 0xFFFFFFFFu; q.strand = 3; q.n_diff = 255; q.is_gap = 255; q.lv_ran = 0; q.n_hits[0] = q.n_hits[1] = 0;
@@ -366,10 +468,15 @@ nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t 
     for (int s = 0; s < 2; ++s) {
         const uint32_t *__restrict__ loci = s ? loci1 : loci0;
         int8_t *__restrict__ accs = s ? acc + n0 : acc;
-        uint64_t rw[WPL];
-        const uint64_t *__restrict__ rrow = c.rd4 + ((size_t)r * 2 + s) * c.W64;
+        uint32_t rw[WPL];
+        const uint32_t *__restrict__ rrow = reinterpret_cast<const uint32_t *>(c.rd4 + ((size_t)r * 2 + s) * c.W64);
+        bool hasN = false;
 #pragma unroll
-        for (int w = 0; w < WPL; ++w) rw[w] = (lane + w * G) < nw ? rrow[lane + w * G] : 0ull;
+        for (int w = 0; w < WPL; ++w) {
+            rw[w] = (lane + w * G) < nw ? rrow[lane + w * G] : 0u;
+            hasN = hasN || ((rw[w] & (rw[w] >> 1) & (rw[w] >> 2) & (rw[w] >> 3) & 0x11111111u) != 0u);
+        }
+        hasN = __any_sync(gmask, hasN);
         bool matched = false;
         uint32_t last = 0xFFFFFFFFu;
         for (uint32_t base = lb[s]; base < le[s]; base += G) {
@@ -378,38 +485,41 @@ nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t 
             int myacc = -1;
             for (int j0 = 0; j0 < cnt; j0 += 4) {
                 uint32_t pos[4]; bool ok[4]; int mt[4];
-                uint64_t q0[4][WPL];
+                uint32_t q0[4][WPL], qx[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     pos[u] = __shfl_sync(gmask, mypos, (j0 + u) & (G - 1), G);
                     ok[u] = (j0 + u) < cnt && (uint64_t)pos[u] + (uint64_t)L <= (uint64_t)c.l;
+                    const uint32_t wbase = pos[u] >> 3;
 #pragma unroll
                     for (int w = 0; w < WPL; ++w) {
                         const int wi = lane + w * G;
-                        q0[u][w] = (ok[u] && wi <= nw) ? m64[(size_t)(pos[u] >> 4) + wi] : 0ull;
+                        q0[u][w] = (ok[u] && wi <= nw) ? mix[wbase + wi] : 0u;
                     }
+                    // the word after this lane's last one; only the last lane cannot get it by shuffle
+                    qx[u] = (ok[u] && lane == G - 1 && G * WPL <= nw) ? mix[wbase + G * WPL] : 0u;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int sh = (int)(pos[u] & 15u) * 4;
+                    const int sh = (int)(pos[u] & 7u) * 4;
                     int m = 0;
 #pragma unroll
                     for (int w = 0; w < WPL; ++w) {
-                        // word wi+1 lives in the next lane; for the last lane it is lane 0's next slot
-                        uint64_t nx = __shfl_down_sync(gmask, q0[u][w], 1, G);
+                        uint32_t nx = __shfl_down_sync(gmask, q0[u][w], 1, G);
                         if (WPL > 1) {
-                            const uint64_t wrap = __shfl_sync(gmask, q0[u][(w + 1 < WPL) ? w + 1 : w], 0, G);
-                            if (lane == G - 1) nx = (w + 1 < WPL) ? wrap : 0ull;
+                            const uint32_t wrap = __shfl_sync(gmask, q0[u][(w + 1 < WPL) ? w + 1 : w], 0, G);
+                            if (lane == G - 1) nx = (w + 1 < WPL) ? wrap : qx[u];
+                        } else if (lane == G - 1) nx = qx[u];
+                        const uint32_t x = __funnelshift_r(q0[u][w], nx, sh) & rw[w];
+                        if (!hasN) m += __popc(x);
+                        else {
+                            uint32_t a = x | (x >> 1);
+                            a |= a >> 2;
+                            m += __popc(a & 0x11111111u);
                         }
-                        const uint64_t x = sh ? ((q0[u][w] >> sh) | (nx << (64 - sh))) : q0[u][w];
-                        uint64_t a = x & rw[w];
-                        a |= a >> 1;
-                        a |= a >> 2;
-                        m += __popcll(a & 0x1111111111111111ull);
                     }
                     mt[u] = m;
                 }
-                // two 16-bit counts per register: two group reductions for four candidates
                 int p01 = mt[0] | (mt[1] << 16), p23 = mt[2] | (mt[3] << 16);
 #pragma unroll
                 for (int o = G / 2; o > 0; o >>= 1) {
@@ -628,12 +738,43 @@ static cudaError_t launch_lv_t(const DevCtx &c, const salt_pair_t *pairs, size_t
     return cudaSuccess;
 }
 
+template <int K>
+static cudaError_t launch_lv_tpp(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k,
+                                 const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
+                                 int8_t *out, int sm_count, cudaStream_t st)
+{
+    const int stride = (lv_tw((int)c.l_max) + lv_pw((int)c.l_max)) | 1;
+    int threads = 128;
+    size_t smem = (size_t)threads * stride * 4;
+    if (smem > 100 * 1024) { threads = 64; smem = (size_t)threads * stride * 4; }
+    const size_t items = worklist ? wl_cap : n;
+    size_t blocks = (items + threads - 1) / threads;
+    const size_t cap = (size_t)sm_count * 16;          // persistent upper bound: warps stride over the rest
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) return cudaSuccess;
+    auto kern = lv_tpp_kernel<K>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    SALT_LAUNCH(kern, (unsigned)blocks, threads, smem, st, c, pairs, n, k, worklist, wl_count, out);
+    SALT_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+// mapping: 0 = choose (thread-per-pair up to k = 15, warp-per-pair beyond), 1 = force warp-per-pair
 cudaError_t launch_lv(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k,
                       const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
-                      int8_t *out, int sm_count, cudaStream_t st)
+                      int8_t *out, int sm_count, cudaStream_t st, int mapping)
 {
     int kmax = k >= 0 ? k : (int)c.l_max / 10;
     if (kmax > LV_MAXK - 1) kmax = LV_MAXK - 1;
+    if (mapping == 0 && c.l_max <= 512) {
+        if (kmax <= 3) return launch_lv_tpp<3>(c, pairs, n, k, worklist, wl_count, wl_cap, out, sm_count, st);
+        if (kmax <= 8) return launch_lv_tpp<8>(c, pairs, n, k, worklist, wl_count, wl_cap, out, sm_count, st);
+        if (kmax <= 10) return launch_lv_tpp<10>(c, pairs, n, k, worklist, wl_count, wl_cap, out, sm_count, st);
+        if (kmax <= 15) return launch_lv_tpp<15>(c, pairs, n, k, worklist, wl_count, wl_cap, out, sm_count, st);
+    }
     if (kmax <= 3) return launch_lv_t<8, 1>(c, pairs, n, k, worklist, wl_count, wl_cap, out, sm_count, st);
     if (kmax <= 7) return launch_lv_t<16, 1>(c, pairs, n, k, worklist, wl_count, wl_cap, out, sm_count, st);
     if (kmax <= 15) return launch_lv_t<32, 1>(c, pairs, n, k, worklist, wl_count, wl_cap, out, sm_count, st);
@@ -703,11 +844,11 @@ cudaError_t launch_nogap_fused(const DevCtx &c, const uint32_t *offs0, const uin
                                uint32_t *lv_count, cudaStream_t st)
 {
     if (!c.n_reads) return cudaSuccess;
-    const int nw = ((int)c.l_max + 15) / 16;
-    if (nw < 8) return launch_nogap_t<8, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
-    if (nw < 16) return launch_nogap_t<16, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
-    if (nw < 32) return launch_nogap_t<32, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
-    return launch_nogap_t<32, 3>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
+    const int nw = ((int)c.l_max + 7) / 8;             // 32-bit words per read
+    if (nw <= 16) return launch_nogap_t<16, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
+    if (nw <= 32) return launch_nogap_t<32, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
+    if (nw <= 64) return launch_nogap_t<32, 2>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
+    return launch_nogap_t<32, 4>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
 }
 
 cudaError_t launch_scan_gap(const DevCtx &c, const uint32_t *offs0, const uint32_t *loci0,

@@ -162,6 +162,7 @@ static inline void __syncthreads() { emu::syncthreads(); }
 
 // ---- scalar intrinsics ------------------------------------------------------------
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh)

@@ -41,6 +41,8 @@ def test_lv(oracle, L, k):
     extra = api.Engine.make_pairs([0, 1], [0, 1], [g.l - L - 4, g.l - L - 3])
     pairs = np.concatenate([pairs, extra])
     got = pc.check_lv(eng, oracle, g, reads, pairs, k)
+    eng.set_lv_mapping(1)          # the warp-per-pair kernel must agree with the thread-per-pair one
+    assert np.array_equal(eng.lv(pairs, k), got)
     assert (got > 0).sum() >= 10
 
 
