@@ -431,15 +431,22 @@ lv_cigar_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8_t *
 // --------------------------------------------------------------------------------------
 // nogap_fused: the whole ungapped stage of one read in one group of G lanes
 // (alnse_check_nogap on strand 0 then strand 1, alnse.c:734-782 + :1079-1083).
-//   - lane i keeps 32-bit words i, i+G, .. of the packed read (8 bases each) in registers while
-//     the read's candidate list is walked, so a candidate costs one coalesced 4-byte window
-//     load per lane; the neighbouring word arrives by shuffle and one funnel shift aligns it
-//   - a read base is one-hot, so popc(window & read) counts matches directly; reads that
-//     contain N (nibble 15) take the nibble-OR path instead (group-uniform choice)
-//   - candidates are fetched G at a time, four windows are in flight together, and their four
-//     counts are reduced across the group packed two per register
-//   - threshold / primary / hit counts follow code_kmismatch (alnse.c:348-370) in list order
-//   - reads with no ungapped hit append their candidates to the Landau-Vishkin worklist
+//   counting  lane i keeps 32-bit words i, i+G, .. of the packed read (8 bases each) in
+//             registers while the read's candidate list is walked, so a candidate costs one
+//             coalesced 4-byte window load per lane; the neighbouring word arrives by shuffle and
+//             one funnel shift aligns it.  A read base is one-hot, so popc(window & read) counts
+//             matches directly; reads containing N (nibble 15) take the nibble-OR path
+//             (group-uniform choice).  Four windows are in flight together and their counts are
+//             reduced across the group packed two per register.
+//   accepting candidates are taken G at a time, lane j owning candidate j.  The reference's
+//             running threshold (code_kmismatch, alnse.c:348-370) is "accept n_j iff
+//             n_j <= min(threshold so far, min of earlier valid n)", i.e. an exclusive prefix
+//             minimum over the lanes; the primary is the first candidate reaching the stage's
+//             minimum, and the first accepted hit of a stage always replaces the primary
+//             (flag_match is local to alnse_check_nogap).  Candidate lists must be sorted
+//             ascending (alnse_locate sorts them), so "pos == previous unskipped pos"
+//             (alnse.c:762) is a comparison with the neighbouring lane.
+//   reads with no ungapped hit append their candidates to the Landau-Vishkin worklist.
 // --------------------------------------------------------------------------------------
 template <int G, int WPL>
 __global__ void __launch_bounds__(256)
@@ -453,12 +460,14 @@ nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t 
     if (r >= c.n_reads) return;                         // whole groups leave together
     const int gshift = (threadIdx.x & 31) / G * G;
     const unsigned gmask = (unsigned)(((1ull << G) - 1ull) << gshift);
+    const unsigned lanes_below = (1u << lane) - 1u;
     const int L = c.rd_len[r];
     const int nw = (L + 7) >> 3;                        // 32-bit words of the read
     const uint32_t *__restrict__ mix = c.mixref;
+    constexpr int BIG = 255;
 
-    salt_verify_out_t q;
-    q.pos = 0xFFFFFFFFu; q.strand = 3; q.n_diff = 255; q.is_gap = 255; q.lv_ran = 0; q.n_hits[0] = q.n_hits[1] = 0;
+    uint32_t prim_pos = 0xFFFFFFFFu;
+    int prim_n = 255, prim_strand = 3, hits[2] = {0, 0};
     int max_diff = T0;
     bool any = false;
     uint32_t lb[2], le[2];
@@ -481,8 +490,9 @@ nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t 
         uint32_t last = 0xFFFFFFFFu;
         for (uint32_t base = lb[s]; base < le[s]; base += G) {
             const int cnt = (int)min((uint32_t)G, le[s] - base);
-            const uint32_t mypos = lane < cnt ? loci[base + lane] : 0u;
-            int myacc = -1;
+            const uint32_t mypos = lane < cnt ? loci[base + lane] : 0xFFFFFFFFu;
+            int mymatches = 0;
+            // ---- counting: four candidates at a time, all lanes cooperate on each window
             for (int j0 = 0; j0 < cnt; j0 += 4) {
                 uint32_t pos[4]; bool ok[4]; int mt[4];
                 uint32_t q0[4][WPL], qx[4];
@@ -526,35 +536,52 @@ nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t 
                     p01 += __shfl_xor_sync(gmask, p01, o, G);
                     p23 += __shfl_xor_sync(gmask, p23, o, G);
                 }
-                mt[0] = p01 & 0xffff; mt[1] = p01 >> 16; mt[2] = p23 & 0xffff; mt[3] = p23 >> 16;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (j0 + u >= cnt) break;
-                    int v = -1;
-                    // alnse.c:762: duplicates and loci past the end are skipped without touching pos0
-                    if (!(pos[u] == last || pos[u] >= c.l)) {
-                        const int nmis = L - mt[u];
-                        const int nd = (ok[u] && nmis <= T0) ? nmis : -1;
-                        if (nd >= 0 && nd <= max_diff) {                    // code_kmismatch, alnse.c:348-370
-                            if (nd < max_diff || !matched) {
-                                max_diff = nd;
-                                q.is_gap = 0; q.n_diff = (uint8_t)nd; q.strand = (uint8_t)s; q.pos = pos[u];
-                            }
-                            matched = true;
-                            q.n_hits[s] += 1;
-                            v = nd;
-                        }
-                        last = pos[u];
-                    }
-                    if (lane == j0 + u) myacc = v;
-                }
+                const int sel = lane - j0;                          // lane j0+u keeps candidate u's count
+                if (sel == 0) mymatches = p01 & 0xffff;
+                if (sel == 1) mymatches = p01 >> 16;
+                if (sel == 2) mymatches = p23 & 0xffff;
+                if (sel == 3) mymatches = p23 >> 16;
             }
-            if (lane < cnt) accs[base + lane] = (int8_t)myacc;
+            // ---- accepting: lane j decides candidate j
+            uint32_t prev = __shfl_up_sync(gmask, mypos, 1, G);
+            if (lane == 0) prev = last;
+            const bool inb = (uint64_t)mypos + (uint64_t)L <= (uint64_t)c.l;
+            const bool skip = lane >= cnt || mypos == prev || mypos >= c.l;          // alnse.c:762
+            const int nmis = L - mymatches;
+            const int key = (!skip && inb && nmis <= T0) ? nmis : BIG;
+            int pm = key;                                                              // inclusive prefix minimum
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) {
+                const int t = __shfl_up_sync(gmask, pm, o, G);
+                if (lane >= o) pm = imin(pm, t);
+            }
+            int ex = __shfl_up_sync(gmask, pm, 1, G);                                 // exclusive
+            if (lane == 0) ex = BIG;
+            const bool accepted = key != BIG && key <= imin(max_diff, ex);
+            const unsigned bal = (__ballot_sync(gmask, accepted) >> gshift) & (unsigned)((1ull << G) - 1ull);
+            if (lane < cnt) accs[base + lane] = (int8_t)(accepted ? key : -1);
+            if (bal) {
+                const int cmin = __shfl_sync(gmask, pm, G - 1, G);                    // minimum over the chunk's valid keys
+                if (cmin < max_diff || !matched) {
+                    // first accepted candidate that reaches the chunk minimum becomes the primary
+                    const unsigned at = (__ballot_sync(gmask, accepted && key == cmin) >> gshift) & (unsigned)((1ull << G) - 1ull);
+                    const int src = __ffs((int)at) - 1;
+                    prim_pos = __shfl_sync(gmask, mypos, src, G);
+                    prim_n = cmin; prim_strand = s;
+                }
+                max_diff = imin(max_diff, cmin);
+                matched = true;
+                hits[s] += __popc(bal);
+            }
+            // last unskipped position carried into the next chunk (sorted lists: the last in-range one)
+            const unsigned unsk = (__ballot_sync(gmask, lane < cnt && !skip) >> gshift) & (unsigned)((1ull << G) - 1ull);
+            if (unsk) last = __shfl_sync(gmask, mypos, 31 - __clz((int)unsk), G);
+            (void)lanes_below;
         }
         any = any || matched;
     }
-    if (!any) {                                          // alnse.c:1022 / :1089: gapped stage for this read
-        q.lv_ran = 1;
+    const bool need_lv = !any;                           // alnse.c:1022 / :1089: gapped stage for this read
+    if (need_lv) {
         const uint32_t c0 = le[0] - lb[0], c1 = le[1] - lb[1];
         if (c0 + c1) {
             uint32_t w = 0;
@@ -570,7 +597,12 @@ nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t 
             }
         }
     }
-    if (lane == 0) rec[r] = q;
+    if (lane == 0) {
+        salt_verify_out_t q;
+        q.pos = prim_pos; q.strand = (uint8_t)prim_strand; q.n_diff = (uint8_t)prim_n;
+        q.is_gap = any ? 0 : 255; q.lv_ran = need_lv ? 1 : 0; q.n_hits[0] = hits[0]; q.n_hits[1] = hits[1];
+        rec[r] = q;
+    }
 }
 
 // --------------------------------------------------------------------------------------

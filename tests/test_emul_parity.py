@@ -82,6 +82,24 @@ def test_verify_stage(emul_lib, oracle, L, lv_T0):
         assert st["lv_ran"] >= 5 and st["gapped"] >= 2 and st["mapped"] >= 30
 
 
+def test_verify_long_lists(emul_lib, oracle):
+    """lists longer than one lane group (several chunks), duplicates that straddle a chunk boundary,
+    loci at/after the end of the reference"""
+    g, reads, pos, strand, cands = pc.make_world(91, L=100, n_reads=10, per_strand=45, indel_frac=0.3, glen=30000)
+    offs0, loci0, offs1, loci1 = cands
+    loci0 = loci0.copy(); loci1 = loci1.copy()
+    for r in range(10):
+        b = int(offs0[r])
+        loci0[b + 15] = loci0[b + 16] = loci0[b + 17]          # run of equal loci across lanes 15|16
+        loci0[b + 31] = loci0[b + 32]
+        e = int(offs1[r + 1])
+        loci1[e - 1] = g.l + 5; loci1[e - 2] = g.l - 50; loci1[e - 3] = g.l - 50   # past the end / too close to it
+    eng = _engine(emul_lib, g)
+    eng.set_reads(reads)
+    pc.check_verify(eng, oracle, g, reads, (offs0, loci0, offs1, loci1), 3, -1)
+    pc.check_verify(eng, oracle, g, reads, (offs0, loci0, offs1, loci1), 3, 3)
+
+
 def test_verify_empty_lists(emul_lib, oracle):
     g, reads, pos, strand, cands = pc.make_world(77, L=100, n_reads=6, per_strand=3, glen=20000)
     z = np.zeros(7, np.uint32); e = np.zeros(0, np.uint32)

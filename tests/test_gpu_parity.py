@@ -70,6 +70,25 @@ def test_verify_stage(oracle, L, lv_T0):
     assert st["lv_ran"] >= 100 and st["gapped"] >= 30 and st["mapped"] >= 800
 
 
+def test_verify_long_lists(oracle):
+    """lists longer than one lane group, duplicates straddling chunk boundaries, loci past the end"""
+    g, reads, pos, strand, cands = pc.make_world(91, glen=100000, L=100, n_reads=300, per_strand=70, indel_frac=0.3)
+    offs0, loci0, offs1, loci1 = cands
+    loci0 = loci0.copy(); loci1 = loci1.copy()
+    for r in range(300):
+        b = int(offs0[r])
+        if offs0[r + 1] - b > 40:
+            loci0[b + 15] = loci0[b + 16] = loci0[b + 17]
+            loci0[b + 31] = loci0[b + 32]
+        e = int(offs1[r + 1])
+        if e - offs1[r] > 4:
+            loci1[e - 1] = g.l + 5; loci1[e - 2] = g.l - 50; loci1[e - 3] = g.l - 50
+    eng = _engine(g)
+    eng.set_reads(reads)
+    pc.check_verify(eng, oracle, g, reads, (offs0, loci0, offs1, loci1), 3, -1)
+    pc.check_verify(eng, oracle, g, reads, (offs0, loci0, offs1, loci1), 3, 3)
+
+
 def test_verify_ragged_and_empty(oracle):
     """ragged read lengths in one chunk, reads without candidates, an empty chunk of lists"""
     rng = np.random.default_rng(5)
