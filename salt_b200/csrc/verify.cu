@@ -431,13 +431,16 @@ lv_cigar_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8_t *
 // --------------------------------------------------------------------------------------
 // nogap_fused: the whole ungapped stage of one read in one group of G lanes
 // (alnse_check_nogap on strand 0 then strand 1, alnse.c:734-782 + :1079-1083).
-//   counting  lane i keeps 32-bit words i, i+G, .. of the packed read (8 bases each) in
-//             registers while the read's candidate list is walked, so a candidate costs one
-//             coalesced 4-byte window load per lane; the neighbouring word arrives by shuffle and
-//             one funnel shift aligns it.  A read base is one-hot, so popc(window & read) counts
-//             matches directly; reads containing N (nibble 15) take the nibble-OR path
-//             (group-uniform choice).  Four windows are in flight together and their counts are
-//             reduced across the group packed two per register.
+//   counting  lane t keeps 64-bit words t, t+G, .. of the packed read (16 bases each) in
+//             registers while the read's candidate list is walked.  A candidate costs one
+//             coalesced, 8-byte-aligned window load per lane (G*8 contiguous bytes per candidate:
+//             one or two L1 wavefronts); the next lane's word arrives by shuffle and two funnel
+//             shifts bring the window to the read's nibble phase.  A read base is one-hot, so
+//             popc(window & read) counts matches directly; reads containing N (nibble 15) take
+//             the nibble-OR path (group-uniform choice).  Four windows are in flight together and
+//             their per-lane counts travel through ONE butterfly, packed PK per register.
+//             G and WPL are chosen so that 16*G*WPL >= l_max + 16: the last lane never needs a
+//             word from beyond the group.
 //   accepting candidates are taken G at a time, lane j owning candidate j.  The reference's
 //             running threshold (code_kmismatch, alnse.c:348-370) is "accept n_j iff
 //             n_j <= min(threshold so far, min of earlier valid n)", i.e. an exclusive prefix
@@ -448,6 +451,124 @@ lv_cigar_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8_t *
 //             (alnse.c:762) is a comparison with the neighbouring lane.
 //   reads with no ungapped hit append their candidates to the Landau-Vishkin worklist.
 // --------------------------------------------------------------------------------------
+// State of one read's ungapped stage, carried across strands and candidate chunks.
+struct NogapState {
+    uint32_t prim_pos; int prim_n, prim_strand, max_diff; bool any;
+};
+
+// One strand of one read per group of G lanes; every loop bound is made warp-uniform (maximum
+// over the warp's groups, idle groups predicated off) so that all shuffles run on the full
+// warp mask without divergence checks.
+template <int G, int WPL, bool HASN>
+__device__ __forceinline__ int nogap_strand(const DevCtx &c, const uint2 *__restrict__ mixl, const uint2 (&rw)[WPL],
+                                            const uint32_t *__restrict__ loci, int8_t *__restrict__ accs,
+                                            uint32_t lbs, uint32_t les, int L, int T0, bool fits, uint32_t lim,
+                                            int nw, int s, int lane, int gshift, NogapState &st)
+{
+    // counts of up to 16*WPL per lane, up to l_max in total: four per register while they fit a byte
+    constexpr int PK = (16 * G * WPL <= 256) ? 4 : 2;
+    constexpr int PB = 32 / PK;
+    constexpr uint32_t PM = PK == 4 ? 0xffu : 0xffffu;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr unsigned gfull = (unsigned)((1ull << G) - 1ull);
+    constexpr int BIG = 255;
+    const int nchunks = (int)((les - lbs + (G - 1)) / G);
+    const int nchunks_w = __reduce_max_sync(FULL, nchunks);
+    bool matched = false;
+    uint32_t last = 0xFFFFFFFFu;
+    int nhits = 0;
+    for (int ci = 0; ci < nchunks_w; ++ci) {
+        const uint32_t base = lbs + (uint32_t)ci * G;
+        const int cnt = ci < nchunks ? (int)min((uint32_t)G, les - base) : 0;
+        const uint32_t truepos = lane < cnt ? loci[base + lane] : 0xFFFFFFFFu;
+        // a read longer than the reference counts nothing; 0xFFFFFFFF > lim switches a lane's window off
+        const uint32_t mypos = fits ? truepos : 0xFFFFFFFFu;
+        const int cnt_w = __reduce_max_sync(FULL, cnt);
+        int mymatches = 0;
+        // ---- counting: four candidates at a time, all lanes of a group cooperate on each window
+        for (int j0 = 0; j0 < cnt_w; j0 += 4) {
+            uint32_t pos[4];
+            uint2 q[4][WPL];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                pos[u] = __shfl_sync(FULL, mypos, (j0 + u) & (G - 1), G);
+                const bool ok = pos[u] <= lim;                          // pos + L <= l, and the lane had a candidate
+                const uint2 *__restrict__ wp = mixl + (pos[u] >> 4);
+#pragma unroll
+                for (int w = 0; w < WPL; ++w)
+                    q[u][w] = (ok && (lane + w * G) < nw) ? wp[w * G] : make_uint2(0u, 0u);
+            }
+            uint32_t packed[4 / PK];
+#pragma unroll
+            for (int k = 0; k < 4 / PK; ++k) packed[k] = 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int sh = (int)(pos[u] & 7u) * 4;
+                const bool hi = (pos[u] & 8u) != 0u;
+                uint32_t m = 0;
+#pragma unroll
+                for (int w = 0; w < WPL; ++w) {
+                    uint32_t n0 = __shfl_down_sync(FULL, q[u][w].x, 1, G);
+                    uint32_t n1 = __shfl_down_sync(FULL, q[u][w].y, 1, G);
+                    if (w + 1 < WPL) {                                  // the last lane's neighbour is lane 0's next word
+                        const uint32_t w0 = __shfl_sync(FULL, q[u][w + 1 < WPL ? w + 1 : w].x, 0, G);
+                        const uint32_t w1 = __shfl_sync(FULL, q[u][w + 1 < WPL ? w + 1 : w].y, 0, G);
+                        if (lane == G - 1) { n0 = w0; n1 = w1; }
+                    }
+                    const uint32_t a = hi ? q[u][w].y : q[u][w].x;
+                    const uint32_t b = hi ? n0 : q[u][w].y;
+                    const uint32_t cc = hi ? n1 : n0;
+                    uint32_t x0 = __funnelshift_r(a, b, sh) & rw[w].x;
+                    uint32_t x1 = __funnelshift_r(b, cc, sh) & rw[w].y;
+                    if (HASN) {
+                        x0 |= x0 >> 1; x0 |= x0 >> 2; x0 &= 0x11111111u;
+                        x1 |= x1 >> 1; x1 |= x1 >> 2; x1 &= 0x11111111u;
+                    }
+                    m += (uint32_t)(__popc(x0) + __popc(x1));
+                }
+                packed[u / PK] += m << (PB * (u % PK));
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1)
+#pragma unroll
+                for (int k = 0; k < 4 / PK; ++k) packed[k] += __shfl_xor_sync(FULL, packed[k], o, G);
+            const int sel = lane - j0;                                  // lane j0+u keeps candidate u's count
+            const uint32_t pv = (PK == 4 || sel < 2) ? packed[0] : packed[4 / PK - 1];
+            if (sel >= 0 && sel < 4) mymatches = (int)((pv >> (PB * (sel % PK))) & PM);
+        }
+        // ---- accepting: lane j decides candidate j
+        uint32_t prev = __shfl_up_sync(FULL, truepos, 1, G);
+        if (lane == 0) prev = last;
+        const bool skip = lane >= cnt || truepos == prev || truepos >= c.l;          // alnse.c:762
+        const int nmis = L - mymatches;
+        const int key = (!skip && mypos <= lim && nmis <= T0) ? nmis : BIG;
+        int pm = key;                                                                // inclusive prefix minimum
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) pm = imin(pm, __shfl_up_sync(FULL, pm, o, G));   // lanes < o get themselves back
+        int ex = __shfl_up_sync(FULL, pm, 1, G);                                     // exclusive
+        if (lane == 0) ex = BIG;
+        const bool accepted = key != BIG && key <= imin(st.max_diff, ex);
+        const unsigned bal = (__ballot_sync(FULL, accepted) >> gshift) & gfull;
+        if (lane < cnt) accs[base + lane] = (int8_t)(accepted ? key : -1);
+        const int cmin = __shfl_sync(FULL, pm, G - 1, G);                            // minimum over the chunk's valid keys
+        // first accepted candidate that reaches the chunk minimum becomes the primary
+        const unsigned at = (__ballot_sync(FULL, accepted && key == cmin) >> gshift) & gfull;
+        const uint32_t cand_pos = __shfl_sync(FULL, truepos, at ? __ffs((int)at) - 1 : 0, G);
+        if (bal) {
+            if (cmin < st.max_diff || !matched) { st.prim_pos = cand_pos; st.prim_n = cmin; st.prim_strand = s; }
+            st.max_diff = imin(st.max_diff, cmin);
+            matched = true;
+            nhits += __popc(bal);
+        }
+        // last unskipped position carried into the next chunk (sorted lists: the last in-range one)
+        const unsigned unsk = (__ballot_sync(FULL, lane < cnt && !skip) >> gshift) & gfull;
+        const uint32_t lastpos = __shfl_sync(FULL, truepos, unsk ? 31 - __clz((int)unsk) : 0, G);
+        if (unsk) last = lastpos;
+    }
+    st.any = st.any || matched;
+    return nhits;
+}
+
 template <int G, int WPL>
 __global__ void __launch_bounds__(256)
 nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t *__restrict__ loci0,
@@ -455,152 +576,62 @@ nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t 
                    int T0, int8_t *__restrict__ acc, salt_verify_out_t *__restrict__ rec,
                    salt_pair_t *__restrict__ lv_pairs, uint32_t *__restrict__ lv_slots, uint32_t *__restrict__ lv_count)
 {
-    const uint32_t r = (uint32_t)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
+    constexpr unsigned FULL = 0xffffffffu;
+    const size_t rr = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool live = rr < (size_t)c.n_reads;           // a dead group runs along with empty lists
+    const uint32_t r = live ? (uint32_t)rr : 0u;
     const int lane = threadIdx.x % G;
-    if (r >= c.n_reads) return;                         // whole groups leave together
     const int gshift = (threadIdx.x & 31) / G * G;
-    const unsigned gmask = (unsigned)(((1ull << G) - 1ull) << gshift);
-    const unsigned lanes_below = (1u << lane) - 1u;
-    const int L = c.rd_len[r];
-    const int nw = (L + 7) >> 3;                        // 32-bit words of the read
-    const uint32_t *__restrict__ mix = c.mixref;
-    constexpr int BIG = 255;
+    const int L = live ? (int)c.rd_len[r] : 0;
+    const int nw = (L + 30) >> 4;                       // aligned 64-bit window words a candidate can touch
+    const uint2 *__restrict__ mixl = reinterpret_cast<const uint2 *>(c.mixref) + lane;
+    const bool fits = c.l >= (uint32_t)L && L > 0;
+    const uint32_t lim = fits ? c.l - (uint32_t)L : 0u; // pos + L <= l  <=>  pos <= lim
 
-    uint32_t prim_pos = 0xFFFFFFFFu;
-    int prim_n = 255, prim_strand = 3, hits[2] = {0, 0};
-    int max_diff = T0;
-    bool any = false;
-    uint32_t lb[2], le[2];
-    lb[0] = offs0[r]; le[0] = offs0[r + 1]; lb[1] = offs1[r]; le[1] = offs1[r + 1];
+    NogapState st;
+    st.prim_pos = 0xFFFFFFFFu; st.prim_n = 255; st.prim_strand = 3; st.max_diff = T0; st.any = false;
+    int hits0 = 0, hits1 = 0;
+    uint32_t lb0 = 0, le0 = 0, lb1 = 0, le1 = 0;
+    if (live) { lb0 = offs0[r]; le0 = offs0[r + 1]; lb1 = offs1[r]; le1 = offs1[r + 1]; }
 
-#pragma unroll
     for (int s = 0; s < 2; ++s) {
         const uint32_t *__restrict__ loci = s ? loci1 : loci0;
         int8_t *__restrict__ accs = s ? acc + n0 : acc;
-        uint32_t rw[WPL];
-        const uint32_t *__restrict__ rrow = reinterpret_cast<const uint32_t *>(c.rd4 + ((size_t)r * 2 + s) * c.W64);
+        const uint32_t lbs = s ? lb1 : lb0, les = s ? le1 : le0;
+        uint2 rw[WPL];
+        const uint2 *__restrict__ rrow = reinterpret_cast<const uint2 *>(c.rd4 + ((size_t)r * 2 + s) * c.W64);
         bool hasN = false;
 #pragma unroll
         for (int w = 0; w < WPL; ++w) {
-            rw[w] = (lane + w * G) < nw ? rrow[lane + w * G] : 0u;
-            hasN = hasN || ((rw[w] & (rw[w] >> 1) & (rw[w] >> 2) & (rw[w] >> 3) & 0x11111111u) != 0u);
+            rw[w] = (live && (uint32_t)(lane + w * G) < c.W64) ? rrow[lane + w * G] : make_uint2(0u, 0u);
+            hasN = hasN || ((rw[w].x & (rw[w].x >> 1) & 0x11111111u) != 0u) || ((rw[w].y & (rw[w].y >> 1) & 0x11111111u) != 0u);
         }
-        hasN = __any_sync(gmask, hasN);
-        bool matched = false;
-        uint32_t last = 0xFFFFFFFFu;
-        for (uint32_t base = lb[s]; base < le[s]; base += G) {
-            const int cnt = (int)min((uint32_t)G, le[s] - base);
-            const uint32_t mypos = lane < cnt ? loci[base + lane] : 0xFFFFFFFFu;
-            int mymatches = 0;
-            // ---- counting: four candidates at a time, all lanes cooperate on each window
-            for (int j0 = 0; j0 < cnt; j0 += 4) {
-                uint32_t pos[4]; bool ok[4]; int mt[4];
-                uint32_t q0[4][WPL], qx[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    pos[u] = __shfl_sync(gmask, mypos, (j0 + u) & (G - 1), G);
-                    ok[u] = (j0 + u) < cnt && (uint64_t)pos[u] + (uint64_t)L <= (uint64_t)c.l;
-                    const uint32_t wbase = pos[u] >> 3;
-#pragma unroll
-                    for (int w = 0; w < WPL; ++w) {
-                        const int wi = lane + w * G;
-                        q0[u][w] = (ok[u] && wi <= nw) ? mix[wbase + wi] : 0u;
-                    }
-                    // the word after this lane's last one; only the last lane cannot get it by shuffle
-                    qx[u] = (ok[u] && lane == G - 1 && G * WPL <= nw) ? mix[wbase + G * WPL] : 0u;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int sh = (int)(pos[u] & 7u) * 4;
-                    int m = 0;
-#pragma unroll
-                    for (int w = 0; w < WPL; ++w) {
-                        uint32_t nx = __shfl_down_sync(gmask, q0[u][w], 1, G);
-                        if (WPL > 1) {
-                            const uint32_t wrap = __shfl_sync(gmask, q0[u][(w + 1 < WPL) ? w + 1 : w], 0, G);
-                            if (lane == G - 1) nx = (w + 1 < WPL) ? wrap : qx[u];
-                        } else if (lane == G - 1) nx = qx[u];
-                        const uint32_t x = __funnelshift_r(q0[u][w], nx, sh) & rw[w];
-                        if (!hasN) m += __popc(x);
-                        else {
-                            uint32_t a = x | (x >> 1);
-                            a |= a >> 2;
-                            m += __popc(a & 0x11111111u);
-                        }
-                    }
-                    mt[u] = m;
-                }
-                int p01 = mt[0] | (mt[1] << 16), p23 = mt[2] | (mt[3] << 16);
-#pragma unroll
-                for (int o = G / 2; o > 0; o >>= 1) {
-                    p01 += __shfl_xor_sync(gmask, p01, o, G);
-                    p23 += __shfl_xor_sync(gmask, p23, o, G);
-                }
-                const int sel = lane - j0;                          // lane j0+u keeps candidate u's count
-                if (sel == 0) mymatches = p01 & 0xffff;
-                if (sel == 1) mymatches = p01 >> 16;
-                if (sel == 2) mymatches = p23 & 0xffff;
-                if (sel == 3) mymatches = p23 >> 16;
-            }
-            // ---- accepting: lane j decides candidate j
-            uint32_t prev = __shfl_up_sync(gmask, mypos, 1, G);
-            if (lane == 0) prev = last;
-            const bool inb = (uint64_t)mypos + (uint64_t)L <= (uint64_t)c.l;
-            const bool skip = lane >= cnt || mypos == prev || mypos >= c.l;          // alnse.c:762
-            const int nmis = L - mymatches;
-            const int key = (!skip && inb && nmis <= T0) ? nmis : BIG;
-            int pm = key;                                                              // inclusive prefix minimum
-#pragma unroll
-            for (int o = 1; o < G; o <<= 1) {
-                const int t = __shfl_up_sync(gmask, pm, o, G);
-                if (lane >= o) pm = imin(pm, t);
-            }
-            int ex = __shfl_up_sync(gmask, pm, 1, G);                                 // exclusive
-            if (lane == 0) ex = BIG;
-            const bool accepted = key != BIG && key <= imin(max_diff, ex);
-            const unsigned bal = (__ballot_sync(gmask, accepted) >> gshift) & (unsigned)((1ull << G) - 1ull);
-            if (lane < cnt) accs[base + lane] = (int8_t)(accepted ? key : -1);
-            if (bal) {
-                const int cmin = __shfl_sync(gmask, pm, G - 1, G);                    // minimum over the chunk's valid keys
-                if (cmin < max_diff || !matched) {
-                    // first accepted candidate that reaches the chunk minimum becomes the primary
-                    const unsigned at = (__ballot_sync(gmask, accepted && key == cmin) >> gshift) & (unsigned)((1ull << G) - 1ull);
-                    const int src = __ffs((int)at) - 1;
-                    prim_pos = __shfl_sync(gmask, mypos, src, G);
-                    prim_n = cmin; prim_strand = s;
-                }
-                max_diff = imin(max_diff, cmin);
-                matched = true;
-                hits[s] += __popc(bal);
-            }
-            // last unskipped position carried into the next chunk (sorted lists: the last in-range one)
-            const unsigned unsk = (__ballot_sync(gmask, lane < cnt && !skip) >> gshift) & (unsigned)((1ull << G) - 1ull);
-            if (unsk) last = __shfl_sync(gmask, mypos, 31 - __clz((int)unsk), G);
-            (void)lanes_below;
-        }
-        any = any || matched;
+        int nh;
+        if (__any_sync(FULL, hasN))      // warp-uniform: the general path is exact for every read
+            nh = nogap_strand<G, WPL, true>(c, mixl, rw, loci, accs, lbs, les, L, T0, fits, lim, nw, s, lane, gshift, st);
+        else
+            nh = nogap_strand<G, WPL, false>(c, mixl, rw, loci, accs, lbs, les, L, T0, fits, lim, nw, s, lane, gshift, st);
+        if (s) hits1 = nh; else hits0 = nh;
     }
-    const bool need_lv = !any;                           // alnse.c:1022 / :1089: gapped stage for this read
+    const bool need_lv = live && !st.any;                // alnse.c:1022 / :1089: gapped stage for this read
+    const uint32_t c0 = le0 - lb0, c1 = le1 - lb1;
+    uint32_t w = 0;
+    if (need_lv && lane == 0 && c0 + c1) w = atomicAdd(lv_count, c0 + c1);
+    w = __shfl_sync(FULL, w, 0, G);
     if (need_lv) {
-        const uint32_t c0 = le[0] - lb[0], c1 = le[1] - lb[1];
-        if (c0 + c1) {
-            uint32_t w = 0;
-            if (lane == 0) w = atomicAdd(lv_count, c0 + c1);
-            w = __shfl_sync(gmask, w, 0, G);
-            for (uint32_t i = lane; i < c0; i += G) {
-                salt_pair_t p; p.rs = r << 1; p.pos = loci0[lb[0] + i];
-                lv_pairs[w + i] = p; lv_slots[w + i] = lb[0] + i;
-            }
-            for (uint32_t i = lane; i < c1; i += G) {
-                salt_pair_t p; p.rs = (r << 1) | 1u; p.pos = loci1[lb[1] + i];
-                lv_pairs[w + c0 + i] = p; lv_slots[w + c0 + i] = (uint32_t)n0 + lb[1] + i;
-            }
+        for (uint32_t i = lane; i < c0; i += G) {
+            salt_pair_t p; p.rs = r << 1; p.pos = loci0[lb0 + i];
+            lv_pairs[w + i] = p; lv_slots[w + i] = lb0 + i;
+        }
+        for (uint32_t i = lane; i < c1; i += G) {
+            salt_pair_t p; p.rs = (r << 1) | 1u; p.pos = loci1[lb1 + i];
+            lv_pairs[w + c0 + i] = p; lv_slots[w + c0 + i] = (uint32_t)n0 + lb1 + i;
         }
     }
-    if (lane == 0) {
+    if (live && lane == 0) {
         salt_verify_out_t q;
-        q.pos = prim_pos; q.strand = (uint8_t)prim_strand; q.n_diff = (uint8_t)prim_n;
-        q.is_gap = any ? 0 : 255; q.lv_ran = need_lv ? 1 : 0; q.n_hits[0] = hits[0]; q.n_hits[1] = hits[1];
+        q.pos = st.prim_pos; q.strand = (uint8_t)st.prim_strand; q.n_diff = (uint8_t)st.prim_n;
+        q.is_gap = st.any ? 0 : 255; q.lv_ran = need_lv ? 1 : 0; q.n_hits[0] = hits0; q.n_hits[1] = hits1;
         rec[r] = q;
     }
 }
@@ -876,11 +907,14 @@ cudaError_t launch_nogap_fused(const DevCtx &c, const uint32_t *offs0, const uin
                                uint32_t *lv_count, cudaStream_t st)
 {
     if (!c.n_reads) return cudaSuccess;
-    const int nw = ((int)c.l_max + 7) / 8;             // 32-bit words per read
-    if (nw <= 16) return launch_nogap_t<16, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
-    if (nw <= 32) return launch_nogap_t<32, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
-    if (nw <= 64) return launch_nogap_t<32, 2>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
-    return launch_nogap_t<32, 4>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
+    // G lanes x WPL 64-bit words per lane cover 16*G*WPL bases; one spare word so the last lane
+    // never needs a neighbour: l_max + 16 <= 16*G*WPL
+    const int lm = (int)c.l_max;
+    if (lm <= 112) return launch_nogap_t<8, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
+    if (lm <= 240) return launch_nogap_t<16, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
+    if (lm <= 496) return launch_nogap_t<32, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
+    if (lm <= 1008) return launch_nogap_t<32, 2>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
+    return launch_nogap_t<32, 3>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
 }
 
 cudaError_t launch_scan_gap(const DevCtx &c, const uint32_t *offs0, const uint32_t *loci0,

@@ -156,6 +156,13 @@ static inline unsigned __ballot_sync(unsigned mask, int pred)
     for (int i = 0; i < 32; ++i) if ((mask >> i & 1u) && tab[i]) r |= 1u << i;
     return r;
 }
+static inline int __reduce_max_sync(unsigned mask, int v)
+{
+    uint32_t tab[32]; emu::gather(mask, (uint32_t)v, tab);
+    int r = (int)0x80000000;
+    for (int i = 0; i < 32; ++i) if (mask >> i & 1u) r = std::max(r, (int)tab[i]);
+    return r;
+}
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { uint32_t tab[32]; emu::gather(mask, 0, tab); }
 static inline void __syncthreads() { emu::syncthreads(); }
