@@ -110,7 +110,7 @@ salt_b200_t *new_handle(int device)
     return h;
 }
 
-const size_t REF_PAD = 256;   // zero bytes after the reference so vector loads may run past the end
+const size_t REF_PAD = 1024;  // zero bytes after the reference so vector loads may run past the end
 
 }  // namespace
 
@@ -475,6 +475,7 @@ int salt_b200_verify_dev(salt_b200_t *h, const uint32_t *d_offs0, const uint32_t
     if (d_acc0 && d_acc1 && d_acc1 != d_acc0 + n0) return fail(SALT_ERR_ARG, "acc1 must follow acc0 contiguously");
     if (d_cigars && (!d_cig_reads || !d_cig_count)) return fail(SALT_ERR_ARG, "cigars need d_cig_reads and d_cig_count");
     if (d_cigars && cigar_stride < 2) return fail(SALT_ERR_ARG, "cigar stride too small");
+    if (reinterpret_cast<uintptr_t>(d_rec) & 15u) return fail(SALT_ERR_ARG, "d_rec must be 16-byte aligned");
     const size_t n = n0 + n1;
     const DevCtx c = h->ctx();
     CU(h->vpairs.need((n + 1) * sizeof(salt_pair_t)));      // LV worklist: pairs ...

@@ -456,89 +456,113 @@ struct NogapState {
     uint32_t prim_pos; int prim_n, prim_strand, max_diff; bool any;
 };
 
+// Window loads of four candidates (lanes jb+J .. jb+J+3 of the group own them).  The owner lane
+// has already turned its candidate into (aligned 64-bit word index, nibble phase) -- see
+// nogap_strand -- so a lane only adds its own offset.  Loads are unconditional: a missing or
+// out-of-range candidate was clamped to the last valid window start; its count is computed and
+// then ignored by the acceptance step.
+template <int G, int WPL, int J>
+__device__ __forceinline__ void nogap_load4(const uint2 *__restrict__ mixl, uint32_t myidx, uint32_t myph, int jb,
+                                            uint32_t (&ph)[4], uint2 (&q)[4][WPL])
+{
+    constexpr unsigned FULL = 0xffffffffu;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const uint32_t idx = __shfl_sync(FULL, myidx, jb + J + u, G);
+        ph[u] = __shfl_sync(FULL, myph, jb + J + u, G);
+        const uint2 *__restrict__ wp = mixl + idx;
+#pragma unroll
+        for (int w = 0; w < WPL; ++w) q[u][w] = wp[w * G];
+    }
+}
+
+// Match counts of four candidates, summed over the group; lane jb+J+u returns candidate u's count
+// in `mine`.  rw = the lane's read words, rwh = the same read moved up by 8 bases (used when the
+// window starts in the upper half of its aligned 64-bit word, so one funnel shift always suffices).
+template <int G, int WPL, int J, bool HASN>
+__device__ __forceinline__ void nogap_count4(const uint32_t (&ph)[4], const uint2 (&q)[4][WPL], const uint2 (&rw)[WPL],
+                                             const uint2 (&rwh)[WPL], int lane, int jb, int &mine)
+{
+    constexpr int PK = (16 * G * WPL <= 256) ? 4 : 2;   // counts per register while they fit their field
+    constexpr int PB = 32 / PK;
+    constexpr uint32_t PM = PK == 4 ? 0xffu : 0xffffu;
+    constexpr unsigned FULL = 0xffffffffu;
+    uint32_t packed[4 / PK];
+#pragma unroll
+    for (int k = 0; k < 4 / PK; ++k) packed[k] = 0u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int sh = (int)ph[u];                              // funnel shifts use the low 5 bits: 4*(pos & 7)
+        const bool hi = (int)ph[u] < 0;                         // bit 31: window starts in the upper 32-bit half
+        uint32_t m = 0;
+#pragma unroll
+        for (int w = 0; w < WPL; ++w) {
+            uint32_t n0 = __shfl_down_sync(FULL, q[u][w].x, 1, G);
+            if (w + 1 < WPL) {                                  // the last lane's neighbour is lane 0's next word
+                const uint32_t w0 = __shfl_sync(FULL, q[u][w + 1 < WPL ? w + 1 : w].x, 0, G);
+                if (lane == G - 1) n0 = w0;
+            }
+            uint32_t x0 = __funnelshift_r(q[u][w].x, q[u][w].y, sh) & (hi ? rwh[w].x : rw[w].x);
+            uint32_t x1 = __funnelshift_r(q[u][w].y, n0, sh) & (hi ? rwh[w].y : rw[w].y);
+            if (HASN) {
+                x0 |= x0 >> 1; x0 |= x0 >> 2; x0 &= 0x11111111u;
+                x1 |= x1 >> 1; x1 |= x1 >> 2; x1 &= 0x11111111u;
+            }
+            m += (uint32_t)(__popc(x0) + __popc(x1));
+        }
+        packed[u / PK] += m << (PB * (u % PK));
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < 4 / PK; ++k) packed[k] += __shfl_xor_sync(FULL, packed[k], o, G);
+    const int sel = lane - jb - J;                              // lane jb+J+u keeps candidate u's count
+    const uint32_t pv = (PK == 4 || sel < 2) ? packed[0] : packed[4 / PK - 1];
+    if (sel >= 0 && sel < 4) mine = (int)((pv >> (PB * (sel % PK))) & PM);
+}
+
 // One strand of one read per group of G lanes; every loop bound is made warp-uniform (maximum
 // over the warp's groups, idle groups predicated off) so that all shuffles run on the full
 // warp mask without divergence checks.
 template <int G, int WPL, bool HASN>
 __device__ __forceinline__ int nogap_strand(const DevCtx &c, const uint2 *__restrict__ mixl, const uint2 (&rw)[WPL],
-                                            const uint32_t *__restrict__ loci, int8_t *__restrict__ accs,
-                                            uint32_t lbs, uint32_t les, int L, int T0, bool fits, uint32_t lim,
-                                            int nw, int s, int lane, int gshift, NogapState &st)
+                                            const uint2 (&rwh)[WPL], const uint32_t *__restrict__ loci,
+                                            int8_t *__restrict__ accs, uint32_t lbs, uint32_t les, uint32_t first,
+                                            int L, int T0, bool fits, uint32_t lim, int s, int lane, int gshift,
+                                            NogapState &st)
 {
-    // counts of up to 16*WPL per lane, up to l_max in total: four per register while they fit a byte
-    constexpr int PK = (16 * G * WPL <= 256) ? 4 : 2;
-    constexpr int PB = 32 / PK;
-    constexpr uint32_t PM = PK == 4 ? 0xffu : 0xffffu;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr unsigned gfull = (unsigned)((1ull << G) - 1ull);
     constexpr int BIG = 255;
     const int nchunks = (int)((les - lbs + (G - 1)) / G);
     const int nchunks_w = __reduce_max_sync(FULL, nchunks);
     bool matched = false;
-    uint32_t last = 0xFFFFFFFFu;
     int nhits = 0;
     for (int ci = 0; ci < nchunks_w; ++ci) {
         const uint32_t base = lbs + (uint32_t)ci * G;
         const int cnt = ci < nchunks ? (int)min((uint32_t)G, les - base) : 0;
-        const uint32_t truepos = lane < cnt ? loci[base + lane] : 0xFFFFFFFFu;
-        // a read longer than the reference counts nothing; 0xFFFFFFFF > lim switches a lane's window off
+        const uint32_t truepos = ci == 0 ? first : (lane < cnt ? loci[base + lane] : 0xFFFFFFFFu);
+        // the element before this lane's candidate in the (sorted) list: alnse.c:762 skips repeats
+        const uint32_t prev = (lane < cnt && base + lane > lbs) ? loci[base + lane - 1] : 0xFFFFFFFFu;
+        // a read longer than the reference counts nothing
         const uint32_t mypos = fits ? truepos : 0xFFFFFFFFu;
+        const uint32_t cpos = min(mypos, lim);                  // what the lanes load for this candidate
+        const uint32_t myidx = cpos >> 4;
+        const uint32_t myph = ((cpos & 7u) << 2) | ((cpos & 8u) << 28);
         const int cnt_w = __reduce_max_sync(FULL, cnt);
         int mymatches = 0;
-        // ---- counting: four candidates at a time, all lanes of a group cooperate on each window
-        for (int j0 = 0; j0 < cnt_w; j0 += 4) {
-            uint32_t pos[4];
-            uint2 q[4][WPL];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                pos[u] = __shfl_sync(FULL, mypos, (j0 + u) & (G - 1), G);
-                const bool ok = pos[u] <= lim;                          // pos + L <= l, and the lane had a candidate
-                const uint2 *__restrict__ wp = mixl + (pos[u] >> 4);
-#pragma unroll
-                for (int w = 0; w < WPL; ++w)
-                    q[u][w] = (ok && (lane + w * G) < nw) ? wp[w * G] : make_uint2(0u, 0u);
-            }
-            uint32_t packed[4 / PK];
-#pragma unroll
-            for (int k = 0; k < 4 / PK; ++k) packed[k] = 0u;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int sh = (int)(pos[u] & 7u) * 4;
-                const bool hi = (pos[u] & 8u) != 0u;
-                uint32_t m = 0;
-#pragma unroll
-                for (int w = 0; w < WPL; ++w) {
-                    uint32_t n0 = __shfl_down_sync(FULL, q[u][w].x, 1, G);
-                    uint32_t n1 = __shfl_down_sync(FULL, q[u][w].y, 1, G);
-                    if (w + 1 < WPL) {                                  // the last lane's neighbour is lane 0's next word
-                        const uint32_t w0 = __shfl_sync(FULL, q[u][w + 1 < WPL ? w + 1 : w].x, 0, G);
-                        const uint32_t w1 = __shfl_sync(FULL, q[u][w + 1 < WPL ? w + 1 : w].y, 0, G);
-                        if (lane == G - 1) { n0 = w0; n1 = w1; }
-                    }
-                    const uint32_t a = hi ? q[u][w].y : q[u][w].x;
-                    const uint32_t b = hi ? n0 : q[u][w].y;
-                    const uint32_t cc = hi ? n1 : n0;
-                    uint32_t x0 = __funnelshift_r(a, b, sh) & rw[w].x;
-                    uint32_t x1 = __funnelshift_r(b, cc, sh) & rw[w].y;
-                    if (HASN) {
-                        x0 |= x0 >> 1; x0 |= x0 >> 2; x0 &= 0x11111111u;
-                        x1 |= x1 >> 1; x1 |= x1 >> 2; x1 &= 0x11111111u;
-                    }
-                    m += (uint32_t)(__popc(x0) + __popc(x1));
-                }
-                packed[u / PK] += m << (PB * (u % PK));
-            }
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1)
-#pragma unroll
-                for (int k = 0; k < 4 / PK; ++k) packed[k] += __shfl_xor_sync(FULL, packed[k], o, G);
-            const int sel = lane - j0;                                  // lane j0+u keeps candidate u's count
-            const uint32_t pv = (PK == 4 || sel < 2) ? packed[0] : packed[4 / PK - 1];
-            if (sel >= 0 && sel < 4) mymatches = (int)((pv >> (PB * (sel % PK))) & PM);
+        // ---- counting: eight candidates in flight, all lanes of a group cooperate on each window
+        for (int jb = 0; jb < (G == 8 ? 1 : cnt_w); jb += 8) {
+            const int jbb = G == 8 ? 0 : jb;
+            const bool more = cnt_w > jbb + 4;
+            uint32_t pa[4], pb[4];
+            uint2 qa[4][WPL], qb[4][WPL];
+            nogap_load4<G, WPL, 0>(mixl, myidx, myph, jbb, pa, qa);
+            if (more) nogap_load4<G, WPL, 4>(mixl, myidx, myph, jbb, pb, qb);
+            nogap_count4<G, WPL, 0, HASN>(pa, qa, rw, rwh, lane, jbb, mymatches);
+            if (more) nogap_count4<G, WPL, 4, HASN>(pb, qb, rw, rwh, lane, jbb, mymatches);
         }
         // ---- accepting: lane j decides candidate j
-        uint32_t prev = __shfl_up_sync(FULL, truepos, 1, G);
-        if (lane == 0) prev = last;
         const bool skip = lane >= cnt || truepos == prev || truepos >= c.l;          // alnse.c:762
         const int nmis = L - mymatches;
         const int key = (!skip && mypos <= lim && nmis <= T0) ? nmis : BIG;
@@ -560,13 +584,37 @@ __device__ __forceinline__ int nogap_strand(const DevCtx &c, const uint2 *__rest
             matched = true;
             nhits += __popc(bal);
         }
-        // last unskipped position carried into the next chunk (sorted lists: the last in-range one)
-        const unsigned unsk = (__ballot_sync(FULL, lane < cnt && !skip) >> gshift) & gfull;
-        const uint32_t lastpos = __shfl_sync(FULL, truepos, unsk ? 31 - __clz((int)unsk) : 0, G);
-        if (unsk) last = lastpos;
     }
     st.any = st.any || matched;
     return nhits;
+}
+
+template <int G, int WPL, bool HASN>
+__device__ __forceinline__ void nogap_read(const DevCtx &c, const uint2 *__restrict__ mixl, const uint2 (&rw0)[WPL],
+                                           const uint2 (&rw1)[WPL], const uint32_t *__restrict__ loci0,
+                                           const uint32_t *__restrict__ loci1, int8_t *__restrict__ acc, size_t n0,
+                                           uint32_t lb0, uint32_t le0, uint32_t lb1, uint32_t le1, uint32_t first0,
+                                           uint32_t first1, int L, int T0, bool fits, uint32_t lim, int lane, int gshift,
+                                           NogapState &st, int &hits0, int &hits1)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    uint2 rwh[WPL];
+#pragma unroll
+    for (int w = 0; w < WPL; ++w) {                     // the read moved up by one 32-bit word (8 bases)
+        uint32_t up = __shfl_up_sync(FULL, rw0[w].y, 1, G);
+        if (lane == 0) up = 0u;
+        if (w > 0) { const uint32_t wrap = __shfl_sync(FULL, rw0[w > 0 ? w - 1 : 0].y, G - 1, G); if (lane == 0) up = wrap; }
+        rwh[w] = make_uint2(up, rw0[w].x);
+    }
+    hits0 = nogap_strand<G, WPL, HASN>(c, mixl, rw0, rwh, loci0, acc, lb0, le0, first0, L, T0, fits, lim, 0, lane, gshift, st);
+#pragma unroll
+    for (int w = 0; w < WPL; ++w) {
+        uint32_t up = __shfl_up_sync(FULL, rw1[w].y, 1, G);
+        if (lane == 0) up = 0u;
+        if (w > 0) { const uint32_t wrap = __shfl_sync(FULL, rw1[w > 0 ? w - 1 : 0].y, G - 1, G); if (lane == 0) up = wrap; }
+        rwh[w] = make_uint2(up, rw1[w].x);
+    }
+    hits1 = nogap_strand<G, WPL, HASN>(c, mixl, rw1, rwh, loci1, acc + n0, lb1, le1, first1, L, T0, fits, lim, 1, lane, gshift, st);
 }
 
 template <int G, int WPL>
@@ -582,8 +630,20 @@ nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t 
     const uint32_t r = live ? (uint32_t)rr : 0u;
     const int lane = threadIdx.x % G;
     const int gshift = (threadIdx.x & 31) / G * G;
+    uint32_t lb0 = 0, le0 = 0, lb1 = 0, le1 = 0;
+    if (live) { lb0 = offs0[r]; le0 = offs0[r + 1]; lb1 = offs1[r]; le1 = offs1[r + 1]; }
     const int L = live ? (int)c.rd_len[r] : 0;
-    const int nw = (L + 30) >> 4;                       // aligned 64-bit window words a candidate can touch
+    // both strands' read words and first candidates are requested before any of them is used
+    uint2 rw0[WPL], rw1[WPL];
+    const uint2 *__restrict__ rrow = reinterpret_cast<const uint2 *>(c.rd4 + (size_t)r * 2 * c.W64);
+#pragma unroll
+    for (int w = 0; w < WPL; ++w) {
+        const bool in = live && (uint32_t)(lane + w * G) < c.W64;
+        rw0[w] = in ? rrow[lane + w * G] : make_uint2(0u, 0u);
+        rw1[w] = in ? rrow[c.W64 + lane + w * G] : make_uint2(0u, 0u);
+    }
+    const uint32_t first0 = lb0 + lane < le0 ? loci0[lb0 + lane] : 0xFFFFFFFFu;
+    const uint32_t first1 = lb1 + lane < le1 ? loci1[lb1 + lane] : 0xFFFFFFFFu;
     const uint2 *__restrict__ mixl = reinterpret_cast<const uint2 *>(c.mixref) + lane;
     const bool fits = c.l >= (uint32_t)L && L > 0;
     const uint32_t lim = fits ? c.l - (uint32_t)L : 0u; // pos + L <= l  <=>  pos <= lim
@@ -591,28 +651,17 @@ nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t 
     NogapState st;
     st.prim_pos = 0xFFFFFFFFu; st.prim_n = 255; st.prim_strand = 3; st.max_diff = T0; st.any = false;
     int hits0 = 0, hits1 = 0;
-    uint32_t lb0 = 0, le0 = 0, lb1 = 0, le1 = 0;
-    if (live) { lb0 = offs0[r]; le0 = offs0[r + 1]; lb1 = offs1[r]; le1 = offs1[r + 1]; }
-
-    for (int s = 0; s < 2; ++s) {
-        const uint32_t *__restrict__ loci = s ? loci1 : loci0;
-        int8_t *__restrict__ accs = s ? acc + n0 : acc;
-        const uint32_t lbs = s ? lb1 : lb0, les = s ? le1 : le0;
-        uint2 rw[WPL];
-        const uint2 *__restrict__ rrow = reinterpret_cast<const uint2 *>(c.rd4 + ((size_t)r * 2 + s) * c.W64);
-        bool hasN = false;
+    bool hasN = false;                                  // N is its own complement: one test serves both strands
 #pragma unroll
-        for (int w = 0; w < WPL; ++w) {
-            rw[w] = (live && (uint32_t)(lane + w * G) < c.W64) ? rrow[lane + w * G] : make_uint2(0u, 0u);
-            hasN = hasN || ((rw[w].x & (rw[w].x >> 1) & 0x11111111u) != 0u) || ((rw[w].y & (rw[w].y >> 1) & 0x11111111u) != 0u);
-        }
-        int nh;
-        if (__any_sync(FULL, hasN))      // warp-uniform: the general path is exact for every read
-            nh = nogap_strand<G, WPL, true>(c, mixl, rw, loci, accs, lbs, les, L, T0, fits, lim, nw, s, lane, gshift, st);
-        else
-            nh = nogap_strand<G, WPL, false>(c, mixl, rw, loci, accs, lbs, les, L, T0, fits, lim, nw, s, lane, gshift, st);
-        if (s) hits1 = nh; else hits0 = nh;
-    }
+    for (int w = 0; w < WPL; ++w)
+        hasN = hasN || ((rw0[w].x & (rw0[w].x >> 1) & 0x11111111u) != 0u) || ((rw0[w].y & (rw0[w].y >> 1) & 0x11111111u) != 0u);
+    if (__any_sync(FULL, hasN))          // warp-uniform: the general path is exact for every read
+        nogap_read<G, WPL, true>(c, mixl, rw0, rw1, loci0, loci1, acc, n0, lb0, le0, lb1, le1, first0, first1, L, T0, fits, lim,
+                                 lane, gshift, st, hits0, hits1);
+    else
+        nogap_read<G, WPL, false>(c, mixl, rw0, rw1, loci0, loci1, acc, n0, lb0, le0, lb1, le1, first0, first1, L, T0, fits, lim,
+                                  lane, gshift, st, hits0, hits1);
+
     const bool need_lv = live && !st.any;                // alnse.c:1022 / :1089: gapped stage for this read
     const uint32_t c0 = le0 - lb0, c1 = le1 - lb1;
     uint32_t w = 0;
@@ -629,10 +678,12 @@ nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t 
         }
     }
     if (live && lane == 0) {
-        salt_verify_out_t q;
-        q.pos = st.prim_pos; q.strand = (uint8_t)st.prim_strand; q.n_diff = (uint8_t)st.prim_n;
-        q.is_gap = st.any ? 0 : 255; q.lv_ran = need_lv ? 1 : 0; q.n_hits[0] = hits0; q.n_hits[1] = hits1;
-        rec[r] = q;
+        uint4 o;                                         // salt_verify_out_t as one 16-byte store
+        o.x = st.prim_pos;
+        o.y = (uint32_t)(st.prim_strand & 255) | ((uint32_t)(st.prim_n & 255) << 8) |
+              ((st.any ? 0u : 255u) << 16) | ((need_lv ? 1u : 0u) << 24);
+        o.z = (uint32_t)hits0; o.w = (uint32_t)hits1;
+        *reinterpret_cast<uint4 *>(rec + r) = o;
     }
 }
 

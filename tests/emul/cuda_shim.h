@@ -29,6 +29,7 @@
 
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct uint2 { unsigned x, y; };
+struct uint4 { unsigned x, y, z, w; };
 static inline uint2 make_uint2(unsigned a, unsigned b) { uint2 r; r.x = a; r.y = b; return r; }
 
 typedef int cudaError_t;
