@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=400_000, help="reads in the bounded CPU-baseline sample")
     ap.add_argument("--sw-tasks", type=int, default=200_000)
     ap.add_argument("--skip-extras", action="store_true", help="skip the sw/lv kernel sweeps")
+    ap.add_argument("--chunk", type=int, default=100_000, help="reads per pipeline chunk in the e2e leg (N_SEQS, aln.h:27)")
     return ap.parse_args()
 
 
@@ -239,10 +240,25 @@ def main():
     n_lv = int(np.frombuffer(d_rec.cpu().numpy().tobytes(), api.VERIFY_DT)["lv_ran"].sum())
     n_gapped = int(d_cigcnt[0].item())
 
+    # PCIe copy peaks beside the e2e number (pinned 256 MiB, best of 3)
+    def copy_peak(to_dev):
+        nb = 256 << 20
+        a = torch.empty(nb, dtype=torch.uint8).pin_memory(); b = torch.empty(nb, dtype=torch.uint8, device=dev)
+        best = 0.0
+        for _ in range(3):
+            c0 = torch.cuda.Event(enable_timing=True); c1 = torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            (b.copy_(a, non_blocking=True) if to_dev else a.copy_(b, non_blocking=True))
+            c1.record(stream); torch.cuda.synchronize(dev)
+            best = max(best, nb / (c0.elapsed_time(c1) * 1e-3) / 1e9)
+        return best
+    pcie_h2d, pcie_d2h = copy_peak(True), copy_peak(False)
+
     # ---------------- e2e: host buffers through the C ABI
     def step_host():
-        ck(lib.salt_b200_set_reads(h, C.byref(reads_t)))
-        ck(lib.salt_b200_verify(h, C.byref(cands), 3, -1, h_rec.data_ptr(), h_acc0.data_ptr(), h_acc1.data_ptr(), h_cig.data_ptr(), 128))
+        # the reference's chunk loop (alnse.c:1414-1440) through the asynchronous slots
+        ck(lib.salt_b200_verify_batch(h, C.byref(reads_t), C.byref(cands), args.chunk, 3, -1, h_rec.data_ptr(),
+                                      h_acc0.data_ptr(), h_acc1.data_ptr(), h_cig.data_ptr(), 128))
     for _ in range(max(1, args.warmup - 1)):
         step_host()
     barrier()
@@ -262,7 +278,8 @@ def main():
            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
            "data": "synthetic", "config": cfg, "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": world * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "ms_per_step": e2e_s * 1e3},
+                   "ms_per_step": e2e_s * 1e3, "chunk_reads": args.chunk, "slots": int(lib.salt_b200_n_slots()),
+                   "pcie_gbs": {"h2d": h2d / e2e_s / 1e9, "d2h": d2h / e2e_s / 1e9, "h2d_copy_peak": pcie_h2d, "d2h_copy_peak": pcie_d2h}},
            "pairs_per_step": int(n0 + n1), "pairs_per_s": world * (n0 + n1) / (ms_step * 1e-3),
            "lv_reads_per_step": n_lv, "gapped_primaries_per_step": n_gapped, "kernels_ms": kernels}
 

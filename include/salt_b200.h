@@ -93,7 +93,8 @@ salt_b200_t *salt_b200_init_from_bases(const char *bases, uint32_t l, const uint
                                        const uint8_t *snp_mask, size_t n_snp, int device);
 int salt_b200_get_mixref(salt_b200_t *h, uint32_t *words_out, size_t n_words);
 
-/* Use an existing CUDA stream (cudaStream_t) for all work of this handle; NULL = own stream. */
+/* Use an existing CUDA stream (cudaStream_t) for the synchronous entry points and the *_dev
+ * variants of this handle (slot 0 of the chunk pipeline); NULL = own stream. */
 int salt_b200_set_stream(salt_b200_t *h, void *cuda_stream);
 int salt_b200_sync(salt_b200_t *h);
 
@@ -151,6 +152,27 @@ int salt_b200_verify(salt_b200_t *h, const salt_cands_t *cands, int nogap_T0, in
                      salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1,
                      char *cigars, int cigar_stride);
 
+/* ---- asynchronous chunk pipeline ------------------------------------------------------------
+ * alnse_core / alnpe_core work through the input in chunks of N_SEQS = 100000 reads
+ * (aln.h:27, alnse.c:1414-1440): read a chunk, run the workers, print.  The engine keeps
+ * salt_b200_n_slots() chunks in flight, each on its own CUDA stream with its own staging in HBM,
+ * so the upload of chunk c+1, the kernels of chunk c and the download of chunk c-1 overlap (and the
+ * host can seed chunk c+1 meanwhile).  Buffers passed to _submit (inputs and outputs; pinned memory
+ * from salt_b200_host_alloc makes the copies truly asynchronous) must stay valid and untouched
+ * until _wait(slot) returns.  Results are exactly those of salt_b200_set_reads + salt_b200_verify
+ * on the same chunk; read ids inside a chunk are chunk-relative. */
+int salt_b200_n_slots(void);
+int salt_b200_verify_submit(salt_b200_t *h, int slot, const salt_reads_t *reads, const salt_cands_t *cands,
+                            int nogap_T0, int lv_T0, salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1,
+                            char *cigars, int cigar_stride);
+int salt_b200_verify_wait(salt_b200_t *h, int slot);
+/* The loop above over a whole batch: reads/cands describe n_reads reads (global CSR offsets);
+ * chunks of chunk_reads reads (0 = 100000) go through the slots round-robin; outputs are indexed
+ * like the inputs.  Returns when every chunk is done. */
+int salt_b200_verify_batch(salt_b200_t *h, const salt_reads_t *reads, const salt_cands_t *cands, uint32_t chunk_reads,
+                           int nogap_T0, int lv_T0, salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1,
+                           char *cigars, int cigar_stride);
+
 /* Landau-Vishkin work mapping: 0 = automatic (one thread per pair with all diagonals in
  * registers for k <= 15, one warp per pair with lanes over diagonals beyond), 1 = always one
  * warp (or sub-warp group) per pair.  Results are identical; this exists for measurement. */
@@ -166,7 +188,7 @@ int salt_b200_mismatch_dev(salt_b200_t *h, const salt_pair_t *d_pairs, size_t n,
 int salt_b200_lv_dev(salt_b200_t *h, const salt_pair_t *d_pairs, size_t n, int k, int8_t *d_out);
 /* Device variant of salt_b200_verify.  CIGARs come back compact: d_cigars[i*stride] belongs to
  * read d_cig_reads[i], i < *d_cig_count (only gapped primaries have one).  Pass d_cigars = NULL
- * to skip them. */
+ * to skip them.  d_rec must be 16-byte aligned. */
 int salt_b200_verify_dev(salt_b200_t *h, const uint32_t *d_offs0, const uint32_t *d_loci0, size_t n0,
                          const uint32_t *d_offs1, const uint32_t *d_loci1, size_t n1,
                          int nogap_T0, int lv_T0, salt_verify_out_t *d_rec, int8_t *d_acc0, int8_t *d_acc1,

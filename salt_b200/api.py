@@ -61,6 +61,9 @@ def _declare(L):
     L.salt_b200_lv_cigar.argtypes = [vp, vp, vp, sz, vp, i32, vp]
     L.salt_b200_ssw.argtypes = [vp, vp, sz, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32]
     L.salt_b200_verify.argtypes = [vp, C.POINTER(CandsT), i32, i32, vp, vp, vp, vp, i32]
+    L.salt_b200_verify_submit.argtypes = [vp, i32, C.POINTER(ReadsT), C.POINTER(CandsT), i32, i32, vp, vp, vp, vp, i32]
+    L.salt_b200_verify_wait.argtypes = [vp, i32]
+    L.salt_b200_verify_batch.argtypes = [vp, C.POINTER(ReadsT), C.POINTER(CandsT), C.c_uint32, i32, i32, vp, vp, vp, vp, i32]
     L.salt_b200_set_max_window.argtypes = [vp, i32]
     L.salt_b200_set_lv_mapping.argtypes = [vp, i32]
     L.salt_b200_mismatch_dev.argtypes = [vp, vp, sz, i32, vp]
@@ -244,6 +247,26 @@ class Engine:
         cig = np.zeros((self.n_reads, cigar_stride), np.uint8) if want_cigars else None
         self._ck(self.L.salt_b200_verify(self.h, C.byref(c), int(nogap_T0), int(lv_T0), _ptr(rec), _ptr(acc0), _ptr(acc1),
                                          _ptr(cig), int(cigar_stride)))
+        return rec, acc0, acc1, cig
+
+
+    def verify_batch(self, codes, roffs, offs0, loci0, offs1, loci1, chunk_reads=100000, nogap_T0=3, lv_T0=-1,
+                     cigar_stride=128, want_cigars=True):
+        """Whole batch through the asynchronous chunk pipeline (salt_b200_verify_batch)."""
+        codes = np.ascontiguousarray(codes, np.uint8).reshape(-1)
+        roffs = np.ascontiguousarray(roffs, np.uint32)
+        offs0 = np.ascontiguousarray(offs0, np.uint32); offs1 = np.ascontiguousarray(offs1, np.uint32)
+        loci0 = np.ascontiguousarray(loci0, np.uint32); loci1 = np.ascontiguousarray(loci1, np.uint32)
+        n = len(roffs) - 1
+        r = ReadsT(_ptr(codes), _ptr(roffs), n)
+        c = CandsT()
+        c.offs[0], c.offs[1] = _ptr(offs0), _ptr(offs1)
+        c.loci[0], c.loci[1] = _ptr(loci0) if len(loci0) else None, _ptr(loci1) if len(loci1) else None
+        rec = np.zeros(n, VERIFY_DT)
+        acc0 = np.empty(len(loci0), np.int8); acc1 = np.empty(len(loci1), np.int8)
+        cig = np.zeros((n, cigar_stride), np.uint8) if want_cigars else None
+        self._ck(self.L.salt_b200_verify_batch(self.h, C.byref(r), C.byref(c), int(chunk_reads), int(nogap_T0), int(lv_T0),
+                                               _ptr(rec), _ptr(acc0), _ptr(acc1), _ptr(cig), int(cigar_stride)))
         return rec, acc0, acc1, cig
 
 

@@ -52,33 +52,66 @@ struct DBuf {
 
 }  // namespace
 
+// One in-flight read chunk: its own stream, its own copy of the chunk's reads and candidate
+// lists in HBM, and the scratch of the verification stage.  Slot 0 also serves the synchronous
+// entry points; the other slots exist so that chunk c+1 can upload while chunk c computes and
+// chunk c-1 downloads (salt_b200_verify_submit / _wait).
+struct Slot {
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    DBuf codes, offs, rd4, rd_len;
+    uint32_t n_reads = 0, W64 = 0, l_max = 0;
+    DBuf c_offs0, c_loci0, c_offs1, c_loci1, vpairs, acc, rec, lvlist, ciglist, counters, cig;
+    // asynchronous verify in flight: where the compact CIGAR list has to be scattered to
+    bool pending = false;
+    char *u_cigars = nullptr; int u_stride = 0;
+    uint8_t *h_stage = nullptr; size_t h_stage_cap = 0;      // pinned: count, read ids, strings
+    uint32_t eager = 0;                                       // list entries already copied by submit
+    uint32_t *h_offs = nullptr; size_t h_offs_cap = 0;        // pinned; salt_b200_verify_batch: the chunk's rebased offsets
+    // optional per-stage timing (salt_b200_profile): events at the boundaries of the stages
+    cudaEvent_t ev_verify[7] = {nullptr};
+    bool have_verify_prof = false;
+
+    void release()
+    {
+        DBuf *all[] = {&codes, &offs, &rd4, &rd_len, &c_offs0, &c_loci0, &c_offs1, &c_loci1, &vpairs, &acc, &rec,
+                       &lvlist, &ciglist, &counters, &cig};
+        for (DBuf *b : all) b->release();
+        if (h_stage) cudaFreeHost(h_stage);
+        h_stage = nullptr; h_stage_cap = 0;
+        if (h_offs) cudaFreeHost(h_offs);
+        h_offs = nullptr; h_offs_cap = 0;
+        for (int i = 0; i < 7; ++i) if (ev_verify[i]) { cudaEventDestroy(ev_verify[i]); ev_verify[i] = nullptr; }
+        if (stream && own_stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
+};
+
+constexpr int SALT_SLOTS = 4;
+constexpr uint32_t CIG_EAGER = 8192;       // CIGARs of a chunk copied back without waiting for their count
+
 struct salt_b200 {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;
-    bool own_stream = true;
     uint32_t *d_mixref = nullptr; uint32_t l = 0;
     uint8_t *d_pac = nullptr; int64_t l_pac = 0;
-    // current read chunk
-    DBuf codes, offs, rd4, rd_len;
-    uint32_t n_reads = 0, W64 = 0, l_max = 0;
-    // staging / scratch
+    Slot slot[SALT_SLOTS];
+    // staging / scratch of the synchronous per-pair and SSW entry points (slot 0's stream)
     DBuf pairs, out8, kbuf, cig, wins, sswout, sswcig, sswscratch;
-    DBuf c_offs0, c_loci0, c_offs1, c_loci1, vpairs, acc, rec, lvlist, ciglist, counters;
     uint64_t launches = 0;
     int lv_mapping = 0;         // 0 = auto, 1 = force warp-per-pair (salt_b200_set_lv_mapping)
     int max_window = 1024;      // widest rescue window the SSW scratch is sized for
-    // optional per-stage timing (salt_b200_profile): events at the boundaries of the stages
     bool profiling = false;
-    cudaEvent_t ev_verify[7] = {nullptr}, ev_ssw[7] = {nullptr};
-    bool have_verify_prof = false, have_ssw_prof = false, verify_prof_cigar = false;
+    cudaEvent_t ev_ssw[7] = {nullptr};
+    bool have_ssw_prof = false;
 
-    DevCtx ctx() const
+    DevCtx ctx(int si = 0) const
     {
+        const Slot &s = slot[si];
         DevCtx c;
         c.mixref = d_mixref; c.l = l; c.pac = d_pac; c.l_pac = l_pac;
-        c.rd4 = rd4.as<uint64_t>(); c.rd_len = rd_len.as<uint16_t>();
-        c.n_reads = n_reads; c.W64 = W64; c.l_max = l_max;
+        c.rd4 = s.rd4.as<uint64_t>(); c.rd_len = s.rd_len.as<uint16_t>();
+        c.n_reads = s.n_reads; c.W64 = s.W64; c.l_max = s.l_max;
         return c;
     }
 };
@@ -104,13 +137,190 @@ salt_b200_t *new_handle(int device)
     h->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
-    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
-        fail(SALT_ERR_CUDA, "cudaStreamCreate", e); delete h; return nullptr;
-    }
+    for (int i = 0; i < SALT_SLOTS; ++i)
+        if ((e = cudaStreamCreateWithFlags(&h->slot[i].stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            fail(SALT_ERR_CUDA, "cudaStreamCreate", e); salt_b200_destroy(h); return nullptr;
+        }
     return h;
 }
 
 const size_t REF_PAD = 1024;  // zero bytes after the reference so vector loads may run past the end
+
+// Upload + pack one chunk of reads into a slot.  Asynchronous on the slot's stream.
+int load_reads(salt_b200_t *h, Slot &s, const salt_reads_t *reads)
+{
+    if (!reads || !reads->offs || (reads->n_reads && !reads->codes)) return fail(SALT_ERR_ARG, "reads is null");
+    if (reads->n_reads >= (1u << 31)) return fail(SALT_ERR_ARG, "too many reads in one chunk");
+    const uint32_t n = reads->n_reads;
+    uint32_t l_max = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t a = reads->offs[i], b = reads->offs[i + 1];
+        if (b < a) return fail(SALT_ERR_ARG, "read offsets not monotone");
+        if (b - a > l_max) l_max = b - a;
+    }
+    if (l_max > 1024) return fail(SALT_ERR_UNSUPPORTED, "reads longer than 1024 bases are not supported");
+    const size_t total = n ? (size_t)reads->offs[n] - reads->offs[0] : 0;
+    if (n && reads->offs[0] != 0) return fail(SALT_ERR_ARG, "read offsets must start at 0");
+    s.n_reads = n; s.l_max = l_max; s.W64 = (l_max + 15) / 16 + 1;
+    CU(s.codes.need(total + 16));
+    CU(s.offs.need(((size_t)n + 1) * 4));
+    CU(s.rd4.need((size_t)n * 2 * s.W64 * 8 + 64));
+    CU(s.rd_len.need((size_t)n * 2 + 64));
+    if (n) {
+        CU(cudaMemcpyAsync(s.codes.p, reads->codes, total, cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(s.offs.p, reads->offs, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, s.stream));
+        CU(launch_pack_reads(s.codes.as<uint8_t>(), s.offs.as<uint32_t>(), n, s.W64, s.rd4.as<uint64_t>(),
+                             s.rd_len.as<uint16_t>(), s.stream));
+        h->launches += 1;
+    }
+    return SALT_OK;
+}
+
+// The verification stage of one slot with every input already in HBM (asynchronous).
+int verify_on_device(salt_b200_t *h, int si, const uint32_t *d_offs0, const uint32_t *d_loci0, size_t n0,
+                     const uint32_t *d_offs1, const uint32_t *d_loci1, size_t n1,
+                     int nogap_T0, int lv_T0, salt_verify_out_t *d_rec, int8_t *d_acc0, int8_t *d_acc1,
+                     char *d_cigars, int cigar_stride, uint32_t *d_cig_reads, uint32_t *d_cig_count)
+{
+    Slot &s = h->slot[si];
+    if (!s.n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    if (!d_offs0 || !d_offs1 || !d_rec) return fail(SALT_ERR_ARG, "null buffer");
+    if (nogap_T0 < 0 || nogap_T0 > 127) return fail(SALT_ERR_ARG, "nogap_T0 must be in 0..127");
+    if (n0 + n1 >= (size_t)1 << 32) return fail(SALT_ERR_ARG, "too many candidates in one chunk");
+    if (d_acc0 && d_acc1 && d_acc1 != d_acc0 + n0) return fail(SALT_ERR_ARG, "acc1 must follow acc0 contiguously");
+    if (d_cigars && (!d_cig_reads || !d_cig_count)) return fail(SALT_ERR_ARG, "cigars need d_cig_reads and d_cig_count");
+    if (d_cigars && cigar_stride < 2) return fail(SALT_ERR_ARG, "cigar stride too small");
+    if (reinterpret_cast<uintptr_t>(d_rec) & 15u) return fail(SALT_ERR_ARG, "d_rec must be 16-byte aligned");
+    const size_t n = n0 + n1;
+    const DevCtx c = h->ctx(si);
+    CU(s.vpairs.need((n + 1) * sizeof(salt_pair_t)));      // LV worklist: pairs ...
+    CU(s.lvlist.need((n + 1) * 4));                         // ... and the acc slot each one reports to
+    CU(s.counters.need(256));
+    int8_t *acc = d_acc0;
+    if (!acc) { CU(s.acc.need(n + 1)); acc = s.acc.as<int8_t>(); }
+    salt_pair_t *lvp = s.vpairs.as<salt_pair_t>();
+    uint32_t *lvs = s.lvlist.as<uint32_t>();
+    uint32_t *cnt = s.counters.as<uint32_t>();        // [0] LV worklist length
+    if (h->profiling)
+        for (int i = 0; i < 7; ++i) if (!s.ev_verify[i]) CU(cudaEventCreate(&s.ev_verify[i]));
+    cudaEvent_t *ev = h->profiling ? s.ev_verify : nullptr;
+#define SALT_EV(i) do { if (ev) CU(cudaEventRecord(ev[i], s.stream)); } while (0)
+    CU(cudaMemsetAsync(cnt, 0, 256, s.stream));
+    if (d_cig_count) CU(cudaMemsetAsync(d_cig_count, 0, 4, s.stream));
+    SALT_EV(0);
+    SALT_EV(1);
+    CU(launch_nogap_fused(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, nogap_T0, acc, d_rec, lvp, lvs, cnt, s.stream));
+    SALT_EV(2);
+    SALT_EV(3);
+    CU(launch_lv(c, lvp, n, lv_T0, lvs, cnt, n, acc, h->sm_count, s.stream, h->lv_mapping));
+    SALT_EV(4);
+    CU(launch_scan_gap(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, lv_T0, acc, d_rec,
+                       d_cigars ? d_cig_reads : nullptr, d_cig_count, s.stream));
+    SALT_EV(5);
+    h->launches += 3;
+    if (d_cigars) {
+        CU(launch_lv_cigar(c, nullptr, nullptr, 0, d_cig_reads, d_cig_count, s.n_reads, d_rec,
+                           d_cigars, cigar_stride, nullptr, h->sm_count, s.stream));
+        h->launches += 1;
+    }
+    SALT_EV(6);
+#undef SALT_EV
+    s.have_verify_prof = h->profiling;
+    return SALT_OK;
+}
+
+// Host-buffer verify of one slot: uploads the candidate lists, runs the stage, queues the
+// downloads.  Returns without waiting; finish_verify completes it.
+int enqueue_verify(salt_b200_t *h, int si, const salt_cands_t *cands, int nogap_T0, int lv_T0,
+                   salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1, char *cigars, int cigar_stride)
+{
+    Slot &s = h->slot[si];
+    if (!cands || !cands->offs[0] || !cands->offs[1] || !rec) return fail(SALT_ERR_ARG, "null buffer");
+    if (!s.n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    if (s.pending) return fail(SALT_ERR_ARG, "slot has a verify in flight: call salt_b200_verify_wait first");
+    const uint32_t nr = s.n_reads;
+    const size_t n0 = cands->offs[0][nr], n1 = cands->offs[1][nr];
+    if ((n0 && !cands->loci[0]) || (n1 && !cands->loci[1])) return fail(SALT_ERR_ARG, "null loci");
+    CU(s.c_offs0.need(((size_t)nr + 1) * 4)); CU(s.c_offs1.need(((size_t)nr + 1) * 4));
+    CU(s.c_loci0.need(n0 * 4 + 4)); CU(s.c_loci1.need(n1 * 4 + 4));
+    CU(s.acc.need(n0 + n1 + 1));
+    CU(s.rec.need((size_t)nr * sizeof(salt_verify_out_t)));
+    s.eager = 0;
+    if (cigars) {
+        if (cigar_stride < 2) return fail(SALT_ERR_ARG, "cigar stride too small");
+        CU(s.cig.need((size_t)nr * cigar_stride));
+        CU(s.ciglist.need(((size_t)nr + 2) * 4));      // [0] count, [1..] read ids
+        s.eager = nr < CIG_EAGER ? nr : CIG_EAGER;
+        const size_t want = 4 + (size_t)s.eager * 4 + (size_t)s.eager * cigar_stride;
+        if (want > s.h_stage_cap) {
+            if (s.h_stage) { CU(cudaFreeHost(s.h_stage)); s.h_stage = nullptr; s.h_stage_cap = 0; }
+            CU(cudaMallocHost(&s.h_stage, want));
+            s.h_stage_cap = want;
+        }
+    }
+    CU(cudaMemcpyAsync(s.c_offs0.p, cands->offs[0], ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaMemcpyAsync(s.c_offs1.p, cands->offs[1], ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, s.stream));
+    if (n0) CU(cudaMemcpyAsync(s.c_loci0.p, cands->loci[0], n0 * 4, cudaMemcpyHostToDevice, s.stream));
+    if (n1) CU(cudaMemcpyAsync(s.c_loci1.p, cands->loci[1], n1 * 4, cudaMemcpyHostToDevice, s.stream));
+    int8_t *acc = s.acc.as<int8_t>();
+    uint32_t *cl = cigars ? s.ciglist.as<uint32_t>() : nullptr;
+    if (int rc = verify_on_device(h, si, s.c_offs0.as<uint32_t>(), s.c_loci0.as<uint32_t>(), n0,
+                                  s.c_offs1.as<uint32_t>(), s.c_loci1.as<uint32_t>(), n1, nogap_T0, lv_T0,
+                                  s.rec.as<salt_verify_out_t>(), acc, acc + n0,
+                                  cigars ? s.cig.as<char>() : nullptr, cigar_stride, cl ? cl + 1 : nullptr, cl))
+        return rc;
+    CU(cudaMemcpyAsync(rec, s.rec.p, (size_t)nr * sizeof(salt_verify_out_t), cudaMemcpyDeviceToHost, s.stream));
+    if (acc0 && n0) CU(cudaMemcpyAsync(acc0, acc, n0, cudaMemcpyDeviceToHost, s.stream));
+    if (acc1 && n1) CU(cudaMemcpyAsync(acc1, acc + n0, n1, cudaMemcpyDeviceToHost, s.stream));
+    if (cigars) {
+        // only gapped primaries have a CIGAR (query_gen_cigar, query.c:282-295): the device keeps a
+        // compact list; its head comes back with the rest of the results, the tail (rare) on demand
+        CU(cudaMemcpyAsync(s.h_stage, cl, 4 + (size_t)s.eager * 4, cudaMemcpyDeviceToHost, s.stream));
+        if (s.eager)
+            CU(cudaMemcpyAsync(s.h_stage + 4 + (size_t)s.eager * 4, s.cig.p, (size_t)s.eager * cigar_stride,
+                               cudaMemcpyDeviceToHost, s.stream));
+    }
+    s.u_cigars = cigars; s.u_stride = cigar_stride;
+    s.pending = true;
+    return SALT_OK;
+}
+
+int finish_verify(salt_b200_t *h, int si)
+{
+    Slot &s = h->slot[si];
+    if (!s.pending) return SALT_OK;
+    s.pending = false;
+    CU(cudaStreamSynchronize(s.stream));
+    if (!s.u_cigars) return SALT_OK;
+    uint32_t n_cig = 0;
+    memcpy(&n_cig, s.h_stage, 4);
+    if (n_cig > s.n_reads) return fail(SALT_ERR_CUDA, "corrupt CIGAR list length");
+    const int stride = s.u_stride;
+    const uint32_t head = n_cig < s.eager ? n_cig : s.eager;
+    const uint32_t *ids = reinterpret_cast<const uint32_t *>(s.h_stage + 4);
+    const char *strs = reinterpret_cast<const char *>(s.h_stage + 4 + (size_t)s.eager * 4);
+    auto scatter = [&](const uint32_t *id, const char *sp, uint32_t m) {
+        // like the reference, touch only the string and its terminator in the caller's buffers
+        for (uint32_t i = 0; i < m; ++i, sp += stride) {
+            const size_t len = strnlen(sp, (size_t)stride - 1);
+            char *dst = s.u_cigars + (size_t)id[i] * stride;
+            memcpy(dst, sp, len);
+            dst[len] = '\0';
+        }
+    };
+    scatter(ids, strs, head);
+    if (n_cig > head) {
+        const uint32_t m = n_cig - head;
+        std::vector<uint32_t> id2(m);
+        std::vector<char> tmp((size_t)m * stride);
+        const uint32_t *cl = s.ciglist.as<uint32_t>();
+        CU(cudaMemcpyAsync(id2.data(), cl + 1 + head, (size_t)m * 4, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaMemcpyAsync(tmp.data(), s.cig.as<char>() + (size_t)head * stride, tmp.size(), cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaStreamSynchronize(s.stream));
+        scatter(id2.data(), tmp.data(), m);
+    }
+    return SALT_OK;
+}
 
 }  // namespace
 
@@ -132,24 +342,25 @@ salt_b200_t *salt_b200_init(const uint32_t *mixref, uint32_t l, const uint8_t *p
     if (!mixref || l == 0) { fail(SALT_ERR_ARG, "mixref is null or empty"); return nullptr; }
     salt_b200_t *h = new_handle(device);
     if (!h) return nullptr;
+    cudaStream_t st = h->slot[0].stream;
     const size_t nb = ((size_t)l + 7) / 8 * 4;
     cudaError_t e;
     if ((e = cudaMalloc(&h->d_mixref, nb + REF_PAD)) != cudaSuccess ||
-        (e = cudaMemsetAsync(reinterpret_cast<uint8_t *>(h->d_mixref) + nb, 0, REF_PAD, h->stream)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(h->d_mixref, mixref, nb, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) {
+        (e = cudaMemsetAsync(reinterpret_cast<uint8_t *>(h->d_mixref) + nb, 0, REF_PAD, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(h->d_mixref, mixref, nb, cudaMemcpyHostToDevice, st)) != cudaSuccess) {
         fail(SALT_ERR_CUDA, "upload mixref", e); salt_b200_destroy(h); return nullptr;
     }
     h->l = l;
     if (pac && l_pac > 0) {
         const size_t pb = ((size_t)l_pac + 3) / 4;
         if ((e = cudaMalloc(&h->d_pac, pb + REF_PAD)) != cudaSuccess ||
-            (e = cudaMemsetAsync(h->d_pac + pb, 0, REF_PAD, h->stream)) != cudaSuccess ||
-            (e = cudaMemcpyAsync(h->d_pac, pac, pb, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) {
+            (e = cudaMemsetAsync(h->d_pac + pb, 0, REF_PAD, st)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(h->d_pac, pac, pb, cudaMemcpyHostToDevice, st)) != cudaSuccess) {
             fail(SALT_ERR_CUDA, "upload pac", e); salt_b200_destroy(h); return nullptr;
         }
         h->l_pac = l_pac;
     }
-    if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) { fail(SALT_ERR_CUDA, "sync", e); salt_b200_destroy(h); return nullptr; }
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { fail(SALT_ERR_CUDA, "sync", e); salt_b200_destroy(h); return nullptr; }
     return h;
 }
 
@@ -159,23 +370,24 @@ salt_b200_t *salt_b200_init_from_bases(const char *bases, uint32_t l, const uint
     if (!bases || l == 0) { fail(SALT_ERR_ARG, "bases is null or empty"); return nullptr; }
     salt_b200_t *h = new_handle(device);
     if (!h) return nullptr;
+    cudaStream_t st = h->slot[0].stream;
     const size_t nb = ((size_t)l + 7) / 8 * 4;
     char *d_bases = nullptr; uint32_t *d_pos = nullptr; uint8_t *d_mask = nullptr;
     cudaError_t e = cudaSuccess;
     do {
         if ((e = cudaMalloc(&h->d_mixref, nb + REF_PAD)) != cudaSuccess) break;
-        if ((e = cudaMemsetAsync(reinterpret_cast<uint8_t *>(h->d_mixref) + nb, 0, REF_PAD, h->stream)) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(reinterpret_cast<uint8_t *>(h->d_mixref) + nb, 0, REF_PAD, st)) != cudaSuccess) break;
         if ((e = cudaMalloc(&d_bases, l)) != cudaSuccess) break;
-        if ((e = cudaMemcpyAsync(d_bases, bases, l, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(d_bases, bases, l, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
         if (n_snp) {
             if ((e = cudaMalloc(&d_pos, n_snp * 4)) != cudaSuccess) break;
             if ((e = cudaMalloc(&d_mask, n_snp)) != cudaSuccess) break;
-            if ((e = cudaMemcpyAsync(d_pos, snp_pos, n_snp * 4, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) break;
-            if ((e = cudaMemcpyAsync(d_mask, snp_mask, n_snp, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) break;
+            if ((e = cudaMemcpyAsync(d_pos, snp_pos, n_snp * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+            if ((e = cudaMemcpyAsync(d_mask, snp_mask, n_snp, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
         }
-        if ((e = launch_build_mixref(d_bases, l, d_pos, d_mask, n_snp, h->d_mixref, h->stream)) != cudaSuccess) break;
+        if ((e = launch_build_mixref(d_bases, l, d_pos, d_mask, n_snp, h->d_mixref, st)) != cudaSuccess) break;
         h->launches += n_snp ? 2 : 1;
-        e = cudaStreamSynchronize(h->stream);
+        e = cudaStreamSynchronize(st);
     } while (0);
     if (d_bases) cudaFree(d_bases);
     if (d_pos) cudaFree(d_pos);
@@ -190,8 +402,8 @@ int salt_b200_get_mixref(salt_b200_t *h, uint32_t *words_out, size_t n_words)
     if (int rc = use_device(h)) return rc;
     const size_t have = ((size_t)h->l + 7) / 8;
     if (!words_out || n_words < have) return fail(SALT_ERR_ARG, "output too small");
-    CU(cudaMemcpyAsync(words_out, h->d_mixref, have * 4, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpyAsync(words_out, h->d_mixref, have * 4, cudaMemcpyDeviceToHost, h->slot[0].stream));
+    CU(cudaStreamSynchronize(h->slot[0].stream));
     return SALT_OK;
 }
 
@@ -199,31 +411,36 @@ void salt_b200_destroy(salt_b200_t *h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream && h->own_stream) { cudaStreamSynchronize(h->stream); }
-    DBuf *all[] = {&h->codes, &h->offs, &h->rd4, &h->rd_len, &h->pairs, &h->out8, &h->kbuf, &h->cig, &h->wins,
-                   &h->sswout, &h->sswcig, &h->sswscratch, &h->c_offs0, &h->c_loci0, &h->c_offs1, &h->c_loci1,
-                   &h->vpairs, &h->acc, &h->rec, &h->lvlist, &h->ciglist, &h->counters};
+    for (int i = 0; i < SALT_SLOTS; ++i) {
+        if (h->slot[i].stream) cudaStreamSynchronize(h->slot[i].stream);
+        h->slot[i].release();
+    }
+    DBuf *all[] = {&h->pairs, &h->out8, &h->kbuf, &h->cig, &h->wins, &h->sswout, &h->sswcig, &h->sswscratch};
     for (DBuf *b : all) b->release();
-    for (int i = 0; i < 7; ++i) { if (h->ev_verify[i]) cudaEventDestroy(h->ev_verify[i]); if (h->ev_ssw[i]) cudaEventDestroy(h->ev_ssw[i]); }
+    for (int i = 0; i < 7; ++i) if (h->ev_ssw[i]) cudaEventDestroy(h->ev_ssw[i]);
     if (h->d_mixref) cudaFree(h->d_mixref);
     if (h->d_pac) cudaFree(h->d_pac);
-    if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
 int salt_b200_set_stream(salt_b200_t *h, void *cuda_stream)
 {
     if (int rc = use_device(h)) return rc;
-    if (h->own_stream && h->stream) { CU(cudaStreamSynchronize(h->stream)); CU(cudaStreamDestroy(h->stream)); }
-    if (cuda_stream) { h->stream = static_cast<cudaStream_t>(cuda_stream); h->own_stream = false; }
-    else { CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    Slot &s = h->slot[0];
+    if (s.pending) return fail(SALT_ERR_ARG, "slot 0 has a verify in flight");
+    if (s.own_stream && s.stream) { CU(cudaStreamSynchronize(s.stream)); CU(cudaStreamDestroy(s.stream)); s.stream = nullptr; }
+    if (cuda_stream) { s.stream = static_cast<cudaStream_t>(cuda_stream); s.own_stream = false; }
+    else { CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)); s.own_stream = true; }
     return SALT_OK;
 }
 
 int salt_b200_sync(salt_b200_t *h)
 {
     if (int rc = use_device(h)) return rc;
-    CU(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < SALT_SLOTS; ++i) {
+        if (h->slot[i].pending) { if (int rc = finish_verify(h, i)) return rc; }
+        else CU(cudaStreamSynchronize(h->slot[i].stream));
+    }
     return SALT_OK;
 }
 
@@ -248,30 +465,10 @@ uint64_t salt_b200_launch_count(salt_b200_t *h, int reset)
 int salt_b200_set_reads(salt_b200_t *h, const salt_reads_t *reads)
 {
     if (int rc = use_device(h)) return rc;
-    if (!reads || !reads->offs || (reads->n_reads && !reads->codes)) return fail(SALT_ERR_ARG, "reads is null");
-    if (reads->n_reads >= (1u << 31)) return fail(SALT_ERR_ARG, "too many reads in one chunk");
-    const uint32_t n = reads->n_reads;
-    uint32_t l_max = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t a = reads->offs[i], b = reads->offs[i + 1];
-        if (b < a) return fail(SALT_ERR_ARG, "read offsets not monotone");
-        if (b - a > l_max) l_max = b - a;
-    }
-    if (l_max > 1024) return fail(SALT_ERR_UNSUPPORTED, "reads longer than 1024 bases are not supported");
-    const size_t total = n ? reads->offs[n] : 0;
-    h->n_reads = n; h->l_max = l_max; h->W64 = (l_max + 15) / 16 + 1;
-    CU(h->codes.need(total + 16));
-    CU(h->offs.need(((size_t)n + 1) * 4));
-    CU(h->rd4.need((size_t)n * 2 * h->W64 * 8 + 64));
-    CU(h->rd_len.need((size_t)n * 2 + 64));
-    if (n) {
-        CU(cudaMemcpyAsync(h->codes.p, reads->codes, total, cudaMemcpyHostToDevice, h->stream));
-        CU(cudaMemcpyAsync(h->offs.p, reads->offs, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, h->stream));
-        CU(launch_pack_reads(h->codes.as<uint8_t>(), h->offs.as<uint32_t>(), n, h->W64, h->rd4.as<uint64_t>(),
-                             h->rd_len.as<uint16_t>(), h->stream));
-        h->launches += 1;
-    }
-    CU(cudaStreamSynchronize(h->stream));      // the caller's buffers are free to change after return
+    Slot &s = h->slot[0];
+    if (s.pending) return fail(SALT_ERR_ARG, "slot 0 has a verify in flight");
+    if (int rc = load_reads(h, s, reads)) return rc;
+    CU(cudaStreamSynchronize(s.stream));      // the caller's buffers are free to change after return
     return SALT_OK;
 }
 
@@ -281,8 +478,8 @@ int salt_b200_mismatch_dev(salt_b200_t *h, const salt_pair_t *d_pairs, size_t n,
     if (int rc = use_device(h)) return rc;
     if (n && (!d_pairs || !d_out)) return fail(SALT_ERR_ARG, "null buffer");
     if (max_err < 0 || max_err > 127) return fail(SALT_ERR_ARG, "max_err must be in 0..127");
-    if (!h->n_reads) return fail(SALT_ERR_ARG, "no reads set");
-    CU(launch_mismatch(h->ctx(), d_pairs, n, max_err, d_out, h->stream));
+    if (!h->slot[0].n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    CU(launch_mismatch(h->ctx(), d_pairs, n, max_err, d_out, h->slot[0].stream));
     if (n) h->launches += 1;
     return SALT_OK;
 }
@@ -292,12 +489,13 @@ int salt_b200_mismatch(salt_b200_t *h, const salt_pair_t *pairs, size_t n, int m
     if (int rc = use_device(h)) return rc;
     if (n && (!pairs || !out)) return fail(SALT_ERR_ARG, "null buffer");
     if (!n) return SALT_OK;
+    cudaStream_t st = h->slot[0].stream;
     CU(h->pairs.need(n * sizeof(salt_pair_t)));
     CU(h->out8.need(n));
-    CU(cudaMemcpyAsync(h->pairs.p, pairs, n * sizeof(salt_pair_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->pairs.p, pairs, n * sizeof(salt_pair_t), cudaMemcpyHostToDevice, st));
     if (int rc = salt_b200_mismatch_dev(h, h->pairs.as<salt_pair_t>(), n, max_err, h->out8.as<int8_t>())) return rc;
-    CU(cudaMemcpyAsync(out, h->out8.p, n, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpyAsync(out, h->out8.p, n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return SALT_OK;
 }
 
@@ -305,8 +503,8 @@ int salt_b200_lv_dev(salt_b200_t *h, const salt_pair_t *d_pairs, size_t n, int k
 {
     if (int rc = use_device(h)) return rc;
     if (n && (!d_pairs || !d_out)) return fail(SALT_ERR_ARG, "null buffer");
-    if (!h->n_reads) return fail(SALT_ERR_ARG, "no reads set");
-    CU(launch_lv(h->ctx(), d_pairs, n, k, nullptr, nullptr, 0, d_out, h->sm_count, h->stream, h->lv_mapping));
+    if (!h->slot[0].n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    CU(launch_lv(h->ctx(), d_pairs, n, k, nullptr, nullptr, 0, d_out, h->sm_count, h->slot[0].stream, h->lv_mapping));
     if (n) h->launches += 1;
     return SALT_OK;
 }
@@ -316,12 +514,13 @@ int salt_b200_lv(salt_b200_t *h, const salt_pair_t *pairs, size_t n, int k, int8
     if (int rc = use_device(h)) return rc;
     if (n && (!pairs || !out)) return fail(SALT_ERR_ARG, "null buffer");
     if (!n) return SALT_OK;
+    cudaStream_t st = h->slot[0].stream;
     CU(h->pairs.need(n * sizeof(salt_pair_t)));
     CU(h->out8.need(n));
-    CU(cudaMemcpyAsync(h->pairs.p, pairs, n * sizeof(salt_pair_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->pairs.p, pairs, n * sizeof(salt_pair_t), cudaMemcpyHostToDevice, st));
     if (int rc = salt_b200_lv_dev(h, h->pairs.as<salt_pair_t>(), n, k, h->out8.as<int8_t>())) return rc;
-    CU(cudaMemcpyAsync(out, h->out8.p, n, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpyAsync(out, h->out8.p, n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return SALT_OK;
 }
 
@@ -331,29 +530,30 @@ int salt_b200_lv_cigar(salt_b200_t *h, const salt_pair_t *pairs, const uint8_t *
     if (int rc = use_device(h)) return rc;
     if (n && (!pairs || !k_each || !cigars || !out)) return fail(SALT_ERR_ARG, "null buffer");
     if (stride < 2) return fail(SALT_ERR_ARG, "cigar stride too small");
-    if (!h->n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    if (!h->slot[0].n_reads) return fail(SALT_ERR_ARG, "no reads set");
     if (!n) return SALT_OK;
     for (size_t i = 0; i < n; ++i)
         if (k_each[i] >= 31) return fail(SALT_ERR_ARG, "k must be < 31 (LandauVishkin.c:183 asserts)");
+    cudaStream_t st = h->slot[0].stream;
     CU(h->pairs.need(n * sizeof(salt_pair_t)));
     CU(h->out8.need(n));
     CU(h->kbuf.need(n));
     CU(h->cig.need(n * (size_t)stride));
-    CU(cudaMemcpyAsync(h->pairs.p, pairs, n * sizeof(salt_pair_t), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->kbuf.p, k_each, n, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemsetAsync(h->cig.p, 0, n * (size_t)stride, h->stream));
+    CU(cudaMemcpyAsync(h->pairs.p, pairs, n * sizeof(salt_pair_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->kbuf.p, k_each, n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(h->cig.p, 0, n * (size_t)stride, st));
     CU(launch_lv_cigar(h->ctx(), h->pairs.as<salt_pair_t>(), h->kbuf.as<uint8_t>(), n, nullptr, nullptr, 0, nullptr,
-                       h->cig.as<char>(), stride, h->out8.as<int8_t>(), h->sm_count, h->stream));
+                       h->cig.as<char>(), stride, h->out8.as<int8_t>(), h->sm_count, st));
     h->launches += 1;
     std::vector<char> tmp(n * (size_t)stride);
-    CU(cudaMemcpyAsync(tmp.data(), h->cig.p, tmp.size(), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(out, h->out8.p, n, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpyAsync(tmp.data(), h->cig.p, tmp.size(), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out, h->out8.p, n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     // like the reference, touch only the string and its terminator in the caller's buffers
     for (size_t i = 0; i < n; ++i) {
-        const char *s = tmp.data() + i * (size_t)stride;
-        size_t len = strnlen(s, (size_t)stride - 1);
-        memcpy(cigars + i * (size_t)stride, s, len);
+        const char *sp = tmp.data() + i * (size_t)stride;
+        size_t len = strnlen(sp, (size_t)stride - 1);
+        memcpy(cigars + i * (size_t)stride, sp, len);
         cigars[i * (size_t)stride + len] = '\0';
     }
     return SALT_OK;
@@ -397,20 +597,22 @@ int salt_b200_ssw_dev(salt_b200_t *h, const salt_win_t *d_wins, size_t n, int us
     if (int rc = use_device(h)) return rc;
     if (n && (!d_wins || !d_out || !d_cigars)) return fail(SALT_ERR_ARG, "null buffer");
     if (cigar_stride < 1) return fail(SALT_ERR_ARG, "cigar stride too small");
-    if (!h->n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    if (!h->slot[0].n_reads) return fail(SALT_ERR_ARG, "no reads set");
     if (use_pac && !h->d_pac) return fail(SALT_ERR_ARG, "no pac uploaded");
     SswParams prm;
     if (int rc = fill_ssw_params(prm, use_pac, mat, n_sym, gapO, gapE, flag, filters, filterd, mask_len)) return rc;
     int maxpos = 0;
     for (int i = 0; i < n_sym * n_sym; ++i) if (mat[i] > maxpos) maxpos = mat[i];
-    if ((int64_t)maxpos * (int64_t)h->l_max >= 32000) return fail(SALT_ERR_UNSUPPORTED, "scores would overflow int16");
+    if ((int64_t)maxpos * (int64_t)h->slot[0].l_max >= 32000) return fail(SALT_ERR_UNSUPPORTED, "scores would overflow int16");
     if (!n) return SALT_OK;
     const int max_cols = h->max_window;
     size_t lay[8];
-    const size_t need = ssw_scratch_bytes(n, max_cols, (int)h->l_max, lay);
+    const size_t need = ssw_scratch_bytes(n, max_cols, (int)h->slot[0].l_max, lay);
     CU(h->sswscratch.need(need));
+    if (h->profiling)
+        for (int i = 0; i < 7; ++i) if (!h->ev_ssw[i]) CU(cudaEventCreate(&h->ev_ssw[i]));
     CU(launch_ssw(h->ctx(), d_wins, n, prm, h->sswscratch.p, h->sswscratch.cap, max_cols, d_out, d_cigars,
-                  cigar_stride, h->sm_count, h->stream, &h->launches, h->profiling ? h->ev_ssw : nullptr));
+                  cigar_stride, h->sm_count, h->slot[0].stream, &h->launches, h->profiling ? h->ev_ssw : nullptr));
     h->have_ssw_prof = h->profiling;
     return SALT_OK;
 }
@@ -440,6 +642,7 @@ int salt_b200_ssw(salt_b200_t *h, const salt_win_t *wins, size_t n, int use_pac,
     if (n && (!wins || !out || !cigars)) return fail(SALT_ERR_ARG, "null buffer");
     if (cigar_stride < 1) return fail(SALT_ERR_ARG, "cigar stride too small");
     if (!n) return SALT_OK;
+    cudaStream_t st = h->slot[0].stream;
     uint32_t widest = 1;
     for (size_t i = 0; i < n; ++i)
         if (wins[i].end >= wins[i].start && wins[i].end - wins[i].start + 1 > widest) widest = wins[i].end - wins[i].start + 1;
@@ -448,14 +651,14 @@ int salt_b200_ssw(salt_b200_t *h, const salt_win_t *wins, size_t n, int use_pac,
     CU(h->wins.need(n * sizeof(salt_win_t)));
     CU(h->sswout.need(n * sizeof(salt_ssw_out_t)));
     CU(h->sswcig.need(n * (size_t)cigar_stride * 4));
-    CU(cudaMemcpyAsync(h->wins.p, wins, n * sizeof(salt_win_t), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemsetAsync(h->sswcig.p, 0, n * (size_t)cigar_stride * 4, h->stream));
+    CU(cudaMemcpyAsync(h->wins.p, wins, n * sizeof(salt_win_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(h->sswcig.p, 0, n * (size_t)cigar_stride * 4, st));
     if (int rc = salt_b200_ssw_dev(h, h->wins.as<salt_win_t>(), n, use_pac, mat, n_sym, gapO, gapE, flag, filters,
                                    filterd, mask_len, h->sswout.as<salt_ssw_out_t>(), h->sswcig.as<uint32_t>(), cigar_stride))
         return rc;
-    CU(cudaMemcpyAsync(out, h->sswout.p, n * sizeof(salt_ssw_out_t), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(cigars, h->sswcig.p, n * (size_t)cigar_stride * 4, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpyAsync(out, h->sswout.p, n * sizeof(salt_ssw_out_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(cigars, h->sswcig.p, n * (size_t)cigar_stride * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     for (size_t i = 0; i < n; ++i)
         if (out[i].cigarLen < 0) return fail(SALT_ERR_UNSUPPORTED, "a window was invalid or its traceback band exceeded the engine limit");
     return SALT_OK;
@@ -468,115 +671,84 @@ int salt_b200_verify_dev(salt_b200_t *h, const uint32_t *d_offs0, const uint32_t
                          char *d_cigars, int cigar_stride, uint32_t *d_cig_reads, uint32_t *d_cig_count)
 {
     if (int rc = use_device(h)) return rc;
-    if (!h->n_reads) return fail(SALT_ERR_ARG, "no reads set");
-    if (!d_offs0 || !d_offs1 || !d_rec) return fail(SALT_ERR_ARG, "null buffer");
-    if (nogap_T0 < 0 || nogap_T0 > 127) return fail(SALT_ERR_ARG, "nogap_T0 must be in 0..127");
-    if (n0 + n1 >= (size_t)1 << 32) return fail(SALT_ERR_ARG, "too many candidates in one chunk");
-    if (d_acc0 && d_acc1 && d_acc1 != d_acc0 + n0) return fail(SALT_ERR_ARG, "acc1 must follow acc0 contiguously");
-    if (d_cigars && (!d_cig_reads || !d_cig_count)) return fail(SALT_ERR_ARG, "cigars need d_cig_reads and d_cig_count");
-    if (d_cigars && cigar_stride < 2) return fail(SALT_ERR_ARG, "cigar stride too small");
-    if (reinterpret_cast<uintptr_t>(d_rec) & 15u) return fail(SALT_ERR_ARG, "d_rec must be 16-byte aligned");
-    const size_t n = n0 + n1;
-    const DevCtx c = h->ctx();
-    CU(h->vpairs.need((n + 1) * sizeof(salt_pair_t)));      // LV worklist: pairs ...
-    CU(h->lvlist.need((n + 1) * 4));                         // ... and the acc slot each one reports to
-    CU(h->counters.need(256));
-    int8_t *acc = d_acc0;
-    if (!acc) { CU(h->acc.need(n + 1)); acc = h->acc.as<int8_t>(); }
-    salt_pair_t *lvp = h->vpairs.as<salt_pair_t>();
-    uint32_t *lvs = h->lvlist.as<uint32_t>();
-    uint32_t *cnt = h->counters.as<uint32_t>();        // [0] LV worklist length
-    cudaEvent_t *ev = h->profiling ? h->ev_verify : nullptr;
-#define SALT_EV(i) do { if (ev) CU(cudaEventRecord(ev[i], h->stream)); } while (0)
-    CU(cudaMemsetAsync(cnt, 0, 256, h->stream));
-    if (d_cig_count) CU(cudaMemsetAsync(d_cig_count, 0, 4, h->stream));
-    SALT_EV(0);
-    SALT_EV(1);
-    CU(launch_nogap_fused(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, nogap_T0, acc, d_rec, lvp, lvs, cnt, h->stream));
-    SALT_EV(2);
-    SALT_EV(3);
-    CU(launch_lv(c, lvp, n, lv_T0, lvs, cnt, n, acc, h->sm_count, h->stream, h->lv_mapping));
-    SALT_EV(4);
-    CU(launch_scan_gap(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, lv_T0, acc, d_rec,
-                       d_cigars ? d_cig_reads : nullptr, d_cig_count, h->stream));
-    SALT_EV(5);
-    h->launches += 3;
-    if (d_cigars) {
-        CU(launch_lv_cigar(c, nullptr, nullptr, 0, d_cig_reads, d_cig_count, h->n_reads, d_rec,
-                           d_cigars, cigar_stride, nullptr, h->sm_count, h->stream));
-        h->launches += 1;
-    }
-    SALT_EV(6);
-#undef SALT_EV
-    h->have_verify_prof = h->profiling;
-    return SALT_OK;
+    if (h->slot[0].pending) return fail(SALT_ERR_ARG, "slot 0 has a verify in flight");
+    return verify_on_device(h, 0, d_offs0, d_loci0, n0, d_offs1, d_loci1, n1, nogap_T0, lv_T0, d_rec, d_acc0, d_acc1,
+                            d_cigars, cigar_stride, d_cig_reads, d_cig_count);
 }
 
 int salt_b200_verify(salt_b200_t *h, const salt_cands_t *cands, int nogap_T0, int lv_T0,
                      salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1, char *cigars, int cigar_stride)
 {
     if (int rc = use_device(h)) return rc;
-    if (!cands || !cands->offs[0] || !cands->offs[1] || !rec) return fail(SALT_ERR_ARG, "null buffer");
-    if (!h->n_reads) return fail(SALT_ERR_ARG, "no reads set");
-    const uint32_t nr = h->n_reads;
-    const size_t n0 = cands->offs[0][nr], n1 = cands->offs[1][nr];
-    if ((n0 && !cands->loci[0]) || (n1 && !cands->loci[1])) return fail(SALT_ERR_ARG, "null loci");
-    CU(h->c_offs0.need(((size_t)nr + 1) * 4)); CU(h->c_offs1.need(((size_t)nr + 1) * 4));
-    CU(h->c_loci0.need(n0 * 4 + 4)); CU(h->c_loci1.need(n1 * 4 + 4));
-    CU(h->acc.need(n0 + n1 + 1));
-    CU(h->rec.need((size_t)nr * sizeof(salt_verify_out_t)));
-    if (cigars) {
-        if (cigar_stride < 2) return fail(SALT_ERR_ARG, "cigar stride too small");
-        CU(h->cig.need((size_t)nr * cigar_stride));
-        CU(h->ciglist.need(((size_t)nr + 2) * 4));      // [0] count, [1..] read ids
-    }
-    CU(cudaMemcpyAsync(h->c_offs0.p, cands->offs[0], ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->c_offs1.p, cands->offs[1], ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, h->stream));
-    if (n0) CU(cudaMemcpyAsync(h->c_loci0.p, cands->loci[0], n0 * 4, cudaMemcpyHostToDevice, h->stream));
-    if (n1) CU(cudaMemcpyAsync(h->c_loci1.p, cands->loci[1], n1 * 4, cudaMemcpyHostToDevice, h->stream));
-    int8_t *acc = h->acc.as<int8_t>();
-    uint32_t *cl = cigars ? h->ciglist.as<uint32_t>() : nullptr;
-    if (int rc = salt_b200_verify_dev(h, h->c_offs0.as<uint32_t>(), h->c_loci0.as<uint32_t>(), n0,
-                                      h->c_offs1.as<uint32_t>(), h->c_loci1.as<uint32_t>(), n1, nogap_T0, lv_T0,
-                                      h->rec.as<salt_verify_out_t>(), acc, acc + n0,
-                                      cigars ? h->cig.as<char>() : nullptr, cigar_stride, cl ? cl + 1 : nullptr, cl))
-        return rc;
-    CU(cudaMemcpyAsync(rec, h->rec.p, (size_t)nr * sizeof(salt_verify_out_t), cudaMemcpyDeviceToHost, h->stream));
-    if (acc0 && n0) CU(cudaMemcpyAsync(acc0, acc, n0, cudaMemcpyDeviceToHost, h->stream));
-    if (acc1 && n1) CU(cudaMemcpyAsync(acc1, acc + n0, n1, cudaMemcpyDeviceToHost, h->stream));
-    uint32_t n_cig = 0;
-    if (cigars) CU(cudaMemcpyAsync(&n_cig, cl, 4, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    if (cigars && n_cig) {
-        // only gapped primaries have a CIGAR to fetch (query_gen_cigar, query.c:282-295): bring back
-        // the compact list and copy each string into the caller's per-read buffer
-        std::vector<uint32_t> ids(n_cig);
-        std::vector<char> tmp((size_t)n_cig * cigar_stride);
-        CU(cudaMemcpyAsync(ids.data(), cl + 1, (size_t)n_cig * 4, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaMemcpyAsync(tmp.data(), h->cig.p, tmp.size(), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        for (uint32_t i = 0; i < n_cig; ++i) {
-            const char *sp = tmp.data() + (size_t)i * cigar_stride;
-            const size_t len = strnlen(sp, (size_t)cigar_stride - 1);
-            char *dst = cigars + (size_t)ids[i] * cigar_stride;
-            memcpy(dst, sp, len);
-            dst[len] = '\0';
+    if (int rc = enqueue_verify(h, 0, cands, nogap_T0, lv_T0, rec, acc0, acc1, cigars, cigar_stride)) return rc;
+    return finish_verify(h, 0);
+}
+
+int salt_b200_n_slots(void) { return SALT_SLOTS; }
+
+int salt_b200_verify_submit(salt_b200_t *h, int slot, const salt_reads_t *reads, const salt_cands_t *cands,
+                            int nogap_T0, int lv_T0, salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1,
+                            char *cigars, int cigar_stride)
+{
+    if (int rc = use_device(h)) return rc;
+    if (slot < 0 || slot >= SALT_SLOTS) return fail(SALT_ERR_ARG, "slot out of range");
+    Slot &s = h->slot[slot];
+    if (s.pending) return fail(SALT_ERR_ARG, "slot has a verify in flight: call salt_b200_verify_wait first");
+    if (int rc = load_reads(h, s, reads)) return rc;
+    if (!s.n_reads) return SALT_OK;
+    return enqueue_verify(h, slot, cands, nogap_T0, lv_T0, rec, acc0, acc1, cigars, cigar_stride);
+}
+
+int salt_b200_verify_wait(salt_b200_t *h, int slot)
+{
+    if (int rc = use_device(h)) return rc;
+    if (slot < 0 || slot >= SALT_SLOTS) return fail(SALT_ERR_ARG, "slot out of range");
+    return finish_verify(h, slot);
+}
+
+int salt_b200_verify_batch(salt_b200_t *h, const salt_reads_t *reads, const salt_cands_t *cands, uint32_t chunk_reads,
+                           int nogap_T0, int lv_T0, salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1,
+                           char *cigars, int cigar_stride)
+{
+    if (int rc = use_device(h)) return rc;
+    if (!reads || !reads->offs || !cands || !cands->offs[0] || !cands->offs[1] || !rec) return fail(SALT_ERR_ARG, "null buffer");
+    if (chunk_reads == 0) chunk_reads = 100000;          // N_SEQS, aln.h:27
+    const uint32_t n = reads->n_reads;
+    int rc = SALT_OK;
+    uint32_t k = 0;
+    for (uint32_t b = 0; b < n && rc == SALT_OK; b += chunk_reads, ++k) {
+        const int si = (int)(k % SALT_SLOTS);
+        if ((rc = finish_verify(h, si)) != SALT_OK) break;
+        const uint32_t m = n - b < chunk_reads ? n - b : chunk_reads;
+        // per-chunk views need offsets that start at 0: rebased copies in pinned memory, owned by the slot
+        Slot &sl = h->slot[si];
+        if (sl.h_offs_cap < 3 * ((size_t)m + 1)) {
+            if (sl.h_offs) { cudaFreeHost(sl.h_offs); sl.h_offs = nullptr; sl.h_offs_cap = 0; }
+            const size_t want = 3 * ((size_t)(m > chunk_reads ? m : chunk_reads) + 1);
+            if (cudaMallocHost(&sl.h_offs, want * 4) != cudaSuccess) { rc = fail(SALT_ERR_NOMEM, "pinned offsets"); break; }
+            sl.h_offs_cap = want;
         }
+        uint32_t *r_ = sl.h_offs, *a_ = r_ + (m + 1), *b_ = a_ + (m + 1);
+        const uint32_t rb = reads->offs[b], c0 = cands->offs[0][b], c1 = cands->offs[1][b];
+        for (uint32_t i = 0; i <= m; ++i) {
+            r_[i] = reads->offs[b + i] - rb; a_[i] = cands->offs[0][b + i] - c0; b_[i] = cands->offs[1][b + i] - c1;
+        }
+        salt_reads_t rv; rv.codes = reads->codes + rb; rv.offs = r_; rv.n_reads = m;
+        salt_cands_t cv; cv.offs[0] = a_; cv.offs[1] = b_;
+        cv.loci[0] = cands->loci[0] ? cands->loci[0] + c0 : nullptr; cv.loci[1] = cands->loci[1] ? cands->loci[1] + c1 : nullptr;
+        rc = salt_b200_verify_submit(h, si, &rv, &cv, nogap_T0, lv_T0, rec + b, acc0 ? acc0 + c0 : nullptr,
+                                     acc1 ? acc1 + c1 : nullptr, cigars ? cigars + (size_t)b * cigar_stride : nullptr, cigar_stride);
     }
-    return SALT_OK;
+    for (int si = 0; si < SALT_SLOTS; ++si) { const int r2 = finish_verify(h, si); if (rc == SALT_OK) rc = r2; }
+    return rc;
 }
 
 int salt_b200_profile(salt_b200_t *h, int enable)
 {
     if (int rc = use_device(h)) return rc;
-    if (enable) {
-        for (int i = 0; i < 7; ++i) {
-            if (!h->ev_verify[i]) CU(cudaEventCreate(&h->ev_verify[i]));
-            if (!h->ev_ssw[i]) CU(cudaEventCreate(&h->ev_ssw[i]));
-        }
-    }
     h->profiling = enable != 0;
-    h->have_verify_prof = h->have_ssw_prof = false;
+    h->have_ssw_prof = false;
+    for (int i = 0; i < SALT_SLOTS; ++i) h->slot[i].have_verify_prof = false;
     return SALT_OK;
 }
 
@@ -584,10 +756,11 @@ int salt_b200_profile_read(salt_b200_t *h, float *ms /* [12] */)
 {
     if (int rc = use_device(h)) return rc;
     if (!ms) return fail(SALT_ERR_ARG, "null buffer");
-    CU(cudaStreamSynchronize(h->stream));
+    Slot &s = h->slot[0];
+    CU(cudaStreamSynchronize(s.stream));
     for (int i = 0; i < 12; ++i) ms[i] = -1.f;
-    if (h->have_verify_prof)
-        for (int i = 0; i < 6; ++i) CU(cudaEventElapsedTime(&ms[i], h->ev_verify[i], h->ev_verify[i + 1]));
+    if (s.have_verify_prof)
+        for (int i = 0; i < 6; ++i) CU(cudaEventElapsedTime(&ms[i], s.ev_verify[i], s.ev_verify[i + 1]));
     if (h->have_ssw_prof)
         for (int i = 0; i < 6; ++i) CU(cudaEventElapsedTime(&ms[6 + i], h->ev_ssw[i], h->ev_ssw[i + 1]));
     return SALT_OK;

@@ -89,6 +89,20 @@ def check_verify(eng, oracle, g, reads, cands, nogap_T0=3, lv_T0=-1, stride=128)
     return stats
 
 
+def check_verify_batch(eng, reads, cands, chunk_reads, nogap_T0=3, lv_T0=-1, stride=128):
+    """The asynchronous chunk pipeline must return exactly what the one-shot stage returns
+    (which check_verify pins against the oracle)."""
+    offs0, loci0, offs1, loci1 = cands
+    n, L = reads.shape
+    eng.set_reads(reads)
+    want = eng.verify(offs0, loci0, offs1, loci1, nogap_T0, lv_T0, stride)
+    roffs = (np.arange(n + 1, dtype=np.uint64) * L).astype(np.uint32)
+    got = eng.verify_batch(reads, roffs, offs0, loci0, offs1, loci1, chunk_reads, nogap_T0, lv_T0, stride)
+    for a, b, name in zip(got, want, ("rec", "acc0", "acc1", "cigars")):
+        assert a.tobytes() == b.tobytes(), name
+    return want[0]
+
+
 def make_windows(g, reads, pos, strand, L, rng, width=401):
     """Rescue-like windows: the read's true locus somewhere inside a `width`-base window,
     plus a few decoy windows and windows clipped at the ends of the reference."""

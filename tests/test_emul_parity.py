@@ -100,6 +100,15 @@ def test_verify_long_lists(emul_lib, oracle):
     pc.check_verify(eng, oracle, g, reads, (offs0, loci0, offs1, loci1), 3, 3)
 
 
+def test_verify_batch_pipeline(emul_lib, oracle):
+    """chunks of 7 reads through the 4 slots: slot reuse, last partial chunk, compact CIGAR return"""
+    g, reads, pos, strand, cands = pc.make_world(123, L=100, n_reads=60, per_strand=4, indel_frac=0.4, glen=30000)
+    eng = _engine(emul_lib, g)
+    rec = pc.check_verify_batch(eng, reads, cands, 7)
+    assert (rec["is_gap"] == 1).sum() >= 3
+    pc.check_verify_batch(eng, reads, cands, 1000)
+
+
 def test_verify_empty_lists(emul_lib, oracle):
     g, reads, pos, strand, cands = pc.make_world(77, L=100, n_reads=6, per_strand=3, glen=20000)
     z = np.zeros(7, np.uint32); e = np.zeros(0, np.uint32)

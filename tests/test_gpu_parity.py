@@ -89,6 +89,16 @@ def test_verify_long_lists(oracle):
     pc.check_verify(eng, oracle, g, reads, (offs0, loci0, offs1, loci1), 3, 3)
 
 
+def test_verify_batch_pipeline(oracle):
+    """the asynchronous chunk pipeline (4 slots) against the one-shot stage, several chunk sizes"""
+    g, reads, pos, strand, cands = pc.make_world(321, glen=400000, L=100, n_reads=5000, per_strand=6, indel_frac=0.3, sub_rate=0.02)
+    eng = _engine(g)
+    rec = pc.check_verify_batch(eng, reads, cands, 333)
+    assert (rec["is_gap"] == 1).sum() >= 100
+    pc.check_verify_batch(eng, reads, cands, 1024)
+    pc.check_verify_batch(eng, reads, cands, 100000)
+
+
 def test_verify_ragged_and_empty(oracle):
     """ragged read lengths in one chunk, reads without candidates, an empty chunk of lists"""
     rng = np.random.default_rng(5)
