@@ -178,6 +178,12 @@ int salt_b200_verify_batch(salt_b200_t *h, const salt_reads_t *reads, const salt
  * warp (or sub-warp group) per pair.  Results are identical; this exists for measurement. */
 int salt_b200_set_lv_mapping(salt_b200_t *h, int mapping);
 
+/* Pigeonhole pre-filter in front of Landau-Vishkin (default on): a pair can only be within k
+ * differences if at least plen/8 - k of the read's full 8-base words match the window exactly on
+ * some diagonal |d| <= k; pairs failing that get -1 without running Landau-Vishkin.  Results are
+ * identical with the filter off; the switch exists for measurement and tests. */
+int salt_b200_set_lv_filter(salt_b200_t *h, int enable);
+
 /* Widest rescue window (in bases) the *_dev SSW entry point must handle; the host entry point
  * sets it from its arguments.  Default 1024. */
 int salt_b200_set_max_window(salt_b200_t *h, int cols);

@@ -1,0 +1,74 @@
+/*
+ * salt_host.h -- host-side C layer over libsalt_b200.so: the part of salt's per-chunk loop that
+ * sits between seeding and SAM output, re-staged for a batched engine.
+ *
+ * In the reference every worker thread runs, per read,
+ *     seed + locate  ->  alnse_check_nogap / alnse_check_withgap  ->  query_set_hits  ->  query_gen_cigar
+ * (alnse.c:1045-1100 alnse_overlap_alt, alnse.c:985-1040 alnse_overlap, query.c:282-333).
+ * With the GPU engine the middle step is done for a whole chunk at once, so the loop becomes
+ *     workers: seed + locate, push (read, sorted loci) into a pinned chunk queue      [salt_chunk_add_read]
+ *     main   : submit the chunk to a pipeline slot, keep seeding the next chunk        [salt_chunk_submit]
+ *     main   : wait; per read rebuild aux->hits, run query_set_hits / gen_mapq         [salt_chunk_wait, salt_chunk_result]
+ * Plain C, no CUDA types.  Compiled by gcc into libsalt_host.so, which links libsalt_b200.so.
+ */
+#ifndef SALT_HOST_H
+#define SALT_HOST_H
+#include <stddef.h>
+#include <stdint.h>
+#include "salt_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SALT_MAX_HITS 16            /* aln_opt->max_hits is 5 in the reference (aln.h:139) */
+
+/* hit_t (query.h:28-33) */
+typedef struct { uint32_t pos; uint8_t n_diff; uint8_t is_gap; uint16_t strand; } salt_hit_t;
+
+/* What the verification stage leaves in query_t for one read (query.h:37-64):
+ * pos/strand/n_diff/is_gap (alnse.c:348-393), hits[2] + b0/b1/mapq (query_set_hits, query.c:297-333;
+ * gen_mapq, query.c:270-281), cigar (query_gen_cigar, query.c:282-295). */
+typedef struct {
+    uint32_t pos;                    /* 0xFFFFFFFF = unmapped */
+    uint8_t strand, n_diff, is_gap;  /* 3 / 255 / 255 when unmapped */
+    int b0, b1;
+    uint32_t mapq;
+    int n_alt[2];
+    salt_hit_t alt[2][SALT_MAX_HITS];
+    char cigar[128];                 /* "" when unmapped; "<l_seq>M" for an ungapped primary */
+} salt_read_result_t;
+
+typedef struct salt_chunk salt_chunk_t;
+
+/* Pinned queues for one chunk: up to max_reads reads, max_bases read bases, max_cands candidate
+ * loci per strand.  (N_SEQS = 100000 reads per chunk in the reference, aln.h:27.) */
+salt_chunk_t *salt_chunk_new(uint32_t max_reads, size_t max_bases, size_t max_cands);
+void salt_chunk_free(salt_chunk_t *c);
+void salt_chunk_reset(salt_chunk_t *c);
+uint32_t salt_chunk_n_reads(const salt_chunk_t *c);
+
+/* Append read i = salt_chunk_n_reads() with its candidate loci per strand as alnse_locate[_alt]
+ * leaves them in aux->loci (sorted ascending).  seq: codes 0..4 (query->seq).  Call in read order
+ * from one thread (e.g. after the seeding workers have joined, alnse.c:1428).  Returns the read's
+ * index in the chunk, or a negative SALT_ERR_* when a queue is full. */
+int salt_chunk_add_read(salt_chunk_t *c, const uint8_t *seq, uint32_t l_seq,
+                        const uint32_t *loci0, uint32_t n0, const uint32_t *loci1, uint32_t n1);
+
+/* Send the chunk through pipeline slot `slot` (salt_b200_verify_submit) / wait for it.
+ * nogap_T0 = 3 (alnse.c:1016,1079); lv_T0 < 0 = l_seq/10, the SE rule (alnse.c:1090), 3 = PE (alnse.c:1027). */
+int salt_chunk_submit(salt_b200_t *h, int slot, salt_chunk_t *c, int nogap_T0, int lv_T0);
+int salt_chunk_wait(salt_b200_t *h, int slot, salt_chunk_t *c);
+
+/* After salt_chunk_wait: the query_t fields of read i, with query_set_hits(max_hits) applied to
+ * the accepted hits exactly as the reference does (including its use of element 0's n_diff,
+ * query.c:317-318). */
+int salt_chunk_result(const salt_chunk_t *c, uint32_t i, int max_hits, salt_read_result_t *out);
+
+/* aux->hits of read i on one strand, in acceptance order.  Returns the number written (<= cap). */
+int salt_chunk_hits(const salt_chunk_t *c, uint32_t i, int strand, salt_hit_t *out, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SALT_HOST_H */

@@ -66,6 +66,7 @@ def _declare(L):
     L.salt_b200_verify_batch.argtypes = [vp, C.POINTER(ReadsT), C.POINTER(CandsT), C.c_uint32, i32, i32, vp, vp, vp, vp, i32]
     L.salt_b200_set_max_window.argtypes = [vp, i32]
     L.salt_b200_set_lv_mapping.argtypes = [vp, i32]
+    L.salt_b200_set_lv_filter.argtypes = [vp, i32]
     L.salt_b200_mismatch_dev.argtypes = [vp, vp, sz, i32, vp]
     L.salt_b200_lv_dev.argtypes = [vp, vp, sz, i32, vp]
     L.salt_b200_verify_dev.argtypes = [vp, vp, vp, sz, vp, vp, sz, i32, i32, vp, vp, vp, vp, i32, vp, vp]
@@ -179,6 +180,9 @@ class Engine:
 
     def set_lv_mapping(self, mapping):
         self._ck(self.L.salt_b200_set_lv_mapping(self.h, int(mapping)))
+
+    def set_lv_filter(self, enable):
+        self._ck(self.L.salt_b200_set_lv_filter(self.h, int(enable)))
 
     def launch_count(self, reset=False):
         return int(self.L.salt_b200_launch_count(self.h, int(reset)))

@@ -43,7 +43,22 @@ def build(force=False, verbose=False):
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
+    build_host(force or bool(procs))
     return OUT
+
+
+HOST_OUT = os.path.join(HERE, "libsalt_host.so")
+
+
+def build_host(force=False, engine=OUT, out=HOST_OUT):
+    """libsalt_host.so: the host-side C layer (include/salt_host.h), gcc, linked against the engine."""
+    src = os.path.join(HERE, "host", "salt_host.c")
+    hdrs = [os.path.join(HERE, "..", "include", f) for f in ("salt_host.h", "salt_b200.h")]
+    if force or _stale(out, [src, engine] + hdrs):
+        d, f = os.path.split(engine)
+        subprocess.check_call([os.environ.get("CC", "gcc"), "-O2", "-std=gnu11", "-Wall", "-Wextra", "-fPIC", "-shared",
+                               "-o", out, src, "-L" + d, "-l:" + f, "-Wl,-rpath," + d, "-Wl,-rpath,$ORIGIN"])
+    return out
 
 
 if __name__ == "__main__":

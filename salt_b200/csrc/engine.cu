@@ -61,7 +61,7 @@ struct Slot {
     bool own_stream = true;
     DBuf codes, offs, rd4, rd_len;
     uint32_t n_reads = 0, W64 = 0, l_max = 0;
-    DBuf c_offs0, c_loci0, c_offs1, c_loci1, vpairs, acc, rec, lvlist, ciglist, counters, cig;
+    DBuf c_offs0, c_loci0, c_offs1, c_loci1, vpairs, acc, rec, lvlist, ciglist, counters, cig, fpairs, fslots;
     // asynchronous verify in flight: where the compact CIGAR list has to be scattered to
     bool pending = false;
     char *u_cigars = nullptr; int u_stride = 0;
@@ -75,7 +75,7 @@ struct Slot {
     void release()
     {
         DBuf *all[] = {&codes, &offs, &rd4, &rd_len, &c_offs0, &c_loci0, &c_offs1, &c_loci1, &vpairs, &acc, &rec,
-                       &lvlist, &ciglist, &counters, &cig};
+                       &lvlist, &ciglist, &counters, &cig, &fpairs, &fslots};
         for (DBuf *b : all) b->release();
         if (h_stage) cudaFreeHost(h_stage);
         h_stage = nullptr; h_stage_cap = 0;
@@ -93,9 +93,12 @@ constexpr uint32_t CIG_EAGER = 8192;       // CIGARs of a chunk copied back with
 struct salt_b200 {
     int device = 0;
     int sm_count = 148;
+    uint8_t *d_mixref_alloc = nullptr;      // allocation: REF_FRONT zero bytes, the words, REF_PAD zero bytes
     uint32_t *d_mixref = nullptr; uint32_t l = 0;
     uint8_t *d_pac = nullptr; int64_t l_pac = 0;
     Slot slot[SALT_SLOTS];
+    DBuf fpairs, fslots, fcount;            // LV filter survivors of the per-pair entry point
+    int lv_filter = 1;                      // pigeonhole filter in front of Landau-Vishkin (salt_b200_set_lv_filter)
     // staging / scratch of the synchronous per-pair and SSW entry points (slot 0's stream)
     DBuf pairs, out8, kbuf, cig, wins, sswout, sswcig, sswscratch;
     uint64_t launches = 0;
@@ -145,6 +148,17 @@ salt_b200_t *new_handle(int device)
 }
 
 const size_t REF_PAD = 1024;  // zero bytes after the reference so vector loads may run past the end
+const size_t REF_FRONT = 256; // zero bytes before it: the LV filter looks 32 bases to the left of a window
+
+// device allocation of the reference words with zeroed padding on both sides
+cudaError_t alloc_mixref(salt_b200_t *h, size_t nb, cudaStream_t st)
+{
+    cudaError_t e = cudaMalloc(&h->d_mixref_alloc, REF_FRONT + nb + REF_PAD);
+    if (e != cudaSuccess) return e;
+    h->d_mixref = reinterpret_cast<uint32_t *>(h->d_mixref_alloc + REF_FRONT);
+    if ((e = cudaMemsetAsync(h->d_mixref_alloc, 0, REF_FRONT, st)) != cudaSuccess) return e;
+    return cudaMemsetAsync(h->d_mixref_alloc + REF_FRONT + nb, 0, REF_PAD, st);
+}
 
 // Upload + pack one chunk of reads into a slot.  Asynchronous on the slot's stream.
 int load_reads(salt_b200_t *h, Slot &s, const salt_reads_t *reads)
@@ -196,6 +210,12 @@ int verify_on_device(salt_b200_t *h, int si, const uint32_t *d_offs0, const uint
     CU(s.vpairs.need((n + 1) * sizeof(salt_pair_t)));      // LV worklist: pairs ...
     CU(s.lvlist.need((n + 1) * 4));                         // ... and the acc slot each one reports to
     CU(s.counters.need(256));
+    LvFilterScratch fs{nullptr, nullptr, nullptr};
+    if (h->lv_filter) {
+        CU(s.fpairs.need((n + 1) * sizeof(salt_pair_t)));
+        CU(s.fslots.need((n + 1) * 4));
+        fs.pairs = s.fpairs.as<salt_pair_t>(); fs.slots = s.fslots.as<uint32_t>(); fs.count = s.counters.as<uint32_t>() + 8;
+    }
     int8_t *acc = d_acc0;
     if (!acc) { CU(s.acc.need(n + 1)); acc = s.acc.as<int8_t>(); }
     salt_pair_t *lvp = s.vpairs.as<salt_pair_t>();
@@ -212,12 +232,12 @@ int verify_on_device(salt_b200_t *h, int si, const uint32_t *d_offs0, const uint
     CU(launch_nogap_fused(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, nogap_T0, acc, d_rec, lvp, lvs, cnt, s.stream));
     SALT_EV(2);
     SALT_EV(3);
-    CU(launch_lv(c, lvp, n, lv_T0, lvs, cnt, n, acc, h->sm_count, s.stream, h->lv_mapping));
+    CU(launch_lv(c, lvp, n, lv_T0, lvs, cnt, n, acc, h->sm_count, s.stream, h->lv_mapping, h->lv_filter ? &fs : nullptr));
     SALT_EV(4);
     CU(launch_scan_gap(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, lv_T0, acc, d_rec,
                        d_cigars ? d_cig_reads : nullptr, d_cig_count, s.stream));
     SALT_EV(5);
-    h->launches += 3;
+    h->launches += h->lv_filter ? 4 : 3;
     if (d_cigars) {
         CU(launch_lv_cigar(c, nullptr, nullptr, 0, d_cig_reads, d_cig_count, s.n_reads, d_rec,
                            d_cigars, cigar_stride, nullptr, h->sm_count, s.stream));
@@ -345,8 +365,7 @@ salt_b200_t *salt_b200_init(const uint32_t *mixref, uint32_t l, const uint8_t *p
     cudaStream_t st = h->slot[0].stream;
     const size_t nb = ((size_t)l + 7) / 8 * 4;
     cudaError_t e;
-    if ((e = cudaMalloc(&h->d_mixref, nb + REF_PAD)) != cudaSuccess ||
-        (e = cudaMemsetAsync(reinterpret_cast<uint8_t *>(h->d_mixref) + nb, 0, REF_PAD, st)) != cudaSuccess ||
+    if ((e = alloc_mixref(h, nb, st)) != cudaSuccess ||
         (e = cudaMemcpyAsync(h->d_mixref, mixref, nb, cudaMemcpyHostToDevice, st)) != cudaSuccess) {
         fail(SALT_ERR_CUDA, "upload mixref", e); salt_b200_destroy(h); return nullptr;
     }
@@ -375,8 +394,7 @@ salt_b200_t *salt_b200_init_from_bases(const char *bases, uint32_t l, const uint
     char *d_bases = nullptr; uint32_t *d_pos = nullptr; uint8_t *d_mask = nullptr;
     cudaError_t e = cudaSuccess;
     do {
-        if ((e = cudaMalloc(&h->d_mixref, nb + REF_PAD)) != cudaSuccess) break;
-        if ((e = cudaMemsetAsync(reinterpret_cast<uint8_t *>(h->d_mixref) + nb, 0, REF_PAD, st)) != cudaSuccess) break;
+        if ((e = alloc_mixref(h, nb, st)) != cudaSuccess) break;
         if ((e = cudaMalloc(&d_bases, l)) != cudaSuccess) break;
         if ((e = cudaMemcpyAsync(d_bases, bases, l, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
         if (n_snp) {
@@ -415,10 +433,11 @@ void salt_b200_destroy(salt_b200_t *h)
         if (h->slot[i].stream) cudaStreamSynchronize(h->slot[i].stream);
         h->slot[i].release();
     }
-    DBuf *all[] = {&h->pairs, &h->out8, &h->kbuf, &h->cig, &h->wins, &h->sswout, &h->sswcig, &h->sswscratch};
+    DBuf *all[] = {&h->pairs, &h->out8, &h->kbuf, &h->cig, &h->wins, &h->sswout, &h->sswcig, &h->sswscratch,
+                   &h->fpairs, &h->fslots, &h->fcount};
     for (DBuf *b : all) b->release();
     for (int i = 0; i < 7; ++i) if (h->ev_ssw[i]) cudaEventDestroy(h->ev_ssw[i]);
-    if (h->d_mixref) cudaFree(h->d_mixref);
+    if (h->d_mixref_alloc) cudaFree(h->d_mixref_alloc);
     if (h->d_pac) cudaFree(h->d_pac);
     delete h;
 }
@@ -504,8 +523,16 @@ int salt_b200_lv_dev(salt_b200_t *h, const salt_pair_t *d_pairs, size_t n, int k
     if (int rc = use_device(h)) return rc;
     if (n && (!d_pairs || !d_out)) return fail(SALT_ERR_ARG, "null buffer");
     if (!h->slot[0].n_reads) return fail(SALT_ERR_ARG, "no reads set");
-    CU(launch_lv(h->ctx(), d_pairs, n, k, nullptr, nullptr, 0, d_out, h->sm_count, h->slot[0].stream, h->lv_mapping));
-    if (n) h->launches += 1;
+    LvFilterScratch fs{nullptr, nullptr, nullptr};
+    if (h->lv_filter && n) {
+        CU(h->fpairs.need((n + 1) * sizeof(salt_pair_t)));
+        CU(h->fslots.need((n + 1) * 4));
+        CU(h->fcount.need(256));
+        fs.pairs = h->fpairs.as<salt_pair_t>(); fs.slots = h->fslots.as<uint32_t>(); fs.count = h->fcount.as<uint32_t>();
+    }
+    CU(launch_lv(h->ctx(), d_pairs, n, k, nullptr, nullptr, 0, d_out, h->sm_count, h->slot[0].stream, h->lv_mapping,
+                 h->lv_filter ? &fs : nullptr));
+    if (n) h->launches += h->lv_filter ? 2 : 1;
     return SALT_OK;
 }
 
@@ -622,6 +649,13 @@ int salt_b200_set_lv_mapping(salt_b200_t *h, int mapping)
     if (!h) return fail(SALT_ERR_ARG, "null handle");
     if (mapping != 0 && mapping != 1) return fail(SALT_ERR_ARG, "mapping must be 0 (auto) or 1 (warp per pair)");
     h->lv_mapping = mapping;
+    return SALT_OK;
+}
+
+int salt_b200_set_lv_filter(salt_b200_t *h, int enable)
+{
+    if (!h) return fail(SALT_ERR_ARG, "null handle");
+    h->lv_filter = enable ? 1 : 0;
     return SALT_OK;
 }
 

@@ -11,9 +11,12 @@ namespace salt {
 cudaError_t launch_pack_reads(const uint8_t *codes, const uint32_t *offs, uint32_t n_reads, uint32_t W64,
                               uint64_t *rd4, uint16_t *rd_len, cudaStream_t st);
 cudaError_t launch_mismatch(const DevCtx &c, const salt_pair_t *pairs, size_t n, int max_err, int8_t *out, cudaStream_t st);
+struct LvFilterScratch {      // survivors of the pigeonhole filter: room for every input pair
+    salt_pair_t *pairs; uint32_t *slots; uint32_t *count;
+};
 cudaError_t launch_lv(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k,
                       const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
-                      int8_t *out, int sm_count, cudaStream_t st, int mapping = 0);
+                      int8_t *out, int sm_count, cudaStream_t st, int mapping = 0, const LvFilterScratch *f = nullptr);
 cudaError_t launch_lv_cigar(const DevCtx &c, const salt_pair_t *pairs, const uint8_t *k_each, size_t n,
                             const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
                             const salt_verify_out_t *rec, char *cigars, int stride, int8_t *out,

@@ -318,6 +318,140 @@ lv_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_f
 }
 
 // --------------------------------------------------------------------------------------
+// lv_filter: an exact pigeonhole pre-filter in front of Landau-Vishkin.  One thread per pair,
+// registers only, no divergence.
+//
+// computeEditDistance returns e <= k only if the pattern aligns to a prefix of the text with
+// e edits, every other column being a match under salt's AND test (LandauVishkin.c:42-53,
+// :85-95), on diagonals |d| <= e.  Cut the pattern into its nf = plen/8 full 8-base words.
+// An edit spoils at most one word, so at least nf - k words are edit-free, and an edit-free
+// word matches the text on ONE diagonal d, |d| <= k.  Hence
+//
+//      #{ w < nf : exists d in [-k,k], all 8 nibbles of P_w & T(8w+d ..) non-zero }  >=  nf - k
+//
+// is necessary for a result >= 0.  Text outside [0, textLen) is read from the real reference
+// instead of the zeros the reference sees; that can only add matches, so the filter stays
+// conservative (it never rejects a pair the reference accepts).  A random decoy passes with
+// probability ~1e-5 (needs two 8-mer hits at L=100, k=10); it would otherwise walk all k levels
+// of Landau-Vishkin, the worst case.  Survivors are compacted into a worklist for the LV kernels.
+//
+// Work per pair: the 2k+1 diagonals are swept by moving a register copy of the window one
+// nibble per step (16 funnel shifts) and testing the 12 words of a 96-base tile (AND, has-zero-
+// nibble, running minimum): ~64 integer ops per diagonal.  Reads longer than 96 bases take
+// several tiles.  Work items as in lv_kernel.
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lv_haszero(uint32_t x)      // non-zero iff some nibble of x is zero
+{
+    return (x - 0x11111111u) & ~x & 0x88888888u;
+}
+
+__global__ void __launch_bounds__(128)
+lv_filter_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_fixed,
+                 const uint32_t *__restrict__ slots, const uint32_t *__restrict__ wl_count,
+                 int8_t *__restrict__ out, salt_pair_t *__restrict__ pass_pairs, uint32_t *__restrict__ pass_slots,
+                 uint32_t *__restrict__ pass_count)
+{
+    constexpr int TW = 12;                              // pattern words per tile (96 bases)
+    const size_t count = slots ? (size_t)*wl_count : n;
+    const size_t step = (size_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    // mixref is preceded by zero padding (engine.cu), so a window may start 32 bases before pos = 0
+    const uint2 *__restrict__ mix = reinterpret_cast<const uint2 *>(c.mixref);
+    for (size_t base = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < count; base += step) {
+        const size_t it = base + lane;
+        const bool live = it < count;
+        salt_pair_t p; p.rs = 0; p.pos = 0;
+        if (live) p = pairs[it];
+        const uint32_t rid = p.rs >> 1;
+        const int plen = (live && rid < c.n_reads) ? (int)c.rd_len[rid] : 0;
+        const int tlen = plen + 4;                                  // alnse.c:373
+        const bool ok = plen > 0 && (uint64_t)p.pos + (uint64_t)tlen <= (uint64_t)c.l;   // editdistance.c:178
+        int k = k_fixed >= 0 ? k_fixed : plen / 10;                 // alnse.c:1090
+        k = imin(k, LV_MAXK - 1);                                   // LandauVishkin.c:31
+        const int nf = plen >> 3;
+        const int need = nf - k;
+        const int kw = __reduce_max_sync(0xffffffffu, ok ? k : 0);
+        const int nfw = __reduce_max_sync(0xffffffffu, (ok && need > 0) ? nf : 0);
+        int found = 0;
+        const uint32_t *__restrict__ prow = reinterpret_cast<const uint32_t *>(c.rd4 + (size_t)p.rs * c.W64);
+        for (int t0 = 0; t0 < nfw; t0 += TW) {                      // warp-uniform tile loop
+            // ---- window of the tile: TA[u] holds text nibbles 8u-32 .. 8u-25 relative to pos + 8*t0
+            const int64_t g0 = (int64_t)p.pos + 8 * t0 - 32;        // first nibble, may be negative (front padding)
+            const int a = (int)(g0 & 15);
+            const uint2 *__restrict__ src = mix + (g0 >> 4);
+            uint32_t raw[22];
+#pragma unroll
+            for (int i = 0; i < 11; ++i) {
+                const uint2 v = ok ? src[i] : make_uint2(0u, 0u);
+                raw[2 * i] = v.x; raw[2 * i + 1] = v.y;
+            }
+            uint32_t TA[20];
+            {
+                const int sh = (a & 7) * 4;
+                const bool hi = (a & 8) != 0;
+#pragma unroll
+                for (int u = 0; u < 20; ++u) {
+                    const uint32_t lo = hi ? raw[u + 1] : raw[u];
+                    const uint32_t up = hi ? raw[u + 2] : raw[u + 1];
+                    TA[u] = __funnelshift_r(lo, up, sh);
+                }
+            }
+            uint32_t P[TW], m[TW];
+#pragma unroll
+            for (int j = 0; j < TW; ++j) {
+                P[j] = (ok && t0 + j < nf) ? prow[t0 + j] : 0u;     // words past the last full one never match
+                m[j] = lv_haszero(P[j] & TA[j + 4]);                // diagonal 0
+            }
+            // ---- diagonals +1 .. +k: the window moves down one nibble per step
+            {
+                uint32_t W[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) W[j] = TA[j + 4];
+                for (int d = 1; d <= kw; ++d) {
+#pragma unroll
+                    for (int j = 0; j < 15; ++j) W[j] = __funnelshift_r(W[j], W[j + 1], 4);
+                    W[15] >>= 4;
+                    if (d <= k) {
+#pragma unroll
+                        for (int j = 0; j < TW; ++j) m[j] = min(m[j], lv_haszero(P[j] & W[j]));
+                    }
+                }
+            }
+            // ---- diagonals -1 .. -k: the window moves up one nibble per step
+            {
+                uint32_t W[16];                                     // W[j] <-> TA[j]: tile words sit at j = 4..15
+#pragma unroll
+                for (int j = 0; j < 16; ++j) W[j] = TA[j];
+                for (int d = 1; d <= kw; ++d) {
+#pragma unroll
+                    for (int j = 15; j > 0; --j) W[j] = __funnelshift_l(W[j - 1], W[j], 4);
+                    W[0] <<= 4;
+                    if (d <= k) {
+#pragma unroll
+                        for (int j = 0; j < TW; ++j) m[j] = min(m[j], lv_haszero(P[j] & W[j + 4]));
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < TW; ++j) found += (m[j] == 0u && t0 + j < nf) ? 1 : 0;
+        }
+        const bool pass = ok && (need <= 0 || found >= need);
+        // ---- survivors go to the LV worklist, everything else is decided here
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        uint32_t w0 = 0;
+        if (lane == 0 && bal) w0 = atomicAdd(pass_count, (uint32_t)__popc(bal));
+        w0 = __shfl_sync(0xffffffffu, w0, 0);
+        const size_t slot = slots ? slots[live ? it : 0] : it;
+        if (pass) {
+            const uint32_t at = w0 + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+            pass_pairs[at] = p; pass_slots[at] = (uint32_t)slot;
+        } else if (live) {
+            out[slot] = (int8_t)-1;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------
 // lv_cigar: one warp per pair, 64 diagonals (2 per lane), furthest-reaching and action
 // tables kept in shared memory for the backtrace, which lane 0 performs.
 // Work items: (pairs[i], k_each[i]) -> cigars + i*stride, or, when `worklist` is non-null,
@@ -618,7 +752,7 @@ __device__ __forceinline__ void nogap_read(const DevCtx &c, const uint2 *__restr
 }
 
 template <int G, int WPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, G == 8 ? 4 : 1)
 nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t *__restrict__ loci0,
                    const uint32_t *__restrict__ offs1, const uint32_t *__restrict__ loci1, size_t n0,
                    int T0, int8_t *__restrict__ acc, salt_verify_out_t *__restrict__ rec,
@@ -877,9 +1011,9 @@ static cudaError_t launch_lv_tpp(const DevCtx &c, const salt_pair_t *pairs, size
 }
 
 // mapping: 0 = choose (thread-per-pair up to k = 15, warp-per-pair beyond), 1 = force warp-per-pair
-cudaError_t launch_lv(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k,
-                      const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
-                      int8_t *out, int sm_count, cudaStream_t st, int mapping)
+static cudaError_t launch_lv_core(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k,
+                                  const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
+                                  int8_t *out, int sm_count, cudaStream_t st, int mapping)
 {
     int kmax = k >= 0 ? k : (int)c.l_max / 10;
     if (kmax > LV_MAXK - 1) kmax = LV_MAXK - 1;
@@ -893,6 +1027,32 @@ cudaError_t launch_lv(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k
     if (kmax <= 7) return launch_lv_t<16, 1>(c, pairs, n, k, worklist, wl_count, wl_cap, out, sm_count, st);
     if (kmax <= 15) return launch_lv_t<32, 1>(c, pairs, n, k, worklist, wl_count, wl_cap, out, sm_count, st);
     return launch_lv_t<32, 2>(c, pairs, n, k, worklist, wl_count, wl_cap, out, sm_count, st);
+}
+
+// Landau-Vishkin over a pair list.  With a filter scratch (room for the whole list) the pigeonhole
+// filter runs first and only its survivors reach the LV kernels; results are identical either way.
+cudaError_t launch_lv(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k,
+                      const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
+                      int8_t *out, int sm_count, cudaStream_t st, int mapping, const LvFilterScratch *f)
+{
+    const size_t items = worklist ? wl_cap : n;
+    if (!items) return cudaSuccess;
+    if (!f || !f->pairs || !f->slots || !f->count)
+        return launch_lv_core(c, pairs, n, k, worklist, wl_count, wl_cap, out, sm_count, st, mapping);
+    cudaError_t e = cudaMemsetAsync(f->count, 0, 4, st);
+    if (e != cudaSuccess) return e;
+    const int threads = 128;
+    size_t blocks = (items + threads - 1) / threads;
+    const size_t cap = (size_t)sm_count * 32;            // persistent upper bound: warps stride over the rest
+    if (blocks > cap) blocks = cap;
+    SALT_LAUNCH(lv_filter_kernel, (unsigned)blocks, threads, 0, st, c, pairs, n, k, worklist, wl_count, out,
+                f->pairs, f->slots, f->count);
+    SALT_LAUNCH_CHECK();
+    // Survivors are mostly true hits and their +-1..3 shifted twins, which stop after a few levels.
+    // Measured on B200 (profiles/): inside the verify stage (few survivors per launch) one thread per
+    // pair is faster, on flat decoy-heavy lists (many survivors) one warp per pair is.
+    return launch_lv_core(c, f->pairs, items, k, f->slots, f->count, items, out, sm_count, st,
+                          mapping == 0 ? (worklist ? 0 : 1) : mapping);
 }
 
 cudaError_t launch_lv_cigar(const DevCtx &c, const salt_pair_t *pairs, const uint8_t *k_each, size_t n,

@@ -1,0 +1,154 @@
+/* salt_host.c -- see include/salt_host.h.  Host-side C over the C ABI of libsalt_b200.so. */
+#include "../../include/salt_host.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+struct salt_chunk {
+    uint32_t max_reads; size_t max_bases, max_cands;
+    uint32_t n_reads;
+    /* pinned inputs */
+    uint8_t *codes; uint32_t *roffs;
+    uint32_t *offs[2]; uint32_t *loci[2];
+    /* pinned outputs */
+    salt_verify_out_t *rec; int8_t *acc[2]; char *cigars;
+    int lv_T0; int done;
+};
+
+static void *pinned(size_t bytes) { return salt_b200_host_alloc(bytes ? bytes : 1); }
+
+salt_chunk_t *salt_chunk_new(uint32_t max_reads, size_t max_bases, size_t max_cands)
+{
+    salt_chunk_t *c = (salt_chunk_t *)calloc(1, sizeof *c);
+    if (!c) return NULL;
+    c->max_reads = max_reads; c->max_bases = max_bases; c->max_cands = max_cands;
+    c->codes = (uint8_t *)pinned(max_bases + 16);
+    c->roffs = (uint32_t *)pinned(((size_t)max_reads + 1) * 4);
+    c->rec = (salt_verify_out_t *)pinned((size_t)max_reads * sizeof(salt_verify_out_t));
+    c->cigars = (char *)pinned((size_t)max_reads * 128);
+    for (int s = 0; s < 2; ++s) {
+        c->offs[s] = (uint32_t *)pinned(((size_t)max_reads + 1) * 4);
+        c->loci[s] = (uint32_t *)pinned(max_cands * 4 + 4);
+        c->acc[s] = (int8_t *)pinned(max_cands + 1);
+    }
+    if (!c->codes || !c->roffs || !c->rec || !c->cigars || !c->offs[0] || !c->offs[1] || !c->loci[0] ||
+        !c->loci[1] || !c->acc[0] || !c->acc[1]) { salt_chunk_free(c); return NULL; }
+    salt_chunk_reset(c);
+    return c;
+}
+
+void salt_chunk_free(salt_chunk_t *c)
+{
+    if (!c) return;
+    salt_b200_host_free(c->codes); salt_b200_host_free(c->roffs); salt_b200_host_free(c->rec);
+    salt_b200_host_free(c->cigars);
+    for (int s = 0; s < 2; ++s) { salt_b200_host_free(c->offs[s]); salt_b200_host_free(c->loci[s]); salt_b200_host_free(c->acc[s]); }
+    free(c);
+}
+
+void salt_chunk_reset(salt_chunk_t *c)
+{
+    c->n_reads = 0; c->done = 0;
+    c->roffs[0] = 0; c->offs[0][0] = 0; c->offs[1][0] = 0;
+}
+
+uint32_t salt_chunk_n_reads(const salt_chunk_t *c) { return c->n_reads; }
+
+int salt_chunk_add_read(salt_chunk_t *c, const uint8_t *seq, uint32_t l_seq,
+                        const uint32_t *loci0, uint32_t n0, const uint32_t *loci1, uint32_t n1)
+{
+    const uint32_t i = c->n_reads;
+    if (i >= c->max_reads) return SALT_ERR_NOMEM;
+    if ((size_t)c->roffs[i] + l_seq > c->max_bases) return SALT_ERR_NOMEM;
+    if ((size_t)c->offs[0][i] + n0 > c->max_cands || (size_t)c->offs[1][i] + n1 > c->max_cands) return SALT_ERR_NOMEM;
+    if (l_seq && !seq) return SALT_ERR_ARG;
+    memcpy(c->codes + c->roffs[i], seq, l_seq);
+    c->roffs[i + 1] = c->roffs[i] + l_seq;
+    if (n0) memcpy(c->loci[0] + c->offs[0][i], loci0, (size_t)n0 * 4);
+    if (n1) memcpy(c->loci[1] + c->offs[1][i], loci1, (size_t)n1 * 4);
+    c->offs[0][i + 1] = c->offs[0][i] + n0;
+    c->offs[1][i + 1] = c->offs[1][i] + n1;
+    c->n_reads = i + 1;
+    return (int)i;
+}
+
+int salt_chunk_submit(salt_b200_t *h, int slot, salt_chunk_t *c, int nogap_T0, int lv_T0)
+{
+    salt_reads_t r; salt_cands_t k;
+    r.codes = c->codes; r.offs = c->roffs; r.n_reads = c->n_reads;
+    k.offs[0] = c->offs[0]; k.offs[1] = c->offs[1]; k.loci[0] = c->loci[0]; k.loci[1] = c->loci[1];
+    c->lv_T0 = lv_T0; c->done = 0;
+    if (!c->n_reads) return SALT_OK;
+    /* query->cigar starts out empty (kstring, query.c:208-209): gapped primaries get theirs from the GPU */
+    for (uint32_t i = 0; i < c->n_reads; ++i) c->cigars[(size_t)i * 128] = '\0';
+    return salt_b200_verify_submit(h, slot, &r, &k, nogap_T0, lv_T0, c->rec, c->acc[0], c->acc[1], c->cigars, 128);
+}
+
+int salt_chunk_wait(salt_b200_t *h, int slot, salt_chunk_t *c)
+{
+    int rc = c->n_reads ? salt_b200_verify_wait(h, slot) : SALT_OK;
+    if (rc == SALT_OK) c->done = 1;
+    return rc;
+}
+
+int salt_chunk_hits(const salt_chunk_t *c, uint32_t i, int strand, salt_hit_t *out, int cap)
+{
+    if (!c->done || i >= c->n_reads || strand < 0 || strand > 1) return SALT_ERR_ARG;
+    const salt_verify_out_t *q = &c->rec[i];
+    const uint8_t gapped = q->lv_ran ? 1 : 0;        /* all hits of a read come from one stage (alnse.c:1089) */
+    int n = 0;
+    for (uint32_t j = c->offs[strand][i]; j < c->offs[strand][i + 1] && n < cap; ++j) {
+        if (c->acc[strand][j] < 0) continue;
+        out[n].pos = c->loci[strand][j]; out[n].n_diff = (uint8_t)c->acc[strand][j];
+        out[n].is_gap = gapped; out[n].strand = (uint16_t)strand;
+        ++n;
+    }
+    return n;
+}
+
+static uint32_t gen_mapq(uint32_t b0, uint32_t b1)            /* query.c:270-281 */
+{
+    if (b0 == 0) return 0;
+    uint32_t mapq = (uint32_t)(255.0 * ((double)abs((int)(b0 - b1)) / (double)b0));
+    return mapq < 254 ? mapq : 254;
+}
+
+int salt_chunk_result(const salt_chunk_t *c, uint32_t i, int max_hits, salt_read_result_t *out)
+{
+    if (!c->done || i >= c->n_reads || !out || max_hits < 0 || max_hits > SALT_MAX_HITS) return SALT_ERR_ARG;
+    const salt_verify_out_t *q = &c->rec[i];
+    memset(out, 0, sizeof *out);
+    out->pos = q->pos; out->strand = q->strand; out->n_diff = q->n_diff; out->is_gap = q->is_gap;
+    /* query_set_hits (query.c:297-333).  The reference compares a->n_diff -- element 0 of the strand's
+     * hit vector -- for every j (:317-318); kept.  tot_hits == max_hits is tested after every visited hit. */
+    const uint8_t gapped = q->lv_ran ? 1 : 0;
+    int tot = 0;
+    out->b0 = q->n_diff; out->b1 = 100000;
+    for (int s = 0; s < 2; ++s) {
+        int first_nd = -1;
+        for (uint32_t j = c->offs[s][i]; j < c->offs[s][i + 1]; ++j) {
+            const int nd = c->acc[s][j];
+            if (nd < 0) continue;                                 /* not in aux->hits */
+            if (first_nd < 0) first_nd = nd;
+            const uint32_t pos = c->loci[s][j];
+            if (pos != 0xFFFFFFFFu && pos != q->pos) {            /* last_pos stays (uint32_t)-1 in the reference */
+                if (first_nd <= (int)q->n_diff) {
+                    if (first_nd <= out->b1) out->b1 = first_nd;
+                    salt_hit_t *hh = &out->alt[s][out->n_alt[s]++];
+                    hh->pos = pos; hh->n_diff = (uint8_t)nd; hh->is_gap = gapped; hh->strand = (uint16_t)s;
+                    ++tot;
+                }
+                if (tot == max_hits) goto done;
+            }
+        }
+    }
+done:
+    out->mapq = gen_mapq((uint32_t)out->b0, (uint32_t)out->b1);
+    /* query_gen_cigar (query.c:282-295) */
+    if (q->pos != 0xFFFFFFFFu) {
+        if (q->is_gap) { strncpy(out->cigar, c->cigars + (size_t)i * 128, 127); out->cigar[127] = '\0'; }
+        else snprintf(out->cigar, sizeof out->cigar, "%dM", (int)(c->roffs[i + 1] - c->roffs[i]));
+    }
+    return SALT_OK;
+}

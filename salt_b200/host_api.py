@@ -1,0 +1,90 @@
+"""ctypes binding of libsalt_host.so (include/salt_host.h) -- the host-side C layer that re-stages
+salt's per-chunk loop around the batched engine.  Forwarding only; used by tests and examples."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import api
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB_PATH = os.path.join(HERE, "libsalt_host.so")
+SALT_MAX_HITS = 16
+
+
+class HitT(C.Structure):          # hit_t, query.h:28-33
+    _fields_ = [("pos", C.c_uint32), ("n_diff", C.c_uint8), ("is_gap", C.c_uint8), ("strand", C.c_uint16)]
+
+
+class ReadResultT(C.Structure):
+    _fields_ = [("pos", C.c_uint32), ("strand", C.c_uint8), ("n_diff", C.c_uint8), ("is_gap", C.c_uint8),
+                ("b0", C.c_int), ("b1", C.c_int), ("mapq", C.c_uint32), ("n_alt", C.c_int * 2),
+                ("alt", (HitT * SALT_MAX_HITS) * 2), ("cigar", C.c_char * 128)]
+
+
+def declare(L):
+    vp, i32, u32, sz = C.c_void_p, C.c_int, C.c_uint32, C.c_size_t
+    L.salt_chunk_new.restype = vp
+    L.salt_chunk_new.argtypes = [u32, sz, sz]
+    L.salt_chunk_free.argtypes = [vp]; L.salt_chunk_free.restype = None
+    L.salt_chunk_reset.argtypes = [vp]; L.salt_chunk_reset.restype = None
+    L.salt_chunk_n_reads.argtypes = [vp]; L.salt_chunk_n_reads.restype = u32
+    L.salt_chunk_add_read.argtypes = [vp, vp, u32, vp, u32, vp, u32]
+    L.salt_chunk_submit.argtypes = [vp, i32, vp, i32, i32]
+    L.salt_chunk_wait.argtypes = [vp, i32, vp]
+    L.salt_chunk_result.argtypes = [vp, u32, i32, C.POINTER(ReadResultT)]
+    L.salt_chunk_hits.argtypes = [vp, u32, i32, C.POINTER(HitT), i32]
+    return L
+
+
+def load(path=HOST_LIB_PATH):
+    if not os.path.exists(path):
+        raise api.SaltError(-105, "libsalt_host.so is not built (python -m salt_b200.build)")
+    return declare(C.CDLL(path))
+
+
+class Chunk:
+    """One pinned chunk queue (salt_chunk_t)."""
+
+    def __init__(self, hostlib, max_reads, max_bases, max_cands):
+        self.H = hostlib
+        self.c = hostlib.salt_chunk_new(int(max_reads), int(max_bases), int(max_cands))
+        if not self.c:
+            raise api.SaltError(-103, "salt_chunk_new failed")
+
+    def close(self):
+        if self.c:
+            self.H.salt_chunk_free(self.c); self.c = None
+
+    def reset(self):
+        self.H.salt_chunk_reset(self.c)
+
+    def add_read(self, seq, loci0, loci1):
+        seq = np.ascontiguousarray(seq, np.uint8)
+        l0 = np.ascontiguousarray(loci0, np.uint32); l1 = np.ascontiguousarray(loci1, np.uint32)
+        rc = self.H.salt_chunk_add_read(self.c, seq.ctypes.data, len(seq), l0.ctypes.data if len(l0) else None, len(l0),
+                                        l1.ctypes.data if len(l1) else None, len(l1))
+        if rc < 0:
+            raise api.SaltError(rc, "chunk queue full")
+        return rc
+
+    def submit(self, eng, slot, nogap_T0=3, lv_T0=-1):
+        eng._ck(self.H.salt_chunk_submit(eng.h, int(slot), self.c, int(nogap_T0), int(lv_T0)))
+
+    def wait(self, eng, slot):
+        eng._ck(self.H.salt_chunk_wait(eng.h, int(slot), self.c))
+
+    def result(self, i, max_hits=5):
+        r = ReadResultT()
+        rc = self.H.salt_chunk_result(self.c, int(i), int(max_hits), C.byref(r))
+        if rc != 0:
+            raise api.SaltError(rc, "salt_chunk_result")
+        alts = [[(h.pos, h.n_diff, h.is_gap, h.strand) for h in r.alt[s][:r.n_alt[s]]] for s in (0, 1)]
+        return (r.pos, r.strand, r.n_diff, r.is_gap, r.b0, r.b1, r.mapq), alts, r.cigar.decode()
+
+    def hits(self, i, strand, cap=4096):
+        buf = (HitT * cap)()
+        n = self.H.salt_chunk_hits(self.c, int(i), int(strand), buf, cap)
+        if n < 0:
+            raise api.SaltError(n, "salt_chunk_hits")
+        return [(h.pos, h.n_diff, h.is_gap, h.strand) for h in buf[:n]]

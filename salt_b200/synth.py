@@ -132,6 +132,36 @@ def sample_reads(g, n, L, seed=2, sub_rate=0.01, indel_frac=0.0, max_indel=3, n_
     return np.ascontiguousarray(reads), pos.astype(np.uint32), strand
 
 
+def edit_rich_reads(g, n, L, n_edits, seed=4):
+    """Forward-strand reads carrying about n_edits[i] scattered edits each (substitutions, 1-base
+    insertions and deletions at random places) -- the adversarial case for the Landau-Vishkin
+    pigeonhole filter, where every edit tries to spoil a different 8-base word.
+    Returns (reads[n,L], pos[n]) with strand 0."""
+    rng = np.random.default_rng(seed)
+    reads = np.zeros((n, L), np.uint8)
+    pos = rng.integers(40, g.l - 2 * L - 80, n).astype(np.uint32)
+    for i in range(n):
+        src = g.codes[int(pos[i]):int(pos[i]) + 2 * L].astype(np.uint8) & 3
+        out = []
+        j = 0
+        where = set(rng.choice(np.arange(2, L - 2), size=min(int(n_edits[i]), L - 4), replace=False).tolist())
+        while len(out) < L:
+            if len(out) in where:
+                where.discard(len(out))
+                kind = rng.integers(0, 3)
+                if kind == 0:
+                    out.append((int(src[j]) + int(rng.integers(1, 4))) & 3); j += 1      # substitution
+                elif kind == 1:
+                    out.append(int(rng.integers(0, 4)))                                  # insertion in the read
+                else:
+                    j += 1                                                               # deletion from the read
+                    out.append(int(src[j])); j += 1
+            else:
+                out.append(int(src[j])); j += 1
+        reads[i] = out[:L]
+    return reads, pos
+
+
 def make_candidates(g, true_pos, strand, L, per_strand=8, seed=3, shift_frac=0.25, lv_pad=4):
     """CSR candidate lists per strand: (offs0, loci0, offs1, loci1).
 

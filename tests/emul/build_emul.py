@@ -16,5 +16,16 @@ def build(force=False):
     return OUT
 
 
+HOST_OUT = os.path.join(HERE, "libsalt_host_emul.so")
+
+
+def build_host(force=False):
+    """the host-side C layer linked against the emulated engine (CPU tests of the host logic)"""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from salt_b200 import build as b
+    return b.build_host(force=force, engine=build(), out=HOST_OUT)
+
+
 if __name__ == "__main__":
     print(build(True))

@@ -177,6 +177,10 @@ static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh)
 {
     sh &= 31u; return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
 }
+static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh)
+{
+    sh &= 31u; return sh ? (hi << sh) | (lo >> (32 - sh)) : hi;
+}
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 using std::min;

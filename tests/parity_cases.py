@@ -48,6 +48,26 @@ def check_lv(eng, oracle, g, reads, pairs, k):
     return got
 
 
+def check_lv_filter(eng, oracle, g, L, k, n, seed):
+    """Reads with about k scattered edits at their true locus (and +-1..3 shifted loci): the
+    pigeonhole filter must never reject what the reference accepts, and filter on/off must agree."""
+    rng = np.random.default_rng(seed)
+    kk = k if k >= 0 else L // 10
+    n_edits = rng.integers(max(0, kk - 3), kk + 3, n)
+    reads, pos = synth.edit_rich_reads(g, n, L, n_edits, seed=seed + 1)
+    eng.set_reads(reads)
+    rid = np.arange(n, dtype=np.uint32)
+    shift = rng.integers(-3, 4, n)
+    pairs = np.concatenate([api.Engine.make_pairs(rid, np.zeros(n, np.uint32), pos),
+                            api.Engine.make_pairs(rid, np.zeros(n, np.uint32), (pos.astype(np.int64) + shift).astype(np.uint32))])
+    eng.set_lv_filter(1)
+    got = check_lv(eng, oracle, g, reads, pairs, k)
+    eng.set_lv_filter(0)
+    assert np.array_equal(eng.lv(pairs, k), got)
+    eng.set_lv_filter(1)
+    return int((got >= 0).sum()), int((got == kk).sum())
+
+
 def check_lv_cigar(eng, oracle, g, reads, pairs, k_each, stride):
     out, buf = eng.lv_cigar(pairs, k_each, stride, fill=0x7e)
     n_gapped = 0
@@ -101,6 +121,60 @@ def check_verify_batch(eng, reads, cands, chunk_reads, nogap_T0=3, lv_T0=-1, str
     for a, b, name in zip(got, want, ("rec", "acc0", "acc1", "cigars")):
         assert a.tobytes() == b.tobytes(), name
     return want[0]
+
+
+def check_host_chunks(eng, hostlib, oracle, g, reads, cands, chunk_reads, nogap_T0=3, lv_T0=-1, max_hits=5):
+    """The host-side C layer (include/salt_host.h): chunk queues through the pipeline slots, then
+    query_set_hits / gen_mapq / query_gen_cigar per read -- against the oracle's verify_read."""
+    from salt_b200 import host_api
+    offs0, loci0, offs1, loci1 = cands
+    n, L = reads.shape
+    n_slots = 4
+    chunks = [host_api.Chunk(hostlib, chunk_reads, chunk_reads * L, chunk_reads * 64 + 4096) for _ in range(n_slots)]
+    owner = [None] * n_slots
+    n_gapped = 0
+
+    def drain(si):
+        nonlocal n_gapped
+        if owner[si] is None:
+            return
+        b = owner[si]; ch = chunks[si]
+        ch.wait(eng, si)
+        for i in range(ch.H.salt_chunk_n_reads(ch.c)):
+            r = b + i
+            seq = np.ascontiguousarray(reads[r]); rseq = np.ascontiguousarray(synth.revcomp(reads[r]))
+            l0 = loci0[offs0[r]:offs0[r + 1]]; l1 = loci1[offs1[r]:offs1[r + 1]]
+            prim, hits, alts = oracle.verify_read(g.mixref, g.l, seq, rseq, l0, l1, nogap_T0,
+                                                  (L // 10 if lv_T0 < 0 else lv_T0), max_hits)
+            gp, galts, gcig = ch.result(i, max_hits)
+            assert gp == prim, (r, gp, prim)
+            assert galts == alts, (r, galts, alts)
+            for s in (0, 1):
+                assert ch.hits(i, s) == hits[s], (r, s)
+            if prim[0] == 0xFFFFFFFF:
+                assert gcig == ""
+            elif prim[3] == 0:
+                assert gcig == "%dM" % L
+            else:
+                want = oracle.ed_diff_withcigar(g.mixref, prim[0], rseq if prim[1] else seq, prim[2], 128)
+                assert gcig == want[1], (r, gcig, want)
+                n_gapped += 1
+        owner[si] = None
+
+    k = 0
+    for b in range(0, n, chunk_reads):
+        si = k % n_slots; k += 1
+        drain(si)
+        ch = chunks[si]; ch.reset()
+        for r in range(b, min(n, b + chunk_reads)):
+            ch.add_read(reads[r], loci0[offs0[r]:offs0[r + 1]], loci1[offs1[r]:offs1[r + 1]])
+        ch.submit(eng, si, nogap_T0, lv_T0)
+        owner[si] = b
+    for si in range(n_slots):
+        drain(si)
+    for ch in chunks:
+        ch.close()
+    return n_gapped
 
 
 def make_windows(g, reads, pos, strand, L, rng, width=401):

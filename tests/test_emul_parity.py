@@ -52,6 +52,14 @@ def test_lv(emul_lib, oracle, L, k):
     assert (got > 0).sum() >= 3
 
 
+@pytest.mark.parametrize("L,k", [(100, -1), (100, 3), (64, 6), (150, -1), (250, -1), (40, 4)])
+def test_lv_filter_adversarial(emul_lib, oracle, L, k):
+    g = synth.Genome(30000, snp_rate=0.02, seed=7)
+    eng = _engine(emul_lib, g)
+    found, at_k = pc.check_lv_filter(eng, oracle, g, L, k, 40 if L <= 150 else 16, seed=900 + L + k)
+    assert found >= 8
+
+
 @pytest.mark.parametrize("L", [100, 250])
 def test_lv_cigar(emul_lib, oracle, L):
     g, reads, pos, strand, cands = pc.make_world(300 + L, L=L, n_reads=24, per_strand=3, indel_frac=0.8, sub_rate=0.02)
@@ -107,6 +115,17 @@ def test_verify_batch_pipeline(emul_lib, oracle):
     rec = pc.check_verify_batch(eng, reads, cands, 7)
     assert (rec["is_gap"] == 1).sum() >= 3
     pc.check_verify_batch(eng, reads, cands, 1000)
+
+
+def test_host_layer_chunks(emul_lib, oracle):
+    """include/salt_host.h over the (emulated) engine: pinned chunk queues, slots, query_set_hits/mapq/cigar"""
+    import build_emul
+    from salt_b200 import host_api
+    hostlib = host_api.load(build_emul.build_host())
+    g, reads, pos, strand, cands = pc.make_world(222, L=100, n_reads=50, per_strand=5, indel_frac=0.4, glen=30000)
+    eng = _engine(emul_lib, g)
+    assert pc.check_host_chunks(eng, hostlib, oracle, g, reads, cands, 9) >= 3
+    assert pc.check_host_chunks(eng, hostlib, oracle, g, reads, cands, 9, 3, 3, max_hits=2) >= 1
 
 
 def test_verify_empty_lists(emul_lib, oracle):

@@ -46,6 +46,15 @@ def test_lv(oracle, L, k):
     assert (got > 0).sum() >= 10
 
 
+@pytest.mark.parametrize("L,k", [(100, -1), (100, 3), (100, 8), (64, 6), (150, -1), (250, -1), (40, 4), (100, 30), (300, 25)])
+def test_lv_filter_adversarial(oracle, L, k):
+    """about k scattered edits per read: the pigeonhole filter may not reject what the reference accepts"""
+    g = synth.Genome(300000, snp_rate=0.02, seed=7)
+    eng = _engine(g)
+    found, at_k = pc.check_lv_filter(eng, oracle, g, L, k, 1500, seed=900 + L + k)
+    assert found >= 300
+
+
 @pytest.mark.parametrize("L", [100, 150, 250])
 def test_lv_cigar(oracle, L):
     g, reads, pos, strand, cands = pc.make_world(300 + L, glen=300000, L=L, n_reads=400, per_strand=3, indel_frac=0.8, sub_rate=0.02)
@@ -97,6 +106,18 @@ def test_verify_batch_pipeline(oracle):
     assert (rec["is_gap"] == 1).sum() >= 100
     pc.check_verify_batch(eng, reads, cands, 1024)
     pc.check_verify_batch(eng, reads, cands, 100000)
+
+
+def test_host_layer_chunks(oracle):
+    """include/salt_host.h over the CUDA engine: pinned chunk queues through the slots, then
+    query_set_hits / gen_mapq / query_gen_cigar per read, against the oracle"""
+    from salt_b200 import host_api
+    hostlib = host_api.load()
+    g, reads, pos, strand, cands = pc.make_world(654, glen=300000, L=100, n_reads=2000, per_strand=6, indel_frac=0.3, sub_rate=0.02)
+    eng = _engine(g)
+    assert pc.check_host_chunks(eng, hostlib, oracle, g, reads, cands, 300) >= 50
+    assert pc.check_host_chunks(eng, hostlib, oracle, g, reads[:600], tuple(
+        c[:601] if i % 2 == 0 else c for i, c in enumerate(cands)), 128, 3, 3, max_hits=3) >= 5
 
 
 def test_verify_ragged_and_empty(oracle):
