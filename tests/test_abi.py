@@ -26,6 +26,19 @@ def test_exports_match_header(lib):
     assert lib.salt_b200_abi_version() == 1
 
 
+def test_host_layer_exports():
+    """include/salt_host.h and the level-0 shim: every declared symbol is exported"""
+    hdr = open(os.path.join(ROOT, "include", "salt_host.h")).read()
+    names = sorted(set(re.findall(r"\b(salt_chunk_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 9
+    H = C.CDLL(os.path.join(os.path.dirname(api.LIB_PATH), "libsalt_host.so"))
+    for n in names:
+        assert hasattr(H, n), n
+    S = C.CDLL(os.path.join(os.path.dirname(api.LIB_PATH), "libsalt_level0.so"))
+    for n in ("ed_mismatch", "ed_diff", "ed_diff_withcigar", "salt_level0_attach"):      # editdistance.h:20-22
+        assert hasattr(S, n), n
+
+
 def test_struct_sizes():
     assert api.PAIR_DT.itemsize == 8 and api.WIN_DT.itemsize == 12
     assert api.SSW_DT.itemsize == 28 and api.VERIFY_DT.itemsize == 16

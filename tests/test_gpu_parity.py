@@ -120,6 +120,32 @@ def test_host_layer_chunks(oracle):
         c[:601] if i % 2 == 0 else c for i, c in enumerate(cands)), 128, 3, 3, max_hits=3) >= 5
 
 
+def test_level0_symbol_shim(oracle):
+    """the reference's own per-pair symbols (editdistance.h:20-22) served by the engine, batch of one"""
+    import ctypes as C
+    import os
+    g, reads, pos, strand, cands = pc.make_world(88, glen=100000, L=100, n_reads=40, per_strand=3, indel_frac=0.5)
+    eng = _engine(g)
+    S = C.CDLL(os.path.join(os.path.dirname(api.LIB_PATH), "libsalt_level0.so"))
+    S.salt_level0_attach.argtypes = [C.c_void_p, C.c_uint32]
+    S.salt_level0_attach(eng.h, g.l)
+    vp = C.c_void_p
+    S.ed_mismatch.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_int]
+    S.ed_diff.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.c_int]
+    S.ed_diff_withcigar.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int]
+    n_gap = 0
+    for r in range(len(reads)):
+        seq = np.ascontiguousarray(synth.revcomp(reads[r]) if strand[r] else reads[r]); p = int(pos[r])
+        assert S.ed_mismatch(None, p, seq.ctypes.data, 100, 3) == oracle.ed_mismatch(g.mixref, p, seq, 3)
+        assert S.ed_diff(None, g.l, p, 104, seq.ctypes.data, 100, 10) == oracle.ed_diff(g.mixref, g.l, p, seq, 10)
+        buf = C.create_string_buffer(128)
+        e = S.ed_diff_withcigar(None, p, 104, seq.ctypes.data, 100, 10, buf, 128, 1, 0)
+        want = oracle.ed_diff_withcigar(g.mixref, p, seq, 10, 128)
+        assert (e, buf.value.decode()) == want
+        n_gap += "I" in want[1] or "D" in want[1]
+    assert n_gap >= 5
+
+
 def test_verify_ragged_and_empty(oracle):
     """ragged read lengths in one chunk, reads without candidates, an empty chunk of lists"""
     rng = np.random.default_rng(5)
