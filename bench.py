@@ -128,8 +128,27 @@ def cpu_reference_run(args, wl, n_sample, steps, warmup):
                        "running thresholds, %d host threads, gcc -O2" % (n, len(wl["reads"]), pairs, cores))
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Everything libraries print to fd 1 (NCCL's version banner, for one) goes to stderr; the one JSON
+    line is written to the real stdout by _emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
     args = parse()
+    _claim_stdout()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = {"workload": "configs[1]: synthetic %d Mbp genome + %.1f%% SNPs, %d x %d bp SE reads per GPU, %d candidates/read/strand "
@@ -144,7 +163,7 @@ def main():
         wl = make_workload(args, seed=11)
         r = cpu_reference_run(args, wl, args.cpu_sample, args.steps, args.warmup)
         val = r["n"] / r["sec"]
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        _emit(({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec"] * 1e3,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                           "config": cfg,
@@ -312,7 +331,7 @@ def main():
         except Exception as ex:   # the checker is optional for the bench line
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
     if rank == 0:
-        print(json.dumps(out))
+        _emit(out)
     if world > 1:
         dist.destroy_process_group()
 

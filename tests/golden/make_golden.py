@@ -121,7 +121,7 @@ def main():
         words, tot, rc = orc.RefIdx().build_mixref(fa, sn, outp)
     d["idx_fasta"] = np.frombuffer("".join(">%s\n%s\n" % r for r in recs).encode(), np.uint8)
     d["idx_snps"] = np.frombuffer("".join("%s\t%d\t%s\t%s\n" % r for r in rows).encode(), np.uint8)
-    if tot % 8:          # nibbles past l in the last word are uninitialised heap in the reference (mixRef.c:117)
+    if tot % 8:          # nibbles past l in the last word are uninitialised heap in the reference (realloc, mixRef.c:135)
         words = words.copy(); words[-1] &= np.uint32((1 << (4 * (tot % 8))) - 1)
     d["idx_words"] = words; d["idx_l"] = np.uint32(tot)
     np.savez_compressed(OUT, **d)

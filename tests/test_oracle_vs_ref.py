@@ -186,7 +186,7 @@ def test_build_mixref(oracle):
                 f.write("%s\t%d\t%s\t%s\n" % r)
         words_ref, l_ref, rc = refidx.build_mixref(fa, sn, out)
     words, l = oracle.build_mixref(recs, rows)
-    # the reference malloc()s its word array (Index_src/mixRef.c:117): nibbles past l in the last word are
+    # the reference realloc()s its word array (Index_src/mixRef.c:135): nibbles past l in the last word are
     # whatever the heap held, so only the l valid nibbles are comparable
     if l % 8:
         words_ref = words_ref.copy(); words_ref[-1] &= np.uint32((1 << (4 * (l % 8))) - 1)
