@@ -61,7 +61,7 @@ struct Slot {
     bool own_stream = true;
     DBuf codes, offs, rd4, rd_len;
     uint32_t n_reads = 0, W64 = 0, l_max = 0;
-    DBuf c_offs0, c_loci0, c_offs1, c_loci1, vpairs, acc, rec, lvlist, ciglist, counters, cig, fpairs, fslots;
+    DBuf c_offs0, c_loci0, c_offs1, c_loci1, vpairs, acc, rec, lvlist, ciglist, counters, cig, fpairs, fslots, lvreads;
     // asynchronous verify in flight: where the compact CIGAR list has to be scattered to
     bool pending = false;
     char *u_cigars = nullptr; int u_stride = 0;
@@ -75,7 +75,7 @@ struct Slot {
     void release()
     {
         DBuf *all[] = {&codes, &offs, &rd4, &rd_len, &c_offs0, &c_loci0, &c_offs1, &c_loci1, &vpairs, &acc, &rec,
-                       &lvlist, &ciglist, &counters, &cig, &fpairs, &fslots};
+                       &lvlist, &ciglist, &counters, &cig, &fpairs, &fslots, &lvreads};
         for (DBuf *b : all) b->release();
         if (h_stage) cudaFreeHost(h_stage);
         h_stage = nullptr; h_stage_cap = 0;
@@ -210,6 +210,7 @@ int verify_on_device(salt_b200_t *h, int si, const uint32_t *d_offs0, const uint
     CU(s.vpairs.need((n + 1) * sizeof(salt_pair_t)));      // LV worklist: pairs ...
     CU(s.lvlist.need((n + 1) * 4));                         // ... and the acc slot each one reports to
     CU(s.counters.need(256));
+    CU(s.lvreads.need(((size_t)s.n_reads + 1) * 4));        // reads that reach the gapped stage
     LvFilterScratch fs{nullptr, nullptr, nullptr};
     if (h->lv_filter) {
         CU(s.fpairs.need((n + 1) * sizeof(salt_pair_t)));
@@ -229,13 +230,14 @@ int verify_on_device(salt_b200_t *h, int si, const uint32_t *d_offs0, const uint
     if (d_cig_count) CU(cudaMemsetAsync(d_cig_count, 0, 4, s.stream));
     SALT_EV(0);
     SALT_EV(1);
-    CU(launch_nogap_fused(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, nogap_T0, acc, d_rec, lvp, lvs, cnt, s.stream));
+    CU(launch_nogap_fused(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, nogap_T0, acc, d_rec, lvp, lvs, cnt,
+                          s.lvreads.as<uint32_t>(), s.stream));
     SALT_EV(2);
     SALT_EV(3);
     CU(launch_lv(c, lvp, n, lv_T0, lvs, cnt, n, acc, h->sm_count, s.stream, h->lv_mapping, h->lv_filter ? &fs : nullptr));
     SALT_EV(4);
-    CU(launch_scan_gap(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, lv_T0, acc, d_rec,
-                       d_cigars ? d_cig_reads : nullptr, d_cig_count, s.stream));
+    CU(launch_scan_gap(c, d_offs0, d_loci0, d_offs1, d_loci1, n0, lv_T0, acc, d_rec, s.lvreads.as<uint32_t>(), cnt + 1,
+                       d_cigars ? d_cig_reads : nullptr, d_cig_count, h->sm_count, s.stream));
     SALT_EV(5);
     h->launches += h->lv_filter ? 4 : 3;
     if (d_cigars) {

@@ -30,10 +30,11 @@ cudaError_t launch_scan_nogap(const DevCtx &c, const uint32_t *offs0, const uint
 cudaError_t launch_nogap_fused(const DevCtx &c, const uint32_t *offs0, const uint32_t *loci0,
                                const uint32_t *offs1, const uint32_t *loci1, size_t n0, int T0,
                                int8_t *acc, salt_verify_out_t *rec, salt_pair_t *lv_pairs, uint32_t *lv_slots,
-                               uint32_t *lv_count, cudaStream_t st);
+                               uint32_t *lv_count /* [0] pairs, [1] reads */, uint32_t *lv_reads, cudaStream_t st);
 cudaError_t launch_scan_gap(const DevCtx &c, const uint32_t *offs0, const uint32_t *loci0,
                             const uint32_t *offs1, const uint32_t *loci1, size_t n0, int lv_T0,
-                            int8_t *acc, salt_verify_out_t *rec, uint32_t *cig_list, uint32_t *cig_count, cudaStream_t st);
+                            int8_t *acc, salt_verify_out_t *rec, const uint32_t *lv_reads, const uint32_t *lv_read_count,
+                            uint32_t *cig_list, uint32_t *cig_count, int sm_count, cudaStream_t st);
 
 // mixref.cu
 cudaError_t launch_build_mixref(const char *bases, uint32_t l, const uint32_t *snp_pos, const uint8_t *snp_mask,

@@ -756,7 +756,8 @@ __global__ void __launch_bounds__(256, G == 8 ? 4 : 1)
 nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t *__restrict__ loci0,
                    const uint32_t *__restrict__ offs1, const uint32_t *__restrict__ loci1, size_t n0,
                    int T0, int8_t *__restrict__ acc, salt_verify_out_t *__restrict__ rec,
-                   salt_pair_t *__restrict__ lv_pairs, uint32_t *__restrict__ lv_slots, uint32_t *__restrict__ lv_count)
+                   salt_pair_t *__restrict__ lv_pairs, uint32_t *__restrict__ lv_slots, uint32_t *__restrict__ lv_count,
+                   uint32_t *__restrict__ lv_reads)
 {
     constexpr unsigned FULL = 0xffffffffu;
     const size_t rr = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -799,7 +800,10 @@ nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t 
     const bool need_lv = live && !st.any;                // alnse.c:1022 / :1089: gapped stage for this read
     const uint32_t c0 = le0 - lb0, c1 = le1 - lb1;
     uint32_t w = 0;
-    if (need_lv && lane == 0 && c0 + c1) w = atomicAdd(lv_count, c0 + c1);
+    if (need_lv && lane == 0) {
+        if (c0 + c1) w = atomicAdd(lv_count, c0 + c1);
+        lv_reads[atomicAdd(lv_count + 1, 1u)] = r;       // the reads scan_gap has to visit
+    }
     w = __shfl_sync(FULL, w, 0, G);
     if (need_lv) {
         for (uint32_t i = lane; i < c0; i += G) {
@@ -911,20 +915,23 @@ __global__ void __launch_bounds__(128)
 scan_gap_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t *__restrict__ loci0,
                 const uint32_t *__restrict__ offs1, const uint32_t *__restrict__ loci1, size_t n0,
                 int lv_T0, int8_t *__restrict__ acc, salt_verify_out_t *__restrict__ rec,
+                const uint32_t *__restrict__ lv_reads, const uint32_t *__restrict__ lv_read_count,
                 uint32_t *__restrict__ cig_list, uint32_t *__restrict__ cig_count)
 {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= c.n_reads) return;
-    salt_verify_out_t q = rec[r];
-    if (!q.lv_ran) return;
-    const int L = c.rd_len[r];
-    int max_diff = lv_T0 >= 0 ? lv_T0 : L / 10;
-    const uint32_t guard = (uint32_t)L + 4u;
-    const int d0 = scan_stage(loci0, offs0[r], offs0[r + 1], acc, c.l, guard, max_diff, 0, 1, q);
-    if (d0 != -1 && d0 < max_diff) max_diff = d0;
-    (void)scan_stage(loci1, offs1[r], offs1[r + 1], acc + n0, c.l, guard, max_diff, 1, 1, q);
-    rec[r] = q;
-    if (q.is_gap == 1 && cig_list) cig_list[atomicAdd(cig_count, 1u)] = r;
+    // one thread per read that reached the gapped stage (the list nogap_fused wrote)
+    const uint32_t count = *lv_read_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint32_t r = lv_reads[i];
+        salt_verify_out_t q = rec[r];
+        const int L = c.rd_len[r];
+        int max_diff = lv_T0 >= 0 ? lv_T0 : L / 10;
+        const uint32_t guard = (uint32_t)L + 4u;
+        const int d0 = scan_stage(loci0, offs0[r], offs0[r + 1], acc, c.l, guard, max_diff, 0, 1, q);
+        if (d0 != -1 && d0 < max_diff) max_diff = d0;
+        (void)scan_stage(loci1, offs1[r], offs1[r + 1], acc + n0, c.l, guard, max_diff, 1, 1, q);
+        rec[r] = q;
+        if (q.is_gap == 1 && cig_list) cig_list[atomicAdd(cig_count, 1u)] = r;
+    }
 }
 
 // --------------------------------------------------------------------------------------
@@ -1102,12 +1109,12 @@ template <int G, int WPL>
 static cudaError_t launch_nogap_t(const DevCtx &c, const uint32_t *offs0, const uint32_t *loci0,
                                   const uint32_t *offs1, const uint32_t *loci1, size_t n0, int T0,
                                   int8_t *acc, salt_verify_out_t *rec, salt_pair_t *lv_pairs, uint32_t *lv_slots,
-                                  uint32_t *lv_count, cudaStream_t st)
+                                  uint32_t *lv_count, uint32_t *lv_reads, cudaStream_t st)
 {
     auto kern = nogap_fused_kernel<G, WPL>;
     const size_t threads = (size_t)c.n_reads * G;
     SALT_LAUNCH(kern, (unsigned)((threads + 255) / 256), 256, 0, st, c, offs0, loci0, offs1, loci1, n0, T0, acc, rec,
-                lv_pairs, lv_slots, lv_count);
+                lv_pairs, lv_slots, lv_count, lv_reads);
     SALT_LAUNCH_CHECK();
     return cudaSuccess;
 }
@@ -1115,25 +1122,30 @@ static cudaError_t launch_nogap_t(const DevCtx &c, const uint32_t *offs0, const 
 cudaError_t launch_nogap_fused(const DevCtx &c, const uint32_t *offs0, const uint32_t *loci0,
                                const uint32_t *offs1, const uint32_t *loci1, size_t n0, int T0,
                                int8_t *acc, salt_verify_out_t *rec, salt_pair_t *lv_pairs, uint32_t *lv_slots,
-                               uint32_t *lv_count, cudaStream_t st)
+                               uint32_t *lv_count, uint32_t *lv_reads, cudaStream_t st)
 {
     if (!c.n_reads) return cudaSuccess;
     // G lanes x WPL 64-bit words per lane cover 16*G*WPL bases; one spare word so the last lane
     // never needs a neighbour: l_max + 16 <= 16*G*WPL
     const int lm = (int)c.l_max;
-    if (lm <= 112) return launch_nogap_t<8, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
-    if (lm <= 240) return launch_nogap_t<16, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
-    if (lm <= 496) return launch_nogap_t<32, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
-    if (lm <= 1008) return launch_nogap_t<32, 2>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
-    return launch_nogap_t<32, 3>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, st);
+    if (lm <= 112) return launch_nogap_t<8, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, lv_reads, st);
+    if (lm <= 240) return launch_nogap_t<16, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, lv_reads, st);
+    if (lm <= 496) return launch_nogap_t<32, 1>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, lv_reads, st);
+    if (lm <= 1008) return launch_nogap_t<32, 2>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, lv_reads, st);
+    return launch_nogap_t<32, 3>(c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_pairs, lv_slots, lv_count, lv_reads, st);
 }
 
 cudaError_t launch_scan_gap(const DevCtx &c, const uint32_t *offs0, const uint32_t *loci0,
                             const uint32_t *offs1, const uint32_t *loci1, size_t n0, int lv_T0,
-                            int8_t *acc, salt_verify_out_t *rec, uint32_t *cig_list, uint32_t *cig_count, cudaStream_t st)
+                            int8_t *acc, salt_verify_out_t *rec, const uint32_t *lv_reads, const uint32_t *lv_read_count,
+                            uint32_t *cig_list, uint32_t *cig_count, int sm_count, cudaStream_t st)
 {
     if (!c.n_reads) return cudaSuccess;
-    SALT_LAUNCH(scan_gap_kernel, (c.n_reads + 127) / 128, 128, 0, st, c, offs0, loci0, offs1, loci1, n0, lv_T0, acc, rec, cig_list, cig_count);
+    size_t blocks = ((size_t)c.n_reads + 127) / 128;
+    const size_t cap = (size_t)sm_count * 8;             // the list is usually a few percent of the reads
+    if (blocks > cap) blocks = cap;
+    SALT_LAUNCH(scan_gap_kernel, (unsigned)blocks, 128, 0, st, c, offs0, loci0, offs1, loci1, n0, lv_T0, acc, rec,
+                lv_reads, lv_read_count, cig_list, cig_count);
     SALT_LAUNCH_CHECK();
     return cudaSuccess;
 }
