@@ -319,6 +319,8 @@ def main():
                            "algorithmic_bytes_per_pair": bytes_per_pair, "kernel_ms": mm_ms, "dominant_kernel_of_step": dom}
 
     # ---------------- kernel-level extras: LV and SW sweeps (N=1 only)
+    # the e2e leg left slot 0 holding its last chunk: the sweeps index the whole batch again
+    ck(lib.salt_b200_set_reads(h, C.byref(reads_t)))
     if world == 1 and not args.skip_extras:
         out["lv"] = bench_lv(eng, lib, h, wl, args, dev, stream)
         out["sw"] = bench_sw(eng, lib, h, wl, args, dev, stream)

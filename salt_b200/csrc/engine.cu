@@ -632,7 +632,7 @@ int salt_b200_ssw_dev(salt_b200_t *h, const salt_win_t *d_wins, size_t n, int us
     if (int rc = fill_ssw_params(prm, use_pac, mat, n_sym, gapO, gapE, flag, filters, filterd, mask_len)) return rc;
     int maxpos = 0;
     for (int i = 0; i < n_sym * n_sym; ++i) if (mat[i] > maxpos) maxpos = mat[i];
-    if ((int64_t)maxpos * (int64_t)h->slot[0].l_max >= 32000) return fail(SALT_ERR_UNSUPPORTED, "scores would overflow int16");
+    if ((int64_t)maxpos * (int64_t)h->slot[0].l_max >= 24000) return fail(SALT_ERR_UNSUPPORTED, "scores would overflow int16");
     if (!n) return SALT_OK;
     const int max_cols = h->max_window;
     size_t lay[8];

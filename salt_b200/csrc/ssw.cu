@@ -129,13 +129,25 @@ sw_prep_kernel(SwDev d)
 // --------------------------------------------------------------------------------------
 __device__ __forceinline__ int half_of(uint32_t x, int h) { return h ? s16hi(x) : s16lo(x); }
 
+// keep a loop-invariant value in its register: without this ptxas re-derives it from the kernel
+// parameters inside the column loop to save a register, which costs more issue slots than it saves
+#if defined(__CUDA_ARCH__)
+#define SALT_PIN32(x) asm volatile("" : "+r"(x))
+#define SALT_PIN64(x) asm volatile("" : "+l"(x))
+#else
+#define SALT_PIN32(x) (void)(x)
+#define SALT_PIN64(x) (void)(x)
+#endif
+
 template <int G, int S, bool REV>
 __global__ void __launch_bounds__(128)
 sw_dp_kernel(SwDev d)
 {
     constexpr int NQ = (S + 3) / 4;
+    constexpr int SP = (S + 3) / 4 * 4;                  // snapshot row stride: whole uint4s
+    constexpr unsigned FULL = 0xffffffffu;
     __shared__ uint2 s_tab[17];
-    SALT_DYN_SMEM(uint32_t, s_snap);                     // [thread][2][S]
+    SALT_DYN_SMEM(uint32_t, s_snap);                     // [thread][2][SP]
     if (threadIdx.x < 17) {
         const uint32_t *tb = reinterpret_cast<const uint32_t *>(d.prm.table);
         s_tab[threadIdx.x] = make_uint2(tb[2 * threadIdx.x], tb[2 * threadIdx.x + 1]);
@@ -143,11 +155,11 @@ sw_dp_kernel(SwDev d)
     __syncthreads();
     constexpr int GPC = 128 / G;
     const int gl = threadIdx.x / G, j = threadIdx.x % G;
-    const size_t pair = (size_t)blockIdx.x * GPC + gl;
-    if (pair >= d.n_pairs) return;
+    const size_t pair_raw = (size_t)blockIdx.x * GPC + gl;
+    const bool live = pair_raw < d.n_pairs;              // dead groups run along on empty tasks (warp-uniform flow)
+    const size_t pair = live ? pair_raw : 0;
     const int gshift = (threadIdx.x & 31) / G * G;
-    const unsigned gmask = (unsigned)(((1ull << G) - 1ull) << gshift);
-    uint32_t *snap = s_snap + (size_t)threadIdx.x * 2 * S;
+    uint32_t *snap = s_snap + (size_t)threadIdx.x * 2 * SP;
 
     int rows[2], cols[2], off[2], aux_read_end[2], aux_ref_end[2];
     uint32_t term = 0;
@@ -155,7 +167,7 @@ sw_dp_kernel(SwDev d)
     for (int h = 0; h < 2; ++h) {
         const size_t t = pair * 2 + h;
         rows[h] = 0; cols[h] = 0; aux_read_end[h] = 0; aux_ref_end[h] = 0;
-        if (t < d.n_tasks) {
+        if (live && t < d.n_tasks) {
             const int32_t *f = d.fwd + t * 8;
             const int fl = f[F_FLAGS];
             if (!REV) {
@@ -167,12 +179,12 @@ sw_dp_kernel(SwDev d)
             } else if (fl & FL_DO_REV) {
                 aux_read_end[h] = f[F_READ_END1]; aux_ref_end[h] = f[F_REF_END1];
                 rows[h] = aux_read_end[h] + 1; cols[h] = aux_ref_end[h] + 1;
-                term |= (uint32_t)(uint16_t)f[F_SCORE1] << (16 * h);
+                term |= (uint32_t)(uint16_t)(f[F_SCORE1] + SW_BIAS) << (16 * h);      // compared in the biased domain
             }
         }
         off[h] = G * S - 8 * ((rows[h] + 7) / 8);
     }
-    const int maxcols = cols[0] > cols[1] ? cols[0] : cols[1];
+    int maxcols = cols[0] > cols[1] ? cols[0] : cols[1];
 
     SwStrip<S> st;
     st.clear();
@@ -181,19 +193,22 @@ sw_dp_kernel(SwDev d)
         st.sel0[q] = d.rsel[(pair * 2 + 0) * (size_t)(G * NQ) + j * NQ + q];
         st.sel1[q] = d.rsel[(pair * 2 + 1) * (size_t)(G * NQ) + j * NQ + q];
     }
-    const uint32_t negO = s16x2(-d.prm.gapO, -d.prm.gapO), negE = s16x2(-d.prm.gapE, -d.prm.gapE);
+    uint32_t negO = s16x2(-d.prm.gapO, -d.prm.gapO);
+    uint32_t negE = 0u - ((uint32_t)d.prm.gapE | ((uint32_t)d.prm.gapE << 16));   // one 32-bit subtraction for both halves
+    SALT_PIN32(negO); SALT_PIN32(negE);
     const uint2 *__restrict__ win = d.win2 + pair * d.CW;
     uint32_t *__restrict__ mcol = d.maxcol2 + pair * (size_t)d.MC;
+    SALT_PIN64(win); SALT_PIN64(mcol);
 
-    uint32_t Hrecv = 0, Hrecv2 = 0, Frecv = 0, Crecv = 0, best = 0;
+    uint32_t Hrecv = SW_BIAS2, Hrecv2 = SW_BIAS2, Frecv = SW_BIAS2, Crecv = SW_BIAS2, best = SW_BIAS2;
     int bcol[2] = {0, 0};
     uint2 wreg = make_uint2(0, 0);
     int done = 0;                                        // REV, lane G-1: bit h = half h reached score1
     if (REV) done = (cols[0] == 0 ? 1 : 0) | (cols[1] == 0 ? 2 : 0);
-    const int nsteps = maxcols + G - 1;
+    const int nsteps = __reduce_max_sync(FULL, maxcols + G - 1);    // warp-uniform: every shuffle runs on the full mask
     for (int t = 0; t < nsteps; ++t) {
         const int c = t - j;
-        uint32_t Hbot = 0, Fout = 0, cm = 0;
+        uint32_t Hbot = SW_BIAS2, Fout = SW_BIAS2, cm = SW_BIAS2;
         if (c >= 0 && c < maxcols) {
             if ((c & 7) == 0) wreg = win[c >> 3];
             const int sh = 4 * (c & 7);
@@ -201,28 +216,34 @@ sw_dp_kernel(SwDev d)
             if (c >= cols[0]) sym0 = SW_SYM_PADCOL;
             if (c >= cols[1]) sym1 = SW_SYM_PADCOL;
             const uint2 ta = s_tab[sym0], tb = s_tab[sym1];
-            uint32_t F = j == 0 ? 0u : Frecv;
-            const uint32_t diag = j == 0 ? 0u : Hrecv2;
+            uint32_t F = j == 0 ? SW_BIAS2 : Frecv;
+            const uint32_t diag = j == 0 ? SW_BIAS2 : Hrecv2;
             const uint32_t sm = st.column(ta.x, ta.y, tb.x, tb.y, diag, F, negO, negE);
             Hbot = st.H[S - 1]; Fout = F;
-            cm = vmax2(j == 0 ? 0u : Crecv, sm);
+            cm = vmax2(j == 0 ? SW_BIAS2 : Crecv, sm);
             const uint32_t nb = vmax2(best, sm);
             if (nb != best) {                            // this strip's maximum rose: remember where
                 const uint32_t ch = nb ^ best;
                 if (ch & 0xffffu) {
                     bcol[0] = c;
 #pragma unroll
-                    for (int i = 0; i < S; ++i) snap[i] = st.H[i];
+                    for (int i = 0; i < SP; i += 4)
+                        *reinterpret_cast<uint4 *>(snap + i) = make_uint4(st.H[i], i + 1 < S ? st.H[i + 1 < S ? i + 1 : 0] : 0u,
+                                                                          i + 2 < S ? st.H[i + 2 < S ? i + 2 : 0] : 0u,
+                                                                          i + 3 < S ? st.H[i + 3 < S ? i + 3 : 0] : 0u);
                 }
                 if (ch >> 16) {
                     bcol[1] = c;
 #pragma unroll
-                    for (int i = 0; i < S; ++i) snap[S + i] = st.H[i];
+                    for (int i = 0; i < SP; i += 4)
+                        *reinterpret_cast<uint4 *>(snap + SP + i) = make_uint4(st.H[i], i + 1 < S ? st.H[i + 1 < S ? i + 1 : 0] : 0u,
+                                                                               i + 2 < S ? st.H[i + 2 < S ? i + 2 : 0] : 0u,
+                                                                               i + 3 < S ? st.H[i + 3 < S ? i + 3 : 0] : 0u);
                 }
                 best = nb;
             }
             if (j == G - 1) {
-                if (!REV) mcol[c] = cm;
+                if (!REV) mcol[c] = cm - SW_BIAS2;       // no borrow: both halves >= the bias
                 else {
                     if (c < cols[0] && (cm & 0xffffu) == (term & 0xffffu)) done |= 1;
                     if (c < cols[1] && (cm >> 16) == (term >> 16)) done |= 2;
@@ -230,20 +251,26 @@ sw_dp_kernel(SwDev d)
             }
         }
         Hrecv2 = Hrecv;
-        Hrecv = __shfl_up_sync(gmask, Hbot, 1, G);
-        Frecv = __shfl_up_sync(gmask, Fout, 1, G);
-        Crecv = __shfl_up_sync(gmask, cm, 1, G);
+        Hrecv = __shfl_up_sync(FULL, Hbot, 1, G);
+        Frecv = __shfl_up_sync(FULL, Fout, 1, G);
+        Crecv = __shfl_up_sync(FULL, cm, 1, G);
         if (REV) {
-            if (__shfl_sync(gmask, done, G - 1, G) == 3) break;
+            // a task pair that reached score1 on both halves stops computing (ssw.c:500); the warp leaves
+            // the loop when all of its pairs have
+            const bool gdone = __shfl_sync(FULL, done, G - 1, G) == 3;
+            if (gdone) maxcols = 0;
+            if (__all_sync(FULL, gdone)) break;
         }
     }
-    __syncwarp(gmask);
+    __syncwarp();
+    // the epilogue branches per task pair (mask length, flags): group masks from here on
+    const unsigned gmask = (unsigned)(((1ull << G) - 1ull) << gshift);
 
     // ---- combine the strips: global maximum, first column reaching it, smallest row there
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const size_t t = pair * 2 + h;
-        const int bh = half_of(best, h);
+        const int bh = half_of(best, h) - SW_BIAS;
         int m = bh;
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) m = imax(m, __shfl_xor_sync(gmask, m, o, G));
@@ -255,7 +282,7 @@ sw_dp_kernel(SwDev d)
         int row = 0;
         if (j == winner && m > 0) {
             for (int i = 0; i < S; ++i)
-                if (half_of(snap[h * S + i], h) == m) { row = j * S + i - off[h]; break; }
+                if (half_of(snap[h * SP + i], h) - SW_BIAS == m) { row = j * S + i - off[h]; break; }
         }
         row = __shfl_sync(gmask, row, winner, G);
         int end_read = 0;
@@ -263,8 +290,8 @@ sw_dp_kernel(SwDev d)
         else end_read = imin(rows[h] - 1, row);
         if (rows[h] > 0 && end_read > rows[h] - 1) end_read = rows[h] - 1;
 
-        if (t >= d.n_tasks) continue;
-        int32_t *f = d.fwd + t * 8;
+        const bool wr = live && t < d.n_tasks;            // absent tasks run along (full-mask shuffles below)
+        int32_t *f = d.fwd + (wr ? t : 0) * 8;
         if (!REV) {
             // second-best score outside the mask around ref_end1 (ssw.c:537-550)
             int s2 = 0, e2 = 0x7fffffff;
@@ -283,14 +310,14 @@ sw_dp_kernel(SwDev d)
                 }
                 if (s2 == 0) e2 = 0;
             } else { s2 = 0; e2 = -1; }
-            if (j == 0 && (f[F_FLAGS] & FL_VALID)) {
+            if (wr && j == 0 && (f[F_FLAGS] & FL_VALID)) {
                 f[F_SCORE1] = m; f[F_REF_END1] = ec; f[F_READ_END1] = end_read;
                 f[F_SCORE2] = s2; f[F_REF_END2] = e2;
                 const int flag = d.prm.flag;
                 const bool do_rev = !(flag == 0 || (flag == 2 && m < d.prm.filters));      // ssw.c:824
                 f[F_FLAGS] = FL_VALID | (do_rev ? FL_DO_REV : 0);
             }
-        } else if (j == 0 && (f[F_FLAGS] & FL_DO_REV)) {
+        } else if (wr && j == 0 && (f[F_FLAGS] & FL_DO_REV)) {
             const int rb = aux_ref_end[h] - ec, qb = aux_read_end[h] - end_read;       // ssw.c:836-837
             f[F_REF_BEGIN1] = rb; f[F_READ_BEGIN1] = qb;
             const int flag = d.prm.flag, score1 = f[F_SCORE1];
@@ -442,9 +469,15 @@ sw_banded_kernel(BandDev d)
 // --------------------------------------------------------------------------------------
 struct SwShape { int G, S; };
 
+// Strip shapes.  Fewer, taller strips amortise the per-column work (score lookup, three shuffles,
+// best tracking) over more rows and shorten the systolic fill; 4 threads x 26 rows serves the
+// 100 bp case (104 padded rows), 8 threads per pair the longer reads.
 static SwShape pick_shape(int l_max)
 {
     const int seg = (l_max + 7) / 8;                 // rows needed = 8*seg
+    static const int s4[] = {16, 26};
+    if (!getenv("SALT_SW_G8"))
+        for (int s : s4) if (2 * seg <= s) return {4, s};
     static const int s8[] = {8, 13, 16, 19, 24, 32};
     for (int s : s8) if (seg <= s) return {8, s};
     if (8 * seg <= 16 * 32) return {16, 32};
@@ -478,7 +511,7 @@ static cudaError_t run_dp(const SwDev &d, bool rev, cudaStream_t st)
 {
     constexpr int GPC = 128 / G;
     const size_t blocks = (d.n_pairs + GPC - 1) / GPC;
-    const size_t smem = 128 * 2 * S * sizeof(uint32_t);
+    const size_t smem = 128 * 2 * ((S + 3) / 4 * 4) * sizeof(uint32_t);
     if (rev) {
         auto kern = sw_dp_kernel<G, S, true>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -494,6 +527,8 @@ static cudaError_t run_dp(const SwDev &d, bool rev, cudaStream_t st)
 static cudaError_t dispatch_dp(const SwDev &d, bool rev, cudaStream_t st)
 {
     switch (d.G * 100 + d.S) {
+    case 416: return run_dp<4, 16>(d, rev, st);
+    case 426: return run_dp<4, 26>(d, rev, st);
     case 808: return run_dp<8, 8>(d, rev, st);
     case 813: return run_dp<8, 13>(d, rev, st);
     case 816: return run_dp<8, 16>(d, rev, st);

@@ -30,6 +30,7 @@
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct uint2 { unsigned x, y; };
 struct uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { uint4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
 static inline uint2 make_uint2(unsigned a, unsigned b) { uint2 r; r.x = a; r.y = b; return r; }
 
 typedef int cudaError_t;
@@ -165,6 +166,7 @@ static inline int __reduce_max_sync(unsigned mask, int v)
     return r;
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { uint32_t tab[32]; emu::gather(mask, 0, tab); }
 static inline void __syncthreads() { emu::syncthreads(); }
 
