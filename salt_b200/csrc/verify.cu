@@ -327,7 +327,7 @@ lv_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_f
 // An edit spoils at most one word, so at least nf - k words are edit-free, and an edit-free
 // word matches the text on ONE diagonal d, |d| <= k.  Hence
 //
-//      #{ w < nf : exists d in [-k,k], all 8 nibbles of P_w & T(8w+d ..) non-zero }  >=  nf - k
+//      #{ w < nf : exists d in [-k, min(k,(k+4)/2)], all 8 nibbles of P_w & T(8w+d ..) non-zero }  >=  nf - k
 //
 // is necessary for a result >= 0.  Text outside [0, textLen) is read from the real reference
 // instead of the zeros the reference sees; that can only add matches, so the filter stays
@@ -370,7 +370,12 @@ lv_filter_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int 
         k = imin(k, LV_MAXK - 1);                                   // LandauVishkin.c:31
         const int nf = plen >> 3;
         const int need = nf - k;
+        // The alignment must end with the pattern consumed inside the text: final diagonal <= tlen - plen
+        // = 4.  Being on diagonal d > 4 costs d edits to get there and d - 4 to come back, so positive
+        // diagonals beyond (k + 4) / 2 cannot be part of a k-difference alignment.
+        const int kp = imin(k, (k + 4) >> 1);
         const int kw = __reduce_max_sync(0xffffffffu, ok ? k : 0);
+        const int kpw = __reduce_max_sync(0xffffffffu, ok ? kp : 0);
         const int nfw = __reduce_max_sync(0xffffffffu, (ok && need > 0) ? nf : 0);
         int found = 0;
         const uint32_t *__restrict__ prow = reinterpret_cast<const uint32_t *>(c.rd4 + (size_t)p.rs * c.W64);
@@ -407,11 +412,11 @@ lv_filter_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int 
                 uint32_t W[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) W[j] = TA[j + 4];
-                for (int d = 1; d <= kw; ++d) {
+                for (int d = 1; d <= kpw; ++d) {
 #pragma unroll
                     for (int j = 0; j < 15; ++j) W[j] = __funnelshift_r(W[j], W[j + 1], 4);
                     W[15] >>= 4;
-                    if (d <= k) {
+                    if (d <= kp) {
 #pragma unroll
                         for (int j = 0; j < TW; ++j) m[j] = min(m[j], lv_haszero(P[j] & W[j]));
                     }
