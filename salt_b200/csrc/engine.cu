@@ -241,7 +241,8 @@ int verify_on_device(salt_b200_t *h, int si, const uint32_t *d_offs0, const uint
     SALT_EV(5);
     h->launches += h->lv_filter ? 4 : 3;
     if (d_cigars) {
-        CU(launch_lv_cigar(c, nullptr, nullptr, 0, d_cig_reads, d_cig_count, s.n_reads, d_rec,
+        const int kmax = lv_T0 >= 0 ? lv_T0 : (int)s.l_max / 10;     // a gapped primary's n_diff never exceeds the stage threshold
+        CU(launch_lv_cigar(c, nullptr, nullptr, 0, d_cig_reads, d_cig_count, s.n_reads, d_rec, kmax,
                            d_cigars, cigar_stride, nullptr, h->sm_count, s.stream));
         h->launches += 1;
     }
@@ -561,8 +562,11 @@ int salt_b200_lv_cigar(salt_b200_t *h, const salt_pair_t *pairs, const uint8_t *
     if (stride < 2) return fail(SALT_ERR_ARG, "cigar stride too small");
     if (!h->slot[0].n_reads) return fail(SALT_ERR_ARG, "no reads set");
     if (!n) return SALT_OK;
-    for (size_t i = 0; i < n; ++i)
+    int kmax = 0;
+    for (size_t i = 0; i < n; ++i) {
         if (k_each[i] >= 31) return fail(SALT_ERR_ARG, "k must be < 31 (LandauVishkin.c:183 asserts)");
+        if (k_each[i] > kmax) kmax = k_each[i];
+    }
     cudaStream_t st = h->slot[0].stream;
     CU(h->pairs.need(n * sizeof(salt_pair_t)));
     CU(h->out8.need(n));
@@ -571,7 +575,7 @@ int salt_b200_lv_cigar(salt_b200_t *h, const salt_pair_t *pairs, const uint8_t *
     CU(cudaMemcpyAsync(h->pairs.p, pairs, n * sizeof(salt_pair_t), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(h->kbuf.p, k_each, n, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(h->cig.p, 0, n * (size_t)stride, st));
-    CU(launch_lv_cigar(h->ctx(), h->pairs.as<salt_pair_t>(), h->kbuf.as<uint8_t>(), n, nullptr, nullptr, 0, nullptr,
+    CU(launch_lv_cigar(h->ctx(), h->pairs.as<salt_pair_t>(), h->kbuf.as<uint8_t>(), n, nullptr, nullptr, 0, nullptr, kmax,
                        h->cig.as<char>(), stride, h->out8.as<int8_t>(), h->sm_count, st));
     h->launches += 1;
     std::vector<char> tmp(n * (size_t)stride);

@@ -19,7 +19,7 @@ cudaError_t launch_lv(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k
                       int8_t *out, int sm_count, cudaStream_t st, int mapping = 0, const LvFilterScratch *f = nullptr);
 cudaError_t launch_lv_cigar(const DevCtx &c, const salt_pair_t *pairs, const uint8_t *k_each, size_t n,
                             const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
-                            const salt_verify_out_t *rec, char *cigars, int stride, int8_t *out,
+                            const salt_verify_out_t *rec, int kmax, char *cigars, int stride, int8_t *out,
                             int sm_count, cudaStream_t st);
 cudaError_t launch_expand(const uint32_t *offs0, const uint32_t *loci0, size_t n0,
                           const uint32_t *offs1, const uint32_t *loci1, size_t n1,

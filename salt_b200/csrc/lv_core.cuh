@@ -75,11 +75,12 @@ struct CigarOut {
 };
 
 // Backtrace + emission of computeEditDistanceWithCigar, useM = 1 (LandauVishkin.c:380-462).
-// Lt/At are the furthest-reaching table and action table, row-major [e][LV_ND], diagonal d
-// at column d + LV_ND/2.  Returns e or -2 (buffer too small).
-SALT_HD int lv_cigar_emit(const int16_t *Lt, const char *At, int e, int d, char *buf, int buflen)
+// Lt/At are the furthest-reaching table and action table, row-major [e][nd], diagonal d
+// at column d + nd/2.  Returns e or -2 (buffer too small).
+SALT_HD int lv_cigar_emit(const int16_t *Lt, const char *At, int nd, int e, int d, char *buf, int buflen)
 {
-    constexpr int C = LV_ND / 2;
+    const int LV_ND = nd;
+    const int C = nd / 2;
     char act[LV_MAXK + 1]; int run[LV_MAXK + 1];
     int cd = d;
     for (int ce = e; ce >= 1; --ce) {

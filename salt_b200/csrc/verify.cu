@@ -462,26 +462,27 @@ lv_filter_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int 
 // Work items: (pairs[i], k_each[i]) -> cigars + i*stride, or, when `worklist` is non-null,
 // read ids whose primary (rec[rid]) is gapped -> cigars + (list index)*stride (query.c:282-295).
 // --------------------------------------------------------------------------------------
-struct LvCigarSmem {
-    int16_t L[LV_MAXK][LV_ND];
-    char A[LV_MAXK][LV_ND];
-};
+// shared-memory words one warp of lv_cigar needs: L (int16) and A (char) tables of `rows` levels x nd
+// diagonals, then the staged text and pattern
+__host__ __device__ inline size_t lv_cigar_tab_words(int rows, int nd) { return ((size_t)rows * nd * 3 + 3) / 4; }
 
+template <int DPL>
 __global__ void __launch_bounds__(128)
 lv_cigar_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8_t *__restrict__ k_each, size_t n,
                 const uint32_t *__restrict__ worklist, const uint32_t *__restrict__ wl_count,
-                const salt_verify_out_t *__restrict__ rec,
+                const salt_verify_out_t *__restrict__ rec, int rows,
                 char *__restrict__ cigars, int stride, int8_t *__restrict__ out)
 {
     SALT_DYN_SMEM(uint32_t, smem);
-    constexpr int G = 32, DPL = 2, C = LV_ND / 2;
+    constexpr int G = 32, ND = 32 * DPL, C = ND / 2;
     const int TW = lv_tw((int)c.l_max), PW = lv_pw((int)c.l_max);
     const int wl = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int warps = blockDim.x / 32;
-    const size_t per_warp = (sizeof(LvCigarSmem) + 3) / 4 + TW + PW;
+    const size_t per_warp = lv_cigar_tab_words(rows, ND) + TW + PW;
     uint32_t *base = smem + (size_t)wl * per_warp;
-    LvCigarSmem *tab = reinterpret_cast<LvCigarSmem *>(base);
-    uint32_t *T = base + (sizeof(LvCigarSmem) + 3) / 4;
+    int16_t *tabL = reinterpret_cast<int16_t *>(base);                  // [rows][ND]
+    char *tabA = reinterpret_cast<char *>(tabL + (size_t)rows * ND);    // [rows][ND]
+    uint32_t *T = base + lv_cigar_tab_words(rows, ND);
     uint32_t *P = T + TW;
     const unsigned gmask = 0xffffffffu;
     const size_t groups = (size_t)gridDim.x * warps;
@@ -501,7 +502,7 @@ lv_cigar_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8_t *
         const int plen = rid < c.n_reads ? (int)c.rd_len[rid] : 0;
         const int tlen = plen + 4;
         int result = -1;
-        const bool ok = plen > 0 && k < LV_MAXK && (uint64_t)p.pos + (uint64_t)tlen <= (uint64_t)c.l;
+        const bool ok = plen > 0 && k < LV_MAXK && k < rows && k < C && (uint64_t)p.pos + (uint64_t)tlen <= (uint64_t)c.l;
         if (ok) {
             lv_stage<G>(c, p.rs, p.pos, plen, tlen, T, P, TW, PW, lane);
             __syncwarp();
@@ -514,7 +515,7 @@ lv_cigar_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8_t *
                 for (int q = 0; q < DPL; ++q) {
                     const int d = lane * DPL + q - C;
                     Lp[q] = d == 0 ? L0 : -2;
-                    tab->L[0][d + C] = (int16_t)Lp[q];
+                    tabL[d + C] = (int16_t)Lp[q];
                 }
                 int found_e = -1, found_d = 0;
                 for (int e = 1; e <= k; ++e) {
@@ -536,11 +537,11 @@ lv_cigar_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8_t *
                             best = lv_extend(T, P, best, d, plen, tlen);
                             if (best == plen) myrank = imin(myrank, lv_cigar_rank(d));
                             Ln[q] = best;
-                            tab->A[e][d + C] = a;
+                            tabA[e * ND + d + C] = a;
                         } else {
                             Ln[q] = -2;
                         }
-                        tab->L[e][d + C] = (int16_t)Ln[q];
+                        tabL[e * ND + d + C] = (int16_t)Ln[q];
                     }
                     int r = myrank;
 #pragma unroll
@@ -556,7 +557,7 @@ lv_cigar_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8_t *
                 __syncwarp();
                 if (lane == 0) {
                     if (found_e < 0) { if (stride > 0) buf[0] = '\0'; result = -1; }
-                    else result = lv_cigar_emit(&tab->L[0][0], &tab->A[0][0], found_e, found_d, buf, stride);
+                    else result = lv_cigar_emit(tabL, tabA, ND, found_e, found_d, buf, stride);
                 }
             }
             __syncwarp();
@@ -1067,26 +1068,42 @@ cudaError_t launch_lv(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k
                           mapping == 0 ? (worklist ? 0 : 1) : mapping);
 }
 
-cudaError_t launch_lv_cigar(const DevCtx &c, const salt_pair_t *pairs, const uint8_t *k_each, size_t n,
-                            const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
-                            const salt_verify_out_t *rec, char *cigars, int stride, int8_t *out,
-                            int sm_count, cudaStream_t st)
+template <int DPL>
+static cudaError_t launch_lv_cigar_t(const DevCtx &c, const salt_pair_t *pairs, const uint8_t *k_each, size_t n,
+                                     const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
+                                     const salt_verify_out_t *rec, int rows, char *cigars, int stride, int8_t *out,
+                                     int sm_count, cudaStream_t st)
 {
     constexpr int threads = 128, warps = threads / 32;
-    const size_t per_warp = ((sizeof(LvCigarSmem) + 3) / 4 + lv_tw((int)c.l_max) + lv_pw((int)c.l_max)) * 4;
+    const size_t per_warp = (lv_cigar_tab_words(rows, 32 * DPL) + lv_tw((int)c.l_max) + lv_pw((int)c.l_max)) * 4;
     const size_t smem = per_warp * warps;
     const size_t items = worklist ? wl_cap : n;
     size_t blocks = (items + warps - 1) / warps;
-    const size_t cap = (size_t)sm_count * 8;
+    const size_t cap = (size_t)sm_count * 16;
     if (blocks > cap) blocks = cap;
     if (blocks == 0) return cudaSuccess;
+    auto kern = lv_cigar_kernel<DPL>;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(lv_cigar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    SALT_LAUNCH(lv_cigar_kernel, (unsigned)blocks, threads, smem, st, c, pairs, k_each, n, worklist, wl_count, rec, cigars, stride, out);
+    SALT_LAUNCH(kern, (unsigned)blocks, threads, smem, st, c, pairs, k_each, n, worklist, wl_count, rec, rows, cigars, stride, out);
     SALT_LAUNCH_CHECK();
     return cudaSuccess;
+}
+
+// kmax: upper bound of the k the items carry (levels kept in shared memory = kmax + 1; up to 15
+// differences fit 32 diagonals, one per lane)
+cudaError_t launch_lv_cigar(const DevCtx &c, const salt_pair_t *pairs, const uint8_t *k_each, size_t n,
+                            const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
+                            const salt_verify_out_t *rec, int kmax, char *cigars, int stride, int8_t *out,
+                            int sm_count, cudaStream_t st)
+{
+    if (kmax < 0) kmax = 0;
+    if (kmax > LV_MAXK - 1) kmax = LV_MAXK - 1;
+    if (kmax <= 15)
+        return launch_lv_cigar_t<1>(c, pairs, k_each, n, worklist, wl_count, wl_cap, rec, kmax + 1, cigars, stride, out, sm_count, st);
+    return launch_lv_cigar_t<2>(c, pairs, k_each, n, worklist, wl_count, wl_cap, rec, kmax + 1, cigars, stride, out, sm_count, st);
 }
 
 cudaError_t launch_expand(const uint32_t *offs0, const uint32_t *loci0, size_t n0,
