@@ -1,0 +1,35 @@
+"""TEST INFRASTRUCTURE: the SIMT-emulated engine built with AddressSanitizer and zero allocation slack, driven
+through verify / mismatch / LV / SSW with candidates at both ends of the reference.  compute-sanitizer is not
+available on the GPU pool, so out-of-bounds accesses in kernel logic are hunted here.
+    g++ -std=c++17 -O1 -g -fPIC -shared -pthread -fsanitize=address -DSALT_EMUL_SLACK=0 -o /tmp/libsalt_b200_emul_asan.so tests/emul/emul_lib.cpp
+    LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 python tests/emul/asan_check.py"""
+import sys, ctypes as C, numpy as np
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import parity_cases as pc
+from salt_b200 import api, synth
+from oracle import orc
+lib = api._declare(C.CDLL("/tmp/libsalt_b200_emul_asan.so"))
+o = orc.Oracle()
+for L, glen in ((100, 30000), (150, 30000), (250, 30000), (37, 20000), (700, 40000)):
+    n = 40 if L <= 150 else 10
+    g, reads, pos, strand, cands = pc.make_world(400 + L, L=L, n_reads=n, per_strand=5, indel_frac=0.35, glen=glen,
+                                                 sub_rate=0.02 if L <= 150 else 0.004)
+    # candidates right at both ends of the reference
+    offs0, loci0, offs1, loci1 = cands
+    loci0 = loci0.copy(); loci0[0] = 0; loci0[offs0[1] - 1] = max(loci0[offs0[1] - 2], g.l - L)
+    e = int(offs1[n]); loci1 = loci1.copy(); loci1[e - 1] = g.l - L - 4; loci1[e - 2] = min(loci1[e-2], g.l - L - 5)
+    eng = api.Engine(g.mixref, g.l, g.pac, g.l, lib=lib)
+    eng.set_reads(reads)
+    pc.check_verify(eng, o, g, reads, (offs0, loci0, offs1, loci1), 3, -1)
+    pc.check_verify(eng, o, g, reads, (offs0, loci0, offs1, loci1), 3, 3)
+    pairs = pc.flat_pairs((offs0, loci0, offs1, loci1), n)
+    pc.check_mismatch(eng, o, g, reads, pairs[:60], 3)
+    pc.check_lv(eng, o, g, reads, pairs[:60], -1)
+    rng = np.random.default_rng(L)
+    if L <= 250:
+        wins = pc.make_windows(g, reads[:12], pos[:12], strand[:12], L, rng, 301)
+        pc.check_ssw(eng, o, g, reads, wins, False, api.salt_score_mat2(), 16, cigar_stride=96)
+    eng.close()
+    print("asan ok", L, flush=True)

@@ -199,9 +199,12 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { p->m
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, int) { *s = (void *)1; return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
-template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)calloc(n + 64, 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+#ifndef SALT_EMUL_SLACK
+#define SALT_EMUL_SLACK 64
+#endif
+template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)calloc(n + SALT_EMUL_SLACK, 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
-template <class T> static inline cudaError_t cudaMallocHost(T **p, size_t n) { *p = (T *)calloc(n + 64, 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+template <class T> static inline cudaError_t cudaMallocHost(T **p, size_t n) { *p = (T *)calloc(n + SALT_EMUL_SLACK, 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
