@@ -21,12 +21,6 @@ cudaError_t launch_lv_cigar(const DevCtx &c, const salt_pair_t *pairs, const uin
                             const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
                             const salt_verify_out_t *rec, int kmax, char *cigars, int stride, int8_t *out,
                             int sm_count, cudaStream_t st);
-cudaError_t launch_expand(const uint32_t *offs0, const uint32_t *loci0, size_t n0,
-                          const uint32_t *offs1, const uint32_t *loci1, size_t n1,
-                          uint32_t n_reads, salt_pair_t *pairs, cudaStream_t st);
-cudaError_t launch_scan_nogap(const DevCtx &c, const uint32_t *offs0, const uint32_t *loci0,
-                              const uint32_t *offs1, const uint32_t *loci1, size_t n0, int T0,
-                              int8_t *acc, salt_verify_out_t *rec, uint32_t *lv_list, uint32_t *lv_count, cudaStream_t st);
 cudaError_t launch_nogap_fused(const DevCtx &c, const uint32_t *offs0, const uint32_t *loci0,
                                const uint32_t *offs1, const uint32_t *loci1, size_t n0, int T0,
                                int8_t *acc, salt_verify_out_t *rec, salt_pair_t *lv_pairs, uint32_t *lv_slots,

@@ -5,7 +5,9 @@
 //   mismatch        ed_mismatch                                          (editdistance.c:88-163)
 //   lv              ed_diff -> computeEditDistance                       (editdistance.c:174, LandauVishkin.c:19)
 //   lv_cigar        ed_diff_withcigar -> computeEditDistanceWithCigar    (editdistance.c:234, LandauVishkin.c:176)
-//   expand / scan   alnse_check_nogap / alnse_check_withgap + overlap    (alnse.c:734, :871, :1014-1036, :1077-1097)
+//   nogap_fused     alnse_check_nogap x2 + running threshold + primary     (alnse.c:734, :1014-1036, :1077-1097)
+//   lv_filter       exact pigeonhole pre-filter in front of Landau-Vishkin
+//   scan_gap        alnse_check_withgap's acceptance logic                 (alnse.c:871, :372-393)
 #if !defined(SALT_EMUL)
 #include <cuda_runtime.h>
 #endif
@@ -47,44 +49,87 @@ pack_reads_kernel(const uint8_t *__restrict__ codes, const uint32_t *__restrict_
 }
 
 // --------------------------------------------------------------------------------------
-// mismatch: G lanes per pair, one 64-bit word (16 bases) per lane per iteration.
-// The window is fetched as aligned 64-bit words (coalesced across the group) and funnel
-// shifted to the read's nibble phase; a match is (ref & read) != 0 per nibble.
+// mismatch: batched ed_mismatch on a flat pair list (editdistance.c:88-163).  G lanes per pair,
+// lane t owning 64-bit words t, t+G, .. of the packed read and of the aligned window -- the
+// counting scheme of nogap_fused below (one coalesced 8-byte-aligned window load per lane, the next
+// lane's low word by shuffle, one funnel shift each way, popc of window AND read) without the
+// read reuse, since neighbouring pairs may belong to different reads.  Four pairs are in flight per
+// group; control flow is warp-uniform so the shuffles run on the full mask.
+// G*WPL*16 >= l_max + 16 (launcher), so the last lane never needs a word from beyond the group.
 // --------------------------------------------------------------------------------------
-template <int G>
+template <int G, int WPL>
 __global__ void __launch_bounds__(256)
 mismatch_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int max_err, int8_t *__restrict__ out)
 {
-    const size_t gid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int U = 4;                                 // pairs per group per pass
     const int lane = threadIdx.x % G;
-    const bool live = gid < n;
-    salt_pair_t p; p.rs = 0; p.pos = 0;
-    if (live) p = pairs[gid];
-    const uint32_t rid = p.rs >> 1;
-    bool bad = !live || rid >= c.n_reads;
-    const int L = bad ? 0 : (int)c.rd_len[rid];
-    bad = bad || ((uint64_t)p.pos + (uint64_t)L > (uint64_t)c.l) || L == 0;
-    int matches = 0;
-    if (!bad) {
-        const uint64_t *__restrict__ r = c.rd4 + (size_t)p.rs * c.W64;
-        const uint64_t *__restrict__ m64 = reinterpret_cast<const uint64_t *>(c.mixref);
-        const int nw = (L + 15) >> 4;
-        const size_t base = p.pos >> 4;
-        const int sh = (p.pos & 15) * 4;
-        for (int w = lane; w < nw; w += G) {
-            const uint64_t q0 = m64[base + w], q1 = m64[base + w + 1];
-            const uint64_t x = sh ? ((q0 >> sh) | (q1 << (64 - sh))) : q0;
-            uint64_t m = x & r[w];
-            m |= m >> 1;
-            m |= m >> 2;
-            matches += __popcll(m & 0x1111111111111111ull);
-        }
-    }
+    const size_t group = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const size_t ngroups = ((size_t)gridDim.x * blockDim.x) / G;
+    const uint2 *__restrict__ mixl = reinterpret_cast<const uint2 *>(c.mixref) + lane;
+    const size_t passes = (n + ngroups * U - 1) / (ngroups * U);          // identical for every group
+    for (size_t ps = 0; ps < passes; ++ps) {
+        const size_t first = (ps * ngroups + group) * U;
+        uint2 q[U][WPL], rw[U][WPL], rwh[U][WPL];
+        uint32_t ph[U]; int Ls[U]; bool good[U];
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) matches += __shfl_xor_sync(0xffffffffu, matches, o, G);
-    if (lane == 0 && live) {
-        const int nmis = L - matches;
-        out[gid] = (int8_t)((bad || nmis > max_err) ? -1 : nmis);
+        for (int u = 0; u < U; ++u) {
+            const size_t i = first + u;
+            salt_pair_t p; p.rs = 0; p.pos = 0;
+            if (i < n) p = pairs[i];
+            const uint32_t rid = p.rs >> 1;
+            const bool live = i < n && rid < c.n_reads;
+            const int L = live ? (int)c.rd_len[rid] : 0;
+            Ls[u] = L;
+            good[u] = live && L > 0 && (uint64_t)p.pos + (uint64_t)L <= (uint64_t)c.l;
+            const uint32_t cpos = good[u] ? p.pos : 0u;                  // a bad pair counts window 0 and is ignored
+            ph[u] = ((cpos & 7u) << 2) | ((cpos & 8u) << 28);
+            const uint2 *__restrict__ wp = mixl + (cpos >> 4);
+            const uint2 *__restrict__ rrow = reinterpret_cast<const uint2 *>(c.rd4 + (size_t)(live ? p.rs : 0u) * c.W64);
+#pragma unroll
+            for (int w = 0; w < WPL; ++w) {
+                q[u][w] = wp[w * G];
+                rw[u][w] = (live && (uint32_t)(lane + w * G) < c.W64) ? rrow[lane + w * G] : make_uint2(0u, 0u);
+            }
+        }
+        uint32_t packed[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int sh = (int)ph[u];
+            const bool hi = (int)ph[u] < 0;
+            uint32_t m = 0;
+#pragma unroll
+            for (int w = 0; w < WPL; ++w) {
+                uint32_t up = __shfl_up_sync(FULL, rw[u][w].y, 1, G);     // the read moved up by one 32-bit word
+                if (lane == 0) up = 0u;
+                if (w > 0) { const uint32_t wrap = __shfl_sync(FULL, rw[u][w > 0 ? w - 1 : 0].y, G - 1, G); if (lane == 0) up = wrap; }
+                rwh[u][w] = make_uint2(up, rw[u][w].x);
+                uint32_t n0 = __shfl_down_sync(FULL, q[u][w].x, 1, G);
+                if (w + 1 < WPL) {
+                    const uint32_t w0 = __shfl_sync(FULL, q[u][w + 1 < WPL ? w + 1 : w].x, 0, G);
+                    if (lane == G - 1) n0 = w0;
+                }
+                uint32_t x0 = __funnelshift_r(q[u][w].x, q[u][w].y, sh) & (hi ? rwh[u][w].x : rw[u][w].x);
+                uint32_t x1 = __funnelshift_r(q[u][w].y, n0, sh) & (hi ? rwh[u][w].y : rw[u][w].y);
+                // general form (reads may contain N = 15): a matching nibble is a non-zero nibble
+                x0 |= x0 >> 1; x0 |= x0 >> 2; x0 &= 0x11111111u;
+                x1 |= x1 >> 1; x1 |= x1 >> 2; x1 &= 0x11111111u;
+                m += (uint32_t)(__popc(x0) + __popc(x1));
+            }
+            packed[u] = m;
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < U; ++u) packed[u] += __shfl_xor_sync(FULL, packed[u], o, G);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t i = first + u;
+            if (lane == u && i < n) {
+                const int nmis = Ls[u] - (int)packed[u];
+                out[i] = (int8_t)((!good[u] || nmis > max_err) ? -1 : nmis);
+            }
+        }
     }
 }
 
@@ -832,37 +877,11 @@ nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t 
 }
 
 // --------------------------------------------------------------------------------------
-// expand: CSR candidate lists -> flat pair array (strand 0 lists first, then strand 1).
-// One thread per candidate; the owning read is found by binary search in the offsets.
+// Acceptance scan of the gapped stage.  The LV kernels return e iff e <= T0; the reference calls
+// them with a threshold that tightens as candidates are accepted, which is equivalent to accepting
+// candidate i iff e_i <= min(T0, min_{j<i} e_j) in list order, strand 0 then strand 1
+// (code_kdiff, alnse.c:372-393).  One thread per read that reached the stage walks its lists.
 // --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-expand_kernel(const uint32_t *__restrict__ offs0, const uint32_t *__restrict__ loci0, size_t n0,
-              const uint32_t *__restrict__ offs1, const uint32_t *__restrict__ loci1, size_t n1,
-              uint32_t n_reads, salt_pair_t *__restrict__ pairs)
-{
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n0 + n1) return;
-    const uint32_t strand = i >= n0;
-    const uint32_t *offs = strand ? offs1 : offs0;
-    const uint32_t j = (uint32_t)(strand ? i - n0 : i);
-    uint32_t lo = 0, hi = n_reads;                  // find r with offs[r] <= j < offs[r+1]
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (offs[mid] <= j) lo = mid; else hi = mid;
-    }
-    salt_pair_t p;
-    p.rs = (lo << 1) | strand;
-    p.pos = strand ? loci1[j] : loci0[j];
-    pairs[i] = p;
-}
-
-// --------------------------------------------------------------------------------------
-// Acceptance scans.  The kernels above return n iff n <= T0; the reference calls them with
-// a threshold that tightens as candidates are accepted, which is equivalent to accepting
-// candidate i iff n_i <= min(T0, min_{j<i} n_j) in list order, strand 0 then strand 1
-// (code_kmismatch / code_kdiff, alnse.c:348-393).  One thread per read walks its lists.
-// --------------------------------------------------------------------------------------
-struct StageState { int max_diff; };
 
 __device__ __forceinline__ int scan_stage(const uint32_t *__restrict__ loci, uint32_t b, uint32_t e,
                                           int8_t *__restrict__ acc, uint32_t l_mref, uint32_t guard,
@@ -888,33 +907,6 @@ __device__ __forceinline__ int scan_stage(const uint32_t *__restrict__ loci, uin
         last = pos;
     }
     return matched ? max_diff : -1;
-}
-
-__global__ void __launch_bounds__(128)
-scan_nogap_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t *__restrict__ loci0,
-                  const uint32_t *__restrict__ offs1, const uint32_t *__restrict__ loci1, size_t n0,
-                  int T0, int8_t *__restrict__ acc, salt_verify_out_t *__restrict__ rec,
-                  uint32_t *__restrict__ lv_list, uint32_t *__restrict__ lv_count)
-{
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= c.n_reads) return;
-    salt_verify_out_t q;
-    q.pos = 0xFFFFFFFFu; q.strand = 3; q.n_diff = 255; q.is_gap = 255; q.lv_ran = 0; q.n_hits[0] = q.n_hits[1] = 0;
-    int max_diff = T0;
-    const uint32_t b0 = offs0[r], e0 = offs0[r + 1], b1 = offs1[r], e1 = offs1[r + 1];
-    const int m0 = scan_stage(loci0, b0, e0, acc, c.l, 0, max_diff, 0, 0, q);
-    if (m0 != -1 && m0 < max_diff) max_diff = m0;
-    const int m1 = scan_stage(loci1, b1, e1, acc + n0, c.l, 0, max_diff, 1, 0, q);
-    if (m0 == -1 && m1 == -1) {                      // alnse.c:1022 / :1089
-        q.lv_ran = 1;
-        const uint32_t cnt = (e0 - b0) + (e1 - b1);
-        if (cnt) {
-            uint32_t w = atomicAdd(lv_count, cnt);
-            for (uint32_t i = b0; i < e0; ++i) lv_list[w++] = i;
-            for (uint32_t i = b1; i < e1; ++i) lv_list[w++] = (uint32_t)n0 + i;
-        }
-    }
-    rec[r] = q;
 }
 
 __global__ void __launch_bounds__(128)
@@ -955,25 +947,28 @@ cudaError_t launch_pack_reads(const uint8_t *codes, const uint32_t *offs, uint32
     return cudaSuccess;
 }
 
+template <int G, int WPL>
+static cudaError_t launch_mismatch_t(const DevCtx &c, const salt_pair_t *pairs, size_t n, int max_err, int8_t *out, cudaStream_t st)
+{
+    const size_t groups = (n + 3) / 4;
+    size_t blocks = (groups * G + 255) / 256;
+    const size_t cap = 148 * 64;                         // grid-stride beyond that
+    if (blocks > cap) blocks = cap;
+    auto kern = mismatch_kernel<G, WPL>;
+    SALT_LAUNCH(kern, (unsigned)blocks, 256, 0, st, c, pairs, n, max_err, out);
+    SALT_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
 cudaError_t launch_mismatch(const DevCtx &c, const salt_pair_t *pairs, size_t n, int max_err, int8_t *out, cudaStream_t st)
 {
     if (!n) return cudaSuccess;
-    const int nw = ((int)c.l_max + 15) / 16;
-    if (nw <= 4) {
-        constexpr int G = 4;
-        auto kern = mismatch_kernel<G>;
-        SALT_LAUNCH(kern, (unsigned)((n * G + 255) / 256), 256, 0, st, c, pairs, n, max_err, out);
-    } else if (nw <= 8) {
-        constexpr int G = 8;
-        auto kern = mismatch_kernel<G>;
-        SALT_LAUNCH(kern, (unsigned)((n * G + 255) / 256), 256, 0, st, c, pairs, n, max_err, out);
-    } else {
-        constexpr int G = 16;
-        auto kern = mismatch_kernel<G>;
-        SALT_LAUNCH(kern, (unsigned)((n * G + 255) / 256), 256, 0, st, c, pairs, n, max_err, out);
-    }
-    SALT_LAUNCH_CHECK();
-    return cudaSuccess;
+    const int lm = (int)c.l_max;                        // l_max + 16 <= 16*G*WPL, as for nogap_fused
+    if (lm <= 112) return launch_mismatch_t<8, 1>(c, pairs, n, max_err, out, st);
+    if (lm <= 240) return launch_mismatch_t<16, 1>(c, pairs, n, max_err, out, st);
+    if (lm <= 496) return launch_mismatch_t<32, 1>(c, pairs, n, max_err, out, st);
+    if (lm <= 1008) return launch_mismatch_t<32, 2>(c, pairs, n, max_err, out, st);
+    return launch_mismatch_t<32, 3>(c, pairs, n, max_err, out, st);
 }
 
 template <int G, int DPL>
@@ -1104,27 +1099,6 @@ cudaError_t launch_lv_cigar(const DevCtx &c, const salt_pair_t *pairs, const uin
     if (kmax <= 15)
         return launch_lv_cigar_t<1>(c, pairs, k_each, n, worklist, wl_count, wl_cap, rec, kmax + 1, cigars, stride, out, sm_count, st);
     return launch_lv_cigar_t<2>(c, pairs, k_each, n, worklist, wl_count, wl_cap, rec, kmax + 1, cigars, stride, out, sm_count, st);
-}
-
-cudaError_t launch_expand(const uint32_t *offs0, const uint32_t *loci0, size_t n0,
-                          const uint32_t *offs1, const uint32_t *loci1, size_t n1,
-                          uint32_t n_reads, salt_pair_t *pairs, cudaStream_t st)
-{
-    const size_t n = n0 + n1;
-    if (!n) return cudaSuccess;
-    SALT_LAUNCH(expand_kernel, (unsigned)((n + 255) / 256), 256, 0, st, offs0, loci0, n0, offs1, loci1, n1, n_reads, pairs);
-    SALT_LAUNCH_CHECK();
-    return cudaSuccess;
-}
-
-cudaError_t launch_scan_nogap(const DevCtx &c, const uint32_t *offs0, const uint32_t *loci0,
-                              const uint32_t *offs1, const uint32_t *loci1, size_t n0, int T0,
-                              int8_t *acc, salt_verify_out_t *rec, uint32_t *lv_list, uint32_t *lv_count, cudaStream_t st)
-{
-    if (!c.n_reads) return cudaSuccess;
-    SALT_LAUNCH(scan_nogap_kernel, (c.n_reads + 127) / 128, 128, 0, st, c, offs0, loci0, offs1, loci1, n0, T0, acc, rec, lv_list, lv_count);
-    SALT_LAUNCH_CHECK();
-    return cudaSuccess;
 }
 
 template <int G, int WPL>
