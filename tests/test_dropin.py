@@ -1,0 +1,53 @@
+"""End-to-end SAM parity (BASELINE.json configs[0] shape): the reference's own `salt` binary and
+`salt_dropin` -- the same reference sources with ONE function (alnse_core) replaced by
+oracle/dropin/alnse_core_gpu.c, which sends the verification stage to libsalt_b200.so -- must print
+identical SAM for the same index and reads.  Both binaries and the reference indexer are built from
+the reference tree by oracle/Makefile in the build container and travel in oracle/_ref/; the index
+is built on the spot (the 12-mer lookup table alone is 64 MiB)."""
+import os
+import subprocess
+
+import pytest
+
+import dropin_data
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+pytestmark = pytest.mark.gpu
+
+
+def _have():
+    return all(os.path.exists(os.path.join(REFDIR, b)) for b in ("salt", "salt-idx", "salt_dropin"))
+
+
+def _run(cmd, cwd, out):
+    with open(out, "w") as f:
+        p = subprocess.run(cmd, cwd=cwd, stdout=f, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return p.stderr
+
+
+def _sam_body(path):
+    return [ln for ln in open(path).read().split("\n") if not ln.startswith("@PG")]     # @PG carries date + command line
+
+
+@pytest.mark.parametrize("flags", [["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500", "-t", "1"],     # run_se_test.sh:12
+                                   ["-r", "1", "-l", "100", "-t", "1"]])
+def test_se_sam_identical(tmp_path, flags):
+    if not _have():
+        pytest.skip("oracle/_ref programs not built (reference tree absent at build time)")
+    d = str(tmp_path)
+    fa, sn, fq = dropin_data.write_inputs(d)
+    _run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], d, os.path.join(d, "idx.log"))
+    _run([os.path.join(REFDIR, "salt")] + flags + ["idx", "reads.fq"], d, os.path.join(d, "ref.sam"))
+    err = _run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", "reads.fq"], d, os.path.join(d, "gpu.sam"))
+    assert "verification on libsalt_b200" in err
+    want, got = _sam_body(os.path.join(d, "ref.sam")), _sam_body(os.path.join(d, "gpu.sam"))
+    assert len(want) == len(got) and len(want) > 6000
+    for a, b in zip(want, got):
+        assert a == b
+    body = [ln.split("\t") for ln in want if ln and not ln.startswith("@")]
+    assert sum(1 for f in body if f[1] == "4") >= 30                       # unmapped reads exist
+    assert sum(1 for f in body if "I" in f[5] or "D" in f[5]) >= 300       # gapped CIGARs exist
+    assert sum(1 for f in body if any(x.startswith("XA:") for x in f[11:])) >= 1
