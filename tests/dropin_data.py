@@ -38,3 +38,47 @@ def write_inputs(outdir, glen=150_000, n_reads=6000, L=100, seed=5):
         for i, r in enumerate(reads):
             f.write("@r%d\n%s\n+\n%s\n" % (i, "".join("ACGTN"[c] for c in r), "I" * L))
     return fa, sn, fq
+
+
+def write_pe_inputs(outdir, glen=150_000, n_pairs=3000, L=100, seed=9):
+    """Genome + SNP table as write_inputs; mates 1/2 as two FASTQ files, insert ~ N(500, 40) (the bounds of
+    run_pe_test.sh are 350..650).  A tenth of the second mates is too divergent to verify and has to be rescued."""
+    fa, sn, _ = write_inputs(outdir, glen=glen, n_reads=10, L=L, seed=seed)
+    rng = np.random.default_rng(seed + 17)
+    g = synth.Genome(glen, snp_rate=0.01, n_rate=0.0, seed=seed)
+    codes = (g.codes & 3).astype(np.uint8)
+
+    def noisy(seq, rate, indel):
+        out = []
+        i = 0
+        while len(out) < L and i < len(seq):
+            u = rng.random()
+            if u < rate:
+                out.append((int(seq[i]) + int(rng.integers(1, 4))) & 3); i += 1
+            elif u < rate + indel:
+                if rng.random() < 0.5:
+                    out.append(int(rng.integers(0, 4)))
+                else:
+                    i += 1
+            else:
+                out.append(int(seq[i])); i += 1
+        while len(out) < L:
+            out.append(int(rng.integers(0, 4)))
+        return np.array(out[:L], np.uint8)
+
+    f1 = open(os.path.join(outdir, "r1.fq"), "w"); f2 = open(os.path.join(outdir, "r2.fq"), "w")
+    for i in range(n_pairs):
+        ins = int(np.clip(rng.normal(500, 40), 360, 640))
+        p = int(rng.integers(0, glen - ins - 20))
+        hard = i % 10 == 3
+        a = noisy(codes[p:p + L + 12], 0.01, 0.002)
+        b = noisy(codes[p + ins - L:p + ins + 12], 0.09 if hard else 0.01, 0.02 if hard else 0.002)
+        b = synth.revcomp(b[None, :])[0]
+        if rng.random() < 0.5:                       # fragment from the other strand: swap roles
+            a, b = b, a
+        if i % 97 == 0:
+            b = rng.integers(0, 4, L, dtype=np.uint8)   # a mate that maps nowhere
+        for f, r in ((f1, a), (f2, b)):
+            f.write("@p%d\n%s\n+\n%s\n" % (i, "".join("ACGTN"[c] for c in r), "I" * L))
+    f1.close(); f2.close()
+    return fa, sn, os.path.join(outdir, "r1.fq"), os.path.join(outdir, "r2.fq")

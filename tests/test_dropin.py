@@ -51,3 +51,24 @@ def test_se_sam_identical(tmp_path, flags):
     assert sum(1 for f in body if f[1] == "4") >= 30                       # unmapped reads exist
     assert sum(1 for f in body if "I" in f[5] or "D" in f[5]) >= 300       # gapped CIGARs exist
     assert sum(1 for f in body if any(x.startswith("XA:") for x in f[11:])) >= 1
+
+
+@pytest.mark.parametrize("flags", [["-d", "-p", "-e", "-l", "100", "-c", "-a", "350", "-b", "650", "-r", "5", "-t", "1"]])   # run_pe_test.sh:14
+def test_pe_sam_identical(tmp_path, flags):
+    """paired-end: both mates verified on the GPU with the PE thresholds, then the reference's own pairing2 /
+    mate rescue / alnpe_sam"""
+    if not _have():
+        pytest.skip("oracle/_ref programs not built (reference tree absent at build time)")
+    d = str(tmp_path)
+    dropin_data.write_pe_inputs(d)
+    _run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], d, os.path.join(d, "idx.log"))
+    _run([os.path.join(REFDIR, "salt")] + flags + ["idx", "r1.fq", "r2.fq"], d, os.path.join(d, "ref.sam"))
+    err = _run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", "r1.fq", "r2.fq"], d, os.path.join(d, "gpu.sam"))
+    assert "verification on libsalt_b200" in err
+    want, got = _sam_body(os.path.join(d, "ref.sam")), _sam_body(os.path.join(d, "gpu.sam"))
+    assert len(want) == len(got) and len(want) > 6000
+    for a, b in zip(want, got):
+        assert a == b
+    body = [ln.split("\t") for ln in want if ln and not ln.startswith("@")]
+    assert sum(1 for f in body if int(f[1]) & 2) >= 4000                  # properly paired records
+    assert sum(1 for f in body if "S" in f[5]) >= 20                      # soft-clipped = rescued by Smith-Waterman
