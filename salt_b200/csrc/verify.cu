@@ -19,33 +19,65 @@
 namespace salt {
 
 // --------------------------------------------------------------------------------------
-// pack_reads: one thread per 64-bit output word (16 bases).
+// pack_reads: eight lanes per read-strand, lane t writing 64-bit words t, t+8, .. (16 bases each).
+// A code c becomes the nibble 1 << c, N (and anything above 3) becomes 15: one shift of a 20-bit
+// table.  Strand 1 is the reverse complement (query.c:46-64): base i comes from L-1-i with 3 - c.
 // --------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_nib(uint32_t c, bool comp)
+{
+    c = c > 4u ? 4u : c;
+    // forward: 0,1,2,3,N -> 1,2,4,8,15     complement: 0,1,2,3,N -> 8,4,2,1,15
+    return ((comp ? 0xF1248u : 0xF8421u) >> (4u * c)) & 15u;
+}
+
 __global__ void __launch_bounds__(256)
 pack_reads_kernel(const uint8_t *__restrict__ codes, const uint32_t *__restrict__ offs, uint32_t n_reads,
                   uint32_t W64, uint64_t *__restrict__ rd4, uint16_t *__restrict__ rd_len)
 {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)n_reads * 2 * W64;
-    if (idx >= total) return;
-    const uint32_t w = (uint32_t)(idx % W64);
-    const uint32_t rs = (uint32_t)(idx / W64);
-    const uint32_t rid = rs >> 1, strand = rs & 1;
+    const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;      // read-strand
+    const int lane = threadIdx.x & 7;
+    if (g >= (size_t)n_reads * 2) return;
+    const uint32_t rid = (uint32_t)(g >> 1);
+    const bool rev = (g & 1) != 0;
     const uint32_t o = offs[rid];
     const int L = (int)(offs[rid + 1] - o);
-    uint64_t word = 0;
+    const uint8_t *__restrict__ src = codes + o;
+    uint64_t *__restrict__ dst = rd4 + g * W64;
+    for (uint32_t w = lane; w < W64; w += 8) {
+        const int i0 = (int)w * 16;
+        uint64_t word = 0;
+        if (i0 < L) {
+            const int nb = L - i0 < 16 ? L - i0 : 16;
+            if (!rev) {
+                if (nb == 16 && ((o + (uint32_t)i0) & 3u) == 0u) {              // four aligned 32-bit loads
+                    const uint32_t *__restrict__ s4 = reinterpret_cast<const uint32_t *>(src + i0);
 #pragma unroll
-    for (int b = 0; b < 16; ++b) {
-        const int i = (int)w * 16 + b;
-        if (i < L) {
-            unsigned c = strand ? codes[o + (L - 1 - i)] : codes[o + i];
-            if (strand && c < 4) c = 3 - c;
-            const uint64_t nib = c > 3 ? 15u : (1u << c);
-            word |= nib << (4 * b);
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t v = s4[k];
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) word |= (uint64_t)pack_nib((v >> (8 * b)) & 255u, false) << (4 * (4 * k + b));
+                    }
+                } else {
+                    for (int b = 0; b < nb; ++b) word |= (uint64_t)pack_nib(src[i0 + b], false) << (4 * b);
+                }
+            } else {
+                const int top = L - 1 - i0;                                     // base i0 of the strand comes from here
+                if (nb == 16 && ((o + (uint32_t)(top - 15)) & 3u) == 0u) {
+                    const uint32_t *__restrict__ s4 = reinterpret_cast<const uint32_t *>(src + top - 15);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t v = s4[k];                               // bytes top-15+4k .. top-12+4k
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) word |= (uint64_t)pack_nib((v >> (8 * b)) & 255u, true) << (4 * (15 - 4 * k - b));
+                    }
+                } else {
+                    for (int b = 0; b < nb; ++b) word |= (uint64_t)pack_nib(src[top - b], true) << (4 * b);
+                }
+            }
         }
+        dst[w] = word;
     }
-    rd4[idx] = word;
-    if (w == 0 && strand == 0) rd_len[rid] = (uint16_t)L;
+    if (lane == 0 && !rev) rd_len[rid] = (uint16_t)L;
 }
 
 // --------------------------------------------------------------------------------------
@@ -940,7 +972,7 @@ scan_gap_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t *__
 cudaError_t launch_pack_reads(const uint8_t *codes, const uint32_t *offs, uint32_t n_reads, uint32_t W64,
                               uint64_t *rd4, uint16_t *rd_len, cudaStream_t st)
 {
-    const size_t total = (size_t)n_reads * 2 * W64;
+    const size_t total = (size_t)n_reads * 2 * 8;        // eight lanes per read-strand
     if (!total) return cudaSuccess;
     SALT_LAUNCH(pack_reads_kernel, (unsigned)((total + 255) / 256), 256, 0, st, codes, offs, n_reads, W64, rd4, rd_len);
     SALT_LAUNCH_CHECK();
