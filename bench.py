@@ -314,8 +314,16 @@ def main():
         bytes_per_pair = (L + 1) // 2 + 8 + 2          # window nibbles + pair descriptor + result (60 B at L=100)
         mm_ms = kernels.get("nogap_fused", float("nan"))
         ach = (n0 + n1) * bytes_per_pair / (mm_ms * 1e-3) / 1e9
+        # dram__bytes_read+write of that kernel per launch, from the committed ncu --set full capture of this same
+        # workload (scaled by pairs if the run uses another size)
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1k_nogap_traffic.json")))
+            traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * (n0 + n1) / tr["pairs_per_launch"]
+        except Exception:
+            pass
         out["roofline"] = {"kernel": "nogap_fused_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                           "frac": ach / hbm, "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                           "frac": ach / hbm, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
                            "algorithmic_bytes_per_pair": bytes_per_pair, "kernel_ms": mm_ms, "dominant_kernel_of_step": dom}
 
     # ---------------- kernel-level extras: LV and SW sweeps (N=1 only)
