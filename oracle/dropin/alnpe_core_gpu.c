@@ -7,10 +7,19 @@
  *            alnse_locate (the first half of alnse_overlap, alnse.c:1001-1004)
  *   phase 2  the verification stage of all mates on the GPU with the paired-end thresholds
  *            (nogap 3, gapped 3: alnse.c:1016,1027) + query_set_hits -- salt_host.h
- *   phase 3  the reference's own pairing2 / pairing_singleton (mate rescue included) and alnpe_sam.
- * Only phase 2 leaves the reference's code.  (Batching phase 3's Smith-Waterman rescues through
- * salt_b200_ssw needs pairing2 re-staged; the kernel itself is parity-tested
- * against ssw_align separately.)
+ *   phase 3  the reference's own pairing2 / pairing_singleton and alnpe_sam, with the mate-rescue
+ *            Smith-Waterman of the whole chunk done in ONE salt_b200_ssw call per flavour:
+ *            alnpe.c is also compiled with its calls to ssw_init / ssw_align / init_destroy /
+ *            align_destroy renamed to the hooks below.  Pass 1 runs pairing with hooks that only RECORD
+ *            which (mate, strand, window) a rescue asks for and answer "not found" (the queries are
+ *            snapshotted and restored around it); the recorded windows go to the GPU; pass 2 runs pairing
+ *            again with hooks that REPLAY the GPU's s_align records, so every decision and every field
+ *            update after a rescue is still the reference's own code.  Window coordinates are not visible
+ *            to the hooks; they are recomputed from the anchor mate with pairing2's / pairing_singleton's
+ *            arithmetic (alnpe.c:206-252, :413-466) and checked byte for byte against the window the
+ *            reference unpacked -- a request that does not check, or that the engine declines (window
+ *            touching the end of the reference, CIGAR longer than the stride), runs the reference's own
+ *            ssw_align instead and is counted.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -19,20 +28,171 @@
 #include "kvec.h"
 #include "aln.h"
 #include "sam.h"
+#include "ssw.h"
 #include "salt_host.h"
 
 #define DROPIN_PE_MAX_N_PERSEQ 5          /* alnpe.c:481 */
 #define DROPIN_CHUNK_READS 20000u
 #define DROPIN_CHUNK_CANDS (20000u * 256u)
+#define DROPIN_CIG_STRIDE 64
 
 int pairing2(index_t *index, query_t *q0, query_t *q1, const aln_opt_t *aln_opt);
 int pairing_singleton(index_t *index, query_t *q0, query_t *q1, aln_opt_t *aln_opt);
 void alnpe_sam(index_t *index, query_t *q, const aln_opt_t *opt);
+extern int8_t score_mat[25], score_mat2[256];       /* alnpe.c:52-73 */
 
 static void die(const char *what)
 {
     fprintf(stderr, "[salt_dropin/pe] %s: %s\n", what, salt_b200_last_error());
     exit(1);
+}
+
+/* ------------------------------------------------------------------ rescue hooks */
+typedef struct { const int8_t *read; int32_t len; const int8_t *mat; int32_t n; s_profile *real; } hook_profile_t;
+typedef struct {
+    int pair, mate, strand, flavour;       /* flavour 16 = mixRef masks (snpaln_sw_snpaware), 5 = pac (snpaln_sw) */
+    uint32_t start, end;
+    int on_gpu;                             /* 0 = the reference's own ssw_align serves it */
+} rescue_req_t;
+
+enum { MODE_RECORD = 1, MODE_REPLAY = 2 };
+static struct {
+    int mode, func;                         /* func 2 = pairing2, 1 = pairing_singleton */
+    index_t *index; const aln_opt_t *opt;
+    query_t *q[2]; int pair; int chunk_idx[2];
+    rescue_req_t *req; size_t n_req, m_req, cursor;
+    salt_ssw_out_t *res; uint32_t *cig; size_t *res_of;     /* GPU results, indexed through res_of[request] */
+    size_t n_cpu;
+} H;
+
+static int identify(const hook_profile_t *p, int *mate, int *strand)
+{
+    int m, s, i;
+    for (m = 0; m < 2; ++m)
+        for (s = 0; s < 2; ++s) {
+            const uint8_t *seq = s ? H.q[m]->rseq : H.q[m]->seq;
+            if (H.q[m]->l_seq != p->len) continue;
+            if (p->n == 5) { if ((const uint8_t *)p->read == seq) { *mate = m; *strand = s; return 1; } continue; }
+            for (i = 0; i < p->len; ++i) if ((uint8_t)p->read[i] != (uint8_t)(1u << seq[i])) break;
+            if (i == p->len) { *mate = m; *strand = s; return 1; }
+        }
+    return 0;
+}
+
+/* the window pairing2 (func 2) / pairing_singleton (func 1) hands to its rescue call when `a` anchors and `t` is rescued */
+static int window_of(const query_t *a, const query_t *t, int t_strand, uint32_t *start, uint32_t *end)
+{
+    const uint32_t l2 = a->l_seq + t->l_seq, l_pac = H.index->bntseq->l_pac;
+    const uint32_t min_isize = H.opt->min_tlen > l2 ? H.opt->min_tlen - l2 : 0;
+    const uint32_t max_isize = H.opt->max_tlen > l2 ? H.opt->max_tlen - l2 : 0;
+    uint32_t s, e;
+    if (a->pos == 0xFFFFFFFF) return 0;
+    if (a->strand == 0) {                   /* anchor forward: mate expected downstream, on the other strand */
+        if (t_strand != 1) return 0;
+        s = a->pos + min_isize + a->l_seq;
+        e = a->pos + max_isize + a->l_seq + t->l_seq;
+    } else {
+        if (t_strand != 0) return 0;
+        s = a->pos > max_isize + t->l_seq ? a->pos - max_isize - t->l_seq : 0;
+        e = a->pos > min_isize ? a->pos - min_isize : 0;
+    }
+    if (H.func == 2) { e = e >= l_pac ? l_pac : e; }
+    else { s = s < l_pac - 1 ? s : l_pac - 1; e = e < l_pac - 1 ? e : l_pac - 1; }
+    *start = s; *end = e;
+    return 1;
+}
+
+static int window_matches(int flavour, uint32_t start, uint32_t end, const int8_t *ref, int32_t refLen)
+{
+    uint32_t i;
+    if (end < start || (int64_t)end - start + 1 != refLen) return 0;
+    if (end >= H.index->mixRef->l) return 0;             /* the engine does not read past the reference */
+    for (i = 0; i < (uint32_t)refLen; ++i) {
+        const uint32_t p = start + i;
+        const int sym = flavour == 16 ? (int)((H.index->mixRef->seq[p >> 3] >> (4 * (p & 7))) & 15)
+                                      : (int)((H.index->pac[p >> 2] >> ((~p & 3) << 1)) & 3);
+        if (sym != ref[i]) return 0;
+    }
+    return 1;
+}
+
+s_profile *dropin_ssw_init(const int8_t *read, const int32_t readLen, const int8_t *mat, const int32_t n, const int8_t score_size)
+{
+    hook_profile_t *p = calloc(1, sizeof *p);
+    p->read = read; p->len = readLen; p->mat = mat; p->n = n;
+    p->real = ssw_init(read, readLen, mat, n, score_size);          /* cheap; only used when a request falls back */
+    return (s_profile *)p;
+}
+
+void dropin_init_destroy(s_profile *pp)
+{
+    hook_profile_t *p = (hook_profile_t *)pp;
+    init_destroy(p->real);
+    free(p);
+}
+
+void dropin_align_destroy(s_align *a) { if (a) { free(a->cigar); free(a); } }
+
+s_align *dropin_ssw_align(const s_profile *pp, const int8_t *ref, int32_t refLen, const uint8_t gapO, const uint8_t gapE,
+                          const uint8_t flag, const uint16_t filters, const int32_t filterd, const int32_t maskLen)
+{
+    const hook_profile_t *p = (const hook_profile_t *)pp;
+    int mate = 0, strand = 0;
+    uint32_t start = 0, end = 0;
+    const int known = identify(p, &mate, &strand) && window_of(H.q[1 - mate], H.q[mate], strand, &start, &end) &&
+                      window_matches(p->n, start, end, ref, refLen) && H.chunk_idx[mate] >= 0;
+    if (H.mode == MODE_RECORD) {
+        if (H.n_req == H.m_req) { H.m_req = H.m_req ? H.m_req * 2 : 1024; H.req = realloc(H.req, H.m_req * sizeof *H.req); }
+        rescue_req_t *r = &H.req[H.n_req++];
+        r->pair = H.pair; r->mate = mate; r->strand = strand; r->flavour = p->n; r->start = start; r->end = end; r->on_gpu = known;
+        s_align *a = calloc(1, sizeof *a);              /* "nothing found": read span 1 < filterd, so the caller moves on */
+        return a;
+    }
+    /* replay: the k-th rescue call of this pair gets the k-th recorded request's answer */
+    if (H.cursor >= H.n_req || H.req[H.cursor].pair != H.pair) { fprintf(stderr, "[salt_dropin/pe] replay ran out of requests\n"); exit(1); }
+    const rescue_req_t *r = &H.req[H.cursor];
+    const size_t ri = H.res_of[H.cursor];
+    ++H.cursor;
+    if (r->on_gpu && (!known || r->mate != mate || r->strand != strand || r->start != start || r->end != end)) {
+        fprintf(stderr, "[salt_dropin/pe] replay diverged from the recorded run\n"); exit(1);
+    }
+    if (!r->on_gpu || H.res[ri].cigarLen < 0 || H.res[ri].cigarLen > DROPIN_CIG_STRIDE) {
+        ++H.n_cpu;
+        s_align *a = ssw_align(p->real, ref, refLen, gapO, gapE, flag, filters, filterd, maskLen);
+        /* the caller frees through dropin_align_destroy: same layout, same free()s (ssw.c:858-862) */
+        return a;
+    }
+    s_align *a = calloc(1, sizeof *a);
+    const salt_ssw_out_t *o = &H.res[ri];
+    a->score1 = o->score1; a->score2 = o->score2; a->ref_begin1 = o->ref_begin1; a->ref_end1 = o->ref_end1;
+    a->read_begin1 = o->read_begin1; a->read_end1 = o->read_end1; a->ref_end2 = o->ref_end2; a->cigarLen = o->cigarLen;
+    if (o->cigarLen > 0) {
+        a->cigar = malloc((size_t)o->cigarLen * 4);
+        memcpy(a->cigar, H.cig + ri * DROPIN_CIG_STRIDE, (size_t)o->cigarLen * 4);
+    }
+    return a;
+}
+
+/* ------------------------------------------------------------------ query snapshots around the recording pass */
+typedef struct {
+    uint32_t pos, seq_start, seq_end; int strand, b0, b1; uint8_t n_diff, is_gap, mapq;
+    size_t cig_l; char cig[256]; size_t nh[2];
+} qsnap_t;
+
+static void snap(const query_t *q, qsnap_t *s)
+{
+    s->pos = q->pos; s->seq_start = q->seq_start; s->seq_end = q->seq_end; s->strand = q->strand; s->b0 = q->b0; s->b1 = q->b1;
+    s->n_diff = q->n_diff; s->is_gap = q->is_gap; s->mapq = q->mapq; s->cig_l = q->cigar->l;
+    memcpy(s->cig, q->cigar->s, q->cigar->m < sizeof s->cig ? q->cigar->m : sizeof s->cig);
+    s->nh[0] = q->hits[0].n; s->nh[1] = q->hits[1].n;
+}
+
+static void unsnap(query_t *q, const qsnap_t *s)
+{
+    q->pos = s->pos; q->seq_start = s->seq_start; q->seq_end = s->seq_end; q->strand = s->strand; q->b0 = s->b0; q->b1 = s->b1;
+    q->n_diff = s->n_diff; q->is_gap = s->is_gap; q->mapq = s->mapq; q->cigar->l = s->cig_l;
+    memcpy(q->cigar->s, s->cig, q->cigar->m < sizeof s->cig ? q->cigar->m : sizeof s->cig);
+    q->hits[0].n = s->nh[0]; q->hits[1].n = s->nh[1];
 }
 
 /* what alnse_overlap leaves in query_t after its checks and query_set_hits (alnse.c:1014-1036) */
@@ -49,6 +209,84 @@ static void apply_result(query_t *query, const aln_opt_t *aln_opt, const salt_ch
             h.pos = r.alt[s][j].pos; h.n_diff = r.alt[s][j].n_diff; h.is_gap = r.alt[s][j].is_gap; h.strand = r.alt[s][j].strand;
             kv_push(hit_t, query->hits[s], h);
         }
+}
+
+static void run_pairing(index_t *index, query_t *q0, query_t *q1, aln_opt_t *aln_opt)      /* alnpe.c:507-517 */
+{
+    if (q0->pos != 0xFFFFFFFF && q1->pos != 0xFFFFFFFF) { H.func = 2; pairing2(index, q0, q1, aln_opt); }
+    else if (q0->pos != 0xFFFFFFFF || q1->pos != 0xFFFFFFFF) { H.func = 1; pairing_singleton(index, q0, q1, aln_opt); }
+}
+
+/* pairs [first, upto) of the chunk: record, one GPU batch per flavour, replay + SAM */
+static void pair_and_emit(salt_b200_t *gpu, index_t *index, aln_opt_t *aln_opt, query_t *multi_seqs, const int *slot_of,
+                          int first, int upto)
+{
+    int j;
+    size_t k;
+    H.index = index; H.opt = aln_opt; H.n_req = 0;
+    H.mode = MODE_RECORD;
+    for (j = first; j < upto; j += 2) {
+        query_t *q0 = multi_seqs + j, *q1 = multi_seqs + j + 1;
+        qsnap_t s0, s1;
+        H.q[0] = q0; H.q[1] = q1; H.pair = j; H.chunk_idx[0] = slot_of[j]; H.chunk_idx[1] = slot_of[j + 1];
+        snap(q0, &s0); snap(q1, &s1);
+        run_pairing(index, q0, q1, aln_opt);
+        unsnap(q0, &s0); unsnap(q1, &s1);
+    }
+    /* the windows the recording pass asked for, grouped by flavour */
+    H.res = realloc(H.res, (H.n_req + 1) * sizeof *H.res);
+    H.cig = realloc(H.cig, (H.n_req + 1) * DROPIN_CIG_STRIDE * 4);
+    H.res_of = realloc(H.res_of, (H.n_req + 1) * sizeof *H.res_of);
+    salt_win_t *wins = malloc((H.n_req + 1) * sizeof *wins);
+    size_t n_out = 0;
+    int flavour;
+    for (flavour = 16; flavour >= 5; flavour -= 11) {
+        const size_t base = n_out;
+        size_t m = 0;
+        for (k = 0; k < H.n_req; ++k) {
+            const rescue_req_t *r = &H.req[k];
+            if (r->flavour != flavour) continue;
+            H.res_of[k] = base + m;
+            if (!r->on_gpu) { H.res[base + m].cigarLen = -1; ++m; continue; }
+            /* a window the engine may still decline comes back with cigarLen < 0: it gets its own call below */
+            ++m;
+        }
+        /* compact GPU list */
+        size_t g = 0, *map = malloc((m + 1) * sizeof *map);
+        for (k = 0; k < H.n_req; ++k) {
+            const rescue_req_t *r = &H.req[k];
+            if (r->flavour != flavour || !r->on_gpu) continue;
+            const int ci = slot_of[r->pair + r->mate];
+            wins[g].rs = ((uint32_t)ci << 1) | (uint32_t)r->strand; wins[g].start = r->start; wins[g].end = r->end;
+            map[g++] = H.res_of[k];
+        }
+        if (g) {
+            salt_ssw_out_t *o = malloc(g * sizeof *o);
+            uint32_t *cg = calloc(g * DROPIN_CIG_STRIDE, 4);
+            const int rc = salt_b200_ssw(gpu, wins, g, flavour == 5, flavour == 5 ? score_mat : score_mat2, flavour, aln_opt->gap_op,
+                                         aln_opt->gap_ex, 2, aln_opt->filters, aln_opt->filterd, -1, o, cg, DROPIN_CIG_STRIDE);
+            if (rc != SALT_OK && rc != SALT_ERR_UNSUPPORTED) die("salt_b200_ssw");
+            for (k = 0; k < g; ++k) {
+                H.res[map[k]] = o[k];
+                memcpy(H.cig + map[k] * DROPIN_CIG_STRIDE, cg + k * DROPIN_CIG_STRIDE, DROPIN_CIG_STRIDE * 4);
+            }
+            free(o); free(cg);
+        }
+        free(map);
+        n_out = base + m;
+    }
+    free(wins);
+    H.mode = MODE_REPLAY; H.cursor = 0;
+    for (j = first; j < upto; j += 2) {
+        query_t *q0 = multi_seqs + j, *q1 = multi_seqs + j + 1;
+        H.q[0] = q0; H.q[1] = q1; H.pair = j; H.chunk_idx[0] = slot_of[j]; H.chunk_idx[1] = slot_of[j + 1];
+        run_pairing(index, q0, q1, aln_opt);
+        if (H.cursor < H.n_req && H.req[H.cursor].pair == j) {
+            /* a rescue that succeeds ends pairing early: skip the requests recorded after it */
+            while (H.cursor < H.n_req && H.req[H.cursor].pair == j) ++H.cursor;
+        }
+        alnpe_sam(index, multi_seqs + j, aln_opt);
+    }
 }
 
 int alnpe_core(const opt_t *opt)
@@ -71,8 +309,10 @@ int alnpe_core(const opt_t *opt)
     aln_samhead(opt, index->bntseq);
 
     int n, tot = 0;
+    size_t n_rescue = 0;
     query_t *multi_seqs = calloc(N_SEQS, sizeof(query_t));
     int *slot_of = calloc(N_SEQS, sizeof(int));
+    char *verified = calloc(N_SEQS, 1);
     while ((n = query_read_multiPairedSeqs(qs, N_SEQS, multi_seqs)) > 0) {
         if (opt->max_tlen == 0) { fprintf(stderr, "infer isize func haven't been implemented\n"); break; }
         int first = 0;                               /* mates [first, i) are queued; first is always even */
@@ -81,21 +321,27 @@ int alnpe_core(const opt_t *opt)
             int flush = (i == n);
             if (!flush) {
                 query_t *query = multi_seqs + i;
-                slot_of[i] = -1;
-                if (query->n_ambiguous > DROPIN_PE_MAX_N_PERSEQ) continue;               /* alnpe.c:495 */
-                if (query->l_seq - aln_opt->l_seed + 1 > aux[0]->n_sai_range) {
-                    int n_sai_range = query->l_seq - aln_opt->l_seed + 1;
-                    aux_resize(aux[0], n_sai_range);
-                    aux_resize(aux[1], n_sai_range);
-                }
-                aux_reset(aux[0]);
-                aux_reset(aux[1]);
-                alnse_seed_overlap(index, query->l_seq, query->seq, aln_opt, aux[0]);
-                alnse_locate(index, query->l_seq, aln_opt->max_locate, aux[0]);
-                alnse_seed_overlap(index, query->l_seq, query->rseq, aln_opt, aux[1]);
-                alnse_locate(index, query->l_seq, aln_opt->max_locate, aux[1]);
-                int at = salt_chunk_add_read(ck, query->seq, query->l_seq, aux[0]->loci.a, aux[0]->loci.n,
+                int at;
+                slot_of[i] = -1; verified[i] = 0;
+                if (query->n_ambiguous > DROPIN_PE_MAX_N_PERSEQ) {
+                    /* alnpe.c:495 skips its verification; the mate still has to be on the device for a possible rescue */
+                    at = salt_chunk_add_read(ck, query->seq, query->l_seq, NULL, 0, NULL, 0);
+                } else {
+                    if (query->l_seq - aln_opt->l_seed + 1 > aux[0]->n_sai_range) {
+                        int n_sai_range = query->l_seq - aln_opt->l_seed + 1;
+                        aux_resize(aux[0], n_sai_range);
+                        aux_resize(aux[1], n_sai_range);
+                    }
+                    aux_reset(aux[0]);
+                    aux_reset(aux[1]);
+                    alnse_seed_overlap(index, query->l_seq, query->seq, aln_opt, aux[0]);
+                    alnse_locate(index, query->l_seq, aln_opt->max_locate, aux[0]);
+                    alnse_seed_overlap(index, query->l_seq, query->rseq, aln_opt, aux[1]);
+                    alnse_locate(index, query->l_seq, aln_opt->max_locate, aux[1]);
+                    at = salt_chunk_add_read(ck, query->seq, query->l_seq, aux[0]->loci.a, aux[0]->loci.n,
                                              aux[1]->loci.a, aux[1]->loci.n);
+                    verified[i] = 1;
+                }
                 if (at == SALT_ERR_NOMEM && salt_chunk_n_reads(ck) > 0) flush = 2;       /* queue full */
                 else if (at < 0) die("salt_chunk_add_read");
                 else slot_of[i] = at;
@@ -109,13 +355,9 @@ int alnpe_core(const opt_t *opt)
                     if (salt_chunk_wait(gpu, 0, ck) != SALT_OK) die("salt_chunk_wait");
                 }
                 for (j = first; j < upto; ++j)
-                    if (slot_of[j] >= 0) apply_result(multi_seqs + j, aln_opt, ck, (uint32_t)slot_of[j]);
-                for (j = first; j + 1 < upto + 1 && j < upto; j += 2) {                  /* alnpe.c:507-519 */
-                    query_t *q0 = multi_seqs + j, *q1 = multi_seqs + j + 1;
-                    if (q0->pos != 0xFFFFFFFF && q1->pos != 0xFFFFFFFF) pairing2(index, q0, q1, aln_opt);
-                    else if (q0->pos != 0xFFFFFFFF || q1->pos != 0xFFFFFFFF) pairing_singleton(index, q0, q1, aln_opt);
-                    alnpe_sam(index, multi_seqs + j, aln_opt);
-                }
+                    if (verified[j]) apply_result(multi_seqs + j, aln_opt, ck, (uint32_t)slot_of[j]);
+                pair_and_emit(gpu, index, aln_opt, multi_seqs, slot_of, first, upto);
+                n_rescue += H.n_req;
                 first = upto;
                 salt_chunk_reset(ck);
                 if (flush == 2) i = upto - 1;        /* re-queue from the first mate not yet verified */
@@ -132,11 +374,12 @@ int alnpe_core(const opt_t *opt)
         memset(multi_seqs, '\0', sizeof(query_t) * N_SEQS);
         fprintf(stderr, "alned %d reads!\n", tot);
     }
+    fprintf(stderr, "[salt_dropin/pe] rescue windows recorded: %zu, served by the reference's own ssw_align: %zu\n", n_rescue, H.n_cpu);
     aux_destroy(aux[0]);
     aux_destroy(aux[1]);
     query_close(qs[0]);
     query_close(qs[1]);
-    free(multi_seqs); free(slot_of);
+    free(multi_seqs); free(slot_of); free(verified);
     salt_chunk_free(ck);
     salt_b200_destroy(gpu);
     alnpe_index_destroy(index);

@@ -65,6 +65,9 @@ def test_pe_sam_identical(tmp_path, flags):
     _run([os.path.join(REFDIR, "salt")] + flags + ["idx", "r1.fq", "r2.fq"], d, os.path.join(d, "ref.sam"))
     err = _run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", "r1.fq", "r2.fq"], d, os.path.join(d, "gpu.sam"))
     assert "verification on libsalt_b200" in err
+    import re
+    m = re.search(r"rescue windows recorded: (\d+), served by the reference's own ssw_align: (\d+)", err)
+    assert m and int(m.group(1)) >= 200 and int(m.group(2)) <= int(m.group(1)) // 20, err[-500:]    # the rescues ran on the GPU
     want, got = _sam_body(os.path.join(d, "ref.sam")), _sam_body(os.path.join(d, "gpu.sam"))
     assert len(want) == len(got) and len(want) > 6000
     for a, b in zip(want, got):
