@@ -93,11 +93,26 @@ sw_prep_kernel(SwDev d)
     }
     if (item < d.CW) {                                  // window word: columns 8*item .. 8*item+7
         uint32_t word = 0;
-        for (int b = 0; b < 8; ++b) {
-            const int col = item * 8 + b;
-            if (col < cols) {
-                const uint32_t p = REV ? start + (uint32_t)(ref_end - col) : start + (uint32_t)col;
-                word |= (uint32_t)sw_ref_symbol(d.c, d.prm.use_pac, p) << (4 * b);
+        const int col0 = item * 8;
+        if (!d.prm.use_pac && col0 < cols) {
+            // eight mask nibbles with one funnel shift of two aligned reference words (the reference is
+            // padded on both sides, engine.cu); the reverse pass wants them in descending order
+            const int nv = cols - col0 < 8 ? cols - col0 : 8;
+            const int64_t p0 = REV ? (int64_t)start + ref_end - col0 - 7 : (int64_t)start + col0;   // lowest position of the group
+            const uint32_t *__restrict__ mw = d.c.mixref + (p0 >> 3);
+            uint32_t x = __funnelshift_r(mw[0], mw[1], 4 * (int)(p0 & 7));
+            if (REV) {
+                x = __byte_perm(x, 0u, 0x0123);                                   // byte order, then the nibbles in each byte
+                x = ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);
+            }
+            word = nv < 8 ? (x & ((1u << (4 * nv)) - 1u)) : x;
+        } else {
+            for (int b = 0; b < 8; ++b) {
+                const int col = col0 + b;
+                if (col < cols) {
+                    const uint32_t p = REV ? start + (uint32_t)(ref_end - col) : start + (uint32_t)col;
+                    word |= (uint32_t)sw_ref_symbol(d.c, d.prm.use_pac, p) << (4 * b);
+                }
             }
         }
         uint32_t *dst = reinterpret_cast<uint32_t *>(d.win2 + (t >> 1) * d.CW + item);
@@ -375,7 +390,9 @@ sw_banded_kernel(BandDev d)
     const int read0 = o.read_begin1;
     const int score = o.score1, gapO = d.prm.gapO, gapE = d.prm.gapE;
     int band = abs(refLen - readLen) + 1;                                    // ssw.c:845
-    uint8_t *dirs = d.dirs + tid * d.slot;
+    // direction bytes of the 32 tasks of a warp are interleaved ([cell][lane]): the tasks of a warp walk
+    // their bands in step, so a warp's byte stores and traceback loads land in one 32-byte sector
+    uint8_t *dirs = d.dirs + (tid >> 5) * (d.slot * 32) + (tid & 31);
     int hb[2 * BWMAX + 5], eb[2 * BWMAX + 5], hc[2 * BWMAX + 5];
     int max = 0, wd = 0;
     bool overflow = false;
@@ -391,7 +408,7 @@ sw_banded_kernel(BandDev d)
             const int edge = end + 1 < width - 1 ? end + 1 : width - 1;
             int fcur = 0;
             hb[0] = eb[0] = hb[edge] = eb[edge] = hc[0] = 0;
-            uint8_t *dl = dirs + (size_t)wd * i;
+            uint8_t *dl = dirs + (size_t)wd * i * 32;
             const int rc = sw_read_code(d.c, w.rs, read0 + i);
             for (int j = beg; j <= end; ++j) {
                 u = band_u(band, i, j);
@@ -412,7 +429,7 @@ sw_banded_kernel(BandDev d)
                 hc[u] = t1 > t2 ? t1 : t2;
                 if (hc[u] > max) max = hc[u];
                 const int dh = t1 <= t2 ? 1 : (e1 > f1 ? de : df);
-                dl[band_d(band, i, j)] = sw_dir_pack(de, df, dh);
+                dl[band_d(band, i, j) * 32] = sw_dir_pack(de, df, dh);
             }
             for (int j = 1; j <= u; ++j) hb[j] = hc[j];
         }
@@ -438,7 +455,7 @@ sw_banded_kernel(BandDev d)
     while (i > 0) {
         const int x = band_d(band, i, j);
         if (x < 0 || x >= wd || j < 0) { bad = true; break; }
-        const int code = sw_dir_get(dirs[(size_t)wd * i + x], state);
+        const int code = sw_dir_get(dirs[((size_t)wd * i + x) * 32], state);
         switch (code) {
         case 1: --i; --j; state = 2; fop = 0; break;
         case 2: --i; state = 0; fop = 1; break;

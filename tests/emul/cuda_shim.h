@@ -183,6 +183,13 @@ static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh)
 {
     sh &= 31u; return sh ? (hi << sh) | (lo >> (32 - sh)) : hi;
 }
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel)
+{
+    unsigned long long src = (unsigned long long)a | ((unsigned long long)b << 32);
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) r |= (unsigned)((src >> (8 * ((sel >> (4 * i)) & 7u))) & 255u) << (8 * i);
+    return r;
+}
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 using std::min;
