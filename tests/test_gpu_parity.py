@@ -229,3 +229,42 @@ def test_build_mixref_on_device(oracle):
     mask = np.array([oracle.lib.orc_allele_mask(r[2].encode()) for r in rows], np.uint8)
     eng = api.Engine.from_bases(fasta, pos, mask)
     assert np.array_equal(eng.get_mixref(), want)
+
+
+def test_error_paths():
+    """misuse is reported through return codes and salt_b200_last_error(), never by exiting"""
+    import ctypes as C
+    g, reads, pos, strand, cands = pc.make_world(5, glen=50000, L=100, n_reads=20, per_strand=2)
+    eng = _engine(g, pac=False)
+    L_ = eng.L
+    pairs = api.Engine.make_pairs([0], [0], [10])
+    with pytest.raises(api.SaltError) as e:
+        eng.mismatch(pairs, 3)                                   # no reads set yet
+    assert e.value.code == -101
+    eng.set_reads(reads)
+    with pytest.raises(api.SaltError):
+        eng.mismatch(pairs, 500)                                 # max_err out of range
+    with pytest.raises(api.SaltError):
+        eng.lv_cigar(pairs, np.array([31], np.uint8))            # LandauVishkin.c:183 asserts k < 31
+    wins = np.zeros(1, api.WIN_DT); wins["end"] = 300
+    with pytest.raises(api.SaltError) as e:
+        eng.ssw(wins, api.salt_score_mat2(), 16, False, gapO=1, gapE=1)      # gapO <= gapE is not reproduced
+    assert e.value.code == -104
+    with pytest.raises(api.SaltError):
+        eng.ssw(wins, api.salt_score_mat(), 5, True)             # no pac uploaded
+    # a slot cannot take a second chunk before it was waited for; bad slot numbers are refused
+    offs0, loci0, offs1, loci1 = cands
+    n = len(reads)
+    codes = np.ascontiguousarray(reads).reshape(-1); roffs = (np.arange(n + 1) * 100).astype(np.uint32)
+    r = api.ReadsT(codes.ctypes.data, roffs.ctypes.data, n)
+    c = api.CandsT(); c.offs[0], c.offs[1] = offs0.ctypes.data, offs1.ctypes.data; c.loci[0], c.loci[1] = loci0.ctypes.data, loci1.ctypes.data
+    rec = np.zeros(n, api.VERIFY_DT)
+    assert L_.salt_b200_verify_submit(eng.h, 9, C.byref(r), C.byref(c), 3, -1, rec.ctypes.data, None, None, None, 0) == -101
+    assert L_.salt_b200_verify_submit(eng.h, 1, C.byref(r), C.byref(c), 3, -1, rec.ctypes.data, None, None, None, 0) == 0
+    assert L_.salt_b200_verify_submit(eng.h, 1, C.byref(r), C.byref(c), 3, -1, rec.ctypes.data, None, None, None, 0) == -101
+    assert L_.salt_b200_verify_wait(eng.h, 1) == 0
+    assert (rec["pos"] != 0xFFFFFFFF).sum() >= 10
+    # a window that leaves the reference comes back flagged, not crashed
+    wins = np.zeros(2, api.WIN_DT); wins["start"] = [10, g.l - 50]; wins["end"] = [310, g.l + 20]
+    with pytest.raises(api.SaltError):
+        eng.ssw(wins, api.salt_score_mat2(), 16, False)
