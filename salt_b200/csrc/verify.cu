@@ -997,8 +997,8 @@ cudaError_t launch_mismatch(const DevCtx &c, const salt_pair_t *pairs, size_t n,
     if (!n) return cudaSuccess;
     const int lm = (int)c.l_max;                        // l_max + 16 <= 16*G*WPL, as for nogap_fused
     if (lm <= 112) return launch_mismatch_t<8, 1>(c, pairs, n, max_err, out, st);
-    if (lm <= 240) return launch_mismatch_t<16, 1>(c, pairs, n, max_err, out, st);
-    if (lm <= 496) return launch_mismatch_t<32, 1>(c, pairs, n, max_err, out, st);
+    if (lm <= 240) return launch_mismatch_t<8, 2>(c, pairs, n, max_err, out, st);
+    if (lm <= 496) return launch_mismatch_t<16, 2>(c, pairs, n, max_err, out, st);
     if (lm <= 1008) return launch_mismatch_t<32, 2>(c, pairs, n, max_err, out, st);
     return launch_mismatch_t<32, 3>(c, pairs, n, max_err, out, st);
 }
