@@ -479,9 +479,53 @@ lv_filter_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int 
                 }
             }
             uint32_t P[TW], m[TW];
+            bool hasN = false;
 #pragma unroll
             for (int j = 0; j < TW; ++j) {
                 P[j] = (ok && t0 + j < nf) ? prow[t0 + j] : 0u;     // words past the last full one never match
+                hasN = hasN || ((P[j] & (P[j] >> 1) & 0x11111111u) != 0u);
+            }
+            // A read base is one-hot, so "all eight nibbles of P & W non-zero" is "P & ~W == 0": one LOP3 and
+            // a running minimum per word and diagonal.  N (15) matches any non-empty mask, which that test
+            // does not express: a warp holding such a read takes the general has-zero-nibble form (warp-uniform).
+            if (!__any_sync(0xffffffffu, hasN)) {
+#pragma unroll
+                for (int j = 0; j < TW; ++j) m[j] = (t0 + j < nf && ok) ? (P[j] & ~TA[j + 4]) : 1u;           // diagonal 0
+                {
+                    uint32_t W[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) W[j] = TA[j + 4];
+                    for (int d = 1; d <= kpw; ++d) {
+#pragma unroll
+                        for (int j = 0; j < 15; ++j) W[j] = __funnelshift_r(W[j], W[j + 1], 4);
+                        W[15] >>= 4;
+                        if (d <= kp) {
+#pragma unroll
+                            for (int j = 0; j < TW; ++j) m[j] = min(m[j], P[j] & ~W[j]);
+                        }
+                    }
+                }
+                {
+                    uint32_t W[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) W[j] = TA[j];
+                    for (int d = 1; d <= kw; ++d) {
+#pragma unroll
+                        for (int j = 15; j > 0; --j) W[j] = __funnelshift_l(W[j - 1], W[j], 4);
+                        W[0] <<= 4;
+                        if (d <= k) {
+#pragma unroll
+                            for (int j = 0; j < TW; ++j) m[j] = min(m[j], P[j] & ~W[j + 4]);
+                        }
+                    }
+                }
+                // an absent word (P = 0) would pass "P & ~W == 0": it was seeded with 1 and min() keeps 0 out only
+                // if every test is masked too
+#pragma unroll
+                for (int j = 0; j < TW; ++j) if (!(t0 + j < nf && ok)) m[j] = 1u;
+            } else {
+#pragma unroll
+            for (int j = 0; j < TW; ++j) {
                 m[j] = lv_haszero(P[j] & TA[j + 4]);                // diagonal 0
             }
             // ---- diagonals +1 .. +k: the window moves down one nibble per step
@@ -513,6 +557,7 @@ lv_filter_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int 
                         for (int j = 0; j < TW; ++j) m[j] = min(m[j], lv_haszero(P[j] & W[j + 4]));
                     }
                 }
+            }
             }
 #pragma unroll
             for (int j = 0; j < TW; ++j) found += (m[j] == 0u && t0 + j < nf) ? 1 : 0;
