@@ -217,6 +217,59 @@ __host__ __device__ inline int lv_tw(int l_max) { return (l_max + 4 + 64) / 8 + 
 __host__ __device__ inline int lv_pw(int l_max) { return (l_max + 64) / 8 + 2; }
 
 // --------------------------------------------------------------------------------------
+// Group-cooperative longest common extension (same result as lv_extend, lv_core.cuh).
+// Every lane first looks at the gate and at the first 8 symbols of ITS diagonal; almost all
+// diagonals stop there.  The few that run on (the diagonal the read really lies on) are then
+// finished one at a time by the whole group, lane t testing symbols [8t, 8t+8) of each block of 8G
+// beyond the point reached, so a 100-base extension costs one ballot instead of a dozen dependent
+// iterations of one lane while the others wait.
+// --------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ int lv_extend_group(const uint32_t *T, const uint32_t *P, int best, int d, bool active,
+                                               int plen, int tlen, int lane, unsigned gmask, int gshift)
+{
+    constexpr unsigned gfull = (unsigned)((1ull << G) - 1ull);
+    const int lim = imin(plen, tlen - d);
+    bool more = false;
+    if (active) {
+        const uint32_t pc = nib8(P, best), tc = nib8(T, d + best);
+        const uint32_t pb = pc & 15u, tb = tc & 15u;
+        if (pb == tb) {                                             // equality gate (LandauVishkin.c:79)
+            if (pb == 0) best = lim;                                // both exhausted: the 8-byte x == 0 shortcut
+            else {
+                const uint32_t z = zero_nibbles(pc & tc);
+                if (z) best = imin(best + first_set_nibble(z), lim);
+                else if (best + 8 >= lim) best = lim;
+                else { best += 8; more = true; }
+            }
+        }
+    }
+    unsigned todo = (__ballot_sync(gmask, more) >> gshift) & gfull;
+    while (todo) {
+        const int src = __ffs((int)todo) - 1;
+        todo &= todo - 1;
+        const int b = __shfl_sync(gmask, best, src, G);
+        const int dd = __shfl_sync(gmask, d, src, G);
+        const int e = imin(plen, tlen - dd);
+        int res = e;
+        for (int base = b; base < e; base += 8 * G) {
+            const int off = base + 8 * lane;
+            // lanes past the end report a stop at their first symbol; the min() below clamps it
+            const uint32_t z = off < e ? zero_nibbles(nib8(P, off) & nib8(T, dd + off)) : 1u;
+            const unsigned bal = (__ballot_sync(gmask, z != 0) >> gshift) & gfull;
+            if (bal) {
+                const int first = __ffs((int)bal) - 1;
+                const int idx = __shfl_sync(gmask, z ? first_set_nibble(z) : 0, first, G);
+                res = imin(base + 8 * first + idx, e);
+                break;
+            }
+        }
+        if (lane == src) best = res;
+    }
+    return best;
+}
+
+// --------------------------------------------------------------------------------------
 // lv: G lanes per pair, DPL diagonals per lane (diagonal d = lane*DPL + q - G*DPL/2).
 // Furthest-reaching values of the previous level live in registers; neighbours are
 // exchanged with __shfl_up/down inside the group.  The diagonal order of the reference
@@ -276,13 +329,10 @@ lv_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_fixed
                         const int left = q == 0 ? lft : Lp[q - 1];
                         const int right = q == DPL - 1 ? rgt : Lp[q + 1];
                         int best = imax(imax(Lp[q] + 1, left), right + 1);
-                        if (d >= -e && d <= e) {
-                            best = lv_extend(T, P, best, d, plen, tlen);
-                            hit = hit || best == plen;
-                            Ln[q] = best;
-                        } else {
-                            Ln[q] = -2;
-                        }
+                        const bool act = d >= -e && d <= e;
+                        best = lv_extend_group<G>(T, P, best, d, act, plen, tlen, lane, gmask, gshift);
+                        hit = hit || (act && best == plen);
+                        Ln[q] = act ? best : -2;
                     }
                     if (__any_sync(gmask, hit)) { result = e; break; }
 #pragma unroll
@@ -655,8 +705,9 @@ lv_cigar_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8_t *
                         int best = Lp[q] + 1; char a = 'X';                // LandauVishkin.c:249-260
                         if (left > best) { best = left; a = 'D'; }
                         if (right > best) { best = right; a = 'I'; }
-                        if (d >= -e && d <= e) {
-                            best = lv_extend(T, P, best, d, plen, tlen);
+                        const bool act = d >= -e && d <= e;
+                        best = lv_extend_group<G>(T, P, best, d, act, plen, tlen, lane, gmask, 0);
+                        if (act) {
                             if (best == plen) myrank = imin(myrank, lv_cigar_rank(d));
                             Ln[q] = best;
                             tabA[e * ND + d + C] = a;
