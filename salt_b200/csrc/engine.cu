@@ -59,9 +59,12 @@ struct DBuf {
 struct Slot {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
-    DBuf codes, offs, rd4, rd_len;
+    DBuf codes, offs3, rd4, rd_len;                           // offs3: read offsets, then the two candidate-offset arrays
     uint32_t n_reads = 0, W64 = 0, l_max = 0;
-    DBuf c_offs0, c_loci0, c_offs1, c_loci1, vpairs, acc, rec, lvlist, ciglist, counters, cig, fpairs, fslots, lvreads;
+    bool offs_merged = false;                                 // all three offset arrays arrived in one copy
+    uint32_t *d_roffs() const { return offs3.as<uint32_t>(); }
+    uint32_t *d_coffs(int strand) const { return offs3.as<uint32_t>() + (size_t)(strand + 1) * ((size_t)n_reads + 1); }
+    DBuf c_loci0, c_loci1, vpairs, acc, rec, lvlist, ciglist, counters, cig, fpairs, fslots, lvreads;
     // asynchronous verify in flight: where the compact CIGAR list has to be scattered to
     bool pending = false;
     char *u_cigars = nullptr; int u_stride = 0;
@@ -74,7 +77,7 @@ struct Slot {
 
     void release()
     {
-        DBuf *all[] = {&codes, &offs, &rd4, &rd_len, &c_offs0, &c_loci0, &c_offs1, &c_loci1, &vpairs, &acc, &rec,
+        DBuf *all[] = {&codes, &offs3, &rd4, &rd_len, &c_loci0, &c_loci1, &vpairs, &acc, &rec,
                        &lvlist, &ciglist, &counters, &cig, &fpairs, &fslots, &lvreads};
         for (DBuf *b : all) b->release();
         if (h_stage) cudaFreeHost(h_stage);
@@ -161,7 +164,9 @@ cudaError_t alloc_mixref(salt_b200_t *h, size_t nb, cudaStream_t st)
 }
 
 // Upload + pack one chunk of reads into a slot.  Asynchronous on the slot's stream.
-int load_reads(salt_b200_t *h, Slot &s, const salt_reads_t *reads)
+// `with` non-null: if the caller keeps the read offsets and both candidate-offset arrays back to back in host
+// memory (salt_b200_verify_batch and the host layer's chunk queues do), all three travel in one copy.
+int load_reads(salt_b200_t *h, Slot &s, const salt_reads_t *reads, const salt_cands_t *with = nullptr)
 {
     if (!reads || !reads->offs || (reads->n_reads && !reads->codes)) return fail(SALT_ERR_ARG, "reads is null");
     if (reads->n_reads >= (1u << 31)) return fail(SALT_ERR_ARG, "too many reads in one chunk");
@@ -177,13 +182,14 @@ int load_reads(salt_b200_t *h, Slot &s, const salt_reads_t *reads)
     if (n && reads->offs[0] != 0) return fail(SALT_ERR_ARG, "read offsets must start at 0");
     s.n_reads = n; s.l_max = l_max; s.W64 = (l_max + 15) / 16 + 1;
     CU(s.codes.need(total + 16));
-    CU(s.offs.need(((size_t)n + 1) * 4));
+    CU(s.offs3.need(3 * ((size_t)n + 1) * 4));
     CU(s.rd4.need((size_t)n * 2 * s.W64 * 8 + 64));
     CU(s.rd_len.need((size_t)n * 2 + 64));
     if (n) {
         CU(cudaMemcpyAsync(s.codes.p, reads->codes, total, cudaMemcpyHostToDevice, s.stream));
-        CU(cudaMemcpyAsync(s.offs.p, reads->offs, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, s.stream));
-        CU(launch_pack_reads(s.codes.as<uint8_t>(), s.offs.as<uint32_t>(), n, s.W64, s.rd4.as<uint64_t>(),
+        s.offs_merged = with && with->offs[0] == reads->offs + ((size_t)n + 1) && with->offs[1] == with->offs[0] + ((size_t)n + 1);
+        CU(cudaMemcpyAsync(s.offs3.p, reads->offs, (s.offs_merged ? 3 : 1) * ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, s.stream));
+        CU(launch_pack_reads(s.codes.as<uint8_t>(), s.d_roffs(), n, s.W64, s.rd4.as<uint64_t>(),
                              s.rd_len.as<uint16_t>(), s.stream));
         h->launches += 1;
     }
@@ -264,7 +270,6 @@ int enqueue_verify(salt_b200_t *h, int si, const salt_cands_t *cands, int nogap_
     const uint32_t nr = s.n_reads;
     const size_t n0 = cands->offs[0][nr], n1 = cands->offs[1][nr];
     if ((n0 && !cands->loci[0]) || (n1 && !cands->loci[1])) return fail(SALT_ERR_ARG, "null loci");
-    CU(s.c_offs0.need(((size_t)nr + 1) * 4)); CU(s.c_offs1.need(((size_t)nr + 1) * 4));
     CU(s.c_loci0.need(n0 * 4 + 4)); CU(s.c_loci1.need(n1 * 4 + 4));
     CU(s.acc.need(n0 + n1 + 1));
     CU(s.rec.need((size_t)nr * sizeof(salt_verify_out_t)));
@@ -281,14 +286,17 @@ int enqueue_verify(salt_b200_t *h, int si, const salt_cands_t *cands, int nogap_
             s.h_stage_cap = want;
         }
     }
-    CU(cudaMemcpyAsync(s.c_offs0.p, cands->offs[0], ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, s.stream));
-    CU(cudaMemcpyAsync(s.c_offs1.p, cands->offs[1], ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, s.stream));
+    if (!s.offs_merged) {
+        CU(cudaMemcpyAsync(s.d_coffs(0), cands->offs[0], ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(s.d_coffs(1), cands->offs[1], ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, s.stream));
+    }
+    s.offs_merged = false;                               // one use: a later verify on the same reads uploads its own lists
     if (n0) CU(cudaMemcpyAsync(s.c_loci0.p, cands->loci[0], n0 * 4, cudaMemcpyHostToDevice, s.stream));
     if (n1) CU(cudaMemcpyAsync(s.c_loci1.p, cands->loci[1], n1 * 4, cudaMemcpyHostToDevice, s.stream));
     int8_t *acc = s.acc.as<int8_t>();
     uint32_t *cl = cigars ? s.ciglist.as<uint32_t>() : nullptr;
-    if (int rc = verify_on_device(h, si, s.c_offs0.as<uint32_t>(), s.c_loci0.as<uint32_t>(), n0,
-                                  s.c_offs1.as<uint32_t>(), s.c_loci1.as<uint32_t>(), n1, nogap_T0, lv_T0,
+    if (int rc = verify_on_device(h, si, s.d_coffs(0), s.c_loci0.as<uint32_t>(), n0,
+                                  s.d_coffs(1), s.c_loci1.as<uint32_t>(), n1, nogap_T0, lv_T0,
                                   s.rec.as<salt_verify_out_t>(), acc, acc + n0,
                                   cigars ? s.cig.as<char>() : nullptr, cigar_stride, cl ? cl + 1 : nullptr, cl))
         return rc;
@@ -734,7 +742,7 @@ int salt_b200_verify_submit(salt_b200_t *h, int slot, const salt_reads_t *reads,
     if (slot < 0 || slot >= SALT_SLOTS) return fail(SALT_ERR_ARG, "slot out of range");
     Slot &s = h->slot[slot];
     if (s.pending) return fail(SALT_ERR_ARG, "slot has a verify in flight: call salt_b200_verify_wait first");
-    if (int rc = load_reads(h, s, reads)) return rc;
+    if (int rc = load_reads(h, s, reads, cands)) return rc;
     if (!s.n_reads) return SALT_OK;
     return enqueue_verify(h, slot, cands, nogap_T0, lv_T0, rec, acc0, acc1, cigars, cigar_stride);
 }

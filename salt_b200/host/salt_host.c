@@ -9,7 +9,7 @@ struct salt_chunk {
     uint32_t max_reads; size_t max_bases, max_cands;
     uint32_t n_reads;
     /* pinned inputs */
-    uint8_t *codes; uint32_t *roffs;
+    uint8_t *codes; uint32_t *offs_all; uint32_t *roffs;
     uint32_t *offs[2]; uint32_t *loci[2];
     /* pinned outputs */
     salt_verify_out_t *rec; int8_t *acc[2]; char *cigars;
@@ -24,11 +24,14 @@ salt_chunk_t *salt_chunk_new(uint32_t max_reads, size_t max_bases, size_t max_ca
     if (!c) return NULL;
     c->max_reads = max_reads; c->max_bases = max_bases; c->max_cands = max_cands;
     c->codes = (uint8_t *)pinned(max_bases + 16);
-    c->roffs = (uint32_t *)pinned(((size_t)max_reads + 1) * 4);
+    /* read offsets and the two candidate-offset arrays share one allocation; salt_chunk_submit lays them back to
+       back for the chunk's actual read count so that the engine uploads them in one copy */
+    c->offs_all = (uint32_t *)pinned(6 * ((size_t)max_reads + 1) * 4);
+    c->roffs = c->offs_all;
     c->rec = (salt_verify_out_t *)pinned((size_t)max_reads * sizeof(salt_verify_out_t));
     c->cigars = (char *)pinned((size_t)max_reads * 128);
     for (int s = 0; s < 2; ++s) {
-        c->offs[s] = (uint32_t *)pinned(((size_t)max_reads + 1) * 4);
+        c->offs[s] = c->offs_all ? c->offs_all + (size_t)(s + 1) * ((size_t)max_reads + 1) : NULL;
         c->loci[s] = (uint32_t *)pinned(max_cands * 4 + 4);
         c->acc[s] = (int8_t *)pinned(max_cands + 1);
     }
@@ -41,9 +44,9 @@ salt_chunk_t *salt_chunk_new(uint32_t max_reads, size_t max_bases, size_t max_ca
 void salt_chunk_free(salt_chunk_t *c)
 {
     if (!c) return;
-    salt_b200_host_free(c->codes); salt_b200_host_free(c->roffs); salt_b200_host_free(c->rec);
+    salt_b200_host_free(c->codes); salt_b200_host_free(c->offs_all); salt_b200_host_free(c->rec);
     salt_b200_host_free(c->cigars);
-    for (int s = 0; s < 2; ++s) { salt_b200_host_free(c->offs[s]); salt_b200_host_free(c->loci[s]); salt_b200_host_free(c->acc[s]); }
+    for (int s = 0; s < 2; ++s) { salt_b200_host_free(c->loci[s]); salt_b200_host_free(c->acc[s]); }
     free(c);
 }
 
@@ -76,8 +79,12 @@ int salt_chunk_add_read(salt_chunk_t *c, const uint8_t *seq, uint32_t l_seq,
 int salt_chunk_submit(salt_b200_t *h, int slot, salt_chunk_t *c, int nogap_T0, int lv_T0)
 {
     salt_reads_t r; salt_cands_t k;
-    r.codes = c->codes; r.offs = c->roffs; r.n_reads = c->n_reads;
-    k.offs[0] = c->offs[0]; k.offs[1] = c->offs[1]; k.loci[0] = c->loci[0]; k.loci[1] = c->loci[1];
+    /* compact copy of the three offset arrays, back to back, in the second half of the allocation */
+    const size_t m1 = (size_t)c->n_reads + 1;
+    uint32_t *pk = c->offs_all + 3 * ((size_t)c->max_reads + 1);
+    memcpy(pk, c->roffs, m1 * 4); memcpy(pk + m1, c->offs[0], m1 * 4); memcpy(pk + 2 * m1, c->offs[1], m1 * 4);
+    r.codes = c->codes; r.offs = pk; r.n_reads = c->n_reads;
+    k.offs[0] = pk + m1; k.offs[1] = pk + 2 * m1; k.loci[0] = c->loci[0]; k.loci[1] = c->loci[1];
     c->lv_T0 = lv_T0; c->done = 0;
     if (!c->n_reads) return SALT_OK;
     /* query->cigar starts out empty (kstring, query.c:208-209): gapped primaries get theirs from the GPU */
