@@ -931,7 +931,7 @@ __device__ __forceinline__ void nogap_read(const DevCtx &c, const uint2 *__restr
 }
 
 template <int G, int WPL>
-__global__ void __launch_bounds__(256, (G == 8 && WPL == 1) ? 4 : (WPL == 2 && G <= 16) ? 3 : 1)
+__global__ void __launch_bounds__(64, (G == 8 && WPL == 1) ? 16 : (WPL == 2 && G <= 16) ? 12 : 4)
 nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t *__restrict__ loci0,
                    const uint32_t *__restrict__ offs1, const uint32_t *__restrict__ loci1, size_t n0,
                    int T0, int8_t *__restrict__ acc, salt_verify_out_t *__restrict__ rec,
@@ -1237,7 +1237,7 @@ static cudaError_t launch_nogap_t(const DevCtx &c, const uint32_t *offs0, const 
 {
     auto kern = nogap_fused_kernel<G, WPL>;
     const size_t threads = (size_t)c.n_reads * G;
-    SALT_LAUNCH(kern, (unsigned)((threads + 255) / 256), 256, 0, st, c, offs0, loci0, offs1, loci1, n0, T0, acc, rec,
+    SALT_LAUNCH(kern, (unsigned)((threads + 63) / 64), 64, 0, st, c, offs0, loci0, offs1, loci1, n0, T0, acc, rec,
                 lv_pairs, lv_slots, lv_count, lv_reads);
     SALT_LAUNCH_CHECK();
     return cudaSuccess;
