@@ -75,3 +75,40 @@ def test_pe_sam_identical(tmp_path, flags):
     body = [ln.split("\t") for ln in want if ln and not ln.startswith("@")]
     assert sum(1 for f in body if int(f[1]) & 2) >= 4000                  # properly paired records
     assert sum(1 for f in body if "S" in f[5]) >= 20                      # soft-clipped = rescued by Smith-Waterman
+
+
+def test_mixref_builder_matches_salt_idx(tmp_path, oracle):
+    """row A: the SNP-aware reference built on the device from FASTA bases + SNP rows equals the PREFIX.ref file
+    the reference's own indexer (salt-idx -> build_mixRef, Index_src/mixRef.c:93) writes"""
+    import numpy as np
+    from salt_b200 import api
+    if not _have():
+        pytest.skip("oracle/_ref programs not built (reference tree absent at build time)")
+    d = str(tmp_path)
+    fa, sn, fq = dropin_data.write_inputs(d, n_reads=10)
+    _run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], d, os.path.join(d, "idx.log"))
+    raw = np.fromfile(os.path.join(d, "idx.ref"), np.uint32)
+    l, words = int(raw[0]), raw[1:].copy()
+    recs, name = [], None
+    for ln in open(fa):
+        ln = ln.strip()
+        if ln.startswith(">"):
+            name = ln[1:]; recs.append([name, []])
+        else:
+            recs[-1][1].append(ln)
+    recs = [(n, "".join(p)) for n, p in recs]
+    offs = {}
+    tot = 0
+    for n, sq in recs:
+        offs[n] = tot; tot += len(sq)
+    assert tot == l
+    pos, mask = [], []
+    for ln in open(sn):
+        c, p1, al, rf = ln.rstrip("\n").split("\t")
+        pos.append(offs[c] + int(p1) - 1); mask.append(oracle.lib.orc_allele_mask(al.encode()))
+    eng = api.Engine.from_bases("".join(sq for _, sq in recs), np.array(pos, np.uint32), np.array(mask, np.uint8), device=0)
+    got = eng.get_mixref()
+    if l % 8:                                  # nibbles past l in the file's last word are uninitialised heap (realloc, mixRef.c:135)
+        words[-1] &= np.uint32((1 << (4 * (l % 8))) - 1)
+    assert len(got) == len(words) and np.array_equal(got, words)
+    assert (np.bitwise_count(words) > 8).sum() > 100 if hasattr(np, "bitwise_count") else True      # SNP sites carry extra allele bits
