@@ -206,7 +206,7 @@ int salt_b200_ssw_dev(salt_b200_t *h, const salt_win_t *d_wins, size_t n, int us
 
 /* Per-stage device timing (CUDA events on the handle's stream around each kernel).
  * After a verify / ssw call with profiling enabled, salt_b200_profile_read synchronises and fills
- * ms[0..5]  = (unused), nogap_fused, (unused), lv, scan_gap, lv_cigar   (verify stage)
+ * ms[0..5]  = (unused), nogap_fused, (unused), lv (pre-filter + Landau-Vishkin), scan_gap, lv_cigar   (verify stage)
  * ms[6..11] = prep_fwd, dp_fwd, prep_rev, dp_rev, banded, banded_overflow (ssw)
  * with -1 for stages that did not run. */
 int salt_b200_profile(salt_b200_t *h, int enable);
