@@ -373,7 +373,7 @@ def bench_lv(eng, lib, h, wl, args, dev, stream):
         sec = e0.elapsed_time(e1) * 1e-3 / 3
         res["k%d" % k] = {"pairs_per_s": len(pairs) / sec, "gcups_equiv": len(pairs) * L * (L + 4) / sec / 1e9, "ms": sec * 1e3}
     # the two work mappings at the SE default k = L/10 (north star: warp per candidate, lanes over diagonals)
-    for mapping, name in ((1, "warp_per_pair_k10"), (0, "thread_per_pair_k10")):
+    for mapping, name in ((1, "warp_per_pair_k10"), (2, "thread_per_pair_k10")):
         lib.salt_b200_set_lv_mapping(h, mapping)
         lib.salt_b200_lv_dev(h, d_pairs.data_ptr(), len(pairs), 10, d_out.data_ptr())
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)

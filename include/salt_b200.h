@@ -174,8 +174,9 @@ int salt_b200_verify_batch(salt_b200_t *h, const salt_reads_t *reads, const salt
                            char *cigars, int cigar_stride);
 
 /* Landau-Vishkin work mapping: 0 = automatic (one thread per pair with all diagonals in
- * registers for k <= 15, one warp per pair with lanes over diagonals beyond), 1 = always one
- * warp (or sub-warp group) per pair.  Results are identical; this exists for measurement. */
+ * registers for k <= 15 inside the verify stage, one warp per pair with lanes over diagonals
+ * beyond that and on flat pair lists), 1 = always one warp (or sub-warp group) per pair,
+ * 2 = one thread per pair whenever k <= 15.  Results are identical; this exists for measurement. */
 int salt_b200_set_lv_mapping(salt_b200_t *h, int mapping);
 
 /* Pigeonhole pre-filter in front of Landau-Vishkin (default on): a pair can only be within k

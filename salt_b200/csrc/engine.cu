@@ -105,7 +105,7 @@ struct salt_b200 {
     // staging / scratch of the synchronous per-pair and SSW entry points (slot 0's stream)
     DBuf pairs, out8, kbuf, cig, wins, sswout, sswcig, sswscratch;
     uint64_t launches = 0;
-    int lv_mapping = 0;         // 0 = auto, 1 = force warp-per-pair (salt_b200_set_lv_mapping)
+    int lv_mapping = 0;         // 0 = auto, 1 = warp per pair, 2 = thread per pair (salt_b200_set_lv_mapping)
     int max_window = 1024;      // widest rescue window the SSW scratch is sized for
     bool profiling = false;
     cudaEvent_t ev_ssw[7] = {nullptr};
@@ -661,7 +661,7 @@ int salt_b200_ssw_dev(salt_b200_t *h, const salt_win_t *d_wins, size_t n, int us
 int salt_b200_set_lv_mapping(salt_b200_t *h, int mapping)
 {
     if (!h) return fail(SALT_ERR_ARG, "null handle");
-    if (mapping != 0 && mapping != 1) return fail(SALT_ERR_ARG, "mapping must be 0 (auto) or 1 (warp per pair)");
+    if (mapping < 0 || mapping > 2) return fail(SALT_ERR_ARG, "mapping must be 0 (auto), 1 (warp per pair) or 2 (thread per pair)");
     h->lv_mapping = mapping;
     return SALT_OK;
 }

@@ -37,6 +37,38 @@ SALT_HD int lv_extend(const uint32_t *T, const uint32_t *P, int best, int d, int
     return imin(best, e);
 }
 
+// lv_extend split in two for thread-per-pair kernels: the gate and the first 8 symbols here,
+// the rest in lv_extend_more.  Most diagonals stop inside the first word; the few that run on
+// (`more`) are finished after the level's diagonal loop, where the lanes of a warp that have one
+// iterate together instead of one after the other.
+SALT_HD int lv_extend_first(const uint32_t *T, const uint32_t *P, int best, int d, int plen, int tlen, bool &more)
+{
+    const int e = imin(plen, tlen - d);
+    const uint32_t pc = nib8(P, best), tc = nib8(T, d + best);
+    const uint32_t pb = pc & 15u, tb = tc & 15u;
+    more = false;
+    if (pb != tb) return best;
+    if (pb == 0) return e;
+    const uint32_t z = zero_nibbles(pc & tc);
+    if (z) return imin(best + first_set_nibble(z), e);
+    if (best + 8 >= e) return e;
+    more = true;
+    return best + 8;
+}
+
+// continuation of lv_extend_first from `best` < endl(d), all symbols before it matched
+SALT_HD int lv_extend_more(const uint32_t *T, const uint32_t *P, int best, int d, int plen, int tlen)
+{
+    const int e = imin(plen, tlen - d);
+    for (;;) {
+        const uint32_t z = zero_nibbles(nib8(P, best) & nib8(T, d + best));
+        if (z) { best += first_set_nibble(z); break; }
+        best += 8;
+        if (best >= e) break;
+    }
+    return imin(best, e);
+}
+
 // Level-0 extension from (0,0), no gate (LandauVishkin.c:41-58).  Single-thread form; the
 // kernels use a cooperative version with the same result.
 SALT_HD int lv_extend0(const uint32_t *T, const uint32_t *P, int plen, int tlen)

@@ -421,6 +421,7 @@ lv_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_f
                 for (int e = 1; e <= k; ++e) {
                     int Ln[2 * K + 1];
                     bool hit = false;
+                    int pend_di = -1, pend_best = 0;                // one deferred long extension per level
 #pragma unroll
                     for (int di = 0; di < 2 * K + 1; ++di) {
                         const int d = di - K;
@@ -428,14 +429,24 @@ lv_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_f
                         if (d >= -e && d <= e) {
                             const int left = di > 0 ? Lp[di > 0 ? di - 1 : 0] : -2;
                             const int right = di < 2 * K ? Lp[di < 2 * K ? di + 1 : 0] + 1 : -1;
-                            v = lv_extend(T, P, imax(imax(Lp[di] + 1, left), right), d, plen, tlen);
+                            bool more;
+                            v = lv_extend_first(T, P, imax(imax(Lp[di] + 1, left), right), d, plen, tlen, more);
+                            if (more) {
+                                if (pend_di < 0) { pend_di = di; pend_best = v; }
+                                else v = lv_extend_more(T, P, v, d, plen, tlen);
+                            }
                             hit = hit || v == plen;
                         }
                         Ln[di] = v;
                     }
+                    int pend_v = 0;
+                    if (pend_di >= 0) {
+                        pend_v = lv_extend_more(T, P, pend_best, pend_di - K, plen, tlen);
+                        hit = hit || pend_v == plen;
+                    }
                     if (hit) { result = e; break; }
 #pragma unroll
-                    for (int i = 0; i < 2 * K + 1; ++i) Lp[i] = Ln[i];
+                    for (int i = 0; i < 2 * K + 1; ++i) Lp[i] = i == pend_di ? pend_v : Ln[i];
                 }
             }
         }
@@ -1153,7 +1164,7 @@ static cudaError_t launch_lv_core(const DevCtx &c, const salt_pair_t *pairs, siz
 {
     int kmax = k >= 0 ? k : (int)c.l_max / 10;
     if (kmax > LV_MAXK - 1) kmax = LV_MAXK - 1;
-    if (mapping == 0 && c.l_max <= 512) {
+    if (mapping != 1 && c.l_max <= 512) {
         if (kmax <= 3) return launch_lv_tpp<3>(c, pairs, n, k, worklist, wl_count, wl_cap, out, sm_count, st);
         if (kmax <= 8) return launch_lv_tpp<8>(c, pairs, n, k, worklist, wl_count, wl_cap, out, sm_count, st);
         if (kmax <= 10) return launch_lv_tpp<10>(c, pairs, n, k, worklist, wl_count, wl_cap, out, sm_count, st);
@@ -1184,11 +1195,10 @@ cudaError_t launch_lv(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k
     SALT_LAUNCH(lv_filter_kernel, (unsigned)blocks, threads, 0, st, c, pairs, n, k, worklist, wl_count, out,
                 f->pairs, f->slots, f->count);
     SALT_LAUNCH_CHECK();
-    // Survivors are mostly true hits and their +-1..3 shifted twins, which stop after a few levels.
-    // Measured on B200 (profiles/): inside the verify stage (few survivors per launch) one thread per
-    // pair is faster, on flat decoy-heavy lists (many survivors) one warp per pair is.
-    return launch_lv_core(c, f->pairs, items, k, f->slots, f->count, items, out, sm_count, st,
-                          mapping == 0 ? (worklist ? 0 : 1) : mapping);
+    // Survivors are mostly true hits and their +-1..3 shifted twins, which stop after a few levels:
+    // one thread per pair (long extensions deferred to the end of a level) beats one warp per pair on
+    // both the verify stage's worklists and flat decoy-heavy lists (profiles/r1r_lv_split.txt).
+    return launch_lv_core(c, f->pairs, items, k, f->slots, f->count, items, out, sm_count, st, mapping);
 }
 
 template <int DPL>

@@ -107,7 +107,7 @@ def test_gpu_pairs(gold, tag, L):
     assert np.array_equal(eng.mismatch(pairs, 0), gold[tag + "_mm0"])
     for filt in (1, 0):
         eng.set_lv_filter(filt)
-        for mapping in (0, 1):
+        for mapping in (0, 1, 2):
             eng.set_lv_mapping(mapping)
             assert np.array_equal(eng.lv(pairs, -1), gold[tag + "_lvk"]), (filt, mapping)
             assert np.array_equal(eng.lv(pairs, 3), gold[tag + "_lv3"]), (filt, mapping)
