@@ -40,11 +40,13 @@ SALT_HD int lv_extend(const uint32_t *T, const uint32_t *P, int best, int d, int
 // lv_extend split in two for thread-per-pair kernels: the gate and the first 8 symbols here,
 // the rest in lv_extend_more.  Most diagonals stop inside the first word; the few that run on
 // (`more`) are finished after the level's diagonal loop, where the lanes of a warp that have one
-// iterate together instead of one after the other.
-SALT_HD int lv_extend_first(const uint32_t *T, const uint32_t *P, int best, int d, int plen, int tlen, bool &more)
+// iterate together instead of one after the other.  `toff`: nibble offset of text position 0 inside T
+// (a kernel may keep the window as the raw 16-byte-aligned reference words it loaded).
+SALT_HD int lv_extend_first(const uint32_t *T, const uint32_t *P, int best, int d, int plen, int tlen, bool &more,
+                            int toff = 0)
 {
     const int e = imin(plen, tlen - d);
-    const uint32_t pc = nib8(P, best), tc = nib8(T, d + best);
+    const uint32_t pc = nib8(P, best), tc = nib8(T, toff + d + best);
     const uint32_t pb = pc & 15u, tb = tc & 15u;
     more = false;
     if (pb != tb) return best;
@@ -57,11 +59,11 @@ SALT_HD int lv_extend_first(const uint32_t *T, const uint32_t *P, int best, int 
 }
 
 // continuation of lv_extend_first from `best` < endl(d), all symbols before it matched
-SALT_HD int lv_extend_more(const uint32_t *T, const uint32_t *P, int best, int d, int plen, int tlen)
+SALT_HD int lv_extend_more(const uint32_t *T, const uint32_t *P, int best, int d, int plen, int tlen, int toff = 0)
 {
     const int e = imin(plen, tlen - d);
     for (;;) {
-        const uint32_t z = zero_nibbles(nib8(P, best) & nib8(T, d + best));
+        const uint32_t z = zero_nibbles(nib8(P, best) & nib8(T, toff + d + best));
         if (z) { best += first_set_nibble(z); break; }
         best += 8;
         if (best >= e) break;
@@ -71,12 +73,12 @@ SALT_HD int lv_extend_more(const uint32_t *T, const uint32_t *P, int best, int d
 
 // Level-0 extension from (0,0), no gate (LandauVishkin.c:41-58).  Single-thread form; the
 // kernels use a cooperative version with the same result.
-SALT_HD int lv_extend0(const uint32_t *T, const uint32_t *P, int plen, int tlen)
+SALT_HD int lv_extend0(const uint32_t *T, const uint32_t *P, int plen, int tlen, int toff = 0)
 {
     const int e = imin(plen, tlen);
     int i = 0;
     while (i < e) {
-        const uint32_t z = zero_nibbles(nib8(P, i) & nib8(T, i));
+        const uint32_t z = zero_nibbles(nib8(P, i) & nib8(T, toff + i));
         if (z) { i += first_set_nibble(z); break; }
         i += 8;
     }

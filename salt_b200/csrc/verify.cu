@@ -215,6 +215,12 @@ __device__ __forceinline__ int lv_level0(const uint32_t *T, const uint32_t *P, i
 // Shared-memory words needed per pair for a chunk whose longest read is l_max.
 __host__ __device__ inline int lv_tw(int l_max) { return (l_max + 4 + 64) / 8 + 2; }
 __host__ __device__ inline int lv_pw(int l_max) { return (l_max + 64) / 8 + 2; }
+// thread-per-pair kernel: window kept as raw 16-byte-aligned reference words (up to 31 nibbles in front)
+__host__ __device__ inline int lv_twr(int l_max) { return ((31 + l_max + 4 + 64) / 8 + 2 + 3) & ~3; }
+__device__ __forceinline__ uint32_t lv_tailmask(int r)             // keep the low r nibbles (r <= 0: none, r >= 8: all)
+{
+    return r >= 8 ? 0xffffffffu : (r <= 0 ? 0u : (1u << (4 * r)) - 1u);
+}
 
 // --------------------------------------------------------------------------------------
 // Group-cooperative longest common extension (same result as lv_extend, lv_core.cuh).
@@ -361,8 +367,8 @@ lv_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_f
               int8_t *__restrict__ out)
 {
     SALT_DYN_SMEM(uint32_t, smem);
-    const int TW = lv_tw((int)c.l_max), PW = lv_pw((int)c.l_max);
-    const int stride = (TW + PW) | 1;
+    const int TW = lv_twr((int)c.l_max), PW = lv_pw((int)c.l_max);
+    const int stride = (TW + PW) | 1;                  // odd: the 32 rows of a warp sit in 32 different banks
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *wbase = smem + (size_t)warp * 32 * stride;
     uint32_t *T = wbase + (size_t)lane * stride;
@@ -380,30 +386,32 @@ lv_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_f
         const int plen = (live && rid < c.n_reads) ? (int)c.rd_len[rid] : 0;
         const int tlen = plen + 4;                                  // alnse.c:373
         const bool ok = plen > 0 && (uint64_t)p.pos + (uint64_t)tlen <= (uint64_t)c.l;   // editdistance.c:178
-        // ---- cooperative staging of the warp's 32 windows and reads
-        for (int j = 0; j < 32; ++j) {
-            const uint32_t pos_j = __shfl_sync(0xffffffffu, p.pos, j);
-            const uint32_t rs_j = __shfl_sync(0xffffffffu, p.rs, j);
-            const int tlen_j = __shfl_sync(0xffffffffu, ok ? tlen : 0, j);
-            if (tlen_j == 0) continue;
-            uint32_t *Tj = wbase + (size_t)j * stride;
-            uint32_t *Pj = Tj + TW;
-            const uint32_t *__restrict__ r32 = reinterpret_cast<const uint32_t *>(c.rd4 + (size_t)rs_j * c.W64);
-            const int have = (int)c.W64 * 2;
-            for (int i = lane; i < TW + PW; i += 32) {
-                if (i < TW) {
-                    const int valid = tlen_j - 8 * i;
-                    uint32_t x = 0;
-                    if (valid > 0) {
-                        const uint32_t o = pos_j + 8u * (uint32_t)i;
-                        x = __funnelshift_r(mix[o >> 3], mix[(o >> 3) + 1], (int)(o & 7u) * 4);
-                        if (valid < 8) x &= (1u << (4 * valid)) - 1u;
-                    }
-                    Tj[i] = x;
-                } else {
-                    const int pi = i - TW;
-                    Pj[pi] = pi < have ? r32[pi] : 0u;
-                }
+        // ---- every lane stages its own row: the window as the raw reference words from the 16-byte boundary
+        // below pos (text position 0 is nibble `toff` of the row; nibbles from toff + tlen on are cleared, the
+        // text is "0 beyond textLen"), then the packed read.  Wide independent loads, one row per bank.
+        int toff = 0;
+        if (ok) {
+            const uint32_t w0 = (p.pos >> 3) & ~3u;
+            toff = (int)(p.pos - 8u * w0);
+            const int tend = toff + tlen;
+            const uint4 *__restrict__ src = reinterpret_cast<const uint4 *>(mix + w0);
+#pragma unroll 4
+            for (int v = 0; v < TW / 4; ++v) {
+                const int rem = tend - 32 * v;                      // valid nibbles from this vector's first one
+                uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                if (rem > 0) x = src[v];
+                T[4 * v + 0] = x.x & lv_tailmask(rem);
+                T[4 * v + 1] = x.y & lv_tailmask(rem - 8);
+                T[4 * v + 2] = x.z & lv_tailmask(rem - 16);
+                T[4 * v + 3] = x.w & lv_tailmask(rem - 24);
+            }
+            const uint2 *__restrict__ r2 = reinterpret_cast<const uint2 *>(c.rd4 + (size_t)p.rs * c.W64);
+#pragma unroll 4
+            for (int i = 0; i < PW; i += 2) {
+                uint2 y = make_uint2(0u, 0u);
+                if ((i >> 1) < (int)c.W64) y = r2[i >> 1];
+                P[i] = y.x;
+                if (i + 1 < PW) P[i + 1] = y.y;
             }
         }
         __syncwarp();
@@ -411,7 +419,7 @@ lv_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_f
         if (ok) {
             int k = k_fixed >= 0 ? k_fixed : plen / 10;             // alnse.c:1090
             k = imin(imin(k, LV_MAXK - 1), K);                      // LandauVishkin.c:31
-            const int L0 = lv_extend0(T, P, plen, tlen);
+            const int L0 = lv_extend0(T, P, plen, tlen, toff);
             if (L0 == plen) result = 0;
             else {
                 int Lp[2 * K + 1];
@@ -430,10 +438,10 @@ lv_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_f
                             const int left = di > 0 ? Lp[di > 0 ? di - 1 : 0] : -2;
                             const int right = di < 2 * K ? Lp[di < 2 * K ? di + 1 : 0] + 1 : -1;
                             bool more;
-                            v = lv_extend_first(T, P, imax(imax(Lp[di] + 1, left), right), d, plen, tlen, more);
+                            v = lv_extend_first(T, P, imax(imax(Lp[di] + 1, left), right), d, plen, tlen, more, toff);
                             if (more) {
                                 if (pend_di < 0) { pend_di = di; pend_best = v; }
-                                else v = lv_extend_more(T, P, v, d, plen, tlen);
+                                else v = lv_extend_more(T, P, v, d, plen, tlen, toff);
                             }
                             hit = hit || v == plen;
                         }
@@ -441,7 +449,7 @@ lv_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_f
                     }
                     int pend_v = 0;
                     if (pend_di >= 0) {
-                        pend_v = lv_extend_more(T, P, pend_best, pend_di - K, plen, tlen);
+                        pend_v = lv_extend_more(T, P, pend_best, pend_di - K, plen, tlen, toff);
                         hit = hit || pend_v == plen;
                     }
                     if (hit) { result = e; break; }
@@ -1138,7 +1146,7 @@ static cudaError_t launch_lv_tpp(const DevCtx &c, const salt_pair_t *pairs, size
                                  const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
                                  int8_t *out, int sm_count, cudaStream_t st)
 {
-    const int stride = (lv_tw((int)c.l_max) + lv_pw((int)c.l_max)) | 1;
+    const int stride = (lv_twr((int)c.l_max) + lv_pw((int)c.l_max)) | 1;
     int threads = 128;
     size_t smem = (size_t)threads * stride * 4;
     if (smem > 100 * 1024) { threads = 64; smem = (size_t)threads * stride * 4; }
