@@ -249,7 +249,7 @@ int verify_on_device(salt_b200_t *h, int si, const uint32_t *d_offs0, const uint
     if (d_cigars) {
         const int kmax = lv_T0 >= 0 ? lv_T0 : (int)s.l_max / 10;     // a gapped primary's n_diff never exceeds the stage threshold
         CU(launch_lv_cigar(c, nullptr, nullptr, 0, d_cig_reads, d_cig_count, s.n_reads, d_rec, kmax,
-                           d_cigars, cigar_stride, nullptr, h->sm_count, s.stream));
+                           d_cigars, cigar_stride, nullptr, h->sm_count, s.stream, h->lv_mapping));
         h->launches += 1;
     }
     SALT_EV(6);
@@ -584,7 +584,7 @@ int salt_b200_lv_cigar(salt_b200_t *h, const salt_pair_t *pairs, const uint8_t *
     CU(cudaMemcpyAsync(h->kbuf.p, k_each, n, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(h->cig.p, 0, n * (size_t)stride, st));
     CU(launch_lv_cigar(h->ctx(), h->pairs.as<salt_pair_t>(), h->kbuf.as<uint8_t>(), n, nullptr, nullptr, 0, nullptr, kmax,
-                       h->cig.as<char>(), stride, h->out8.as<int8_t>(), h->sm_count, st));
+                       h->cig.as<char>(), stride, h->out8.as<int8_t>(), h->sm_count, st, h->lv_mapping));
     h->launches += 1;
     std::vector<char> tmp(n * (size_t)stride);
     CU(cudaMemcpyAsync(tmp.data(), h->cig.p, tmp.size(), cudaMemcpyDeviceToHost, st));

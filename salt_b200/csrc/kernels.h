@@ -20,7 +20,7 @@ cudaError_t launch_lv(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k
 cudaError_t launch_lv_cigar(const DevCtx &c, const salt_pair_t *pairs, const uint8_t *k_each, size_t n,
                             const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
                             const salt_verify_out_t *rec, int kmax, char *cigars, int stride, int8_t *out,
-                            int sm_count, cudaStream_t st);
+                            int sm_count, cudaStream_t st, int mapping);
 cudaError_t launch_nogap_fused(const DevCtx &c, const uint32_t *offs0, const uint32_t *loci0,
                                const uint32_t *offs1, const uint32_t *loci1, size_t n0, int T0,
                                int8_t *acc, salt_verify_out_t *rec, salt_pair_t *lv_pairs, uint32_t *lv_slots,

@@ -108,25 +108,33 @@ struct CigarOut {
     }
 };
 
+// Table layouts of the CIGAR variant: entry (e, d) of the furthest-reaching / action tables.
+struct LvRectIdx {                       // row-major [e][nd], diagonal d at column d + nd/2
+    int nd;
+    SALT_HD int operator()(int e, int d) const { return e * nd + d + nd / 2; }
+};
+struct LvTriIdx {                        // level e holds diagonals -e..e only: row e starts at e*e
+    SALT_HD int operator()(int e, int d) const { return e * e + d + e; }
+};
+
 // Backtrace + emission of computeEditDistanceWithCigar, useM = 1 (LandauVishkin.c:380-462).
-// Lt/At are the furthest-reaching table and action table, row-major [e][nd], diagonal d
-// at column d + nd/2.  Returns e or -2 (buffer too small).
-SALT_HD int lv_cigar_emit(const int16_t *Lt, const char *At, int nd, int e, int d, char *buf, int buflen)
+// Lt/At are the furthest-reaching table and action table addressed through `at`.
+// Returns e or -2 (buffer too small).
+template <class Idx>
+SALT_HD int lv_cigar_emit_t(const int16_t *Lt, const char *At, Idx at, int e, int d, char *buf, int buflen)
 {
-    const int LV_ND = nd;
-    const int C = nd / 2;
     char act[LV_MAXK + 1]; int run[LV_MAXK + 1];
     int cd = d;
     for (int ce = e; ce >= 1; --ce) {
-        const char a = At[ce * LV_ND + cd + C];
+        const char a = At[at(ce, cd)];
         act[ce] = a;
-        const int here = Lt[ce * LV_ND + cd + C];
-        if (a == 'I') { run[ce] = here - Lt[(ce - 1) * LV_ND + cd + 1 + C] - 1; cd += 1; }
-        else if (a == 'D') { run[ce] = here - Lt[(ce - 1) * LV_ND + cd - 1 + C]; cd -= 1; }
-        else { run[ce] = here - Lt[(ce - 1) * LV_ND + cd + C] - 1; }
+        const int here = Lt[at(ce, cd)];
+        if (a == 'I') { run[ce] = here - Lt[at(ce - 1, cd + 1)] - 1; cd += 1; }
+        else if (a == 'D') { run[ce] = here - Lt[at(ce - 1, cd - 1)]; cd -= 1; }
+        else { run[ce] = here - Lt[at(ce - 1, cd)] - 1; }
     }
     CigarOut o{buf, buflen};
-    int accM = Lt[C];
+    int accM = Lt[at(0, 0)];
     int ce = 1;
     while (ce <= e) {
         const char a = act[ce]; int cnt = 1;
@@ -142,6 +150,11 @@ SALT_HD int lv_cigar_emit(const int16_t *Lt, const char *At, int nd, int e, int 
     if (accM != 0) { if (!o.put(accM, 'M')) return -2; }
     if (o.len > 0) *o.buf = '\0';
     return e;
+}
+
+SALT_HD int lv_cigar_emit(const int16_t *Lt, const char *At, int nd, int e, int d, char *buf, int buflen)
+{
+    return lv_cigar_emit_t(Lt, At, LvRectIdx{nd}, e, d, buf, buflen);
 }
 
 }  // namespace salt

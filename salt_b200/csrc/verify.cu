@@ -351,6 +351,38 @@ lv_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_fixed
     }
 }
 
+// Thread-per-pair staging: the lane fills its own row with the window as the raw reference words from the
+// 16-byte boundary below pos (text position 0 is nibble `toff` of the row, returned; nibbles from
+// toff + tlen on are cleared -- the text is "0 beyond textLen"), then the packed read.  Wide independent
+// loads; with an odd row stride the 32 rows of a warp sit in 32 different banks.
+__device__ __forceinline__ int lv_stage_own(const DevCtx &c, const salt_pair_t p, int tlen, uint32_t *T, uint32_t *P,
+                                            int TW, int PW)
+{
+    const uint32_t w0 = (p.pos >> 3) & ~3u;
+    const int toff = (int)(p.pos - 8u * w0);
+    const int tend = toff + tlen;
+    const uint4 *__restrict__ src = reinterpret_cast<const uint4 *>(c.mixref + w0);
+#pragma unroll 4
+    for (int v = 0; v < TW / 4; ++v) {
+        const int rem = tend - 32 * v;                      // valid nibbles from this vector's first one
+        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+        if (rem > 0) x = src[v];
+        T[4 * v + 0] = x.x & lv_tailmask(rem);
+        T[4 * v + 1] = x.y & lv_tailmask(rem - 8);
+        T[4 * v + 2] = x.z & lv_tailmask(rem - 16);
+        T[4 * v + 3] = x.w & lv_tailmask(rem - 24);
+    }
+    const uint2 *__restrict__ r2 = reinterpret_cast<const uint2 *>(c.rd4 + (size_t)p.rs * c.W64);
+#pragma unroll 4
+    for (int i = 0; i < PW; i += 2) {
+        uint2 y = make_uint2(0u, 0u);
+        if ((i >> 1) < (int)c.W64) y = r2[i >> 1];
+        P[i] = y.x;
+        if (i + 1 < PW) P[i + 1] = y.y;
+    }
+    return toff;
+}
+
 // --------------------------------------------------------------------------------------
 // lv_tpp: one THREAD per pair, all 2K+1 diagonals of a level in registers (loops over the
 // diagonals are fully unrolled, so L[e-1][d-1], L[e-1][d], L[e-1][d+1] are plain registers).
@@ -375,7 +407,6 @@ lv_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_f
     uint32_t *P = T + TW;
     const size_t count = slots ? (size_t)*wl_count : n;
     const size_t step = (size_t)gridDim.x * blockDim.x;
-    const uint32_t *__restrict__ mix = c.mixref;
 
     for (size_t base = (size_t)blockIdx.x * blockDim.x + (size_t)warp * 32; base < count; base += step) {
         const size_t it = base + lane;
@@ -386,34 +417,7 @@ lv_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_f
         const int plen = (live && rid < c.n_reads) ? (int)c.rd_len[rid] : 0;
         const int tlen = plen + 4;                                  // alnse.c:373
         const bool ok = plen > 0 && (uint64_t)p.pos + (uint64_t)tlen <= (uint64_t)c.l;   // editdistance.c:178
-        // ---- every lane stages its own row: the window as the raw reference words from the 16-byte boundary
-        // below pos (text position 0 is nibble `toff` of the row; nibbles from toff + tlen on are cleared, the
-        // text is "0 beyond textLen"), then the packed read.  Wide independent loads, one row per bank.
-        int toff = 0;
-        if (ok) {
-            const uint32_t w0 = (p.pos >> 3) & ~3u;
-            toff = (int)(p.pos - 8u * w0);
-            const int tend = toff + tlen;
-            const uint4 *__restrict__ src = reinterpret_cast<const uint4 *>(mix + w0);
-#pragma unroll 4
-            for (int v = 0; v < TW / 4; ++v) {
-                const int rem = tend - 32 * v;                      // valid nibbles from this vector's first one
-                uint4 x = make_uint4(0u, 0u, 0u, 0u);
-                if (rem > 0) x = src[v];
-                T[4 * v + 0] = x.x & lv_tailmask(rem);
-                T[4 * v + 1] = x.y & lv_tailmask(rem - 8);
-                T[4 * v + 2] = x.z & lv_tailmask(rem - 16);
-                T[4 * v + 3] = x.w & lv_tailmask(rem - 24);
-            }
-            const uint2 *__restrict__ r2 = reinterpret_cast<const uint2 *>(c.rd4 + (size_t)p.rs * c.W64);
-#pragma unroll 4
-            for (int i = 0; i < PW; i += 2) {
-                uint2 y = make_uint2(0u, 0u);
-                if ((i >> 1) < (int)c.W64) y = r2[i >> 1];
-                P[i] = y.x;
-                if (i + 1 < PW) P[i + 1] = y.y;
-            }
-        }
+        const int toff = ok ? lv_stage_own(c, p, tlen, T, P, TW, PW) : 0;
         __syncwarp();
         int result = -1;
         if (ok) {
@@ -757,6 +761,122 @@ lv_cigar_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8_t *
             buf[0] = '\0';
         }
         if (lane == 0 && out) out[slot] = (int8_t)result;
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// lv_cigar_tpp: computeEditDistanceWithCigar (LandauVishkin.c:200-462) with one THREAD per pair, for the
+// case the verify stage produces: many pairs whose k is the small number of differences already found.
+// Furthest-reaching values of the current level live in registers as in lv_tpp; the history the
+// backtrace needs is a per-thread triangular table in shared memory (level e keeps diagonals -e..e, entry
+// e*e + d + e: (K+1)^2 int16 values and as many action bytes).  Every lane emits its own string.
+// Same staging, deferred long extensions and bank layout as lv_tpp.
+// --------------------------------------------------------------------------------------
+__host__ __device__ constexpr int lv_cigar_tpp_tab_words(int K) { return ((K + 1) * (K + 1) * 3 + 3) / 4; }
+
+template <int K>
+__global__ void __launch_bounds__(128)
+lv_cigar_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8_t *__restrict__ k_each, size_t n,
+                    const uint32_t *__restrict__ worklist, const uint32_t *__restrict__ wl_count,
+                    const salt_verify_out_t *__restrict__ rec,
+                    char *__restrict__ cigars, int stride, int8_t *__restrict__ out)
+{
+    SALT_DYN_SMEM(uint32_t, smem);
+    const int TW = lv_twr((int)c.l_max), PW = lv_pw((int)c.l_max);
+    constexpr int TABW = lv_cigar_tpp_tab_words(K);
+    const int rstride = (TW + PW + TABW) | 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *T = smem + ((size_t)warp * 32 + lane) * rstride;
+    uint32_t *P = T + TW;
+    int16_t *tabL = reinterpret_cast<int16_t *>(P + PW);               // [(K+1)^2]
+    char *tabA = reinterpret_cast<char *>(tabL + (K + 1) * (K + 1));   // [(K+1)^2]
+    const LvTriIdx at;
+    const size_t count = worklist ? (size_t)*wl_count : n;
+    const size_t step = (size_t)gridDim.x * blockDim.x;
+
+    for (size_t base = (size_t)blockIdx.x * blockDim.x + (size_t)warp * 32; base < count; base += step) {
+        const size_t it = base + lane;
+        const bool live = it < count;
+        salt_pair_t p; p.rs = 0; p.pos = 0; int k = 0;
+        const size_t slot = it;
+        if (live) {
+            if (worklist) {
+                const uint32_t rid = worklist[it];
+                const salt_verify_out_t r = rec[rid];
+                p.rs = (rid << 1) | (r.strand & 1); p.pos = r.pos; k = r.n_diff;   // compact: slot = list index
+            } else {
+                p = pairs[it]; k = k_each[it];
+            }
+        }
+        char *buf = cigars + slot * (size_t)stride;
+        const uint32_t rid = p.rs >> 1;
+        const int plen = (live && rid < c.n_reads) ? (int)c.rd_len[rid] : 0;
+        const int tlen = plen + 4;
+        const bool ok = plen > 0 && k <= K && (uint64_t)p.pos + (uint64_t)tlen <= (uint64_t)c.l;
+        const int toff = ok ? lv_stage_own(c, p, tlen, T, P, TW, PW) : 0;
+        __syncwarp();
+        int result = -1;
+        if (ok) {
+            const int L0 = lv_extend0(T, P, plen, tlen, toff);
+            if (L0 == plen) {
+                CigarOut o{buf, stride};
+                result = o.put(plen, 'M') ? 0 : -2;
+            } else {
+                int Lp[2 * K + 1];
+#pragma unroll
+                for (int i = 0; i < 2 * K + 1; ++i) Lp[i] = -2;
+                Lp[K] = L0;
+                tabL[0] = (int16_t)L0;
+                int found_e = -1, found_d = 0;
+                for (int e = 1; e <= k; ++e) {
+                    int Ln[2 * K + 1];
+                    int myrank = 1 << 20;
+                    int pend_di = -1, pend_best = 0;
+#pragma unroll
+                    for (int di = 0; di < 2 * K + 1; ++di) {
+                        const int d = di - K;
+                        int v = -2;
+                        if (d >= -e && d <= e) {
+                            const int left = di > 0 ? Lp[di > 0 ? di - 1 : 0] : -2;
+                            const int right = di < 2 * K ? Lp[di < 2 * K ? di + 1 : 0] + 1 : -1;
+                            int best = Lp[di] + 1; char a = 'X';                // LandauVishkin.c:249-260
+                            if (left > best) { best = left; a = 'D'; }
+                            if (right > best) { best = right; a = 'I'; }
+                            bool more;
+                            v = lv_extend_first(T, P, best, d, plen, tlen, more, toff);
+                            if (more) {
+                                if (pend_di < 0) { pend_di = di; pend_best = v; }
+                                else v = lv_extend_more(T, P, v, d, plen, tlen, toff);
+                            }
+                            if (v == plen) myrank = imin(myrank, lv_cigar_rank(d));
+                            tabA[at(e, d)] = a;
+                            tabL[at(e, d)] = (int16_t)v;
+                        }
+                        Ln[di] = v;
+                    }
+                    int pend_v = 0;
+                    if (pend_di >= 0) {
+                        const int d = pend_di - K;
+                        pend_v = lv_extend_more(T, P, pend_best, d, plen, tlen, toff);
+                        if (pend_v == plen) myrank = imin(myrank, lv_cigar_rank(d));
+                        tabL[at(e, d)] = (int16_t)pend_v;
+                    }
+                    if (myrank < (1 << 20)) {
+                        found_e = e;
+                        found_d = myrank == 0 ? 0 : ((myrank & 1) ? -(myrank + 1) / 2 : myrank / 2);
+                        break;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2 * K + 1; ++i) Lp[i] = i == pend_di ? pend_v : Ln[i];
+                }
+                if (found_e < 0) { if (stride > 0) buf[0] = '\0'; result = -1; }
+                else result = lv_cigar_emit_t(tabL, tabA, at, found_e, found_d, buf, stride);
+            }
+        } else if (live && stride > 0 && plen > 0 && k < LV_MAXK) {
+            buf[0] = '\0';
+        }
+        if (live && out) out[slot] = (int8_t)result;
+        __syncwarp();
     }
 }
 
@@ -1233,15 +1353,45 @@ static cudaError_t launch_lv_cigar_t(const DevCtx &c, const salt_pair_t *pairs, 
     return cudaSuccess;
 }
 
+template <int K>
+static cudaError_t launch_lv_cigar_tpp(const DevCtx &c, const salt_pair_t *pairs, const uint8_t *k_each, size_t n,
+                                       const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
+                                       const salt_verify_out_t *rec, char *cigars, int stride, int8_t *out,
+                                       int sm_count, cudaStream_t st)
+{
+    const int rstride = (lv_twr((int)c.l_max) + lv_pw((int)c.l_max) + lv_cigar_tpp_tab_words(K)) | 1;
+    int threads = 128;
+    size_t smem = (size_t)threads * rstride * 4;
+    if (smem > 72 * 1024) { threads = 64; smem = (size_t)threads * rstride * 4; }
+    const size_t items = worklist ? wl_cap : n;
+    size_t blocks = (items + threads - 1) / threads;
+    const size_t cap = (size_t)sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) return cudaSuccess;
+    auto kern = lv_cigar_tpp_kernel<K>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    SALT_LAUNCH(kern, (unsigned)blocks, threads, smem, st, c, pairs, k_each, n, worklist, wl_count, rec, cigars, stride, out);
+    SALT_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
 // kmax: upper bound of the k the items carry (levels kept in shared memory = kmax + 1; up to 15
 // differences fit 32 diagonals, one per lane)
 cudaError_t launch_lv_cigar(const DevCtx &c, const salt_pair_t *pairs, const uint8_t *k_each, size_t n,
                             const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
                             const salt_verify_out_t *rec, int kmax, char *cigars, int stride, int8_t *out,
-                            int sm_count, cudaStream_t st)
+                            int sm_count, cudaStream_t st, int mapping)
 {
     if (kmax < 0) kmax = 0;
     if (kmax > LV_MAXK - 1) kmax = LV_MAXK - 1;
+    if (mapping != 1 && c.l_max <= 512) {               // thread per pair: see lv_cigar_tpp_kernel
+        if (kmax <= 4) return launch_lv_cigar_tpp<4>(c, pairs, k_each, n, worklist, wl_count, wl_cap, rec, cigars, stride, out, sm_count, st);
+        if (kmax <= 10) return launch_lv_cigar_tpp<10>(c, pairs, k_each, n, worklist, wl_count, wl_cap, rec, cigars, stride, out, sm_count, st);
+        if (kmax <= 15) return launch_lv_cigar_tpp<15>(c, pairs, k_each, n, worklist, wl_count, wl_cap, rec, cigars, stride, out, sm_count, st);
+    }
     if (kmax <= 15)
         return launch_lv_cigar_t<1>(c, pairs, k_each, n, worklist, wl_count, wl_cap, rec, kmax + 1, cigars, stride, out, sm_count, st);
     return launch_lv_cigar_t<2>(c, pairs, k_each, n, worklist, wl_count, wl_cap, rec, kmax + 1, cigars, stride, out, sm_count, st);

@@ -73,6 +73,14 @@ def test_lv_cigar(emul_lib, oracle, L):
     gapped = pc.check_lv_cigar(eng, oracle, g, reads, pairs, k_each, 128)
     assert gapped >= 5
     pc.check_lv_cigar(eng, oracle, g, reads, pairs, k_each, 6)
+    # thresholds the thread-per-pair kernels take (k <= 4, <= 10, <= 15), then the same through the warp kernel
+    for mapping in (0, 1):
+        eng.set_lv_mapping(mapping)
+        for ks in ([1, 2, 3, 4], [2, 5, 10], [12, 15]):
+            kk = rng.choice(ks, len(pairs)).astype(np.uint8)
+            pc.check_lv_cigar(eng, oracle, g, reads, pairs, kk, 128)
+            pc.check_lv_cigar(eng, oracle, g, reads, pairs, kk, 5)
+    eng.set_lv_mapping(0)
     pc.check_lv_cigar(eng, oracle, g, reads, pc.flat_pairs(cands, len(reads))[:24], np.full(24, 10, np.uint8), 256)
 
 
