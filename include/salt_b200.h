@@ -64,6 +64,16 @@ typedef struct {
     int32_t cigarLen;
 } salt_ssw_out_t;
 
+/* One alignment whose SAM tail is wanted: the read as aligned (strand bit of rs), its leftmost
+ * reference base and the read offset the alignment starts at (query->seq_start: 0 in SE, the
+ * soft-clip length after a mate rescue, alnpe.c:301).  pos = 0xFFFFFFFF: unmapped, no tags. */
+typedef struct { uint32_t rs; uint32_t pos; uint32_t seq_start; } salt_mdnm_in_t;
+
+/* nm: the NM value.  md_len: characters of the MD value (excluding the NUL); -2 = MD buffer too
+ * small (string truncated), -3 = an M run reaches past the end of the reference (the reference
+ * asserts there, sam.c:270).  n_xv: entries of the XV list (at most 64, sam.c:242). */
+typedef struct { int32_t nm; int16_t md_len; uint16_t n_xv; } salt_mdnm_out_t;
+
 /* Per-read outcome of the verification stage: the query_t fields that
  * alnse_check_nogap / alnse_check_withgap set (alnse.c:348-393), plus hit counts. */
 typedef struct {
@@ -138,6 +148,15 @@ int salt_b200_ssw(salt_b200_t *h, const salt_win_t *wins, size_t n, int use_pac,
                   const int8_t *mat, int n_sym, int gapO, int gapE, int flag,
                   int filters, int filterd, int mask_len,
                   salt_ssw_out_t *out, uint32_t *cigars, int cigar_stride);
+
+/* MD / NM / XV of n alignments of the reads resident in `slot` (0 = the read set of the synchronous
+ * entry points; a pipeline slot keeps its chunk's reads until it is submitted again) --
+ * sam_add_md_nm (sam.c:246-328), the tags behind `-d`.  cigars: n NUL-terminated M/I/D strings (query->cigar->s, no soft clips),
+ * cigar_stride bytes apart.  md: n strings of md_stride bytes ("MD:Z:" value only).  xv: n rows
+ * of xv_stride uint16 read offsets (relative to seq_start); a row holds the first
+ * min(n_xv, xv_stride) entries.  Needs the 2-bit pac given to salt_b200_init. */
+int salt_b200_md_nm(salt_b200_t *h, int slot, const salt_mdnm_in_t *items, size_t n, const char *cigars, int cigar_stride,
+                    char *md, int md_stride, uint16_t *xv, int xv_stride, salt_mdnm_out_t *out);
 
 /* The whole verification stage for a chunk, as alnse_overlap_alt (SE) / alnse_overlap (PE)
  * run it after seeding (alnse.c:1077-1097 / :1014-1036):

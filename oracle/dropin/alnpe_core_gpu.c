@@ -39,6 +39,7 @@
 int pairing2(index_t *index, query_t *q0, query_t *q1, const aln_opt_t *aln_opt);
 int pairing_singleton(index_t *index, query_t *q0, query_t *q1, aln_opt_t *aln_opt);
 void alnpe_sam(index_t *index, query_t *q, const aln_opt_t *opt);
+void dropin_tail_prepare(salt_b200_t *gpu, int slot, const query_t *multi_seqs, const int *slot_of, int first, int upto);
 extern int8_t score_mat[25], score_mat2[256];       /* alnpe.c:52-73 */
 
 static void die(const char *what)
@@ -285,8 +286,10 @@ static void pair_and_emit(salt_b200_t *gpu, index_t *index, aln_opt_t *aln_opt, 
             /* a rescue that succeeds ends pairing early: skip the requests recorded after it */
             while (H.cursor < H.n_req && H.req[H.cursor].pair == j) ++H.cursor;
         }
-        alnpe_sam(index, multi_seqs + j, aln_opt);
     }
+    /* every query_t of the chunk is final: its MD/NM/XV tags in one GPU call, then the SAM records */
+    if (aln_opt->print_nm_md) dropin_tail_prepare(gpu, 0, multi_seqs, slot_of, first, upto);
+    for (j = first; j < upto; j += 2) alnpe_sam(index, multi_seqs + j, aln_opt);
 }
 
 int alnpe_core(const opt_t *opt)

@@ -33,7 +33,10 @@ static void die(const char *what)
     exit(1);
 }
 
-/* alnse_core1's per-read work after verification: results -> query_t -> SAM (alnse.c:1306-1307 / :1342-1345) */
+void dropin_tail_prepare(salt_b200_t *gpu, int slot, const query_t *multi_seqs, const int *slot_of, int first, int upto);
+
+/* alnse_core1's per-read work after verification: results -> query_t (alnse.c:1306 / :1342-1344); the SAM line
+ * follows once the chunk's MD/NM/XV tags are back from the GPU */
 static void finish_read(index_t *index, query_t *query, const aln_opt_t *aln_opt, const salt_chunk_t *ck, uint32_t i)
 {
     salt_read_result_t r;
@@ -53,7 +56,6 @@ static void finish_read(index_t *index, query_t *query, const aln_opt_t *aln_opt
         if (query->is_gap) strncpy(query->cigar->s, r.cigar, query->cigar->m - 1);
         else ksprintf(query->cigar, "%dM", query->l_seq);
     }
-    aln_samse(index, query, aln_opt);
 }
 
 int alnse_core(const opt_t *opt)
@@ -115,6 +117,9 @@ int alnse_core(const opt_t *opt)
                 }
                 for (j = first; j < upto; ++j)
                     if (slot_of[j] >= 0) finish_read(index, multiSeqs + j, aln_opt, ck, (uint32_t)slot_of[j]);
+                if (aln_opt->print_nm_md) dropin_tail_prepare(gpu, 0, multiSeqs, slot_of, first, upto);
+                for (j = first; j < upto; ++j)
+                    if (slot_of[j] >= 0) aln_samse(index, multiSeqs + j, aln_opt);     /* alnse.c:1307 / :1345 */
                 first = upto;
                 salt_chunk_reset(ck);
             }

@@ -591,6 +591,68 @@ typedef struct {
     int n_alt[2];                                                /* query->hits[strand] after query_set_hits */
 } orc_verify_t;
 
+/* ------------------------------------------------------------------------ */
+/* SAM tail: MD / NM / XV of one alignment (sam.c:246-328, sam_add_md_nm).   */
+/* `seq` is the read as aligned (query->seq or ->rseq), codes 0..4; `cigar`  */
+/* is query->cigar->s (M/I/D runs only, soft clips are printed elsewhere).   */
+/* Appends exactly what the reference appends to the SAM line; returns the   */
+/* text length, or -3 where the reference's assert(ref_pos < l_pac) fires.   */
+/* Quirks kept: no "0" between adjacent mismatches, a deletion flushes the   */
+/* match run, XV lists read offsets (relative to seq_start) of mismatching   */
+/* bases that hit a non-reference SNP allele, at most 64 of them.            */
+/* ------------------------------------------------------------------------ */
+static inline unsigned orc_pac(const uint8_t *pac, uint32_t p) { return pac[p >> 2] >> ((~p & 3) << 1) & 3; }   /* sam.c:244 */
+
+ORC_EXPORT int orc_md_nm(const uint32_t *mixref, const uint8_t *pac, uint32_t l_pac, const uint8_t *seq, int l_seq,
+                         uint32_t pos, uint32_t seq_start, const char *cigar, char *out, int cap)
+{
+    if (pos == 0xFFFFFFFFu) { if (cap > 0) out[0] = 0; return 0; }        /* sam.c:248 */
+    char buf[8192]; int o = 0;
+#define MD_PUT(...) do { o += snprintf(buf + o, sizeof buf - (size_t)o, __VA_ARGS__); } while (0)
+    int nm = 0, n_match = 0, n_rs = 0, rs[64];
+    uint32_t ref_pos = pos;
+    int si = (int)seq_start;                                               /* index into seq */
+    MD_PUT("\tMD:Z:");
+    const char *c = cigar;
+    while (*c) {
+        char *end; long n = strtol(c, &end, 10); c = end;
+        const char op = *c;
+        if (op == 'M') {
+            for (long i = 0; i < n; ++i) {
+                if (ref_pos >= l_pac) return -3;                           /* sam.c:270 assert */
+                const unsigned bt = orc_pac(pac, ref_pos);
+                const unsigned rd = (si >= 0 && si < l_seq) ? seq[si] : 4u;
+                if (bt == rd) n_match += 1;
+                else {
+                    const unsigned meta = orc_nib(mixref, ref_pos);
+                    if ((meta & (1u << rd)) != 0 && n_rs < 64) rs[n_rs++] = si - (int)seq_start;   /* sam.c:281-286 */
+                    nm += 1;
+                    if (n_match != 0) MD_PUT("%d", n_match);
+                    n_match = 0;
+                    MD_PUT("%c", "ACGTN"[bt]);
+                }
+                ref_pos += 1; si += 1;
+            }
+        } else if (op == 'I') { nm += (int)n; si += (int)n; }
+        else if (op == 'D') {
+            if (n_match != 0) MD_PUT("%d", n_match);
+            n_match = 0; nm += (int)n;
+            MD_PUT("^");
+            for (long i = 0; i < n; ++i) { MD_PUT("%c", "ACGTN"[orc_pac(pac, ref_pos)]); ref_pos += 1; }
+        }
+        if (*c) c += 1;
+    }
+    if (n_match != 0) MD_PUT("%d", n_match);
+    MD_PUT("\tNM:i:%u", (unsigned)nm);
+    if (n_rs > 0) {
+        MD_PUT("\tXV:i:");
+        for (int i = 0; i < n_rs; ++i) { if (i) MD_PUT(","); MD_PUT("%d", rs[i]); }
+    }
+#undef MD_PUT
+    if (cap > 0) { int m = o < cap - 1 ? o : cap - 1; memcpy(out, buf, (size_t)m); out[m] = 0; }
+    return o;
+}
+
 static uint32_t orc_gen_mapq(uint32_t b0, uint32_t b1)       /* query.c:270-281 */
 {
     if (b0 == 0) return 0;

@@ -25,7 +25,8 @@ def build(force=False):
     if force or not os.path.exists(os.path.join(HERE, "liboracle.so")) or \
             os.path.getmtime(os.path.join(HERE, "liboracle.so")) < os.path.getmtime(os.path.join(HERE, "oracle.c")):
         subprocess.check_call(["make", "-s", "-C", HERE, os.path.join(HERE, "liboracle.so")])
-    if os.path.isdir("/root/reference/Align_src") and (force or not os.path.exists(os.path.join(HERE, "_ref", "libsaltref.so"))):
+    if os.path.isdir("/root/reference/Align_src") and (force or not all(
+            os.path.exists(os.path.join(HERE, "_ref", f)) for f in ("libsaltref.so", "libsaltref_sam.so"))):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
 
 
@@ -68,6 +69,7 @@ class Oracle:
                                         C.c_int, C.c_int, C.POINTER(AlignRec), u32p, C.c_int]
         L.orc_rescue_pac.argtypes = [u8p, C.c_uint32, C.c_uint32, u8p, C.c_int, i8p, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.POINTER(AlignRec), u32p, C.c_int]
+        L.orc_md_nm.argtypes = [u32p, u8p, C.c_uint32, u8p, C.c_int, C.c_uint32, C.c_uint32, C.c_char_p, C.c_char_p, C.c_int]
         L.orc_score_mat2.argtypes = [i8p]
         L.orc_score_mat.argtypes = [i8p]
         L.orc_mixref_put_seq.argtypes = [u32p, C.c_uint32, C.c_char_p, C.c_uint32]
@@ -134,6 +136,13 @@ class Oracle:
         return m
 
     # --- per-pair kernels -------------------------------------------------
+    def md_nm(self, mixref, pac, l_pac, seq, pos, seq_start, cigar, cap=4096):
+        """text sam_add_md_nm appends for the read as aligned (`seq` = query->seq or ->rseq); -3 = reference assert"""
+        buf = C.create_string_buffer(cap)
+        n = self.lib.orc_md_nm(_p(mixref, u32p), _p(pac, u8p), int(l_pac), _p(seq, u8p), len(seq), int(pos), int(seq_start),
+                               cigar.encode(), buf, cap)
+        return n if n < 0 else buf.value.decode()
+
     def ed_mismatch(self, mixref, pos, seq, max_err):
         return self.lib.orc_ed_mismatch(_p(mixref, u32p), int(pos), _p(seq, u8p), len(seq), int(max_err))
 
@@ -297,6 +306,26 @@ class Ref:
         idx = np.arange(start, end + 1, dtype=np.int64)
         ref = ((pac[idx >> 2] >> ((~idx & 3) << 1).astype(np.uint8)) & 3).astype(np.int8)
         return self.ssw_align(seq.astype(np.int8), mat, 5, ref, gapO, gapE, 2, filters, filterd, len(seq) // 2)
+
+
+class RefSam:
+    """The reference's own sam_add_md_nm (sam.c:246) behind oracle/dropin/sam_harness.c."""
+
+    def __init__(self):
+        build()
+        self.lib = C.CDLL(os.path.join(HERE, "_ref", "libsaltref_sam.so"))
+        self.lib.ref_sam_md_nm.argtypes = [u32p, C.c_uint32, u8p, u8p, u8p, C.c_int, C.c_uint32, C.c_int, C.c_uint32,
+                                           C.c_char_p, C.c_char_p, C.c_int]
+
+    def md_nm(self, mixref, l, pac, seq, rseq, pos, strand, seq_start, cigar, cap=4096):
+        buf = C.create_string_buffer(cap)
+        self.lib.ref_sam_md_nm(_p(mixref, u32p), int(l), _p(pac, u8p), _p(seq, u8p), _p(rseq, u8p), len(seq), int(pos),
+                               int(strand), int(seq_start), cigar.encode(), buf, cap)
+        return buf.value.decode()
+
+
+def ref_sam_available():
+    return os.path.exists(os.path.join(HERE, "_ref", "libsaltref_sam.so"))
 
 
 class RefIdx:

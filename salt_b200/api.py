@@ -18,6 +18,8 @@ ERRORS = {-101: "SALT_ERR_ARG", -102: "SALT_ERR_CUDA", -103: "SALT_ERR_NOMEM",
 
 PAIR_DT = np.dtype([("rs", np.uint32), ("pos", np.uint32)])
 WIN_DT = np.dtype([("rs", np.uint32), ("start", np.uint32), ("end", np.uint32)])
+MDNM_IN_DT = np.dtype([("rs", np.uint32), ("pos", np.uint32), ("seq_start", np.uint32)])
+MDNM_OUT_DT = np.dtype([("nm", np.int32), ("md_len", np.int16), ("n_xv", np.uint16)])
 SSW_DT = np.dtype([("score1", np.uint16), ("score2", np.uint16), ("ref_begin1", np.int32), ("ref_end1", np.int32),
                    ("read_begin1", np.int32), ("read_end1", np.int32), ("ref_end2", np.int32), ("cigarLen", np.int32)])
 VERIFY_DT = np.dtype([("pos", np.uint32), ("strand", np.uint8), ("n_diff", np.uint8), ("is_gap", np.uint8),
@@ -59,6 +61,7 @@ def _declare(L):
     L.salt_b200_mismatch.argtypes = [vp, vp, sz, i32, vp]
     L.salt_b200_lv.argtypes = [vp, vp, sz, i32, vp]
     L.salt_b200_lv_cigar.argtypes = [vp, vp, vp, sz, vp, i32, vp]
+    L.salt_b200_md_nm.argtypes = [vp, i32, vp, sz, vp, i32, vp, i32, vp, i32, vp]
     L.salt_b200_ssw.argtypes = [vp, vp, sz, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32]
     L.salt_b200_verify.argtypes = [vp, C.POINTER(CandsT), i32, i32, vp, vp, vp, vp, i32]
     L.salt_b200_verify_submit.argtypes = [vp, i32, C.POINTER(ReadsT), C.POINTER(CandsT), i32, i32, vp, vp, vp, vp, i32]
@@ -219,6 +222,33 @@ class Engine:
         out = np.empty(len(pairs), np.int8)
         self._ck(self.L.salt_b200_lv(self.h, _ptr(pairs), len(pairs), int(k), _ptr(out)))
         return out
+
+    def md_nm(self, rs, pos, seq_start, cigars, md_stride=128, xv_stride=64, cigar_stride=None, slot=0):
+        """sam_add_md_nm for alignments of the current read set.  cigars: list of str.  Returns
+        (out records, md strings as a [n, md_stride] uint8 array, xv [n, xv_stride] uint16)."""
+        n = len(pos)
+        items = np.zeros(n, MDNM_IN_DT)
+        items["rs"] = rs; items["pos"] = pos; items["seq_start"] = seq_start
+        if cigar_stride is None:
+            cigar_stride = max([len(c) for c in cigars] + [1]) + 1
+        cg = np.zeros((n, cigar_stride), np.uint8)
+        for i, c in enumerate(cigars):
+            b = np.frombuffer(c.encode(), np.uint8)
+            cg[i, :len(b)] = b
+        md = np.zeros((n, md_stride), np.uint8)
+        xv = np.zeros((n, max(xv_stride, 1)), np.uint16)
+        out = np.zeros(n, MDNM_OUT_DT)
+        self._ck(self.L.salt_b200_md_nm(self.h, int(slot), _ptr(items), n, _ptr(cg), cigar_stride, _ptr(md), md_stride,
+                                        _ptr(xv) if xv_stride > 0 else None, xv_stride, _ptr(out)))
+        return out, md, xv
+
+    @staticmethod
+    def md_nm_text(out, md, xv, i):
+        """the text sam_add_md_nm appends for item i, from the engine's record"""
+        s = "\tMD:Z:" + cstr(md[i]) + "\tNM:i:%u" % out["nm"][i]
+        if out["n_xv"][i]:
+            s += "\tXV:i:" + ",".join(str(int(v)) for v in xv[i, :out["n_xv"][i]])
+        return s
 
     def lv_cigar(self, pairs, k_each, stride=128, fill=0):
         pairs = np.ascontiguousarray(pairs, PAIR_DT)

@@ -103,7 +103,7 @@ struct salt_b200 {
     DBuf fpairs, fslots, fcount;            // LV filter survivors of the per-pair entry point
     int lv_filter = 1;                      // pigeonhole filter in front of Landau-Vishkin (salt_b200_set_lv_filter)
     // staging / scratch of the synchronous per-pair and SSW entry points (slot 0's stream)
-    DBuf pairs, out8, kbuf, cig, wins, sswout, sswcig, sswscratch;
+    DBuf pairs, out8, kbuf, cig, wins, sswout, sswcig, sswscratch, md_in, md_cig, md_str, md_xv, md_out;
     uint64_t launches = 0;
     int lv_mapping = 0;         // 0 = auto, 1 = warp per pair, 2 = thread per pair (salt_b200_set_lv_mapping)
     int max_window = 1024;      // widest rescue window the SSW scratch is sized for
@@ -445,7 +445,7 @@ void salt_b200_destroy(salt_b200_t *h)
         h->slot[i].release();
     }
     DBuf *all[] = {&h->pairs, &h->out8, &h->kbuf, &h->cig, &h->wins, &h->sswout, &h->sswcig, &h->sswscratch,
-                   &h->fpairs, &h->fslots, &h->fcount};
+                   &h->fpairs, &h->fslots, &h->fcount, &h->md_in, &h->md_cig, &h->md_str, &h->md_xv, &h->md_out};
     for (DBuf *b : all) b->release();
     for (int i = 0; i < 7; ++i) if (h->ev_ssw[i]) cudaEventDestroy(h->ev_ssw[i]);
     if (h->d_mixref_alloc) cudaFree(h->d_mixref_alloc);
@@ -597,6 +597,41 @@ int salt_b200_lv_cigar(salt_b200_t *h, const salt_pair_t *pairs, const uint8_t *
         memcpy(cigars + i * (size_t)stride, sp, len);
         cigars[i * (size_t)stride + len] = '\0';
     }
+    return SALT_OK;
+}
+
+// ------------------------------------------------------------------ SAM tail
+int salt_b200_md_nm(salt_b200_t *h, int slot, const salt_mdnm_in_t *items, size_t n, const char *cigars, int cigar_stride,
+                    char *md, int md_stride, uint16_t *xv, int xv_stride, salt_mdnm_out_t *out)
+{
+    if (int rc = use_device(h)) return rc;
+    if (n && (!items || !cigars || !md || !out)) return fail(SALT_ERR_ARG, "null buffer");
+    if (cigar_stride < 2 || md_stride < 2) return fail(SALT_ERR_ARG, "string stride too small");
+    if (xv_stride < 0 || xv_stride > 64 || (xv_stride > 0 && !xv)) return fail(SALT_ERR_ARG, "xv_stride must be 0..64 with a buffer");
+    if (!h->d_pac) return fail(SALT_ERR_ARG, "MD/NM need the 2-bit pac (salt_b200_init was given none)");
+    if (slot < 0 || slot >= SALT_SLOTS) return fail(SALT_ERR_ARG, "slot out of range");
+    Slot &s = h->slot[slot];
+    if (!s.n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    if (s.pending) return fail(SALT_ERR_ARG, "slot has a verify in flight: call salt_b200_verify_wait first");
+    if (!n) return SALT_OK;
+    cudaStream_t st = s.stream;
+    const size_t xs = (size_t)(xv_stride > 0 ? xv_stride : 1);
+    CU(h->md_in.need(n * sizeof(salt_mdnm_in_t)));
+    CU(h->md_cig.need(n * (size_t)cigar_stride));
+    CU(h->md_str.need(n * (size_t)md_stride));
+    CU(h->md_xv.need(n * xs * 2));
+    CU(h->md_out.need(n * sizeof(salt_mdnm_out_t)));
+    CU(cudaMemcpyAsync(h->md_in.p, items, n * sizeof(salt_mdnm_in_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->md_cig.p, cigars, n * (size_t)cigar_stride, cudaMemcpyHostToDevice, st));
+    if (xv_stride > 0) CU(cudaMemsetAsync(h->md_xv.p, 0, n * xs * 2, st));
+    CU(launch_md_nm(h->ctx(slot), s.codes.as<uint8_t>(), s.d_roffs(), h->md_in.as<salt_mdnm_in_t>(), n, h->md_cig.as<char>(),
+                    cigar_stride, h->md_str.as<char>(), md_stride, h->md_xv.as<uint16_t>(), xv_stride,
+                    h->md_out.as<salt_mdnm_out_t>(), st));
+    h->launches += 1;
+    CU(cudaMemcpyAsync(md, h->md_str.p, n * (size_t)md_stride, cudaMemcpyDeviceToHost, st));
+    if (xv_stride > 0) CU(cudaMemcpyAsync(xv, h->md_xv.p, n * xs * 2, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out, h->md_out.p, n * sizeof(salt_mdnm_out_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return SALT_OK;
 }
 

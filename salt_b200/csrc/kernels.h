@@ -1,4 +1,4 @@
-// kernels.h -- launchers implemented in verify.cu / ssw.cu / mixref.cu, used by engine.cu.
+// kernels.h -- launchers implemented in verify.cu / ssw.cu / samtail.cu / mixref.cu, used by engine.cu.
 #pragma once
 #if !defined(SALT_EMUL)
 #include <cuda_runtime.h>
@@ -29,6 +29,11 @@ cudaError_t launch_scan_gap(const DevCtx &c, const uint32_t *offs0, const uint32
                             const uint32_t *offs1, const uint32_t *loci1, size_t n0, int lv_T0,
                             int8_t *acc, salt_verify_out_t *rec, const uint32_t *lv_reads, const uint32_t *lv_read_count,
                             uint32_t *cig_list, uint32_t *cig_count, int sm_count, cudaStream_t st);
+
+// samtail.cu
+cudaError_t launch_md_nm(const DevCtx &c, const uint8_t *codes, const uint32_t *roffs, const salt_mdnm_in_t *items, size_t n,
+                         const char *cigars, int cstride, char *md, int mstride, uint16_t *xv, int xstride,
+                         salt_mdnm_out_t *out, cudaStream_t st);
 
 // mixref.cu
 cudaError_t launch_build_mixref(const char *bases, uint32_t l, const uint32_t *snp_pos, const uint8_t *snp_mask,

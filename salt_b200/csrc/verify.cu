@@ -1387,6 +1387,13 @@ cudaError_t launch_lv_cigar(const DevCtx &c, const salt_pair_t *pairs, const uin
 {
     if (kmax < 0) kmax = 0;
     if (kmax > LV_MAXK - 1) kmax = LV_MAXK - 1;
+    // One thread per pair issues a quarter of the instructions but is a long serial chain per warp: it pays
+    // once there are enough pairs to fill the machine with such warps (2 M-read chunk, 75 k gapped primaries:
+    // 88 us against 112 us), while a 100 k-read chunk's ~4 k pairs finish sooner spread one per warp
+    // (23 us against 46 us; profiles/r1r_launches_bench_summary.txt).  A verify-stage worklist holds the
+    // gapped primaries, a few percent of the chunk's reads.
+    const size_t expect = worklist ? wl_cap / 25 : n;
+    if (mapping == 0 && expect < 32768) mapping = 1;
     if (mapping != 1 && c.l_max <= 512) {               // thread per pair: see lv_cigar_tpp_kernel
         if (kmax <= 4) return launch_lv_cigar_tpp<4>(c, pairs, k_each, n, worklist, wl_count, wl_cap, rec, cigars, stride, out, sm_count, st);
         if (kmax <= 10) return launch_lv_cigar_tpp<10>(c, pairs, k_each, n, worklist, wl_count, wl_cap, rec, cigars, stride, out, sm_count, st);

@@ -19,6 +19,15 @@ def oracle():
 
 
 @pytest.fixture(scope="session")
+def refsam():
+    from oracle import orc
+    orc.build()
+    if not orc.ref_sam_available():
+        pytest.skip("oracle/_ref/libsaltref_sam.so not built (reference tree absent)")
+    return orc.RefSam()
+
+
+@pytest.fixture(scope="session")
 def ref():
     from oracle import orc
     if not orc.ref_available():

@@ -10,5 +10,6 @@ thread_local CtaState *t_cta = nullptr;
 
 #include "../../salt_b200/csrc/verify.cu"
 #include "../../salt_b200/csrc/ssw.cu"
+#include "../../salt_b200/csrc/samtail.cu"
 #include "../../salt_b200/csrc/mixref.cu"
 #include "../../salt_b200/csrc/engine.cu"

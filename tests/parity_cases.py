@@ -217,3 +217,70 @@ def check_ssw(eng, oracle, g, reads, wins, use_pac, mat, n_sym, gapO=3, gapE=1, 
         assert np.array_equal(cig[i][:rec[7]], wc), ("ssw cigar", i, cig[i][:rec[7]], wc)
         gapped += any((int(c) & 15) != 0 for c in wc)
     return gapped
+
+
+def random_cigar(rng, qlen, max_ops=5):
+    """A random M/I/D run string consuming exactly qlen read bases (what query->cigar->s may hold)."""
+    ops = []
+    left = qlen
+    n_ops = int(rng.integers(0, max_ops))
+    for _ in range(n_ops):
+        if left < 12:
+            break
+        m = int(rng.integers(1, left - 8))
+        ops.append("%dM" % m); left -= m
+        if rng.random() < 0.5:
+            ops.append("%dD" % int(rng.integers(1, 5)))
+        else:
+            i = int(rng.integers(1, min(5, left - 2)))
+            ops.append("%dI" % i); left -= i
+    ops.append("%dM" % left)
+    return "".join(ops)
+
+
+def mdnm_cases(g, reads, pos, strand, seed, clip_frac=0.3):
+    """(seq as aligned, rseq partner, pos, strand, seq_start, cigar) per read, with random soft clips and gaps."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for r in range(len(reads)):
+        L = reads.shape[1]
+        seq = np.ascontiguousarray(reads[r]); rseq = np.ascontiguousarray(synth.revcomp(reads[r]))
+        s0 = int(rng.integers(1, 20)) if rng.random() < clip_frac else 0
+        s1 = int(rng.integers(1, 20)) if rng.random() < clip_frac else 0
+        cig = random_cigar(rng, L - s0 - s1)
+        out.append((seq, rseq, int(pos[r]) + s0, int(strand[r]), s0, cig))
+    return out
+
+
+def check_md_nm(eng, oracle, g, reads, pos, strand, seed, md_stride=128):
+    """salt_b200_md_nm against the oracle's sam_add_md_nm text, alignment by alignment (random M/I/D strings,
+    soft-clip starts, both strands), plus the unmapped / too-small-buffer / past-the-end codes."""
+    cases = mdnm_cases(g, reads, pos, strand, seed)
+    eng.set_reads(reads)
+    rid = np.arange(len(reads), dtype=np.uint32)
+    rs = (rid << 1) | np.array([c[3] for c in cases], np.uint32)
+    p = np.array([c[2] for c in cases], np.uint32); s0 = np.array([c[4] for c in cases], np.uint32)
+    cigs = [c[5] for c in cases]
+    out, md, xv = eng.md_nm(rs, p, s0, cigs, md_stride=md_stride)
+    n_xv = 0
+    for i, (seq, rseq, pp, st, ss, cig) in enumerate(cases):
+        want = oracle.md_nm(g.mixref, g.pac, g.l, rseq if st else seq, pp, ss, cig)
+        assert out["md_len"][i] >= 0, (i, out[i])
+        got = api.Engine.md_nm_text(out, md, xv, i)
+        assert got == want, (i, pp, st, ss, cig, got, want)
+        n_xv += int(out["n_xv"][i] > 0)
+    # unmapped: no tags; an M run past the end of the reference: -3 (the reference asserts); tiny MD buffer: -2
+    out2, md2, _ = eng.md_nm(rs[:3], np.array([0xFFFFFFFF, g.l - 50, p[2]], np.uint32), np.zeros(3, np.uint32),
+                             ["100M", "100M", cigs[2]], md_stride=128)
+    assert out2["md_len"][0] == 0 and out2["nm"][0] == 0 and md2[0, 0] == 0
+    assert out2["md_len"][1] == -3
+    assert oracle.md_nm(g.mixref, g.pac, g.l, cases[1][1] if cases[1][3] else cases[1][0], g.l - 50, 0, "100M") == -3
+    out3, md3, _ = eng.md_nm(rs, p, s0, cigs, md_stride=4)
+    for i in range(len(cases)):
+        full = api.cstr(md[i])
+        if len(full) > 3:
+            assert out3["md_len"][i] == -2 and api.cstr(md3[i]) == full[:3], (i, full, api.cstr(md3[i]))
+        else:
+            assert out3["md_len"][i] == len(full) and api.cstr(md3[i]) == full
+        assert out3["nm"][i] == out["nm"][i]
+    return n_xv

@@ -125,6 +125,14 @@ def test_verify_batch_pipeline(emul_lib, oracle):
     pc.check_verify_batch(eng, reads, cands, 1000)
 
 
+def test_md_nm(emul_lib, oracle):
+    """SAM tail kernel (MD/NM/XV, sam.c:246-328) against the oracle"""
+    g = synth.Genome(40000, snp_rate=0.03, seed=15)
+    reads, pos, strand = synth.sample_reads(g, 60, 100, seed=16, sub_rate=0.03, indel_frac=0.3, n_frac=0.01)
+    eng = _engine(emul_lib, g, with_pac=True)
+    assert pc.check_md_nm(eng, oracle, g, reads, pos, strand, 17, md_stride=264) >= 3
+
+
 def test_host_layer_chunks(emul_lib, oracle):
     """include/salt_host.h over the (emulated) engine: pinned chunk queues, slots, query_set_hits/mapq/cigar"""
     import build_emul

@@ -116,6 +116,15 @@ def test_verify_batch_pipeline(oracle):
     pc.check_verify_batch(eng, reads, cands, 100000)
 
 
+@pytest.mark.parametrize("L", [100, 250])
+def test_md_nm(oracle, L):
+    """SAM tail kernel (MD/NM/XV, sam.c:246-328) against the oracle, 4000 alignments per length"""
+    g = synth.Genome(400000, snp_rate=0.03, seed=15 + L)
+    reads, pos, strand = synth.sample_reads(g, 4000, L, seed=16, sub_rate=0.03, indel_frac=0.3, n_frac=0.01)
+    eng = _engine(g)
+    assert pc.check_md_nm(eng, oracle, g, reads, pos, strand, 17, md_stride=2 * L + 64) >= 200
+
+
 def test_host_layer_chunks(oracle):
     """include/salt_host.h over the CUDA engine: pinned chunk queues through the slots, then
     query_set_hits / gen_mapq / query_gen_cigar per read, against the oracle"""

@@ -191,3 +191,21 @@ def test_build_mixref(oracle):
     if l % 8:
         words_ref = words_ref.copy(); words_ref[-1] &= np.uint32((1 << (4 * (l % 8))) - 1)
     assert l == l_ref and np.array_equal(words, words_ref)
+
+
+def test_md_nm(oracle, refsam):
+    """sam_add_md_nm (sam.c:246-328): MD/NM/XV text for random M/I/D strings, soft-clip starts, both strands,
+    read-N and SNP sites matched by non-reference alleles -- oracle.c's restatement vs the reference's own code."""
+    import parity_cases as pc
+    g = synth.Genome(60000, snp_rate=0.03, seed=5)
+    reads, pos, strand = synth.sample_reads(g, N_FAST * 3, 100, seed=6, sub_rate=0.03, indel_frac=0.3, n_frac=0.01)
+    n_xv = 0
+    for seq, rseq, p, st, s0, cig in pc.mdnm_cases(g, reads, pos, strand, 7):
+        want = refsam.md_nm(g.mixref, g.l, g.pac, seq, rseq, p, st, s0, cig)
+        got = oracle.md_nm(g.mixref, g.pac, g.l, rseq if st else seq, p, s0, cig)
+        assert got == want, (p, st, s0, cig, got, want)
+        n_xv += "XV:i:" in want
+    assert n_xv > 20
+    # unmapped reads get nothing (sam.c:248)
+    assert refsam.md_nm(g.mixref, g.l, g.pac, reads[0], reads[0], 0xFFFFFFFF, 0, 0, "100M") == ""
+    assert oracle.md_nm(g.mixref, g.pac, g.l, reads[0], 0xFFFFFFFF, 0, "100M") == ""
