@@ -40,6 +40,7 @@ int pairing2(index_t *index, query_t *q0, query_t *q1, const aln_opt_t *aln_opt)
 int pairing_singleton(index_t *index, query_t *q0, query_t *q1, aln_opt_t *aln_opt);
 void alnpe_sam(index_t *index, query_t *q, const aln_opt_t *opt);
 void dropin_tail_prepare(salt_b200_t *gpu, int slot, const query_t *multi_seqs, const int *slot_of, int first, int upto);
+void dropin_tail_report(void);
 extern int8_t score_mat[25], score_mat2[256];       /* alnpe.c:52-73 */
 
 static void die(const char *what)
@@ -288,7 +289,7 @@ static void pair_and_emit(salt_b200_t *gpu, index_t *index, aln_opt_t *aln_opt, 
         }
     }
     /* every query_t of the chunk is final: its MD/NM/XV tags in one GPU call, then the SAM records */
-    if (aln_opt->print_nm_md) dropin_tail_prepare(gpu, 0, multi_seqs, slot_of, first, upto);
+    if (aln_opt->print_nm_md || aln_opt->print_xa_cigar) dropin_tail_prepare(gpu, 0, multi_seqs, slot_of, first, upto);
     for (j = first; j < upto; j += 2) alnpe_sam(index, multi_seqs + j, aln_opt);
 }
 
@@ -384,6 +385,7 @@ int alnpe_core(const opt_t *opt)
     query_close(qs[1]);
     free(multi_seqs); free(slot_of); free(verified);
     salt_chunk_free(ck);
+    dropin_tail_report();
     salt_b200_destroy(gpu);
     alnpe_index_destroy(index);
     aln_opt_destroy(aln_opt);

@@ -34,6 +34,7 @@ static void die(const char *what)
 }
 
 void dropin_tail_prepare(salt_b200_t *gpu, int slot, const query_t *multi_seqs, const int *slot_of, int first, int upto);
+void dropin_tail_report(void);
 
 /* alnse_core1's per-read work after verification: results -> query_t (alnse.c:1306 / :1342-1344); the SAM line
  * follows once the chunk's MD/NM/XV tags are back from the GPU */
@@ -117,7 +118,7 @@ int alnse_core(const opt_t *opt)
                 }
                 for (j = first; j < upto; ++j)
                     if (slot_of[j] >= 0) finish_read(index, multiSeqs + j, aln_opt, ck, (uint32_t)slot_of[j]);
-                if (aln_opt->print_nm_md) dropin_tail_prepare(gpu, 0, multiSeqs, slot_of, first, upto);
+                if (aln_opt->print_nm_md || aln_opt->print_xa_cigar) dropin_tail_prepare(gpu, 0, multiSeqs, slot_of, first, upto);
                 for (j = first; j < upto; ++j)
                     if (slot_of[j] >= 0) aln_samse(index, multiSeqs + j, aln_opt);     /* alnse.c:1307 / :1345 */
                 first = upto;
@@ -137,6 +138,7 @@ int alnse_core(const opt_t *opt)
     free(multiSeqs); free(slot_of);
     query_close(qs);
     salt_chunk_free(ck);
+    dropin_tail_report();
     salt_b200_destroy(gpu);
     alnse_index_destroy(index);
     aln_opt_destroy(aln_opt);

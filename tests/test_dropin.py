@@ -48,6 +48,14 @@ def test_se_sam_identical(tmp_path, flags):
     for a, b in zip(want, got):
         assert a == b
     body = [ln.split("\t") for ln in want if ln and not ln.startswith("@")]
+    if "-d" in flags:        # the MD/NM/XV tags and the XA alternates' CIGARs in that SAM came from the GPU
+        import re
+        m = re.search(r"MD/NM/XV tags prepared (\d+) printed (\d+), XA CIGARs prepared (\d+) printed (\d+)", err)
+        n_md = sum(1 for f in body if any(x.startswith("MD:Z:") for x in f[11:]))
+        n_xa_gapped = sum(sum(1 for alt in x[5:].split(";") if alt and ("I" in alt.split(",")[2] or "D" in alt.split(",")[2]))
+                          for f in body for x in f[11:] if x.startswith("XA:Z:"))
+        assert m and int(m.group(2)) == n_md and n_md >= 5000, (m and m.groups(), n_md)
+        assert int(m.group(4)) == n_xa_gapped and int(m.group(3)) >= int(m.group(4)), (m.groups(), n_xa_gapped)
     assert sum(1 for f in body if f[1] == "4") >= 30                       # unmapped reads exist
     assert sum(1 for f in body if "I" in f[5] or "D" in f[5]) >= 300       # gapped CIGARs exist
     assert sum(1 for f in body if any(x.startswith("XA:") for x in f[11:])) >= 1
