@@ -67,5 +67,15 @@ SALT_HD int first_set_nibble(uint32_t z)   // z != 0, bits only at 4i
 
 SALT_HD int imin(int a, int b) { return a < b ? a : b; }
 SALT_HD int imax(int a, int b) { return a > b ? a : b; }
+// three-input unsigned minimum: one VIMNMX3 on sm_100a
+SALT_HD uint32_t salt_min3u(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    return __vimin3_u32(a, b, c);
+#else
+    const uint32_t t = a < b ? a : b;
+    return t < c ? t : c;
+#endif
+}
 
 }  // namespace salt

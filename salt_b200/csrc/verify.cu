@@ -495,6 +495,23 @@ __device__ __forceinline__ uint32_t lv_haszero(uint32_t x)      // non-zero iff 
     return (x - 0x11111111u) & ~x & 0x88888888u;
 }
 
+// One word offset A of the filter's diagonal sweep: shifts s_first..s_last (nibbles) of the window words
+// TA[j + A], TA[j + A + 1] against the tile's 12 pattern words (one-hot reads: a word matches iff P & ~W == 0).
+template <int A>
+__device__ __forceinline__ void lv_filter_block(const uint32_t (&TA)[20], const uint32_t (&P)[12], uint32_t (&m)[12],
+                                                int s_first, int s_last)
+{
+    for (int s = s_first; s <= s_last; s += 2) {
+        const int sh0 = 4 * s, sh1 = 4 * (s + 1 <= s_last ? s + 1 : s);
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            const uint32_t x0 = P[j] & ~__funnelshift_r(TA[j + A], TA[j + A + 1], sh0);
+            const uint32_t x1 = P[j] & ~__funnelshift_r(TA[j + A], TA[j + A + 1], sh1);
+            m[j] = salt_min3u(m[j], x0, x1);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128)
 lv_filter_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_fixed,
                  const uint32_t *__restrict__ slots, const uint32_t *__restrict__ wl_count,
@@ -564,34 +581,18 @@ lv_filter_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int 
             if (!__any_sync(0xffffffffu, hasN)) {
 #pragma unroll
                 for (int j = 0; j < TW; ++j) m[j] = (t0 + j < nf && ok) ? (P[j] & ~TA[j + 4]) : 1u;           // diagonal 0
-                {
-                    uint32_t W[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) W[j] = TA[j + 4];
-                    for (int d = 1; d <= kpw; ++d) {
-#pragma unroll
-                        for (int j = 0; j < 15; ++j) W[j] = __funnelshift_r(W[j], W[j + 1], 4);
-                        W[15] >>= 4;
-                        if (d <= kp) {
-#pragma unroll
-                            for (int j = 0; j < TW; ++j) m[j] = min(m[j], P[j] & ~W[j]);
-                        }
-                    }
-                }
-                {
-                    uint32_t W[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) W[j] = TA[j];
-                    for (int d = 1; d <= kw; ++d) {
-#pragma unroll
-                        for (int j = 15; j > 0; --j) W[j] = __funnelshift_l(W[j - 1], W[j], 4);
-                        W[0] <<= 4;
-                        if (d <= k) {
-#pragma unroll
-                            for (int j = 0; j < TW; ++j) m[j] = min(m[j], P[j] & ~W[j + 4]);
-                        }
-                    }
-                }
+                // Diagonal +d looks at text nibble 8j + d of the tile, i.e. TA[j + 4 + (d >> 3)] shifted by d & 7
+                // nibbles; diagonal -d at nibble 8j + t - 32 with t = 32 - d, i.e. TA[j + (t >> 3)] shifted by t & 7.
+                // Each block below covers the eight shifts of one word offset (static register indices), two
+                // diagonals per step so that one three-input minimum folds both.  The sweep runs to the warp's
+                // largest k: a diagonal beyond a lane's own k can only add matches, the filter stays exact.
+                lv_filter_block<4>(TA, P, m, 1, imin(7, kpw));
+                if (kpw >= 8) lv_filter_block<5>(TA, P, m, 0, imin(7, kpw - 8));
+                if (kpw >= 16) lv_filter_block<6>(TA, P, m, 0, imin(7, kpw - 16));
+                lv_filter_block<3>(TA, P, m, 8 - imin(8, kw), kw >= 1 ? 7 : -1);
+                if (kw >= 9) lv_filter_block<2>(TA, P, m, 16 - imin(16, kw), 7);
+                if (kw >= 17) lv_filter_block<1>(TA, P, m, 24 - imin(24, kw), 7);
+                if (kw >= 25) lv_filter_block<0>(TA, P, m, 32 - imin(32, kw), 7);
                 // an absent word (P = 0) would pass "P & ~W == 0": it was seeded with 1 and min() keeps 0 out only
                 // if every test is masked too
 #pragma unroll
