@@ -146,6 +146,33 @@ def _emit(obj):
     _REAL_STDOUT.flush()
 
 
+def _bind_to_gpu_numa_node(local):
+    """Several ranks share the host: run this one (and first-touch its pinned buffers) on the NUMA node its
+    GPU hangs off, so that every rank's H2D/D2H traffic stays on its own socket.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                                  # sysfs uses a 4-digit PCI domain
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return "unknown"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "node%d (%d cpus)" % (node, len(cpus))
+    except Exception as e:                                 # noqa: BLE001 -- affinity is an optimisation only
+        return "unbound (%s)" % type(e).__name__
+    return "unbound"
+
+
 def main():
     args = parse()
     _claim_stdout()
@@ -178,6 +205,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
+        cfg["numa"] = _bind_to_gpu_numa_node(local)       # pinned host buffers next to this rank's GPU
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     wl = make_workload(args, seed=11 + rank)
