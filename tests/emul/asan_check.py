@@ -27,6 +27,14 @@ for L, glen in ((100, 30000), (150, 30000), (250, 30000), (37, 20000), (700, 400
     pairs = pc.flat_pairs((offs0, loci0, offs1, loci1), n)
     pc.check_mismatch(eng, o, g, reads, pairs[:60], 3)
     pc.check_lv(eng, o, g, reads, pairs[:60], -1)
+    for mapping in (1, 2):                       # warp-per-pair and thread-per-pair LV, CIGAR kernels of both kinds
+        eng.set_lv_mapping(mapping)
+        pc.check_lv(eng, o, g, reads, pairs[:40], 3)
+        tp = api.Engine.make_pairs(np.arange(n, dtype=np.uint32), strand, pos)
+        pc.check_lv_cigar(eng, o, g, reads, tp, np.full(n, min(15, L // 10 + 2), np.uint8), 128)
+    eng.set_lv_mapping(0)
+    cases_seed = 1000 + L
+    pc.check_md_nm(eng, o, g, reads, pos, strand, cases_seed, md_stride=2 * L + 64)
     rng = np.random.default_rng(L)
     if L <= 250:
         wins = pc.make_windows(g, reads[:12], pos[:12], strand[:12], L, rng, 301)
