@@ -1148,33 +1148,50 @@ nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t 
 // Acceptance scan of the gapped stage.  The LV kernels return e iff e <= T0; the reference calls
 // them with a threshold that tightens as candidates are accepted, which is equivalent to accepting
 // candidate i iff e_i <= min(T0, min_{j<i} e_j) in list order, strand 0 then strand 1
-// (code_kdiff, alnse.c:372-393).  One thread per read that reached the stage walks its lists.
+// (code_kdiff, alnse.c:372-393).  Eight lanes per read that reached the stage walk its lists, eight
+// candidates per step.
 // --------------------------------------------------------------------------------------
 
-__device__ __forceinline__ int scan_stage(const uint32_t *__restrict__ loci, uint32_t b, uint32_t e,
-                                          int8_t *__restrict__ acc, uint32_t l_mref, uint32_t guard,
-                                          int max_diff, int strand, int gapped, salt_verify_out_t &q)
+// One strand of one read, eight lanes over eight candidates at a time: the same acceptance as nogap_strand
+// (exclusive prefix minimum over the lanes, then the running threshold), fed with the LV results in acc.
+__device__ __forceinline__ void scan_strand(const uint32_t *__restrict__ loci, uint32_t b, uint32_t e,
+                                            int8_t *__restrict__ accs, uint32_t l_mref, uint32_t guard, int strand,
+                                            int lane, int gshift, unsigned gmask, int &max_diff, salt_verify_out_t &q)
 {
-    bool matched = false;
-    uint32_t last = 0xFFFFFFFFu;
-    for (uint32_t i = b; i < e; ++i) {
-        const uint32_t pos = loci[i];
-        // alnse.c:762 (nogap: pos >= l) / :894 (withgap: pos + l_seq + 4 >= l, uint32 arithmetic)
-        if (pos == last || (uint32_t)(pos + guard) >= l_mref) { acc[i] = -1; continue; }
-        const int nd = acc[i];
-        if (nd >= 0 && nd <= max_diff) {
-            if (nd < max_diff || !matched) {
-                max_diff = nd;
-                q.is_gap = (uint8_t)gapped; q.n_diff = (uint8_t)nd; q.strand = (uint8_t)strand; q.pos = pos;
-            }
-            matched = true;
-            q.n_hits[strand] += 1;
-        } else {
-            acc[i] = -1;
+    constexpr int G = 8, BIG = 255;
+    bool matched = false;                                           // per stage call (alnse.c:883)
+    for (uint32_t base = b; base < e; base += G) {
+        const uint32_t idx = base + (uint32_t)lane;
+        const bool in = idx < e;
+        const uint32_t pos = in ? loci[idx] : 0xFFFFFFFFu;
+        const uint32_t prev = (in && idx > b) ? loci[idx - 1] : 0xFFFFFFFFu;
+        // alnse.c:894: repeats of the previous locus and pos + l_seq + 4 >= l (uint32 arithmetic) are skipped
+        const bool skip = !in || pos == prev || (uint32_t)(pos + guard) >= l_mref;
+        const int nd = in ? (int)accs[idx] : -1;
+        const int key = (!skip && nd >= 0) ? nd : BIG;
+        int pm = key;                                               // inclusive prefix minimum over the group
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+            const int up = __shfl_up_sync(gmask, pm, o, G);
+            if (lane >= o) pm = imin(pm, up);
         }
-        last = pos;
+        int ex = __shfl_up_sync(gmask, pm, 1, G);
+        if (lane == 0) ex = BIG;
+        const bool accepted = key != BIG && key <= imin(max_diff, ex);
+        const unsigned bal = (__ballot_sync(gmask, accepted) >> gshift) & 0xffu;
+        if (in) accs[idx] = (int8_t)(accepted ? key : -1);
+        const int cmin = __shfl_sync(gmask, pm, G - 1, G);
+        const unsigned at = (__ballot_sync(gmask, accepted && key == cmin) >> gshift) & 0xffu;
+        const uint32_t cand_pos = __shfl_sync(gmask, pos, at ? __ffs((int)at) - 1 : 0, G);
+        if (bal) {
+            if (cmin < max_diff || !matched) {                      // first success, then every strict improvement
+                q.is_gap = 1; q.n_diff = (uint8_t)cmin; q.strand = (uint8_t)strand; q.pos = cand_pos;
+            }
+            max_diff = imin(max_diff, cmin);
+            matched = true;
+            q.n_hits[strand] += __popc(bal);
+        }
     }
-    return matched ? max_diff : -1;
 }
 
 __global__ void __launch_bounds__(128)
@@ -1184,19 +1201,27 @@ scan_gap_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t *__
                 const uint32_t *__restrict__ lv_reads, const uint32_t *__restrict__ lv_read_count,
                 uint32_t *__restrict__ cig_list, uint32_t *__restrict__ cig_count)
 {
-    // one thread per read that reached the gapped stage (the list nogap_fused wrote)
+    // eight lanes per read that reached the gapped stage (the list nogap_fused wrote)
+    constexpr int G = 8;
     const uint32_t count = *lv_read_count;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x % G;
+    const int gshift = (threadIdx.x & 31) / G * G;
+    const unsigned gmask = 0xffu << gshift;
+    const uint32_t groups = gridDim.x * blockDim.x / G;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) / G; i < count; i += groups) {
         const uint32_t r = lv_reads[i];
         salt_verify_out_t q = rec[r];
         const int L = c.rd_len[r];
-        int max_diff = lv_T0 >= 0 ? lv_T0 : L / 10;
+        int max_diff = lv_T0 >= 0 ? lv_T0 : L / 10;                  // alnse.c:1090 / :1027
         const uint32_t guard = (uint32_t)L + 4u;
-        const int d0 = scan_stage(loci0, offs0[r], offs0[r + 1], acc, c.l, guard, max_diff, 0, 1, q);
-        if (d0 != -1 && d0 < max_diff) max_diff = d0;
-        (void)scan_stage(loci1, offs1[r], offs1[r + 1], acc + n0, c.l, guard, max_diff, 1, 1, q);
-        rec[r] = q;
-        if (q.is_gap == 1 && cig_list) cig_list[atomicAdd(cig_count, 1u)] = r;
+        // strand 1 starts from the threshold strand 0 left (alnse.c:1092-1094)
+        const uint32_t b0 = offs0[r], e0 = offs0[r + 1], b1 = offs1[r], e1 = offs1[r + 1];   // all four before the first use
+        scan_strand(loci0, b0, e0, acc, c.l, guard, 0, lane, gshift, gmask, max_diff, q);
+        scan_strand(loci1, b1, e1, acc + n0, c.l, guard, 1, lane, gshift, gmask, max_diff, q);
+        if (lane == 0) {
+            rec[r] = q;
+            if (q.is_gap == 1 && cig_list) cig_list[atomicAdd(cig_count, 1u)] = r;
+        }
     }
 }
 
@@ -1443,8 +1468,8 @@ cudaError_t launch_scan_gap(const DevCtx &c, const uint32_t *offs0, const uint32
                             uint32_t *cig_list, uint32_t *cig_count, int sm_count, cudaStream_t st)
 {
     if (!c.n_reads) return cudaSuccess;
-    size_t blocks = ((size_t)c.n_reads + 127) / 128;
-    const size_t cap = (size_t)sm_count * 8;             // the list is usually a few percent of the reads
+    size_t blocks = ((size_t)c.n_reads * 8 + 127) / 128;      // eight lanes per listed read
+    const size_t cap = (size_t)sm_count * 32;            // the list is usually a few percent of the reads
     if (blocks > cap) blocks = cap;
     SALT_LAUNCH(scan_gap_kernel, (unsigned)blocks, 128, 0, st, c, offs0, loci0, offs1, loci1, n0, lv_T0, acc, rec,
                 lv_reads, lv_read_count, cig_list, cig_count);
