@@ -65,6 +65,15 @@ int salt_chunk_wait(salt_b200_t *h, int slot, salt_chunk_t *c);
  * query.c:317-318). */
 int salt_chunk_result(const salt_chunk_t *c, uint32_t i, int max_hits, salt_read_result_t *out);
 
+/* The SAM tail of the chunk's primaries (sam_add_md_nm, sam.c:246-328; option -d): MD string, NM and
+ * XV of every mapped read from ONE salt_b200_md_nm call on the reads still resident in `slot`.
+ * Call after salt_chunk_wait and before the slot is submitted again.  Needs the 2-bit pac. */
+int salt_chunk_tail(salt_b200_t *h, int slot, salt_chunk_t *c);
+
+/* Read i after salt_chunk_tail: the "MD:Z:" value ("" for an unmapped read), *nm = the NM value,
+ * *xv / *n_xv = the XV read offsets (NULL / 0 when there are none).  NULL on misuse. */
+const char *salt_chunk_md(const salt_chunk_t *c, uint32_t i, int *nm, const uint16_t **xv, int *n_xv);
+
 /* aux->hits of read i on one strand, in acceptance order.  Returns the number written (<= cap). */
 int salt_chunk_hits(const salt_chunk_t *c, uint32_t i, int strand, salt_hit_t *out, int cap);
 

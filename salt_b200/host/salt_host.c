@@ -14,7 +14,12 @@ struct salt_chunk {
     /* pinned outputs */
     salt_verify_out_t *rec; int8_t *acc[2]; char *cigars;
     int lv_T0; int done;
+    /* SAM tail (salt_chunk_tail): per read, rows of the arrays below; -1 = unmapped */
+    int tail_done; int32_t *tail_row; salt_mdnm_out_t *tail_out; char *tail_md; uint16_t *tail_xv;
 };
+
+#define TAIL_MD_STRIDE 256
+#define TAIL_XV_STRIDE 64
 
 static void *pinned(size_t bytes) { return salt_b200_host_alloc(bytes ? bytes : 1); }
 
@@ -46,13 +51,14 @@ void salt_chunk_free(salt_chunk_t *c)
     if (!c) return;
     salt_b200_host_free(c->codes); salt_b200_host_free(c->offs_all); salt_b200_host_free(c->rec);
     salt_b200_host_free(c->cigars);
+    free(c->tail_row); free(c->tail_out); free(c->tail_md); free(c->tail_xv);
     for (int s = 0; s < 2; ++s) { salt_b200_host_free(c->loci[s]); salt_b200_host_free(c->acc[s]); }
     free(c);
 }
 
 void salt_chunk_reset(salt_chunk_t *c)
 {
-    c->n_reads = 0; c->done = 0;
+    c->n_reads = 0; c->done = 0; c->tail_done = 0;
     c->roffs[0] = 0; c->offs[0][0] = 0; c->offs[1][0] = 0;
 }
 
@@ -158,4 +164,50 @@ done:
         else snprintf(out->cigar, sizeof out->cigar, "%dM", (int)(c->roffs[i + 1] - c->roffs[i]));
     }
     return SALT_OK;
+}
+
+/* sam_add_md_nm for the whole chunk (sam.c:246-328): one GPU call on the slot's resident reads */
+int salt_chunk_tail(salt_b200_t *h, int slot, salt_chunk_t *c)
+{
+    if (!c || !c->done) return SALT_ERR_ARG;
+    const uint32_t n = c->n_reads;
+    uint32_t m = 0, i;
+    c->tail_row = realloc(c->tail_row, ((size_t)n + 1) * sizeof *c->tail_row);
+    if (!c->tail_row) return SALT_ERR_NOMEM;
+    for (i = 0; i < n; ++i) c->tail_row[i] = c->rec[i].pos != 0xFFFFFFFFu ? (int32_t)m++ : -1;
+    c->tail_done = 1;
+    if (!m) return SALT_OK;
+    salt_mdnm_in_t *in = malloc((size_t)m * sizeof *in);
+    char *cg = calloc((size_t)m, 128);
+    c->tail_out = realloc(c->tail_out, (size_t)m * sizeof *c->tail_out);
+    c->tail_md = realloc(c->tail_md, (size_t)m * TAIL_MD_STRIDE);
+    c->tail_xv = realloc(c->tail_xv, (size_t)m * TAIL_XV_STRIDE * sizeof *c->tail_xv);
+    if (!in || !cg || !c->tail_out || !c->tail_md || !c->tail_xv) { free(in); free(cg); c->tail_done = 0; return SALT_ERR_NOMEM; }
+    for (i = 0; i < n; ++i) {
+        const int32_t k = c->tail_row[i];
+        if (k < 0) continue;
+        const salt_verify_out_t *q = &c->rec[i];
+        in[k].rs = (i << 1) | (uint32_t)(q->strand & 1); in[k].pos = q->pos; in[k].seq_start = 0;     /* query.c:284 */
+        if (q->is_gap) { strncpy(cg + (size_t)k * 128, c->cigars + (size_t)i * 128, 127); }          /* query.c:288 */
+        else snprintf(cg + (size_t)k * 128, 128, "%dM", (int)(c->roffs[i + 1] - c->roffs[i]));       /* query.c:291 */
+    }
+    const int rc = salt_b200_md_nm(h, slot, in, m, cg, 128, c->tail_md, TAIL_MD_STRIDE, c->tail_xv, TAIL_XV_STRIDE, c->tail_out);
+    free(in); free(cg);
+    if (rc != SALT_OK) c->tail_done = 0;
+    return rc;
+}
+
+const char *salt_chunk_md(const salt_chunk_t *c, uint32_t i, int *nm, const uint16_t **xv, int *n_xv)
+{
+    if (!c || !c->tail_done || i >= c->n_reads) return NULL;
+    const int32_t k = c->tail_row[i];
+    if (nm) *nm = 0;
+    if (xv) *xv = NULL;
+    if (n_xv) *n_xv = 0;
+    if (k < 0) return "";
+    if (c->tail_out[k].md_len < 0) return NULL;                     /* -2 / -3: see salt_mdnm_out_t */
+    if (nm) *nm = c->tail_out[k].nm;
+    if (n_xv) *n_xv = c->tail_out[k].n_xv;
+    if (xv && c->tail_out[k].n_xv) *xv = c->tail_xv + (size_t)k * TAIL_XV_STRIDE;
+    return c->tail_md + (size_t)k * TAIL_MD_STRIDE;
 }

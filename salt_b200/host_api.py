@@ -34,6 +34,9 @@ def declare(L):
     L.salt_chunk_wait.argtypes = [vp, i32, vp]
     L.salt_chunk_result.argtypes = [vp, u32, i32, C.POINTER(ReadResultT)]
     L.salt_chunk_hits.argtypes = [vp, u32, i32, C.POINTER(HitT), i32]
+    L.salt_chunk_tail.argtypes = [vp, i32, vp]
+    L.salt_chunk_md.argtypes = [vp, u32, C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(C.c_int)]
+    L.salt_chunk_md.restype = C.c_char_p
     return L
 
 
@@ -81,6 +84,17 @@ class Chunk:
             raise api.SaltError(rc, "salt_chunk_result")
         alts = [[(h.pos, h.n_diff, h.is_gap, h.strand) for h in r.alt[s][:r.n_alt[s]]] for s in (0, 1)]
         return (r.pos, r.strand, r.n_diff, r.is_gap, r.b0, r.b1, r.mapq), alts, r.cigar.decode()
+
+    def tail(self, eng, slot):
+        eng._ck(self.H.salt_chunk_tail(eng.h, int(slot), self.c))
+
+    def md(self, i):
+        """(MD value, NM, XV offsets) of read i after tail(); MD is '' for an unmapped read"""
+        nm = C.c_int(); nx = C.c_int(); xv = C.POINTER(C.c_uint16)()
+        md = self.H.salt_chunk_md(self.c, int(i), C.byref(nm), C.byref(xv), C.byref(nx))
+        if md is None:
+            raise api.SaltError(-101, "salt_chunk_md")
+        return md.decode(), nm.value, [int(xv[k]) for k in range(nx.value)]
 
     def hits(self, i, strand, cap=4096):
         buf = (HitT * cap)()

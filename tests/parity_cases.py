@@ -123,7 +123,7 @@ def check_verify_batch(eng, reads, cands, chunk_reads, nogap_T0=3, lv_T0=-1, str
     return want[0]
 
 
-def check_host_chunks(eng, hostlib, oracle, g, reads, cands, chunk_reads, nogap_T0=3, lv_T0=-1, max_hits=5):
+def check_host_chunks(eng, hostlib, oracle, g, reads, cands, chunk_reads, nogap_T0=3, lv_T0=-1, max_hits=5, with_tail=False):
     """The host-side C layer (include/salt_host.h): chunk queues through the pipeline slots, then
     query_set_hits / gen_mapq / query_gen_cigar per read -- against the oracle's verify_read."""
     from salt_b200 import host_api
@@ -140,6 +140,8 @@ def check_host_chunks(eng, hostlib, oracle, g, reads, cands, chunk_reads, nogap_
             return
         b = owner[si]; ch = chunks[si]
         ch.wait(eng, si)
+        if with_tail:
+            ch.tail(eng, si)
         for i in range(ch.H.salt_chunk_n_reads(ch.c)):
             r = b + i
             seq = np.ascontiguousarray(reads[r]); rseq = np.ascontiguousarray(synth.revcomp(reads[r]))
@@ -159,6 +161,13 @@ def check_host_chunks(eng, hostlib, oracle, g, reads, cands, chunk_reads, nogap_
                 want = oracle.ed_diff_withcigar(g.mixref, prim[0], rseq if prim[1] else seq, prim[2], 128)
                 assert gcig == want[1], (r, gcig, want)
                 n_gapped += 1
+            if with_tail:                      # salt_chunk_tail: the MD/NM/XV tags of the primary (sam.c:246-328)
+                md, nm, xv = ch.md(i)
+                if prim[0] == 0xFFFFFFFF:
+                    assert (md, nm, xv) == ("", 0, [])
+                else:
+                    text = "\tMD:Z:%s\tNM:i:%u" % (md, nm) + ("\tXV:i:" + ",".join(map(str, xv)) if xv else "")
+                    assert text == oracle.md_nm(g.mixref, g.pac, g.l, rseq if prim[1] else seq, prim[0], 0, gcig), (r, text)
         owner[si] = None
 
     k = 0

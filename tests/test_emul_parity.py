@@ -139,8 +139,8 @@ def test_host_layer_chunks(emul_lib, oracle):
     from salt_b200 import host_api
     hostlib = host_api.load(build_emul.build_host())
     g, reads, pos, strand, cands = pc.make_world(222, L=100, n_reads=50, per_strand=5, indel_frac=0.4, glen=30000)
-    eng = _engine(emul_lib, g)
-    assert pc.check_host_chunks(eng, hostlib, oracle, g, reads, cands, 9) >= 3
+    eng = _engine(emul_lib, g, with_pac=True)
+    assert pc.check_host_chunks(eng, hostlib, oracle, g, reads, cands, 9, with_tail=True) >= 3
     assert pc.check_host_chunks(eng, hostlib, oracle, g, reads, cands, 9, 3, 3, max_hits=2) >= 1
 
 

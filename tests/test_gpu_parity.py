@@ -132,7 +132,7 @@ def test_host_layer_chunks(oracle):
     hostlib = host_api.load()
     g, reads, pos, strand, cands = pc.make_world(654, glen=300000, L=100, n_reads=2000, per_strand=6, indel_frac=0.3, sub_rate=0.02)
     eng = _engine(g)
-    assert pc.check_host_chunks(eng, hostlib, oracle, g, reads, cands, 300) >= 50
+    assert pc.check_host_chunks(eng, hostlib, oracle, g, reads, cands, 300, with_tail=True) >= 50
     assert pc.check_host_chunks(eng, hostlib, oracle, g, reads[:600], tuple(
         c[:601] if i % 2 == 0 else c for i, c in enumerate(cands)), 128, 3, 3, max_hits=3) >= 5
 
