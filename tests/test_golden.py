@@ -8,6 +8,7 @@ import pytest
 from salt_b200 import api, synth
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "salt_golden_v1.npz")
+GOLD_MDNM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "salt_golden_mdnm_v1.npz")
 TAGS = (("a", 100), ("b", 150), ("c", 250), ("d", 37))
 
 
@@ -36,7 +37,30 @@ def _parse_idx(G):
     return recs, rows
 
 
+@pytest.fixture(scope="module")
+def gold_mdnm():
+    return np.load(GOLD_MDNM)
+
+
+def _txt(row):
+    return bytes(row).split(b"\0")[0].decode()
+
+
 # ------------------------------------------------------------------ CPU: oracle vs golden
+@pytest.mark.parametrize("tag,L", TAGS)
+def test_oracle_md_nm(oracle, gold, gold_mdnm, tag, L):
+    """MD/NM/XV text of the reference's own sam_add_md_nm (tests/golden/make_golden_mdnm.py)"""
+    M = gold_mdnm
+    n_xv = 0
+    for i in range(len(M[tag + "_pos"])):
+        s = int(M[tag + "_strand"][i])
+        got = oracle.md_nm(gold[tag + "_mixref"], gold[tag + "_pac"], int(gold[tag + "_l"]), _seq(gold, tag, i, s),
+                           int(M[tag + "_pos"][i]), int(M[tag + "_seq_start"][i]), _txt(M[tag + "_cigar"][i]))
+        assert got == _txt(M[tag + "_text"][i]), (tag, i)
+        n_xv += "XV:i:" in got
+    assert n_xv >= 3
+
+
 @pytest.mark.parametrize("tag,L", TAGS)
 def test_oracle_pairs(oracle, gold, tag, L):
     mix, l, pac, reads, pos, strand, cands = _world(gold, tag)
@@ -117,6 +141,18 @@ def test_gpu_pairs(gold, tag, L):
     assert np.array_equal(out, gold[tag + "_cig_e"])
     for r in range(n):
         assert api.cstr(buf[r]) == api.cstr(gold[tag + "_cig_s"][r])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,L", TAGS)
+def test_gpu_md_nm(gold, gold_mdnm, tag, L):
+    M = gold_mdnm
+    eng = _engine(gold, tag)
+    n = len(M[tag + "_pos"])
+    rs = (np.arange(n, dtype=np.uint32) << 1) | M[tag + "_strand"].astype(np.uint32)
+    out, md, xv = eng.md_nm(rs, M[tag + "_pos"], M[tag + "_seq_start"], [_txt(c) for c in M[tag + "_cigar"]], md_stride=4 * L + 128)
+    for i in range(n):
+        assert api.Engine.md_nm_text(out, md, xv, i) == _txt(M[tag + "_text"][i]), (tag, i)
 
 
 @pytest.mark.gpu
