@@ -70,12 +70,47 @@ def make_workload(args, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML in-process (a query takes ~0.1 ms, the
+    timed region of the default run only a few ms), `nvidia-smi -lms` as the fallback."""
+
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, dev):
-        self.dev = dev; self.rows = []; self.p = None
+        self.dev = dev; self.rows = []; self.p = None; self.h = None; self.stop_flag = False; self.t = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            pr = torch.cuda.get_device_properties(self.dev)
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:                                  # noqa: BLE001 -- older torch: fall back to the index
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.dev)
+
+    def _sample_nvml(self):
+        nv, h = self.nv, self.h
+        try:
+            reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        except Exception:                                  # noqa: BLE001
+            reasons = 0
+        self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(reasons)))
+
+    def _loop(self):
+        while not self.stop_flag:
+            self._sample_nvml()
+            time.sleep(0.0005)
 
     def start(self):
+        try:
+            self.nv, self.h = self._nvml_handle()
+            self.max_mhz = float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            self._sample_nvml()
+            self.t = threading.Thread(target=self._loop, daemon=True); self.t.start()
+            return
+        except Exception:                                  # noqa: BLE001
+            self.h = None
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
@@ -90,6 +125,17 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.h is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1.0)
+            self._sample_nvml()
+            sm = [r[0] for r in self.rows]
+            bits = 0
+            for r in self.rows:
+                bits |= r[1]
+            busy = sorted(sm)[len(sm) // 2:]
+            return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                    "reasons": [n for b, n in self.REASONS if bits & b], "source": "nvml"}
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -100,7 +146,7 @@ class ClockSampler:
         reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
         busy = sorted(sm)[len(sm) // 2:] if sm else []
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": reasons}
+                "samples": len(sm), "reasons": reasons, "source": "nvidia-smi"}
 
 
 def cpu_reference_run(args, wl, n_sample, steps, warmup):
