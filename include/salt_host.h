@@ -77,6 +77,33 @@ const char *salt_chunk_md(const salt_chunk_t *c, uint32_t i, int *nm, const uint
 /* aux->hits of read i on one strand, in acceptance order.  Returns the number written (<= cap). */
 int salt_chunk_hits(const salt_chunk_t *c, uint32_t i, int strand, salt_hit_t *out, int cap);
 
+/* ---- paired-end: what happens to a pair after both mates went through the verification stage ----
+ * pairing2 (alnpe.c:94-257, both mates mapped) and pairing_singleton (alnpe.c:395-473, one mapped)
+ * re-staged as a PLAN: either the pair is proper as it stands or through one combination of the mates'
+ * alternates (no rescue), or up to two mate-rescue windows have to be aligned with Smith-Waterman, in the
+ * order the reference tries them (the second only if the first finds nothing).  A chunk's windows can then
+ * go to salt_b200_ssw in one call per flavour, without a host round trip per pair. */
+typedef struct {
+    int mate;                        /* the mate aligned into the window (the other one anchors it) */
+    int strand;                      /* that mate's strand there */
+    int flavour;                     /* 16: SNP-aware, mixRef masks + score_mat2 (snpaln_sw_snpaware, alnpe.c:261);
+                                        5: plain, 2-bit pac + score_mat (snpaln_sw, alnpe.c:330) */
+    uint32_t start, end;             /* reference bases [start, end] inclusive */
+} salt_rescue_t;
+
+typedef struct {
+    int paired;                      /* 1: proper pair without rescue; hit[m] = what mate m's primary becomes */
+    salt_hit_t hit[2];
+    int n_win;                       /* 0..2 rescue windows */
+    salt_rescue_t win[2];
+} salt_pair_plan_t;
+
+/* r0 / r1: the two mates' results (salt_chunk_result, PE thresholds); l0 / l1: their lengths;
+ * min_tlen / max_tlen: the -a / -b options (aln.h:127-128); l_pac: reference length.
+ * Returns SALT_OK, or SALT_ERR_ARG where the reference would exit (a window starting past the reference). */
+int salt_pair_plan(const salt_read_result_t *r0, uint32_t l0, const salt_read_result_t *r1, uint32_t l1,
+                   uint32_t min_tlen, uint32_t max_tlen, uint32_t l_pac, salt_pair_plan_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -219,6 +219,59 @@ static void run_pairing(index_t *index, query_t *q0, query_t *q1, aln_opt_t *aln
     else if (q0->pos != 0xFFFFFFFF || q1->pos != 0xFFFFFFFF) { H.func = 1; pairing_singleton(index, q0, q1, aln_opt); }
 }
 
+/* ---- salt_pair_plan (include/salt_host.h) checked against the reference's own pairing, pair by pair ---- */
+static size_t plan_checked, plan_paired, plan_windows, plan_mismatch;
+
+static void result_of_query(const query_t *q, salt_read_result_t *r)       /* the query_t fields the verification stage set */
+{
+    int s; size_t i;
+    memset(r, 0, sizeof *r);
+    r->pos = q->pos; r->strand = (uint8_t)q->strand; r->n_diff = q->n_diff; r->is_gap = q->is_gap;
+    for (s = 0; s < 2; ++s) {
+        r->n_alt[s] = (int)q->hits[s].n;
+        for (i = 0; i < q->hits[s].n && i < SALT_MAX_HITS; ++i) {
+            const hit_t *h = q->hits[s].a + i;
+            r->alt[s][i].pos = h->pos; r->alt[s][i].n_diff = h->n_diff; r->alt[s][i].is_gap = h->is_gap; r->alt[s][i].strand = h->strand;
+        }
+    }
+}
+
+static int plan_of(const query_t *q0, const query_t *q1, const aln_opt_t *opt, uint32_t l_pac, salt_pair_plan_t *plan)
+{
+    salt_read_result_t r0, r1;
+    result_of_query(q0, &r0); result_of_query(q1, &r1);
+    return salt_pair_plan(&r0, (uint32_t)q0->l_seq, &r1, (uint32_t)q1->l_seq, (uint32_t)opt->min_tlen, (uint32_t)opt->max_tlen, l_pac, plan);
+}
+
+static void check_plan(const salt_pair_plan_t *plan, int plan_rc, const query_t *q0, const query_t *q1, size_t req0)
+{
+    const size_t n_req = H.n_req - req0;
+    int ok = plan_rc == SALT_OK;
+    int w;
+    ++plan_checked;
+    if (plan->paired) {
+        const query_t *q[2] = {q0, q1};
+        ++plan_paired;
+        ok = ok && n_req == 0;
+        for (w = 0; w < 2; ++w)
+            ok = ok && q[w]->pos == plan->hit[w].pos && q[w]->strand == (int)plan->hit[w].strand &&
+                 q[w]->n_diff == plan->hit[w].n_diff && q[w]->is_gap == plan->hit[w].is_gap;
+    } else {
+        plan_windows += (size_t)plan->n_win;
+        ok = ok && n_req == (size_t)plan->n_win;
+        for (w = 0; ok && w < plan->n_win; ++w) {
+            const rescue_req_t *r = &H.req[req0 + w];
+            ok = r->mate == plan->win[w].mate && r->strand == plan->win[w].strand && r->flavour == plan->win[w].flavour &&
+                 r->start == plan->win[w].start && r->end == plan->win[w].end;
+        }
+    }
+    if (!ok) {
+        if (plan_mismatch < 5) fprintf(stderr, "[salt_dropin/pe] salt_pair_plan disagrees with the reference on %s (rc %d, paired %d, windows %d, recorded %zu)\n",
+                                       q0->name, plan_rc, plan->paired, plan->n_win, n_req);
+        ++plan_mismatch;
+    }
+}
+
 /* pairs [first, upto) of the chunk: record, one GPU batch per flavour, replay + SAM */
 static void pair_and_emit(salt_b200_t *gpu, index_t *index, aln_opt_t *aln_opt, query_t *multi_seqs, const int *slot_of,
                           int first, int upto)
@@ -232,7 +285,13 @@ static void pair_and_emit(salt_b200_t *gpu, index_t *index, aln_opt_t *aln_opt, 
         qsnap_t s0, s1;
         H.q[0] = q0; H.q[1] = q1; H.pair = j; H.chunk_idx[0] = slot_of[j]; H.chunk_idx[1] = slot_of[j + 1];
         snap(q0, &s0); snap(q1, &s1);
+        /* the host layer's re-staged pairing (salt_pair_plan) must predict what the reference's pairing2 /
+           pairing_singleton is about to do: no rescue and these primaries, or exactly these windows in this order */
+        salt_pair_plan_t plan;
+        const size_t req0 = H.n_req;
+        const int plan_rc = plan_of(q0, q1, aln_opt, index->bntseq->l_pac, &plan);
         run_pairing(index, q0, q1, aln_opt);
+        check_plan(&plan, plan_rc, q0, q1, req0);
         unsnap(q0, &s0); unsnap(q1, &s1);
     }
     /* the windows the recording pass asked for, grouped by flavour */
@@ -379,6 +438,8 @@ int alnpe_core(const opt_t *opt)
         fprintf(stderr, "alned %d reads!\n", tot);
     }
     fprintf(stderr, "[salt_dropin/pe] rescue windows recorded: %zu, served by the reference's own ssw_align: %zu\n", n_rescue, H.n_cpu);
+    fprintf(stderr, "[salt_dropin/pe] salt_pair_plan: %zu pairs checked against pairing2/pairing_singleton, %zu proper without rescue, "
+                    "%zu windows planned, %zu mismatches\n", plan_checked, plan_paired, plan_windows, plan_mismatch);
     aux_destroy(aux[0]);
     aux_destroy(aux[1]);
     query_close(qs[0]);

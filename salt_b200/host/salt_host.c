@@ -211,3 +211,90 @@ const char *salt_chunk_md(const salt_chunk_t *c, uint32_t i, int *nm, const uint
     if (xv && c->tail_out[k].n_xv) *xv = c->tail_xv + (size_t)k * TAIL_XV_STRIDE;
     return c->tail_md + (size_t)k * TAIL_MD_STRIDE;
 }
+
+/* ------------------------------------------------------------------ paired-end plan (alnpe.c:94-257, :395-473) */
+enum { PP_IN_RANGE, PP_LOW, PP_HIGH };
+static int pp_in_range(uint32_t a, uint32_t b, uint32_t small, uint32_t large)     /* CHECK_IN_RANGE, alnpe.c:76-81 */
+{
+    const uint32_t r = a < b ? b - a : a - b;
+    if (a > b || r < small) return PP_LOW;
+    if (r > large) return PP_HIGH;
+    return PP_IN_RANGE;
+}
+
+/* the hit x hit scan of pairing2 (alnpe.c:131-191): forward hits of one mate against backward hits of the other.
+ * The reference never advances its lower bound (`j == jj;` is a comparison, alnpe.c:154): every forward hit scans
+ * the backward hits from the first one and stops at the first that lies beyond the insert range. */
+static void pp_scan(const salt_read_result_t *f, uint32_t lf, const salt_read_result_t *b, uint32_t min_isize,
+                    uint32_t max_isize, uint32_t *min_errors, salt_hit_t *bf, salt_hit_t *bb)
+{
+    for (int i = 0; i < f->n_alt[0]; ++i) {
+        const uint32_t pos0 = f->alt[0][i].pos;
+        for (int j = 0; j < b->n_alt[1]; ++j) {
+            const int range = pp_in_range(pos0 + lf, b->alt[1][j].pos, min_isize, max_isize);
+            if (range == PP_IN_RANGE) {
+                const uint32_t e = (uint32_t)f->alt[0][i].n_diff + b->alt[1][j].n_diff;
+                if (e < *min_errors) { *min_errors = e; *bf = f->alt[0][i]; *bb = b->alt[1][j]; }
+            } else if (range == PP_HIGH) break;
+        }
+    }
+}
+
+/* the window in which mate t is looked for when mate a anchors (alnpe.c:206-252 / :413-466) */
+static int pp_window(const salt_read_result_t *a, uint32_t la, uint32_t lt, int t_mate, uint32_t min_isize,
+                     uint32_t max_isize, uint32_t l_pac, int singleton, salt_rescue_t *w)
+{
+    uint32_t s, e;
+    if (a->strand == 0) {                    /* anchor forward: the mate lies downstream on the other strand */
+        s = a->pos + min_isize + la;
+        e = a->pos + max_isize + la + lt;
+        w->strand = 1;
+    } else {
+        s = a->pos > max_isize + lt ? a->pos - max_isize - lt : 0;
+        e = a->pos > min_isize ? a->pos - min_isize : 0;
+        w->strand = 0;
+    }
+    if (singleton) { s = s < l_pac - 1 ? s : l_pac - 1; e = e < l_pac - 1 ? e : l_pac - 1; }   /* __min(.., l_pac-1), alnpe.c:417-420 */
+    else e = e >= l_pac ? l_pac : e;                                                          /* alnpe.c:212 */
+    w->mate = t_mate; w->flavour = singleton ? 5 : 16; w->start = s; w->end = e;
+    return s >= l_pac ? SALT_ERR_ARG : SALT_OK;       /* alnpe.c:265-268 / :334-337: the reference exits */
+}
+
+int salt_pair_plan(const salt_read_result_t *r0, uint32_t l0, const salt_read_result_t *r1, uint32_t l1,
+                   uint32_t min_tlen, uint32_t max_tlen, uint32_t l_pac, salt_pair_plan_t *out)
+{
+    if (!r0 || !r1 || !out) return SALT_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    const uint32_t l2 = l0 + l1;
+    const uint32_t min_isize = min_tlen > l2 ? min_tlen - l2 : 0, max_isize = max_tlen > l2 ? max_tlen - l2 : 0;
+    const int m0 = r0->pos != 0xFFFFFFFFu, m1 = r1->pos != 0xFFFFFFFFu;
+    if (!m0 && !m1) return SALT_OK;                                   /* alnpe.c:513-517: nothing to do */
+    int rc = SALT_OK;
+    if (m0 && m1) {                                                    /* pairing2 */
+        const salt_hit_t p0 = {r0->pos, r0->n_diff, r0->is_gap, r0->strand}, p1 = {r1->pos, r1->n_diff, r1->is_gap, r1->strand};
+        if ((r0->strand == 0 && r1->strand == 1 && r0->pos < r1->pos &&
+             pp_in_range(r0->pos + l0, r1->pos, min_isize, max_isize) == PP_IN_RANGE) ||
+            (r1->strand == 0 && r0->strand == 1 && r1->pos < r0->pos &&
+             pp_in_range(r1->pos + l1, r0->pos, min_isize, max_isize) == PP_IN_RANGE)) {
+            out->paired = 1; out->hit[0] = p0; out->hit[1] = p1;      /* the primaries pair as they are (alnpe.c:109-127) */
+            return SALT_OK;
+        }
+        uint32_t min_errors = 0xFFFFFFFFu;
+        salt_hit_t b0 = p0, b1 = p1;
+        pp_scan(r0, l0, r1, min_isize, max_isize, &min_errors, &b0, &b1);     /* mate 0 forward, mate 1 backward */
+        pp_scan(r1, l1, r0, min_isize, max_isize, &min_errors, &b1, &b0);     /* mate 1 forward, mate 0 backward */
+        if (min_errors != 0xFFFFFFFFu) { out->paired = 1; out->hit[0] = b0; out->hit[1] = b1; return SALT_OK; }
+        /* rescue: mate 1 around mate 0, then mate 0 around mate 1 (alnpe.c:206-252) */
+        int rc0 = pp_window(r0, l0, l1, 1, min_isize, max_isize, l_pac, 0, &out->win[0]);
+        int rc1 = pp_window(r1, l1, l0, 0, min_isize, max_isize, l_pac, 0, &out->win[1]);
+        out->n_win = 2;
+        rc = rc0 != SALT_OK ? rc0 : rc1;
+    } else if (m0) {                                                   /* pairing_singleton, mate 0 anchors */
+        rc = pp_window(r0, l0, l1, 1, min_isize, max_isize, l_pac, 1, &out->win[0]);
+        out->n_win = 1;
+    } else {
+        rc = pp_window(r1, l1, l0, 0, min_isize, max_isize, l_pac, 1, &out->win[0]);
+        out->n_win = 1;
+    }
+    return rc;
+}

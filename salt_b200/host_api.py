@@ -22,6 +22,33 @@ class ReadResultT(C.Structure):
                 ("alt", (HitT * SALT_MAX_HITS) * 2), ("cigar", C.c_char * 128)]
 
 
+class RescueT(C.Structure):       # salt_rescue_t
+    _fields_ = [("mate", C.c_int), ("strand", C.c_int), ("flavour", C.c_int), ("start", C.c_uint32), ("end", C.c_uint32)]
+
+
+class PairPlanT(C.Structure):     # salt_pair_plan_t
+    _fields_ = [("paired", C.c_int), ("hit", HitT * 2), ("n_win", C.c_int), ("win", RescueT * 2)]
+
+
+def make_result(pos=0xFFFFFFFF, strand=3, n_diff=255, is_gap=255, alt0=(), alt1=()):
+    """a salt_read_result_t from (pos, strand, n_diff, is_gap) and alternates [(pos, n_diff, is_gap), ...] per strand"""
+    r = ReadResultT()
+    r.pos, r.strand, r.n_diff, r.is_gap = pos, strand, n_diff, is_gap
+    for s, alts in enumerate((alt0, alt1)):
+        r.n_alt[s] = len(alts)
+        for j, (p, nd, g) in enumerate(alts):
+            r.alt[s][j].pos, r.alt[s][j].n_diff, r.alt[s][j].is_gap, r.alt[s][j].strand = p, nd, g, s
+    return r
+
+
+def pair_plan(L, r0, l0, r1, l1, min_tlen, max_tlen, l_pac):
+    plan = PairPlanT()
+    rc = L.salt_pair_plan(C.byref(r0), int(l0), C.byref(r1), int(l1), int(min_tlen), int(max_tlen), int(l_pac), C.byref(plan))
+    wins = [(w.mate, w.strand, w.flavour, w.start, w.end) for w in plan.win[:plan.n_win]]
+    hits = [(h.pos, h.strand, h.n_diff, h.is_gap) for h in plan.hit] if plan.paired else None
+    return rc, hits, wins
+
+
 def declare(L):
     vp, i32, u32, sz = C.c_void_p, C.c_int, C.c_uint32, C.c_size_t
     L.salt_chunk_new.restype = vp
@@ -37,6 +64,7 @@ def declare(L):
     L.salt_chunk_tail.argtypes = [vp, i32, vp]
     L.salt_chunk_md.argtypes = [vp, u32, C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(C.c_int)]
     L.salt_chunk_md.restype = C.c_char_p
+    L.salt_pair_plan.argtypes = [C.POINTER(ReadResultT), u32, C.POINTER(ReadResultT), u32, u32, u32, u32, C.POINTER(PairPlanT)]
     return L
 
 

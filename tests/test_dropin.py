@@ -76,6 +76,9 @@ def test_pe_sam_identical(tmp_path, flags):
     import re
     m = re.search(r"rescue windows recorded: (\d+), served by the reference's own ssw_align: (\d+)", err)
     assert m and int(m.group(1)) >= 200 and int(m.group(2)) <= int(m.group(1)) // 20, err[-500:]    # the rescues ran on the GPU
+    # the host layer's re-staged pairing predicted every decision of the reference's pairing2 / pairing_singleton
+    m = re.search(r"salt_pair_plan: (\d+) pairs checked .*?, (\d+) proper without rescue, (\d+) windows planned, (\d+) mismatches", err)
+    assert m and int(m.group(1)) >= 2900 and int(m.group(2)) >= 2000 and int(m.group(3)) >= 200 and int(m.group(4)) == 0, err[-800:]
     want, got = _sam_body(os.path.join(d, "ref.sam")), _sam_body(os.path.join(d, "gpu.sam"))
     assert len(want) == len(got) and len(want) > 6000
     for a, b in zip(want, got):

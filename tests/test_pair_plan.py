@@ -1,0 +1,66 @@
+"""salt_pair_plan (include/salt_host.h): pairing2 / pairing_singleton (alnpe.c:94-257, :395-473) re-staged as a plan.
+Hand-made cases here (no GPU: the function is host C); tests/test_dropin.py checks it on the GPU box against the
+reference's own pairing for every pair of the paired-end run."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
+from salt_b200 import host_api
+
+L_PAC = 1_000_000
+A, B = 350, 650           # -a / -b of Test/Run_test/run_pe_test.sh:14 -> insert between mates 150..450 for 100 bp reads
+
+
+@pytest.fixture(scope="module")
+def H():
+    import build_emul                                   # the host layer linked against the CPU-run engine: loads without a GPU
+    return host_api.load(build_emul.build_host())
+
+
+def plan(H, r0, r1, l0=100, l1=100, a=A, b=B, l_pac=L_PAC):
+    return host_api.pair_plan(H, r0, l0, r1, l1, a, b, l_pac)
+
+
+def test_primaries_pair_as_they_are(H):
+    r0 = host_api.make_result(5000, 0, 1, 0); r1 = host_api.make_result(5400, 1, 2, 1)      # gap 300 between end of 0 and start of 1
+    assert plan(H, r0, r1) == (0, [(5000, 0, 1, 0), (5400, 1, 2, 1)], [])
+    assert plan(H, r1, r0) == (0, [(5400, 1, 2, 1), (5000, 0, 1, 0)], [])                   # mate 1 forward, mate 0 backward
+    # both unmapped: nothing to do
+    assert plan(H, host_api.make_result(), host_api.make_result()) == (0, None, [])
+
+
+def test_alternates_pair_with_fewest_errors(H):
+    # primaries too far apart, but two combinations of alternates lie in range: the one with fewer differences wins,
+    # ties keep the first found (strict <, alnpe.c:146)
+    r0 = host_api.make_result(5000, 0, 0, 0, alt0=[(90000, 2, 0), (70000, 1, 1)])
+    r1 = host_api.make_result(200000, 1, 0, 0, alt1=[(70350, 1, 0), (90400, 3, 0)])
+    rc, hits, wins = plan(H, r0, r1)
+    assert (rc, wins) == (0, []) and hits == [(70000, 0, 1, 1), (70350, 1, 1, 0)]
+    # the reverse orientation list is scanned too (mate 1 forward x mate 0 backward)
+    r0 = host_api.make_result(5000, 0, 0, 0, alt1=[(30400, 2, 0)])
+    r1 = host_api.make_result(200000, 1, 0, 0, alt0=[(30000, 0, 0)])
+    assert plan(H, r0, r1)[1] == [(30400, 1, 2, 0), (30000, 0, 0, 0)]
+
+
+def test_rescue_windows_both_mapped(H):
+    # same strand: no proper pair anywhere -> mate 1 around mate 0, then mate 0 around mate 1 (SNP-aware flavour)
+    r0 = host_api.make_result(5000, 0, 1, 0); r1 = host_api.make_result(300000, 0, 0, 0)
+    rc, hits, wins = plan(H, r0, r1)
+    assert rc == 0 and hits is None
+    assert wins == [(1, 1, 16, 5000 + 150 + 100, 5000 + 450 + 200), (0, 1, 16, 300000 + 150 + 100, 300000 + 450 + 200)]
+    # backward anchors look upstream; near the start of the reference the window is clipped at 0
+    r0 = host_api.make_result(5000, 1, 1, 0); r1 = host_api.make_result(300, 1, 0, 0)
+    assert plan(H, r0, r1)[2] == [(1, 0, 16, 5000 - 450 - 100, 5000 - 150), (0, 0, 16, 0, 150)]
+    # forward anchor at the end of the reference: end clamps to l_pac (not l_pac - 1, alnpe.c:212)
+    r0 = host_api.make_result(L_PAC - 400, 0, 1, 0); r1 = host_api.make_result(300, 0, 0, 0)
+    assert plan(H, r0, r1)[2][0] == (1, 1, 16, L_PAC - 400 + 250, L_PAC)
+
+
+def test_singleton_window(H):
+    r0 = host_api.make_result(5000, 0, 1, 0); un = host_api.make_result()
+    assert plan(H, r0, un) == (0, None, [(1, 1, 5, 5250, 5650)])                           # plain flavour (snpaln_sw)
+    assert plan(H, un, r0) == (0, None, [(0, 1, 5, 5250, 5650)])
+    end = host_api.make_result(L_PAC - 120, 0, 0, 0)                                       # both ends clamp to l_pac - 1
+    assert plan(H, end, un)[2] == [(1, 1, 5, L_PAC - 1, L_PAC - 1)]
