@@ -220,7 +220,7 @@ static void run_pairing(index_t *index, query_t *q0, query_t *q1, aln_opt_t *aln
 }
 
 /* ---- salt_pair_plan (include/salt_host.h) checked against the reference's own pairing, pair by pair ---- */
-static size_t plan_checked, plan_paired, plan_windows, plan_mismatch;
+static size_t plan_checked, plan_paired, plan_windows, plan_mismatch, plan_used;
 
 static void result_of_query(const query_t *q, salt_read_result_t *r)       /* the query_t fields the verification stage set */
 {
@@ -280,7 +280,25 @@ static void pair_and_emit(salt_b200_t *gpu, index_t *index, aln_opt_t *aln_opt, 
     size_t k;
     H.index = index; H.opt = aln_opt; H.n_req = 0;
     H.mode = MODE_RECORD;
-    for (j = first; j < upto; j += 2) {
+    /* SALT_DROPIN_PLAN=1: the windows come from salt_pair_plan alone -- the re-staged flow (plan, one GPU batch,
+       apply) -- instead of from a recording run of the reference's pairing; the replay below still refuses to
+       continue if the reference then asks for anything else */
+    const int use_plan = getenv("SALT_DROPIN_PLAN") && atoi(getenv("SALT_DROPIN_PLAN")) != 0;
+    for (j = first; use_plan && j < upto; j += 2) {
+        query_t *q0 = multi_seqs + j, *q1 = multi_seqs + j + 1;
+        salt_pair_plan_t plan;
+        int w;
+        if (plan_of(q0, q1, aln_opt, index->bntseq->l_pac, &plan) != SALT_OK) die("salt_pair_plan");
+        ++plan_used;
+        for (w = 0; w < plan.n_win; ++w) {
+            if (H.n_req == H.m_req) { H.m_req = H.m_req ? H.m_req * 2 : 1024; H.req = realloc(H.req, H.m_req * sizeof *H.req); }
+            rescue_req_t *r = &H.req[H.n_req++];
+            r->pair = j; r->mate = plan.win[w].mate; r->strand = plan.win[w].strand; r->flavour = plan.win[w].flavour;
+            r->start = plan.win[w].start; r->end = plan.win[w].end;
+            r->on_gpu = r->end >= r->start && r->end < index->mixRef->l && slot_of[j + r->mate] >= 0;
+        }
+    }
+    for (j = first; !use_plan && j < upto; j += 2) {
         query_t *q0 = multi_seqs + j, *q1 = multi_seqs + j + 1;
         qsnap_t s0, s1;
         H.q[0] = q0; H.q[1] = q1; H.pair = j; H.chunk_idx[0] = slot_of[j]; H.chunk_idx[1] = slot_of[j + 1];
@@ -439,7 +457,8 @@ int alnpe_core(const opt_t *opt)
     }
     fprintf(stderr, "[salt_dropin/pe] rescue windows recorded: %zu, served by the reference's own ssw_align: %zu\n", n_rescue, H.n_cpu);
     fprintf(stderr, "[salt_dropin/pe] salt_pair_plan: %zu pairs checked against pairing2/pairing_singleton, %zu proper without rescue, "
-                    "%zu windows planned, %zu mismatches\n", plan_checked, plan_paired, plan_windows, plan_mismatch);
+                    "%zu windows planned, %zu mismatches; %zu pairs scheduled from the plan alone\n", plan_checked, plan_paired, plan_windows,
+            plan_mismatch, plan_used);
     aux_destroy(aux[0]);
     aux_destroy(aux[1]);
     query_close(qs[0]);

@@ -21,9 +21,10 @@ def _have():
     return all(os.path.exists(os.path.join(REFDIR, b)) for b in ("salt", "salt-idx", "salt_dropin"))
 
 
-def _run(cmd, cwd, out):
+def _run(cmd, cwd, out, env=None):
     with open(out, "w") as f:
-        p = subprocess.run(cmd, cwd=cwd, stdout=f, stderr=subprocess.PIPE, text=True, timeout=900)
+        p = subprocess.run(cmd, cwd=cwd, stdout=f, stderr=subprocess.PIPE, text=True, timeout=900,
+                           env=dict(os.environ, **env) if env else None)
     assert p.returncode == 0, p.stderr[-2000:]
     return p.stderr
 
@@ -83,6 +84,12 @@ def test_pe_sam_identical(tmp_path, flags):
     assert len(want) == len(got) and len(want) > 6000
     for a, b in zip(want, got):
         assert a == b
+    # the re-staged flow: rescue windows scheduled from salt_pair_plan alone (no recording run of the reference's pairing)
+    err2 = _run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", "r1.fq", "r2.fq"], d, os.path.join(d, "gpu2.sam"),
+                env={"SALT_DROPIN_PLAN": "1"})
+    m2 = re.search(r"(\d+) pairs scheduled from the plan alone", err2)
+    assert m2 and int(m2.group(1)) >= 2900
+    assert _sam_body(os.path.join(d, "gpu2.sam")) == want
     body = [ln.split("\t") for ln in want if ln and not ln.startswith("@")]
     assert sum(1 for f in body if int(f[1]) & 2) >= 4000                  # properly paired records
     assert sum(1 for f in body if "S" in f[5]) >= 20                      # soft-clipped = rescued by Smith-Waterman
