@@ -104,6 +104,27 @@ typedef struct {
 int salt_pair_plan(const salt_read_result_t *r0, uint32_t l0, const salt_read_result_t *r1, uint32_t l1,
                    uint32_t min_tlen, uint32_t max_tlen, uint32_t l_pac, salt_pair_plan_t *out);
 
+/* What one mate looks like after pairing -- the query_t fields alnpe_sam prints (sam.c:331-455). */
+typedef struct {
+    uint32_t pos;                    /* 0xFFFFFFFF = unmapped */
+    uint8_t strand, n_diff, is_gap;  /* n_diff / is_gap keep the verification stage's values after a rescue, as in the reference */
+    uint32_t seq_start, seq_end;     /* aligned part of the read (soft clips around it, sam.c:392-394) */
+    int b0, b1; uint32_t mapq;
+    int cigar_kind;                  /* 0 none (unmapped); 1 "<l_seq>M"; 2 the verification stage's CIGAR (r->cigar);
+                                        3 Smith-Waterman ops of the rescue; 4 NOT filled: a gapped alternate became the
+                                        primary, its CIGAR is one salt_b200_lv_cigar item (pos, strand, k = n_diff) */
+    char cigar[256];
+} salt_mate_final_t;
+
+/* Apply a plan: `ssw` / `ssw_cigars` (cigar_stride uint32 per window: len << 4 | op, op 0/1/2 = M/I/D) are the
+ * salt_b200_ssw results of plan->win[0 .. n_win), in that order; filters / filterd the accept rule of
+ * snpaln_sw[_snpaware] (alnpe.c:295 / :362: score1 >= filters and aligned read span >= filterd).  The first window
+ * that passes rescues its mate; the other mate keeps its primary.  Returns 1 when the pair ends up aligned as a
+ * pair (PAIRED_ALNED), 0 otherwise, negative SALT_ERR_* on misuse. */
+int salt_pair_apply(const salt_pair_plan_t *plan, const salt_read_result_t *r0, uint32_t l0,
+                    const salt_read_result_t *r1, uint32_t l1, const salt_ssw_out_t *ssw, const uint32_t *ssw_cigars,
+                    int cigar_stride, int filters, int filterd, salt_mate_final_t out[2]);
+
 #ifdef __cplusplus
 }
 #endif

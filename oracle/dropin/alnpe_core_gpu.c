@@ -221,12 +221,16 @@ static void run_pairing(index_t *index, query_t *q0, query_t *q1, aln_opt_t *aln
 
 /* ---- salt_pair_plan (include/salt_host.h) checked against the reference's own pairing, pair by pair ---- */
 static size_t plan_checked, plan_paired, plan_windows, plan_mismatch, plan_used;
+static size_t apply_checked, apply_skipped, apply_mismatch, apply_rescued, apply_swapped;
+static const salt_chunk_t *H_ck;          /* the chunk whose results the pairs under way came from */
+static salt_b200_t *H_gpu;
 
 static void result_of_query(const query_t *q, salt_read_result_t *r)       /* the query_t fields the verification stage set */
 {
     int s; size_t i;
     memset(r, 0, sizeof *r);
     r->pos = q->pos; r->strand = (uint8_t)q->strand; r->n_diff = q->n_diff; r->is_gap = q->is_gap;
+    r->b0 = q->b0; r->b1 = q->b1; r->mapq = q->mapq;
     for (s = 0; s < 2; ++s) {
         r->n_alt[s] = (int)q->hits[s].n;
         for (i = 0; i < q->hits[s].n && i < SALT_MAX_HITS; ++i) {
@@ -269,6 +273,66 @@ static void check_plan(const salt_pair_plan_t *plan, int plan_rc, const query_t 
         if (plan_mismatch < 5) fprintf(stderr, "[salt_dropin/pe] salt_pair_plan disagrees with the reference on %s (rc %d, paired %d, windows %d, recorded %zu)\n",
                                        q0->name, plan_rc, plan->paired, plan->n_win, n_req);
         ++plan_mismatch;
+    }
+}
+
+/* ---- salt_pair_apply checked against where the reference's pairing ends, pair by pair ---- */
+static int results_for_apply(const query_t *q0, const query_t *q1, int ci0, int ci1, salt_read_result_t *r0, salt_read_result_t *r1)
+{
+    const query_t *q[2] = {q0, q1};
+    salt_read_result_t *r[2] = {r0, r1};
+    const int ci[2] = {ci0, ci1};
+    int m;
+    for (m = 0; m < 2; ++m) {
+        result_of_query(q[m], r[m]);
+        if (q[m]->pos != 0xFFFFFFFF && q[m]->is_gap) {          /* the verification stage's CIGAR of a gapped primary */
+            salt_read_result_t full;
+            if (ci[m] < 0 || salt_chunk_result(H_ck, (uint32_t)ci[m], H.opt->max_hits, &full) != SALT_OK) return 0;
+            memcpy(r[m]->cigar, full.cigar, sizeof full.cigar);
+        }
+    }
+    return 1;
+}
+
+static void check_apply(const salt_pair_plan_t *plan, const salt_read_result_t *r0, const salt_read_result_t *r1,
+                        const query_t *q0, const query_t *q1, size_t k0, const aln_opt_t *opt)
+{
+    const query_t *q[2] = {q0, q1};
+    salt_ssw_out_t ssw[2];
+    uint32_t cig[2 * DROPIN_CIG_STRIDE];
+    salt_mate_final_t fin[2];
+    int w, m, ok = 1;
+    for (w = 0; w < plan->n_win; ++w) {                           /* the GPU answers of this pair's windows, in plan order */
+        const size_t k = k0 + (size_t)w;
+        if (k >= H.n_req || H.req[k].pair != H.pair || !H.req[k].on_gpu) { ++apply_skipped; return; }
+        const size_t ri = H.res_of[k];
+        if (H.res[ri].cigarLen < 0 || H.res[ri].cigarLen > DROPIN_CIG_STRIDE) { ++apply_skipped; return; }
+        ssw[w] = H.res[ri];
+        memcpy(cig + (size_t)w * DROPIN_CIG_STRIDE, H.cig + ri * DROPIN_CIG_STRIDE, DROPIN_CIG_STRIDE * 4);
+    }
+    const int rc = salt_pair_apply(plan, r0, (uint32_t)q0->l_seq, r1, (uint32_t)q1->l_seq, ssw, cig, DROPIN_CIG_STRIDE,
+                                   opt->filters, opt->filterd, fin);
+    ++apply_checked;
+    ok = rc >= 0;
+    for (m = 0; ok && m < 2; ++m) {
+        const salt_mate_final_t *f = &fin[m];
+        ok = q[m]->pos == f->pos && (f->pos == 0xFFFFFFFF || (q[m]->strand == (int)f->strand && q[m]->n_diff == f->n_diff &&
+             q[m]->is_gap == f->is_gap && q[m]->seq_start == f->seq_start && q[m]->seq_end == f->seq_end)) &&
+             q[m]->b0 == f->b0 && q[m]->b1 == f->b1 && q[m]->mapq == (uint8_t)f->mapq;
+        if (!ok || f->pos == 0xFFFFFFFF) continue;
+        if (f->cigar_kind == 3) ++apply_rescued;
+        if (f->cigar_kind == 4) {                                 /* a gapped alternate became the primary: one LV+CIGAR item */
+            salt_pair_t p; uint8_t k = f->n_diff; int8_t e; char buf[256];
+            ++apply_swapped;
+            p.rs = ((uint32_t)H.chunk_idx[m] << 1) | f->strand; p.pos = f->pos;
+            memset(buf, 0, sizeof buf);
+            if (H.chunk_idx[m] < 0 || salt_b200_lv_cigar(H_gpu, &p, &k, 1, buf, sizeof buf, &e) != SALT_OK) { ok = 0; continue; }
+            ok = strcmp(buf, q[m]->cigar->s) == 0;
+        } else ok = strcmp(f->cigar, q[m]->cigar->s) == 0;
+    }
+    if (!ok) {
+        if (apply_mismatch < 5) fprintf(stderr, "[salt_dropin/pe] salt_pair_apply disagrees with the reference on %s\n", q0->name);
+        ++apply_mismatch;
     }
 }
 
@@ -359,7 +423,16 @@ static void pair_and_emit(salt_b200_t *gpu, index_t *index, aln_opt_t *aln_opt, 
     for (j = first; j < upto; j += 2) {
         query_t *q0 = multi_seqs + j, *q1 = multi_seqs + j + 1;
         H.q[0] = q0; H.q[1] = q1; H.pair = j; H.chunk_idx[0] = slot_of[j]; H.chunk_idx[1] = slot_of[j + 1];
+        /* salt_pair_apply (include/salt_host.h) must end where the reference's pairing ends */
+        salt_read_result_t pr0, pr1;
+        salt_pair_plan_t plan;
+        const size_t k0 = H.cursor;
+        const int have_plan = results_for_apply(q0, q1, slot_of[j], slot_of[j + 1], &pr0, &pr1) &&
+                              salt_pair_plan(&pr0, (uint32_t)q0->l_seq, &pr1, (uint32_t)q1->l_seq, (uint32_t)aln_opt->min_tlen,
+                                             (uint32_t)aln_opt->max_tlen, index->bntseq->l_pac, &plan) == SALT_OK;
         run_pairing(index, q0, q1, aln_opt);
+        if (have_plan) check_apply(&plan, &pr0, &pr1, q0, q1, k0, aln_opt);
+        else ++apply_skipped;
         if (H.cursor < H.n_req && H.req[H.cursor].pair == j) {
             /* a rescue that succeeds ends pairing early: skip the requests recorded after it */
             while (H.cursor < H.n_req && H.req[H.cursor].pair == j) ++H.cursor;
@@ -437,6 +510,7 @@ int alnpe_core(const opt_t *opt)
                 }
                 for (j = first; j < upto; ++j)
                     if (verified[j]) apply_result(multi_seqs + j, aln_opt, ck, (uint32_t)slot_of[j]);
+                H_ck = ck; H_gpu = gpu;
                 pair_and_emit(gpu, index, aln_opt, multi_seqs, slot_of, first, upto);
                 n_rescue += H.n_req;
                 first = upto;
@@ -459,6 +533,9 @@ int alnpe_core(const opt_t *opt)
     fprintf(stderr, "[salt_dropin/pe] salt_pair_plan: %zu pairs checked against pairing2/pairing_singleton, %zu proper without rescue, "
                     "%zu windows planned, %zu mismatches; %zu pairs scheduled from the plan alone\n", plan_checked, plan_paired, plan_windows,
             plan_mismatch, plan_used);
+    fprintf(stderr, "[salt_dropin/pe] salt_pair_apply: %zu pairs checked against the reference's final query_t (%zu rescued mates, "
+                    "%zu alternates promoted with a fresh CIGAR), %zu not checked (rescue not on the GPU), %zu mismatches\n",
+            apply_checked, apply_rescued, apply_swapped, apply_skipped, apply_mismatch);
     aux_destroy(aux[0]);
     aux_destroy(aux[1]);
     query_close(qs[0]);

@@ -298,3 +298,52 @@ int salt_pair_plan(const salt_read_result_t *r0, uint32_t l0, const salt_read_re
     }
     return rc;
 }
+
+/* query_gen_cigar (query.c:282-295) for a mate whose primary is `h` */
+static void pp_keep(const salt_read_result_t *r, uint32_t l, const salt_hit_t *h, int swapped, salt_mate_final_t *o)
+{
+    memset(o, 0, sizeof *o);
+    o->pos = h->pos; o->strand = (uint8_t)h->strand; o->n_diff = h->n_diff; o->is_gap = h->is_gap;
+    o->b0 = r->b0; o->b1 = r->b1; o->mapq = r->mapq;
+    o->seq_start = 0; o->seq_end = l - 1;
+    if (o->pos == 0xFFFFFFFFu) { o->cigar_kind = 0; return; }
+    if (!o->is_gap) { o->cigar_kind = 1; snprintf(o->cigar, sizeof o->cigar, "%dM", (int)l); }
+    else if (!swapped) { o->cigar_kind = 2; strncpy(o->cigar, r->cigar, sizeof o->cigar - 1); }
+    else o->cigar_kind = 4;
+}
+
+int salt_pair_apply(const salt_pair_plan_t *plan, const salt_read_result_t *r0, uint32_t l0,
+                    const salt_read_result_t *r1, uint32_t l1, const salt_ssw_out_t *ssw, const uint32_t *ssw_cigars,
+                    int cigar_stride, int filters, int filterd, salt_mate_final_t out[2])
+{
+    if (!plan || !r0 || !r1 || !out || (plan->n_win > 0 && (!ssw || !ssw_cigars))) return SALT_ERR_ARG;
+    const salt_read_result_t *r[2] = {r0, r1};
+    const uint32_t l[2] = {l0, l1};
+    const salt_hit_t prim[2] = {{r0->pos, r0->n_diff, r0->is_gap, r0->strand}, {r1->pos, r1->n_diff, r1->is_gap, r1->strand}};
+    if (plan->paired) {
+        for (int m = 0; m < 2; ++m) {
+            const int swapped = plan->hit[m].pos != prim[m].pos || plan->hit[m].strand != prim[m].strand;
+            pp_keep(r[m], l[m], &plan->hit[m], swapped, &out[m]);
+        }
+        return 1;
+    }
+    pp_keep(r0, l0, &prim[0], 0, &out[0]);
+    pp_keep(r1, l1, &prim[1], 0, &out[1]);
+    for (int w = 0; w < plan->n_win; ++w) {
+        const salt_ssw_out_t *a = &ssw[w];
+        if (!((int)a->score1 >= filters && a->read_end1 - a->read_begin1 + 1 >= filterd)) continue;     /* alnpe.c:295 / :362 */
+        salt_mate_final_t *o = &out[plan->win[w].mate];
+        o->b0 = a->score1; o->b1 = a->score2; o->mapq = gen_mapq((uint32_t)o->b0, (uint32_t)o->b1);
+        o->pos = (uint32_t)a->ref_begin1 + plan->win[w].start; o->strand = (uint8_t)plan->win[w].strand;
+        o->seq_start = (uint32_t)a->read_begin1; o->seq_end = (uint32_t)a->read_end1;
+        o->cigar_kind = 3;
+        size_t at = 0;
+        o->cigar[0] = 0;
+        for (int j = 0; j < a->cigarLen && j < cigar_stride && at + 16 < sizeof o->cigar; ++j) {
+            const uint32_t c = ssw_cigars[(size_t)w * (size_t)cigar_stride + (size_t)j];
+            at += (size_t)snprintf(o->cigar + at, sizeof o->cigar - at, "%u%c", c >> 4, "MID"[c & 15]);
+        }
+        return 1;
+    }
+    return 0;
+}

@@ -80,6 +80,10 @@ def test_pe_sam_identical(tmp_path, flags):
     # the host layer's re-staged pairing predicted every decision of the reference's pairing2 / pairing_singleton
     m = re.search(r"salt_pair_plan: (\d+) pairs checked .*?, (\d+) proper without rescue, (\d+) windows planned, (\d+) mismatches", err)
     assert m and int(m.group(1)) >= 2900 and int(m.group(2)) >= 2000 and int(m.group(3)) >= 200 and int(m.group(4)) == 0, err[-800:]
+    # ... and salt_pair_apply reproduced the final state of both mates (primaries, rescued mates with their soft clips and
+    # Smith-Waterman CIGARs, alternates promoted to primary)
+    m = re.search(r"salt_pair_apply: (\d+) pairs checked .*?\((\d+) rescued mates, (\d+) alternates promoted.*?(\d+) not checked.*?(\d+) mismatches", err)
+    assert m and int(m.group(1)) >= 2800 and int(m.group(2)) >= 100 and int(m.group(5)) == 0, err[-800:]
     want, got = _sam_body(os.path.join(d, "ref.sam")), _sam_body(os.path.join(d, "gpu.sam"))
     assert len(want) == len(got) and len(want) > 6000
     for a, b in zip(want, got):
