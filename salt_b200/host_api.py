@@ -30,6 +30,31 @@ class PairPlanT(C.Structure):     # salt_pair_plan_t
     _fields_ = [("paired", C.c_int), ("hit", HitT * 2), ("n_win", C.c_int), ("win", RescueT * 2)]
 
 
+class SswOutT(C.Structure):       # salt_ssw_out_t
+    _fields_ = [("score1", C.c_uint16), ("score2", C.c_uint16), ("ref_begin1", C.c_int32), ("ref_end1", C.c_int32),
+                ("read_begin1", C.c_int32), ("read_end1", C.c_int32), ("ref_end2", C.c_int32), ("cigarLen", C.c_int32)]
+
+
+class MateFinalT(C.Structure):    # salt_mate_final_t
+    _fields_ = [("pos", C.c_uint32), ("strand", C.c_uint8), ("n_diff", C.c_uint8), ("is_gap", C.c_uint8),
+                ("seq_start", C.c_uint32), ("seq_end", C.c_uint32), ("b0", C.c_int), ("b1", C.c_int), ("mapq", C.c_uint32),
+                ("cigar_kind", C.c_int), ("cigar", C.c_char * 256)]
+
+
+def pair_apply(L, plan_c, r0, l0, r1, l1, ssw, cigars, filters=0, filterd=20, stride=8):
+    """ssw: list of (score1, score2, ref_begin1, ref_end1, read_begin1, read_end1); cigars: list of [(len, op), ...]"""
+    n = len(ssw)
+    so = (SswOutT * max(n, 1))(); cg = (C.c_uint32 * (max(n, 1) * stride))()
+    for w, (a, ops) in enumerate(zip(ssw, cigars)):
+        so[w].score1, so[w].score2, so[w].ref_begin1, so[w].ref_end1, so[w].read_begin1, so[w].read_end1 = a
+        so[w].cigarLen = len(ops)
+        for j, (ln, op) in enumerate(ops):
+            cg[w * stride + j] = (ln << 4) | op
+    out = (MateFinalT * 2)()
+    rc = L.salt_pair_apply(C.byref(plan_c), C.byref(r0), int(l0), C.byref(r1), int(l1), so, cg, stride, int(filters), int(filterd), out)
+    return rc, [(o.pos, o.strand, o.n_diff, o.is_gap, o.seq_start, o.seq_end, o.b0, o.b1, o.mapq, o.cigar_kind, o.cigar.decode()) for o in out]
+
+
 def make_result(pos=0xFFFFFFFF, strand=3, n_diff=255, is_gap=255, alt0=(), alt1=()):
     """a salt_read_result_t from (pos, strand, n_diff, is_gap) and alternates [(pos, n_diff, is_gap), ...] per strand"""
     r = ReadResultT()
@@ -41,11 +66,13 @@ def make_result(pos=0xFFFFFFFF, strand=3, n_diff=255, is_gap=255, alt0=(), alt1=
     return r
 
 
-def pair_plan(L, r0, l0, r1, l1, min_tlen, max_tlen, l_pac):
+def pair_plan(L, r0, l0, r1, l1, min_tlen, max_tlen, l_pac, raw=False):
     plan = PairPlanT()
     rc = L.salt_pair_plan(C.byref(r0), int(l0), C.byref(r1), int(l1), int(min_tlen), int(max_tlen), int(l_pac), C.byref(plan))
     wins = [(w.mate, w.strand, w.flavour, w.start, w.end) for w in plan.win[:plan.n_win]]
     hits = [(h.pos, h.strand, h.n_diff, h.is_gap) for h in plan.hit] if plan.paired else None
+    if raw:
+        return plan
     return rc, hits, wins
 
 
@@ -65,6 +92,7 @@ def declare(L):
     L.salt_chunk_md.argtypes = [vp, u32, C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(C.c_int)]
     L.salt_chunk_md.restype = C.c_char_p
     L.salt_pair_plan.argtypes = [C.POINTER(ReadResultT), u32, C.POINTER(ReadResultT), u32, u32, u32, u32, C.POINTER(PairPlanT)]
+    L.salt_pair_apply.argtypes = [C.POINTER(PairPlanT), C.POINTER(ReadResultT), u32, C.POINTER(ReadResultT), u32, vp, vp, i32, i32, i32, vp]
     return L
 
 

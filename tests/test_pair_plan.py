@@ -64,3 +64,30 @@ def test_singleton_window(H):
     assert plan(H, un, r0) == (0, None, [(0, 1, 5, 5250, 5650)])
     end = host_api.make_result(L_PAC - 120, 0, 0, 0)                                       # both ends clamp to l_pac - 1
     assert plan(H, end, un)[2] == [(1, 1, 5, L_PAC - 1, L_PAC - 1)]
+
+
+def test_apply(H):
+    """salt_pair_apply: what both mates look like after pairing (the query_t fields alnpe_sam prints)"""
+    # proper pair through alternates: mate 0 takes a gapped alternate (its CIGAR is left to one LV+CIGAR item, kind 4),
+    # mate 1 an ungapped one ("100M"); b0/b1/mapq stay what the verification stage left
+    r0 = host_api.make_result(5000, 0, 0, 0, alt0=[(70000, 1, 1)]); r0.b0, r0.b1, r0.mapq = 0, 1, 17
+    r1 = host_api.make_result(200000, 1, 0, 0, alt1=[(70350, 1, 0)]); r1.b0, r1.b1, r1.mapq = 0, 100000, 37
+    pl = host_api.pair_plan(H, r0, 100, r1, 100, A, B, L_PAC, raw=True)
+    rc, fin = host_api.pair_apply(H, pl, r0, 100, r1, 100, [], [])
+    assert rc == 1
+    assert fin[0] == (70000, 0, 1, 1, 0, 99, 0, 1, 17, 4, "") and fin[1] == (70350, 1, 1, 0, 0, 99, 0, 100000, 37, 1, "100M")
+    # rescue: the first window finds nothing long enough, the second rescues mate 0 with soft clips on both sides
+    r0 = host_api.make_result(5000, 0, 1, 1); r0.cigar = b"40M1I59M"; r0.b0, r0.b1, r0.mapq = 1, 100000, 30
+    r1 = host_api.make_result(300000, 0, 2, 0); r1.b0, r1.b1, r1.mapq = 2, 100000, 25
+    pl = host_api.pair_plan(H, r0, 100, r1, 100, A, B, L_PAC, raw=True)
+    assert pl.n_win == 2
+    ssw = [(12, 0, 3, 14, 0, 11), (80, 30, 120, 206, 5, 92)]
+    rc, fin = host_api.pair_apply(H, pl, r0, 100, r1, 100, ssw, [[(12, 0)], [(50, 0), (1, 2), (38, 0)]])
+    assert rc == 1
+    w1 = pl.win[1]
+    assert (w1.mate, w1.strand) == (0, 1)
+    assert fin[0][:6] == (w1.start + 120, 1, 1, 1, 5, 92) and fin[0][6:8] == (80, 30) and fin[0][9:] == (3, "50M1D38M")
+    assert fin[1] == (300000, 0, 2, 0, 0, 99, 2, 100000, 25, 1, "100M")           # the anchor keeps its primary
+    # both windows fail: both mates keep their primaries, the gapped one its verification-stage CIGAR
+    rc, fin = host_api.pair_apply(H, pl, r0, 100, r1, 100, [(12, 0, 3, 14, 0, 11), (15, 0, 0, 10, 0, 9)], [[(12, 0)], [(10, 0)]])
+    assert rc == 0 and fin[0] == (5000, 0, 1, 1, 0, 99, 1, 100000, 30, 2, "40M1I59M") and fin[1][9:] == (1, "100M")
