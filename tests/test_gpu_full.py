@@ -130,3 +130,46 @@ def test_ssw_full_windows(big, oracle):
     ok = out["cigarLen"] <= 32
     assert np.array_equal(span[ok], (out["read_end1"] - out["read_begin1"] + 1)[ok].astype(np.int64))
     pc.check_ssw(eng, oracle, g, wl["reads"], wins[rng.choice(nt, 400, replace=False)], False, api.salt_score_mat2(), 16, cigar_stride=64)
+
+
+def test_sam_tail_consistency(big, oracle):
+    """MD/NM/XV of every mapped primary of the full-size run (sam.c:246-328): the MD string must account for exactly the
+    reference bases the CIGAR spans (match counts + letters = M + D bases), NM = mismatches + inserted + deleted bases,
+    XV entries are read offsets of mismatches; a random sample is compared with the oracle text."""
+    import re
+    wl, eng, (rec, a0, a1, cig) = big
+    n, L = wl["reads"].shape
+    eng.set_reads(wl["reads"])
+    mapped = np.nonzero(rec["pos"] != 0xFFFFFFFF)[0]
+    cigs = [api.cstr(cig[r]) if rec["is_gap"][r] == 1 else "%dM" % L for r in mapped]
+    rs = (mapped.astype(np.uint32) << 1) | rec["strand"][mapped].astype(np.uint32)
+    out, md, xv = eng.md_nm(rs, rec["pos"][mapped], np.zeros(len(mapped), np.uint32), cigs, md_stride=256)
+    assert (out["md_len"] >= 0).all()
+    op = re.compile(r"(\d+)([MID])"); tok = re.compile(r"(\d+)|\^([ACGT]+)|([ACGT])")
+    rng = np.random.default_rng(5)
+    check = set(rng.choice(len(mapped), 3000, replace=False).tolist()) | set(np.nonzero(rec["is_gap"][mapped] == 1)[0][:3000].tolist())
+    for i in check:
+        m_len = sum(int(a) for a, b in op.findall(cigs[i]) if b == "M")
+        i_len = sum(int(a) for a, b in op.findall(cigs[i]) if b == "I")
+        d_len = sum(int(a) for a, b in op.findall(cigs[i]) if b == "D")
+        s = api.cstr(md[i])
+        assert len(s) == out["md_len"][i]
+        matches = mism = dels = 0
+        for num, de, mm in tok.findall(s):
+            if num:
+                matches += int(num)
+            elif de:
+                dels += len(de)
+            else:
+                mism += 1
+        # the reference prints no "0" between a deletion and a mismatch right after it, so "^CCA" may be two deleted
+        # bases and a mismatch: only the total number of letters is well defined
+        letters = mism + dels
+        assert matches + letters == m_len + d_len and dels >= d_len, (cigs[i], s)
+        assert out["nm"][i] == letters + i_len
+        assert out["n_xv"][i] <= letters - d_len and (xv[i, :out["n_xv"][i]] < L).all()
+    for i in list(check)[:400]:
+        r = int(mapped[i]); s = int(rec["strand"][r])
+        seq = np.ascontiguousarray(synth.revcomp(wl["reads"][r]) if s else wl["reads"][r])
+        g = wl["g"]
+        assert api.Engine.md_nm_text(out, md, xv, i) == oracle.md_nm(g.mixref, g.pac, g.l, seq, int(rec["pos"][r]), 0, cigs[i])
