@@ -406,6 +406,7 @@ def main():
     if world == 1 and not args.skip_extras:
         out["lv"] = bench_lv(eng, lib, h, wl, args, dev, stream)
         out["sw"] = bench_sw(eng, lib, h, wl, args, dev, stream)
+        out["sam_tail"] = bench_sam_tail(eng, wl, args, d_rec, d_cig, d_cigreads, d_cigcnt)
 
     if rank == 0 and world == 1:
         try:
@@ -462,6 +463,39 @@ def bench_lv(eng, lib, h, wl, args, dev, stream):
     res["pairs"] = len(pairs)
     res["note"] = "GCUPS-equivalent = L*(L+4) DP cells per pair (SURVEY §8d); ~94% of pairs are decoys (worst case for LV)"
     return res
+
+
+def bench_sam_tail(eng, wl, args, d_rec, d_cig, d_cigreads, d_cigcnt):
+    """MD/NM/XV (sam_add_md_nm) of every mapped primary of the batch through salt_b200_md_nm: host buffers in and out,
+    one kernel; wall time of the call (its copies included)."""
+    from salt_b200 import api
+    L = args.read_len
+    rec = np.frombuffer(d_rec.cpu().numpy().tobytes(), api.VERIFY_DT)
+    ng = int(d_cigcnt[0].item())
+    lst = d_cigreads[:ng].cpu().numpy().astype(np.int64)
+    cg = d_cig.cpu().numpy().reshape(-1, 128)[:ng]
+    mapped = np.nonzero(rec["pos"] != 0xFFFFFFFF)[0]
+    stride = 24
+    cigs = np.zeros((len(mapped), stride), np.uint8)
+    cigs[:, :len("%dM" % L)] = np.frombuffer(("%dM" % L).encode(), np.uint8)
+    where = np.full(len(rec), -1, np.int64); where[mapped] = np.arange(len(mapped))
+    ok = (where[lst] >= 0) & (cg[:, stride - 1] == 0)
+    cigs[where[lst[ok]]] = cg[ok, :stride]
+    items = np.zeros(len(mapped), api.MDNM_IN_DT)
+    items["rs"] = (mapped.astype(np.uint32) << 1) | rec["strand"][mapped]; items["pos"] = rec["pos"][mapped]
+    md = np.zeros((len(mapped), 128), np.uint8); xv = np.zeros((len(mapped), 8), np.uint16); out = np.zeros(len(mapped), api.MDNM_OUT_DT)
+
+    def run():
+        eng._ck(eng.L.salt_b200_md_nm(eng.h, 0, api._ptr(items), len(items), api._ptr(cigs), stride, api._ptr(md), 128,
+                                      api._ptr(xv), 8, api._ptr(out)))
+    run()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        run()
+    sec = (time.perf_counter() - t0) / 3
+    return {"alignments": int(len(mapped)), "ms": sec * 1e3, "alignments_per_s": len(mapped) / sec,
+            "nm_mean": float(out["nm"].mean()), "md_overflow": int((out["md_len"] < 0).sum()),
+            "note": "pageable numpy buffers in and out; the kernel itself is a small part of the call"}
 
 
 def bench_sw(eng, lib, h, wl, args, dev, stream):
