@@ -57,7 +57,7 @@ typedef struct {
     int on_gpu;                             /* 0 = the reference's own ssw_align serves it */
 } rescue_req_t;
 
-enum { MODE_RECORD = 1, MODE_REPLAY = 2 };
+enum { MODE_RECORD = 1, MODE_REPLAY = 2, MODE_DIRECT = 3 };     /* DIRECT: the hooks pass straight through to the reference's ssw_align */
 static struct {
     int mode, func;                         /* func 2 = pairing2, 1 = pairing_singleton */
     index_t *index; const aln_opt_t *opt;
@@ -143,6 +143,7 @@ s_align *dropin_ssw_align(const s_profile *pp, const int8_t *ref, int32_t refLen
     uint32_t start = 0, end = 0;
     const int known = identify(p, &mate, &strand) && window_of(H.q[1 - mate], H.q[mate], strand, &start, &end) &&
                       window_matches(p->n, start, end, ref, refLen) && H.chunk_idx[mate] >= 0;
+    if (H.mode == MODE_DIRECT) return ssw_align(p->real, ref, refLen, gapO, gapE, flag, filters, filterd, maskLen);
     if (H.mode == MODE_RECORD) {
         if (H.n_req == H.m_req) { H.m_req = H.m_req ? H.m_req * 2 : 1024; H.req = realloc(H.req, H.m_req * sizeof *H.req); }
         rescue_req_t *r = &H.req[H.n_req++];
@@ -221,7 +222,7 @@ static void run_pairing(index_t *index, query_t *q0, query_t *q1, aln_opt_t *aln
 
 /* ---- salt_pair_plan (include/salt_host.h) checked against the reference's own pairing, pair by pair ---- */
 static size_t plan_checked, plan_paired, plan_windows, plan_mismatch, plan_used;
-static size_t apply_checked, apply_skipped, apply_mismatch, apply_rescued, apply_swapped;
+static size_t apply_checked, apply_skipped, apply_mismatch, apply_rescued, apply_swapped, apply_final, apply_fallback;
 static const salt_chunk_t *H_ck;          /* the chunk whose results the pairs under way came from */
 static salt_b200_t *H_gpu;
 
@@ -336,6 +337,46 @@ static void check_apply(const salt_pair_plan_t *plan, const salt_read_result_t *
     }
 }
 
+/* SALT_DROPIN_PLAN=2: write what salt_pair_apply decided into the two query_t; 0 = this pair needs the reference's pairing */
+static int apply_to_queries(const salt_pair_plan_t *plan, const salt_read_result_t *r0, const salt_read_result_t *r1,
+                            query_t *q0, query_t *q1, size_t k0, const aln_opt_t *opt)
+{
+    query_t *q[2] = {q0, q1};
+    salt_ssw_out_t ssw[2];
+    uint32_t cig[2 * DROPIN_CIG_STRIDE];
+    salt_mate_final_t fin[2];
+    char fresh[2][256];
+    int w, m;
+    for (w = 0; w < plan->n_win; ++w) {
+        const size_t k = k0 + (size_t)w;
+        if (k >= H.n_req || H.req[k].pair != H.pair || !H.req[k].on_gpu) return 0;
+        const size_t ri = H.res_of[k];
+        if (H.res[ri].cigarLen < 0 || H.res[ri].cigarLen > DROPIN_CIG_STRIDE) return 0;
+        ssw[w] = H.res[ri];
+        memcpy(cig + (size_t)w * DROPIN_CIG_STRIDE, H.cig + ri * DROPIN_CIG_STRIDE, DROPIN_CIG_STRIDE * 4);
+    }
+    if (salt_pair_apply(plan, r0, (uint32_t)q0->l_seq, r1, (uint32_t)q1->l_seq, ssw, cig, DROPIN_CIG_STRIDE,
+                        opt->filters, opt->filterd, fin) < 0) return 0;
+    for (m = 0; m < 2; ++m)                                       /* a gapped alternate promoted to primary: its CIGAR */
+        if (fin[m].pos != 0xFFFFFFFF && fin[m].cigar_kind == 4) {
+            salt_pair_t p; uint8_t k = fin[m].n_diff; int8_t e;
+            if (H.chunk_idx[m] < 0) return 0;
+            p.rs = ((uint32_t)H.chunk_idx[m] << 1) | fin[m].strand; p.pos = fin[m].pos;
+            memset(fresh[m], 0, sizeof fresh[m]);
+            if (salt_b200_lv_cigar(H_gpu, &p, &k, 1, fresh[m], sizeof fresh[m], &e) != SALT_OK || e != (int8_t)k) return 0;
+        }
+    for (m = 0; m < 2; ++m) {
+        const salt_mate_final_t *f = &fin[m];
+        if (f->pos == 0xFFFFFFFF) continue;                      /* an unmapped mate is left as the verification stage left it */
+        q[m]->pos = f->pos; q[m]->strand = f->strand; q[m]->n_diff = f->n_diff; q[m]->is_gap = f->is_gap;
+        q[m]->seq_start = f->seq_start; q[m]->seq_end = f->seq_end;
+        q[m]->b0 = f->b0; q[m]->b1 = f->b1; q[m]->mapq = (uint8_t)f->mapq;
+        q[m]->cigar->l = 0;
+        kputs(f->cigar_kind == 4 ? fresh[m] : f->cigar, q[m]->cigar);
+    }
+    return 1;
+}
+
 /* pairs [first, upto) of the chunk: record, one GPU batch per flavour, replay + SAM */
 static void pair_and_emit(salt_b200_t *gpu, index_t *index, aln_opt_t *aln_opt, query_t *multi_seqs, const int *slot_of,
                           int first, int upto)
@@ -347,7 +388,8 @@ static void pair_and_emit(salt_b200_t *gpu, index_t *index, aln_opt_t *aln_opt, 
     /* SALT_DROPIN_PLAN=1: the windows come from salt_pair_plan alone -- the re-staged flow (plan, one GPU batch,
        apply) -- instead of from a recording run of the reference's pairing; the replay below still refuses to
        continue if the reference then asks for anything else */
-    const int use_plan = getenv("SALT_DROPIN_PLAN") && atoi(getenv("SALT_DROPIN_PLAN")) != 0;
+    const int plan_mode = getenv("SALT_DROPIN_PLAN") ? atoi(getenv("SALT_DROPIN_PLAN")) : 0;
+    const int use_plan = plan_mode != 0;
     for (j = first; use_plan && j < upto; j += 2) {
         query_t *q0 = multi_seqs + j, *q1 = multi_seqs + j + 1;
         salt_pair_plan_t plan;
@@ -430,6 +472,15 @@ static void pair_and_emit(salt_b200_t *gpu, index_t *index, aln_opt_t *aln_opt, 
         const int have_plan = results_for_apply(q0, q1, slot_of[j], slot_of[j + 1], &pr0, &pr1) &&
                               salt_pair_plan(&pr0, (uint32_t)q0->l_seq, &pr1, (uint32_t)q1->l_seq, (uint32_t)aln_opt->min_tlen,
                                              (uint32_t)aln_opt->max_tlen, index->bntseq->l_pac, &plan) == SALT_OK;
+        /* SALT_DROPIN_PLAN=2: the reference's pairing is out of the loop -- salt_pair_apply writes the mates' final
+           fields from the plan and the GPU's answers; a pair with a window the GPU did not serve goes through the
+           reference's pairing with its own Smith-Waterman */
+        if (plan_mode == 2) {
+            if (have_plan && apply_to_queries(&plan, &pr0, &pr1, q0, q1, k0, aln_opt)) ++apply_final;
+            else { H.mode = MODE_DIRECT; run_pairing(index, q0, q1, aln_opt); H.mode = MODE_REPLAY; ++apply_fallback; }
+            while (H.cursor < H.n_req && H.req[H.cursor].pair == j) ++H.cursor;
+            continue;
+        }
         run_pairing(index, q0, q1, aln_opt);
         if (have_plan) check_apply(&plan, &pr0, &pr1, q0, q1, k0, aln_opt);
         else ++apply_skipped;
@@ -536,6 +587,8 @@ int alnpe_core(const opt_t *opt)
     fprintf(stderr, "[salt_dropin/pe] salt_pair_apply: %zu pairs checked against the reference's final query_t (%zu rescued mates, "
                     "%zu alternates promoted with a fresh CIGAR), %zu not checked (rescue not on the GPU), %zu mismatches\n",
             apply_checked, apply_rescued, apply_swapped, apply_skipped, apply_mismatch);
+    fprintf(stderr, "[salt_dropin/pe] pairs finished by salt_pair_apply alone: %zu, handed back to the reference's pairing: %zu\n",
+            apply_final, apply_fallback);
     aux_destroy(aux[0]);
     aux_destroy(aux[1]);
     query_close(qs[0]);

@@ -94,6 +94,12 @@ def test_pe_sam_identical(tmp_path, flags):
     m2 = re.search(r"(\d+) pairs scheduled from the plan alone", err2)
     assert m2 and int(m2.group(1)) >= 2900
     assert _sam_body(os.path.join(d, "gpu2.sam")) == want
+    # ... and with the reference's pairing out of the loop altogether: plan -> GPU batch -> salt_pair_apply -> query_t
+    err3 = _run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", "r1.fq", "r2.fq"], d, os.path.join(d, "gpu3.sam"),
+                env={"SALT_DROPIN_PLAN": "2"})
+    m3 = re.search(r"pairs finished by salt_pair_apply alone: (\d+), handed back to the reference's pairing: (\d+)", err3)
+    assert m3 and int(m3.group(1)) >= 2900 and int(m3.group(2)) <= 30, err3[-600:]
+    assert _sam_body(os.path.join(d, "gpu3.sam")) == want
     body = [ln.split("\t") for ln in want if ln and not ln.startswith("@")]
     assert sum(1 for f in body if int(f[1]) & 2) >= 4000                  # properly paired records
     assert sum(1 for f in body if "S" in f[5]) >= 20                      # soft-clipped = rescued by Smith-Waterman
