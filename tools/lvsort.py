@@ -37,3 +37,12 @@ coarse = np.where(es <= 3, 0, 1)
 run(surv[np.argsort(coarse, kind="stable")], "lv_tpp two buckets (e<=3)")
 coarse3 = np.digitize(es, [3, 6])
 run(surv[np.argsort(coarse3, kind="stable")], "lv_tpp three buckets")
+# a predictor available before LV runs: do the read's first 8 bases match the window on diagonal 0?  (a +-1..3 shifted twin
+# does not, although all its words match on the shifted diagonal)
+rid = (surv["rs"] >> 1).astype(np.int64); st = (surv["rs"] & 1).astype(bool); pos = surv["pos"].astype(np.int64)
+rd = wl["reads"][rid]
+rd = np.where(st[:, None], (np.where(rd[:, ::-1] < 4, 3 - rd[:, ::-1], rd[:, ::-1])), rd)[:, :8]
+m = g.masks[pos[:, None] + np.arange(8)[None, :]]
+first_ok = (((m >> np.minimum(rd, 3)) & 1).astype(bool) | (rd == 4)).all(axis=1)
+print("first word matches on diagonal 0: %.1f%% of survivors; mean e there %.2f, elsewhere %.2f" % (100 * first_ok.mean(), es[first_ok].mean(), es[~first_ok].mean()))
+run(surv[np.argsort(~first_ok, kind="stable")], "lv_tpp two buckets (first word)")
