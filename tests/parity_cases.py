@@ -256,6 +256,8 @@ def mdnm_cases(g, reads, pos, strand, seed, clip_frac=0.3):
         seq = np.ascontiguousarray(reads[r]); rseq = np.ascontiguousarray(synth.revcomp(reads[r]))
         s0 = int(rng.integers(1, 20)) if rng.random() < clip_frac else 0
         s1 = int(rng.integers(1, 20)) if rng.random() < clip_frac else 0
+        if L - s0 - s1 < 16:                       # short reads: keep an aligned part worth the name
+            s0 = s1 = 0
         cig = random_cigar(rng, L - s0 - s1)
         out.append((seq, rseq, int(pos[r]) + s0, int(strand[r]), s0, cig))
     return out
