@@ -18,6 +18,11 @@ from salt_b200 import api  # noqa: E402
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 o = orc.Oracle()
+try:
+    from salt_b200 import host_api
+    hostlib = host_api.load()
+except Exception:                                    # noqa: BLE001
+    hostlib = None
 rng = np.random.default_rng(seed0)
 t0 = time.time(); it = 0; tot_reads = 0
 while time.time() - t0 < budget:
@@ -33,6 +38,12 @@ while time.time() - t0 < budget:
     eng.set_lv_filter(int(rng.integers(0, 2))); eng.set_lv_mapping(int(rng.integers(0, 3)))
     nog = int(rng.choice([0, 1, 3, 5])); lvT = int(rng.choice([-1, -1, 3, 0, 7, int(rng.integers(0, 31))]))
     pc.check_verify(eng, o, g, reads, cands, nog, lvT)
+    if it % 4 == 1:                                  # the asynchronous chunk pipeline and the host layer on the same world
+        pc.check_verify_batch(eng, reads, cands, int(rng.integers(1, n + 5)), nog, lvT)
+        eng.set_reads(reads)
+    if it % 8 == 3 and hostlib is not None:
+        pc.check_host_chunks(eng, hostlib, o, g, reads, cands, int(rng.integers(5, n + 5)), nog, lvT, max_hits=int(rng.integers(1, 9)), with_tail=True)
+        eng.set_reads(reads)
     pairs = pc.flat_pairs(cands, n)
     sel = rng.choice(len(pairs), min(len(pairs), 150), replace=False)
     pc.check_mismatch(eng, o, g, reads, pairs[sel], int(rng.integers(0, 8)))
