@@ -26,7 +26,7 @@ def build(force=False):
             os.path.getmtime(os.path.join(HERE, "liboracle.so")) < os.path.getmtime(os.path.join(HERE, "oracle.c")):
         subprocess.check_call(["make", "-s", "-C", HERE, os.path.join(HERE, "liboracle.so")])
     if os.path.isdir("/root/reference/Align_src") and (force or not all(
-            os.path.exists(os.path.join(HERE, "_ref", f)) for f in ("libsaltref.so", "libsaltref_sam.so"))):
+            os.path.exists(os.path.join(HERE, "_ref", f)) for f in ("libsaltref.so", "libsaltref_sam.so", "libsaltref_pair.so"))):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
 
 
@@ -322,6 +322,39 @@ class RefSam:
         self.lib.ref_sam_md_nm(_p(mixref, u32p), int(l), _p(pac, u8p), _p(seq, u8p), _p(rseq, u8p), len(seq), int(pos),
                                int(strand), int(seq_start), cigar.encode(), buf, cap)
         return buf.value.decode()
+
+
+class RefPair:
+    """The reference's own pairing2 / pairing_singleton (alnpe.c) behind oracle/dropin/pair_harness.c; rescues always fail."""
+
+    def __init__(self):
+        build()
+        self.lib = C.CDLL(os.path.join(HERE, "_ref", "libsaltref_pair.so"))
+        self.lib.ref_pairing.argtypes = [C.c_uint32, C.c_int, C.c_int, u32p, C.POINTER(C.c_int), u32p, C.POINTER(C.c_int), C.c_int,
+                                         u32p, C.POINTER(C.c_int), C.c_char_p]
+
+    def pairing(self, l_pac, min_tlen, max_tlen, prim, l_seq, hits):
+        """prim: [(pos, strand, n_diff, is_gap)] x2; hits[m][s] = [(pos, n_diff, is_gap), ...].
+        Returns (paired, [(pos, strand, n_diff, is_gap, seq_start, seq_end)] x2, windows, cigars)."""
+        mx = 16
+        qf = np.array(prim, np.uint32).reshape(-1)
+        ls = (C.c_int * 2)(*l_seq)
+        hh = np.zeros((2, 2, mx, 3), np.uint32); nh = (C.c_int * 4)()
+        for m in range(2):
+            for s in range(2):
+                nh[m * 2 + s] = len(hits[m][s])
+                for i, h in enumerate(hits[m][s]):
+                    hh[m, s, i] = h
+        out_q = np.zeros(12, np.uint32); out_w = (C.c_int * 20)(); cg = C.create_string_buffer(128)
+        r = self.lib.ref_pairing(int(l_pac), int(min_tlen), int(max_tlen), _p(qf, u32p), ls, _p(hh, u32p), nh, mx, _p(out_q, u32p), out_w, cg)
+        n = r & 255
+        wins = [tuple(out_w[i * 5 + j] & 0xFFFFFFFF if j >= 3 else out_w[i * 5 + j] for j in range(5)) for i in range(n)]
+        cigs = [cg.raw[m * 64:(m + 1) * 64].split(b"\0")[0].decode() for m in range(2)]
+        return r >> 8, [tuple(int(x) for x in out_q[m * 6:(m + 1) * 6]) for m in range(2)], wins, cigs
+
+
+def ref_pair_available():
+    return os.path.exists(os.path.join(HERE, "_ref", "libsaltref_pair.so"))
 
 
 def ref_sam_available():

@@ -91,3 +91,52 @@ def test_apply(H):
     # both windows fail: both mates keep their primaries, the gapped one its verification-stage CIGAR
     rc, fin = host_api.pair_apply(H, pl, r0, 100, r1, 100, [(12, 0, 3, 14, 0, 11), (15, 0, 0, 10, 0, 9)], [[(12, 0)], [(10, 0)]])
     assert rc == 0 and fin[0] == (5000, 0, 1, 1, 0, 99, 1, 100000, 30, 2, "40M1I59M") and fin[1][9:] == (1, "100M")
+
+
+def test_against_reference_pairing(H):
+    """salt_pair_plan / salt_pair_apply against the reference's own pairing2 / pairing_singleton (oracle/_ref/
+    libsaltref_pair.so: alnpe.c unmodified, its rescue functions replaced by recorders that find nothing) on random
+    primaries and alternate lists -- proper pairs through alternates included, which the drop-in's data never produce."""
+    import numpy as np
+    from oracle import orc
+    orc.build()
+    if not orc.ref_pair_available():
+        pytest.skip("oracle/_ref/libsaltref_pair.so not built (reference tree absent)")
+    ref = orc.RefPair()
+    rng = np.random.default_rng(77)
+    l_pac = 60000
+    n_paired = n_alt = n_win = 0
+    for it in range(4000):
+        l = [int(rng.choice([100, 100, 150, 37])), int(rng.choice([100, 100, 250]))]
+        a, b = int(rng.choice([350, 0, 200])), int(rng.choice([650, 300, 1000]))
+        centre = int(rng.integers(2000, l_pac - 3000))
+
+        def near():
+            return int(np.clip(centre + rng.integers(-1500, 1500), 0, l_pac - 300))
+        prim = []
+        for m in range(2):
+            if rng.random() < 0.12:
+                prim.append((0xFFFFFFFF, 3, 255, 255))
+            else:
+                prim.append((near() if rng.random() < 0.8 else int(rng.integers(0, l_pac - 300)), int(rng.integers(0, 2)), int(rng.integers(0, 6)), 0))
+        hits = [[sorted({(near(), int(rng.integers(0, 6)), 0) for _ in range(int(rng.integers(0, 6)))}) if prim[m][0] != 0xFFFFFFFF else []
+                 for s in range(2)] for m in range(2)]
+        hits = [[[h for h in hs if h[0] != prim[m][0]][:5] for hs in hits[m]] for m in range(2)]
+        paired, fq, wins, cigs = ref.pairing(l_pac, a, b, prim, l, hits)
+        r = [host_api.make_result(*prim[m], alt0=hits[m][0], alt1=hits[m][1]) for m in range(2)]
+        rc, phits, pwins = host_api.pair_plan(H, r[0], l[0], r[1], l[1], a, b, l_pac)
+        assert pwins == [tuple(int(x) for x in w) for w in wins], (it, prim, hits, pwins, wins)
+        assert (phits is not None) == (paired == 1 and not wins), (it, prim, hits, phits, paired)
+        pl = host_api.pair_plan(H, r[0], l[0], r[1], l[1], a, b, l_pac, raw=True)
+        nw = len(pwins)
+        rc2, fin = host_api.pair_apply(H, pl, r[0], l[0], r[1], l[1], [(0, 0, 0, 0, 0, 0)] * nw, [[]] * nw)      # every rescue fails
+        assert rc2 == (1 if phits is not None else 0)
+        for m in range(2):
+            if fq[m][0] == 0xFFFFFFFF:
+                assert fin[m][0] == 0xFFFFFFFF
+                continue
+            assert fin[m][:6] == fq[m], (it, m, fin[m], fq[m])
+            assert fin[m][10] == cigs[m], (it, m, fin[m], cigs[m])
+        n_paired += phits is not None; n_win += nw
+        n_alt += phits is not None and [h[:2] for h in phits] != [p[:2] for p in prim]
+    assert n_paired > 500 and n_alt > 100 and n_win > 1000, (n_paired, n_alt, n_win)
