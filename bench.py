@@ -330,7 +330,11 @@ def main():
             prof.setdefault(k, []).append(v)
     eng.profile(False)
     kernels = {k: float(np.mean(v)) for k, v in prof.items()}
-    n_lv = int(np.frombuffer(d_rec.cpu().numpy().tobytes(), api.VERIFY_DT)["lv_ran"].sum())
+    rec_np = np.frombuffer(d_rec.cpu().numpy().tobytes(), api.VERIFY_DT)
+    n_lv = int(rec_np["lv_ran"].sum())
+    # candidate pairs of the reads that reached the gapped stage: each is one Landau-Vishkin problem
+    lv_mask = rec_np["lv_ran"] == 1
+    n_lv_pairs = int((np.diff(wl["offs0"].astype(np.int64))[lv_mask].sum() + np.diff(wl["offs1"].astype(np.int64))[lv_mask].sum()))
     n_gapped = int(d_cigcnt[0].item())
 
     # PCIe copy peaks beside the e2e number (pinned 256 MiB, best of 3)
@@ -374,6 +378,9 @@ def main():
                    "ms_per_step": e2e_s * 1e3, "chunk_reads": args.chunk, "slots": int(lib.salt_b200_n_slots()),
                    "pcie_gbs": {"h2d": h2d / e2e_s / 1e9, "d2h": d2h / e2e_s / 1e9, "h2d_copy_peak": pcie_h2d, "d2h_copy_peak": pcie_d2h}},
            "pairs_per_step": int(n0 + n1), "pairs_per_s": world * (n0 + n1) / (ms_step * 1e-3),
+           # SURVEY 8(d) whole-job figure: DP-cell equivalents of the step (L per ungapped pair, L*(L+4) per LV pair) / time
+           "tcups_equivalent": world * ((n0 + n1) * L + n_lv_pairs * L * (L + 4)) / (ms_step * 1e-3) / 1e12,
+           "lv_pairs_per_step": n_lv_pairs,
            "lv_reads_per_step": n_lv, "gapped_primaries_per_step": n_gapped, "kernels_ms": kernels}
 
     if rank == 0:
