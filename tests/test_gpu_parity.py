@@ -269,6 +269,18 @@ def test_error_paths():
     assert e.value.code == -104
     with pytest.raises(api.SaltError):
         eng.ssw(wins, api.salt_score_mat(), 5, True)             # no pac uploaded
+    # SAM tail: needs the 2-bit pac, sane strides, an existing slot
+    with pytest.raises(api.SaltError) as e:
+        eng.md_nm(np.array([0], np.uint32), np.array([10], np.uint32), np.array([0], np.uint32), ["100M"])      # engine built without pac
+    assert e.value.code == -101 and "pac" in str(e.value)
+    eng2 = _engine(g)
+    eng2.set_reads(reads)
+    for kw in (dict(md_stride=1), dict(xv_stride=65), dict(slot=7)):
+        with pytest.raises(api.SaltError):
+            eng2.md_nm(np.array([0], np.uint32), np.array([10], np.uint32), np.array([0], np.uint32), ["100M"], **kw)
+    out, md, xv = eng2.md_nm(np.array([0, 1 << 20], np.uint32), np.array([10, 10], np.uint32), np.zeros(2, np.uint32), ["100M", "100M"])
+    assert out["md_len"][0] > 0 and out["md_len"][1] == 0 and md[1, 0] == 0            # a read id outside the chunk: no tags
+    eng2.close()
     # a slot cannot take a second chunk before it was waited for; bad slot numbers are refused
     offs0, loci0, offs1, loci1 = cands
     n = len(reads)
