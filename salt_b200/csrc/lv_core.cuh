@@ -120,8 +120,8 @@ struct LvTriIdx {                        // level e holds diagonals -e..e only: 
 // Backtrace + emission of computeEditDistanceWithCigar, useM = 1 (LandauVishkin.c:380-462).
 // Lt/At are the furthest-reaching table and action table addressed through `at`.
 // Returns e or -2 (buffer too small).
-template <class Idx>
-SALT_HD int lv_cigar_emit_t(const int16_t *Lt, const char *At, Idx at, int e, int d, char *buf, int buflen)
+template <class Idx, class LT>
+SALT_HD int lv_cigar_emit_t(const LT *Lt, const char *At, Idx at, int e, int d, char *buf, int buflen)
 {
     char act[LV_MAXK + 1]; int run[LV_MAXK + 1];
     int cd = d;

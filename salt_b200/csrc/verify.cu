@@ -216,7 +216,10 @@ __device__ __forceinline__ int lv_level0(const uint32_t *T, const uint32_t *P, i
 __host__ __device__ inline int lv_tw(int l_max) { return (l_max + 4 + 64) / 8 + 2; }
 __host__ __device__ inline int lv_pw(int l_max) { return (l_max + 64) / 8 + 2; }
 // thread-per-pair kernel: window kept as raw 16-byte-aligned reference words (up to 31 nibbles in front)
-__host__ __device__ inline int lv_twr(int l_max) { return ((31 + l_max + 4 + 64) / 8 + 2 + 3) & ~3; }
+// The thread-per-pair kernels never look past nibble toff + textLen + 2 of the window or patternLen + 1 of the read
+// (extensions stop at endl(d), lv_core.cuh), each plus the 8 nibbles and the next word nib8 touches.
+__host__ __device__ inline int lv_twr(int l_max) { return ((31 + l_max + 4 + 10) / 8 + 2 + 3) & ~3; }
+__host__ __device__ inline int lv_pwt(int l_max) { return (l_max + 10) / 8 + 2; }
 __device__ __forceinline__ uint32_t lv_tailmask(int r)             // keep the low r nibbles (r <= 0: none, r >= 8: all)
 {
     return r >= 8 ? 0xffffffffu : (r <= 0 ? 0u : (1u << (4 * r)) - 1u);
@@ -399,7 +402,7 @@ lv_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_f
               int8_t *__restrict__ out)
 {
     SALT_DYN_SMEM(uint32_t, smem);
-    const int TW = lv_twr((int)c.l_max), PW = lv_pw((int)c.l_max);
+    const int TW = lv_twr((int)c.l_max), PW = lv_pwt((int)c.l_max);
     const int stride = (TW + PW) | 1;                  // odd: the 32 rows of a warp sit in 32 different banks
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *wbase = smem + (size_t)warp * 32 * stride;
@@ -804,9 +807,9 @@ __host__ __device__ constexpr int cta_sort_words(int threads) { return 64 + thre
 // e*e + d + e: (K+1)^2 int16 values and as many action bytes).  Every lane emits its own string.
 // Same staging, deferred long extensions and bank layout as lv_tpp.
 // --------------------------------------------------------------------------------------
-__host__ __device__ constexpr int lv_cigar_tpp_tab_words(int K) { return ((K + 1) * (K + 1) * 3 + 3) / 4; }
+__host__ __device__ constexpr int lv_cigar_tpp_tab_words(int K, int lbytes) { return ((K + 1) * (K + 1) * (lbytes + 1) + 3) / 4; }
 
-template <int K>
+template <int K, class LT>
 __global__ void __launch_bounds__(128)
 lv_cigar_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8_t *__restrict__ k_each, size_t n,
                     const uint32_t *__restrict__ worklist, const uint32_t *__restrict__ wl_count,
@@ -814,14 +817,14 @@ lv_cigar_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8
                     char *__restrict__ cigars, int stride, int8_t *__restrict__ out)
 {
     SALT_DYN_SMEM(uint32_t, smem);
-    const int TW = lv_twr((int)c.l_max), PW = lv_pw((int)c.l_max);
-    constexpr int TABW = lv_cigar_tpp_tab_words(K);
+    const int TW = lv_twr((int)c.l_max), PW = lv_pwt((int)c.l_max);
+    constexpr int TABW = lv_cigar_tpp_tab_words(K, (int)sizeof(LT));
     const int rstride = (TW + PW + TABW) | 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *sort_area = smem;
     uint32_t *T = smem + cta_sort_words((int)blockDim.x) + ((size_t)warp * 32 + lane) * rstride;
     uint32_t *P = T + TW;
-    int16_t *tabL = reinterpret_cast<int16_t *>(P + PW);               // [(K+1)^2]
+    LT *tabL = reinterpret_cast<LT *>(P + PW);                         // [(K+1)^2]: uint8 while reads are <= 253 bases, else int16
     char *tabA = reinterpret_cast<char *>(tabL + (K + 1) * (K + 1));   // [(K+1)^2]
     const LvTriIdx at;
     const size_t count = worklist ? (size_t)*wl_count : n;
@@ -865,7 +868,7 @@ lv_cigar_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8
 #pragma unroll
                 for (int i = 0; i < 2 * K + 1; ++i) Lp[i] = -2;
                 Lp[K] = L0;
-                tabL[0] = (int16_t)L0;
+                tabL[0] = (LT)L0;
                 int found_e = -1, found_d = 0;
                 for (int e = 1; e <= k; ++e) {
                     int Ln[2 * K + 1];
@@ -889,7 +892,7 @@ lv_cigar_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8
                             }
                             if (v == plen) myrank = imin(myrank, lv_cigar_rank(d));
                             tabA[at(e, d)] = a;
-                            tabL[at(e, d)] = (int16_t)v;
+                            tabL[at(e, d)] = (LT)v;
                         }
                         Ln[di] = v;
                     }
@@ -898,7 +901,7 @@ lv_cigar_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, const uint8
                         const int d = pend_di - K;
                         pend_v = lv_extend_more(T, P, pend_best, d, plen, tlen, toff);
                         if (pend_v == plen) myrank = imin(myrank, lv_cigar_rank(d));
-                        tabL[at(e, d)] = (int16_t)pend_v;
+                        tabL[at(e, d)] = (LT)pend_v;
                     }
                     if (myrank < (1 << 20)) {
                         found_e = e;
@@ -1330,7 +1333,7 @@ static cudaError_t launch_lv_tpp(const DevCtx &c, const salt_pair_t *pairs, size
                                  const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
                                  int8_t *out, int sm_count, cudaStream_t st)
 {
-    const int stride = (lv_twr((int)c.l_max) + lv_pw((int)c.l_max)) | 1;
+    const int stride = (lv_twr((int)c.l_max) + lv_pwt((int)c.l_max)) | 1;
     int threads = 128;
     size_t smem = (size_t)threads * stride * 4;
     if (smem > 100 * 1024) { threads = 64; smem = (size_t)threads * stride * 4; }
@@ -1417,13 +1420,13 @@ static cudaError_t launch_lv_cigar_t(const DevCtx &c, const salt_pair_t *pairs, 
     return cudaSuccess;
 }
 
-template <int K>
-static cudaError_t launch_lv_cigar_tpp(const DevCtx &c, const salt_pair_t *pairs, const uint8_t *k_each, size_t n,
-                                       const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
-                                       const salt_verify_out_t *rec, char *cigars, int stride, int8_t *out,
-                                       int sm_count, cudaStream_t st)
+template <int K, class LT>
+static cudaError_t launch_lv_cigar_tpp_t(const DevCtx &c, const salt_pair_t *pairs, const uint8_t *k_each, size_t n,
+                                         const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
+                                         const salt_verify_out_t *rec, char *cigars, int stride, int8_t *out,
+                                         int sm_count, cudaStream_t st)
 {
-    const int rstride = (lv_twr((int)c.l_max) + lv_pw((int)c.l_max) + lv_cigar_tpp_tab_words(K)) | 1;
+    const int rstride = (lv_twr((int)c.l_max) + lv_pwt((int)c.l_max) + lv_cigar_tpp_tab_words(K, (int)sizeof(LT))) | 1;
     int threads = 128;
     size_t smem = ((size_t)threads * rstride + cta_sort_words(threads)) * 4;
     if (smem > 73 * 1024) { threads = 64; smem = ((size_t)threads * rstride + cta_sort_words(threads)) * 4; }
@@ -1432,7 +1435,7 @@ static cudaError_t launch_lv_cigar_tpp(const DevCtx &c, const salt_pair_t *pairs
     const size_t cap = (size_t)sm_count * 16;
     if (blocks > cap) blocks = cap;
     if (blocks == 0) return cudaSuccess;
-    auto kern = lv_cigar_tpp_kernel<K>;
+    auto kern = lv_cigar_tpp_kernel<K, LT>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1440,6 +1443,19 @@ static cudaError_t launch_lv_cigar_tpp(const DevCtx &c, const salt_pair_t *pairs
     SALT_LAUNCH(kern, (unsigned)blocks, threads, smem, st, c, pairs, k_each, n, worklist, wl_count, rec, cigars, stride, out);
     SALT_LAUNCH_CHECK();
     return cudaSuccess;
+}
+
+// furthest-reaching values fit a byte while reads are at most 253 bases: a third less shared memory per thread, 4 CTAs per
+// SM instead of 3 at K = 10 -- the kernel is latency-bound, occupancy is what it lacks
+template <int K>
+static cudaError_t launch_lv_cigar_tpp(const DevCtx &c, const salt_pair_t *pairs, const uint8_t *k_each, size_t n,
+                                       const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
+                                       const salt_verify_out_t *rec, char *cigars, int stride, int8_t *out,
+                                       int sm_count, cudaStream_t st)
+{
+    if (c.l_max <= 253)
+        return launch_lv_cigar_tpp_t<K, uint8_t>(c, pairs, k_each, n, worklist, wl_count, wl_cap, rec, cigars, stride, out, sm_count, st);
+    return launch_lv_cigar_tpp_t<K, int16_t>(c, pairs, k_each, n, worklist, wl_count, wl_cap, rec, cigars, stride, out, sm_count, st);
 }
 
 // kmax: upper bound of the k the items carry (levels kept in shared memory = kmax + 1; up to 15
