@@ -396,7 +396,7 @@ __device__ __forceinline__ int lv_stage_own(const DevCtx &c, const salt_pair_t p
 // Work items as in lv_kernel.
 // --------------------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(128, K <= 10 ? 8 : 4)
+__global__ void __launch_bounds__(128, K <= 10 ? 10 : 4)
 lv_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_fixed,
               const uint32_t *__restrict__ slots, const uint32_t *__restrict__ wl_count,
               int8_t *__restrict__ out)
