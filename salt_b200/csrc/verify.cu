@@ -1112,7 +1112,7 @@ __device__ __forceinline__ void nogap_read(const DevCtx &c, const uint2 *__restr
 }
 
 template <int G, int WPL>
-__global__ void __launch_bounds__(64, (G == 8 && WPL == 1) ? 16 : (WPL == 2 && G <= 16) ? 12 : 4)
+__global__ void __launch_bounds__(64, (G == 8 && WPL == 1) ? 18 : (WPL == 2 && G <= 16) ? 12 : 4)
 nogap_fused_kernel(DevCtx c, const uint32_t *__restrict__ offs0, const uint32_t *__restrict__ loci0,
                    const uint32_t *__restrict__ offs1, const uint32_t *__restrict__ loci1, size_t n0,
                    int T0, int8_t *__restrict__ acc, salt_verify_out_t *__restrict__ rec,
