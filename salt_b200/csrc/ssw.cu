@@ -155,7 +155,7 @@ __device__ __forceinline__ int half_of(uint32_t x, int h) { return h ? s16hi(x) 
 #endif
 
 template <int G, int S, bool REV>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (G == 4 && S == 26) ? 5 : 1)
 sw_dp_kernel(SwDev d)
 {
     constexpr int NQ = (S + 3) / 4;
