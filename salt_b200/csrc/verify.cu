@@ -515,7 +515,7 @@ __device__ __forceinline__ void lv_filter_block(const uint32_t (&TA)[20], const 
     }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)           // 80 registers, no spills; 7 and 8 spill (4 CTAs unbounded: 112 registers)
 lv_filter_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_fixed,
                  const uint32_t *__restrict__ slots, const uint32_t *__restrict__ wl_count,
                  int8_t *__restrict__ out, salt_pair_t *__restrict__ pass_pairs, uint32_t *__restrict__ pass_slots,
