@@ -143,7 +143,10 @@ int salt_b200_lv_cigar(salt_b200_t *h, const salt_pair_t *pairs, const uint8_t *
  * reads one past its array) is scored as mat[n_sym*n_sym-1].
  * mask_len < 0 means l_seq/2 (alnpe.c:287).  Requires gapO > gapE.
  * cigars: n * cigar_stride uint32 (len<<4|op, op 0/1/2 = M/I/D); out[i].cigarLen is the
- * true length even if it exceeds cigar_stride. */
+ * true length even if it exceeds cigar_stride (the row then holds only the last cigar_stride ops).
+ * A window the engine declines does not fail the batch: out[i].cigarLen = -1 (read id outside the
+ * chunk, start > end, end > l -- end == l is served, position l scoring as symbol 0 -- or wider than
+ * the widest supported window), -2 (traceback band beyond 512, ssw.c:570-631 keeps doubling). */
 int salt_b200_ssw(salt_b200_t *h, const salt_win_t *wins, size_t n, int use_pac,
                   const int8_t *mat, int n_sym, int gapO, int gapE, int flag,
                   int filters, int filterd, int mask_len,

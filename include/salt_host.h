@@ -62,7 +62,7 @@ int salt_chunk_wait(salt_b200_t *h, int slot, salt_chunk_t *c);
 
 /* After salt_chunk_wait: the query_t fields of read i, with query_set_hits(max_hits) applied to
  * the accepted hits exactly as the reference does (including its use of element 0's n_diff,
- * query.c:317-318). */
+ * query.c:317-318).  1 <= max_hits <= SALT_MAX_HITS. */
 int salt_chunk_result(const salt_chunk_t *c, uint32_t i, int max_hits, salt_read_result_t *out);
 
 /* The SAM tail of the chunk's primaries (sam_add_md_nm, sam.c:246-328; option -d): MD string, NM and
@@ -120,7 +120,8 @@ typedef struct {
  * salt_b200_ssw results of plan->win[0 .. n_win), in that order; filters / filterd the accept rule of
  * snpaln_sw[_snpaware] (alnpe.c:295 / :362: score1 >= filters and aligned read span >= filterd).  The first window
  * that passes rescues its mate; the other mate keeps its primary.  Returns 1 when the pair ends up aligned as a
- * pair (PAIRED_ALNED), 0 otherwise, negative SALT_ERR_* on misuse. */
+ * pair (PAIRED_ALNED), 0 otherwise, negative SALT_ERR_* on misuse; SALT_ERR_UNSUPPORTED when the rescuing window has
+ * no complete CIGAR (declined by the engine, longer than cigar_stride, or longer than the 256-byte string). */
 int salt_pair_apply(const salt_pair_plan_t *plan, const salt_read_result_t *r0, uint32_t l0,
                     const salt_read_result_t *r1, uint32_t l1, const salt_ssw_out_t *ssw, const uint32_t *ssw_cigars,
                     int cigar_stride, int filters, int filterd, salt_mate_final_t out[2]);

@@ -401,7 +401,7 @@ static void pair_and_emit(salt_b200_t *gpu, index_t *index, aln_opt_t *aln_opt, 
             rescue_req_t *r = &H.req[H.n_req++];
             r->pair = j; r->mate = plan.win[w].mate; r->strand = plan.win[w].strand; r->flavour = plan.win[w].flavour;
             r->start = plan.win[w].start; r->end = plan.win[w].end;
-            r->on_gpu = r->end >= r->start && r->end < index->mixRef->l && slot_of[j + r->mate] >= 0;
+            r->on_gpu = r->end >= r->start && r->end <= index->mixRef->l && slot_of[j + r->mate] >= 0;
         }
     }
     for (j = first; !use_plan && j < upto; j += 2) {

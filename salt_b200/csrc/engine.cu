@@ -103,7 +103,7 @@ struct salt_b200 {
     DBuf fpairs, fslots, fcount;            // LV filter survivors of the per-pair entry point
     int lv_filter = 1;                      // pigeonhole filter in front of Landau-Vishkin (salt_b200_set_lv_filter)
     // staging / scratch of the synchronous per-pair and SSW entry points (slot 0's stream)
-    DBuf pairs, out8, kbuf, cig, wins, sswout, sswcig, sswscratch, md_in, md_cig, md_str, md_xv, md_out;
+    DBuf pairs, out8, kbuf, cig, wins, sswout, sswcig, sswscratch, sswovf, md_in, md_cig, md_str, md_xv, md_out;
     uint64_t launches = 0;
     int lv_mapping = 0;         // 0 = auto, 1 = warp per pair, 2 = thread per pair (salt_b200_set_lv_mapping)
     int max_window = 1024;      // widest rescue window the SSW scratch is sized for
@@ -444,7 +444,7 @@ void salt_b200_destroy(salt_b200_t *h)
         if (h->slot[i].stream) cudaStreamSynchronize(h->slot[i].stream);
         h->slot[i].release();
     }
-    DBuf *all[] = {&h->pairs, &h->out8, &h->kbuf, &h->cig, &h->wins, &h->sswout, &h->sswcig, &h->sswscratch,
+    DBuf *all[] = {&h->pairs, &h->out8, &h->kbuf, &h->cig, &h->wins, &h->sswout, &h->sswcig, &h->sswscratch, &h->sswovf,
                    &h->fpairs, &h->fslots, &h->fcount, &h->md_in, &h->md_cig, &h->md_str, &h->md_xv, &h->md_out};
     for (DBuf *b : all) b->release();
     for (int i = 0; i < 7; ++i) if (h->ev_ssw[i]) cudaEventDestroy(h->ev_ssw[i]);
@@ -685,10 +685,12 @@ int salt_b200_ssw_dev(salt_b200_t *h, const salt_win_t *d_wins, size_t n, int us
     size_t lay[8];
     const size_t need = ssw_scratch_bytes(n, max_cols, (int)h->slot[0].l_max, lay);
     CU(h->sswscratch.need(need));
+    CU(h->sswovf.need(ssw_overflow_bytes((int)h->slot[0].l_max)));     // per handle: two handles never share direction bytes
     if (h->profiling)
         for (int i = 0; i < 7; ++i) if (!h->ev_ssw[i]) CU(cudaEventCreate(&h->ev_ssw[i]));
     CU(launch_ssw(h->ctx(), d_wins, n, prm, h->sswscratch.p, h->sswscratch.cap, max_cols, d_out, d_cigars,
-                  cigar_stride, h->sm_count, h->slot[0].stream, &h->launches, h->profiling ? h->ev_ssw : nullptr));
+                  cigar_stride, h->sm_count, h->slot[0].stream, &h->launches, h->profiling ? h->ev_ssw : nullptr,
+                  h->sswovf.as<uint8_t>()));
     h->have_ssw_prof = h->profiling;
     return SALT_OK;
 }
@@ -742,9 +744,7 @@ int salt_b200_ssw(salt_b200_t *h, const salt_win_t *wins, size_t n, int use_pac,
     CU(cudaMemcpyAsync(out, h->sswout.p, n * sizeof(salt_ssw_out_t), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(cigars, h->sswcig.p, n * (size_t)cigar_stride * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    for (size_t i = 0; i < n; ++i)
-        if (out[i].cigarLen < 0) return fail(SALT_ERR_UNSUPPORTED, "a window was invalid or its traceback band exceeded the engine limit");
-    return SALT_OK;
+    return SALT_OK;                                   // declined windows are reported per item: out[i].cigarLen < 0
 }
 
 // ------------------------------------------------------------------ verification stage

@@ -57,6 +57,9 @@ size_t ssw_scratch_bytes(size_t n_tasks, int max_cols, int max_rows, size_t *lay
 cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const SswParams &prm,
                        void *scratch, size_t scratch_bytes, int max_cols,
                        salt_ssw_out_t *out, uint32_t *cigars, int cigar_stride, int sm_count, cudaStream_t st,
-                       uint64_t *launches, cudaEvent_t *ev /* null or [7]: boundaries of the 6 stages */);
+                       uint64_t *launches, cudaEvent_t *ev /* null or [7]: boundaries of the 6 stages */,
+                       uint8_t *ovf_dirs /* ssw_overflow_bytes(l_max) of scratch for bands wider than 16, or null */);
+constexpr unsigned SSW_OVF_THREADS = 128;
+size_t ssw_overflow_bytes(int max_rows);
 
 }  // namespace salt

@@ -73,7 +73,8 @@ sw_prep_kernel(SwDev d)
         const salt_win_t w = d.wins[t];
         const uint32_t rid = w.rs >> 1;
         const int64_t lim = d.prm.use_pac ? d.c.l_pac : (int64_t)d.c.l;
-        const bool ok = rid < d.c.n_reads && w.start <= w.end && (int64_t)w.end < lim &&
+        const bool ok = rid < d.c.n_reads && w.start <= w.end && (int64_t)w.end <= lim &&      // end == l is what alnpe.c:213-252 clamps to: position l reads the zero pad
+                       
                         (!d.prm.use_pac || d.c.pac != nullptr) &&
                         (int64_t)(w.end - w.start + 1) <= (int64_t)d.MC;
         if (!REV) {
@@ -371,9 +372,11 @@ sw_banded_kernel(BandDev d)
     for (int i = threadIdx.x; i < 17 * 8; i += blockDim.x) s_tab[i] = d.prm.table[i];
     __syncthreads();
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t t;
-    if (OVERFLOW) { if (tid >= (size_t)min(*d.in_count, d.ovf_cap)) return; t = d.in_list[tid]; }
-    else { if (tid >= d.n_tasks) return; t = tid; }
+    // overflow pass: ovf_cap threads, each with its own wide direction scratch, walk the whole list
+    const size_t n_items = OVERFLOW ? (size_t)*d.in_count : d.n_tasks;
+    const size_t item_step = OVERFLOW ? (size_t)d.ovf_cap : n_items;
+    for (size_t item = tid; item < n_items; item += item_step) {
+    const size_t t = OVERFLOW ? (size_t)d.in_list[item] : item;
     const int32_t *f = d.fwd + t * 8;
     const int fl = f[F_FLAGS];
     salt_ssw_out_t o;
@@ -382,7 +385,7 @@ sw_banded_kernel(BandDev d)
     o.read_begin1 = f[F_READ_BEGIN1]; o.read_end1 = f[F_READ_END1];
     o.ref_end2 = f[F_REF_END2]; o.cigarLen = 0;
     if (!(fl & FL_VALID)) { o.ref_end2 = -1; o.cigarLen = -1; }
-    if (!(fl & FL_DO_CIGAR)) { if (!OVERFLOW) d.out[t] = o; return; }
+    if (!(fl & FL_DO_CIGAR)) { if (!OVERFLOW) d.out[t] = o; continue; }
 
     const salt_win_t w = d.wins[t];
     const int refLen = o.ref_end1 - o.ref_begin1 + 1, readLen = o.read_end1 - o.read_begin1 + 1;
@@ -437,13 +440,12 @@ sw_banded_kernel(BandDev d)
     } while (max < score);
 
     if (overflow) {
-        if (!OVERFLOW) {
-            const uint32_t k = atomicAdd(d.ovf_count, 1u);
-            if (k < d.ovf_cap) { d.ovf_list[k] = (uint32_t)t; o.cigarLen = 0; }
-            else o.cigarLen = -2;
-        } else o.cigarLen = -2;
+        if (!OVERFLOW && d.ovf_list) {
+            const uint32_t k = atomicAdd(d.ovf_count, 1u);     // the list has room for every task
+            d.ovf_list[k] = (uint32_t)t; o.cigarLen = 0;
+        } else o.cigarLen = -2;                                // band beyond the engine's widest (BWMAX of the overflow pass)
         d.out[t] = o;
-        return;
+        continue;
     }
     band /= 2;
 
@@ -468,17 +470,16 @@ sw_banded_kernel(BandDev d)
         if (fop == prev) ++e;
         else { emit((uint32_t)e << 4 | (uint32_t)prev); prev = fop; e = 1; }
     }
-    if (bad) { o.cigarLen = -3; d.out[t] = o; return; }
+    if (bad) { o.cigarLen = -3; d.out[t] = o; continue; }
     if (fop == 0) emit((uint32_t)(e + 1) << 4);
     else { emit((uint32_t)e << 4 | (uint32_t)fop); emit(16u); }
     const int stored = l < d.cigar_stride ? l : d.cigar_stride;
     for (int a = 0, b = stored - 1; a < b; ++a, --b) { const uint32_t tmp = cg[a]; cg[a] = cg[b]; cg[b] = tmp; }
-    if (l > d.cigar_stride) {
-        // keep the FIRST cigar_stride ops of the true cigar: they are the last ones produced.
-        // (callers size the stride for the worst case; cigarLen still reports the true length)
-    }
+    // l > cigar_stride: the row holds the LAST cigar_stride ops of the true cigar (the first ones the traceback
+    // produced), reversed into order; cigarLen reports the true length so the caller can tell the row is partial
     o.cigarLen = l;
     d.out[t] = o;
+    }
 }
 
 // --------------------------------------------------------------------------------------
@@ -558,15 +559,17 @@ static cudaError_t dispatch_dp(const SwDev &d, bool rev, cudaStream_t st)
     return cudaErrorInvalidValue;
 }
 
-// Overflow scratch for wide bands: allocated on first use, kept for the process lifetime.
-static uint8_t *g_ovf_dirs[64] = {nullptr};
-static const size_t OVF_SLOT = (size_t)(2 * 512 + 1) * 1024;     // band <= 512, rows <= 1024
-static const uint32_t OVF_CAP = 256;
+// Overflow pass for bands wider than 16: SSW_OVF_THREADS threads, each with direction scratch for band <= 512
+// over the chunk's longest read, walk the overflow list however long it is.  The scratch belongs to the handle.
+size_t ssw_overflow_bytes(int max_rows)
+{
+    return (size_t)SSW_OVF_THREADS * (size_t)(2 * 512 + 1) * (size_t)(8 * ((max_rows + 7) / 8));
+}
 
 cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const SswParams &prm,
                        void *scratch, size_t scratch_bytes, int max_cols,
                        salt_ssw_out_t *out, uint32_t *cigars, int cigar_stride, int sm_count, cudaStream_t st,
-                       uint64_t *launches, cudaEvent_t *ev)
+                       uint64_t *launches, cudaEvent_t *ev, uint8_t *ovf_dirs)
 {
 #define SALT_EV(i) do { if (ev) cudaEventRecord(ev[i], st); } while (0)
     (void)sm_count;
@@ -608,23 +611,19 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
     b.dirs = base + lay[4];
     b.slot = (size_t)(2 * 16 + 1) * (size_t)(8 * (((int)c.l_max + 7) / 8));
     b.ovf_list = reinterpret_cast<uint32_t *>(base + lay[5]);
-    b.ovf_count = ovf_count; b.ovf_cap = OVF_CAP;
+    b.ovf_count = ovf_count; b.ovf_cap = SSW_OVF_THREADS;
+    if (!ovf_dirs) b.ovf_list = nullptr;                  // no overflow scratch: wide bands come back with cigarLen = -2
     b.in_list = nullptr; b.in_count = nullptr;
     b.out = out; b.cigars = cigars; b.cigar_stride = cigar_stride;
     { auto kern = sw_banded_kernel<16, false>; SALT_LAUNCH(kern, (unsigned)((n + 127) / 128), 128, 0, st, b); }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     SALT_EV(5);
 
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64) {
-        if (!g_ovf_dirs[dev]) {
-            if ((e = cudaMalloc(&g_ovf_dirs[dev], OVF_SLOT * OVF_CAP)) != cudaSuccess) return e;
-        }
+    if (ovf_dirs) {
         BandDev b2 = b;
-        b2.dirs = g_ovf_dirs[dev]; b2.slot = OVF_SLOT;
+        b2.dirs = ovf_dirs; b2.slot = (size_t)(2 * 512 + 1) * (size_t)(8 * (((int)c.l_max + 7) / 8));
         b2.in_list = b.ovf_list; b2.in_count = ovf_count;
-        { auto kern = sw_banded_kernel<512, true>; SALT_LAUNCH(kern, (OVF_CAP + 127) / 128, 128, 0, st, b2); }
+        { auto kern = sw_banded_kernel<512, true>; SALT_LAUNCH(kern, (SSW_OVF_THREADS + 127) / 128, 128, 0, st, b2); }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     SALT_EV(6);

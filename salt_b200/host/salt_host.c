@@ -129,7 +129,8 @@ static uint32_t gen_mapq(uint32_t b0, uint32_t b1)            /* query.c:270-281
 
 int salt_chunk_result(const salt_chunk_t *c, uint32_t i, int max_hits, salt_read_result_t *out)
 {
-    if (!c->done || i >= c->n_reads || !out || max_hits < 0 || max_hits > SALT_MAX_HITS) return SALT_ERR_ARG;
+    /* max_hits < 1 would never meet the reference's `tot_hits == max_hits` stop test (query.c:327) and run past alt[] */
+    if (!c->done || i >= c->n_reads || !out || max_hits < 1 || max_hits > SALT_MAX_HITS) return SALT_ERR_ARG;
     const salt_verify_out_t *q = &c->rec[i];
     memset(out, 0, sizeof *out);
     out->pos = q->pos; out->strand = q->strand; out->n_diff = q->n_diff; out->is_gap = q->is_gap;
@@ -339,8 +340,12 @@ int salt_pair_apply(const salt_pair_plan_t *plan, const salt_read_result_t *r0, 
         o->cigar_kind = 3;
         size_t at = 0;
         o->cigar[0] = 0;
-        for (int j = 0; j < a->cigarLen && j < cigar_stride && at + 16 < sizeof o->cigar; ++j) {
+        /* a rescued mate without its whole CIGAR is an error, not a shorter string: the engine declined the window
+           (cigarLen < 0), the row was too short for it (cigarLen > cigar_stride) or it does not fit 256 bytes */
+        if (a->cigarLen < 0 || a->cigarLen > cigar_stride) return SALT_ERR_UNSUPPORTED;
+        for (int j = 0; j < a->cigarLen; ++j) {
             const uint32_t c = ssw_cigars[(size_t)w * (size_t)cigar_stride + (size_t)j];
+            if (at + 16 >= sizeof o->cigar) return SALT_ERR_UNSUPPORTED;
             at += (size_t)snprintf(o->cigar + at, sizeof o->cigar - at, "%u%c", c >> 4, "MID"[c & 15]);
         }
         return 1;

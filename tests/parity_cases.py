@@ -228,6 +228,29 @@ def check_ssw(eng, oracle, g, reads, wins, use_pac, mat, n_sym, gapO=3, gapE=1, 
     return gapped
 
 
+def check_ssw_wide_bands(eng, oracle, seed, n_reads=150, L=100, glen=20003):
+    """Every read lacks `gap` >= 16 reference bases in its middle, so banded_sw's first band (|refLen - readLen| + 1,
+    ssw.c:845) is already wider than the main pass serves: all of them go through the overflow pass, more of them
+    than it has threads.  Plus windows that end AT l, which alnpe.c:213-252 clamps to (position l reads as symbol 0)."""
+    rng = np.random.default_rng(seed)
+    g = synth.Genome(glen, snp_rate=0.01, n_rate=0.0, seed=seed)           # glen % 8 != 0: position l is in the last word
+    codes = np.log2(np.maximum(synth.unpack_mixref(g.mixref, 0, g.l) & -synth.unpack_mixref(g.mixref, 0, g.l).astype(np.int8), 1)).astype(np.uint8)
+    reads = np.zeros((n_reads, L), np.uint8); wins = np.zeros(n_reads, api.WIN_DT)
+    for i in range(n_reads):
+        gap = int(rng.integers(16, 40)); a = int(rng.integers(40, 61))
+        p = int(rng.integers(200, g.l - 600))
+        reads[i] = np.concatenate([codes[p:p + a], codes[p + a + gap:p + gap + L]])
+        start = p - int(rng.integers(0, 150)); end = start + 400
+        if i % 10 == 0:
+            end = g.l; start = g.l - 400
+            q = g.l - L - gap - int(rng.integers(0, 100))
+            reads[i] = np.concatenate([codes[q:q + a], codes[q + a + gap:q + gap + L]])
+        wins[i] = (i << 1, start, end)
+    eng.set_reads(reads)
+    gapped = check_ssw(eng, oracle, g, reads, wins, False, api.salt_score_mat2(), 16)
+    return gapped
+
+
 def random_cigar(rng, qlen, max_ops=5):
     """A random M/I/D run string consuming exactly qlen read bases (what query->cigar->s may hold)."""
     ops = []

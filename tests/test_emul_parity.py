@@ -165,6 +165,12 @@ def test_ssw_mixref(emul_lib, oracle, L, width):
     assert gapped >= 3
 
 
+def test_ssw_wide_bands_and_end_at_l(emul_lib, oracle):
+    g = synth.Genome(20003, snp_rate=0.01, n_rate=0.0, seed=77)
+    eng = _engine(emul_lib, g)
+    assert pc.check_ssw_wide_bands(eng, oracle, 77) >= 120
+
+
 def test_ssw_pac_and_params(emul_lib, oracle):
     L = 100
     g, reads, pos, strand, _ = pc.make_world(600, L=L, n_reads=11, per_strand=2, indel_frac=0.7, sub_rate=0.04,

@@ -295,5 +295,14 @@ def test_error_paths():
     assert (rec["pos"] != 0xFFFFFFFF).sum() >= 10
     # a window that leaves the reference comes back flagged, not crashed
     wins = np.zeros(2, api.WIN_DT); wins["start"] = [10, g.l - 50]; wins["end"] = [310, g.l + 20]
-    with pytest.raises(api.SaltError):
-        eng.ssw(wins, api.salt_score_mat2(), 16, False)
+    o, _ = eng.ssw(wins, api.salt_score_mat2(), 16, False)
+    assert int(o["cigarLen"][0]) >= 0 and int(o["cigarLen"][1]) == -1      # declined per item, the batch goes through
+
+
+@pytest.mark.gpu
+def test_ssw_wide_bands_and_end_at_l(oracle):
+    """bands wider than the main pass, more of them than the overflow pass has threads; windows clamped to end == l"""
+    g = synth.Genome(20003, snp_rate=0.01, n_rate=0.0, seed=77)
+    eng = _engine(g, pac=False)
+    assert pc.check_ssw_wide_bands(eng, oracle, 77, n_reads=700) >= 600
+    eng.close()
