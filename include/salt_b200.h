@@ -195,6 +195,42 @@ int salt_b200_verify_batch(salt_b200_t *h, const salt_reads_t *reads, const salt
                            int nogap_T0, int lv_T0, salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1,
                            char *cigars, int cigar_stride);
 
+/* ---- compact transport ------------------------------------------------------------------------
+ * The verification stage is bound by the host link, not by the kernels, so a caller
+ * that controls its own queues can send a chunk in fewer bytes: bases at 2 or 4 bits instead of the
+ * reference's one byte per base (query->seq, query.c:177-181 -- the FASTQ parser can emit either for
+ * free), read lengths and per-read candidate counts instead of three 32-bit offset arrays.  The engine
+ * rebuilds codes and offsets on the device; results are identical to salt_b200_verify_submit on the
+ * same chunk.
+ *   base_bits 2: codes 0..3, base p of the stream in bits 2*(p&3) of byte p>>2; an N is sent as any
+ *                code and its stream position listed in n_pos (ascending).
+ *   base_bits 4: codes 0..4, base p in bits 4*(p&1) of byte p>>1.
+ * Reads lie back to back in the stream; read 0's first base is stream position base_start (so a view
+ * into a longer stream needs no re-packing).  `bases` must be readable up to the byte holding the last
+ * base.  lens == NULL: every read has l_seq bases.  n_cand[s][i] = candidates of read i on strand s
+ * (count_bits 16 or 32); loci[s] = the lists themselves, reads back to back, as in salt_cands_t. */
+typedef struct {
+    uint32_t n_reads;
+    int base_bits;
+    const uint8_t *bases;
+    uint32_t base_start;
+    const uint16_t *lens;
+    uint32_t l_seq;
+    const uint32_t *n_pos;
+    size_t n_n;
+    int count_bits;
+    const void *n_cand[2];
+    const uint32_t *loci[2];
+} salt_packed_chunk_t;
+
+/* salt_b200_set_reads / _verify_submit / _verify_batch for the compact format (n_cand / loci are not
+ * read by _set_reads_packed). */
+int salt_b200_set_reads_packed(salt_b200_t *h, const salt_packed_chunk_t *pc);
+int salt_b200_verify_submit_packed(salt_b200_t *h, int slot, const salt_packed_chunk_t *pc, int nogap_T0, int lv_T0,
+                                   salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1, char *cigars, int cigar_stride);
+int salt_b200_verify_batch_packed(salt_b200_t *h, const salt_packed_chunk_t *pc, uint32_t chunk_reads, int nogap_T0, int lv_T0,
+                                  salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1, char *cigars, int cigar_stride);
+
 /* Landau-Vishkin work mapping: 0 = automatic (one thread per pair with all diagonals in
  * registers for k <= 15 inside the verify stage, one warp per pair with lanes over diagonals
  * beyond that and on flat pair lists), 1 = always one warp (or sub-warp group) per pair,

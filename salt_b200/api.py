@@ -41,6 +41,29 @@ class CandsT(C.Structure):
     _fields_ = [("offs", C.c_void_p * 2), ("loci", C.c_void_p * 2)]
 
 
+class PackedChunkT(C.Structure):
+    """salt_packed_chunk_t (include/salt_b200.h): the compact host->device transport of a chunk."""
+    _fields_ = [("n_reads", C.c_uint32), ("base_bits", C.c_int), ("bases", C.c_void_p), ("base_start", C.c_uint32),
+                ("lens", C.c_void_p), ("l_seq", C.c_uint32), ("n_pos", C.c_void_p), ("n_n", C.c_size_t),
+                ("count_bits", C.c_int), ("n_cand", C.c_void_p * 2), ("loci", C.c_void_p * 2)]
+
+
+def pack_bases(codes, bits, base_start=0):
+    """codes 0..4 (flat uint8 stream) -> (packed bytes, positions of N) in the transport layout: base p of the stream
+    in bits `bits`*(p mod 8/bits) of byte p / (8/bits), lowest bits first.  The stream's first base sits at
+    position base_start.  What a FASTQ parser would emit directly; numpy here because the tests are Python."""
+    codes = np.ascontiguousarray(codes, np.uint8).reshape(-1)
+    per = 8 // bits
+    n_pos = np.nonzero(codes > 3)[0].astype(np.uint32) + np.uint32(base_start)
+    c = np.minimum(codes, 4) if bits == 4 else np.where(codes > 3, 0, codes).astype(np.uint8)
+    c = np.concatenate([np.zeros(base_start, np.uint8), c, np.zeros((-(len(c) + base_start)) % per + per, np.uint8)])
+    c = c.reshape(-1, per).astype(np.uint32)
+    out = np.zeros(len(c), np.uint32)
+    for e in range(per):
+        out |= c[:, e] << (bits * e)
+    return out.astype(np.uint8), (n_pos if bits == 2 else np.zeros(0, np.uint32))
+
+
 def _declare(L):
     vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
     L.salt_b200_last_error.restype = C.c_char_p
@@ -67,6 +90,10 @@ def _declare(L):
     L.salt_b200_verify_submit.argtypes = [vp, i32, C.POINTER(ReadsT), C.POINTER(CandsT), i32, i32, vp, vp, vp, vp, i32]
     L.salt_b200_verify_wait.argtypes = [vp, i32]
     L.salt_b200_verify_batch.argtypes = [vp, C.POINTER(ReadsT), C.POINTER(CandsT), C.c_uint32, i32, i32, vp, vp, vp, vp, i32]
+    if hasattr(L, "salt_b200_set_reads_packed"):
+        L.salt_b200_set_reads_packed.argtypes = [vp, C.POINTER(PackedChunkT)]
+        L.salt_b200_verify_submit_packed.argtypes = [vp, i32, C.POINTER(PackedChunkT), i32, i32, vp, vp, vp, vp, i32]
+        L.salt_b200_verify_batch_packed.argtypes = [vp, C.POINTER(PackedChunkT), C.c_uint32, i32, i32, vp, vp, vp, vp, i32]
     L.salt_b200_set_max_window.argtypes = [vp, i32]
     L.salt_b200_set_lv_mapping.argtypes = [vp, i32]
     L.salt_b200_set_lv_filter.argtypes = [vp, i32]
@@ -301,6 +328,45 @@ class Engine:
         cig = np.zeros((n, cigar_stride), np.uint8) if want_cigars else None
         self._ck(self.L.salt_b200_verify_batch(self.h, C.byref(r), C.byref(c), int(chunk_reads), int(nogap_T0), int(lv_T0),
                                                _ptr(rec), _ptr(acc0), _ptr(acc1), _ptr(cig), int(cigar_stride)))
+        return rec, acc0, acc1, cig
+
+
+    def packed_chunk(self, codes, roffs, offs0, loci0, offs1, loci1, bits=2, count_bits=16, base_start=0, uniform=None):
+        """Build a salt_packed_chunk_t (and the arrays it points into, which the caller must keep alive) from the
+        plain CSR description of a batch."""
+        codes = np.ascontiguousarray(codes, np.uint8).reshape(-1)
+        roffs = np.ascontiguousarray(roffs, np.int64)
+        keep = {}
+        keep["bases"], keep["n_pos"] = pack_bases(codes, bits, base_start)
+        lens = np.diff(roffs)
+        if uniform is None:
+            uniform = len(lens) > 0 and bool((lens == lens[0]).all())
+        keep["lens"] = None if uniform else lens.astype(np.uint16)
+        cdt = np.uint16 if count_bits == 16 else np.uint32
+        keep["cnt0"] = np.diff(np.asarray(offs0, np.int64)).astype(cdt); keep["cnt1"] = np.diff(np.asarray(offs1, np.int64)).astype(cdt)
+        keep["loci0"] = np.ascontiguousarray(loci0, np.uint32); keep["loci1"] = np.ascontiguousarray(loci1, np.uint32)
+        pc = PackedChunkT()
+        pc.n_reads = len(lens); pc.base_bits = bits; pc.bases = _ptr(keep["bases"]); pc.base_start = base_start
+        pc.lens = _ptr(keep["lens"]); pc.l_seq = int(lens[0]) if uniform and len(lens) else 0
+        pc.n_pos = _ptr(keep["n_pos"]) if len(keep["n_pos"]) else None; pc.n_n = len(keep["n_pos"])
+        pc.count_bits = count_bits
+        pc.n_cand[0], pc.n_cand[1] = _ptr(keep["cnt0"]), _ptr(keep["cnt1"])
+        pc.loci[0] = _ptr(keep["loci0"]) if len(keep["loci0"]) else None
+        pc.loci[1] = _ptr(keep["loci1"]) if len(keep["loci1"]) else None
+        return pc, keep
+
+    def set_reads_packed(self, pc):
+        self._ck(self.L.salt_b200_set_reads_packed(self.h, C.byref(pc)))
+        self.n_reads = int(pc.n_reads)
+
+    def verify_batch_packed(self, pc, n0, n1, chunk_reads=100000, nogap_T0=3, lv_T0=-1, cigar_stride=128, want_cigars=True):
+        """salt_b200_verify_batch_packed: the chunk pipeline fed in the compact transport format."""
+        n = int(pc.n_reads)
+        rec = np.zeros(n, VERIFY_DT)
+        acc0 = np.empty(n0, np.int8); acc1 = np.empty(n1, np.int8)
+        cig = np.zeros((n, cigar_stride), np.uint8) if want_cigars else None
+        self._ck(self.L.salt_b200_verify_batch_packed(self.h, C.byref(pc), int(chunk_reads), int(nogap_T0), int(lv_T0),
+                                                      _ptr(rec), _ptr(acc0), _ptr(acc1), _ptr(cig), int(cigar_stride)))
         return rec, acc0, acc1, cig
 
 

@@ -65,6 +65,7 @@ struct Slot {
     uint32_t *d_roffs() const { return offs3.as<uint32_t>(); }
     uint32_t *d_coffs(int strand) const { return offs3.as<uint32_t>() + (size_t)(strand + 1) * ((size_t)n_reads + 1); }
     DBuf c_loci0, c_loci1, vpairs, acc, rec, lvlist, ciglist, counters, cig, fpairs, fslots, lvreads;
+    DBuf pk_bases, pk_lens, pk_cnt, pk_npos, pk_scan;          // compact transport (salt_packed_chunk_t): raw uploads + scan scratch
     // asynchronous verify in flight: where the compact CIGAR list has to be scattered to
     bool pending = false;
     char *u_cigars = nullptr; int u_stride = 0;
@@ -78,7 +79,8 @@ struct Slot {
     void release()
     {
         DBuf *all[] = {&codes, &offs3, &rd4, &rd_len, &c_loci0, &c_loci1, &vpairs, &acc, &rec,
-                       &lvlist, &ciglist, &counters, &cig, &fpairs, &fslots, &lvreads};
+                       &lvlist, &ciglist, &counters, &cig, &fpairs, &fslots, &lvreads,
+                       &pk_bases, &pk_lens, &pk_cnt, &pk_npos, &pk_scan};
         for (DBuf *b : all) b->release();
         if (h_stage) cudaFreeHost(h_stage);
         h_stage = nullptr; h_stage_cap = 0;
@@ -258,19 +260,13 @@ int verify_on_device(salt_b200_t *h, int si, const uint32_t *d_offs0, const uint
     return SALT_OK;
 }
 
-// Host-buffer verify of one slot: uploads the candidate lists, runs the stage, queues the
-// downloads.  Returns without waiting; finish_verify completes it.
-int enqueue_verify(salt_b200_t *h, int si, const salt_cands_t *cands, int nogap_T0, int lv_T0,
-                   salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1, char *cigars, int cigar_stride)
+// Second half of a host-buffer verify: the slot's candidate offsets and loci are in HBM (n0 / n1 of them);
+// run the stage and queue the downloads.  Returns without waiting; finish_verify completes it.
+int run_and_download(salt_b200_t *h, int si, size_t n0, size_t n1, int nogap_T0, int lv_T0,
+                     salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1, char *cigars, int cigar_stride)
 {
     Slot &s = h->slot[si];
-    if (!cands || !cands->offs[0] || !cands->offs[1] || !rec) return fail(SALT_ERR_ARG, "null buffer");
-    if (!s.n_reads) return fail(SALT_ERR_ARG, "no reads set");
-    if (s.pending) return fail(SALT_ERR_ARG, "slot has a verify in flight: call salt_b200_verify_wait first");
     const uint32_t nr = s.n_reads;
-    const size_t n0 = cands->offs[0][nr], n1 = cands->offs[1][nr];
-    if ((n0 && !cands->loci[0]) || (n1 && !cands->loci[1])) return fail(SALT_ERR_ARG, "null loci");
-    CU(s.c_loci0.need(n0 * 4 + 4)); CU(s.c_loci1.need(n1 * 4 + 4));
     CU(s.acc.need(n0 + n1 + 1));
     CU(s.rec.need((size_t)nr * sizeof(salt_verify_out_t)));
     s.eager = 0;
@@ -286,13 +282,6 @@ int enqueue_verify(salt_b200_t *h, int si, const salt_cands_t *cands, int nogap_
             s.h_stage_cap = want;
         }
     }
-    if (!s.offs_merged) {
-        CU(cudaMemcpyAsync(s.d_coffs(0), cands->offs[0], ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, s.stream));
-        CU(cudaMemcpyAsync(s.d_coffs(1), cands->offs[1], ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, s.stream));
-    }
-    s.offs_merged = false;                               // one use: a later verify on the same reads uploads its own lists
-    if (n0) CU(cudaMemcpyAsync(s.c_loci0.p, cands->loci[0], n0 * 4, cudaMemcpyHostToDevice, s.stream));
-    if (n1) CU(cudaMemcpyAsync(s.c_loci1.p, cands->loci[1], n1 * 4, cudaMemcpyHostToDevice, s.stream));
     int8_t *acc = s.acc.as<int8_t>();
     uint32_t *cl = cigars ? s.ciglist.as<uint32_t>() : nullptr;
     if (int rc = verify_on_device(h, si, s.d_coffs(0), s.c_loci0.as<uint32_t>(), n0,
@@ -313,6 +302,136 @@ int enqueue_verify(salt_b200_t *h, int si, const salt_cands_t *cands, int nogap_
     }
     s.u_cigars = cigars; s.u_stride = cigar_stride;
     s.pending = true;
+    return SALT_OK;
+}
+
+// Host-buffer verify of one slot: uploads the candidate lists, runs the stage, queues the
+// downloads.  Returns without waiting; finish_verify completes it.
+int enqueue_verify(salt_b200_t *h, int si, const salt_cands_t *cands, int nogap_T0, int lv_T0,
+                   salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1, char *cigars, int cigar_stride)
+{
+    Slot &s = h->slot[si];
+    if (!cands || !cands->offs[0] || !cands->offs[1] || !rec) return fail(SALT_ERR_ARG, "null buffer");
+    if (!s.n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    if (s.pending) return fail(SALT_ERR_ARG, "slot has a verify in flight: call salt_b200_verify_wait first");
+    const uint32_t nr = s.n_reads;
+    const size_t n0 = cands->offs[0][nr], n1 = cands->offs[1][nr];
+    if ((n0 && !cands->loci[0]) || (n1 && !cands->loci[1])) return fail(SALT_ERR_ARG, "null loci");
+    CU(s.c_loci0.need(n0 * 4 + 4)); CU(s.c_loci1.need(n1 * 4 + 4));
+    if (!s.offs_merged) {
+        CU(cudaMemcpyAsync(s.d_coffs(0), cands->offs[0], ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(s.d_coffs(1), cands->offs[1], ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, s.stream));
+    }
+    s.offs_merged = false;                               // one use: a later verify on the same reads uploads its own lists
+    if (n0) CU(cudaMemcpyAsync(s.c_loci0.p, cands->loci[0], n0 * 4, cudaMemcpyHostToDevice, s.stream));
+    if (n1) CU(cudaMemcpyAsync(s.c_loci1.p, cands->loci[1], n1 * 4, cudaMemcpyHostToDevice, s.stream));
+    return run_and_download(h, si, n0, n1, nogap_T0, lv_T0, rec, acc0, acc1, cigars, cigar_stride);
+}
+
+// One chunk in the compact transport format: what is known on the host about it.
+struct PackedView {
+    const salt_packed_chunk_t *pc;
+    uint32_t first = 0, n = 0;            // reads [first, first + n) of pc
+    uint64_t base_pos = 0;                // stream position of the view's first base
+    uint64_t n_bases = 0;
+    size_t np_lo = 0, np_hi = 0;          // range of pc->n_pos inside the view
+    size_t c0 = 0, c1 = 0, n0 = 0, n1 = 0;   // where the view's loci start in pc->loci[] and how many there are
+    uint32_t l_max = 0;
+};
+
+inline uint32_t packed_count(const salt_packed_chunk_t *pc, int strand, uint32_t i)
+{
+    return pc->count_bits == 16 ? (uint32_t)static_cast<const uint16_t *>(pc->n_cand[strand])[i]
+                                : static_cast<const uint32_t *>(pc->n_cand[strand])[i];
+}
+
+int check_packed(const salt_packed_chunk_t *pc, bool need_cands)
+{
+    if (!pc) return fail(SALT_ERR_ARG, "packed chunk is null");
+    if (pc->base_bits != 2 && pc->base_bits != 4) return fail(SALT_ERR_ARG, "base_bits must be 2 or 4");
+    if (pc->n_reads && !pc->bases) return fail(SALT_ERR_ARG, "bases is null");
+    if (pc->n_reads >= (1u << 31)) return fail(SALT_ERR_ARG, "too many reads");
+    if (!pc->lens && (pc->l_seq == 0 || pc->l_seq > 1024)) return fail(SALT_ERR_ARG, "l_seq must be 1..1024 when lens is null");
+    if (pc->n_n && (!pc->n_pos || pc->base_bits != 2)) return fail(SALT_ERR_ARG, "n_pos belongs to 2-bit streams");
+    if (need_cands) {
+        if (pc->count_bits != 16 && pc->count_bits != 32) return fail(SALT_ERR_ARG, "count_bits must be 16 or 32");
+        if (pc->n_reads && (!pc->n_cand[0] || !pc->n_cand[1])) return fail(SALT_ERR_ARG, "n_cand is null");
+    }
+    return SALT_OK;
+}
+
+// Extend `v` (which ends at read v.first + v.n) by the next m reads of its chunk: host-side sums only.
+int grow_view(PackedView &v, uint32_t m, bool with_cands)
+{
+    const salt_packed_chunk_t *pc = v.pc;
+    for (uint32_t i = v.first + v.n; i < v.first + v.n + m; ++i) {
+        const uint32_t L = pc->lens ? pc->lens[i] : pc->l_seq;
+        if (L > v.l_max) v.l_max = L;
+        v.n_bases += L;
+        if (with_cands) { v.n0 += packed_count(pc, 0, i); v.n1 += packed_count(pc, 1, i); }
+    }
+    v.n += m;
+    if (v.l_max > 1024) return fail(SALT_ERR_UNSUPPORTED, "reads longer than 1024 bases are not supported");
+    if (v.n_bases >= ((uint64_t)1 << 32) || v.n0 + v.n1 >= ((size_t)1 << 32)) return fail(SALT_ERR_ARG, "chunk too large: bases and candidates are 32-bit offsets");
+    const uint64_t end = v.base_pos + v.n_bases;
+    v.np_hi = v.np_lo;
+    while (v.np_hi < pc->n_n && pc->n_pos[v.np_hi] < end) ++v.np_hi;
+    return SALT_OK;
+}
+
+// Upload one view and rebuild codes / offsets / packed reads in the slot.  Asynchronous on the slot's stream.
+int load_packed(salt_b200_t *h, Slot &s, const PackedView &v, bool with_cands)
+{
+    const salt_packed_chunk_t *pc = v.pc;
+    const uint32_t n = v.n;
+    s.n_reads = n; s.l_max = v.l_max; s.W64 = (v.l_max + 15) / 16 + 1;
+    s.offs_merged = false;
+    if (!n) return SALT_OK;
+    const uint32_t per = 8u / (uint32_t)pc->base_bits;                 // bases per byte
+    const uint64_t byte_lo = v.base_pos / per, byte_hi = (v.base_pos + v.n_bases + per - 1) / per;
+    const uint32_t phase = (uint32_t)(v.base_pos % per);
+    CU(s.codes.need((v.n_bases + 3) / 4 * 4 + 16));
+    CU(s.offs3.need(3 * ((size_t)n + 1) * 4));
+    CU(s.rd4.need((size_t)n * 2 * s.W64 * 8 + 64));
+    CU(s.rd_len.need((size_t)n * 2 + 64));
+    CU(s.pk_bases.need(byte_hi - byte_lo + 8));
+    CU(s.pk_scan.need(3 * (size_t)scan3_blocks(n) * 4 + 16));
+    CU(cudaMemcpyAsync(s.pk_bases.p, pc->bases + byte_lo, byte_hi - byte_lo, cudaMemcpyHostToDevice, s.stream));
+    Scan3 sc{};
+    sc.n = n; sc.partial = s.pk_scan.as<uint32_t>();
+    sc.out[0] = s.d_roffs(); sc.out[1] = s.d_coffs(0); sc.out[2] = s.d_coffs(1);
+    if (pc->lens) {
+        CU(s.pk_lens.need((size_t)n * 2 + 16));
+        CU(cudaMemcpyAsync(s.pk_lens.p, pc->lens + v.first, (size_t)n * 2, cudaMemcpyHostToDevice, s.stream));
+        sc.in[0] = s.pk_lens.p; sc.width[0] = 16;
+    } else { sc.in[0] = nullptr; sc.uniform[0] = pc->l_seq; sc.width[0] = 32; }
+    if (with_cands) {
+        const size_t cb = (size_t)pc->count_bits / 8;
+        const size_t stride = ((size_t)n * cb + 15) / 16 * 16;
+        CU(s.pk_cnt.need(2 * stride + 16));
+        for (int k = 0; k < 2; ++k) {
+            uint8_t *dst = s.pk_cnt.as<uint8_t>() + k * stride;
+            CU(cudaMemcpyAsync(dst, static_cast<const uint8_t *>(pc->n_cand[k]) + (size_t)v.first * cb, (size_t)n * cb,
+                               cudaMemcpyHostToDevice, s.stream));
+            sc.in[1 + k] = dst; sc.width[1 + k] = pc->count_bits;
+        }
+    }
+    CU(launch_scan3(sc, with_cands ? 3 : 1, s.stream));
+    const size_t nn = v.np_hi - v.np_lo;
+    if (nn) {
+        CU(s.pk_npos.need(nn * 4));
+        CU(cudaMemcpyAsync(s.pk_npos.p, pc->n_pos + v.np_lo, nn * 4, cudaMemcpyHostToDevice, s.stream));
+    }
+    CU(launch_unpack_bases(s.pk_bases.as<uint8_t>(), phase, pc->base_bits, (size_t)v.n_bases, s.codes.as<uint8_t>(),
+                           s.pk_npos.as<uint32_t>(), nn, (uint32_t)v.base_pos, s.stream));
+    CU(launch_pack_reads(s.codes.as<uint8_t>(), s.d_roffs(), n, s.W64, s.rd4.as<uint64_t>(), s.rd_len.as<uint16_t>(), s.stream));
+    h->launches += 5 + (nn ? 1 : 0);
+    if (with_cands) {
+        if ((v.n0 && !pc->loci[0]) || (v.n1 && !pc->loci[1])) return fail(SALT_ERR_ARG, "null loci");
+        CU(s.c_loci0.need(v.n0 * 4 + 4)); CU(s.c_loci1.need(v.n1 * 4 + 4));
+        if (v.n0) CU(cudaMemcpyAsync(s.c_loci0.p, pc->loci[0] + v.c0, v.n0 * 4, cudaMemcpyHostToDevice, s.stream));
+        if (v.n1) CU(cudaMemcpyAsync(s.c_loci1.p, pc->loci[1] + v.c1, v.n1 * 4, cudaMemcpyHostToDevice, s.stream));
+    }
     return SALT_OK;
 }
 
@@ -821,6 +940,68 @@ int salt_b200_verify_batch(salt_b200_t *h, const salt_reads_t *reads, const salt
         cv.loci[0] = cands->loci[0] ? cands->loci[0] + c0 : nullptr; cv.loci[1] = cands->loci[1] ? cands->loci[1] + c1 : nullptr;
         rc = salt_b200_verify_submit(h, si, &rv, &cv, nogap_T0, lv_T0, rec + b, acc0 ? acc0 + c0 : nullptr,
                                      acc1 ? acc1 + c1 : nullptr, cigars ? cigars + (size_t)b * cigar_stride : nullptr, cigar_stride);
+    }
+    for (int si = 0; si < SALT_SLOTS; ++si) { const int r2 = finish_verify(h, si); if (rc == SALT_OK) rc = r2; }
+    return rc;
+}
+
+// ------------------------------------------------------------------ compact transport
+int salt_b200_set_reads_packed(salt_b200_t *h, const salt_packed_chunk_t *pc)
+{
+    if (int rc = use_device(h)) return rc;
+    if (int rc = check_packed(pc, false)) return rc;
+    Slot &s = h->slot[0];
+    if (s.pending) return fail(SALT_ERR_ARG, "slot 0 has a verify in flight");
+    PackedView v; v.pc = pc; v.base_pos = pc->base_start;
+    while (v.np_lo < pc->n_n && pc->n_pos[v.np_lo] < v.base_pos) ++v.np_lo;
+    if (int rc = grow_view(v, pc->n_reads, false)) return rc;
+    if (int rc = load_packed(h, s, v, false)) return rc;
+    CU(cudaStreamSynchronize(s.stream));
+    return SALT_OK;
+}
+
+int salt_b200_verify_submit_packed(salt_b200_t *h, int slot, const salt_packed_chunk_t *pc, int nogap_T0, int lv_T0,
+                                   salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1, char *cigars, int cigar_stride)
+{
+    if (int rc = use_device(h)) return rc;
+    if (slot < 0 || slot >= SALT_SLOTS) return fail(SALT_ERR_ARG, "slot out of range");
+    if (int rc = check_packed(pc, true)) return rc;
+    if (!rec) return fail(SALT_ERR_ARG, "null buffer");
+    Slot &s = h->slot[slot];
+    if (s.pending) return fail(SALT_ERR_ARG, "slot has a verify in flight: call salt_b200_verify_wait first");
+    PackedView v; v.pc = pc; v.base_pos = pc->base_start;
+    while (v.np_lo < pc->n_n && pc->n_pos[v.np_lo] < v.base_pos) ++v.np_lo;
+    if (int rc = grow_view(v, pc->n_reads, true)) return rc;
+    if (int rc = load_packed(h, s, v, true)) return rc;
+    if (!s.n_reads) return SALT_OK;
+    return run_and_download(h, slot, v.n0, v.n1, nogap_T0, lv_T0, rec, acc0, acc1, cigars, cigar_stride);
+}
+
+int salt_b200_verify_batch_packed(salt_b200_t *h, const salt_packed_chunk_t *pc, uint32_t chunk_reads, int nogap_T0, int lv_T0,
+                                  salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1, char *cigars, int cigar_stride)
+{
+    if (int rc = use_device(h)) return rc;
+    if (int rc = check_packed(pc, true)) return rc;
+    if (!rec) return fail(SALT_ERR_ARG, "null buffer");
+    if (chunk_reads == 0) chunk_reads = 100000;          // N_SEQS, aln.h:27
+    int rc = SALT_OK;
+    PackedView v; v.pc = pc; v.base_pos = pc->base_start;
+    while (v.np_lo < pc->n_n && pc->n_pos[v.np_lo] < v.base_pos) ++v.np_lo;
+    v.np_hi = v.np_lo;
+    uint32_t k = 0;
+    for (uint32_t b = 0; b < pc->n_reads && rc == SALT_OK; b += chunk_reads, ++k) {
+        const int si = (int)(k % SALT_SLOTS);
+        if ((rc = finish_verify(h, si)) != SALT_OK) break;
+        const uint32_t m = pc->n_reads - b < chunk_reads ? pc->n_reads - b : chunk_reads;
+        // the next view starts where the last one ended
+        PackedView w; w.pc = pc; w.first = b; w.base_pos = v.base_pos + v.n_bases; w.np_lo = v.np_hi;
+        w.c0 = v.c0 + v.n0; w.c1 = v.c1 + v.n1;
+        if ((rc = grow_view(w, m, true)) != SALT_OK) break;
+        v = w;
+        Slot &sl = h->slot[si];
+        if ((rc = load_packed(h, sl, v, true)) != SALT_OK) break;
+        rc = run_and_download(h, si, v.n0, v.n1, nogap_T0, lv_T0, rec + b, acc0 ? acc0 + v.c0 : nullptr,
+                              acc1 ? acc1 + v.c1 : nullptr, cigars ? cigars + (size_t)b * cigar_stride : nullptr, cigar_stride);
     }
     for (int si = 0; si < SALT_SLOTS; ++si) { const int r2 = finish_verify(h, si); if (rc == SALT_OK) rc = r2; }
     return rc;

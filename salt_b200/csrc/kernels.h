@@ -39,6 +39,21 @@ cudaError_t launch_md_nm(const DevCtx &c, const uint8_t *codes, const uint32_t *
 cudaError_t launch_build_mixref(const char *bases, uint32_t l, const uint32_t *snp_pos, const uint8_t *snp_mask,
                                 size_t n_snp, uint32_t *words, cudaStream_t st);
 
+// transport.cu: the compact chunk format (salt_packed_chunk_t)
+struct Scan3 {                // exclusive prefix sums: out[k][0..n] from n counts each
+    const void *in[3];        // null = every count is uniform[k]
+    int width[3];             // 16 or 32 bits per count
+    uint32_t uniform[3];
+    uint32_t *out[3];
+    size_t n;
+    uint32_t *partial;        // 3 * scan3_blocks(n) words of scratch
+    uint32_t n_blocks;        // filled by the launcher
+};
+uint32_t scan3_blocks(size_t n);
+cudaError_t launch_scan3(Scan3 a, int n_arrays, cudaStream_t st);
+cudaError_t launch_unpack_bases(const uint8_t *in, uint32_t phase, int bits, size_t n_bases, uint8_t *codes,
+                                const uint32_t *n_pos, size_t n_n, uint32_t origin, cudaStream_t st);
+
 // ssw.cu
 struct SswParams {
     int use_pac, n_sym, gapO, gapE, flag, filters, filterd, mask_len;

@@ -89,6 +89,7 @@ template <class F>
 static inline void launch(dim3 grid, dim3 block, size_t smem, F body)
 {
     std::vector<unsigned char> dyn(smem + 64);
+    for (unsigned by = 0; by < grid.y; ++by)
     for (unsigned b = 0; b < grid.x; ++b) {
         CtaState cta;
         cta.warps = std::vector<WarpMon>((block.x + 31) / 32);
@@ -97,8 +98,8 @@ static inline void launch(dim3 grid, dim3 block, size_t smem, F body)
         std::vector<std::thread> th;
         th.reserve(block.x);
         for (unsigned t = 0; t < block.x; ++t)
-            th.emplace_back([&, t, b] {
-                t_threadIdx = dim3(t); t_blockIdx = dim3(b); t_blockDim = block; t_gridDim = grid; t_cta = &cta;
+            th.emplace_back([&, t, b, by] {
+                t_threadIdx = dim3(t); t_blockIdx = dim3(b, by); t_blockDim = block; t_gridDim = grid; t_cta = &cta;
                 body();
             });
         for (auto &x : th) x.join();

@@ -123,6 +123,37 @@ def check_verify_batch(eng, reads, cands, chunk_reads, nogap_T0=3, lv_T0=-1, str
     return want[0]
 
 
+def check_verify_packed(eng, reads_list, cands, chunk_reads, nogap_T0=3, lv_T0=-1, stride=128, variants=None):
+    """The compact transport (salt_packed_chunk_t: 2/4-bit bases, lengths, per-read candidate counts) must give
+    exactly what the plain format gives, for every packing flavour, through views that start mid-byte.
+    reads_list: list of 1-D code arrays (ragged allowed)."""
+    offs0, loci0, offs1, loci1 = cands
+    lens = np.array([len(r) for r in reads_list], np.int64)
+    roffs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    codes = np.concatenate(reads_list).astype(np.uint8) if len(reads_list) else np.zeros(0, np.uint8)
+    eng.set_reads(codes, roffs)
+    want = eng.verify(offs0, loci0, offs1, loci1, nogap_T0, lv_T0, stride)
+    n_variants = 0
+    for bits in (2, 4):
+        for count_bits in (16, 32):
+            for base_start in (0, 3):
+                if variants is not None and (bits, count_bits, base_start) not in variants:
+                    continue
+                pk, keep = eng.packed_chunk(codes, roffs, offs0, loci0, offs1, loci1, bits=bits, count_bits=count_bits,
+                                            base_start=base_start)
+                got = eng.verify_batch_packed(pk, len(loci0), len(loci1), chunk_reads, nogap_T0, lv_T0, stride)
+                for a, b, name in zip(got, want, ("rec", "acc0", "acc1", "cigars")):
+                    assert a.tobytes() == b.tobytes(), (name, bits, count_bits, base_start)
+                n_variants += 1
+    # the synchronous read upload in the compact format feeds the per-pair entry points the same reads
+    pk, keep = eng.packed_chunk(codes, roffs, offs0, loci0, offs1, loci1, bits=2, base_start=1)
+    eng.set_reads_packed(pk)
+    got = eng.verify(offs0, loci0, offs1, loci1, nogap_T0, lv_T0, stride)
+    for a, b, name in zip(got, want, ("rec", "acc0", "acc1", "cigars")):
+        assert a.tobytes() == b.tobytes(), ("set_reads_packed", name)
+    return n_variants
+
+
 def check_host_chunks(eng, hostlib, oracle, g, reads, cands, chunk_reads, nogap_T0=3, lv_T0=-1, max_hits=5, with_tail=False):
     """The host-side C layer (include/salt_host.h): chunk queues through the pipeline slots, then
     query_set_hits / gen_mapq / query_gen_cigar per read -- against the oracle's verify_read."""

@@ -125,6 +125,22 @@ def test_verify_batch_pipeline(emul_lib, oracle):
     pc.check_verify_batch(eng, reads, cands, 1000)
 
 
+def test_verify_packed_transport(emul_lib, oracle):
+    """compact transport: every packing flavour, uniform and ragged read lengths, reads with N, views starting mid-byte"""
+    g, reads, pos, strand, cands = pc.make_world(321, L=100, n_reads=30, per_strand=3, indel_frac=0.4, glen=30000, n_frac=0.02)
+    eng = _engine(emul_lib, g)
+    assert pc.check_verify_packed(eng, [r for r in reads], cands, 7) == 8
+    # ragged: reads cut to different lengths (their candidate lists stay valid loci)
+    rng = np.random.default_rng(5)
+    ragged = [r[:int(rng.integers(37, 101))] for r in reads]
+    pc.check_verify_packed(eng, ragged, cands, 11, lv_T0=3, variants=[(2, 16, 3), (4, 32, 0)])
+    # an empty batch
+    z = np.zeros(1, np.uint32); e = np.zeros(0, np.uint32)
+    pk, keep = eng.packed_chunk(np.zeros(0, np.uint8), z, z, e, z, e)
+    rec, a0, a1, cig = eng.verify_batch_packed(pk, 0, 0, 7)
+    assert len(rec) == 0
+
+
 def test_md_nm(emul_lib, oracle):
     """SAM tail kernel (MD/NM/XV, sam.c:246-328) against the oracle"""
     g = synth.Genome(40000, snp_rate=0.03, seed=15)

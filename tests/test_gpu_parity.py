@@ -306,3 +306,16 @@ def test_ssw_wide_bands_and_end_at_l(oracle):
     eng = _engine(g, pac=False)
     assert pc.check_ssw_wide_bands(eng, oracle, 77, n_reads=700) >= 600
     eng.close()
+
+
+@pytest.mark.gpu
+def test_verify_packed_transport(oracle):
+    """compact transport (2/4-bit bases, lengths, per-read counts) == plain format, all flavours, ragged reads, N bases"""
+    g, reads, pos, strand, cands = pc.make_world(321, L=150, n_reads=5000, per_strand=5, indel_frac=0.3, glen=400000, n_frac=0.01)
+    eng = _engine(g)
+    assert pc.check_verify_packed(eng, [r for r in reads], cands, 700) == 8
+    rng = np.random.default_rng(5)
+    ragged = [r[:int(rng.integers(37, 151))] for r in reads]
+    pc.check_verify_packed(eng, ragged, cands, 1100, lv_T0=3)
+    pc.check_verify_packed(eng, ragged, cands, 100000)
+    eng.close()
