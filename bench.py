@@ -50,13 +50,22 @@ def parse():
     ap.add_argument("--sw-tasks", type=int, default=200_000)
     ap.add_argument("--skip-extras", action="store_true", help="skip the sw/lv kernel sweeps")
     ap.add_argument("--chunk", type=int, default=100_000, help="reads per pipeline chunk in the e2e leg (N_SEQS, aln.h:27)")
+    ap.add_argument("--no-traffic-probe", action="store_true", help="skip the ncu subprocess that measures the dominant kernel's DRAM bytes")
+    ap.add_argument("--traffic-probe-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--probe-dir", default="", help=argparse.SUPPRESS)
+    ap.add_argument("--pe-pairs", type=int, default=200_000, help="pairs in the paired-end pipeline leg (0 = skip)")
     return ap.parse_args()
 
 
 def make_workload(args, seed):
     from salt_b200 import synth
     t0 = time.time()
-    g = synth.Genome(args.genome, snp_rate=args.snp_rate, seed=seed)
+    if args.genome > 500_000_000:
+        # configs[2]-sized reference: block-wise generator, the same genome on every rank (the reference is replicated),
+        # reads differ per rank
+        g = synth.BigGenome(args.genome, snp_rate=args.snp_rate, seed=11, n_records=24)
+    else:
+        g = synth.Genome(args.genome, snp_rate=args.snp_rate, seed=seed)
     n, L = args.reads, args.read_len
     reads = np.empty((n, L), np.uint8); pos = np.empty(n, np.uint32); strand = np.empty(n, np.uint8)
     chunk = 250_000
@@ -174,6 +183,79 @@ def cpu_reference_run(args, wl, n_sample, steps, warmup):
                        "running thresholds, %d host threads, gcc -O2" % (n, len(wl["reads"]), pairs, cores))
 
 
+def traffic_probe_child(path):
+    """Child of traffic_probe(): the device-resident verification stage on the workload the parent saved, three
+    times, so that ncu (which wraps this process) can capture one warm launch of the dominant kernel."""
+    import torch
+    from salt_b200 import api
+    z = np.load(os.path.join(path, "wl.npz"))
+    mixref = np.load(os.path.join(path, "mixref.npy"), mmap_mode="r")
+    eng = api.Engine(mixref, int(z["l"]), None, 0, device=0)
+    n, L = z["reads"].shape
+    eng.set_reads(z["reads"])
+    dev = torch.device("cuda", 0)
+    d = [torch.from_numpy(z[k]).to(dev) for k in ("offs0", "loci0", "offs1", "loci1")]
+    n0, n1 = len(z["loci0"]), len(z["loci1"])
+    d_rec = torch.empty(n * 16, dtype=torch.uint8, device=dev); d_acc = torch.empty(n0 + n1 + 16, dtype=torch.int8, device=dev)
+    for _ in range(3):
+        rc = eng.L.salt_b200_verify_dev(eng.h, d[0].data_ptr(), d[1].data_ptr(), n0, d[2].data_ptr(), d[3].data_ptr(), n1, 3, -1,
+                                        d_rec.data_ptr(), d_acc.data_ptr(), d_acc.data_ptr() + n0, None, 0, None, None)
+        assert rc == 0
+    eng.sync()
+    eng.close()
+
+
+def traffic_probe(wl, timeout_s=420):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE warm nogap_fused launch on this run's workload, measured by
+    an ncu subprocess wrapped around traffic_probe_child (ncu replays the kernel; the number never touches a timing).
+    Returns (bytes, detail dict) or (None, reason)."""
+    import shutil
+    import tempfile
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, {"error": "ncu not found"}
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    path = tempfile.mkdtemp(prefix="salt_bench_", dir=base)
+    try:
+        np.savez(os.path.join(path, "wl.npz"), reads=wl["reads"], offs0=wl["offs0"], loci0=wl["loci0"], offs1=wl["offs1"],
+                 loci1=wl["loci1"], l=np.int64(wl["g"].l))
+        np.save(os.path.join(path, "mixref.npy"), wl["g"].mixref)
+        csv = os.path.join(path, "ncu.csv")
+        metrics = "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct," \
+                  "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed,smsp__issue_active.avg.pct_of_peak_sustained_elapsed"
+        cmd = [ncu, "--metrics", metrics, "--clock-control", "none", "-k", "regex:nogap_fused", "--launch-skip", "2",
+               "--launch-count", "1", "--csv", "--log-file", csv, sys.executable, os.path.abspath(__file__),
+               "--traffic-probe-child", "--probe-dir", path]
+        env = dict(os.environ)
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout_s, env=env)
+        if r.returncode != 0 or not os.path.exists(csv):
+            return None, {"error": "ncu exit %d: %s" % (r.returncode, r.stdout[-300:])}
+        vals = {}
+        import csv as _csv
+        rows = [row for row in _csv.reader(open(csv)) if len(row) > 5]
+        hdr = next(i for i, row in enumerate(rows) if "Metric Name" in row)
+        ci = {name: rows[hdr].index(name) for name in ("Metric Name", "Metric Unit", "Metric Value")}
+        for row in rows[hdr + 1:]:
+            v = float(row[ci["Metric Value"]].replace(",", ""))
+            unit = row[ci["Metric Unit"]].lower()
+            scale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3,
+                     "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "second": 1}.get(unit, 1)
+            vals[row[ci["Metric Name"]]] = v * scale
+        tot = vals.get("dram__bytes_read.sum", 0.0) + vals.get("dram__bytes_write.sum", 0.0)
+        return (tot if tot > 0 else None), {"dram_bytes_read": vals.get("dram__bytes_read.sum"), "dram_bytes_write": vals.get("dram__bytes_write.sum"),
+                                            "ncu_kernel_s": vals.get("gpu__time_duration.sum"),
+                                            "l2_hit_pct": vals.get("lts__t_sector_hit_rate.pct"),
+                                            "l1_lsu_wavefront_pct": vals.get("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+                                            "issue_active_pct": vals.get("smsp__issue_active.avg.pct_of_peak_sustained_elapsed"),
+                                            "how": "ncu subprocess on this run's workload, launch 3 of nogap_fused (warm), --clock-control none"}
+    except Exception as ex:                                # noqa: BLE001 -- the probe is evidence, not the measurement
+        return None, {"error": repr(ex)}
+    finally:
+        shutil.rmtree(path, ignore_errors=True)
+
+
 _REAL_STDOUT = None
 
 
@@ -221,11 +303,14 @@ def _bind_to_gpu_numa_node(local):
 
 def main():
     args = parse()
+    if args.traffic_probe_child:
+        return traffic_probe_child(args.probe_dir)
     _claim_stdout()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    cfg = {"workload": "configs[1]: synthetic %d Mbp genome + %.1f%% SNPs, %d x %d bp SE reads per GPU, %d candidates/read/strand "
-                       "(true locus + decoys), sub 1%%, 2%% reads with an indel" % (args.genome // 1_000_000, args.snp_rate * 100,
+    which = "configs[1]" if args.genome <= 500_000_000 else "configs[2]-sized reference (24 records, snp144-like density), verify stage"
+    cfg = {"workload": "%s: synthetic %d Mbp genome + %.2f%% SNPs, %d x %d bp SE reads per GPU, %d candidates/read/strand "
+                       "(true locus + decoys), sub 1%%, 2%% reads with an indel" % (which, args.genome // 1_000_000, args.snp_rate * 100,
                                                                                   args.reads, args.read_len, args.cands),
            "nogap_T0": 3, "lv_T0": "l_seq/10", "parallelism": "reads sharded per GPU, reference replicated, no collective on the data path",
            "l2": "per-step inputs+outputs (~0.7 GB) exceed the 126 MB L2"}
@@ -250,8 +335,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local)
+    numa = None
     if world > 1:
-        cfg["numa"] = _bind_to_gpu_numa_node(local)       # pinned host buffers next to this rank's GPU
+        numa = _bind_to_gpu_numa_node(local)              # pinned host buffers next to this rank's GPU
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     wl = make_workload(args, seed=11 + rank)
@@ -337,12 +423,14 @@ def main():
     n_lv_pairs = int((np.diff(wl["offs0"].astype(np.int64))[lv_mask].sum() + np.diff(wl["offs1"].astype(np.int64))[lv_mask].sum()))
     n_gapped = int(d_cigcnt[0].item())
 
-    # PCIe copy peaks beside the e2e number (pinned 256 MiB, best of 3)
+    # PCIe copy peaks beside the e2e number (pinned 256 MiB, best of 3), all ranks copying at the same time: the ranks
+    # of one box share the host's memory / PCIe complex, so a rank-local peak would overstate what the pipeline can get
     def copy_peak(to_dev):
         nb = 256 << 20
         a = torch.empty(nb, dtype=torch.uint8).pin_memory(); b = torch.empty(nb, dtype=torch.uint8, device=dev)
         best = 0.0
         for _ in range(3):
+            barrier()
             c0 = torch.cuda.Event(enable_timing=True); c1 = torch.cuda.Event(enable_timing=True)
             c0.record(stream)
             (b.copy_(a, non_blocking=True) if to_dev else a.copy_(b, non_blocking=True))
@@ -351,24 +439,47 @@ def main():
         return best
     pcie_h2d, pcie_d2h = copy_peak(True), copy_peak(False)
 
-    # ---------------- e2e: host buffers through the C ABI
-    def step_host():
-        # the reference's chunk loop (alnse.c:1414-1440) through the asynchronous slots
+    # ---------------- e2e: host buffers through the C ABI, the reference's chunk loop (alnse.c:1414-1440) through the
+    # asynchronous slots.  Headline: the compact transport (2-bit bases + per-read counts, salt_packed_chunk_t);
+    # beside it the plain format (one byte per base + three offset arrays) the reference's own structures map to.
+    pk_bases, pk_npos = api.pack_bases(wl["reads"].reshape(-1), 2)
+    h_bases = pin(pk_bases); h_npos = pin(pk_npos) if len(pk_npos) else None
+    h_c0 = pin(np.diff(wl["offs0"].astype(np.int64)).astype(np.uint16)); h_c1 = pin(np.diff(wl["offs1"].astype(np.int64)).astype(np.uint16))
+    pkc = api.PackedChunkT()
+    pkc.n_reads = n; pkc.base_bits = 2; pkc.bases = h_bases.data_ptr(); pkc.base_start = 0; pkc.lens = None; pkc.l_seq = L
+    pkc.n_pos = h_npos.data_ptr() if h_npos is not None else None; pkc.n_n = len(pk_npos); pkc.count_bits = 16
+    pkc.n_cand[0], pkc.n_cand[1] = h_c0.data_ptr(), h_c1.data_ptr()
+    pkc.loci[0], pkc.loci[1] = h_l0.data_ptr(), h_l1.data_ptr()
+
+    def step_host_packed():
+        ck(lib.salt_b200_verify_batch_packed(h, C.byref(pkc), args.chunk, 3, -1, h_rec.data_ptr(),
+                                             h_acc0.data_ptr(), h_acc1.data_ptr(), h_cig.data_ptr(), 128))
+
+    def step_host_plain():
         ck(lib.salt_b200_verify_batch(h, C.byref(reads_t), C.byref(cands), args.chunk, 3, -1, h_rec.data_ptr(),
                                       h_acc0.data_ptr(), h_acc1.data_ptr(), h_cig.data_ptr(), 128))
-    for _ in range(max(1, args.warmup - 1)):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_host()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    te = torch.tensor([e2e_s], device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
-    h2d = h_codes.numel() + 4 * (h_roffs.numel() + h_o0.numel() + h_o1.numel() + n0 + n1)
+
+    def time_host(fn):
+        for _ in range(max(1, args.warmup - 1)):
+            fn()
+        barrier()
+        eng.launch_count(reset=True)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        barrier()
+        sec = (time.perf_counter() - t0) / args.steps
+        te = torch.tensor([sec], device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return float(te.item()), eng.launch_count() // args.steps
+
+    plain_s, _ = time_host(step_host_plain)
+    rec_plain = h_rec.numpy().copy()
+    e2e_s, e2e_launches = time_host(step_host_packed)
+    assert h_rec.numpy().tobytes() == rec_plain.tobytes(), "compact and plain transport disagree"
+    h2d_plain = h_codes.numel() + 4 * (h_roffs.numel() + h_o0.numel() + h_o1.numel() + n0 + n1)
+    h2d = h_bases.numel() + 4 * len(pk_npos) + 2 * (h_c0.numel() + h_c1.numel()) + 4 * (n0 + n1)
     d2h = n * 16 + n0 + n1 + n_gapped * (128 + 4) + 4
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -376,12 +487,19 @@ def main():
            "data": "synthetic", "config": cfg, "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": world * n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "ms_per_step": e2e_s * 1e3, "chunk_reads": args.chunk, "slots": int(lib.salt_b200_n_slots()),
-                   "pcie_gbs": {"h2d": h2d / e2e_s / 1e9, "d2h": d2h / e2e_s / 1e9, "h2d_copy_peak": pcie_h2d, "d2h_copy_peak": pcie_d2h}},
+                   "gpu_launches_per_step": int(e2e_launches),
+                   "transport": "salt_b200_verify_batch_packed: 2-bit bases, uint16 candidate counts, uint32 loci; pinned host buffers",
+                   "h2d_bytes_per_read": h2d / n,
+                   "pcie_gbs": {"h2d": h2d / e2e_s / 1e9, "d2h": d2h / e2e_s / 1e9, "h2d_copy_peak": pcie_h2d, "d2h_copy_peak": pcie_d2h,
+                                "copy_peak_how": "256 MiB pinned, best of 3, all %d ranks copying concurrently" % world},
+                   "floor_ms": h2d / (pcie_h2d * 1e9) * 1e3,
+                   "plain_format": {"value": world * n / plain_s, "ms_per_step": plain_s * 1e3, "h2d_bytes_per_step": int(h2d_plain),
+                                    "transport": "salt_b200_verify_batch: one byte per base, three uint32 offset arrays"}},
            "pairs_per_step": int(n0 + n1), "pairs_per_s": world * (n0 + n1) / (ms_step * 1e-3),
            # SURVEY 8(d) whole-job figure: DP-cell equivalents of the step (L per ungapped pair, L*(L+4) per LV pair) / time
            "tcups_equivalent": world * ((n0 + n1) * L + n_lv_pairs * L * (L + 4)) / (ms_step * 1e-3) / 1e12,
            "lv_pairs_per_step": n_lv_pairs,
-           "lv_reads_per_step": n_lv, "gapped_primaries_per_step": n_gapped, "kernels_ms": kernels}
+           "lv_reads_per_step": n_lv, "gapped_primaries_per_step": n_gapped, "kernels_ms": kernels, "numa": numa}
 
     if rank == 0:
         peaks = {}
@@ -395,17 +513,19 @@ def main():
         bytes_per_pair = (L + 1) // 2 + 8 + 2          # window nibbles + pair descriptor + result (60 B at L=100)
         mm_ms = kernels.get("nogap_fused", float("nan"))
         ach = (n0 + n1) * bytes_per_pair / (mm_ms * 1e-3) / 1e9
-        # dram__bytes_read+write of that kernel per launch, from the committed ncu --set full capture of this same
-        # workload (scaled by pairs if the run uses another size)
-        traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1k_nogap_traffic.json")))
-            traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * (n0 + n1) / tr["pairs_per_launch"]
-        except Exception:
-            pass
+        traffic, tdetail = (None, {"skipped": True})
+        if not args.no_traffic_probe and world == 1:
+            traffic, tdetail = traffic_probe(wl)
         out["roofline"] = {"kernel": "nogap_fused_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
                            "frac": ach / hbm, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
-                           "algorithmic_bytes_per_pair": bytes_per_pair, "kernel_ms": mm_ms, "dominant_kernel_of_step": dom}
+                           "algorithmic_bytes_per_pair": bytes_per_pair, "kernel_ms": mm_ms, "dominant_kernel_of_step": dom,
+                           "traffic_probe": tdetail,
+                           # what the DRAM actually moved in the kernel's own time (live event timing, not ncu's)
+                           "dram_gbs": (traffic / (mm_ms * 1e-3) / 1e9) if traffic else None,
+                           "dram_frac": (traffic / (mm_ms * 1e-3) / 1e9 / hbm) if traffic else None,
+                           "note": "achieved/frac = ALGORITHMIC bytes / kernel time (HBM-equivalent); dram_gbs/dram_frac = "
+                                   "measured DRAM bytes / kernel time.  When the reference fits the 126 MB L2 the kernel is "
+                                   "L1/issue-bound and dram_frac is far below frac; at GRCh38 size the window gathers miss L2."}
 
     # ---------------- kernel-level extras: LV and SW sweeps (N=1 only)
     # the e2e leg left slot 0 holding its last chunk: the sweeps index the whole batch again

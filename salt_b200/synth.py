@@ -81,6 +81,52 @@ class Genome:
         return "".join("ACGT"[c] if m else "N" for c, m in zip(self.codes, self.masks))
 
 
+class _MaskView:
+    """g.masks[idx] for a genome that keeps only the packed words: the allele mask is the mixRef nibble."""
+
+    def __init__(self, words):
+        self.words = words
+
+    def __getitem__(self, idx):
+        idx = np.asarray(idx, np.int64)
+        return ((self.words[idx >> 3] >> (4 * (idx & 7)).astype(np.uint32)) & 15).astype(np.uint8)
+
+
+class BigGenome:
+    """Genome for reference sizes where whole-array temporaries do not fit (BASELINE configs[2]: 3.1 Gbp, snp144-like
+    density): generated and packed block by block, same layouts and same SNP rule as Genome; `n_records` equal records
+    mimic the 24 FASTA records of GRCh38 (the records are simply concatenated, as bns/mixRef do: l = sum of lengths).
+    Keeps codes (1 B/base), mixref (4 bit/base) and pac (2 bit/base); masks are read back from mixref."""
+
+    def __init__(self, length, snp_rate=0.0047, seed=1, multi_allele=0.03, n_records=24, block=1 << 26):
+        self.l = int(length)
+        self.n_records = n_records
+        self.record_len = [self.l // n_records + (1 if i < self.l % n_records else 0) for i in range(n_records)]
+        self.codes = np.empty(self.l, np.uint8)
+        self.mixref = np.zeros((self.l + 7) // 8, np.uint32)
+        self.pac = np.zeros((self.l + 3) // 4, np.uint8)
+        n_snp = 0
+        for bi, b0 in enumerate(range(0, self.l, block)):          # block is a multiple of 8: whole words and bytes
+            b1 = min(self.l, b0 + block)
+            rng = np.random.default_rng([seed, bi])
+            c = rng.integers(0, 4, b1 - b0, dtype=np.uint8)
+            self.codes[b0:b1] = c
+            m = np.left_shift(np.uint8(1), c)
+            k = int((b1 - b0) * snp_rate)
+            if k:
+                sp = np.unique(rng.integers(0, b1 - b0, k))
+                alt = (c[sp] + rng.integers(1, 4, len(sp), dtype=np.uint8)) & 3
+                m[sp] |= np.left_shift(np.uint8(1), alt)
+                two = rng.random(len(sp)) < multi_allele
+                alt2 = (c[sp] + rng.integers(1, 4, len(sp), dtype=np.uint8)) & 3
+                m[sp[two]] |= np.left_shift(np.uint8(1), alt2[two])
+                n_snp += len(sp)
+            self.mixref[b0 >> 3:(b1 + 7) >> 3] = pack_mixref(m)
+            self.pac[b0 >> 2:(b1 + 3) >> 2] = pack_pac(c)
+        self.n_snp = n_snp
+        self.masks = _MaskView(self.mixref)
+
+
 def sample_reads(g, n, L, seed=2, sub_rate=0.01, indel_frac=0.0, max_indel=3, n_frac=0.0):
     """Return (reads[n,L] codes in sequencing orientation, true_pos[n], strand[n]).
 

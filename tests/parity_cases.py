@@ -154,6 +154,59 @@ def check_verify_packed(eng, reads_list, cands, chunk_reads, nogap_T0=3, lv_T0=-
     return n_variants
 
 
+class SparseWorld:
+    """A reference of l bases that is zero (N) everywhere except around a few loci: large coordinates without
+    gigabytes of random bases.  .mixref / .l like synth.Genome; reads come from the filled windows."""
+
+    def __init__(self, l, centres, L, seed, span=480):
+        rng = np.random.default_rng(seed)
+        self.l = int(l)
+        self.mixref = np.zeros((self.l + 7) // 8 + 1, np.uint32)        # one spare word: the oracle may look at position l
+        self.windows = []
+        for c in centres:
+            a = max(0, min(int(c) - span // 2, self.l - 1))
+            b = min(self.l, a + span)
+            m = synth.fuzz_masks(b - a, int(rng.integers(1 << 30)), snp=0.03, nfrac=0.002)
+            for i, v in enumerate(m):
+                p = a + i
+                self.mixref[p >> 3] |= np.uint32(int(v) << (4 * (p & 7)))
+            self.windows.append((a, b, m))
+        self.L = L
+
+    def reads_and_candidates(self, per_window, seed, extra_loci=()):
+        """per_window reads from every window (forward strand, a few edits), each with its true locus, small shifts,
+        decoys inside other windows and the `extra_loci` (end-of-reference / beyond-the-end cases) on both strands."""
+        rng = np.random.default_rng(seed)
+        L = self.L
+        reads, cand0, cand1 = [], [], []
+        for (a, b, m) in self.windows:
+            for _ in range(per_window):
+                if b - a < L + 12:
+                    continue
+                o = int(rng.integers(0, b - a - L - 8))
+                kind = rng.random()
+                rd = synth.fuzz_read_from_masks(m[o:], L, rng, sub=0.015, indel=0.012 if kind < 0.4 else 0.0, nfrac=0.003)
+                if rng.random() < 0.5:
+                    reads.append(rd); mine = cand0
+                    other = cand1
+                else:
+                    reads.append(synth.revcomp(rd)); mine = cand1
+                    other = cand0
+                true = a + o
+                decoys = [w[0] + int(rng.integers(0, max(1, w[1] - w[0] - L))) for w in self.windows[::3]]
+                lst = sorted(set([true, max(0, true - 2), true + 1, true + 3] + decoys + list(extra_loci)))
+                mine.append(np.array(lst, np.uint32))
+                other.append(np.array(sorted(set(decoys[:4] + list(extra_loci))), np.uint32))
+        reads = np.array(reads, np.uint8)
+
+        def csr(lists):
+            offs = np.zeros(len(lists) + 1, np.uint32)
+            offs[1:] = np.cumsum([len(x) for x in lists])
+            return offs, (np.concatenate(lists) if lists else np.zeros(0, np.uint32)).astype(np.uint32)
+        o0, l0 = csr(cand0); o1, l1 = csr(cand1)
+        return reads, (o0, l0, o1, l1)
+
+
 def check_host_chunks(eng, hostlib, oracle, g, reads, cands, chunk_reads, nogap_T0=3, lv_T0=-1, max_hits=5, with_tail=False):
     """The host-side C layer (include/salt_host.h): chunk queues through the pipeline slots, then
     query_set_hits / gen_mapq / query_gen_cigar per read -- against the oracle's verify_read."""

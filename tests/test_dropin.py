@@ -140,3 +140,50 @@ def test_mixref_builder_matches_salt_idx(tmp_path, oracle):
         words[-1] &= np.uint32((1 << (4 * (l % 8))) - 1)
     assert len(got) == len(words) and np.array_equal(got, words)
     assert (np.bitwise_count(words) > 8).sum() > 100 if hasattr(np, "bitwise_count") else True      # SNP sites carry extra allele bits
+
+
+C0 = os.path.join(REFDIR, "config0")
+
+
+def _config0_index(d):
+    """BASELINE configs[0] as shipped (Test/Run_test/run_test.sh): the bundled two-copy lambda genome, reads from the
+    bundled wgsim with -S 11, the SNP table from the script's own awk line -- staged by oracle/Makefile under
+    oracle/_ref/config0 together with the reference program's SAM (-t 4).  The index is built here (run_test.sh:32)."""
+    if not (_have() and os.path.exists(os.path.join(C0, "pe.sam"))):
+        pytest.skip("oracle/_ref/config0 not staged (reference tree absent at build time)")
+    _run([os.path.join(REFDIR, "salt-idx"), "-k", "19", os.path.join(C0, "Genome.fa"), os.path.join(C0, "hapmap.txt"), "idx"],
+         d, os.path.join(d, "idx.log"))
+
+
+def _same_sam(want_path, got_path, min_lines):
+    want, got = _sam_body(want_path), _sam_body(got_path)
+    assert len(want) == len(got) and len(want) >= min_lines, (len(want), len(got))
+    for i, (a, b) in enumerate(zip(want, got)):
+        assert a == b, (i, a, b)
+    return [ln.split("\t") for ln in want if ln and not ln.startswith("@")]
+
+
+@pytest.mark.parametrize("threads", ["4", "1"])
+def test_config0_se_sam_identical(tmp_path, threads):
+    """run_se_test.sh:12 flags on the bundled genome: every read ties between the two lambda copies (strand-1-wins and
+    first-hit rules decide the primary), 5 % mutated reads against their own SNP table"""
+    d = str(tmp_path)
+    _config0_index(d)
+    flags = ["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500", "-t", threads]
+    err = _run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", os.path.join(C0, "Read1.fq")], d, os.path.join(d, "gpu.sam"))
+    assert "verification on libsalt_b200" in err
+    body = _same_sam(os.path.join(C0, "se.sam"), os.path.join(d, "gpu.sam"), 20000)
+    assert sum(1 for f in body if any(x.startswith("XA:") for x in f[11:])) >= 15000      # the duplicate copy is always an alternate
+
+
+@pytest.mark.parametrize("threads", ["4"])
+def test_config0_pe_sam_identical(tmp_path, threads):
+    """run_pe_test.sh:14 flags (what run_test.sh actually runs, :37)"""
+    d = str(tmp_path)
+    _config0_index(d)
+    flags = ["-d", "-p", "-e", "-l", "100", "-c", "-a", "350", "-b", "650", "-r", "5", "-t", threads]
+    err = _run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", os.path.join(C0, "Read1.fq"), os.path.join(C0, "Read2.fq")],
+               d, os.path.join(d, "gpu.sam"), env={"SALT_DROPIN_PLAN": "2"})
+    assert "verification on libsalt_b200" in err
+    body = _same_sam(os.path.join(C0, "pe.sam"), os.path.join(d, "gpu.sam"), 40000)
+    assert sum(1 for f in body if int(f[1]) & 2) >= 30000

@@ -319,3 +319,78 @@ def test_verify_packed_transport(oracle):
     pc.check_verify_packed(eng, ragged, cands, 1100, lv_T0=3)
     pc.check_verify_packed(eng, ragged, cands, 100000)
     eng.close()
+
+
+@pytest.mark.gpu
+def test_verify_max_list_lengths(oracle):
+    """the longest lists the reference allows: max_locate = 1000 candidates per read in SE (aln.c:47, alnse.c:678) and
+    MAX_LOC_POS = 262144 per strand in PE (alnse.c:42,533), with duplicates everywhere a lane group / chunk boundary
+    could fall; one of the huge-list reads only matches with a gap, so the gapped stage sees all 524 288 pairs"""
+    L = 100
+    g, reads, pos, strand, cands = pc.make_world(4242, glen=3_000_000, L=L, n_reads=24, per_strand=4, indel_frac=0.0, sub_rate=0.01)
+    rng = np.random.default_rng(99)
+    # read 1 gets a 2-base deletion so that no ungapped candidate passes
+    src = synth.unpack_mixref(g.mixref, int(pos[1]), L + 8)
+    code = np.array([[b for b in range(4) if (int(m) >> b) & 1][0] if m else 0 for m in src], np.uint8)
+    rd = np.concatenate([code[:50], code[52:L + 2]])
+    reads[1] = synth.revcomp(rd) if strand[1] else rd
+    lists = [[], []]
+    hi = g.l - L - 5
+    for r in range(len(reads)):
+        want = 262144 if r < 2 else (500 if r < 12 else 6)
+        for s_ in (0, 1):
+            loci = np.unique(rng.integers(0, hi, want + want // 8))[:want].astype(np.int64)
+            if strand[r] == s_:
+                loci[rng.integers(0, len(loci))] = int(pos[r])
+                loci[rng.integers(0, len(loci))] = int(pos[r]) + 1
+            loci.sort()
+            step = 4093 if want > 1000 else 37
+            loci[step::step] = loci[step - 1:-1:step]            # duplicates (alnse.c:762 skips pos1 == pos0)
+            if want >= 500:
+                loci[-1] = g.l + 7; loci[-2] = g.l - 20           # past the end / window leaving the reference
+            lists[s_].append(loci.astype(np.uint32))
+
+    def csr(ls):
+        offs = np.zeros(len(ls) + 1, np.uint32); offs[1:] = np.cumsum([len(x) for x in ls])
+        return offs, np.concatenate(ls)
+    o0, l0 = csr(lists[0]); o1, l1 = csr(lists[1])
+    eng = _engine(g)
+    eng.set_reads(reads)
+    st = pc.check_verify(eng, oracle, g, reads, (o0, l0, o1, l1), 3, -1)
+    assert st["lv_ran"] >= 1 and st["gapped"] >= 1 and st["mapped"] >= 20
+    pc.check_verify(eng, oracle, g, reads, (o0, l0, o1, l1), 3, 3)
+    # the same lists through the chunk pipeline and the compact transport (32-bit counts: 262144 > 65535)
+    pc.check_verify_batch(eng, reads, (o0, l0, o1, l1), 5)
+    pc.check_verify_packed(eng, [r for r in reads], (o0, l0, o1, l1), 5, variants=[(2, 32, 3)])
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_large_coordinates(oracle):
+    """a reference longer than 2^31 bases: loci just below / across 2^31, in the last KiB before l, pos + L + 4 >= l,
+    pos >= l and pos near 2^32 -- the 32-bit position arithmetic of every kernel on the path"""
+    L = 100
+    l = (1 << 31) + 12_345_677
+    centres = [300, (1 << 31) - 200, (1 << 31) - 40, (1 << 31) + 250, (1 << 30) + 77, 3_000_000_001 % l, l - 900, l - 245, l - 60,
+               (1 << 31) + 8_000_000, 123_456_789, l - 5000]
+    w = pc.SparseWorld(l, centres, L, seed=5)
+    extra = [l - L - 4, l - L - 3, l - L, l - L + 1, l - 1, l, l + 5, 0xFFFFFFF0, 0xFFFFFFFF - L]
+    reads, cands = w.reads_and_candidates(12, seed=6, extra_loci=extra)
+    eng = api.Engine(w.mixref, w.l, None, 0, device=0)
+    eng.set_reads(reads)
+    st = pc.check_verify(eng, oracle, w, reads, cands, 3, -1)
+    assert st["mapped"] >= 60 and st["gapped"] >= 5
+    pc.check_verify(eng, oracle, w, reads, cands, 3, 3)
+    # per-pair entry points on the same loci
+    pairs = pc.flat_pairs(cands, len(reads))
+    pc.check_mismatch(eng, oracle, w, reads, pairs, 3)
+    pc.check_lv(eng, oracle, w, reads, pairs[::3], 10)
+    # mate-rescue windows at large coordinates, one of them clamped to end == l
+    wins = np.zeros(len(reads), api.WIN_DT)
+    offs0, loci0, offs1, loci1 = cands
+    for i in range(len(reads)):
+        a, b, _ = w.windows[i // 12] if i // 12 < len(w.windows) else w.windows[-1]
+        wins[i] = ((i << 1) | (0 if offs0[i + 1] - offs0[i] > offs1[i + 1] - offs1[i] else 1), a, min(b + 30, l))
+    gapped = pc.check_ssw(eng, oracle, w, reads, wins, False, api.salt_score_mat2(), 16)
+    assert gapped >= 3
+    eng.close()
