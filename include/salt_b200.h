@@ -231,6 +231,54 @@ int salt_b200_verify_submit_packed(salt_b200_t *h, int slot, const salt_packed_c
 int salt_b200_verify_batch_packed(salt_b200_t *h, const salt_packed_chunk_t *pc, uint32_t chunk_reads, int nogap_T0, int lv_T0,
                                   salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1, char *cigars, int cigar_stride);
 
+/* ---- seeding + locate on the device ------------------------------------
+ * The reference spends > 90 % of its time producing the candidate lists (alnse_seed_overlap, alnse.c:199-312;
+ * alnse_locate_alt, alnse.c:633-731).  With its FM-indexes resident in HBM the engine produces the identical
+ * sorted lists itself, so a chunk needs only its reads uploaded and the lists never cross the host link.
+ *
+ * salt_fm_index_t carries the arrays exactly as the reference's loaders leave them in memory
+ * (indexio.c:23-50): the BWA-layout BWT and sampled SA of the primary reference (bwt.h:44-57: PREFIX.C.bwt,
+ * PREFIX.C.sa; sa[0] = (uint32_t)-1, bwtio.c:46), the 12-mer lookup table (lookup.h:21-25: PREFIX.C.lkt) and the
+ * backward SNP-context index (rbwt.h:60-80: PREFIX.R.backward.bwt / .occ / .sa).  cum[0] = 0 as Rbwt_restore_bwt
+ * sets it (rbwt.c:262). */
+typedef struct {
+    const uint32_t *c_bwt; size_t c_bwt_words;           /* bwt_t::bwt, bwt_size */
+    uint32_t c_primary, c_seq_len, c_L2[5];
+    const uint32_t *c_sa; uint32_t c_n_sa, c_sa_intv;
+    const uint32_t *lkt; uint32_t lkt_len;                /* lookupTable_t::item (4^lkt_len + 1 entries), maxLookupLen */
+    const uint32_t *r_bwt; size_t r_bwt_words;            /* rbwt_t::bwtCode, bwtSizeInWord */
+    const uint32_t *r_occ; size_t r_occ_words;            /* occValue, occSizeInWord */
+    const uint32_t *r_occ_major; size_t r_occ_major_words;
+    const uint32_t *r_sa_sharp; size_t r_n_sa_sharp;      /* saValueSharp, saValueSizeSharp */
+    uint32_t r_cum[6], r_inv_sa0, r_text_len;             /* cumulativeFreq, inverseSa0, textLength */
+} salt_fm_index_t;
+
+/* aln_opt_t fields the seeding reads (aln.h:121-151): l_seed (persisted by the indexer in PREFIX.R.seedLen),
+ * l_overlap (defaults to l_seed), max_seed (-n), max_locate (-m), seed_only_ref (-R). */
+typedef struct { int l_seed, l_overlap, max_seed, max_locate, seed_only_ref; } salt_seed_opt_t;
+
+/* Upload the indexes once (the handle keeps its own copy). */
+int salt_b200_set_index(salt_b200_t *h, const salt_fm_index_t *ix);
+
+/* alnse_seed_overlap + alnse_locate_alt for both strands of every read resident in `slot` (uploaded by
+ * salt_b200_set_reads[_packed]; slot 0 for the synchronous entry points).  The sorted lists stay on the device as the
+ * slot's candidate lists -- salt_b200_verify_seeded consumes them in place -- and are optionally downloaded:
+ * offs0 / offs1 (n_reads + 1 each) and loci0 / loci1 (cap0 / cap1 entries of room; SALT_ERR_NOMEM if a strand has
+ * more) may be NULL.  *n0 / *n1 receive the totals.  Limits: at most 64 seed starts per strand
+ * ((l_seq - l_seed) / l_overlap + 1), max_locate <= 16384, l_seed >= the lookup length. */
+int salt_b200_seed_locate(salt_b200_t *h, int slot, const salt_seed_opt_t *opt, uint32_t *offs0, uint32_t *offs1,
+                          uint32_t *loci0, size_t cap0, uint32_t *loci1, size_t cap1, size_t *n0, size_t *n1);
+
+/* salt_b200_verify on the lists salt_b200_seed_locate left in the slot.  acc0 / acc1 need the totals it reported. */
+int salt_b200_verify_seeded(salt_b200_t *h, int slot, int nogap_T0, int lv_T0, salt_verify_out_t *rec,
+                            int8_t *acc0, int8_t *acc1, char *cigars, int cigar_stride);
+
+/* The whole single-end stage of alnse_overlap_alt (alnse.c:1045-1100) for a batch in the compact transport format
+ * (n_cand / loci of `pc` are not read): per chunk of chunk_reads reads, upload the reads, seed, locate, verify, and
+ * download the per-read records (and CIGARs).  Chunks go through the pipeline slots like salt_b200_verify_batch. */
+int salt_b200_align_batch_packed(salt_b200_t *h, const salt_packed_chunk_t *pc, const salt_seed_opt_t *opt, uint32_t chunk_reads,
+                                 int nogap_T0, int lv_T0, salt_verify_out_t *rec, char *cigars, int cigar_stride);
+
 /* Landau-Vishkin work mapping: 0 = automatic (one thread per pair with all diagonals in
  * registers for k <= 15 inside the verify stage, one warp per pair with lanes over diagonals
  * beyond that and on flat pair lists), 1 = always one warp (or sub-warp group) per pair,

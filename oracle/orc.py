@@ -373,3 +373,40 @@ class RefIdx:
         rc = self.lib.build_mixRef(fa_path.encode(), snp_path.encode(), out_path.encode())
         raw = np.fromfile(out_path, np.uint32)
         return raw[1:].copy(), int(raw[0]), rc
+
+
+class SeedRef:
+    """The reference's own seeding + locate and index loader (oracle/_ref/libsaltref_seed.so, built from the unmodified
+    sources by oracle/Makefile around oracle/dropin/seed_harness.c): the oracle of row f1."""
+
+    PATH = os.path.join(HERE, "_ref", "libsaltref_seed.so")
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(cls.PATH)
+
+    def __init__(self, prefix):
+        self.lib = C.CDLL(self.PATH)
+        self.lib.seedref_open.restype = C.c_void_p
+        self.lib.seedref_open.argtypes = [C.c_char_p]
+        self.lib.seedref_close.argtypes = [C.c_void_p]
+        self.lib.seedref_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]
+        self.ix = self.lib.seedref_open(prefix.encode())
+
+    def run(self, codes, roffs, l_seed, l_overlap, max_seed, max_locate, seed_only_ref=0):
+        codes = np.ascontiguousarray(codes, np.uint8).reshape(-1); roffs = np.ascontiguousarray(roffs, np.uint32)
+        n = len(roffs) - 1
+        cap = n * max_locate + 16
+        offs0 = np.zeros(n + 1, np.uint32); offs1 = np.zeros(n + 1, np.uint32)
+        loci0 = np.zeros(cap, np.uint32); loci1 = np.zeros(cap, np.uint32)
+        rc = self.lib.seedref_run(self.ix, codes.ctypes.data, roffs.ctypes.data, n, l_seed, l_overlap if l_overlap > 0 else l_seed,
+                                  max_seed, max_locate, seed_only_ref, offs0.ctypes.data, loci0.ctypes.data, cap,
+                                  offs1.ctypes.data, loci1.ctypes.data, cap)
+        assert rc == 0
+        return offs0, loci0[:offs0[-1]].copy(), offs1, loci1[:offs1[-1]].copy()
+
+    def close(self):
+        if self.ix:
+            self.lib.seedref_close(self.ix)
+            self.ix = None

@@ -94,6 +94,13 @@ def _declare(L):
         L.salt_b200_set_reads_packed.argtypes = [vp, C.POINTER(PackedChunkT)]
         L.salt_b200_verify_submit_packed.argtypes = [vp, i32, C.POINTER(PackedChunkT), i32, i32, vp, vp, vp, vp, i32]
         L.salt_b200_verify_batch_packed.argtypes = [vp, C.POINTER(PackedChunkT), C.c_uint32, i32, i32, vp, vp, vp, vp, i32]
+    if hasattr(L, "salt_b200_set_index"):
+        from .index_io import FmIndexT, SeedOptT
+        szp = C.POINTER(C.c_size_t)
+        L.salt_b200_set_index.argtypes = [vp, C.POINTER(FmIndexT)]
+        L.salt_b200_seed_locate.argtypes = [vp, i32, C.POINTER(SeedOptT), vp, vp, vp, sz, vp, sz, szp, szp]
+        L.salt_b200_verify_seeded.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32]
+        L.salt_b200_align_batch_packed.argtypes = [vp, C.POINTER(PackedChunkT), C.POINTER(SeedOptT), C.c_uint32, i32, i32, vp, vp, i32]
     L.salt_b200_set_max_window.argtypes = [vp, i32]
     L.salt_b200_set_lv_mapping.argtypes = [vp, i32]
     L.salt_b200_set_lv_filter.argtypes = [vp, i32]
@@ -354,6 +361,45 @@ class Engine:
         pc.loci[0] = _ptr(keep["loci0"]) if len(keep["loci0"]) else None
         pc.loci[1] = _ptr(keep["loci1"]) if len(keep["loci1"]) else None
         return pc, keep
+
+    # ---- seeding + locate (row f1) --------------------------------------------------------
+    def set_index(self, fm):
+        """fm: index_io.FmIndex (kept alive by the caller until this returns; the engine keeps its own copy)."""
+        st = fm.struct()
+        self._ck(self.L.salt_b200_set_index(self.h, C.byref(st)))
+
+    @staticmethod
+    def seed_opt(l_seed, l_overlap=0, max_seed=50, max_locate=1000, seed_only_ref=0):
+        from .index_io import SeedOptT
+        return SeedOptT(int(l_seed), int(l_overlap) if l_overlap > 0 else int(l_seed), int(max_seed), int(max_locate), int(seed_only_ref))
+
+    def seed_locate(self, opt, slot=0, download=True):
+        """alnse_seed_overlap + alnse_locate_alt for the reads in `slot`: (offs0, loci0, offs1, loci1) or just the totals."""
+        n0 = C.c_size_t(0); n1 = C.c_size_t(0)
+        self._ck(self.L.salt_b200_seed_locate(self.h, int(slot), C.byref(opt), None, None, None, 0, None, 0, C.byref(n0), C.byref(n1)))
+        if not download:
+            return n0.value, n1.value
+        offs0 = np.zeros(self.n_reads + 1, np.uint32); offs1 = np.zeros(self.n_reads + 1, np.uint32)
+        loci0 = np.zeros(n0.value, np.uint32); loci1 = np.zeros(n1.value, np.uint32)
+        self._ck(self.L.salt_b200_seed_locate(self.h, int(slot), C.byref(opt), _ptr(offs0), _ptr(offs1), _ptr(loci0), len(loci0),
+                                              _ptr(loci1), len(loci1), C.byref(n0), C.byref(n1)))
+        return offs0, loci0, offs1, loci1
+
+    def verify_seeded(self, n0, n1, nogap_T0=3, lv_T0=-1, cigar_stride=128, slot=0):
+        rec = np.zeros(self.n_reads, VERIFY_DT)
+        acc0 = np.empty(n0, np.int8); acc1 = np.empty(n1, np.int8)
+        cig = np.zeros((self.n_reads, cigar_stride), np.uint8)
+        self._ck(self.L.salt_b200_verify_seeded(self.h, int(slot), int(nogap_T0), int(lv_T0), _ptr(rec), _ptr(acc0), _ptr(acc1),
+                                                _ptr(cig), int(cigar_stride)))
+        return rec, acc0, acc1, cig
+
+    def align_batch_packed(self, pc, opt, chunk_reads=100000, nogap_T0=3, lv_T0=-1, cigar_stride=128):
+        n = int(pc.n_reads)
+        rec = np.zeros(n, VERIFY_DT)
+        cig = np.zeros((n, cigar_stride), np.uint8)
+        self._ck(self.L.salt_b200_align_batch_packed(self.h, C.byref(pc), C.byref(opt), int(chunk_reads), int(nogap_T0), int(lv_T0),
+                                                     _ptr(rec), _ptr(cig), int(cigar_stride)))
+        return rec, cig
 
     def set_reads_packed(self, pc):
         self._ck(self.L.salt_b200_set_reads_packed(self.h, C.byref(pc)))

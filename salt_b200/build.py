@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsalt_b200.so")
-SOURCES = ["engine.cu", "verify.cu", "ssw.cu", "samtail.cu", "mixref.cu", "transport.cu"]
+SOURCES = ["engine.cu", "verify.cu", "ssw.cu", "samtail.cu", "mixref.cu", "transport.cu", "seed.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "--use_fast_math"]

@@ -66,6 +66,10 @@ struct Slot {
     uint32_t *d_coffs(int strand) const { return offs3.as<uint32_t>() + (size_t)(strand + 1) * ((size_t)n_reads + 1); }
     DBuf c_loci0, c_loci1, vpairs, acc, rec, lvlist, ciglist, counters, cig, fpairs, fslots, lvreads;
     DBuf pk_bases, pk_lens, pk_cnt, pk_npos, pk_scan;          // compact transport (salt_packed_chunk_t): raw uploads + scan scratch
+    DBuf sd_sai, sd_counts, sd_lists;                          // seeding scratch: intervals, per-strand counts, fixed-stride lists
+    uint32_t *h_tot = nullptr;                                  // pinned: the two list totals of a seeded chunk
+    size_t seeded_n0 = 0, seeded_n1 = 0; int seeded = 0;        // 1: totals in flight, 2: lists gathered into c_loci0/1
+    int seed_max_locate = 0;
     // asynchronous verify in flight: where the compact CIGAR list has to be scattered to
     bool pending = false;
     char *u_cigars = nullptr; int u_stride = 0;
@@ -80,12 +84,14 @@ struct Slot {
     {
         DBuf *all[] = {&codes, &offs3, &rd4, &rd_len, &c_loci0, &c_loci1, &vpairs, &acc, &rec,
                        &lvlist, &ciglist, &counters, &cig, &fpairs, &fslots, &lvreads,
-                       &pk_bases, &pk_lens, &pk_cnt, &pk_npos, &pk_scan};
+                       &pk_bases, &pk_lens, &pk_cnt, &pk_npos, &pk_scan, &sd_sai, &sd_counts, &sd_lists};
         for (DBuf *b : all) b->release();
         if (h_stage) cudaFreeHost(h_stage);
         h_stage = nullptr; h_stage_cap = 0;
         if (h_offs) cudaFreeHost(h_offs);
         h_offs = nullptr; h_offs_cap = 0;
+        if (h_tot) cudaFreeHost(h_tot);
+        h_tot = nullptr;
         for (int i = 0; i < 7; ++i) if (ev_verify[i]) { cudaEventDestroy(ev_verify[i]); ev_verify[i] = nullptr; }
         if (stream && own_stream) cudaStreamDestroy(stream);
         stream = nullptr;
@@ -106,6 +112,8 @@ struct salt_b200 {
     int lv_filter = 1;                      // pigeonhole filter in front of Landau-Vishkin (salt_b200_set_lv_filter)
     // staging / scratch of the synchronous per-pair and SSW entry points (slot 0's stream)
     DBuf pairs, out8, kbuf, cig, wins, sswout, sswcig, sswscratch, sswovf, md_in, md_cig, md_str, md_xv, md_out;
+    DBuf ix_cbwt, ix_csa, ix_lkt, ix_rbwt, ix_rocc, ix_rmaj, ix_rsa;      // FM-indexes (salt_b200_set_index)
+    FmIndexDev fm{}; bool have_index = false;
     uint64_t launches = 0;
     int lv_mapping = 0;         // 0 = auto, 1 = warp per pair, 2 = thread per pair (salt_b200_set_lv_mapping)
     int max_window = 1024;      // widest rescue window the SSW scratch is sized for
@@ -435,6 +443,71 @@ int load_packed(salt_b200_t *h, Slot &s, const PackedView &v, bool with_cands)
     return SALT_OK;
 }
 
+// ---- seeding + locate (row f1) -----------------------------------------------------------------------
+int check_seed_opt(const salt_b200_t *h, const Slot &s, const salt_seed_opt_t *o, int *max_seeds)
+{
+    if (!h->have_index) return fail(SALT_ERR_ARG, "no FM-index uploaded: call salt_b200_set_index first");
+    if (!o) return fail(SALT_ERR_ARG, "seed options are null");
+    if (o->l_seed < h->fm.l_lkt || o->l_seed > 1024) return fail(SALT_ERR_ARG, "l_seed must be at least the lookup length");
+    if (o->l_overlap < 1) return fail(SALT_ERR_UNSUPPORTED, "l_overlap < 1: the reference's non-overlap seeding is not served");
+    if (o->max_seed < 0) return fail(SALT_ERR_ARG, "max_seed must be >= 0");
+    if (o->max_locate < 1 || o->max_locate > 16384) return fail(SALT_ERR_UNSUPPORTED, "max_locate must be in 1..16384");
+    const int ms = s.l_max >= (uint32_t)o->l_seed ? (int)((s.l_max - (uint32_t)o->l_seed) / (uint32_t)o->l_overlap) + 1 : 1;
+    if (ms > 64) return fail(SALT_ERR_UNSUPPORTED, "more than 64 seed starts per strand");
+    *max_seeds = ms;
+    return SALT_OK;
+}
+
+// Phase A of a seeded chunk: seed, locate, scan the counts into the slot's candidate offsets, start the download of
+// the two totals.  Asynchronous.
+int seed_enqueue(salt_b200_t *h, int si, const salt_seed_opt_t *o)
+{
+    Slot &s = h->slot[si];
+    int max_seeds = 1;
+    if (int rc = check_seed_opt(h, s, o, &max_seeds)) return rc;
+    const uint32_t n = s.n_reads;
+    s.seeded = 0; s.seeded_n0 = s.seeded_n1 = 0; s.seed_max_locate = o->max_locate;
+    if (!s.h_tot) CU(cudaMallocHost(&s.h_tot, 16));
+    s.h_tot[0] = s.h_tot[1] = 0;
+    if (!n) { s.seeded = 1; return SALT_OK; }
+    SeedOpt so{o->l_seed, o->l_overlap, o->max_seed, o->max_locate, o->seed_only_ref};
+    CU(s.sd_sai.need(seed_sai_bytes(n, max_seeds)));
+    CU(s.sd_counts.need((size_t)n * 2 * 4 + 16));
+    CU(s.sd_lists.need((size_t)n * 2 * (size_t)o->max_locate * 4 + 16));
+    CU(s.pk_scan.need(3 * (size_t)scan3_blocks(n) * 4 + 16));
+    CU(launch_seed(h->fm, so, s.codes.as<uint8_t>(), s.d_roffs(), n, max_seeds, s.sd_sai.as<SeedSai>(), s.stream));
+    CU(launch_locate(h->fm, so, s.d_roffs(), n, max_seeds, h->l, s.sd_sai.as<SeedSai>(), s.sd_counts.as<uint32_t>(),
+                     s.sd_lists.as<uint32_t>(), s.stream));
+    Scan3 sc{};
+    sc.n = n; sc.partial = s.pk_scan.as<uint32_t>();
+    sc.in[0] = s.sd_counts.as<uint32_t>(); sc.in[1] = s.sd_counts.as<uint32_t>() + n; sc.width[0] = sc.width[1] = 32;
+    sc.out[0] = s.d_coffs(0); sc.out[1] = s.d_coffs(1);
+    CU(launch_scan3(sc, 2, s.stream));
+    CU(cudaMemcpyAsync(&s.h_tot[0], s.d_coffs(0) + n, 4, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaMemcpyAsync(&s.h_tot[1], s.d_coffs(1) + n, 4, cudaMemcpyDeviceToHost, s.stream));
+    h->launches += 5;
+    s.offs_merged = false;
+    s.seeded = 1;
+    return SALT_OK;
+}
+
+// Phase B: wait for the totals, gather the fixed-stride lists into the slot's CSR candidate arrays.
+int seed_finish(salt_b200_t *h, int si)
+{
+    Slot &s = h->slot[si];
+    if (s.seeded != 1) return s.seeded == 2 ? SALT_OK : fail(SALT_ERR_ARG, "slot was not seeded");
+    CU(cudaStreamSynchronize(s.stream));
+    s.seeded_n0 = s.h_tot[0]; s.seeded_n1 = s.h_tot[1];
+    CU(s.c_loci0.need(s.seeded_n0 * 4 + 4)); CU(s.c_loci1.need(s.seeded_n1 * 4 + 4));
+    if (s.n_reads) {
+        CU(launch_seed_gather(s.sd_lists.as<uint32_t>(), s.seed_max_locate, s.d_coffs(0), s.d_coffs(1), s.n_reads,
+                              s.c_loci0.as<uint32_t>(), s.c_loci1.as<uint32_t>(), s.stream));
+        h->launches += 1;
+    }
+    s.seeded = 2;
+    return SALT_OK;
+}
+
 int finish_verify(salt_b200_t *h, int si)
 {
     Slot &s = h->slot[si];
@@ -563,7 +636,7 @@ void salt_b200_destroy(salt_b200_t *h)
         if (h->slot[i].stream) cudaStreamSynchronize(h->slot[i].stream);
         h->slot[i].release();
     }
-    DBuf *all[] = {&h->pairs, &h->out8, &h->kbuf, &h->cig, &h->wins, &h->sswout, &h->sswcig, &h->sswscratch, &h->sswovf,
+    DBuf *all[] = {&h->pairs, &h->out8, &h->kbuf, &h->cig, &h->wins, &h->sswout, &h->sswcig, &h->sswscratch, &h->sswovf, &h->ix_cbwt, &h->ix_csa, &h->ix_lkt, &h->ix_rbwt, &h->ix_rocc, &h->ix_rmaj, &h->ix_rsa,
                    &h->fpairs, &h->fslots, &h->fcount, &h->md_in, &h->md_cig, &h->md_str, &h->md_xv, &h->md_out};
     for (DBuf *b : all) b->release();
     for (int i = 0; i < 7; ++i) if (h->ev_ssw[i]) cudaEventDestroy(h->ev_ssw[i]);
@@ -1003,6 +1076,120 @@ int salt_b200_verify_batch_packed(salt_b200_t *h, const salt_packed_chunk_t *pc,
         rc = run_and_download(h, si, v.n0, v.n1, nogap_T0, lv_T0, rec + b, acc0 ? acc0 + v.c0 : nullptr,
                               acc1 ? acc1 + v.c1 : nullptr, cigars ? cigars + (size_t)b * cigar_stride : nullptr, cigar_stride);
     }
+    for (int si = 0; si < SALT_SLOTS; ++si) { const int r2 = finish_verify(h, si); if (rc == SALT_OK) rc = r2; }
+    return rc;
+}
+
+// ------------------------------------------------------------------ seeding + locate
+int salt_b200_set_index(salt_b200_t *h, const salt_fm_index_t *ix)
+{
+    if (int rc = use_device(h)) return rc;
+    if (!ix || !ix->c_bwt || !ix->c_sa || !ix->lkt || !ix->r_bwt || !ix->r_occ || !ix->r_occ_major || !ix->r_sa_sharp)
+        return fail(SALT_ERR_ARG, "an index array is null");
+    if (ix->lkt_len < 1 || ix->lkt_len > 14) return fail(SALT_ERR_ARG, "lookup length out of range");
+    if (ix->c_sa_intv < 1 || ix->c_n_sa < 1) return fail(SALT_ERR_ARG, "suffix-array sampling is empty");
+    cudaStream_t st = h->slot[0].stream;
+    const size_t lkt_items = ((size_t)1 << (2 * ix->lkt_len)) + 1;
+    // the SNP-context BWT is read up to the next 256-character boundary past its end (rbwt.c:248 sizes it that way)
+    const size_t rpad = (ix->r_bwt_words * 8 + 256) / 256 * 256 / 8 + 1;
+    CU(h->ix_cbwt.need(ix->c_bwt_words * 4 + 64)); CU(h->ix_csa.need((size_t)ix->c_n_sa * 4));
+    CU(h->ix_lkt.need(lkt_items * 4)); CU(h->ix_rbwt.need(rpad * 4 + 64)); CU(h->ix_rocc.need(ix->r_occ_words * 4 + 64));
+    CU(h->ix_rmaj.need(ix->r_occ_major_words * 4 + 64)); CU(h->ix_rsa.need(ix->r_n_sa_sharp * 4 + 4));
+    CU(cudaMemsetAsync(h->ix_rbwt.p, 0, rpad * 4 + 64, st));
+    CU(cudaMemcpyAsync(h->ix_cbwt.p, ix->c_bwt, ix->c_bwt_words * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->ix_csa.p, ix->c_sa, (size_t)ix->c_n_sa * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->ix_lkt.p, ix->lkt, lkt_items * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->ix_rbwt.p, ix->r_bwt, ix->r_bwt_words * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->ix_rocc.p, ix->r_occ, ix->r_occ_words * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->ix_rmaj.p, ix->r_occ_major, ix->r_occ_major_words * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->ix_rsa.p, ix->r_sa_sharp, ix->r_n_sa_sharp * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    FmIndexDev &f = h->fm;
+    f.cbwt = h->ix_cbwt.as<uint32_t>(); f.c_primary = ix->c_primary; f.c_seq_len = ix->c_seq_len;
+    for (int i = 0; i < 5; ++i) f.c_L2[i] = ix->c_L2[i];
+    f.c_sa = h->ix_csa.as<uint32_t>(); f.c_sa_intv = ix->c_sa_intv; f.c_n_sa = ix->c_n_sa;
+    f.lkt = h->ix_lkt.as<uint32_t>(); f.l_lkt = (int)ix->lkt_len;
+    f.r_bwt = h->ix_rbwt.as<uint32_t>(); f.r_occ = h->ix_rocc.as<uint32_t>(); f.r_occ_major = h->ix_rmaj.as<uint32_t>();
+    f.r_sa_sharp = h->ix_rsa.as<uint32_t>(); f.r_n_sa_sharp = (uint32_t)ix->r_n_sa_sharp;
+    for (int i = 0; i < 6; ++i) f.r_cum[i] = ix->r_cum[i];
+    f.r_inv_sa0 = ix->r_inv_sa0; f.r_text_len = ix->r_text_len;
+    h->have_index = true;
+    return SALT_OK;
+}
+
+int salt_b200_seed_locate(salt_b200_t *h, int slot, const salt_seed_opt_t *opt, uint32_t *offs0, uint32_t *offs1,
+                          uint32_t *loci0, size_t cap0, uint32_t *loci1, size_t cap1, size_t *n0, size_t *n1)
+{
+    if (int rc = use_device(h)) return rc;
+    if (slot < 0 || slot >= SALT_SLOTS) return fail(SALT_ERR_ARG, "slot out of range");
+    Slot &s = h->slot[slot];
+    if (s.pending) return fail(SALT_ERR_ARG, "slot has a verify in flight: call salt_b200_verify_wait first");
+    if (!s.n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    if (int rc = seed_enqueue(h, slot, opt)) return rc;
+    if (int rc = seed_finish(h, slot)) return rc;
+    if (n0) *n0 = s.seeded_n0;
+    if (n1) *n1 = s.seeded_n1;
+    if ((loci0 && cap0 < s.seeded_n0) || (loci1 && cap1 < s.seeded_n1)) return fail(SALT_ERR_NOMEM, "loci buffer too small for the lists");
+    const size_t m1 = (size_t)s.n_reads + 1;
+    if (offs0) CU(cudaMemcpyAsync(offs0, s.d_coffs(0), m1 * 4, cudaMemcpyDeviceToHost, s.stream));
+    if (offs1) CU(cudaMemcpyAsync(offs1, s.d_coffs(1), m1 * 4, cudaMemcpyDeviceToHost, s.stream));
+    if (loci0 && s.seeded_n0) CU(cudaMemcpyAsync(loci0, s.c_loci0.p, s.seeded_n0 * 4, cudaMemcpyDeviceToHost, s.stream));
+    if (loci1 && s.seeded_n1) CU(cudaMemcpyAsync(loci1, s.c_loci1.p, s.seeded_n1 * 4, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    return SALT_OK;
+}
+
+int salt_b200_verify_seeded(salt_b200_t *h, int slot, int nogap_T0, int lv_T0, salt_verify_out_t *rec,
+                            int8_t *acc0, int8_t *acc1, char *cigars, int cigar_stride)
+{
+    if (int rc = use_device(h)) return rc;
+    if (slot < 0 || slot >= SALT_SLOTS) return fail(SALT_ERR_ARG, "slot out of range");
+    Slot &s = h->slot[slot];
+    if (s.pending) return fail(SALT_ERR_ARG, "slot has a verify in flight: call salt_b200_verify_wait first");
+    if (!rec) return fail(SALT_ERR_ARG, "null buffer");
+    if (s.seeded != 2) return fail(SALT_ERR_ARG, "slot holds no seeded lists: call salt_b200_seed_locate first");
+    if (!s.n_reads) return SALT_OK;
+    if (int rc = run_and_download(h, slot, s.seeded_n0, s.seeded_n1, nogap_T0, lv_T0, rec, acc0, acc1, cigars, cigar_stride)) return rc;
+    return finish_verify(h, slot);
+}
+
+int salt_b200_align_batch_packed(salt_b200_t *h, const salt_packed_chunk_t *pc, const salt_seed_opt_t *opt, uint32_t chunk_reads,
+                                 int nogap_T0, int lv_T0, salt_verify_out_t *rec, char *cigars, int cigar_stride)
+{
+    if (int rc = use_device(h)) return rc;
+    if (int rc = check_packed(pc, false)) return rc;
+    if (!rec) return fail(SALT_ERR_ARG, "null buffer");
+    if (chunk_reads == 0) chunk_reads = 100000;          // N_SEQS, aln.h:27
+    int rc = SALT_OK;
+    PackedView v; v.pc = pc; v.base_pos = pc->base_start;
+    while (v.np_lo < pc->n_n && pc->n_pos[v.np_lo] < v.base_pos) ++v.np_lo;
+    v.np_hi = v.np_lo;
+    // chunk k: upload + seed + locate are queued first; the totals of chunk k-1 are awaited only then, so the device
+    // always has the next chunk's seeding to do while the host sizes and queues the previous chunk's verification
+    int prev_slot = -1; uint32_t prev_b = 0;
+    auto verify_prev = [&]() -> int {
+        if (prev_slot < 0) return SALT_OK;
+        Slot &sp = h->slot[prev_slot];
+        if (int r2 = seed_finish(h, prev_slot)) return r2;
+        const int ps = prev_slot; prev_slot = -1;
+        if (!sp.n_reads) return SALT_OK;
+        return run_and_download(h, ps, sp.seeded_n0, sp.seeded_n1, nogap_T0, lv_T0, rec + prev_b, nullptr, nullptr,
+                                cigars ? cigars + (size_t)prev_b * cigar_stride : nullptr, cigar_stride);
+    };
+    uint32_t k = 0;
+    for (uint32_t b = 0; b < pc->n_reads && rc == SALT_OK; b += chunk_reads, ++k) {
+        const int si = (int)(k % SALT_SLOTS);
+        if ((rc = finish_verify(h, si)) != SALT_OK) break;
+        const uint32_t m = pc->n_reads - b < chunk_reads ? pc->n_reads - b : chunk_reads;
+        PackedView w; w.pc = pc; w.first = b; w.base_pos = v.base_pos + v.n_bases; w.np_lo = v.np_hi;
+        if ((rc = grow_view(w, m, false)) != SALT_OK) break;
+        v = w;
+        if ((rc = load_packed(h, h->slot[si], v, false)) != SALT_OK) break;
+        if ((rc = seed_enqueue(h, si, opt)) != SALT_OK) break;
+        if ((rc = verify_prev()) != SALT_OK) break;
+        prev_slot = si; prev_b = b;
+    }
+    if (rc == SALT_OK) rc = verify_prev();
     for (int si = 0; si < SALT_SLOTS; ++si) { const int r2 = finish_verify(h, si); if (rc == SALT_OK) rc = r2; }
     return rc;
 }

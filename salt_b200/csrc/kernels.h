@@ -54,6 +54,26 @@ cudaError_t launch_scan3(Scan3 a, int n_arrays, cudaStream_t st);
 cudaError_t launch_unpack_bases(const uint8_t *in, uint32_t phase, int bits, size_t n_bases, uint8_t *codes,
                                 const uint32_t *n_pos, size_t n_n, uint32_t origin, cudaStream_t st);
 
+// seed.cu: single-end seeding + locate on the reference's FM-indexes (row f1)
+struct FmIndexDev {
+    // primary reference ("C part"): BWA layout, bwt.h:44-57
+    const uint32_t *cbwt; uint32_t c_primary, c_seq_len; uint32_t c_L2[5];
+    const uint32_t *c_sa; uint32_t c_sa_intv, c_n_sa;
+    const uint32_t *lkt; int l_lkt;                       // lookup.h:21-25
+    // SNP-context index, backward direction ("R part"): rbwt.h:60-80
+    const uint32_t *r_bwt, *r_occ, *r_occ_major, *r_sa_sharp;
+    uint32_t r_cum[6], r_inv_sa0, r_text_len, r_n_sa_sharp;
+};
+struct SeedOpt { int l_seed, l_overlap, max_seed, max_locate, seed_only_ref; };
+struct SeedSai { uint32_t sp, ep, offset; };              // sai_t, aln.h:91-95
+size_t seed_sai_bytes(uint32_t n_reads, int max_seeds);
+cudaError_t launch_seed(const FmIndexDev &ix, const SeedOpt &opt, const uint8_t *codes, const uint32_t *roffs, uint32_t n_reads,
+                        int max_seeds, SeedSai *sai, cudaStream_t st);
+cudaError_t launch_locate(const FmIndexDev &ix, const SeedOpt &opt, const uint32_t *roffs, uint32_t n_reads, int max_seeds,
+                          uint32_t ref_l, SeedSai *sai, uint32_t *counts, uint32_t *lists, cudaStream_t st);
+cudaError_t launch_seed_gather(const uint32_t *lists, int max_locate, const uint32_t *offs0, const uint32_t *offs1,
+                               uint32_t n_reads, uint32_t *loci0, uint32_t *loci1, cudaStream_t st);
+
 // ssw.cu
 struct SswParams {
     int use_pac, n_sym, gapO, gapE, flag, filters, filterd, mask_len;

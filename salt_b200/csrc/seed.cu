@@ -1,0 +1,441 @@
+// seed.cu -- sm_100a kernels for salt's single-end seeding + locate:
+//
+//   alnse_seed_overlap   alnse.c:199-312   per seed start: 12-mer lookup (lookup.h:39) + backward search on the
+//                                          primary-reference FM-index (bwt.c:281 bwt_match_exact_alt, :140 bwt_2occ),
+//                                          the same on the SNP-context FM-index (rbwt.c:619, :159), both extended to the
+//                                          left while the interval is wider than max_seed; intervals sorted by width
+//   alnse_locate_alt     alnse.c:633-731   suffix-array walks (bwt.c:89 bwt_sa, rbwt.c:316 Rbwt_back_bwt_sa), position
+//                                          minus seed offset in uint32 arithmetic, at most max_locate loci, sorted
+//
+// The index arrives exactly as the reference's loaders leave it in memory (indexio.c:23-50): PREFIX.C.bwt / .C.sa
+// (BWA layout: 128-base blocks of 4 counts + 8 words), PREFIX.C.lkt, PREFIX.R.backward.{bwt,occ,sa}.
+//
+// Mapping: seed_kernel runs one thread per (read, strand, seed start) -- every LF step is a dependent random access,
+// so parallelism across seeds is what hides HBM latency; locate_kernel runs one warp per (read, strand): lane 0 orders
+// the intervals with the reference's own (unstable) introsort so that ties break identically, the lanes walk the
+// suffix array for 32 rows at a time, a ballot + prefix count reproduces "stop at max_locate" exactly, and the list is
+// sorted in shared memory (bitonic).  Results are the candidate lists of the slot: the verification stage consumes
+// them in place, they never cross the host link.
+#if !defined(SALT_EMUL)
+#include <cuda_runtime.h>
+#endif
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace salt {
+
+// ---------------------------------------------------------------- primary-reference FM-index (bwt.h layout)
+__device__ __forceinline__ uint32_t c_count16(uint32_t x, int c, int m)
+{
+    // bases of a 16-base word sit 2 bits each, first base in the top bits (bwt.h:62 bwt_B0); count c among the first m
+    uint32_t y = ((c & 2) ? x : ~x) >> 1 & ((c & 1) ? x : ~x) & 0x55555555u;
+    if (m < 16) y &= ~((1u << (2 * (16 - m))) - 1u);
+    return (uint32_t)__popc(y);
+}
+
+// bwt_occ (bwt.c:106-129): occurrences of c in B[0..k]
+__device__ __forceinline__ uint32_t c_occ(const FmIndexDev &ix, uint32_t k, int c)
+{
+    if (k == ix.c_seq_len) return ix.c_L2[c + 1] - ix.c_L2[c];
+    if (k == 0xFFFFFFFFu) return 0u;
+    if (k >= ix.c_primary) --k;
+    const uint32_t *__restrict__ p = ix.cbwt + (size_t)(k >> 7) * 12;
+    uint32_t n = p[c];
+    const int in_block = (int)(k & 127u) + 1;           // bases of this block to count
+    p += 4;
+    for (int w = 0; w * 16 < in_block; ++w) {
+        const int m = in_block - w * 16;
+        n += c_count16(p[w], c, m < 16 ? m : 16);
+    }
+    return n;
+}
+
+__device__ __forceinline__ int c_B0(const FmIndexDev &ix, uint32_t k)
+{
+    return (int)(ix.cbwt[(size_t)(k >> 7) * 12 + 4 + ((k & 127u) >> 4)] >> ((~k & 0xfu) << 1) & 3u);
+}
+
+// bwt_invPsi (bwt.h:67-72)
+__device__ __forceinline__ uint32_t c_inv_psi(const FmIndexDev &ix, uint32_t k)
+{
+    if (k == ix.c_primary) return 0u;
+    const int c = k < ix.c_primary ? c_B0(ix, k) : c_B0(ix, k - 1);
+    return ix.c_L2[c] + c_occ(ix, k, c);
+}
+
+// bwt_sa (bwt.c:89-104)
+__device__ __forceinline__ uint32_t c_sa(const FmIndexDev &ix, uint32_t k)
+{
+    uint32_t sa = 0;
+    while (k % ix.c_sa_intv != 0) { ++sa; k = c_inv_psi(ix, k); }
+    return sa + ix.c_sa[k / ix.c_sa_intv];
+}
+
+// one backward-search step (bwt.c:293-299): returns false when the interval empties
+__device__ __forceinline__ bool c_step(const FmIndexDev &ix, int c, uint32_t &k, uint32_t &l)
+{
+    const uint32_t ok = c_occ(ix, k - 1, c), ol = c_occ(ix, l, c);      // bwt_2occ is an optimised pair of bwt_occ
+    k = ix.c_L2[c] + ok + 1;
+    l = ix.c_L2[c] + ol;
+    return k <= l;
+}
+
+// ---------------------------------------------------------------- SNP-context FM-index (rbwt.h layout)
+// occurrences of c among BWT characters [a, b): 4 bits each, first character in the top nibble (rbwt.h:113-117)
+__device__ __forceinline__ uint32_t r_count(const uint32_t *__restrict__ code, uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t n = 0;
+    const uint32_t pat = c * 0x11111111u;
+    for (uint32_t w = a >> 3; w <= ((b - 1) >> 3); ++w) {
+        uint32_t x = code[w] ^ pat;                       // matching nibbles become 0
+        x |= x >> 1; x |= x >> 2;
+        uint32_t m = ~x & 0x11111111u;
+        const uint32_t lo = w * 8, hi = lo + 8;           // characters of this word
+        if (a > lo) m &= 0xFFFFFFFFu >> (4 * (a - lo));                  // drop the first a-lo characters (top nibbles)
+        if (b < hi) m &= ~((1u << (4 * (hi - b))) - 1u);                 // drop the last hi-b characters
+        n += (uint32_t)__popc(m);
+    }
+    return n;
+}
+
+// Rbwt_BWTOccValue (rbwt.c:159-189) with BWTOccValueExplicit (:38-79): bidirectional explicit counts every 256
+// characters (16 bit, two per word) on top of major counts every 65536
+__device__ __forceinline__ uint32_t r_occ(const FmIndexDev &ix, uint32_t index, uint32_t c)
+{
+    if (index > ix.r_inv_sa0) --index;
+    const uint32_t e = (index + 127u) >> 8, at = e << 8;
+    const uint32_t minor = ix.r_occ[(size_t)(e >> 1) * 5 + c];
+    uint32_t v = ix.r_occ_major[(size_t)(at >> 16) * 5 + c] + ((e & 1u) ? (minor & 0xFFFFu) : (minor >> 16));
+    if (at < index) v += r_count(ix.r_bwt, at, index, c);
+    else if (at > index) v -= r_count(ix.r_bwt, index, at, c);
+    return v;
+}
+
+__device__ __forceinline__ uint32_t r_nt(const FmIndexDev &ix, uint32_t pos)       // Rbwt_bwt2nt, rbwt.h:101-121
+{
+    if (pos == ix.r_inv_sa0) return 4u;
+    if (pos > ix.r_inv_sa0) --pos;
+    return (ix.r_bwt[pos >> 3] >> (4u * (7u - (pos & 7u)))) & 15u;
+}
+
+// Rbwt_back_bwt_sa (rbwt.c:316-333)
+__device__ __forceinline__ uint32_t r_sa(const FmIndexDev &ix, uint32_t i)
+{
+    uint32_t step = 0;
+    const uint32_t n_acgt = ix.r_cum[4];
+    while (i <= n_acgt) {
+        const uint32_t c = r_nt(ix, i);
+        i = ix.r_cum[c] + r_occ(ix, i, c) + 1;
+        ++step;
+    }
+    return ix.r_sa_sharp[i - n_acgt - 1] + step - 1;
+}
+
+__device__ __forceinline__ bool r_step(const FmIndexDev &ix, uint32_t c, uint32_t &k, uint32_t &l)
+{
+    const uint32_t nk = ix.r_cum[c] + r_occ(ix, k, c) + 1;
+    const uint32_t nl = ix.r_cum[c] + r_occ(ix, l + 1, c);
+    k = nk; l = nl;
+    return k <= l;
+}
+
+// ---------------------------------------------------------------- reads
+// code of base i of strand s of a read: query->seq / query->rseq (query.c:46-64: reverse, 3-c for c < 4)
+__device__ __forceinline__ int seed_code(const uint8_t *__restrict__ codes, int L, int strand, int i)
+{
+    if (!strand) return codes[i];
+    const int c = codes[L - 1 - i];
+    return c < 4 ? 3 - c : c;
+}
+
+// ---------------------------------------------------------------- alnse_seed_overlap, one seed start per thread
+__global__ void __launch_bounds__(128)
+seed_kernel(FmIndexDev ix, SeedOpt opt, const uint8_t *__restrict__ codes, const uint32_t *__restrict__ roffs,
+            uint32_t n_reads, int max_seeds, SeedSai *__restrict__ sai /* [rs][2][max_seeds] */)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t rs = tid / (unsigned)max_seeds;
+    const int si = (int)(tid % (unsigned)max_seeds);
+    if (rs >= (size_t)n_reads * 2) return;
+    const uint32_t r = (uint32_t)(rs >> 1);
+    const int strand = (int)(rs & 1);
+    const uint32_t o = roffs[r];
+    const int L = (int)(roffs[r + 1] - o);
+    const uint8_t *__restrict__ rd = codes + o;
+    SeedSai *out = sai + rs * 2 * (size_t)max_seeds;
+    SeedSai none; none.sp = 1; none.ep = 0; none.offset = 0;
+    out[si] = none; out[max_seeds + si] = none;
+    const int seed_start = si * opt.l_overlap;                       // alnse.c:226-228
+    if (L < opt.l_seed || seed_start > L - opt.l_seed) return;
+    const int seed_end = seed_start + opt.l_seed - 1;
+
+    // ---- primary reference: 12-mer lookup, then the rest of the seed, then extension to the left
+    {
+        uint32_t k = 1, l = 0;
+        uint32_t item = 0; bool has_n = false;
+        for (int i = seed_end - ix.l_lkt + 1; i <= seed_end; ++i) {   // LKT_seq2LktItem, lookup.c:163-176
+            const int c = seed_code(rd, L, strand, i);
+            if (c > 3) has_n = true;
+            item = (item << 2) | (uint32_t)(c & 3);
+        }
+        if (!has_n) { k = ix.lkt[item]; l = ix.lkt[item + 1] - 1; }  // lookup.h:39-52
+        bool ok = k <= l;
+        for (int i = opt.l_seed - ix.l_lkt - 1; ok && i >= 0; --i) { // bwt_match_exact_alt on seq[seed_start .. +l_seed-l_lkt)
+            const int c = seed_code(rd, L, strand, seed_start + i);
+            if (c > 3) { ok = false; break; }
+            ok = c_step(ix, c, k, l);
+        }
+        if (ok) {
+            int l_extend = 0;
+            while (l - k > (uint32_t)opt.max_seed && l_extend < seed_start) {      // alnse.c:249-259
+                const int c = seed_code(rd, L, strand, seed_start - l_extend - 1);
+                if (c > 3) break;
+                uint32_t nk = k, nl = l;
+                if (!c_step(ix, c, nk, nl)) break;
+                k = nk; l = nl;
+                ++l_extend;
+                if (l - k <= (uint32_t)opt.max_seed) break;
+            }
+            SeedSai s; s.sp = k; s.ep = l; s.offset = (uint32_t)(seed_start - l_extend);
+            out[si] = s;
+        }
+    }
+    if (opt.seed_only_ref) return;
+    // ---- SNP-context index: the whole seed backwards (Rbwt_exact_match_backward, rbwt.c:619-649), then extension
+    {
+        uint32_t k = 0, l = ix.r_text_len;
+        bool ok = true;
+        int step = 0;
+        while (k <= l && step < opt.l_seed) {
+            const int c = seed_code(rd, L, strand, seed_start + opt.l_seed - step - 1);
+            if (c > 3) { ok = false; break; }
+            r_step(ix, (uint32_t)c, k, l);
+            ++step;
+        }
+        if (ok && l >= k) {
+            int l_extend = 0;
+            while (l - k > (uint32_t)opt.max_seed && l_extend < seed_start) {      // alnse.c:280-291
+                // the reference indexes cumulativeFreq / occ with the raw code here: an N (4) extends over '#'
+                const uint32_t c = (uint32_t)seed_code(rd, L, strand, seed_start - l_extend - 1);
+                const uint32_t okk = r_occ(ix, k, c), oll = r_occ(ix, l + 1, c);
+                if (okk + 1 > oll) break;
+                k = ix.r_cum[c] + okk + 1;
+                l = ix.r_cum[c] + oll;
+                ++l_extend;
+                if (l - k <= (uint32_t)opt.max_seed) break;
+            }
+            SeedSai s; s.sp = k; s.ep = l; s.offset = (uint32_t)(seed_start - l_extend);
+            out[max_seeds + si] = s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- ks_introsort_sai (ksort.h:180-226, alnse.c:35-38)
+// The reference's sort is not stable, and which interval comes first decides whose loci survive the max_locate cut:
+// the same algorithm (median-of-three pivot moved to the end, Hoare partition, ranges of <= 17 left to one final
+// insertion sort, comb sort when the depth budget runs out) is run here on the same input order.
+__device__ __forceinline__ bool sai_lt(const SeedSai &a, const SeedSai &b) { return a.ep - a.sp < b.ep - b.sp; }
+
+__device__ void sai_insertsort(SeedSai *s, SeedSai *t)             // __ks_insertsort, ksort.h:148-155
+{
+    for (SeedSai *i = s + 1; i < t; ++i)
+        for (SeedSai *j = i; j > s && sai_lt(*j, *(j - 1)); --j) { const SeedSai tmp = *j; *j = *(j - 1); *(j - 1) = tmp; }
+}
+
+__device__ void sai_combsort(int n, SeedSai *a)                     // ks_combsort, ksort.h:156-178
+{
+    const double shrink = 1.2473309501039786540366528676643;
+    int do_swap;
+    int gap = n;
+    do {
+        if (gap > 2) {
+            gap = (int)(gap / shrink);
+            if (gap == 9 || gap == 10) gap = 11;
+        }
+        do_swap = 0;
+        for (SeedSai *i = a; i < a + n - gap; ++i) {
+            SeedSai *j = i + gap;
+            if (sai_lt(*j, *i)) { const SeedSai tmp = *i; *i = *j; *j = tmp; do_swap = 1; }
+        }
+    } while (do_swap || gap > 2);
+    if (gap != 1) sai_insertsort(a, a + n);
+}
+
+__device__ void sai_introsort(int n, SeedSai *a)
+{
+    if (n < 1) return;
+    if (n == 2) { if (sai_lt(a[1], a[0])) { const SeedSai tmp = a[0]; a[0] = a[1]; a[1] = tmp; } return; }
+    int d;
+    for (d = 2; (1 << d) < n; ++d);
+    struct Frame { SeedSai *left, *right; int depth; };
+    Frame stack[64];
+    Frame *top = stack;
+    SeedSai *s = a, *t = a + (n - 1);
+    d <<= 1;
+    for (;;) {
+        if (s < t) {
+            if (--d == 0) { sai_combsort((int)(t - s) + 1, s); t = s; continue; }
+            SeedSai *i = s, *j = t, *k = i + ((j - i) >> 1) + 1;
+            if (sai_lt(*k, *i)) { if (sai_lt(*k, *j)) k = j; }
+            else k = sai_lt(*j, *i) ? i : j;
+            const SeedSai rp = *k;
+            if (k != t) { const SeedSai tmp = *k; *k = *t; *t = tmp; }
+            for (;;) {
+                do ++i; while (sai_lt(*i, rp));
+                do --j; while (i <= j && sai_lt(rp, *j));
+                if (j <= i) break;
+                const SeedSai tmp = *i; *i = *j; *j = tmp;
+            }
+            { const SeedSai tmp = *i; *i = *t; *t = tmp; }
+            if (i - s > t - i) {
+                if (i - s > 16) { top->left = s; top->right = i - 1; top->depth = d; ++top; }
+                s = t - i > 16 ? i + 1 : t;
+            } else {
+                if (t - i > 16) { top->left = i + 1; top->right = t; top->depth = d; ++top; }
+                t = i - s > 16 ? i - 1 : s;
+            }
+        } else {
+            if (top == stack) { sai_insertsort(a, a + n); return; }
+            --top; s = top->left; t = top->right; d = top->depth;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- alnse_locate_alt, one warp per (read, strand)
+// shared memory per warp: max_seeds sai (12 B each), then cap2 = pow2 >= max_locate loci
+__global__ void __launch_bounds__(128)
+locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, uint32_t n_reads, int max_seeds, int cap2,
+              uint32_t ref_l, SeedSai *__restrict__ sai, uint32_t *__restrict__ counts /* [2][n_reads] */,
+              uint32_t *__restrict__ lists /* [rs][max_locate] */)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    SALT_DYN_SMEM(uint32_t, s_mem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = (size_t)max_seeds * 3 + (size_t)cap2;
+    SeedSai *s_sai = reinterpret_cast<SeedSai *>(s_mem + warp * per_warp);
+    uint32_t *s_loci = s_mem + warp * per_warp + (size_t)max_seeds * 3;
+    const size_t rs_raw = (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    const bool live = rs_raw < (size_t)n_reads * 2;
+    const size_t rs = live ? rs_raw : 0;
+    const uint32_t r = (uint32_t)(rs >> 1);
+    const uint32_t l_seq = live ? roffs[r + 1] - roffs[r] : 0u;
+    const uint32_t max_locate = (uint32_t)opt.max_locate;
+    SeedSai *g = sai + rs * 2 * (size_t)max_seeds;
+    uint32_t n = 0;                                                   // aux->loci.n
+    for (int part = 0; part < 2 && live; ++part) {                    // 0: sai_C, 1: sai_backwardR (sai_forwardR is empty here)
+        // compact the valid intervals in seed order, sort them as the reference does
+        int m = 0;
+        if (lane == 0) {
+            for (int i = 0; i < max_seeds; ++i) { const SeedSai v = g[part * max_seeds + i]; if (v.sp <= v.ep) s_sai[m++] = v; }
+            sai_introsort(m, s_sai);
+        }
+        m = __shfl_sync(FULL, m, 0);
+        __syncwarp();
+        for (int i = 0; i < m && n < max_locate; ++i) {
+            const SeedSai v = s_sai[i];
+            uint32_t skip = 1;
+            if (part == 1) { skip = (v.ep + 1 - v.sp) / 0x40000u; if ((int)skip <= 0) skip = 1; }    // alnse.c:702-703
+            // rows sp, sp+skip, .. <= ep; 32 at a time
+            const uint64_t rows = ((uint64_t)(v.ep - v.sp)) / skip + 1;
+            for (uint64_t b = 0; b < rows && n < max_locate; b += 32) {
+                const uint64_t idx = b + (uint64_t)lane;
+                bool keep = false;
+                uint32_t pos = 0;
+                if (idx < rows) {
+                    const uint32_t j = v.sp + (uint32_t)idx * skip;
+                    pos = (part == 0 ? c_sa(ix, j) : r_sa(ix, j)) - v.offset;          // uint32 arithmetic, may wrap (alnse.c:669)
+                    keep = !(pos + l_seq > ref_l);
+                    if (part == 1 && pos > ref_l) keep = false;                       // alnse.c:711
+                }
+                const unsigned bal = __ballot_sync(FULL, keep);
+                const uint32_t rank = (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                if (keep && n + rank < max_locate) s_loci[n + rank] = pos;
+                n = min(max_locate, n + (uint32_t)__popc(bal));
+            }
+        }
+        __syncwarp();
+    }
+    // ks_introsort(uint32_t) of the list: any correct sort gives the same array; bitonic over cap2 padded with ~0
+    for (uint32_t i = n + lane; i < (uint32_t)cap2; i += 32) s_loci[i] = 0xFFFFFFFFu;
+    __syncwarp();
+    // a pad value can equal a real (wrapped) locus 0xFFFFFFFF: equal keys, so the sorted prefix is still right
+    for (uint32_t k = 2; k <= (uint32_t)cap2; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = lane; i < (uint32_t)cap2; i += 32) {
+                const uint32_t p = i ^ j;
+                if (p > i) {
+                    const uint32_t a = s_loci[i], b = s_loci[p];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { s_loci[i] = b; s_loci[p] = a; }
+                }
+            }
+            __syncwarp();
+        }
+    if (live) {
+        uint32_t *dst = lists + rs * (size_t)max_locate;
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = s_loci[i];
+        if (lane == 0) counts[(rs & 1) * (size_t)n_reads + r] = n;
+    }
+}
+
+// CSR gather: strand s of read r takes counts[s][r] loci from its fixed-stride row
+__global__ void __launch_bounds__(256)
+seed_gather_kernel(const uint32_t *__restrict__ lists, int max_locate, const uint32_t *__restrict__ offs0,
+                   const uint32_t *__restrict__ offs1, uint32_t n_reads, uint32_t *__restrict__ loci0, uint32_t *__restrict__ loci1)
+{
+    const size_t rs = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;         // eight lanes per list
+    const int lane = threadIdx.x & 7;
+    if (rs >= (size_t)n_reads * 2) return;
+    const uint32_t r = (uint32_t)(rs >> 1);
+    const uint32_t *__restrict__ offs = (rs & 1) ? offs1 : offs0;
+    uint32_t *__restrict__ dst = ((rs & 1) ? loci1 : loci0) + offs[r];
+    const uint32_t n = offs[r + 1] - offs[r];
+    const uint32_t *__restrict__ src = lists + rs * (size_t)max_locate;
+    for (uint32_t i = lane; i < n; i += 8) dst[i] = src[i];
+}
+
+// ---------------------------------------------------------------- launchers
+size_t seed_sai_bytes(uint32_t n_reads, int max_seeds) { return (size_t)n_reads * 2 * 2 * (size_t)max_seeds * sizeof(SeedSai); }
+
+cudaError_t launch_seed(const FmIndexDev &ix, const SeedOpt &opt, const uint8_t *codes, const uint32_t *roffs, uint32_t n_reads,
+                        int max_seeds, SeedSai *sai, cudaStream_t st)
+{
+    const size_t total = (size_t)n_reads * 2 * (size_t)max_seeds;
+    if (!total) return cudaSuccess;
+    SALT_LAUNCH(seed_kernel, (unsigned)((total + 127) / 128), 128, 0, st, ix, opt, codes, roffs, n_reads, max_seeds, sai);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_locate(const FmIndexDev &ix, const SeedOpt &opt, const uint32_t *roffs, uint32_t n_reads, int max_seeds,
+                          uint32_t ref_l, SeedSai *sai, uint32_t *counts, uint32_t *lists, cudaStream_t st)
+{
+    if (!n_reads) return cudaSuccess;
+    int cap2 = 32;
+    while (cap2 < opt.max_locate) cap2 <<= 1;
+    const size_t per_warp = ((size_t)max_seeds * 3 + (size_t)cap2) * 4;
+    int warps = 4;
+    while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
+    if (per_warp * warps > 200 * 1024) return cudaErrorInvalidValue;
+    const size_t smem = per_warp * warps;
+    auto kern = locate_kernel;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const size_t n_rs = (size_t)n_reads * 2;
+    SALT_LAUNCH(kern, (unsigned)((n_rs + warps - 1) / warps), warps * 32, smem, st, ix, opt, roffs, n_reads, max_seeds, cap2,
+                ref_l, sai, counts, lists);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_seed_gather(const uint32_t *lists, int max_locate, const uint32_t *offs0, const uint32_t *offs1,
+                               uint32_t n_reads, uint32_t *loci0, uint32_t *loci1, cudaStream_t st)
+{
+    const size_t total = (size_t)n_reads * 2 * 8;
+    if (!total) return cudaSuccess;
+    SALT_LAUNCH(seed_gather_kernel, (unsigned)((total + 255) / 256), 256, 0, st, lists, max_locate, offs0, offs1, n_reads, loci0, loci1);
+    return cudaGetLastError();
+}
+
+}  // namespace salt

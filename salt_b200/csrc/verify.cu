@@ -956,7 +956,7 @@ struct NogapState {
 // out-of-range candidate was clamped to the last valid window start; its count is computed and
 // then ignored by the acceptance step.
 template <int G, int WPL, int J>
-__device__ __forceinline__ void nogap_load4(const uint2 *__restrict__ mixl, uint32_t myidx, uint32_t myph, int jb,
+__device__ __forceinline__ void nogap_load4(const uint2 *__restrict__ mixl, uint32_t myidx, uint32_t myph, int jb, int wlim,
                                             uint32_t (&ph)[4], uint2 (&q)[4][WPL])
 {
     constexpr unsigned FULL = 0xffffffffu;
@@ -966,7 +966,13 @@ __device__ __forceinline__ void nogap_load4(const uint2 *__restrict__ mixl, uint
         ph[u] = __shfl_sync(FULL, myph, jb + J + u, G);
         const uint2 *__restrict__ wp = mixl + idx;
 #pragma unroll
-        for (int w = 0; w < WPL; ++w) q[u][w] = wp[w * G];
+        for (int w = 0; w < WPL; ++w) {
+            // a window of L bases starting at most 15 bases into its aligned word ends in word (L + 14) / 16: lanes whose
+            // word lies beyond that do not touch memory (their read words are zero anyway).  With the reference in DRAM
+            // (GRCh38-sized) the kernel is bound by the sectors it fetches, so the unused tail of the span is time.
+            if (w == 0 && WPL == 1 && G <= 8) q[u][w] = wp[0];
+            else q[u][w] = (w * G < wlim) ? wp[w * G] : make_uint2(0u, 0u);
+        }
     }
 }
 
@@ -1030,6 +1036,7 @@ __device__ __forceinline__ int nogap_strand(const DevCtx &c, const uint2 *__rest
     constexpr int BIG = 255;
     const int nchunks = (int)((les - lbs + (G - 1)) / G);
     const int nchunks_w = __reduce_max_sync(FULL, nchunks);
+    const int wlim = (L + 14) / 16 + 1 - lane;              // this lane loads word lane + w*G iff w*G < wlim
     bool matched = false;
     int nhits = 0;
     for (int ci = 0; ci < nchunks_w; ++ci) {
@@ -1051,8 +1058,8 @@ __device__ __forceinline__ int nogap_strand(const DevCtx &c, const uint2 *__rest
             const bool more = cnt_w > jbb + 4;
             uint32_t pa[4], pb[4];
             uint2 qa[4][WPL], qb[4][WPL];
-            nogap_load4<G, WPL, 0>(mixl, myidx, myph, jbb, pa, qa);
-            if (more) nogap_load4<G, WPL, 4>(mixl, myidx, myph, jbb, pb, qb);
+            nogap_load4<G, WPL, 0>(mixl, myidx, myph, jbb, wlim, pa, qa);
+            if (more) nogap_load4<G, WPL, 4>(mixl, myidx, myph, jbb, wlim, pb, qb);
             nogap_count4<G, WPL, 0, HASN>(pa, qa, rw, rwh, lane, jbb, mymatches);
             if (more) nogap_count4<G, WPL, 4, HASN>(pb, qb, rw, rwh, lane, jbb, mymatches);
         }

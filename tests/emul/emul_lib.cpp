@@ -13,4 +13,5 @@ thread_local CtaState *t_cta = nullptr;
 #include "../../salt_b200/csrc/samtail.cu"
 #include "../../salt_b200/csrc/mixref.cu"
 #include "../../salt_b200/csrc/transport.cu"
+#include "../../salt_b200/csrc/seed.cu"
 #include "../../salt_b200/csrc/engine.cu"
