@@ -7,9 +7,11 @@
  * oracle/_ref/libsaltref_seed.so.  tests/ use it as the oracle of row f1: the device must emit the identical
  * sorted candidate lists.  Nothing of the reference is copied here; this file only calls its functions.
  */
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "aln.h"          /* pulls in indexio.h (no include guard there) */
 
@@ -95,5 +97,85 @@ int seedref_run(void *p, const uint8_t *codes, const uint32_t *roffs, uint32_t n
     }
     free(rseq);
     aux_destroy(aux);
+    return rc;
+}
+
+/* The same on n_threads pthreads (contiguous blocks of reads, one aux_t per thread, as alnse_core_thread keeps one per
+ * worker): the CPU side of the seeding throughput comparison.  Returns the wall time in seconds through *sec. */
+typedef struct {
+    index_t *ix; const uint8_t *codes; const uint32_t *roffs; uint32_t first, upto; aln_opt_t opt; uint32_t l_max;
+    uint32_t *cnt0, *cnt1;            /* per read list lengths (shared arrays, disjoint ranges) */
+    uint32_t *buf[2]; size_t n[2], cap[2];
+} seed_job_t;
+
+static void *seed_worker(void *arg)
+{
+    seed_job_t *J = (seed_job_t *)arg;
+    aux_t *aux = aux_init((int)J->l_max + J->opt.l_seed, J->opt.l_seed);
+    uint8_t *rseq = malloc(J->l_max + 1);
+    uint32_t r;
+    for (r = J->first; r < J->upto; ++r) {
+        const uint8_t *seq = J->codes + J->roffs[r];
+        const uint32_t L = J->roffs[r + 1] - J->roffs[r];
+        uint32_t i; int s;
+        for (i = 0; i < L; ++i) { uint8_t c = seq[L - 1 - i]; rseq[i] = c < 4 ? 3 - c : c; }
+        for (s = 0; s < 2; ++s) {
+            aux_reset(aux);
+            if ((int)L >= J->opt.l_seed) {
+                alnse_seed_overlap(J->ix, L, s ? rseq : seq, &J->opt, aux);
+                alnse_locate_alt(J->ix, L, J->opt.max_locate, aux);
+            }
+            if (J->n[s] + aux->loci.n > J->cap[s]) {
+                J->cap[s] = (J->n[s] + aux->loci.n) * 2 + 1024;
+                J->buf[s] = realloc(J->buf[s], J->cap[s] * 4);
+            }
+            memcpy(J->buf[s] + J->n[s], aux->loci.a, aux->loci.n * 4);
+            J->n[s] += aux->loci.n;
+            (s ? J->cnt1 : J->cnt0)[r] = (uint32_t)aux->loci.n;
+        }
+    }
+    free(rseq);
+    aux_destroy(aux);
+    return NULL;
+}
+
+int seedref_run_mt(void *p, const uint8_t *codes, const uint32_t *roffs, uint32_t n_reads, int l_seed, int l_overlap,
+                   int max_seed, int max_locate, int seed_only_ref, int n_threads, uint32_t *offs0, uint32_t *loci0, size_t cap0,
+                   uint32_t *offs1, uint32_t *loci1, size_t cap1, double *sec)
+{
+    if (n_threads < 1) n_threads = 1;
+    seed_job_t *J = calloc((size_t)n_threads, sizeof *J);
+    pthread_t *th = calloc((size_t)n_threads, sizeof *th);
+    uint32_t *cnt0 = calloc((size_t)n_reads + 1, 4), *cnt1 = calloc((size_t)n_reads + 1, 4);
+    uint32_t r, l_max = 1;
+    int t, rc = 0;
+    for (r = 0; r < n_reads; ++r) if (roffs[r + 1] - roffs[r] > l_max) l_max = roffs[r + 1] - roffs[r];
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (t = 0; t < n_threads; ++t) {
+        memset(&J[t].opt, 0, sizeof J[t].opt);
+        J[t].opt.l_seed = l_seed; J[t].opt.l_overlap = l_overlap; J[t].opt.max_seed = max_seed;
+        J[t].opt.max_locate = (uint32_t)max_locate; J[t].opt.seed_only_ref = seed_only_ref;
+        J[t].ix = (index_t *)p; J[t].codes = codes; J[t].roffs = roffs; J[t].l_max = l_max; J[t].cnt0 = cnt0; J[t].cnt1 = cnt1;
+        J[t].first = (uint32_t)((uint64_t)n_reads * (uint64_t)t / (uint64_t)n_threads);
+        J[t].upto = (uint32_t)((uint64_t)n_reads * (uint64_t)(t + 1) / (uint64_t)n_threads);
+        pthread_create(&th[t], NULL, seed_worker, &J[t]);
+    }
+    for (t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (sec) *sec = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    size_t n0 = 0, n1 = 0;
+    for (t = 0; t < n_threads; ++t) {
+        if (n0 + J[t].n[0] > cap0 || n1 + J[t].n[1] > cap1) rc = -1;
+        else {
+            if (J[t].n[0]) memcpy(loci0 + n0, J[t].buf[0], J[t].n[0] * 4);
+            if (J[t].n[1]) memcpy(loci1 + n1, J[t].buf[1], J[t].n[1] * 4);
+        }
+        n0 += J[t].n[0]; n1 += J[t].n[1];
+        free(J[t].buf[0]); free(J[t].buf[1]);
+    }
+    offs0[0] = offs1[0] = 0;
+    for (r = 0; r < n_reads; ++r) { offs0[r + 1] = offs0[r] + cnt0[r]; offs1[r + 1] = offs1[r] + cnt1[r]; }
+    free(cnt0); free(cnt1); free(J); free(th);
     return rc;
 }

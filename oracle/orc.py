@@ -406,6 +406,25 @@ class SeedRef:
         assert rc == 0
         return offs0, loci0[:offs0[-1]].copy(), offs1, loci1[:offs1[-1]].copy()
 
+    def run_mt(self, codes, roffs, l_seed, l_overlap, max_seed, max_locate, n_threads, seed_only_ref=0):
+        """the same on n_threads pthreads; returns (lists..., seconds)"""
+        codes = np.ascontiguousarray(codes, np.uint8).reshape(-1); roffs = np.ascontiguousarray(roffs, np.uint32)
+        n = len(roffs) - 1
+        cap = n * 64 + 1024
+        while True:
+            offs0 = np.zeros(n + 1, np.uint32); offs1 = np.zeros(n + 1, np.uint32)
+            loci0 = np.zeros(cap, np.uint32); loci1 = np.zeros(cap, np.uint32)
+            sec = C.c_double(0.0)
+            self.lib.seedref_run_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                                                C.POINTER(C.c_double)]
+            rc = self.lib.seedref_run_mt(self.ix, codes.ctypes.data, roffs.ctypes.data, n, l_seed, l_overlap if l_overlap > 0 else l_seed,
+                                         max_seed, max_locate, seed_only_ref, n_threads, offs0.ctypes.data, loci0.ctypes.data, cap,
+                                         offs1.ctypes.data, loci1.ctypes.data, cap, C.byref(sec))
+            if rc == 0:
+                return offs0, loci0[:offs0[-1]].copy(), offs1, loci1[:offs1[-1]].copy(), sec.value
+            cap *= 4
+
     def close(self):
         if self.ix:
             self.lib.seedref_close(self.ix)

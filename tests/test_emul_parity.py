@@ -213,3 +213,31 @@ def test_build_mixref_on_device(emul_lib, oracle):
     eng = api.Engine.from_bases(fasta, pos, mask, lib=emul_lib)
     assert np.array_equal(eng.get_mixref(), want)
     assert np.array_equal(want, g.mixref)
+
+
+def test_seed_locate_lists(emul_lib, tmp_path):
+    """row f1 on the emulator: the device's candidate lists equal the reference's own alnse_seed_overlap +
+    alnse_locate_alt (libsaltref_seed.so) on an index written by the reference's salt-idx -- repeat-rich genome,
+    ragged reads, N in reads and reference, six option sets"""
+    import seed_cases as sc
+    from oracle import orc
+    from salt_b200 import index_io
+    if not sc.have_ref():
+        pytest.skip("oracle/_ref not built (reference tree absent at build time)")
+    rng = np.random.default_rng(3)
+    g, is_n = sc.repeat_genome(rng, n_units=24, unit_len=900, n_rate=0.001)
+    prefix = sc.write_index(str(tmp_path), g, is_n, rng)
+    fm = index_io.FmIndex(prefix)
+    codes, roffs = sc.sample_reads(g, rng, 14)
+    ref = orc.SeedRef(prefix)
+    eng = api.Engine(fm.mixref, fm.l, None, 0, lib=emul_lib)
+    eng.set_index(fm)
+    assert sc.check_lists(eng, ref, fm, codes, roffs) > 500
+    # and the verification stage on the lists the seeding left on the device == on the same lists uploaded
+    opt = api.Engine.seed_opt(fm.l_seed, 0, 50, 500)
+    offs0, loci0, offs1, loci1 = eng.seed_locate(opt)
+    got = eng.verify_seeded(len(loci0), len(loci1))
+    want = eng.verify(offs0, loci0, offs1, loci1)
+    for a, b, name in zip(got, want, ("rec", "acc0", "acc1", "cigars")):
+        assert a.tobytes() == b.tobytes(), name
+    ref.close(); eng.close()
