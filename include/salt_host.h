@@ -60,6 +60,12 @@ int salt_chunk_add_read(salt_chunk_t *c, const uint8_t *seq, uint32_t l_seq,
 int salt_chunk_submit(salt_b200_t *h, int slot, salt_chunk_t *c, int nogap_T0, int lv_T0);
 int salt_chunk_wait(salt_b200_t *h, int slot, salt_chunk_t *c);
 
+/* Seeding on the device: the chunk's reads were added with n0 = n1 = 0; this uploads them,
+ * runs alnse_seed_overlap + alnse_locate_alt and the verification stage on the GPU (salt_b200_set_index must have been
+ * called), and brings the candidate lists back into the chunk so that salt_chunk_result / salt_chunk_hits work as
+ * after salt_chunk_wait.  Synchronous, slot 0.  SALT_ERR_NOMEM when the lists exceed the chunk's max_cands. */
+int salt_chunk_seed_verify(salt_b200_t *h, salt_chunk_t *c, const salt_seed_opt_t *opt, int nogap_T0, int lv_T0);
+
 /* After salt_chunk_wait: the query_t fields of read i, with query_set_hits(max_hits) applied to
  * the accepted hits exactly as the reference does (including its use of element 0's n_diff,
  * query.c:317-318).  1 <= max_hits <= SALT_MAX_HITS. */

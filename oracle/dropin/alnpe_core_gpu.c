@@ -21,6 +21,7 @@
  *            touching the end of the reference, CIGAR longer than the stride), runs the reference's own
  *            ssw_align instead and is counted.
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -494,6 +495,42 @@ static void pair_and_emit(salt_b200_t *gpu, index_t *index, aln_opt_t *aln_opt, 
     for (j = first; j < upto; j += 2) alnpe_sam(index, multi_seqs + j, aln_opt);
 }
 
+/* phase 1 on -t worker threads, as alnpe_core runs alnpe_core1 on them (alnpe.c:482-528, :596-606): every worker its own
+ * aux_t pair, mates interleaved statically (alnpe.c:487) */
+typedef struct { uint32_t *a[2]; uint32_t n[2], m[2]; int skip; } pe_seeded_t;
+typedef struct { int tid, n_threads, n; index_t *index; query_t *queries; aln_opt_t *aln_opt; pe_seeded_t *out; aux_t *aux[2]; } pe_seed_thread_t;
+
+static void *pe_seed_worker(void *arg)
+{
+    pe_seed_thread_t *T = (pe_seed_thread_t *)arg;
+    int i, s;
+    for (i = T->tid; i < T->n; i += T->n_threads) {
+        query_t *query = T->queries + i;
+        pe_seeded_t *o = T->out + i;
+        o->n[0] = o->n[1] = 0;
+        o->skip = query->n_ambiguous > DROPIN_PE_MAX_N_PERSEQ;       /* alnpe.c:495 */
+        if (o->skip) continue;
+        if (query->l_seq - T->aln_opt->l_seed + 1 > T->aux[0]->n_sai_range) {
+            int n_sai_range = query->l_seq - T->aln_opt->l_seed + 1;
+            aux_resize(T->aux[0], n_sai_range);
+            aux_resize(T->aux[1], n_sai_range);
+        }
+        aux_reset(T->aux[0]);
+        aux_reset(T->aux[1]);
+        alnse_seed_overlap(T->index, query->l_seq, query->seq, T->aln_opt, T->aux[0]);
+        alnse_locate(T->index, query->l_seq, T->aln_opt->max_locate, T->aux[0]);
+        alnse_seed_overlap(T->index, query->l_seq, query->rseq, T->aln_opt, T->aux[1]);
+        alnse_locate(T->index, query->l_seq, T->aln_opt->max_locate, T->aux[1]);
+        for (s = 0; s < 2; ++s) {
+            const uint32_t k = (uint32_t)T->aux[s]->loci.n;
+            if (k > o->m[s]) { o->m[s] = k + 16; o->a[s] = realloc(o->a[s], (size_t)o->m[s] * 4); }
+            memcpy(o->a[s], T->aux[s]->loci.a, (size_t)k * 4);
+            o->n[s] = k;
+        }
+    }
+    return NULL;
+}
+
 int alnpe_core(const opt_t *opt)
 {
     int i;
@@ -508,9 +545,16 @@ int alnpe_core(const opt_t *opt)
     queryio_t *qs[2];
     qs[0] = query_open(opt->fn_read1);
     qs[1] = query_open(opt->fn_read2);
-    aux_t *aux[2];
-    aux[0] = aux_init(opt->l_read, opt->l_seed);
-    aux[1] = aux_init(opt->l_read, opt->l_seed);
+    const int n_threads = opt->n_threads > 1 ? opt->n_threads : 1;
+    pe_seed_thread_t *T = calloc((size_t)n_threads, sizeof *T);
+    pthread_t *th = calloc((size_t)n_threads, sizeof *th);
+    pe_seeded_t *seeds = calloc(N_SEQS, sizeof *seeds);
+    int t;
+    for (t = 0; t < n_threads; ++t) {
+        T[t].tid = t; T[t].n_threads = n_threads; T[t].index = index; T[t].aln_opt = aln_opt;
+        T[t].aux[0] = aux_init(opt->l_read, opt->l_seed);
+        T[t].aux[1] = aux_init(opt->l_read, opt->l_seed);
+    }
     aln_samhead(opt, index->bntseq);
 
     int n, tot = 0;
@@ -521,6 +565,12 @@ int alnpe_core(const opt_t *opt)
     while ((n = query_read_multiPairedSeqs(qs, N_SEQS, multi_seqs)) > 0) {
         if (opt->max_tlen == 0) { fprintf(stderr, "infer isize func haven't been implemented\n"); break; }
         int first = 0;                               /* mates [first, i) are queued; first is always even */
+        for (t = 0; t < n_threads; ++t) { T[t].n = n; T[t].queries = multi_seqs; T[t].out = seeds; }
+        if (n_threads == 1) pe_seed_worker(&T[0]);
+        else {
+            for (t = 0; t < n_threads; ++t) pthread_create(&th[t], NULL, pe_seed_worker, &T[t]);
+            for (t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+        }
         salt_chunk_reset(ck);
         for (i = 0; i <= n; ++i) {
             int flush = (i == n);
@@ -528,23 +578,11 @@ int alnpe_core(const opt_t *opt)
                 query_t *query = multi_seqs + i;
                 int at;
                 slot_of[i] = -1; verified[i] = 0;
-                if (query->n_ambiguous > DROPIN_PE_MAX_N_PERSEQ) {
+                if (seeds[i].skip) {
                     /* alnpe.c:495 skips its verification; the mate still has to be on the device for a possible rescue */
                     at = salt_chunk_add_read(ck, query->seq, query->l_seq, NULL, 0, NULL, 0);
                 } else {
-                    if (query->l_seq - aln_opt->l_seed + 1 > aux[0]->n_sai_range) {
-                        int n_sai_range = query->l_seq - aln_opt->l_seed + 1;
-                        aux_resize(aux[0], n_sai_range);
-                        aux_resize(aux[1], n_sai_range);
-                    }
-                    aux_reset(aux[0]);
-                    aux_reset(aux[1]);
-                    alnse_seed_overlap(index, query->l_seq, query->seq, aln_opt, aux[0]);
-                    alnse_locate(index, query->l_seq, aln_opt->max_locate, aux[0]);
-                    alnse_seed_overlap(index, query->l_seq, query->rseq, aln_opt, aux[1]);
-                    alnse_locate(index, query->l_seq, aln_opt->max_locate, aux[1]);
-                    at = salt_chunk_add_read(ck, query->seq, query->l_seq, aux[0]->loci.a, aux[0]->loci.n,
-                                             aux[1]->loci.a, aux[1]->loci.n);
+                    at = salt_chunk_add_read(ck, query->seq, query->l_seq, seeds[i].a[0], seeds[i].n[0], seeds[i].a[1], seeds[i].n[1]);
                     verified[i] = 1;
                 }
                 if (at == SALT_ERR_NOMEM && salt_chunk_n_reads(ck) > 0) flush = 2;       /* queue full */
@@ -589,8 +627,10 @@ int alnpe_core(const opt_t *opt)
             apply_checked, apply_rescued, apply_swapped, apply_skipped, apply_mismatch);
     fprintf(stderr, "[salt_dropin/pe] pairs finished by salt_pair_apply alone: %zu, handed back to the reference's pairing: %zu\n",
             apply_final, apply_fallback);
-    aux_destroy(aux[0]);
-    aux_destroy(aux[1]);
+    fprintf(stderr, "[salt_dropin/pe] %d seeding threads\n", n_threads);
+    for (t = 0; t < n_threads; ++t) { aux_destroy(T[t].aux[0]); aux_destroy(T[t].aux[1]); }
+    for (i = 0; i < N_SEQS; ++i) { free(seeds[i].a[0]); free(seeds[i].a[1]); }
+    free(T); free(th); free(seeds);
     query_close(qs[0]);
     query_close(qs[1]);
     free(multi_seqs); free(slot_of); free(verified);

@@ -14,9 +14,11 @@
  *
  * Nothing from the reference is copied here: this file only CALLS its functions.
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "kvec.h"
 #include "aln.h"
@@ -59,9 +61,58 @@ static void finish_read(index_t *index, query_t *query, const aln_opt_t *aln_opt
     }
 }
 
+/* ---- seeding on the host: the reference's own alnse_seed_overlap / alnse_locate_alt on -t worker threads, as
+ * alnse_core_thread runs them (alnse.c:1282-1310, :1423-1428); every worker keeps its own aux_t pair ------------- */
+typedef struct { uint32_t *a[2]; uint32_t n[2], m[2]; int skip; } seeded_read_t;
+typedef struct {
+    int tid, n_threads, n; index_t *index; query_t *queries; aln_opt_t *aln_opt; seeded_read_t *out; aux_t *aux[2];
+} seed_thread_t;
+
+static void *seed_worker(void *arg)
+{
+    seed_thread_t *T = (seed_thread_t *)arg;
+    int i, s;
+    for (i = T->tid; i < T->n; i += T->n_threads) {              /* static interleave, as alnse_core1 (alnse.c:1321) */
+        query_t *query = T->queries + i;
+        seeded_read_t *o = T->out + i;
+        o->n[0] = o->n[1] = 0;
+        o->skip = query->n_ambiguous > DROPIN_MAX_N_PERSEQ;      /* alnse.c:1296 / :1328 */
+        if (o->skip) continue;
+        if (query->l_seq - T->aln_opt->l_seed + 1 > T->aux[0]->n_sai_range) {
+            int n_sai_range = query->l_seq - T->aln_opt->l_seed + 1;
+            aux_resize(T->aux[0], n_sai_range);
+            aux_resize(T->aux[1], n_sai_range);
+        }
+        aux_reset(T->aux[0]);
+        aux_reset(T->aux[1]);
+        /* the first half of alnse_overlap_alt (alnse.c:1065-1068) */
+        alnse_seed_overlap(T->index, query->l_seq, query->seq, T->aln_opt, T->aux[0]);
+        alnse_locate_alt(T->index, query->l_seq, T->aln_opt->max_locate, T->aux[0]);
+        alnse_seed_overlap(T->index, query->l_seq, query->rseq, T->aln_opt, T->aux[1]);
+        alnse_locate_alt(T->index, query->l_seq, T->aln_opt->max_locate, T->aux[1]);
+        for (s = 0; s < 2; ++s) {
+            const uint32_t k = (uint32_t)T->aux[s]->loci.n;
+            if (k > o->m[s]) { o->m[s] = k + 16; o->a[s] = realloc(o->a[s], (size_t)o->m[s] * 4); }
+            memcpy(o->a[s], T->aux[s]->loci.a, (size_t)k * 4);
+            o->n[s] = k;
+        }
+    }
+    return NULL;
+}
+
+static double now_s(void)
+{
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+
 int alnse_core(const opt_t *opt)
 {
-    fprintf(stderr, "[alnse_core/gpu]:  Start single end alignment (verification on libsalt_b200)\n");
+    const char *seed_env = getenv("SALT_DROPIN_SEED");
+    const int gpu_seed = seed_env && !strcmp(seed_env, "gpu");
+    fprintf(stderr, "[alnse_core/gpu]:  Start single end alignment (verification on libsalt_b200%s)\n",
+            gpu_seed ? ", seeding + locate on libsalt_b200" : "");
     aln_opt_t *aln_opt = aln_opt_init(opt);
     index_t *index = alnse_index_reload(opt->fn_index);
     if (aln_opt->extend_algo == EXTEND_SW || aln_opt->l_overlap <= 0) {
@@ -70,59 +121,118 @@ int alnse_core(const opt_t *opt)
     }
     salt_b200_t *gpu = salt_b200_init(index->mixRef->seq, index->mixRef->l, index->pac, index->bntseq->l_pac, 0);
     if (!gpu) die("salt_b200_init");
-    salt_chunk_t *ck = salt_chunk_new(DROPIN_CHUNK_READS, (size_t)DROPIN_CHUNK_READS * 1024, DROPIN_CHUNK_CANDS);
-    if (!ck) die("salt_chunk_new");
-    aux_t *aux[2];
-    aux[0] = aux_init(opt->l_read, opt->l_seed);
-    aux[1] = aux_init(opt->l_read, opt->l_seed);
-
+    salt_seed_opt_t sopt;
+    sopt.l_seed = aln_opt->l_seed; sopt.l_overlap = aln_opt->l_overlap; sopt.max_seed = aln_opt->max_seed;
+    sopt.max_locate = (int)aln_opt->max_locate; sopt.seed_only_ref = aln_opt->seed_only_ref;
+    if (gpu_seed) {
+        /* the FM-indexes exactly as the reference's loaders left them in memory (indexio.c:23-50) */
+        salt_fm_index_t fx;
+        int i;
+        rbwt_t *r = index->rbwt2->rbwt1;
+        memset(&fx, 0, sizeof fx);
+        fx.c_bwt = index->cbwt->bwt; fx.c_bwt_words = index->cbwt->bwt_size;
+        fx.c_primary = index->cbwt->primary; fx.c_seq_len = index->cbwt->seq_len;
+        for (i = 0; i < 5; ++i) fx.c_L2[i] = index->cbwt->L2[i];
+        fx.c_sa = index->cbwt->sa; fx.c_n_sa = index->cbwt->n_sa; fx.c_sa_intv = (uint32_t)index->cbwt->sa_intv;
+        fx.lkt = index->lkt->item; fx.lkt_len = index->lkt->maxLookupLen;
+        fx.r_bwt = r->bwtCode; fx.r_bwt_words = r->bwtSizeInWord;
+        fx.r_occ = r->occValue; fx.r_occ_words = r->occSizeInWord;
+        fx.r_occ_major = r->occValueMajor; fx.r_occ_major_words = r->occMajorSizeInWord;
+        fx.r_sa_sharp = r->saValueSharp; fx.r_n_sa_sharp = r->saValueSizeSharp;
+        for (i = 0; i < 6; ++i) fx.r_cum[i] = r->cumulativeFreq[i];
+        fx.r_inv_sa0 = r->inverseSa0; fx.r_text_len = r->textLength;
+        if (salt_b200_set_index(gpu, &fx) != SALT_OK) die("salt_b200_set_index");
+    }
+    /* two chunk queues: while the GPU verifies one, the host finishes (hit selection, SAM text) the other */
+    salt_chunk_t *ck[2];
+    int c;
+    for (c = 0; c < 2; ++c) {
+        ck[c] = salt_chunk_new(DROPIN_CHUNK_READS, (size_t)DROPIN_CHUNK_READS * 1024, DROPIN_CHUNK_CANDS);
+        if (!ck[c]) die("salt_chunk_new");
+    }
+    const int n_threads = opt->n_threads > 1 ? opt->n_threads : 1;
+    seed_thread_t *T = calloc((size_t)n_threads, sizeof *T);
+    pthread_t *th = calloc((size_t)n_threads, sizeof *th);
+    int t;
+    for (t = 0; t < n_threads; ++t) {
+        T[t].tid = t; T[t].n_threads = n_threads; T[t].index = index; T[t].aln_opt = aln_opt;
+        T[t].aux[0] = aux_init(opt->l_read, opt->l_seed);
+        T[t].aux[1] = aux_init(opt->l_read, opt->l_seed);
+    }
     queryio_t *qs = query_open(opt->fn_read1);
     query_t *multiSeqs = calloc(N_SEQS, sizeof(query_t));
-    int *slot_of = calloc(N_SEQS, sizeof(int));        /* index of read i in the GPU chunk being filled */
+    seeded_read_t *seeds = calloc(N_SEQS, sizeof(seeded_read_t));
+    int *slot_of = calloc(N_SEQS, sizeof(int));        /* index of read i in the GPU chunk that holds it */
     aln_samhead(opt, index->bntseq);
-    int n, i, n_tot = 0;
+    int n, i, n_tot = 0, n_chunks = 0;
+    double t_seed = 0, t_gpu_wait = 0, t_finish = 0;
     while ((n = query_read_multiSeqs(qs, N_SEQS, multiSeqs)) > 0) {
         n_tot += n;
-        int first = 0;                                 /* reads [first, i) are queued in ck */
-        salt_chunk_reset(ck);
-        for (i = 0; i <= n; ++i) {
-            int flush = (i == n);
-            if (!flush) {
-                query_t *query = multiSeqs + i;
-                slot_of[i] = -1;
-                if (query->n_ambiguous > DROPIN_MAX_N_PERSEQ) continue;          /* alnse.c:1328 */
-                if (query->l_seq - aln_opt->l_seed + 1 > aux[0]->n_sai_range) {
-                    int n_sai_range = query->l_seq - aln_opt->l_seed + 1;
-                    aux_resize(aux[0], n_sai_range);
-                    aux_resize(aux[1], n_sai_range);
-                }
-                aux_reset(aux[0]);
-                aux_reset(aux[1]);
-                /* seeding + locate: the reference's own code, the first half of alnse_overlap_alt (alnse.c:1065-1068) */
-                alnse_seed_overlap(index, query->l_seq, query->seq, aln_opt, aux[0]);
-                alnse_locate_alt(index, query->l_seq, aln_opt->max_locate, aux[0]);
-                alnse_seed_overlap(index, query->l_seq, query->rseq, aln_opt, aux[1]);
-                alnse_locate_alt(index, query->l_seq, aln_opt->max_locate, aux[1]);
-                int at = salt_chunk_add_read(ck, query->seq, query->l_seq, aux[0]->loci.a, aux[0]->loci.n,
-                                             aux[1]->loci.a, aux[1]->loci.n);
-                if (at == SALT_ERR_NOMEM && salt_chunk_n_reads(ck) > 0) { flush = 1; --i; }   /* queue full: verify what is queued, retry */
-                else if (at < 0) die("salt_chunk_add_read");
-                else slot_of[i] = at;
+        double t0 = now_s();
+        if (!gpu_seed) {
+            for (t = 0; t < n_threads; ++t) { T[t].n = n; T[t].queries = multiSeqs; T[t].out = seeds; }
+            if (n_threads == 1) seed_worker(&T[0]);
+            else {
+                for (t = 0; t < n_threads; ++t) pthread_create(&th[t], NULL, seed_worker, &T[t]);
+                for (t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
             }
-            if (flush) {
-                int upto = (i < n) ? i + 1 : n, j;
-                if (salt_chunk_n_reads(ck) > 0) {
-                    /* SE thresholds: nogap 3 (alnse.c:1079), gapped l_seq/10 (alnse.c:1090) */
-                    if (salt_chunk_submit(gpu, 0, ck, 3, -1) != SALT_OK) die("salt_chunk_submit");
-                    if (salt_chunk_wait(gpu, 0, ck) != SALT_OK) die("salt_chunk_wait");
+        } else {
+            for (i = 0; i < n; ++i) { seeds[i].skip = multiSeqs[i].n_ambiguous > DROPIN_MAX_N_PERSEQ; seeds[i].n[0] = seeds[i].n[1] = 0; }
+        }
+        t_seed += now_s() - t0;
+        /* sub-chunks [first, upto) go to slots 0 / 1 alternately; chunk k-1 is finished on the host while k is on the GPU */
+        int first = 0, k = 0;
+        int pend_first = -1, pend_upto = -1, pend_c = -1;
+        while (first < n || pend_c >= 0) {
+            int upto = first, cur = -1;
+            if (first < n) {
+                cur = k & 1;
+                salt_chunk_reset(ck[cur]);
+                for (i = first; i < n; ++i) {
+                    slot_of[i] = -1;
+                    if (seeds[i].skip) continue;
+                    query_t *query = multiSeqs + i;
+                    int at = salt_chunk_add_read(ck[cur], query->seq, query->l_seq, seeds[i].a[0], seeds[i].n[0], seeds[i].a[1], seeds[i].n[1]);
+                    if (at == SALT_ERR_NOMEM && salt_chunk_n_reads(ck[cur]) > 0) break;       /* queue full: verify what is queued */
+                    if (at < 0) die("salt_chunk_add_read");
+                    slot_of[i] = at;
+                    if (gpu_seed && salt_chunk_n_reads(ck[cur]) * (size_t)sopt.max_locate >= DROPIN_CHUNK_CANDS) { ++i; break; }
                 }
-                for (j = first; j < upto; ++j)
-                    if (slot_of[j] >= 0) finish_read(index, multiSeqs + j, aln_opt, ck, (uint32_t)slot_of[j]);
-                if (aln_opt->print_nm_md || aln_opt->print_xa_cigar) dropin_tail_prepare(gpu, 0, multiSeqs, slot_of, first, upto);
-                for (j = first; j < upto; ++j)
+                upto = i;
+                double tg = now_s();
+                if (gpu_seed) {
+                    /* SE thresholds: nogap 3 (alnse.c:1079), gapped l_seq/10 (alnse.c:1090) */
+                    if (salt_chunk_seed_verify(gpu, ck[cur], &sopt, 3, -1) != SALT_OK) die("salt_chunk_seed_verify");
+                } else if (salt_chunk_n_reads(ck[cur]) > 0) {
+                    if (salt_chunk_submit(gpu, cur, ck[cur], 3, -1) != SALT_OK) die("salt_chunk_submit");
+                }
+                t_gpu_wait += now_s() - tg;
+                ++n_chunks;
+            }
+            if (pend_c >= 0) {                          /* finish the previous sub-chunk while the GPU works on this one */
+                int j;
+                double tg = now_s();
+                if (!gpu_seed && salt_chunk_wait(gpu, pend_c, ck[pend_c]) != SALT_OK) die("salt_chunk_wait");
+                t_gpu_wait += now_s() - tg;
+                double tf = now_s();
+                for (j = pend_first; j < pend_upto; ++j)
+                    if (slot_of[j] >= 0) finish_read(index, multiSeqs + j, aln_opt, ck[pend_c], (uint32_t)slot_of[j]);
+                if (aln_opt->print_nm_md || aln_opt->print_xa_cigar)
+                    dropin_tail_prepare(gpu, gpu_seed ? 0 : pend_c, multiSeqs, slot_of, pend_first, pend_upto);
+                for (j = pend_first; j < pend_upto; ++j)
                     if (slot_of[j] >= 0) aln_samse(index, multiSeqs + j, aln_opt);     /* alnse.c:1307 / :1345 */
-                first = upto;
-                salt_chunk_reset(ck);
+                t_finish += now_s() - tf;
+                pend_c = -1;
+            }
+            if (cur >= 0) {
+                if (gpu_seed) {
+                    /* synchronous on slot 0: finish right away (the tail needs the slot's reads still resident) */
+                    pend_c = cur; pend_first = first; pend_upto = upto;
+                    first = upto; ++k;
+                    continue;
+                }
+                pend_c = cur; pend_first = first; pend_upto = upto;
+                first = upto; ++k;
             }
         }
         for (i = 0; i < n; ++i) {
@@ -133,11 +243,15 @@ int alnse_core(const opt_t *opt)
         memset(multiSeqs, 0, N_SEQS * sizeof(query_t));
         fprintf(stderr, "%d reads have been aligned!\n", n_tot);
     }
-    aux_destroy(aux[0]);
-    aux_destroy(aux[1]);
+    fprintf(stderr, "[salt_dropin] %d reads, %d GPU chunks, %d seeding threads: seeding %s %.3f s, GPU calls (exposed wait) %.3f s, "
+                    "hit selection + SAM text %.3f s\n", n_tot, n_chunks, n_threads, gpu_seed ? "(on the GPU, inside the GPU calls)" : "on the host",
+            t_seed, t_gpu_wait, t_finish);
+    for (t = 0; t < n_threads; ++t) { aux_destroy(T[t].aux[0]); aux_destroy(T[t].aux[1]); }
+    for (i = 0; i < N_SEQS; ++i) { free(seeds[i].a[0]); free(seeds[i].a[1]); }
+    free(T); free(th); free(seeds);
     free(multiSeqs); free(slot_of);
     query_close(qs);
-    salt_chunk_free(ck);
+    salt_chunk_free(ck[0]); salt_chunk_free(ck[1]);
     dropin_tail_report();
     salt_b200_destroy(gpu);
     alnse_index_destroy(index);

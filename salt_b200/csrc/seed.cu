@@ -303,7 +303,7 @@ __device__ void sai_introsort(int n, SeedSai *a)
 }
 
 // ---------------------------------------------------------------- alnse_locate_alt, one warp per (read, strand)
-// shared memory per warp: max_seeds sai (12 B each), then cap2 = pow2 >= max_locate loci
+// shared memory per warp: max_seeds sai (12 B each), max_seeds + 1 row offsets (64 bit), then cap2 = pow2 >= max_locate loci
 __global__ void __launch_bounds__(128)
 locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, uint32_t n_reads, int max_seeds, int cap2,
               uint32_t ref_l, SeedSai *__restrict__ sai, uint32_t *__restrict__ counts /* [2][n_reads] */,
@@ -312,9 +312,11 @@ locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, ui
     constexpr unsigned FULL = 0xffffffffu;
     SALT_DYN_SMEM(uint32_t, s_mem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t per_warp = (size_t)max_seeds * 3 + (size_t)cap2;
+    const size_t per_warp = (size_t)max_seeds * 3 + 2 * ((size_t)max_seeds + 2) + (size_t)cap2;
     SeedSai *s_sai = reinterpret_cast<SeedSai *>(s_mem + warp * per_warp);
-    uint32_t *s_loci = s_mem + warp * per_warp + (size_t)max_seeds * 3;
+    // row offsets are 64 bit: an interval that could not be narrowed may span the whole suffix array
+    unsigned long long *s_row = reinterpret_cast<unsigned long long *>(s_mem + warp * per_warp + (((size_t)max_seeds * 3 + 1) & ~(size_t)1));
+    uint32_t *s_loci = s_mem + warp * per_warp + (size_t)max_seeds * 3 + 2 * ((size_t)max_seeds + 2);
     const size_t rs_raw = (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
     const bool live = rs_raw < (size_t)n_reads * 2;
     const size_t rs = live ? rs_raw : 0;
@@ -324,45 +326,57 @@ locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, ui
     SeedSai *g = sai + rs * 2 * (size_t)max_seeds;
     uint32_t n = 0;                                                   // aux->loci.n
     for (int part = 0; part < 2 && live; ++part) {                    // 0: sai_C, 1: sai_backwardR (sai_forwardR is empty here)
-        // compact the valid intervals in seed order, sort them as the reference does
+        // compact the valid intervals in seed order, sort them as the reference does, lay their rows end to end
         int m = 0;
         if (lane == 0) {
             for (int i = 0; i < max_seeds; ++i) { const SeedSai v = g[part * max_seeds + i]; if (v.sp <= v.ep) s_sai[m++] = v; }
             sai_introsort(m, s_sai);
+            unsigned long long acc = 0;
+            for (int i = 0; i < m; ++i) {
+                const SeedSai v = s_sai[i];
+                uint32_t skip = 1;
+                if (part == 1) { skip = (v.ep + 1 - v.sp) / 0x40000u; if ((int)skip <= 0) skip = 1; }    // alnse.c:702-703
+                s_row[i] = acc;
+                acc += ((unsigned long long)(v.ep - v.sp)) / skip + 1;                                   // rows sp, sp+skip, .. <= ep
+            }
+            s_row[m] = acc;
         }
         m = __shfl_sync(FULL, m, 0);
         __syncwarp();
-        for (int i = 0; i < m && n < max_locate; ++i) {
-            const SeedSai v = s_sai[i];
-            uint32_t skip = 1;
-            if (part == 1) { skip = (v.ep + 1 - v.sp) / 0x40000u; if ((int)skip <= 0) skip = 1; }    // alnse.c:702-703
-            // rows sp, sp+skip, .. <= ep; 32 at a time
-            const uint64_t rows = ((uint64_t)(v.ep - v.sp)) / skip + 1;
-            for (uint64_t b = 0; b < rows && n < max_locate; b += 32) {
-                const uint64_t idx = b + (uint64_t)lane;
-                bool keep = false;
-                uint32_t pos = 0;
-                if (idx < rows) {
-                    const uint32_t j = v.sp + (uint32_t)idx * skip;
-                    pos = (part == 0 ? c_sa(ix, j) : r_sa(ix, j)) - v.offset;          // uint32 arithmetic, may wrap (alnse.c:669)
-                    keep = !(pos + l_seq > ref_l);
-                    if (part == 1 && pos > ref_l) keep = false;                       // alnse.c:711
-                }
-                const unsigned bal = __ballot_sync(FULL, keep);
-                const uint32_t rank = (uint32_t)__popc(bal & ((1u << lane) - 1u));
-                if (keep && n + rank < max_locate) s_loci[n + rank] = pos;
-                n = min(max_locate, n + (uint32_t)__popc(bal));
+        const unsigned long long rows = m ? s_row[m] : 0ull;
+        // the reference walks interval after interval, row after row, and stops at max_locate pushes: the same order,
+        // 32 rows at a time over the concatenation of all intervals
+        for (unsigned long long b = 0; b < rows && n < max_locate; b += 32) {
+            const unsigned long long flat = b + (unsigned long long)lane;
+            bool keep = false;
+            uint32_t pos = 0;
+            if (flat < rows) {
+                int lo = 0, hi = m - 1;                               // last interval whose first row is <= flat
+                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_row[mid] <= flat) lo = mid; else hi = mid - 1; }
+                const SeedSai v = s_sai[lo];
+                uint32_t skip = 1;
+                if (part == 1) { skip = (v.ep + 1 - v.sp) / 0x40000u; if ((int)skip <= 0) skip = 1; }
+                const uint32_t j = v.sp + (uint32_t)(flat - s_row[lo]) * skip;
+                pos = (part == 0 ? c_sa(ix, j) : r_sa(ix, j)) - v.offset;              // uint32 arithmetic, may wrap (alnse.c:669)
+                keep = !(pos + l_seq > ref_l);
+                if (part == 1 && pos > ref_l) keep = false;                           // alnse.c:711
             }
+            const unsigned bal = __ballot_sync(FULL, keep);
+            const uint32_t rank = (uint32_t)__popc(bal & ((1u << lane) - 1u));
+            if (keep && n + rank < max_locate) s_loci[n + rank] = pos;
+            n = min(max_locate, n + (uint32_t)__popc(bal));
         }
         __syncwarp();
     }
-    // ks_introsort(uint32_t) of the list: any correct sort gives the same array; bitonic over cap2 padded with ~0
-    for (uint32_t i = n + lane; i < (uint32_t)cap2; i += 32) s_loci[i] = 0xFFFFFFFFu;
+    // ks_introsort(uint32_t) of the list: any correct sort gives the same array; bitonic over the next power of two,
+    // padded with ~0 (a pad can equal a real, wrapped locus 0xFFFFFFFF: equal keys, the sorted prefix is still right)
+    uint32_t n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (uint32_t i = n + lane; i < n2; i += 32) s_loci[i] = 0xFFFFFFFFu;
     __syncwarp();
-    // a pad value can equal a real (wrapped) locus 0xFFFFFFFF: equal keys, so the sorted prefix is still right
-    for (uint32_t k = 2; k <= (uint32_t)cap2; k <<= 1)
+    for (uint32_t k = 2; k <= n2; k <<= 1)
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = lane; i < (uint32_t)cap2; i += 32) {
+            for (uint32_t i = lane; i < n2; i += 32) {
                 const uint32_t p = i ^ j;
                 if (p > i) {
                     const uint32_t a = s_loci[i], b = s_loci[p];
@@ -413,7 +427,7 @@ cudaError_t launch_locate(const FmIndexDev &ix, const SeedOpt &opt, const uint32
     if (!n_reads) return cudaSuccess;
     int cap2 = 32;
     while (cap2 < opt.max_locate) cap2 <<= 1;
-    const size_t per_warp = ((size_t)max_seeds * 3 + (size_t)cap2) * 4;
+    const size_t per_warp = ((size_t)max_seeds * 3 + 2 * ((size_t)max_seeds + 2) + (size_t)cap2) * 4;
     int warps = 4;
     while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
     if (per_warp * warps > 200 * 1024) return cudaErrorInvalidValue;

@@ -105,6 +105,23 @@ int salt_chunk_wait(salt_b200_t *h, int slot, salt_chunk_t *c)
     return rc;
 }
 
+int salt_chunk_seed_verify(salt_b200_t *h, salt_chunk_t *c, const salt_seed_opt_t *opt, int nogap_T0, int lv_T0)
+{
+    if (!h || !c || !opt) return SALT_ERR_ARG;
+    c->lv_T0 = lv_T0; c->done = 0;
+    if (!c->n_reads) { c->done = 1; return SALT_OK; }
+    salt_reads_t r; r.codes = c->codes; r.offs = c->roffs; r.n_reads = c->n_reads;
+    int rc = salt_b200_set_reads(h, &r);
+    if (rc != SALT_OK) return rc;
+    size_t n0 = 0, n1 = 0;
+    rc = salt_b200_seed_locate(h, 0, opt, c->offs[0], c->offs[1], c->loci[0], c->max_cands, c->loci[1], c->max_cands, &n0, &n1);
+    if (rc != SALT_OK) return rc;
+    for (uint32_t i = 0; i < c->n_reads; ++i) c->cigars[(size_t)i * 128] = '\0';
+    rc = salt_b200_verify_seeded(h, 0, nogap_T0, lv_T0, c->rec, c->acc[0], c->acc[1], c->cigars, 128);
+    if (rc == SALT_OK) c->done = 1;
+    return rc;
+}
+
 int salt_chunk_hits(const salt_chunk_t *c, uint32_t i, int strand, salt_hit_t *out, int cap)
 {
     if (!c->done || i >= c->n_reads || strand < 0 || strand > 1) return SALT_ERR_ARG;

@@ -33,17 +33,24 @@ def _sam_body(path):
     return [ln for ln in open(path).read().split("\n") if not ln.startswith("@PG")]     # @PG carries date + command line
 
 
-@pytest.mark.parametrize("flags", [["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500", "-t", "1"],     # run_se_test.sh:12
-                                   ["-r", "1", "-l", "100", "-t", "1"]])
-def test_se_sam_identical(tmp_path, flags):
+@pytest.mark.parametrize("flags,seed", [(["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500", "-t", "1"], "host"),     # run_se_test.sh:12
+                                        (["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500", "-t", "4"], "host"),     # ... as shipped: 4 seeding threads
+                                        (["-r", "1", "-l", "100", "-t", "1"], "host"),
+                                        (["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500", "-t", "4"], "gpu"),      # seeding + locate on the device too
+                                        (["-r", "1", "-l", "100", "-t", "1"], "gpu")])
+def test_se_sam_identical(tmp_path, flags, seed):
     if not _have():
         pytest.skip("oracle/_ref programs not built (reference tree absent at build time)")
     d = str(tmp_path)
     fa, sn, fq = dropin_data.write_inputs(d)
     _run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], d, os.path.join(d, "idx.log"))
     _run([os.path.join(REFDIR, "salt")] + flags + ["idx", "reads.fq"], d, os.path.join(d, "ref.sam"))
-    err = _run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", "reads.fq"], d, os.path.join(d, "gpu.sam"))
+    err = _run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", "reads.fq"], d, os.path.join(d, "gpu.sam"),
+               env={"SALT_DROPIN_SEED": seed})
     assert "verification on libsalt_b200" in err
+    assert ("seeding + locate on libsalt_b200" in err) == (seed == "gpu")
+    if seed == "host":
+        assert "%s seeding threads" % flags[flags.index("-t") + 1] in err
     want, got = _sam_body(os.path.join(d, "ref.sam")), _sam_body(os.path.join(d, "gpu.sam"))
     assert len(want) == len(got) and len(want) > 6000
     for a, b in zip(want, got):
@@ -163,15 +170,17 @@ def _same_sam(want_path, got_path, min_lines):
     return [ln.split("\t") for ln in want if ln and not ln.startswith("@")]
 
 
-@pytest.mark.parametrize("threads", ["4", "1"])
-def test_config0_se_sam_identical(tmp_path, threads):
+@pytest.mark.parametrize("threads,seed", [("4", "host"), ("1", "host"), ("4", "gpu")])
+def test_config0_se_sam_identical(tmp_path, threads, seed):
     """run_se_test.sh:12 flags on the bundled genome: every read ties between the two lambda copies (strand-1-wins and
     first-hit rules decide the primary), 5 % mutated reads against their own SNP table"""
     d = str(tmp_path)
     _config0_index(d)
     flags = ["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500", "-t", threads]
-    err = _run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", os.path.join(C0, "Read1.fq")], d, os.path.join(d, "gpu.sam"))
+    err = _run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", os.path.join(C0, "Read1.fq")], d, os.path.join(d, "gpu.sam"),
+               env={"SALT_DROPIN_SEED": seed})
     assert "verification on libsalt_b200" in err
+    assert ("seeding + locate on libsalt_b200" in err) == (seed == "gpu")
     body = _same_sam(os.path.join(C0, "se.sam"), os.path.join(d, "gpu.sam"), 20000)
     assert sum(1 for f in body if any(x.startswith("XA:") for x in f[11:])) >= 100
 
