@@ -534,6 +534,8 @@ def main():
         out["lv"] = bench_lv(eng, lib, h, wl, args, dev, stream)
         out["sw"] = bench_sw(eng, lib, h, wl, args, dev, stream)
         out["sam_tail"] = bench_sam_tail(eng, wl, args, d_rec, d_cig, d_cigreads, d_cigcnt)
+        if args.pe_pairs > 0:
+            out["pe"] = bench_pe(eng, wl, args)
 
     if rank == 0 and world == 1:
         try:
@@ -546,6 +548,90 @@ def main():
         _emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_pe(eng, wl, args):
+    """Paired-end pipeline through the host layer from HOST buffers (alnpe_core re-staged, alnpe.c:530-615): per chunk of
+    pairs salt_chunk_add_reads (pageable -> pinned queues), salt_chunk_submit with the PE thresholds 3 / 3, salt_chunk_wait,
+    salt_chunk_pair = query_set_hits + pairing plans + one Smith-Waterman batch per rescue flavour + apply + MD/NM/XV of every
+    mapped mate.  Chunks alternate between pipeline slots so that chunk k verifies while chunk k-1 pairs."""
+    from salt_b200 import host_api, synth
+    H = host_api.load()
+    g = wl["g"]; L = args.read_len; npairs = args.pe_pairs
+    reads, pos, strand = synth.sample_pairs(g, npairs, L, seed=77, hard_frac=0.05, junk_frac=0.005)
+    offs0, loci0, offs1, loci1 = synth.make_candidates(g, pos, strand, L, per_strand=args.cands, seed=78)
+    n = 2 * npairs
+    roffs = (np.arange(n + 1, dtype=np.uint64) * L).astype(np.uint32)
+    cpairs = 50_000                                      # N_SEQS = 100000 reads per chunk (aln.h:27)
+    n_slots = 2
+    cap_c = 0
+    for b in range(0, npairs, cpairs):
+        r0, r1 = 2 * b, 2 * min(npairs, b + cpairs)
+        cap_c = max(cap_c, int(offs0[r1]) - int(offs0[r0]), int(offs1[r1]) - int(offs1[r0]))
+    chunks = [host_api.Chunk(H, 2 * cpairs + 8, (2 * cpairs + 8) * L, cap_c + 64) for _ in range(n_slots)]
+    min_tlen, max_tlen = 250, 550                        # aln.c defaults (-a / -b)
+    stats = []
+    finals_keep = []
+
+    def run():
+        stats.clear(); finals_keep.clear()
+        pend = None
+        k = 0
+        for b in range(0, npairs, cpairs):
+            m = min(cpairs, npairs - b)
+            ch = chunks[k % n_slots]; slot = k % n_slots
+            ch.reset()
+            r0, r1 = 2 * b, 2 * (b + m)
+            ch.add_reads(reads.reshape(-1), roffs[r0:r1 + 1], offs0[r0:r1 + 1], loci0, offs1[r0:r1 + 1], loci1)
+            ch.submit(eng, slot, 3, 3)
+            if pend is not None:
+                pc_, ps_, pm_ = pend
+                pc_.wait(eng, ps_)
+                f, to, tm, st = pc_.pair(eng, ps_, pm_, min_tlen, max_tlen, g.l)
+                stats.append(st); finals_keep.append((f, to))
+            pend = (ch, slot, m); k += 1
+        pc_, ps_, pm_ = pend
+        pc_.wait(eng, ps_)
+        f, to, tm, st = pc_.pair(eng, ps_, pm_, min_tlen, max_tlen, g.l)
+        stats.append(st); finals_keep.append((f, to))
+    run()
+    t0 = time.perf_counter()
+    reps = 2
+    for _ in range(reps):
+        run()
+    sec = (time.perf_counter() - t0) / reps
+    tot = {k: sum(getattr(s_, k) for s_ in stats) for k in ("pairs", "proper", "windows16", "windows5", "rescued", "promoted", "declined")}
+    ms = {k: sum(getattr(s_, k) for s_ in stats) for k in ("ms_plan", "ms_ssw", "ms_apply", "ms_tail")}
+    mapped = sum(int((to["md_len"] > 0).sum()) for _, to in finals_keep)
+    cells = (tot["windows16"] + tot["windows5"]) * (8 * ((L + 7) // 8)) * 401
+    res = {"pairs": npairs, "read_len": L, "reads_per_s": 2 * npairs / sec, "ms": sec * 1e3, "chunk_pairs": cpairs,
+           "insert": "N(400,50)", "tlen_bounds": [min_tlen, max_tlen], "counts": tot, "stage_ms_host_wall": ms,
+           "mapped_mates_with_tags": mapped, "rescue_frac_of_pairs": (tot["windows16"] + tot["windows5"]) / max(1, npairs),
+           "sw_gcups_fwd_cells": cells / max(1e-9, ms["ms_ssw"] * 1e-3) / 1e9,
+           "how": "wall time from pageable host arrays through salt_chunk_add_reads / _submit / _wait / salt_chunk_pair (two slots "
+                  "alternating), results in host memory"}
+    for ch in chunks:
+        ch.close()
+    # the reference's functions beside it (bounded sample): verification with the PE thresholds + ssw_align on as many windows
+    try:
+        from oracle import orc
+        o = orc.Oracle(); ref = orc.Ref() if orc.ref_available() else None
+        cores = os.cpu_count() or 1
+        ns = min(n, 200_000)
+        sec_v, *_ = o.verify_batch(g.mixref, g.l, np.ascontiguousarray(reads[:ns]).reshape(-1), roffs[:ns + 1], offs0[:ns + 1].copy(),
+                                   loci0[:offs0[ns]], offs1[:ns + 1].copy(), loci1[:offs1[ns]], 3, 3, n_threads=cores, ref=ref)
+        nw = max(1, int((tot["windows16"] + tot["windows5"]) * ns / n))
+        nw = min(nw, 4000 * cores)
+        rd = reads[1:2 * nw:2]
+        rd = np.where(strand[1:2 * nw:2, None] == 1, synth.revcomp(rd), rd)
+        st_ = np.maximum(0, pos[1:2 * nw:2].astype(np.int64) - 150); en_ = np.minimum(g.l - 1, st_ + 400)
+        sec_w, _ = o.ssw_batch(g.mixref, np.ascontiguousarray(rd).reshape(-1), L, st_.astype(np.uint32), en_.astype(np.uint32),
+                               o.score_mat2(), 3, 1, n_threads=cores, ref=ref)
+        res["cpu"] = {"reads_per_s": ns / (sec_v + sec_w), "verify_s": sec_v, "ssw_s": sec_w, "windows": int(len(rd)), "cores": cores,
+                      "kind": "reference" if ref else "port", "sample": "%d mates, %d rescue windows" % (ns, len(rd))}
+    except Exception as ex:                                # noqa: BLE001
+        res["cpu"] = {"error": repr(ex)}
+    return res
 
 
 def bench_lv(eng, lib, h, wl, args, dev, stream):

@@ -279,6 +279,11 @@ int salt_b200_verify_seeded(salt_b200_t *h, int slot, int nogap_T0, int lv_T0, s
 int salt_b200_align_batch_packed(salt_b200_t *h, const salt_packed_chunk_t *pc, const salt_seed_opt_t *opt, uint32_t chunk_reads,
                                  int nogap_T0, int lv_T0, salt_verify_out_t *rec, char *cigars, int cigar_stride);
 
+/* The per-pair entry points (salt_b200_mismatch / _lv / _lv_cigar / _ssw and their _dev variants) work on the reads of
+ * slot 0 unless told otherwise: after salt_b200_verify_wait(slot) a chunk's reads stay resident in that slot until it
+ * is submitted again, so the paired-end stage can run its mate rescues on them (alnpe.c:206-252) without a re-upload. */
+int salt_b200_use_slot(salt_b200_t *h, int slot);
+
 /* Landau-Vishkin work mapping: 0 = automatic (one thread per pair with all diagonals in
  * registers for k <= 15 inside the verify stage, one warp per pair with lanes over diagonals
  * beyond that and on flat pair lists), 1 = always one warp (or sub-warp group) per pair,

@@ -132,6 +132,43 @@ int salt_pair_apply(const salt_pair_plan_t *plan, const salt_read_result_t *r0, 
                     const salt_read_result_t *r1, uint32_t l1, const salt_ssw_out_t *ssw, const uint32_t *ssw_cigars,
                     int cigar_stride, int filters, int filterd, salt_mate_final_t out[2]);
 
+/* Append n reads at once (the chunk's queues are plain arrays: this is three memcpys and three offset loops).
+ * roffs / offs0 / offs1: n + 1 offsets each, any base (they are rebased).  Returns the index of the first read added. */
+int salt_chunk_add_reads(salt_chunk_t *c, const uint8_t *codes, const uint32_t *roffs, uint32_t n,
+                         const uint32_t *offs0, const uint32_t *loci0, const uint32_t *offs1, const uint32_t *loci1);
+
+/* ---- the paired-end stage of one chunk: alnpe_core1 after seeding (alnpe.c:482-528) re-staged for batches ----------
+ * The chunk holds mates 2i, 2i+1 of pair i and has been through salt_chunk_submit (PE thresholds 3 / 3) and
+ * salt_chunk_wait on `slot`.  This runs, for the whole chunk: query_set_hits per mate (salt_chunk_result), pairing2 /
+ * pairing_singleton as plans (salt_pair_plan), ONE salt_b200_ssw call per rescue flavour on the reads still resident
+ * in the slot, salt_pair_apply, one salt_b200_lv_cigar call for gapped alternates that became primaries, and one
+ * salt_b200_md_nm call for the MD / NM / XV tags of every mapped mate (with_tail != 0; needs the 2-bit pac).
+ * out[i] = the two mates of pair i as alnpe_sam would print them; md / nm / xv of mate m of pair i are at row 2i+m. */
+typedef struct {
+    salt_mate_final_t mate[2];
+    int paired;                      /* PAIRED_ALNED */
+} salt_pair_final_t;
+typedef struct {
+    size_t pairs, proper, windows16, windows5, rescued, promoted, declined;
+    double ms_plan, ms_ssw, ms_apply, ms_tail;
+} salt_pe_stats_t;
+int salt_chunk_pair(salt_b200_t *h, int slot, salt_chunk_t *c, uint32_t min_tlen, uint32_t max_tlen, uint32_t l_pac,
+                    int max_hits, const int8_t *mat16 /* score_mat2, 256 */, const int8_t *mat5 /* score_mat, 25 */,
+                    int gapO, int gapE, int filters, int filterd, int with_tail,
+                    salt_pair_final_t *out, salt_mdnm_out_t *tail_out, char *tail_md, int md_stride, salt_pe_stats_t *stats);
+
+/* ---- several GPUs in one process (reads shard, the reference is replicated, no collective) ----
+ * salt is one process (alnse.c:1414-1440); this keeps it one: one handle per device, the batch split into contiguous
+ * shares, every share through its device's own chunk pipeline on its own host thread, every result written at the
+ * position of its read -- input order by construction. */
+typedef struct salt_multi salt_multi_t;
+salt_multi_t *salt_multi_init(const uint32_t *mixref, uint32_t l, const uint8_t *pac, int64_t l_pac, const int *devices, int n_devices);
+void salt_multi_destroy(salt_multi_t *m);
+int salt_multi_n(const salt_multi_t *m);
+salt_b200_t *salt_multi_handle(salt_multi_t *m, int i);
+int salt_multi_verify_batch_packed(salt_multi_t *m, const salt_packed_chunk_t *pc, uint32_t chunk_reads, int nogap_T0, int lv_T0,
+                                   salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1, char *cigars, int cigar_stride);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,7 +57,7 @@ def build_host(force=False, engine=OUT, out=HOST_OUT):
     if force or _stale(out, [src, engine] + hdrs):
         d, f = os.path.split(engine)
         subprocess.check_call([os.environ.get("CC", "gcc"), "-O2", "-std=gnu11", "-Wall", "-Wextra", "-fPIC", "-shared",
-                               "-o", out, src, "-L" + d, "-l:" + f, "-Wl,-rpath," + d, "-Wl,-rpath,$ORIGIN"])
+                               "-o", out, src, "-L" + d, "-l:" + f, "-Wl,-rpath," + d, "-Wl,-rpath,$ORIGIN", "-lpthread"])
     l0 = os.path.join(os.path.dirname(out), "libsalt_level0" + ("_emul" if out.endswith("_emul.so") else "") + ".so")
     src0 = os.path.join(HERE, "host", "level0_shim.c")
     if force or _stale(l0, [src0, engine] + hdrs):

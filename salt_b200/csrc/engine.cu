@@ -115,6 +115,7 @@ struct salt_b200 {
     DBuf ix_cbwt, ix_csa, ix_lkt, ix_rbwt, ix_rocc, ix_rmaj, ix_rsa;      // FM-indexes (salt_b200_set_index)
     FmIndexDev fm{}; bool have_index = false;
     uint64_t launches = 0;
+    int cur = 0;                // slot whose reads the per-pair / SSW entry points work on (salt_b200_use_slot)
     int lv_mapping = 0;         // 0 = auto, 1 = warp per pair, 2 = thread per pair (salt_b200_set_lv_mapping)
     int max_window = 1024;      // widest rescue window the SSW scratch is sized for
     bool profiling = false;
@@ -700,8 +701,8 @@ int salt_b200_mismatch_dev(salt_b200_t *h, const salt_pair_t *d_pairs, size_t n,
     if (int rc = use_device(h)) return rc;
     if (n && (!d_pairs || !d_out)) return fail(SALT_ERR_ARG, "null buffer");
     if (max_err < 0 || max_err > 127) return fail(SALT_ERR_ARG, "max_err must be in 0..127");
-    if (!h->slot[0].n_reads) return fail(SALT_ERR_ARG, "no reads set");
-    CU(launch_mismatch(h->ctx(), d_pairs, n, max_err, d_out, h->slot[0].stream));
+    if (!h->slot[h->cur].n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    CU(launch_mismatch(h->ctx(h->cur), d_pairs, n, max_err, d_out, h->slot[h->cur].stream));
     if (n) h->launches += 1;
     return SALT_OK;
 }
@@ -711,7 +712,7 @@ int salt_b200_mismatch(salt_b200_t *h, const salt_pair_t *pairs, size_t n, int m
     if (int rc = use_device(h)) return rc;
     if (n && (!pairs || !out)) return fail(SALT_ERR_ARG, "null buffer");
     if (!n) return SALT_OK;
-    cudaStream_t st = h->slot[0].stream;
+    cudaStream_t st = h->slot[h->cur].stream;
     CU(h->pairs.need(n * sizeof(salt_pair_t)));
     CU(h->out8.need(n));
     CU(cudaMemcpyAsync(h->pairs.p, pairs, n * sizeof(salt_pair_t), cudaMemcpyHostToDevice, st));
@@ -725,7 +726,7 @@ int salt_b200_lv_dev(salt_b200_t *h, const salt_pair_t *d_pairs, size_t n, int k
 {
     if (int rc = use_device(h)) return rc;
     if (n && (!d_pairs || !d_out)) return fail(SALT_ERR_ARG, "null buffer");
-    if (!h->slot[0].n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    if (!h->slot[h->cur].n_reads) return fail(SALT_ERR_ARG, "no reads set");
     LvFilterScratch fs{nullptr, nullptr, nullptr};
     if (h->lv_filter && n) {
         CU(h->fpairs.need((n + 1) * sizeof(salt_pair_t)));
@@ -733,7 +734,7 @@ int salt_b200_lv_dev(salt_b200_t *h, const salt_pair_t *d_pairs, size_t n, int k
         CU(h->fcount.need(256));
         fs.pairs = h->fpairs.as<salt_pair_t>(); fs.slots = h->fslots.as<uint32_t>(); fs.count = h->fcount.as<uint32_t>();
     }
-    CU(launch_lv(h->ctx(), d_pairs, n, k, nullptr, nullptr, 0, d_out, h->sm_count, h->slot[0].stream, h->lv_mapping,
+    CU(launch_lv(h->ctx(h->cur), d_pairs, n, k, nullptr, nullptr, 0, d_out, h->sm_count, h->slot[h->cur].stream, h->lv_mapping,
                  h->lv_filter ? &fs : nullptr));
     if (n) h->launches += h->lv_filter ? 2 : 1;
     return SALT_OK;
@@ -744,7 +745,7 @@ int salt_b200_lv(salt_b200_t *h, const salt_pair_t *pairs, size_t n, int k, int8
     if (int rc = use_device(h)) return rc;
     if (n && (!pairs || !out)) return fail(SALT_ERR_ARG, "null buffer");
     if (!n) return SALT_OK;
-    cudaStream_t st = h->slot[0].stream;
+    cudaStream_t st = h->slot[h->cur].stream;
     CU(h->pairs.need(n * sizeof(salt_pair_t)));
     CU(h->out8.need(n));
     CU(cudaMemcpyAsync(h->pairs.p, pairs, n * sizeof(salt_pair_t), cudaMemcpyHostToDevice, st));
@@ -760,14 +761,14 @@ int salt_b200_lv_cigar(salt_b200_t *h, const salt_pair_t *pairs, const uint8_t *
     if (int rc = use_device(h)) return rc;
     if (n && (!pairs || !k_each || !cigars || !out)) return fail(SALT_ERR_ARG, "null buffer");
     if (stride < 2) return fail(SALT_ERR_ARG, "cigar stride too small");
-    if (!h->slot[0].n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    if (!h->slot[h->cur].n_reads) return fail(SALT_ERR_ARG, "no reads set");
     if (!n) return SALT_OK;
     int kmax = 0;
     for (size_t i = 0; i < n; ++i) {
         if (k_each[i] >= 31) return fail(SALT_ERR_ARG, "k must be < 31 (LandauVishkin.c:183 asserts)");
         if (k_each[i] > kmax) kmax = k_each[i];
     }
-    cudaStream_t st = h->slot[0].stream;
+    cudaStream_t st = h->slot[h->cur].stream;
     CU(h->pairs.need(n * sizeof(salt_pair_t)));
     CU(h->out8.need(n));
     CU(h->kbuf.need(n));
@@ -775,7 +776,7 @@ int salt_b200_lv_cigar(salt_b200_t *h, const salt_pair_t *pairs, const uint8_t *
     CU(cudaMemcpyAsync(h->pairs.p, pairs, n * sizeof(salt_pair_t), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(h->kbuf.p, k_each, n, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(h->cig.p, 0, n * (size_t)stride, st));
-    CU(launch_lv_cigar(h->ctx(), h->pairs.as<salt_pair_t>(), h->kbuf.as<uint8_t>(), n, nullptr, nullptr, 0, nullptr, kmax,
+    CU(launch_lv_cigar(h->ctx(h->cur), h->pairs.as<salt_pair_t>(), h->kbuf.as<uint8_t>(), n, nullptr, nullptr, 0, nullptr, kmax,
                        h->cig.as<char>(), stride, h->out8.as<int8_t>(), h->sm_count, st, h->lv_mapping));
     h->launches += 1;
     std::vector<char> tmp(n * (size_t)stride);
@@ -865,25 +866,34 @@ int salt_b200_ssw_dev(salt_b200_t *h, const salt_win_t *d_wins, size_t n, int us
     if (int rc = use_device(h)) return rc;
     if (n && (!d_wins || !d_out || !d_cigars)) return fail(SALT_ERR_ARG, "null buffer");
     if (cigar_stride < 1) return fail(SALT_ERR_ARG, "cigar stride too small");
-    if (!h->slot[0].n_reads) return fail(SALT_ERR_ARG, "no reads set");
+    if (!h->slot[h->cur].n_reads) return fail(SALT_ERR_ARG, "no reads set");
     if (use_pac && !h->d_pac) return fail(SALT_ERR_ARG, "no pac uploaded");
     SswParams prm;
     if (int rc = fill_ssw_params(prm, use_pac, mat, n_sym, gapO, gapE, flag, filters, filterd, mask_len)) return rc;
     int maxpos = 0;
     for (int i = 0; i < n_sym * n_sym; ++i) if (mat[i] > maxpos) maxpos = mat[i];
-    if ((int64_t)maxpos * (int64_t)h->slot[0].l_max >= 24000) return fail(SALT_ERR_UNSUPPORTED, "scores would overflow int16");
+    if ((int64_t)maxpos * (int64_t)h->slot[h->cur].l_max >= 24000) return fail(SALT_ERR_UNSUPPORTED, "scores would overflow int16");
     if (!n) return SALT_OK;
     const int max_cols = h->max_window;
     size_t lay[8];
-    const size_t need = ssw_scratch_bytes(n, max_cols, (int)h->slot[0].l_max, lay);
+    const size_t need = ssw_scratch_bytes(n, max_cols, (int)h->slot[h->cur].l_max, lay);
     CU(h->sswscratch.need(need));
-    CU(h->sswovf.need(ssw_overflow_bytes((int)h->slot[0].l_max)));     // per handle: two handles never share direction bytes
+    CU(h->sswovf.need(ssw_overflow_bytes((int)h->slot[h->cur].l_max)));     // per handle: two handles never share direction bytes
     if (h->profiling)
         for (int i = 0; i < 7; ++i) if (!h->ev_ssw[i]) CU(cudaEventCreate(&h->ev_ssw[i]));
-    CU(launch_ssw(h->ctx(), d_wins, n, prm, h->sswscratch.p, h->sswscratch.cap, max_cols, d_out, d_cigars,
-                  cigar_stride, h->sm_count, h->slot[0].stream, &h->launches, h->profiling ? h->ev_ssw : nullptr,
+    CU(launch_ssw(h->ctx(h->cur), d_wins, n, prm, h->sswscratch.p, h->sswscratch.cap, max_cols, d_out, d_cigars,
+                  cigar_stride, h->sm_count, h->slot[h->cur].stream, &h->launches, h->profiling ? h->ev_ssw : nullptr,
                   h->sswovf.as<uint8_t>()));
     h->have_ssw_prof = h->profiling;
+    return SALT_OK;
+}
+
+int salt_b200_use_slot(salt_b200_t *h, int slot)
+{
+    if (!h) return fail(SALT_ERR_ARG, "null handle");
+    if (slot < 0 || slot >= SALT_SLOTS) return fail(SALT_ERR_ARG, "slot out of range");
+    if (h->slot[slot].pending) return fail(SALT_ERR_ARG, "slot has a verify in flight: call salt_b200_verify_wait first");
+    h->cur = slot;
     return SALT_OK;
 }
 
@@ -919,7 +929,7 @@ int salt_b200_ssw(salt_b200_t *h, const salt_win_t *wins, size_t n, int use_pac,
     if (n && (!wins || !out || !cigars)) return fail(SALT_ERR_ARG, "null buffer");
     if (cigar_stride < 1) return fail(SALT_ERR_ARG, "cigar stride too small");
     if (!n) return SALT_OK;
-    cudaStream_t st = h->slot[0].stream;
+    cudaStream_t st = h->slot[h->cur].stream;
     uint32_t widest = 1;
     for (size_t i = 0; i < n; ++i)
         if (wins[i].end >= wins[i].start && wins[i].end - wins[i].start + 1 > widest) widest = wins[i].end - wins[i].start + 1;

@@ -312,7 +312,7 @@ locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, ui
     constexpr unsigned FULL = 0xffffffffu;
     SALT_DYN_SMEM(uint32_t, s_mem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t per_warp = (size_t)max_seeds * 3 + 2 * ((size_t)max_seeds + 2) + (size_t)cap2;
+    const size_t per_warp = ((size_t)max_seeds * 3 + 2 * ((size_t)max_seeds + 2) + (size_t)cap2 + 1) & ~(size_t)1;   // even: 64-bit row offsets inside
     SeedSai *s_sai = reinterpret_cast<SeedSai *>(s_mem + warp * per_warp);
     // row offsets are 64 bit: an interval that could not be narrowed may span the whole suffix array
     unsigned long long *s_row = reinterpret_cast<unsigned long long *>(s_mem + warp * per_warp + (((size_t)max_seeds * 3 + 1) & ~(size_t)1));
@@ -427,7 +427,7 @@ cudaError_t launch_locate(const FmIndexDev &ix, const SeedOpt &opt, const uint32
     if (!n_reads) return cudaSuccess;
     int cap2 = 32;
     while (cap2 < opt.max_locate) cap2 <<= 1;
-    const size_t per_warp = ((size_t)max_seeds * 3 + 2 * ((size_t)max_seeds + 2) + (size_t)cap2) * 4;
+    const size_t per_warp = (((size_t)max_seeds * 3 + 2 * ((size_t)max_seeds + 2) + (size_t)cap2 + 1) & ~(size_t)1) * 4;
     int warps = 4;
     while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
     if (per_warp * warps > 200 * 1024) return cudaErrorInvalidValue;

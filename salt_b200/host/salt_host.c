@@ -1,9 +1,11 @@
 /* salt_host.c -- see include/salt_host.h.  Host-side C over the C ABI of libsalt_b200.so. */
 #include "../../include/salt_host.h"
 
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 struct salt_chunk {
     uint32_t max_reads; size_t max_bases, max_cands;
@@ -368,4 +370,250 @@ int salt_pair_apply(const salt_pair_plan_t *plan, const salt_read_result_t *r0, 
         return 1;
     }
     return 0;
+}
+
+/* ------------------------------------------------------------------ bulk queueing */
+int salt_chunk_add_reads(salt_chunk_t *c, const uint8_t *codes, const uint32_t *roffs, uint32_t n,
+                         const uint32_t *offs0, const uint32_t *loci0, const uint32_t *offs1, const uint32_t *loci1)
+{
+    if (!c || !roffs || !offs0 || !offs1 || (n && !codes)) return SALT_ERR_ARG;
+    const uint32_t at = c->n_reads;
+    const size_t nb = (size_t)roffs[n] - roffs[0], n0 = (size_t)offs0[n] - offs0[0], n1 = (size_t)offs1[n] - offs1[0];
+    if ((size_t)at + n > c->max_reads || (size_t)c->roffs[at] + nb > c->max_bases ||
+        (size_t)c->offs[0][at] + n0 > c->max_cands || (size_t)c->offs[1][at] + n1 > c->max_cands) return SALT_ERR_NOMEM;
+    if ((n0 && !loci0) || (n1 && !loci1)) return SALT_ERR_ARG;
+    memcpy(c->codes + c->roffs[at], codes + roffs[0], nb);
+    if (n0) memcpy(c->loci[0] + c->offs[0][at], loci0 + offs0[0], n0 * 4);
+    if (n1) memcpy(c->loci[1] + c->offs[1][at], loci1 + offs1[0], n1 * 4);
+    const uint32_t rb = c->roffs[at] - roffs[0], b0 = c->offs[0][at] - offs0[0], b1 = c->offs[1][at] - offs1[0];
+    for (uint32_t i = 1; i <= n; ++i) {
+        c->roffs[at + i] = roffs[i] + rb; c->offs[0][at + i] = offs0[i] + b0; c->offs[1][at + i] = offs1[i] + b1;
+    }
+    c->n_reads = at + n;
+    return (int)at;
+}
+
+/* ------------------------------------------------------------------ paired-end stage of a chunk */
+static double ms_now(void)
+{
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return 1e3 * (double)t.tv_sec + 1e-6 * (double)t.tv_nsec;
+}
+
+#define PE_CIG_STRIDE 64
+
+int salt_chunk_pair(salt_b200_t *h, int slot, salt_chunk_t *c, uint32_t min_tlen, uint32_t max_tlen, uint32_t l_pac,
+                    int max_hits, const int8_t *mat16, const int8_t *mat5, int gapO, int gapE, int filters, int filterd,
+                    int with_tail, salt_pair_final_t *out, salt_mdnm_out_t *tail_out, char *tail_md, int md_stride,
+                    salt_pe_stats_t *stats)
+{
+    if (!h || !c || !c->done || !out || !mat16 || !mat5 || (c->n_reads & 1)) return SALT_ERR_ARG;
+    if (with_tail && (!tail_out || !tail_md || md_stride < 2)) return SALT_ERR_ARG;
+    const uint32_t np = c->n_reads / 2;
+    salt_pe_stats_t st;
+    memset(&st, 0, sizeof st);
+    st.pairs = np;
+    int rc = SALT_OK;
+    salt_read_result_t *res = malloc((size_t)c->n_reads * sizeof *res + 1);
+    salt_pair_plan_t *plan = malloc((size_t)np * sizeof *plan + 1);
+    /* windows by flavour; win_at[2 * pair + w] = row of the plan's w-th window in its flavour's batch */
+    salt_win_t *win[2] = {malloc(((size_t)np * 2 + 1) * sizeof(salt_win_t)), malloc(((size_t)np * 2 + 1) * sizeof(salt_win_t))};
+    uint32_t *win_at = malloc(((size_t)np * 2 + 1) * 4);
+    size_t nw[2] = {0, 0};
+    salt_ssw_out_t *so[2] = {NULL, NULL};
+    uint32_t *sc[2] = {NULL, NULL};
+    if (!res || !plan || !win[0] || !win[1] || !win_at) { rc = SALT_ERR_NOMEM; goto done; }
+
+    double t0 = ms_now();
+    for (uint32_t i = 0; i < c->n_reads && rc == SALT_OK; ++i) rc = salt_chunk_result(c, i, max_hits, &res[i]);
+    for (uint32_t p = 0; p < np && rc == SALT_OK; ++p) {
+        const uint32_t l0 = c->roffs[2 * p + 1] - c->roffs[2 * p], l1 = c->roffs[2 * p + 2] - c->roffs[2 * p + 1];
+        rc = salt_pair_plan(&res[2 * p], l0, &res[2 * p + 1], l1, min_tlen, max_tlen, l_pac, &plan[p]);
+        if (rc != SALT_OK) break;
+        if (plan[p].paired) ++st.proper;
+        for (int w = 0; w < plan[p].n_win; ++w) {
+            const salt_rescue_t *rw = &plan[p].win[w];
+            const int f = rw->flavour == 5;
+            salt_win_t *o = &win[f][nw[f]];
+            o->rs = ((2 * p + (uint32_t)rw->mate) << 1) | (uint32_t)rw->strand; o->start = rw->start; o->end = rw->end;
+            win_at[2 * p + (uint32_t)w] = (uint32_t)nw[f]++;
+        }
+    }
+    st.windows16 = nw[0]; st.windows5 = nw[1];
+    st.ms_plan = ms_now() - t0;
+    if (rc != SALT_OK) goto done;
+
+    /* one Smith-Waterman batch per flavour on the chunk's resident reads (alnpe.c:261 / :330) */
+    t0 = ms_now();
+    if ((rc = salt_b200_use_slot(h, slot)) != SALT_OK) goto done;
+    for (int f = 0; f < 2 && rc == SALT_OK; ++f) {
+        if (!nw[f]) continue;
+        so[f] = malloc(nw[f] * sizeof(salt_ssw_out_t));
+        sc[f] = calloc(nw[f] * PE_CIG_STRIDE, 4);
+        if (!so[f] || !sc[f]) { rc = SALT_ERR_NOMEM; break; }
+        rc = salt_b200_ssw(h, win[f], nw[f], f, f ? mat5 : mat16, f ? 5 : 16, gapO, gapE, 2, filters, filterd, -1, so[f], sc[f], PE_CIG_STRIDE);
+    }
+    st.ms_ssw = ms_now() - t0;
+    if (rc != SALT_OK) { salt_b200_use_slot(h, 0); goto done; }
+
+    t0 = ms_now();
+    size_t n_k4 = 0;
+    for (uint32_t p = 0; p < np; ++p) {
+        const uint32_t l0 = c->roffs[2 * p + 1] - c->roffs[2 * p], l1 = c->roffs[2 * p + 2] - c->roffs[2 * p + 1];
+        salt_ssw_out_t ws[2];
+        uint32_t wc[2 * PE_CIG_STRIDE];
+        for (int w = 0; w < plan[p].n_win; ++w) {
+            const int f = plan[p].win[w].flavour == 5;
+            const uint32_t at = win_at[2 * p + (uint32_t)w];
+            ws[w] = so[f][at];
+            memcpy(wc + w * PE_CIG_STRIDE, sc[f] + (size_t)at * PE_CIG_STRIDE, PE_CIG_STRIDE * 4);
+            if (ws[w].cigarLen < 0) ++st.declined;
+        }
+        const int r = salt_pair_apply(&plan[p], &res[2 * p], l0, &res[2 * p + 1], l1, ws, wc, PE_CIG_STRIDE, filters, filterd, out[p].mate);
+        if (r < 0) { rc = r; break; }
+        out[p].paired = r;
+        for (int m = 0; m < 2; ++m) {
+            if (out[p].mate[m].cigar_kind == 3) ++st.rescued;
+            if (out[p].mate[m].cigar_kind == 4) ++n_k4;
+        }
+    }
+    if (rc == SALT_OK && n_k4) {
+        /* gapped alternates that became primaries: their CIGARs in one salt_b200_lv_cigar call (query.c:288) */
+        salt_pair_t *pp = malloc(n_k4 * sizeof *pp);
+        uint8_t *kk = malloc(n_k4);
+        char *cg = calloc(n_k4, 128);
+        int8_t *eo = malloc(n_k4);
+        size_t q = 0;
+        if (!pp || !kk || !cg || !eo) rc = SALT_ERR_NOMEM;
+        for (uint32_t p = 0; p < np && rc == SALT_OK; ++p)
+            for (int m = 0; m < 2; ++m)
+                if (out[p].mate[m].cigar_kind == 4) {
+                    pp[q].rs = ((2 * p + (uint32_t)m) << 1) | (uint32_t)(out[p].mate[m].strand & 1); pp[q].pos = out[p].mate[m].pos;
+                    kk[q] = out[p].mate[m].n_diff > 30 ? 30 : out[p].mate[m].n_diff; ++q;
+                }
+        if (rc == SALT_OK) rc = salt_b200_lv_cigar(h, pp, kk, n_k4, cg, 128, eo);
+        q = 0;
+        for (uint32_t p = 0; p < np && rc == SALT_OK; ++p)
+            for (int m = 0; m < 2; ++m)
+                if (out[p].mate[m].cigar_kind == 4) { strncpy(out[p].mate[m].cigar, cg + q * 128, 127); ++q; ++st.promoted; }
+        free(pp); free(kk); free(cg); free(eo);
+    }
+    salt_b200_use_slot(h, 0);
+    st.ms_apply = ms_now() - t0;
+    if (rc != SALT_OK) goto done;
+
+    if (with_tail) {
+        /* sam_add_md_nm of every mapped mate (sam.c:246-328) in one call on the slot's reads */
+        t0 = ms_now();
+        const uint32_t n = c->n_reads;
+        salt_mdnm_in_t *in = malloc((size_t)n * sizeof *in + 1);
+        char *cg = malloc((size_t)n * 128 + 1);
+        if (!in || !cg) rc = SALT_ERR_NOMEM;
+        for (uint32_t i = 0; i < n && rc == SALT_OK; ++i) {
+            const salt_mate_final_t *mf = &out[i / 2].mate[i & 1];
+            in[i].rs = (i << 1) | (uint32_t)(mf->strand & 1); in[i].pos = mf->pos; in[i].seq_start = mf->seq_start;
+            memcpy(cg + (size_t)i * 128, mf->cigar, 128);
+            cg[(size_t)i * 128 + 127] = 0;
+        }
+        if (rc == SALT_OK) rc = salt_b200_md_nm(h, slot, in, n, cg, 128, tail_md, md_stride, NULL, 0, tail_out);
+        free(in); free(cg);
+        st.ms_tail = ms_now() - t0;
+    }
+done:
+    free(res); free(plan); free(win[0]); free(win[1]); free(win_at);
+    free(so[0]); free(so[1]); free(sc[0]); free(sc[1]);
+    if (stats) *stats = st;
+    return rc;
+}
+
+/* ------------------------------------------------------------------ several GPUs in one process */
+struct salt_multi { int n; salt_b200_t **h; };
+
+salt_multi_t *salt_multi_init(const uint32_t *mixref, uint32_t l, const uint8_t *pac, int64_t l_pac, const int *devices, int n_devices)
+{
+    if (n_devices < 1 || !devices) return NULL;
+    salt_multi_t *m = calloc(1, sizeof *m);
+    if (!m) return NULL;
+    m->h = calloc((size_t)n_devices, sizeof *m->h);
+    if (!m->h) { free(m); return NULL; }
+    m->n = n_devices;
+    for (int i = 0; i < n_devices; ++i) {
+        m->h[i] = salt_b200_init(mixref, l, pac, l_pac, devices[i]);
+        if (!m->h[i]) { salt_multi_destroy(m); return NULL; }
+    }
+    return m;
+}
+
+void salt_multi_destroy(salt_multi_t *m)
+{
+    if (!m) return;
+    for (int i = 0; i < m->n; ++i) if (m->h[i]) salt_b200_destroy(m->h[i]);
+    free(m->h); free(m);
+}
+
+int salt_multi_n(const salt_multi_t *m) { return m ? m->n : 0; }
+salt_b200_t *salt_multi_handle(salt_multi_t *m, int i) { return (m && i >= 0 && i < m->n) ? m->h[i] : NULL; }
+
+typedef struct {
+    salt_b200_t *h; salt_packed_chunk_t view; uint32_t chunk_reads; int nogap_T0, lv_T0;
+    salt_verify_out_t *rec; int8_t *acc0, *acc1; char *cigars; int cigar_stride; int rc;
+} multi_job_t;
+
+static void *multi_worker(void *arg)
+{
+    multi_job_t *J = (multi_job_t *)arg;
+    J->rc = J->view.n_reads ? salt_b200_verify_batch_packed(J->h, &J->view, J->chunk_reads, J->nogap_T0, J->lv_T0, J->rec, J->acc0,
+                                                           J->acc1, J->cigars, J->cigar_stride) : SALT_OK;
+    return NULL;
+}
+
+static uint32_t pk_count(const salt_packed_chunk_t *pc, int s, uint32_t i)
+{
+    return pc->count_bits == 16 ? ((const uint16_t *)pc->n_cand[s])[i] : ((const uint32_t *)pc->n_cand[s])[i];
+}
+
+int salt_multi_verify_batch_packed(salt_multi_t *m, const salt_packed_chunk_t *pc, uint32_t chunk_reads, int nogap_T0, int lv_T0,
+                                   salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1, char *cigars, int cigar_stride)
+{
+    if (!m || !pc || !rec || (pc->count_bits != 16 && pc->count_bits != 32) || (pc->n_reads && (!pc->n_cand[0] || !pc->n_cand[1])))
+        return SALT_ERR_ARG;
+    if (chunk_reads == 0) chunk_reads = 100000;
+    const int G = m->n;
+    multi_job_t *J = calloc((size_t)G, sizeof *J);
+    pthread_t *th = calloc((size_t)G, sizeof *th);
+    if (!J || !th) { free(J); free(th); return SALT_ERR_NOMEM; }
+    /* contiguous shares on chunk boundaries; one pass over the lengths and counts finds where each share starts */
+    const uint32_t n_chunks = (pc->n_reads + chunk_reads - 1) / chunk_reads;
+    uint64_t base = pc->base_start; size_t c0 = 0, c1 = 0, np = 0;
+    uint32_t r = 0;
+    const size_t cb = (size_t)pc->count_bits / 8;
+    for (int g = 0; g < G; ++g) {
+        const uint32_t first_chunk = (uint32_t)((uint64_t)n_chunks * (uint64_t)g / (uint64_t)G);
+        const uint32_t upto_chunk = (uint32_t)((uint64_t)n_chunks * (uint64_t)(g + 1) / (uint64_t)G);
+        const uint32_t first = first_chunk * chunk_reads;
+        uint32_t upto = upto_chunk * chunk_reads; if (upto > pc->n_reads) upto = pc->n_reads;
+        multi_job_t *j = &J[g];
+        j->h = m->h[g]; j->chunk_reads = chunk_reads; j->nogap_T0 = nogap_T0; j->lv_T0 = lv_T0; j->cigar_stride = cigar_stride;
+        j->view = *pc;
+        j->view.n_reads = upto - first;
+        j->view.base_start = (uint32_t)base;
+        j->view.lens = pc->lens ? pc->lens + first : NULL;
+        while (np < pc->n_n && pc->n_pos[np] < base) ++np;
+        j->view.n_pos = pc->n_pos ? pc->n_pos + np : NULL; j->view.n_n = pc->n_n - np;
+        j->view.n_cand[0] = (const uint8_t *)pc->n_cand[0] + (size_t)first * cb;
+        j->view.n_cand[1] = (const uint8_t *)pc->n_cand[1] + (size_t)first * cb;
+        j->view.loci[0] = pc->loci[0] ? pc->loci[0] + c0 : NULL; j->view.loci[1] = pc->loci[1] ? pc->loci[1] + c1 : NULL;
+        j->rec = rec + first; j->acc0 = acc0 ? acc0 + c0 : NULL; j->acc1 = acc1 ? acc1 + c1 : NULL;
+        j->cigars = cigars ? cigars + (size_t)first * cigar_stride : NULL;
+        for (; r < upto; ++r) {
+            base += pc->lens ? pc->lens[r] : pc->l_seq;
+            c0 += pk_count(pc, 0, r); c1 += pk_count(pc, 1, r);
+        }
+    }
+    for (int g = 0; g < G; ++g) pthread_create(&th[g], NULL, multi_worker, &J[g]);
+    int rc = SALT_OK;
+    for (int g = 0; g < G; ++g) { pthread_join(th[g], NULL); if (rc == SALT_OK) rc = J[g].rc; }
+    free(J); free(th);
+    return rc;
 }

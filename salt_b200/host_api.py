@@ -41,6 +41,16 @@ class MateFinalT(C.Structure):    # salt_mate_final_t
                 ("cigar_kind", C.c_int), ("cigar", C.c_char * 256)]
 
 
+class PairFinalT(C.Structure):    # salt_pair_final_t
+    _fields_ = [("mate", MateFinalT * 2), ("paired", C.c_int)]
+
+
+class PeStatsT(C.Structure):      # salt_pe_stats_t
+    _fields_ = [("pairs", C.c_size_t), ("proper", C.c_size_t), ("windows16", C.c_size_t), ("windows5", C.c_size_t),
+                ("rescued", C.c_size_t), ("promoted", C.c_size_t), ("declined", C.c_size_t),
+                ("ms_plan", C.c_double), ("ms_ssw", C.c_double), ("ms_apply", C.c_double), ("ms_tail", C.c_double)]
+
+
 def pair_apply(L, plan_c, r0, l0, r1, l1, ssw, cigars, filters=0, filterd=20, stride=8):
     """ssw: list of (score1, score2, ref_begin1, ref_end1, read_begin1, read_end1); cigars: list of [(len, op), ...]"""
     n = len(ssw)
@@ -91,6 +101,17 @@ def declare(L):
     L.salt_chunk_tail.argtypes = [vp, i32, vp]
     L.salt_chunk_md.argtypes = [vp, u32, C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(C.c_int)]
     L.salt_chunk_md.restype = C.c_char_p
+    if hasattr(L, "salt_chunk_pair"):
+        from .index_io import SeedOptT
+        L.salt_chunk_add_reads.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp]
+        L.salt_chunk_seed_verify.argtypes = [vp, vp, C.POINTER(SeedOptT), i32, i32]
+        L.salt_chunk_pair.argtypes = [vp, i32, vp, u32, u32, u32, i32, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, C.POINTER(PeStatsT)]
+        L.salt_multi_init.restype = vp
+        L.salt_multi_init.argtypes = [vp, u32, vp, C.c_int64, vp, i32]
+        L.salt_multi_destroy.argtypes = [vp]; L.salt_multi_destroy.restype = None
+        L.salt_multi_n.argtypes = [vp]
+        L.salt_multi_handle.restype = vp; L.salt_multi_handle.argtypes = [vp, i32]
+        L.salt_multi_verify_batch_packed.argtypes = [vp, C.POINTER(api.PackedChunkT), u32, i32, i32, vp, vp, vp, vp, i32]
     L.salt_pair_plan.argtypes = [C.POINTER(ReadResultT), u32, C.POINTER(ReadResultT), u32, u32, u32, u32, C.POINTER(PairPlanT)]
     L.salt_pair_apply.argtypes = [C.POINTER(PairPlanT), C.POINTER(ReadResultT), u32, C.POINTER(ReadResultT), u32, vp, vp, i32, i32, i32, vp]
     return L
@@ -126,6 +147,32 @@ class Chunk:
         if rc < 0:
             raise api.SaltError(rc, "chunk queue full")
         return rc
+
+    def add_reads(self, codes, roffs, offs0, loci0, offs1, loci1):
+        codes = np.ascontiguousarray(codes, np.uint8).reshape(-1); roffs = np.ascontiguousarray(roffs, np.uint32)
+        offs0 = np.ascontiguousarray(offs0, np.uint32); offs1 = np.ascontiguousarray(offs1, np.uint32)
+        loci0 = np.ascontiguousarray(loci0, np.uint32); loci1 = np.ascontiguousarray(loci1, np.uint32)
+        rc = self.H.salt_chunk_add_reads(self.c, codes.ctypes.data, roffs.ctypes.data, len(roffs) - 1, offs0.ctypes.data,
+                                         loci0.ctypes.data if len(loci0) else None, offs1.ctypes.data,
+                                         loci1.ctypes.data if len(loci1) else None)
+        if rc < 0:
+            raise api.SaltError(rc, "chunk queue full")
+        return rc
+
+    def pair(self, eng, slot, n_pairs, min_tlen, max_tlen, l_pac, max_hits=5, gapO=3, gapE=1, filters=0, filterd=20, with_tail=True,
+             md_stride=128):
+        """salt_chunk_pair: the paired-end stage of the chunk.  Returns (finals, tail_out, tail_md, stats)."""
+        out = (PairFinalT * max(n_pairs, 1))()
+        tail_out = np.zeros(2 * n_pairs, api.MDNM_OUT_DT); tail_md = np.zeros((2 * n_pairs, md_stride), np.uint8)
+        st = PeStatsT()
+        m16 = api.salt_score_mat2(); m5 = api.salt_score_mat()
+        eng._ck(self.H.salt_chunk_pair(eng.h, int(slot), self.c, int(min_tlen), int(max_tlen), int(l_pac), int(max_hits),
+                                       m16.ctypes.data, m5.ctypes.data, int(gapO), int(gapE), int(filters), int(filterd), int(with_tail),
+                                       out, tail_out.ctypes.data, tail_md.ctypes.data, int(md_stride), C.byref(st)))
+        return out, tail_out, tail_md, st
+
+    def seed_verify(self, eng, opt, nogap_T0=3, lv_T0=-1):
+        eng._ck(self.H.salt_chunk_seed_verify(eng.h, self.c, C.byref(opt), int(nogap_T0), int(lv_T0)))
 
     def submit(self, eng, slot, nogap_T0=3, lv_T0=-1):
         eng._ck(self.H.salt_chunk_submit(eng.h, int(slot), self.c, int(nogap_T0), int(lv_T0)))

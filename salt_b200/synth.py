@@ -178,6 +178,45 @@ def sample_reads(g, n, L, seed=2, sub_rate=0.01, indel_frac=0.0, max_indel=3, n_
     return np.ascontiguousarray(reads), pos.astype(np.uint32), strand
 
 
+def sample_pairs(g, n_pairs, L, seed=6, insert_mean=400, insert_sd=50, sub_rate=0.01, hard_frac=0.05, hard_sub=0.09,
+                 junk_frac=0.0):
+    """Paired-end reads (insert ~ N(400, 50)): mates interleaved (row 2i = mate 0, 2i+1 = mate 1 of pair i).
+    Mate 0 reads the forward strand at p, mate 1 the reverse strand of [p+ins-L, p+ins); half of the pairs come from
+    the other strand (roles swapped).  A fraction hard_frac of the second mates carries hard_sub substitutions and an
+    indel, so the verification stage cannot place it and the pair needs a Smith-Waterman mate rescue; junk_frac of the
+    second mates are random (singleton pairs).  Returns (reads[2n, L], true_pos[2n], strand[2n])."""
+    rng = np.random.default_rng(seed)
+    ins = np.clip(rng.normal(insert_mean, insert_sd, n_pairs), L + 20, insert_mean + 4 * insert_sd).astype(np.int64)
+    p = rng.integers(0, g.l - ins.max() - 16, n_pairs)
+    col = np.arange(L)[None, :]
+    a = g.codes[p[:, None] + col].astype(np.uint8)
+    pos_b = p + ins - L
+    b = g.codes[pos_b[:, None] + col].astype(np.uint8)
+    for arr in (a, b):
+        e = rng.random(arr.shape) < sub_rate
+        arr[e] = (arr[e] + rng.integers(1, 4, int(e.sum()), dtype=np.uint8)) & 3
+    hard = rng.random(n_pairs) < hard_frac
+    if hard.any():
+        hb = b[hard]
+        e = rng.random(hb.shape) < hard_sub
+        hb[e] = (hb[e] + rng.integers(1, 4, int(e.sum()), dtype=np.uint8)) & 3
+        cut = rng.integers(L // 3, 2 * L // 3, len(hb))
+        for i in range(len(hb)):                       # a 2-base deletion from the read
+            hb[i, cut[i]:-2] = hb[i, cut[i] + 2:]
+        b[hard] = hb
+    junk = rng.random(n_pairs) < junk_frac
+    if junk.any():
+        b[junk] = rng.integers(0, 4, (int(junk.sum()), L), dtype=np.uint8)
+    b = revcomp(b)
+    flip = rng.random(n_pairs) < 0.5
+    reads = np.empty((2 * n_pairs, L), np.uint8); pos = np.empty(2 * n_pairs, np.uint32); strand = np.empty(2 * n_pairs, np.uint8)
+    # flipped fragment: what was read forward is now reverse-complemented and vice versa
+    reads[0::2] = np.where(flip[:, None], revcomp(a), a); reads[1::2] = np.where(flip[:, None], revcomp(b), b)
+    pos[0::2] = p; pos[1::2] = pos_b
+    strand[0::2] = flip.astype(np.uint8); strand[1::2] = 1 - flip.astype(np.uint8)
+    return np.ascontiguousarray(reads), pos, strand
+
+
 def edit_rich_reads(g, n, L, n_edits, seed=4):
     """Forward-strand reads carrying about n_edits[i] scattered edits each (substitutions, 1-base
     insertions and deletions at random places) -- the adversarial case for the Landau-Vishkin

@@ -335,6 +335,58 @@ def check_ssw_wide_bands(eng, oracle, seed, n_reads=150, L=100, glen=20003):
     return gapped
 
 
+def check_chunk_pair(eng, hostlib, g, n_pairs, L, seed, min_tlen=250, max_tlen=550):
+    """salt_chunk_pair (the paired-end stage of a whole chunk: plans, one Smith-Waterman batch per flavour, apply, CIGARs
+    of promoted alternates, MD/NM) against the same stage composed pair by pair from the pieces that the reference's own
+    pairing pins (tests/test_pair_plan.py, the PE drop-in): salt_chunk_result, salt_pair_plan, salt_b200_ssw,
+    salt_pair_apply, salt_b200_md_nm."""
+    import ctypes as C
+    from salt_b200 import host_api
+    reads, pos, strand = synth.sample_pairs(g, n_pairs, L, seed=seed, hard_frac=0.15, junk_frac=0.04)
+    offs0, loci0, offs1, loci1 = synth.make_candidates(g, pos, strand, L, per_strand=4, seed=seed + 1)
+    n = 2 * n_pairs
+    roffs = (np.arange(n + 1) * L).astype(np.uint32)
+    ch = host_api.Chunk(hostlib, n + 8, (n + 8) * L, len(loci0) + len(loci1) + 64)
+    assert ch.add_reads(reads, roffs, offs0, loci0, offs1, loci1) == 0
+    ch.submit(eng, 0, 3, 3); ch.wait(eng, 0)
+    finals, tail_out, tail_md, st = ch.pair(eng, 0, n_pairs, min_tlen, max_tlen, g.l)
+    assert st.pairs == n_pairs
+    m16 = api.salt_score_mat2(); m5 = api.salt_score_mat()
+    n_rescued = 0
+    for p in range(n_pairs):
+        rr = []
+        for m in (0, 1):
+            r = host_api.ReadResultT()
+            assert hostlib.salt_chunk_result(ch.c, 2 * p + m, 5, C.byref(r)) == 0
+            rr.append(r)
+        plan = host_api.pair_plan(hostlib, rr[0], L, rr[1], L, min_tlen, max_tlen, g.l, raw=True)
+        ssw, cigs = [], []
+        for w in plan.win[:plan.n_win]:
+            wins = np.zeros(1, api.WIN_DT); wins[0] = (((2 * p + w.mate) << 1) | w.strand, w.start, w.end)
+            o, cg = eng.ssw(wins, m5 if w.flavour == 5 else m16, w.flavour, w.flavour == 5)
+            ssw.append(tuple(int(o[0][f]) for f in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1")))
+            cigs.append([(int(c) >> 4, int(c) & 15) for c in cg[0][:int(o[0]["cigarLen"])]])
+        rc, want = host_api.pair_apply(hostlib, plan, rr[0], L, rr[1], L, ssw, cigs, stride=64)
+        assert rc == finals[p].paired, (p, rc, finals[p].paired)
+        for m in (0, 1):
+            f = finals[p].mate[m]
+            got = (f.pos, f.strand, f.n_diff, f.is_gap, f.seq_start, f.seq_end, f.b0, f.b1, f.mapq, f.cigar_kind)
+            assert got == want[m][:10], (p, m, got, want[m])
+            if f.cigar_kind != 4:
+                assert f.cigar.decode() == want[m][10], (p, m, f.cigar, want[m][10])
+            n_rescued += f.cigar_kind == 3
+            # the tags of this mate
+            if f.pos != 0xFFFFFFFF:
+                o, md, xv = eng.md_nm(np.array([((2 * p + m) << 1) | (f.strand & 1)], np.uint32), np.array([f.pos], np.uint32),
+                                      np.array([f.seq_start], np.uint32), [f.cigar.decode()], md_stride=128, xv_stride=0)
+                assert int(tail_out["nm"][2 * p + m]) == int(o["nm"][0]) and api.cstr(tail_md[2 * p + m]) == api.cstr(md[0]), (p, m)
+            else:
+                assert int(tail_out["md_len"][2 * p + m]) == 0
+    assert st.rescued == n_rescued
+    ch.close()
+    return st
+
+
 def random_cigar(rng, qlen, max_ops=5):
     """A random M/I/D run string consuming exactly qlen read bases (what query->cigar->s may hold)."""
     ops = []

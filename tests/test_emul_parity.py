@@ -241,3 +241,15 @@ def test_seed_locate_lists(emul_lib, tmp_path):
     for a, b, name in zip(got, want, ("rec", "acc0", "acc1", "cigars")):
         assert a.tobytes() == b.tobytes(), name
     ref.close(); eng.close()
+
+
+def test_chunk_pair_stage(emul_lib, oracle):
+    """the paired-end stage of a chunk in one call == the stage composed pair by pair"""
+    import build_emul
+    from salt_b200 import host_api
+    hostlib = host_api.load(build_emul.build_host())
+    g = synth.Genome(40000, snp_rate=0.01, seed=77)
+    eng = _engine(emul_lib, g, with_pac=True)
+    st = pc.check_chunk_pair(eng, hostlib, g, 24, 100, seed=9)
+    assert st.windows16 + st.windows5 >= 3 and st.rescued >= 1 and st.proper >= 10
+    eng.close()

@@ -394,3 +394,46 @@ def test_large_coordinates(oracle):
     gapped = pc.check_ssw(eng, oracle, w, reads, wins, False, api.salt_score_mat2(), 16)
     assert gapped >= 3
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L", [100, 150])
+def test_chunk_pair_stage(L):
+    """the paired-end stage of a whole chunk (salt_chunk_pair) == the stage composed pair by pair"""
+    from salt_b200 import host_api
+    hostlib = host_api.load()
+    g = synth.Genome(300000, snp_rate=0.01, seed=70 + L)
+    eng = _engine(g)
+    st = pc.check_chunk_pair(eng, hostlib, g, 400, L, seed=9 + L)
+    assert st.windows16 + st.windows5 >= 40 and st.rescued >= 20 and st.proper >= 250
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_multi_gpu_in_process_matches_single():
+    """salt_multi_*: one process, one handle per device, contiguous shares on their own host threads -- the output must
+    equal the single-device output byte for byte (two handles on one device when the box has a single GPU)"""
+    import ctypes as C
+    from salt_b200 import host_api
+    hostlib = host_api.load()
+    g, reads, pos, strand, cands = pc.make_world(555, glen=400000, L=100, n_reads=9000, per_strand=6, indel_frac=0.3, n_frac=0.005)
+    offs0, loci0, offs1, loci1 = cands
+    n, L = reads.shape
+    roffs = (np.arange(n + 1) * L).astype(np.uint32)
+    eng = _engine(g)
+    pk, keep = eng.packed_chunk(reads, roffs, offs0, loci0, offs1, loci1, bits=2)
+    want = eng.verify_batch_packed(pk, len(loci0), len(loci1), chunk_reads=700)
+    ndev = int(eng.L.salt_b200_device_count())
+    for devs in ([0, 1 % ndev], [0, 1 % ndev, 2 % ndev]):
+        darr = (C.c_int * len(devs))(*devs)
+        m = hostlib.salt_multi_init(g.mixref.ctypes.data, g.l, g.pac.ctypes.data, g.l, darr, len(devs))
+        assert m and hostlib.salt_multi_n(m) == len(devs)
+        rec = np.zeros(n, api.VERIFY_DT); acc0 = np.empty(len(loci0), np.int8); acc1 = np.empty(len(loci1), np.int8)
+        cig = np.zeros((n, 128), np.uint8)
+        rc = hostlib.salt_multi_verify_batch_packed(m, C.byref(pk), 700, 3, -1, rec.ctypes.data, acc0.ctypes.data, acc1.ctypes.data,
+                                                    cig.ctypes.data, 128)
+        assert rc == 0
+        for a, b, name in zip((rec, acc0, acc1, cig), want, ("rec", "acc0", "acc1", "cigars")):
+            assert a.tobytes() == b.tobytes(), (name, devs)
+        hostlib.salt_multi_destroy(m)
+    eng.close()
