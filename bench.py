@@ -533,7 +533,7 @@ def main():
     if world == 1 and not args.skip_extras:
         out["lv"] = bench_lv(eng, lib, h, wl, args, dev, stream)
         out["sw"] = bench_sw(eng, lib, h, wl, args, dev, stream)
-        out["sam_tail"] = bench_sam_tail(eng, wl, args, d_rec, d_cig, d_cigreads, d_cigcnt)
+        out["sam_tail"] = bench_sam_tail(eng, lib, h, pkc, args, n, n0, n1, (h_rec, h_acc0, h_acc1, h_cig))
         if args.pe_pairs > 0:
             out["pe"] = bench_pe(eng, wl, args)
 
@@ -557,6 +557,7 @@ def bench_pe(eng, wl, args):
     mapped mate.  Chunks alternate between pipeline slots so that chunk k verifies while chunk k-1 pairs."""
     from salt_b200 import host_api, synth
     H = host_api.load()
+    H.salt_host_set_threads(os.cpu_count() or 1)       # the reference pairs on its -t workers too
     g = wl["g"]; L = args.read_len; npairs = args.pe_pairs
     reads, pos, strand = synth.sample_pairs(g, npairs, L, seed=77, hard_frac=0.05, junk_frac=0.005)
     offs0, loci0, offs1, loci1 = synth.make_candidates(g, pos, strand, L, per_strand=args.cands, seed=78)
@@ -587,12 +588,12 @@ def bench_pe(eng, wl, args):
             if pend is not None:
                 pc_, ps_, pm_ = pend
                 pc_.wait(eng, ps_)
-                f, to, tm, st = pc_.pair(eng, ps_, pm_, min_tlen, max_tlen, g.l)
+                f, to, tm, st = pc_.pair(eng, ps_, pm_, min_tlen, max_tlen, g.l, md_stride=64)
                 stats.append(st); finals_keep.append((f, to))
             pend = (ch, slot, m); k += 1
         pc_, ps_, pm_ = pend
         pc_.wait(eng, ps_)
-        f, to, tm, st = pc_.pair(eng, ps_, pm_, min_tlen, max_tlen, g.l)
+        f, to, tm, st = pc_.pair(eng, ps_, pm_, min_tlen, max_tlen, g.l, md_stride=64)
         stats.append(st); finals_keep.append((f, to))
     run()
     t0 = time.perf_counter()
@@ -608,6 +609,7 @@ def bench_pe(eng, wl, args):
            "insert": "N(400,50)", "tlen_bounds": [min_tlen, max_tlen], "counts": tot, "stage_ms_host_wall": ms,
            "mapped_mates_with_tags": mapped, "rescue_frac_of_pairs": (tot["windows16"] + tot["windows5"]) / max(1, npairs),
            "sw_gcups_fwd_cells": cells / max(1e-9, ms["ms_ssw"] * 1e-3) / 1e9,
+           "host_threads": os.cpu_count() or 1,
            "how": "wall time from pageable host arrays through salt_chunk_add_reads / _submit / _wait / salt_chunk_pair (two slots "
                   "alternating), results in host memory"}
     for ch in chunks:
@@ -678,37 +680,73 @@ def bench_lv(eng, lib, h, wl, args, dev, stream):
     return res
 
 
-def bench_sam_tail(eng, wl, args, d_rec, d_cig, d_cigreads, d_cigcnt):
-    """MD/NM/XV (sam_add_md_nm) of every mapped primary of the batch through salt_b200_md_nm: host buffers in and out,
-    one kernel; wall time of the call (its copies included)."""
+def bench_sam_tail(eng, lib, h, pkc, args, n, n0, n1, pins):
+    """MD/NM/XV (sam_add_md_nm, sam.c:246-328) of every primary of the batch on the chunk pipeline: per chunk
+    salt_b200_verify_submit_packed -> _verify_wait -> salt_b200_tail_primaries on the slot (positions, strands and CIGARs are
+    already on the device; tags come back packed into pinned buffers).  Reported: the whole loop, and the same loop without the
+    tail calls, so that the difference is what the SAM tail costs on top of the verification stage."""
+    import torch
     from salt_b200 import api
+    h_rec, h_acc0, h_acc1, h_cig = pins
+    chunk = args.chunk
     L = args.read_len
-    rec = np.frombuffer(d_rec.cpu().numpy().tobytes(), api.VERIFY_DT)
-    ng = int(d_cigcnt[0].item())
-    lst = d_cigreads[:ng].cpu().numpy().astype(np.int64)
-    cg = d_cig.cpu().numpy().reshape(-1, 128)[:ng]
-    mapped = np.nonzero(rec["pos"] != 0xFFFFFFFF)[0]
-    stride = 24
-    cigs = np.zeros((len(mapped), stride), np.uint8)
-    cigs[:, :len("%dM" % L)] = np.frombuffer(("%dM" % L).encode(), np.uint8)
-    where = np.full(len(rec), -1, np.int64); where[mapped] = np.arange(len(mapped))
-    ok = (where[lst] >= 0) & (cg[:, stride - 1] == 0)
-    cigs[where[lst[ok]]] = cg[ok, :stride]
-    items = np.zeros(len(mapped), api.MDNM_IN_DT)
-    items["rs"] = (mapped.astype(np.uint32) << 1) | rec["strand"][mapped]; items["pos"] = rec["pos"][mapped]
-    md = np.zeros((len(mapped), 128), np.uint8); xv = np.zeros((len(mapped), 8), np.uint16); out = np.zeros(len(mapped), api.MDNM_OUT_DT)
+    n_slots = int(lib.salt_b200_n_slots())
+    h_out = torch.empty(n * 8, dtype=torch.uint8).pin_memory(); h_offs = torch.empty((chunk + 1) * n_slots, dtype=torch.int32).pin_memory()
+    md_cap = chunk * 48
+    h_md = torch.empty(md_cap * n_slots, dtype=torch.uint8).pin_memory()
+    h_xv = torch.empty(n * 8, dtype=torch.int16).pin_memory()
+    c0 = np.frombuffer(C.string_at(pkc.n_cand[0], 2 * n), np.uint16).astype(np.int64); c1 = np.frombuffer(C.string_at(pkc.n_cand[1], 2 * n), np.uint16).astype(np.int64)
+    o0 = np.concatenate([[0], np.cumsum(c0)]); o1 = np.concatenate([[0], np.cumsum(c1)])
+    views = []
+    for b in range(0, n, chunk):
+        m = min(chunk, n - b)
+        v = api.PackedChunkT()
+        v.n_reads = m; v.base_bits = 2; v.bases = pkc.bases; v.base_start = b * L; v.lens = None; v.l_seq = L
+        v.n_pos = pkc.n_pos; v.n_n = pkc.n_n; v.count_bits = 16
+        v.n_cand[0] = pkc.n_cand[0] + 2 * b; v.n_cand[1] = pkc.n_cand[1] + 2 * b
+        v.loci[0] = pkc.loci[0] + 4 * int(o0[b]); v.loci[1] = pkc.loci[1] + 4 * int(o1[b])
+        views.append((b, m, v))
+    stat = {"md_bytes": 0, "nm": 0}
 
-    def run():
-        eng._ck(eng.L.salt_b200_md_nm(eng.h, 0, api._ptr(items), len(items), api._ptr(cigs), stride, api._ptr(md), 128,
-                                      api._ptr(xv), 8, api._ptr(out)))
-    run()
-    t0 = time.perf_counter()
-    for _ in range(3):
-        run()
-    sec = (time.perf_counter() - t0) / 3
-    return {"alignments": int(len(mapped)), "ms": sec * 1e3, "alignments_per_s": len(mapped) / sec,
-            "nm_mean": float(out["nm"].mean()), "md_overflow": int((out["md_len"] < 0).sum()),
-            "note": "pageable numpy buffers in and out; the kernel itself is a small part of the call"}
+    def ck(rc):
+        if rc != 0:
+            raise RuntimeError(lib.salt_b200_last_error().decode())
+
+    def finish(k, with_tail):
+        b, m, v = views[k]; si = k % n_slots
+        ck(lib.salt_b200_verify_wait(h, si))
+        if with_tail:
+            nb = C.c_size_t(0)
+            ck(lib.salt_b200_tail_primaries(h, si, h_out.data_ptr() + 8 * b, h_offs.data_ptr() + 4 * (chunk + 1) * si,
+                                            h_md.data_ptr() + md_cap * si, md_cap, C.byref(nb), h_xv.data_ptr() + 16 * b, 8))
+            stat["md_bytes"] += nb.value
+
+    def run(with_tail):
+        stat["md_bytes"] = 0
+        for k, (b, m, v) in enumerate(views):
+            si = k % n_slots
+            if k >= n_slots:
+                finish(k - n_slots, with_tail)
+            ck(lib.salt_b200_verify_submit_packed(h, si, C.byref(v), 3, -1, h_rec.data_ptr() + 16 * b, h_acc0.data_ptr() + int(o0[b]),
+                                                  h_acc1.data_ptr() + int(o1[b]), h_cig.data_ptr() + 128 * b, 128))
+        for k in range(max(0, len(views) - n_slots), len(views)):
+            finish(k, with_tail)
+    res = {}
+    for with_tail in (False, True):
+        run(with_tail)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            run(with_tail)
+        torch.cuda.synchronize()
+        res[with_tail] = (time.perf_counter() - t0) / 3
+    out = np.frombuffer(h_out.numpy().tobytes(), api.MDNM_OUT_DT)
+    mapped = int((out["md_len"] > 0).sum())
+    return {"alignments": mapped, "ms_verify_loop": res[False] * 1e3, "ms_verify_plus_tail_loop": res[True] * 1e3,
+            "ms": (res[True] - res[False]) * 1e3, "alignments_per_s": mapped / max(1e-9, res[True] - res[False]),
+            "nm_mean": float(out["nm"][out["md_len"] > 0].mean()) if mapped else 0.0, "md_overflow": int((out["md_len"] < 0).sum()),
+            "md_bytes": int(stat["md_bytes"]), "d2h_bytes": int(stat["md_bytes"] + n * (8 + 16 + 4)),
+            "note": "salt_b200_tail_primaries per chunk on the pipeline slots, pinned outputs; ms = loop with tails minus loop without"}
 
 
 def bench_sw(eng, lib, h, wl, args, dev, stream):

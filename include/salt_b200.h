@@ -161,6 +161,14 @@ int salt_b200_ssw(salt_b200_t *h, const salt_win_t *wins, size_t n, int use_pac,
 int salt_b200_md_nm(salt_b200_t *h, int slot, const salt_mdnm_in_t *items, size_t n, const char *cigars, int cigar_stride,
                     char *md, int md_stride, uint16_t *xv, int xv_stride, salt_mdnm_out_t *out);
 
+/* The same tags for the PRIMARIES of the chunk just verified in `slot` (salt_b200_verify / _verify_wait, with CIGARs):
+ * positions, strands and CIGARs are already on the device, so nothing crosses the host link on the way in, and the MD
+ * strings come back packed -- string i (NUL-terminated, "" for an unmapped read) starts at md_packed[md_offs[i]];
+ * *md_bytes = md_offs[n_reads] bytes in all (SALT_ERR_NOMEM when md_cap is smaller).  out / xv as in salt_b200_md_nm,
+ * one row per read of the chunk.  This is sam_add_md_nm for a whole chunk of aln_samse records (sam.c:87, :246-328). */
+int salt_b200_tail_primaries(salt_b200_t *h, int slot, salt_mdnm_out_t *out, uint32_t *md_offs, char *md_packed, size_t md_cap,
+                             size_t *md_bytes, uint16_t *xv, int xv_stride);
+
 /* The whole verification stage for a chunk, as alnse_overlap_alt (SE) / alnse_overlap (PE)
  * run it after seeding (alnse.c:1077-1097 / :1014-1036):
  *   nogap on strand 0 then 1 with threshold nogap_T0 (3) tightening as candidates are

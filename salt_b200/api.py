@@ -101,6 +101,9 @@ def _declare(L):
         L.salt_b200_seed_locate.argtypes = [vp, i32, C.POINTER(SeedOptT), vp, vp, vp, sz, vp, sz, szp, szp]
         L.salt_b200_verify_seeded.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32]
         L.salt_b200_align_batch_packed.argtypes = [vp, C.POINTER(PackedChunkT), C.POINTER(SeedOptT), C.c_uint32, i32, i32, vp, vp, i32]
+    if hasattr(L, "salt_b200_tail_primaries"):
+        L.salt_b200_tail_primaries.argtypes = [vp, i32, vp, vp, vp, sz, C.POINTER(C.c_size_t), vp, i32]
+        L.salt_b200_use_slot.argtypes = [vp, i32]
     L.salt_b200_set_max_window.argtypes = [vp, i32]
     L.salt_b200_set_lv_mapping.argtypes = [vp, i32]
     L.salt_b200_set_lv_filter.argtypes = [vp, i32]
@@ -275,6 +278,18 @@ class Engine:
         self._ck(self.L.salt_b200_md_nm(self.h, int(slot), _ptr(items), n, _ptr(cg), cigar_stride, _ptr(md), md_stride,
                                         _ptr(xv) if xv_stride > 0 else None, xv_stride, _ptr(out)))
         return out, md, xv
+
+    def tail_primaries(self, slot=0, xv_stride=64, md_cap=None):
+        """MD / NM / XV of the primaries of the chunk just verified in `slot` (salt_b200_tail_primaries).
+        Returns (out records, md_offs, packed md bytes, xv rows)."""
+        n = self.n_reads
+        out = np.zeros(n, MDNM_OUT_DT); offs = np.zeros(n + 1, np.uint32)
+        cap = md_cap if md_cap is not None else n * 300 + 16
+        packed = np.zeros(cap, np.uint8); xv = np.zeros((n, max(xv_stride, 1)), np.uint16)
+        nb = C.c_size_t(0)
+        self._ck(self.L.salt_b200_tail_primaries(self.h, int(slot), _ptr(out), _ptr(offs), _ptr(packed), cap, C.byref(nb),
+                                                 _ptr(xv) if xv_stride > 0 else None, int(xv_stride)))
+        return out, offs, packed[:nb.value], xv
 
     @staticmethod
     def md_nm_text(out, md, xv, i):

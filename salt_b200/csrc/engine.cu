@@ -66,6 +66,8 @@ struct Slot {
     uint32_t *d_coffs(int strand) const { return offs3.as<uint32_t>() + (size_t)(strand + 1) * ((size_t)n_reads + 1); }
     DBuf c_loci0, c_loci1, vpairs, acc, rec, lvlist, ciglist, counters, cig, fpairs, fslots, lvreads;
     DBuf pk_bases, pk_lens, pk_cnt, pk_npos, pk_scan;          // compact transport (salt_packed_chunk_t): raw uploads + scan scratch
+    DBuf tl_md, tl_out, tl_len, tl_offs, tl_packed, tl_cigrow, tl_xv;   // SAM tail of the chunk's primaries
+    bool have_rec = false; int rec_cig_stride = 0;                // the slot's rec / cig buffers hold a finished verify
     DBuf sd_sai, sd_counts, sd_lists;                          // seeding scratch: intervals, per-strand counts, fixed-stride lists
     uint32_t *h_tot = nullptr;                                  // pinned: the two list totals of a seeded chunk
     size_t seeded_n0 = 0, seeded_n1 = 0; int seeded = 0;        // 1: totals in flight, 2: lists gathered into c_loci0/1
@@ -84,7 +86,8 @@ struct Slot {
     {
         DBuf *all[] = {&codes, &offs3, &rd4, &rd_len, &c_loci0, &c_loci1, &vpairs, &acc, &rec,
                        &lvlist, &ciglist, &counters, &cig, &fpairs, &fslots, &lvreads,
-                       &pk_bases, &pk_lens, &pk_cnt, &pk_npos, &pk_scan, &sd_sai, &sd_counts, &sd_lists};
+                       &pk_bases, &pk_lens, &pk_cnt, &pk_npos, &pk_scan, &sd_sai, &sd_counts, &sd_lists,
+                       &tl_md, &tl_out, &tl_len, &tl_offs, &tl_packed, &tl_cigrow, &tl_xv};
         for (DBuf *b : all) b->release();
         if (h_stage) cudaFreeHost(h_stage);
         h_stage = nullptr; h_stage_cap = 0;
@@ -191,7 +194,7 @@ int load_reads(salt_b200_t *h, Slot &s, const salt_reads_t *reads, const salt_ca
     if (l_max > 1024) return fail(SALT_ERR_UNSUPPORTED, "reads longer than 1024 bases are not supported");
     const size_t total = n ? (size_t)reads->offs[n] - reads->offs[0] : 0;
     if (n && reads->offs[0] != 0) return fail(SALT_ERR_ARG, "read offsets must start at 0");
-    s.n_reads = n; s.l_max = l_max; s.W64 = (l_max + 15) / 16 + 1;
+    s.n_reads = n; s.l_max = l_max; s.W64 = (l_max + 15) / 16 + 1; s.have_rec = false;
     CU(s.codes.need(total + 16));
     CU(s.offs3.need(3 * ((size_t)n + 1) * 4));
     CU(s.rd4.need((size_t)n * 2 * s.W64 * 8 + 64));
@@ -311,6 +314,7 @@ int run_and_download(salt_b200_t *h, int si, size_t n0, size_t n1, int nogap_T0,
     }
     s.u_cigars = cigars; s.u_stride = cigar_stride;
     s.pending = true;
+    s.have_rec = true; s.rec_cig_stride = cigars ? cigar_stride : 0;
     return SALT_OK;
 }
 
@@ -393,7 +397,7 @@ int load_packed(salt_b200_t *h, Slot &s, const PackedView &v, bool with_cands)
 {
     const salt_packed_chunk_t *pc = v.pc;
     const uint32_t n = v.n;
-    s.n_reads = n; s.l_max = v.l_max; s.W64 = (v.l_max + 15) / 16 + 1;
+    s.n_reads = n; s.l_max = v.l_max; s.W64 = (v.l_max + 15) / 16 + 1; s.have_rec = false;
     s.offs_merged = false;
     if (!n) return SALT_OK;
     const uint32_t per = 8u / (uint32_t)pc->base_bits;                 // bases per byte
@@ -454,7 +458,7 @@ int check_seed_opt(const salt_b200_t *h, const Slot &s, const salt_seed_opt_t *o
     if (o->max_seed < 0) return fail(SALT_ERR_ARG, "max_seed must be >= 0");
     if (o->max_locate < 1 || o->max_locate > 16384) return fail(SALT_ERR_UNSUPPORTED, "max_locate must be in 1..16384");
     const int ms = s.l_max >= (uint32_t)o->l_seed ? (int)((s.l_max - (uint32_t)o->l_seed) / (uint32_t)o->l_overlap) + 1 : 1;
-    if (ms > 64) return fail(SALT_ERR_UNSUPPORTED, "more than 64 seed starts per strand");
+    if (ms > 1024) return fail(SALT_ERR_UNSUPPORTED, "more than 1024 seed starts per strand");
     *max_seeds = ms;
     return SALT_OK;
 }
@@ -825,6 +829,48 @@ int salt_b200_md_nm(salt_b200_t *h, int slot, const salt_mdnm_in_t *items, size_
     if (xv_stride > 0) CU(cudaMemcpyAsync(xv, h->md_xv.p, n * xs * 2, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(out, h->md_out.p, n * sizeof(salt_mdnm_out_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return SALT_OK;
+}
+
+int salt_b200_tail_primaries(salt_b200_t *h, int slot, salt_mdnm_out_t *out, uint32_t *md_offs, char *md_packed, size_t md_cap,
+                             size_t *md_bytes, uint16_t *xv, int xv_stride)
+{
+    if (int rc = use_device(h)) return rc;
+    if (slot < 0 || slot >= SALT_SLOTS) return fail(SALT_ERR_ARG, "slot out of range");
+    Slot &s = h->slot[slot];
+    if (s.pending) return fail(SALT_ERR_ARG, "slot has a verify in flight: call salt_b200_verify_wait first");
+    if (!s.have_rec || !s.n_reads) return fail(SALT_ERR_ARG, "slot holds no verified chunk");
+    if (!s.rec_cig_stride) return fail(SALT_ERR_ARG, "the chunk was verified without CIGARs: gapped primaries would have no tags");
+    if (!h->d_pac) return fail(SALT_ERR_ARG, "MD/NM need the 2-bit pac (salt_b200_init was given none)");
+    if (!out || !md_offs || !md_packed) return fail(SALT_ERR_ARG, "null buffer");
+    if (xv_stride < 0 || xv_stride > 64 || (xv_stride > 0 && !xv)) return fail(SALT_ERR_ARG, "xv_stride must be 0..64 with a buffer");
+    const uint32_t n = s.n_reads;
+    const int mstride = 2 * (int)s.l_max + 16 < 64 ? 64 : 2 * (int)s.l_max + 16;     // an MD string never needs more than ~2 characters per base
+    const size_t xs = (size_t)(xv_stride > 0 ? xv_stride : 1);
+    cudaStream_t st = s.stream;
+    CU(s.tl_md.need((size_t)n * mstride)); CU(s.tl_out.need((size_t)n * sizeof(salt_mdnm_out_t)));
+    CU(s.tl_len.need((size_t)n * 4 + 16)); CU(s.tl_offs.need(((size_t)n + 1) * 4)); CU(s.tl_cigrow.need((size_t)n * 4));
+    CU(s.tl_xv.need((size_t)n * xs * 2)); CU(s.pk_scan.need(3 * (size_t)scan3_blocks(n) * 4 + 16));
+    if (xv_stride > 0) CU(cudaMemsetAsync(s.tl_xv.p, 0, (size_t)n * xs * 2, st));
+    const uint32_t *cl = s.ciglist.as<uint32_t>();
+    CU(launch_tail_primaries(h->ctx(slot), s.codes.as<uint8_t>(), s.d_roffs(), s.rec.as<salt_verify_out_t>(), cl + 1, cl,
+                             s.cig.as<char>(), s.rec_cig_stride, s.tl_cigrow.as<int32_t>(), s.tl_md.as<char>(), mstride,
+                             s.tl_xv.as<uint16_t>(), xv_stride, s.tl_out.as<salt_mdnm_out_t>(), s.tl_len.as<uint32_t>(), st));
+    Scan3 sc{};
+    sc.n = n; sc.partial = s.pk_scan.as<uint32_t>(); sc.in[0] = s.tl_len.p; sc.width[0] = 32; sc.out[0] = s.tl_offs.as<uint32_t>();
+    CU(launch_scan3(sc, 1, st));
+    CU(cudaMemcpyAsync(md_offs, s.tl_offs.p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out, s.tl_out.p, (size_t)n * sizeof(salt_mdnm_out_t), cudaMemcpyDeviceToHost, st));
+    if (xv_stride > 0) CU(cudaMemcpyAsync(xv, s.tl_xv.p, (size_t)n * xs * 2, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const size_t total = md_offs[n];
+    if (md_bytes) *md_bytes = total;
+    if (total > md_cap) return fail(SALT_ERR_NOMEM, "packed MD buffer too small");
+    CU(s.tl_packed.need(total + 16));
+    CU(launch_tail_pack(s.tl_md.as<char>(), mstride, s.tl_offs.as<uint32_t>(), n, s.tl_packed.as<char>(), st));
+    CU(cudaMemcpyAsync(md_packed, s.tl_packed.p, total, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    h->launches += 7;
     return SALT_OK;
 }
 

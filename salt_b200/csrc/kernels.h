@@ -35,6 +35,12 @@ cudaError_t launch_md_nm(const DevCtx &c, const uint8_t *codes, const uint32_t *
                          const char *cigars, int cstride, char *md, int mstride, uint16_t *xv, int xstride,
                          salt_mdnm_out_t *out, cudaStream_t st);
 
+cudaError_t launch_tail_primaries(const DevCtx &c, const uint8_t *codes, const uint32_t *roffs, const salt_verify_out_t *rec,
+                                  const uint32_t *cig_reads, const uint32_t *cig_count, const char *cigs, int cstride,
+                                  int32_t *cig_row, char *md, int mstride, uint16_t *xv, int xstride, salt_mdnm_out_t *out,
+                                  uint32_t *md_bytes, cudaStream_t st);
+cudaError_t launch_tail_pack(const char *md, int mstride, const uint32_t *offs, uint32_t n, char *packed, cudaStream_t st);
+
 // mixref.cu
 cudaError_t launch_build_mixref(const char *bases, uint32_t l, const uint32_t *snp_pos, const uint8_t *snp_mask,
                                 size_t n_snp, uint32_t *words, cudaStream_t st);

@@ -402,6 +402,92 @@ static double ms_now(void)
 }
 
 #define PE_CIG_STRIDE 64
+#define PE_TAIL_CIG 64               /* bytes per mate for the M/I/D string sent to salt_b200_md_nm (longer ones: 256) */
+
+/* host threads for the per-pair loops (hit selection, plans, apply): the reference runs them on its -t workers */
+static int g_host_threads = 1;
+void salt_host_set_threads(int n) { g_host_threads = n < 1 ? 1 : (n > 256 ? 256 : n); }
+
+typedef struct {
+    void (*fn)(void *ctx, uint32_t first, uint32_t upto);
+    void *ctx; uint32_t first, upto;
+} pfor_job_t;
+static void *pfor_tramp(void *a) { pfor_job_t *j = (pfor_job_t *)a; j->fn(j->ctx, j->first, j->upto); return NULL; }
+static void pfor(uint32_t n, void (*fn)(void *, uint32_t, uint32_t), void *ctx)
+{
+    int T = g_host_threads;
+    if ((uint32_t)T > n / 256 + 1) T = (int)(n / 256 + 1);
+    if (T <= 1) { fn(ctx, 0, n); return; }
+    pfor_job_t job[256]; pthread_t th[256];
+    for (int t = 0; t < T; ++t) {
+        job[t].fn = fn; job[t].ctx = ctx;
+        job[t].first = (uint32_t)((uint64_t)n * (uint64_t)t / (uint64_t)T); job[t].upto = (uint32_t)((uint64_t)n * (uint64_t)(t + 1) / (uint64_t)T);
+        pthread_create(&th[t], NULL, pfor_tramp, &job[t]);
+    }
+    for (int t = 0; t < T; ++t) pthread_join(th[t], NULL);
+}
+
+typedef struct {
+    salt_chunk_t *c; int max_hits; uint32_t min_tlen, max_tlen, l_pac; int filters, filterd;
+    salt_read_result_t *res; salt_pair_plan_t *plan; uint32_t *win_at;
+    salt_ssw_out_t *so[2]; uint32_t *sc[2];
+    salt_pair_final_t *out; salt_mdnm_in_t *tin; char *tcg; int tcs;
+    int rc;                                  /* first error of any thread (benign race: any error fails the call) */
+    size_t declined, rescued, k4, long_cigar;
+    pthread_mutex_t mu;
+} pe_ctx_t;
+
+static void pe_plan_range(void *a, uint32_t first, uint32_t upto)
+{
+    pe_ctx_t *X = (pe_ctx_t *)a;
+    salt_chunk_t *c = X->c;
+    for (uint32_t p = first; p < upto; ++p) {
+        int rc = salt_chunk_result(c, 2 * p, X->max_hits, &X->res[2 * p]);
+        if (rc == SALT_OK) rc = salt_chunk_result(c, 2 * p + 1, X->max_hits, &X->res[2 * p + 1]);
+        const uint32_t l0 = c->roffs[2 * p + 1] - c->roffs[2 * p], l1 = c->roffs[2 * p + 2] - c->roffs[2 * p + 1];
+        if (rc == SALT_OK) rc = salt_pair_plan(&X->res[2 * p], l0, &X->res[2 * p + 1], l1, X->min_tlen, X->max_tlen, X->l_pac, &X->plan[p]);
+        if (rc != SALT_OK) { X->rc = rc; return; }
+    }
+}
+
+static void pe_apply_range(void *a, uint32_t first, uint32_t upto)
+{
+    pe_ctx_t *X = (pe_ctx_t *)a;
+    salt_chunk_t *c = X->c;
+    size_t declined = 0, rescued = 0, k4 = 0, long_cigar = 0;
+    for (uint32_t p = first; p < upto; ++p) {
+        const uint32_t l0 = c->roffs[2 * p + 1] - c->roffs[2 * p], l1 = c->roffs[2 * p + 2] - c->roffs[2 * p + 1];
+        salt_ssw_out_t ws[2];
+        uint32_t wc[2 * PE_CIG_STRIDE];
+        const salt_pair_plan_t *pl = &X->plan[p];
+        for (int w = 0; w < pl->n_win; ++w) {
+            const int f = pl->win[w].flavour == 5;
+            const uint32_t at = X->win_at[2 * p + (uint32_t)w];
+            ws[w] = X->so[f][at];
+            memcpy(wc + w * PE_CIG_STRIDE, X->sc[f] + (size_t)at * PE_CIG_STRIDE, PE_CIG_STRIDE * 4);
+            if (ws[w].cigarLen < 0) ++declined;
+        }
+        const int r = salt_pair_apply(pl, &X->res[2 * p], l0, &X->res[2 * p + 1], l1, ws, wc, PE_CIG_STRIDE, X->filters, X->filterd,
+                                      X->out[p].mate);
+        if (r < 0) { X->rc = r; return; }
+        X->out[p].paired = r;
+        for (int m = 0; m < 2; ++m) {
+            const salt_mate_final_t *mf = &X->out[p].mate[m];
+            if (mf->cigar_kind == 3) ++rescued;
+            if (mf->cigar_kind == 4) ++k4;
+            if (X->tin) {                                /* the mate's row of the SAM-tail batch */
+                const uint32_t i = 2 * p + (uint32_t)m;
+                X->tin[i].rs = (i << 1) | (uint32_t)(mf->strand & 1); X->tin[i].pos = mf->pos; X->tin[i].seq_start = mf->seq_start;
+                const size_t len = strnlen(mf->cigar, sizeof mf->cigar);
+                if (len >= (size_t)X->tcs) ++long_cigar;
+                else memcpy(X->tcg + (size_t)i * (size_t)X->tcs, mf->cigar, len + 1);
+            }
+        }
+    }
+    pthread_mutex_lock(&X->mu);
+    X->declined += declined; X->rescued += rescued; X->k4 += k4; X->long_cigar += long_cigar;
+    pthread_mutex_unlock(&X->mu);
+}
 
 int salt_chunk_pair(salt_b200_t *h, int slot, salt_chunk_t *c, uint32_t min_tlen, uint32_t max_tlen, uint32_t l_pac,
                     int max_hits, const int8_t *mat16, const int8_t *mat5, int gapO, int gapE, int filters, int filterd,
@@ -415,71 +501,61 @@ int salt_chunk_pair(salt_b200_t *h, int slot, salt_chunk_t *c, uint32_t min_tlen
     memset(&st, 0, sizeof st);
     st.pairs = np;
     int rc = SALT_OK;
-    salt_read_result_t *res = malloc((size_t)c->n_reads * sizeof *res + 1);
-    salt_pair_plan_t *plan = malloc((size_t)np * sizeof *plan + 1);
+    pe_ctx_t X;
+    memset(&X, 0, sizeof X);
+    pthread_mutex_init(&X.mu, NULL);
+    X.c = c; X.max_hits = max_hits; X.min_tlen = min_tlen; X.max_tlen = max_tlen; X.l_pac = l_pac; X.filters = filters; X.filterd = filterd;
+    X.out = out; X.rc = SALT_OK;
+    X.res = malloc((size_t)c->n_reads * sizeof *X.res + 1);
+    X.plan = malloc((size_t)np * sizeof *X.plan + 1);
     /* windows by flavour; win_at[2 * pair + w] = row of the plan's w-th window in its flavour's batch */
     salt_win_t *win[2] = {malloc(((size_t)np * 2 + 1) * sizeof(salt_win_t)), malloc(((size_t)np * 2 + 1) * sizeof(salt_win_t))};
-    uint32_t *win_at = malloc(((size_t)np * 2 + 1) * 4);
+    X.win_at = malloc(((size_t)np * 2 + 1) * 4);
     size_t nw[2] = {0, 0};
-    salt_ssw_out_t *so[2] = {NULL, NULL};
-    uint32_t *sc[2] = {NULL, NULL};
-    if (!res || !plan || !win[0] || !win[1] || !win_at) { rc = SALT_ERR_NOMEM; goto done; }
+    if (!X.res || !X.plan || !win[0] || !win[1] || !X.win_at) { rc = SALT_ERR_NOMEM; goto done; }
 
     double t0 = ms_now();
-    for (uint32_t i = 0; i < c->n_reads && rc == SALT_OK; ++i) rc = salt_chunk_result(c, i, max_hits, &res[i]);
-    for (uint32_t p = 0; p < np && rc == SALT_OK; ++p) {
-        const uint32_t l0 = c->roffs[2 * p + 1] - c->roffs[2 * p], l1 = c->roffs[2 * p + 2] - c->roffs[2 * p + 1];
-        rc = salt_pair_plan(&res[2 * p], l0, &res[2 * p + 1], l1, min_tlen, max_tlen, l_pac, &plan[p]);
-        if (rc != SALT_OK) break;
-        if (plan[p].paired) ++st.proper;
-        for (int w = 0; w < plan[p].n_win; ++w) {
-            const salt_rescue_t *rw = &plan[p].win[w];
+    pfor(np, pe_plan_range, &X);                          /* query_set_hits of both mates + the pair's plan */
+    if ((rc = X.rc) != SALT_OK) goto done;
+    for (uint32_t p = 0; p < np; ++p) {
+        if (X.plan[p].paired) ++st.proper;
+        for (int w = 0; w < X.plan[p].n_win; ++w) {
+            const salt_rescue_t *rw = &X.plan[p].win[w];
             const int f = rw->flavour == 5;
             salt_win_t *o = &win[f][nw[f]];
             o->rs = ((2 * p + (uint32_t)rw->mate) << 1) | (uint32_t)rw->strand; o->start = rw->start; o->end = rw->end;
-            win_at[2 * p + (uint32_t)w] = (uint32_t)nw[f]++;
+            X.win_at[2 * p + (uint32_t)w] = (uint32_t)nw[f]++;
         }
     }
     st.windows16 = nw[0]; st.windows5 = nw[1];
     st.ms_plan = ms_now() - t0;
-    if (rc != SALT_OK) goto done;
 
     /* one Smith-Waterman batch per flavour on the chunk's resident reads (alnpe.c:261 / :330) */
     t0 = ms_now();
     if ((rc = salt_b200_use_slot(h, slot)) != SALT_OK) goto done;
     for (int f = 0; f < 2 && rc == SALT_OK; ++f) {
         if (!nw[f]) continue;
-        so[f] = malloc(nw[f] * sizeof(salt_ssw_out_t));
-        sc[f] = calloc(nw[f] * PE_CIG_STRIDE, 4);
-        if (!so[f] || !sc[f]) { rc = SALT_ERR_NOMEM; break; }
-        rc = salt_b200_ssw(h, win[f], nw[f], f, f ? mat5 : mat16, f ? 5 : 16, gapO, gapE, 2, filters, filterd, -1, so[f], sc[f], PE_CIG_STRIDE);
+        X.so[f] = malloc(nw[f] * sizeof(salt_ssw_out_t));
+        X.sc[f] = calloc(nw[f] * PE_CIG_STRIDE, 4);
+        if (!X.so[f] || !X.sc[f]) { rc = SALT_ERR_NOMEM; break; }
+        rc = salt_b200_ssw(h, win[f], nw[f], f, f ? mat5 : mat16, f ? 5 : 16, gapO, gapE, 2, filters, filterd, -1, X.so[f], X.sc[f], PE_CIG_STRIDE);
     }
     st.ms_ssw = ms_now() - t0;
     if (rc != SALT_OK) { salt_b200_use_slot(h, 0); goto done; }
 
     t0 = ms_now();
-    size_t n_k4 = 0;
-    for (uint32_t p = 0; p < np; ++p) {
-        const uint32_t l0 = c->roffs[2 * p + 1] - c->roffs[2 * p], l1 = c->roffs[2 * p + 2] - c->roffs[2 * p + 1];
-        salt_ssw_out_t ws[2];
-        uint32_t wc[2 * PE_CIG_STRIDE];
-        for (int w = 0; w < plan[p].n_win; ++w) {
-            const int f = plan[p].win[w].flavour == 5;
-            const uint32_t at = win_at[2 * p + (uint32_t)w];
-            ws[w] = so[f][at];
-            memcpy(wc + w * PE_CIG_STRIDE, sc[f] + (size_t)at * PE_CIG_STRIDE, PE_CIG_STRIDE * 4);
-            if (ws[w].cigarLen < 0) ++st.declined;
-        }
-        const int r = salt_pair_apply(&plan[p], &res[2 * p], l0, &res[2 * p + 1], l1, ws, wc, PE_CIG_STRIDE, filters, filterd, out[p].mate);
-        if (r < 0) { rc = r; break; }
-        out[p].paired = r;
-        for (int m = 0; m < 2; ++m) {
-            if (out[p].mate[m].cigar_kind == 3) ++st.rescued;
-            if (out[p].mate[m].cigar_kind == 4) ++n_k4;
-        }
+    if (with_tail) {
+        X.tcs = PE_TAIL_CIG;
+        X.tin = malloc((size_t)c->n_reads * sizeof *X.tin + 1);
+        X.tcg = malloc((size_t)c->n_reads * (size_t)X.tcs + 1);
+        if (!X.tin || !X.tcg) { rc = SALT_ERR_NOMEM; salt_b200_use_slot(h, 0); goto done; }
     }
-    if (rc == SALT_OK && n_k4) {
+    pfor(np, pe_apply_range, &X);
+    rc = X.rc;
+    st.declined = X.declined; st.rescued = X.rescued;
+    if (rc == SALT_OK && X.k4) {
         /* gapped alternates that became primaries: their CIGARs in one salt_b200_lv_cigar call (query.c:288) */
+        const size_t n_k4 = X.k4;
         salt_pair_t *pp = malloc(n_k4 * sizeof *pp);
         uint8_t *kk = malloc(n_k4);
         char *cg = calloc(n_k4, 128);
@@ -496,7 +572,13 @@ int salt_chunk_pair(salt_b200_t *h, int slot, salt_chunk_t *c, uint32_t min_tlen
         q = 0;
         for (uint32_t p = 0; p < np && rc == SALT_OK; ++p)
             for (int m = 0; m < 2; ++m)
-                if (out[p].mate[m].cigar_kind == 4) { strncpy(out[p].mate[m].cigar, cg + q * 128, 127); ++q; ++st.promoted; }
+                if (out[p].mate[m].cigar_kind == 4) {
+                    strncpy(out[p].mate[m].cigar, cg + q * 128, 127);
+                    if (X.tcg) { strncpy(X.tcg + (size_t)(2 * p + (uint32_t)m) * (size_t)X.tcs, cg + q * 128, (size_t)X.tcs - 1);
+                                 X.tcg[(size_t)(2 * p + (uint32_t)m) * (size_t)X.tcs + (size_t)X.tcs - 1] = 0;
+                                 if (strlen(cg + q * 128) >= (size_t)X.tcs) ++X.long_cigar; }
+                    ++q; ++st.promoted;
+                }
         free(pp); free(kk); free(cg); free(eo);
     }
     salt_b200_use_slot(h, 0);
@@ -507,22 +589,23 @@ int salt_chunk_pair(salt_b200_t *h, int slot, salt_chunk_t *c, uint32_t min_tlen
         /* sam_add_md_nm of every mapped mate (sam.c:246-328) in one call on the slot's reads */
         t0 = ms_now();
         const uint32_t n = c->n_reads;
-        salt_mdnm_in_t *in = malloc((size_t)n * sizeof *in + 1);
-        char *cg = malloc((size_t)n * 128 + 1);
-        if (!in || !cg) rc = SALT_ERR_NOMEM;
-        for (uint32_t i = 0; i < n && rc == SALT_OK; ++i) {
-            const salt_mate_final_t *mf = &out[i / 2].mate[i & 1];
-            in[i].rs = (i << 1) | (uint32_t)(mf->strand & 1); in[i].pos = mf->pos; in[i].seq_start = mf->seq_start;
-            memcpy(cg + (size_t)i * 128, mf->cigar, 128);
-            cg[(size_t)i * 128 + 127] = 0;
+        if (X.long_cigar) {                               /* rare: a CIGAR of 64+ characters -- redo the batch's strings at full width */
+            free(X.tcg);
+            X.tcs = 256;
+            X.tcg = malloc((size_t)n * 256 + 1);
+            if (!X.tcg) rc = SALT_ERR_NOMEM;
+            for (uint32_t i = 0; i < n && rc == SALT_OK; ++i) {
+                memcpy(X.tcg + (size_t)i * 256, out[i / 2].mate[i & 1].cigar, 256);
+                X.tcg[(size_t)i * 256 + 255] = 0;
+            }
         }
-        if (rc == SALT_OK) rc = salt_b200_md_nm(h, slot, in, n, cg, 128, tail_md, md_stride, NULL, 0, tail_out);
-        free(in); free(cg);
+        if (rc == SALT_OK) rc = salt_b200_md_nm(h, slot, X.tin, n, X.tcg, X.tcs, tail_md, md_stride, NULL, 0, tail_out);
         st.ms_tail = ms_now() - t0;
     }
 done:
-    free(res); free(plan); free(win[0]); free(win[1]); free(win_at);
-    free(so[0]); free(so[1]); free(sc[0]); free(sc[1]);
+    free(X.res); free(X.plan); free(win[0]); free(win[1]); free(X.win_at);
+    free(X.so[0]); free(X.so[1]); free(X.sc[0]); free(X.sc[1]); free(X.tin); free(X.tcg);
+    pthread_mutex_destroy(&X.mu);
     if (stats) *stats = st;
     return rc;
 }

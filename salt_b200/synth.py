@@ -210,9 +210,9 @@ def sample_pairs(g, n_pairs, L, seed=6, insert_mean=400, insert_sd=50, sub_rate=
     b = revcomp(b)
     flip = rng.random(n_pairs) < 0.5
     reads = np.empty((2 * n_pairs, L), np.uint8); pos = np.empty(2 * n_pairs, np.uint32); strand = np.empty(2 * n_pairs, np.uint8)
-    # flipped fragment: what was read forward is now reverse-complemented and vice versa
-    reads[0::2] = np.where(flip[:, None], revcomp(a), a); reads[1::2] = np.where(flip[:, None], revcomp(b), b)
-    pos[0::2] = p; pos[1::2] = pos_b
+    # fragment from the other strand: mate 0 is the reverse-strand read at the far end, mate 1 the forward read
+    reads[0::2] = np.where(flip[:, None], b, a); reads[1::2] = np.where(flip[:, None], a, b)
+    pos[0::2] = np.where(flip, pos_b, p); pos[1::2] = np.where(flip, p, pos_b)
     strand[0::2] = flip.astype(np.uint8); strand[1::2] = 1 - flip.astype(np.uint8)
     return np.ascontiguousarray(reads), pos, strand
 

@@ -335,6 +335,29 @@ def check_ssw_wide_bands(eng, oracle, seed, n_reads=150, L=100, glen=20003):
     return gapped
 
 
+def check_tail_primaries(eng, oracle, g, reads, cands, nogap_T0=3, lv_T0=-1):
+    """salt_b200_tail_primaries (tags of a verified chunk's primaries, nothing uploaded, MD strings packed) against
+    salt_b200_md_nm on the same alignments (which check_md_nm pins against the oracle and the golden vectors)."""
+    offs0, loci0, offs1, loci1 = cands
+    eng.set_reads(reads)
+    rec, acc0, acc1, cig = eng.verify(offs0, loci0, offs1, loci1, nogap_T0, lv_T0, 128)
+    out, offs, packed, xv = eng.tail_primaries(0)
+    n, L = reads.shape
+    cigs = [api.cstr(cig[i]) if rec["is_gap"][i] == 1 else "%dM" % L for i in range(n)]
+    rs = (np.arange(n, dtype=np.uint32) << 1) | (rec["strand"].astype(np.uint32) & 1)
+    want, md, xv2 = eng.md_nm(rs, rec["pos"], np.zeros(n, np.uint32), cigs, md_stride=320)
+    n_gapped = 0
+    for i in range(n):
+        a = bytes(packed[offs[i]:offs[i + 1]])
+        assert a.endswith(b"\0")
+        assert a[:-1].decode() == api.cstr(md[i]), (i, a, api.cstr(md[i]))
+        assert tuple(out[i]) == tuple(want[i]), (i, out[i], want[i])
+        assert np.array_equal(xv[i][:out["n_xv"][i]], xv2[i][:want["n_xv"][i]])
+        n_gapped += rec["is_gap"][i] == 1
+    assert int(offs[-1]) == len(packed)
+    return n_gapped
+
+
 def check_chunk_pair(eng, hostlib, g, n_pairs, L, seed, min_tlen=250, max_tlen=550):
     """salt_chunk_pair (the paired-end stage of a whole chunk: plans, one Smith-Waterman batch per flavour, apply, CIGARs
     of promoted alternates, MD/NM) against the same stage composed pair by pair from the pieces that the reference's own

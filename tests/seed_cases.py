@@ -68,7 +68,8 @@ def sample_reads(g, rng, n, ragged=True, sub=0.02, n_every=7):
     return np.concatenate(reads), roffs
 
 
-OPTION_SETS = ((0, 0, 50, 500, 0),        # run_se_test.sh: -n 20 sets max_diff, -m 500
+OPTION_SETS = ((0, 1, 50, 500, 0),        # run_se_test.sh:12: -r 1 (a seed at every position: up to l_seq - l_seed + 1 intervals per index), -m 500
+               (0, 0, 50, 500, 0),        # the same with the default seed spacing (l_overlap = l_seed)
                (0, 0, 2, 7, 0),           # tight caps: extension runs long, every list is cut
                (0, 5, 0, 1000, 0),        # overlapping seeds, extension until unique
                (0, 0, 1000, 33, 0),       # no extension, wide intervals against a small max_locate

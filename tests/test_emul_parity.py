@@ -253,3 +253,10 @@ def test_chunk_pair_stage(emul_lib, oracle):
     st = pc.check_chunk_pair(eng, hostlib, g, 24, 100, seed=9)
     assert st.windows16 + st.windows5 >= 3 and st.rescued >= 1 and st.proper >= 10
     eng.close()
+
+
+def test_tail_primaries(emul_lib, oracle):
+    g, reads, pos, strand, cands = pc.make_world(808, L=100, n_reads=40, per_strand=3, indel_frac=0.4, glen=30000, sub_rate=0.03)
+    eng = _engine(emul_lib, g, with_pac=True)
+    assert pc.check_tail_primaries(eng, oracle, g, reads, cands) >= 3
+    eng.close()

@@ -437,3 +437,13 @@ def test_multi_gpu_in_process_matches_single():
             assert a.tobytes() == b.tobytes(), (name, devs)
         hostlib.salt_multi_destroy(m)
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L", [100, 250])
+def test_tail_primaries(oracle, L):
+    """tags of a verified chunk's primaries from device-resident records and CIGARs, MD strings packed"""
+    g, reads, pos, strand, cands = pc.make_world(808 + L, L=L, n_reads=3000, per_strand=4, indel_frac=0.4, glen=300000, sub_rate=0.03)
+    eng = _engine(g)
+    assert pc.check_tail_primaries(eng, oracle, g, reads, cands) >= 200
+    eng.close()
