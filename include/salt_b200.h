@@ -94,6 +94,14 @@ int salt_b200_device_count(void);
 salt_b200_t *salt_b200_init(const uint32_t *mixref, uint32_t l, const uint8_t *pac, int64_t l_pac, int device);
 void salt_b200_destroy(salt_b200_t *h);
 
+/* A second handle on the same device that shares the first one's resident reference (and FM-indexes) but has its own
+ * streams, slots and scratch: what each of the reference's -t worker threads takes (a handle is single-threaded).  The
+ * parent must outlive it. */
+salt_b200_t *salt_b200_attach(salt_b200_t *parent);
+
+/* Replace the resident reference of a handle that owns one (re-using its allocation when the new one fits). */
+int salt_b200_reload_ref(salt_b200_t *h, const uint32_t *mixref, uint32_t l, const uint8_t *pac, int64_t l_pac);
+
 /* Build the SNP-aware reference on the device from raw bases and SNP rows instead of
  * uploading it: Index_src/mixRef.c:93-197 (build_mixRef) + Index_src/hapmap.c:92-158.
  * bases: ASCII, all records concatenated; snp_pos: 0-based global positions; snp_mask: allele

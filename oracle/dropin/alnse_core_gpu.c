@@ -209,7 +209,10 @@ int alnse_core(const opt_t *opt)
                 t_gpu_wait += now_s() - tg;
                 ++n_chunks;
             }
-            if (pend_c >= 0) {                          /* finish the previous sub-chunk while the GPU works on this one */
+            /* host seeding: finish the previous sub-chunk while the GPU verifies this one.  Device seeding is synchronous
+               on slot 0 (the slot's resident reads feed the SAM tail), so there the sub-chunk just verified is finished at once */
+            if (gpu_seed && cur >= 0) { pend_c = cur; pend_first = first; pend_upto = upto; first = upto; ++k; cur = -1; }
+            if (pend_c >= 0) {
                 int j;
                 double tg = now_s();
                 if (!gpu_seed && salt_chunk_wait(gpu, pend_c, ck[pend_c]) != SALT_OK) die("salt_chunk_wait");
@@ -224,16 +227,7 @@ int alnse_core(const opt_t *opt)
                 t_finish += now_s() - tf;
                 pend_c = -1;
             }
-            if (cur >= 0) {
-                if (gpu_seed) {
-                    /* synchronous on slot 0: finish right away (the tail needs the slot's reads still resident) */
-                    pend_c = cur; pend_first = first; pend_upto = upto;
-                    first = upto; ++k;
-                    continue;
-                }
-                pend_c = cur; pend_first = first; pend_upto = upto;
-                first = upto; ++k;
-            }
+            if (cur >= 0) { pend_c = cur; pend_first = first; pend_upto = upto; first = upto; ++k; }
         }
         for (i = 0; i < n; ++i) {
             query_t *query = multiSeqs + i;

@@ -44,7 +44,7 @@ static void dropin_xa_prepare(salt_b200_t *gpu, int slot, const query_t *multi_s
     size_t i, n = 0, cap = 0;
     salt_pair_t *pairs = NULL; uint8_t *k_each = NULL;
     T.n_xa = 0; T.xa_cursor = 0;
-    if (slot != 0) { fprintf(stderr, "[salt_dropin] XA CIGARs use the read set of slot 0\n"); exit(1); }
+    if (salt_b200_use_slot(gpu, slot) != SALT_OK) tail_die("salt_b200_use_slot");      /* the per-pair entry points follow the chunk's slot */
     for (j = first; j < upto; ++j) {
         const query_t *q = multi_seqs + j;
         if (slot_of[j] < 0) continue;
@@ -69,6 +69,7 @@ static void dropin_xa_prepare(salt_b200_t *gpu, int slot, const query_t *multi_s
         memset(T.xa_cig, 0, n * TAIL_XA_STRIDE);
         if (salt_b200_lv_cigar(gpu, pairs, k_each, n, T.xa_cig, TAIL_XA_STRIDE, T.xa_e) != SALT_OK) tail_die("salt_b200_lv_cigar");
     }
+    salt_b200_use_slot(gpu, 0);
     T.n_xa = n; T.tot_xa += n;
     free(pairs); free(k_each);
 }

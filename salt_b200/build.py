@@ -63,7 +63,7 @@ def build_host(force=False, engine=OUT, out=HOST_OUT):
     if force or _stale(l0, [src0, engine] + hdrs):
         d, f = os.path.split(engine)
         subprocess.check_call([os.environ.get("CC", "gcc"), "-O2", "-std=gnu11", "-Wall", "-Wextra", "-fPIC", "-shared",
-                               "-fvisibility=hidden", "-o", l0, src0, "-L" + d, "-l:" + f, "-Wl,-rpath," + d, "-Wl,-rpath,$ORIGIN"])
+                               "-fvisibility=hidden", "-o", l0, src0, "-L" + d, "-l:" + f, "-Wl,-rpath," + d, "-Wl,-rpath,$ORIGIN", "-lpthread"])
     return out
 
 

@@ -110,6 +110,8 @@ struct salt_b200 {
     uint8_t *d_mixref_alloc = nullptr;      // allocation: REF_FRONT zero bytes, the words, REF_PAD zero bytes
     uint32_t *d_mixref = nullptr; uint32_t l = 0;
     uint8_t *d_pac = nullptr; int64_t l_pac = 0;
+    size_t ref_cap = 0, pac_cap = 0;        // bytes allocated for the words / the pac (salt_b200_reload_ref)
+    bool borrowed = false;                  // reference (and index) belong to the handle this one was attached to
     Slot slot[SALT_SLOTS];
     DBuf fpairs, fslots, fcount;            // LV filter survivors of the per-pair entry point
     int lv_filter = 1;                      // pigeonhole filter in front of Landau-Vishkin (salt_b200_set_lv_filter)
@@ -173,6 +175,7 @@ cudaError_t alloc_mixref(salt_b200_t *h, size_t nb, cudaStream_t st)
     cudaError_t e = cudaMalloc(&h->d_mixref_alloc, REF_FRONT + nb + REF_PAD);
     if (e != cudaSuccess) return e;
     h->d_mixref = reinterpret_cast<uint32_t *>(h->d_mixref_alloc + REF_FRONT);
+    h->ref_cap = nb;
     if ((e = cudaMemsetAsync(h->d_mixref_alloc, 0, REF_FRONT, st)) != cudaSuccess) return e;
     return cudaMemsetAsync(h->d_mixref_alloc + REF_FRONT + nb, 0, REF_PAD, st);
 }
@@ -585,7 +588,7 @@ salt_b200_t *salt_b200_init(const uint32_t *mixref, uint32_t l, const uint8_t *p
             (e = cudaMemcpyAsync(h->d_pac, pac, pb, cudaMemcpyHostToDevice, st)) != cudaSuccess) {
             fail(SALT_ERR_CUDA, "upload pac", e); salt_b200_destroy(h); return nullptr;
         }
-        h->l_pac = l_pac;
+        h->l_pac = l_pac; h->pac_cap = pb;
     }
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { fail(SALT_ERR_CUDA, "sync", e); salt_b200_destroy(h); return nullptr; }
     return h;
@@ -623,6 +626,50 @@ salt_b200_t *salt_b200_init_from_bases(const char *bases, uint32_t l, const uint
     return h;
 }
 
+salt_b200_t *salt_b200_attach(salt_b200_t *parent)
+{
+    if (!parent) { fail(SALT_ERR_ARG, "null handle"); return nullptr; }
+    salt_b200_t *h = new_handle(parent->device);
+    if (!h) return nullptr;
+    h->borrowed = true;
+    h->d_mixref = parent->d_mixref; h->l = parent->l; h->d_pac = parent->d_pac; h->l_pac = parent->l_pac;
+    h->fm = parent->fm; h->have_index = parent->have_index;
+    h->lv_filter = parent->lv_filter; h->lv_mapping = parent->lv_mapping;
+    return h;
+}
+
+int salt_b200_reload_ref(salt_b200_t *h, const uint32_t *mixref, uint32_t l, const uint8_t *pac, int64_t l_pac)
+{
+    if (int rc = use_device(h)) return rc;
+    if (h->borrowed) return fail(SALT_ERR_ARG, "an attached handle does not own its reference");
+    if (!mixref || l == 0) return fail(SALT_ERR_ARG, "mixref is null or empty");
+    for (int i = 0; i < SALT_SLOTS; ++i) if (h->slot[i].pending) return fail(SALT_ERR_ARG, "a slot has a verify in flight");
+    cudaStream_t st = h->slot[0].stream;
+    const size_t nb = ((size_t)l + 7) / 8 * 4;
+    if (nb > h->ref_cap) {
+        CU(cudaStreamSynchronize(st));
+        if (h->d_mixref_alloc) { CU(cudaFree(h->d_mixref_alloc)); h->d_mixref_alloc = nullptr; h->d_mixref = nullptr; h->ref_cap = 0; }
+        CU(alloc_mixref(h, nb + nb / 2 + 256, st));
+    }
+    CU(cudaMemcpyAsync(h->d_mixref, mixref, nb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(reinterpret_cast<uint8_t *>(h->d_mixref) + nb, 0, REF_PAD, st));      // zero pad right behind the new end
+    h->l = l;
+    if (pac && l_pac > 0) {
+        const size_t pb = ((size_t)l_pac + 3) / 4;
+        if (pb > h->pac_cap) {
+            CU(cudaStreamSynchronize(st));
+            if (h->d_pac) { CU(cudaFree(h->d_pac)); h->d_pac = nullptr; h->pac_cap = 0; }
+            CU(cudaMalloc(&h->d_pac, pb + pb / 2 + 256 + REF_PAD));
+            h->pac_cap = pb + pb / 2 + 256;
+        }
+        CU(cudaMemcpyAsync(h->d_pac, pac, pb, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(h->d_pac + pb, 0, REF_PAD, st));
+        h->l_pac = l_pac;
+    } else h->l_pac = 0;
+    CU(cudaStreamSynchronize(st));
+    return SALT_OK;
+}
+
 int salt_b200_get_mixref(salt_b200_t *h, uint32_t *words_out, size_t n_words)
 {
     if (int rc = use_device(h)) return rc;
@@ -645,8 +692,10 @@ void salt_b200_destroy(salt_b200_t *h)
                    &h->fpairs, &h->fslots, &h->fcount, &h->md_in, &h->md_cig, &h->md_str, &h->md_xv, &h->md_out};
     for (DBuf *b : all) b->release();
     for (int i = 0; i < 7; ++i) if (h->ev_ssw[i]) cudaEventDestroy(h->ev_ssw[i]);
-    if (h->d_mixref_alloc) cudaFree(h->d_mixref_alloc);
-    if (h->d_pac) cudaFree(h->d_pac);
+    if (!h->borrowed) {                     // an attached handle only points at its parent's reference and indexes
+        if (h->d_mixref_alloc) cudaFree(h->d_mixref_alloc);
+        if (h->d_pac) cudaFree(h->d_pac);
+    }
     delete h;
 }
 

@@ -35,7 +35,9 @@ def test_host_layer_exports():
     for n in names:
         assert hasattr(H, n), n
     S = C.CDLL(os.path.join(os.path.dirname(api.LIB_PATH), "libsalt_level0.so"))
-    for n in ("ed_mismatch", "ed_diff", "ed_diff_withcigar", "salt_level0_attach"):      # editdistance.h:20-22
+    for n in ("ed_mismatch", "ed_diff", "ed_diff_withcigar", "salt_level0_attach",        # editdistance.h:20-22
+              "computeEditDistance", "computeEditDistanceWithCigar",                      # LandauVishkin.h:45, :50
+              "ssw_init", "ssw_align", "init_destroy", "align_destroy"):                  # ssw.h:71, :111, :76, :124
         assert hasattr(S, n), n
 
 

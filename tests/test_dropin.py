@@ -196,3 +196,28 @@ def test_config0_pe_sam_identical(tmp_path, threads):
     assert "verification on libsalt_b200" in err
     body = _same_sam(os.path.join(C0, "pe.sam"), os.path.join(d, "gpu.sam"), 40000)
     assert sum(1 for f in body if int(f[1]) & 2) >= 30000
+
+
+@pytest.mark.parametrize("mode", ["se-t1", "se-t4", "pe-t2"])
+def test_level0_program_sam_identical(tmp_path, mode):
+    """Level 0: the reference's UNMODIFIED objects minus editdistance.o / LandauVishkin.o / ssw.o, linked
+    against libsalt_level0.so (oracle/_ref/salt_level0) -- every ed_mismatch / ed_diff / ed_diff_withcigar / ssw_* call of the
+    reference's own loops is a batch-of-one GPU call, from several worker threads at once -- prints the reference's SAM"""
+    if not (_have() and os.path.exists(os.path.join(REFDIR, "salt_level0"))):
+        pytest.skip("oracle/_ref programs not built (reference tree absent at build time)")
+    d = str(tmp_path)
+    if mode.startswith("se"):
+        dropin_data.write_inputs(d, glen=60_000, n_reads=500)
+        files = ["reads.fq"]
+        flags = ["-d", "-r", "5", "-l", "100", "-n", "20", "-c", "-m", "500", "-t", mode[-1]]
+    else:
+        dropin_data.write_pe_inputs(d, glen=60_000, n_pairs=250)
+        files = ["r1.fq", "r2.fq"]
+        flags = ["-d", "-p", "-e", "-l", "100", "-c", "-a", "350", "-b", "650", "-r", "5", "-t", mode[-1]]
+    _run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], d, os.path.join(d, "idx.log"))
+    _run([os.path.join(REFDIR, "salt")] + flags + ["idx"] + files, d, os.path.join(d, "ref.sam"))
+    _run([os.path.join(REFDIR, "salt_level0")] + flags + ["idx"] + files, d, os.path.join(d, "l0.sam"))
+    body = _same_sam(os.path.join(d, "ref.sam"), os.path.join(d, "l0.sam"), 500)
+    assert sum(1 for f in body if f[1] != "4") >= 400
+    if mode.startswith("pe"):
+        assert sum(1 for f in body if "S" in f[5]) >= 3          # rescued by ssw_align on the GPU

@@ -161,6 +161,49 @@ def test_level0_symbol_shim(oracle):
         assert (e, buf.value.decode()) == want
         n_gap += "I" in want[1] or "D" in want[1]
     assert n_gap >= 5
+    # LandauVishkin.h:45 / :50 on caller-supplied bytes (text = allele masks, pattern = one-hot / 15), as ed_diff calls them
+    S.computeEditDistance.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int]
+    S.computeEditDistanceWithCigar.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int]
+    onehot = np.array([1, 2, 4, 8, 15], np.uint8)
+    for r in range(0, len(reads), 2):
+        seq = np.ascontiguousarray(synth.revcomp(reads[r]) if strand[r] else reads[r]); p = int(pos[r])
+        text = np.ascontiguousarray(synth.unpack_mixref(g.mixref, p, 104)); pat = np.ascontiguousarray(onehot[seq])
+        assert S.computeEditDistance(text.ctypes.data, 104, pat.ctypes.data, 100, 10) == oracle.ed_diff(g.mixref, g.l, p, seq, 10)
+        buf = C.create_string_buffer(128)
+        e = S.computeEditDistanceWithCigar(text.ctypes.data, 104, pat.ctypes.data, 100, 10, buf, 128, 1, 0)
+        assert (e, buf.value.decode()) == oracle.ed_diff_withcigar(g.mixref, p, seq, 10, 128)
+    # ssw.h:71 / :111 / :76 / :124 with the reference's ownership rules: borrowed read / mat, calloc'd s_align, malloc'd cigar
+    class SAlign(C.Structure):
+        _fields_ = [("score1", C.c_uint16), ("score2", C.c_uint16), ("ref_begin1", C.c_int32), ("ref_end1", C.c_int32),
+                    ("read_begin1", C.c_int32), ("read_end1", C.c_int32), ("ref_end2", C.c_int32), ("cigar", C.POINTER(C.c_uint32)),
+                    ("cigarLen", C.c_int32)]
+    S.ssw_init.restype = vp; S.ssw_init.argtypes = [vp, C.c_int32, vp, C.c_int32, C.c_int8]
+    S.ssw_align.restype = C.POINTER(SAlign)
+    S.ssw_align.argtypes = [vp, vp, C.c_int32, C.c_uint8, C.c_uint8, C.c_uint8, C.c_uint16, C.c_int32, C.c_int32]
+    S.init_destroy.argtypes = [vp]; S.align_destroy.argtypes = [C.POINTER(SAlign)]
+    m16 = api.salt_score_mat2(); m5 = api.salt_score_mat()
+    pad16 = np.concatenate([m16, m16[-1:]])
+    n_sw_gap = 0
+    for r in range(0, len(reads), 3):
+        seq = np.ascontiguousarray(synth.revcomp(reads[r]) if strand[r] else reads[r]); p = max(0, int(pos[r]) - 150)
+        for n_sym in (16, 5):
+            if n_sym == 16:
+                ref = synth.unpack_mixref(g.mixref, p, 401).astype(np.int8); rd = (1 << seq.astype(np.int32)).astype(np.int8); mat = m16
+            else:
+                idx = np.arange(p, p + 401)
+                ref = ((g.pac[idx >> 2] >> ((~idx & 3) << 1).astype(np.uint8)) & 3).astype(np.int8); rd = seq.astype(np.int8); mat = m5
+            ref = np.ascontiguousarray(ref); rd = np.ascontiguousarray(rd)
+            prof = S.ssw_init(rd.ctypes.data, 100, mat.ctypes.data, n_sym, 1)
+            a = S.ssw_align(prof, ref.ctypes.data, 401, 3, 1, 2, 0, 20, 50)
+            assert a
+            rc, want, wc = oracle.ssw_align(rd, pad16 if n_sym == 16 else m5, n_sym, ref, 3, 1, 2, 0, 20, 50)
+            got = (a.contents.score1, a.contents.score2, a.contents.ref_begin1, a.contents.ref_end1, a.contents.read_begin1,
+                   a.contents.read_end1, a.contents.ref_end2, a.contents.cigarLen)
+            assert got == want, (r, n_sym, got, want)
+            assert [a.contents.cigar[i] for i in range(want[7])] == [int(c) for c in wc]
+            n_sw_gap += any((int(c) & 15) != 0 for c in wc)
+            S.align_destroy(a); S.init_destroy(prof)
+    assert n_sw_gap >= 2
 
 
 def test_verify_ragged_and_empty(oracle):
