@@ -159,6 +159,35 @@ int salt_chunk_pair(salt_b200_t *h, int slot, salt_chunk_t *c, uint32_t min_tlen
                     int gapO, int gapE, int filters, int filterd, int with_tail,
                     salt_pair_final_t *out, salt_mdnm_out_t *tail_out, char *tail_md, int md_stride, salt_pe_stats_t *stats);
 
+/* ---- input side: FASTQ text -> the compact transport, in one pass ---------------------------
+ * What query_read_seq does per record (query.c:146-239) -- name up to the first blank with a trailing "/<digit>" trimmed
+ * (:140-144), comment, bases through nst_nt4_table (A/C/G/T in either case -> 0..3, anything else -> 4 and counted in
+ * n_ambiguous), quality string -- but emitting the bases directly at 2 bits per base with the N positions on the side,
+ * i.e. a salt_packed_chunk_t ready for salt_b200_set_reads_packed / _verify_submit_packed / _align_batch_packed.  The
+ * reverse complement (query->rseq, query.c:46-64) is made on the device.  kseq's grammar is kept: '@' or '>' records,
+ * sequence and quality may span lines, the quality block ends when it is as long as the sequence.
+ * All arrays are the caller's; name / comment / quality stay in `text` and are returned as offsets.  (A record without a
+ * comment reports an empty one; the reference's query->comment holds the previous record's there, query.c:160 -- it is
+ * never printed.) */
+typedef struct {
+    uint8_t *bases; size_t bases_cap;        /* in: room for bases_cap bases (bases_cap / 4 bytes, + 1); out: 2-bit stream */
+    uint32_t *n_pos; size_t n_pos_cap;       /* stream positions of non-ACGT bases */
+    uint16_t *lens; uint16_t *n_ambiguous;   /* per read (max_reads entries each) */
+    uint32_t *name_off; uint16_t *name_len;  /* per read: the trimmed name inside `text` */
+    uint32_t *comment_off; uint16_t *comment_len;
+    uint32_t *qual_off;                      /* per read: first quality character inside `text` (0xFFFFFFFF: none; multi-line
+                                                quality blocks are reported by their first line) */
+    /* results */
+    uint32_t n_reads; size_t n_bases, n_n;
+} salt_fastq_t;
+
+/* Parse complete records from text[0, len) until max_reads records, a full array, or the end of the text.
+ * final != 0: the text ends the input (a last record without a trailing newline is complete).  *consumed = bytes of
+ * text used by the records returned; the caller re-presents the rest together with the next block.
+ * Returns the number of records, or a negative SALT_ERR_*: SALT_ERR_ARG on malformed input (a quality block shorter than
+ * its sequence at the end of the input, a read longer than 65535 bases). */
+int salt_fastq_pack(const char *text, size_t len, int final, uint32_t max_reads, salt_fastq_t *out, size_t *consumed);
+
 /* ---- several GPUs in one process (reads shard, the reference is replicated, no collective) ----
  * salt is one process (alnse.c:1414-1440); this keeps it one: one handle per device, the batch split into contiguous
  * shares, every share through its device's own chunk pipeline on its own host thread, every result written at the

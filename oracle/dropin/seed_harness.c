@@ -179,3 +179,31 @@ int seedref_run_mt(void *p, const uint8_t *codes, const uint32_t *roffs, uint32_
     free(cnt0); free(cnt1); free(J); free(th);
     return rc;
 }
+
+/* The reference's own FASTQ reader (query_open / query_read_seq, query.c:66-239): codes, lengths, ambiguity counts, names,
+ * comments and quality strings of up to max_reads records -- the oracle of the input side (row f4). */
+int seedref_read_fastq(const char *fn, uint32_t max_reads, uint8_t *codes, size_t codes_cap, uint32_t *roffs, uint16_t *n_amb,
+                       char *names, char *comments, char *quals, int text_stride)
+{
+    queryio_t *qs = query_open(fn);
+    query_t q;
+    uint32_t n = 0;
+    size_t at = 0;
+    roffs[0] = 0;
+    memset(&q, 0, sizeof q);
+    while (n < max_reads && query_read_seq(qs, &q) > 0) {
+        if (at + (size_t)q.l_seq > codes_cap) break;
+        memcpy(codes + at, q.seq, (size_t)q.l_seq);
+        at += (size_t)q.l_seq;
+        roffs[n + 1] = (uint32_t)at;
+        n_amb[n] = (uint16_t)q.n_ambiguous;
+        strncpy(names + (size_t)n * text_stride, q.name ? q.name : "", (size_t)text_stride - 1);
+        strncpy(comments + (size_t)n * text_stride, q.comment ? q.comment : "", (size_t)text_stride - 1);
+        strncpy(quals + (size_t)n * text_stride, q.qual ? (const char *)q.qual : "", (size_t)text_stride - 1);
+        query_destroy(&q);
+        memset(&q, 0, sizeof q);
+        ++n;
+    }
+    query_close(qs);
+    return (int)n;
+}

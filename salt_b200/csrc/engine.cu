@@ -68,6 +68,7 @@ struct Slot {
     DBuf pk_bases, pk_lens, pk_cnt, pk_npos, pk_scan;          // compact transport (salt_packed_chunk_t): raw uploads + scan scratch
     DBuf tl_md, tl_out, tl_len, tl_offs, tl_packed, tl_cigrow, tl_xv;   // SAM tail of the chunk's primaries
     bool have_rec = false; int rec_cig_stride = 0;                // the slot's rec / cig buffers hold a finished verify
+    DBuf sd_long;                                               // (read, strand) ids whose lists need the long sort, [0] = count
     DBuf sd_sai, sd_counts, sd_lists;                          // seeding scratch: intervals, per-strand counts, fixed-stride lists
     uint32_t *h_tot = nullptr;                                  // pinned: the two list totals of a seeded chunk
     size_t seeded_n0 = 0, seeded_n1 = 0; int seeded = 0;        // 1: totals in flight, 2: lists gathered into c_loci0/1
@@ -86,7 +87,7 @@ struct Slot {
     {
         DBuf *all[] = {&codes, &offs3, &rd4, &rd_len, &c_loci0, &c_loci1, &vpairs, &acc, &rec,
                        &lvlist, &ciglist, &counters, &cig, &fpairs, &fslots, &lvreads,
-                       &pk_bases, &pk_lens, &pk_cnt, &pk_npos, &pk_scan, &sd_sai, &sd_counts, &sd_lists,
+                       &pk_bases, &pk_lens, &pk_cnt, &pk_npos, &pk_scan, &sd_sai, &sd_counts, &sd_lists, &sd_long,
                        &tl_md, &tl_out, &tl_len, &tl_offs, &tl_packed, &tl_cigrow, &tl_xv};
         for (DBuf *b : all) b->release();
         if (h_stage) cudaFreeHost(h_stage);
@@ -484,8 +485,9 @@ int seed_enqueue(salt_b200_t *h, int si, const salt_seed_opt_t *o)
     CU(s.sd_lists.need((size_t)n * 2 * (size_t)o->max_locate * 4 + 16));
     CU(s.pk_scan.need(3 * (size_t)scan3_blocks(n) * 4 + 16));
     CU(launch_seed(h->fm, so, s.codes.as<uint8_t>(), s.d_roffs(), n, max_seeds, s.sd_sai.as<SeedSai>(), s.stream));
+    CU(s.sd_long.need(((size_t)n * 2 + 4) * 4));
     CU(launch_locate(h->fm, so, s.d_roffs(), n, max_seeds, h->l, s.sd_sai.as<SeedSai>(), s.sd_counts.as<uint32_t>(),
-                     s.sd_lists.as<uint32_t>(), s.stream));
+                     s.sd_lists.as<uint32_t>(), s.sd_long.as<uint32_t>() + 4, s.sd_long.as<uint32_t>(), h->sm_count, s.stream));
     Scan3 sc{};
     sc.n = n; sc.partial = s.pk_scan.as<uint32_t>();
     sc.in[0] = s.sd_counts.as<uint32_t>(); sc.in[1] = s.sd_counts.as<uint32_t>() + n; sc.width[0] = sc.width[1] = 32;
@@ -493,7 +495,7 @@ int seed_enqueue(salt_b200_t *h, int si, const salt_seed_opt_t *o)
     CU(launch_scan3(sc, 2, s.stream));
     CU(cudaMemcpyAsync(&s.h_tot[0], s.d_coffs(0) + n, 4, cudaMemcpyDeviceToHost, s.stream));
     CU(cudaMemcpyAsync(&s.h_tot[1], s.d_coffs(1) + n, 4, cudaMemcpyDeviceToHost, s.stream));
-    h->launches += 5;
+    h->launches += 6;
     s.offs_merged = false;
     s.seeded = 1;
     return SALT_OK;

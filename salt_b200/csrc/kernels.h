@@ -76,7 +76,8 @@ size_t seed_sai_bytes(uint32_t n_reads, int max_seeds);
 cudaError_t launch_seed(const FmIndexDev &ix, const SeedOpt &opt, const uint8_t *codes, const uint32_t *roffs, uint32_t n_reads,
                         int max_seeds, SeedSai *sai, cudaStream_t st);
 cudaError_t launch_locate(const FmIndexDev &ix, const SeedOpt &opt, const uint32_t *roffs, uint32_t n_reads, int max_seeds,
-                          uint32_t ref_l, SeedSai *sai, uint32_t *counts, uint32_t *lists, cudaStream_t st);
+                          uint32_t ref_l, SeedSai *sai, uint32_t *counts, uint32_t *lists, uint32_t *long_list /* 2*n_reads */,
+                          uint32_t *long_count, int sm_count, cudaStream_t st);
 cudaError_t launch_seed_gather(const uint32_t *lists, int max_locate, const uint32_t *offs0, const uint32_t *offs1,
                                uint32_t n_reads, uint32_t *loci0, uint32_t *loci1, cudaStream_t st);
 

@@ -72,10 +72,35 @@ __device__ __forceinline__ uint32_t c_sa(const FmIndexDev &ix, uint32_t k)
     return sa + ix.c_sa[k / ix.c_sa_intv];
 }
 
-// one backward-search step (bwt.c:293-299): returns false when the interval empties
+// occurrences of c among the block-relative bases [a, b] of one 128-base block (p = its eight 16-base words)
+__device__ __forceinline__ uint32_t c_count_range(const uint32_t *__restrict__ p, int a, int b, int c)
+{
+    uint32_t n = 0;
+    for (int w = a >> 4; w <= (b >> 4); ++w) {
+        const uint32_t x = p[w];
+        uint32_t y = ((c & 2) ? x : ~x) >> 1 & ((c & 1) ? x : ~x) & 0x55555555u;
+        const int lo = w << 4;
+        if (a > lo) y &= 0xFFFFFFFFu >> (2 * (a - lo));                  // drop bases before a (top bits)
+        if (b < lo + 15) y &= ~((1u << (2 * (lo + 15 - b))) - 1u);       // drop bases after b
+        n += (uint32_t)__popc(y);
+    }
+    return n;
+}
+
+// one backward-search step (bwt.c:293-299): returns false when the interval empties.  bwt_2occ (bwt.c:140-176) is an
+// optimised pair of bwt_occ calls; so is this: when both ends fall into one 128-base block -- the usual case once the
+// interval has narrowed -- the second count is the first plus the occurrences in between.
 __device__ __forceinline__ bool c_step(const FmIndexDev &ix, int c, uint32_t &k, uint32_t &l)
 {
-    const uint32_t ok = c_occ(ix, k - 1, c), ol = c_occ(ix, l, c);      // bwt_2occ is an optimised pair of bwt_occ
+    const uint32_t km = k - 1;
+    uint32_t ok, ol;
+    const bool plain = km == 0xFFFFFFFFu || km == ix.c_seq_len || l == ix.c_seq_len || l == 0xFFFFFFFFu;
+    const uint32_t kk = km >= ix.c_primary ? km - 1 : km, ll = l >= ix.c_primary ? l - 1 : l;
+    if (!plain && (kk >> 7) == (ll >> 7) && kk <= ll) {
+        ok = c_occ(ix, km, c);
+        ol = ok;
+        if (ll > kk) ol += c_count_range(ix.cbwt + (size_t)(kk >> 7) * 12 + 4, (int)(kk & 127u) + 1, (int)(ll & 127u), c);
+    } else { ok = c_occ(ix, km, c); ol = c_occ(ix, l, c); }
     k = ix.c_L2[c] + ok + 1;
     l = ix.c_L2[c] + ol;
     return k <= l;
@@ -83,20 +108,28 @@ __device__ __forceinline__ bool c_step(const FmIndexDev &ix, int c, uint32_t &k,
 
 // ---------------------------------------------------------------- SNP-context FM-index (rbwt.h layout)
 // occurrences of c among BWT characters [a, b): 4 bits each, first character in the top nibble (rbwt.h:113-117)
+__device__ __forceinline__ uint32_t r_match8(uint32_t word, uint32_t pat)
+{
+    uint32_t x = word ^ pat;                              // matching nibbles become 0
+    x |= x >> 1; x |= x >> 2;
+    return ~x & 0x11111111u;
+}
+
 __device__ __forceinline__ uint32_t r_count(const uint32_t *__restrict__ code, uint32_t a, uint32_t b, uint32_t c)
 {
-    uint32_t n = 0;
     const uint32_t pat = c * 0x11111111u;
-    for (uint32_t w = a >> 3; w <= ((b - 1) >> 3); ++w) {
-        uint32_t x = code[w] ^ pat;                       // matching nibbles become 0
-        x |= x >> 1; x |= x >> 2;
-        uint32_t m = ~x & 0x11111111u;
-        const uint32_t lo = w * 8, hi = lo + 8;           // characters of this word
-        if (a > lo) m &= 0xFFFFFFFFu >> (4 * (a - lo));                  // drop the first a-lo characters (top nibbles)
-        if (b < hi) m &= ~((1u << (4 * (hi - b))) - 1u);                 // drop the last hi-b characters
-        n += (uint32_t)__popc(m);
+    const uint32_t wa = a >> 3, wb = (b - 1) >> 3;        // b > a
+    uint32_t first = r_match8(code[wa], pat);
+    if (a & 7u) first &= 0xFFFFFFFFu >> (4 * (a & 7u));                  // drop the characters before a (top nibbles)
+    if (wa == wb) {
+        if (b & 7u) first &= ~((1u << (4 * (8 - (b & 7u)))) - 1u);       // ... and those from b on
+        return (uint32_t)__popc(first);
     }
-    return n;
+    uint32_t n = (uint32_t)__popc(first);
+    for (uint32_t w = wa + 1; w < wb; ++w) n += (uint32_t)__popc(r_match8(code[w], pat));
+    uint32_t last = r_match8(code[wb], pat);
+    if (b & 7u) last &= ~((1u << (4 * (8 - (b & 7u)))) - 1u);
+    return n + (uint32_t)__popc(last);
 }
 
 // Rbwt_BWTOccValue (rbwt.c:159-189) with BWTOccValueExplicit (:38-79): bidirectional explicit counts every 256
@@ -132,11 +165,23 @@ __device__ __forceinline__ uint32_t r_sa(const FmIndexDev &ix, uint32_t i)
     return ix.r_sa_sharp[i - n_acgt - 1] + step - 1;
 }
 
+// The pair Rbwt_BWTOccValue(k, c), Rbwt_BWTOccValue(l + 1, c) of one backward step (rbwt.c:641-642).  Both are plain
+// occurrence counts, so when the two (adjusted) indexes are close the second is the first plus the occurrences in
+// between -- identical values, about half the words read once the interval has narrowed.
+__device__ __forceinline__ void r_occ2(const FmIndexDev &ix, uint32_t k, uint32_t l1, uint32_t c, uint32_t &ok, uint32_t &ol)
+{
+    ok = r_occ(ix, k, c);
+    const uint32_t ka = k > ix.r_inv_sa0 ? k - 1 : k, la = l1 > ix.r_inv_sa0 ? l1 - 1 : l1;
+    if (la >= ka && la - ka <= 64u) ol = la > ka ? ok + r_count(ix.r_bwt, ka, la, c) : ok;
+    else ol = r_occ(ix, l1, c);
+}
+
 __device__ __forceinline__ bool r_step(const FmIndexDev &ix, uint32_t c, uint32_t &k, uint32_t &l)
 {
-    const uint32_t nk = ix.r_cum[c] + r_occ(ix, k, c) + 1;
-    const uint32_t nl = ix.r_cum[c] + r_occ(ix, l + 1, c);
-    k = nk; l = nl;
+    uint32_t ok, ol;
+    r_occ2(ix, k, l + 1, c, ok, ol);
+    k = ix.r_cum[c] + ok + 1;
+    l = ix.r_cum[c] + ol;
     return k <= l;
 }
 
@@ -218,7 +263,8 @@ seed_kernel(FmIndexDev ix, SeedOpt opt, const uint8_t *__restrict__ codes, const
             while (l - k > (uint32_t)opt.max_seed && l_extend < seed_start) {      // alnse.c:280-291
                 // the reference indexes cumulativeFreq / occ with the raw code here: an N (4) extends over '#'
                 const uint32_t c = (uint32_t)seed_code(rd, L, strand, seed_start - l_extend - 1);
-                const uint32_t okk = r_occ(ix, k, c), oll = r_occ(ix, l + 1, c);
+                uint32_t okk, oll;
+                r_occ2(ix, k, l + 1, c, okk, oll);
                 if (okk + 1 > oll) break;
                 k = ix.r_cum[c] + okk + 1;
                 l = ix.r_cum[c] + oll;
@@ -302,30 +348,43 @@ __device__ void sai_introsort(int n, SeedSai *a)
     }
 }
 
-// ---------------------------------------------------------------- alnse_locate_alt, one warp per (read, strand)
-// shared memory per warp: max_seeds sai (12 B each), max_seeds + 1 row offsets (64 bit), then cap2 = pow2 >= max_locate loci
-__global__ void __launch_bounds__(128)
-locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, uint32_t n_reads, int max_seeds, int cap2,
-              uint32_t ref_l, SeedSai *__restrict__ sai, uint32_t *__restrict__ counts /* [2][n_reads] */,
-              uint32_t *__restrict__ lists /* [rs][max_locate] */)
+// ---------------------------------------------------------------- alnse_locate_alt, eight lanes per (read, strand)
+// A strand's lists are short on most genomes (a handful of intervals of a few rows each), so a whole warp per strand
+// idles; eight lanes do.  Loci go straight to the strand's row of the fixed-stride list array; lists of up to
+// LOC_SMALL entries are then sorted by the group in shared memory, longer ones are queued for sort_long_kernel.
+// Shared memory per group: max_seeds sai (12 B), max_seeds + 1 row offsets (64 bit), LOC_SMALL loci.
+constexpr int LOC_G = 8;
+constexpr int LOC_SMALL = 64;
+
+__device__ __forceinline__ size_t locate_group_words(int max_seeds)
 {
-    constexpr unsigned FULL = 0xffffffffu;
+    return (((size_t)max_seeds * 3 + 1) & ~(size_t)1) + 2 * ((size_t)max_seeds + 2) + LOC_SMALL;
+}
+
+__global__ void __launch_bounds__(128)
+locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, uint32_t n_reads, int max_seeds,
+              uint32_t ref_l, SeedSai *__restrict__ sai, uint32_t *__restrict__ counts /* [2][n_reads] */,
+              uint32_t *__restrict__ lists /* [rs][max_locate] */, uint32_t *__restrict__ long_list, uint32_t *__restrict__ long_count)
+{
     SALT_DYN_SMEM(uint32_t, s_mem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t per_warp = ((size_t)max_seeds * 3 + 2 * ((size_t)max_seeds + 2) + (size_t)cap2 + 1) & ~(size_t)1;   // even: 64-bit row offsets inside
-    SeedSai *s_sai = reinterpret_cast<SeedSai *>(s_mem + warp * per_warp);
+    const int grp = threadIdx.x / LOC_G, lane = threadIdx.x % LOC_G;
+    const int gshift = (threadIdx.x & 31) / LOC_G * LOC_G;
+    const unsigned gmask = 0xFFu << gshift;
+    const size_t per_group = locate_group_words(max_seeds);
+    uint32_t *base = s_mem + grp * per_group;
+    SeedSai *s_sai = reinterpret_cast<SeedSai *>(base);
     // row offsets are 64 bit: an interval that could not be narrowed may span the whole suffix array
-    unsigned long long *s_row = reinterpret_cast<unsigned long long *>(s_mem + warp * per_warp + (((size_t)max_seeds * 3 + 1) & ~(size_t)1));
-    uint32_t *s_loci = s_mem + warp * per_warp + (size_t)max_seeds * 3 + 2 * ((size_t)max_seeds + 2);
-    const size_t rs_raw = (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
-    const bool live = rs_raw < (size_t)n_reads * 2;
-    const size_t rs = live ? rs_raw : 0;
+    unsigned long long *s_row = reinterpret_cast<unsigned long long *>(base + (((size_t)max_seeds * 3 + 1) & ~(size_t)1));
+    uint32_t *s_small = base + (((size_t)max_seeds * 3 + 1) & ~(size_t)1) + 2 * ((size_t)max_seeds + 2);
+    const size_t rs = (size_t)blockIdx.x * (blockDim.x / LOC_G) + grp;
+    if (rs >= (size_t)n_reads * 2) return;                           // whole groups leave together: group masks below
     const uint32_t r = (uint32_t)(rs >> 1);
-    const uint32_t l_seq = live ? roffs[r + 1] - roffs[r] : 0u;
+    const uint32_t l_seq = roffs[r + 1] - roffs[r];
     const uint32_t max_locate = (uint32_t)opt.max_locate;
     SeedSai *g = sai + rs * 2 * (size_t)max_seeds;
+    uint32_t *dst = lists + rs * (size_t)max_locate;
     uint32_t n = 0;                                                   // aux->loci.n
-    for (int part = 0; part < 2 && live; ++part) {                    // 0: sai_C, 1: sai_backwardR (sai_forwardR is empty here)
+    for (int part = 0; part < 2; ++part) {                            // 0: sai_C, 1: sai_backwardR (sai_forwardR is empty here)
         // compact the valid intervals in seed order, sort them as the reference does, lay their rows end to end
         int m = 0;
         if (lane == 0) {
@@ -341,12 +400,12 @@ locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, ui
             }
             s_row[m] = acc;
         }
-        m = __shfl_sync(FULL, m, 0);
-        __syncwarp();
+        m = __shfl_sync(gmask, m, gshift);
+        __syncwarp(gmask);
         const unsigned long long rows = m ? s_row[m] : 0ull;
         // the reference walks interval after interval, row after row, and stops at max_locate pushes: the same order,
-        // 32 rows at a time over the concatenation of all intervals
-        for (unsigned long long b = 0; b < rows && n < max_locate; b += 32) {
+        // eight rows at a time over the concatenation of all intervals
+        for (unsigned long long b = 0; b < rows && n < max_locate; b += LOC_G) {
             const unsigned long long flat = b + (unsigned long long)lane;
             bool keep = false;
             uint32_t pos = 0;
@@ -361,35 +420,75 @@ locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, ui
                 keep = !(pos + l_seq > ref_l);
                 if (part == 1 && pos > ref_l) keep = false;                           // alnse.c:711
             }
-            const unsigned bal = __ballot_sync(FULL, keep);
+            const unsigned bal = (__ballot_sync(gmask, keep) >> gshift) & 0xFFu;
             const uint32_t rank = (uint32_t)__popc(bal & ((1u << lane) - 1u));
-            if (keep && n + rank < max_locate) s_loci[n + rank] = pos;
+            if (keep && n + rank < max_locate) dst[n + rank] = pos;
             n = min(max_locate, n + (uint32_t)__popc(bal));
         }
-        __syncwarp();
+        __syncwarp(gmask);
     }
-    // ks_introsort(uint32_t) of the list: any correct sort gives the same array; bitonic over the next power of two,
-    // padded with ~0 (a pad can equal a real, wrapped locus 0xFFFFFFFF: equal keys, the sorted prefix is still right)
-    uint32_t n2 = 1;
+    if (lane == 0) counts[(rs & 1) * (size_t)n_reads + r] = n;
+    if (n > LOC_SMALL) {                                              // ks_introsort(uint32_t) of a long list: sort_long_kernel
+        if (lane == 0) long_list[atomicAdd(long_count, 1u)] = (uint32_t)rs;
+        return;
+    }
+    if (n < 2) return;
+    // any correct sort gives the reference's array: bitonic over the next power of two, padded with ~0 (a pad can equal a
+    // real, wrapped locus 0xFFFFFFFF: equal keys, the sorted prefix is still right)
+    __threadfence_block();
+    __syncwarp(gmask);
+    uint32_t n2 = 2;
     while (n2 < n) n2 <<= 1;
-    for (uint32_t i = n + lane; i < n2; i += 32) s_loci[i] = 0xFFFFFFFFu;
-    __syncwarp();
+    for (uint32_t i = lane; i < n2; i += LOC_G) s_small[i] = i < n ? dst[i] : 0xFFFFFFFFu;
+    __syncwarp(gmask);
     for (uint32_t k = 2; k <= n2; k <<= 1)
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = lane; i < n2; i += 32) {
+            for (uint32_t i = lane; i < n2; i += LOC_G) {
                 const uint32_t p = i ^ j;
                 if (p > i) {
-                    const uint32_t a = s_loci[i], b = s_loci[p];
+                    const uint32_t a = s_small[i], b2 = s_small[p];
                     const bool up = (i & k) == 0;
-                    if ((a > b) == up) { s_loci[i] = b; s_loci[p] = a; }
+                    if ((a > b2) == up) { s_small[i] = b2; s_small[p] = a; }
                 }
             }
-            __syncwarp();
+            __syncwarp(gmask);
         }
-    if (live) {
-        uint32_t *dst = lists + rs * (size_t)max_locate;
+    for (uint32_t i = lane; i < n; i += LOC_G) dst[i] = s_small[i];
+}
+
+// lists longer than LOC_SMALL: one warp per queued (read, strand), bitonic in shared memory over cap2 >= max_locate
+__global__ void __launch_bounds__(128)
+sort_long_kernel(const uint32_t *__restrict__ long_list, const uint32_t *__restrict__ long_count, uint32_t n_reads, int max_locate,
+                 int cap2, const uint32_t *__restrict__ counts, uint32_t *__restrict__ lists)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    SALT_DYN_SMEM(uint32_t, s_mem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *s_loci = s_mem + (size_t)warp * (size_t)cap2;
+    const uint32_t total = *long_count;
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + warp; e < total; e += n_warps) {
+        const uint32_t rs = long_list[e];
+        const uint32_t n = counts[(rs & 1) * (size_t)n_reads + (rs >> 1)];
+        uint32_t *dst = lists + (size_t)rs * (size_t)max_locate;
+        uint32_t n2 = 2;
+        while (n2 < n) n2 <<= 1;
+        for (uint32_t i = lane; i < n2; i += 32) s_loci[i] = i < n ? dst[i] : 0xFFFFFFFFu;
+        __syncwarp(FULL);
+        for (uint32_t k = 2; k <= n2; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t i = lane; i < n2; i += 32) {
+                    const uint32_t p = i ^ j;
+                    if (p > i) {
+                        const uint32_t a = s_loci[i], b = s_loci[p];
+                        const bool up = (i & k) == 0;
+                        if ((a > b) == up) { s_loci[i] = b; s_loci[p] = a; }
+                    }
+                }
+                __syncwarp(FULL);
+            }
         for (uint32_t i = lane; i < n; i += 32) dst[i] = s_loci[i];
-        if (lane == 0) counts[(rs & 1) * (size_t)n_reads + r] = n;
+        __syncwarp(FULL);
     }
 }
 
@@ -422,24 +521,36 @@ cudaError_t launch_seed(const FmIndexDev &ix, const SeedOpt &opt, const uint8_t 
 }
 
 cudaError_t launch_locate(const FmIndexDev &ix, const SeedOpt &opt, const uint32_t *roffs, uint32_t n_reads, int max_seeds,
-                          uint32_t ref_l, SeedSai *sai, uint32_t *counts, uint32_t *lists, cudaStream_t st)
+                          uint32_t ref_l, SeedSai *sai, uint32_t *counts, uint32_t *lists, uint32_t *long_list, uint32_t *long_count,
+                          int sm_count, cudaStream_t st)
 {
     if (!n_reads) return cudaSuccess;
-    int cap2 = 32;
-    while (cap2 < opt.max_locate) cap2 <<= 1;
-    const size_t per_warp = (((size_t)max_seeds * 3 + 2 * ((size_t)max_seeds + 2) + (size_t)cap2 + 1) & ~(size_t)1) * 4;
-    int warps = 4;
-    while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
-    if (per_warp * warps > 200 * 1024) return cudaErrorInvalidValue;
-    const size_t smem = per_warp * warps;
-    auto kern = locate_kernel;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+    cudaError_t e = cudaMemsetAsync(long_count, 0, 4, st);
+    if (e != cudaSuccess) return e;
+    const size_t per_group = ((((size_t)max_seeds * 3 + 1) & ~(size_t)1) + 2 * ((size_t)max_seeds + 2) + LOC_SMALL) * 4;
+    int groups = 16;                                        // 128 threads
+    while (groups > 4 && per_group * groups > 96 * 1024) groups >>= 1;
+    const size_t smem = per_group * groups;
+    {
+        auto kern = locate_kernel;
+        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        const size_t n_rs = (size_t)n_reads * 2;
+        SALT_LAUNCH(kern, (unsigned)((n_rs + groups - 1) / groups), groups * LOC_G, smem, st, ix, opt, roffs, n_reads, max_seeds, ref_l, sai,
+                    counts, lists, long_list, long_count);
     }
-    const size_t n_rs = (size_t)n_reads * 2;
-    SALT_LAUNCH(kern, (unsigned)((n_rs + warps - 1) / warps), warps * 32, smem, st, ix, opt, roffs, n_reads, max_seeds, cap2,
-                ref_l, sai, counts, lists);
+    if (opt.max_locate > LOC_SMALL) {
+        int cap2 = 2 * LOC_SMALL;
+        while (cap2 < opt.max_locate) cap2 <<= 1;
+        int warps = 4;
+        while (warps > 1 && (size_t)cap2 * 4 * warps > 96 * 1024) warps >>= 1;
+        const size_t smem2 = (size_t)cap2 * 4 * warps;
+        auto kern = sort_long_kernel;
+        if (smem2 > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)) != cudaSuccess) return e;
+        const size_t want = ((size_t)n_reads * 2 + warps - 1) / warps;
+        const size_t cap = (size_t)sm_count * 8;
+        SALT_LAUNCH(kern, (unsigned)(want < cap ? want : cap), warps * 32, smem2, st, long_list, long_count, n_reads, opt.max_locate, cap2,
+                    counts, lists);
+    }
     return cudaGetLastError();
 }
 

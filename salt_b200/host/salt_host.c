@@ -700,3 +700,94 @@ int salt_multi_verify_batch_packed(salt_multi_t *m, const salt_packed_chunk_t *p
     free(J); free(th);
     return rc;
 }
+
+/* ------------------------------------------------------------------ FASTQ -> compact transport (query.c:146-239) */
+static inline int fq_is_blank(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
+
+int salt_fastq_pack(const char *text, size_t len, int final, uint32_t max_reads, salt_fastq_t *o, size_t *consumed)
+{
+    if (!text || !o || !o->bases || !o->lens || !o->n_ambiguous || !o->name_off || !o->name_len || !consumed) return SALT_ERR_ARG;
+    /* nst_nt4_table (bntseq.c): A/a C/c G/g T/t -> 0..3, '-' and everything else -> 4 (5 for '-' is > 3 all the same) */
+    static uint8_t nt4[256]; static int nt4_ready;
+    if (!nt4_ready) {
+        memset(nt4, 4, sizeof nt4);
+        nt4['A'] = nt4['a'] = 0; nt4['C'] = nt4['c'] = 1; nt4['G'] = nt4['g'] = 2; nt4['T'] = nt4['t'] = 3;
+        nt4_ready = 1;
+    }
+    uint32_t n = 0;
+    size_t nb = o->n_bases = 0, nn = o->n_n = 0;
+    size_t p = 0;
+    *consumed = 0;
+    o->n_reads = 0;
+    if (o->bases_cap) memset(o->bases, 0, o->bases_cap / 4 + 1);
+    while (n < max_reads) {
+        /* kseq: skip to the next header character */
+        while (p < len && text[p] != '@' && text[p] != '>') ++p;
+        if (p >= len) break;
+        const size_t rec = p++;
+        size_t q = p;
+        while (q < len && !fq_is_blank(text[q])) ++q;
+        if (q >= len && !final) break;
+        size_t name_a = p, name_b = q;
+        if (name_b - name_a > 2 && text[name_b - 2] == '/' && text[name_b - 1] >= '0' && text[name_b - 1] <= '9') name_b -= 2;   /* trim_readno */
+        size_t com_a = q, com_b = q;
+        if (q < len && text[q] != '\n') {                                   /* comment: the rest of the header line */
+            com_a = q + 1;
+            while (q < len && text[q] != '\n') ++q;
+            com_b = q;
+            while (com_b > com_a && text[com_b - 1] == '\r') --com_b;
+        }
+        if (q >= len && !final) break;
+        p = q < len ? q + 1 : q;
+        /* sequence lines until a line starting with '+', '>' or '@' */
+        const size_t base0 = nb; size_t amb = 0, nn0 = nn;
+        int complete = 0, has_plus = 0;
+        while (1) {
+            if (p >= len) { complete = final; break; }
+            const char c0 = text[p];
+            if (c0 == '+') { has_plus = 1; complete = 1; break; }
+            if (c0 == '>' || c0 == '@') { complete = 1; break; }
+            while (p < len && text[p] != '\n') {
+                const unsigned char ch = (unsigned char)text[p++];
+                if (ch <= ' ') continue;                                     /* kseq keeps graphic characters only */
+                if (nb >= o->bases_cap) goto full;
+                const unsigned v = nt4[ch];
+                if (v > 3) { ++amb; if (o->n_pos) { if (nn >= o->n_pos_cap) goto full; o->n_pos[nn] = (uint32_t)nb; } ++nn; }
+                else o->bases[nb >> 2] |= (uint8_t)(v << (2 * (nb & 3)));
+                ++nb;
+            }
+            if (p < len) ++p; else { complete = final; break; }
+        }
+        if (!complete) { nb = base0; nn = nn0; break; }
+        const size_t L = nb - base0;
+        if (L > 65535) return SALT_ERR_ARG;
+        size_t qual_at = (size_t)-1;
+        if (has_plus) {
+            while (p < len && text[p] != '\n') ++p;                          /* the rest of the '+' line */
+            if (p >= len) { if (!final) { nb = base0; nn = nn0; break; } }
+            else ++p;
+            qual_at = p;
+            size_t ql = 0;
+            while (ql < L && p < len) { const unsigned char ch = (unsigned char)text[p++]; if (ch > ' ') ++ql; }
+            if (ql < L) { if (final) return SALT_ERR_ARG; nb = base0; nn = nn0; break; }
+            while (p < len && text[p] != '\n') ++p;                          /* kseq reads whole lines */
+            if (p < len) ++p; else if (!final) { nb = base0; nn = nn0; break; }
+        }
+        if (L == 0) { /* query_read_seq stops at an empty record (l_seq <= 0, query.c:155) */ *consumed = p; break; }
+        o->lens[n] = (uint16_t)L; o->n_ambiguous[n] = (uint16_t)(amb > 65535 ? 65535 : amb);
+        o->name_off[n] = (uint32_t)name_a; o->name_len[n] = (uint16_t)(name_b - name_a);
+        if (o->comment_off) { o->comment_off[n] = (uint32_t)com_a; o->comment_len[n] = (uint16_t)(com_b - com_a); }
+        if (o->qual_off) o->qual_off[n] = qual_at == (size_t)-1 ? 0xFFFFFFFFu : (uint32_t)qual_at;
+        ++n;
+        *consumed = p;
+        (void)rec;
+        continue;
+full:
+        /* an array filled up inside this record: give back what belongs to it and stop before it */
+        for (size_t k = base0; k < nb; ++k) o->bases[k >> 2] &= (uint8_t)~(3u << (2 * (k & 3)));
+        nb = base0; nn = nn0;
+        break;
+    }
+    o->n_reads = n; o->n_bases = nb; o->n_n = nn;
+    return (int)n;
+}
