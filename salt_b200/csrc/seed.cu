@@ -348,15 +348,22 @@ __device__ void sai_introsort(int n, SeedSai *a)
     }
 }
 
-// ---------------------------------------------------------------- alnse_locate_alt, eight lanes per (read, strand)
-// A strand's lists are short on most genomes (a handful of intervals of a few rows each), so a whole warp per strand
-// idles; eight lanes do.  Loci go straight to the strand's row of the fixed-stride list array; lists of up to
-// LOC_SMALL entries are then sorted by the group in shared memory, longer ones are queued for sort_long_kernel.
-// Shared memory per group: max_seeds sai (12 B), max_seeds + 1 row offsets (64 bit), LOC_SMALL loci.
+// ---------------------------------------------------------------- alnse_locate_alt, sixteen (read, strand)s per CTA
+// A strand's lists are short on most genomes (a handful of intervals of a few rows each) while a suffix-array walk is
+// long (up to sa_intv - 1 LF steps on the primary index, up to a whole local pattern on the SNP-context index), so rows
+// are the unit of parallel work, not strands: eight lanes own a strand for the bookkeeping (interval order, the
+// max_locate cut, the final sort), but the walks of ALL sixteen strands of a CTA are laid end to end and shared out
+// over its 128 threads, one index at a time, so that every lane walks and all lanes run the same code.
+// Loci go straight to the strand's row of the fixed-stride list array; lists of up to LOC_SMALL entries are then
+// sorted by the group in shared memory, longer ones are queued for sort_long_kernel.
+// Shared memory: per group max_seeds sai (12 B), max_seeds + 1 row offsets (64 bit), LOC_SMALL loci; per CTA the staging
+// of one round of walks.
 constexpr int LOC_G = 8;
+constexpr int LOC_GROUPS = 16;                 // per CTA of 128 threads
 constexpr int LOC_SMALL = 64;
+constexpr int LOC_STAGE = 1024;                // walks per round and CTA
 
-__device__ __forceinline__ size_t locate_group_words(int max_seeds)
+__host__ __device__ __forceinline__ size_t locate_group_words(int max_seeds)
 {
     return (((size_t)max_seeds * 3 + 1) & ~(size_t)1) + 2 * ((size_t)max_seeds + 2) + LOC_SMALL;
 }
@@ -367,6 +374,12 @@ locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, ui
               uint32_t *__restrict__ lists /* [rs][max_locate] */, uint32_t *__restrict__ long_list, uint32_t *__restrict__ long_count)
 {
     SALT_DYN_SMEM(uint32_t, s_mem);
+    __shared__ uint32_t s_pos[LOC_STAGE];
+    __shared__ uint8_t s_keep[LOC_STAGE];
+    __shared__ uint32_t s_want[LOC_GROUPS + 1];                       // exclusive prefix of the groups' shares of a round
+    __shared__ unsigned long long s_done[LOC_GROUPS];                 // rows of the current part already walked
+    __shared__ uint32_t s_n[LOC_GROUPS];                              // aux->loci.n
+    __shared__ int s_m[LOC_GROUPS];                                   // valid intervals of the current part
     const int grp = threadIdx.x / LOC_G, lane = threadIdx.x % LOC_G;
     const int gshift = (threadIdx.x & 31) / LOC_G * LOC_G;
     const unsigned gmask = 0xFFu << gshift;
@@ -376,20 +389,20 @@ locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, ui
     // row offsets are 64 bit: an interval that could not be narrowed may span the whole suffix array
     unsigned long long *s_row = reinterpret_cast<unsigned long long *>(base + (((size_t)max_seeds * 3 + 1) & ~(size_t)1));
     uint32_t *s_small = base + (((size_t)max_seeds * 3 + 1) & ~(size_t)1) + 2 * ((size_t)max_seeds + 2);
-    const size_t rs = (size_t)blockIdx.x * (blockDim.x / LOC_G) + grp;
-    if (rs >= (size_t)n_reads * 2) return;                           // whole groups leave together: group masks below
-    const uint32_t r = (uint32_t)(rs >> 1);
-    const uint32_t l_seq = roffs[r + 1] - roffs[r];
+    const size_t rs0 = (size_t)blockIdx.x * LOC_GROUPS;
+    const size_t rs = rs0 + grp;
+    const bool live = rs < (size_t)n_reads * 2;                       // dead groups run along with nothing to do
     const uint32_t max_locate = (uint32_t)opt.max_locate;
-    SeedSai *g = sai + rs * 2 * (size_t)max_seeds;
-    uint32_t *dst = lists + rs * (size_t)max_locate;
-    uint32_t n = 0;                                                   // aux->loci.n
+    if (lane == 0) s_n[grp] = 0;
     for (int part = 0; part < 2; ++part) {                            // 0: sai_C, 1: sai_backwardR (sai_forwardR is empty here)
-        // compact the valid intervals in seed order, sort them as the reference does, lay their rows end to end
-        int m = 0;
+        // ---- plan: the valid intervals in seed order, sorted as the reference sorts them, their rows laid end to end
         if (lane == 0) {
-            for (int i = 0; i < max_seeds; ++i) { const SeedSai v = g[part * max_seeds + i]; if (v.sp <= v.ep) s_sai[m++] = v; }
-            sai_introsort(m, s_sai);
+            int m = 0;
+            if (live) {
+                const SeedSai *g = sai + rs * 2 * (size_t)max_seeds + (size_t)part * max_seeds;
+                for (int i = 0; i < max_seeds; ++i) { const SeedSai v = g[i]; if (v.sp <= v.ep) s_sai[m++] = v; }
+                sai_introsort(m, s_sai);
+            }
             unsigned long long acc = 0;
             for (int i = 0; i < m; ++i) {
                 const SeedSai v = s_sai[i];
@@ -399,34 +412,73 @@ locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, ui
                 acc += ((unsigned long long)(v.ep - v.sp)) / skip + 1;                                   // rows sp, sp+skip, .. <= ep
             }
             s_row[m] = acc;
+            s_m[grp] = m; s_done[grp] = 0;
         }
-        m = __shfl_sync(gmask, m, gshift);
-        __syncwarp(gmask);
-        const unsigned long long rows = m ? s_row[m] : 0ull;
-        // the reference walks interval after interval, row after row, and stops at max_locate pushes: the same order,
-        // eight rows at a time over the concatenation of all intervals
-        for (unsigned long long b = 0; b < rows && n < max_locate; b += LOC_G) {
-            const unsigned long long flat = b + (unsigned long long)lane;
-            bool keep = false;
-            uint32_t pos = 0;
-            if (flat < rows) {
-                int lo = 0, hi = m - 1;                               // last interval whose first row is <= flat
-                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_row[mid] <= flat) lo = mid; else hi = mid - 1; }
-                const SeedSai v = s_sai[lo];
+        __syncthreads();
+        // ---- rounds: every strand asks for the rows it may still push, all threads walk them, every strand takes its own
+        for (;;) {
+            if (threadIdx.x == 0) {
+                uint32_t acc = 0;
+                for (int gi = 0; gi < LOC_GROUPS; ++gi) {
+                    s_want[gi] = acc;
+                    const unsigned long long *row_g = reinterpret_cast<const unsigned long long *>(
+                        s_mem + gi * per_group + (((size_t)max_seeds * 3 + 1) & ~(size_t)1));
+                    const unsigned long long left = s_m[gi] ? row_g[s_m[gi]] - s_done[gi] : 0ull;
+                    const uint32_t room = max_locate - s_n[gi];          // the reference stops at max_locate pushes (alnse.c:678)
+                    uint32_t w = (uint32_t)(left < (unsigned long long)room ? left : (unsigned long long)room);
+                    if (w > (uint32_t)LOC_STAGE - acc) w = (uint32_t)LOC_STAGE - acc;
+                    acc += w;
+                }
+                s_want[LOC_GROUPS] = acc;
+            }
+            __syncthreads();
+            const uint32_t total = s_want[LOC_GROUPS];
+            if (total == 0) break;
+            for (uint32_t f = threadIdx.x; f < total; f += blockDim.x) {
+                int gi = 0;
+                while (gi + 1 < LOC_GROUPS && s_want[gi + 1] <= f) ++gi;
+                const uint32_t *gb = s_mem + gi * per_group;
+                const SeedSai *sai_g = reinterpret_cast<const SeedSai *>(gb);
+                const unsigned long long *row_g = reinterpret_cast<const unsigned long long *>(gb + (((size_t)max_seeds * 3 + 1) & ~(size_t)1));
+                const unsigned long long flat = s_done[gi] + (unsigned long long)(f - s_want[gi]);
+                int lo = 0, hi = s_m[gi] - 1;                          // last interval whose first row is <= flat
+                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (row_g[mid] <= flat) lo = mid; else hi = mid - 1; }
+                const SeedSai v = sai_g[lo];
                 uint32_t skip = 1;
                 if (part == 1) { skip = (v.ep + 1 - v.sp) / 0x40000u; if ((int)skip <= 0) skip = 1; }
-                const uint32_t j = v.sp + (uint32_t)(flat - s_row[lo]) * skip;
-                pos = (part == 0 ? c_sa(ix, j) : r_sa(ix, j)) - v.offset;              // uint32 arithmetic, may wrap (alnse.c:669)
-                keep = !(pos + l_seq > ref_l);
-                if (part == 1 && pos > ref_l) keep = false;                           // alnse.c:711
+                const uint32_t j = v.sp + (uint32_t)(flat - row_g[lo]) * skip;
+                const uint32_t pos = (part == 0 ? c_sa(ix, j) : r_sa(ix, j)) - v.offset;      // uint32 arithmetic, may wrap (alnse.c:669)
+                const size_t rsg = rs0 + (size_t)gi;
+                const uint32_t l_seq = roffs[(rsg >> 1) + 1] - roffs[rsg >> 1];
+                bool keep = !(pos + l_seq > ref_l);
+                if (part == 1 && pos > ref_l) keep = false;                                   // alnse.c:711
+                s_pos[f] = pos; s_keep[f] = keep ? 1 : 0;
             }
-            const unsigned bal = (__ballot_sync(gmask, keep) >> gshift) & 0xFFu;
-            const uint32_t rank = (uint32_t)__popc(bal & ((1u << lane) - 1u));
-            if (keep && n + rank < max_locate) dst[n + rank] = pos;
-            n = min(max_locate, n + (uint32_t)__popc(bal));
+            __syncthreads();
+            // each strand pushes its rows in order
+            {
+                const uint32_t f0 = s_want[grp], cnt = s_want[grp + 1] - f0;
+                uint32_t n = s_n[grp];
+                uint32_t *dst = lists + rs * (size_t)max_locate;
+                for (uint32_t b = 0; b < cnt; b += LOC_G) {
+                    const uint32_t i = b + (uint32_t)lane;
+                    const bool keep = i < cnt && s_keep[f0 + i] != 0;
+                    const unsigned bal = (__ballot_sync(gmask, keep) >> gshift) & 0xFFu;
+                    const uint32_t rank = (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                    if (keep && n + rank < max_locate) dst[n + rank] = s_pos[f0 + i];
+                    n = min(max_locate, n + (uint32_t)__popc(bal));
+                }
+                __syncwarp(gmask);
+                if (lane == 0) { s_n[grp] = n; s_done[grp] += cnt; }
+            }
+            __syncthreads();
         }
-        __syncwarp(gmask);
+        __syncthreads();
     }
+    if (!live) return;
+    const uint32_t r = (uint32_t)(rs >> 1);
+    const uint32_t n = s_n[grp];
+    uint32_t *dst = lists + rs * (size_t)max_locate;
     if (lane == 0) counts[(rs & 1) * (size_t)n_reads + r] = n;
     if (n > LOC_SMALL) {                                              // ks_introsort(uint32_t) of a long list: sort_long_kernel
         if (lane == 0) long_list[atomicAdd(long_count, 1u)] = (uint32_t)rs;
@@ -527,10 +579,10 @@ cudaError_t launch_locate(const FmIndexDev &ix, const SeedOpt &opt, const uint32
     if (!n_reads) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(long_count, 0, 4, st);
     if (e != cudaSuccess) return e;
-    const size_t per_group = ((((size_t)max_seeds * 3 + 1) & ~(size_t)1) + 2 * ((size_t)max_seeds + 2) + LOC_SMALL) * 4;
-    int groups = 16;                                        // 128 threads
-    while (groups > 4 && per_group * groups > 96 * 1024) groups >>= 1;
+    const size_t per_group = locate_group_words(max_seeds) * 4;
+    const int groups = LOC_GROUPS;                          // 128 threads
     const size_t smem = per_group * groups;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
     {
         auto kern = locate_kernel;
         if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;

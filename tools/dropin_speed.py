@@ -1,9 +1,8 @@
 #!/usr/bin/env python
 """End-to-end wall time of the reference `salt` and of `salt_dropin` (same sources, verification stage and
 paired-end rescues on the GPU) on one synthetic data set, single-end and paired-end, with the SAM
-comparison.  Both programs seed on ONE host thread here (-t 1; the drop-in's driver is single-threaded),
-so the difference is what the GPU removes from the per-read critical path; seeding itself (>90 % of the
-reference's time) is untouched.  Prints one JSON object."""
+comparison, at -t 1 and at all host threads, with the drop-in seeding on the host (the reference's own functions on -t
+workers) or on the device (SALT_DROPIN_SEED=gpu).  Prints one JSON object."""
 import json
 import os
 import subprocess
@@ -31,28 +30,51 @@ def body(path):
 
 
 def main():
+    """SE with the flags of run_se_test.sh:12 (-r 1: a seed at every read position) and with the default seed spacing, at -t 1 and
+    at all host threads: the reference, the drop-in seeding on the host (-t workers), the drop-in seeding on the device."""
     glen = int(os.environ.get("GENOME", "5000000")); n = int(os.environ.get("READS", "200000"))
-    res = {"genome_bp": glen, "reads": n}
+    threads = os.cpu_count() or 1
+    res = {"genome_bp": glen, "reads": n, "host_threads": threads}
     with tempfile.TemporaryDirectory() as d:
         dropin_data.write_inputs(d, glen=glen, n_reads=n)
         t, _ = run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], d, os.path.join(d, "idx.log"))
         res["index_s"] = round(t, 2)
-        flags = ["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500", "-t", "1"]
-        t_ref, _ = run([os.path.join(REFDIR, "salt")] + flags + ["idx", "reads.fq"], d, os.path.join(d, "ref.sam"))
-        t_gpu, _ = run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", "reads.fq"], d, os.path.join(d, "gpu.sam"))
-        same = body(os.path.join(d, "ref.sam")) == body(os.path.join(d, "gpu.sam"))
-        res["se"] = {"reference_s": round(t_ref, 2), "dropin_s": round(t_gpu, 2), "reference_reads_per_s": round((n + 40) / t_ref),
-                     "dropin_reads_per_s": round((n + 40) / t_gpu), "sam_identical": same}
+        res["se"] = []
+        for name, base in (("run_se_test.sh:12 (-r 1)", ["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500"]),
+                           ("default seed spacing", ["-d", "-l", "100", "-n", "20", "-c", "-m", "500"])):
+            for t_ in sorted({1, threads}):
+                flags = base + ["-t", str(t_)]
+                row = {"flags": " ".join(flags), "what": name}
+                t_ref, _ = run([os.path.join(REFDIR, "salt")] + flags + ["idx", "reads.fq"], d, os.path.join(d, "ref.sam"))
+                row["reference_s"] = round(t_ref, 2); row["reference_reads_per_s"] = round((n + 40) / t_ref)
+                want = body(os.path.join(d, "ref.sam"))
+                for mode in ("host", "gpu"):
+                    if mode == "gpu" and t_ != 1:
+                        continue                                  # -t only drives host seeding
+                    env = dict(os.environ, SALT_DROPIN_SEED=mode)
+                    t0 = time.time()
+                    with open(os.path.join(d, "gpu.sam"), "w") as f:
+                        p = subprocess.run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", "reads.fq"], cwd=d, stdout=f,
+                                           stderr=subprocess.PIPE, text=True, env=env)
+                    assert p.returncode == 0, p.stderr[-1500:]
+                    dt = time.time() - t0
+                    key = "dropin_%s_seeding" % mode
+                    row[key + "_s"] = round(dt, 2); row[key + "_reads_per_s"] = round((n + 40) / dt)
+                    row[key + "_sam_identical"] = body(os.path.join(d, "gpu.sam")) == want
+                    row[key + "_phases"] = [ln for ln in p.stderr.split("\n") if ln.startswith("[salt_dropin] ") and "seeding" in ln][-1:]
+                res["se"].append(row)
         npairs = n // 2
         dropin_data.write_pe_inputs(d, glen=glen, n_pairs=npairs)
         run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], d, os.path.join(d, "idx.log"))
-        flags = ["-d", "-p", "-e", "-l", "100", "-c", "-a", "350", "-b", "650", "-r", "5", "-t", "1"]
-        t_ref, _ = run([os.path.join(REFDIR, "salt")] + flags + ["idx", "r1.fq", "r2.fq"], d, os.path.join(d, "ref.sam"))
-        t_gpu, err = run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", "r1.fq", "r2.fq"], d, os.path.join(d, "gpu.sam"))
-        same = body(os.path.join(d, "ref.sam")) == body(os.path.join(d, "gpu.sam"))
-        res["pe"] = {"reference_s": round(t_ref, 2), "dropin_s": round(t_gpu, 2), "reference_reads_per_s": round(2 * npairs / t_ref),
-                     "dropin_reads_per_s": round(2 * npairs / t_gpu), "sam_identical": same,
-                     "rescue": [ln for ln in err.split("\n") if "rescue windows" in ln][-1:]}
+        res["pe"] = []
+        for t_ in sorted({1, threads}):
+            flags = ["-d", "-p", "-e", "-l", "100", "-c", "-a", "350", "-b", "650", "-r", "5", "-t", str(t_)]
+            t_ref, _ = run([os.path.join(REFDIR, "salt")] + flags + ["idx", "r1.fq", "r2.fq"], d, os.path.join(d, "ref.sam"))
+            t_gpu, err = run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", "r1.fq", "r2.fq"], d, os.path.join(d, "gpu.sam"))
+            same = body(os.path.join(d, "ref.sam")) == body(os.path.join(d, "gpu.sam"))
+            res["pe"].append({"flags": " ".join(flags), "reference_s": round(t_ref, 2), "dropin_s": round(t_gpu, 2),
+                              "reference_reads_per_s": round(2 * npairs / t_ref), "dropin_reads_per_s": round(2 * npairs / t_gpu),
+                              "sam_identical": same, "rescue": [ln for ln in err.split("\n") if "rescue windows" in ln][-1:]})
     print(json.dumps(res, indent=1))
 
 
