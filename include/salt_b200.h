@@ -303,7 +303,9 @@ int salt_b200_use_slot(salt_b200_t *h, int slot);
 /* Landau-Vishkin work mapping: 0 = automatic (one thread per pair with all diagonals in
  * registers for k <= 15 inside the verify stage, one warp per pair with lanes over diagonals
  * beyond that and on flat pair lists), 1 = always one warp (or sub-warp group) per pair,
- * 2 = one thread per pair whenever k <= 15.  Results are identical; this exists for measurement. */
+ * 2 = one thread per pair whenever k <= 15.  Adding 16 runs the thread-per-pair kernel in one pass instead of two (three
+ * levels for every survivor of the pre-filter, the full depth only for the pairs that need it).  Results are identical;
+ * this exists for measurement. */
 int salt_b200_set_lv_mapping(salt_b200_t *h, int mapping);
 
 /* Pigeonhole pre-filter in front of Landau-Vishkin (default on): a pair can only be within k

@@ -37,6 +37,7 @@ static void die(const char *what)
 
 void dropin_tail_prepare(salt_b200_t *gpu, int slot, const query_t *multi_seqs, const int *slot_of, int first, int upto);
 void dropin_tail_report(void);
+void dropin_tail_begin_read(int j);
 
 /* alnse_core1's per-read work after verification: results -> query_t (alnse.c:1306 / :1342-1344); the SAM line
  * follows once the chunk's MD/NM/XV tags are back from the GPU */
@@ -100,6 +101,32 @@ static void *seed_worker(void *arg)
     return NULL;
 }
 
+/* hit selection and SAM text of a sub-chunk on the -t workers, as alnse_core_thread does both per read (alnse.c:1306-1307) */
+typedef struct { int tid, n_threads, first, upto, phase; index_t *index; query_t *queries; aln_opt_t *aln_opt; const salt_chunk_t *ck; const int *slot_of; } fin_thread_t;
+static void *finish_worker(void *arg)
+{
+    fin_thread_t *F = (fin_thread_t *)arg;
+    int j;
+    for (j = F->first + F->tid; j < F->upto; j += F->n_threads) {
+        if (F->slot_of[j] < 0) continue;
+        if (F->phase == 0) finish_read(F->index, F->queries + j, F->aln_opt, F->ck, (uint32_t)F->slot_of[j]);
+        else { dropin_tail_begin_read(j); aln_samse(F->index, F->queries + j, F->aln_opt); }      /* alnse.c:1307 / :1345 */
+    }
+    return NULL;
+}
+static void finish_parallel(int n_threads, pthread_t *th, fin_thread_t *F, int phase, int first, int upto, index_t *index, query_t *queries,
+                            aln_opt_t *aln_opt, const salt_chunk_t *ck, const int *slot_of)
+{
+    int t;
+    for (t = 0; t < n_threads; ++t) {
+        F[t].tid = t; F[t].n_threads = n_threads; F[t].first = first; F[t].upto = upto; F[t].phase = phase;
+        F[t].index = index; F[t].queries = queries; F[t].aln_opt = aln_opt; F[t].ck = ck; F[t].slot_of = slot_of;
+    }
+    if (n_threads == 1) { finish_worker(&F[0]); return; }
+    for (t = 0; t < n_threads; ++t) pthread_create(&th[t], NULL, finish_worker, &F[t]);
+    for (t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+}
+
 static double now_s(void)
 {
     struct timespec t;
@@ -152,6 +179,7 @@ int alnse_core(const opt_t *opt)
     }
     const int n_threads = opt->n_threads > 1 ? opt->n_threads : 1;
     seed_thread_t *T = calloc((size_t)n_threads, sizeof *T);
+    fin_thread_t *Fin = calloc((size_t)n_threads, sizeof *Fin);
     pthread_t *th = calloc((size_t)n_threads, sizeof *th);
     int t;
     for (t = 0; t < n_threads; ++t) {
@@ -218,12 +246,11 @@ int alnse_core(const opt_t *opt)
                 if (!gpu_seed && salt_chunk_wait(gpu, pend_c, ck[pend_c]) != SALT_OK) die("salt_chunk_wait");
                 t_gpu_wait += now_s() - tg;
                 double tf = now_s();
-                for (j = pend_first; j < pend_upto; ++j)
-                    if (slot_of[j] >= 0) finish_read(index, multiSeqs + j, aln_opt, ck[pend_c], (uint32_t)slot_of[j]);
+                (void)j;
+                finish_parallel(n_threads, th, Fin, 0, pend_first, pend_upto, index, multiSeqs, aln_opt, ck[pend_c], slot_of);
                 if (aln_opt->print_nm_md || aln_opt->print_xa_cigar)
                     dropin_tail_prepare(gpu, gpu_seed ? 0 : pend_c, multiSeqs, slot_of, pend_first, pend_upto);
-                for (j = pend_first; j < pend_upto; ++j)
-                    if (slot_of[j] >= 0) aln_samse(index, multiSeqs + j, aln_opt);     /* alnse.c:1307 / :1345 */
+                finish_parallel(n_threads, th, Fin, 1, pend_first, pend_upto, index, multiSeqs, aln_opt, ck[pend_c], slot_of);
                 t_finish += now_s() - tf;
                 pend_c = -1;
             }
@@ -242,7 +269,7 @@ int alnse_core(const opt_t *opt)
             t_seed, t_gpu_wait, t_finish);
     for (t = 0; t < n_threads; ++t) { aux_destroy(T[t].aux[0]); aux_destroy(T[t].aux[1]); }
     for (i = 0; i < N_SEQS; ++i) { free(seeds[i].a[0]); free(seeds[i].a[1]); }
-    free(T); free(th); free(seeds);
+    free(T); free(th); free(seeds); free(Fin);
     free(multiSeqs); free(slot_of);
     query_close(qs);
     salt_chunk_free(ck[0]); salt_chunk_free(ck[1]);

@@ -27,9 +27,12 @@ static struct {
     salt_mdnm_out_t *out; char *md; uint16_t *xv;
     /* gapped XA alternates in the order sam_add_xa visits them (sam.c:195-197) */
     size_t n_xa, xa_cursor;
+    size_t *xa_first; int n_first;  /* per query: its first row among the XA alternates */
     size_t tot_md, tot_xa, used_md, used_xa;       /* prepared on the GPU / printed into SAM lines */
     const uint8_t **xa_seq; uint32_t *xa_pos; int8_t *xa_e; char *xa_cig;
 } T;
+
+static __thread size_t t_xa_cursor;
 
 static void tail_die(const char *what)
 {
@@ -43,10 +46,13 @@ static void dropin_xa_prepare(salt_b200_t *gpu, int slot, const query_t *multi_s
     int j, strand;
     size_t i, n = 0, cap = 0;
     salt_pair_t *pairs = NULL; uint8_t *k_each = NULL;
-    T.n_xa = 0; T.xa_cursor = 0;
+    T.n_xa = 0; T.xa_cursor = 0; t_xa_cursor = 0;
+    T.xa_first = realloc(T.xa_first, (size_t)(upto + 1) * sizeof *T.xa_first); T.n_first = upto;
+    for (j = 0; j < upto; ++j) T.xa_first[j] = 0;
     if (salt_b200_use_slot(gpu, slot) != SALT_OK) tail_die("salt_b200_use_slot");      /* the per-pair entry points follow the chunk's slot */
     for (j = first; j < upto; ++j) {
         const query_t *q = multi_seqs + j;
+        T.xa_first[j] = n;
         if (slot_of[j] < 0) continue;
         for (strand = 0; strand < 2; ++strand)
             for (i = 0; i < q->hits[strand].n; ++i) {
@@ -74,15 +80,19 @@ static void dropin_xa_prepare(salt_b200_t *gpu, int slot, const query_t *multi_s
     free(pairs); free(k_each);
 }
 
+/* The SAM text of a chunk may be written by several threads (as the reference's workers do, alnse.c:1307): each thread
+ * announces the read it is about to print, and the XA hook then walks that read's own alternates. */
+void dropin_tail_begin_read(int j) { t_xa_cursor = (T.xa_first && j >= 0 && j < T.n_first) ? T.xa_first[j] : 0; }
+
 /* replaces the ed_diff_withcigar call at sam.c:218 (renamed with -D on sam.c only) */
 int dropin_xa_cigar(const uint32_t *mixRef, uint32_t ref_st, uint32_t l_ref, const uint8_t *seq, uint32_t l_seq,
                     int max_k_diff, char *cigarBuf, int cigarLen, int useM, int cigarFormat)
 {
     (void)mixRef; (void)l_ref; (void)l_seq; (void)max_k_diff; (void)useM; (void)cigarFormat;
-    while (T.xa_cursor < T.n_xa && !(T.xa_seq[T.xa_cursor] == seq && T.xa_pos[T.xa_cursor] == ref_st)) ++T.xa_cursor;
-    if (T.xa_cursor >= T.n_xa) { fprintf(stderr, "[salt_dropin] no XA CIGAR prepared for pos %u\n", ref_st); exit(1); }
-    const size_t k = T.xa_cursor++;
-    ++T.used_xa;
+    while (t_xa_cursor < T.n_xa && !(T.xa_seq[t_xa_cursor] == seq && T.xa_pos[t_xa_cursor] == ref_st)) ++t_xa_cursor;
+    if (t_xa_cursor >= T.n_xa) { fprintf(stderr, "[salt_dropin] no XA CIGAR prepared for pos %u\n", ref_st); exit(1); }
+    const size_t k = t_xa_cursor++;
+    __atomic_fetch_add(&T.used_xa, 1, __ATOMIC_RELAXED);
     strncpy(cigarBuf, T.xa_cig + k * TAIL_XA_STRIDE, (size_t)cigarLen - 1);
     return T.xa_e[k];
 }
@@ -131,7 +141,7 @@ void sam_add_md_nm(kstring_t *s, index_t *index, query_t *q)
     if (j < 0 || j >= T.n_q || T.idx[j] < 0) { fprintf(stderr, "[salt_dropin] no SAM tail prepared for %s\n", q->name); exit(1); }
     const int k = T.idx[j];
     if (T.out[k].md_len < 0) { fprintf(stderr, "[salt_dropin] MD of %s: engine code %d\n", q->name, T.out[k].md_len); exit(1); }
-    ++T.used_md;
+    __atomic_fetch_add(&T.used_md, 1, __ATOMIC_RELAXED);
     ksprintf(s, "\tMD:Z:%s", T.md + (size_t)k * TAIL_MD_STRIDE);
     ksprintf(s, "\tNM:i:%u", (unsigned)T.out[k].nm);
     if (T.out[k].n_xv > 0) {

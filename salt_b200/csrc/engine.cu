@@ -64,7 +64,7 @@ struct Slot {
     bool offs_merged = false;                                 // all three offset arrays arrived in one copy
     uint32_t *d_roffs() const { return offs3.as<uint32_t>(); }
     uint32_t *d_coffs(int strand) const { return offs3.as<uint32_t>() + (size_t)(strand + 1) * ((size_t)n_reads + 1); }
-    DBuf c_loci0, c_loci1, vpairs, acc, rec, lvlist, ciglist, counters, cig, fpairs, fslots, lvreads;
+    DBuf c_loci0, c_loci1, vpairs, acc, rec, lvlist, ciglist, counters, cig, fpairs, fslots, lvreads, fpairs2, fslots2;
     DBuf pk_bases, pk_lens, pk_cnt, pk_npos, pk_scan;          // compact transport (salt_packed_chunk_t): raw uploads + scan scratch
     DBuf tl_md, tl_out, tl_len, tl_offs, tl_packed, tl_cigrow, tl_xv;   // SAM tail of the chunk's primaries
     bool have_rec = false; int rec_cig_stride = 0;                // the slot's rec / cig buffers hold a finished verify
@@ -86,7 +86,7 @@ struct Slot {
     void release()
     {
         DBuf *all[] = {&codes, &offs3, &rd4, &rd_len, &c_loci0, &c_loci1, &vpairs, &acc, &rec,
-                       &lvlist, &ciglist, &counters, &cig, &fpairs, &fslots, &lvreads,
+                       &lvlist, &ciglist, &counters, &cig, &fpairs, &fslots, &lvreads, &fpairs2, &fslots2,
                        &pk_bases, &pk_lens, &pk_cnt, &pk_npos, &pk_scan, &sd_sai, &sd_counts, &sd_lists, &sd_long,
                        &tl_md, &tl_out, &tl_len, &tl_offs, &tl_packed, &tl_cigrow, &tl_xv};
         for (DBuf *b : all) b->release();
@@ -116,6 +116,8 @@ struct salt_b200 {
     Slot slot[SALT_SLOTS];
     DBuf fpairs, fslots, fcount;            // LV filter survivors of the per-pair entry point
     int lv_filter = 1;                      // pigeonhole filter in front of Landau-Vishkin (salt_b200_set_lv_filter)
+    int lv_two_pass = 1;                    // Landau-Vishkin in two passes behind the filter (salt_b200_set_lv_mapping bit 4 clears it)
+    DBuf fpairs2, fslots2;                  // second-pass list of the per-pair entry point
     // staging / scratch of the synchronous per-pair and SSW entry points (slot 0's stream)
     DBuf pairs, out8, kbuf, cig, wins, sswout, sswcig, sswscratch, sswovf, md_in, md_cig, md_str, md_xv, md_out;
     DBuf ix_cbwt, ix_csa, ix_lkt, ix_rbwt, ix_rocc, ix_rmaj, ix_rsa;      // FM-indexes (salt_b200_set_index)
@@ -240,6 +242,11 @@ int verify_on_device(salt_b200_t *h, int si, const uint32_t *d_offs0, const uint
         CU(s.fpairs.need((n + 1) * sizeof(salt_pair_t)));
         CU(s.fslots.need((n + 1) * 4));
         fs.pairs = s.fpairs.as<salt_pair_t>(); fs.slots = s.fslots.as<uint32_t>(); fs.count = s.counters.as<uint32_t>() + 8;
+        if (h->lv_two_pass) {
+            CU(s.fpairs2.need((n + 1) * sizeof(salt_pair_t)));
+            CU(s.fslots2.need((n + 1) * 4));
+            fs.pairs2 = s.fpairs2.as<salt_pair_t>(); fs.slots2 = s.fslots2.as<uint32_t>(); fs.count2 = s.counters.as<uint32_t>() + 12;
+        }
     }
     int8_t *acc = d_acc0;
     if (!acc) { CU(s.acc.need(n + 1)); acc = s.acc.as<int8_t>(); }
@@ -691,7 +698,7 @@ void salt_b200_destroy(salt_b200_t *h)
         h->slot[i].release();
     }
     DBuf *all[] = {&h->pairs, &h->out8, &h->kbuf, &h->cig, &h->wins, &h->sswout, &h->sswcig, &h->sswscratch, &h->sswovf, &h->ix_cbwt, &h->ix_csa, &h->ix_lkt, &h->ix_rbwt, &h->ix_rocc, &h->ix_rmaj, &h->ix_rsa,
-                   &h->fpairs, &h->fslots, &h->fcount, &h->md_in, &h->md_cig, &h->md_str, &h->md_xv, &h->md_out};
+                   &h->fpairs, &h->fslots, &h->fcount, &h->fpairs2, &h->fslots2, &h->md_in, &h->md_cig, &h->md_str, &h->md_xv, &h->md_out};
     for (DBuf *b : all) b->release();
     for (int i = 0; i < 7; ++i) if (h->ev_ssw[i]) cudaEventDestroy(h->ev_ssw[i]);
     if (!h->borrowed) {                     // an attached handle only points at its parent's reference and indexes
@@ -788,6 +795,11 @@ int salt_b200_lv_dev(salt_b200_t *h, const salt_pair_t *d_pairs, size_t n, int k
         CU(h->fslots.need((n + 1) * 4));
         CU(h->fcount.need(256));
         fs.pairs = h->fpairs.as<salt_pair_t>(); fs.slots = h->fslots.as<uint32_t>(); fs.count = h->fcount.as<uint32_t>();
+        if (h->lv_two_pass) {
+            CU(h->fpairs2.need((n + 1) * sizeof(salt_pair_t)));
+            CU(h->fslots2.need((n + 1) * 4));
+            fs.pairs2 = h->fpairs2.as<salt_pair_t>(); fs.slots2 = h->fslots2.as<uint32_t>(); fs.count2 = h->fcount.as<uint32_t>() + 4;
+        }
     }
     CU(launch_lv(h->ctx(h->cur), d_pairs, n, k, nullptr, nullptr, 0, d_out, h->sm_count, h->slot[h->cur].stream, h->lv_mapping,
                  h->lv_filter ? &fs : nullptr));
@@ -997,8 +1009,9 @@ int salt_b200_use_slot(salt_b200_t *h, int slot)
 int salt_b200_set_lv_mapping(salt_b200_t *h, int mapping)
 {
     if (!h) return fail(SALT_ERR_ARG, "null handle");
-    if (mapping < 0 || mapping > 2) return fail(SALT_ERR_ARG, "mapping must be 0 (auto), 1 (warp per pair) or 2 (thread per pair)");
-    h->lv_mapping = mapping;
+    if (mapping < 0 || (mapping & 15) > 2 || mapping > 18) return fail(SALT_ERR_ARG, "mapping must be 0 (auto), 1 (warp per pair) or 2 (thread per pair), + 16 for a single pass");
+    h->lv_mapping = mapping & 15;
+    h->lv_two_pass = (mapping & 16) ? 0 : 1;
     return SALT_OK;
 }
 

@@ -13,7 +13,9 @@ cudaError_t launch_pack_reads(const uint8_t *codes, const uint32_t *offs, uint32
 cudaError_t launch_mismatch(const DevCtx &c, const salt_pair_t *pairs, size_t n, int max_err, int8_t *out, cudaStream_t st);
 struct LvFilterScratch {      // survivors of the pigeonhole filter: room for every input pair
     salt_pair_t *pairs; uint32_t *slots; uint32_t *count;
+    salt_pair_t *pairs2 = nullptr; uint32_t *slots2 = nullptr; uint32_t *count2 = nullptr;   // second Landau-Vishkin pass (optional)
 };
+struct LvDefer { salt_pair_t *pairs; uint32_t *slots; uint32_t *count; };    // where a first pass queues the pairs it does not finish
 cudaError_t launch_lv(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k,
                       const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
                       int8_t *out, int sm_count, cudaStream_t st, int mapping = 0, const LvFilterScratch *f = nullptr);

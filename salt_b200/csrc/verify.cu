@@ -399,7 +399,7 @@ template <int K>
 __global__ void __launch_bounds__(128, K <= 10 ? 10 : 4)
 lv_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_fixed,
               const uint32_t *__restrict__ slots, const uint32_t *__restrict__ wl_count,
-              int8_t *__restrict__ out)
+              int8_t *__restrict__ out, LvDefer df)
 {
     SALT_DYN_SMEM(uint32_t, smem);
     const int TW = lv_twr((int)c.l_max), PW = lv_pwt((int)c.l_max);
@@ -423,9 +423,14 @@ lv_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_f
         const int toff = ok ? lv_stage_own(c, p, tlen, T, P, TW, PW) : 0;
         __syncwarp();
         int result = -1;
+        bool defer = false;
         if (ok) {
             int k = k_fixed >= 0 ? k_fixed : plen / 10;             // alnse.c:1090
-            k = imin(imin(k, LV_MAXK - 1), K);                      // LandauVishkin.c:31
+            k = imin(k, LV_MAXK - 1);                               // LandauVishkin.c:31
+            // first pass of two (df.pairs set): only the first K levels are walked here; a pair that needs more goes to
+            // the list of the second pass, so that the lanes of a warp stop within a few levels of each other
+            if (df.pairs && k > K) defer = true;
+            k = imin(k, K);
             const int L0 = lv_extend0(T, P, plen, tlen, toff);
             if (L0 == plen) result = 0;
             else {
@@ -465,7 +470,17 @@ lv_tpp_kernel(DevCtx c, const salt_pair_t *__restrict__ pairs, size_t n, int k_f
                 }
             }
         }
-        if (live) out[slots ? slots[it] : it] = (int8_t)result;
+        defer = defer && result < 0;                                // within the first K levels: final
+        if (df.pairs) {
+            const unsigned bal = __ballot_sync(0xffffffffu, live && defer);
+            uint32_t at = 0;
+            if (bal) {
+                if (lane == 0) at = atomicAdd(df.count, (uint32_t)__popc(bal));
+                at = __shfl_sync(0xffffffffu, at, 0) + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+            }
+            if (live && defer) { df.pairs[at] = p; df.slots[at] = slots ? slots[it] : (uint32_t)it; }
+        }
+        if (live && !defer) out[slots ? slots[it] : it] = (int8_t)result;
         __syncwarp();
     }
 }
@@ -1338,7 +1353,7 @@ static cudaError_t launch_lv_t(const DevCtx &c, const salt_pair_t *pairs, size_t
 template <int K>
 static cudaError_t launch_lv_tpp(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k,
                                  const uint32_t *worklist, const uint32_t *wl_count, size_t wl_cap,
-                                 int8_t *out, int sm_count, cudaStream_t st)
+                                 int8_t *out, int sm_count, cudaStream_t st, LvDefer df = LvDefer{nullptr, nullptr, nullptr})
 {
     const int stride = (lv_twr((int)c.l_max) + lv_pwt((int)c.l_max)) | 1;
     int threads = 128;
@@ -1354,7 +1369,7 @@ static cudaError_t launch_lv_tpp(const DevCtx &c, const salt_pair_t *pairs, size
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    SALT_LAUNCH(kern, (unsigned)blocks, threads, smem, st, c, pairs, n, k, worklist, wl_count, out);
+    SALT_LAUNCH(kern, (unsigned)blocks, threads, smem, st, c, pairs, n, k, worklist, wl_count, out, df);
     SALT_LAUNCH_CHECK();
     return cudaSuccess;
 }
@@ -1400,6 +1415,18 @@ cudaError_t launch_lv(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k
     // Survivors are mostly true hits and their +-1..3 shifted twins, which stop after a few levels:
     // one thread per pair (long extensions deferred to the end of a level) beats one warp per pair on
     // both the verify stage's worklists and flat decoy-heavy lists (profiles/r1r_lv_split.txt).
+    int kmax = k >= 0 ? k : (int)c.l_max / 10;
+    if (kmax > LV_MAXK - 1) kmax = LV_MAXK - 1;
+    // (measured: 0.76 -> 0.67 ms on a flat 7.8 M-pair list at k = 10, but 0.166 -> 0.181 ms on the verify stage's 1.2 M-pair
+    // worklist, where the second launch and the re-staging cost more than the idle lanes: large lists only)
+    if (mapping != 1 && c.l_max <= 512 && kmax > 3 && kmax <= 15 && items >= 3000000 && f->pairs2 && f->slots2 && f->count2) {
+        // two passes: three levels for everybody (most survivors end there), the full depth only for the rest -- the
+        // lanes of a warp then finish within a few levels of each other instead of waiting for the one deep pair
+        if ((e = cudaMemsetAsync(f->count2, 0, 4, st)) != cudaSuccess) return e;
+        LvDefer df{f->pairs2, f->slots2, f->count2};
+        if ((e = launch_lv_tpp<3>(c, f->pairs, items, k, f->slots, f->count, items, out, sm_count, st, df)) != cudaSuccess) return e;
+        return launch_lv_core(c, f->pairs2, items, k, f->slots2, f->count2, items, out, sm_count, st, mapping);
+    }
     return launch_lv_core(c, f->pairs, items, k, f->slots, f->count, items, out, sm_count, st, mapping);
 }
 

@@ -49,8 +49,6 @@ def main():
                 row["reference_s"] = round(t_ref, 2); row["reference_reads_per_s"] = round((n + 40) / t_ref)
                 want = body(os.path.join(d, "ref.sam"))
                 for mode in ("host", "gpu"):
-                    if mode == "gpu" and t_ != 1:
-                        continue                                  # -t only drives host seeding
                     env = dict(os.environ, SALT_DROPIN_SEED=mode)
                     t0 = time.time()
                     with open(os.path.join(d, "gpu.sam"), "w") as f:
