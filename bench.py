@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--traffic-probe-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--probe-dir", default="", help=argparse.SUPPRESS)
     ap.add_argument("--pe-pairs", type=int, default=200_000, help="pairs in the paired-end pipeline leg (0 = skip)")
+    ap.add_argument("--seed-reads", type=int, default=400_000, help="reads in the seeding + locate leg (0 = skip)")
+    ap.add_argument("--seed-genome", type=int, default=10_000_000, help="genome of the seeding leg (its index is built by salt-idx)")
     return ap.parse_args()
 
 
@@ -536,6 +538,8 @@ def main():
         out["sam_tail"] = bench_sam_tail(eng, lib, h, pkc, args, n, n0, n1, (h_rec, h_acc0, h_acc1, h_cig))
         if args.pe_pairs > 0:
             out["pe"] = bench_pe(eng, wl, args)
+        if args.seed_reads > 0:
+            out["seeding"] = bench_seeding(args)
 
     if rank == 0 and world == 1:
         try:
@@ -636,6 +640,24 @@ def bench_pe(eng, wl, args):
     return res
 
 
+def bench_seeding(args):
+    """Row f1 beside the headline: single-end seeding + locate on the device, and the whole single-end stage from reads
+    alone, against the reference's own functions on all host threads (tools/seed_bench.py at a size that fits the
+    default run).  Needs the reference's indexer and seeding harness from oracle/_ref (input preparation and the CPU
+    side); without them the block says so."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import seed_bench
+        import seed_cases
+        if not seed_cases.have_ref():
+            return {"unavailable": "oracle/_ref/salt-idx / libsaltref_seed.so not built (no reference tree at build time)"}
+        a = argparse.Namespace(genome=args.seed_genome, reads=args.seed_reads, read_len=args.read_len, repeat_frac=0.10,
+                               cpu_sample=min(args.seed_reads, 200_000), chunk=args.chunk, max_seed=50, max_locate=1000)
+        return seed_bench.run(a)
+    except Exception as ex:                                # noqa: BLE001 -- an extra, never the headline
+        return {"error": repr(ex)}
+
+
 def bench_lv(eng, lib, h, wl, args, dev, stream):
     """Landau-Vishkin kernel alone on decoy-heavy pair lists (every candidate of the first reads), k = 2..10."""
     import torch
@@ -714,12 +736,12 @@ def bench_sam_tail(eng, lib, h, pkc, args, n, n0, n1, pins):
 
     def finish(k, with_tail):
         b, m, v = views[k]; si = k % n_slots
-        ck(lib.salt_b200_verify_wait(h, si))
         if with_tail:
             nb = C.c_size_t(0)
-            ck(lib.salt_b200_tail_primaries(h, si, h_out.data_ptr() + 8 * b, h_offs.data_ptr() + 4 * (chunk + 1) * si,
-                                            h_md.data_ptr() + md_cap * si, md_cap, C.byref(nb), h_xv.data_ptr() + 16 * b, 8))
+            ck(lib.salt_b200_tail_wait(h, si, C.byref(nb)))        # completes the verify of the slot as well
             stat["md_bytes"] += nb.value
+        else:
+            ck(lib.salt_b200_verify_wait(h, si))
 
     def run(with_tail):
         stat["md_bytes"] = 0
@@ -729,6 +751,9 @@ def bench_sam_tail(eng, lib, h, pkc, args, n, n0, n1, pins):
                 finish(k - n_slots, with_tail)
             ck(lib.salt_b200_verify_submit_packed(h, si, C.byref(v), 3, -1, h_rec.data_ptr() + 16 * b, h_acc0.data_ptr() + int(o0[b]),
                                                   h_acc1.data_ptr() + int(o1[b]), h_cig.data_ptr() + 128 * b, 128))
+            if with_tail:                                          # queued right behind the verify, on the same stream
+                ck(lib.salt_b200_tail_submit(h, si, h_out.data_ptr() + 8 * b, h_offs.data_ptr() + 4 * (chunk + 1) * si,
+                                             h_md.data_ptr() + md_cap * si, md_cap, h_xv.data_ptr() + 16 * b, 8))
         for k in range(max(0, len(views) - n_slots), len(views)):
             finish(k, with_tail)
     res = {}
@@ -746,7 +771,7 @@ def bench_sam_tail(eng, lib, h, pkc, args, n, n0, n1, pins):
             "ms": (res[True] - res[False]) * 1e3, "alignments_per_s": mapped / max(1e-9, res[True] - res[False]),
             "nm_mean": float(out["nm"][out["md_len"] > 0].mean()) if mapped else 0.0, "md_overflow": int((out["md_len"] < 0).sum()),
             "md_bytes": int(stat["md_bytes"]), "d2h_bytes": int(stat["md_bytes"] + n * (8 + 16 + 4)),
-            "note": "salt_b200_tail_primaries per chunk on the pipeline slots, pinned outputs; ms = loop with tails minus loop without"}
+            "note": "salt_b200_tail_submit right behind every salt_b200_verify_submit_packed, salt_b200_tail_wait per slot, pinned outputs; ms = loop with tails minus loop without"}
 
 
 def bench_sw(eng, lib, h, wl, args, dev, stream):

@@ -177,6 +177,13 @@ int salt_b200_md_nm(salt_b200_t *h, int slot, const salt_mdnm_in_t *items, size_
 int salt_b200_tail_primaries(salt_b200_t *h, int slot, salt_mdnm_out_t *out, uint32_t *md_offs, char *md_packed, size_t md_cap,
                              size_t *md_bytes, uint16_t *xv, int xv_stride);
 
+/* The same, asynchronous: _tail_submit queues the work on the slot's stream -- also right behind a
+ * salt_b200_verify_submit[_packed] of the same slot, without waiting for it -- and _tail_wait completes both.  The buffers
+ * must stay valid until _tail_wait returns. */
+int salt_b200_tail_submit(salt_b200_t *h, int slot, salt_mdnm_out_t *out, uint32_t *md_offs, char *md_packed, size_t md_cap,
+                          uint16_t *xv, int xv_stride);
+int salt_b200_tail_wait(salt_b200_t *h, int slot, size_t *md_bytes);
+
 /* The whole verification stage for a chunk, as alnse_overlap_alt (SE) / alnse_overlap (PE)
  * run it after seeding (alnse.c:1077-1097 / :1014-1036):
  *   nogap on strand 0 then 1 with threshold nogap_T0 (3) tightening as candidates are

@@ -104,6 +104,8 @@ def _declare(L):
     if hasattr(L, "salt_b200_tail_primaries"):
         L.salt_b200_tail_primaries.argtypes = [vp, i32, vp, vp, vp, sz, C.POINTER(C.c_size_t), vp, i32]
         L.salt_b200_use_slot.argtypes = [vp, i32]
+        L.salt_b200_tail_submit.argtypes = [vp, i32, vp, vp, vp, sz, vp, i32]
+        L.salt_b200_tail_wait.argtypes = [vp, i32, C.POINTER(C.c_size_t)]
     L.salt_b200_set_max_window.argtypes = [vp, i32]
     L.salt_b200_set_lv_mapping.argtypes = [vp, i32]
     L.salt_b200_set_lv_filter.argtypes = [vp, i32]

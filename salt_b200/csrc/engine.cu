@@ -66,7 +66,8 @@ struct Slot {
     uint32_t *d_coffs(int strand) const { return offs3.as<uint32_t>() + (size_t)(strand + 1) * ((size_t)n_reads + 1); }
     DBuf c_loci0, c_loci1, vpairs, acc, rec, lvlist, ciglist, counters, cig, fpairs, fslots, lvreads, fpairs2, fslots2;
     DBuf pk_bases, pk_lens, pk_cnt, pk_npos, pk_scan;          // compact transport (salt_packed_chunk_t): raw uploads + scan scratch
-    DBuf tl_md, tl_out, tl_len, tl_offs, tl_packed, tl_cigrow, tl_xv;   // SAM tail of the chunk's primaries
+    DBuf tl_md, tl_out, tl_len, tl_offs, tl_packed, tl_cigrow, tl_xv, tl_scan;   // SAM tail of the chunk's primaries
+    bool tail_pending = false; size_t tail_eager = 0, tail_cap = 0; uint32_t *tail_offs = nullptr; char *tail_md = nullptr;
     bool have_rec = false; int rec_cig_stride = 0;                // the slot's rec / cig buffers hold a finished verify
     DBuf sd_long;                                               // (read, strand) ids whose lists need the long sort, [0] = count
     DBuf sd_sai, sd_counts, sd_lists;                          // seeding scratch: intervals, per-strand counts, fixed-stride lists
@@ -88,7 +89,7 @@ struct Slot {
         DBuf *all[] = {&codes, &offs3, &rd4, &rd_len, &c_loci0, &c_loci1, &vpairs, &acc, &rec,
                        &lvlist, &ciglist, &counters, &cig, &fpairs, &fslots, &lvreads, &fpairs2, &fslots2,
                        &pk_bases, &pk_lens, &pk_cnt, &pk_npos, &pk_scan, &sd_sai, &sd_counts, &sd_lists, &sd_long,
-                       &tl_md, &tl_out, &tl_len, &tl_offs, &tl_packed, &tl_cigrow, &tl_xv};
+                       &tl_md, &tl_out, &tl_len, &tl_offs, &tl_packed, &tl_cigrow, &tl_xv, &tl_scan};
         for (DBuf *b : all) b->release();
         if (h_stage) cudaFreeHost(h_stage);
         h_stage = nullptr; h_stage_cap = 0;
@@ -895,46 +896,88 @@ int salt_b200_md_nm(salt_b200_t *h, int slot, const salt_mdnm_in_t *items, size_
     return SALT_OK;
 }
 
-int salt_b200_tail_primaries(salt_b200_t *h, int slot, salt_mdnm_out_t *out, uint32_t *md_offs, char *md_packed, size_t md_cap,
-                             size_t *md_bytes, uint16_t *xv, int xv_stride)
+// Queue the tags of the slot's primaries behind whatever the slot's stream still has to do (a verify just submitted
+// included): kernels, scan, packing and the downloads, with the first `eager` bytes of the packed MD stream copied
+// without waiting for its length.  tail_finish completes it.
+static int tail_enqueue(salt_b200_t *h, int slot, salt_mdnm_out_t *out, uint32_t *md_offs, char *md_packed, size_t md_cap,
+                        uint16_t *xv, int xv_stride)
 {
-    if (int rc = use_device(h)) return rc;
     if (slot < 0 || slot >= SALT_SLOTS) return fail(SALT_ERR_ARG, "slot out of range");
     Slot &s = h->slot[slot];
-    if (s.pending) return fail(SALT_ERR_ARG, "slot has a verify in flight: call salt_b200_verify_wait first");
     if (!s.have_rec || !s.n_reads) return fail(SALT_ERR_ARG, "slot holds no verified chunk");
     if (!s.rec_cig_stride) return fail(SALT_ERR_ARG, "the chunk was verified without CIGARs: gapped primaries would have no tags");
     if (!h->d_pac) return fail(SALT_ERR_ARG, "MD/NM need the 2-bit pac (salt_b200_init was given none)");
     if (!out || !md_offs || !md_packed) return fail(SALT_ERR_ARG, "null buffer");
     if (xv_stride < 0 || xv_stride > 64 || (xv_stride > 0 && !xv)) return fail(SALT_ERR_ARG, "xv_stride must be 0..64 with a buffer");
+    if (s.tail_pending) return fail(SALT_ERR_ARG, "slot has a tail in flight: call salt_b200_tail_wait first");
     const uint32_t n = s.n_reads;
     const int mstride = 2 * (int)s.l_max + 16 < 64 ? 64 : 2 * (int)s.l_max + 16;     // an MD string never needs more than ~2 characters per base
     const size_t xs = (size_t)(xv_stride > 0 ? xv_stride : 1);
     cudaStream_t st = s.stream;
     CU(s.tl_md.need((size_t)n * mstride)); CU(s.tl_out.need((size_t)n * sizeof(salt_mdnm_out_t)));
     CU(s.tl_len.need((size_t)n * 4 + 16)); CU(s.tl_offs.need(((size_t)n + 1) * 4)); CU(s.tl_cigrow.need((size_t)n * 4));
-    CU(s.tl_xv.need((size_t)n * xs * 2)); CU(s.pk_scan.need(3 * (size_t)scan3_blocks(n) * 4 + 16));
+    CU(s.tl_xv.need((size_t)n * xs * 2)); CU(s.tl_scan.need(3 * (size_t)scan3_blocks(n) * 4 + 16));
+    CU(s.tl_packed.need((size_t)n * mstride + 16));                   // worst case: known before the lengths are
     if (xv_stride > 0) CU(cudaMemsetAsync(s.tl_xv.p, 0, (size_t)n * xs * 2, st));
     const uint32_t *cl = s.ciglist.as<uint32_t>();
     CU(launch_tail_primaries(h->ctx(slot), s.codes.as<uint8_t>(), s.d_roffs(), s.rec.as<salt_verify_out_t>(), cl + 1, cl,
                              s.cig.as<char>(), s.rec_cig_stride, s.tl_cigrow.as<int32_t>(), s.tl_md.as<char>(), mstride,
                              s.tl_xv.as<uint16_t>(), xv_stride, s.tl_out.as<salt_mdnm_out_t>(), s.tl_len.as<uint32_t>(), st));
     Scan3 sc{};
-    sc.n = n; sc.partial = s.pk_scan.as<uint32_t>(); sc.in[0] = s.tl_len.p; sc.width[0] = 32; sc.out[0] = s.tl_offs.as<uint32_t>();
+    sc.n = n; sc.partial = s.tl_scan.as<uint32_t>(); sc.in[0] = s.tl_len.p; sc.width[0] = 32; sc.out[0] = s.tl_offs.as<uint32_t>();
     CU(launch_scan3(sc, 1, st));
+    CU(launch_tail_pack(s.tl_md.as<char>(), mstride, s.tl_offs.as<uint32_t>(), n, s.tl_packed.as<char>(), st));
     CU(cudaMemcpyAsync(md_offs, s.tl_offs.p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(out, s.tl_out.p, (size_t)n * sizeof(salt_mdnm_out_t), cudaMemcpyDeviceToHost, st));
     if (xv_stride > 0) CU(cudaMemcpyAsync(xv, s.tl_xv.p, (size_t)n * xs * 2, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    const size_t total = md_offs[n];
-    if (md_bytes) *md_bytes = total;
-    if (total > md_cap) return fail(SALT_ERR_NOMEM, "packed MD buffer too small");
-    CU(s.tl_packed.need(total + 16));
-    CU(launch_tail_pack(s.tl_md.as<char>(), mstride, s.tl_offs.as<uint32_t>(), n, s.tl_packed.as<char>(), st));
-    CU(cudaMemcpyAsync(md_packed, s.tl_packed.p, total, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    size_t eager = (size_t)n * 12;                                    // typical MD strings are a handful of characters
+    if (eager > md_cap) eager = md_cap;
+    if (eager > (size_t)n * mstride) eager = (size_t)n * mstride;
+    if (eager) CU(cudaMemcpyAsync(md_packed, s.tl_packed.p, eager, cudaMemcpyDeviceToHost, st));
+    s.tail_pending = true; s.tail_eager = eager; s.tail_offs = md_offs; s.tail_md = md_packed; s.tail_cap = md_cap;
     h->launches += 7;
     return SALT_OK;
+}
+
+static int tail_finish(salt_b200_t *h, int slot, size_t *md_bytes)
+{
+    Slot &s = h->slot[slot];
+    if (!s.tail_pending) return fail(SALT_ERR_ARG, "slot has no tail in flight");
+    s.tail_pending = false;
+    if (s.pending) { if (int rc = finish_verify(h, slot)) return rc; }      // same stream: the verify is complete too
+    else CU(cudaStreamSynchronize(s.stream));
+    const size_t total = s.tail_offs[s.n_reads];
+    if (md_bytes) *md_bytes = total;
+    if (total > s.tail_cap) return fail(SALT_ERR_NOMEM, "packed MD buffer too small");
+    if (total > s.tail_eager) {
+        CU(cudaMemcpyAsync(s.tail_md + s.tail_eager, s.tl_packed.as<char>() + s.tail_eager, total - s.tail_eager, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaStreamSynchronize(s.stream));
+    }
+    return SALT_OK;
+}
+
+int salt_b200_tail_submit(salt_b200_t *h, int slot, salt_mdnm_out_t *out, uint32_t *md_offs, char *md_packed, size_t md_cap,
+                          uint16_t *xv, int xv_stride)
+{
+    if (int rc = use_device(h)) return rc;
+    return tail_enqueue(h, slot, out, md_offs, md_packed, md_cap, xv, xv_stride);
+}
+
+int salt_b200_tail_wait(salt_b200_t *h, int slot, size_t *md_bytes)
+{
+    if (int rc = use_device(h)) return rc;
+    if (slot < 0 || slot >= SALT_SLOTS) return fail(SALT_ERR_ARG, "slot out of range");
+    return tail_finish(h, slot, md_bytes);
+}
+
+int salt_b200_tail_primaries(salt_b200_t *h, int slot, salt_mdnm_out_t *out, uint32_t *md_offs, char *md_packed, size_t md_cap,
+                             size_t *md_bytes, uint16_t *xv, int xv_stride)
+{
+    if (int rc = use_device(h)) return rc;
+    if (slot < 0 || slot >= SALT_SLOTS) return fail(SALT_ERR_ARG, "slot out of range");
+    if (h->slot[slot].pending) return fail(SALT_ERR_ARG, "slot has a verify in flight: call salt_b200_verify_wait first");
+    if (int rc = tail_enqueue(h, slot, out, md_offs, md_packed, md_cap, xv, xv_stride)) return rc;
+    return tail_finish(h, slot, md_bytes);
 }
 
 // ------------------------------------------------------------------ SSW

@@ -355,6 +355,24 @@ def check_tail_primaries(eng, oracle, g, reads, cands, nogap_T0=3, lv_T0=-1):
         assert np.array_equal(xv[i][:out["n_xv"][i]], xv2[i][:want["n_xv"][i]])
         n_gapped += rec["is_gap"][i] == 1
     assert int(offs[-1]) == len(packed)
+    # the asynchronous flavour: tail queued right behind a verify that is still in flight, both completed by _tail_wait
+    import ctypes as C
+    roffs = (np.arange(n + 1) * L).astype(np.uint32)
+    codes = np.ascontiguousarray(reads).reshape(-1)
+    r = api.ReadsT(codes.ctypes.data, roffs.ctypes.data, n)
+    cd = api.CandsT(); cd.offs[0], cd.offs[1] = offs0.ctypes.data, offs1.ctypes.data
+    cd.loci[0], cd.loci[1] = loci0.ctypes.data, loci1.ctypes.data
+    rec2 = np.zeros(n, api.VERIFY_DT); cig2 = np.zeros((n, 128), np.uint8)
+    out2 = np.zeros(n, api.MDNM_OUT_DT); offs2 = np.zeros(n + 1, np.uint32); packed2 = np.zeros(len(packed) + 64, np.uint8)
+    xvb = np.zeros((n, 64), np.uint16)
+    Lb = eng.L
+    for cap in (len(packed2), len(packed)):             # roomy, and exactly enough (the eager copy must not overrun it)
+        eng._ck(Lb.salt_b200_verify_submit(eng.h, 2, C.byref(r), C.byref(cd), nogap_T0, lv_T0, rec2.ctypes.data, None, None, cig2.ctypes.data, 128))
+        eng._ck(Lb.salt_b200_tail_submit(eng.h, 2, out2.ctypes.data, offs2.ctypes.data, packed2.ctypes.data, cap, xvb.ctypes.data, 64))
+        nb = C.c_size_t(0)
+        eng._ck(Lb.salt_b200_tail_wait(eng.h, 2, C.byref(nb)))
+        assert nb.value == len(packed) and rec2.tobytes() == rec.tobytes()
+        assert out2.tobytes() == out.tobytes() and np.array_equal(offs2, offs) and packed2[:nb.value].tobytes() == packed.tobytes()
     return n_gapped
 
 

@@ -31,6 +31,12 @@ def main():
     ap.add_argument("--max-seed", type=int, default=50)
     ap.add_argument("--max-locate", type=int, default=1000)
     args = ap.parse_args()
+    print(json.dumps(run(args)))
+
+
+def run(args, device=0):
+    """args: genome, reads, read_len, repeat_frac, cpu_sample, chunk, max_seed, max_locate"""
+    import shutil
     import torch
     import seed_cases as sc
     from oracle import orc
@@ -58,8 +64,7 @@ def main():
     reads[rc_mask] = synth.revcomp(reads[rc_mask])
     reads = np.ascontiguousarray(reads, np.uint8)
     roffs = (np.arange(n + 1, dtype=np.uint64) * L).astype(np.uint32)
-    dev = torch.device("cuda", 0)
-    eng = api.Engine(fm.mixref, fm.l, None, 0, device=0)
+    eng = api.Engine(fm.mixref, fm.l, None, 0, device=device)
     eng.set_index(fm)
     opt = api.Engine.seed_opt(fm.l_seed, 0, args.max_seed, args.max_locate)
     out = {"genome": args.genome, "reads": n, "read_len": L, "l_seed": fm.l_seed, "max_seed": args.max_seed,
@@ -119,7 +124,9 @@ def main():
     out["lists_identical_on_sample"] = bool(all(np.array_equal(a, b) for a, b in zip(got, (o0, l0, o1, l1))))
     out["speedup_seed_locate"] = out["gpu_seed_locate"]["reads_per_s"] / out["cpu_seed_locate"]["reads_per_s"]
     out["speedup_align_e2e"] = out["gpu_align_e2e"]["reads_per_s"] / out["cpu_seed_verify"]["reads_per_s"]
-    print(json.dumps(out))
+    ref.close(); eng.close()
+    shutil.rmtree(d, ignore_errors=True)
+    return out
 
 
 if __name__ == "__main__":
