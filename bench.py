@@ -555,6 +555,7 @@ def main():
 
 
 def bench_pe(eng, wl, args):
+    from salt_b200 import api
     """Paired-end pipeline through the host layer from HOST buffers (alnpe_core re-staged, alnpe.c:530-615): per chunk of
     pairs salt_chunk_add_reads (pageable -> pinned queues), salt_chunk_submit with the PE thresholds 3 / 3, salt_chunk_wait,
     salt_chunk_pair = query_set_hits + pairing plans + one Smith-Waterman batch per rescue flavour + apply + MD/NM/XV of every
@@ -577,6 +578,8 @@ def bench_pe(eng, wl, args):
     min_tlen, max_tlen = 250, 550                        # aln.c defaults (-a / -b)
     stats = []
     finals_keep = []
+    # the caller's result buffers, one set per slot (a real caller keeps its query_t array)
+    obufs = [((host_api.PairFinalT * cpairs)(), np.zeros(2 * cpairs, api.MDNM_OUT_DT), np.zeros((2 * cpairs, 64), np.uint8)) for _ in range(n_slots)]
 
     def run():
         stats.clear(); finals_keep.clear()
@@ -592,13 +595,13 @@ def bench_pe(eng, wl, args):
             if pend is not None:
                 pc_, ps_, pm_ = pend
                 pc_.wait(eng, ps_)
-                f, to, tm, st = pc_.pair(eng, ps_, pm_, min_tlen, max_tlen, g.l, md_stride=64)
-                stats.append(st); finals_keep.append((f, to))
+                f, to, tm, st = pc_.pair(eng, ps_, pm_, min_tlen, max_tlen, g.l, md_stride=64, bufs=obufs[ps_])
+                stats.append(st); finals_keep.append((f, to[:2 * pm_].copy()))
             pend = (ch, slot, m); k += 1
         pc_, ps_, pm_ = pend
         pc_.wait(eng, ps_)
-        f, to, tm, st = pc_.pair(eng, ps_, pm_, min_tlen, max_tlen, g.l, md_stride=64)
-        stats.append(st); finals_keep.append((f, to))
+        f, to, tm, st = pc_.pair(eng, ps_, pm_, min_tlen, max_tlen, g.l, md_stride=64, bufs=obufs[ps_])
+        stats.append(st); finals_keep.append((f, to[:2 * pm_].copy()))
     run()
     t0 = time.perf_counter()
     reps = 2

@@ -278,7 +278,13 @@ typedef struct {
 
 /* aln_opt_t fields the seeding reads (aln.h:121-151): l_seed (persisted by the indexer in PREFIX.R.seedLen),
  * l_overlap (defaults to l_seed), max_seed (-n), max_locate (-m), seed_only_ref (-R). */
-typedef struct { int l_seed, l_overlap, max_seed, max_locate, seed_only_ref; } salt_seed_opt_t;
+typedef struct {
+    int l_seed, l_overlap, max_seed, max_locate, seed_only_ref;
+    int locate_mode;     /* 0: alnse_locate_alt, the single-end program (alnse.c:633-731); 1: alnse_locate, the paired-end
+                            program (alnse.c:501-631): up to max_locate + 1 rows of every primary-index interval, MAX_LOC_POS
+                            loci in all, and SNP-context intervals wider than max_locate subsampled with rand() */
+    int list_cap;        /* locate_mode 1: room per list on the device, 64..16384 (the reference allows 262144) */
+} salt_seed_opt_t;
 
 /* Upload the indexes once (the handle keeps its own copy). */
 int salt_b200_set_index(salt_b200_t *h, const salt_fm_index_t *ix);
@@ -291,6 +297,12 @@ int salt_b200_set_index(salt_b200_t *h, const salt_fm_index_t *ix);
  * ((l_seq - l_seed) / l_overlap + 1), max_locate <= 16384, l_seed >= the lookup length. */
 int salt_b200_seed_locate(salt_b200_t *h, int slot, const salt_seed_opt_t *opt, uint32_t *offs0, uint32_t *offs1,
                           uint32_t *loci0, size_t cap0, uint32_t *loci1, size_t cap1, size_t *n0, size_t *n1);
+
+/* locate_mode 1 only: per read and strand, bit 0 = an SNP-context interval was wider than max_locate -- the reference
+ * picks a random subset of its rows there (srand(time(0)), alnse.c:538-552), so no list is "the" right one: the interval
+ * is left out and the caller decides (the reference's own functions on the host, or accept the shorter list); bit 1 = the
+ * list filled list_cap before the reference's own limit.  n_reads bytes per strand. */
+int salt_b200_seed_status(salt_b200_t *h, int slot, uint8_t *st0, uint8_t *st1);
 
 /* salt_b200_verify on the lists salt_b200_seed_locate left in the slot.  acc0 / acc1 need the totals it reported. */
 int salt_b200_verify_seeded(salt_b200_t *h, int slot, int nogap_T0, int lv_T0, salt_verify_out_t *rec,

@@ -531,15 +531,115 @@ static void *pe_seed_worker(void *arg)
     return NULL;
 }
 
+/* phase 1 on the device (SALT_DROPIN_SEED=gpu): alnse_seed_overlap + alnse_locate of every mate through
+ * salt_b200_seed_locate(locate_mode 1), in sub-batches; a strand the engine flags (an SNP-context interval the reference
+ * subsamples with rand(), or a list beyond list_cap) gets the reference's own functions on the host instead. */
+#define DROPIN_PE_LIST_CAP 4096
+static size_t gpu_seed_flagged, gpu_seed_reads;
+static void pe_seed_on_gpu(salt_b200_t *gpu, index_t *index, aln_opt_t *aln_opt, query_t *queries, int n, pe_seeded_t *out, aux_t *aux[2])
+{
+    salt_seed_opt_t so;
+    memset(&so, 0, sizeof so);
+    so.l_seed = aln_opt->l_seed; so.l_overlap = aln_opt->l_overlap; so.max_seed = aln_opt->max_seed;
+    so.max_locate = (int)aln_opt->max_locate; so.seed_only_ref = aln_opt->seed_only_ref;
+    so.locate_mode = 1; so.list_cap = DROPIN_PE_LIST_CAP;
+    const int step = 20000;
+    size_t cap = (size_t)step * 64;
+    uint32_t *loci[2] = {malloc(cap * 4), malloc(cap * 4)};
+    uint32_t *offs[2] = {malloc(((size_t)step + 1) * 4), malloc(((size_t)step + 1) * 4)};
+    uint8_t *st[2] = {malloc((size_t)step), malloc((size_t)step)};
+    uint32_t *roffs = malloc(((size_t)step + 1) * 4);
+    int *who = malloc((size_t)step * sizeof *who);
+    int b, i, s;
+    for (b = 0; b < n; b += step) {
+        const int e = b + step < n ? b + step : n;
+        size_t nb = 0; uint32_t m = 0;
+        for (i = b; i < e; ++i) {
+            out[i].n[0] = out[i].n[1] = 0;
+            out[i].skip = queries[i].n_ambiguous > DROPIN_PE_MAX_N_PERSEQ;
+            if (!out[i].skip) nb += (size_t)queries[i].l_seq;
+        }
+        uint8_t *codes = malloc(nb + 16);
+        roffs[0] = 0;
+        for (i = b; i < e; ++i) {
+            if (out[i].skip) continue;
+            memcpy(codes + roffs[m], queries[i].seq, (size_t)queries[i].l_seq);
+            roffs[m + 1] = roffs[m] + (uint32_t)queries[i].l_seq;
+            who[m++] = i;
+        }
+        if (m) {
+            salt_reads_t r; r.codes = codes; r.offs = roffs; r.n_reads = m;
+            if (salt_b200_set_reads(gpu, &r) != SALT_OK) die("salt_b200_set_reads");
+            size_t n0 = 0, n1 = 0;
+            int rc = salt_b200_seed_locate(gpu, 0, &so, offs[0], offs[1], loci[0], cap, loci[1], cap, &n0, &n1);
+            if (rc == SALT_ERR_NOMEM) {
+                cap = (n0 > n1 ? n0 : n1) + 1024;
+                loci[0] = realloc(loci[0], cap * 4); loci[1] = realloc(loci[1], cap * 4);
+                rc = salt_b200_seed_locate(gpu, 0, &so, offs[0], offs[1], loci[0], cap, loci[1], cap, &n0, &n1);
+            }
+            if (rc != SALT_OK) die("salt_b200_seed_locate");
+            if (salt_b200_seed_status(gpu, 0, st[0], st[1]) != SALT_OK) die("salt_b200_seed_status");
+            for (uint32_t k = 0; k < m; ++k) {
+                pe_seeded_t *o = out + who[k];
+                query_t *query = queries + who[k];
+                ++gpu_seed_reads;
+                if (st[0][k] | st[1][k]) {               /* no single right answer on the device: the reference's own functions */
+                    ++gpu_seed_flagged;
+                    if (query->l_seq - aln_opt->l_seed + 1 > aux[0]->n_sai_range) {
+                        aux_resize(aux[0], query->l_seq - aln_opt->l_seed + 1); aux_resize(aux[1], query->l_seq - aln_opt->l_seed + 1);
+                    }
+                    aux_reset(aux[0]); aux_reset(aux[1]);
+                    alnse_seed_overlap(index, query->l_seq, query->seq, aln_opt, aux[0]);
+                    alnse_locate(index, query->l_seq, aln_opt->max_locate, aux[0]);
+                    alnse_seed_overlap(index, query->l_seq, query->rseq, aln_opt, aux[1]);
+                    alnse_locate(index, query->l_seq, aln_opt->max_locate, aux[1]);
+                }
+                for (s = 0; s < 2; ++s) {
+                    const int flagged = (st[0][k] | st[1][k]) != 0;
+                    const uint32_t cnt = flagged ? (uint32_t)aux[s]->loci.n : offs[s][k + 1] - offs[s][k];
+                    const uint32_t *src = flagged ? aux[s]->loci.a : loci[s] + offs[s][k];
+                    if (cnt > o->m[s]) { o->m[s] = cnt + 16; o->a[s] = realloc(o->a[s], (size_t)o->m[s] * 4); }
+                    memcpy(o->a[s], src, (size_t)cnt * 4);
+                    o->n[s] = cnt;
+                }
+            }
+        }
+        free(codes);
+    }
+    free(loci[0]); free(loci[1]); free(offs[0]); free(offs[1]); free(st[0]); free(st[1]); free(roffs); free(who);
+}
+
 int alnpe_core(const opt_t *opt)
 {
     int i;
     aln_opt_t *aln_opt = aln_opt_init(opt);
-    fprintf(stderr, "[alnpe_core/gpu]:  Start paired end alignment (verification on libsalt_b200)\n");
+    const char *seed_env = getenv("SALT_DROPIN_SEED");
+    const int gpu_seed = seed_env && !strcmp(seed_env, "gpu");
+    fprintf(stderr, "[alnpe_core/gpu]:  Start paired end alignment (verification on libsalt_b200%s)\n",
+            gpu_seed ? ", seeding + locate on libsalt_b200" : "");
     index_t *index = alnpe_index_reload(opt->fn_index);
     if (aln_opt->l_overlap <= 0) { fprintf(stderr, "[salt_dropin/pe] only the overlap path is served\n"); exit(1); }
     salt_b200_t *gpu = salt_b200_init(index->mixRef->seq, index->mixRef->l, index->pac, index->bntseq->l_pac, 0);
     if (!gpu) die("salt_b200_init");
+    if (gpu_seed) {
+        /* the FM-indexes exactly as the reference's loaders left them in memory (indexio.c:52-91) */
+        salt_fm_index_t fx;
+        int k;
+        rbwt_t *r = index->rbwt2->rbwt1;
+        memset(&fx, 0, sizeof fx);
+        fx.c_bwt = index->cbwt->bwt; fx.c_bwt_words = index->cbwt->bwt_size;
+        fx.c_primary = index->cbwt->primary; fx.c_seq_len = index->cbwt->seq_len;
+        for (k = 0; k < 5; ++k) fx.c_L2[k] = index->cbwt->L2[k];
+        fx.c_sa = index->cbwt->sa; fx.c_n_sa = index->cbwt->n_sa; fx.c_sa_intv = (uint32_t)index->cbwt->sa_intv;
+        fx.lkt = index->lkt->item; fx.lkt_len = index->lkt->maxLookupLen;
+        fx.r_bwt = r->bwtCode; fx.r_bwt_words = r->bwtSizeInWord;
+        fx.r_occ = r->occValue; fx.r_occ_words = r->occSizeInWord;
+        fx.r_occ_major = r->occValueMajor; fx.r_occ_major_words = r->occMajorSizeInWord;
+        fx.r_sa_sharp = r->saValueSharp; fx.r_n_sa_sharp = r->saValueSizeSharp;
+        for (k = 0; k < 6; ++k) fx.r_cum[k] = r->cumulativeFreq[k];
+        fx.r_inv_sa0 = r->inverseSa0; fx.r_text_len = r->textLength;
+        if (salt_b200_set_index(gpu, &fx) != SALT_OK) die("salt_b200_set_index");
+    }
     salt_chunk_t *ck = salt_chunk_new(DROPIN_CHUNK_READS, (size_t)DROPIN_CHUNK_READS * 1024, DROPIN_CHUNK_CANDS);
     if (!ck) die("salt_chunk_new");
     queryio_t *qs[2];
@@ -566,7 +666,8 @@ int alnpe_core(const opt_t *opt)
         if (opt->max_tlen == 0) { fprintf(stderr, "infer isize func haven't been implemented\n"); break; }
         int first = 0;                               /* mates [first, i) are queued; first is always even */
         for (t = 0; t < n_threads; ++t) { T[t].n = n; T[t].queries = multi_seqs; T[t].out = seeds; }
-        if (n_threads == 1) pe_seed_worker(&T[0]);
+        if (gpu_seed) pe_seed_on_gpu(gpu, index, aln_opt, multi_seqs, n, seeds, T[0].aux);
+        else if (n_threads == 1) pe_seed_worker(&T[0]);
         else {
             for (t = 0; t < n_threads; ++t) pthread_create(&th[t], NULL, pe_seed_worker, &T[t]);
             for (t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
@@ -628,6 +729,8 @@ int alnpe_core(const opt_t *opt)
     fprintf(stderr, "[salt_dropin/pe] pairs finished by salt_pair_apply alone: %zu, handed back to the reference's pairing: %zu\n",
             apply_final, apply_fallback);
     fprintf(stderr, "[salt_dropin/pe] %d seeding threads\n", n_threads);
+    if (gpu_seed) fprintf(stderr, "[salt_dropin/pe] seeded on the GPU: %zu mates, %zu of them handed to the reference's own seeding (flagged lists)\n",
+                          gpu_seed_reads, gpu_seed_flagged);
     for (t = 0; t < n_threads; ++t) { aux_destroy(T[t].aux[0]); aux_destroy(T[t].aux[1]); }
     for (i = 0; i < N_SEQS; ++i) { free(seeds[i].a[0]); free(seeds[i].a[1]); }
     free(T); free(th); free(seeds);

@@ -149,6 +149,7 @@ int alnse_core(const opt_t *opt)
     salt_b200_t *gpu = salt_b200_init(index->mixRef->seq, index->mixRef->l, index->pac, index->bntseq->l_pac, 0);
     if (!gpu) die("salt_b200_init");
     salt_seed_opt_t sopt;
+    memset(&sopt, 0, sizeof sopt);                      /* locate_mode 0: alnse_locate_alt, the single-end program's */
     sopt.l_seed = aln_opt->l_seed; sopt.l_overlap = aln_opt->l_overlap; sopt.max_seed = aln_opt->max_seed;
     sopt.max_locate = (int)aln_opt->max_locate; sopt.seed_only_ref = aln_opt->seed_only_ref;
     if (gpu_seed) {

@@ -17,6 +17,11 @@
 
 void alnse_seed_overlap(index_t *index, uint32_t l_seq, const uint8_t *seq, aln_opt_t *opt, aux_t *aux_data);
 void alnse_locate_alt(index_t *index, uint32_t l_seq, uint32_t max_locate, aux_t *aux_data);
+void alnse_locate(index_t *index, uint32_t l_seq, uint32_t max_locate, aux_t *aux_data);
+
+/* 0: alnse_locate_alt (what alnse_overlap_alt, the single-end program, calls); 1: alnse_locate (alnse_overlap, paired-end) */
+static int g_locate_mode;
+void seedref_set_locate_mode(int m) { g_locate_mode = m; }
 
 void *seedref_open(const char *prefix) { return alnse_index_reload(prefix); }
 void seedref_close(void *ix) { if (ix) alnse_index_destroy((index_t *)ix); }
@@ -84,7 +89,7 @@ int seedref_run(void *p, const uint8_t *codes, const uint32_t *roffs, uint32_t n
             aux_reset(aux);
             if ((int)L >= l_seed) {
                 alnse_seed_overlap(ix, L, s ? rseq : seq, &opt, aux);
-                alnse_locate_alt(ix, L, (uint32_t)max_locate, aux);
+                if (g_locate_mode) alnse_locate(ix, L, (uint32_t)max_locate, aux); else alnse_locate_alt(ix, L, (uint32_t)max_locate, aux);
             }
             size_t *n = s ? &n1 : &n0;
             uint32_t *dst = s ? loci1 : loci0;
@@ -123,7 +128,7 @@ static void *seed_worker(void *arg)
             aux_reset(aux);
             if ((int)L >= J->opt.l_seed) {
                 alnse_seed_overlap(J->ix, L, s ? rseq : seq, &J->opt, aux);
-                alnse_locate_alt(J->ix, L, J->opt.max_locate, aux);
+                if (g_locate_mode) alnse_locate(J->ix, L, J->opt.max_locate, aux); else alnse_locate_alt(J->ix, L, J->opt.max_locate, aux);
             }
             if (J->n[s] + aux->loci.n > J->cap[s]) {
                 J->cap[s] = (J->n[s] + aux->loci.n) * 2 + 1024;

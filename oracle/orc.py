@@ -394,15 +394,18 @@ class SeedRef:
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]
         self.ix = self.lib.seedref_open(prefix.encode())
 
-    def run(self, codes, roffs, l_seed, l_overlap, max_seed, max_locate, seed_only_ref=0):
+    def run(self, codes, roffs, l_seed, l_overlap, max_seed, max_locate, seed_only_ref=0, locate_mode=0, cap_per_read=None):
+        """locate_mode 0: alnse_locate_alt (single-end program), 1: alnse_locate (paired-end program)"""
         codes = np.ascontiguousarray(codes, np.uint8).reshape(-1); roffs = np.ascontiguousarray(roffs, np.uint32)
         n = len(roffs) - 1
-        cap = n * max_locate + 16
+        self.lib.seedref_set_locate_mode(int(locate_mode))
+        cap = n * (cap_per_read or max_locate) + 16
         offs0 = np.zeros(n + 1, np.uint32); offs1 = np.zeros(n + 1, np.uint32)
         loci0 = np.zeros(cap, np.uint32); loci1 = np.zeros(cap, np.uint32)
         rc = self.lib.seedref_run(self.ix, codes.ctypes.data, roffs.ctypes.data, n, l_seed, l_overlap if l_overlap > 0 else l_seed,
                                   max_seed, max_locate, seed_only_ref, offs0.ctypes.data, loci0.ctypes.data, cap,
                                   offs1.ctypes.data, loci1.ctypes.data, cap)
+        self.lib.seedref_set_locate_mode(0)
         assert rc == 0
         return offs0, loci0[:offs0[-1]].copy(), offs1, loci1[:offs1[-1]].copy()
 

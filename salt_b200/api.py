@@ -100,6 +100,7 @@ def _declare(L):
         L.salt_b200_set_index.argtypes = [vp, C.POINTER(FmIndexT)]
         L.salt_b200_seed_locate.argtypes = [vp, i32, C.POINTER(SeedOptT), vp, vp, vp, sz, vp, sz, szp, szp]
         L.salt_b200_verify_seeded.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32]
+        L.salt_b200_seed_status.argtypes = [vp, i32, vp, vp]
         L.salt_b200_align_batch_packed.argtypes = [vp, C.POINTER(PackedChunkT), C.POINTER(SeedOptT), C.c_uint32, i32, i32, vp, vp, i32]
     if hasattr(L, "salt_b200_tail_primaries"):
         L.salt_b200_tail_primaries.argtypes = [vp, i32, vp, vp, vp, sz, C.POINTER(C.c_size_t), vp, i32]
@@ -386,9 +387,15 @@ class Engine:
         self._ck(self.L.salt_b200_set_index(self.h, C.byref(st)))
 
     @staticmethod
-    def seed_opt(l_seed, l_overlap=0, max_seed=50, max_locate=1000, seed_only_ref=0):
+    def seed_opt(l_seed, l_overlap=0, max_seed=50, max_locate=1000, seed_only_ref=0, locate_mode=0, list_cap=0):
         from .index_io import SeedOptT
-        return SeedOptT(int(l_seed), int(l_overlap) if l_overlap > 0 else int(l_seed), int(max_seed), int(max_locate), int(seed_only_ref))
+        return SeedOptT(int(l_seed), int(l_overlap) if l_overlap > 0 else int(l_seed), int(max_seed), int(max_locate), int(seed_only_ref),
+                        int(locate_mode), int(list_cap))
+
+    def seed_status(self, slot=0):
+        st0 = np.zeros(self.n_reads, np.uint8); st1 = np.zeros(self.n_reads, np.uint8)
+        self._ck(self.L.salt_b200_seed_status(self.h, int(slot), _ptr(st0), _ptr(st1)))
+        return st0, st1
 
     def seed_locate(self, opt, slot=0, download=True):
         """alnse_seed_overlap + alnse_locate_alt for the reads in `slot`: (offs0, loci0, offs1, loci1) or just the totals."""

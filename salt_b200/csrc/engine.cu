@@ -69,6 +69,7 @@ struct Slot {
     DBuf tl_md, tl_out, tl_len, tl_offs, tl_packed, tl_cigrow, tl_xv, tl_scan;   // SAM tail of the chunk's primaries
     bool tail_pending = false; size_t tail_eager = 0, tail_cap = 0; uint32_t *tail_offs = nullptr; char *tail_md = nullptr;
     bool have_rec = false; int rec_cig_stride = 0;                // the slot's rec / cig buffers hold a finished verify
+    DBuf sd_status;                                             // per strand: flags of the paired-end flavour of locate
     DBuf sd_long;                                               // (read, strand) ids whose lists need the long sort, [0] = count
     DBuf sd_sai, sd_counts, sd_lists;                          // seeding scratch: intervals, per-strand counts, fixed-stride lists
     uint32_t *h_tot = nullptr;                                  // pinned: the two list totals of a seeded chunk
@@ -88,7 +89,7 @@ struct Slot {
     {
         DBuf *all[] = {&codes, &offs3, &rd4, &rd_len, &c_loci0, &c_loci1, &vpairs, &acc, &rec,
                        &lvlist, &ciglist, &counters, &cig, &fpairs, &fslots, &lvreads, &fpairs2, &fslots2,
-                       &pk_bases, &pk_lens, &pk_cnt, &pk_npos, &pk_scan, &sd_sai, &sd_counts, &sd_lists, &sd_long,
+                       &pk_bases, &pk_lens, &pk_cnt, &pk_npos, &pk_scan, &sd_sai, &sd_counts, &sd_lists, &sd_long, &sd_status,
                        &tl_md, &tl_out, &tl_len, &tl_offs, &tl_packed, &tl_cigrow, &tl_xv, &tl_scan};
         for (DBuf *b : all) b->release();
         if (h_stage) cudaFreeHost(h_stage);
@@ -469,6 +470,8 @@ int check_seed_opt(const salt_b200_t *h, const Slot &s, const salt_seed_opt_t *o
     if (o->l_overlap < 1) return fail(SALT_ERR_UNSUPPORTED, "l_overlap < 1: the reference's non-overlap seeding is not served");
     if (o->max_seed < 0) return fail(SALT_ERR_ARG, "max_seed must be >= 0");
     if (o->max_locate < 1 || o->max_locate > 16384) return fail(SALT_ERR_UNSUPPORTED, "max_locate must be in 1..16384");
+    if (o->locate_mode != 0 && o->locate_mode != 1) return fail(SALT_ERR_ARG, "locate_mode must be 0 (alnse_locate_alt) or 1 (alnse_locate)");
+    if (o->locate_mode == 1 && (o->list_cap < 64 || o->list_cap > 16384)) return fail(SALT_ERR_ARG, "list_cap must be in 64..16384 for locate_mode 1");
     const int ms = s.l_max >= (uint32_t)o->l_seed ? (int)((s.l_max - (uint32_t)o->l_seed) / (uint32_t)o->l_overlap) + 1 : 1;
     if (ms > 1024) return fail(SALT_ERR_UNSUPPORTED, "more than 1024 seed starts per strand");
     *max_seeds = ms;
@@ -483,19 +486,21 @@ int seed_enqueue(salt_b200_t *h, int si, const salt_seed_opt_t *o)
     int max_seeds = 1;
     if (int rc = check_seed_opt(h, s, o, &max_seeds)) return rc;
     const uint32_t n = s.n_reads;
-    s.seeded = 0; s.seeded_n0 = s.seeded_n1 = 0; s.seed_max_locate = o->max_locate;
+    const int stride = o->locate_mode == 1 ? o->list_cap : o->max_locate;
+    s.seeded = 0; s.seeded_n0 = s.seeded_n1 = 0; s.seed_max_locate = stride;
     if (!s.h_tot) CU(cudaMallocHost(&s.h_tot, 16));
     s.h_tot[0] = s.h_tot[1] = 0;
     if (!n) { s.seeded = 1; return SALT_OK; }
-    SeedOpt so{o->l_seed, o->l_overlap, o->max_seed, o->max_locate, o->seed_only_ref};
+    SeedOpt so{o->l_seed, o->l_overlap, o->max_seed, o->max_locate, o->seed_only_ref, o->locate_mode, stride};
     CU(s.sd_sai.need(seed_sai_bytes(n, max_seeds)));
     CU(s.sd_counts.need((size_t)n * 2 * 4 + 16));
-    CU(s.sd_lists.need((size_t)n * 2 * (size_t)o->max_locate * 4 + 16));
+    CU(s.sd_lists.need((size_t)n * 2 * (size_t)stride * 4 + 16));
+    CU(s.sd_status.need((size_t)n * 2 + 16));
     CU(s.pk_scan.need(3 * (size_t)scan3_blocks(n) * 4 + 16));
     CU(launch_seed(h->fm, so, s.codes.as<uint8_t>(), s.d_roffs(), n, max_seeds, s.sd_sai.as<SeedSai>(), s.stream));
     CU(s.sd_long.need(((size_t)n * 2 + 4) * 4));
     CU(launch_locate(h->fm, so, s.d_roffs(), n, max_seeds, h->l, s.sd_sai.as<SeedSai>(), s.sd_counts.as<uint32_t>(),
-                     s.sd_lists.as<uint32_t>(), s.sd_long.as<uint32_t>() + 4, s.sd_long.as<uint32_t>(), h->sm_count, s.stream));
+                     s.sd_lists.as<uint32_t>(), s.sd_long.as<uint32_t>() + 4, s.sd_long.as<uint32_t>(), s.sd_status.as<uint8_t>(), h->sm_count, s.stream));
     Scan3 sc{};
     sc.n = n; sc.partial = s.pk_scan.as<uint32_t>();
     sc.in[0] = s.sd_counts.as<uint32_t>(); sc.in[1] = s.sd_counts.as<uint32_t>() + n; sc.width[0] = sc.width[1] = 32;
@@ -1298,6 +1303,19 @@ int salt_b200_seed_locate(salt_b200_t *h, int slot, const salt_seed_opt_t *opt, 
     if (offs1) CU(cudaMemcpyAsync(offs1, s.d_coffs(1), m1 * 4, cudaMemcpyDeviceToHost, s.stream));
     if (loci0 && s.seeded_n0) CU(cudaMemcpyAsync(loci0, s.c_loci0.p, s.seeded_n0 * 4, cudaMemcpyDeviceToHost, s.stream));
     if (loci1 && s.seeded_n1) CU(cudaMemcpyAsync(loci1, s.c_loci1.p, s.seeded_n1 * 4, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    return SALT_OK;
+}
+
+int salt_b200_seed_status(salt_b200_t *h, int slot, uint8_t *st0, uint8_t *st1)
+{
+    if (int rc = use_device(h)) return rc;
+    if (slot < 0 || slot >= SALT_SLOTS) return fail(SALT_ERR_ARG, "slot out of range");
+    Slot &s = h->slot[slot];
+    if (s.seeded != 2 || !st0 || !st1) return fail(SALT_ERR_ARG, "slot holds no seeded lists, or null buffer");
+    if (!s.n_reads) return SALT_OK;
+    CU(cudaMemcpyAsync(st0, s.sd_status.p, s.n_reads, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaMemcpyAsync(st1, s.sd_status.as<uint8_t>() + s.n_reads, s.n_reads, cudaMemcpyDeviceToHost, s.stream));
     CU(cudaStreamSynchronize(s.stream));
     return SALT_OK;
 }

@@ -72,14 +72,14 @@ struct FmIndexDev {
     const uint32_t *r_bwt, *r_occ, *r_occ_major, *r_sa_sharp;
     uint32_t r_cum[6], r_inv_sa0, r_text_len, r_n_sa_sharp;
 };
-struct SeedOpt { int l_seed, l_overlap, max_seed, max_locate, seed_only_ref; };
+struct SeedOpt { int l_seed, l_overlap, max_seed, max_locate, seed_only_ref, mode /* 0 alnse_locate_alt, 1 alnse_locate */, list_cap /* list stride */; };
 struct SeedSai { uint32_t sp, ep, offset; };              // sai_t, aln.h:91-95
 size_t seed_sai_bytes(uint32_t n_reads, int max_seeds);
 cudaError_t launch_seed(const FmIndexDev &ix, const SeedOpt &opt, const uint8_t *codes, const uint32_t *roffs, uint32_t n_reads,
                         int max_seeds, SeedSai *sai, cudaStream_t st);
 cudaError_t launch_locate(const FmIndexDev &ix, const SeedOpt &opt, const uint32_t *roffs, uint32_t n_reads, int max_seeds,
                           uint32_t ref_l, SeedSai *sai, uint32_t *counts, uint32_t *lists, uint32_t *long_list /* 2*n_reads */,
-                          uint32_t *long_count, int sm_count, cudaStream_t st);
+                          uint32_t *long_count, uint8_t *status /* [2][n_reads] or null */, int sm_count, cudaStream_t st);
 cudaError_t launch_seed_gather(const uint32_t *lists, int max_locate, const uint32_t *offs0, const uint32_t *offs1,
                                uint32_t n_reads, uint32_t *loci0, uint32_t *loci1, cudaStream_t st);
 

@@ -371,7 +371,8 @@ __host__ __device__ __forceinline__ size_t locate_group_words(int max_seeds)
 __global__ void __launch_bounds__(128)
 locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, uint32_t n_reads, int max_seeds,
               uint32_t ref_l, SeedSai *__restrict__ sai, uint32_t *__restrict__ counts /* [2][n_reads] */,
-              uint32_t *__restrict__ lists /* [rs][max_locate] */, uint32_t *__restrict__ long_list, uint32_t *__restrict__ long_count)
+              uint32_t *__restrict__ lists /* [rs][list_cap] */, uint32_t *__restrict__ long_list, uint32_t *__restrict__ long_count,
+              uint8_t *__restrict__ status /* [2][n_reads] */)
 {
     SALT_DYN_SMEM(uint32_t, s_mem);
     __shared__ uint32_t s_pos[LOC_STAGE];
@@ -392,7 +393,14 @@ locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, ui
     const size_t rs0 = (size_t)blockIdx.x * LOC_GROUPS;
     const size_t rs = rs0 + grp;
     const bool live = rs < (size_t)n_reads * 2;                       // dead groups run along with nothing to do
-    const uint32_t max_locate = (uint32_t)opt.max_locate;
+    // mode 0 = alnse_locate_alt (single-end): at most max_locate loci in all.  mode 1 = alnse_locate (paired-end,
+    // alnse.c:501-631): at most max_locate + 1 rows of each primary-index interval (:521), MAX_LOC_POS loci in all (:533),
+    // SNP-context intervals wider than max_locate are subsampled with rand() by the reference (:577-596) -- such an
+    // interval is left out here and the strand is flagged (bit 0), as is a list cut by list_cap < MAX_LOC_POS (bit 1).
+    const bool pe = opt.mode == 1;
+    const uint32_t stride = (uint32_t)opt.list_cap;
+    const uint32_t max_locate = pe ? (stride < 0x40000u ? stride : 0x40000u) : (uint32_t)opt.max_locate;
+    uint32_t flags = 0;
     if (lane == 0) s_n[grp] = 0;
     for (int part = 0; part < 2; ++part) {                            // 0: sai_C, 1: sai_backwardR (sai_forwardR is empty here)
         // ---- plan: the valid intervals in seed order, sorted as the reference sorts them, their rows laid end to end
@@ -406,10 +414,16 @@ locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, ui
             unsigned long long acc = 0;
             for (int i = 0; i < m; ++i) {
                 const SeedSai v = s_sai[i];
-                uint32_t skip = 1;
-                if (part == 1) { skip = (v.ep + 1 - v.sp) / 0x40000u; if ((int)skip <= 0) skip = 1; }    // alnse.c:702-703
                 s_row[i] = acc;
-                acc += ((unsigned long long)(v.ep - v.sp)) / skip + 1;                                   // rows sp, sp+skip, .. <= ep
+                if (!pe) {
+                    uint32_t skip = 1;
+                    if (part == 1) { skip = (v.ep + 1 - v.sp) / 0x40000u; if ((int)skip <= 0) skip = 1; }    // alnse.c:702-703
+                    acc += ((unsigned long long)(v.ep - v.sp)) / skip + 1;                                   // rows sp, sp+skip, .. <= ep
+                } else if (part == 0) {
+                    const unsigned long long w = (unsigned long long)(v.ep - v.sp) + 1;
+                    acc += w < (unsigned long long)opt.max_locate + 1 ? w : (unsigned long long)opt.max_locate + 1;   // alnse.c:521
+                } else if (v.ep - v.sp > (uint32_t)opt.max_locate) flags |= 1u;                              // alnse.c:577: rand()
+                else acc += (unsigned long long)(v.ep - v.sp) + 1;
             }
             s_row[m] = acc;
             s_m[grp] = m; s_done[grp] = 0;
@@ -445,7 +459,7 @@ locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, ui
                 while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (row_g[mid] <= flat) lo = mid; else hi = mid - 1; }
                 const SeedSai v = sai_g[lo];
                 uint32_t skip = 1;
-                if (part == 1) { skip = (v.ep + 1 - v.sp) / 0x40000u; if ((int)skip <= 0) skip = 1; }
+                if (!pe && part == 1) { skip = (v.ep + 1 - v.sp) / 0x40000u; if ((int)skip <= 0) skip = 1; }
                 const uint32_t j = v.sp + (uint32_t)(flat - row_g[lo]) * skip;
                 const uint32_t pos = (part == 0 ? c_sa(ix, j) : r_sa(ix, j)) - v.offset;      // uint32 arithmetic, may wrap (alnse.c:669)
                 const size_t rsg = rs0 + (size_t)gi;
@@ -459,7 +473,7 @@ locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, ui
             {
                 const uint32_t f0 = s_want[grp], cnt = s_want[grp + 1] - f0;
                 uint32_t n = s_n[grp];
-                uint32_t *dst = lists + rs * (size_t)max_locate;
+                uint32_t *dst = lists + rs * (size_t)stride;
                 for (uint32_t b = 0; b < cnt; b += LOC_G) {
                     const uint32_t i = b + (uint32_t)lane;
                     const bool keep = i < cnt && s_keep[f0 + i] != 0;
@@ -478,8 +492,12 @@ locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, ui
     if (!live) return;
     const uint32_t r = (uint32_t)(rs >> 1);
     const uint32_t n = s_n[grp];
-    uint32_t *dst = lists + rs * (size_t)max_locate;
-    if (lane == 0) counts[(rs & 1) * (size_t)n_reads + r] = n;
+    uint32_t *dst = lists + rs * (size_t)stride;
+    if (lane == 0) {
+        counts[(rs & 1) * (size_t)n_reads + r] = n;
+        if (pe && stride < 0x40000u && n == stride) flags |= 2u;
+        if (status) status[(rs & 1) * (size_t)n_reads + r] = (uint8_t)flags;
+    }
     if (n > LOC_SMALL) {                                              // ks_introsort(uint32_t) of a long list: sort_long_kernel
         if (lane == 0) long_list[atomicAdd(long_count, 1u)] = (uint32_t)rs;
         return;
@@ -510,7 +528,7 @@ locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, ui
 
 // lists longer than LOC_SMALL: one warp per queued (read, strand), bitonic in shared memory over cap2 >= max_locate
 __global__ void __launch_bounds__(128)
-sort_long_kernel(const uint32_t *__restrict__ long_list, const uint32_t *__restrict__ long_count, uint32_t n_reads, int max_locate,
+sort_long_kernel(const uint32_t *__restrict__ long_list, const uint32_t *__restrict__ long_count, uint32_t n_reads, int max_locate /* list stride */,
                  int cap2, const uint32_t *__restrict__ counts, uint32_t *__restrict__ lists)
 {
     constexpr unsigned FULL = 0xffffffffu;
@@ -574,7 +592,7 @@ cudaError_t launch_seed(const FmIndexDev &ix, const SeedOpt &opt, const uint8_t 
 
 cudaError_t launch_locate(const FmIndexDev &ix, const SeedOpt &opt, const uint32_t *roffs, uint32_t n_reads, int max_seeds,
                           uint32_t ref_l, SeedSai *sai, uint32_t *counts, uint32_t *lists, uint32_t *long_list, uint32_t *long_count,
-                          int sm_count, cudaStream_t st)
+                          uint8_t *status, int sm_count, cudaStream_t st)
 {
     if (!n_reads) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(long_count, 0, 4, st);
@@ -588,11 +606,11 @@ cudaError_t launch_locate(const FmIndexDev &ix, const SeedOpt &opt, const uint32
         if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         const size_t n_rs = (size_t)n_reads * 2;
         SALT_LAUNCH(kern, (unsigned)((n_rs + groups - 1) / groups), groups * LOC_G, smem, st, ix, opt, roffs, n_reads, max_seeds, ref_l, sai,
-                    counts, lists, long_list, long_count);
+                    counts, lists, long_list, long_count, status);
     }
-    if (opt.max_locate > LOC_SMALL) {
+    if (opt.list_cap > LOC_SMALL) {
         int cap2 = 2 * LOC_SMALL;
-        while (cap2 < opt.max_locate) cap2 <<= 1;
+        while (cap2 < opt.list_cap) cap2 <<= 1;
         int warps = 4;
         while (warps > 1 && (size_t)cap2 * 4 * warps > 96 * 1024) warps >>= 1;
         const size_t smem2 = (size_t)cap2 * 4 * warps;
@@ -600,7 +618,7 @@ cudaError_t launch_locate(const FmIndexDev &ix, const SeedOpt &opt, const uint32
         if (smem2 > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)) != cudaSuccess) return e;
         const size_t want = ((size_t)n_reads * 2 + warps - 1) / warps;
         const size_t cap = (size_t)sm_count * 8;
-        SALT_LAUNCH(kern, (unsigned)(want < cap ? want : cap), warps * 32, smem2, st, long_list, long_count, n_reads, opt.max_locate, cap2,
+        SALT_LAUNCH(kern, (unsigned)(want < cap ? want : cap), warps * 32, smem2, st, long_list, long_count, n_reads, opt.list_cap, cap2,
                     counts, lists);
     }
     return cudaGetLastError();

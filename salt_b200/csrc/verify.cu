@@ -1419,7 +1419,7 @@ cudaError_t launch_lv(const DevCtx &c, const salt_pair_t *pairs, size_t n, int k
     if (kmax > LV_MAXK - 1) kmax = LV_MAXK - 1;
     // (measured: 0.76 -> 0.67 ms on a flat 7.8 M-pair list at k = 10, but 0.166 -> 0.181 ms on the verify stage's 1.2 M-pair
     // worklist, where the second launch and the re-staging cost more than the idle lanes: large lists only)
-    if (mapping != 1 && c.l_max <= 512 && kmax > 3 && kmax <= 15 && items >= 3000000 && f->pairs2 && f->slots2 && f->count2) {
+    if (mapping != 1 && c.l_max <= 512 && kmax > 3 && kmax <= 15 && !worklist && n >= 3000000 && f->pairs2 && f->slots2 && f->count2) {
         // two passes: three levels for everybody (most survivors end there), the full depth only for the rest -- the
         // lanes of a warp then finish within a few levels of each other instead of waiting for the one deep pair
         if ((e = cudaMemsetAsync(f->count2, 0, 4, st)) != cudaSuccess) return e;

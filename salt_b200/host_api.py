@@ -161,10 +161,14 @@ class Chunk:
         return rc
 
     def pair(self, eng, slot, n_pairs, min_tlen, max_tlen, l_pac, max_hits=5, gapO=3, gapE=1, filters=0, filterd=20, with_tail=True,
-             md_stride=128):
-        """salt_chunk_pair: the paired-end stage of the chunk.  Returns (finals, tail_out, tail_md, stats)."""
-        out = (PairFinalT * max(n_pairs, 1))()
-        tail_out = np.zeros(2 * n_pairs, api.MDNM_OUT_DT); tail_md = np.zeros((2 * n_pairs, md_stride), np.uint8)
+             md_stride=128, bufs=None):
+        """salt_chunk_pair: the paired-end stage of the chunk.  Returns (finals, tail_out, tail_md, stats).
+        bufs = (finals, tail_out, tail_md) from an earlier call re-uses the caller's output buffers."""
+        if bufs is not None:
+            out, tail_out, tail_md = bufs
+        else:
+            out = (PairFinalT * max(n_pairs, 1))()
+            tail_out = np.zeros(2 * n_pairs, api.MDNM_OUT_DT); tail_md = np.zeros((2 * n_pairs, md_stride), np.uint8)
         st = PeStatsT()
         m16 = api.salt_score_mat2(); m5 = api.salt_score_mat()
         eng._ck(self.H.salt_chunk_pair(eng.h, int(slot), self.c, int(min_tlen), int(max_tlen), int(l_pac), int(max_hits),

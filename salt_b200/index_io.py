@@ -29,7 +29,7 @@ class FmIndexT(C.Structure):
 
 class SeedOptT(C.Structure):
     _fields_ = [("l_seed", C.c_int), ("l_overlap", C.c_int), ("max_seed", C.c_int), ("max_locate", C.c_int),
-                ("seed_only_ref", C.c_int)]
+                ("seed_only_ref", C.c_int), ("locate_mode", C.c_int), ("list_cap", C.c_int)]
 
 
 class FmIndex:

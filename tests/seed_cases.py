@@ -89,3 +89,30 @@ def check_lists(eng, ref, fm, codes, roffs, option_sets=OPTION_SETS):
             assert np.array_equal(a, b), (name, (ls, lo, ms, ml, ro), len(a), len(b))
         total += int(want[0][-1]) + int(want[2][-1])
     return total
+
+
+PE_OPTION_SETS = ((0, 5, 50, 200), (0, 0, 50, 1000), (0, 5, 3, 6), (0, 7, 1000, 40))   # (l_seed, l_overlap, max_seed, max_locate)
+
+
+def check_lists_pe(eng, ref, fm, codes, roffs, option_sets=PE_OPTION_SETS, list_cap=4096):
+    """the paired-end program's flavour (alnse_seed_overlap + alnse_locate, alnse.c:501-631).  Strands the device flags
+    (an SNP-context interval wider than max_locate: the reference draws rand() there; or a list that filled list_cap) have
+    no single right answer and are only counted."""
+    from salt_b200 import api
+    eng.set_reads(codes, roffs)
+    total = flagged = 0
+    for (ls, lo, ms, ml) in option_sets:
+        ls = ls or fm.l_seed
+        want = ref.run(codes, roffs, ls, lo, ms, ml, 0, locate_mode=1, cap_per_read=20000)
+        got = eng.seed_locate(api.Engine.seed_opt(ls, lo, ms, ml, 0, locate_mode=1, list_cap=list_cap))
+        st = eng.seed_status()
+        for s_ in (0, 1):
+            go, gl, wo, wl = got[2 * s_], got[2 * s_ + 1], want[2 * s_], want[2 * s_ + 1]
+            for r in range(len(roffs) - 1):
+                if st[s_][r]:
+                    flagged += 1
+                    continue
+                a = gl[go[r]:go[r + 1]]; b = wl[wo[r]:wo[r + 1]]
+                assert np.array_equal(a, b), ("pe lists", (ls, lo, ms, ml), s_, r, len(a), len(b))
+                total += len(b)
+    return total, flagged

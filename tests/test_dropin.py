@@ -69,17 +69,20 @@ def test_se_sam_identical(tmp_path, flags, seed):
     assert sum(1 for f in body if any(x.startswith("XA:") for x in f[11:])) >= 1
 
 
-@pytest.mark.parametrize("flags", [["-d", "-p", "-e", "-l", "100", "-c", "-a", "350", "-b", "650", "-r", "5", "-t", "1"]])   # run_pe_test.sh:14
+@pytest.mark.parametrize("flags", [["-d", "-p", "-e", "-l", "100", "-c", "-a", "350", "-b", "650", "-r", "5", "-t", "1"],    # run_pe_test.sh:14
+                                   ["-d", "-p", "-e", "-l", "100", "-c", "-a", "350", "-b", "650", "-r", "5", "-t", "4", "GPUSEED"]])
 def test_pe_sam_identical(tmp_path, flags):
     """paired-end: both mates verified on the GPU with the PE thresholds, then the reference's own pairing2 /
     mate rescue / alnpe_sam"""
     if not _have():
         pytest.skip("oracle/_ref programs not built (reference tree absent at build time)")
     d = str(tmp_path)
+    seed_env = {"SALT_DROPIN_SEED": "gpu"} if "GPUSEED" in flags else {"SALT_DROPIN_SEED": "host"}
+    flags = [f for f in flags if f != "GPUSEED"]
     dropin_data.write_pe_inputs(d)
     _run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], d, os.path.join(d, "idx.log"))
     _run([os.path.join(REFDIR, "salt")] + flags + ["idx", "r1.fq", "r2.fq"], d, os.path.join(d, "ref.sam"))
-    err = _run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", "r1.fq", "r2.fq"], d, os.path.join(d, "gpu.sam"))
+    err = _run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", "r1.fq", "r2.fq"], d, os.path.join(d, "gpu.sam"), env=seed_env)
     assert "verification on libsalt_b200" in err
     import re
     m = re.search(r"rescue windows recorded: (\d+), served by the reference's own ssw_align: (\d+)", err)
@@ -97,13 +100,13 @@ def test_pe_sam_identical(tmp_path, flags):
         assert a == b
     # the re-staged flow: rescue windows scheduled from salt_pair_plan alone (no recording run of the reference's pairing)
     err2 = _run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", "r1.fq", "r2.fq"], d, os.path.join(d, "gpu2.sam"),
-                env={"SALT_DROPIN_PLAN": "1"})
+                env=dict(seed_env, SALT_DROPIN_PLAN="1"))
     m2 = re.search(r"(\d+) pairs scheduled from the plan alone", err2)
     assert m2 and int(m2.group(1)) >= 2900
     assert _sam_body(os.path.join(d, "gpu2.sam")) == want
     # ... and with the reference's pairing out of the loop altogether: plan -> GPU batch -> salt_pair_apply -> query_t
     err3 = _run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", "r1.fq", "r2.fq"], d, os.path.join(d, "gpu3.sam"),
-                env={"SALT_DROPIN_PLAN": "2"})
+                env=dict(seed_env, SALT_DROPIN_PLAN="2"))
     m3 = re.search(r"pairs finished by salt_pair_apply alone: (\d+), handed back to the reference's pairing: (\d+)", err3)
     assert m3 and int(m3.group(1)) >= 2900 and int(m3.group(2)) <= 30, err3[-600:]
     assert _sam_body(os.path.join(d, "gpu3.sam")) == want
@@ -185,15 +188,20 @@ def test_config0_se_sam_identical(tmp_path, threads, seed):
     assert sum(1 for f in body if any(x.startswith("XA:") for x in f[11:])) >= 100
 
 
-@pytest.mark.parametrize("threads", ["4"])
-def test_config0_pe_sam_identical(tmp_path, threads):
-    """run_pe_test.sh:14 flags (what run_test.sh actually runs, :37)"""
+@pytest.mark.parametrize("threads,seed", [("4", "host"), ("4", "gpu")])
+def test_config0_pe_sam_identical(tmp_path, threads, seed):
+    """run_pe_test.sh:14 flags (what run_test.sh actually runs, :37); with seed == "gpu" the paired-end program's seeding +
+    locate (alnse_seed_overlap + alnse_locate) run on the device as well"""
     d = str(tmp_path)
     _config0_index(d)
     flags = ["-d", "-p", "-e", "-l", "100", "-c", "-a", "350", "-b", "650", "-r", "5", "-t", threads]
     err = _run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", os.path.join(C0, "Read1.fq"), os.path.join(C0, "Read2.fq")],
-               d, os.path.join(d, "gpu.sam"), env={"SALT_DROPIN_PLAN": "2"})
+               d, os.path.join(d, "gpu.sam"), env={"SALT_DROPIN_PLAN": "2", "SALT_DROPIN_SEED": seed})
     assert "verification on libsalt_b200" in err
+    if seed == "gpu":
+        import re
+        m = re.search(r"seeded on the GPU: (\d+) mates, (\d+) of them handed", err)
+        assert m and int(m.group(1)) >= 39000 and int(m.group(2)) <= int(m.group(1)) // 10, err[-600:]
     body = _same_sam(os.path.join(C0, "pe.sam"), os.path.join(d, "gpu.sam"), 40000)
     assert sum(1 for f in body if int(f[1]) & 2) >= 30000
 

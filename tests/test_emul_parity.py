@@ -233,6 +233,9 @@ def test_seed_locate_lists(emul_lib, tmp_path):
     eng = api.Engine(fm.mixref, fm.l, None, 0, lib=emul_lib)
     eng.set_index(fm)
     assert sc.check_lists(eng, ref, fm, codes, roffs) > 500
+    # the paired-end program's flavour of locate (alnse_locate)
+    tot, flagged = sc.check_lists_pe(eng, ref, fm, codes, roffs, option_sets=sc.PE_OPTION_SETS[:2])
+    assert tot > 200
     # and the verification stage on the lists the seeding left on the device == on the same lists uploaded
     opt = api.Engine.seed_opt(fm.l_seed, 0, 50, 500)
     offs0, loci0, offs1, loci1 = eng.seed_locate(opt)

@@ -30,6 +30,13 @@ def test_seed_lists_repeat_genome(tmp_path):
     eng = api.Engine(fm.mixref, fm.l, None, 0, device=0)
     eng.set_index(fm)
     assert sc.check_lists(eng, ref, fm, codes, roffs) > 500000
+    # the paired-end program's flavour (alnse_locate): per-interval row caps, MAX_LOC_POS in all; strands with an interval the
+    # reference subsamples with rand() are flagged instead of compared
+    tot, flagged = sc.check_lists_pe(eng, ref, fm, codes, roffs)
+    assert tot > 300000 and flagged < 0.2 * 8 * len(roffs)
+    # a small list_cap: lists that fill it are flagged, everything else still matches
+    tot2, flagged2 = sc.check_lists_pe(eng, ref, fm, codes, roffs, option_sets=sc.PE_OPTION_SETS[:1], list_cap=64)
+    assert flagged2 > 0 and tot2 > 10000
     ref.close(); eng.close()
 
 
