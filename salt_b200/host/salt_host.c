@@ -611,7 +611,39 @@ done:
 }
 
 /* ------------------------------------------------------------------ several GPUs in one process */
-struct salt_multi { int n; salt_b200_t **h; };
+typedef struct {
+    salt_b200_t *h; salt_packed_chunk_t view; uint32_t chunk_reads; int nogap_T0, lv_T0;
+    salt_verify_out_t *rec; int8_t *acc0, *acc1; char *cigars; int cigar_stride; int rc;
+} multi_job_t;
+
+/* one persistent host thread per device: a thread's first CUDA call binds it to its device, which is not free, so the
+   threads live as long as the handle set and are woken per batch */
+typedef struct {
+    pthread_t th; pthread_mutex_t mu; pthread_cond_t cv;
+    int state;                       /* 0 idle, 1 job posted, 2 job done, 3 quit */
+    multi_job_t job;
+} multi_worker_t;
+
+struct salt_multi { int n; salt_b200_t **h; multi_worker_t *w; };
+
+static void *multi_worker(void *arg)
+{
+    multi_worker_t *W = (multi_worker_t *)arg;
+    pthread_mutex_lock(&W->mu);
+    for (;;) {
+        while (W->state != 1 && W->state != 3) pthread_cond_wait(&W->cv, &W->mu);
+        if (W->state == 3) break;
+        pthread_mutex_unlock(&W->mu);
+        multi_job_t *J = &W->job;
+        J->rc = J->view.n_reads ? salt_b200_verify_batch_packed(J->h, &J->view, J->chunk_reads, J->nogap_T0, J->lv_T0, J->rec, J->acc0,
+                                                               J->acc1, J->cigars, J->cigar_stride) : SALT_OK;
+        pthread_mutex_lock(&W->mu);
+        W->state = 2;
+        pthread_cond_broadcast(&W->cv);
+    }
+    pthread_mutex_unlock(&W->mu);
+    return NULL;
+}
 
 salt_multi_t *salt_multi_init(const uint32_t *mixref, uint32_t l, const uint8_t *pac, int64_t l_pac, const int *devices, int n_devices)
 {
@@ -619,11 +651,17 @@ salt_multi_t *salt_multi_init(const uint32_t *mixref, uint32_t l, const uint8_t 
     salt_multi_t *m = calloc(1, sizeof *m);
     if (!m) return NULL;
     m->h = calloc((size_t)n_devices, sizeof *m->h);
-    if (!m->h) { free(m); return NULL; }
+    m->w = calloc((size_t)n_devices, sizeof *m->w);
+    if (!m->h || !m->w) { free(m->h); free(m->w); free(m); return NULL; }
     m->n = n_devices;
     for (int i = 0; i < n_devices; ++i) {
         m->h[i] = salt_b200_init(mixref, l, pac, l_pac, devices[i]);
-        if (!m->h[i]) { salt_multi_destroy(m); return NULL; }
+        if (!m->h[i]) { m->n = i; salt_multi_destroy(m); return NULL; }
+    }
+    for (int i = 0; i < n_devices; ++i) {
+        pthread_mutex_init(&m->w[i].mu, NULL); pthread_cond_init(&m->w[i].cv, NULL);
+        m->w[i].state = 0;
+        pthread_create(&m->w[i].th, NULL, multi_worker, &m->w[i]);
     }
     return m;
 }
@@ -631,25 +669,19 @@ salt_multi_t *salt_multi_init(const uint32_t *mixref, uint32_t l, const uint8_t 
 void salt_multi_destroy(salt_multi_t *m)
 {
     if (!m) return;
-    for (int i = 0; i < m->n; ++i) if (m->h[i]) salt_b200_destroy(m->h[i]);
-    free(m->h); free(m);
+    for (int i = 0; i < m->n; ++i) {
+        if (m->w && m->w[i].th) {
+            pthread_mutex_lock(&m->w[i].mu); m->w[i].state = 3; pthread_cond_broadcast(&m->w[i].cv); pthread_mutex_unlock(&m->w[i].mu);
+            pthread_join(m->w[i].th, NULL);
+            pthread_mutex_destroy(&m->w[i].mu); pthread_cond_destroy(&m->w[i].cv);
+        }
+        if (m->h[i]) salt_b200_destroy(m->h[i]);
+    }
+    free(m->h); free(m->w); free(m);
 }
 
 int salt_multi_n(const salt_multi_t *m) { return m ? m->n : 0; }
 salt_b200_t *salt_multi_handle(salt_multi_t *m, int i) { return (m && i >= 0 && i < m->n) ? m->h[i] : NULL; }
-
-typedef struct {
-    salt_b200_t *h; salt_packed_chunk_t view; uint32_t chunk_reads; int nogap_T0, lv_T0;
-    salt_verify_out_t *rec; int8_t *acc0, *acc1; char *cigars; int cigar_stride; int rc;
-} multi_job_t;
-
-static void *multi_worker(void *arg)
-{
-    multi_job_t *J = (multi_job_t *)arg;
-    J->rc = J->view.n_reads ? salt_b200_verify_batch_packed(J->h, &J->view, J->chunk_reads, J->nogap_T0, J->lv_T0, J->rec, J->acc0,
-                                                           J->acc1, J->cigars, J->cigar_stride) : SALT_OK;
-    return NULL;
-}
 
 static uint32_t pk_count(const salt_packed_chunk_t *pc, int s, uint32_t i)
 {
@@ -663,9 +695,6 @@ int salt_multi_verify_batch_packed(salt_multi_t *m, const salt_packed_chunk_t *p
         return SALT_ERR_ARG;
     if (chunk_reads == 0) chunk_reads = 100000;
     const int G = m->n;
-    multi_job_t *J = calloc((size_t)G, sizeof *J);
-    pthread_t *th = calloc((size_t)G, sizeof *th);
-    if (!J || !th) { free(J); free(th); return SALT_ERR_NOMEM; }
     /* contiguous shares on chunk boundaries; one pass over the lengths and counts finds where each share starts */
     const uint32_t n_chunks = (pc->n_reads + chunk_reads - 1) / chunk_reads;
     uint64_t base = pc->base_start; size_t c0 = 0, c1 = 0, np = 0;
@@ -676,7 +705,7 @@ int salt_multi_verify_batch_packed(salt_multi_t *m, const salt_packed_chunk_t *p
         const uint32_t upto_chunk = (uint32_t)((uint64_t)n_chunks * (uint64_t)(g + 1) / (uint64_t)G);
         const uint32_t first = first_chunk * chunk_reads;
         uint32_t upto = upto_chunk * chunk_reads; if (upto > pc->n_reads) upto = pc->n_reads;
-        multi_job_t *j = &J[g];
+        multi_job_t *j = &m->w[g].job;
         j->h = m->h[g]; j->chunk_reads = chunk_reads; j->nogap_T0 = nogap_T0; j->lv_T0 = lv_T0; j->cigar_stride = cigar_stride;
         j->view = *pc;
         j->view.n_reads = upto - first;
@@ -693,11 +722,16 @@ int salt_multi_verify_batch_packed(salt_multi_t *m, const salt_packed_chunk_t *p
             base += pc->lens ? pc->lens[r] : pc->l_seq;
             c0 += pk_count(pc, 0, r); c1 += pk_count(pc, 1, r);
         }
+        pthread_mutex_lock(&m->w[g].mu); m->w[g].state = 1; pthread_cond_broadcast(&m->w[g].cv); pthread_mutex_unlock(&m->w[g].mu);
     }
-    for (int g = 0; g < G; ++g) pthread_create(&th[g], NULL, multi_worker, &J[g]);
     int rc = SALT_OK;
-    for (int g = 0; g < G; ++g) { pthread_join(th[g], NULL); if (rc == SALT_OK) rc = J[g].rc; }
-    free(J); free(th);
+    for (int g = 0; g < G; ++g) {
+        pthread_mutex_lock(&m->w[g].mu);
+        while (m->w[g].state != 2) pthread_cond_wait(&m->w[g].cv, &m->w[g].mu);
+        m->w[g].state = 0;
+        pthread_mutex_unlock(&m->w[g].mu);
+        if (rc == SALT_OK) rc = m->w[g].job.rc;
+    }
     return rc;
 }
 

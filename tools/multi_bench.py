@@ -48,24 +48,26 @@ def main():
         m = H.salt_multi_init(g.mixref.ctypes.data, g.l, g.pac.ctypes.data, g.l, devs, G)
         assert m
 
-        def run():
-            rc = H.salt_multi_verify_batch_packed(m, C.byref(pk), args.chunk, 3, -1, h_rec.data_ptr(), h_a0.data_ptr(), h_a1.data_ptr(),
-                                                  h_cig.data_ptr(), 128)
-            assert rc == 0
-        run(); run()
-        t0 = time.perf_counter()
-        reps = 5
-        for _ in range(reps):
-            run()
-        sec = (time.perf_counter() - t0) / reps
-        rec = h_rec.numpy().reshape(G, -1)
-        if want is None:
-            want = rec[0].tobytes()
-        same = all(rec[k].tobytes() == want for k in range(G))      # every device's share equals the single-device result
-        out["rows"].append({"devices": G, "reads": n, "ms": sec * 1e3, "reads_per_s": n / sec, "identical_to_single_device": bool(same)})
+        for chunk in (args.chunk, 4 * args.chunk):
+            def run():
+                rc = H.salt_multi_verify_batch_packed(m, C.byref(pk), chunk, 3, -1, h_rec.data_ptr(), h_a0.data_ptr(), h_a1.data_ptr(),
+                                                      h_cig.data_ptr(), 128)
+                assert rc == 0
+            run(); run()
+            t0 = time.perf_counter()
+            reps = 5
+            for _ in range(reps):
+                run()
+            sec = (time.perf_counter() - t0) / reps
+            rec = h_rec.numpy().reshape(G, -1)
+            if want is None:
+                want = rec[0].tobytes()
+            same = all(rec[k].tobytes() == want for k in range(G))      # every device's share equals the single-device result
+            out["rows"].append({"devices": G, "chunk_reads": chunk, "reads": n, "ms": sec * 1e3, "reads_per_s": n / sec,
+                                "identical_to_single_device": bool(same)})
         H.salt_multi_destroy(m)
-    r1 = out["rows"][0]["reads_per_s"]
     for r in out["rows"]:
+        r1 = next(x["reads_per_s"] for x in out["rows"] if x["devices"] == 1 and x["chunk_reads"] == r["chunk_reads"])
         r["efficiency_vs_1"] = r["reads_per_s"] / (r1 * r["devices"])
     print(json.dumps(out))
 
