@@ -441,6 +441,27 @@ def main():
         return best
     pcie_h2d, pcie_d2h = copy_peak(True), copy_peak(False)
 
+    def copy_peak_bidir():
+        """both directions at once (the pipeline uploads chunk c+1 while it downloads chunk c-1), all ranks together"""
+        nb = 256 << 20
+        a = torch.empty(nb, dtype=torch.uint8).pin_memory(); b = torch.empty(nb, dtype=torch.uint8, device=dev)
+        a2 = torch.empty(nb, dtype=torch.uint8).pin_memory(); b2 = torch.empty(nb, dtype=torch.uint8, device=dev)
+        s2 = torch.cuda.Stream(dev)
+        best = (0.0, 0.0)
+        for _ in range(3):
+            barrier()
+            u0 = torch.cuda.Event(enable_timing=True); u1 = torch.cuda.Event(enable_timing=True)
+            d0 = torch.cuda.Event(enable_timing=True); d1 = torch.cuda.Event(enable_timing=True)
+            u0.record(stream); b.copy_(a, non_blocking=True); u1.record(stream)
+            with torch.cuda.stream(s2):
+                d0.record(s2); a2.copy_(b2, non_blocking=True); d1.record(s2)
+            torch.cuda.synchronize(dev)
+            up = nb / (u0.elapsed_time(u1) * 1e-3) / 1e9; down = nb / (d0.elapsed_time(d1) * 1e-3) / 1e9
+            if up + down > sum(best):
+                best = (up, down)
+        return best
+    pcie_bi_h2d, pcie_bi_d2h = copy_peak_bidir()
+
     # ---------------- e2e: host buffers through the C ABI, the reference's chunk loop (alnse.c:1414-1440) through the
     # asynchronous slots.  Headline: the compact transport (2-bit bases + per-read counts, salt_packed_chunk_t);
     # beside it the plain format (one byte per base + three offset arrays) the reference's own structures map to.
@@ -493,6 +514,7 @@ def main():
                    "transport": "salt_b200_verify_batch_packed: 2-bit bases, uint16 candidate counts, uint32 loci; pinned host buffers",
                    "h2d_bytes_per_read": h2d / n,
                    "pcie_gbs": {"h2d": h2d / e2e_s / 1e9, "d2h": d2h / e2e_s / 1e9, "h2d_copy_peak": pcie_h2d, "d2h_copy_peak": pcie_d2h,
+                                "h2d_copy_peak_bidirectional": pcie_bi_h2d, "d2h_copy_peak_bidirectional": pcie_bi_d2h,
                                 "copy_peak_how": "256 MiB pinned, best of 3, all %d ranks copying concurrently" % world},
                    "floor_ms": h2d / (pcie_h2d * 1e9) * 1e3,
                    "plain_format": {"value": world * n / plain_s, "ms_per_step": plain_s * 1e3, "h2d_bytes_per_step": int(h2d_plain),

@@ -69,6 +69,7 @@ struct Slot {
     DBuf tl_md, tl_out, tl_len, tl_offs, tl_packed, tl_cigrow, tl_xv, tl_scan;   // SAM tail of the chunk's primaries
     bool tail_pending = false; size_t tail_eager = 0, tail_cap = 0; uint32_t *tail_offs = nullptr; char *tail_md = nullptr;
     bool have_rec = false; int rec_cig_stride = 0;                // the slot's rec / cig buffers hold a finished verify
+    DBuf cigslim;                                               // 32-byte copies of the CIGAR rows that go back eagerly
     DBuf sd_status;                                             // per strand: flags of the paired-end flavour of locate
     DBuf sd_long;                                               // (read, strand) ids whose lists need the long sort, [0] = count
     DBuf sd_sai, sd_counts, sd_lists;                          // seeding scratch: intervals, per-strand counts, fixed-stride lists
@@ -89,7 +90,7 @@ struct Slot {
     {
         DBuf *all[] = {&codes, &offs3, &rd4, &rd_len, &c_loci0, &c_loci1, &vpairs, &acc, &rec,
                        &lvlist, &ciglist, &counters, &cig, &fpairs, &fslots, &lvreads, &fpairs2, &fslots2,
-                       &pk_bases, &pk_lens, &pk_cnt, &pk_npos, &pk_scan, &sd_sai, &sd_counts, &sd_lists, &sd_long, &sd_status,
+                       &pk_bases, &pk_lens, &pk_cnt, &pk_npos, &pk_scan, &sd_sai, &sd_counts, &sd_lists, &sd_long, &sd_status, &cigslim,
                        &tl_md, &tl_out, &tl_len, &tl_offs, &tl_packed, &tl_cigrow, &tl_xv, &tl_scan};
         for (DBuf *b : all) b->release();
         if (h_stage) cudaFreeHost(h_stage);
@@ -300,7 +301,8 @@ int run_and_download(salt_b200_t *h, int si, size_t n0, size_t n1, int nogap_T0,
         CU(s.cig.need((size_t)nr * cigar_stride));
         CU(s.ciglist.need(((size_t)nr + 2) * 4));      // [0] count, [1..] read ids
         s.eager = nr < CIG_EAGER ? nr : CIG_EAGER;
-        const size_t want = 4 + (size_t)s.eager * 4 + (size_t)s.eager * cigar_stride;
+        const size_t want = 4 + (size_t)s.eager * 4 + (size_t)s.eager * 32;
+        CU(s.cigslim.need((size_t)s.eager * 32 + 32));
         if (want > s.h_stage_cap) {
             if (s.h_stage) { CU(cudaFreeHost(s.h_stage)); s.h_stage = nullptr; s.h_stage_cap = 0; }
             CU(cudaMallocHost(&s.h_stage, want));
@@ -321,9 +323,11 @@ int run_and_download(salt_b200_t *h, int si, size_t n0, size_t n1, int nogap_T0,
         // only gapped primaries have a CIGAR (query_gen_cigar, query.c:282-295): the device keeps a
         // compact list; its head comes back with the rest of the results, the tail (rare) on demand
         CU(cudaMemcpyAsync(s.h_stage, cl, 4 + (size_t)s.eager * 4, cudaMemcpyDeviceToHost, s.stream));
-        if (s.eager)
-            CU(cudaMemcpyAsync(s.h_stage + 4 + (size_t)s.eager * 4, s.cig.p, (size_t)s.eager * cigar_stride,
-                               cudaMemcpyDeviceToHost, s.stream));
+        if (s.eager) {
+            CU(launch_cig_slim(s.cig.as<char>(), cigar_stride, cl, s.eager, s.cigslim.as<char>(), s.stream));
+            h->launches += 1;
+            CU(cudaMemcpyAsync(s.h_stage + 4 + (size_t)s.eager * 4, s.cigslim.p, (size_t)s.eager * 32, cudaMemcpyDeviceToHost, s.stream));
+        }
     }
     s.u_cigars = cigars; s.u_stride = cigar_stride;
     s.pending = true;
@@ -545,16 +549,25 @@ int finish_verify(salt_b200_t *h, int si)
     const uint32_t head = n_cig < s.eager ? n_cig : s.eager;
     const uint32_t *ids = reinterpret_cast<const uint32_t *>(s.h_stage + 4);
     const char *strs = reinterpret_cast<const char *>(s.h_stage + 4 + (size_t)s.eager * 4);
-    auto scatter = [&](const uint32_t *id, const char *sp, uint32_t m) {
+    auto scatter = [&](const uint32_t *id, const char *sp, uint32_t m, int row) {
         // like the reference, touch only the string and its terminator in the caller's buffers
-        for (uint32_t i = 0; i < m; ++i, sp += stride) {
-            const size_t len = strnlen(sp, (size_t)stride - 1);
+        for (uint32_t i = 0; i < m; ++i, sp += row) {
+            if ((unsigned char)sp[0] == 0xFFu) continue;               // a slimmed row that did not fit: fetched below
+            const size_t lim = (size_t)(row < stride ? row : stride) - 1;
+            const size_t len = strnlen(sp, lim);
             char *dst = s.u_cigars + (size_t)id[i] * stride;
             memcpy(dst, sp, len);
             dst[len] = '\0';
         }
     };
-    scatter(ids, strs, head);
+    scatter(ids, strs, head, 32);
+    for (uint32_t i = 0; i < head; ++i)
+        if ((unsigned char)strs[(size_t)i * 32] == 0xFFu) {           // rare: a CIGAR of 32+ characters
+            std::vector<char> one((size_t)stride);
+            CU(cudaMemcpyAsync(one.data(), s.cig.as<char>() + (size_t)i * stride, (size_t)stride, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaStreamSynchronize(s.stream));
+            scatter(ids + i, one.data(), 1, stride);
+        }
     if (n_cig > head) {
         const uint32_t m = n_cig - head;
         std::vector<uint32_t> id2(m);
@@ -563,7 +576,7 @@ int finish_verify(salt_b200_t *h, int si)
         CU(cudaMemcpyAsync(id2.data(), cl + 1 + head, (size_t)m * 4, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaMemcpyAsync(tmp.data(), s.cig.as<char>() + (size_t)head * stride, tmp.size(), cudaMemcpyDeviceToHost, s.stream));
         CU(cudaStreamSynchronize(s.stream));
-        scatter(id2.data(), tmp.data(), m);
+        scatter(id2.data(), tmp.data(), m, stride);
     }
     return SALT_OK;
 }

@@ -57,6 +57,7 @@ struct Scan3 {                // exclusive prefix sums: out[k][0..n] from n coun
     uint32_t *partial;        // 3 * scan3_blocks(n) words of scratch
     uint32_t n_blocks;        // filled by the launcher
 };
+cudaError_t launch_cig_slim(const char *rows, int stride, const uint32_t *count, uint32_t eager, char *slim, cudaStream_t st);
 uint32_t scan3_blocks(size_t n);
 cudaError_t launch_scan3(Scan3 a, int n_arrays, cudaStream_t st);
 cudaError_t launch_unpack_bases(const uint8_t *in, uint32_t phase, int bits, size_t n_bases, uint8_t *codes,

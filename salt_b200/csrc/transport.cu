@@ -133,6 +133,30 @@ patch_n_kernel(const uint32_t *__restrict__ n_pos, size_t n_n, uint32_t origin, 
     if (q < n_bases) codes[q] = 4;
 }
 
+// The CIGARs of a chunk's gapped primaries sit in stride-byte rows (the caller's stride, 128 in the reference); nearly all
+// are a dozen characters.  The rows that go back to the host without waiting for their count are slimmed to 32 bytes
+// (0xFF in byte 0: does not fit, fetched on demand), a quarter of the download.
+__global__ void __launch_bounds__(256)
+cig_slim_kernel(const char *__restrict__ rows, int stride, const uint32_t *__restrict__ count, uint32_t eager, char *__restrict__ slim)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= eager || i >= *count) return;
+    const char *__restrict__ src = rows + (size_t)i * (size_t)stride;
+    char *__restrict__ dst = slim + (size_t)i * 32;
+    int len = 0;
+    while (len < stride - 1 && len < 32 && src[len] != '\0') ++len;
+    if (len >= 32) { dst[0] = (char)0xFF; return; }
+    for (int k = 0; k < len; ++k) dst[k] = src[k];
+    dst[len] = '\0';
+}
+
+cudaError_t launch_cig_slim(const char *rows, int stride, const uint32_t *count, uint32_t eager, char *slim, cudaStream_t st)
+{
+    if (!eager) return cudaSuccess;
+    SALT_LAUNCH(cig_slim_kernel, (eager + 255) / 256, 256, 0, st, rows, stride, count, eager, slim);
+    return cudaGetLastError();
+}
+
 uint32_t scan3_blocks(size_t n) { return (uint32_t)((n + SCAN_TILE - 1) / SCAN_TILE); }
 
 cudaError_t launch_scan3(Scan3 a, int n_arrays, cudaStream_t st)

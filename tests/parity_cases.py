@@ -335,6 +335,27 @@ def check_ssw_wide_bands(eng, oracle, seed, n_reads=150, L=100, glen=20003):
     return gapped
 
 
+def check_long_cigars(eng, oracle, seed, n_reads=40, L=250):
+    """gapped primaries whose CIGAR strings run to 32+ characters (several indels per read): the rows that travel back in the
+    slimmed 32-byte form must fall back to the full row, in the one-shot stage and through the chunk pipeline"""
+    rng = np.random.default_rng(seed)
+    glen = 60000
+    masks = synth.fuzz_masks(glen, seed + 1, snp=0.01, nfrac=0.0)
+    class G:            # the two fields the checks read
+        pass
+    g = G(); g.l = glen; g.mixref = synth.pack_mixref(masks); g.pac = None
+    reads, l0, l1 = [], [], []
+    for i in range(n_reads):
+        p = int(rng.integers(100, glen - 2 * L))
+        rd = synth.fuzz_read_from_masks(masks[p:], L, rng, sub=0.01, indel=0.03, nfrac=0.0)
+        reads.append(rd)
+        l0.append(np.array(sorted({p, max(0, p - 3), int(rng.integers(0, glen - 2 * L))}), np.uint32)); l1.append(np.zeros(0, np.uint32))
+    reads = np.array(reads, np.uint8)
+    offs0 = np.concatenate([[0], np.cumsum([len(x) for x in l0])]).astype(np.uint32); offs1 = np.zeros(n_reads + 1, np.uint32)
+    cands = (offs0, np.concatenate(l0), offs1, np.zeros(0, np.uint32))
+    return g, reads, cands
+
+
 def check_tail_primaries(eng, oracle, g, reads, cands, nogap_T0=3, lv_T0=-1):
     """salt_b200_tail_primaries (tags of a verified chunk's primaries, nothing uploaded, MD strings packed) against
     salt_b200_md_nm on the same alignments (which check_md_nm pins against the oracle and the golden vectors)."""

@@ -263,3 +263,14 @@ def test_tail_primaries(emul_lib, oracle):
     eng = _engine(emul_lib, g, with_pac=True)
     assert pc.check_tail_primaries(eng, oracle, g, reads, cands) >= 3
     eng.close()
+
+
+def test_long_cigars_through_the_slim_download(emul_lib, oracle):
+    g, reads, cands = pc.check_long_cigars(None, oracle, 31, n_reads=24)
+    eng = api.Engine(g.mixref, g.l, None, 0, lib=emul_lib)
+    eng.set_reads(reads)
+    st = pc.check_verify(eng, oracle, g, reads, cands, 3, -1)
+    rec, _, _, cig = eng.verify(*cands)
+    assert st["gapped"] >= 10 and max(len(api.cstr(c)) for c in cig) >= 32
+    pc.check_verify_batch(eng, reads, cands, 5)
+    eng.close()

@@ -490,3 +490,16 @@ def test_tail_primaries(oracle, L):
     eng = _engine(g)
     assert pc.check_tail_primaries(eng, oracle, g, reads, cands) >= 200
     eng.close()
+
+
+@pytest.mark.gpu
+def test_long_cigars_through_the_slim_download(oracle):
+    """CIGAR strings of 32+ characters: the slimmed eager download falls back to the full row"""
+    g, reads, cands = pc.check_long_cigars(None, oracle, 31, n_reads=400)
+    eng = api.Engine(g.mixref, g.l, None, 0, device=0)
+    eng.set_reads(reads)
+    st = pc.check_verify(eng, oracle, g, reads, cands, 3, -1)
+    rec, _, _, cig = eng.verify(*cands)
+    assert st["gapped"] >= 200 and sum(len(api.cstr(c)) >= 32 for c in cig) >= 50
+    pc.check_verify_batch(eng, reads, cands, 64)
+    eng.close()
