@@ -124,6 +124,7 @@ struct salt_b200 {
     // staging / scratch of the synchronous per-pair and SSW entry points (slot 0's stream)
     DBuf pairs, out8, kbuf, cig, wins, sswout, sswcig, sswscratch, sswovf, md_in, md_cig, md_str, md_xv, md_out;
     DBuf ix_cbwt, ix_csa, ix_lkt, ix_rbwt, ix_rocc, ix_rmaj, ix_rsa;      // FM-indexes (salt_b200_set_index)
+    DBuf ix_c32, ix_r64;                                                  // ... and the device's own dense layouts built from them
     FmIndexDev fm{}; bool have_index = false;
     uint64_t launches = 0;
     int cur = 0;                // slot whose reads the per-pair / SSW entry points work on (salt_b200_use_slot)
@@ -716,7 +717,7 @@ void salt_b200_destroy(salt_b200_t *h)
         if (h->slot[i].stream) cudaStreamSynchronize(h->slot[i].stream);
         h->slot[i].release();
     }
-    DBuf *all[] = {&h->pairs, &h->out8, &h->kbuf, &h->cig, &h->wins, &h->sswout, &h->sswcig, &h->sswscratch, &h->sswovf, &h->ix_cbwt, &h->ix_csa, &h->ix_lkt, &h->ix_rbwt, &h->ix_rocc, &h->ix_rmaj, &h->ix_rsa,
+    DBuf *all[] = {&h->pairs, &h->out8, &h->kbuf, &h->cig, &h->wins, &h->sswout, &h->sswcig, &h->sswscratch, &h->sswovf, &h->ix_cbwt, &h->ix_csa, &h->ix_lkt, &h->ix_rbwt, &h->ix_rocc, &h->ix_rmaj, &h->ix_rsa, &h->ix_c32, &h->ix_r64,
                    &h->fpairs, &h->fslots, &h->fcount, &h->fpairs2, &h->fslots2, &h->md_in, &h->md_cig, &h->md_str, &h->md_xv, &h->md_out};
     for (DBuf *b : all) b->release();
     for (int i = 0; i < 7; ++i) if (h->ev_ssw[i]) cudaEventDestroy(h->ev_ssw[i]);
@@ -1294,6 +1295,17 @@ int salt_b200_set_index(salt_b200_t *h, const salt_fm_index_t *ix)
     f.r_sa_sharp = h->ix_rsa.as<uint32_t>(); f.r_n_sa_sharp = (uint32_t)ix->r_n_sa_sharp;
     for (int i = 0; i < 6; ++i) f.r_cum[i] = ix->r_cum[i];
     f.r_inv_sa0 = ix->r_inv_sa0; f.r_text_len = ix->r_text_len;
+    // the device's own layouts of the two BWTs (seed.cu): one aligned line per occurrence count
+    CU(h->ix_c32.need(fm_c32_entries(ix->c_bwt_words) * 32 + 64));
+    CU(h->ix_r64.need(fm_r64_entries(ix->r_text_len) * 64 + 64));
+    f.c32 = h->ix_c32.as<uint4>(); f.r64 = h->ix_r64.as<uint4>();
+    CU(launch_build_dense_index(f, ix->c_bwt_words, rpad, h->ix_c32.as<uint4>(), h->ix_r64.as<uint4>(), st));
+    CU(cudaStreamSynchronize(st));
+    // the file-layout BWT words and count tables have served their purpose (the sampled suffix arrays, the lookup table
+    // and the 4-bit characters -- for Rbwt_bwt2nt -- stay)
+    h->ix_cbwt.release(); h->ix_rocc.release(); h->ix_rmaj.release();
+    f.cbwt = nullptr; f.r_occ = nullptr; f.r_occ_major = nullptr;
+    h->launches += 2;
     h->have_index = true;
     return SALT_OK;
 }

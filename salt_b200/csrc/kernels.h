@@ -69,6 +69,8 @@ struct FmIndexDev {
     const uint32_t *cbwt; uint32_t c_primary, c_seq_len; uint32_t c_L2[5];
     const uint32_t *c_sa; uint32_t c_sa_intv, c_n_sa;
     const uint32_t *lkt; int l_lkt;                       // lookup.h:21-25
+    const uint4 *c32;                                     // device layout: per 32 bases {4 counts}{2 words} (seed.cu)
+    const uint4 *r64;                                     // device layout: per 64 characters {5 counts}{8 words}
     // SNP-context index, backward direction ("R part"): rbwt.h:60-80
     const uint32_t *r_bwt, *r_occ, *r_occ_major, *r_sa_sharp;
     uint32_t r_cum[6], r_inv_sa0, r_text_len, r_n_sa_sharp;
@@ -76,6 +78,9 @@ struct FmIndexDev {
 struct SeedOpt { int l_seed, l_overlap, max_seed, max_locate, seed_only_ref, mode /* 0 alnse_locate_alt, 1 alnse_locate */, list_cap /* list stride */; };
 struct SeedSai { uint32_t sp, ep, offset; };              // sai_t, aln.h:91-95
 size_t seed_sai_bytes(uint32_t n_reads, int max_seeds);
+size_t fm_c32_entries(size_t c_bwt_words);
+size_t fm_r64_entries(uint32_t r_text_len);
+cudaError_t launch_build_dense_index(const FmIndexDev &ix, size_t c_bwt_words, size_t r_bwt_words_padded, uint4 *c32, uint4 *r64, cudaStream_t st);
 cudaError_t launch_seed(const FmIndexDev &ix, const SeedOpt &opt, const uint8_t *codes, const uint32_t *roffs, uint32_t n_reads,
                         int max_seeds, SeedSai *sai, cudaStream_t st);
 cudaError_t launch_locate(const FmIndexDev &ix, const SeedOpt &opt, const uint32_t *roffs, uint32_t n_reads, int max_seeds,

@@ -34,26 +34,50 @@ __device__ __forceinline__ uint32_t c_count16(uint32_t x, int c, int m)
     return (uint32_t)__popc(y);
 }
 
+// The device keeps its own, denser copy of the reference's BWT (built once by build_c32_kernel from the BWA-layout
+// words): per 32 bases one 32-byte entry = the four counts up to the entry's first base + its two 16-base words.  An
+// occurrence count is then ONE aligned 32-byte read and at most two masked popcounts -- no loop, so the lanes of a warp
+// stay together -- where the 128-base blocks of the file layout (bwt.h:44-57) need up to eight words.  HBM is what a
+// B200 has plenty of: 1 byte per base (3.1 GB at GRCh38 size) instead of 0.375.
+__device__ __forceinline__ uint32_t c_pick(const uint4 v, int c) { return c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w; }
+
 // bwt_occ (bwt.c:106-129): occurrences of c in B[0..k]
 __device__ __forceinline__ uint32_t c_occ(const FmIndexDev &ix, uint32_t k, int c)
 {
     if (k == ix.c_seq_len) return ix.c_L2[c + 1] - ix.c_L2[c];
     if (k == 0xFFFFFFFFu) return 0u;
     if (k >= ix.c_primary) --k;
-    const uint32_t *__restrict__ p = ix.cbwt + (size_t)(k >> 7) * 12;
-    uint32_t n = p[c];
-    const int in_block = (int)(k & 127u) + 1;           // bases of this block to count
-    p += 4;
-    for (int w = 0; w * 16 < in_block; ++w) {
-        const int m = in_block - w * 16;
-        n += c_count16(p[w], c, m < 16 ? m : 16);
-    }
+    const uint4 *__restrict__ e = ix.c32 + (size_t)(k >> 5) * 2;
+    const uint4 cnt = e[0], w = e[1];
+    const int r = (int)(k & 31u) + 1;                   // bases of this entry to count: 1..32
+    uint32_t n = c_pick(cnt, c) + c_count16(w.x, c, r < 16 ? r : 16);
+    if (r > 16) n += c_count16(w.y, c, r - 16);
     return n;
 }
 
 __device__ __forceinline__ int c_B0(const FmIndexDev &ix, uint32_t k)
 {
-    return (int)(ix.cbwt[(size_t)(k >> 7) * 12 + 4 + ((k & 127u) >> 4)] >> ((~k & 0xfu) << 1) & 3u);
+    const uint4 w = ix.c32[(size_t)(k >> 5) * 2 + 1];
+    return (int)(((k & 16u) ? w.y : w.x) >> ((~k & 0xfu) << 1) & 3u);
+}
+
+// one entry of the dense table from the file layout: counts of block k/128 plus the words of the block before the entry
+__global__ void __launch_bounds__(256)
+build_c32_kernel(const uint32_t *__restrict__ cbwt, size_t n_words, size_t n_entries, uint4 *__restrict__ c32)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_entries) return;
+    const size_t blk = e >> 2; const int sub = (int)(e & 3);
+    const uint32_t *__restrict__ p = cbwt + blk * 12;
+    auto word = [&](size_t i) { return blk * 12 + i < n_words ? p[i] : 0u; };
+    uint32_t cnt[4];
+    for (int c = 0; c < 4; ++c) {
+        uint32_t n = word((size_t)c);
+        for (int w = 0; w < 2 * sub; ++w) n += c_count16(word(4 + (size_t)w), c, 16);
+        cnt[c] = n;
+    }
+    c32[e * 2] = make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);
+    c32[e * 2 + 1] = make_uint4(word(4 + 2 * (size_t)sub), word(5 + 2 * (size_t)sub), 0u, 0u);
 }
 
 // bwt_invPsi (bwt.h:67-72)
@@ -96,10 +120,14 @@ __device__ __forceinline__ bool c_step(const FmIndexDev &ix, int c, uint32_t &k,
     uint32_t ok, ol;
     const bool plain = km == 0xFFFFFFFFu || km == ix.c_seq_len || l == ix.c_seq_len || l == 0xFFFFFFFFu;
     const uint32_t kk = km >= ix.c_primary ? km - 1 : km, ll = l >= ix.c_primary ? l - 1 : l;
-    if (!plain && (kk >> 7) == (ll >> 7) && kk <= ll) {
-        ok = c_occ(ix, km, c);
+    if (!plain && (kk >> 5) == (ll >> 5) && kk <= ll) {
+        const uint4 *__restrict__ e = ix.c32 + (size_t)(kk >> 5) * 2;
+        const uint4 cnt = e[0], w = e[1];
+        const uint32_t ww[2] = {w.x, w.y};
+        const int rk = (int)(kk & 31u) + 1;
+        ok = c_pick(cnt, c) + c_count16(w.x, c, rk < 16 ? rk : 16) + (rk > 16 ? c_count16(w.y, c, rk - 16) : 0u);
         ol = ok;
-        if (ll > kk) ol += c_count_range(ix.cbwt + (size_t)(kk >> 7) * 12 + 4, (int)(kk & 127u) + 1, (int)(ll & 127u), c);
+        if (ll > kk) ol += c_count_range(ww, (int)(kk & 31u) + 1, (int)(ll & 31u), c);
     } else { ok = c_occ(ix, km, c); ol = c_occ(ix, l, c); }
     k = ix.c_L2[c] + ok + 1;
     l = ix.c_L2[c] + ol;
@@ -132,16 +160,70 @@ __device__ __forceinline__ uint32_t r_count(const uint32_t *__restrict__ code, u
     return n + (uint32_t)__popc(last);
 }
 
-// Rbwt_BWTOccValue (rbwt.c:159-189) with BWTOccValueExplicit (:38-79): bidirectional explicit counts every 256
-// characters (16 bit, two per word) on top of major counts every 65536
-__device__ __forceinline__ uint32_t r_occ(const FmIndexDev &ix, uint32_t index, uint32_t c)
+// occurrences of c among BWT characters [0, index) from the reference's own tables: Rbwt_BWTOccValue (rbwt.c:159-189)
+// with BWTOccValueExplicit (:38-79) -- bidirectional explicit counts every 256 characters (16 bit, two per word) on top
+// of major counts every 65536 -- without the inverseSa0 adjustment.  Used once, to build the dense table below.
+__device__ __forceinline__ uint32_t r_occ_file(const FmIndexDev &ix, uint32_t index, uint32_t c)
 {
-    if (index > ix.r_inv_sa0) --index;
     const uint32_t e = (index + 127u) >> 8, at = e << 8;
     const uint32_t minor = ix.r_occ[(size_t)(e >> 1) * 5 + c];
     uint32_t v = ix.r_occ_major[(size_t)(at >> 16) * 5 + c] + ((e & 1u) ? (minor & 0xFFFFu) : (minor >> 16));
     if (at < index) v += r_count(ix.r_bwt, at, index, c);
     else if (at > index) v -= r_count(ix.r_bwt, index, at, c);
+    return v;
+}
+
+// The device's own layout of the SNP-context index: per 64 characters one 64-byte line = the five counts up to the
+// line's first character (A, C, G, T, #) + its eight 4-bit words.  One aligned line per occurrence count, at most eight
+// words to look at, no second and third table.
+__global__ void __launch_bounds__(256)
+build_r64_kernel(FmIndexDev ix, size_t n_entries, size_t n_words, uint4 *__restrict__ r64)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_entries) return;
+    const uint32_t at = (uint32_t)(e << 6);
+    uint32_t cnt[5];
+    for (uint32_t c = 0; c < 5; ++c) cnt[c] = r_occ_file(ix, at, c);
+    uint32_t w[8];
+    for (int i = 0; i < 8; ++i) { const size_t wi = e * 8 + (size_t)i; w[i] = wi < n_words ? ix.r_bwt[wi] : 0u; }
+    r64[e * 4] = make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);
+    r64[e * 4 + 1] = make_uint4(cnt[4], 0u, 0u, 0u);
+    r64[e * 4 + 2] = make_uint4(w[0], w[1], w[2], w[3]);
+    r64[e * 4 + 3] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// Rbwt_BWTOccValue (rbwt.c:159-189): occurrences of c among the BWT characters before `index` ($ is not encoded)
+__device__ __forceinline__ uint32_t r_occ(const FmIndexDev &ix, uint32_t index, uint32_t c)
+{
+    if (index > ix.r_inv_sa0) --index;
+    const uint4 *__restrict__ e = ix.r64 + (size_t)(index >> 6) * 4;
+    const uint4 c03 = e[0];
+    uint32_t v = c == 4u ? e[1].x : c_pick(c03, (int)c);
+    const uint32_t r = index & 63u;                       // characters of this line to count: 0..63
+    if (r) {
+        const uint32_t pat = c * 0x11111111u;
+        const uint4 a = e[2];
+        const uint32_t wa[4] = {a.x, a.y, a.z, a.w};
+        const uint32_t full = r >> 3, part = r & 7u;      // whole words, characters of the next one
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i) {
+            uint32_t m = r_match8(wa[i], pat);
+            if (i > full || (i == full && part == 0)) m = 0;
+            else if (i == full) m &= ~((1u << (4 * (8 - part))) - 1u);
+            v += (uint32_t)__popc(m);
+        }
+        if (r > 32) {
+            const uint4 b = e[3];
+            const uint32_t wb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (uint32_t i = 0; i < 4; ++i) {
+                uint32_t m = r_match8(wb[i], pat);
+                if (i + 4 > full || (i + 4 == full && part == 0)) m = 0;
+                else if (i + 4 == full) m &= ~((1u << (4 * (8 - part))) - 1u);
+                v += (uint32_t)__popc(m);
+            }
+        }
+    }
     return v;
 }
 
@@ -579,6 +661,17 @@ seed_gather_kernel(const uint32_t *__restrict__ lists, int max_locate, const uin
 }
 
 // ---------------------------------------------------------------- launchers
+size_t fm_c32_entries(size_t c_bwt_words) { return (c_bwt_words + 11) / 12 * 4; }
+size_t fm_r64_entries(uint32_t r_text_len) { return ((size_t)r_text_len >> 6) + 2; }
+
+cudaError_t launch_build_dense_index(const FmIndexDev &ix, size_t c_bwt_words, size_t r_bwt_words_padded, uint4 *c32, uint4 *r64, cudaStream_t st)
+{
+    const size_t nc = fm_c32_entries(c_bwt_words), nr = fm_r64_entries(ix.r_text_len);
+    SALT_LAUNCH(build_c32_kernel, (unsigned)((nc + 255) / 256), 256, 0, st, ix.cbwt, c_bwt_words, nc, c32);
+    SALT_LAUNCH(build_r64_kernel, (unsigned)((nr + 255) / 256), 256, 0, st, ix, nr, r_bwt_words_padded, r64);
+    return cudaGetLastError();
+}
+
 size_t seed_sai_bytes(uint32_t n_reads, int max_seeds) { return (size_t)n_reads * 2 * 2 * (size_t)max_seeds * sizeof(SeedSai); }
 
 cudaError_t launch_seed(const FmIndexDev &ix, const SeedOpt &opt, const uint8_t *codes, const uint32_t *roffs, uint32_t n_reads,

@@ -85,9 +85,14 @@ static inline void syncthreads()
     else c.bcv.wait(lk, [&] { return c.bgen != gen; });
 }
 
+// kernels of different host threads (several handles in one process) run one after the other: __shared__ variables are
+// plain statics here
+static std::mutex g_launch_mu;
+
 template <class F>
 static inline void launch(dim3 grid, dim3 block, size_t smem, F body)
 {
+    std::lock_guard<std::mutex> one_at_a_time(g_launch_mu);
     std::vector<unsigned char> dyn(smem + 64);
     for (unsigned by = 0; by < grid.y; ++by)
     for (unsigned b = 0; b < grid.x; ++b) {

@@ -274,3 +274,30 @@ def test_long_cigars_through_the_slim_download(emul_lib, oracle):
     assert st["gapped"] >= 10 and max(len(api.cstr(c)) for c in cig) >= 32
     pc.check_verify_batch(eng, reads, cands, 5)
     eng.close()
+
+
+def test_multi_handles_in_one_process(emul_lib, oracle):
+    """salt_multi_*: shares on persistent worker threads, results in input order (two emulated handles)"""
+    import ctypes as C
+    import build_emul
+    from salt_b200 import host_api
+    hostlib = host_api.load(build_emul.build_host())
+    g, reads, pos, strand, cands = pc.make_world(556, glen=30000, L=100, n_reads=50, per_strand=3, indel_frac=0.3, n_frac=0.01)
+    offs0, loci0, offs1, loci1 = cands
+    n, L = reads.shape
+    roffs = (np.arange(n + 1) * L).astype(np.uint32)
+    eng = _engine(emul_lib, g)
+    pk, keep = eng.packed_chunk(reads, roffs, offs0, loci0, offs1, loci1, bits=2)
+    want = eng.verify_batch_packed(pk, len(loci0), len(loci1), chunk_reads=7)
+    devs = (C.c_int * 3)(0, 0, 0)
+    m = hostlib.salt_multi_init(g.mixref.ctypes.data, g.l, None, 0, devs, 3)
+    assert m and hostlib.salt_multi_n(m) == 3
+    for rep in range(2):                                   # the workers are reused across calls
+        rec = np.zeros(n, api.VERIFY_DT); acc0 = np.empty(len(loci0), np.int8); acc1 = np.empty(len(loci1), np.int8)
+        cig = np.zeros((n, 128), np.uint8)
+        assert hostlib.salt_multi_verify_batch_packed(m, C.byref(pk), 7, 3, -1, rec.ctypes.data, acc0.ctypes.data, acc1.ctypes.data,
+                                                      cig.ctypes.data, 128) == 0
+        for a, b, name in zip((rec, acc0, acc1, cig), want, ("rec", "acc0", "acc1", "cigars")):
+            assert a.tobytes() == b.tobytes(), (name, rep)
+    hostlib.salt_multi_destroy(m)
+    eng.close()
