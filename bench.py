@@ -562,6 +562,7 @@ def main():
             out["pe"] = bench_pe(eng, wl, args)
         if args.seed_reads > 0:
             out["seeding"] = bench_seeding(args)
+        out["se_host_layer"] = bench_se_host_layer(eng, wl, args)
 
     if rank == 0 and world == 1:
         try:
@@ -663,6 +664,63 @@ def bench_pe(eng, wl, args):
     except Exception as ex:                                # noqa: BLE001
         res["cpu"] = {"error": repr(ex)}
     return res
+
+
+def bench_se_host_layer(eng, wl, args):
+    """The single-end chunk loop as a caller of the HOST LAYER runs it (include/salt_host.h; alnse_core re-staged,
+    INTEGRATION.md section 2): per chunk salt_chunk_add_reads (pageable arrays -> the chunk's pinned queues: one byte per base,
+    CSR lists), salt_chunk_submit, salt_chunk_wait, salt_chunk_results = query_set_hits + gen_mapq + query_gen_cigar of every
+    read on the host threads.  Four chunk queues, one per pipeline slot.  Everything from the caller's arrays to the per-read
+    query_t fields is inside the timed region."""
+    from salt_b200 import host_api
+    H = host_api.load()
+    H.salt_host_set_threads(os.cpu_count() or 1)
+    n, L = args.reads, args.read_len
+    chunk = args.chunk
+    n_slots = 4
+    roffs = (np.arange(n + 1, dtype=np.uint64) * L).astype(np.uint32)
+    o0, l0, o1, l1 = wl["offs0"], wl["loci0"], wl["offs1"], wl["loci1"]
+    cap = 0
+    for b in range(0, n, chunk):
+        e = min(n, b + chunk)
+        cap = max(cap, int(o0[e]) - int(o0[b]), int(o1[e]) - int(o1[b]))
+    chunks = [host_api.Chunk(H, chunk + 8, (chunk + 8) * L, cap + 64) for _ in range(n_slots)]
+    outs = [(host_api.ReadResultT * chunk)() for _ in range(n_slots)]
+    codes = wl["reads"].reshape(-1)
+    mapped = [0]
+
+    def finish(k):
+        ch = chunks[k % n_slots]
+        ch.wait(eng, k % n_slots)
+        rc = H.salt_chunk_results(ch.c, 5, outs[k % n_slots])
+        assert rc == 0
+
+    def run():
+        k = 0
+        for b in range(0, n, chunk):
+            e = min(n, b + chunk)
+            if k >= n_slots:
+                finish(k - n_slots)
+            ch = chunks[k % n_slots]
+            ch.reset()
+            ch.add_reads(codes, roffs[b:e + 1], o0[b:e + 1], l0, o1[b:e + 1], l1)
+            ch.submit(eng, k % n_slots, 3, -1)
+            k += 1
+        for j in range(max(0, k - n_slots), k):
+            finish(j)
+    run()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        run()
+    sec = (time.perf_counter() - t0) / reps
+    last = outs[(((n + chunk - 1) // chunk) - 1) % n_slots]
+    for ch in chunks:
+        ch.close()
+    return {"reads_per_s": n / sec, "ms": sec * 1e3, "chunk_reads": chunk, "host_threads": os.cpu_count() or 1,
+            "last_read_pos": int(last[0].pos),
+            "how": "pageable caller arrays -> salt_chunk_add_reads -> salt_chunk_submit / _wait -> salt_chunk_results (per-read query_t "
+                   "fields on the host threads); plain transport (one byte per base), four chunk queues"}
 
 
 def bench_seeding(args):

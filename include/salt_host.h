@@ -71,6 +71,10 @@ int salt_chunk_seed_verify(salt_b200_t *h, salt_chunk_t *c, const salt_seed_opt_
  * query.c:317-318).  1 <= max_hits <= SALT_MAX_HITS. */
 int salt_chunk_result(const salt_chunk_t *c, uint32_t i, int max_hits, salt_read_result_t *out);
 
+/* salt_chunk_result for every read of the chunk, on the host threads of salt_host_set_threads (the reference does this
+ * per read on its -t workers, alnse.c:1306): out[i] = the query_t fields of read i. */
+int salt_chunk_results(const salt_chunk_t *c, int max_hits, salt_read_result_t *out);
+
 /* The SAM tail of the chunk's primaries (sam_add_md_nm, sam.c:246-328; option -d): MD string, NM and
  * XV of every mapped read from ONE salt_b200_md_nm call on the reads still resident in `slot`.
  * Call after salt_chunk_wait and before the slot is submitted again.  Needs the 2-bit pac. */

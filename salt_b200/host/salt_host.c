@@ -489,6 +489,24 @@ static void pe_apply_range(void *a, uint32_t first, uint32_t upto)
     pthread_mutex_unlock(&X->mu);
 }
 
+typedef struct { const salt_chunk_t *c; int max_hits; salt_read_result_t *out; int rc; } results_ctx_t;
+static void results_range(void *a, uint32_t first, uint32_t upto)
+{
+    results_ctx_t *X = (results_ctx_t *)a;
+    for (uint32_t i = first; i < upto; ++i) {
+        const int rc = salt_chunk_result(X->c, i, X->max_hits, &X->out[i]);
+        if (rc != SALT_OK) { X->rc = rc; return; }
+    }
+}
+
+int salt_chunk_results(const salt_chunk_t *c, int max_hits, salt_read_result_t *out)
+{
+    if (!c || !c->done || !out) return SALT_ERR_ARG;
+    results_ctx_t X = {c, max_hits, out, SALT_OK};
+    pfor(c->n_reads, results_range, &X);
+    return X.rc;
+}
+
 int salt_chunk_pair(salt_b200_t *h, int slot, salt_chunk_t *c, uint32_t min_tlen, uint32_t max_tlen, uint32_t l_pac,
                     int max_hits, const int8_t *mat16, const int8_t *mat5, int gapO, int gapE, int filters, int filterd,
                     int with_tail, salt_pair_final_t *out, salt_mdnm_out_t *tail_out, char *tail_md, int md_stride,
