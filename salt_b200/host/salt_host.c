@@ -151,7 +151,8 @@ int salt_chunk_result(const salt_chunk_t *c, uint32_t i, int max_hits, salt_read
     /* max_hits < 1 would never meet the reference's `tot_hits == max_hits` stop test (query.c:327) and run past alt[] */
     if (!c->done || i >= c->n_reads || !out || max_hits < 1 || max_hits > SALT_MAX_HITS) return SALT_ERR_ARG;
     const salt_verify_out_t *q = &c->rec[i];
-    memset(out, 0, sizeof *out);
+    /* no memset of the 700-byte record: alt[] beyond n_alt[] and cigar[] beyond its terminator are not part of the result */
+    out->n_alt[0] = out->n_alt[1] = 0; out->cigar[0] = '\0';
     out->pos = q->pos; out->strand = q->strand; out->n_diff = q->n_diff; out->is_gap = q->is_gap;
     /* query_set_hits (query.c:297-333).  The reference compares a->n_diff -- element 0 of the strand's
      * hit vector -- for every j (:317-318); kept.  tot_hits == max_hits is tested after every visited hit. */
@@ -372,6 +373,43 @@ int salt_pair_apply(const salt_pair_plan_t *plan, const salt_read_result_t *r0, 
     return 0;
 }
 
+/* host threads for the per-pair loops (hit selection, plans, apply): the reference runs them on its -t workers */
+static int g_host_threads = 1;
+void salt_host_set_threads(int n) { g_host_threads = n < 1 ? 1 : (n > 256 ? 256 : n); }
+
+typedef struct {
+    void (*fn)(void *ctx, uint32_t first, uint32_t upto);
+    void *ctx; uint32_t first, upto;
+} pfor_job_t;
+static void *pfor_tramp(void *a) { pfor_job_t *j = (pfor_job_t *)a; j->fn(j->ctx, j->first, j->upto); return NULL; }
+static void pfor_g(uint32_t n, uint32_t grain, void (*fn)(void *, uint32_t, uint32_t), void *ctx)
+{
+    int T = g_host_threads;
+    if ((uint32_t)T > n / grain + 1) T = (int)(n / grain + 1);
+    if (T <= 1) { fn(ctx, 0, n); return; }
+    pfor_job_t job[256]; pthread_t th[256];
+    for (int t = 0; t < T; ++t) {
+        job[t].fn = fn; job[t].ctx = ctx;
+        job[t].first = (uint32_t)((uint64_t)n * (uint64_t)t / (uint64_t)T); job[t].upto = (uint32_t)((uint64_t)n * (uint64_t)(t + 1) / (uint64_t)T);
+        pthread_create(&th[t], NULL, pfor_tramp, &job[t]);
+    }
+    for (int t = 0; t < T; ++t) pthread_join(th[t], NULL);
+}
+static void pfor(uint32_t n, void (*fn)(void *, uint32_t, uint32_t), void *ctx) { pfor_g(n, 256, fn, ctx); }
+
+
+#define COPY_PIECES 64
+typedef struct { uint8_t *dst[3]; const uint8_t *src[3]; size_t bytes[3]; } copy3_t;
+static void copy3_range(void *a, uint32_t first, uint32_t upto)
+{
+    copy3_t *X = (copy3_t *)a;
+    for (uint32_t i = first; i < upto; ++i) {
+        const int k = (int)(i / COPY_PIECES); const size_t piece = i % COPY_PIECES;
+        const size_t lo = X->bytes[k] * piece / COPY_PIECES, hi = X->bytes[k] * (piece + 1) / COPY_PIECES;
+        if (hi > lo) memcpy(X->dst[k] + lo, X->src[k] + lo, hi - lo);
+    }
+}
+
 /* ------------------------------------------------------------------ bulk queueing */
 int salt_chunk_add_reads(salt_chunk_t *c, const uint8_t *codes, const uint32_t *roffs, uint32_t n,
                          const uint32_t *offs0, const uint32_t *loci0, const uint32_t *offs1, const uint32_t *loci1)
@@ -382,9 +420,12 @@ int salt_chunk_add_reads(salt_chunk_t *c, const uint8_t *codes, const uint32_t *
     if ((size_t)at + n > c->max_reads || (size_t)c->roffs[at] + nb > c->max_bases ||
         (size_t)c->offs[0][at] + n0 > c->max_cands || (size_t)c->offs[1][at] + n1 > c->max_cands) return SALT_ERR_NOMEM;
     if ((n0 && !loci0) || (n1 && !loci1)) return SALT_ERR_ARG;
-    memcpy(c->codes + c->roffs[at], codes + roffs[0], nb);
-    if (n0) memcpy(c->loci[0] + c->offs[0][at], loci0 + offs0[0], n0 * 4);
-    if (n1) memcpy(c->loci[1] + c->offs[1][at], loci1 + offs1[0], n1 * 4);
+    /* three large copies into pinned memory: shared out over the host threads (one thread moves ~5 GB/s) */
+    copy3_t cp = {{c->codes + c->roffs[at], (uint8_t *)(c->loci[0] + c->offs[0][at]), (uint8_t *)(c->loci[1] + c->offs[1][at])},
+                  {codes + roffs[0], (const uint8_t *)(loci0 ? loci0 + offs0[0] : NULL), (const uint8_t *)(loci1 ? loci1 + offs1[0] : NULL)},
+                  {nb, n0 * 4, n1 * 4}};
+    if (nb + n0 * 4 + n1 * 4 < ((size_t)1 << 20)) copy3_range(&cp, 0, 3 * COPY_PIECES);       /* small: not worth the threads */
+    else pfor_g(3 * COPY_PIECES, 4, copy3_range, &cp);
     const uint32_t rb = c->roffs[at] - roffs[0], b0 = c->offs[0][at] - offs0[0], b1 = c->offs[1][at] - offs1[0];
     for (uint32_t i = 1; i <= n; ++i) {
         c->roffs[at + i] = roffs[i] + rb; c->offs[0][at + i] = offs0[i] + b0; c->offs[1][at + i] = offs1[i] + b1;
@@ -403,29 +444,6 @@ static double ms_now(void)
 
 #define PE_CIG_STRIDE 64
 #define PE_TAIL_CIG 64               /* bytes per mate for the M/I/D string sent to salt_b200_md_nm (longer ones: 256) */
-
-/* host threads for the per-pair loops (hit selection, plans, apply): the reference runs them on its -t workers */
-static int g_host_threads = 1;
-void salt_host_set_threads(int n) { g_host_threads = n < 1 ? 1 : (n > 256 ? 256 : n); }
-
-typedef struct {
-    void (*fn)(void *ctx, uint32_t first, uint32_t upto);
-    void *ctx; uint32_t first, upto;
-} pfor_job_t;
-static void *pfor_tramp(void *a) { pfor_job_t *j = (pfor_job_t *)a; j->fn(j->ctx, j->first, j->upto); return NULL; }
-static void pfor(uint32_t n, void (*fn)(void *, uint32_t, uint32_t), void *ctx)
-{
-    int T = g_host_threads;
-    if ((uint32_t)T > n / 256 + 1) T = (int)(n / 256 + 1);
-    if (T <= 1) { fn(ctx, 0, n); return; }
-    pfor_job_t job[256]; pthread_t th[256];
-    for (int t = 0; t < T; ++t) {
-        job[t].fn = fn; job[t].ctx = ctx;
-        job[t].first = (uint32_t)((uint64_t)n * (uint64_t)t / (uint64_t)T); job[t].upto = (uint32_t)((uint64_t)n * (uint64_t)(t + 1) / (uint64_t)T);
-        pthread_create(&th[t], NULL, pfor_tramp, &job[t]);
-    }
-    for (int t = 0; t < T; ++t) pthread_join(th[t], NULL);
-}
 
 typedef struct {
     salt_chunk_t *c; int max_hits; uint32_t min_tlen, max_tlen, l_pac; int filters, filterd;
