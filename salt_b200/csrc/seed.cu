@@ -430,28 +430,28 @@ __device__ void sai_introsort(int n, SeedSai *a)
     }
 }
 
-// ---------------------------------------------------------------- alnse_locate_alt, sixteen (read, strand)s per CTA
+// ---------------------------------------------------------------- alnse_locate[_alt], up to 64 (read, strand)s per CTA
 // A strand's lists are short on most genomes (a handful of intervals of a few rows each) while a suffix-array walk is
 // long (up to sa_intv - 1 LF steps on the primary index, up to a whole local pattern on the SNP-context index), so rows
-// are the unit of parallel work, not strands: eight lanes own a strand for the bookkeeping (interval order, the
-// max_locate cut, the final sort), but the walks of ALL sixteen strands of a CTA are laid end to end and shared out
-// over its 128 threads, one index at a time, so that every lane walks and all lanes run the same code.
-// Loci go straight to the strand's row of the fixed-stride list array; lists of up to LOC_SMALL entries are then
-// sorted by the group in shared memory, longer ones are queued for sort_long_kernel.
-// Shared memory: per group max_seeds sai (12 B), max_seeds + 1 row offsets (64 bit), LOC_SMALL loci; per CTA the staging
-// of one round of walks.
-constexpr int LOC_G = 8;
-constexpr int LOC_GROUPS = 16;                 // per CTA of 128 threads
-constexpr int LOC_SMALL = 64;
-constexpr int LOC_STAGE = 1024;                // walks per round and CTA
+// are the unit of parallel work, not strands.  One thread keeps a strand's books (interval order, the max_locate cut,
+// the final sort of a short list); the walks of ALL strands of the CTA are laid end to end and shared out over its 128
+// threads, one index at a time, several walks per thread, so that every lane walks, all lanes run the same code and
+// long and short walks average out.
+// Loci go straight to the strand's row of the fixed-stride list array; lists of up to LOC_SMALL entries are sorted by
+// their thread in shared memory, longer ones are queued for sort_long_kernel.
+// Shared memory: per strand max_seeds sai (12 B) and max_seeds + 1 row offsets (64 bit); per CTA the staging of one
+// round of walks.
+constexpr int LOC_STRANDS = 64;                // at most, per CTA of 128 threads (fewer when there are many seed starts)
+constexpr int LOC_SMALL = 16;
+constexpr int LOC_STAGE = LOC_STRANDS * LOC_SMALL;   // walks per round and CTA; also the short lists' sorting room
 
-__host__ __device__ __forceinline__ size_t locate_group_words(int max_seeds)
+__host__ __device__ __forceinline__ size_t locate_strand_words(int max_seeds)
 {
-    return (((size_t)max_seeds * 3 + 1) & ~(size_t)1) + 2 * ((size_t)max_seeds + 2) + LOC_SMALL;
+    return (((size_t)max_seeds * 3 + 1) & ~(size_t)1) + 2 * ((size_t)max_seeds + 2);
 }
 
 __global__ void __launch_bounds__(128)
-locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, uint32_t n_reads, int max_seeds,
+locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, uint32_t n_reads, int max_seeds, int strands,
               uint32_t ref_l, SeedSai *__restrict__ sai, uint32_t *__restrict__ counts /* [2][n_reads] */,
               uint32_t *__restrict__ lists /* [rs][list_cap] */, uint32_t *__restrict__ long_list, uint32_t *__restrict__ long_count,
               uint8_t *__restrict__ status /* [2][n_reads] */)
@@ -459,22 +459,19 @@ locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, ui
     SALT_DYN_SMEM(uint32_t, s_mem);
     __shared__ uint32_t s_pos[LOC_STAGE];
     __shared__ uint8_t s_keep[LOC_STAGE];
-    __shared__ uint32_t s_want[LOC_GROUPS + 1];                       // exclusive prefix of the groups' shares of a round
-    __shared__ unsigned long long s_done[LOC_GROUPS];                 // rows of the current part already walked
-    __shared__ uint32_t s_n[LOC_GROUPS];                              // aux->loci.n
-    __shared__ int s_m[LOC_GROUPS];                                   // valid intervals of the current part
-    const int grp = threadIdx.x / LOC_G, lane = threadIdx.x % LOC_G;
-    const int gshift = (threadIdx.x & 31) / LOC_G * LOC_G;
-    const unsigned gmask = 0xFFu << gshift;
-    const size_t per_group = locate_group_words(max_seeds);
-    uint32_t *base = s_mem + grp * per_group;
-    SeedSai *s_sai = reinterpret_cast<SeedSai *>(base);
-    // row offsets are 64 bit: an interval that could not be narrowed may span the whole suffix array
-    unsigned long long *s_row = reinterpret_cast<unsigned long long *>(base + (((size_t)max_seeds * 3 + 1) & ~(size_t)1));
-    uint32_t *s_small = base + (((size_t)max_seeds * 3 + 1) & ~(size_t)1) + 2 * ((size_t)max_seeds + 2);
-    const size_t rs0 = (size_t)blockIdx.x * LOC_GROUPS;
-    const size_t rs = rs0 + grp;
-    const bool live = rs < (size_t)n_reads * 2;                       // dead groups run along with nothing to do
+    __shared__ uint32_t s_want[LOC_STRANDS + 1];                      // exclusive prefix of the strands' shares of a round
+    __shared__ unsigned long long s_done[LOC_STRANDS];                // rows of the current part already walked
+    __shared__ uint32_t s_n[LOC_STRANDS];                             // aux->loci.n
+    __shared__ int s_m[LOC_STRANDS];                                  // valid intervals of the current part
+    const int t = threadIdx.x;
+    const size_t per_strand = locate_strand_words(max_seeds);
+    const size_t row_off = ((size_t)max_seeds * 3 + 1) & ~(size_t)1;  // row offsets are 64 bit: an interval that could not be
+                                                                      // narrowed may span the whole suffix array
+    const size_t rs0 = (size_t)blockIdx.x * (size_t)strands;
+    const size_t rs = rs0 + (size_t)t;
+    const bool mine = t < strands && rs < (size_t)n_reads * 2;        // this thread keeps the books of strand rs
+    SeedSai *my_sai = reinterpret_cast<SeedSai *>(s_mem + (size_t)(t < strands ? t : 0) * per_strand);
+    unsigned long long *my_row = reinterpret_cast<unsigned long long *>(s_mem + (size_t)(t < strands ? t : 0) * per_strand + row_off);
     // mode 0 = alnse_locate_alt (single-end): at most max_locate loci in all.  mode 1 = alnse_locate (paired-end,
     // alnse.c:501-631): at most max_locate + 1 rows of each primary-index interval (:521), MAX_LOC_POS loci in all (:533),
     // SNP-context intervals wider than max_locate are subsampled with rand() by the reference (:577-596) -- such an
@@ -483,20 +480,20 @@ locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, ui
     const uint32_t stride = (uint32_t)opt.list_cap;
     const uint32_t max_locate = pe ? (stride < 0x40000u ? stride : 0x40000u) : (uint32_t)opt.max_locate;
     uint32_t flags = 0;
-    if (lane == 0) s_n[grp] = 0;
+    if (t < LOC_STRANDS) { s_n[t] = 0; s_m[t] = 0; s_done[t] = 0; }
     for (int part = 0; part < 2; ++part) {                            // 0: sai_C, 1: sai_backwardR (sai_forwardR is empty here)
         // ---- plan: the valid intervals in seed order, sorted as the reference sorts them, their rows laid end to end
-        if (lane == 0) {
+        if (t < strands) {
             int m = 0;
-            if (live) {
+            if (mine) {
                 const SeedSai *g = sai + rs * 2 * (size_t)max_seeds + (size_t)part * max_seeds;
-                for (int i = 0; i < max_seeds; ++i) { const SeedSai v = g[i]; if (v.sp <= v.ep) s_sai[m++] = v; }
-                sai_introsort(m, s_sai);
+                for (int i = 0; i < max_seeds; ++i) { const SeedSai v = g[i]; if (v.sp <= v.ep) my_sai[m++] = v; }
+                sai_introsort(m, my_sai);
             }
             unsigned long long acc = 0;
             for (int i = 0; i < m; ++i) {
-                const SeedSai v = s_sai[i];
-                s_row[i] = acc;
+                const SeedSai v = my_sai[i];
+                my_row[i] = acc;
                 if (!pe) {
                     uint32_t skip = 1;
                     if (part == 1) { skip = (v.ep + 1 - v.sp) / 0x40000u; if ((int)skip <= 0) skip = 1; }    // alnse.c:702-703
@@ -507,35 +504,35 @@ locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, ui
                 } else if (v.ep - v.sp > (uint32_t)opt.max_locate) flags |= 1u;                              // alnse.c:577: rand()
                 else acc += (unsigned long long)(v.ep - v.sp) + 1;
             }
-            s_row[m] = acc;
-            s_m[grp] = m; s_done[grp] = 0;
+            my_row[m] = acc;
+            s_m[t] = m; s_done[t] = 0;
         }
         __syncthreads();
         // ---- rounds: every strand asks for the rows it may still push, all threads walk them, every strand takes its own
         for (;;) {
-            if (threadIdx.x == 0) {
+            if (t == 0) {
                 uint32_t acc = 0;
-                for (int gi = 0; gi < LOC_GROUPS; ++gi) {
+                for (int gi = 0; gi < strands; ++gi) {
                     s_want[gi] = acc;
-                    const unsigned long long *row_g = reinterpret_cast<const unsigned long long *>(
-                        s_mem + gi * per_group + (((size_t)max_seeds * 3 + 1) & ~(size_t)1));
+                    const unsigned long long *row_g = reinterpret_cast<const unsigned long long *>(s_mem + (size_t)gi * per_strand + row_off);
                     const unsigned long long left = s_m[gi] ? row_g[s_m[gi]] - s_done[gi] : 0ull;
                     const uint32_t room = max_locate - s_n[gi];          // the reference stops at max_locate pushes (alnse.c:678)
                     uint32_t w = (uint32_t)(left < (unsigned long long)room ? left : (unsigned long long)room);
                     if (w > (uint32_t)LOC_STAGE - acc) w = (uint32_t)LOC_STAGE - acc;
                     acc += w;
                 }
-                s_want[LOC_GROUPS] = acc;
+                s_want[strands] = acc;
             }
             __syncthreads();
-            const uint32_t total = s_want[LOC_GROUPS];
+            const uint32_t total = s_want[strands];
             if (total == 0) break;
-            for (uint32_t f = threadIdx.x; f < total; f += blockDim.x) {
-                int gi = 0;
-                while (gi + 1 < LOC_GROUPS && s_want[gi + 1] <= f) ++gi;
-                const uint32_t *gb = s_mem + gi * per_group;
+            for (uint32_t f = (uint32_t)t; f < total; f += blockDim.x) {
+                int glo = 0, ghi = strands - 1;                        // the strand whose share holds row f
+                while (glo < ghi) { const int mid = (glo + ghi + 1) >> 1; if (s_want[mid] <= f) glo = mid; else ghi = mid - 1; }
+                const int gi = glo;
+                const uint32_t *gb = s_mem + (size_t)gi * per_strand;
                 const SeedSai *sai_g = reinterpret_cast<const SeedSai *>(gb);
-                const unsigned long long *row_g = reinterpret_cast<const unsigned long long *>(gb + (((size_t)max_seeds * 3 + 1) & ~(size_t)1));
+                const unsigned long long *row_g = reinterpret_cast<const unsigned long long *>(gb + row_off);
                 const unsigned long long flat = s_done[gi] + (unsigned long long)(f - s_want[gi]);
                 int lo = 0, hi = s_m[gi] - 1;                          // last interval whose first row is <= flat
                 while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (row_g[mid] <= flat) lo = mid; else hi = mid - 1; }
@@ -551,61 +548,40 @@ locate_kernel(FmIndexDev ix, SeedOpt opt, const uint32_t *__restrict__ roffs, ui
                 s_pos[f] = pos; s_keep[f] = keep ? 1 : 0;
             }
             __syncthreads();
-            // each strand pushes its rows in order
-            {
-                const uint32_t f0 = s_want[grp], cnt = s_want[grp + 1] - f0;
-                uint32_t n = s_n[grp];
-                uint32_t *dst = lists + rs * (size_t)stride;
-                for (uint32_t b = 0; b < cnt; b += LOC_G) {
-                    const uint32_t i = b + (uint32_t)lane;
-                    const bool keep = i < cnt && s_keep[f0 + i] != 0;
-                    const unsigned bal = (__ballot_sync(gmask, keep) >> gshift) & 0xFFu;
-                    const uint32_t rank = (uint32_t)__popc(bal & ((1u << lane) - 1u));
-                    if (keep && n + rank < max_locate) dst[n + rank] = s_pos[f0 + i];
-                    n = min(max_locate, n + (uint32_t)__popc(bal));
+            if (t < strands) {                                         // each strand pushes its rows in order
+                const uint32_t f0 = s_want[t], cnt = s_want[t + 1] - f0;
+                if (cnt) {
+                    uint32_t n = s_n[t];
+                    uint32_t *dst = lists + rs * (size_t)stride;
+                    for (uint32_t i = 0; i < cnt; ++i)
+                        if (s_keep[f0 + i] && n < max_locate) dst[n++] = s_pos[f0 + i];
+                    s_n[t] = n; s_done[t] += cnt;
                 }
-                __syncwarp(gmask);
-                if (lane == 0) { s_n[grp] = n; s_done[grp] += cnt; }
             }
             __syncthreads();
         }
         __syncthreads();
     }
-    if (!live) return;
+    if (!mine) return;
     const uint32_t r = (uint32_t)(rs >> 1);
-    const uint32_t n = s_n[grp];
+    const uint32_t n = s_n[t];
     uint32_t *dst = lists + rs * (size_t)stride;
-    if (lane == 0) {
-        counts[(rs & 1) * (size_t)n_reads + r] = n;
-        if (pe && stride < 0x40000u && n == stride) flags |= 2u;
-        if (status) status[(rs & 1) * (size_t)n_reads + r] = (uint8_t)flags;
-    }
-    if (n > LOC_SMALL) {                                              // ks_introsort(uint32_t) of a long list: sort_long_kernel
-        if (lane == 0) long_list[atomicAdd(long_count, 1u)] = (uint32_t)rs;
-        return;
-    }
+    counts[(rs & 1) * (size_t)n_reads + r] = n;
+    if (pe && stride < 0x40000u && n == stride) flags |= 2u;
+    if (status) status[(rs & 1) * (size_t)n_reads + r] = (uint8_t)flags;
+    if (n > LOC_SMALL) { long_list[atomicAdd(long_count, 1u)] = (uint32_t)rs; return; }     // ks_introsort(uint32_t) of a long list
     if (n < 2) return;
-    // any correct sort gives the reference's array: bitonic over the next power of two, padded with ~0 (a pad can equal a
-    // real, wrapped locus 0xFFFFFFFF: equal keys, the sorted prefix is still right)
-    __threadfence_block();
-    __syncwarp(gmask);
-    uint32_t n2 = 2;
-    while (n2 < n) n2 <<= 1;
-    for (uint32_t i = lane; i < n2; i += LOC_G) s_small[i] = i < n ? dst[i] : 0xFFFFFFFFu;
-    __syncwarp(gmask);
-    for (uint32_t k = 2; k <= n2; k <<= 1)
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = lane; i < n2; i += LOC_G) {
-                const uint32_t p = i ^ j;
-                if (p > i) {
-                    const uint32_t a = s_small[i], b2 = s_small[p];
-                    const bool up = (i & k) == 0;
-                    if ((a > b2) == up) { s_small[i] = b2; s_small[p] = a; }
-                }
-            }
-            __syncwarp(gmask);
-        }
-    for (uint32_t i = lane; i < n; i += LOC_G) dst[i] = s_small[i];
+    // any correct sort gives the reference's array: insertion sort in this strand's corner of the staging area (no other
+    // thread of the CTA touches the staging area after the last round)
+    uint32_t *mine_sorted = s_pos + (size_t)t * LOC_SMALL;
+    for (uint32_t i = 0; i < n; ++i) mine_sorted[i] = dst[i];
+    for (uint32_t i = 1; i < n; ++i) {
+        const uint32_t v = mine_sorted[i];
+        uint32_t j = i;
+        while (j > 0 && mine_sorted[j - 1] > v) { mine_sorted[j] = mine_sorted[j - 1]; --j; }
+        mine_sorted[j] = v;
+    }
+    for (uint32_t i = 0; i < n; ++i) dst[i] = mine_sorted[i];
 }
 
 // lists longer than LOC_SMALL: one warp per queued (read, strand), bitonic in shared memory over cap2 >= max_locate
@@ -690,15 +666,16 @@ cudaError_t launch_locate(const FmIndexDev &ix, const SeedOpt &opt, const uint32
     if (!n_reads) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(long_count, 0, 4, st);
     if (e != cudaSuccess) return e;
-    const size_t per_group = locate_group_words(max_seeds) * 4;
-    const int groups = LOC_GROUPS;                          // 128 threads
-    const size_t smem = per_group * groups;
+    const size_t per_strand = locate_strand_words(max_seeds) * 4;
+    int strands = LOC_STRANDS;                              // per CTA of 128 threads
+    while (strands > 8 && per_strand * strands > 96 * 1024) strands >>= 1;
+    const size_t smem = per_strand * strands;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     {
         auto kern = locate_kernel;
         if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         const size_t n_rs = (size_t)n_reads * 2;
-        SALT_LAUNCH(kern, (unsigned)((n_rs + groups - 1) / groups), groups * LOC_G, smem, st, ix, opt, roffs, n_reads, max_seeds, ref_l, sai,
+        SALT_LAUNCH(kern, (unsigned)((n_rs + strands - 1) / strands), 128, smem, st, ix, opt, roffs, n_reads, max_seeds, strands, ref_l, sai,
                     counts, lists, long_list, long_count, status);
     }
     if (opt.list_cap > LOC_SMALL) {

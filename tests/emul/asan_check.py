@@ -41,3 +41,32 @@ for L, glen in ((100, 30000), (150, 30000), (250, 30000), (37, 20000), (700, 400
         pc.check_ssw(eng, o, g, reads, wins, False, api.salt_score_mat2(), 16, cigar_stride=96)
     eng.close()
     print("asan ok", L, flush=True)
+
+# ---- round 2: compact transport, SAM tail of primaries, wide-band rescues, seeding + locate (both flavours)
+import tempfile
+import seed_cases as sc
+from salt_b200 import index_io
+g, reads, pos, strand, cands = pc.make_world(77, L=100, n_reads=30, per_strand=3, indel_frac=0.4, glen=30000, n_frac=0.02)
+eng = api.Engine(g.mixref, g.l, g.pac, g.l, lib=lib)
+pc.check_verify_packed(eng, [r for r in reads], cands, 7, variants=[(2, 16, 3), (4, 32, 0)])
+rng = np.random.default_rng(5)
+pc.check_verify_packed(eng, [r[:int(rng.integers(37, 101))] for r in reads], cands, 11, variants=[(2, 32, 1)])
+pc.check_tail_primaries(eng, o, g, reads, cands)
+eng.close()
+g3 = synth.Genome(20003, snp_rate=0.01, n_rate=0.0, seed=77)
+eng = api.Engine(g3.mixref, g3.l, None, 0, lib=lib)
+pc.check_ssw_wide_bands(eng, o, 77, n_reads=140)
+eng.close()
+print("asan ok transport / tail / wide bands", flush=True)
+if sc.have_ref():
+    rng = np.random.default_rng(3)
+    gg, is_n = sc.repeat_genome(rng, n_units=16, unit_len=700, n_rate=0.001)
+    prefix = sc.write_index(tempfile.mkdtemp(prefix="salt_asan_"), gg, is_n, rng)
+    fm = index_io.FmIndex(prefix)
+    codes, roffs = sc.sample_reads(gg, rng, 16)
+    ref = orc.SeedRef(prefix)
+    eng = api.Engine(fm.mixref, fm.l, None, 0, lib=lib)
+    eng.set_index(fm)
+    sc.check_lists(eng, ref, fm, codes, roffs, option_sets=sc.OPTION_SETS[:4])
+    sc.check_lists_pe(eng, ref, fm, codes, roffs, option_sets=sc.PE_OPTION_SETS[:2])
+    print("asan ok seeding", flush=True)
