@@ -293,7 +293,7 @@ int salt_b200_set_index(salt_b200_t *h, const salt_fm_index_t *ix);
  * salt_b200_set_reads[_packed]; slot 0 for the synchronous entry points).  The sorted lists stay on the device as the
  * slot's candidate lists -- salt_b200_verify_seeded consumes them in place -- and are optionally downloaded:
  * offs0 / offs1 (n_reads + 1 each) and loci0 / loci1 (cap0 / cap1 entries of room; SALT_ERR_NOMEM if a strand has
- * more) may be NULL.  *n0 / *n1 receive the totals.  Limits: at most 64 seed starts per strand
+ * more) may be NULL.  *n0 / *n1 receive the totals.  Limits: at most 1024 seed starts per strand
  * ((l_seq - l_seed) / l_overlap + 1), max_locate <= 16384, l_seed >= the lookup length. */
 int salt_b200_seed_locate(salt_b200_t *h, int slot, const salt_seed_opt_t *opt, uint32_t *offs0, uint32_t *offs1,
                           uint32_t *loci0, size_t cap0, uint32_t *loci1, size_t cap1, size_t *n0, size_t *n1);

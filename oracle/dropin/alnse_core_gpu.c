@@ -141,11 +141,14 @@ int alnse_core(const opt_t *opt)
     fprintf(stderr, "[alnse_core/gpu]:  Start single end alignment (verification on libsalt_b200%s)\n",
             gpu_seed ? ", seeding + locate on libsalt_b200" : "");
     aln_opt_t *aln_opt = aln_opt_init(opt);
+    double t_start = now_s();
     index_t *index = alnse_index_reload(opt->fn_index);
+    const double t_load = now_s() - t_start;
     if (aln_opt->extend_algo == EXTEND_SW || aln_opt->l_overlap <= 0) {
         fprintf(stderr, "[salt_dropin] only the overlap/LV path (the reference's default) is served\n");
         exit(1);
     }
+    double t_init = now_s();
     salt_b200_t *gpu = salt_b200_init(index->mixRef->seq, index->mixRef->l, index->pac, index->bntseq->l_pac, 0);
     if (!gpu) die("salt_b200_init");
     salt_seed_opt_t sopt;
@@ -178,6 +181,7 @@ int alnse_core(const opt_t *opt)
         ck[c] = salt_chunk_new(DROPIN_CHUNK_READS, (size_t)DROPIN_CHUNK_READS * 1024, DROPIN_CHUNK_CANDS);
         if (!ck[c]) die("salt_chunk_new");
     }
+    t_init = now_s() - t_init;
     const int n_threads = opt->n_threads > 1 ? opt->n_threads : 1;
     seed_thread_t *T = calloc((size_t)n_threads, sizeof *T);
     fin_thread_t *Fin = calloc((size_t)n_threads, sizeof *Fin);
@@ -194,10 +198,11 @@ int alnse_core(const opt_t *opt)
     int *slot_of = calloc(N_SEQS, sizeof(int));        /* index of read i in the GPU chunk that holds it */
     aln_samhead(opt, index->bntseq);
     int n, i, n_tot = 0, n_chunks = 0;
-    double t_seed = 0, t_gpu_wait = 0, t_finish = 0;
+    double t_seed = 0, t_gpu_wait = 0, t_finish = 0, t_select = 0, t_tail = 0, t_read = 0, t_print = 0, t_rd0 = now_s();
     while ((n = query_read_multiSeqs(qs, N_SEQS, multiSeqs)) > 0) {
         n_tot += n;
         double t0 = now_s();
+        t_read += t0 - t_rd0;
         if (!gpu_seed) {
             for (t = 0; t < n_threads; ++t) { T[t].n = n; T[t].queries = multiSeqs; T[t].out = seeds; }
             if (n_threads == 1) seed_worker(&T[0]);
@@ -249,14 +254,18 @@ int alnse_core(const opt_t *opt)
                 double tf = now_s();
                 (void)j;
                 finish_parallel(n_threads, th, Fin, 0, pend_first, pend_upto, index, multiSeqs, aln_opt, ck[pend_c], slot_of);
+                t_select += now_s() - tf;
+                double tt = now_s();
                 if (aln_opt->print_nm_md || aln_opt->print_xa_cigar)
                     dropin_tail_prepare(gpu, gpu_seed ? 0 : pend_c, multiSeqs, slot_of, pend_first, pend_upto);
+                t_tail += now_s() - tt;
                 finish_parallel(n_threads, th, Fin, 1, pend_first, pend_upto, index, multiSeqs, aln_opt, ck[pend_c], slot_of);
                 t_finish += now_s() - tf;
                 pend_c = -1;
             }
             if (cur >= 0) { pend_c = cur; pend_first = first; pend_upto = upto; first = upto; ++k; }
         }
+        double tp = now_s();
         for (i = 0; i < n; ++i) {
             query_t *query = multiSeqs + i;
             puts(query->sam->s);                        /* alnse.c:1433-1439 */
@@ -264,10 +273,15 @@ int alnse_core(const opt_t *opt)
         }
         memset(multiSeqs, 0, N_SEQS * sizeof(query_t));
         fprintf(stderr, "%d reads have been aligned!\n", n_tot);
+        t_rd0 = now_s();
+        t_print += t_rd0 - tp;
     }
     fprintf(stderr, "[salt_dropin] %d reads, %d GPU chunks, %d seeding threads: seeding %s %.3f s, GPU calls (exposed wait) %.3f s, "
                     "hit selection + SAM text %.3f s\n", n_tot, n_chunks, n_threads, gpu_seed ? "(on the GPU, inside the GPU calls)" : "on the host",
             t_seed, t_gpu_wait, t_finish);
+    fprintf(stderr, "[salt_dropin] wall %.3f s: index load (reference loaders) %.3f, GPU init + uploads %.3f, FASTQ reader %.3f, SAM print + free %.3f; "
+                    "of the host finish: hit selection %.3f, GPU tail calls %.3f, SAM text %.3f\n", now_s() - t_start, t_load, t_init, t_read, t_print,
+            t_select, t_tail, t_finish - t_select - t_tail);
     for (t = 0; t < n_threads; ++t) { aux_destroy(T[t].aux[0]); aux_destroy(T[t].aux[1]); }
     for (i = 0; i < N_SEQS; ++i) { free(seeds[i].a[0]); free(seeds[i].a[1]); }
     free(T); free(th); free(seeds); free(Fin);
