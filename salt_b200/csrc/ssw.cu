@@ -357,12 +357,204 @@ struct BandDev {
     SswParams prm;
     uint8_t *dirs; size_t slot;          // per-thread direction scratch
     uint32_t *ovf_list; uint32_t *ovf_count; uint32_t ovf_cap;
-    const uint32_t *in_list; const uint32_t *in_count;   // overflow pass input
+    const uint32_t *in_list; const uint32_t *in_count;   // list-driven passes: their input
+    uint32_t *wide_list; uint32_t *wide_count;           // narrow pass: tasks it hands to the general kernel
     salt_ssw_out_t *out; uint32_t *cigars; int cigar_stride;
 };
 
 __device__ __forceinline__ int band_u(int w, int i, int j) { int x = i - w; if (x < 0) x = 0; return j - x + 1; }
 __device__ __forceinline__ int band_d(int w, int i, int j) { int x = i - w; if (x < 0) x = 0; return j - x; }
+
+// Traceback from the bottom-right corner (ssw.c:634-716); ops are produced last-first and reversed in place.
+// code_at(i, x, state) = direction code 1..5 of cell (row i, band slot x) for the matrix the walk is in
+// (state 0 = E, 1 = F, 2 = H).  Returns the cigar's true length, or -3 when the walk leaves the band.
+template <class CodeAt>
+__device__ __forceinline__ int band_traceback(const CodeAt &code_at, int band, int wd, int readLen, int refLen, uint32_t *cg, int cigar_stride)
+{
+    int i = readLen - 1, j = refLen - 1, e = 0, l = 0, fop = 0, prev = 0, state = 2;
+    bool bad = false;
+    auto emit = [&](uint32_t v) { if (l < cigar_stride) cg[l] = v; ++l; };
+    while (i > 0) {
+        const int x = band_d(band, i, j);
+        if (x < 0 || x >= wd || j < 0) { bad = true; break; }
+        const int code = code_at(i, x, state);
+        switch (code) {
+        case 1: --i; --j; state = 2; fop = 0; break;
+        case 2: --i; state = 0; fop = 1; break;
+        case 3: --i; state = 2; fop = 1; break;
+        case 4: --j; state = 1; fop = 2; break;
+        case 5: --j; state = 2; fop = 2; break;
+        default: bad = true; break;
+        }
+        if (bad) break;
+        if (fop == prev) ++e;
+        else { emit((uint32_t)e << 4 | (uint32_t)prev); prev = fop; e = 1; }
+    }
+    if (bad) return -3;
+    if (fop == 0) emit((uint32_t)(e + 1) << 4);
+    else { emit((uint32_t)e << 4 | (uint32_t)fop); emit(16u); }
+    const int stored = l < cigar_stride ? l : cigar_stride;
+    for (int a = 0, b = stored - 1; a < b; ++a, --b) { const uint32_t tmp = cg[a]; cg[a] = cg[b]; cg[b] = tmp; }
+    // l > cigar_stride: the row holds the LAST cigar_stride ops of the true cigar (the first ones the traceback
+    // produced), reversed into order; the true length tells the caller the row is partial
+    return l;
+}
+
+// ---- narrow bands: banded_sw with band B <= 3 entirely in registers ---------------------------------------------
+// Nearly every rescue window aligns without a gap or with a short one, so banded_sw's first band
+// (|refLen - readLen| + 1, ssw.c:845) is 1, 2 or 3 and succeeds.  For those the three band rows hb / eb / hc of the
+// reference (2B+3 entries each) are registers with compile-time indices, a row's reference symbols are one funnel
+// shift, and a row's direction codes are one 32-bit word (four bits per cell).  Indices follow the reference:
+// cell (i, j) has slot u = j - max(i-B, 0) + 1, its upper neighbour slot u + D with D = [i > B], its left
+// neighbour u - 1.  Needs refLen >= 2B+2 so that no early row is cut short by the window's end (the reference's
+// `edge` is then i+B+1 for rows 0..B and 2B+2 afterwards); everything else goes to the general kernel.
+template <int B>
+struct NarrowBand {
+    static constexpr int W = 2 * B + 3;
+    int hb[W], eb[W], hc[W];
+    int max;
+};
+
+template <int B, int D>
+__device__ __forceinline__ void narrow_row(NarrowBand<B> &s, const DevCtx &c, int use_pac, const int8_t *s_tab, int i, int refLen,
+                                           uint32_t ref0, int rc, int gapO, int gapE, uint32_t *rowdirs)
+{
+    constexpr int W = NarrowBand<B>::W;
+    const int beg = D ? i - B : 0;
+    int end = i + B;
+    if (end > refLen - 1) end = refLen - 1;
+    const int n = end - beg + 1;
+    s.hb[0] = s.eb[0] = s.hc[0] = 0;
+    if (D) { s.hb[W - 1] = 0; s.eb[W - 1] = 0; }
+    else {
+        const int edge = end + 1 < W - 1 ? end + 1 : W - 1;
+#pragma unroll
+        for (int k = 1; k < W; ++k) if (k == edge) { s.hb[k] = 0; s.eb[k] = 0; }
+    }
+    uint32_t symw = 0;
+    if (!use_pac) {
+        const uint32_t p = ref0 + (uint32_t)beg;
+        const uint32_t *__restrict__ mw = c.mixref + (p >> 3);
+        symw = __funnelshift_r(mw[0], mw[1], 4 * (int)(p & 7u));
+    }
+    int fcur = 0;
+    uint32_t dirw = 0;
+#pragma unroll
+    for (int u = 1; u <= 2 * B + 1; ++u) {
+        if (u <= n) {
+            constexpr int dummy = 0; (void)dummy;
+            const int ue = u + D, ud = ue - 1, ub = u - 1;
+            int t1 = (!D && i == 0) ? -gapO : s.hb[ue] - gapO;
+            int t2 = (!D && i == 0) ? -gapE : s.eb[ue] - gapE;
+            const uint32_t e_from_h = t1 > t2 ? 1u : 0u;
+            const int ev = t1 > t2 ? t1 : t2;
+            s.eb[u] = ev;
+            t1 = s.hc[ub] - gapO;
+            t2 = fcur - gapE;
+            const uint32_t f_from_h = t1 > t2 ? 1u : 0u;
+            fcur = t1 > t2 ? t1 : t2;
+            const int e1 = ev > 0 ? ev : 0;
+            const int f1 = fcur > 0 ? fcur : 0;
+            t1 = e1 > f1 ? e1 : f1;
+            const int sym = use_pac ? sw_ref_symbol(c, 1, ref0 + (uint32_t)(beg + u - 1)) : (int)((symw >> (4 * (u - 1))) & 15u);
+            t2 = s.hb[ud] + s_tab[sym * 8 + rc];
+            const int h = t1 > t2 ? t1 : t2;
+            s.hc[u] = h;
+            if (h > s.max) s.max = h;
+            const uint32_t hsel = t1 <= t2 ? 0u : (e1 > f1 ? 1u : 2u);
+            dirw |= (e_from_h | (f_from_h << 1) | (hsel << 2)) << (4 * (u - 1));
+        }
+    }
+#pragma unroll
+    for (int k = 1; k <= 2 * B + 1; ++k) if (k <= n) s.hb[k] = s.hc[k];
+    rowdirs[(size_t)i * 32] = dirw;
+}
+
+// one banded_sw attempt at band B; max carries over between attempts as in the reference's do-while (ssw.c:575-632)
+template <int B>
+__device__ __forceinline__ bool narrow_fill(const DevCtx &c, int use_pac, const int8_t *s_tab, uint32_t rs, int read0, uint32_t ref0,
+                                            int readLen, int refLen, int score, int gapO, int gapE, uint32_t *rowdirs, int &max)
+{
+    NarrowBand<B> s;
+#pragma unroll
+    for (int k = 0; k < NarrowBand<B>::W; ++k) { s.hb[k] = 0; s.eb[k] = 0; s.hc[k] = 0; }
+    s.max = max;
+    const uint64_t *__restrict__ rd = c.rd4 + (size_t)rs * c.W64;
+    uint64_t rw = rd[read0 >> 4];
+    auto code_of = [&](int idx) {
+        if ((idx & 15) == 0) rw = rd[idx >> 4];
+        const unsigned nib = (unsigned)(rw >> (4 * (idx & 15))) & 15u;
+        return nib == 15u ? SW_CODE_N : (31 - __clz(nib));
+    };
+#pragma unroll
+    for (int i = 0; i <= B; ++i)
+        if (i < readLen) narrow_row<B, 0>(s, c, use_pac, s_tab, i, refLen, ref0, code_of(read0 + i), gapO, gapE, rowdirs);
+    for (int i = B + 1; i < readLen; ++i)
+        narrow_row<B, 1>(s, c, use_pac, s_tab, i, refLen, ref0, code_of(read0 + i), gapO, gapE, rowdirs);
+    max = s.max;
+    return s.max >= score;
+}
+
+struct NarrowCodeAt {
+    const uint32_t *rowdirs;
+    __device__ __forceinline__ int operator()(int i, int x, int state) const
+    {
+        const uint32_t nib = (rowdirs[(size_t)i * 32] >> (4 * x)) & 15u;
+        const int ce = (nib & 1u) ? 3 : 2, cf = (nib & 2u) ? 5 : 4;
+        if (state == 0) return ce;
+        if (state == 1) return cf;
+        const uint32_t hs = nib >> 2;
+        return hs == 0u ? 1 : (hs == 1u ? ce : cf);
+    }
+};
+
+__global__ void __launch_bounds__(128)
+sw_banded_narrow_kernel(BandDev d)
+{
+    __shared__ int8_t s_tab[17 * 8];
+    for (int i = threadIdx.x; i < 17 * 8; i += blockDim.x) s_tab[i] = d.prm.table[i];
+    __syncthreads();
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= d.n_tasks) return;
+    const size_t t = tid;
+    const int32_t *f = d.fwd + t * 8;
+    const int fl = f[F_FLAGS];
+    salt_ssw_out_t o;
+    o.score1 = (uint16_t)f[F_SCORE1]; o.score2 = (uint16_t)f[F_SCORE2];
+    o.ref_begin1 = f[F_REF_BEGIN1]; o.ref_end1 = f[F_REF_END1];
+    o.read_begin1 = f[F_READ_BEGIN1]; o.read_end1 = f[F_READ_END1];
+    o.ref_end2 = f[F_REF_END2]; o.cigarLen = 0;
+    if (!(fl & FL_VALID)) { o.ref_end2 = -1; o.cigarLen = -1; }
+    if (!(fl & FL_DO_CIGAR)) { d.out[t] = o; return; }
+
+    const salt_win_t w = d.wins[t];
+    const int refLen = o.ref_end1 - o.ref_begin1 + 1, readLen = o.read_end1 - o.read_begin1 + 1;
+    const uint32_t ref0 = w.start + (uint32_t)o.ref_begin1;
+    const int read0 = o.read_begin1;
+    const int score = o.score1, gapO = d.prm.gapO, gapE = d.prm.gapE;
+    int band = abs(refLen - readLen) + 1;                                    // ssw.c:845
+    // a row's direction word of the 32 tasks of a warp side by side: [row][lane]
+    uint32_t *rowdirs = reinterpret_cast<uint32_t *>(d.dirs + (tid >> 5) * (d.slot * 32)) + (tid & 31);
+    bool ok = false;
+    int max = 0;
+    if (readLen >= 1 && (size_t)readLen * 4 <= d.slot) {
+        if (band == 1 && refLen >= 4) {
+            ok = narrow_fill<1>(d.c, d.prm.use_pac, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
+            if (!ok) band = 2;
+        }
+        if (!ok && band == 2 && refLen >= 6)
+            ok = narrow_fill<2>(d.c, d.prm.use_pac, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
+        else if (!ok && band == 3 && refLen >= 8)
+            ok = narrow_fill<3>(d.c, d.prm.use_pac, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
+    }
+    if (!ok) {                                                               // the general kernel starts this task over
+        d.wide_list[atomicAdd(d.wide_count, 1u)] = (uint32_t)t;
+        return;
+    }
+    NarrowCodeAt at{rowdirs};
+    o.cigarLen = band_traceback(at, band, 2 * band + 1, readLen, refLen, d.cigars + t * (size_t)d.cigar_stride, d.cigar_stride);
+    d.out[t] = o;
+}
 
 template <int BWMAX, bool OVERFLOW>
 __global__ void __launch_bounds__(128)
