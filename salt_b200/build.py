@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
         if p.wait() != 0:
             raise RuntimeError("nvcc failed on " + src)
     if force or procs or _stale(OUT, objs):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-Xlinker", "--exclude-libs,ALL"]
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs + ["-Xlinker", "--exclude-libs,ALL"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

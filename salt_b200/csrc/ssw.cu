@@ -29,6 +29,7 @@ struct SwDev {
     size_t n_pairs;            // ceil(n_tasks / 2)
     int G, S;                  // rows = G*S
     int CW;                    // window words (8 columns each) per pair
+    int item_shift;            // log2 of the prep kernels' padded items per task
     int MC;                    // maxcol stride (columns) per pair
     uint2 *win2;               // [pair][CW]  (.x task 0, .y task 1)
     uint32_t *rsel;            // [task][G*NQ]
@@ -61,10 +62,9 @@ sw_prep_kernel(SwDev d)
     const int NQ = (d.S + 3) / 4;
     const int per_task = d.CW + d.G * NQ;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = d.n_pairs * 2 * (size_t)per_task;
-    if (idx >= total) return;
-    const size_t t = idx / per_task;
-    const int item = (int)(idx % per_task);
+    const size_t t = idx >> d.item_shift;              // a task's items are padded to a power of two: no division
+    const int item = (int)(idx & (((size_t)1 << d.item_shift) - 1));
+    if (t >= d.n_pairs * 2 || item >= per_task) return;
     const bool real = t < d.n_tasks;
     uint32_t rs = 0, start = 0;
     int L = 0, cols = 0, read_end = 0, ref_end = 0;
@@ -442,7 +442,6 @@ __device__ __forceinline__ void narrow_row(NarrowBand<B> &s, const DevCtx &c, in
 #pragma unroll
     for (int u = 1; u <= 2 * B + 1; ++u) {
         if (u <= n) {
-            constexpr int dummy = 0; (void)dummy;
             const int ue = u + D, ud = ue - 1, ub = u - 1;
             int t1 = (!D && i == 0) ? -gapO : s.hb[ue] - gapO;
             int t2 = (!D && i == 0) ? -gapE : s.eb[ue] - gapE;
@@ -556,7 +555,10 @@ sw_banded_narrow_kernel(BandDev d)
     d.out[t] = o;
 }
 
-template <int BWMAX, bool OVERFLOW>
+// The general kernel walks a list: the tasks the narrow pass handed over (FINAL = false: a band beyond BWMAX goes on to
+// the overflow list), or that overflow list (FINAL = true: SSW_OVF_THREADS threads with wide scratch, a band beyond
+// BWMAX is declined per item).  Every thread of the grid strides over the list, however long it is.
+template <int BWMAX, bool FINAL>
 __global__ void __launch_bounds__(128)
 sw_banded_kernel(BandDev d)
 {
@@ -564,20 +566,16 @@ sw_banded_kernel(BandDev d)
     for (int i = threadIdx.x; i < 17 * 8; i += blockDim.x) s_tab[i] = d.prm.table[i];
     __syncthreads();
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    // overflow pass: ovf_cap threads, each with its own wide direction scratch, walk the whole list
-    const size_t n_items = OVERFLOW ? (size_t)*d.in_count : d.n_tasks;
-    const size_t item_step = OVERFLOW ? (size_t)d.ovf_cap : n_items;
+    const size_t n_items = (size_t)*d.in_count;
+    const size_t item_step = (size_t)gridDim.x * blockDim.x;
     for (size_t item = tid; item < n_items; item += item_step) {
-    const size_t t = OVERFLOW ? (size_t)d.in_list[item] : item;
+    const size_t t = (size_t)d.in_list[item];
     const int32_t *f = d.fwd + t * 8;
-    const int fl = f[F_FLAGS];
     salt_ssw_out_t o;
     o.score1 = (uint16_t)f[F_SCORE1]; o.score2 = (uint16_t)f[F_SCORE2];
     o.ref_begin1 = f[F_REF_BEGIN1]; o.ref_end1 = f[F_REF_END1];
     o.read_begin1 = f[F_READ_BEGIN1]; o.read_end1 = f[F_READ_END1];
-    o.ref_end2 = f[F_REF_END2]; o.cigarLen = 0;
-    if (!(fl & FL_VALID)) { o.ref_end2 = -1; o.cigarLen = -1; }
-    if (!(fl & FL_DO_CIGAR)) { if (!OVERFLOW) d.out[t] = o; continue; }
+    o.ref_end2 = f[F_REF_END2]; o.cigarLen = 0;                  // listed tasks are valid and want a cigar
 
     const salt_win_t w = d.wins[t];
     const int refLen = o.ref_end1 - o.ref_begin1 + 1, readLen = o.read_end1 - o.read_begin1 + 1;
@@ -632,7 +630,7 @@ sw_banded_kernel(BandDev d)
     } while (max < score);
 
     if (overflow) {
-        if (!OVERFLOW && d.ovf_list) {
+        if (!FINAL && d.ovf_list) {
             const uint32_t k = atomicAdd(d.ovf_count, 1u);     // the list has room for every task
             d.ovf_list[k] = (uint32_t)t; o.cigarLen = 0;
         } else o.cigarLen = -2;                                // band beyond the engine's widest (BWMAX of the overflow pass)
@@ -641,35 +639,12 @@ sw_banded_kernel(BandDev d)
     }
     band /= 2;
 
-    // trace back from the bottom-right corner (ssw.c:634-716); ops are produced last-first
-    uint32_t *cg = d.cigars + t * (size_t)d.cigar_stride;
-    int i = readLen - 1, j = refLen - 1, e = 0, l = 0, fop = 0, prev = 0, state = 2;
-    bool bad = false;
-    auto emit = [&](uint32_t v) { if (l < d.cigar_stride) cg[l] = v; ++l; };
-    while (i > 0) {
-        const int x = band_d(band, i, j);
-        if (x < 0 || x >= wd || j < 0) { bad = true; break; }
-        const int code = sw_dir_get(dirs[((size_t)wd * i + x) * 32], state);
-        switch (code) {
-        case 1: --i; --j; state = 2; fop = 0; break;
-        case 2: --i; state = 0; fop = 1; break;
-        case 3: --i; state = 2; fop = 1; break;
-        case 4: --j; state = 1; fop = 2; break;
-        case 5: --j; state = 2; fop = 2; break;
-        default: bad = true; break;
-        }
-        if (bad) break;
-        if (fop == prev) ++e;
-        else { emit((uint32_t)e << 4 | (uint32_t)prev); prev = fop; e = 1; }
-    }
-    if (bad) { o.cigarLen = -3; d.out[t] = o; continue; }
-    if (fop == 0) emit((uint32_t)(e + 1) << 4);
-    else { emit((uint32_t)e << 4 | (uint32_t)fop); emit(16u); }
-    const int stored = l < d.cigar_stride ? l : d.cigar_stride;
-    for (int a = 0, b = stored - 1; a < b; ++a, --b) { const uint32_t tmp = cg[a]; cg[a] = cg[b]; cg[b] = tmp; }
-    // l > cigar_stride: the row holds the LAST cigar_stride ops of the true cigar (the first ones the traceback
-    // produced), reversed into order; cigarLen reports the true length so the caller can tell the row is partial
-    o.cigarLen = l;
+    struct ByteCodeAt {
+        const uint8_t *dirs; int wd;
+        __device__ __forceinline__ int operator()(int i, int x, int state) const { return sw_dir_get(dirs[((size_t)wd * i + x) * 32], state); }
+    };
+    ByteCodeAt at{dirs, wd};
+    o.cigarLen = band_traceback(at, band, wd, readLen, refLen, d.cigars + t * (size_t)d.cigar_stride, d.cigar_stride);
     d.out[t] = o;
     }
 }
@@ -696,7 +671,7 @@ static SwShape pick_shape(int l_max)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// layout: [0]=win2 [1]=rsel [2]=maxcol2 [3]=fwd [4]=dirs [5]=ovf_list [6]=ovf_count [7]=total
+// layout: [0]=win2 [1]=rsel [2]=maxcol2 [3]=fwd [4]=dirs [5]=ovf_list [6]=counters [7]=total [8]=wide_list
 size_t ssw_scratch_bytes(size_t n_tasks, int max_cols, int max_rows, size_t *layout)
 {
     const SwShape sh = pick_shape(max_rows);
@@ -712,6 +687,7 @@ size_t ssw_scratch_bytes(size_t n_tasks, int max_cols, int max_rows, size_t *lay
     layout[4] = off; off = align_up(off + align_up(n_tasks, 128) * slot, 256);
     layout[5] = off; off = align_up(off + n_tasks * sizeof(uint32_t), 256);
     layout[6] = off; off = align_up(off + 256, 256);
+    layout[8] = off; off = align_up(off + n_tasks * sizeof(uint32_t), 256);
     layout[7] = off;
     return off;
 }
@@ -764,9 +740,8 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
                        uint64_t *launches, cudaEvent_t *ev, uint8_t *ovf_dirs)
 {
 #define SALT_EV(i) do { if (ev) cudaEventRecord(ev[i], st); } while (0)
-    (void)sm_count;
     if (!n) return cudaSuccess;
-    size_t lay[8];
+    size_t lay[9];
     const size_t need = ssw_scratch_bytes(n, max_cols, (int)c.l_max, lay);
     if (need > scratch_bytes) return cudaErrorMemoryAllocation;
     const SwShape sh = pick_shape((int)c.l_max);
@@ -780,7 +755,9 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
     d.fwd = reinterpret_cast<int32_t *>(base + lay[3]);
     d.prm = prm;
     const int NQ = (sh.S + 3) / 4;
-    const size_t prep_items = d.n_pairs * 2 * (size_t)(d.CW + d.G * NQ);
+    d.item_shift = 0;
+    while ((1 << d.item_shift) < d.CW + d.G * NQ) ++d.item_shift;
+    const size_t prep_items = (d.n_pairs * 2) << d.item_shift;
     const unsigned prep_blocks = (unsigned)((prep_items + 255) / 256);
     cudaError_t e;
     uint32_t *ovf_count = reinterpret_cast<uint32_t *>(base + lay[6]);
@@ -805,9 +782,16 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
     b.ovf_list = reinterpret_cast<uint32_t *>(base + lay[5]);
     b.ovf_count = ovf_count; b.ovf_cap = SSW_OVF_THREADS;
     if (!ovf_dirs) b.ovf_list = nullptr;                  // no overflow scratch: wide bands come back with cigarLen = -2
-    b.in_list = nullptr; b.in_count = nullptr;
+    b.wide_list = reinterpret_cast<uint32_t *>(base + lay[8]); b.wide_count = ovf_count + 1;
+    b.in_list = b.wide_list; b.in_count = b.wide_count;
     b.out = out; b.cigars = cigars; b.cigar_stride = cigar_stride;
-    { auto kern = sw_banded_kernel<16, false>; SALT_LAUNCH(kern, (unsigned)((n + 127) / 128), 128, 0, st, b); }
+    // bands 1..3 in registers for every task; what they hand over (wider first bands, doubled bands) in the general kernel
+    SALT_LAUNCH(sw_banded_narrow_kernel, (unsigned)((n + 127) / 128), 128, 0, st, b);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    {
+        const size_t wide_blocks = (n + 127) / 128 < (size_t)(4 * (sm_count > 0 ? sm_count : 148)) ? (n + 127) / 128 : (size_t)(4 * (sm_count > 0 ? sm_count : 148));
+        auto kern = sw_banded_kernel<16, false>; SALT_LAUNCH(kern, (unsigned)wide_blocks, 128, 0, st, b);
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     SALT_EV(5);
 
@@ -819,7 +803,7 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     SALT_EV(6);
-    if (launches) *launches += 6;
+    if (launches) *launches += 7;
     return cudaSuccess;
 #undef SALT_EV
 }

@@ -335,6 +335,48 @@ def check_ssw_wide_bands(eng, oracle, seed, n_reads=150, L=100, glen=20003):
     return gapped
 
 
+def check_ssw_narrow_bands(eng, oracle, seed, n_reads=120, L=100, glen=20011):
+    """banded_sw's first band is |refLen - readLen| + 1 (ssw.c:845) and doubles until the band holds score1.  Reads built to
+    walk every branch of the narrow-band pass: no gap (band 1), a 1- or 2-base gap (bands 2, 3), a deletion and an
+    insertion of two bases each far apart (equal lengths: band 1 fails, band 2 succeeds), of three or four bases each (bands 1
+    and 2 fail: handed to the general kernel), a 3+-base gap (first band 4+: general kernel), and reads whose alignment is
+    only a few bases long (soft-clipped to less than the band rows)."""
+    rng = np.random.default_rng(seed)
+    g = synth.Genome(glen, snp_rate=0.01, n_rate=0.0, seed=seed)
+    m = synth.unpack_mixref(g.mixref, 0, g.l)
+    codes = np.log2(np.maximum(m & -m.astype(np.int8), 1)).astype(np.uint8)
+    reads = np.zeros((n_reads, L), np.uint8); wins = np.zeros(n_reads, api.WIN_DT)
+    for i in range(n_reads):
+        p = int(rng.integers(300, g.l - 700))
+        kind = i % 8
+        if kind == 0:
+            rd = codes[p:p + L].copy()
+        elif kind in (1, 2):                                      # one gap of 1..2 bases, deletion or insertion
+            k = kind; a = int(rng.integers(30, 70))
+            if rng.random() < 0.5: rd = np.concatenate([codes[p:p + a], codes[p + a + k:p + k + L]])
+            else: rd = np.concatenate([codes[p:p + a], rng.integers(0, 4, k).astype(np.uint8), codes[p + a:p + L - k]])
+        elif kind in (3, 4, 5):                                   # compensating deletion + insertion of k bases
+            k = kind - 1; a = int(rng.integers(20, 30)); b = int(rng.integers(65, 75))
+            rd = np.concatenate([codes[p:p + a], codes[p + a + k:p + b + k], (3 - codes[p + b + k:p + b + 2 * k]), codes[p + b + k:p + L]])[:L]
+        elif kind == 6:                                           # one gap of 3..6 bases
+            k = int(rng.integers(3, 7)); a = int(rng.integers(30, 70))
+            rd = np.concatenate([codes[p:p + a], codes[p + a + k:p + k + L]])
+        else:                                                     # a few matching bases inside noise
+            k = int(rng.integers(6, 14)); a = int(rng.integers(0, L - k))
+            rd = rng.integers(0, 4, L).astype(np.uint8); rd[a:a + k] = codes[p + a:p + a + k]
+        assert len(rd) == L
+        e = rng.random(L) < 0.01
+        rd = rd.copy(); rd[e] = (rd[e] + 1) & 3
+        reads[i] = rd
+        start = p - int(rng.integers(0, 150))
+        wins[i] = (i << 1, start, start + 400)
+    eng.set_reads(reads)
+    gapped = check_ssw(eng, oracle, g, reads, wins, False, api.salt_score_mat2(), 16, cigar_stride=96)
+    if g.pac is not None:
+        check_ssw(eng, oracle, g, reads, wins, True, api.salt_score_mat2(), 16, cigar_stride=96)
+    return gapped
+
+
 def check_long_cigars(eng, oracle, seed, n_reads=40, L=250):
     """gapped primaries whose CIGAR strings run to 32+ characters (several indels per read): the rows that travel back in the
     slimmed 32-byte form must fall back to the full row, in the one-shot stage and through the chunk pipeline"""

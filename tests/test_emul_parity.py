@@ -187,6 +187,13 @@ def test_ssw_wide_bands_and_end_at_l(emul_lib, oracle):
     assert pc.check_ssw_wide_bands(eng, oracle, 77) >= 120
 
 
+def test_ssw_narrow_bands_every_branch(emul_lib, oracle):
+    """bands 1..3 in registers, the doubling 1 -> 2, the hand-over to the general kernel; mixRef and pac scoring"""
+    g = synth.Genome(20011, snp_rate=0.01, n_rate=0.0, seed=9)
+    eng = _engine(emul_lib, g, with_pac=True)
+    assert pc.check_ssw_narrow_bands(eng, oracle, 9) >= 60
+
+
 def test_ssw_pac_and_params(emul_lib, oracle):
     L = 100
     g, reads, pos, strand, _ = pc.make_world(600, L=L, n_reads=11, per_strand=2, indel_frac=0.7, sub_rate=0.04,

@@ -343,6 +343,15 @@ def test_error_paths():
 
 
 @pytest.mark.gpu
+def test_ssw_narrow_bands_every_branch(oracle):
+    """bands 1..3 in registers, the doubling 1 -> 2, the hand-over to the general kernel; mixRef and pac scoring"""
+    g = synth.Genome(20011, snp_rate=0.01, n_rate=0.0, seed=9)
+    eng = _engine(g)
+    assert pc.check_ssw_narrow_bands(eng, oracle, 9, n_reads=1600) >= 800
+    eng.close()
+
+
+@pytest.mark.gpu
 def test_ssw_wide_bands_and_end_at_l(oracle):
     """bands wider than the main pass, more of them than the overflow pass has threads; windows clamped to end == l"""
     g = synth.Genome(20003, snp_rate=0.01, n_rate=0.0, seed=77)
