@@ -34,6 +34,7 @@ def main():
     at all host threads: the reference, the drop-in seeding on the host (-t workers), the drop-in seeding on the device."""
     glen = int(os.environ.get("GENOME", "5000000")); n = int(os.environ.get("READS", "200000"))
     threads = os.cpu_count() or 1
+    tlist = [threads] if os.environ.get("QUICK") else sorted({1, threads})      # QUICK=1: all host threads only
     res = {"genome_bp": glen, "reads": n, "host_threads": threads}
     with tempfile.TemporaryDirectory() as d:
         dropin_data.write_inputs(d, glen=glen, n_reads=n)
@@ -42,7 +43,7 @@ def main():
         res["se"] = []
         for name, base in (("run_se_test.sh:12 (-r 1)", ["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500"]),
                            ("default seed spacing", ["-d", "-l", "100", "-n", "20", "-c", "-m", "500"])):
-            for t_ in sorted({1, threads}):
+            for t_ in tlist:
                 flags = base + ["-t", str(t_)]
                 row = {"flags": " ".join(flags), "what": name}
                 t_ref, _ = run([os.path.join(REFDIR, "salt")] + flags + ["idx", "reads.fq"], d, os.path.join(d, "ref.sam"))
@@ -65,7 +66,7 @@ def main():
         dropin_data.write_pe_inputs(d, glen=glen, n_pairs=npairs)
         run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], d, os.path.join(d, "idx.log"))
         res["pe"] = []
-        for t_ in sorted({1, threads}):
+        for t_ in tlist:
             flags = ["-d", "-p", "-e", "-l", "100", "-c", "-a", "350", "-b", "650", "-r", "5", "-t", str(t_)]
             t_ref, _ = run([os.path.join(REFDIR, "salt")] + flags + ["idx", "r1.fq", "r2.fq"], d, os.path.join(d, "ref.sam"))
             want = body(os.path.join(d, "ref.sam"))
