@@ -415,33 +415,39 @@ struct NarrowBand {
     int max;
 };
 
-template <int B, int D>
-__device__ __forceinline__ void narrow_row(NarrowBand<B> &s, const DevCtx &c, int use_pac, const int8_t *s_tab, int i, int refLen,
+// One row.  D = [i > B] (slot shift against the previous row); FULL: the row holds all 2B+1 cells (no window end in
+// reach), so nothing in it is predicated.
+template <int B, int D, bool PAC, bool FULL>
+__device__ __forceinline__ void narrow_row(NarrowBand<B> &s, const DevCtx &c, const int8_t *s_tab, int i, int refLen,
                                            uint32_t ref0, int rc, int gapO, int gapE, uint32_t *rowdirs)
 {
     constexpr int W = NarrowBand<B>::W;
     const int beg = D ? i - B : 0;
-    int end = i + B;
-    if (end > refLen - 1) end = refLen - 1;
-    const int n = end - beg + 1;
+    int n = 2 * B + 1;
+    if (!FULL) {
+        int end = i + B;
+        if (end > refLen - 1) end = refLen - 1;
+        n = end - beg + 1;
+        if (!D) {
+            const int edge = end + 1 < W - 1 ? end + 1 : W - 1;
+#pragma unroll
+            for (int k = 1; k < W; ++k) if (k == edge) { s.hb[k] = 0; s.eb[k] = 0; }
+        }
+    }
     s.hb[0] = s.eb[0] = s.hc[0] = 0;
     if (D) { s.hb[W - 1] = 0; s.eb[W - 1] = 0; }
-    else {
-        const int edge = end + 1 < W - 1 ? end + 1 : W - 1;
-#pragma unroll
-        for (int k = 1; k < W; ++k) if (k == edge) { s.hb[k] = 0; s.eb[k] = 0; }
-    }
     uint32_t symw = 0;
-    if (!use_pac) {
+    if (!PAC) {
         const uint32_t p = ref0 + (uint32_t)beg;
         const uint32_t *__restrict__ mw = c.mixref + (p >> 3);
         symw = __funnelshift_r(mw[0], mw[1], 4 * (int)(p & 7u));
     }
+    const int8_t *__restrict__ srow = s_tab + rc;
     int fcur = 0;
     uint32_t dirw = 0;
 #pragma unroll
     for (int u = 1; u <= 2 * B + 1; ++u) {
-        if (u <= n) {
+        if (FULL || u <= n) {
             const int ue = u + D, ud = ue - 1, ub = u - 1;
             int t1 = (!D && i == 0) ? -gapO : s.hb[ue] - gapO;
             int t2 = (!D && i == 0) ? -gapE : s.eb[ue] - gapE;
@@ -455,23 +461,23 @@ __device__ __forceinline__ void narrow_row(NarrowBand<B> &s, const DevCtx &c, in
             const int e1 = ev > 0 ? ev : 0;
             const int f1 = fcur > 0 ? fcur : 0;
             t1 = e1 > f1 ? e1 : f1;
-            const int sym = use_pac ? sw_ref_symbol(c, 1, ref0 + (uint32_t)(beg + u - 1)) : (int)((symw >> (4 * (u - 1))) & 15u);
-            t2 = s.hb[ud] + s_tab[sym * 8 + rc];
+            const int sym = PAC ? sw_ref_symbol(c, 1, ref0 + (uint32_t)(beg + u - 1)) : (int)((symw >> (4 * (u - 1))) & 15u);
+            t2 = s.hb[ud] + srow[sym * 8];
             const int h = t1 > t2 ? t1 : t2;
             s.hc[u] = h;
-            if (h > s.max) s.max = h;
+            s.max = h > s.max ? h : s.max;
             const uint32_t hsel = t1 <= t2 ? 0u : (e1 > f1 ? 1u : 2u);
             dirw |= (e_from_h | (f_from_h << 1) | (hsel << 2)) << (4 * (u - 1));
         }
     }
 #pragma unroll
-    for (int k = 1; k <= 2 * B + 1; ++k) if (k <= n) s.hb[k] = s.hc[k];
+    for (int k = 1; k <= 2 * B + 1; ++k) if (FULL || k <= n) s.hb[k] = s.hc[k];
     rowdirs[(size_t)i * 32] = dirw;
 }
 
 // one banded_sw attempt at band B; max carries over between attempts as in the reference's do-while (ssw.c:575-632)
-template <int B>
-__device__ __forceinline__ bool narrow_fill(const DevCtx &c, int use_pac, const int8_t *s_tab, uint32_t rs, int read0, uint32_t ref0,
+template <int B, bool PAC>
+__device__ __forceinline__ bool narrow_fill(const DevCtx &c, const int8_t *s_tab, uint32_t rs, int read0, uint32_t ref0,
                                             int readLen, int refLen, int score, int gapO, int gapE, uint32_t *rowdirs, int &max)
 {
     NarrowBand<B> s;
@@ -487,9 +493,14 @@ __device__ __forceinline__ bool narrow_fill(const DevCtx &c, int use_pac, const 
     };
 #pragma unroll
     for (int i = 0; i <= B; ++i)
-        if (i < readLen) narrow_row<B, 0>(s, c, use_pac, s_tab, i, refLen, ref0, code_of(read0 + i), gapO, gapE, rowdirs);
-    for (int i = B + 1; i < readLen; ++i)
-        narrow_row<B, 1>(s, c, use_pac, s_tab, i, refLen, ref0, code_of(read0 + i), gapO, gapE, rowdirs);
+        if (i < readLen) narrow_row<B, 0, PAC, false>(s, c, s_tab, i, refLen, ref0, code_of(read0 + i), gapO, gapE, rowdirs);
+    int full_end = refLen - B;                                  // rows below it hold all 2B+1 cells: i + B <= refLen - 1
+    if (full_end > readLen) full_end = readLen;
+    int i = B + 1;
+    for (; i < full_end; ++i)
+        narrow_row<B, 1, PAC, true>(s, c, s_tab, i, refLen, ref0, code_of(read0 + i), gapO, gapE, rowdirs);
+    for (; i < readLen; ++i)
+        narrow_row<B, 1, PAC, false>(s, c, s_tab, i, refLen, ref0, code_of(read0 + i), gapO, gapE, rowdirs);
     max = s.max;
     return s.max >= score;
 }
@@ -507,6 +518,7 @@ struct NarrowCodeAt {
     }
 };
 
+template <bool PAC>
 __global__ void __launch_bounds__(128)
 sw_banded_narrow_kernel(BandDev d)
 {
@@ -538,13 +550,13 @@ sw_banded_narrow_kernel(BandDev d)
     int max = 0;
     if (readLen >= 1 && (size_t)readLen * 4 <= d.slot) {
         if (band == 1 && refLen >= 4) {
-            ok = narrow_fill<1>(d.c, d.prm.use_pac, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
+            ok = narrow_fill<1, PAC>(d.c, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
             if (!ok) band = 2;
         }
         if (!ok && band == 2 && refLen >= 6)
-            ok = narrow_fill<2>(d.c, d.prm.use_pac, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
+            ok = narrow_fill<2, PAC>(d.c, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
         else if (!ok && band == 3 && refLen >= 8)
-            ok = narrow_fill<3>(d.c, d.prm.use_pac, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
+            ok = narrow_fill<3, PAC>(d.c, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
     }
     if (!ok) {                                                               // the general kernel starts this task over
         d.wide_list[atomicAdd(d.wide_count, 1u)] = (uint32_t)t;
@@ -555,9 +567,120 @@ sw_banded_narrow_kernel(BandDev d)
     d.out[t] = o;
 }
 
-// The general kernel walks a list: the tasks the narrow pass handed over (FINAL = false: a band beyond BWMAX goes on to
-// the overflow list), or that overflow list (FINAL = true: SSW_OVF_THREADS threads with wide scratch, a band beyond
-// BWMAX is declined per item).  Every thread of the grid strides over the list, however long it is.
+// ---- wide bands: one warp per task, lanes over the band's diagonals ----------------------------------------------------
+// A task the narrow pass hands over has a first band of 4+ (a long gap) or needed its band doubled: a few per thousand,
+// but one thread walking (2B+1) x readLen cells after the other is what the whole stage then waits for.  Here lane k owns
+// diagonal j - i + B = k of the band.  Cell (i, k) needs (i, k-1) [left: H, F], (i-1, k+1) [up: H, E] and (i-1, k) [own
+// previous cell: H], so with lane k working on row i at step s = 2i + k both neighbours finished exactly one step earlier
+// and their values arrive by shuffle; a lane whose cell lies outside the window or the read publishes zeros, which is what
+// banded_sw's zeroed edge slots hold (refLen >= 2B+2, as for the narrow pass; anything else goes to the serial kernel).
+constexpr int COOP_MAXB = 15;                    // 2B+1 <= 31 lanes
+
+struct PlainCodeAt {
+    const uint8_t *dirs; int wd;
+    __device__ __forceinline__ int operator()(int i, int x, int state) const { return sw_dir_get(dirs[(size_t)wd * i + x], state); }
+};
+
+__global__ void __launch_bounds__(128)
+sw_banded_coop_kernel(BandDev d, int rows8, int smem_per_warp)
+{
+    constexpr unsigned FULLM = 0xffffffffu;
+    __shared__ int8_t s_tab[17 * 8];
+    SALT_DYN_SMEM(uint8_t, s_dirs);                                      // [warp][smem_per_warp]
+    for (int i = threadIdx.x; i < 17 * 8; i += blockDim.x) s_tab[i] = d.prm.table[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const size_t n_items = (size_t)*d.in_count;
+    uint8_t *gdirs = d.dirs + warp * ((size_t)(2 * COOP_MAXB + 1) * (size_t)rows8);
+    uint8_t *sdirs = s_dirs + (size_t)(threadIdx.x >> 5) * (size_t)smem_per_warp;
+    for (size_t item = warp; item < n_items; item += n_warps) {
+        const size_t t = (size_t)d.in_list[item];
+        const int32_t *f = d.fwd + t * 8;
+        salt_ssw_out_t o;
+        o.score1 = (uint16_t)f[F_SCORE1]; o.score2 = (uint16_t)f[F_SCORE2];
+        o.ref_begin1 = f[F_REF_BEGIN1]; o.ref_end1 = f[F_REF_END1];
+        o.read_begin1 = f[F_READ_BEGIN1]; o.read_end1 = f[F_READ_END1];
+        o.ref_end2 = f[F_REF_END2]; o.cigarLen = 0;
+        const salt_win_t w = d.wins[t];
+        const int refLen = o.ref_end1 - o.ref_begin1 + 1, readLen = o.read_end1 - o.read_begin1 + 1;
+        const uint32_t ref0 = w.start + (uint32_t)o.ref_begin1;
+        const int read0 = o.read_begin1;
+        const int score = o.score1, gapO = d.prm.gapO, gapE = d.prm.gapE;
+        int band = abs(refLen - readLen) + 1;                                // ssw.c:845
+        int max = 0, wd = 0;
+        bool served = true;
+        uint8_t *dirs = gdirs;
+        do {
+            wd = 2 * band + 1;
+            if (band > COOP_MAXB || refLen < 2 * band + 2 || readLen < 1) { served = false; break; }
+            dirs = (size_t)wd * (size_t)readLen <= (size_t)smem_per_warp ? sdirs : gdirs;
+            const int k = lane;
+            const bool lane_on = k < wd;
+            int Hlast = 0, Elast = 0, Flast = 0, Hown = 0, lmax = 0;
+            // substitution score of the lane's next cell, fetched one round ahead of its use
+            auto score_of = [&](int i, int j) -> int {
+                if (i >= readLen || j < 0 || j >= refLen) return 0;
+                return s_tab[sw_ref_symbol(d.c, d.prm.use_pac, ref0 + (uint32_t)j) * 8 + sw_read_code(d.c, w.rs, read0 + i)];
+            };
+            int sc = 0;
+            {   // first cell of the lane: row i0 = max(0, B - k) rounded to the lane's parity is simply the first i with j >= 0
+                const int i0 = band - k > 0 ? band - k : 0;
+                if (lane_on) sc = score_of(i0, i0 + k - band);
+            }
+            const int n_steps = 2 * (readLen - 1) + wd;
+            for (int s = 0; s < n_steps; ++s) {
+                const int upH = __shfl_down_sync(FULLM, Hlast, 1), upE = __shfl_down_sync(FULLM, Elast, 1);
+                int leftH = __shfl_up_sync(FULLM, Hlast, 1), leftF = __shfl_up_sync(FULLM, Flast, 1);
+                if (lane == 0) { leftH = 0; leftF = 0; }
+                const int d2 = s - k;
+                if (lane_on && d2 >= 0 && !(d2 & 1)) {
+                    const int i = d2 >> 1, j = i + k - band;
+                    int h = 0, e = 0, fv = 0;
+                    if (i < readLen && j >= 0 && j < refLen) {
+                        int t1 = upH - gapO, t2 = upE - gapE;
+                        const int de = t1 > t2 ? 3 : 2;
+                        e = t1 > t2 ? t1 : t2;
+                        t1 = leftH - gapO; t2 = leftF - gapE;
+                        const int df = t1 > t2 ? 5 : 4;
+                        fv = t1 > t2 ? t1 : t2;
+                        const int e1 = e > 0 ? e : 0, f1 = fv > 0 ? fv : 0;
+                        t1 = e1 > f1 ? e1 : f1;
+                        t2 = Hown + sc;
+                        h = t1 > t2 ? t1 : t2;
+                        lmax = h > lmax ? h : lmax;
+                        const int dh = t1 <= t2 ? 1 : (e1 > f1 ? de : df);
+                        dirs[(size_t)wd * i + band_d(band, i, j)] = sw_dir_pack(de, df, dh);
+                        sc = score_of(i + 1, j + 1);
+                    } else if (j < 0) sc = score_of(i + 1, j + 1);       // still above the window's first column
+                    Hown = h; Hlast = h; Elast = e; Flast = fv;
+                }
+            }
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) { const int v = __shfl_xor_sync(FULLM, lmax, o2); lmax = v > lmax ? v : lmax; }
+            max = lmax > max ? lmax : max;
+            band *= 2;
+        } while (max < score);
+        __syncwarp();
+        if (lane == 0) {
+            if (!served) {
+                if (d.ovf_list) { d.ovf_list[atomicAdd(d.ovf_count, 1u)] = (uint32_t)t; o.cigarLen = 0; }
+                else o.cigarLen = -2;
+            } else {
+                band /= 2;
+                PlainCodeAt at{dirs, wd};
+                o.cigarLen = band_traceback(at, band, wd, readLen, refLen, d.cigars + t * (size_t)d.cigar_stride, d.cigar_stride);
+            }
+            d.out[t] = o;
+        }
+        __syncwarp();
+    }
+}
+
+// The serial kernel: one thread per listed task, a literal restatement of banded_sw's arrays (any window shape, every quirk
+// of its edge handling).  It serves what the two passes above hand on (FINAL = true: SSW_OVF_THREADS threads with scratch
+// for bands up to BWMAX = 512, a band beyond that is declined per item); every thread strides over the list.
 template <int BWMAX, bool FINAL>
 __global__ void __launch_bounds__(128)
 sw_banded_kernel(BandDev d)
@@ -786,11 +909,18 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
     b.in_list = b.wide_list; b.in_count = b.wide_count;
     b.out = out; b.cigars = cigars; b.cigar_stride = cigar_stride;
     // bands 1..3 in registers for every task; what they hand over (wider first bands, doubled bands) in the general kernel
-    SALT_LAUNCH(sw_banded_narrow_kernel, (unsigned)((n + 127) / 128), 128, 0, st, b);
+    if (prm.use_pac) { auto kern = sw_banded_narrow_kernel<true>; SALT_LAUNCH(kern, (unsigned)((n + 127) / 128), 128, 0, st, b); }
+    else { auto kern = sw_banded_narrow_kernel<false>; SALT_LAUNCH(kern, (unsigned)((n + 127) / 128), 128, 0, st, b); }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     {
-        const size_t wide_blocks = (n + 127) / 128 < (size_t)(4 * (sm_count > 0 ? sm_count : 148)) ? (n + 127) / 128 : (size_t)(4 * (sm_count > 0 ? sm_count : 148));
-        auto kern = sw_banded_kernel<16, false>; SALT_LAUNCH(kern, (unsigned)wide_blocks, 128, 0, st, b);
+        // one warp per handed-over task; scratch per warp: direction bytes of a band of COOP_MAXB (shared memory when they fit)
+        const int rows8 = 8 * (((int)c.l_max + 7) / 8);
+        const size_t cap = (size_t)(4 * (sm_count > 0 ? sm_count : 148));
+        const size_t coop_blocks = (n + 3) / 4 < cap ? (n + 3) / 4 : cap;
+        int smem_per_warp = (2 * COOP_MAXB + 1) * rows8;
+        if (smem_per_warp > 11 * 1024) smem_per_warp = 11 * 1024;
+        smem_per_warp = (smem_per_warp + 15) / 16 * 16;
+        SALT_LAUNCH(sw_banded_coop_kernel, (unsigned)coop_blocks, 128, (size_t)4 * smem_per_warp, st, b, rows8, smem_per_warp);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     SALT_EV(5);

@@ -339,8 +339,8 @@ def check_ssw_narrow_bands(eng, oracle, seed, n_reads=120, L=100, glen=20011):
     """banded_sw's first band is |refLen - readLen| + 1 (ssw.c:845) and doubles until the band holds score1.  Reads built to
     walk every branch of the narrow-band pass: no gap (band 1), a 1- or 2-base gap (bands 2, 3), a deletion and an
     insertion of two bases each far apart (equal lengths: band 1 fails, band 2 succeeds), of three or four bases each (bands 1
-    and 2 fail: handed to the general kernel), a 3+-base gap (first band 4+: general kernel), and reads whose alignment is
-    only a few bases long (soft-clipped to less than the band rows)."""
+    and 2 fail: handed to the general kernel), a 3+-base gap (first band 4+: general kernel), a 3..14-base gap (first band up to 15, the widest the warp-per-task pass
+    serves) and reads whose alignment is only a few bases long (soft-clipped to less than the band rows)."""
     rng = np.random.default_rng(seed)
     g = synth.Genome(glen, snp_rate=0.01, n_rate=0.0, seed=seed)
     m = synth.unpack_mixref(g.mixref, 0, g.l)
@@ -358,8 +358,8 @@ def check_ssw_narrow_bands(eng, oracle, seed, n_reads=120, L=100, glen=20011):
         elif kind in (3, 4, 5):                                   # compensating deletion + insertion of k bases
             k = kind - 1; a = int(rng.integers(20, 30)); b = int(rng.integers(65, 75))
             rd = np.concatenate([codes[p:p + a], codes[p + a + k:p + b + k], (3 - codes[p + b + k:p + b + 2 * k]), codes[p + b + k:p + L]])[:L]
-        elif kind == 6:                                           # one gap of 3..6 bases
-            k = int(rng.integers(3, 7)); a = int(rng.integers(30, 70))
+        elif kind == 6:                                           # one gap of 3..14 bases: first bands 4..15, one warp per task
+            k = int(rng.integers(3, 15)); a = int(rng.integers(30, 70))
             rd = np.concatenate([codes[p:p + a], codes[p + a + k:p + k + L]])
         else:                                                     # a few matching bases inside noise
             k = int(rng.integers(6, 14)); a = int(rng.integers(0, L - k))

@@ -24,7 +24,7 @@ def main():
     for it in range(2):
         rec, a0, a1, cig = eng.verify(wl["offs0"], wl["loci0"], wl["offs1"], wl["loci1"], 3, -1)
     print("verify: mapped %d lv_ran %d gapped %d" % ((rec["pos"] != 0xFFFFFFFF).sum(), rec["lv_ran"].sum(), (rec["is_gap"] == 1).sum()))
-    nt = min(n, 100000); W = 401; L = args.read_len
+    nt = min(n, int(os.environ.get("PROF_SW_TASKS", "100000"))); W = 401; L = args.read_len
     rng = np.random.default_rng(5)
     start = np.maximum(0, wl["pos"][:nt].astype(np.int64) - rng.integers(0, W - L, nt))
     wins = np.zeros(nt, api.WIN_DT)
