@@ -44,6 +44,17 @@ __device__ __forceinline__ int sw_ref_symbol(const DevCtx &c, int use_pac, uint3
     return (c.mixref[p >> 3] >> (4u * (p & 7u))) & 15u;
 }
 
+// eight consecutive pac symbols starting at position p, one per nibble (lowest nibble first)
+__device__ __forceinline__ uint32_t sw_pac_group(const uint8_t *__restrict__ pac, uint32_t p)
+{
+    const uint8_t *__restrict__ b = pac + (p >> 2);
+    const uint32_t x = ((uint32_t)b[0] << 16) | ((uint32_t)b[1] << 8) | (uint32_t)b[2];      // 12 symbols, first in the top bits
+    uint32_t r = 0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) r |= ((x >> (22 - 2 * (int)((p & 3u) + (uint32_t)m))) & 3u) << (4 * m);
+    return r;
+}
+
 // read code 0..4 of packed read rs at index i (one-hot nibble -> code)
 __device__ __forceinline__ int sw_read_code(const DevCtx &c, uint32_t rs, int i)
 {
@@ -358,7 +369,8 @@ struct BandDev {
     uint8_t *dirs; size_t slot;          // per-thread direction scratch
     uint32_t *ovf_list; uint32_t *ovf_count; uint32_t ovf_cap;
     const uint32_t *in_list; const uint32_t *in_count;   // list-driven passes: their input
-    uint32_t *wide_list; uint32_t *wide_count;           // narrow pass: tasks it hands to the general kernel
+    uint32_t *dp_list; uint32_t *dp_count;               // diagonal pass: tasks that need banded_sw's dynamic program
+    uint32_t *wide_list; uint32_t *wide_count;           // narrow pass: tasks it hands to the warp-per-task kernel
     salt_ssw_out_t *out; uint32_t *cigars; int cigar_stride;
 };
 
@@ -518,16 +530,22 @@ struct NarrowCodeAt {
     }
 };
 
+// ---- the gapless majority: no dynamic program at all ----------------------------------------------------------------------
+// banded_sw runs on the rectangle [ref_begin1, ref_end1] x [read_begin1, read_end1] the two score passes found.  When the
+// rectangle is square and the plain sum P of the substitution scores along its diagonal equals score1, the result is known:
+// the first band is 1; H(i,i) >= P_i along the diagonal, so the band's maximum reaches score1 and the band is not doubled;
+// and at every diagonal cell the traceback takes the diagonal -- were max(E, F, 0) > H(i-1,i-1) + s_i >= P_i at some
+// cell, following the diagonal from there would end above P = score1, the maximum over the whole window (ties go to the
+// diagonal, ssw.c:609).  The cigar is "<readLen>M".  Everything else is listed for the dynamic program.
 template <bool PAC>
 __global__ void __launch_bounds__(128)
-sw_banded_narrow_kernel(BandDev d)
+sw_diag_kernel(BandDev d)
 {
     __shared__ int8_t s_tab[17 * 8];
     for (int i = threadIdx.x; i < 17 * 8; i += blockDim.x) s_tab[i] = d.prm.table[i];
     __syncthreads();
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= d.n_tasks) return;
-    const size_t t = tid;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d.n_tasks) return;
     const int32_t *f = d.fwd + t * 8;
     const int fl = f[F_FLAGS];
     salt_ssw_out_t o;
@@ -537,6 +555,60 @@ sw_banded_narrow_kernel(BandDev d)
     o.ref_end2 = f[F_REF_END2]; o.cigarLen = 0;
     if (!(fl & FL_VALID)) { o.ref_end2 = -1; o.cigarLen = -1; }
     if (!(fl & FL_DO_CIGAR)) { d.out[t] = o; return; }
+    const salt_win_t w = d.wins[t];
+    const int refLen = o.ref_end1 - o.ref_begin1 + 1, readLen = o.read_end1 - o.read_begin1 + 1;
+    if (refLen == readLen && readLen >= 1) {
+        const uint32_t ref0 = w.start + (uint32_t)o.ref_begin1;
+        const int read0 = o.read_begin1;
+        const uint64_t *__restrict__ rd = d.c.rd4 + (size_t)w.rs * d.c.W64;
+        int P = 0;
+        for (int i0 = 0; i0 < readLen; i0 += 8) {
+            const uint32_t p = ref0 + (uint32_t)i0;
+            uint32_t symw;
+            if (PAC) symw = sw_pac_group(d.c.pac, p);
+            else { const uint32_t *__restrict__ mw = d.c.mixref + (p >> 3); symw = __funnelshift_r(mw[0], mw[1], 4 * (int)(p & 7u)); }
+            const int idx = read0 + i0, wi = idx >> 4, sh = 4 * (idx & 15);
+            uint64_t rw = rd[wi] >> sh;
+            if (sh > 32 && wi + 1 < (int)d.c.W64) rw |= rd[wi + 1] << (64 - sh);
+            const uint32_t codes = (uint32_t)rw;
+            const int n8 = readLen - i0 < 8 ? readLen - i0 : 8;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                if (m < n8) {
+                    const unsigned nib = (codes >> (4 * m)) & 15u;
+                    const int rc = nib == 15u ? SW_CODE_N : (31 - __clz(nib));
+                    P += s_tab[((symw >> (4 * m)) & 15u) * 8 + rc];
+                }
+            }
+        }
+        if (P == (int)o.score1) {
+            if (d.cigar_stride > 0) d.cigars[t * (size_t)d.cigar_stride] = (uint32_t)readLen << 4;
+            o.cigarLen = 1;
+            d.out[t] = o;
+            return;
+        }
+    }
+    d.dp_list[atomicAdd(d.dp_count, 1u)] = (uint32_t)t;
+}
+
+template <bool PAC>
+__global__ void __launch_bounds__(128)
+sw_banded_narrow_kernel(BandDev d)
+{
+    __shared__ int8_t s_tab[17 * 8];
+    for (int i = threadIdx.x; i < 17 * 8; i += blockDim.x) s_tab[i] = d.prm.table[i];
+    __syncthreads();
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n_items = (size_t)*d.in_count;
+    const size_t item_step = (size_t)gridDim.x * blockDim.x;
+    for (size_t item = tid; item < n_items; item += item_step) {
+    const size_t t = (size_t)d.in_list[item];
+    const int32_t *f = d.fwd + t * 8;
+    salt_ssw_out_t o;
+    o.score1 = (uint16_t)f[F_SCORE1]; o.score2 = (uint16_t)f[F_SCORE2];
+    o.ref_begin1 = f[F_REF_BEGIN1]; o.ref_end1 = f[F_REF_END1];
+    o.read_begin1 = f[F_READ_BEGIN1]; o.read_end1 = f[F_READ_END1];
+    o.ref_end2 = f[F_REF_END2]; o.cigarLen = 0;                  // listed tasks are valid and want a cigar
 
     const salt_win_t w = d.wins[t];
     const int refLen = o.ref_end1 - o.ref_begin1 + 1, readLen = o.read_end1 - o.read_begin1 + 1;
@@ -558,13 +630,14 @@ sw_banded_narrow_kernel(BandDev d)
         else if (!ok && band == 3 && refLen >= 8)
             ok = narrow_fill<3, PAC>(d.c, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
     }
-    if (!ok) {                                                               // the general kernel starts this task over
+    if (!ok) {                                                               // the warp-per-task kernel starts this task over
         d.wide_list[atomicAdd(d.wide_count, 1u)] = (uint32_t)t;
-        return;
+        continue;
     }
     NarrowCodeAt at{rowdirs};
     o.cigarLen = band_traceback(at, band, 2 * band + 1, readLen, refLen, d.cigars + t * (size_t)d.cigar_stride, d.cigar_stride);
     d.out[t] = o;
+    }
 }
 
 // ---- wide bands: one warp per task, lanes over the band's diagonals ----------------------------------------------------
@@ -619,16 +692,23 @@ sw_banded_coop_kernel(BandDev d, int rows8, int smem_per_warp)
             const int k = lane;
             const bool lane_on = k < wd;
             int Hlast = 0, Elast = 0, Flast = 0, Hown = 0, lmax = 0;
-            // substitution score of the lane's next cell, fetched one round ahead of its use
-            auto score_of = [&](int i, int j) -> int {
-                if (i >= readLen || j < 0 || j >= refLen) return 0;
-                return s_tab[sw_ref_symbol(d.c, d.prm.use_pac, ref0 + (uint32_t)j) * 8 + sw_read_code(d.c, w.rs, read0 + i)];
-            };
-            int sc = 0;
-            {   // first cell of the lane: row i0 = max(0, B - k) rounded to the lane's parity is simply the first i with j >= 0
-                const int i0 = band - k > 0 ? band - k : 0;
-                if (lane_on) sc = score_of(i0, i0 + k - band);
+            // The lane walks its diagonal: row and column advance together.  Eight reference symbols and sixteen read codes
+            // at a time sit in registers, the words behind them are fetched a group ahead, so no step waits on memory.
+            const int i0 = band - k > 0 ? band - k : 0;                    // first row whose column j = i + k - band is >= 0
+            const uint32_t p0 = ref0 + (uint32_t)(i0 + k - band);
+            uint32_t symw = 0, w1 = 0, w2 = 0, wnext = 0;
+            int rsh = 0;
+            if (!d.prm.use_pac) {
+                const uint32_t *__restrict__ mw = d.c.mixref + (p0 >> 3);
+                rsh = 4 * (int)(p0 & 7u);
+                w1 = mw[1]; w2 = mw[2]; wnext = 3;
+                symw = __funnelshift_r(mw[0], w1, rsh);
+            } else {
+                symw = sw_pac_group(d.c.pac, p0); w1 = sw_pac_group(d.c.pac, p0 + 8u);
             }
+            const uint64_t *__restrict__ rd = d.c.rd4 + (size_t)w.rs * d.c.W64;
+            const int rword0 = (read0 + i0) >> 4;
+            uint64_t rw = rword0 < (int)d.c.W64 ? rd[rword0] : 0ull, rwn = rword0 + 1 < (int)d.c.W64 ? rd[rword0 + 1] : 0ull;
             const int n_steps = 2 * (readLen - 1) + wd;
             for (int s = 0; s < n_steps; ++s) {
                 const int upH = __shfl_down_sync(FULLM, Hlast, 1), upE = __shfl_down_sync(FULLM, Elast, 1);
@@ -638,22 +718,41 @@ sw_banded_coop_kernel(BandDev d, int rows8, int smem_per_warp)
                 if (lane_on && d2 >= 0 && !(d2 & 1)) {
                     const int i = d2 >> 1, j = i + k - band;
                     int h = 0, e = 0, fv = 0;
-                    if (i < readLen && j >= 0 && j < refLen) {
-                        int t1 = upH - gapO, t2 = upE - gapE;
-                        const int de = t1 > t2 ? 3 : 2;
-                        e = t1 > t2 ? t1 : t2;
-                        t1 = leftH - gapO; t2 = leftF - gapE;
-                        const int df = t1 > t2 ? 5 : 4;
-                        fv = t1 > t2 ? t1 : t2;
-                        const int e1 = e > 0 ? e : 0, f1 = fv > 0 ? fv : 0;
-                        t1 = e1 > f1 ? e1 : f1;
-                        t2 = Hown + sc;
-                        h = t1 > t2 ? t1 : t2;
-                        lmax = h > lmax ? h : lmax;
-                        const int dh = t1 <= t2 ? 1 : (e1 > f1 ? de : df);
-                        dirs[(size_t)wd * i + band_d(band, i, j)] = sw_dir_pack(de, df, dh);
-                        sc = score_of(i + 1, j + 1);
-                    } else if (j < 0) sc = score_of(i + 1, j + 1);       // still above the window's first column
+                    if (i >= i0) {
+                        const int cell = i - i0;                            // cells of this lane so far
+                        const int sym = (int)((symw >> (4 * (cell & 7))) & 15u);
+                        const int ridx = read0 + i;
+                        const unsigned nib = (unsigned)(rw >> (4 * (ridx & 15))) & 15u;
+                        const int rc = nib == 15u ? SW_CODE_N : (31 - __clz(nib));
+                        if (i < readLen && j < refLen) {
+                            int t1 = upH - gapO, t2 = upE - gapE;
+                            const int de = t1 > t2 ? 3 : 2;
+                            e = t1 > t2 ? t1 : t2;
+                            t1 = leftH - gapO; t2 = leftF - gapE;
+                            const int df = t1 > t2 ? 5 : 4;
+                            fv = t1 > t2 ? t1 : t2;
+                            const int e1 = e > 0 ? e : 0, f1 = fv > 0 ? fv : 0;
+                            t1 = e1 > f1 ? e1 : f1;
+                            t2 = Hown + s_tab[sym * 8 + rc];
+                            h = t1 > t2 ? t1 : t2;
+                            lmax = h > lmax ? h : lmax;
+                            const int dh = t1 <= t2 ? 1 : (e1 > f1 ? de : df);
+                            dirs[(size_t)wd * i + band_d(band, i, j)] = sw_dir_pack(de, df, dh);
+                        }
+                        if ((cell & 7) == 7) {                              // next eight symbols; the words after them are requested now
+                            if (!d.prm.use_pac) {
+                                symw = __funnelshift_r(w1, w2, rsh);
+                                w1 = w2; w2 = d.c.mixref[(p0 >> 3) + wnext]; ++wnext;
+                            } else {
+                                symw = w1; w1 = sw_pac_group(d.c.pac, p0 + (uint32_t)(cell + 9));
+                            }
+                        }
+                        if ((ridx & 15) == 15) {
+                            rw = rwn;
+                            const int nw = (ridx >> 4) + 2;
+                            rwn = nw < (int)d.c.W64 ? rd[nw] : 0ull;
+                        }
+                    }
                     Hown = h; Hlast = h; Elast = e; Flast = fv;
                 }
             }
@@ -794,7 +893,7 @@ static SwShape pick_shape(int l_max)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// layout: [0]=win2 [1]=rsel [2]=maxcol2 [3]=fwd [4]=dirs [5]=ovf_list [6]=counters [7]=total [8]=wide_list
+// layout: [0]=win2 [1]=rsel [2]=maxcol2 [3]=fwd [4]=dirs [5]=ovf_list [6]=counters [7]=total [8]=wide_list [9]=dp_list
 size_t ssw_scratch_bytes(size_t n_tasks, int max_cols, int max_rows, size_t *layout)
 {
     const SwShape sh = pick_shape(max_rows);
@@ -811,6 +910,7 @@ size_t ssw_scratch_bytes(size_t n_tasks, int max_cols, int max_rows, size_t *lay
     layout[5] = off; off = align_up(off + n_tasks * sizeof(uint32_t), 256);
     layout[6] = off; off = align_up(off + 256, 256);
     layout[8] = off; off = align_up(off + n_tasks * sizeof(uint32_t), 256);
+    layout[9] = off; off = align_up(off + n_tasks * sizeof(uint32_t), 256);
     layout[7] = off;
     return off;
 }
@@ -864,7 +964,7 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
 {
 #define SALT_EV(i) do { if (ev) cudaEventRecord(ev[i], st); } while (0)
     if (!n) return cudaSuccess;
-    size_t lay[9];
+    size_t lay[10];
     const size_t need = ssw_scratch_bytes(n, max_cols, (int)c.l_max, lay);
     if (need > scratch_bytes) return cudaErrorMemoryAllocation;
     const SwShape sh = pick_shape((int)c.l_max);
@@ -906,12 +1006,22 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
     b.ovf_count = ovf_count; b.ovf_cap = SSW_OVF_THREADS;
     if (!ovf_dirs) b.ovf_list = nullptr;                  // no overflow scratch: wide bands come back with cigarLen = -2
     b.wide_list = reinterpret_cast<uint32_t *>(base + lay[8]); b.wide_count = ovf_count + 1;
-    b.in_list = b.wide_list; b.in_count = b.wide_count;
+    b.dp_list = reinterpret_cast<uint32_t *>(base + lay[9]); b.dp_count = ovf_count + 2;
     b.out = out; b.cigars = cigars; b.cigar_stride = cigar_stride;
-    // bands 1..3 in registers for every task; what they hand over (wider first bands, doubled bands) in the general kernel
-    if (prm.use_pac) { auto kern = sw_banded_narrow_kernel<true>; SALT_LAUNCH(kern, (unsigned)((n + 127) / 128), 128, 0, st, b); }
-    else { auto kern = sw_banded_narrow_kernel<false>; SALT_LAUNCH(kern, (unsigned)((n + 127) / 128), 128, 0, st, b); }
+    const unsigned task_blocks = (unsigned)((n + 127) / 128);
+    const unsigned list_blocks = task_blocks < (unsigned)(4 * (sm_count > 0 ? sm_count : 148)) ? task_blocks : (unsigned)(4 * (sm_count > 0 ? sm_count : 148));
+    // (1) gapless rectangles: one pass over the diagonal; (2) bands 1..3 in registers for what is left; (3) what they hand
+    // over (wider first bands, doubled bands) one warp per task; (4) the serial kernel for the rest
+    b.in_list = b.dp_list; b.in_count = b.dp_count;
+    if (prm.use_pac) {
+        { auto kern = sw_diag_kernel<true>; SALT_LAUNCH(kern, task_blocks, 128, 0, st, b); }
+        { auto kern = sw_banded_narrow_kernel<true>; SALT_LAUNCH(kern, list_blocks, 128, 0, st, b); }
+    } else {
+        { auto kern = sw_diag_kernel<false>; SALT_LAUNCH(kern, task_blocks, 128, 0, st, b); }
+        { auto kern = sw_banded_narrow_kernel<false>; SALT_LAUNCH(kern, list_blocks, 128, 0, st, b); }
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    b.in_list = b.wide_list; b.in_count = b.wide_count;
     {
         // one warp per handed-over task; scratch per warp: direction bytes of a band of COOP_MAXB (shared memory when they fit)
         const int rows8 = 8 * (((int)c.l_max + 7) / 8);
@@ -933,7 +1043,7 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     SALT_EV(6);
-    if (launches) *launches += 7;
+    if (launches) *launches += 8;
     return cudaSuccess;
 #undef SALT_EV
 }

@@ -57,6 +57,10 @@ g3 = synth.Genome(20003, snp_rate=0.01, n_rate=0.0, seed=77)
 eng = api.Engine(g3.mixref, g3.l, None, 0, lib=lib)
 pc.check_ssw_wide_bands(eng, o, 77, n_reads=140)
 eng.close()
+g4 = synth.Genome(20011, snp_rate=0.01, n_rate=0.0, seed=9)
+eng = api.Engine(g4.mixref, g4.l, g4.pac, g4.l, lib=lib)
+pc.check_ssw_narrow_bands(eng, o, 9, n_reads=64)          # bands 1..3 in registers, warp-per-task bands, both scoring flavours
+eng.close()
 print("asan ok transport / tail / wide bands", flush=True)
 if sc.have_ref():
     rng = np.random.default_rng(3)

@@ -2,7 +2,8 @@
 """Randomised GPU-vs-oracle stress run (beyond the seeded cases of tests/): random read lengths, candidate densities,
 error mixes, thresholds and kernel mappings through the verify stage, the per-pair LV / mismatch / CIGAR entry points,
 the SAM tail and the rescue Smith-Waterman.  Stops at the first mismatch (assert).
-    python tools/fuzz_gpu.py [seconds] [seed]"""
+    python tools/fuzz_gpu.py [seconds] [seed] [ssw]        (third argument "ssw": only the rescue Smith-Waterman, many windows
+                                                            per world, random gap penalties and window widths)"""
 import os
 import sys
 import time
@@ -25,7 +26,25 @@ except Exception:                                    # noqa: BLE001
     hostlib = None
 rng = np.random.default_rng(seed0)
 t0 = time.time(); it = 0; tot_reads = 0
-while time.time() - t0 < budget:
+ssw_only = len(sys.argv) > 3 and sys.argv[3] == "ssw"
+while ssw_only and time.time() - t0 < budget:
+    L = int(rng.choice([37, 64, 100, 101, 150, 250]))
+    n = int(rng.integers(100, 260))
+    g, reads, pos, strand, cands = pc.make_world(int(rng.integers(1 << 30)), glen=int(rng.integers(30000, 120000)), L=L, n_reads=n,
+                                                 per_strand=1, snp_rate=float(rng.choice([0.0, 0.01, 0.05])),
+                                                 n_rate=float(rng.choice([0.0, 0.002])), sub_rate=float(rng.choice([0.0, 0.01, 0.04])),
+                                                 indel_frac=float(rng.choice([0.3, 0.8, 1.0])), n_frac=float(rng.choice([0.0, 0.003])))
+    eng = api.Engine(g.mixref, g.l, g.pac, g.l, device=0)
+    eng.set_reads(reads)
+    wins = pc.make_windows(g, reads, pos, strand, L, rng, int(rng.choice([L + 20, 301, 401, 2 * L + 60])))
+    gapO, gapE = [(3, 1), (5, 2), (2, 1), (6, 1), (4, 3)][int(rng.integers(0, 5))]
+    pac = bool(it % 2)
+    pc.check_ssw(eng, o, g, reads, wins, pac, api.salt_score_mat() if pac else api.salt_score_mat2(), 5 if pac else 16,
+                 gapO=gapO, gapE=gapE, flag=int(rng.choice([2, 1, 6])), filters=int(rng.choice([0, 20, 60])),
+                 filterd=int(rng.choice([20, 5, 300])), mask_len=int(rng.choice([-1, 15, 40])), cigar_stride=int(rng.choice([96, 64])))
+    eng.close()
+    it += 1; tot_reads += n
+while not ssw_only and time.time() - t0 < budget:
     L = int(rng.choice([37, 50, 64, 75, 100, 101, 125, 150, 151, 200, 250, 300]))
     n = int(rng.integers(40, 220 if L <= 150 else 90))
     per = int(rng.integers(1, 14))
