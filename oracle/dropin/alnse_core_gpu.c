@@ -107,7 +107,11 @@ static void *finish_worker(void *arg)
 {
     fin_thread_t *F = (fin_thread_t *)arg;
     int j;
-    for (j = F->first + F->tid; j < F->upto; j += F->n_threads) {
+    /* a contiguous share per worker, not the reference's interleave (alnse.c:1321): neighbouring reads' kstring_t headers share
+       a cache line, and aln_samse updates its header a few hundred times per read */
+    const int span = F->upto - F->first, lo = F->first + (int)((long)span * F->tid / F->n_threads),
+              hi = F->first + (int)((long)span * (F->tid + 1) / F->n_threads);
+    for (j = lo; j < hi; ++j) {
         if (F->slot_of[j] < 0) continue;
         if (F->phase == 0) finish_read(F->index, F->queries + j, F->aln_opt, F->ck, (uint32_t)F->slot_of[j]);
         else { dropin_tail_begin_read(j); aln_samse(F->index, F->queries + j, F->aln_opt); }      /* alnse.c:1307 / :1345 */
@@ -132,6 +136,67 @@ static double now_s(void)
     struct timespec t;
     clock_gettime(CLOCK_MONOTONIC, &t);
     return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+
+/* ---- the reference's FASTQ reader and its SAM printing on their own threads (the reference runs both on the main thread,
+ * between its batches, alnse.c:1414-1440): batch k lives in buffer k % 3; the reader fills it, the main thread aligns it, the
+ * writer prints and frees it.  Output order is the input order: batches are written in sequence. */
+#define DROPIN_BATCH_BUFS 3
+typedef struct {
+    pthread_mutex_t mu; pthread_cond_t cv;
+    queryio_t *qs;
+    query_t *buf[DROPIN_BATCH_BUFS]; int cnt[DROPIN_BATCH_BUFS];
+    int n_read, n_done, n_written, all_done;          /* batches read / aligned / written so far */
+    double t_read, t_print;
+} batch_pipe_t;
+
+static void *reader_thread(void *arg)
+{
+    batch_pipe_t *P = (batch_pipe_t *)arg;
+    int k;
+    for (k = 0;; ++k) {
+        pthread_mutex_lock(&P->mu);
+        while (k - P->n_written >= DROPIN_BATCH_BUFS) pthread_cond_wait(&P->cv, &P->mu);
+        pthread_mutex_unlock(&P->mu);
+        double t0 = now_s();
+        int n = query_read_multiSeqs(P->qs, N_SEQS, P->buf[k % DROPIN_BATCH_BUFS]);
+        P->t_read += now_s() - t0;
+        pthread_mutex_lock(&P->mu);
+        P->cnt[k % DROPIN_BATCH_BUFS] = n; P->n_read = k + 1;
+        pthread_cond_broadcast(&P->cv);
+        pthread_mutex_unlock(&P->mu);
+        if (n <= 0) break;
+    }
+    return NULL;
+}
+
+static void *writer_thread(void *arg)
+{
+    batch_pipe_t *P = (batch_pipe_t *)arg;
+    int k, i, n_tot = 0;
+    for (k = 0;; ++k) {
+        pthread_mutex_lock(&P->mu);
+        while (P->n_done <= k && !P->all_done) pthread_cond_wait(&P->cv, &P->mu);
+        const int have = P->n_done > k;
+        pthread_mutex_unlock(&P->mu);
+        if (!have) break;
+        double t0 = now_s();
+        query_t *q = P->buf[k % DROPIN_BATCH_BUFS];
+        const int n = P->cnt[k % DROPIN_BATCH_BUFS];
+        for (i = 0; i < n; ++i) {
+            puts(q[i].sam->s);                          /* alnse.c:1433-1439 */
+            query_destroy(q + i);
+        }
+        memset(q, 0, N_SEQS * sizeof(query_t));
+        n_tot += n;
+        fprintf(stderr, "%d reads have been aligned!\n", n_tot);
+        P->t_print += now_s() - t0;
+        pthread_mutex_lock(&P->mu);
+        P->n_written = k + 1;
+        pthread_cond_broadcast(&P->cv);
+        pthread_mutex_unlock(&P->mu);
+    }
+    return NULL;
 }
 
 int alnse_core(const opt_t *opt)
@@ -193,16 +258,31 @@ int alnse_core(const opt_t *opt)
         T[t].aux[1] = aux_init(opt->l_read, opt->l_seed);
     }
     queryio_t *qs = query_open(opt->fn_read1);
-    query_t *multiSeqs = calloc(N_SEQS, sizeof(query_t));
+    batch_pipe_t P;
+    memset(&P, 0, sizeof P);
+    pthread_mutex_init(&P.mu, NULL); pthread_cond_init(&P.cv, NULL);
+    P.qs = qs;
+    for (t = 0; t < DROPIN_BATCH_BUFS; ++t) P.buf[t] = calloc(N_SEQS, sizeof(query_t));
     seeded_read_t *seeds = calloc(N_SEQS, sizeof(seeded_read_t));
     int *slot_of = calloc(N_SEQS, sizeof(int));        /* index of read i in the GPU chunk that holds it */
     aln_samhead(opt, index->bntseq);
-    int n, i, n_tot = 0, n_chunks = 0;
-    double t_seed = 0, t_gpu_wait = 0, t_finish = 0, t_select = 0, t_tail = 0, t_read = 0, t_print = 0, t_rd0 = now_s();
-    while ((n = query_read_multiSeqs(qs, N_SEQS, multiSeqs)) > 0) {
+    fflush(stdout);
+    pthread_t th_reader, th_writer;
+    pthread_create(&th_reader, NULL, reader_thread, &P);
+    pthread_create(&th_writer, NULL, writer_thread, &P);
+    int n, i, n_tot = 0, n_chunks = 0, batch;
+    double t_seed = 0, t_gpu_wait = 0, t_finish = 0, t_select = 0, t_tail = 0, t_starved = 0;
+    for (batch = 0;; ++batch) {
+        double tw = now_s();
+        pthread_mutex_lock(&P.mu);
+        while (P.n_read <= batch) pthread_cond_wait(&P.cv, &P.mu);
+        n = P.cnt[batch % DROPIN_BATCH_BUFS];
+        pthread_mutex_unlock(&P.mu);
+        t_starved += now_s() - tw;
+        if (n <= 0) break;
+        query_t *multiSeqs = P.buf[batch % DROPIN_BATCH_BUFS];
         n_tot += n;
         double t0 = now_s();
-        t_read += t0 - t_rd0;
         if (!gpu_seed) {
             for (t = 0; t < n_threads; ++t) { T[t].n = n; T[t].queries = multiSeqs; T[t].out = seeds; }
             if (n_threads == 1) seed_worker(&T[0]);
@@ -265,27 +345,28 @@ int alnse_core(const opt_t *opt)
             }
             if (cur >= 0) { pend_c = cur; pend_first = first; pend_upto = upto; first = upto; ++k; }
         }
-        double tp = now_s();
-        for (i = 0; i < n; ++i) {
-            query_t *query = multiSeqs + i;
-            puts(query->sam->s);                        /* alnse.c:1433-1439 */
-            query_destroy(query);
-        }
-        memset(multiSeqs, 0, N_SEQS * sizeof(query_t));
-        fprintf(stderr, "%d reads have been aligned!\n", n_tot);
-        t_rd0 = now_s();
-        t_print += t_rd0 - tp;
+        pthread_mutex_lock(&P.mu);
+        P.n_done = batch + 1;
+        pthread_cond_broadcast(&P.cv);
+        pthread_mutex_unlock(&P.mu);
     }
+    pthread_mutex_lock(&P.mu);
+    P.all_done = 1;
+    pthread_cond_broadcast(&P.cv);
+    pthread_mutex_unlock(&P.mu);
+    pthread_join(th_reader, NULL);
+    pthread_join(th_writer, NULL);
     fprintf(stderr, "[salt_dropin] %d reads, %d GPU chunks, %d seeding threads: seeding %s %.3f s, GPU calls (exposed wait) %.3f s, "
                     "hit selection + SAM text %.3f s\n", n_tot, n_chunks, n_threads, gpu_seed ? "(on the GPU, inside the GPU calls)" : "on the host",
             t_seed, t_gpu_wait, t_finish);
-    fprintf(stderr, "[salt_dropin] wall %.3f s: index load (reference loaders) %.3f, GPU init + uploads %.3f, FASTQ reader %.3f, SAM print + free %.3f; "
-                    "of the host finish: hit selection %.3f, GPU tail calls %.3f, SAM text %.3f\n", now_s() - t_start, t_load, t_init, t_read, t_print,
-            t_select, t_tail, t_finish - t_select - t_tail);
+    fprintf(stderr, "[salt_dropin] wall %.3f s: index load (reference loaders) %.3f, GPU init + uploads %.3f; main thread: waiting for the reader %.3f, "
+                    "hit selection %.3f, GPU tail calls %.3f, SAM text %.3f; beside it: FASTQ reader thread %.3f, SAM print + free thread %.3f\n",
+            now_s() - t_start, t_load, t_init, t_starved, t_select, t_tail, t_finish - t_select - t_tail, P.t_read, P.t_print);
     for (t = 0; t < n_threads; ++t) { aux_destroy(T[t].aux[0]); aux_destroy(T[t].aux[1]); }
     for (i = 0; i < N_SEQS; ++i) { free(seeds[i].a[0]); free(seeds[i].a[1]); }
     free(T); free(th); free(seeds); free(Fin);
-    free(multiSeqs); free(slot_of);
+    for (t = 0; t < DROPIN_BATCH_BUFS; ++t) free(P.buf[t]);
+    free(slot_of);
     query_close(qs);
     salt_chunk_free(ck[0]); salt_chunk_free(ck[1]);
     dropin_tail_report();
