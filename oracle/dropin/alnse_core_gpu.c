@@ -102,7 +102,7 @@ static void *seed_worker(void *arg)
 }
 
 /* hit selection and SAM text of a sub-chunk on the -t workers, as alnse_core_thread does both per read (alnse.c:1306-1307) */
-typedef struct { int tid, n_threads, first, upto, phase; index_t *index; query_t *queries; aln_opt_t *aln_opt; const salt_chunk_t *ck; const int *slot_of; } fin_thread_t;
+typedef struct { int tid, n_threads, first, upto, phase; index_t *index; query_t *queries; aln_opt_t *aln_opt; const salt_chunk_t *ck; const int *slot_of; char **old_sam; } fin_thread_t;
 static void *finish_worker(void *arg)
 {
     fin_thread_t *F = (fin_thread_t *)arg;
@@ -114,17 +114,25 @@ static void *finish_worker(void *arg)
     for (j = lo; j < hi; ++j) {
         if (F->slot_of[j] < 0) continue;
         if (F->phase == 0) finish_read(F->index, F->queries + j, F->aln_opt, F->ck, (uint32_t)F->slot_of[j]);
-        else { dropin_tail_begin_read(j); aln_samse(F->index, F->queries + j, F->aln_opt); }      /* alnse.c:1307 / :1345 */
+        else {
+            /* The reader allocated sam->s (128 bytes, query.c:215) in ITS malloc arena; growing it from a worker makes realloc
+               lock that one arena for every read of every worker.  Give the line a buffer from this thread's arena instead, large
+               enough that aln_samse rarely grows it; the old one is freed by the thread that allocated it. */
+            kstring_t *ks = F->queries[j].sam;
+            if (ks && ks->m < 1024) { F->old_sam[j] = ks->s; ks->s = malloc(1024); ks->s[0] = '\0'; ks->m = 1024; }
+            dropin_tail_begin_read(j);
+            aln_samse(F->index, F->queries + j, F->aln_opt);                                      /* alnse.c:1307 / :1345 */
+        }
     }
     return NULL;
 }
 static void finish_parallel(int n_threads, pthread_t *th, fin_thread_t *F, int phase, int first, int upto, index_t *index, query_t *queries,
-                            aln_opt_t *aln_opt, const salt_chunk_t *ck, const int *slot_of)
+                            aln_opt_t *aln_opt, const salt_chunk_t *ck, const int *slot_of, char **old_sam)
 {
     int t;
     for (t = 0; t < n_threads; ++t) {
         F[t].tid = t; F[t].n_threads = n_threads; F[t].first = first; F[t].upto = upto; F[t].phase = phase;
-        F[t].index = index; F[t].queries = queries; F[t].aln_opt = aln_opt; F[t].ck = ck; F[t].slot_of = slot_of;
+        F[t].index = index; F[t].queries = queries; F[t].aln_opt = aln_opt; F[t].ck = ck; F[t].slot_of = slot_of; F[t].old_sam = old_sam;
     }
     if (n_threads == 1) { finish_worker(&F[0]); return; }
     for (t = 0; t < n_threads; ++t) pthread_create(&th[t], NULL, finish_worker, &F[t]);
@@ -146,9 +154,24 @@ typedef struct {
     pthread_mutex_t mu; pthread_cond_t cv;
     queryio_t *qs;
     query_t *buf[DROPIN_BATCH_BUFS]; int cnt[DROPIN_BATCH_BUFS];
-    int n_read, n_done, n_written, all_done;          /* batches read / aligned / written so far */
+    char **old_sam[DROPIN_BATCH_BUFS];                /* per read: the reader's first sam buffer, replaced by a worker's */
+    int n_read, n_done, n_written, n_destroyed, all_done;     /* batches read / aligned / written / freed so far */
     double t_read, t_print;
 } batch_pipe_t;
+
+static void batch_destroy(batch_pipe_t *P, int k)
+{
+    query_t *q = P->buf[k % DROPIN_BATCH_BUFS];
+    char **old = P->old_sam[k % DROPIN_BATCH_BUFS];
+    const int n = P->cnt[k % DROPIN_BATCH_BUFS];
+    int i;
+    for (i = 0; i < n; ++i) {
+        free(old[i]); old[i] = NULL;
+        query_destroy(q + i);
+    }
+    memset(q, 0, N_SEQS * sizeof(query_t));
+    P->n_destroyed = k + 1;
+}
 
 static void *reader_thread(void *arg)
 {
@@ -159,6 +182,7 @@ static void *reader_thread(void *arg)
         while (k - P->n_written >= DROPIN_BATCH_BUFS) pthread_cond_wait(&P->cv, &P->mu);
         pthread_mutex_unlock(&P->mu);
         double t0 = now_s();
+        if (k >= DROPIN_BATCH_BUFS) batch_destroy(P, k - DROPIN_BATCH_BUFS);      /* written by now; freed where it was allocated */
         int n = query_read_multiSeqs(P->qs, N_SEQS, P->buf[k % DROPIN_BATCH_BUFS]);
         P->t_read += now_s() - t0;
         pthread_mutex_lock(&P->mu);
@@ -183,11 +207,7 @@ static void *writer_thread(void *arg)
         double t0 = now_s();
         query_t *q = P->buf[k % DROPIN_BATCH_BUFS];
         const int n = P->cnt[k % DROPIN_BATCH_BUFS];
-        for (i = 0; i < n; ++i) {
-            puts(q[i].sam->s);                          /* alnse.c:1433-1439 */
-            query_destroy(q + i);
-        }
-        memset(q, 0, N_SEQS * sizeof(query_t));
+        for (i = 0; i < n; ++i) puts(q[i].sam->s);     /* alnse.c:1433-1439 */
         n_tot += n;
         fprintf(stderr, "%d reads have been aligned!\n", n_tot);
         P->t_print += now_s() - t0;
@@ -262,7 +282,7 @@ int alnse_core(const opt_t *opt)
     memset(&P, 0, sizeof P);
     pthread_mutex_init(&P.mu, NULL); pthread_cond_init(&P.cv, NULL);
     P.qs = qs;
-    for (t = 0; t < DROPIN_BATCH_BUFS; ++t) P.buf[t] = calloc(N_SEQS, sizeof(query_t));
+    for (t = 0; t < DROPIN_BATCH_BUFS; ++t) { P.buf[t] = calloc(N_SEQS, sizeof(query_t)); P.old_sam[t] = calloc(N_SEQS, sizeof(char *)); }
     seeded_read_t *seeds = calloc(N_SEQS, sizeof(seeded_read_t));
     int *slot_of = calloc(N_SEQS, sizeof(int));        /* index of read i in the GPU chunk that holds it */
     aln_samhead(opt, index->bntseq);
@@ -281,6 +301,7 @@ int alnse_core(const opt_t *opt)
         t_starved += now_s() - tw;
         if (n <= 0) break;
         query_t *multiSeqs = P.buf[batch % DROPIN_BATCH_BUFS];
+        char **old_sam = P.old_sam[batch % DROPIN_BATCH_BUFS];
         n_tot += n;
         double t0 = now_s();
         if (!gpu_seed) {
@@ -333,13 +354,13 @@ int alnse_core(const opt_t *opt)
                 t_gpu_wait += now_s() - tg;
                 double tf = now_s();
                 (void)j;
-                finish_parallel(n_threads, th, Fin, 0, pend_first, pend_upto, index, multiSeqs, aln_opt, ck[pend_c], slot_of);
+                finish_parallel(n_threads, th, Fin, 0, pend_first, pend_upto, index, multiSeqs, aln_opt, ck[pend_c], slot_of, old_sam);
                 t_select += now_s() - tf;
                 double tt = now_s();
                 if (aln_opt->print_nm_md || aln_opt->print_xa_cigar)
                     dropin_tail_prepare(gpu, gpu_seed ? 0 : pend_c, multiSeqs, slot_of, pend_first, pend_upto);
                 t_tail += now_s() - tt;
-                finish_parallel(n_threads, th, Fin, 1, pend_first, pend_upto, index, multiSeqs, aln_opt, ck[pend_c], slot_of);
+                finish_parallel(n_threads, th, Fin, 1, pend_first, pend_upto, index, multiSeqs, aln_opt, ck[pend_c], slot_of, old_sam);
                 t_finish += now_s() - tf;
                 pend_c = -1;
             }
@@ -356,16 +377,17 @@ int alnse_core(const opt_t *opt)
     pthread_mutex_unlock(&P.mu);
     pthread_join(th_reader, NULL);
     pthread_join(th_writer, NULL);
+    while (P.n_destroyed < batch) batch_destroy(&P, P.n_destroyed);
     fprintf(stderr, "[salt_dropin] %d reads, %d GPU chunks, %d seeding threads: seeding %s %.3f s, GPU calls (exposed wait) %.3f s, "
                     "hit selection + SAM text %.3f s\n", n_tot, n_chunks, n_threads, gpu_seed ? "(on the GPU, inside the GPU calls)" : "on the host",
             t_seed, t_gpu_wait, t_finish);
     fprintf(stderr, "[salt_dropin] wall %.3f s: index load (reference loaders) %.3f, GPU init + uploads %.3f; main thread: waiting for the reader %.3f, "
-                    "hit selection %.3f, GPU tail calls %.3f, SAM text %.3f; beside it: FASTQ reader thread %.3f, SAM print + free thread %.3f\n",
+                    "hit selection %.3f, GPU tail calls %.3f, SAM text %.3f; beside it: FASTQ reader + free thread %.3f, SAM print thread %.3f\n",
             now_s() - t_start, t_load, t_init, t_starved, t_select, t_tail, t_finish - t_select - t_tail, P.t_read, P.t_print);
     for (t = 0; t < n_threads; ++t) { aux_destroy(T[t].aux[0]); aux_destroy(T[t].aux[1]); }
     for (i = 0; i < N_SEQS; ++i) { free(seeds[i].a[0]); free(seeds[i].a[1]); }
     free(T); free(th); free(seeds); free(Fin);
-    for (t = 0; t < DROPIN_BATCH_BUFS; ++t) free(P.buf[t]);
+    for (t = 0; t < DROPIN_BATCH_BUFS; ++t) { free(P.buf[t]); free(P.old_sam[t]); }
     free(slot_of);
     query_close(qs);
     salt_chunk_free(ck[0]); salt_chunk_free(ck[1]);

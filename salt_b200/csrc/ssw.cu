@@ -371,6 +371,7 @@ struct BandDev {
     const uint32_t *in_list; const uint32_t *in_count;   // list-driven passes: their input
     uint32_t *dp_list; uint32_t *dp_count;               // diagonal pass: tasks that need banded_sw's dynamic program
     uint32_t *wide_list; uint32_t *wide_count;           // narrow pass: tasks it hands to the warp-per-task kernel
+    uint32_t *next_item;                                 // warp-per-task kernel: next unclaimed entry of its list
     salt_ssw_out_t *out; uint32_t *cigars; int cigar_stride;
 };
 
@@ -429,9 +430,9 @@ struct NarrowBand {
 
 // One row.  D = [i > B] (slot shift against the previous row); FULL: the row holds all 2B+1 cells (no window end in
 // reach), so nothing in it is predicated.
-template <int B, int D, bool PAC, bool FULL>
-__device__ __forceinline__ void narrow_row(NarrowBand<B> &s, const DevCtx &c, const int8_t *s_tab, int i, int refLen,
-                                           uint32_t ref0, int rc, int gapO, int gapE, uint32_t *rowdirs)
+template <int B, int D, bool FULL>
+__device__ __forceinline__ void narrow_row(NarrowBand<B> &s, const int8_t *s_tab, int i, int refLen,
+                                           uint32_t symw, int rc, int gapO, int gapE, uint32_t *rowdirs)
 {
     constexpr int W = NarrowBand<B>::W;
     const int beg = D ? i - B : 0;
@@ -448,12 +449,6 @@ __device__ __forceinline__ void narrow_row(NarrowBand<B> &s, const DevCtx &c, co
     }
     s.hb[0] = s.eb[0] = s.hc[0] = 0;
     if (D) { s.hb[W - 1] = 0; s.eb[W - 1] = 0; }
-    uint32_t symw = 0;
-    if (!PAC) {
-        const uint32_t p = ref0 + (uint32_t)beg;
-        const uint32_t *__restrict__ mw = c.mixref + (p >> 3);
-        symw = __funnelshift_r(mw[0], mw[1], 4 * (int)(p & 7u));
-    }
     const int8_t *__restrict__ srow = s_tab + rc;
     int fcur = 0;
     uint32_t dirw = 0;
@@ -473,7 +468,7 @@ __device__ __forceinline__ void narrow_row(NarrowBand<B> &s, const DevCtx &c, co
             const int e1 = ev > 0 ? ev : 0;
             const int f1 = fcur > 0 ? fcur : 0;
             t1 = e1 > f1 ? e1 : f1;
-            const int sym = PAC ? sw_ref_symbol(c, 1, ref0 + (uint32_t)(beg + u - 1)) : (int)((symw >> (4 * (u - 1))) & 15u);
+            const int sym = (int)((symw >> (4 * (u - 1))) & 15u);
             t2 = s.hb[ud] + srow[sym * 8];
             const int h = t1 > t2 ? t1 : t2;
             s.hc[u] = h;
@@ -496,32 +491,57 @@ __device__ __forceinline__ bool narrow_fill(const DevCtx &c, const int8_t *s_tab
 #pragma unroll
     for (int k = 0; k < NarrowBand<B>::W; ++k) { s.hb[k] = 0; s.eb[k] = 0; s.hc[k] = 0; }
     s.max = max;
+    // a row's 2B+1 <= 7 reference symbols are one nibble word; it and the read's code word are requested a row / a word ahead
+    auto row_syms = [&](int i, int D) -> uint32_t {
+        const uint32_t p = ref0 + (uint32_t)(D ? i - B : 0);
+        if (PAC) return sw_pac_group(c.pac, p);
+        const uint32_t *__restrict__ mw = c.mixref + (p >> 3);
+        return __funnelshift_r(mw[0], mw[1], 4 * (int)(p & 7u));
+    };
     const uint64_t *__restrict__ rd = c.rd4 + (size_t)rs * c.W64;
-    uint64_t rw = rd[read0 >> 4];
+    const int W64 = (int)c.W64;
+    uint64_t rw = rd[read0 >> 4], rwn = (read0 >> 4) + 1 < W64 ? rd[(read0 >> 4) + 1] : 0ull;
+    bool first_code = true;
     auto code_of = [&](int idx) {
-        if ((idx & 15) == 0) rw = rd[idx >> 4];
+        if ((idx & 15) == 0 && !first_code) { rw = rwn; rwn = (idx >> 4) + 1 < W64 ? rd[(idx >> 4) + 1] : 0ull; }
+        first_code = false;
         const unsigned nib = (unsigned)(rw >> (4 * (idx & 15))) & 15u;
         return nib == 15u ? SW_CODE_N : (31 - __clz(nib));
     };
 #pragma unroll
     for (int i = 0; i <= B; ++i)
-        if (i < readLen) narrow_row<B, 0, PAC, false>(s, c, s_tab, i, refLen, ref0, code_of(read0 + i), gapO, gapE, rowdirs);
+        if (i < readLen) narrow_row<B, 0, false>(s, s_tab, i, refLen, row_syms(i, 0), code_of(read0 + i), gapO, gapE, rowdirs);
     int full_end = refLen - B;                                  // rows below it hold all 2B+1 cells: i + B <= refLen - 1
     if (full_end > readLen) full_end = readLen;
     int i = B + 1;
-    for (; i < full_end; ++i)
-        narrow_row<B, 1, PAC, true>(s, c, s_tab, i, refLen, ref0, code_of(read0 + i), gapO, gapE, rowdirs);
-    for (; i < readLen; ++i)
-        narrow_row<B, 1, PAC, false>(s, c, s_tab, i, refLen, ref0, code_of(read0 + i), gapO, gapE, rowdirs);
+    uint32_t nxt = row_syms(i, 1);
+    for (; i < full_end; ++i) {
+        const uint32_t cur = nxt;
+        nxt = row_syms(i + 1, 1);
+        narrow_row<B, 1, true>(s, s_tab, i, refLen, cur, code_of(read0 + i), gapO, gapE, rowdirs);
+    }
+    for (; i < readLen; ++i) {
+        const uint32_t cur = nxt;
+        nxt = row_syms(i + 1, 1);
+        narrow_row<B, 1, false>(s, s_tab, i, refLen, cur, code_of(read0 + i), gapO, gapE, rowdirs);
+    }
     max = s.max;
     return s.max >= score;
 }
 
+// direction codes of the narrow pass for the traceback; the walk only moves up one row at a time, so the word of the row
+// above is already on its way when it is needed
 struct NarrowCodeAt {
     const uint32_t *rowdirs;
+    mutable int ci; mutable uint32_t wc, wp;
     __device__ __forceinline__ int operator()(int i, int x, int state) const
     {
-        const uint32_t nib = (rowdirs[(size_t)i * 32] >> (4 * x)) & 15u;
+        if (i != ci) {
+            wc = i == ci - 1 ? wp : rowdirs[(size_t)i * 32];
+            ci = i;
+            wp = i > 0 ? rowdirs[(size_t)(i - 1) * 32] : 0u;
+        }
+        const uint32_t nib = (wc >> (4 * x)) & 15u;
         const int ce = (nib & 1u) ? 3 : 2, cf = (nib & 2u) ? 5 : 4;
         if (state == 0) return ce;
         if (state == 1) return cf;
@@ -634,7 +654,7 @@ sw_banded_narrow_kernel(BandDev d)
         d.wide_list[atomicAdd(d.wide_count, 1u)] = (uint32_t)t;
         continue;
     }
-    NarrowCodeAt at{rowdirs};
+    NarrowCodeAt at{rowdirs, -1000, 0u, 0u};
     o.cigarLen = band_traceback(at, band, 2 * band + 1, readLen, refLen, d.cigars + t * (size_t)d.cigar_stride, d.cigar_stride);
     d.out[t] = o;
     }
@@ -664,11 +684,16 @@ sw_banded_coop_kernel(BandDev d, int rows8, int smem_per_warp)
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
     const size_t n_items = (size_t)*d.in_count;
     uint8_t *gdirs = d.dirs + warp * ((size_t)(2 * COOP_MAXB + 1) * (size_t)rows8);
     uint8_t *sdirs = s_dirs + (size_t)(threadIdx.x >> 5) * (size_t)smem_per_warp;
-    for (size_t item = warp; item < n_items; item += n_warps) {
+    for (;;) {
+        // tasks differ by an order of magnitude (one attempt at band 4 ... four attempts up to band 8): warps take the next
+        // listed task when they are free instead of a fixed share
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(d.next_item, 1u);
+        item = __shfl_sync(FULLM, item, 0);
+        if ((size_t)item >= n_items) break;
         const size_t t = (size_t)d.in_list[item];
         const int32_t *f = d.fwd + t * 8;
         salt_ssw_out_t o;
@@ -1006,7 +1031,7 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
     b.ovf_count = ovf_count; b.ovf_cap = SSW_OVF_THREADS;
     if (!ovf_dirs) b.ovf_list = nullptr;                  // no overflow scratch: wide bands come back with cigarLen = -2
     b.wide_list = reinterpret_cast<uint32_t *>(base + lay[8]); b.wide_count = ovf_count + 1;
-    b.dp_list = reinterpret_cast<uint32_t *>(base + lay[9]); b.dp_count = ovf_count + 2;
+    b.dp_list = reinterpret_cast<uint32_t *>(base + lay[9]); b.dp_count = ovf_count + 2; b.next_item = ovf_count + 3;
     b.out = out; b.cigars = cigars; b.cigar_stride = cigar_stride;
     const unsigned task_blocks = (unsigned)((n + 127) / 128);
     const unsigned list_blocks = task_blocks < (unsigned)(4 * (sm_count > 0 ? sm_count : 148)) ? task_blocks : (unsigned)(4 * (sm_count > 0 ? sm_count : 148));
@@ -1025,7 +1050,7 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
     {
         // one warp per handed-over task; scratch per warp: direction bytes of a band of COOP_MAXB (shared memory when they fit)
         const int rows8 = 8 * (((int)c.l_max + 7) / 8);
-        const size_t cap = (size_t)(4 * (sm_count > 0 ? sm_count : 148));
+        const size_t cap = (size_t)(8 * (sm_count > 0 ? sm_count : 148));
         const size_t coop_blocks = (n + 3) / 4 < cap ? (n + 3) / 4 : cap;
         int smem_per_warp = (2 * COOP_MAXB + 1) * rows8;
         if (smem_per_warp > 11 * 1024) smem_per_warp = 11 * 1024;
