@@ -371,6 +371,7 @@ struct BandDev {
     const uint32_t *in_list; const uint32_t *in_count;   // list-driven passes: their input
     uint32_t *dp_list; uint32_t *dp_count;               // diagonal pass: tasks that need banded_sw's dynamic program
     uint32_t *wide_list; uint32_t *wide_count;           // narrow pass: tasks it hands to the warp-per-task kernel
+    uint32_t *wide_aux;                                  // per entry of wide_list: band to try next | maximum so far << 16
     uint32_t *next_item;                                 // warp-per-task kernel: next unclaimed entry of its list
     salt_ssw_out_t *out; uint32_t *cigars; int cigar_stride;
 };
@@ -645,13 +646,18 @@ sw_banded_narrow_kernel(BandDev d)
             ok = narrow_fill<1, PAC>(d.c, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
             if (!ok) band = 2;
         }
-        if (!ok && band == 2 && refLen >= 6)
+        if (!ok && band == 2 && refLen >= 6) {
             ok = narrow_fill<2, PAC>(d.c, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
-        else if (!ok && band == 3 && refLen >= 8)
+            if (!ok) band = 4;
+        } else if (!ok && band == 3 && refLen >= 8) {
             ok = narrow_fill<3, PAC>(d.c, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
+            if (!ok) band = 6;
+        }
     }
-    if (!ok) {                                                               // the warp-per-task kernel starts this task over
-        d.wide_list[atomicAdd(d.wide_count, 1u)] = (uint32_t)t;
+    if (!ok) {                               // the warp-per-task kernel goes on where this one stopped: next band, maximum so far
+        const uint32_t k = atomicAdd(d.wide_count, 1u);
+        d.wide_list[k] = (uint32_t)t;
+        d.wide_aux[k] = (uint32_t)(band < 0xffff ? band : 0xffff) | ((uint32_t)max << 16);
         continue;
     }
     NarrowCodeAt at{rowdirs, -1000, 0u, 0u};
@@ -706,8 +712,9 @@ sw_banded_coop_kernel(BandDev d, int rows8, int smem_per_warp)
         const uint32_t ref0 = w.start + (uint32_t)o.ref_begin1;
         const int read0 = o.read_begin1;
         const int score = o.score1, gapO = d.prm.gapO, gapE = d.prm.gapE;
-        int band = abs(refLen - readLen) + 1;                                // ssw.c:845
-        int max = 0, wd = 0;
+        const uint32_t aux = d.wide_aux[item];                               // where the narrow pass stopped (ssw.c:845 and the doublings it tried)
+        int band = (int)(aux & 0xffffu);
+        int max = (int)(aux >> 16), wd = 0;
         bool served = true;
         uint8_t *dirs = gdirs;
         do {
@@ -918,7 +925,7 @@ static SwShape pick_shape(int l_max)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// layout: [0]=win2 [1]=rsel [2]=maxcol2 [3]=fwd [4]=dirs [5]=ovf_list [6]=counters [7]=total [8]=wide_list [9]=dp_list
+// layout: [0]=win2 [1]=rsel [2]=maxcol2 [3]=fwd [4]=dirs [5]=ovf_list [6]=counters [7]=total [8]=wide_list [9]=dp_list [10]=wide_aux
 size_t ssw_scratch_bytes(size_t n_tasks, int max_cols, int max_rows, size_t *layout)
 {
     const SwShape sh = pick_shape(max_rows);
@@ -936,6 +943,7 @@ size_t ssw_scratch_bytes(size_t n_tasks, int max_cols, int max_rows, size_t *lay
     layout[6] = off; off = align_up(off + 256, 256);
     layout[8] = off; off = align_up(off + n_tasks * sizeof(uint32_t), 256);
     layout[9] = off; off = align_up(off + n_tasks * sizeof(uint32_t), 256);
+    layout[10] = off; off = align_up(off + n_tasks * sizeof(uint32_t), 256);
     layout[7] = off;
     return off;
 }
@@ -989,7 +997,7 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
 {
 #define SALT_EV(i) do { if (ev) cudaEventRecord(ev[i], st); } while (0)
     if (!n) return cudaSuccess;
-    size_t lay[10];
+    size_t lay[11];
     const size_t need = ssw_scratch_bytes(n, max_cols, (int)c.l_max, lay);
     if (need > scratch_bytes) return cudaErrorMemoryAllocation;
     const SwShape sh = pick_shape((int)c.l_max);
@@ -1032,6 +1040,7 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
     if (!ovf_dirs) b.ovf_list = nullptr;                  // no overflow scratch: wide bands come back with cigarLen = -2
     b.wide_list = reinterpret_cast<uint32_t *>(base + lay[8]); b.wide_count = ovf_count + 1;
     b.dp_list = reinterpret_cast<uint32_t *>(base + lay[9]); b.dp_count = ovf_count + 2; b.next_item = ovf_count + 3;
+    b.wide_aux = reinterpret_cast<uint32_t *>(base + lay[10]);
     b.out = out; b.cigars = cigars; b.cigar_stride = cigar_stride;
     const unsigned task_blocks = (unsigned)((n + 127) / 128);
     const unsigned list_blocks = task_blocks < (unsigned)(4 * (sm_count > 0 ? sm_count : 148)) ? task_blocks : (unsigned)(4 * (sm_count > 0 ? sm_count : 148));
