@@ -74,6 +74,8 @@ def _declare(L):
     L.salt_b200_get_mixref.argtypes = [vp, vp, sz]
     L.salt_b200_destroy.argtypes = [vp]
     L.salt_b200_destroy.restype = None
+    L.salt_b200_attach.argtypes = [vp]
+    L.salt_b200_attach.restype = vp
     L.salt_b200_set_stream.argtypes = [vp, vp]
     L.salt_b200_sync.argtypes = [vp]
     L.salt_b200_host_alloc.restype = vp
@@ -183,6 +185,17 @@ class Engine:
             raise SaltError(-102, self.L.salt_b200_last_error().decode())
         self.l = len(b); self.n_reads = 0
         return self
+
+    def attach(self):
+        """A second handle for another host thread: own streams, slots and scratch, this handle's resident reference and
+        indexes (salt_b200_attach).  This handle must outlive it."""
+        other = Engine.__new__(Engine)
+        other.L = self.L
+        other.h = self.L.salt_b200_attach(self.h)
+        if not other.h:
+            raise SaltError(-102, self.L.salt_b200_last_error().decode())
+        other.l = self.l; other.n_reads = 0; other._parent = self
+        return other
 
     def _ck(self, rc):
         if rc != SALT_OK:

@@ -462,6 +462,34 @@ def test_chunk_pair_stage(L):
 
 
 @pytest.mark.gpu
+def test_chunk_pair_stage_two_driver_threads():
+    """two host threads, each with its own attached handle (salt_b200_attach) and its own chunk, run the paired-end stage of
+    different chunks at the same time on one device: each must equal its pair-by-pair composition"""
+    import threading
+    from salt_b200 import host_api
+    hostlib = host_api.load()
+    g = synth.Genome(300000, snp_rate=0.01, seed=171)
+    eng = _engine(g)
+    engs = [eng, eng.attach(), eng.attach()]
+    out = [None] * len(engs); errs = []
+
+    def drive(i):
+        try:
+            for rep in range(3):
+                out[i] = pc.check_chunk_pair(engs[i], hostlib, g, 300, 100, seed=40 + 7 * i + rep)
+        except BaseException as ex:                      # noqa: BLE001
+            errs.append((i, repr(ex)))
+    ths = [threading.Thread(target=drive, args=(i,)) for i in range(len(engs))]
+    for t in ths: t.start()
+    for t in ths: t.join()
+    assert not errs, errs
+    assert all(o is not None and o.rescued >= 10 for o in out)
+    for e in engs[1:]:
+        e.close()
+    eng.close()
+
+
+@pytest.mark.gpu
 def test_multi_gpu_in_process_matches_single():
     """salt_multi_*: one process, one handle per device, contiguous shares on their own host threads -- the output must
     equal the single-device output byte for byte (two handles on one device when the box has a single GPU)"""
