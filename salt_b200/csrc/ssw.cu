@@ -32,7 +32,6 @@ struct SwDev {
     int item_shift;            // log2 of the prep kernels' padded items per task
     int MC;                    // maxcol stride (columns) per pair
     uint2 *win2;               // [pair][CW]  (.x task 0, .y task 1)
-    uint32_t *rsel;            // [task][G*NQ]
     uint32_t *maxcol2;         // [pair][MC]  packed column maxima
     int32_t *fwd;              // [task][8]
     SswParams prm;
@@ -64,14 +63,13 @@ __device__ __forceinline__ int sw_read_code(const DevCtx &c, uint32_t rs, int i)
 }
 
 // --------------------------------------------------------------------------------------
-// prep: one thread per output word.  Items per task: CW window words, then G*NQ selectors.
+// prep: one thread per window word (eight reference symbols of a task); the read-code selectors are made by the DP kernel.
 // --------------------------------------------------------------------------------------
 template <bool REV>
 __global__ void __launch_bounds__(256)
 sw_prep_kernel(SwDev d)
 {
-    const int NQ = (d.S + 3) / 4;
-    const int per_task = d.CW + d.G * NQ;
+    const int per_task = d.CW;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t t = idx >> d.item_shift;              // a task's items are padded to a power of two: no division
     const int item = (int)(idx & (((size_t)1 << d.item_shift) - 1));
@@ -103,7 +101,7 @@ sw_prep_kernel(SwDev d)
             }
         }
     }
-    if (item < d.CW) {                                  // window word: columns 8*item .. 8*item+7
+    {                                                   // window word: columns 8*item .. 8*item+7
         uint32_t word = 0;
         const int col0 = item * 8;
         if (!d.prm.use_pac && col0 < cols) {
@@ -129,25 +127,6 @@ sw_prep_kernel(SwDev d)
         }
         uint32_t *dst = reinterpret_cast<uint32_t *>(d.win2 + (t >> 1) * d.CW + item);
         dst[t & 1] = word;
-    } else {                                            // selector word: rows 4q..4q+3 of thread j
-        const int k = item - d.CW;
-        const int j = k / NQ, q = k % NQ;
-        const int R = 8 * ((L + 7) / 8);
-        const int off = d.G * d.S - R;
-        uint32_t sel = 0;
-        for (int r = 0; r < 4; ++r) {
-            const int i = 4 * q + r;
-            int code = SW_CODE_TOP;
-            if (i < d.S) {
-                const int row = j * d.S + i - off;
-                if (row >= 0) {
-                    if (row < L) code = sw_read_code(d.c, rs, REV ? read_end - row : row);
-                    else code = SW_CODE_TAIL;
-                }
-            }
-            sel |= (uint32_t)code << (4 * r);
-        }
-        d.rsel[t * (size_t)(d.G * NQ) + k] = sel;
     }
 }
 
@@ -189,7 +168,7 @@ sw_dp_kernel(SwDev d)
     uint32_t *snap = s_snap + (size_t)threadIdx.x * 2 * SP;
 
     int rows[2], cols[2], off[2], aux_read_end[2], aux_ref_end[2];
-    uint32_t term = 0;
+    uint32_t term = 0, task_rs[2] = {0u, 0u};
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const size_t t = pair * 2 + h;
@@ -200,10 +179,12 @@ sw_dp_kernel(SwDev d)
             if (!REV) {
                 if (fl & FL_VALID) {
                     const salt_win_t w = d.wins[t];
+                    task_rs[h] = w.rs;
                     rows[h] = d.c.rd_len[w.rs >> 1];
                     cols[h] = (int)(w.end - w.start + 1);
                 }
             } else if (fl & FL_DO_REV) {
+                task_rs[h] = d.wins[t].rs;
                 aux_read_end[h] = f[F_READ_END1]; aux_ref_end[h] = f[F_REF_END1];
                 rows[h] = aux_read_end[h] + 1; cols[h] = aux_ref_end[h] + 1;
                 term |= (uint32_t)(uint16_t)(f[F_SCORE1] + SW_BIAS) << (16 * h);      // compared in the biased domain
@@ -215,10 +196,27 @@ sw_dp_kernel(SwDev d)
 
     SwStrip<S> st;
     st.clear();
+    // read-code selectors of this thread's S rows (four rows per word): rows above the read score -128 against everything,
+    // the read's own rows carry its codes (the reverse pass walks the read backwards from read_end1, ssw.c:827-832), the
+    // padded rows [L, 8*ceil(L/8)) score 0
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-        st.sel0[q] = d.rsel[(pair * 2 + 0) * (size_t)(G * NQ) + j * NQ + q];
-        st.sel1[q] = d.rsel[(pair * 2 + 1) * (size_t)(G * NQ) + j * NQ + q];
+    for (int h = 0; h < 2; ++h) {
+        const int Lh = rows[h];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            uint32_t sel = 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int i = 4 * q + r;
+                int code = SW_CODE_TOP;
+                if (i < S) {
+                    const int row = j * S + i - off[h];
+                    if (row >= 0) code = row < Lh ? sw_read_code(d.c, task_rs[h], REV ? aux_read_end[h] - row : row) : SW_CODE_TAIL;
+                }
+                sel |= (uint32_t)code << (4 * r);
+            }
+            if (h == 0) st.sel0[q] = sel; else st.sel1[q] = sel;
+        }
     }
     uint32_t negO = s16x2(-d.prm.gapO, -d.prm.gapO);
     uint32_t negE = 0u - ((uint32_t)d.prm.gapE | ((uint32_t)d.prm.gapE << 16));   // one 32-bit subtraction for both halves
@@ -925,16 +923,15 @@ static SwShape pick_shape(int l_max)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// layout: [0]=win2 [1]=rsel [2]=maxcol2 [3]=fwd [4]=dirs [5]=ovf_list [6]=counters [7]=total [8]=wide_list [9]=dp_list [10]=wide_aux
+// layout: [0]=win2 [1]=unused [2]=maxcol2 [3]=fwd [4]=dirs [5]=ovf_list [6]=counters [7]=total [8]=wide_list [9]=dp_list [10]=wide_aux
 size_t ssw_scratch_bytes(size_t n_tasks, int max_cols, int max_rows, size_t *layout)
 {
     const SwShape sh = pick_shape(max_rows);
-    const int NQ = (sh.S + 3) / 4;
     const size_t pairs = (n_tasks + 1) / 2;
     const int CW = (max_cols + 7) / 8 + 1;
     size_t off = 0;
     layout[0] = off; off = align_up(off + pairs * CW * sizeof(uint2), 256);
-    layout[1] = off; off = align_up(off + pairs * 2 * sh.G * NQ * sizeof(uint32_t), 256);
+    layout[1] = off;                                  // (selectors: made inside the DP kernel since round 2)
     layout[2] = off; off = align_up(off + pairs * (size_t)max_cols * sizeof(uint32_t), 256);
     layout[3] = off; off = align_up(off + pairs * 2 * 8 * sizeof(int32_t), 256);
     const size_t slot = (size_t)(2 * 16 + 1) * (size_t)(8 * ((max_rows + 7) / 8));
@@ -1006,13 +1003,11 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
     d.c = c; d.wins = wins; d.n_tasks = n; d.n_pairs = (n + 1) / 2;
     d.G = sh.G; d.S = sh.S; d.CW = (max_cols + 7) / 8 + 1; d.MC = max_cols;
     d.win2 = reinterpret_cast<uint2 *>(base + lay[0]);
-    d.rsel = reinterpret_cast<uint32_t *>(base + lay[1]);
     d.maxcol2 = reinterpret_cast<uint32_t *>(base + lay[2]);
     d.fwd = reinterpret_cast<int32_t *>(base + lay[3]);
     d.prm = prm;
-    const int NQ = (sh.S + 3) / 4;
     d.item_shift = 0;
-    while ((1 << d.item_shift) < d.CW + d.G * NQ) ++d.item_shift;
+    while ((1 << d.item_shift) < d.CW) ++d.item_shift;
     const size_t prep_items = (d.n_pairs * 2) << d.item_shift;
     const unsigned prep_blocks = (unsigned)((prep_items + 255) / 256);
     cudaError_t e;
