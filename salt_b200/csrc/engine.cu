@@ -1046,7 +1046,7 @@ int salt_b200_ssw_dev(salt_b200_t *h, const salt_win_t *d_wins, size_t n, int us
     if ((int64_t)maxpos * (int64_t)h->slot[h->cur].l_max >= 24000) return fail(SALT_ERR_UNSUPPORTED, "scores would overflow int16");
     if (!n) return SALT_OK;
     const int max_cols = h->max_window;
-    size_t lay[11];
+    size_t lay[13];
     const size_t need = ssw_scratch_bytes(n, max_cols, (int)h->slot[h->cur].l_max, lay);
     CU(h->sswscratch.need(need));
     CU(h->sswovf.need(ssw_overflow_bytes((int)h->slot[h->cur].l_max)));     // per handle: two handles never share direction bytes

@@ -370,6 +370,7 @@ struct BandDev {
     uint32_t *dp_list; uint32_t *dp_count;               // diagonal pass: tasks that need banded_sw's dynamic program
     uint32_t *wide_list; uint32_t *wide_count;           // narrow pass: tasks it hands to the warp-per-task kernel
     uint32_t *wide_aux;                                  // per entry of wide_list: band to try next | maximum so far << 16
+    uint32_t *coop_list; uint32_t *coop_aux; uint32_t *coop_count;   // medium pass: what it hands to the warp-per-task kernel
     uint32_t *next_item;                                 // warp-per-task kernel: next unclaimed entry of its list
     salt_ssw_out_t *out; uint32_t *cigars; int cigar_stride;
 };
@@ -429,9 +430,10 @@ struct NarrowBand {
 
 // One row.  D = [i > B] (slot shift against the previous row); FULL: the row holds all 2B+1 cells (no window end in
 // reach), so nothing in it is predicated.
-template <int B, int D, bool FULL>
+// DW: the word holding a row's 2B+1 symbols / direction codes (four bits each): uint32_t up to B = 3, uint64_t up to B = 7.
+template <int B, int D, bool FULL, class DW>
 __device__ __forceinline__ void narrow_row(NarrowBand<B> &s, const int8_t *s_tab, int i, int refLen,
-                                           uint32_t symw, int rc, int gapO, int gapE, uint32_t *rowdirs)
+                                           DW symw, int rc, int gapO, int gapE, DW *rowdirs)
 {
     constexpr int W = NarrowBand<B>::W;
     const int beg = D ? i - B : 0;
@@ -450,7 +452,7 @@ __device__ __forceinline__ void narrow_row(NarrowBand<B> &s, const int8_t *s_tab
     if (D) { s.hb[W - 1] = 0; s.eb[W - 1] = 0; }
     const int8_t *__restrict__ srow = s_tab + rc;
     int fcur = 0;
-    uint32_t dirw = 0;
+    DW dirw = 0;
 #pragma unroll
     for (int u = 1; u <= 2 * B + 1; ++u) {
         if (FULL || u <= n) {
@@ -473,7 +475,7 @@ __device__ __forceinline__ void narrow_row(NarrowBand<B> &s, const int8_t *s_tab
             s.hc[u] = h;
             s.max = h > s.max ? h : s.max;
             const uint32_t hsel = t1 <= t2 ? 0u : (e1 > f1 ? 1u : 2u);
-            dirw |= (e_from_h | (f_from_h << 1) | (hsel << 2)) << (4 * (u - 1));
+            dirw |= (DW)(e_from_h | (f_from_h << 1) | (hsel << 2)) << (4 * (u - 1));
         }
     }
 #pragma unroll
@@ -482,20 +484,29 @@ __device__ __forceinline__ void narrow_row(NarrowBand<B> &s, const int8_t *s_tab
 }
 
 // one banded_sw attempt at band B; max carries over between attempts as in the reference's do-while (ssw.c:575-632)
-template <int B, bool PAC>
+template <int B, bool PAC, class DW>
 __device__ __forceinline__ bool narrow_fill(const DevCtx &c, const int8_t *s_tab, uint32_t rs, int read0, uint32_t ref0,
-                                            int readLen, int refLen, int score, int gapO, int gapE, uint32_t *rowdirs, int &max)
+                                            int readLen, int refLen, int score, int gapO, int gapE, DW *rowdirs, int &max)
 {
+    static_assert(4 * (2 * B + 1) <= 8 * (int)sizeof(DW), "a row's codes must fit the word");
     NarrowBand<B> s;
 #pragma unroll
     for (int k = 0; k < NarrowBand<B>::W; ++k) { s.hb[k] = 0; s.eb[k] = 0; s.hc[k] = 0; }
     s.max = max;
-    // a row's 2B+1 <= 7 reference symbols are one nibble word; it and the read's code word are requested a row / a word ahead
-    auto row_syms = [&](int i, int D) -> uint32_t {
+    // a row's 2B+1 reference symbols are one nibble word; it and the read's code word are requested a row / a word ahead
+    auto row_syms = [&](int i, int D) -> DW {
         const uint32_t p = ref0 + (uint32_t)(D ? i - B : 0);
-        if (PAC) return sw_pac_group(c.pac, p);
+        if (PAC) {
+            uint64_t v = sw_pac_group(c.pac, p);
+            if (sizeof(DW) > 4) v |= (uint64_t)sw_pac_group(c.pac, p + 8u) << 32;
+            return (DW)v;
+        }
         const uint32_t *__restrict__ mw = c.mixref + (p >> 3);
-        return __funnelshift_r(mw[0], mw[1], 4 * (int)(p & 7u));
+        const int sh = 4 * (int)(p & 7u);
+        const uint32_t w1 = mw[1];
+        uint64_t v = __funnelshift_r(mw[0], w1, sh);
+        if (sizeof(DW) > 4) v |= (uint64_t)__funnelshift_r(w1, mw[2], sh) << 32;
+        return (DW)v;
     };
     const uint64_t *__restrict__ rd = c.rd4 + (size_t)rs * c.W64;
     const int W64 = (int)c.W64;
@@ -509,20 +520,20 @@ __device__ __forceinline__ bool narrow_fill(const DevCtx &c, const int8_t *s_tab
     };
 #pragma unroll
     for (int i = 0; i <= B; ++i)
-        if (i < readLen) narrow_row<B, 0, false>(s, s_tab, i, refLen, row_syms(i, 0), code_of(read0 + i), gapO, gapE, rowdirs);
+        if (i < readLen) narrow_row<B, 0, false, DW>(s, s_tab, i, refLen, row_syms(i, 0), code_of(read0 + i), gapO, gapE, rowdirs);
     int full_end = refLen - B;                                  // rows below it hold all 2B+1 cells: i + B <= refLen - 1
     if (full_end > readLen) full_end = readLen;
     int i = B + 1;
-    uint32_t nxt = row_syms(i, 1);
+    DW nxt = row_syms(i, 1);
     for (; i < full_end; ++i) {
-        const uint32_t cur = nxt;
+        const DW cur = nxt;
         nxt = row_syms(i + 1, 1);
-        narrow_row<B, 1, true>(s, s_tab, i, refLen, cur, code_of(read0 + i), gapO, gapE, rowdirs);
+        narrow_row<B, 1, true, DW>(s, s_tab, i, refLen, cur, code_of(read0 + i), gapO, gapE, rowdirs);
     }
     for (; i < readLen; ++i) {
-        const uint32_t cur = nxt;
+        const DW cur = nxt;
         nxt = row_syms(i + 1, 1);
-        narrow_row<B, 1, false>(s, s_tab, i, refLen, cur, code_of(read0 + i), gapO, gapE, rowdirs);
+        narrow_row<B, 1, false, DW>(s, s_tab, i, refLen, cur, code_of(read0 + i), gapO, gapE, rowdirs);
     }
     max = s.max;
     return s.max >= score;
@@ -530,17 +541,18 @@ __device__ __forceinline__ bool narrow_fill(const DevCtx &c, const int8_t *s_tab
 
 // direction codes of the narrow pass for the traceback; the walk only moves up one row at a time, so the word of the row
 // above is already on its way when it is needed
+template <class DW>
 struct NarrowCodeAt {
-    const uint32_t *rowdirs;
-    mutable int ci; mutable uint32_t wc, wp;
+    const DW *rowdirs;
+    mutable int ci; mutable DW wc, wp;
     __device__ __forceinline__ int operator()(int i, int x, int state) const
     {
         if (i != ci) {
             wc = i == ci - 1 ? wp : rowdirs[(size_t)i * 32];
             ci = i;
-            wp = i > 0 ? rowdirs[(size_t)(i - 1) * 32] : 0u;
+            wp = i > 0 ? rowdirs[(size_t)(i - 1) * 32] : (DW)0;
         }
-        const uint32_t nib = (wc >> (4 * x)) & 15u;
+        const uint32_t nib = (uint32_t)(wc >> (4 * x)) & 15u;
         const int ce = (nib & 1u) ? 3 : 2, cf = (nib & 2u) ? 5 : 4;
         if (state == 0) return ce;
         if (state == 1) return cf;
@@ -641,14 +653,14 @@ sw_banded_narrow_kernel(BandDev d)
     int max = 0;
     if (readLen >= 1 && (size_t)readLen * 4 <= d.slot) {
         if (band == 1 && refLen >= 4) {
-            ok = narrow_fill<1, PAC>(d.c, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
+            ok = narrow_fill<1, PAC, uint32_t>(d.c, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
             if (!ok) band = 2;
         }
         if (!ok && band == 2 && refLen >= 6) {
-            ok = narrow_fill<2, PAC>(d.c, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
+            ok = narrow_fill<2, PAC, uint32_t>(d.c, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
             if (!ok) band = 4;
         } else if (!ok && band == 3 && refLen >= 8) {
-            ok = narrow_fill<3, PAC>(d.c, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
+            ok = narrow_fill<3, PAC, uint32_t>(d.c, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max);
             if (!ok) band = 6;
         }
     }
@@ -658,9 +670,62 @@ sw_banded_narrow_kernel(BandDev d)
         d.wide_aux[k] = (uint32_t)(band < 0xffff ? band : 0xffff) | ((uint32_t)max << 16);
         continue;
     }
-    NarrowCodeAt at{rowdirs, -1000, 0u, 0u};
+    NarrowCodeAt<uint32_t> at{rowdirs, -1000, 0u, 0u};
     o.cigarLen = band_traceback(at, band, 2 * band + 1, readLen, refLen, d.cigars + t * (size_t)d.cigar_stride, d.cigar_stride);
     d.out[t] = o;
+    }
+}
+
+// ---- bands 4..7: still one thread per task and registers only (a row's fifteen codes are one 64-bit word) ---------------
+// Indel-rich reads (several gaps per read, BASELINE configs[4]) put most rescue windows here; a warp per task would spend
+// a hundred instructions per step on nine to fifteen lanes.  Walks the list the narrow pass left (task, band to try,
+// maximum so far), makes ONE attempt at that band and either finishes the task or passes it on with the doubled band.
+template <bool PAC>
+__global__ void __launch_bounds__(128)
+sw_banded_medium_kernel(BandDev d)
+{
+    __shared__ int8_t s_tab[17 * 8];
+    for (int i = threadIdx.x; i < 17 * 8; i += blockDim.x) s_tab[i] = d.prm.table[i];
+    __syncthreads();
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n_items = (size_t)*d.in_count;
+    const size_t item_step = (size_t)gridDim.x * blockDim.x;
+    for (size_t item = tid; item < n_items; item += item_step) {
+        const size_t t = (size_t)d.in_list[item];
+        const uint32_t aux = d.wide_aux[item];
+        int band = (int)(aux & 0xffffu), max = (int)(aux >> 16);
+        const int32_t *f = d.fwd + t * 8;
+        salt_ssw_out_t o;
+        o.score1 = (uint16_t)f[F_SCORE1]; o.score2 = (uint16_t)f[F_SCORE2];
+        o.ref_begin1 = f[F_REF_BEGIN1]; o.ref_end1 = f[F_REF_END1];
+        o.read_begin1 = f[F_READ_BEGIN1]; o.read_end1 = f[F_READ_END1];
+        o.ref_end2 = f[F_REF_END2]; o.cigarLen = 0;
+        const salt_win_t w = d.wins[t];
+        const int refLen = o.ref_end1 - o.ref_begin1 + 1, readLen = o.read_end1 - o.read_begin1 + 1;
+        const uint32_t ref0 = w.start + (uint32_t)o.ref_begin1;
+        const int read0 = o.read_begin1;
+        const int score = o.score1, gapO = d.prm.gapO, gapE = d.prm.gapE;
+        uint64_t *rowdirs = reinterpret_cast<uint64_t *>(d.dirs + (tid >> 5) * (d.slot * 32)) + (tid & 31);
+        bool ok = false;
+        if (band >= 4 && band <= 7 && readLen >= 1 && refLen >= 2 * band + 2 && (size_t)readLen * 8 <= d.slot) {
+            const int b0 = band;
+            switch (b0) {
+            case 4: ok = narrow_fill<4, PAC, uint64_t>(d.c, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max); break;
+            case 5: ok = narrow_fill<5, PAC, uint64_t>(d.c, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max); break;
+            case 6: ok = narrow_fill<6, PAC, uint64_t>(d.c, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max); break;
+            default: ok = narrow_fill<7, PAC, uint64_t>(d.c, s_tab, w.rs, read0, ref0, readLen, refLen, score, gapO, gapE, rowdirs, max); break;
+            }
+            if (!ok) band = 2 * b0;
+        }
+        if (!ok) {
+            const uint32_t k = atomicAdd(d.coop_count, 1u);
+            d.coop_list[k] = (uint32_t)t;
+            d.coop_aux[k] = (uint32_t)(band < 0xffff ? band : 0xffff) | ((uint32_t)max << 16);
+            continue;
+        }
+        NarrowCodeAt<uint64_t> at{rowdirs, -1000, 0ull, 0ull};
+        o.cigarLen = band_traceback(at, band, 2 * band + 1, readLen, refLen, d.cigars + t * (size_t)d.cigar_stride, d.cigar_stride);
+        d.out[t] = o;
     }
 }
 
@@ -710,7 +775,7 @@ sw_banded_coop_kernel(BandDev d, int rows8, int smem_per_warp)
         const uint32_t ref0 = w.start + (uint32_t)o.ref_begin1;
         const int read0 = o.read_begin1;
         const int score = o.score1, gapO = d.prm.gapO, gapE = d.prm.gapE;
-        const uint32_t aux = d.wide_aux[item];                               // where the narrow pass stopped (ssw.c:845 and the doublings it tried)
+        const uint32_t aux = d.coop_aux[item];                               // where the passes before stopped (ssw.c:845 and the doublings they tried)
         int band = (int)(aux & 0xffffu);
         int max = (int)(aux >> 16), wd = 0;
         bool served = true;
@@ -923,7 +988,7 @@ static SwShape pick_shape(int l_max)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// layout: [0]=win2 [1]=unused [2]=maxcol2 [3]=fwd [4]=dirs [5]=ovf_list [6]=counters [7]=total [8]=wide_list [9]=dp_list [10]=wide_aux
+// layout: [0]=win2 [1]=unused [2]=maxcol2 [3]=fwd [4]=dirs [5]=ovf_list [6]=counters [7]=total [8]=wide_list [9]=dp_list [10]=wide_aux [11]=coop_list [12]=coop_aux
 size_t ssw_scratch_bytes(size_t n_tasks, int max_cols, int max_rows, size_t *layout)
 {
     const SwShape sh = pick_shape(max_rows);
@@ -941,6 +1006,8 @@ size_t ssw_scratch_bytes(size_t n_tasks, int max_cols, int max_rows, size_t *lay
     layout[8] = off; off = align_up(off + n_tasks * sizeof(uint32_t), 256);
     layout[9] = off; off = align_up(off + n_tasks * sizeof(uint32_t), 256);
     layout[10] = off; off = align_up(off + n_tasks * sizeof(uint32_t), 256);
+    layout[11] = off; off = align_up(off + n_tasks * sizeof(uint32_t), 256);
+    layout[12] = off; off = align_up(off + n_tasks * sizeof(uint32_t), 256);
     layout[7] = off;
     return off;
 }
@@ -994,7 +1061,7 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
 {
 #define SALT_EV(i) do { if (ev) cudaEventRecord(ev[i], st); } while (0)
     if (!n) return cudaSuccess;
-    size_t lay[11];
+    size_t lay[13];
     const size_t need = ssw_scratch_bytes(n, max_cols, (int)c.l_max, lay);
     if (need > scratch_bytes) return cudaErrorMemoryAllocation;
     const SwShape sh = pick_shape((int)c.l_max);
@@ -1039,8 +1106,8 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
     b.out = out; b.cigars = cigars; b.cigar_stride = cigar_stride;
     const unsigned task_blocks = (unsigned)((n + 127) / 128);
     const unsigned list_blocks = task_blocks < (unsigned)(4 * (sm_count > 0 ? sm_count : 148)) ? task_blocks : (unsigned)(4 * (sm_count > 0 ? sm_count : 148));
-    // (1) gapless rectangles: one pass over the diagonal; (2) bands 1..3 in registers for what is left; (3) what they hand
-    // over (wider first bands, doubled bands) one warp per task; (4) the serial kernel for the rest
+    // (1) gapless rectangles: one pass over the diagonal; (2) bands 1..3 and (3) bands 4..7 in registers, a thread per task;
+    // (4) what they hand over (wider bands) one warp per task; (5) the serial kernel for the rest
     b.in_list = b.dp_list; b.in_count = b.dp_count;
     if (prm.use_pac) {
         { auto kern = sw_diag_kernel<true>; SALT_LAUNCH(kern, task_blocks, 128, 0, st, b); }
@@ -1050,7 +1117,13 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
         { auto kern = sw_banded_narrow_kernel<false>; SALT_LAUNCH(kern, list_blocks, 128, 0, st, b); }
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    b.coop_list = reinterpret_cast<uint32_t *>(base + lay[11]); b.coop_aux = reinterpret_cast<uint32_t *>(base + lay[12]);
+    b.coop_count = ovf_count + 4;
     b.in_list = b.wide_list; b.in_count = b.wide_count;
+    if (prm.use_pac) { auto kern = sw_banded_medium_kernel<true>; SALT_LAUNCH(kern, list_blocks, 128, 0, st, b); }
+    else { auto kern = sw_banded_medium_kernel<false>; SALT_LAUNCH(kern, list_blocks, 128, 0, st, b); }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    b.in_list = b.coop_list; b.in_count = b.coop_count;
     {
         // one warp per handed-over task; scratch per warp: direction bytes of a band of COOP_MAXB (shared memory when they fit)
         const int rows8 = 8 * (((int)c.l_max + 7) / 8);
@@ -1072,7 +1145,7 @@ cudaError_t launch_ssw(const DevCtx &c, const salt_win_t *wins, size_t n, const 
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     SALT_EV(6);
-    if (launches) *launches += 8;
+    if (launches) *launches += 9;
     return cudaSuccess;
 #undef SALT_EV
 }

@@ -338,8 +338,8 @@ def check_ssw_wide_bands(eng, oracle, seed, n_reads=150, L=100, glen=20003):
 def check_ssw_narrow_bands(eng, oracle, seed, n_reads=120, L=100, glen=20011):
     """banded_sw's first band is |refLen - readLen| + 1 (ssw.c:845) and doubles until the band holds score1.  Reads built to
     walk every branch of the narrow-band pass: no gap (band 1), a 1- or 2-base gap (bands 2, 3), a deletion and an
-    insertion of two bases each far apart (equal lengths: band 1 fails, band 2 succeeds), of three or four bases each (bands 1
-    and 2 fail: handed to the general kernel), a 3+-base gap (first band 4+: general kernel), a 3..14-base gap (first band up to 15, the widest the warp-per-task pass
+    insertion of two bases each far apart (equal lengths: band 1 fails, band 2 succeeds), of three to six bases each (bands 1,
+    2 and then 4 fail: handed on to the 4..7 pass and to the warp-per-task kernel), a 3+-base gap (first band 4+: general kernel), a 3..14-base gap (first band up to 15, the widest the warp-per-task pass
     serves) and reads whose alignment is only a few bases long (soft-clipped to less than the band rows)."""
     rng = np.random.default_rng(seed)
     g = synth.Genome(glen, snp_rate=0.01, n_rate=0.0, seed=seed)
@@ -356,7 +356,7 @@ def check_ssw_narrow_bands(eng, oracle, seed, n_reads=120, L=100, glen=20011):
             if rng.random() < 0.5: rd = np.concatenate([codes[p:p + a], codes[p + a + k:p + k + L]])
             else: rd = np.concatenate([codes[p:p + a], rng.integers(0, 4, k).astype(np.uint8), codes[p + a:p + L - k]])
         elif kind in (3, 4, 5):                                   # compensating deletion + insertion of k bases
-            k = kind - 1; a = int(rng.integers(20, 30)); b = int(rng.integers(65, 75))
+            k = 2 + (i // 8 + kind) % 5; a = int(rng.integers(20, 30)); b = int(rng.integers(60, 70))      # 2..6: bands 1, 2 (and 4) fail
             rd = np.concatenate([codes[p:p + a], codes[p + a + k:p + b + k], (3 - codes[p + b + k:p + b + 2 * k]), codes[p + b + k:p + L]])[:L]
         elif kind == 6:                                           # one gap of 3..14 bases: first bands 4..15, one warp per task
             k = int(rng.integers(3, 15)); a = int(rng.integers(30, 70))
