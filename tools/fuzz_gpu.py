@@ -43,6 +43,13 @@ while ssw_only and time.time() - t0 < budget:
                  gapO=gapO, gapE=gapE, flag=int(rng.choice([2, 1, 6])), filters=int(rng.choice([0, 20, 60])),
                  filterd=int(rng.choice([20, 5, 300])), mask_len=int(rng.choice([-1, 15, 40])), cigar_stride=int(rng.choice([96, 64])))
     eng.close()
+    if it % 4 == 0:                                  # every branch of the traceback stage on a fresh seed (gaps of 1..14, compensating gaps)
+        from salt_b200 import synth
+        sd = int(rng.integers(1 << 20))
+        g2 = synth.Genome(20011, snp_rate=0.01, n_rate=0.0, seed=sd)
+        eng = api.Engine(g2.mixref, g2.l, g2.pac, g2.l, device=0)
+        pc.check_ssw_narrow_bands(eng, o, sd, n_reads=160, L=int(rng.choice([100, 150])))
+        eng.close()
     it += 1; tot_reads += n
 while not ssw_only and time.time() - t0 < budget:
     L = int(rng.choice([37, 50, 64, 75, 100, 101, 125, 150, 151, 200, 250, 300]))
