@@ -218,8 +218,8 @@ sw_dp_kernel(SwDev d)
             if (h == 0) st.sel0[q] = sel; else st.sel1[q] = sel;
         }
     }
-    uint32_t negO = 0u - ((uint32_t)d.prm.gapO | ((uint32_t)d.prm.gapO << 16));   // one 32-bit subtraction for both halves of H
-    uint32_t negE = s16x2(-d.prm.gapE, -d.prm.gapE);
+    uint32_t negO = s16x2(-d.prm.gapO, -d.prm.gapO);
+    uint32_t negE = 0u - ((uint32_t)d.prm.gapE | ((uint32_t)d.prm.gapE << 16));   // one 32-bit subtraction for both halves
     SALT_PIN32(negO); SALT_PIN32(negE);
     const uint2 *__restrict__ win = d.win2 + pair * d.CW;
     uint32_t *__restrict__ mcol = d.maxcol2 + pair * (size_t)d.MC;

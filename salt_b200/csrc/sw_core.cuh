@@ -9,14 +9,15 @@
 //
 //     h  = max(Hdiag + s, E)           VIADDMNMX.S16x2
 //     h  = max(h, F, 0)                VIMNMX3.S16x2
-//     t  = h - gapO                    VIADD (32-bit, see below), shared by the two lines after it
-//     E' = max(E - gapE, t)            VIADDMNMX.S16x2
-//     F' = max(F - gapE, t)            VIADDMNMX.S16x2
+//     E' = max(h - gapO, E - gapE)     VIADD + VIADDMNMX.S16x2
+//     F' = max(h - gapO, F - gapE)     VIADD + VIADDMNMX.S16x2
+// (h - gapO computed once for both saves an instruction per cell pair and measured 10 % SLOWER: it puts a third
+// instruction on the F chain that runs down the strip's rows, and at five CTAs per SM that chain is what a warp waits on.)
 //
-// All of H, E, F carry a constant bias SW_BIAS in both halves ("0" is SW_BIAS).  H is floored at the bias, so
-// subtracting gapO from both of its halves is one 32-bit integer subtraction that never borrows across the
-// halves: a plain 32-bit VIADD instead of the SIMD VIADD.16x2 (6 % faster on B200 in round 1; forcing it onto
-// the FMA pipe as IMAD measured slower again).
+// All of H, E, F carry a constant bias SW_BIAS in both halves ("0" is SW_BIAS).  With every half
+// >= SW_BIAS - gapO > gapE, subtracting gapE from both halves is one 32-bit integer subtraction
+// that never borrows across the halves: a plain 32-bit VIADD instead of the SIMD VIADD.16x2, which
+// measured 6 % faster on B200 (forcing it onto the FMA pipe as IMAD measured slower again).
 // E and F are allowed to go below the bias (>= SW_BIAS - gapO); the reference floors them at 0
 // with saturating unsigned subtraction (ssw.c:458-466), which yields the same H because h is
 // floored itself.  Substitution scores come from an 8-byte row of the score table per
@@ -105,7 +106,7 @@ struct SwStrip {
     // negO: (-gapO, -gapO) as s16x2; negE32: -(gapE | gapE << 16) as a 32-bit integer.
     // Returns the strip maximum; leaves the new bottom H in H[S-1] and F leaving the strip in F.
     SALT_HD uint32_t column(uint32_t t0lo, uint32_t t0hi, uint32_t t1lo, uint32_t t1hi,
-                            uint32_t diag, uint32_t &F, uint32_t negO32, uint32_t negE)
+                            uint32_t diag, uint32_t &F, uint32_t negO, uint32_t negE32)
     {
         uint32_t sm = SW_BIAS2, hprev = SW_BIAS2;
 #pragma unroll
@@ -125,9 +126,8 @@ struct SwStrip {
                     H[i] = h;
                     if (i & 1) sm = vmax3(sm, hprev, h);         // the strip maximum takes two rows per instruction
                     else hprev = h;
-                    const uint32_t t = h + negO32;               // h - gapO in both halves, shared by E and F (h >= bias: no borrow)
-                    E[i] = vaddmax(E[i], negE, t);
-                    F = vaddmax(F, negE, t);
+                    E[i] = vaddmax(h, negO, E[i] + negE32);
+                    F = vaddmax(h, negO, F + negE32);
                 }
             }
         }
