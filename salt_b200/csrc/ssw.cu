@@ -83,7 +83,6 @@ sw_prep_kernel(SwDev d)
         const uint32_t rid = w.rs >> 1;
         const int64_t lim = d.prm.use_pac ? d.c.l_pac : (int64_t)d.c.l;
         const bool ok = rid < d.c.n_reads && w.start <= w.end && (int64_t)w.end <= lim &&      // end == l is what alnpe.c:213-252 clamps to: position l reads the zero pad
-                       
                         (!d.prm.use_pac || d.c.pac != nullptr) &&
                         (int64_t)(w.end - w.start + 1) <= (int64_t)d.MC;
         if (!REV) {
@@ -420,7 +419,7 @@ __device__ __forceinline__ int band_traceback(const CodeAt &code_at, int band, i
 // shift, and a row's direction codes are one 32-bit word (four bits per cell).  Indices follow the reference:
 // cell (i, j) has slot u = j - max(i-B, 0) + 1, its upper neighbour slot u + D with D = [i > B], its left
 // neighbour u - 1.  Needs refLen >= 2B+2 so that no early row is cut short by the window's end (the reference's
-// `edge` is then i+B+1 for rows 0..B and 2B+2 afterwards); everything else goes to the general kernel.
+// `edge` is then i+B+1 for rows 0..B and 2B+2 afterwards); everything else goes to the serial kernel.
 template <int B>
 struct NarrowBand {
     static constexpr int W = 2 * B + 3;
@@ -991,7 +990,6 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 // layout: [0]=win2 [1]=unused [2]=maxcol2 [3]=fwd [4]=dirs [5]=ovf_list [6]=counters [7]=total [8]=wide_list [9]=dp_list [10]=wide_aux [11]=coop_list [12]=coop_aux
 size_t ssw_scratch_bytes(size_t n_tasks, int max_cols, int max_rows, size_t *layout)
 {
-    const SwShape sh = pick_shape(max_rows);
     const size_t pairs = (n_tasks + 1) / 2;
     const int CW = (max_cols + 7) / 8 + 1;
     size_t off = 0;
