@@ -180,7 +180,7 @@ def cpu_reference_run(args, wl, n_sample, steps, warmup):
         if it >= warmup:
             times.append(sec)
     pairs = int(o0[-1]) + int(o1[-1])
-    return dict(kind=kind, cores=cores, n=n, pairs=pairs, sec=float(np.mean(times)), times=times,
+    return dict(kind=kind, cores=cores, n=n, pairs=pairs, sec=float(np.mean(times)), times=times, recs=recs, acc0=a0, acc1=a1,
                 sample="first %d of %d reads of the same workload (%d candidate pairs), verify stage with the reference's "
                        "running thresholds, %d host threads, gcc -O2" % (n, len(wl["reads"]), pairs, cores))
 
@@ -501,6 +501,7 @@ def main():
     rec_plain = h_rec.numpy().copy()
     e2e_s, e2e_launches = time_host(step_host_packed)
     assert h_rec.numpy().tobytes() == rec_plain.tobytes(), "compact and plain transport disagree"
+    acc_e2e = (h_acc0.numpy().copy(), h_acc1.numpy().copy())      # compared with the reference's own output below
     h2d_plain = h_codes.numel() + 4 * (h_roffs.numel() + h_o0.numel() + h_o1.numel() + n0 + n1)
     h2d = h_bases.numel() + 4 * len(pk_npos) + 2 * (h_c0.numel() + h_c1.numel()) + 4 * (n0 + n1)
     d2h = n * 16 + n0 + n1 + n_gapped * (128 + 4) + 4
@@ -569,6 +570,24 @@ def main():
             r = cpu_reference_run(args, wl, args.cpu_sample, 1, 0)
             out["cpu_baseline"] = {"value": r["n"] / r["sec"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                                    "sample": r["sample"], "pairs_per_s": r["pairs"] / r["sec"]}
+            # the sample doubles as a bit-exact check of the e2e leg at this run's full size: primaries and per-candidate
+            # results of the reference's own functions against what came back over the C ABI
+            try:
+                ns = r["n"]
+                got = rec_plain.view(api.VERIFY_DT)[:ns]
+                want = r["recs"]
+                wpos = np.fromiter((w.pos for w in want), np.uint32, ns); wst = np.fromiter((w.strand for w in want), np.int64, ns)
+                wnd = np.fromiter((w.n_diff for w in want), np.int64, ns); wgap = np.fromiter((w.is_gap for w in want), np.int64, ns)
+                mapped = wpos != 0xFFFFFFFF
+                same = (np.array_equal(got["pos"], wpos) and np.array_equal(got["strand"][mapped], wst[mapped])
+                        and np.array_equal(got["n_diff"][mapped], wnd[mapped]) and np.array_equal(got["is_gap"][mapped], wgap[mapped]))
+                o0e, o1e = int(wl["offs0"][ns]), int(wl["offs1"][ns])
+                same_acc = np.array_equal(acc_e2e[0][:o0e], r["acc0"]) and np.array_equal(acc_e2e[1][:o1e], r["acc1"])
+                out["cpu_baseline"]["gpu_e2e_identical_on_sample"] = bool(same and same_acc)
+                out["cpu_baseline"]["sample_checked"] = "%d reads, %d candidate results, %d mapped, %d gapped" % (
+                    ns, o0e + o1e, int(mapped.sum()), int((wgap[mapped] == 1).sum()))
+            except Exception as ex:                      # noqa: BLE001
+                out["cpu_baseline"]["gpu_e2e_identical_on_sample"] = "not compared: %r" % (ex,)
         except Exception as ex:   # the checker is optional for the bench line
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
     if rank == 0:
