@@ -204,7 +204,7 @@ int load_reads(salt_b200_t *h, Slot &s, const salt_reads_t *reads, const salt_ca
     if (l_max > 1024) return fail(SALT_ERR_UNSUPPORTED, "reads longer than 1024 bases are not supported");
     const size_t total = n ? (size_t)reads->offs[n] - reads->offs[0] : 0;
     if (n && reads->offs[0] != 0) return fail(SALT_ERR_ARG, "read offsets must start at 0");
-    s.n_reads = n; s.l_max = l_max; s.W64 = (l_max + 15) / 16 + 1; s.have_rec = false;
+    s.n_reads = n; s.l_max = l_max; s.W64 = (l_max + 15) / 16 + 1; s.have_rec = false; s.seeded = 0;      // lists seeded from the reads that were here are gone with them
     CU(s.codes.need(total + 16));
     CU(s.offs3.need(3 * ((size_t)n + 1) * 4));
     CU(s.rd4.need((size_t)n * 2 * s.W64 * 8 + 64));
@@ -415,7 +415,7 @@ int load_packed(salt_b200_t *h, Slot &s, const PackedView &v, bool with_cands)
 {
     const salt_packed_chunk_t *pc = v.pc;
     const uint32_t n = v.n;
-    s.n_reads = n; s.l_max = v.l_max; s.W64 = (v.l_max + 15) / 16 + 1; s.have_rec = false;
+    s.n_reads = n; s.l_max = v.l_max; s.W64 = (v.l_max + 15) / 16 + 1; s.have_rec = false; s.seeded = 0;
     s.offs_merged = false;
     if (!n) return SALT_OK;
     const uint32_t per = 8u / (uint32_t)pc->base_bits;                 // bases per byte

@@ -253,6 +253,56 @@ def test_seed_locate_lists(emul_lib, tmp_path):
     ref.close(); eng.close()
 
 
+def test_seed_error_paths(emul_lib, tmp_path):
+    """the seeding entry points refuse what they cannot reproduce exactly instead of guessing (same codes on the GPU build:
+    the checks are host code in engine.cu)"""
+    import ctypes as C
+    import seed_cases as sc
+    from salt_b200 import index_io
+    if not sc.have_ref():
+        pytest.skip("oracle/_ref not built (reference tree absent at build time)")
+    rng = np.random.default_rng(5)
+    g, is_n = sc.repeat_genome(rng, n_units=8, unit_len=700, n_rate=0.0)
+    prefix = sc.write_index(str(tmp_path), g, is_n, rng)
+    fm = index_io.FmIndex(prefix)
+    codes, roffs = sc.sample_reads(g, rng, 6)
+    n_reads = len(roffs) - 1
+    eng = api.Engine(fm.mixref, fm.l, None, 0, lib=emul_lib)
+    eng.set_reads(codes, roffs)
+    good = api.Engine.seed_opt(fm.l_seed, 0, 50, 500)
+
+    def code_of(opt, **kw):
+        try:
+            eng.seed_locate(opt, **kw)
+        except api.SaltError as ex:
+            return ex.code
+        return 0
+    assert code_of(good) == -101                                   # no index uploaded yet
+    eng.set_index(fm)
+    assert code_of(good) == 0
+    assert code_of(api.Engine.seed_opt(8, 8, 50, 500)) == -101      # seed shorter than the lookup table's k-mer
+    bad = api.Engine.seed_opt(fm.l_seed, 0, 50, 500); bad.l_overlap = 0
+    assert code_of(bad) == -104                                    # the reference's non-overlap seeding is another function
+    assert code_of(api.Engine.seed_opt(fm.l_seed, 0, -1, 500)) == -101
+    assert code_of(api.Engine.seed_opt(fm.l_seed, 0, 50, 0)) == -104
+    assert code_of(api.Engine.seed_opt(fm.l_seed, 0, 50, 20000)) == -104
+    assert code_of(api.Engine.seed_opt(fm.l_seed, 0, 50, 500, locate_mode=2)) == -101
+    assert code_of(api.Engine.seed_opt(fm.l_seed, 0, 50, 500, locate_mode=1, list_cap=8)) == -101
+    assert code_of(api.Engine.seed_opt(fm.l_seed, 0, 50, 500, locate_mode=1, list_cap=4096)) == 0
+    # room for the download smaller than a strand's list: SALT_ERR_NOMEM, and the totals are still reported
+    n0 = C.c_size_t(0); n1 = C.c_size_t(0)
+    offs0 = np.zeros(n_reads + 1, np.uint32); offs1 = np.zeros(n_reads + 1, np.uint32)
+    tiny = np.zeros(1, np.uint32)
+    rc = eng.L.salt_b200_seed_locate(eng.h, 0, C.byref(good), api._ptr(offs0), api._ptr(offs1), api._ptr(tiny), 1, api._ptr(tiny), 1,
+                                     C.byref(n0), C.byref(n1))
+    assert rc == -103 and n0.value > 1
+    # verification of seeded lists needs a seeded slot
+    eng.set_reads(codes, roffs)
+    with pytest.raises(api.SaltError):
+        eng.verify_seeded(10, 10)
+    eng.close()
+
+
 def test_chunk_pair_stage(emul_lib, oracle):
     """the paired-end stage of a chunk in one call == the stage composed pair by pair"""
     import build_emul

@@ -37,6 +37,16 @@ def test_seed_lists_repeat_genome(tmp_path):
     # a small list_cap: lists that fill it are flagged, everything else still matches
     tot2, flagged2 = sc.check_lists_pe(eng, ref, fm, codes, roffs, option_sets=sc.PE_OPTION_SETS[:1], list_cap=64)
     assert flagged2 > 0 and tot2 > 10000
+    # misuse is refused, not guessed at (the full list of refusals: tests/test_emul_parity.py::test_seed_error_paths, same host code)
+    opt = api.Engine.seed_opt(fm.l_seed, 0, 50, 500)
+    eng.set_reads(codes[:roffs[50]], roffs[:51])
+    n0, n1 = eng.seed_locate(opt, download=False)
+    eng.verify_seeded(n0, n1)
+    eng.set_reads(codes[:roffs[50]], roffs[:51])                 # new reads in the slot: the lists seeded from the old ones are gone
+    with pytest.raises(api.SaltError):
+        eng.verify_seeded(n0, n1)
+    with pytest.raises(api.SaltError):
+        eng.seed_locate(api.Engine.seed_opt(fm.l_seed, 0, 50, 20000), download=False)
     ref.close(); eng.close()
 
 
