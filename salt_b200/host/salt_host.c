@@ -15,7 +15,8 @@ struct salt_chunk {
     uint32_t *offs[2]; uint32_t *loci[2];
     /* pinned outputs */
     salt_verify_out_t *rec; int8_t *acc[2]; char *cigars;
-    int lv_T0; int done;
+    int lv_T0; int done;          /* done: results of the queued reads are in the output arrays */
+    int submitted, slot;          /* in flight on pipeline slot `slot` since salt_chunk_submit */
     /* SAM tail (salt_chunk_tail): per read, rows of the arrays below; -1 = unmapped */
     int tail_done; int32_t *tail_row; salt_mdnm_out_t *tail_out; char *tail_md; uint16_t *tail_xv;
 };
@@ -60,7 +61,7 @@ void salt_chunk_free(salt_chunk_t *c)
 
 void salt_chunk_reset(salt_chunk_t *c)
 {
-    c->n_reads = 0; c->done = 0; c->tail_done = 0;
+    c->n_reads = 0; c->done = 0; c->submitted = 0; c->tail_done = 0;
     c->roffs[0] = 0; c->offs[0][0] = 0; c->offs[1][0] = 0;
 }
 
@@ -70,6 +71,7 @@ int salt_chunk_add_read(salt_chunk_t *c, const uint8_t *seq, uint32_t l_seq,
                         const uint32_t *loci0, uint32_t n0, const uint32_t *loci1, uint32_t n1)
 {
     const uint32_t i = c->n_reads;
+    if (c->done || c->submitted) return SALT_ERR_ARG;          /* in flight, or holding results: salt_chunk_reset first */
     if (i >= c->max_reads) return SALT_ERR_NOMEM;
     if ((size_t)c->roffs[i] + l_seq > c->max_bases) return SALT_ERR_NOMEM;
     if ((size_t)c->offs[0][i] + n0 > c->max_cands || (size_t)c->offs[1][i] + n1 > c->max_cands) return SALT_ERR_NOMEM;
@@ -87,6 +89,7 @@ int salt_chunk_add_read(salt_chunk_t *c, const uint8_t *seq, uint32_t l_seq,
 int salt_chunk_submit(salt_b200_t *h, int slot, salt_chunk_t *c, int nogap_T0, int lv_T0)
 {
     salt_reads_t r; salt_cands_t k;
+    if (!h || !c || c->submitted) return SALT_ERR_ARG;         /* one submit per fill; salt_chunk_wait ends it */
     /* compact copy of the three offset arrays, back to back, in the second half of the allocation */
     const size_t m1 = (size_t)c->n_reads + 1;
     uint32_t *pk = c->offs_all + 3 * ((size_t)c->max_reads + 1);
@@ -94,22 +97,28 @@ int salt_chunk_submit(salt_b200_t *h, int slot, salt_chunk_t *c, int nogap_T0, i
     r.codes = c->codes; r.offs = pk; r.n_reads = c->n_reads;
     k.offs[0] = pk + m1; k.offs[1] = pk + 2 * m1; k.loci[0] = c->loci[0]; k.loci[1] = c->loci[1];
     c->lv_T0 = lv_T0; c->done = 0;
-    if (!c->n_reads) return SALT_OK;
+    if (!c->n_reads) { c->submitted = 1; c->slot = slot; return SALT_OK; }
     /* query->cigar starts out empty (kstring, query.c:208-209): gapped primaries get theirs from the GPU */
     for (uint32_t i = 0; i < c->n_reads; ++i) c->cigars[(size_t)i * 128] = '\0';
-    return salt_b200_verify_submit(h, slot, &r, &k, nogap_T0, lv_T0, c->rec, c->acc[0], c->acc[1], c->cigars, 128);
+    const int rc = salt_b200_verify_submit(h, slot, &r, &k, nogap_T0, lv_T0, c->rec, c->acc[0], c->acc[1], c->cigars, 128);
+    if (rc == SALT_OK) { c->submitted = 1; c->slot = slot; }
+    return rc;
 }
 
 int salt_chunk_wait(salt_b200_t *h, int slot, salt_chunk_t *c)
 {
+    if (!h || !c) return SALT_ERR_ARG;
+    if (!c->submitted) return c->done ? SALT_OK : SALT_ERR_ARG;        /* waiting twice is harmless; waiting for nothing is a bug */
+    if (slot != c->slot) return SALT_ERR_ARG;                          /* the chunk went to another slot */
     int rc = c->n_reads ? salt_b200_verify_wait(h, slot) : SALT_OK;
+    c->submitted = 0;
     if (rc == SALT_OK) c->done = 1;
     return rc;
 }
 
 int salt_chunk_seed_verify(salt_b200_t *h, salt_chunk_t *c, const salt_seed_opt_t *opt, int nogap_T0, int lv_T0)
 {
-    if (!h || !c || !opt) return SALT_ERR_ARG;
+    if (!h || !c || !opt || c->submitted) return SALT_ERR_ARG;
     c->lv_T0 = lv_T0; c->done = 0;
     if (!c->n_reads) { c->done = 1; return SALT_OK; }
     salt_reads_t r; r.codes = c->codes; r.offs = c->roffs; r.n_reads = c->n_reads;
@@ -415,6 +424,7 @@ int salt_chunk_add_reads(salt_chunk_t *c, const uint8_t *codes, const uint32_t *
                          const uint32_t *offs0, const uint32_t *loci0, const uint32_t *offs1, const uint32_t *loci1)
 {
     if (!c || !roffs || !offs0 || !offs1 || (n && !codes)) return SALT_ERR_ARG;
+    if (c->done || c->submitted) return SALT_ERR_ARG;          /* in flight, or holding results: salt_chunk_reset first */
     const uint32_t at = c->n_reads;
     const size_t nb = (size_t)roffs[n] - roffs[0], n0 = (size_t)offs0[n] - offs0[0], n1 = (size_t)offs1[n] - offs1[0];
     if ((size_t)at + n > c->max_reads || (size_t)c->roffs[at] + nb > c->max_bases ||

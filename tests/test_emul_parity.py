@@ -303,6 +303,82 @@ def test_seed_error_paths(emul_lib, tmp_path):
     eng.close()
 
 
+def test_transport_and_handle_error_paths(emul_lib):
+    """malformed compact chunks, slots out of range, tags of a slot that holds no verified chunk, reloading the reference of a
+    handle that only borrows it: refused with SALT_ERR_ARG, nothing guessed"""
+    g, reads, pos, strand, cands = pc.make_world(5, L=100, n_reads=12, per_strand=3, indel_frac=0.3, glen=20000)
+    eng = api.Engine(g.mixref, g.l, g.pac, g.l, lib=emul_lib)
+    offs0, loci0, offs1, loci1 = cands
+    roffs = (np.arange(len(reads) + 1) * 100).astype(np.uint32)
+    res = eng.packed_chunk(reads.reshape(-1), roffs, offs0, loci0, offs1, loci1)
+    pk = res[0] if isinstance(res, tuple) else res
+
+    def code_of(fn):
+        try:
+            fn()
+        except api.SaltError as ex:
+            return ex.code
+        return 0
+    run = lambda: eng.verify_batch_packed(pk, len(loci0), len(loci1), 5)
+    assert code_of(run) == 0
+    for field, val in (("base_bits", 3), ("base_bits", 0), ("count_bits", 8), ("bases", None), ("l_seq", 0)):
+        old = getattr(pk, field)
+        setattr(pk, field, val)
+        assert code_of(run) == -101, field
+        setattr(pk, field, old)
+    assert code_of(run) == 0
+    eng.set_reads(reads)
+    assert code_of(lambda: eng.tail_primaries()) == -101            # nothing verified in the slot since its reads changed
+    assert code_of(lambda: eng._ck(eng.L.salt_b200_use_slot(eng.h, 99))) == -101
+    assert code_of(lambda: eng._ck(eng.L.salt_b200_use_slot(eng.h, -1))) == -101
+    other = eng.attach()
+    assert code_of(lambda: other._ck(eng.L.salt_b200_reload_ref(other.h, api._ptr(g.mixref), g.l, None, 0))) == -101
+    assert not eng.L.salt_b200_attach(None)
+    other.close(); eng.close()
+
+
+def test_chunk_queue_misuse_is_refused(emul_lib):
+    """the host layer's chunk queues keep their own state: results before (or without) a submit, waiting on the wrong slot or
+    for nothing, appending to a chunk that is in flight or holds results, a second submit: SALT_ERR_ARG, never stale data"""
+    import build_emul
+    from salt_b200 import host_api
+    H = host_api.load(build_emul.build_host())
+    g, reads, pos, strand, cands = pc.make_world(5, L=100, n_reads=12, per_strand=3, indel_frac=0.3, glen=20000)
+    eng = api.Engine(g.mixref, g.l, g.pac, g.l, lib=emul_lib)
+    offs0, loci0, offs1, loci1 = cands
+    n = len(reads); roffs = (np.arange(n + 1) * 100).astype(np.uint32)
+    ch = host_api.Chunk(H, n + 2, (n + 2) * 100, len(loci0) + len(loci1) + 8)
+
+    def code_of(fn):
+        try:
+            fn()
+        except api.SaltError as ex:
+            return ex.code
+        return 0
+    add = lambda: ch.add_reads(reads.reshape(-1), roffs, offs0, loci0, offs1, loci1)
+    assert code_of(lambda: ch.result(0)) == -101
+    assert code_of(lambda: ch.wait(eng, 0)) == -101                 # nothing was submitted
+    assert code_of(add) == 0
+    assert code_of(lambda: ch.result(0)) == -101                    # queued, not verified
+    assert code_of(lambda: ch.pair(eng, 0, n // 2, 250, 550, g.l)) == -101
+    assert code_of(lambda: ch.submit(eng, 9, 3, 3)) == -101
+    assert code_of(lambda: ch.submit(eng, 0, 3, 3)) == 0
+    assert code_of(lambda: ch.submit(eng, 0, 3, 3)) == -101         # already in flight
+    assert code_of(add) == -101                                     # ... and its queues are not the caller's to write
+    assert code_of(lambda: ch.wait(eng, 1)) == -101                 # it went to slot 0
+    assert code_of(lambda: ch.wait(eng, 0)) == 0
+    assert code_of(lambda: ch.wait(eng, 0)) == 0                    # waiting twice is harmless
+    assert code_of(lambda: ch.result(n)) == -101
+    assert code_of(lambda: ch.result(0, 0)) == -101 and code_of(lambda: ch.result(0, 17)) == -101
+    assert code_of(lambda: ch.result(0)) == 0
+    assert code_of(add) == -101                                     # holds results: reset first
+    ch.reset()
+    assert code_of(lambda: ch.result(0)) == -101
+    assert code_of(add) == 0
+    assert code_of(lambda: ch.seed_verify(eng, api.Engine.seed_opt(19, 0, 50, 500))) == -101      # no index uploaded
+    ch.close(); eng.close()
+
+
 def test_chunk_pair_stage(emul_lib, oracle):
     """the paired-end stage of a chunk in one call == the stage composed pair by pair"""
     import build_emul
