@@ -158,6 +158,8 @@ typedef struct {
 } salt_pe_stats_t;
 /* host threads for salt_chunk_pair's per-pair loops (the reference runs its pairing on the -t workers, alnpe.c:596-606) */
 void salt_host_set_threads(int n);
+/* per-read / per-pair loops shorter than `items` per thread stay on fewer threads (256 by default; tests lower it) */
+void salt_host_set_grain(uint32_t items);
 int salt_chunk_pair(salt_b200_t *h, int slot, salt_chunk_t *c, uint32_t min_tlen, uint32_t max_tlen, uint32_t l_pac,
                     int max_hits, const int8_t *mat16 /* score_mat2, 256 */, const int8_t *mat5 /* score_mat, 25 */,
                     int gapO, int gapE, int filters, int filterd, int with_tail,

@@ -107,6 +107,7 @@ def declare(L):
         L.salt_chunk_seed_verify.argtypes = [vp, vp, C.POINTER(SeedOptT), i32, i32]
         L.salt_chunk_pair.argtypes = [vp, i32, vp, u32, u32, u32, i32, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, C.POINTER(PeStatsT)]
         L.salt_host_set_threads.argtypes = [i32]; L.salt_host_set_threads.restype = None
+        L.salt_host_set_grain.argtypes = [C.c_uint32]; L.salt_host_set_grain.restype = None
         L.salt_chunk_results.argtypes = [vp, i32, vp]
         L.salt_multi_init.restype = vp
         L.salt_multi_init.argtypes = [vp, u32, vp, C.c_int64, vp, i32]

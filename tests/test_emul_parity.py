@@ -391,6 +391,41 @@ def test_chunk_pair_stage(emul_lib, oracle):
     eng.close()
 
 
+def test_chunk_pair_stage_on_host_threads(emul_lib, oracle):
+    """the host layer's per-read / per-pair loops on its persistent thread pool: same results with 1, 3 and 5 host threads
+    (the pool is rebuilt when the count changes), and from two driver threads with their own handles and pools at once"""
+    import threading
+    import build_emul
+    from salt_b200 import host_api
+    hostlib = host_api.load(build_emul.build_host())
+    g = synth.Genome(40000, snp_rate=0.01, seed=78)
+    eng = _engine(emul_lib, g, with_pac=True)
+    hostlib.salt_host_set_grain(2)                       # 24 pairs are enough to spread over the threads
+    try:
+        for nthr in (3, 1, 5):
+            hostlib.salt_host_set_threads(nthr)
+            st = pc.check_chunk_pair(eng, hostlib, g, 24, 100, seed=9)
+            assert st.windows16 + st.windows5 >= 3 and st.rescued >= 1
+        hostlib.salt_host_set_threads(4)
+        engs = [eng, eng.attach()]
+        errs = []
+
+        def drive(i):
+            try:
+                for rep in range(2):
+                    pc.check_chunk_pair(engs[i], hostlib, g, 20, 100, seed=30 + 5 * i + rep)
+            except BaseException as ex:                  # noqa: BLE001
+                errs.append((i, repr(ex)))
+        ths = [threading.Thread(target=drive, args=(i,)) for i in range(2)]
+        for t in ths: t.start()
+        for t in ths: t.join()
+        assert not errs, errs
+        engs[1].close()
+    finally:
+        hostlib.salt_host_set_threads(1); hostlib.salt_host_set_grain(256)
+    eng.close()
+
+
 def test_tail_primaries(emul_lib, oracle):
     g, reads, pos, strand, cands = pc.make_world(808, L=100, n_reads=40, per_strand=3, indel_frac=0.4, glen=30000, sub_rate=0.03)
     eng = _engine(emul_lib, g, with_pac=True)
