@@ -75,26 +75,27 @@ def main():
             rec = np.frombuffer(d_rec.cpu().numpy().tobytes(), api.VERIFY_DT)
             blk["verify_" + rule] = {"ms": ms, "reads_per_s": n_reads / ms * 1e3, "pairs_per_s": (n0 + n1) / ms * 1e3,
                                      "mapped_frac": float((rec["pos"] != 0xFFFFFFFF).mean()), "gapped_stage_frac": float(rec["lv_ran"].mean())}
-        # mate rescue
-        W = {100: 401, 150: 401, 250: 301}[L]
-        nt = min(n_reads, 200_000)
-        rng = np.random.default_rng(5)
-        start = np.maximum(0, pos[:nt].astype(np.int64) - rng.integers(0, W - L, nt))
-        wins = np.zeros(nt, api.WIN_DT); wins["rs"] = (np.arange(nt, dtype=np.uint32) << 1) | strand[:nt]
-        wins["start"] = start; wins["end"] = np.minimum(g.l - 1, start + W - 1)
-        d_w = torch.from_numpy(wins.view(np.uint8)).to(dev); d_so = torch.empty(nt * 28, dtype=torch.uint8, device=dev)
-        d_sc = torch.empty(nt * 64, dtype=torch.int32, device=dev)
-        mat = api.salt_score_mat2()
-        lib.salt_b200_set_max_window(h, (W + 7) // 8 * 8)
-        ms = timed(lambda: lib.salt_b200_ssw_dev(h, d_w.data_ptr(), nt, 0, mat.ctypes.data, 16, 3, 1, 2, 0, 20, -1, d_so.data_ptr(),
-                                                 d_sc.data_ptr(), 64), stream, dev)
-        eng.profile(True)
-        lib.salt_b200_ssw_dev(h, d_w.data_ptr(), nt, 0, mat.ctypes.data, 16, 3, 1, 2, 0, 20, -1, d_so.data_ptr(), d_sc.data_ptr(), 64)
-        stg = {k_: v for k_, v in eng.profile_read().items() if k_.startswith("ssw")}
-        eng.profile(False)
-        cells = nt * (8 * ((L + 7) // 8)) * W
-        blk["ssw"] = {"tasks": nt, "window": W, "ms": ms, "tasks_per_s": nt / ms * 1e3, "tcups_fwd_cells_pipeline": cells / ms / 1e9,
-                      "tcups_fwd_kernel": cells / stg["ssw_dp_fwd"] / 1e9, "stages_ms": stg}
+        # mate rescue: the window the default insert bounds give (alnpe.c:213-252), and for 250 bp also the 551-wide window of
+        # wide insert bounds (-a 250 -b 1050)
+        for key, W in [("ssw", {100: 401, 150: 401, 250: 301}[L])] + ([("ssw_551", 551)] if L == 250 else []):
+            nt = min(n_reads, 200_000)
+            rng = np.random.default_rng(5)
+            start = np.maximum(0, pos[:nt].astype(np.int64) - rng.integers(0, W - L, nt))
+            wins = np.zeros(nt, api.WIN_DT); wins["rs"] = (np.arange(nt, dtype=np.uint32) << 1) | strand[:nt]
+            wins["start"] = start; wins["end"] = np.minimum(g.l - 1, start + W - 1)
+            d_w = torch.from_numpy(wins.view(np.uint8)).to(dev); d_so = torch.empty(nt * 28, dtype=torch.uint8, device=dev)
+            d_sc = torch.empty(nt * 64, dtype=torch.int32, device=dev)
+            mat = api.salt_score_mat2()
+            lib.salt_b200_set_max_window(h, (W + 7) // 8 * 8)
+            ms = timed(lambda: lib.salt_b200_ssw_dev(h, d_w.data_ptr(), nt, 0, mat.ctypes.data, 16, 3, 1, 2, 0, 20, -1, d_so.data_ptr(),
+                                                     d_sc.data_ptr(), 64), stream, dev)
+            eng.profile(True)
+            lib.salt_b200_ssw_dev(h, d_w.data_ptr(), nt, 0, mat.ctypes.data, 16, 3, 1, 2, 0, 20, -1, d_so.data_ptr(), d_sc.data_ptr(), 64)
+            stg = {k_: v for k_, v in eng.profile_read().items() if k_.startswith("ssw")}
+            eng.profile(False)
+            cells = nt * (8 * ((L + 7) // 8)) * W
+            blk[key] = {"tasks": nt, "window": W, "ms": ms, "tasks_per_s": nt / ms * 1e3, "tcups_fwd_cells_pipeline": cells / ms / 1e9,
+                        "tcups_fwd_kernel": cells / stg["ssw_dp_fwd"] / 1e9, "stages_ms": stg}
         out["blocks"].append(blk)
         eng.close()
         print("done", tag, file=sys.stderr)
