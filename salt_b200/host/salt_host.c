@@ -853,6 +853,45 @@ int salt_multi_verify_batch_packed(salt_multi_t *m, const salt_packed_chunk_t *p
 /* ------------------------------------------------------------------ FASTQ -> compact transport (query.c:146-239) */
 static inline int fq_is_blank(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
 
+/* The 2-bit base stream is written through a small bit accumulator (no read-modify-write per base); bases arrive eight at a
+ * time when a sequence line holds nothing but A/C/G/T in either case, which eight bytes are tested for at once. */
+typedef struct { uint8_t *out; size_t byte; uint64_t acc; int bits; } fq_bitw_t;
+static inline void fq_put(fq_bitw_t *w, uint64_t v, int nbits)
+{
+    w->acc |= v << w->bits; w->bits += nbits;
+    while (w->bits >= 8) { w->out[w->byte++] = (uint8_t)w->acc; w->acc >>= 8; w->bits -= 8; }
+}
+#define FQ_ONES 0x0101010101010101ULL
+static inline uint64_t fq_eq_bytes(uint64_t x, unsigned c)        /* 0x80 in every byte of x that equals c */
+{
+    const uint64_t y = x ^ (FQ_ONES * c);
+    const uint64_t t = ((y & (FQ_ONES * 0x7F)) + (FQ_ONES * 0x7F)) | y;          /* bit 7 set iff the byte is non-zero */
+    return ~t & (FQ_ONES * 0x80);
+}
+static inline int fq_has_blank(uint64_t x) { return ((x - FQ_ONES * 0x21) & ~x & (FQ_ONES * 0x80)) != 0; }   /* some byte <= ' ' */
+#if defined(__SSE2__)
+#include <emmintrin.h>
+/* sixteen bases at once: 1 and *packed = their 32 code bits when all sixteen are A/C/G/T in either case, else 0 */
+static inline int fq_pack16(const char *src, uint32_t *packed)
+{
+    const __m128i x = _mm_loadu_si128((const __m128i *)src);
+    const __m128i u = _mm_and_si128(x, _mm_set1_epi8((char)0xDF));
+    const __m128i ok = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(u, _mm_set1_epi8('A')), _mm_cmpeq_epi8(u, _mm_set1_epi8('C'))),
+                                    _mm_or_si128(_mm_cmpeq_epi8(u, _mm_set1_epi8('G')), _mm_cmpeq_epi8(u, _mm_set1_epi8('T'))));
+    if (_mm_movemask_epi8(ok) != 0xFFFF) return 0;
+    __m128i t = _mm_and_si128(_mm_xor_si128(_mm_srli_epi16(x, 1), _mm_srli_epi16(x, 2)), _mm_set1_epi8(3));
+    t = _mm_and_si128(_mm_or_si128(t, _mm_srli_epi16(t, 6)), _mm_set1_epi16(0x000F));
+    t = _mm_and_si128(_mm_or_si128(t, _mm_srli_epi32(t, 12)), _mm_set1_epi32(0x000000FF));
+    t = _mm_packus_epi16(_mm_packs_epi32(t, t), _mm_setzero_si128());
+    *packed = (uint32_t)_mm_cvtsi128_si32(t);
+    return 1;
+}
+static inline int fq_blank16(const char *src)          /* some byte <= ' ' (or >= 0x80: left to the byte loop) among sixteen */
+{
+    return _mm_movemask_epi8(_mm_cmplt_epi8(_mm_loadu_si128((const __m128i *)src), _mm_set1_epi8(0x21))) != 0;
+}
+#endif
+
 int salt_fastq_pack(const char *text, size_t len, int final, uint32_t max_reads, salt_fastq_t *o, size_t *consumed)
 {
     if (!text || !o || !o->bases || !o->lens || !o->n_ambiguous || !o->name_off || !o->name_len || !consumed) return SALT_ERR_ARG;
@@ -868,7 +907,8 @@ int salt_fastq_pack(const char *text, size_t len, int final, uint32_t max_reads,
     size_t p = 0;
     *consumed = 0;
     o->n_reads = 0;
-    if (o->bases_cap) memset(o->bases, 0, o->bases_cap / 4 + 1);
+    fq_bitw_t w = {o->bases, 0, 0, 0};
+    size_t dirty = 0;                      /* bytes a given-back record may have written */
     while (n < max_reads) {
         /* kseq: skip to the next header character */
         while (p < len && text[p] != '@' && text[p] != '>') ++p;
@@ -882,45 +922,104 @@ int salt_fastq_pack(const char *text, size_t len, int final, uint32_t max_reads,
         size_t com_a = q, com_b = q;
         if (q < len && text[q] != '\n') {                                   /* comment: the rest of the header line */
             com_a = q + 1;
-            while (q < len && text[q] != '\n') ++q;
+            const char *e = (const char *)memchr(text + q, '\n', len - q);
+            q = e ? (size_t)(e - text) : len;
             com_b = q;
             while (com_b > com_a && text[com_b - 1] == '\r') --com_b;
         }
         if (q >= len && !final) break;
         p = q < len ? q + 1 : q;
         /* sequence lines until a line starting with '+', '>' or '@' */
-        const size_t base0 = nb; size_t amb = 0, nn0 = nn;
+        const size_t base0 = nb, nn0 = nn; size_t amb = 0;
+        const fq_bitw_t w0 = w;
         int complete = 0, has_plus = 0;
         while (1) {
             if (p >= len) { complete = final; break; }
             const char c0 = text[p];
             if (c0 == '+') { has_plus = 1; complete = 1; break; }
             if (c0 == '>' || c0 == '@') { complete = 1; break; }
-            while (p < len && text[p] != '\n') {
+            const char *e = (const char *)memchr(text + p, '\n', len - p);
+            const size_t le = e ? (size_t)(e - text) : len;                  /* end of this line (or of the block) */
+            if (nb + (le - p) > o->bases_cap) goto full;                     /* conservative: blanks inside the line count too */
+#if defined(__SSE2__)
+            while (p + 16 <= le) {
+                uint32_t v;
+                if (!fq_pack16(text + p, &v)) break;
+                fq_put(&w, v, 32);
+                nb += 16; p += 16;
+            }
+#endif
+            while (p + 8 <= le) {
+                uint64_t x; memcpy(&x, text + p, 8);
+                const uint64_t u = x & (FQ_ONES * 0xDF);                     /* upper case */
+                const uint64_t ok = fq_eq_bytes(u, 'A') | fq_eq_bytes(u, 'C') | fq_eq_bytes(u, 'G') | fq_eq_bytes(u, 'T');
+                if (ok != FQ_ONES * 0x80) break;                             /* something else in these eight: one at a time below */
+                uint64_t t = ((x >> 1) ^ (x >> 2)) & (FQ_ONES * 3);          /* A C G T (either case) -> 0 1 2 3 */
+                t = (t | (t >> 6)) & 0x000F000F000F000FULL;
+                t = (t | (t >> 12)) & 0x000000FF000000FFULL;
+                t = (t | (t >> 24)) & 0xFFFFULL;
+                fq_put(&w, t, 16);
+                nb += 8; p += 8;
+            }
+            while (p < le) {
+#if defined(__SSE2__)
+                if (p + 16 <= le) {                                          /* back to sixteen at a time after the odd byte(s) */
+                    uint32_t v;
+                    if (fq_pack16(text + p, &v)) { fq_put(&w, v, 32); nb += 16; p += 16; continue; }
+                }
+#endif
+                if (p + 8 <= le) {
+                    uint64_t x; memcpy(&x, text + p, 8);
+                    const uint64_t u = x & (FQ_ONES * 0xDF);
+                    const uint64_t ok = fq_eq_bytes(u, 'A') | fq_eq_bytes(u, 'C') | fq_eq_bytes(u, 'G') | fq_eq_bytes(u, 'T');
+                    if (ok == FQ_ONES * 0x80) {
+                        uint64_t t = ((x >> 1) ^ (x >> 2)) & (FQ_ONES * 3);
+                        t = (t | (t >> 6)) & 0x000F000F000F000FULL;
+                        t = (t | (t >> 12)) & 0x000000FF000000FFULL;
+                        t = (t | (t >> 24)) & 0xFFFFULL;
+                        fq_put(&w, t, 16);
+                        nb += 8; p += 8;
+                        continue;
+                    }
+                }
                 const unsigned char ch = (unsigned char)text[p++];
                 if (ch <= ' ') continue;                                     /* kseq keeps graphic characters only */
-                if (nb >= o->bases_cap) goto full;
                 const unsigned v = nt4[ch];
-                if (v > 3) { ++amb; if (o->n_pos) { if (nn >= o->n_pos_cap) goto full; o->n_pos[nn] = (uint32_t)nb; } ++nn; }
-                else o->bases[nb >> 2] |= (uint8_t)(v << (2 * (nb & 3)));
+                if (v > 3) {
+                    ++amb;
+                    if (o->n_pos) { if (nn >= o->n_pos_cap) goto full; o->n_pos[nn] = (uint32_t)nb; }
+                    ++nn;
+                    fq_put(&w, 0, 2);
+                } else fq_put(&w, v, 2);
                 ++nb;
             }
             if (p < len) ++p; else { complete = final; break; }
         }
-        if (!complete) { nb = base0; nn = nn0; break; }
+        if (!complete) { nb = base0; nn = nn0; dirty = w.byte + 1; w = w0; break; }
         const size_t L = nb - base0;
         if (L > 65535) return SALT_ERR_ARG;
         size_t qual_at = (size_t)-1;
         if (has_plus) {
-            while (p < len && text[p] != '\n') ++p;                          /* the rest of the '+' line */
-            if (p >= len) { if (!final) { nb = base0; nn = nn0; break; } }
+            const char *e = (const char *)memchr(text + p, '\n', len - p);   /* the rest of the '+' line */
+            p = e ? (size_t)(e - text) : len;
+            if (p >= len) { if (!final) { nb = base0; nn = nn0; dirty = w.byte + 1; w = w0; break; } }
             else ++p;
             qual_at = p;
             size_t ql = 0;
+            if (p + L <= len) {                                              /* the usual case: L graphic characters in a row */
+                size_t k = 0; int blank = 0;
+#if defined(__SSE2__)
+                for (; k + 16 <= L; k += 16) if (fq_blank16(text + p + k)) { blank = 1; break; }
+#endif
+                for (; !blank && k + 8 <= L; k += 8) { uint64_t x; memcpy(&x, text + p + k, 8); if (fq_has_blank(x)) { blank = 1; break; } }
+                if (!blank) for (; k < L; ++k) if ((unsigned char)text[p + k] <= ' ') { blank = 1; break; }
+                if (!blank) { ql = L; p += L; }
+            }
             while (ql < L && p < len) { const unsigned char ch = (unsigned char)text[p++]; if (ch > ' ') ++ql; }
-            if (ql < L) { if (final) return SALT_ERR_ARG; nb = base0; nn = nn0; break; }
-            while (p < len && text[p] != '\n') ++p;                          /* kseq reads whole lines */
-            if (p < len) ++p; else if (!final) { nb = base0; nn = nn0; break; }
+            if (ql < L) { if (final) return SALT_ERR_ARG; nb = base0; nn = nn0; dirty = w.byte + 1; w = w0; break; }
+            e = (const char *)memchr(text + p, '\n', len - p);               /* kseq reads whole lines */
+            p = e ? (size_t)(e - text) : len;
+            if (p < len) ++p; else if (!final) { nb = base0; nn = nn0; dirty = w.byte + 1; w = w0; break; }
         }
         if (L == 0) { /* query_read_seq stops at an empty record (l_seq <= 0, query.c:155) */ *consumed = p; break; }
         o->lens[n] = (uint16_t)L; o->n_ambiguous[n] = (uint16_t)(amb > 65535 ? 65535 : amb);
@@ -933,9 +1032,16 @@ int salt_fastq_pack(const char *text, size_t len, int final, uint32_t max_reads,
         continue;
 full:
         /* an array filled up inside this record: give back what belongs to it and stop before it */
-        for (size_t k = base0; k < nb; ++k) o->bases[k >> 2] &= (uint8_t)~(3u << (2 * (k & 3)));
-        nb = base0; nn = nn0;
+        nb = base0; nn = nn0; dirty = w.byte + 1; w = w0;
         break;
+    }
+    /* the last, partly filled byte; whatever a given-back record left behind it is cleared */
+    {
+        size_t end = w.byte;
+        if (w.bits > 0) o->bases[end++] = (uint8_t)w.acc;
+        const size_t room = o->bases_cap / 4 + 1;
+        if (dirty > room) dirty = room;
+        if (end < dirty) memset(o->bases + end, 0, dirty - end);
     }
     o->n_reads = n; o->n_bases = nb; o->n_n = nn;
     return (int)n;
