@@ -194,6 +194,14 @@ typedef struct {
  * its sequence at the end of the input, a read longer than 65535 bases). */
 int salt_fastq_pack(const char *text, size_t len, int final, uint32_t max_reads, salt_fastq_t *out, size_t *consumed);
 
+/* Cut points for parsing one FASTQ text on several host threads: cuts[0] = 0 < cuts[1] < ... < cuts[parts] = len, every inner
+ * cut the offset of a four-line record's header (a line starting with '@' whose next-but-one line starts with '+'; a quality
+ * line may start with '@', the line two below it is then a sequence line).  Each part is a text of its own for
+ * salt_fastq_pack(final = 1) and travels as chunks of its own.  cuts needs n_parts + 1 entries.  Returns the number of parts
+ * made (fewer than asked when the text is short), SALT_ERR_UNSUPPORTED when no such header is found where a cut is due
+ * (records spanning several lines, FASTA): parse on one thread. */
+int salt_fastq_split(const char *text, size_t len, int n_parts, size_t *cuts);
+
 /* ---- several GPUs in one process (reads shard, the reference is replicated, no collective) ----
  * salt is one process (alnse.c:1414-1440); this keeps it one: one handle per device, the batch split into contiguous
  * shares, every share through its device's own chunk pipeline on its own host thread, every result written at the

@@ -1046,3 +1046,40 @@ full:
     o->n_reads = n; o->n_bases = nb; o->n_n = nn;
     return (int)n;
 }
+
+/* Cut points for parsing one FASTQ text on several threads (salt_fastq_pack is re-entrant, and every part can travel as
+ * chunks of its own: the compact transport does not care where a chunk's bases start).  A cut is the offset of a line that
+ * starts with '@' and whose next-but-one line starts with '+': a record header of the usual four-line layout.  A quality line
+ * may start with '@' too, but the line two below it is then a sequence line. */
+int salt_fastq_split(const char *text, size_t len, int n_parts, size_t *cuts)
+{
+    if (!text || !cuts || n_parts < 1) return SALT_ERR_ARG;
+    int made = 0;
+    cuts[0] = 0;
+    for (int k = 1; k < n_parts; ++k) {
+        size_t s = (size_t)((unsigned long long)len * (unsigned long long)k / (unsigned long long)n_parts);
+        if (s <= cuts[made]) continue;
+        const char *e = (const char *)memchr(text + s, '\n', len - s);
+        if (!e) break;                                          /* the rest is one line: no further cut */
+        s = (size_t)(e - text) + 1;
+        int found = 0;
+        for (int tries = 0; tries < 4096 && s < len; ++tries) {
+            const char *e1 = (const char *)memchr(text + s, '\n', len - s);
+            if (!e1) break;
+            const size_t l1 = (size_t)(e1 - text) + 1;
+            if (text[s] == '@' && l1 < len) {
+                const char *e2 = (const char *)memchr(text + l1, '\n', len - l1);
+                if (e2) {
+                    const size_t l2 = (size_t)(e2 - text) + 1;
+                    if (l2 < len && text[l2] == '+') { found = 1; break; }
+                }
+            }
+            s = l1;
+        }
+        if (!found) { if (s >= len) break; return SALT_ERR_UNSUPPORTED; }       /* records span several lines: parse on one thread */
+        if (s > cuts[made]) cuts[++made] = s;
+    }
+    cuts[++made] = len;
+    return made;
+}
+

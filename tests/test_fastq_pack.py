@@ -126,3 +126,41 @@ def test_fastq_pack_matches_reference_reader(tmp_path, block, per_call, clean):
             assert com == api.cstr(coms[i]), (i, com, api.cstr(coms[i]))
         assert qual == api.cstr(quals[i]), (i, qual[:20], api.cstr(quals[i])[:20])
     assert sum(r[1] for r in recs) > (100 if clean else 1000)
+
+
+def test_fastq_split_parts_equal_the_whole(tmp_path):
+    """salt_fastq_split: four-line records whose quality lines start with '@' or '+' as often as chance allows; the parts parsed
+    one by one give the same records as the whole text; multi-line records are declined"""
+    H = _hostlib()
+    H.salt_fastq_split.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]
+    H.salt_fastq_split.restype = C.c_int
+    rng = np.random.default_rng(23)
+    lines = []
+    for i in range(3000):
+        L = int(rng.integers(30, 160))
+        seq = "".join("ACGTN"[k] for k in rng.choice(5, L, p=[0.245, 0.245, 0.245, 0.245, 0.02]))
+        qual = "".join(chr(33 + int(k)) for k in rng.integers(0, 41, L))
+        if i % 3 == 0: qual = "@" + qual[1:]
+        if i % 3 == 1: qual = "+" + qual[1:]
+        if i % 7 == 0: qual = "@@" + qual[2:]
+        lines.append("@r%d%s\n%s\n+%s\n%s\n" % (i, " c%d" % i if i % 5 == 0 else "", seq, "r%d" % i if i % 4 == 0 else "", qual))
+    text = "".join(lines).encode()
+    whole = _parse_all(H, text, 1 << 26, 1000000)
+    assert len(whole) == 3000
+    for parts in (2, 5, 16, 64):
+        cuts = (C.c_size_t * (parts + 1))()
+        made = H.salt_fastq_split(text, len(text), parts, cuts)
+        assert 1 <= made <= parts and cuts[0] == 0 and cuts[made] == len(text)
+        got = []
+        for k in range(made):
+            assert cuts[k] < cuts[k + 1] and (k == 0 or text[cuts[k]:cuts[k] + 1] == b"@")
+            got += _parse_all(H, text[cuts[k]:cuts[k + 1]], 1 << 26, 1000000)
+        assert len(got) == len(whole), parts
+        for a, b in zip(got, whole):
+            assert np.array_equal(a[0], b[0]) and a[1:] == b[1:]
+    # records whose sequence spans lines have no such header pattern everywhere: declined, never cut wrongly
+    multi = b"".join(b"@m%d\nACGTACGT\nACGT\n+\nIIIIIIII\nIIII\n" % i for i in range(200))
+    cuts = (C.c_size_t * 9)()
+    assert H.salt_fastq_split(multi, len(multi), 8, cuts) in (-104, 1)
+    fasta = b"".join(b">f%d\nACGTACGTAC\n" % i for i in range(200))
+    assert H.salt_fastq_split(fasta, len(fasta), 4, cuts) in (-104, 1)        # no header of that shape anywhere: one part

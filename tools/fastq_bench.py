@@ -55,6 +55,46 @@ def main():
     out = {"reads": n, "read_len": L, "fastq_bytes": len(text),
            "salt_fastq_pack": {"reads_per_s": n / best, "mb_per_s": len(text) / best / 1e6, "threads": 1, "n_positions": int(fq.n_n),
                                "out_bytes_per_read": (L + 3) // 4 + 2 + 2 + 4 + 2 + 4 + 2 + 4}}
+    # several host threads: salt_fastq_split cuts the text at record headers, every part is parsed on its own thread into its own
+    # arrays (each part travels as chunks of its own)
+    import threading
+    H.salt_fastq_split.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]
+    H.salt_fastq_split.restype = C.c_int
+    out["threads"] = []
+    for T in [t for t in (2, 4, 8, 16, 32) if t <= (os.cpu_count() or 1)]:
+        cuts = (C.c_size_t * (T + 1))()
+        t0 = time.perf_counter()
+        made = H.salt_fastq_split(text, len(text), T, cuts)
+        assert made >= 1, made
+        parts = []
+        for k in range(made):
+            ln = cuts[k + 1] - cuts[k]
+            mr = n // made + n // (4 * made) + 1024
+            b = np.zeros(ln // 8 + 16, np.uint8); npos = np.zeros(max(1024, ln // 100), np.uint32)
+            ar = {key: np.zeros(mr, dt) for key, dt in (("lens", np.uint16), ("n_ambiguous", np.uint16), ("name_off", np.uint32),
+                                                        ("name_len", np.uint16), ("comment_off", np.uint32), ("comment_len", np.uint16),
+                                                        ("qual_off", np.uint32))}
+            parts.append((b, npos, ar, mr))
+        t_alloc = time.perf_counter() - t0
+        counts = [0] * made
+        base_addr = C.cast(C.c_char_p(text), C.c_void_p).value
+
+        def work(k):
+            b, npos, ar, mr = parts[k]
+            fq = FastqT(b.ctypes.data, len(b) * 4 - 8, npos.ctypes.data, len(npos), *(ar[key].ctypes.data for key in
+                        ("lens", "n_ambiguous", "name_off", "name_len", "comment_off", "comment_len", "qual_off")), 0, 0, 0)
+            used = C.c_size_t(0)
+            counts[k] = H.salt_fastq_pack(C.cast(base_addr + cuts[k], C.c_char_p), cuts[k + 1] - cuts[k], 1, mr, C.byref(fq), C.byref(used))
+        bestT = None
+        for _ in range(6):
+            ths = [threading.Thread(target=work, args=(k,)) for k in range(made)]
+            t0 = time.perf_counter()
+            for th in ths: th.start()
+            for th in ths: th.join()
+            dt = time.perf_counter() - t0
+            bestT = dt if bestT is None else min(bestT, dt)
+        assert sum(counts) == n, (counts, n)
+        out["threads"].append({"threads": made, "reads_per_s": n / bestT, "mb_per_s": len(text) / bestT / 1e6})
     ref = os.path.join(ROOT, "oracle", "_ref", "libsaltref_seed.so")
     if os.path.exists(ref):
         R = C.CDLL(ref)
