@@ -379,6 +379,69 @@ def test_chunk_queue_misuse_is_refused(emul_lib):
     ch.close(); eng.close()
 
 
+def test_fastq_text_to_verified_records(emul_lib):
+    """the input side end to end: FASTQ text -> salt_fastq_pack -> the arrays it filled ARE a salt_packed_chunk_t (2-bit bases,
+    N positions, lengths) -> salt_b200_verify_batch_packed, against the same reads uploaded one byte per base; the text is also
+    cut with salt_fastq_split and every part sent as a chunk of its own"""
+    import ctypes as C
+    import build_emul
+    from salt_b200 import host_api
+    from test_fastq_pack import FastqT
+    H = host_api.load(build_emul.build_host())
+    H.salt_fastq_pack.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(FastqT), C.POINTER(C.c_size_t)]
+    H.salt_fastq_split.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]
+    g, reads, pos, strand, cands = pc.make_world(909, L=100, n_reads=40, per_strand=3, indel_frac=0.3, glen=30000, n_frac=0.03)
+    rng = np.random.default_rng(4)
+    reads_list = [r[:int(rng.integers(60, 101))] for r in reads]            # ragged
+    offs0, loci0, offs1, loci1 = cands
+    text = b"".join(b"@r%d/1 c\n%s\n+\n%s\n" % (i, bytes(b"ACGTN"[c] for c in r), b"I" * len(r)) for i, r in enumerate(reads_list))
+    eng = api.Engine(g.mixref, g.l, g.pac, g.l, lib=emul_lib)
+    lens = np.array([len(r) for r in reads_list]); roffs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    eng.set_reads(np.concatenate(reads_list).astype(np.uint8), roffs)
+    want = eng.verify(offs0, loci0, offs1, loci1, 3, -1)
+
+    def run_part(t, first_read):
+        """parse one text, send what the parser filled as one compact chunk; returns (n_reads, results)"""
+        cap = len(t) + 8
+        bases = np.zeros(cap // 4 + 2, np.uint8); n_pos = np.zeros(cap, np.uint32)
+        m = 64
+        arrs = {k: np.zeros(m, dt) for k, dt in (("lens", np.uint16), ("n_ambiguous", np.uint16), ("name_off", np.uint32),
+                                                  ("name_len", np.uint16), ("comment_off", np.uint32), ("comment_len", np.uint16),
+                                                  ("qual_off", np.uint32))}
+        fq = FastqT(bases.ctypes.data, cap, n_pos.ctypes.data, cap, *(arrs[k].ctypes.data for k in
+                    ("lens", "n_ambiguous", "name_off", "name_len", "comment_off", "comment_len", "qual_off")), 0, 0, 0)
+        used = C.c_size_t(0)
+        n = H.salt_fastq_pack(t, len(t), 1, m, C.byref(fq), C.byref(used))
+        assert n > 0
+        a, b = first_read, first_read + n
+        c0 = np.diff(offs0[a:b + 1].astype(np.int64)).astype(np.uint16); c1 = np.diff(offs1[a:b + 1].astype(np.int64)).astype(np.uint16)
+        l0 = np.ascontiguousarray(loci0[offs0[a]:offs0[b]]); l1 = np.ascontiguousarray(loci1[offs1[a]:offs1[b]])
+        pk = api.PackedChunkT()
+        pk.n_reads = n; pk.base_bits = 2; pk.bases = bases.ctypes.data; pk.base_start = 0
+        pk.lens = arrs["lens"].ctypes.data; pk.l_seq = 0
+        pk.n_pos = n_pos.ctypes.data if fq.n_n else None; pk.n_n = fq.n_n; pk.count_bits = 16
+        pk.n_cand[0], pk.n_cand[1] = c0.ctypes.data, c1.ctypes.data
+        pk.loci[0], pk.loci[1] = (l0.ctypes.data if len(l0) else None), (l1.ctypes.data if len(l1) else None)
+        return n, eng.verify_batch_packed(pk, len(l0), len(l1), 16, 3, -1)
+
+    n, got = run_part(text, 0)
+    assert n == len(reads_list)
+    for x, y, name in zip(got, want, ("rec", "acc0", "acc1", "cigars")):
+        assert x.tobytes() == y.tobytes(), name
+    cuts = (C.c_size_t * 5)()
+    made = H.salt_fastq_split(text, len(text), 4, cuts)
+    assert made >= 2
+    first = 0
+    for k in range(made):
+        n, got = run_part(text[cuts[k]:cuts[k + 1]], first)
+        assert got[0].tobytes() == want[0][first:first + n].tobytes(), ("rec of part", k)
+        assert got[1].tobytes() == want[1][offs0[first]:offs0[first + n]].tobytes() and got[2].tobytes() == want[2][offs1[first]:offs1[first + n]].tobytes()
+        assert got[3].tobytes() == want[3][first:first + n].tobytes()
+        first += n
+    assert first == len(reads_list)
+    eng.close()
+
+
 def test_chunk_pair_stage(emul_lib, oracle):
     """the paired-end stage of a chunk in one call == the stage composed pair by pair"""
     import build_emul
