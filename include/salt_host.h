@@ -214,6 +214,39 @@ salt_b200_t *salt_multi_handle(salt_multi_t *m, int i);
 int salt_multi_verify_batch_packed(salt_multi_t *m, const salt_packed_chunk_t *pc, uint32_t chunk_reads, int nogap_T0, int lv_T0,
                                    salt_verify_out_t *rec, int8_t *acc0, int8_t *acc1, char *cigars, int cigar_stride);
 
+/* ---- SAM text (aln_samse sam.c:86-180, alnpe_sam sam.c:331-455, sam_add_xa :186-240,
+ * bns_coor_pac2real bntseq.c:269-303) ----------------------------------------------------------------------------
+ * One SAM line per read from the fields the stages above produce, byte for byte what the reference's formatter leaves in
+ * query->sam: no per-field vsnprintf, no allocation -- the line goes into the caller's buffer. */
+typedef struct {
+    int n_seqs; const char *const *names; const int64_t *offsets;      /* bntseq->anns[i].name / .offset */
+    int64_t l_pac;
+} salt_sam_refs_t;
+
+typedef struct {
+    const char *name;                /* query->name (already trimmed) */
+    const uint8_t *seq;              /* codes 0..4, forward strand; the reverse complement is made here (query.c:46-64) */
+    const char *qual;                /* NULL or "" prints '*' */
+    uint32_t l_seq;
+    uint32_t pos;                    /* 0xFFFFFFFF = unmapped */
+    uint8_t strand; uint32_t mapq;
+    const char *cigar;               /* query->cigar->s */
+    uint32_t seq_start, seq_end;     /* soft clips around the aligned part (paired-end lines only, sam.c:392-394) */
+    int n_alt[2]; const salt_hit_t *alt[2];           /* query->hits[strand] */
+    const char *const *xa_cigars;    /* CIGARs of the gapped alternates that get printed, in the order sam_add_xa visits them */
+    const char *md; uint32_t nm; const uint16_t *xv; int n_xv;         /* tags of sam_add_md_nm; md == NULL: not printed */
+} salt_sam_read_t;
+
+/* aln_samse: the single-end line (no trailing newline; the reference prints it with puts).  print_xa_cigar: option -c.
+ * Returns the line's length; SALT_ERR_NOMEM when it does not fit cap (nothing useful is left in out), SALT_ERR_ARG when a
+ * position lies outside the reference (the reference exits there). */
+int salt_sam_se(const salt_sam_refs_t *refs, const salt_sam_read_t *q, int print_xa_cigar, const char *rg_id, char *out, size_t cap);
+
+/* alnpe_sam: the two lines of a pair, each with its trailing newline as the reference leaves them in query->sam.
+ * len[0] / len[1] receive the lengths. */
+int salt_sam_pe(const salt_sam_refs_t *refs, const salt_sam_read_t q[2], uint32_t min_tlen, uint32_t max_tlen, int print_xa_cigar,
+                const char *rg_id, char *out0, size_t cap0, char *out1, size_t cap1, int len[2]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,8 @@ static void die(const char *what)
 void dropin_tail_prepare(salt_b200_t *gpu, int slot, const query_t *multi_seqs, const int *slot_of, int first, int upto);
 void dropin_tail_report(void);
 void dropin_tail_begin_read(int j);
+int dropin_tail_get(int j, const char **md, unsigned *nm, const uint16_t **xv, int *n_xv);
+const char *dropin_xa_row(int j, int k);
 
 /* alnse_core1's per-read work after verification: results -> query_t (alnse.c:1306 / :1342-1344); the SAM line
  * follows once the chunk's MD/NM/XV tags are back from the GPU */
@@ -103,6 +105,38 @@ static void *seed_worker(void *arg)
 
 /* hit selection and SAM text of a sub-chunk on the -t workers, as alnse_core_thread does both per read (alnse.c:1306-1307) */
 typedef struct { int tid, n_threads, first, upto, phase; index_t *index; query_t *queries; aln_opt_t *aln_opt; const salt_chunk_t *ck; const int *slot_of; char **old_sam; } fin_thread_t;
+
+/* SALT_DROPIN_SAM=native: the line is written by the host layer's own formatter (salt_sam_se, byte-identical to aln_samse:
+ * tests/test_sam_text.py) from the same query_t fields and the tags / XA CIGARs the GPU prepared */
+static int g_native_sam;
+static salt_sam_refs_t g_sam_refs;
+static void native_samse(int j, query_t *query, const aln_opt_t *aln_opt)
+{
+    salt_sam_read_t r;
+    const char *xa[2 * SALT_MAX_HITS + 2];
+    int s, i, k = 0;
+    memset(&r, 0, sizeof r);
+    r.name = query->name; r.seq = query->seq; r.qual = (const char *)query->qual; r.l_seq = (uint32_t)query->l_seq;
+    r.pos = query->pos; r.strand = (uint8_t)query->strand; r.mapq = query->mapq; r.cigar = query->cigar->s;
+    r.seq_start = query->seq_start; r.seq_end = query->seq_end;
+    for (s = 0; s < 2; ++s) {
+        r.n_alt[s] = (int)query->hits[s].n; r.alt[s] = (const salt_hit_t *)query->hits[s].a;       /* hit_t and salt_hit_t share their layout */
+        if (aln_opt->print_xa_cigar)
+            for (i = 0; i < r.n_alt[s]; ++i)
+                if (query->hits[s].a[i].pos != query->pos && query->hits[s].a[i].is_gap && k < 2 * SALT_MAX_HITS) { xa[k] = dropin_xa_row(j, k); ++k; }
+    }
+    r.xa_cigars = xa;
+    unsigned nm = 0; int n_xv = 0; const char *md = NULL; const uint16_t *xv = NULL;
+    if (aln_opt->print_nm_md && query->pos != 0xFFFFFFFF && dropin_tail_get(j, &md, &nm, &xv, &n_xv)) { r.md = md; r.nm = nm; r.xv = xv; r.n_xv = n_xv; }
+    kstring_t *ks = query->sam;
+    for (;;) {
+        const int n = salt_sam_se(&g_sam_refs, &r, aln_opt->print_xa_cigar, aln_opt->rg_id, ks->s, ks->m);
+        if (n >= 0) { ks->l = (size_t)n; return; }
+        if (n != SALT_ERR_NOMEM) { fprintf(stderr, "[salt_dropin] salt_sam_se failed on %s (%d)\n", query->name, n); exit(1); }
+        ks->m = ks->m ? 2 * ks->m : 1024; ks->s = realloc(ks->s, ks->m);
+    }
+}
+
 static void *finish_worker(void *arg)
 {
     fin_thread_t *F = (fin_thread_t *)arg;
@@ -120,8 +154,11 @@ static void *finish_worker(void *arg)
                enough that aln_samse rarely grows it; the old one is freed by the thread that allocated it. */
             kstring_t *ks = F->queries[j].sam;
             if (ks && ks->m < 1024) { F->old_sam[j] = ks->s; ks->s = malloc(1024); ks->s[0] = '\0'; ks->m = 1024; }
-            dropin_tail_begin_read(j);
-            aln_samse(F->index, F->queries + j, F->aln_opt);                                      /* alnse.c:1307 / :1345 */
+            if (g_native_sam) native_samse(j, F->queries + j, F->aln_opt);
+            else {
+                dropin_tail_begin_read(j);
+                aln_samse(F->index, F->queries + j, F->aln_opt);                                  /* alnse.c:1307 / :1345 */
+            }
         }
     }
     return NULL;
@@ -276,6 +313,17 @@ int alnse_core(const opt_t *opt)
         T[t].tid = t; T[t].n_threads = n_threads; T[t].index = index; T[t].aln_opt = aln_opt;
         T[t].aux[0] = aux_init(opt->l_read, opt->l_seed);
         T[t].aux[1] = aux_init(opt->l_read, opt->l_seed);
+    }
+    {
+        const char *e = getenv("SALT_DROPIN_SAM");
+        g_native_sam = e && !strcmp(e, "native");
+        if (g_native_sam) {
+            bntseq_t *bns = index->bntseq;
+            const char **nm = calloc((size_t)bns->n_seqs, sizeof *nm); int64_t *of = calloc((size_t)bns->n_seqs, sizeof *of);
+            for (int i = 0; i < bns->n_seqs; ++i) { nm[i] = bns->anns[i].name; of[i] = bns->anns[i].offset; }
+            g_sam_refs.n_seqs = bns->n_seqs; g_sam_refs.names = nm; g_sam_refs.offsets = of; g_sam_refs.l_pac = bns->l_pac;
+            fprintf(stderr, "[salt_dropin] SAM lines by salt_sam_se\n");
+        }
     }
     queryio_t *qs = query_open(opt->fn_read1);
     batch_pipe_t P;

@@ -154,6 +154,27 @@ void sam_add_md_nm(kstring_t *s, index_t *index, query_t *q)
     }
 }
 
+/* For the host layer's own SAM formatter (salt_sam_se, SALT_DROPIN_SAM=native): the tags of read j and the CIGAR of its k-th
+ * printed gapped alternate, as prepared by dropin_tail_prepare.  Returns 0 when read j has no tags (unmapped / not prepared). */
+int dropin_tail_get(int j, const char **md, unsigned *nm, const uint16_t **xv, int *n_xv)
+{
+    if (j < 0 || j >= T.n_q || !T.idx || T.idx[j] < 0) return 0;
+    const int k = T.idx[j];
+    if (T.out[k].md_len < 0) { fprintf(stderr, "[salt_dropin] MD of read %d: engine code %d\n", j, T.out[k].md_len); exit(1); }
+    *md = T.md + (size_t)k * TAIL_MD_STRIDE; *nm = (unsigned)T.out[k].nm;
+    *xv = T.xv + (size_t)k * TAIL_XV_STRIDE; *n_xv = T.out[k].n_xv;
+    __atomic_fetch_add(&T.used_md, 1, __ATOMIC_RELAXED);
+    return 1;
+}
+const char *dropin_xa_row(int j, int k)
+{
+    if (!T.xa_first || j < 0 || j >= T.n_first) return NULL;
+    const size_t row = T.xa_first[j] + (size_t)k;
+    if (row >= T.n_xa) return NULL;
+    __atomic_fetch_add(&T.used_xa, 1, __ATOMIC_RELAXED);
+    return T.xa_cig + row * TAIL_XA_STRIDE;
+}
+
 void dropin_tail_report(void)
 {
     fprintf(stderr, "[salt_dropin] SAM tail from the GPU: MD/NM/XV tags prepared %zu printed %zu, XA CIGARs prepared %zu printed %zu\n",

@@ -1083,3 +1083,179 @@ int salt_fastq_split(const char *text, size_t len, int n_parts, size_t *cuts)
     return made;
 }
 
+/* ------------------------------------------------------------------ SAM text (sam.c:86-180, :186-240, :331-455) */
+typedef struct { char *s; size_t l, cap; int ovf; } sam_buf_t;
+static inline void sb_putc(sam_buf_t *b, char c) { if (b->l + 1 < b->cap) b->s[b->l] = c; else b->ovf = 1; ++b->l; }
+static inline void sb_puts(sam_buf_t *b, const char *t) { while (*t) sb_putc(b, *t++); }
+static inline void sb_putu(sam_buf_t *b, uint64_t v)
+{
+    char tmp[24]; int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) sb_putc(b, tmp[--n]);
+}
+static inline void sb_puti(sam_buf_t *b, int64_t v) { if (v < 0) { sb_putc(b, '-'); sb_putu(b, (uint64_t)(-v)); } else sb_putu(b, (uint64_t)v); }
+
+/* bns_coor_pac2real (bntseq.c:269-284): the record a coordinate lies in */
+static int sam_rid(const salt_sam_refs_t *r, int64_t pac_coor)
+{
+    int left = 0, mid = 0, right = r->n_seqs;
+    while (left < right) {
+        mid = (left + right) >> 1;
+        if (pac_coor >= r->offsets[mid]) {
+            if (mid == r->n_seqs - 1) break;
+            if (pac_coor < r->offsets[mid + 1]) break;
+            left = mid + 1;
+        } else right = mid;
+    }
+    return mid;
+}
+
+static void sam_seq_qual(sam_buf_t *b, const salt_sam_read_t *q)
+{
+    const uint32_t L = q->l_seq;
+    const int has_qual = q->qual && q->qual[0];
+    if (q->strand == 1) {                                    /* query->rseq: reversed, A<->T C<->G, N stays (query.c:46-64) */
+        for (uint32_t j = 0; j < L; ++j) { const uint8_t c = q->seq[L - 1 - j]; sb_putc(b, "ACGTN"[c < 4 ? 3 - c : 4]); }
+        sb_putc(b, '\t');
+        if (has_qual) for (uint32_t j = L; j-- > 0;) sb_putc(b, q->qual[j]);
+        else sb_putc(b, '*');
+    } else {
+        for (uint32_t j = 0; j < L; ++j) sb_putc(b, "ACGTN"[q->seq[j] < 4 ? q->seq[j] : 4]);
+        sb_putc(b, '\t');
+        if (has_qual) sb_puts(b, q->qual); else sb_putc(b, '*');
+    }
+}
+
+/* sam_add_xa (sam.c:186-240) */
+static int sam_xa(sam_buf_t *b, const salt_sam_refs_t *r, const salt_sam_read_t *q, int is_cigar)
+{
+    int first = 1, k_gap = 0;
+    for (int strand = 0; strand < 2; ++strand)
+        for (int i = 0; i < q->n_alt[strand]; ++i) {
+            const salt_hit_t *h = q->alt[strand] + i;
+            if (h->pos == q->pos) continue;
+            if ((int64_t)h->pos >= r->l_pac) return SALT_ERR_ARG;
+            if (first) { sb_puts(b, "\tXA:Z:"); first = 0; }
+            const int rid = sam_rid(r, (int64_t)h->pos);
+            sb_puts(b, r->names[rid]); sb_putc(b, ',');
+            sb_putc(b, "+-"[strand]); sb_puti(b, (int64_t)h->pos - r->offsets[rid] + 1); sb_putc(b, ',');
+            if (is_cigar) {
+                if (h->is_gap) {
+                    if (!q->xa_cigars || !q->xa_cigars[k_gap]) return SALT_ERR_ARG;
+                    sb_puts(b, q->xa_cigars[k_gap++]); sb_putc(b, ',');
+                } else { sb_putu(b, q->l_seq); sb_puts(b, "M,"); }
+            } else sb_puts(b, "*,");
+            sb_putu(b, h->n_diff); sb_putc(b, ';');
+        }
+    return SALT_OK;
+}
+
+static void sam_tags(sam_buf_t *b, const salt_sam_read_t *q, const char *rg_id)
+{
+    if (q->md && q->pos != 0xFFFFFFFFu) {                    /* sam_add_md_nm (sam.c:246-328) */
+        sb_puts(b, "\tMD:Z:"); sb_puts(b, q->md);
+        sb_puts(b, "\tNM:i:"); sb_putu(b, q->nm);
+        if (q->n_xv > 0) {
+            sb_puts(b, "\tXV:i:");
+            for (int i = 0; i < q->n_xv; ++i) { if (i) sb_putc(b, ','); sb_putu(b, q->xv[i]); }
+        }
+    }
+    if (rg_id) { sb_puts(b, "\tRG:Z:"); sb_puts(b, rg_id); }
+}
+
+int salt_sam_se(const salt_sam_refs_t *refs, const salt_sam_read_t *q, int print_xa_cigar, const char *rg_id, char *out, size_t cap)
+{
+    if (!refs || !q || !out || !cap || !q->name || (q->l_seq && !q->seq)) return SALT_ERR_ARG;
+    sam_buf_t b = {out, 0, cap, 0};
+    sb_puts(&b, q->name); sb_putc(&b, '\t');
+    if (q->pos == 0xFFFFFFFFu) {                             /* sam.c:104-122: no tags, the read as it was sequenced */
+        sb_puts(&b, "4\t*\t0\t0\t*\t*\t0\t0\t");
+        for (uint32_t j = 0; j < q->l_seq; ++j) sb_putc(&b, "ACGTN"[q->seq[j] < 4 ? q->seq[j] : 4]);
+        sb_putc(&b, '\t');
+        if (q->qual) sb_puts(&b, q->qual); else sb_putc(&b, '*');
+    } else {
+        if ((int64_t)q->pos >= refs->l_pac || !q->cigar) return SALT_ERR_ARG;
+        const int rid = sam_rid(refs, (int64_t)q->pos);
+        sb_putu(&b, q->strand ? 16u : 0u); sb_putc(&b, '\t');
+        sb_puts(&b, refs->names[rid]); sb_putc(&b, '\t');
+        sb_puti(&b, (int64_t)q->pos - refs->offsets[rid] + 1); sb_putc(&b, '\t');
+        sb_putu(&b, q->mapq); sb_putc(&b, '\t');
+        sb_puts(&b, q->cigar);
+        sb_puts(&b, "\t*\t0\t0\t");
+        sam_seq_qual(&b, q);
+        const int rc = sam_xa(&b, refs, q, print_xa_cigar);
+        if (rc != SALT_OK) return rc;
+        sam_tags(&b, q, rg_id);
+    }
+    if (b.ovf || b.l >= cap) return SALT_ERR_NOMEM;
+    out[b.l] = '\0';
+    return (int)b.l;
+}
+
+int salt_sam_pe(const salt_sam_refs_t *refs, const salt_sam_read_t q[2], uint32_t min_tlen, uint32_t max_tlen, int print_xa_cigar,
+                const char *rg_id, char *out0, size_t cap0, char *out1, size_t cap1, int len[2])
+{
+    if (!refs || !q || !out0 || !out1 || !cap0 || !cap1 || !len) return SALT_ERR_ARG;
+    int rid[2] = {-1, -1}, is_map[2] = {0, 0};
+    uint32_t pos[2] = {0, 0};
+    for (int i = 0; i < 2; ++i) {
+        if (!q[i].name || (q[i].l_seq && !q[i].seq)) return SALT_ERR_ARG;
+        if (q[i].pos != 0xFFFFFFFFu) {
+            if ((int64_t)q[i].pos >= refs->l_pac || !q[i].cigar) return SALT_ERR_ARG;
+            is_map[i] = 1;
+            rid[i] = sam_rid(refs, (int64_t)q[i].pos);
+            pos[i] = (uint32_t)((int64_t)q[i].pos - refs->offsets[rid[i]] + 1);
+        }
+    }
+    int tlen = 0;                                            /* sam.c:352-358, its second branch reads q[1].seq_start as written there */
+    if (is_map[0] && is_map[1]) {
+        if (rid[0] != rid[1]) tlen = 0;
+        else if (pos[0] < pos[1]) tlen = (int)(pos[1] + q[1].seq_end - q[1].seq_start + 1 - pos[0]);
+        else tlen = (int)(pos[0] + q[0].seq_end - q[1].seq_start + 1 - pos[1]);
+        if ((uint32_t)tlen > max_tlen || (uint32_t)tlen < min_tlen) tlen = 0;
+    }
+    char *outs[2] = {out0, out1}; const size_t caps[2] = {cap0, cap1};
+    for (int i = 0; i < 2; ++i) {
+        sam_buf_t b = {outs[i], 0, caps[i], 0};
+        sb_puts(&b, q[i].name); sb_putc(&b, '\t');
+        unsigned flag = 0x1;
+        if (!is_map[i]) flag |= 0x4;
+        if (!is_map[1 - i]) flag |= 0x8;
+        if (q[i].strand == 1) flag |= 0x10;
+        if (q[1 - i].strand == 1) flag |= 0x20;
+        if (tlen != 0) flag |= 0x2;
+        flag |= i == 0 ? 0x40 : 0x80;
+        sb_putu(&b, flag); sb_putc(&b, '\t');
+        if (is_map[i]) {
+            sb_puts(&b, refs->names[rid[i]]); sb_putc(&b, '\t');
+            sb_putu(&b, pos[i]); sb_putc(&b, '\t');
+            sb_putu(&b, q[i].mapq); sb_putc(&b, '\t');
+            if (q[i].seq_start != 0) { sb_puti(&b, (int)q[i].seq_start); sb_putc(&b, 'S'); }
+            sb_puts(&b, q[i].cigar);
+            if (q[i].seq_end != q[i].l_seq - 1) { sb_puti(&b, (int)(q[i].l_seq - q[i].seq_end - 1)); sb_putc(&b, 'S'); }
+            sb_putc(&b, '\t');
+        } else if (is_map[1 - i]) {
+            sb_puts(&b, refs->names[rid[1 - i]]); sb_putc(&b, '\t');
+            sb_putu(&b, pos[1 - i]); sb_putc(&b, '\t');
+            sb_puts(&b, "255\t*\t");
+        } else sb_puts(&b, "*\t0\t255\t*\t");
+        if (is_map[1 - i]) {                                 /* Rnext, Pnext */
+            if (rid[i] == rid[1 - i] || !is_map[i]) sb_puts(&b, "=\t");
+            else { sb_puts(&b, refs->names[rid[1 - i]]); sb_putc(&b, '\t'); }
+            sb_putu(&b, pos[1 - i]); sb_putc(&b, '\t');
+        } else sb_puts(&b, "*\t0\t");
+        if (tlen != 0) {
+            if (q[i].pos >= q[1 - i].pos) sb_putc(&b, '-');
+            sb_puti(&b, tlen); sb_putc(&b, '\t');
+        } else sb_puts(&b, "0\t");
+        sam_seq_qual(&b, &q[i]);
+        const int rc = sam_xa(&b, refs, &q[i], print_xa_cigar);
+        if (rc != SALT_OK) return rc;
+        sam_tags(&b, &q[i], rg_id);
+        sb_putc(&b, '\n');
+        if (b.ovf || b.l >= caps[i]) return SALT_ERR_NOMEM;
+        outs[i][b.l] = '\0';
+        len[i] = (int)b.l;
+    }
+    return SALT_OK;
+}

@@ -37,7 +37,10 @@ def _sam_body(path):
                                         (["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500", "-t", "4"], "host"),     # ... as shipped: 4 seeding threads
                                         (["-r", "1", "-l", "100", "-t", "1"], "host"),
                                         (["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500", "-t", "4"], "gpu"),      # seeding + locate on the device too
-                                        (["-r", "1", "-l", "100", "-t", "1"], "gpu")])
+                                        (["-r", "1", "-l", "100", "-t", "1"], "gpu"),
+                                        # ... and the SAM lines written by salt_sam_se instead of the reference's aln_samse
+                                        (["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500", "-t", "4"], "gpu+sam"),
+                                        (["-r", "1", "-l", "100", "-t", "2"], "host+sam")])
 def test_se_sam_identical(tmp_path, flags, seed):
     if not _have():
         pytest.skip("oracle/_ref programs not built (reference tree absent at build time)")
@@ -45,10 +48,12 @@ def test_se_sam_identical(tmp_path, flags, seed):
     fa, sn, fq = dropin_data.write_inputs(d)
     _run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], d, os.path.join(d, "idx.log"))
     _run([os.path.join(REFDIR, "salt")] + flags + ["idx", "reads.fq"], d, os.path.join(d, "ref.sam"))
+    native = seed.endswith("+sam"); seed = seed.split("+")[0]
     err = _run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", "reads.fq"], d, os.path.join(d, "gpu.sam"),
-               env={"SALT_DROPIN_SEED": seed})
+               env={"SALT_DROPIN_SEED": seed, "SALT_DROPIN_SAM": "native" if native else "reference"})
     assert "verification on libsalt_b200" in err
     assert ("seeding + locate on libsalt_b200" in err) == (seed == "gpu")
+    assert ("SAM lines by salt_sam_se" in err) == native
     if seed == "host":
         assert "%s seeding threads" % flags[flags.index("-t") + 1] in err
     want, got = _sam_body(os.path.join(d, "ref.sam")), _sam_body(os.path.join(d, "gpu.sam"))
@@ -173,15 +178,17 @@ def _same_sam(want_path, got_path, min_lines):
     return [ln.split("\t") for ln in want if ln and not ln.startswith("@")]
 
 
-@pytest.mark.parametrize("threads,seed", [("4", "host"), ("1", "host"), ("4", "gpu")])
+@pytest.mark.parametrize("threads,seed", [("4", "host"), ("1", "host"), ("4", "gpu"), ("4", "gpu+sam")])
 def test_config0_se_sam_identical(tmp_path, threads, seed):
     """run_se_test.sh:12 flags on the bundled genome: every read ties between the two lambda copies (strand-1-wins and
     first-hit rules decide the primary), 5 % mutated reads against their own SNP table"""
     d = str(tmp_path)
     _config0_index(d)
     flags = ["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500", "-t", threads]
+    native = seed.endswith("+sam"); seed = seed.split("+")[0]
     err = _run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", os.path.join(C0, "Read1.fq")], d, os.path.join(d, "gpu.sam"),
-               env={"SALT_DROPIN_SEED": seed})
+               env={"SALT_DROPIN_SEED": seed, "SALT_DROPIN_SAM": "native" if native else "reference"})
+    assert ("SAM lines by salt_sam_se" in err) == native
     assert "verification on libsalt_b200" in err
     assert ("seeding + locate on libsalt_b200" in err) == (seed == "gpu")
     body = _same_sam(os.path.join(C0, "se.sam"), os.path.join(d, "gpu.sam"), 20000)

@@ -60,19 +60,22 @@ def main():
                 t_ref, _ = run([os.path.join(REFDIR, "salt")] + flags + ["idx", "reads.fq"], d, os.path.join(d, "ref.sam"))
                 row["reference_s"] = round(t_ref, 2); row["reference_reads_per_s"] = round((n + 40) / t_ref)
                 want = body(os.path.join(d, "ref.sam"))
-                for mode in ("host", "gpu"):
-                    env = dict(os.environ, SALT_DROPIN_SEED=mode)
+                for mode in ("host", "gpu", "gpu+sam"):          # +sam: SAM lines by the host layer's salt_sam_se instead of aln_samse
+                    env = dict(os.environ, SALT_DROPIN_SEED=mode.split("+")[0], SALT_DROPIN_SAM="native" if mode.endswith("+sam") else "reference")
                     t0 = time.time()
                     with open(os.path.join(d, "gpu.sam"), "w") as f:
                         p = subprocess.run([os.path.join(REFDIR, "salt_dropin")] + flags + ["idx", "reads.fq"], cwd=d, stdout=f,
                                            stderr=subprocess.PIPE, text=True, env=env)
                     assert p.returncode == 0, p.stderr[-1500:]
                     dt = time.time() - t0
-                    key = "dropin_%s_seeding" % mode
+                    key = "dropin_%s_seeding" % mode.replace("+", "_")
                     row[key + "_s"] = round(dt, 2); row[key + "_reads_per_s"] = round((n + 40) / dt)
                     row[key + "_sam_identical"] = body(os.path.join(d, "gpu.sam")) == want
                     row[key + "_phases"] = [ln for ln in p.stderr.split("\n") if ln.startswith("[salt_dropin] ")][-2:]
                 res["se"].append(row)
+        if os.environ.get("SKIP_PE"):
+            print(json.dumps(res, indent=1))
+            return
         npairs = n // 2
         dropin_data.write_pe_inputs(d, glen=glen, n_pairs=npairs)
         run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], d, os.path.join(d, "idx.log"))
