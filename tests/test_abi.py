@@ -29,8 +29,8 @@ def test_exports_match_header(lib):
 def test_host_layer_exports():
     """include/salt_host.h and the level-0 shim: every declared symbol is exported"""
     hdr = open(os.path.join(ROOT, "include", "salt_host.h")).read()
-    names = sorted(set(re.findall(r"\b(salt_chunk_[a-z0-9_]+)\s*\(", hdr)))
-    assert len(names) >= 9
+    names = sorted(set(re.findall(r"\b(salt_(?:chunk|pair|multi|fastq|sam|host)_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 25 and "salt_sam_se" in names and "salt_fastq_split" in names and "salt_multi_init" in names
     H = C.CDLL(os.path.join(os.path.dirname(api.LIB_PATH), "libsalt_host.so"))
     for n in names:
         assert hasattr(H, n), n
