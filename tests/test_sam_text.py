@@ -211,3 +211,55 @@ def test_sam_pe_lines(world, oracle):
                 f = int(o[0].value.split(b"\t")[1])
                 seen.add((bool(f & 2), bool(f & 4), bool(f & 8)))
     assert (True, False, False) in seen and (False, True, False) in seen and (False, False, True) in seen
+
+
+def test_sam_lines_large_coordinates(oracle):
+    """24 records, 3.1 Gbp: positions beyond 2^31 map to the right record and print as the reference prints them (no tags, no XA
+    CIGARs here: those would need the 3.1 Gbp reference itself; they do not depend on the coordinate arithmetic)"""
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref not built (reference tree absent at build time)")
+    H = _hostlib(); R = C.CDLL(REF)
+    l = 3_100_000_000
+    names = [b"chr%d" % (i + 1) for i in range(24)]
+    offsets = [i * (l // 24) + (i * 7919) % 1000 for i in range(24)]; offsets[0] = 0
+    refs, keep = _refs(names, offsets, l)
+    nm = (C.c_char_p * 24)(*names); of = (C.c_int64 * 24)(*offsets)
+    dummy = np.zeros(64, np.uint32); dpac = np.zeros(64, np.uint8)
+    rng = np.random.default_rng(12)
+    out = [C.create_string_buffer(4096) for _ in range(4)]
+    ln = (C.c_int * 2)(); rln = (C.c_int * 2)()
+    H.salt_sam_se.restype = C.c_int; R.ref_sam_se.restype = C.c_int
+
+    class Bare:
+        pass
+
+    def mk(pos, strand, alts):
+        b = Bare()
+        b.seq = rng.integers(0, 5, 100).astype(np.uint8); b.rseq = np.ascontiguousarray(synth.revcomp(b.seq))
+        b.qual = bytes(33 + int(k) for k in rng.integers(0, 41, 100)); b.name = b"q%d" % pos
+        b.alts = alts; b.ralt = [np.array([x for (p, nd, gap) in a for x in (p, nd, gap)], np.uint32) for a in alts]
+        b.halt = [(HitT * max(1, len(a)))(*[HitT(p, nd, gap, s) for (p, nd, gap) in a]) for s, a in enumerate(alts)]
+        m = SamReadT(); t = RefReadT()
+        for r in (m, t):
+            r.name = b.name; r.seq = b.seq.ctypes.data; r.qual = b.qual; r.l_seq = 100; r.pos = pos; r.mapq = 60; r.cigar = b"100M"
+            r.seq_start = 0; r.seq_end = 99
+            for s in (0, 1):
+                r.n_alt[s] = len(alts[s])
+        m.strand = strand; t.strand = strand; t.rseq = b.rseq.ctypes.data
+        for s in (0, 1):
+            m.alt[s] = C.cast(b.halt[s], C.POINTER(HitT)); t.alt[s] = b.ralt[s].ctypes.data if len(b.ralt[s]) else None
+        b.m, b.t = m, t
+        return b
+    edge = [offsets[k] for k in (1, 12, 23)] + [offsets[k] - 1 for k in (1, 12, 23)] + [l - 101, 2**31 - 1, 2**31, 2**31 + 5, 4_000_000 % l]
+    poss = edge + [int(x) for x in rng.integers(0, l - 101, 40)]
+    items = [mk(p, i % 2, [[(int(rng.integers(0, l - 101)), 3, 0)], [(int(rng.integers(2**31, l - 101)), 1, 0)]] if i % 3 else [[], []])
+             for i, p in enumerate(poss)]
+    for b in items:
+        n = H.salt_sam_se(C.byref(refs), C.byref(b.m), 0, None, out[0], 4096)
+        m = R.ref_sam_se(dummy.ctypes.data, C.c_uint32(l), dpac.ctypes.data, 24, nm, of, C.byref(b.t), 0, 0, None, out[1], 4096)
+        assert n == m and out[0].value == out[1].value, (out[0].value, out[1].value)
+    for a, b in zip(items[::2], items[1::2]):
+        mine = (SamReadT * 2)(a.m, b.m); theirs = (RefReadT * 2)(a.t, b.t)
+        assert H.salt_sam_pe(C.byref(refs), mine, 250, 550, 0, b"g", out[0], 4096, out[1], 4096, ln) == 0
+        R.ref_sam_pe(dummy.ctypes.data, C.c_uint32(l), dpac.ctypes.data, 24, nm, of, theirs, 250, 550, 0, 0, b"g", out[2], 4096, out[3], 4096, rln)
+        assert out[0].value == out[2].value and out[1].value == out[3].value, (out[0].value, out[2].value)
