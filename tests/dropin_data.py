@@ -7,10 +7,14 @@ import numpy as np
 from salt_b200 import synth
 
 
-def write_inputs(outdir, glen=150_000, n_reads=6000, L=100, seed=5):
+def write_inputs(outdir, glen=150_000, n_reads=6000, L=100, seed=5, two_copies=False):
     os.makedirs(outdir, exist_ok=True)
     rng = np.random.default_rng(seed + 991)      # not the genome's own stream
     g = synth.Genome(glen, snp_rate=0.01, n_rate=0.0, seed=seed)
+    if two_copies:                               # the second half repeats the first (SNPs included): every read has an alternate
+        half = glen // 2
+        g.codes[half:2 * half] = g.codes[:half]; g.masks[half:2 * half] = g.masks[:half]
+        g.snp_pos = np.flatnonzero((g.masks & (g.masks - 1)) != 0)
     # two records, so that coordinate translation (bns_coor_pac2real) is exercised
     cut = glen * 3 // 5
     fasta = g.fasta()

@@ -1,0 +1,60 @@
+"""tools/salt_se.py -- the single-end program built from this repository's libraries only (FASTQ parser, seeding + locate +
+verification, hit selection, tags, XA CIGARs, SAM lines; no reference code in the loop) -- against the reference program itself
+(oracle/_ref/salt) on an index written by the reference's salt-idx.  Runs on the SIMT emulator, so the input is small; the GPU
+version of the same comparison at scale is the drop-in's (tests/test_dropin.py)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools")); sys.path.insert(0, os.path.join(ROOT, "tests", "emul"))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+import ctypes as C  # noqa: E402
+
+import dropin_data  # noqa: E402
+from salt_b200 import api, host_api  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emul_lib():
+    import build_emul
+    return api._declare(C.CDLL(build_emul.build()))
+
+
+@pytest.mark.parametrize("flags,kw", [
+    (["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500"], dict(l_overlap=1, max_locate=500, print_xa_cigar=True, print_nm_md=True)),
+    (["-l", "100", "-g", "grp7"], dict(rg_id=b"grp7")),
+])
+def test_single_end_program_from_own_parts(tmp_path, emul_lib, flags, kw):
+    if not all(os.path.exists(os.path.join(REFDIR, f)) for f in ("salt", "salt-idx")):
+        pytest.skip("oracle/_ref programs not built (reference tree absent at build time)")
+    import build_emul
+    import salt_se
+    d = str(tmp_path)
+    dropin_data.write_inputs(d, glen=12000, n_reads=36, seed=11, two_copies=True)     # alternates (XA) for every read
+    run = lambda cmd, out: subprocess.run(cmd, cwd=d, stdout=open(os.path.join(d, out), "w"), stderr=subprocess.PIPE, check=True)
+    run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], "idx.log")
+    run([os.path.join(REFDIR, "salt")] + flags + ["-t", "1", "idx", "reads.fq"], "ref.sam")
+    want = [ln for ln in open(os.path.join(d, "ref.sam"), "rb").read().split(b"\n") if not ln.startswith(b"@")]
+    while want and want[-1] == b"":
+        want.pop()
+    H = host_api.load(build_emul.build_host())
+    body, names, lens = salt_se.align(emul_lib, H, os.path.join(d, "idx"), os.path.join(d, "reads.fq"), chunk_reads=40, **kw)
+    assert len(body) == len(want) == 76
+    for i, (a, b) in enumerate(zip(body, want)):
+        assert a == b, (i, a, b)
+    mapped = [ln for ln in body if ln.split(b"\t")[2] != b"*"]
+    assert len(mapped) >= 30
+    assert sum(b"\tXA:Z:" in ln for ln in mapped) >= 25
+    if kw.get("print_nm_md"):
+        assert all(b"\tMD:Z:" in ln and b"\tNM:i:" in ln for ln in mapped)
+        assert sum(1 for ln in mapped if b"I" in ln.split(b"\t")[5] or b"D" in ln.split(b"\t")[5]) >= 2        # gapped primaries (and XA CIGARs)
+    # the header lines this tool writes are the reference's too (except @PG)
+    head = [ln for ln in open(os.path.join(d, "ref.sam"), "rb").read().split(b"\n") if ln.startswith(b"@") and not ln.startswith(b"@PG")]
+    mine = [b"@HD\tVN:ec1fec2\tSO:unsorted"] + [b"@SQ\tSN:%s\tLN:%d" % (n, l) for n, l in zip(names, lens)] + \
+           [b"@RG\tID:%s" % (kw["rg_id"] if kw.get("rg_id") else b"(null)")]
+    assert head == mine
