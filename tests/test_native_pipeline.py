@@ -58,3 +58,25 @@ def test_single_end_program_from_own_parts(tmp_path, emul_lib, flags, kw):
     mine = [b"@HD\tVN:ec1fec2\tSO:unsorted"] + [b"@SQ\tSN:%s\tLN:%d" % (n, l) for n, l in zip(names, lens)] + \
            [b"@RG\tID:%s" % (kw["rg_id"] if kw.get("rg_id") else b"(null)")]
     assert head == mine
+
+
+@pytest.mark.gpu
+def test_single_end_program_from_own_parts_on_the_gpu(tmp_path):
+    """the same comparison on the device, 3 040 reads, two reference records, shipped flags"""
+    if not all(os.path.exists(os.path.join(REFDIR, f)) for f in ("salt", "salt-idx")):
+        pytest.skip("oracle/_ref programs not built (reference tree absent at build time)")
+    import salt_se
+    d = str(tmp_path)
+    dropin_data.write_inputs(d, glen=150000, n_reads=3000, seed=17, two_copies=True)
+    run = lambda cmd, out: subprocess.run(cmd, cwd=d, stdout=open(os.path.join(d, out), "w"), stderr=subprocess.PIPE, check=True)
+    run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], "idx.log")
+    run([os.path.join(REFDIR, "salt"), "-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500", "-t", "4", "idx", "reads.fq"], "ref.sam")
+    want = [ln for ln in open(os.path.join(d, "ref.sam"), "rb").read().split(b"\n") if not ln.startswith(b"@")]
+    while want and want[-1] == b"":
+        want.pop()
+    body, names, lens = salt_se.align(None, host_api.load(), os.path.join(d, "idx"), os.path.join(d, "reads.fq"), l_overlap=1, max_locate=500,
+                                      print_xa_cigar=True, print_nm_md=True, chunk_reads=1000)
+    assert len(body) == len(want) == 3040
+    for i, (a, b) in enumerate(zip(body, want)):
+        assert a == b, (i, a, b)
+    assert sum(b"\tXA:Z:" in ln for ln in body) >= 2500
