@@ -44,12 +44,16 @@ def write_inputs(outdir, glen=150_000, n_reads=6000, L=100, seed=5, two_copies=F
     return fa, sn, fq
 
 
-def write_pe_inputs(outdir, glen=150_000, n_pairs=3000, L=100, seed=9):
+def write_pe_inputs(outdir, glen=150_000, n_pairs=3000, L=100, seed=9, two_copies=False):
     """Genome + SNP table as write_inputs; mates 1/2 as two FASTQ files, insert ~ N(500, 40) (the bounds of
-    run_pe_test.sh are 350..650).  A tenth of the second mates is too divergent to verify and has to be rescued."""
-    fa, sn, _ = write_inputs(outdir, glen=glen, n_reads=10, L=L, seed=seed)
+    run_pe_test.sh are 350..650).  A tenth of the second mates is too divergent to verify and has to be rescued.
+    two_copies: the second half of the genome repeats the first, so every mate has an alternate (XA, pairing over alternates)."""
+    fa, sn, _ = write_inputs(outdir, glen=glen, n_reads=10, L=L, seed=seed, two_copies=two_copies)
     rng = np.random.default_rng(seed + 17)
     g = synth.Genome(glen, snp_rate=0.01, n_rate=0.0, seed=seed)
+    if two_copies:
+        half = glen // 2
+        g.codes[half:2 * half] = g.codes[:half]
     codes = (g.codes & 3).astype(np.uint8)
 
     def noisy(seq, rate, indel):

@@ -60,6 +60,47 @@ def test_single_end_program_from_own_parts(tmp_path, emul_lib, flags, kw):
     assert head == mine
 
 
+def _pe_reference(d, flags, **data_kw):
+    dropin_data.write_pe_inputs(d, **data_kw)
+    run = lambda cmd, out: subprocess.run(cmd, cwd=d, stdout=open(os.path.join(d, out), "w"), stderr=subprocess.PIPE, check=True)
+    run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], "idx.log")
+    run([os.path.join(REFDIR, "salt")] + flags + ["idx", "r1.fq", "r2.fq"], "ref.sam")
+    text = open(os.path.join(d, "ref.sam"), "rb").read()
+    return [ln + b"\n" for ln in text.split(b"\n") if ln and not ln.startswith(b"@")]        # alnpe_sam's lines, blank separators dropped
+
+
+@pytest.mark.parametrize("flags,kw,copies", [
+    (["-d", "-p", "-e", "-l", "100", "-c", "-a", "350", "-b", "650", "-r", "5"],                                # run_pe_test.sh:14
+     dict(min_tlen=350, max_tlen=650, l_overlap=5, print_xa_cigar=True, print_nm_md=True), True),
+    (["-p", "-l", "100", "-a", "350", "-b", "650", "-g", "grp7"], dict(min_tlen=350, max_tlen=650, rg_id=b"grp7"), False),
+])
+def test_paired_end_program_from_own_parts(tmp_path, emul_lib, flags, kw, copies):
+    """tools/salt_pe.py -- FASTQ parser, seeding + locate (paired-end flavour), verification, pairing plans, mate rescue,
+    tags, XA CIGARs, SAM lines, all from this repository's libraries -- against the reference program's own output"""
+    if not all(os.path.exists(os.path.join(REFDIR, f)) for f in ("salt", "salt-idx")):
+        pytest.skip("oracle/_ref programs not built (reference tree absent at build time)")
+    import build_emul
+    import salt_pe
+    d = str(tmp_path)
+    want = _pe_reference(d, flags + ["-t", "1"], glen=12000, n_pairs=40, seed=21, two_copies=copies)
+    H = host_api.load(build_emul.build_host())
+    st = {}
+    body, names, lens = salt_pe.align(emul_lib, H, os.path.join(d, "idx"), os.path.join(d, "r1.fq"), os.path.join(d, "r2.fq"),
+                                      chunk_pairs=25, stats=st, **kw)
+    assert len(body) == len(want) == 80
+    for i, (a, b) in enumerate(zip(body, want)):
+        assert a == b, (i, a, b)
+    assert st["flagged_mates"] == 0 and st["declined"] == 0
+    assert st["pairs"] == 40 and st["windows16"] + st["windows5"] >= 3 and st["rescued"] >= 2, st
+    f = [ln.split(b"\t") for ln in body]
+    assert sum(1 for x in f if int(x[1]) & 2) >= 50                       # properly paired records
+    assert sum(1 for x in f if b"S" in x[5]) >= 1                         # soft-clipped = rescued by Smith-Waterman
+    if copies:
+        assert sum(b"\tXA:Z:" in ln for ln in body) >= 40
+    if kw.get("print_nm_md"):
+        assert all(b"\tMD:Z:" in ln for ln, x in zip(body, f) if x[5] != b"*")
+
+
 @pytest.mark.gpu
 def test_single_end_program_from_own_parts_on_the_gpu(tmp_path):
     """the same comparison on the device, 3 040 reads, two reference records, shipped flags"""
@@ -80,3 +121,20 @@ def test_single_end_program_from_own_parts_on_the_gpu(tmp_path):
     for i, (a, b) in enumerate(zip(body, want)):
         assert a == b, (i, a, b)
     assert sum(b"\tXA:Z:" in ln for ln in body) >= 2500
+
+
+@pytest.mark.gpu
+def test_paired_end_program_from_own_parts_on_the_gpu(tmp_path):
+    """the same comparison on the device: 3 000 pairs, two reference records, the flags of run_pe_test.sh:14, four reference threads"""
+    if not all(os.path.exists(os.path.join(REFDIR, f)) for f in ("salt", "salt-idx")):
+        pytest.skip("oracle/_ref programs not built (reference tree absent at build time)")
+    import salt_pe
+    d = str(tmp_path)
+    want = _pe_reference(d, ["-d", "-p", "-e", "-l", "100", "-c", "-a", "350", "-b", "650", "-r", "5", "-t", "4"])
+    st = {}
+    body, names, lens = salt_pe.align(None, host_api.load(), os.path.join(d, "idx"), os.path.join(d, "r1.fq"), os.path.join(d, "r2.fq"),
+                                      min_tlen=350, max_tlen=650, l_overlap=5, print_xa_cigar=True, print_nm_md=True, chunk_pairs=1000, stats=st)
+    assert len(body) == len(want) == 6000
+    for i, (a, b) in enumerate(zip(body, want)):
+        assert a == b, (i, a, b)
+    assert st["flagged_mates"] == 0 and st["declined"] == 0 and st["rescued"] >= 100 and st["proper"] >= 2000, st
