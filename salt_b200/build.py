@@ -64,6 +64,23 @@ def build_host(force=False, engine=OUT, out=HOST_OUT):
         d, f = os.path.split(engine)
         subprocess.check_call([os.environ.get("CC", "gcc"), "-O2", "-std=gnu11", "-Wall", "-Wextra", "-fPIC", "-shared",
                                "-fvisibility=hidden", "-o", l0, src0, "-L" + d, "-l:" + f, "-Wl,-rpath," + d, "-Wl,-rpath,$ORIGIN", "-lpthread"])
+    build_aln(force, engine=engine, hostlib=out)
+    return out
+
+
+def build_aln(force=False, engine=OUT, hostlib=HOST_OUT):
+    """salt_aln: the aligner as a program of its own (host/salt_aln.c) over libsalt_host.so + libsalt_b200.so; next to the host
+    library it links (salt_b200/salt_aln, or tests/emul/salt_aln_emul over the emulated engine)."""
+    src = os.path.join(HERE, "host", "salt_aln.c")
+    emul = hostlib.endswith("_emul.so")
+    out = os.path.join(os.path.dirname(hostlib), "salt_aln_emul" if emul else "salt_aln")
+    hdrs = [os.path.join(HERE, "..", "include", f) for f in ("salt_host.h", "salt_b200.h")]
+    if force or _stale(out, [src, engine, hostlib] + hdrs):
+        d, f = os.path.split(engine)
+        dh, fh = os.path.split(hostlib)
+        subprocess.check_call([os.environ.get("CC", "gcc"), "-O2", "-std=gnu11", "-Wall", "-Wextra", "-I" + os.path.join(HERE, "..", "include"),
+                               "-o", out, src, "-L" + dh, "-l:" + fh, "-L" + d, "-l:" + f, "-Wl,-rpath," + d, "-Wl,-rpath," + dh,
+                               "-Wl,-rpath,$ORIGIN", "-lpthread"])
     return out
 
 

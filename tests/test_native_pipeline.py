@@ -138,3 +138,81 @@ def test_paired_end_program_from_own_parts_on_the_gpu(tmp_path):
     for i, (a, b) in enumerate(zip(body, want)):
         assert a == b, (i, a, b)
     assert st["flagged_mates"] == 0 and st["declined"] == 0 and st["rescued"] >= 100 and st["proper"] >= 2000, st
+
+
+# ---- salt_aln: the same two programs as one C executable (salt_b200/host/salt_aln.c) --------------------------------------------
+
+def _sam_lines(path):
+    return [ln for ln in open(path, "rb").read().split(b"\n") if not ln.startswith(b"@PG")]      # @PG carries date + command line
+
+
+def _many_n(path, every, n_bases):
+    """a stretch of N in every `every`-th record of a FASTQ file (mates with more than five are not aligned, alnpe.c:491)"""
+    lines = open(path).read().split("\n")
+    for r in range(0, len(lines) // 4, every):
+        s = lines[4 * r + 1]
+        lines[4 * r + 1] = s[:20] + "N" * n_bases + s[20 + n_bases:]
+    open(path, "w").write("\n".join(lines))
+
+
+def _aln_case(d, exe, paired, flags, threads, batch, env=None):
+    run = lambda cmd, out: subprocess.run(cmd, cwd=d, stdout=open(os.path.join(d, out), "w"), stderr=subprocess.PIPE, check=True,
+                                          env=dict(os.environ, **env) if env else None)
+    files = ["r1.fq", "r2.fq"] if paired else ["reads.fq"]
+    run([os.path.join(REFDIR, "salt")] + flags + ["-t", "2", "idx"] + files, "ref.sam")
+    p = subprocess.run([exe] + flags + ["-t", str(threads)] + (["-B", str(batch)] if batch else []) + ["idx"] + files, cwd=d,
+                       stdout=open(os.path.join(d, "mine.sam"), "w"), stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr[-1500:]
+    want, got = _sam_lines(os.path.join(d, "ref.sam")), _sam_lines(os.path.join(d, "mine.sam"))
+    assert len(want) == len(got)
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert a == b, (i, a, b)
+    return want, p.stderr
+
+
+def test_salt_aln_program_on_the_emulator(tmp_path):
+    """salt_aln over the emulated engine against the reference program: header lines and every record identical, single-end and
+    paired-end, several batches, more host threads than the reference run, mates with too many N"""
+    if not all(os.path.exists(os.path.join(REFDIR, f)) for f in ("salt", "salt-idx")):
+        pytest.skip("oracle/_ref programs not built (reference tree absent at build time)")
+    import build_emul
+    from salt_b200 import build as b
+    exe = b.build_aln(engine=build_emul.build(), hostlib=build_emul.build_host())
+    d = str(tmp_path)
+    dropin_data.write_inputs(d, glen=12000, n_reads=60, seed=31, two_copies=True)
+    subprocess.run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], cwd=d, stdout=open(os.path.join(d, "idx.log"), "w"),
+                   stderr=subprocess.PIPE, check=True)
+    want, err = _aln_case(d, exe, False, ["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500"], 3, 48)
+    assert sum(b"\tXA:Z:" in ln for ln in want) >= 40 and sum(b"\tMD:Z:" in ln for ln in want) >= 50
+    assert "100 reads" in err
+    _aln_case(d, exe, False, ["-l", "100", "-g", "grp7"], 1, 0)
+    dropin_data.write_pe_inputs(d, glen=12000, n_pairs=50, seed=31, two_copies=True)
+    _many_n(os.path.join(d, "r2.fq"), 7, 8)
+    want, err = _aln_case(d, exe, True, ["-d", "-p", "-e", "-l", "100", "-c", "-a", "350", "-b", "650", "-r", "5"], 3, 40)
+    f = [ln.split(b"\t") for ln in want if ln and not ln.startswith(b"@")]
+    assert len(f) == 100 and sum(1 for x in f if int(x[1]) & 2) >= 60 and sum(1 for x in f if b"S" in x[5]) >= 3
+    assert "pairs 50:" in err and "windows declined 0" in err
+    _aln_case(d, exe, True, ["-p", "-l", "100", "-a", "350", "-b", "650", "-g", "grp7"], 2, 0)
+
+
+@pytest.mark.gpu
+def test_salt_aln_program_on_the_gpu(tmp_path):
+    """salt_b200/salt_aln on the device against the reference program at -t 4: 6 040 single-end reads with the shipped flags, 3 000 pairs
+    with the flags of run_pe_test.sh:14 (every seventh second mate with eight N: not aligned, rescued through its mate)"""
+    if not all(os.path.exists(os.path.join(REFDIR, f)) for f in ("salt", "salt-idx")):
+        pytest.skip("oracle/_ref programs not built (reference tree absent at build time)")
+    from salt_b200 import build as b
+    exe = b.build_aln()
+    d = str(tmp_path)
+    dropin_data.write_inputs(d)
+    subprocess.run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], cwd=d, stdout=open(os.path.join(d, "idx.log"), "w"),
+                   stderr=subprocess.PIPE, check=True)
+    want, err = _aln_case(d, exe, False, ["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500"], 4, 2500)
+    assert len(want) > 6000 and "6040 reads" in err
+    _aln_case(d, exe, False, ["-l", "100"], 16, 0)
+    dropin_data.write_pe_inputs(d)
+    _many_n(os.path.join(d, "r2.fq"), 7, 8)
+    want, err = _aln_case(d, exe, True, ["-d", "-p", "-e", "-l", "100", "-c", "-a", "350", "-b", "650", "-r", "5"], 4, 2500)
+    assert "pairs 3000:" in err and "windows declined 0" in err
+    f = [ln.split(b"\t") for ln in want if ln and not ln.startswith(b"@")]
+    assert sum(1 for x in f if int(x[1]) & 2) >= 4000 and sum(1 for x in f if b"S" in x[5]) >= 20
