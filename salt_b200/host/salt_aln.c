@@ -243,10 +243,18 @@ static uint32_t reader_next(reader_t *r, uint32_t want)
         return (uint32_t)n;
     }
 }
-/* read i's bases as one code per byte (query->seq, query.c:177-181) */
+/* read i's bases as one code per byte (query->seq, query.c:177-181): four bases per table look-up */
+static uint32_t unpack4[256];
+static void unpack_init(void)
+{
+    for (uint32_t b = 0; b < 256; ++b) unpack4[b] = (b & 3) | ((b >> 2 & 3) << 8) | ((b >> 4 & 3) << 16) | ((b >> 6 & 3) << 24);
+}
 static void unpack_read(const salt_fastq_t *q, uint32_t base0, uint32_t L, uint8_t *out)
 {
-    for (uint32_t k = 0; k < L; ++k) { const uint32_t p = base0 + k; out[k] = (uint8_t)((q->bases[p >> 2] >> (2 * (p & 3))) & 3); }
+    uint32_t k = 0, p = base0;
+    for (; k < L && (p & 3); ++k, ++p) out[k] = (uint8_t)((q->bases[p >> 2] >> (2 * (p & 3))) & 3);
+    for (; k + 4 <= L; k += 4, p += 4) memcpy(out + k, &unpack4[q->bases[p >> 2]], 4);
+    for (; k < L; ++k, ++p) out[k] = (uint8_t)((q->bases[p >> 2] >> (2 * (p & 3))) & 3);
 }
 /* codes of reads [0, n) of the batch into dst[dst_off[i * stride] ...]; the N positions of the stream are ascending */
 typedef struct { const reader_t *r; uint32_t n; uint8_t *dst; const uint32_t *dst_off; int stride; } unpack_arg_t;
@@ -279,7 +287,7 @@ static inline char *out_room(outbuf_t *o, size_t need)
 }
 
 typedef struct {
-    double index, gpu_init, parse, gpu, select, tail, text, write;
+    double index, gpu_init, parse, gpu, select, tail, text, write, write_wait;
     size_t reads, flagged, md_tags, xa_cigars;
     salt_pe_stats_t pe;
 } stats_t;
@@ -320,14 +328,66 @@ static void xa_collect(xa_t *x, salt_b200_t *h, const salt_read_result_t *res, c
     }
 }
 
-static void write_shares(outbuf_t *ob, int n_thr, stats_t *st)
+/* The shares of a batch are written by a thread of their own while the next batch is under way: two sets of buffers, the
+ * main thread formats into one while the writer drains the other. */
+typedef struct {
+    pthread_t th; pthread_mutex_t mu; pthread_cond_t cv;
+    outbuf_t *set[2]; int n_thr;
+    int job, busy, quit, failed;          /* job: the set being written while busy */
+    double secs;
+} writer_t;
+static void *writer_main(void *p)
 {
-    const double t0 = now();
-    for (int t = 0; t < n_thr; ++t) {
-        if (ob[t].len && fwrite(ob[t].s, 1, ob[t].len, stdout) != ob[t].len) { fprintf(stderr, "[salt_aln] write error\n"); exit(1); }
-        ob[t].len = 0;
+    writer_t *w = (writer_t *)p;
+    pthread_mutex_lock(&w->mu);
+    for (;;) {
+        while (!w->busy && !w->quit) pthread_cond_wait(&w->cv, &w->mu);
+        if (!w->busy) break;
+        outbuf_t *ob = w->set[w->job];
+        pthread_mutex_unlock(&w->mu);
+        const double t0 = now();
+        int bad = 0;
+        for (int t = 0; t < w->n_thr; ++t) {
+            if (ob[t].len && fwrite(ob[t].s, 1, ob[t].len, stdout) != ob[t].len) bad = 1;
+            ob[t].len = 0;
+        }
+        const double dt = now() - t0;
+        pthread_mutex_lock(&w->mu);
+        w->secs += dt; w->failed |= bad; w->busy = 0;
+        pthread_cond_broadcast(&w->cv);
     }
-    st->write += now() - t0;
+    pthread_mutex_unlock(&w->mu);
+    return NULL;
+}
+static void writer_start(writer_t *w, int n_thr)
+{
+    memset(w, 0, sizeof *w);
+    pthread_mutex_init(&w->mu, NULL); pthread_cond_init(&w->cv, NULL);
+    w->n_thr = n_thr;
+    for (int k = 0; k < 2; ++k) w->set[k] = (outbuf_t *)xcalloc((size_t)n_thr, sizeof(outbuf_t));
+    if (pthread_create(&w->th, NULL, writer_main, w) != 0) { fprintf(stderr, "[salt_aln] cannot start the writer thread\n"); exit(1); }
+}
+/* hand set `k` to the writer (after it has finished the other one) and return the set to format into next */
+static int writer_submit(writer_t *w, int k)
+{
+    pthread_mutex_lock(&w->mu);
+    while (w->busy) pthread_cond_wait(&w->cv, &w->mu);
+    if (w->failed) { fprintf(stderr, "[salt_aln] write error\n"); exit(1); }
+    w->job = k; w->busy = 1;
+    pthread_cond_broadcast(&w->cv);
+    pthread_mutex_unlock(&w->mu);
+    return k ^ 1;
+}
+static void writer_finish(writer_t *w, stats_t *st)
+{
+    pthread_mutex_lock(&w->mu);
+    while (w->busy) pthread_cond_wait(&w->cv, &w->mu);
+    w->quit = 1;
+    pthread_cond_broadcast(&w->cv);
+    pthread_mutex_unlock(&w->mu);
+    pthread_join(w->th, NULL);
+    if (w->failed) { fprintf(stderr, "[salt_aln] write error\n"); exit(1); }
+    st->write += w->secs;
 }
 
 typedef struct {
@@ -393,8 +453,10 @@ static void run_se(const opts_t *o, const index_files_t *ix, salt_b200_t *h, sta
     salt_read_result_t *res = (salt_read_result_t *)xmalloc((size_t)B * sizeof *res);
     xa_t xa; memset(&xa, 0, sizeof xa); xa.first = (uint32_t *)xmalloc(((size_t)B + 1) * 4);
     const int n_thr = o->n_threads;
-    outbuf_t *ob = (outbuf_t *)xcalloc((size_t)n_thr, sizeof *ob);
+    writer_t wr; writer_start(&wr, n_thr);
+    int cur = 0;
     for (;;) {
+        outbuf_t *ob = wr.set[cur];
         double t0 = now();
         const uint32_t n = reader_next(&rd, B);
         if (!n) break;
@@ -449,10 +511,12 @@ static void run_se(const opts_t *o, const index_files_t *ix, salt_b200_t *h, sta
         st->md_tags += ta.md_tags;
         const int failed = ta.failed;
         if (failed) die("salt_sam_se / salt_chunk_md", SALT_ERR_ARG);
-        st->text += now() - t0;
-        write_shares(ob, n_thr, st);
+        st->text += now() - t0; t0 = now();
+        cur = writer_submit(&wr, cur);
+        st->write_wait += now() - t0;
         st->reads += n;
     }
+    writer_finish(&wr, st);
     salt_chunk_free(ck);
 }
 
@@ -543,9 +607,11 @@ static void run_pe(const opts_t *o, const index_files_t *ix, salt_b200_t *h, sta
     if (o->print_nm_md) { tcig = (char *)xmalloc((size_t)M * 256); tmd = (char *)xmalloc((size_t)M * MD_STRIDE); txv = (uint16_t *)xmalloc((size_t)M * XV_STRIDE * 2); }
     xa_t xa; memset(&xa, 0, sizeof xa); xa.first = (uint32_t *)xmalloc(((size_t)M + 1) * 4);
     const int n_thr = o->n_threads;
-    outbuf_t *ob = (outbuf_t *)xcalloc((size_t)n_thr, sizeof *ob);
+    writer_t wr; writer_start(&wr, n_thr);
+    int cur = 0;
     for (uint32_t i = 0; i < M; ++i) row_of[i] = (int32_t)i;
     for (;;) {
+        outbuf_t *ob = wr.set[cur];
         double t0 = now();
         uint32_t n0 = reader_next(&rd[0], P);
         const uint32_t n1 = reader_next(&rd[1], n0 ? n0 : 1);
@@ -639,10 +705,12 @@ static void run_pe(const opts_t *o, const index_files_t *ix, salt_b200_t *h, sta
         run_shares(n_thr, pe_text_share, &ta);
         const int failed = ta.failed;
         if (failed) die("salt_sam_pe", SALT_ERR_ARG);
-        st->text += now() - t0;
-        write_shares(ob, n_thr, st);
+        st->text += now() - t0; t0 = now();
+        cur = writer_submit(&wr, cur);
+        st->write_wait += now() - t0;
         st->reads += n;
     }
+    writer_finish(&wr, st);
     salt_chunk_free(ck);
 }
 
@@ -685,6 +753,7 @@ int main(int argc, char **argv)
     if (o.batch < 2) o.batch = 2;
     if (o.paired && o.max_tlen == 0) { fprintf(stderr, "infer isize func haven't been implemented\n"); return 1; }          /* alnpe.c:583 */
     salt_host_set_threads(o.n_threads);
+    unpack_init();
     stats_t st;
     memset(&st, 0, sizeof st);
     const double t_start = now();
@@ -711,9 +780,9 @@ int main(int argc, char **argv)
     salt_b200_destroy(h);
     const double wall = now() - t_start;
     fprintf(stderr, "[salt_aln] %zu reads in %.3f s (%.0f reads/s): index files %.3f, GPU init + uploads %.3f; FASTQ -> codes %.3f, "
-                    "seeding + locate + verification %.3f, %s %.3f, tags + XA CIGARs %.3f, SAM text %.3f, write %.3f  (%d host threads)\n",
+                    "seeding + locate + verification %.3f, %s %.3f, tags + XA CIGARs %.3f, SAM text %.3f, waiting for the writer thread %.3f (it wrote for %.3f)  (%d host threads)\n",
             st.reads, wall, (double)st.reads / wall, st.index, st.gpu_init, st.parse, st.gpu,
-            o.paired ? "pair stage + hit selection" : "hit selection", st.select, st.tail, st.text, st.write, o.n_threads);
+            o.paired ? "pair stage + hit selection" : "hit selection", st.select, st.tail, st.text, st.write_wait, st.write, o.n_threads);
     fprintf(stderr, "[salt_aln] MD/NM/XV tags from the GPU: %zu, XA CIGARs from the GPU: %zu\n", st.md_tags, st.xa_cigars);
     if (o.paired)
         fprintf(stderr, "[salt_aln] pairs %zu: proper without rescue %zu, rescue windows %zu SNP-aware + %zu plain, mates rescued %zu, alternates promoted %zu, "

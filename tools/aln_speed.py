@@ -1,0 +1,133 @@
+#!/usr/bin/env python
+"""Whole-program wall time of the reference `salt` against salt_b200/salt_aln (this repository's own program: no reference code
+in the loop) on one synthetic data set and the reference's own index, single-end (shipped flags of run_se_test.sh:12 and the
+default seed spacing) and paired-end (run_pe_test.sh:14), at all host threads, with the SAM comparison.  Prints one JSON object
+and rewrites it after every step (OUT=path), so a run that is cut short still leaves what it measured.
+
+    GENOME=5000000 READS=600000 PAIRS=200000 OUT=gpurun_out/aln_speed.json python tools/aln_speed.py
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import dropin_data  # noqa: E402
+from salt_b200 import synth  # noqa: E402
+
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+ALN = os.environ.get("SALT_ALN", os.path.join(ROOT, "salt_b200", "salt_aln"))
+
+
+def write_fastq(path, reads, prefix):
+    """fixed-width records, assembled as one byte matrix"""
+    n, L = reads.shape
+    name = np.char.zfill(np.arange(n).astype("U8"), 8).astype("S8").view(np.uint8).reshape(n, 8)
+    rec = np.empty((n, 1 + len(prefix) + 8 + 1 + L + 3 + L + 1), np.uint8)
+    c = 0
+    rec[:, c] = ord("@"); c += 1
+    rec[:, c:c + len(prefix)] = np.frombuffer(prefix.encode(), np.uint8); c += len(prefix)
+    rec[:, c:c + 8] = name; c += 8
+    rec[:, c] = 10; c += 1
+    rec[:, c:c + L] = np.frombuffer(b"ACGTN", np.uint8)[reads]; c += L
+    rec[:, c:c + 3] = np.frombuffer(b"\n+\n", np.uint8); c += 3
+    rec[:, c:c + L] = ord("I"); c += L
+    rec[:, c] = 10
+    rec.tofile(path)
+
+
+def timed(cmd, cwd, out, env=None):
+    t0 = time.time()
+    with open(out, "w") as f:
+        p = subprocess.run(cmd, cwd=cwd, stdout=f, stderr=subprocess.PIPE, text=True, env=env)
+    if p.returncode != 0:
+        raise RuntimeError(p.stderr[-1500:])
+    return time.time() - t0, p.stderr
+
+
+def same_sam(a, b):
+    """identical except the @PG line"""
+    x = subprocess.run("grep -v '^@PG' %s | md5sum; grep -v '^@PG' %s | md5sum" % (a, b), shell=True, capture_output=True, text=True).stdout.split()
+    return len(x) == 4 and x[0] == x[2]
+
+
+def main():
+    glen = int(os.environ.get("GENOME", "5000000")); n = int(os.environ.get("READS", "400000")); npairs = int(os.environ.get("PAIRS", "100000"))
+    threads = int(os.environ.get("THREADS", str(os.cpu_count() or 1)))
+    out_path = os.environ.get("OUT")
+    res = {"genome_bp": glen, "reads": n, "pairs": npairs, "host_threads": threads, "program": "salt_b200/salt_aln (no reference code in the loop)"}
+
+    def flush():
+        if out_path:
+            with open(out_path, "w") as f:
+                json.dump(res, f, indent=1)
+    # The boxes of this pool run without the driver's persistence mode: a process that finds the GPU idle pays 2.4-3.1 s of device
+    # initialisation.  One context held open here for the whole run is what nvidia-persistenced does on a production host
+    # (HOLD_CONTEXT=0 switches it off); salt_aln prints its own "GPU init + uploads" either way.
+    held = None
+    if os.environ.get("HOLD_CONTEXT", "1") != "0":
+        try:
+            from salt_b200 import api
+            held = api.Engine(np.zeros(64, np.uint32), 256, None, 0, device=0)
+        except Exception as ex:                               # noqa: BLE001
+            res["context_hold_failed"] = repr(ex)[:200]
+    res["cuda_context_held_open_by_this_script"] = held is not None
+    with tempfile.TemporaryDirectory() as d:
+        t0 = time.time()
+        dropin_data.write_inputs(d, glen=glen, n_reads=10)
+        g = synth.Genome(glen, snp_rate=0.01, n_rate=0.0, seed=5)
+        reads = np.concatenate([synth.sample_reads(g, min(200000, n - b), 100, seed=100 + b, sub_rate=0.012, indel_frac=0.15, n_frac=0.001)[0]
+                                for b in range(0, n, 200000)])
+        write_fastq(os.path.join(d, "reads.fq"), reads, "r")
+        res["data_s"] = round(time.time() - t0, 2)
+        t, _ = timed([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], d, os.path.join(d, "idx.log"))
+        res["index_s"] = round(t, 2); flush()
+        res["se"] = []
+        for what, base in (("default seed spacing", ["-d", "-l", "100", "-n", "20", "-c", "-m", "500"]),
+                           ("run_se_test.sh:12 (-r 1: a seed at every position)", ["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500"])):
+            flags = base + ["-t", str(threads)]
+            row = {"flags": " ".join(flags), "what": what}
+            try:
+                t_ref, _ = timed([os.path.join(REFDIR, "salt")] + flags + ["idx", "reads.fq"], d, os.path.join(d, "ref.sam"))
+                row["reference_s"] = round(t_ref, 2); row["reference_reads_per_s"] = round(n / t_ref)
+                best = None
+                for rep in range(2):
+                    t_mine, err = timed([ALN] + flags + ["idx", "reads.fq"], d, os.path.join(d, "mine.sam"))
+                    if best is None or t_mine < best[0]:
+                        best = (t_mine, err)
+                row["salt_aln_s"] = round(best[0], 2); row["salt_aln_reads_per_s"] = round(n / best[0])
+                row["speedup"] = round(t_ref / best[0], 2)
+                row["sam_identical"] = same_sam(os.path.join(d, "ref.sam"), os.path.join(d, "mine.sam"))
+                row["salt_aln_phases"] = [ln for ln in best[1].split("\n") if ln.startswith("[salt_aln]")]
+            except Exception as ex:                           # noqa: BLE001
+                row["error"] = str(ex)[-600:]
+            res["se"].append(row); flush()
+        if npairs:
+            try:
+                t0 = time.time()
+                pr = synth.sample_pairs(g, npairs, 100, seed=9, insert_mean=500, insert_sd=40, hard_frac=0.1, junk_frac=0.01)[0]
+                write_fastq(os.path.join(d, "r1.fq"), pr[0::2], "p"); write_fastq(os.path.join(d, "r2.fq"), pr[1::2], "p")
+                flags = ["-d", "-p", "-e", "-l", "100", "-c", "-a", "350", "-b", "650", "-r", "5", "-t", str(threads)]
+                row = {"flags": " ".join(flags), "what": "run_pe_test.sh:14", "data_s": round(time.time() - t0, 2)}
+                t_ref, _ = timed([os.path.join(REFDIR, "salt")] + flags + ["idx", "r1.fq", "r2.fq"], d, os.path.join(d, "ref.sam"))
+                row["reference_s"] = round(t_ref, 2); row["reference_reads_per_s"] = round(2 * npairs / t_ref)
+                t_mine, err = timed([ALN] + flags + ["idx", "r1.fq", "r2.fq"], d, os.path.join(d, "mine.sam"))
+                row["salt_aln_s"] = round(t_mine, 2); row["salt_aln_reads_per_s"] = round(2 * npairs / t_mine)
+                row["speedup"] = round(t_ref / t_mine, 2)
+                row["sam_identical"] = same_sam(os.path.join(d, "ref.sam"), os.path.join(d, "mine.sam"))
+                row["salt_aln_phases"] = [ln for ln in err.split("\n") if ln.startswith("[salt_aln]")]
+            except Exception as ex:                           # noqa: BLE001
+                row = {"error": str(ex)[-600:]}
+            res["pe"] = [row]; flush()
+    if held is not None:
+        held.close()
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main()
