@@ -204,7 +204,7 @@ def test_salt_aln_program_on_the_gpu(tmp_path):
     from salt_b200 import build as b
     exe = b.build_aln()
     d = str(tmp_path)
-    dropin_data.write_inputs(d)
+    dropin_data.write_inputs(d, seed=9)              # the genome write_pe_inputs uses: one index for both halves of the test
     subprocess.run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], cwd=d, stdout=open(os.path.join(d, "idx.log"), "w"),
                    stderr=subprocess.PIPE, check=True)
     want, err = _aln_case(d, exe, False, ["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500"], 4, 2500)
