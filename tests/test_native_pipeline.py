@@ -216,3 +216,58 @@ def test_salt_aln_program_on_the_gpu(tmp_path):
     assert "pairs 3000:" in err and "windows declined 0" in err
     f = [ln.split(b"\t") for ln in want if ln and not ln.startswith(b"@")]
     assert sum(1 for x in f if int(x[1]) & 2) >= 4000 and sum(1 for x in f if b"S" in x[5]) >= 20
+
+
+def test_salt_aln_ragged_inputs_on_the_emulator(tmp_path):
+    """reads of 19 .. 150 bases in one file (the seed length included), lower case, runs of N, all-N and random reads, names
+    with a /1 suffix and comments, mates of different lengths; seed options -v -s -m -r, a read group with a blank"""
+    if not all(os.path.exists(os.path.join(REFDIR, f)) for f in ("salt", "salt-idx")):
+        pytest.skip("oracle/_ref programs not built (reference tree absent at build time)")
+    import build_emul
+    from salt_b200 import build as b, synth
+    exe = b.build_aln(engine=build_emul.build(), hostlib=build_emul.build_host())
+    d = str(tmp_path)
+    glen, seed = 20000, 4
+    rng = np.random.default_rng(seed)
+    dropin_data.write_inputs(d, glen=glen, n_reads=10, seed=seed, two_copies=True)
+    g = synth.Genome(glen, snp_rate=0.01, n_rate=0.0, seed=seed)
+    g.codes[glen // 2:] = g.codes[:glen // 2]
+    codes = (g.codes & 3).astype(np.uint8)
+    subprocess.run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], cwd=d, stdout=open(os.path.join(d, "idx.log"), "w"),
+                   stderr=subprocess.PIPE, check=True)
+
+    def reads(n, lens):
+        out = []
+        for _ in range(n):
+            L = int(rng.choice(lens)); p = int(rng.integers(0, glen - L - 10))
+            r = codes[p:p + L].copy()
+            e = rng.random(L) < 0.02
+            r[e] = (r[e] + rng.integers(1, 4, int(e.sum()))) & 3
+            if rng.random() < 0.2 and L > 30:
+                c = int(rng.integers(10, L - 10)); r = np.concatenate([r[:c], r[c + 1:], codes[p + L:p + L + 1]])
+            if rng.random() < 0.5:
+                r = synth.revcomp(r[None, :])[0]
+            s = "".join("ACGT"[c] for c in r)
+            u = rng.random()
+            if u < 0.1:
+                s = s.lower()
+            elif u < 0.2:
+                k = int(rng.integers(1, 12)); a = int(rng.integers(0, max(1, L - k))); s = s[:a] + "N" * k + s[a + k:]
+            elif u < 0.25:
+                s = "N" * L
+            elif u < 0.3:
+                s = "".join("ACGT"[c] for c in rng.integers(0, 4, L))
+            out.append(s)
+        return out
+
+    def write(name, seqs, suffix):
+        with open(os.path.join(d, name), "w") as f:
+            for i, s in enumerate(seqs):
+                q = "".join(chr(33 + int(x)) for x in rng.integers(0, 41, len(s)))
+                f.write("@q%d%s\n%s\n+\n%s\n" % (i, suffix if i % 2 else " a comment", s, q))
+    lens = [19, 36, 50, 75, 100, 125, 150]       # (250-base reads too: checked off-line, the emulator needs minutes for them)
+    write("reads.fq", reads(32, lens), "/1")
+    _aln_case(d, exe, False, ["-d", "-r", "4", "-c", "-m", "500", "-v", "-s", "5", "-g", "x y"], 3, 20)
+    write("r1.fq", reads(16, lens), "/1"); write("r2.fq", reads(16, lens), "/2")
+    want, err = _aln_case(d, exe, True, ["-p", "-d", "-c", "-a", "100", "-b", "5000", "-r", "9"], 3, 0)
+    assert "pairs 16:" in err
