@@ -192,11 +192,10 @@ static void reader_alloc(reader_t *r, size_t cap)
     q->bases_cap = cap; q->bases = (uint8_t *)xrealloc(q->bases, cap / 4 + 16);
     q->n_pos_cap = cap / 4 + 1024; q->n_pos = (uint32_t *)xrealloc(q->n_pos, q->n_pos_cap * 4);
 }
-static void reader_open(reader_t *r, const char *fn, uint32_t max_reads)
+static void reader_init(reader_t *r, FILE *f, uint32_t max_reads)
 {
     memset(r, 0, sizeof *r);
-    r->f = strcmp(fn, "-") ? fopen(fn, "rb") : stdin;
-    if (!r->f) { fprintf(stderr, "[salt_aln] cannot open %s: %s\n", fn, strerror(errno)); exit(1); }
+    r->f = f;
     r->max_reads = max_reads;
     salt_fastq_t *q = &r->fq;
     q->lens = (uint16_t *)xmalloc((size_t)max_reads * 2); q->n_ambiguous = (uint16_t *)xmalloc((size_t)max_reads * 2);
@@ -243,6 +242,76 @@ static uint32_t reader_next(reader_t *r, uint32_t want)
         return (uint32_t)n;
     }
 }
+/* Two frames per input file and a thread that fills the one the program is not looking at: while a batch is aligned and
+ * printed, the next one is read and parsed.  The unparsed tail of a frame's text opens the next frame. */
+typedef struct {
+    reader_t fr[2]; int cur;                      /* fr[cur]: the batch the program holds */
+    uint32_t want, n_ready;
+    pthread_t th; pthread_mutex_t mu; pthread_cond_t cv;
+    int kick, ready, quit;
+    double secs;
+} stream_t;
+static void *stream_main(void *p)
+{
+    stream_t *s = (stream_t *)p;
+    pthread_mutex_lock(&s->mu);
+    for (;;) {
+        while (!s->kick && !s->quit) pthread_cond_wait(&s->cv, &s->mu);
+        if (s->quit) break;
+        s->kick = 0;
+        const reader_t *a = &s->fr[s->cur]; reader_t *b = &s->fr[s->cur ^ 1];
+        const uint32_t want = s->want;
+        pthread_mutex_unlock(&s->mu);
+        const double t0 = now();
+        const size_t left = a->len - a->used;
+        if (b->cap < left || b->cap < a->cap) reader_alloc(b, a->cap > left ? a->cap : left);
+        memcpy(b->text, a->text + a->used, left);
+        b->len = left; b->used = 0; b->eof = a->eof;
+        const uint32_t n = reader_next(b, want);
+        const double dt = now() - t0;
+        pthread_mutex_lock(&s->mu);
+        s->n_ready = n; s->ready = 1; s->secs += dt;
+        pthread_cond_broadcast(&s->cv);
+    }
+    pthread_mutex_unlock(&s->mu);
+    return NULL;
+}
+static void stream_kick(stream_t *s, uint32_t want)
+{
+    pthread_mutex_lock(&s->mu);
+    s->want = want; s->kick = 1;
+    pthread_cond_broadcast(&s->cv);
+    pthread_mutex_unlock(&s->mu);
+}
+static void stream_open(stream_t *s, const char *fn, uint32_t max_reads)
+{
+    memset(s, 0, sizeof *s);
+    FILE *f = strcmp(fn, "-") ? fopen(fn, "rb") : stdin;
+    if (!f) { fprintf(stderr, "[salt_aln] cannot open %s: %s\n", fn, strerror(errno)); exit(1); }
+    reader_init(&s->fr[0], f, max_reads); reader_init(&s->fr[1], f, max_reads);
+    pthread_mutex_init(&s->mu, NULL); pthread_cond_init(&s->cv, NULL);
+    if (pthread_create(&s->th, NULL, stream_main, s) != 0) { fprintf(stderr, "[salt_aln] cannot start the reader thread\n"); exit(1); }
+    stream_kick(s, max_reads);
+}
+/* the batch that was asked for with the last stream_kick: its frame, *n records (0 at the end of the input) */
+static const reader_t *stream_get(stream_t *s, uint32_t *n)
+{
+    pthread_mutex_lock(&s->mu);
+    while (!s->ready) pthread_cond_wait(&s->cv, &s->mu);
+    s->ready = 0; s->cur ^= 1; *n = s->n_ready;
+    pthread_mutex_unlock(&s->mu);
+    return &s->fr[s->cur];
+}
+static double stream_close(stream_t *s)
+{
+    pthread_mutex_lock(&s->mu);
+    s->quit = 1;
+    pthread_cond_broadcast(&s->cv);
+    pthread_mutex_unlock(&s->mu);
+    pthread_join(s->th, NULL);
+    return s->secs;
+}
+
 /* read i's bases as one code per byte (query->seq, query.c:177-181): four bases per table look-up */
 static uint32_t unpack4[256];
 static void unpack_init(void)
@@ -287,7 +356,7 @@ static inline char *out_room(outbuf_t *o, size_t need)
 }
 
 typedef struct {
-    double index, gpu_init, parse, gpu, select, tail, text, write, write_wait;
+    double index, gpu_init, parse, parse_beside, gpu, select, tail, text, write, write_wait;
     size_t reads, flagged, md_tags, xa_cigars;
     salt_pe_stats_t pe;
 } stats_t;
@@ -435,8 +504,8 @@ static void se_text_share(int t, int T, void *arg)
 /* ---- single-end ----------------------------------------------------------------------------------------------------------- */
 static void run_se(const opts_t *o, const index_files_t *ix, salt_b200_t *h, stats_t *st)
 {
-    reader_t rd;
-    reader_open(&rd, o->fn[0], o->batch);
+    stream_t in;
+    stream_open(&in, o->fn[0], o->batch);
     salt_seed_opt_t so;
     memset(&so, 0, sizeof so);
     so.l_seed = ix->l_seed; so.l_overlap = o->l_overlap > 0 ? o->l_overlap : ix->l_seed; so.max_seed = o->max_seed;
@@ -458,20 +527,22 @@ static void run_se(const opts_t *o, const index_files_t *ix, salt_b200_t *h, sta
     for (;;) {
         outbuf_t *ob = wr.set[cur];
         double t0 = now();
-        const uint32_t n = reader_next(&rd, B);
+        uint32_t n = 0;
+        const reader_t *rd = stream_get(&in, &n);
         if (!n) break;
-        const salt_fastq_t *q = &rd.fq;
-        const size_t nb = rd.roffs[n];
+        stream_kick(&in, B);                      /* the next batch is read and parsed while this one is aligned */
+        const salt_fastq_t *q = &rd->fq;
+        const size_t nb = rd->roffs[n];
         if (nb + 16 > codes_cap) { codes_cap = nb * 2 + 16; codes = (uint8_t *)xrealloc(codes, codes_cap); kcodes = (uint8_t *)xrealloc(kcodes, codes_cap); }
-        unpack_batch(&rd, n, codes, rd.roffs, 1, o->n_threads);
+        unpack_batch(rd, n, codes, rd->roffs, 1, o->n_threads);
         /* reads with more than MAX_N_PERSEQ ambiguous bases are not aligned; their SAM line stays empty (alnse.c:1296) */
         uint32_t nk = 0; int all = 1;
         for (uint32_t i = 0; i < n; ++i) { row_of[i] = q->n_ambiguous[i] <= MAX_N_PERSEQ_SE ? (int32_t)nk++ : -1; all &= row_of[i] >= 0; }
-        const uint8_t *cc = codes; const uint32_t *rr = rd.roffs;
+        const uint8_t *cc = codes; const uint32_t *rr = rd->roffs;
         if (!all) {
             kroffs[0] = 0; nk = 0;
             for (uint32_t i = 0; i < n; ++i) if (row_of[i] >= 0) {
-                memcpy(kcodes + kroffs[nk], codes + rd.roffs[i], q->lens[i]);
+                memcpy(kcodes + kroffs[nk], codes + rd->roffs[i], q->lens[i]);
                 kroffs[nk + 1] = kroffs[nk] + q->lens[i]; ++nk;
             }
             cc = kcodes; rr = kroffs;
@@ -506,7 +577,7 @@ static void run_se(const opts_t *o, const index_files_t *ix, salt_b200_t *h, sta
             st->xa_cigars += xa.n;
         } else memset(xa.first, 0, ((size_t)n + 1) * 4);
         st->tail += now() - t0; t0 = now();
-        se_text_t ta = {o, ix, &rd, ck, codes, row_of, res, &xa, ob, n, 0, 0};
+        se_text_t ta = {o, ix, rd, ck, codes, row_of, res, &xa, ob, n, 0, 0};
         run_shares(n_thr, se_text_share, &ta);
         st->md_tags += ta.md_tags;
         const int failed = ta.failed;
@@ -517,11 +588,12 @@ static void run_se(const opts_t *o, const index_files_t *ix, salt_b200_t *h, sta
         st->reads += n;
     }
     writer_finish(&wr, st);
+    st->parse_beside += stream_close(&in);
     salt_chunk_free(ck);
 }
 
 typedef struct {
-    const opts_t *o; const index_files_t *ix; const reader_t *rd; const uint8_t *codes; const uint32_t *roffs; const salt_pair_final_t *fin;
+    const opts_t *o; const index_files_t *ix; const reader_t *const *rd; const uint8_t *codes; const uint32_t *roffs; const salt_pair_final_t *fin;
     const salt_read_result_t *res; const xa_t *xa; const int32_t *tag_row; const char *tmd; const uint16_t *txv; const salt_mdnm_out_t *tout;
     outbuf_t *ob; uint32_t np; int failed;
 } pe_text_t;
@@ -537,7 +609,7 @@ static void pe_text_share(int t, int T, void *arg)
         memset(s, 0, sizeof s);
         for (int m = 0; m < 2; ++m) {
             const uint32_t i = 2 * p + (uint32_t)m;
-            const reader_t *rd = &a->rd[m]; const salt_fastq_t *q = &rd->fq;
+            const reader_t *rd = a->rd[m]; const salt_fastq_t *q = &rd->fq;
             const salt_mate_final_t *f = &a->fin[p].mate[m];
             const salt_read_result_t *r = a->res + i;
             s[m].name = rd->text + q->name_off[p]; s[m].seq = a->codes + a->roffs[i];
@@ -575,8 +647,9 @@ static void pe_text_share(int t, int T, void *arg)
 static void run_pe(const opts_t *o, const index_files_t *ix, salt_b200_t *h, stats_t *st)
 {
     const uint32_t P = o->batch / 2 ? o->batch / 2 : 1;          /* pairs per batch: N_SEQS reads (query_read_multiPairedSeqs) */
-    reader_t rd[2];
-    reader_open(&rd[0], o->fn[0], P); reader_open(&rd[1], o->fn[1], P);
+    stream_t in[2];
+    stream_open(&in[0], o->fn[0], P); stream_open(&in[1], o->fn[1], P);
+    int last = 0;
     salt_seed_opt_t so;
     memset(&so, 0, sizeof so);
     so.l_seed = ix->l_seed; so.l_overlap = o->l_overlap > 0 ? o->l_overlap : ix->l_seed; so.max_seed = o->max_seed;
@@ -613,22 +686,24 @@ static void run_pe(const opts_t *o, const index_files_t *ix, salt_b200_t *h, sta
     for (;;) {
         outbuf_t *ob = wr.set[cur];
         double t0 = now();
-        uint32_t n0 = reader_next(&rd[0], P);
-        const uint32_t n1 = reader_next(&rd[1], n0 ? n0 : 1);
+        if (last) break;
+        uint32_t n0 = 0, n1 = 0;
+        const reader_t *rd[2];
+        rd[0] = stream_get(&in[0], &n0); rd[1] = stream_get(&in[1], &n1);
         if (!n0 || !n1) break;
-        if (n1 < n0) {                              /* the second file ended first: the surplus of the first is not aligned */
-            fprintf(stderr, "[salt_aln] %s has fewer records than %s: stopping after the last complete pair\n", o->fn[1], o->fn[0]);
-            n0 = n1; rd[0].eof = 1; rd[0].len = rd[0].used = 0;
-        }
+        if (n0 != n1) {                             /* one file ended first: the surplus of the other is not aligned */
+            fprintf(stderr, "[salt_aln] %s and %s hold different numbers of records: stopping after the last complete pair\n", o->fn[0], o->fn[1]);
+            n0 = n0 < n1 ? n0 : n1; last = 1;
+        } else { stream_kick(&in[0], P); stream_kick(&in[1], P); }
         const uint32_t np = n0, n = 2 * np;
         roffs[0] = 0;
         for (uint32_t p = 0; p < np; ++p) {
-            roffs[2 * p + 1] = roffs[2 * p] + rd[0].fq.lens[p];
-            roffs[2 * p + 2] = roffs[2 * p + 1] + rd[1].fq.lens[p];
+            roffs[2 * p + 1] = roffs[2 * p] + rd[0]->fq.lens[p];
+            roffs[2 * p + 2] = roffs[2 * p + 1] + rd[1]->fq.lens[p];
         }
         const size_t nb = roffs[n];
         if (nb + 16 > codes_cap) { codes_cap = nb * 2 + 16; codes = (uint8_t *)xrealloc(codes, codes_cap); }
-        unpack_batch(&rd[0], np, codes, roffs, 2, o->n_threads); unpack_batch(&rd[1], np, codes, roffs + 1, 2, o->n_threads);
+        unpack_batch(rd[0], np, codes, roffs, 2, o->n_threads); unpack_batch(rd[1], np, codes, roffs + 1, 2, o->n_threads);
         st->parse += now() - t0; t0 = now();
         /* phase 1: candidate lists of every mate, both strands (alnse_seed_overlap + alnse_locate, alnse.c:1010-1013) */
         salt_reads_t rs; rs.codes = codes; rs.offs = roffs; rs.n_reads = n;
@@ -647,13 +722,13 @@ static void run_pe(const opts_t *o, const index_files_t *ix, salt_b200_t *h, sta
         for (uint32_t i = 0; i < n; ++i) st->flagged += (stt[0][i] | stt[1][i]) != 0;
         /* a mate with more than MAX_N_PERSEQ ambiguous bases is not aligned (alnpe.c:491); it can still be rescued */
         int any_skip = 0;
-        for (uint32_t i = 0; i < n; ++i) any_skip |= rd[i & 1].fq.n_ambiguous[i >> 1] > MAX_N_PERSEQ_PE;
+        for (uint32_t i = 0; i < n; ++i) any_skip |= rd[i & 1]->fq.n_ambiguous[i >> 1] > MAX_N_PERSEQ_PE;
         if (any_skip)
             for (int s = 0; s < 2; ++s) {
                 uint32_t w = 0, a = 0;                  /* w: end of the compacted lists so far; a: start of mate i's original list */
                 for (uint32_t i = 0; i < n; ++i) {
                     const uint32_t b = offs[s][i + 1];
-                    if (rd[i & 1].fq.n_ambiguous[i >> 1] <= MAX_N_PERSEQ_PE) { memmove(loci[s] + w, loci[s] + a, (size_t)(b - a) * 4); w += b - a; }
+                    if (rd[i & 1]->fq.n_ambiguous[i >> 1] <= MAX_N_PERSEQ_PE) { memmove(loci[s] + w, loci[s] + a, (size_t)(b - a) * 4); w += b - a; }
                     a = b; offs[s][i + 1] = w;
                 }
                 if (s) c1 = w; else c0 = w;
@@ -711,6 +786,7 @@ static void run_pe(const opts_t *o, const index_files_t *ix, salt_b200_t *h, sta
         st->reads += n;
     }
     writer_finish(&wr, st);
+    st->parse_beside += stream_close(&in[0]) + stream_close(&in[1]);
     salt_chunk_free(ck);
 }
 
@@ -779,9 +855,9 @@ int main(int argc, char **argv)
     fflush(stdout);
     salt_b200_destroy(h);
     const double wall = now() - t_start;
-    fprintf(stderr, "[salt_aln] %zu reads in %.3f s (%.0f reads/s): index files %.3f, GPU init + uploads %.3f; FASTQ -> codes %.3f, "
+    fprintf(stderr, "[salt_aln] %zu reads in %.3f s (%.0f reads/s): index files %.3f, GPU init + uploads %.3f; FASTQ -> codes %.3f (waiting for the reader thread and unpacking; it parsed for %.3f beside), "
                     "seeding + locate + verification %.3f, %s %.3f, tags + XA CIGARs %.3f, SAM text %.3f, waiting for the writer thread %.3f (it wrote for %.3f)  (%d host threads)\n",
-            st.reads, wall, (double)st.reads / wall, st.index, st.gpu_init, st.parse, st.gpu,
+            st.reads, wall, (double)st.reads / wall, st.index, st.gpu_init, st.parse, st.parse_beside, st.gpu,
             o.paired ? "pair stage + hit selection" : "hit selection", st.select, st.tail, st.text, st.write_wait, st.write, o.n_threads);
     fprintf(stderr, "[salt_aln] MD/NM/XV tags from the GPU: %zu, XA CIGARs from the GPU: %zu\n", st.md_tags, st.xa_cigars);
     if (o.paired)
