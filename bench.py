@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--pe-pairs", type=int, default=200_000, help="pairs in the paired-end pipeline leg (0 = skip)")
     ap.add_argument("--seed-reads", type=int, default=400_000, help="reads in the seeding + locate leg (0 = skip)")
     ap.add_argument("--seed-genome", type=int, default=10_000_000, help="genome of the seeding leg (its index is built by salt-idx)")
+    ap.add_argument("--program-reads", type=int, default=400_000,
+                    help="reads of the whole-program leg: salt_b200/salt_aln against the reference program, SAM compared (0 = skip)")
     return ap.parse_args()
 
 
@@ -564,6 +566,8 @@ def main():
         if args.seed_reads > 0:
             out["seeding"] = bench_seeding(args)
         out["se_host_layer"] = bench_se_host_layer(eng, wl, args)
+        if args.program_reads > 0:
+            out["program"] = bench_program(args)
 
     if rank == 0 and world == 1:
         try:
@@ -823,6 +827,21 @@ def bench_seeding(args):
         a = argparse.Namespace(genome=args.seed_genome, reads=args.seed_reads, read_len=args.read_len, repeat_frac=0.10,
                                cpu_sample=min(args.seed_reads, 200_000), chunk=args.chunk, max_seed=50, max_locate=1000)
         return seed_bench.run(a)
+    except Exception as ex:                                # noqa: BLE001 -- an extra, never the headline
+        return {"error": repr(ex)}
+
+
+def bench_program(args):
+    """The aligner as a program (salt_b200/salt_aln: no reference code in the loop) against the reference program itself at all
+    host threads, whole-process wall time, SAM compared (tools/aln_speed.py at a size that fits the default run).  This process
+    holds a CUDA context while they run, as nvidia-persistenced would.  Needs oracle/_ref/salt and salt-idx (input preparation
+    and the CPU side); without them the block says so."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import aln_speed
+        if not aln_speed.have_programs():
+            return {"unavailable": "oracle/_ref/salt, salt-idx or salt_b200/salt_aln not built"}
+        return aln_speed.run(5_000_000, args.program_reads, args.program_reads // 4, os.cpu_count() or 1, None, hold_context=False)
     except Exception as ex:                                # noqa: BLE001 -- an extra, never the headline
         return {"error": repr(ex)}
 

@@ -15,7 +15,7 @@
  *                --salt_b200_md_nm / salt_b200_lv_cigar--> --salt_sam_pe--> SAM
  *
  * Reads go through in batches of N_SEQS (aln.h:27); the per-read host work of a batch (unpacking, SAM text) runs on -t
- * threads.  tests/test_native_pipeline.py runs the program on the SIMT emulator against oracle/_ref/salt.
+ * threads.  tests/test_native_pipeline.py runs the program on the SIMT emulator and on the GPU against the reference program.
  *
  * One deliberate difference (paired-end only): where an SNP-context interval is wider than -m the reference locates a random
  * subset of its rows (srand(time(0)) / rand(), alnse.c:538-552), so two runs of the reference itself differ there; the

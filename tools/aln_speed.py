@@ -57,9 +57,16 @@ def same_sam(a, b):
 
 
 def main():
-    glen = int(os.environ.get("GENOME", "5000000")); n = int(os.environ.get("READS", "400000")); npairs = int(os.environ.get("PAIRS", "100000"))
-    threads = int(os.environ.get("THREADS", str(os.cpu_count() or 1)))
-    out_path = os.environ.get("OUT")
+    res = run(int(os.environ.get("GENOME", "5000000")), int(os.environ.get("READS", "400000")), int(os.environ.get("PAIRS", "100000")),
+              int(os.environ.get("THREADS", str(os.cpu_count() or 1))), os.environ.get("OUT"), os.environ.get("HOLD_CONTEXT", "1") != "0")
+    print(json.dumps(res, indent=1))
+
+
+def have_programs():
+    return all(os.path.exists(p) for p in (os.path.join(REFDIR, "salt"), os.path.join(REFDIR, "salt-idx"), ALN))
+
+
+def run(glen, n, npairs, threads, out_path=None, hold_context=True):
     res = {"genome_bp": glen, "reads": n, "pairs": npairs, "host_threads": threads, "program": "salt_b200/salt_aln (no reference code in the loop)"}
 
     def flush():
@@ -70,7 +77,7 @@ def main():
     # initialisation.  One context held open here for the whole run is what nvidia-persistenced does on a production host
     # (HOLD_CONTEXT=0 switches it off); salt_aln prints its own "GPU init + uploads" either way.
     held = None
-    if os.environ.get("HOLD_CONTEXT", "1") != "0":
+    if hold_context:
         try:
             from salt_b200 import api
             held = api.Engine(np.zeros(64, np.uint32), 256, None, 0, device=0)
@@ -126,7 +133,7 @@ def main():
             res["pe"] = [row]; flush()
     if held is not None:
         held.close()
-    print(json.dumps(res, indent=1))
+    return res
 
 
 if __name__ == "__main__":
