@@ -8,7 +8,7 @@
  * alnpe.c:530-660) on an index written by its salt-idx, with the same options and the same SAM (except the @PG line):
  *
  *   single-end   FASTQ text --salt_fastq_pack--> reads --salt_chunk_seed_verify (seeding, locate, verification on the GPU)-->
- *                --salt_chunk_results (hit selection, mapq, CIGAR)--> --salt_chunk_tail / salt_b200_lv_cigar (MD NM XV, XA CIGARs)-->
+ *                --salt_chunk_results (hit selection, mapq, CIGAR)--> --salt_b200_tail_primaries / salt_b200_lv_cigar (MD NM XV, XA CIGARs)-->
  *                --salt_sam_se--> SAM
  *   paired-end   two FASTQ texts --salt_fastq_pack--> mates 2i, 2i+1 --salt_b200_seed_locate (paired-end flavour)-->
  *                --salt_chunk_submit / _wait (thresholds 3 / 3)--> --salt_chunk_pair (pairing plans, mate rescue, apply)-->
@@ -462,6 +462,8 @@ static void writer_finish(writer_t *w, stats_t *st)
 typedef struct {
     const opts_t *o; const index_files_t *ix; const reader_t *rd; const salt_chunk_t *ck; const uint8_t *codes; const int32_t *row_of;
     const salt_read_result_t *res; const xa_t *xa; outbuf_t *ob; uint32_t n; size_t md_tags; int failed;
+    /* tags of the chunk's primaries as salt_b200_tail_primaries returns them (row = the read's row in the chunk); NULL: salt_chunk_md */
+    const salt_mdnm_out_t *t_out; const uint32_t *t_offs; const char *t_md; const uint16_t *t_xv;
 } se_text_t;
 static void se_text_share(int t, int T, void *arg)
 {
@@ -483,7 +485,12 @@ static void se_text_share(int t, int T, void *arg)
         s.xa_cigars = a->xa->ptr ? a->xa->ptr + a->xa->first[i] : NULL;
         if (o->print_nm_md && r->pos != UNMAPPED) {
             int nm = 0, n_xv = 0; const uint16_t *xv = NULL;
-            s.md = salt_chunk_md(a->ck, (uint32_t)a->row_of[i], &nm, &xv, &n_xv);
+            if (a->t_out) {
+                const salt_mdnm_out_t *to = &a->t_out[a->row_of[i]];
+                if (to->md_len < 0) { failed = 1; break; }                  /* -2 / -3: see salt_mdnm_out_t */
+                s.md = a->t_md + a->t_offs[a->row_of[i]]; nm = to->nm; n_xv = to->n_xv;
+                xv = n_xv ? a->t_xv + (size_t)a->row_of[i] * XV_STRIDE : NULL;
+            } else s.md = salt_chunk_md(a->ck, (uint32_t)a->row_of[i], &nm, &xv, &n_xv);
             if (!s.md) { failed = 1; break; }
             s.nm = (uint32_t)nm; s.xv = xv; s.n_xv = n_xv; ++md_tags;
         }
@@ -521,6 +528,8 @@ static void run_se(const opts_t *o, const index_files_t *ix, salt_b200_t *h, sta
     uint32_t *primary = (uint32_t *)xmalloc((size_t)B * 4);
     salt_read_result_t *res = (salt_read_result_t *)xmalloc((size_t)B * sizeof *res);
     xa_t xa; memset(&xa, 0, sizeof xa); xa.first = (uint32_t *)xmalloc(((size_t)B + 1) * 4);
+    salt_mdnm_out_t *t_out = NULL; uint32_t *t_offs = NULL; uint16_t *t_xv = NULL; char *t_md = NULL; size_t t_md_cap = 0;   /* pinned */
+    int tail_fast_ok = 1;
     const int n_thr = o->n_threads;
     writer_t wr; writer_start(&wr, n_thr);
     int cur = 0;
@@ -566,7 +575,29 @@ static void run_se(const opts_t *o, const index_files_t *ix, salt_b200_t *h, sta
             break;
         }
         st->gpu += now() - t0; t0 = now();
-        if (o->print_nm_md && nk) { const int rc = salt_chunk_tail(h, 0, ck); if (rc != SALT_OK) die("salt_chunk_tail", rc); }
+        int fast_tail = 0;
+        if (o->print_nm_md && nk) {
+            /* sam_add_md_nm for every primary of the chunk (sam.c:246-328).  The records, strands and CIGARs of the chunk just
+               verified are still on the device: salt_b200_tail_primaries makes the tags from them and sends the MD strings back
+               packed.  Should it decline, salt_chunk_tail builds the same tags item by item. */
+            if (!t_out) {
+                t_out = (salt_mdnm_out_t *)salt_b200_host_alloc((size_t)B * sizeof *t_out); t_offs = (uint32_t *)salt_b200_host_alloc(((size_t)B + 1) * 4);
+                t_xv = (uint16_t *)salt_b200_host_alloc((size_t)B * XV_STRIDE * 2);
+                t_md_cap = (size_t)B * 48; t_md = (char *)salt_b200_host_alloc(t_md_cap);
+            }
+            if (tail_fast_ok && t_out && t_offs && t_xv && t_md) {
+                size_t bytes = 0;
+                int rc = salt_b200_tail_primaries(h, 0, t_out, t_offs, t_md, t_md_cap, &bytes, t_xv, XV_STRIDE);
+                if (rc == SALT_ERR_NOMEM && bytes > t_md_cap) {              /* longer MD strings than the buffer: once more with room */
+                    salt_b200_host_free(t_md);
+                    t_md_cap = bytes + bytes / 4 + 4096; t_md = (char *)salt_b200_host_alloc(t_md_cap);
+                    rc = t_md ? salt_b200_tail_primaries(h, 0, t_out, t_offs, t_md, t_md_cap, &bytes, t_xv, XV_STRIDE) : SALT_ERR_NOMEM;
+                }
+                if (rc == SALT_OK) fast_tail = 1;
+                else { tail_fast_ok = 0; fprintf(stderr, "[salt_aln] salt_b200_tail_primaries declined (%d: %s): tags through salt_chunk_tail\n", rc, salt_b200_last_error()); }
+            }
+            if (!fast_tail) { const int rc = salt_chunk_tail(h, 0, ck); if (rc != SALT_OK) die("salt_chunk_tail", rc); }
+        }
         st->tail += now() - t0; t0 = now();
         if (nk) { const int rc = salt_chunk_results(ck, MAX_HITS, res); if (rc != SALT_OK) die("salt_chunk_results", rc); }
         for (uint32_t i = 0; i < n; ++i) primary[i] = row_of[i] >= 0 ? res[row_of[i]].pos : UNMAPPED;
@@ -577,7 +608,7 @@ static void run_se(const opts_t *o, const index_files_t *ix, salt_b200_t *h, sta
             st->xa_cigars += xa.n;
         } else memset(xa.first, 0, ((size_t)n + 1) * 4);
         st->tail += now() - t0; t0 = now();
-        se_text_t ta = {o, ix, rd, ck, codes, row_of, res, &xa, ob, n, 0, 0};
+        se_text_t ta = {o, ix, rd, ck, codes, row_of, res, &xa, ob, n, 0, 0, fast_tail ? t_out : NULL, t_offs, t_md, t_xv};
         run_shares(n_thr, se_text_share, &ta);
         st->md_tags += ta.md_tags;
         const int failed = ta.failed;
