@@ -35,7 +35,9 @@
 #define MAX_N_PERSEQ_SE 200           /* alnse.c:1281 */
 #define MAX_N_PERSEQ_PE 5             /* alnpe.c:477 */
 #define MAX_HITS 5                    /* aln.h:139 */
-#define PE_LIST_CAP 4096              /* room per candidate list on the device (the reference allows 262144, alnse.c:42) */
+#define PE_LIST_CAP 1024              /* room per candidate list on the device to start with: a batch whose lists fill it is located
+                                         again with four times the room, up to the engine's 16384 (the reference allows 262144,
+                                         alnse.c:42); the scratch is n_mates x 2 x this x 4 bytes */
 #define XA_STRIDE 256                 /* sam.c:216 */
 #define MD_STRIDE 512
 #define XV_STRIDE 64                  /* sam.c:242 */
@@ -45,7 +47,7 @@ typedef struct {
     int paired, n_threads, l_overlap, max_seed, max_locate, seed_only_ref, print_xa_cigar, print_nm_md, device;
     uint32_t min_tlen, max_tlen;
     const char *rg_id, *prefix, *fn[2];
-    uint32_t batch;
+    uint32_t batch; int list_cap;
 } opts_t;
 
 static double now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; }
@@ -357,7 +359,7 @@ static inline char *out_room(outbuf_t *o, size_t need)
 
 typedef struct {
     double index, gpu_init, parse, parse_beside, gpu, select, tail, text, write, write_wait;
-    size_t reads, flagged, md_tags, xa_cigars;
+    size_t reads, flagged, cut, relocated, md_tags, xa_cigars;
     salt_pe_stats_t pe;
 } stats_t;
 
@@ -684,7 +686,7 @@ static void run_pe(const opts_t *o, const index_files_t *ix, salt_b200_t *h, sta
     salt_seed_opt_t so;
     memset(&so, 0, sizeof so);
     so.l_seed = ix->l_seed; so.l_overlap = o->l_overlap > 0 ? o->l_overlap : ix->l_seed; so.max_seed = o->max_seed;
-    so.max_locate = o->max_locate; so.seed_only_ref = o->seed_only_ref; so.locate_mode = 1; so.list_cap = PE_LIST_CAP;
+    so.max_locate = o->max_locate; so.seed_only_ref = o->seed_only_ref; so.locate_mode = 1; so.list_cap = o->list_cap;
     int8_t mat16[256], mat5[25];
     /* salt's two Smith-Waterman matrices by their rule (alnpe.c:52-73): SNP-aware 16 x 16, rows 1 2 4 8 score +1 where the
        column shares the row's bit, everything else -3; 2-bit 5 x 5, +1 / -3, N scores -1 */
@@ -741,16 +743,23 @@ static void run_pe(const opts_t *o, const index_files_t *ix, salt_b200_t *h, sta
         int rc = salt_b200_set_reads(h, &rs);
         if (rc != SALT_OK) die("salt_b200_set_reads", rc);
         size_t c0 = 0, c1 = 0;
-        rc = salt_b200_seed_locate(h, 0, &so, offs[0], offs[1], loci[0], loci_cap, loci[1], loci_cap, &c0, &c1);
-        if (rc == SALT_ERR_NOMEM) {
-            loci_cap = (c0 > c1 ? c0 : c1) + 1024;
-            loci[0] = (uint32_t *)xrealloc(loci[0], loci_cap * 4); loci[1] = (uint32_t *)xrealloc(loci[1], loci_cap * 4);
+        for (;;) {
             rc = salt_b200_seed_locate(h, 0, &so, offs[0], offs[1], loci[0], loci_cap, loci[1], loci_cap, &c0, &c1);
+            if (rc == SALT_ERR_NOMEM) {
+                loci_cap = (c0 > c1 ? c0 : c1) + 1024;
+                loci[0] = (uint32_t *)xrealloc(loci[0], loci_cap * 4); loci[1] = (uint32_t *)xrealloc(loci[1], loci_cap * 4);
+                rc = salt_b200_seed_locate(h, 0, &so, offs[0], offs[1], loci[0], loci_cap, loci[1], loci_cap, &c0, &c1);
+            }
+            if (rc != SALT_OK) die("salt_b200_seed_locate", rc);
+            rc = salt_b200_seed_status(h, 0, stt[0], stt[1]);
+            if (rc != SALT_OK) die("salt_b200_seed_status", rc);
+            int cut = 0;                            /* bit 1: a list filled the room it was given before the reference's own limit */
+            for (uint32_t i = 0; i < n; ++i) cut |= (stt[0][i] | stt[1][i]) & 2;
+            if (!cut || so.list_cap >= 16384) break;
+            so.list_cap = so.list_cap * 4 > 16384 ? 16384 : so.list_cap * 4;       /* kept for the batches that follow */
+            ++st->relocated;
         }
-        if (rc != SALT_OK) die("salt_b200_seed_locate", rc);
-        rc = salt_b200_seed_status(h, 0, stt[0], stt[1]);
-        if (rc != SALT_OK) die("salt_b200_seed_status", rc);
-        for (uint32_t i = 0; i < n; ++i) st->flagged += (stt[0][i] | stt[1][i]) != 0;
+        for (uint32_t i = 0; i < n; ++i) { st->flagged += ((stt[0][i] | stt[1][i]) & 1) != 0; st->cut += ((stt[0][i] | stt[1][i]) & 2) != 0; }
         /* a mate with more than MAX_N_PERSEQ ambiguous bases is not aligned (alnpe.c:491); it can still be rescued */
         int any_skip = 0;
         for (uint32_t i = 0; i < n; ++i) any_skip |= rd[i & 1]->fq.n_ambiguous[i >> 1] > MAX_N_PERSEQ_PE;
@@ -833,9 +842,9 @@ int main(int argc, char **argv)
 {
     opts_t o;
     memset(&o, 0, sizeof o);
-    o.n_threads = 1; o.l_overlap = -1; o.min_tlen = 250; o.max_tlen = 550; o.max_seed = 50; o.max_locate = 1000; o.batch = N_SEQS;   /* opt_init, aln.c:28-57 */
+    o.n_threads = 1; o.l_overlap = -1; o.min_tlen = 250; o.max_tlen = 550; o.max_seed = 50; o.max_locate = 1000; o.batch = N_SEQS; o.list_cap = PE_LIST_CAP;   /* opt_init, aln.c:28-57 */
     int c;
-    while ((c = getopt(argc, argv, "t:n:hpa:b:g:es:m:l:cdvr:M:O:E:X:D:B:")) >= 0) {
+    while ((c = getopt(argc, argv, "t:n:hpa:b:g:es:m:l:cdvr:M:O:E:X:D:B:L:")) >= 0) {
         switch (c) {
         case 't': o.n_threads = atoi(optarg); break;
         case 'p': o.paired = 1; break;
@@ -850,6 +859,7 @@ int main(int argc, char **argv)
         case 'r': o.l_overlap = atoi(optarg); break;
         case 'D': o.device = atoi(optarg); break;
         case 'B': o.batch = (uint32_t)atoi(optarg); break;                       /* reads per batch (tests) */
+        case 'L': o.list_cap = atoi(optarg); break;                              /* paired-end: first list room on the device (tests) */
         case 'n': case 'l': case 'e': case 'M': case 'O': case 'E': case 'X': break;
         default: return usage();
         }
@@ -858,6 +868,8 @@ int main(int argc, char **argv)
     o.prefix = argv[optind]; o.fn[0] = argv[optind + 1]; o.fn[1] = o.paired ? argv[optind + 2] : NULL;
     if (o.n_threads < 1) o.n_threads = 1;
     if (o.batch < 2) o.batch = 2;
+    if (o.list_cap < 64) o.list_cap = 64;
+    if (o.list_cap > 16384) o.list_cap = 16384;
     if (o.paired && o.max_tlen == 0) { fprintf(stderr, "infer isize func haven't been implemented\n"); return 1; }          /* alnpe.c:583 */
     salt_host_set_threads(o.n_threads);
     unpack_init();
@@ -893,7 +905,9 @@ int main(int argc, char **argv)
     fprintf(stderr, "[salt_aln] MD/NM/XV tags from the GPU: %zu, XA CIGARs from the GPU: %zu\n", st.md_tags, st.xa_cigars);
     if (o.paired)
         fprintf(stderr, "[salt_aln] pairs %zu: proper without rescue %zu, rescue windows %zu SNP-aware + %zu plain, mates rescued %zu, alternates promoted %zu, "
-                        "windows declined %zu, mates with an SNP-context interval wider than -m (left out, the reference draws at random) %zu\n",
-                st.pe.pairs, st.pe.proper, st.pe.windows16, st.pe.windows5, st.pe.rescued, st.pe.promoted, st.pe.declined, st.flagged);
+                        "windows declined %zu, mates with an SNP-context interval wider than -m (left out, the reference draws at random) %zu, "
+                        "batches located again with more list room %zu, mates with a list cut at 16384 loci %zu\n",
+                st.pe.pairs, st.pe.proper, st.pe.windows16, st.pe.windows5, st.pe.rescued, st.pe.promoted, st.pe.declined, st.flagged,
+                st.relocated, st.cut);
     return 0;
 }

@@ -155,12 +155,12 @@ def _many_n(path, every, n_bases):
     open(path, "w").write("\n".join(lines))
 
 
-def _aln_case(d, exe, paired, flags, threads, batch, env=None):
+def _aln_case(d, exe, paired, flags, threads, batch, env=None, extra=()):
     run = lambda cmd, out: subprocess.run(cmd, cwd=d, stdout=open(os.path.join(d, out), "w"), stderr=subprocess.PIPE, check=True,
                                           env=dict(os.environ, **env) if env else None)
     files = ["r1.fq", "r2.fq"] if paired else ["reads.fq"]
     run([os.path.join(REFDIR, "salt")] + flags + ["-t", "2", "idx"] + files, "ref.sam")
-    p = subprocess.run([exe] + flags + ["-t", str(threads)] + (["-B", str(batch)] if batch else []) + ["idx"] + files, cwd=d,
+    p = subprocess.run([exe] + flags + list(extra) + ["-t", str(threads)] + (["-B", str(batch)] if batch else []) + ["idx"] + files, cwd=d,
                        stdout=open(os.path.join(d, "mine.sam"), "w"), stderr=subprocess.PIPE, text=True)
     assert p.returncode == 0, p.stderr[-1500:]
     want, got = _sam_lines(os.path.join(d, "ref.sam")), _sam_lines(os.path.join(d, "mine.sam"))
@@ -192,7 +192,9 @@ def test_salt_aln_program_on_the_emulator(tmp_path):
     f = [ln.split(b"\t") for ln in want if ln and not ln.startswith(b"@")]
     assert len(f) == 100 and sum(1 for x in f if int(x[1]) & 2) >= 60 and sum(1 for x in f if b"S" in x[5]) >= 3
     assert "pairs 50:" in err and "windows declined 0" in err
-    _aln_case(d, exe, True, ["-p", "-l", "100", "-a", "350", "-b", "650", "-g", "grp7"], 2, 0)
+    # candidate lists longer than the room they are first given on the device (-L 64): the batch is located again with more
+    want, err = _aln_case(d, exe, True, ["-p", "-l", "100", "-a", "350", "-b", "650", "-g", "grp7", "-r", "2"], 2, 0, extra=["-L", "64"])
+    assert "located again with more list room 1," in err and "cut at 16384 loci 0" in err
 
 
 @pytest.mark.gpu
