@@ -44,7 +44,7 @@ def write_fastq(path, reads, prefix):
 def timed(cmd, cwd, out, env=None):
     t0 = time.time()
     with open(out, "w") as f:
-        p = subprocess.run(cmd, cwd=cwd, stdout=f, stderr=subprocess.PIPE, text=True, env=env)
+        p = subprocess.run(cmd, cwd=cwd, stdout=f, stderr=subprocess.PIPE, text=True, env=env, timeout=600)
     if p.returncode != 0:
         raise RuntimeError(p.stderr[-1500:])
     return time.time() - t0, p.stderr
