@@ -273,3 +273,41 @@ def test_salt_aln_ragged_inputs_on_the_emulator(tmp_path):
     write("r1.fq", reads(16, lens), "/1"); write("r2.fq", reads(16, lens), "/2")
     want, err = _aln_case(d, exe, True, ["-p", "-d", "-c", "-a", "100", "-b", "5000", "-r", "9"], 3, 0)
     assert "pairs 16:" in err
+
+
+def test_salt_aln_error_paths_on_the_emulator(tmp_path):
+    """what the program does with input it cannot use: a message and a non-zero exit code, never a partial SAM passed off as whole"""
+    if not os.path.exists(os.path.join(REFDIR, "salt-idx")):
+        pytest.skip("oracle/_ref programs not built (reference tree absent at build time)")
+    import build_emul
+    from salt_b200 import build as b
+    exe = b.build_aln(engine=build_emul.build(), hostlib=build_emul.build_host())
+    d = str(tmp_path)
+    run = lambda args: subprocess.run([exe] + args, cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    p = run([])
+    assert p.returncode == 1 and "Usage: salt_aln" in p.stderr
+    p = run(["-p", "idx", "only_one.fq"])
+    assert p.returncode == 1 and "Usage: salt_aln" in p.stderr
+    open(os.path.join(d, "reads.fq"), "w").write("@r0\nACGTACGTACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIII\n")
+    p = run(["nothing_here", "reads.fq"])
+    assert p.returncode == 1 and "cannot open nothing_here.C.bwt" in p.stderr and p.stdout == ""
+    dropin_data.write_pe_inputs(d, glen=12000, n_pairs=6, seed=3)
+    subprocess.run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], cwd=d, stdout=open(os.path.join(d, "idx.log"), "w"),
+                   stderr=subprocess.PIPE, check=True)
+    p = run(["idx", "no_such_reads.fq"])
+    assert p.returncode == 1 and "cannot open no_such_reads.fq" in p.stderr
+    open(os.path.join(d, "broken.fq"), "w").write("@r0\nACGTACGTACGTACGTACGTACGTACGT\n+\nIIII")            # quality shorter than the sequence
+    p = run(["idx", "broken.fq"])
+    assert p.returncode == 1 and "malformed FASTQ" in p.stderr
+    open(os.path.join(d, "empty.fq"), "w").write("")
+    p = run(["idx", "empty.fq"])
+    assert p.returncode == 0 and "0 reads" in p.stderr
+    assert [ln[:3] for ln in p.stdout.split("\n") if ln] == ["@HD", "@SQ", "@SQ", "@RG", "@PG"]
+    # the second file two records short: the complete pairs are aligned, the surplus is reported, not silently dropped
+    lines = open(os.path.join(d, "r2.fq")).read().split("\n")
+    open(os.path.join(d, "r2_short.fq"), "w").write("\n".join(lines[:16]) + "\n")
+    p = run(["-p", "-a", "350", "-b", "650", "idx", "r1.fq", "r2_short.fq"])
+    assert p.returncode == 0 and "different numbers of records" in p.stderr and "pairs 4:" in p.stderr
+    assert sum(1 for ln in p.stdout.split("\n") if ln and not ln.startswith("@")) == 8
+    p = run(["-p", "-b", "0", "idx", "r1.fq", "r2.fq"])                  # alnpe.c:583
+    assert p.returncode == 1 and "infer isize" in p.stderr
