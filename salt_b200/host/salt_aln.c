@@ -913,6 +913,10 @@ int main(int argc, char **argv)
                         "batches located again with more list room %zu, mates with a list cut at 16384 loci %zu\n",
                 st.pe.pairs, st.pe.proper, st.pe.windows16, st.pe.windows5, st.pe.rescued, st.pe.promoted, st.pe.declined, st.flagged,
                 st.relocated, st.cut);
+    if (o.paired && (st.pe.declined || st.cut || st.flagged))
+        fprintf(stderr, "[salt_aln] WARNING: %zu rescue windows beyond what the engine serves (traceback band over 512), %zu candidate lists cut, %zu "
+                        "intervals the reference samples at random: the mates concerned may be placed differently from the reference program's output\n",
+                st.pe.declined, st.cut, st.flagged);
     if (teardown) return 0;
     /* Everything is written.  The process ends here without freeing the device and pinned allocations one by one and without
        the CUDA runtime's exit handlers: the driver reclaims all of it with the process, in a fraction of the time. */
