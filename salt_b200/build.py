@@ -80,7 +80,7 @@ def build_aln(force=False, engine=OUT, hostlib=HOST_OUT):
         dh, fh = os.path.split(hostlib)
         subprocess.check_call([os.environ.get("CC", "gcc"), "-O2", "-std=gnu11", "-Wall", "-Wextra", "-I" + os.path.join(HERE, "..", "include"),
                                "-o", out, src, "-L" + dh, "-l:" + fh, "-L" + d, "-l:" + f, "-Wl,-rpath," + d, "-Wl,-rpath," + dh,
-                               "-Wl,-rpath,$ORIGIN", "-lpthread"])
+                               "-Wl,-rpath,$ORIGIN", "-lpthread", "-lz"])
     return out
 
 

@@ -2,7 +2,7 @@
  * salt_aln.c -- the aligner as a program of its own, built from this repository's libraries only (libsalt_host.so over
  * libsalt_b200.so): no reference code in the loop.
  *
- *     salt_aln [-p] [-a N] [-b N] [-r N] [-m N] [-s N] [-c] [-d] [-v] [-g RG] [-t N] PREFIX reads.fq [mates.fq] > out.sam
+ *     salt_aln [-p] [-a N] [-b N] [-r N] [-m N] [-s N] [-c] [-d] [-v] [-g RG] [-t N] PREFIX reads.fq[.gz] [mates.fq[.gz]] > out.sam
  *
  * The counterpart of the reference's `salt` (opt_parse, aln.c:138-226; alnse_core, alnse.c:1353-1480; alnpe_core,
  * alnpe.c:530-660) on an index written by its salt-idx, with the same options and the same SAM (except the @PG line):
@@ -29,6 +29,7 @@
 #include <string.h>
 #include <time.h>
 #include <unistd.h>
+#include <zlib.h>
 #include <pthread.h>
 #include "salt_host.h"
 
@@ -181,7 +182,7 @@ static void load_index(const char *prefix, index_files_t *ix)
 
 /* ---- FASTQ input: blocks of text through salt_fastq_pack ------------------------------------------------------------------ */
 typedef struct {
-    FILE *f; int eof;
+    gzFile f; int eof;                            /* plain or gzip-compressed text, as the reference's reader takes it (query.c:112) */
     char *text; size_t cap, len, used;            /* text[used, len) has not been parsed yet */
     salt_fastq_t fq;                              /* arrays for up to max_reads records */
     uint32_t max_reads;
@@ -195,7 +196,7 @@ static void reader_alloc(reader_t *r, size_t cap)
     q->bases_cap = cap; q->bases = (uint8_t *)xrealloc(q->bases, cap / 4 + 16);
     q->n_pos_cap = cap / 4 + 1024; q->n_pos = (uint32_t *)xrealloc(q->n_pos, q->n_pos_cap * 4);
 }
-static void reader_init(reader_t *r, FILE *f, uint32_t max_reads)
+static void reader_init(reader_t *r, gzFile f, uint32_t max_reads)
 {
     memset(r, 0, sizeof *r);
     r->f = f;
@@ -215,9 +216,11 @@ static uint32_t reader_next(reader_t *r, uint32_t want)
     for (;;) {
         if (r->used) { memmove(r->text, r->text + r->used, r->len - r->used); r->len -= r->used; r->used = 0; }
         while (!r->eof && r->len < r->cap) {
-            const size_t got = fread(r->text + r->len, 1, r->cap - r->len, r->f);
+            const size_t room = r->cap - r->len;
+            const int got = gzread(r->f, r->text + r->len, (unsigned)(room < ((size_t)1 << 30) ? room : ((size_t)1 << 30)));
+            if (got < 0) { int e = 0; fprintf(stderr, "[salt_aln] read error: %s\n", gzerror(r->f, &e)); exit(1); }
             if (got == 0) r->eof = 1;
-            r->len += got;
+            r->len += (size_t)got;
         }
         size_t consumed = 0;
         const int n = salt_fastq_pack(r->text, r->len, r->eof, want, &r->fq, &consumed);
@@ -289,8 +292,9 @@ static void stream_kick(stream_t *s, uint32_t want)
 static void stream_open(stream_t *s, const char *fn, uint32_t max_reads)
 {
     memset(s, 0, sizeof *s);
-    FILE *f = strcmp(fn, "-") ? fopen(fn, "rb") : stdin;
+    gzFile f = strcmp(fn, "-") ? gzopen(fn, "rb") : gzdopen(0, "rb");
     if (!f) { fprintf(stderr, "[salt_aln] cannot open %s: %s\n", fn, strerror(errno)); exit(1); }
+    gzbuffer(f, 1u << 20);
     reader_init(&s->fr[0], f, max_reads); reader_init(&s->fr[1], f, max_reads);
     pthread_mutex_init(&s->mu, NULL); pthread_cond_init(&s->cv, NULL);
     if (pthread_create(&s->th, NULL, stream_main, s) != 0) { fprintf(stderr, "[salt_aln] cannot start the reader thread\n"); exit(1); }

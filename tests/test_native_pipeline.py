@@ -155,10 +155,10 @@ def _many_n(path, every, n_bases):
     open(path, "w").write("\n".join(lines))
 
 
-def _aln_case(d, exe, paired, flags, threads, batch, env=None, extra=()):
+def _aln_case(d, exe, paired, flags, threads, batch, env=None, extra=(), files=None):
     run = lambda cmd, out: subprocess.run(cmd, cwd=d, stdout=open(os.path.join(d, out), "w"), stderr=subprocess.PIPE, check=True,
                                           env=dict(os.environ, **env) if env else None)
-    files = ["r1.fq", "r2.fq"] if paired else ["reads.fq"]
+    files = files or (["r1.fq", "r2.fq"] if paired else ["reads.fq"])
     run([os.path.join(REFDIR, "salt")] + flags + ["-t", "2", "idx"] + files, "ref.sam")
     p = subprocess.run([exe] + flags + list(extra) + ["-t", str(threads)] + (["-B", str(batch)] if batch else []) + ["idx"] + files, cwd=d,
                        stdout=open(os.path.join(d, "mine.sam"), "w"), stderr=subprocess.PIPE, text=True)
@@ -185,7 +185,9 @@ def test_salt_aln_program_on_the_emulator(tmp_path):
     want, err = _aln_case(d, exe, False, ["-d", "-r", "1", "-l", "100", "-n", "20", "-c", "-m", "500"], 3, 48)
     assert sum(b"\tXA:Z:" in ln for ln in want) >= 40 and sum(b"\tMD:Z:" in ln for ln in want) >= 50
     assert "100 reads" in err
-    _aln_case(d, exe, False, ["-l", "100", "-g", "grp7"], 1, 0)
+    import gzip
+    open(os.path.join(d, "reads.fq.gz"), "wb").write(gzip.compress(open(os.path.join(d, "reads.fq"), "rb").read()))
+    _aln_case(d, exe, False, ["-l", "100", "-g", "grp7"], 1, 0, files=["reads.fq.gz"])          # gzip input, as the reference's reader takes it
     dropin_data.write_pe_inputs(d, glen=12000, n_pairs=50, seed=31, two_copies=True)
     _many_n(os.path.join(d, "r2.fq"), 7, 8)
     want, err = _aln_case(d, exe, True, ["-d", "-p", "-e", "-l", "100", "-c", "-a", "350", "-b", "650", "-r", "5"], 3, 40)
