@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--seed-genome", type=int, default=10_000_000, help="genome of the seeding leg (its index is built by salt-idx)")
     ap.add_argument("--program-reads", type=int, default=400_000,
                     help="reads of the whole-program leg: salt_b200/salt_aln against the reference program, SAM compared (0 = skip)")
+    ap.add_argument("--program-genome", type=int, default=5_000_000, help="genome of the whole-program leg (its index is built by salt-idx)")
     return ap.parse_args()
 
 
@@ -841,7 +842,7 @@ def bench_program(args):
         import aln_speed
         if not aln_speed.have_programs():
             return {"unavailable": "oracle/_ref/salt, salt-idx or salt_b200/salt_aln not built"}
-        return aln_speed.run(5_000_000, args.program_reads, args.program_reads // 4, os.cpu_count() or 1, None, hold_context=False)
+        return aln_speed.run(args.program_genome, args.program_reads, args.program_reads // 4, os.cpu_count() or 1, None, hold_context=False)
     except Exception as ex:                                # noqa: BLE001 -- an extra, never the headline
         return {"error": repr(ex)}
 
