@@ -839,7 +839,7 @@ static int usage(void)
 {
     fprintf(stderr, "Usage: salt_aln [-p] [-a min_tlen] [-b max_tlen] [-r seed_step] [-m max_locate] [-s max_seed] [-c] [-d] [-v]\n"
                     "                [-g read_group] [-t threads] [-D device] <index prefix> <reads.fq> [mates.fq]\n"
-                    "       (the options of the reference's `salt`, aln.c:138-226; -n -l -e -M -O -E -X are accepted and, as there, unused)\n");
+                    "       (the options of the reference's `salt`, aln.c:138-226; -n -l -e -M -O -E are accepted and, as there, unused; -X 1 is refused)\n");
     return 1;
 }
 
@@ -865,7 +865,14 @@ int main(int argc, char **argv)
         case 'D': o.device = atoi(optarg); break;
         case 'B': o.batch = (uint32_t)atoi(optarg); break;                       /* reads per batch (tests) */
         case 'L': o.list_cap = atoi(optarg); break;                              /* paired-end: first list room on the device (tests) */
-        case 'n': case 'l': case 'e': case 'M': case 'O': case 'E': case 'X': break;
+        case 'X':
+            if (atoi(optarg) != 0) {              /* EXTEND_SW (aln.h:29): alnse_overlap_sw, alnse.c:1338 */
+                fprintf(stderr, "[salt_aln] -X %s: the Smith-Waterman extension of single-end reads is not served -- the reference itself aborts on "
+                                "that path (LandauVishkin.c:183)\n", optarg);
+                return 1;
+            }
+            break;
+        case 'n': case 'l': case 'e': case 'M': case 'O': case 'E': break;
         default: return usage();
         }
     }

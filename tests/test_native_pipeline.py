@@ -290,6 +290,8 @@ def test_salt_aln_error_paths_on_the_emulator(tmp_path):
     assert p.returncode == 1 and "Usage: salt_aln" in p.stderr
     p = run(["-p", "idx", "only_one.fq"])
     assert p.returncode == 1 and "Usage: salt_aln" in p.stderr
+    p = run(["-X", "1", "idx", "reads.fq"])                             # row H: the reference aborts on that path
+    assert p.returncode == 1 and "not served" in p.stderr
     open(os.path.join(d, "reads.fq"), "w").write("@r0\nACGTACGTACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIII\n")
     p = run(["nothing_here", "reads.fq"])
     assert p.returncode == 1 and "cannot open nothing_here.C.bwt" in p.stderr and p.stdout == ""
