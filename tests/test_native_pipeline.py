@@ -315,3 +315,30 @@ def test_salt_aln_error_paths_on_the_emulator(tmp_path):
     assert sum(1 for ln in p.stdout.split("\n") if ln and not ln.startswith("@")) == 8
     p = run(["-p", "-b", "0", "idx", "r1.fq", "r2.fq"])                  # alnpe.c:583
     assert p.returncode == 1 and "infer isize" in p.stderr
+
+
+def test_salt_aln_skips_reads_with_too_many_n_on_the_emulator(tmp_path):
+    """single-end reads with more than 200 ambiguous bases are not aligned and leave an empty line (alnse.c:1281, :1296); the others
+    of the batch are compacted around them"""
+    if not all(os.path.exists(os.path.join(REFDIR, f)) for f in ("salt", "salt-idx")):
+        pytest.skip("oracle/_ref programs not built (reference tree absent at build time)")
+    import build_emul
+    from salt_b200 import build as b, synth
+    exe = b.build_aln(engine=build_emul.build(), hostlib=build_emul.build_host())
+    d = str(tmp_path)
+    glen = 20000
+    dropin_data.write_inputs(d, glen=glen, n_reads=10, seed=8)
+    codes = (synth.Genome(glen, snp_rate=0.01, n_rate=0.0, seed=8).codes & 3).astype(np.uint8)
+    rng = np.random.default_rng(1)
+    with open(os.path.join(d, "reads.fq"), "w") as f:
+        for i in range(8):
+            L = 250; p = int(rng.integers(0, glen - L - 5)); s = "".join("ACGT"[c] for c in codes[p:p + L])
+            if i in (2, 7):
+                s = s[:20] + "N" * (201 + i) + s[221 + i:]
+            if i == 5:
+                s = s[:20] + "N" * 200 + s[220:]                  # exactly the limit: still aligned
+            f.write("@r%d\n%s\n+\n%s\n" % (i, s, "I" * L))
+    subprocess.run([os.path.join(REFDIR, "salt-idx"), "-k", "19", "ref.fa", "snps.txt", "idx"], cwd=d, stdout=open(os.path.join(d, "idx.log"), "w"),
+                   stderr=subprocess.PIPE, check=True)
+    want, err = _aln_case(d, exe, False, ["-c", "-l", "250"], 2, 5)
+    assert sum(1 for ln in want[4:-1] if ln == b"") == 2 and "8 reads" in err
