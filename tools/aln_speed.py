@@ -56,6 +56,18 @@ def same_sam(a, b):
     return len(x) == 4 and x[0] == x[2]
 
 
+def steady_state(n_reads, phases):
+    """reads/s over the per-read phases of salt_aln's own breakdown (everything but start-up: index files, GPU init + uploads)"""
+    import re
+    try:
+        ln = [x for x in phases if " reads in " in x][0]
+        keys = ("FASTQ -> codes", "seeding \\+ locate \\+ verification", "hit selection", "tags \\+ XA CIGARs", "SAM text", "waiting for the writer thread")
+        t = sum(float(re.search(k + r" (\d+\.\d+)", ln).group(1)) for k in keys)
+        return round(n_reads / t) if t > 0 else None
+    except Exception:                                         # noqa: BLE001
+        return None
+
+
 def main():
     res = run(int(os.environ.get("GENOME", "5000000")), int(os.environ.get("READS", "400000")), int(os.environ.get("PAIRS", "100000")),
               int(os.environ.get("THREADS", str(os.cpu_count() or 1))), os.environ.get("OUT"), os.environ.get("HOLD_CONTEXT", "1") != "0")
@@ -111,6 +123,7 @@ def run(glen, n, npairs, threads, out_path=None, hold_context=True):
                 row["speedup"] = round(t_ref / best[0], 2)
                 row["sam_identical"] = same_sam(os.path.join(d, "ref.sam"), os.path.join(d, "mine.sam"))
                 row["salt_aln_phases"] = [ln for ln in best[1].split("\n") if ln.startswith("[salt_aln]")]
+                row["salt_aln_steady_state_reads_per_s"] = steady_state(n, row["salt_aln_phases"])
             except Exception as ex:                           # noqa: BLE001
                 row["error"] = str(ex)[-600:]
             res["se"].append(row); flush()
@@ -128,6 +141,7 @@ def run(glen, n, npairs, threads, out_path=None, hold_context=True):
                 row["speedup"] = round(t_ref / t_mine, 2)
                 row["sam_identical"] = same_sam(os.path.join(d, "ref.sam"), os.path.join(d, "mine.sam"))
                 row["salt_aln_phases"] = [ln for ln in err.split("\n") if ln.startswith("[salt_aln]")]
+                row["salt_aln_steady_state_reads_per_s"] = steady_state(2 * npairs, row["salt_aln_phases"])
             except Exception as ex:                           # noqa: BLE001
                 row = {"error": str(ex)[-600:]}
             res["pe"] = [row]; flush()
