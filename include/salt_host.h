@@ -147,7 +147,9 @@ int salt_chunk_add_reads(salt_chunk_t *c, const uint8_t *codes, const uint32_t *
  * pairing_singleton as plans (salt_pair_plan), ONE salt_b200_ssw call per rescue flavour on the reads still resident
  * in the slot, salt_pair_apply, one salt_b200_lv_cigar call for gapped alternates that became primaries, and one
  * salt_b200_md_nm call for the MD / NM / XV tags of every mapped mate (with_tail != 0; needs the 2-bit pac).
- * out[i] = the two mates of pair i as alnpe_sam would print them; md / nm / xv of mate m of pair i are at row 2i+m. */
+ * out[i] = the two mates of pair i as alnpe_sam would print them; md / nm of mate m of pair i are at row 2i+m (tail_out[].n_xv counts
+ * the XV entries; the offsets themselves are not returned here: a caller that prints XV asks salt_b200_md_nm for the finals, as
+ * salt_aln does). */
 typedef struct {
     salt_mate_final_t mate[2];
     int paired;                      /* PAIRED_ALNED */
